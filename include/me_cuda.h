@@ -1,0 +1,168 @@
+/*
+ * me_cuda.h -- C ABI of libme_cuda.so: the B200 (sm_100a) motion-estimation path for the JM 12.4 H.264
+ * reference encoder `lencod`.  Plain C, plain pointers and sizes; no CUDA or torch types cross this boundary.
+ *
+ * What it replaces in the reference (paths relative to the reference tree, file:line):
+ *   - integer-pel fast full search      lencod/src/me_fullfast.c:491 (SetupFastFullPelSearch), :210 (SetupLargerBlocks),
+ *                                       :833 (FastFullPelBlockMotionSearch)
+ *   - quarter-pel plane generation      lencod/src/img_luma.c:45 (getSubImagesLuma), lencod/src/image.c:1601
+ *   - sub-pel refinement (SAD / SATD)   lencod/src/me_fullsearch.c:341 (SubPelBlockMotionSearch),
+ *                                       lencod/src/me_distortion.c:351,657,182,272
+ *   - bi-predictive search              lencod/src/me_fullsearch.c:164 (FullPelBlockMotionBiPred), :520 (SubPelBlockSearchBiPred),
+ *                                       lencod/src/me_distortion.c:482,824
+ *   - reference-plane addressing        lencod/src/refbuf.c:25,37 (FastLine4X / UMVLine4X)
+ *
+ * Two ways in:
+ *   (1) drop-in calls with the reference's own signatures (me_cuda_FastFullPelBlockMotionSearch, ...), one call per
+ *       block search, synchronous -- what the SearchMode dispatch of mv-search.c:741-748,790-826,958-1021 binds to;
+ *   (2) the frame-batch call me_cuda_frame_search(): every (macroblock, list, ref) search of a picture in one
+ *       launch sequence -- the throughput path bench.py measures.
+ * Both run the same device code.  There is no CPU fallback: every entry point fails (non-zero / error handler) when
+ * no CUDA device is usable.
+ *
+ * All calls must come from one host thread (the reference is single-threaded and non-reentrant).
+ */
+#ifndef ME_CUDA_H
+#define ME_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ME_CUDA_ABI_VERSION 1
+
+/* JM's pixel type in the FRExt build: `typedef unsigned short imgpel` (lencod/inc/global.h:50). */
+typedef unsigned short me_imgpel;
+
+/* Opaque handle of a reference picture whose 16 quarter-pel planes live in device memory (0 = invalid). */
+typedef int32_t me_ref_handle;
+
+#define ME_NUM_PARTITIONS 41   /* 1 + 2 + 2 + 4 + 8 + 8 + 16 blocks of types 1..7 (SetupLargerBlocks, me_fullfast.c:210-273) */
+#define ME_IMG_PAD 20          /* IMG_PAD_SIZE, lencod/inc/defines.h:107 */
+
+/* Slice types as in lencod/inc/global.h (P_SLICE = 0, B_SLICE = 1). */
+#define ME_P_SLICE 0
+#define ME_B_SLICE 1
+
+/* Encoder-wide parameters, read once (mirrors what Init_Motion_Search_Module, mv-search.c:290-433, and
+ * InitializeFastFullIntegerSearch, me_fullfast.c:71-141, take from `input` and `img`). */
+typedef struct me_cuda_params {
+  int32_t abi_version;          /* ME_CUDA_ABI_VERSION */
+  int32_t width, height;        /* coded luma size (img->width, img->height): multiples of 16 */
+  int32_t bit_depth;            /* must be 8 (img->max_imgpel_value == 255) */
+  int32_t search_range;         /* input->search_range */
+  int32_t max_num_references;   /* img->max_num_references */
+  int32_t rdopt;                /* input->rdopt */
+  int32_t full_search;          /* input->full_search (cfg RestrictSearchRange): 2 = same range for every reference */
+  int32_t me_metric[3];         /* input->MEErrorMetric[F_PEL,H_PEL,Q_PEL]: 0 SAD, 1 SSE, 2 Hadamard SAD */
+  int32_t transform8x8;         /* input->Transform8x8Mode != 0 */
+  int32_t mv_limit_min_y;       /* LEVELMVLIMIT[img->LevelIndex][0], mv-search.h:36 */
+  int32_t mv_limit_max_y;       /* LEVELMVLIMIT[img->LevelIndex][1] */
+  int32_t chroma_me_enable;     /* input->ChromaMEEnable: must be 0 (chroma ME not implemented) */
+  int32_t weighted_me;          /* weighted-prediction ME active: must be 0 */
+  int32_t device;               /* CUDA device ordinal; -1: env ME_CUDA_DEVICE, else 0 */
+  int32_t reserved[8];
+} me_cuda_params;
+
+/* error handling: the drop-in search calls return a cost like the reference functions do, so failures are reported
+ * through a handler (default: print to stderr and abort()).  A JM build installs error(text, code) (filehandle.c:38). */
+typedef void (*me_cuda_error_fn)(const char *text, int code);
+void        me_cuda_set_error_handler(me_cuda_error_fn fn);
+const char *me_cuda_last_error(void);
+
+/* ---- life cycle: Init_Motion_Search_Module (mv-search.c:431) / Clear_Motion_Search_Module (mv-search.c:461) ---- */
+int  me_cuda_init(const me_cuda_params *p);            /* 0 on success */
+void me_cuda_shutdown(void);
+
+/* ---- reference pictures: body of getSubImagesLuma (img_luma.c:45), called from UnifiedOneForthPix (image.c:1642) ----
+ * imgY_rows: h row pointers of w reconstructed luma samples (StorablePicture::imgY, mbuffer.h:52).
+ * host_sub : NULL, or JM's imgY_sub[4][4][h+40][w+40] (mbuffer.h:53) to be filled with the 16 planes, because
+ *            the encoder's motion compensation (macroblock.c:816) still reads them on the host. */
+int me_cuda_ref_create(const me_imgpel *const *imgY_rows, int w, int h, me_imgpel ****host_sub, me_ref_handle *out);
+/* same, from a contiguous 8-bit plane (bench / tests) */
+int me_cuda_ref_create_u8(const uint8_t *luma, int stride, int w, int h, me_ref_handle *out);
+/* free_storable_picture (mbuffer.c:556-600) */
+int me_cuda_ref_destroy(me_ref_handle h);
+/* copy one of the 16 planes back: dst[(h+40)][dst_stride], plane index as Pic[fy][fx] (refbuf.c:27) */
+int me_cuda_ref_download_plane(me_ref_handle h, int fy, int fx, uint8_t *dst, int dst_stride);
+
+/* ---- current picture: pCurImg after ReadOneFrame (image.c:409-421) ---- */
+int me_cuda_set_current(const me_imgpel *const *rows, int w, int h);
+int me_cuda_set_current_u8(const uint8_t *luma, int stride, int w, int h);
+
+/* ---- reference lists: mirror of listX[list + list_offset][0..n-1] (mbuffer.h:174) for the slice being coded ---- */
+int me_cuda_set_ref_list(int list, int n, const me_ref_handle *handles);
+/* img->type of the slice being coded (ME_P_SLICE / ME_B_SLICE); only the !rdopt zero-vector bonus depends on it */
+int me_cuda_set_slice_type(int slice_type);
+
+/* ---- per macroblock: ResetFastFullIntegerSearch (me_fullfast.c:197, called macroblock.c:509) ---- */
+int me_cuda_mb_begin(int opix_x, int opix_y);
+
+/* ---- per (list, ref) of the macroblock: SetupFastFullPelSearch (me_fullfast.c:491).  The caller supplies the 16x16
+ * motion-vector predictor (SetMotionVectorPredictor(..., 0, 0, 16, 16), me_fullfast.c:550) which stays host code. ---- */
+int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y);
+int me_cuda_ffs_is_set_up(int list, int ref);
+
+/* ---- drop-in block searches; arguments and return value as the reference functions, minus the unused orig_pic
+ * (the library reads the original block from the current picture).  mv in/out as in the reference. ---- */
+int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                         short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                         int search_range, int min_mcost, int lambda_factor);   /* me_fullfast.h:21 */
+int me_cuda_SubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                    short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                    int search_pos2, int search_pos4, int min_mcost,
+                                    const int *lambda_factor);                                  /* me_fullsearch.h:126 */
+int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                     short pred_mv_x1, short pred_mv_y1, short pred_mv_x2, short pred_mv_y2,
+                                     short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                     int search_range, int min_mcost, int lambda_factor);       /* me_fullsearch.h:122 */
+int me_cuda_SubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                    short pred_mv_x, short pred_mv_y,
+                                    short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                    int search_pos2, int search_pos4, int min_mcost,
+                                    const int *lambda_factor);                                  /* me_fullsearch.h:129 */
+
+/* ---- frame batch (no single reference call site: it is PartitionMotionSearch, mv-search.c:1378, for every
+ * macroblock x list x ref of a picture at once, with the predictors supplied by the caller) ----
+ * Partition order p = 0..40: type 1 {0}; type 2 {0,8}; type 3 {0,2}; type 4 {0,2,8,10}; type 5 {0,2,..,14};
+ * type 6 {0,1,2,3,8,9,10,11}; type 7 {0..15}; numbers are the top-left 4x4 block index 4*row+col inside the
+ * macroblock, i.e. BlockSAD[list][ref][type][index] of me_fullfast.c:855. */
+typedef struct me_mb_job {
+  int16_t opix_x, opix_y;               /* macroblock origin in the current picture (img->opix_x/y) */
+  int8_t  list, ref;                    /* reference = handle set by me_cuda_set_ref_list(list)[ref] */
+  int8_t  slice_type;                   /* ME_P_SLICE / ME_B_SLICE */
+  int8_t  reserved;
+  int16_t pmv16[2];                     /* 16x16 predictor -> search centre (me_fullfast.c:550-566) */
+  int16_t pmv[ME_NUM_PARTITIONS][2];    /* predictor of every partition, quarter-pel (x, y) */
+  int32_t lambda[3];                    /* lambda_factor[F_PEL,H_PEL,Q_PEL] (defines.h:125) */
+} me_mb_job;                            /* 188 bytes */
+
+typedef struct me_mb_result {
+  int16_t mv[ME_NUM_PARTITIONS][2];     /* final quarter-pel vector (what BlockMotionSearch writes to all_mv, mv-search.c:855) */
+  int32_t cost[ME_NUM_PARTITIONS];      /* min_mcost returned by BlockMotionSearch (mv-search.c:1042) */
+} me_mb_result;                         /* 328 bytes */
+
+typedef struct me_mb_result_int {       /* optional: the integer-pel stage on its own (mv in integer pels, as *mv_x of me_fullfast.c:900) */
+  int16_t mv[ME_NUM_PARTITIONS][2];
+  int32_t cost[ME_NUM_PARTITIONS];
+} me_mb_result_int;
+
+/* host buffers in, host buffers out; synchronous.  out_int may be NULL. */
+int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, me_mb_result_int *out_int);
+
+/* ---- device-resident variants for measurement (bench.py): pointers are CUDA device pointers, `stream` is a
+ * cudaStream_t passed as void* (NULL = the library's own stream).  Asynchronous. ---- */
+int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, void *d_out_int, void *stream);
+int me_cuda_ref_create_device(const void *d_luma_u8, int stride, int w, int h, void *stream, me_ref_handle *out);
+int me_cuda_set_current_device(const void *d_luma_u8, int stride, int w, int h, void *stream);
+void *me_cuda_stream(void);                 /* the library's stream (cudaStream_t) */
+int   me_cuda_sync(void);                   /* cudaStreamSynchronize on it */
+/* number of kernels this library has launched since init (bench.py reports it as gpu_launches) */
+int64_t me_cuda_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ME_CUDA_H */

@@ -1,0 +1,213 @@
+"""ctypes binding of oracle/liboracle_me.so -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+The product path (h.264_b200/, libme_cuda.so) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle_me.so")
+
+NUM_PART = 41
+PART_TYPE = [1, 2, 2, 3, 3, 4, 4, 4, 4] + [5] * 8 + [6] * 8 + [7] * 16
+PART_BLK = [0, 0, 8, 0, 2, 0, 2, 8, 10, 0, 2, 4, 6, 8, 10, 12, 14, 0, 1, 2, 3, 8, 9, 10, 11] + list(range(16))
+BLOCK_SIZE = {1: (16, 16), 2: (16, 8), 3: (8, 16), 4: (8, 8), 5: (8, 4), 6: (4, 8), 7: (4, 4)}
+INT_MAX = 2147483647
+
+
+def part_index(blocktype, blk):
+    """partition number p of (block type, top-left 4x4 block index)"""
+    for p in range(NUM_PART):
+        if PART_TYPE[p] == blocktype and PART_BLK[p] == blk:
+            return p
+    raise KeyError((blocktype, blk))
+
+
+class OraCfg(C.Structure):
+    _fields_ = [("search_range", C.c_int), ("rdopt", C.c_int), ("full_search", C.c_int),
+                ("metric", C.c_int * 3), ("transform8x8", C.c_int),
+                ("mv_limit_min_y", C.c_int), ("mv_limit_max_y", C.c_int)]
+
+
+class MbJob(C.Structure):
+    _pack_ = 1
+    _fields_ = [("opix_x", C.c_int16), ("opix_y", C.c_int16), ("list", C.c_int8), ("ref", C.c_int8),
+                ("slice_type", C.c_int8), ("reserved", C.c_int8), ("pmv16", C.c_int16 * 2),
+                ("pmv", (C.c_int16 * 2) * NUM_PART), ("lambda_", C.c_int32 * 3)]
+
+
+class MbResult(C.Structure):
+    _fields_ = [("mv", (C.c_int16 * 2) * NUM_PART), ("cost", C.c_int32 * NUM_PART)]
+
+
+# numpy views of the same layouts (used for bulk job arrays)
+JOB_DTYPE = np.dtype([("opix_x", "<i2"), ("opix_y", "<i2"), ("list", "i1"), ("ref", "i1"), ("slice_type", "i1"),
+                      ("reserved", "i1"), ("pmv16", "<i2", (2,)), ("pmv", "<i2", (NUM_PART, 2)),
+                      ("lambda", "<i4", (3,))])
+RESULT_DTYPE = np.dtype([("mv", "<i2", (NUM_PART, 2)), ("cost", "<i4", (NUM_PART,))])
+assert JOB_DTYPE.itemsize == 188 and C.sizeof(MbJob) == 188
+assert RESULT_DTYPE.itemsize == 328 and C.sizeof(MbResult) == 328
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "me_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        vp, ip, sp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_short)
+        L.ora_ref_create.restype = vp
+        L.ora_ref_create.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.ora_ref_destroy.argtypes = [vp]
+        L.ora_ref_plane.restype = vp
+        L.ora_ref_plane.argtypes = [vp, C.c_int, C.c_int]
+        L.ora_spiral.argtypes = [C.c_int, vp, vp]
+        L.ora_mvbits.argtypes = [C.c_int]
+        L.ora_mv_cost.argtypes = [C.c_int] * 5
+        L.ora_setup_range.argtypes = [C.POINTER(OraCfg), C.c_int]
+        L.ora_block_search_range.argtypes = [C.POINTER(OraCfg), C.c_int, C.c_int]
+        L.ora_search_centre.argtypes = [C.POINTER(OraCfg)] + [C.c_int] * 5 + [ip, ip]
+        L.ora_ffs_surfaces.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp] + [C.c_int] * 5 + [vp]
+        L.ora_ffs_block.argtypes = [C.POINTER(OraCfg), vp] + [C.c_int] * 10 + [sp, sp]
+        L.ora_sad_block.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int]
+        L.ora_satd_block.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int]
+        L.ora_hadamard4x4.argtypes = [vp]
+        L.ora_hadamard8x8.argtypes = [vp]
+        L.ora_subpel.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp] + [C.c_int] * 7 + [sp, sp, C.c_int, C.c_int, C.c_int, ip]
+        L.ora_bipred_fullpel.argtypes = ([C.POINTER(OraCfg), vp, C.c_int, vp, vp] + [C.c_int] * 7
+                                         + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int])
+        L.ora_bipred_subpel.argtypes = ([C.POINTER(OraCfg), vp, C.c_int, vp, vp] + [C.c_int] * 5
+                                        + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int, ip])
+        L.ora_mb_search.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def make_cfg(search_range=32, rdopt=1, full_search=2, metric=(0, 2, 2), transform8x8=0,
+             mv_limit_min_y=-511, mv_limit_max_y=511):
+    c = OraCfg()
+    c.search_range, c.rdopt, c.full_search = search_range, rdopt, full_search
+    c.metric[0], c.metric[1], c.metric[2] = metric
+    c.transform8x8 = transform8x8
+    c.mv_limit_min_y, c.mv_limit_max_y = mv_limit_min_y, mv_limit_max_y
+    return c
+
+
+def spiral(R):
+    n = (2 * R + 1) ** 2
+    sx = np.zeros(n, np.int16)
+    sy = np.zeros(n, np.int16)
+    lib().ora_spiral(R, sx.ctypes.data, sy.ctypes.data)
+    return sx, sy
+
+
+class Ref:
+    """16 quarter-pel planes of one reconstructed luma picture (uint8 HxW)."""
+
+    def __init__(self, luma):
+        luma = np.ascontiguousarray(luma, np.uint8)
+        self.h, self.w = luma.shape
+        self.hp, self.wp = self.h + 40, self.w + 40
+        self._luma = luma
+        self.ptr = lib().ora_ref_create(luma.ctypes.data, luma.strides[0], self.w, self.h)
+
+    def plane(self, fy, fx):
+        p = lib().ora_ref_plane(self.ptr, fy, fx)
+        buf = (C.c_uint8 * (self.hp * self.wp)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(self.hp, self.wp)
+
+    def planes(self):
+        return np.stack([np.stack([self.plane(fy, fx) for fx in range(4)]) for fy in range(4)])
+
+    def close(self):
+        if self.ptr:
+            lib().ora_ref_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _shorts(*vals):
+    return [C.c_short(v) for v in vals]
+
+
+def ffs_surfaces(cfg, cur, ref, opix_x, opix_y, cx, cy, rng):
+    P = (2 * rng + 1) ** 2
+    out = np.zeros((NUM_PART, P), np.int32)
+    lib().ora_ffs_surfaces(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr, opix_x, opix_y, cx, cy, rng,
+                           out.ctypes.data)
+    return out
+
+
+def ffs_block(cfg, surf_p, setup_range, opix_x, opix_y, cx, cy, pmv_x, pmv_y, search_range, min_mcost, lam):
+    mx, my = _shorts(0, 0)
+    surf_p = np.ascontiguousarray(surf_p, np.int32)
+    cost = lib().ora_ffs_block(C.byref(cfg), surf_p.ctypes.data, setup_range, opix_x, opix_y, cx, cy,
+                               pmv_x, pmv_y, search_range, min_mcost, lam, C.byref(mx), C.byref(my))
+    return mx.value, my.value, cost
+
+
+def search_centre(cfg, ref_idx, opix_x, opix_y, pmv16_x, pmv16_y):
+    cx, cy = C.c_int(0), C.c_int(0)
+    lib().ora_search_centre(C.byref(cfg), ref_idx, opix_x, opix_y, pmv16_x, pmv16_y, C.byref(cx), C.byref(cy))
+    return cx.value, cy.value
+
+
+def subpel(cfg, cur, ref, pic_pix_x, pic_pix_y, blocktype, ref_idx, slice_type, pmv_x, pmv_y, mv_x, mv_y,
+           min_mcost, lam, search_pos2=9, search_pos4=9):
+    mx, my = _shorts(mv_x, mv_y)
+    lam3 = (C.c_int * 3)(*lam)
+    cost = lib().ora_subpel(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr, pic_pix_x, pic_pix_y, blocktype,
+                            ref_idx, slice_type, pmv_x, pmv_y, C.byref(mx), C.byref(my), search_pos2, search_pos4,
+                            min_mcost, lam3)
+    return mx.value, my.value, cost
+
+
+def bipred_fullpel(cfg, cur, ref1, ref2, pic_pix_x, pic_pix_y, blocktype, pmv1, pmv2, mv, s_mv, search_range,
+                   min_mcost, lam):
+    mx, my, sx, sy = _shorts(mv[0], mv[1], s_mv[0], s_mv[1])
+    cost = lib().ora_bipred_fullpel(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref1.ptr, ref2.ptr,
+                                    pic_pix_x, pic_pix_y, blocktype, pmv1[0], pmv1[1], pmv2[0], pmv2[1],
+                                    C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy), search_range, min_mcost, lam)
+    return mx.value, my.value, cost
+
+
+def bipred_subpel(cfg, cur, ref1, ref2, pic_pix_x, pic_pix_y, blocktype, pmv, mv, s_mv, min_mcost, lam,
+                  search_pos2=9, search_pos4=9):
+    mx, my, sx, sy = _shorts(mv[0], mv[1], s_mv[0], s_mv[1])
+    lam3 = (C.c_int * 3)(*lam)
+    cost = lib().ora_bipred_subpel(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref1.ptr, ref2.ptr,
+                                   pic_pix_x, pic_pix_y, blocktype, pmv[0], pmv[1],
+                                   C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy), search_pos2, search_pos4,
+                                   min_mcost, lam3)
+    return mx.value, my.value, cost
+
+
+def mb_search(cfg, cur, ref, jobs):
+    """jobs: numpy array of JOB_DTYPE (all against the same reference picture).  Returns (final, integer-pel)."""
+    jobs = np.ascontiguousarray(jobs)
+    out = np.zeros(len(jobs), RESULT_DTYPE)
+    out_int = np.zeros(len(jobs), RESULT_DTYPE)
+    L = lib()
+    for i in range(len(jobs)):
+        L.ora_mb_search(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr,
+                        jobs.ctypes.data + i * JOB_DTYPE.itemsize,
+                        out.ctypes.data + i * RESULT_DTYPE.itemsize,
+                        out_int.ctypes.data + i * RESULT_DTYPE.itemsize)
+    return out, out_int

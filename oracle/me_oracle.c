@@ -1,0 +1,529 @@
+/*
+ * me_oracle.c -- TEST INFRASTRUCTURE (see me_oracle.h).  A straight, slow, scalar restatement of what the
+ * reference encoder computes on the motion-estimation hot path.  Written from the behaviour of the reference
+ * (citations = reference file:line that each function follows); no reference code is reused.
+ *
+ * Parity pin: tests/test_oracle_golden.py (committed fixtures made from reference traces) and
+ * tests/test_oracle_ref.py (live traces of oracle/_ref/lencod_trace when that binary is present).
+ */
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "me_oracle.h"
+
+#define PAD ME_IMG_PAD
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int iabs_(int v) { return v < 0 ? -v : v; }
+
+/* ------------------------------------------------------------------------------------------------ tables */
+
+/* partition p -> (block type, top-left 4x4 block index); order documented in include/me_cuda.h */
+const int8_t ora_part_type[ME_NUM_PARTITIONS] = {
+  1, 2, 2, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 6,
+  7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7 };
+const int8_t ora_part_blk[ME_NUM_PARTITIONS] = {
+  0, 0, 8, 0, 2, 0, 2, 8, 10, 0, 2, 4, 6, 8, 10, 12, 14, 0, 1, 2, 3, 8, 9, 10, 11,
+  0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15 };
+
+/* input->blc_size[type][0..1] (configfile.c:805-841) */
+void ora_block_size(int blocktype, int *bsx, int *bsy)
+{
+  static const int sx[8] = { 16, 16, 16, 8, 8, 8, 4, 4 };
+  static const int sy[8] = { 16, 16, 8, 16, 8, 4, 8, 4 };
+  *bsx = sx[blocktype];
+  *bsy = sy[blocktype];
+}
+
+int ora_num_positions(int range) { return (2 * range + 1) * (2 * range + 1); }
+
+/* spiral_search_x/y (mv-search.c:366-393): centre, then ring by ring; inside a ring first the top/bottom rows
+ * (without corners) left to right alternating top, bottom; then the left/right columns top to bottom. */
+void ora_spiral(int range, int16_t *sx, int16_t *sy)
+{
+  int k = 0, l, i;
+  sx[k] = 0; sy[k] = 0; k++;
+  for (l = 1; l <= (range > 1 ? range : 1); l++) {
+    for (i = -l + 1; i < l; i++) {
+      sx[k] = (int16_t)i;  sy[k] = (int16_t)-l; k++;
+      sx[k] = (int16_t)i;  sy[k] = (int16_t)l;  k++;
+    }
+    for (i = -l; i <= l; i++) {
+      sx[k] = (int16_t)-l; sy[k] = (int16_t)i;  k++;
+      sx[k] = (int16_t)l;  sy[k] = (int16_t)i;  k++;
+    }
+  }
+}
+
+/* mvbits[] (mv-search.c:333-341): length of the signed Exp-Golomb code of d */
+int ora_mvbits(int d)
+{
+  int a = iabs_(d), n = 0;
+  if (a == 0) return 1;
+  while (a >> (n + 1)) n++;          /* n = floor(log2 a) */
+  return 2 * n + 3;
+}
+
+/* MV_COST_SMP (defines.h:126-128): 32-bit int product, arithmetic shift */
+int ora_mv_cost(int f, int cx, int cy, int px, int py)
+{
+  return (f * (ora_mvbits(cx - px) + ora_mvbits(cy - py))) >> 16;
+}
+
+/* ------------------------------------------------------------------------------------------------ planes */
+
+ora_ref *ora_ref_create(const uint8_t *luma, int stride, int w, int h)
+{
+  ora_ref *r = (ora_ref *)calloc(1, sizeof *r);
+  int wp = w + 2 * PAD, hp = h + 2 * PAD, x, y, fy, fx;
+  int32_t *tmp = (int32_t *)malloc(sizeof(int32_t) * (size_t)wp * hp);
+  uint8_t *G, *b, *hh, *j;
+  r->w = w; r->h = h; r->wp = wp; r->hp = hp;
+  for (fy = 0; fy < 4; fy++)
+    for (fx = 0; fx < 4; fx++)
+      r->plane[fy][fx] = (uint8_t *)malloc((size_t)wp * hp);
+  G = r->plane[0][0]; b = r->plane[0][2]; hh = r->plane[2][0]; j = r->plane[2][2];
+
+#define AT(P, yy, xx) ((P)[(size_t)(yy) * wp + (xx)])
+#define CX(v) clampi((v), 0, wp - 1)
+#define CY(v) clampi((v), 0, hp - 1)
+  /* integer plane with replicated border (getSubImageInteger, img_luma.c:120-166) */
+  for (y = 0; y < hp; y++)
+    for (x = 0; x < wp; x++)
+      AT(G, y, x) = luma[(size_t)clampi(y - PAD, 0, h - 1) * stride + clampi(x - PAD, 0, w - 1)];
+  /* horizontal half-pel: taps (1,-5,20,20,-5,1) over the padded integer plane, columns clamped to the padded
+   * plane; the unrounded sum is kept for the centre position (getHorSubImageSixTap, img_luma.c:181-280) */
+  for (y = 0; y < hp; y++)
+    for (x = 0; x < wp; x++) {
+      int s = 20 * (AT(G, y, x) + AT(G, y, CX(x + 1))) - 5 * (AT(G, y, CX(x - 1)) + AT(G, y, CX(x + 2)))
+              + (AT(G, y, CX(x - 2)) + AT(G, y, CX(x + 3)));
+      AT(tmp, y, x) = s;
+      AT(b, y, x) = (uint8_t)clampi((s + 16) >> 5, 0, 255);
+    }
+  /* vertical half-pel (getVerSubImageSixTap, img_luma.c:293-380) */
+  for (y = 0; y < hp; y++)
+    for (x = 0; x < wp; x++) {
+      int s = 20 * (AT(G, y, x) + AT(G, CY(y + 1), x)) - 5 * (AT(G, CY(y - 1), x) + AT(G, CY(y + 2), x))
+              + (AT(G, CY(y - 2), x) + AT(G, CY(y + 3), x));
+      AT(hh, y, x) = (uint8_t)clampi((s + 16) >> 5, 0, 255);
+    }
+  /* centre half-pel from the unrounded horizontal sums (getVerSubImageSixTapTmp, img_luma.c:390-470) */
+  for (y = 0; y < hp; y++)
+    for (x = 0; x < wp; x++) {
+      int s = 20 * (AT(tmp, y, x) + AT(tmp, CY(y + 1), x)) - 5 * (AT(tmp, CY(y - 1), x) + AT(tmp, CY(y + 2), x))
+              + (AT(tmp, CY(y - 2), x) + AT(tmp, CY(y + 3), x));
+      AT(j, y, x) = (uint8_t)clampi((s + 512) >> 10, 0, 255);
+    }
+  /* quarter-pel positions: rounded averages of two neighbours (img_luma.c:483-639) */
+  for (y = 0; y < hp; y++)
+    for (x = 0; x < wp; x++) {
+      int x1 = CX(x + 1), y1 = CY(y + 1);
+      int g = AT(G, y, x), bb = AT(b, y, x), hv = AT(hh, y, x), jj = AT(j, y, x);
+      AT(r->plane[0][1], y, x) = (uint8_t)((g + bb + 1) >> 1);
+      AT(r->plane[1][0], y, x) = (uint8_t)((g + hv + 1) >> 1);
+      AT(r->plane[1][1], y, x) = (uint8_t)((bb + hv + 1) >> 1);
+      AT(r->plane[1][2], y, x) = (uint8_t)((bb + jj + 1) >> 1);
+      AT(r->plane[2][1], y, x) = (uint8_t)((hv + jj + 1) >> 1);
+      AT(r->plane[0][3], y, x) = (uint8_t)((bb + AT(G, y, x1) + 1) >> 1);
+      AT(r->plane[1][3], y, x) = (uint8_t)((bb + AT(hh, y, x1) + 1) >> 1);
+      AT(r->plane[2][3], y, x) = (uint8_t)((jj + AT(hh, y, x1) + 1) >> 1);
+      AT(r->plane[3][0], y, x) = (uint8_t)((hv + AT(G, y1, x) + 1) >> 1);
+      AT(r->plane[3][1], y, x) = (uint8_t)((hv + AT(b, y1, x) + 1) >> 1);
+      AT(r->plane[3][2], y, x) = (uint8_t)((jj + AT(b, y1, x) + 1) >> 1);
+      AT(r->plane[3][3], y, x) = (uint8_t)((AT(b, y1, x) + AT(hh, y, x1) + 1) >> 1);
+    }
+#undef AT
+#undef CX
+#undef CY
+  free(tmp);
+  return r;
+}
+
+void ora_ref_destroy(ora_ref *r)
+{
+  int fy, fx;
+  if (!r) return;
+  for (fy = 0; fy < 4; fy++)
+    for (fx = 0; fx < 4; fx++) free(r->plane[fy][fx]);
+  free(r);
+}
+
+const uint8_t *ora_ref_plane(const ora_ref *r, int fy, int fx) { return r->plane[fy][fx]; }
+
+/* UMVLine4X (refbuf.c:37-43) with size_x_pad = w + 2*20 - 1 - 16 (mbuffer.c:421-422).  FastLine4X (refbuf.c:25)
+ * yields the same pixels whenever the reference chooses it: it is only chosen where the clamp is a no-op or where
+ * both addresses lie in the edge-replicated region in which every plane is constant along the row / column. */
+const uint8_t *ora_umv_line(const ora_ref *r, int y4, int x4)
+{
+  int xp = clampi(x4 >> 2, 0, r->w + 2 * PAD - 1 - 16);
+  int yp = clampi(y4 >> 2, 0, r->h + 2 * PAD - 1 - 16);
+  return r->plane[y4 & 3][x4 & 3] + (size_t)yp * r->wp + xp;
+}
+
+/* ------------------------------------------------------------------------------------------------ integer pel */
+
+/* max_search_range[list][ref] (me_fullfast.c:127-140) */
+int ora_setup_range(const ora_cfg *c, int ref)
+{
+  return (c->full_search == 2 || ref == 0) ? c->search_range : c->search_range / 2;
+}
+
+/* mv-search.c:1411-1416 */
+int ora_block_search_range(const ora_cfg *c, int ref, int blocktype)
+{
+  int r1 = (ref < 1 ? ref : 1) + 1;
+  if (c->full_search == 2) return c->search_range;
+  if (c->full_search == 1) return c->search_range / r1;
+  return c->search_range / (r1 * (blocktype < 2 ? blocktype : 2));
+}
+
+/* search centre (me_fullfast.c:550-566): predictor / 4 with C truncation, clips, plus macroblock origin */
+void ora_search_centre(const ora_cfg *c, int ref, int opix_x, int opix_y, int pmv16_x, int pmv16_y,
+                       int *centre_x, int *centre_y)
+{
+  int r = ora_setup_range(c, ref);
+  int cx = pmv16_x / 4, cy = pmv16_y / 4;
+  if (!c->rdopt) { cx = clampi(cx, -r, r); cy = clampi(cy, -r, r); }
+  cx = clampi(cx, -2047 + r, 2047 - r);
+  cy = clampi(cy, c->mv_limit_min_y + r, c->mv_limit_max_y - r);
+  *centre_x = cx + opix_x;
+  *centre_y = cy + opix_y;
+}
+
+/* SetupFastFullPelSearch main loop (me_fullfast.c:619-774, unweighted luma branch) + SetupLargerBlocks (:210-273).
+ * dist_method is SAD for MEErrorMetric[0]==0 and squared error for anything else (me_fullfast.c:512). */
+void ora_ffs_surfaces(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                      int opix_x, int opix_y, int centre_x, int centre_y, int range, int32_t *surf)
+{
+  int P = ora_num_positions(range), pos, p, by, bx, y, x;
+  int16_t *sx = (int16_t *)malloc(sizeof(int16_t) * P), *sy = (int16_t *)malloc(sizeof(int16_t) * P);
+  int leaf[16];
+  ora_spiral(range, sx, sy);
+  for (pos = 0; pos < P; pos++) {
+    const uint8_t *rp = ora_umv_line(r, (centre_y + sy[pos] + PAD) << 2, (centre_x + sx[pos] + PAD) << 2);
+    memset(leaf, 0, sizeof leaf);
+    for (y = 0; y < 16; y++)
+      for (x = 0; x < 16; x++) {
+        int d = (int)rp[(size_t)y * r->wp + x] - (int)cur[(size_t)(opix_y + y) * cur_stride + opix_x + x];
+        leaf[(y >> 2) * 4 + (x >> 2)] += c->metric[0] ? d * d : iabs_(d);
+      }
+    for (p = 0; p < ME_NUM_PARTITIONS; p++) {
+      int bsx, bsy, s = 0, b = ora_part_blk[p];
+      ora_block_size(ora_part_type[p], &bsx, &bsy);
+      for (by = 0; by < bsy / 4; by++)
+        for (bx = 0; bx < bsx / 4; bx++) s += leaf[b + 4 * by + bx];
+      surf[(size_t)p * P + pos] = s;
+    }
+  }
+  free(sx); free(sy);
+}
+
+/* FastFullPelBlockMotionSearch (me_fullfast.c:833-903).  surf_p: the surface of this partition.
+ * Returns the minimum cost; mv_x, mv_y receive the integer-pel vector relative to the block. */
+int ora_ffs_block(const ora_cfg *c, const int32_t *surf_p, int setup_range, int opix_x, int opix_y,
+                  int centre_x, int centre_y, int pmv_x, int pmv_y, int search_range, int min_mcost,
+                  int lambda_factor, short *mv_x, short *mv_y)
+{
+  int Pset = ora_num_positions(setup_range);
+  int P = ora_num_positions(search_range);
+  int offx = centre_x - opix_x, offy = centre_y - opix_y, pos, best = 0;
+  int16_t *sx = (int16_t *)malloc(sizeof(int16_t) * Pset), *sy = (int16_t *)malloc(sizeof(int16_t) * Pset);
+  ora_spiral(setup_range, sx, sy);
+  if (P > Pset) P = Pset;            /* the reference would read past its arrays; no configuration does this */
+  if (!c->rdopt) {
+    /* the zero vector is scored first and keeps ties (me_fullfast.c:602-616, 867-876) */
+    for (pos = 0; pos < Pset; pos++)
+      if (sx[pos] == -offx && sy[pos] == -offy) break;
+    if (pos < Pset) {
+      int m = surf_p[pos] + ora_mv_cost(lambda_factor, 0, 0, pmv_x, pmv_y);
+      if (m < min_mcost) { min_mcost = m; best = pos; }
+    }
+  }
+  for (pos = 0; pos < P; pos++) {
+    if (surf_p[pos] < min_mcost) {
+      int m = surf_p[pos] + ora_mv_cost(lambda_factor, (offx + sx[pos]) << 2, (offy + sy[pos]) << 2, pmv_x, pmv_y);
+      if (m < min_mcost) { min_mcost = m; best = pos; }
+    }
+  }
+  *mv_x = (short)(offx + sx[best]);
+  *mv_y = (short)(offy + sy[best]);
+  free(sx); free(sy);
+  return min_mcost;
+}
+
+/* ------------------------------------------------------------------------------------------------ distortion */
+
+/* HadamardSAD4x4 (me_distortion.c:182-264): 2-D 4-point Hadamard, sum of magnitudes, (s+1)>>1.
+ * The order of the butterflies does not affect the sum of magnitudes, so a plain separable form is used. */
+int ora_hadamard4x4(const int *d)
+{
+  int t[16], i, s = 0;
+  for (i = 0; i < 4; i++) {                       /* rows */
+    int a = d[4 * i], b = d[4 * i + 1], c = d[4 * i + 2], e = d[4 * i + 3];
+    int p = a + e, q = b + c, u = a - e, v = b - c;
+    t[4 * i] = p + q; t[4 * i + 1] = p - q; t[4 * i + 2] = u + v; t[4 * i + 3] = u - v;
+  }
+  for (i = 0; i < 4; i++) {                       /* columns */
+    int a = t[i], b = t[4 + i], c = t[8 + i], e = t[12 + i];
+    int p = a + e, q = b + c, u = a - e, v = b - c;
+    s += iabs_(p + q) + iabs_(p - q) + iabs_(u + v) + iabs_(u - v);
+  }
+  return (s + 1) >> 1;
+}
+
+/* HadamardSAD8x8 (me_distortion.c:272-343): (sum of magnitudes + 2) >> 2 */
+int ora_hadamard8x8(const int *d)
+{
+  int m[64], i, k, s = 0, stage;
+  memcpy(m, d, sizeof m);
+  for (i = 0; i < 8; i++)                          /* rows: three butterfly stages */
+    for (stage = 4; stage >= 1; stage >>= 1)
+      for (k = 0; k < 8; k++)
+        if (!(k & stage)) {
+          int a = m[8 * i + k], b = m[8 * i + k + stage];
+          m[8 * i + k] = a + b; m[8 * i + k + stage] = a - b;
+        }
+  for (i = 0; i < 8; i++)                          /* columns */
+    for (stage = 4; stage >= 1; stage >>= 1)
+      for (k = 0; k < 8; k++)
+        if (!(k & stage)) {
+          int a = m[8 * k + i], b = m[8 * (k + stage) + i];
+          m[8 * k + i] = a + b; m[8 * (k + stage) + i] = a - b;
+        }
+  for (i = 0; i < 64; i++) s += iabs_(m[i]);
+  return (s + 2) >> 2;
+}
+
+/* computeSAD (me_distortion.c:351-405), luma only.  The reference's early exits return partial sums that the
+ * callers then discard (they are >= the running minimum), so the full sum is equivalent. */
+int ora_sad_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4)
+{
+  const uint8_t *rp = ora_umv_line(r, y4, x4);
+  int x, y, s = 0;
+  for (y = 0; y < bsy; y++)
+    for (x = 0; x < bsx; x++) s += iabs_((int)src[(size_t)y * src_stride + x] - (int)rp[(size_t)y * r->wp + x]);
+  return s;
+}
+
+static int sse_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4)
+{
+  const uint8_t *rp = ora_umv_line(r, y4, x4);
+  int x, y, s = 0;
+  for (y = 0; y < bsy; y++)
+    for (x = 0; x < bsx; x++) {
+      int d = (int)src[(size_t)y * src_stride + x] - (int)rp[(size_t)y * r->wp + x];
+      s += d * d;
+    }
+  return s;
+}
+
+/* computeSATD (me_distortion.c:657-726): the reference fetches every 4x4 (or 8x8) tile with its own get_line call,
+ * i.e. the origin clamp applies per tile. */
+int ora_satd_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4, int use8x8)
+{
+  int n = use8x8 ? 8 : 4, bx, by, x, y, s = 0, d[64];
+  for (by = 0; by < bsy; by += n)
+    for (bx = 0; bx < bsx; bx += n) {
+      const uint8_t *rp = ora_umv_line(r, y4 + (by << 2), x4 + (bx << 2));
+      for (y = 0; y < n; y++)
+        for (x = 0; x < n; x++)
+          d[y * n + x] = (int)src[(size_t)(by + y) * src_stride + bx + x] - (int)rp[(size_t)y * r->wp + x];
+      s += use8x8 ? ora_hadamard8x8(d) : ora_hadamard4x4(d);
+    }
+  return s;
+}
+
+static int unipred(const ora_cfg *c, int level, const uint8_t *src, int stride, int bsx, int bsy,
+                   const ora_ref *r, int x4, int y4, int use8x8)
+{
+  switch (c->metric[level]) {       /* computeUniPred[] set-up, mv-search.c:400-424 */
+    case 0:  return ora_sad_block(src, stride, bsx, bsy, r, x4, y4);
+    case 1:  return sse_block(src, stride, bsx, bsy, r, x4, y4);
+    default: return ora_satd_block(src, stride, bsx, bsy, r, x4, y4, use8x8);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ sub-pel */
+
+/* sub-pel patterns are spiral entries 0..8 (search range 1): (0,0) (0,-1) (0,1) (-1,-1) (1,-1) (-1,0) (1,0) (-1,1) (1,1) */
+static void first_spiral(int n, int16_t *sx, int16_t *sy)
+{
+  int16_t tx[9], ty[9];
+  int i;
+  ora_spiral(1, tx, ty);
+  for (i = 0; i < n && i < 9; i++) { sx[i] = tx[i]; sy[i] = ty[i]; }
+}
+
+/* start_me_refinement_hp/qp (mv-search.c:396-397) with ChromaMEEnable == 0 */
+static int start_hp(const ora_cfg *c) { return c->metric[0] != c->metric[1] ? 0 : 1; }
+static int start_qp(const ora_cfg *c) { return c->metric[1] != c->metric[2] ? 0 : 1; }
+
+/* SubPelBlockMotionSearch (me_fullsearch.c:341-511) */
+int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+               int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type,
+               int pmv_x, int pmv_y, short *mv_x, short *mv_y, int search_pos2, int search_pos4,
+               int min_mcost, const int *lambda)
+{
+  int bsx, bsy, pos, best, mcost, cx, cy;
+  int use8x8 = c->transform8x8 && blocktype <= 4;                 /* test8x8transform, mv-search.c:640 */
+  int check0 = (!c->rdopt && slice_type != ME_B_SLICE && ref == 0 && blocktype == 1 && *mv_x == 0 && *mv_y == 0);
+  int p4x = (pic_pix_x + PAD) << 2, p4y = (pic_pix_y + PAD) << 2;
+  int shp = start_hp(c), sqp = start_qp(c);
+  int max_pos2 = (!shp && search_pos2 < 1) ? 1 : search_pos2;
+  const uint8_t *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
+  int16_t sx[9], sy[9];
+  ora_block_size(blocktype, &bsx, &bsy);
+  first_spiral(9, sx, sy);
+
+  for (best = 0, pos = shp; pos < max_pos2; pos++) {              /* half-pel: spiral_hpel_search = 2 * spiral */
+    cx = *mv_x + 2 * sx[pos]; cy = *mv_y + 2 * sy[pos];
+    mcost = ora_mv_cost(lambda[1], cx, cy, pmv_x, pmv_y);
+    if (mcost >= min_mcost) continue;
+    mcost += unipred(c, 1, src, cur_stride, bsx, bsy, r, cx + p4x, cy + p4y, use8x8);
+    if (pos == 0 && check0) mcost -= (lambda[1] * 16) >> 16;      /* WEIGHTED_COST(lambda, 16), :439-442 */
+    if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
+  }
+  if (best) { *mv_x += 2 * sx[best]; *mv_y += 2 * sy[best]; }
+  if (!sqp) min_mcost = INT_MAX;
+
+  for (best = 0, pos = sqp; pos < search_pos4; pos++) {           /* quarter-pel */
+    cx = *mv_x + sx[pos]; cy = *mv_y + sy[pos];
+    mcost = ora_mv_cost(lambda[2], cx, cy, pmv_x, pmv_y);
+    if (mcost >= min_mcost) continue;
+    mcost += unipred(c, 2, src, cur_stride, bsx, bsy, r, cx + p4x, cy + p4y, use8x8);
+    if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
+  }
+  if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }
+  return min_mcost;
+}
+
+/* ------------------------------------------------------------------------------------------------ bi-pred */
+
+/* computeBiPredSAD1 / computeBiPredSATD1 (me_distortion.c:482-548, 824-899): prediction = (p1 + p2 + 1) >> 1.
+ * SAD fetches each picture once per block; SATD once per transform tile. */
+static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stride, int bsx, int bsy,
+                       const ora_ref *r1, int x41, int y41, const ora_ref *r2, int x42, int y42, int use8x8)
+{
+  int metric = c->metric[level], s = 0, x, y, bx, by, d[64];
+  if (metric == 0 || metric == 1) {
+    const uint8_t *a = ora_umv_line(r1, y41, x41), *b = ora_umv_line(r2, y42, x42);
+    for (y = 0; y < bsy; y++)
+      for (x = 0; x < bsx; x++) {
+        int e = (int)src[(size_t)y * stride + x] - (((int)a[(size_t)y * r1->wp + x] + (int)b[(size_t)y * r2->wp + x] + 1) >> 1);
+        s += metric ? e * e : iabs_(e);
+      }
+    return s;
+  } else {
+    int n = use8x8 ? 8 : 4;
+    for (by = 0; by < bsy; by += n)
+      for (bx = 0; bx < bsx; bx += n) {
+        const uint8_t *a = ora_umv_line(r1, y41 + (by << 2), x41 + (bx << 2));
+        const uint8_t *b = ora_umv_line(r2, y42 + (by << 2), x42 + (bx << 2));
+        for (y = 0; y < n; y++)
+          for (x = 0; x < n; x++)
+            d[y * n + x] = (int)src[(size_t)(by + y) * stride + bx + x]
+                           - (((int)a[(size_t)y * r1->wp + x] + (int)b[(size_t)y * r2->wp + x] + 1) >> 1);
+        s += use8x8 ? ora_hadamard8x8(d) : ora_hadamard4x4(d);
+      }
+    return s;
+  }
+}
+
+/* FullPelBlockMotionBiPred (me_fullsearch.c:164-332), unweighted.  r1 = listX[list][ref] read at the fixed vector
+ * (s_mv), r2 = listX[list^1][0] read at the candidate.  Vectors are integer pel.  Note the reference stores the
+ * centres in `short` (:196-199). */
+int ora_bipred_fullpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+                       int pic_pix_x, int pic_pix_y, int blocktype,
+                       int pmv_x1, int pmv_y1, int pmv_x2, int pmv_y2,
+                       short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
+                       int search_range, int min_mcost, int lambda_factor)
+{
+  int P = ora_num_positions(search_range), pos, best = 0, bsx, bsy;
+  int16_t *sx = (int16_t *)malloc(sizeof(int16_t) * (P > 9 ? P : 9)), *sy = (int16_t *)malloc(sizeof(int16_t) * (P > 9 ? P : 9));
+  int px1 = (pic_pix_x << 2) + pmv_x1, py1 = (pic_pix_y << 2) + pmv_y1;
+  int px2 = (pic_pix_x << 2) + pmv_x2, py2 = (pic_pix_y << 2) + pmv_y2;
+  short cx0 = (short)(pic_pix_x + *mv_x), cy0 = (short)(pic_pix_y + *mv_y);
+  short fx0 = (short)(pic_pix_x + *s_mv_x), fy0 = (short)(pic_pix_y + *s_mv_y);
+  const uint8_t *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
+  ora_block_size(blocktype, &bsx, &bsy);
+  ora_spiral(search_range, sx, sy);
+  for (pos = 0; pos < P; pos++) {
+    int cx = (cx0 + sx[pos]) << 2, cy = (cy0 + sy[pos]) << 2;
+    int mcost = ora_mv_cost(lambda_factor, fx0 << 2, fy0 << 2, px1, py1) + ora_mv_cost(lambda_factor, cx, cy, px2, py2);
+    if (mcost >= min_mcost) continue;
+    mcost += bipred_dist(c, 0, src, cur_stride, bsx, bsy, r1, (fx0 << 2) + 4 * PAD, (fy0 << 2) + 4 * PAD,
+                         r2, cx + 4 * PAD, cy + 4 * PAD, 0);
+    if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
+  }
+  if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }
+  free(sx); free(sy);
+  return min_mcost;
+}
+
+/* SubPelBlockSearchBiPred (me_fullsearch.c:520-754), unweighted.  Vectors are quarter pel; only the searched
+ * vector carries a rate term (:666, :729). */
+int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+                      int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y,
+                      short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
+                      int search_pos2, int search_pos4, int min_mcost, const int *lambda)
+{
+  int bsx, bsy, pos, best, mcost, cx, cy;
+  int use8x8 = c->transform8x8 && blocktype <= 4;
+  int p4x = (pic_pix_x + PAD) << 2, p4y = (pic_pix_y + PAD) << 2;
+  int smx = *s_mv_x + p4x, smy = *s_mv_y + p4y;
+  int shp = start_hp(c), sqp = start_qp(c);
+  int max_pos2 = (!shp && search_pos2 < 1) ? 1 : search_pos2;
+  const uint8_t *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
+  int16_t sx[9], sy[9];
+  ora_block_size(blocktype, &bsx, &bsy);
+  first_spiral(9, sx, sy);
+
+  for (best = 0, pos = shp; pos < max_pos2; pos++) {
+    cx = *mv_x + 2 * sx[pos]; cy = *mv_y + 2 * sy[pos];
+    mcost = ora_mv_cost(lambda[1], cx, cy, pmv_x, pmv_y);
+    if (mcost >= min_mcost) continue;
+    mcost += bipred_dist(c, 1, src, cur_stride, bsx, bsy, r1, smx, smy, r2, cx + p4x, cy + p4y, use8x8);
+    if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
+  }
+  if (best) { *mv_x += 2 * sx[best]; *mv_y += 2 * sy[best]; }
+  if (!sqp) min_mcost = INT_MAX;
+  for (best = 0, pos = sqp; pos < search_pos4; pos++) {
+    cx = *mv_x + sx[pos]; cy = *mv_y + sy[pos];
+    mcost = ora_mv_cost(lambda[2], cx, cy, pmv_x, pmv_y);
+    if (mcost >= min_mcost) continue;
+    mcost += bipred_dist(c, 2, src, cur_stride, bsx, bsy, r1, smx, smy, r2, cx + p4x, cy + p4y, use8x8);
+    if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
+  }
+  if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }
+  return min_mcost;
+}
+
+/* ------------------------------------------------------------------------------------------------ batch job */
+
+/* PartitionMotionSearch -> BlockMotionSearch (mv-search.c:1378, :560) for the 41 partitions of one
+ * (macroblock, list, ref): integer-pel search (:745), mv <<= 2 (:770-774), min_mcost reset when the half-pel
+ * metric differs (:785-788), sub-pel refinement with 9/9 positions (:823). */
+void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                   const me_mb_job *job, me_mb_result *out, me_mb_result_int *out_int)
+{
+  int range = ora_setup_range(c, job->ref), P = ora_num_positions(range), p, cx, cy;
+  int32_t *surf = (int32_t *)malloc(sizeof(int32_t) * (size_t)ME_NUM_PARTITIONS * P);
+  ora_search_centre(c, job->ref, job->opix_x, job->opix_y, job->pmv16[0], job->pmv16[1], &cx, &cy);
+  ora_ffs_surfaces(c, cur, cur_stride, r, job->opix_x, job->opix_y, cx, cy, range, surf);
+  for (p = 0; p < ME_NUM_PARTITIONS; p++) {
+    int t = ora_part_type[p], b = ora_part_blk[p];
+    int ppx = job->opix_x + 4 * (b & 3), ppy = job->opix_y + 4 * (b >> 2);
+    short mx, my;
+    int cost = ora_ffs_block(c, surf + (size_t)p * P, range, job->opix_x, job->opix_y, cx, cy,
+                             job->pmv[p][0], job->pmv[p][1], ora_block_search_range(c, job->ref, t),
+                             INT_MAX, job->lambda[0], &mx, &my);
+    if (out_int) { out_int->mv[p][0] = mx; out_int->mv[p][1] = my; out_int->cost[p] = cost; }
+    mx = (short)(mx << 2); my = (short)(my << 2);
+    if (!start_hp(c)) cost = INT_MAX;
+    cost = ora_subpel(c, cur, cur_stride, r, ppx, ppy, t, job->ref, job->slice_type,
+                      job->pmv[p][0], job->pmv[p][1], &mx, &my, 9, 9, cost, job->lambda);
+    out->mv[p][0] = mx; out->mv[p][1] = my; out->cost[p] = cost;
+  }
+  free(surf);
+}

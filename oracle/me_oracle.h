@@ -1,0 +1,94 @@
+/*
+ * me_oracle.h -- TEST INFRASTRUCTURE.  CPU restatement (plain C) of the reference algorithm for the
+ * motion-estimation hot path of JM 12.4 lencod.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg may use it; the product (libme_cuda.so) never links or calls it.
+ *
+ * Parity pin: every function here is checked against call traces and plane dumps of the UNMODIFIED reference
+ * encoder (oracle/_ref/lencod_trace, built by oracle/Makefile from the reference sources) and against the golden
+ * fixtures committed in tests/golden/ that were produced from those traces (tests/golden/make_golden.py).
+ */
+#ifndef ME_ORACLE_H
+#define ME_ORACLE_H
+
+#include <stdint.h>
+#include "../include/me_cuda.h"   /* struct layouts of the batch interface only */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ora_cfg {
+  int search_range;        /* input->search_range */
+  int rdopt;               /* input->rdopt */
+  int full_search;         /* input->full_search */
+  int metric[3];           /* input->MEErrorMetric[] */
+  int transform8x8;        /* input->Transform8x8Mode */
+  int mv_limit_min_y, mv_limit_max_y;  /* LEVELMVLIMIT[LevelIndex][0..1] */
+} ora_cfg;
+
+typedef struct ora_ref {
+  int w, h, wp, hp;        /* picture and padded (+40) sizes */
+  uint8_t *plane[4][4];    /* [vertical fraction][horizontal fraction], hp rows of wp bytes */
+} ora_ref;
+
+/* tables */
+int  ora_num_positions(int range);
+void ora_spiral(int range, int16_t *sx, int16_t *sy);   /* (2*range+1)^2 entries */
+int  ora_mvbits(int d);
+int  ora_mv_cost(int lambda_factor, int cx, int cy, int px, int py);
+extern const int8_t ora_part_type[ME_NUM_PARTITIONS];    /* block type 1..7 of partition p */
+extern const int8_t ora_part_blk[ME_NUM_PARTITIONS];     /* top-left 4x4 block index (4*row+col) of partition p */
+void ora_block_size(int blocktype, int *bsx, int *bsy);
+
+/* quarter-pel planes (getSubImagesLuma, img_luma.c:45-639) */
+ora_ref *ora_ref_create(const uint8_t *luma, int stride, int w, int h);
+void     ora_ref_destroy(ora_ref *r);
+const uint8_t *ora_ref_plane(const ora_ref *r, int fy, int fx);
+
+/* plane access with JM's origin clamp (UMVLine4X, refbuf.c:37): pointer to the first pixel of a block row */
+const uint8_t *ora_umv_line(const ora_ref *r, int y4, int x4);
+
+/* integer-pel fast full search */
+int  ora_setup_range(const ora_cfg *c, int ref);
+void ora_search_centre(const ora_cfg *c, int ref, int opix_x, int opix_y, int pmv16_x, int pmv16_y,
+                       int *centre_x, int *centre_y);
+/* surf: 41 surfaces of ora_num_positions(range) ints each, partition order of me_cuda.h */
+void ora_ffs_surfaces(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                      int opix_x, int opix_y, int centre_x, int centre_y, int range, int32_t *surf);
+int  ora_ffs_block(const ora_cfg *c, const int32_t *surf_p, int setup_range, int opix_x, int opix_y,
+                   int centre_x, int centre_y, int pmv_x, int pmv_y, int search_range, int min_mcost,
+                   int lambda_factor, short *mv_x, short *mv_y);
+/* search range PartitionMotionSearch passes down (mv-search.c:1411-1416) */
+int  ora_block_search_range(const ora_cfg *c, int ref, int blocktype);
+
+/* distortion */
+int ora_sad_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4);
+int ora_satd_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4, int use8x8);
+int ora_hadamard4x4(const int *d);
+int ora_hadamard8x8(const int *d);
+
+/* sub-pel refinement (SubPelBlockMotionSearch, me_fullsearch.c:341) */
+int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+               int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type,
+               int pmv_x, int pmv_y, short *mv_x, short *mv_y, int search_pos2, int search_pos4,
+               int min_mcost, const int *lambda);
+
+/* bi-predictive searches (me_fullsearch.c:164, :520): r1 is read at the fixed vector, r2 at the candidate */
+int ora_bipred_fullpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+                       int pic_pix_x, int pic_pix_y, int blocktype,
+                       int pmv_x1, int pmv_y1, int pmv_x2, int pmv_y2,
+                       short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
+                       int search_range, int min_mcost, int lambda_factor);
+int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+                      int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y,
+                      short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
+                      int search_pos2, int search_pos4, int min_mcost, const int *lambda);
+
+/* one batch job = PartitionMotionSearch for all 41 partitions of one (macroblock, list, ref) */
+void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                   const me_mb_job *job, me_mb_result *out, me_mb_result_int *out_int);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

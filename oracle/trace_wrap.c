@@ -1,0 +1,293 @@
+/*
+ * trace_wrap.c -- TEST INFRASTRUCTURE (oracle side).  Not part of the product path.
+ *
+ * A call tracer for the UNMODIFIED reference encoder.  The reference objects are compiled
+ * from /root/reference/lencod/src where they lie (oracle/Makefile) and linked with
+ *     -Wl,--wrap=FastFullPelBlockMotionSearch,--wrap=SubPelBlockMotionSearch,...
+ * so that every cross-translation-unit call of a hot-path function lands here first.
+ * Each wrapper records the arguments, forwards to the real function (__real_X) and
+ * records the results.  Nothing in the encoder's behaviour changes: the bitstream of the
+ * traced binary stays byte-identical to the plain one (tests/test_oracle_ref.py checks it).
+ *
+ * Functions intercepted (reference file:line of the definition):
+ *   FastFullPelBlockMotionSearch   lencod/src/me_fullfast.c:833   (called mv-search.c:745)
+ *   SubPelBlockMotionSearch        lencod/src/me_fullsearch.c:341 (called mv-search.c:799,823)
+ *   FullPelBlockMotionBiPred       lencod/src/me_fullsearch.c:164 (called mv-search.c:960)
+ *   SubPelBlockSearchBiPred        lencod/src/me_fullsearch.c:520 (called mv-search.c:998,1018)
+ *   ResetFastFullIntegerSearch     lencod/src/me_fullfast.c:197   (called macroblock.c:509)
+ *   getSubImagesLuma               lencod/src/img_luma.c:45       (called image.c:1642)
+ *   encode_one_frame               lencod/src/image.c:346         (called lencod.c:341)
+ *
+ * Output (directory named by env ME_TRACE_DIR, default "."):
+ *   trace.bin          fixed-size records, 32 little-endian int32 each (layout: REC_* below)
+ *   cur_<n>.y          original luma of coded picture n (8-bit, W*H bytes)
+ *   ref_<id>.y         reconstructed luma a set of quarter-pel planes was built from
+ *   ref_<id>.sub       the 16 planes as the reference produced them, [4][4][H+40][W+40] bytes
+ *                      (only when ME_TRACE_PLANES=1)
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "global.h"
+#include "image.h"
+#include "mbuffer.h"
+#include "me_distortion.h"
+
+#define REC_INTS 32
+enum { REC_FFS = 1, REC_SUBPEL = 2, REC_BI_FULL = 3, REC_BI_SUB = 4, REC_REFPIC = 5, REC_CURPIC = 6 };
+
+extern const int LEVELMVLIMIT[17][6];
+extern void SetMotionVectorPredictor (short pmv[2], char **refPic, short ***tmp_mv, short ref_frame,
+                                      int list, int block_x, int block_y, int blockshape_x, int blockshape_y);
+
+static FILE *trace_fp = NULL;
+static const char *trace_dir = ".";
+static int dump_planes = 0;
+static int coded_pic_no = -1;      /* incremented per encode_one_frame */
+static int cur_dumped_for = -2;
+
+/* picture-pointer -> id table for reference pictures */
+#define MAX_TRACKED 64
+static struct { StorablePicture *p; int id; } tracked[MAX_TRACKED];
+static int n_tracked = 0, next_ref_id = 0;
+
+/* private mirror of the static search_setup_done/search_center of me_fullfast.c:41-46 */
+static int setup_done[2][32];
+static int centre_x[2][32], centre_y[2][32], setup_range[2][32];
+
+static void trace_open(void)
+{
+  char path[1024];
+  const char *d;
+  if (trace_fp) return;
+  d = getenv("ME_TRACE_DIR");
+  if (d && *d) trace_dir = d;
+  dump_planes = getenv("ME_TRACE_PLANES") && atoi(getenv("ME_TRACE_PLANES"));
+  snprintf(path, sizeof path, "%s/trace.bin", trace_dir);
+  trace_fp = fopen(path, "wb");
+  if (!trace_fp) { perror(path); exit(97); }
+}
+
+static void put(const int *rec) { trace_open(); fwrite(rec, sizeof(int), REC_INTS, trace_fp); }
+
+static int ref_id_of(StorablePicture *p)
+{
+  int i;
+  for (i = n_tracked - 1; i >= 0; i--) if (tracked[i].p == p) return tracked[i].id;
+  return -1;
+}
+
+static void dump_luma(const char *name, imgpel **rows, int w, int h)
+{
+  char path[1024];
+  FILE *f;
+  int x, y;
+  unsigned char *line = (unsigned char *)malloc(w);
+  snprintf(path, sizeof path, "%s/%s", trace_dir, name);
+  f = fopen(path, "wb");
+  if (!f) { perror(path); exit(97); }
+  for (y = 0; y < h; y++) {
+    for (x = 0; x < w; x++) line[x] = (unsigned char)rows[y][x];
+    fwrite(line, 1, w, f);
+  }
+  fclose(f);
+  free(line);
+}
+
+static void dump_current_if_needed(void)
+{
+  char name[64];
+  int rec[REC_INTS] = {0};
+  if (cur_dumped_for == coded_pic_no) return;
+  cur_dumped_for = coded_pic_no;
+  snprintf(name, sizeof name, "cur_%d.y", coded_pic_no);
+  dump_luma(name, pCurImg, img->width, img->height);
+  rec[0] = REC_CURPIC; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->width; rec[4] = img->height;
+  rec[5] = img->framepoc; rec[6] = img->qp;
+  put(rec);
+}
+
+/* ---------------------------------------------------------------- frame counter */
+int __real_encode_one_frame(void);
+int __wrap_encode_one_frame(void)
+{
+  trace_open();
+  coded_pic_no++;
+  return __real_encode_one_frame();
+}
+
+/* ---------------------------------------------------------------- plane generation */
+void __real_getSubImagesLuma(StorablePicture *s);
+void __wrap_getSubImagesLuma(StorablePicture *s)
+{
+  int rec[REC_INTS] = {0};
+  char name[64];
+  int id;
+  trace_open();
+  __real_getSubImagesLuma(s);
+  /* 4:4:4 calls this three times per picture (Y,U,V); only the luma pass is traced */
+  if (s->p_curr_img != s->imgY) return;
+  id = next_ref_id++;
+  if (n_tracked == MAX_TRACKED) { memmove(&tracked[0], &tracked[1], sizeof(tracked[0]) * (MAX_TRACKED - 1)); n_tracked--; }
+  tracked[n_tracked].p = s; tracked[n_tracked].id = id; n_tracked++;
+  snprintf(name, sizeof name, "ref_%d.y", id);
+  dump_luma(name, s->imgY, s->size_x, s->size_y);
+  if (dump_planes) {
+    char path[1024];
+    FILE *f;
+    int fy, fx, y, x;
+    int wp = s->size_x_padded, hp = s->size_y_padded;
+    unsigned char *line = (unsigned char *)malloc(wp);
+    snprintf(path, sizeof path, "%s/ref_%d.sub", trace_dir, id);
+    f = fopen(path, "wb");
+    if (!f) { perror(path); exit(97); }
+    for (fy = 0; fy < 4; fy++)
+      for (fx = 0; fx < 4; fx++)
+        for (y = 0; y < hp; y++) {
+          for (x = 0; x < wp; x++) line[x] = (unsigned char)s->imgY_sub[fy][fx][y][x];
+          fwrite(line, 1, wp, f);
+        }
+    fclose(f);
+    free(line);
+  }
+  rec[0] = REC_REFPIC; rec[1] = id; rec[2] = s->size_x; rec[3] = s->size_y; rec[4] = coded_pic_no;
+  rec[5] = s->poc;
+  put(rec);
+}
+
+/* ---------------------------------------------------------------- per-MB reset */
+void __real_ResetFastFullIntegerSearch(void);
+void __wrap_ResetFastFullIntegerSearch(void)
+{
+  memset(setup_done, 0, sizeof setup_done);
+  __real_ResetFastFullIntegerSearch();
+}
+
+static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* ---------------------------------------------------------------- integer-pel fast full search */
+int __real_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                        int blocktype, short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                        int search_range, int min_mcost, int lambda_factor);
+int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                        int blocktype, short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                        int search_range, int min_mcost, int lambda_factor)
+{
+  int rec[REC_INTS] = {0};
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  int cost;
+  dump_current_if_needed();
+  if (!setup_done[list][ref]) {
+    /* what SetupFastFullPelSearch is about to derive (me_fullfast.c:505,550-566) */
+    short pmv[2];
+    int r = (input->full_search == 2 || ref == 0) ? input->search_range : input->search_range / 2;
+    int cx, cy;
+    SetMotionVectorPredictor(pmv, enc_picture->ref_idx[list], enc_picture->mv[list], ref, list, 0, 0, 16, 16);
+    cx = pmv[0] / 4; cy = pmv[1] / 4;
+    if (!input->rdopt) { cx = clip3(-r, r, cx); cy = clip3(-r, r, cy); }
+    cx = clip3(-2047 + r, 2047 - r, cx);
+    cy = clip3(LEVELMVLIMIT[img->LevelIndex][0] + r, LEVELMVLIMIT[img->LevelIndex][1] - r, cy);
+    centre_x[list][ref] = cx + img->opix_x;
+    centre_y[list][ref] = cy + img->opix_y;
+    setup_range[list][ref] = r;
+    setup_done[list][ref] = 1;
+    rec[22] = 1;                      /* this call triggered the setup */
+    rec[23] = pmv[0]; rec[24] = pmv[1];
+  }
+  rec[0] = REC_FFS; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->opix_x; rec[4] = img->opix_y;
+  rec[5] = list; rec[6] = ref; rec[7] = blocktype; rec[8] = pic_pix_x; rec[9] = pic_pix_y;
+  rec[10] = pred_mv_x; rec[11] = pred_mv_y; rec[12] = search_range; rec[13] = lambda_factor; rec[14] = min_mcost;
+  rec[15] = centre_x[list][ref]; rec[16] = centre_y[list][ref]; rec[17] = setup_range[list][ref];
+  rec[21] = ref_id_of(listX[list + list_offset][ref]);
+  rec[25] = input->rdopt;
+  cost = __real_FastFullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
+                                             pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
+  rec[18] = *mv_x; rec[19] = *mv_y; rec[20] = cost;
+  put(rec);
+  return cost;
+}
+
+/* ---------------------------------------------------------------- sub-pel refinement */
+int __real_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                   int blocktype, short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                   int search_pos2, int search_pos4, int min_mcost, int *lambda_factor);
+int __wrap_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                   int blocktype, short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                   int search_pos2, int search_pos4, int min_mcost, int *lambda_factor)
+{
+  int rec[REC_INTS] = {0};
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  int cost;
+  dump_current_if_needed();
+  rec[0] = REC_SUBPEL; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->opix_x; rec[4] = img->opix_y;
+  rec[5] = list; rec[6] = ref; rec[7] = blocktype; rec[8] = pic_pix_x; rec[9] = pic_pix_y;
+  rec[10] = pred_mv_x; rec[11] = pred_mv_y; rec[12] = *mv_x; rec[13] = *mv_y; rec[14] = min_mcost;
+  rec[15] = lambda_factor[0]; rec[16] = lambda_factor[1]; rec[17] = lambda_factor[2];
+  rec[21] = ref_id_of(listX[list + list_offset][ref]);
+  rec[22] = test8x8transform; rec[23] = start_me_refinement_hp; rec[24] = start_me_refinement_qp;
+  rec[25] = input->rdopt; rec[26] = search_pos2; rec[27] = search_pos4;
+  cost = __real_SubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
+                                        pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+  rec[18] = *mv_x; rec[19] = *mv_y; rec[20] = cost;
+  put(rec);
+  return cost;
+}
+
+/* ---------------------------------------------------------------- bi-predictive integer-pel search */
+int __real_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                    int blocktype, short pred_mv_x1, short pred_mv_y1, short pred_mv_x2, short pred_mv_y2,
+                                    short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                    int search_range, int min_mcost, int lambda_factor);
+int __wrap_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                    int blocktype, short pred_mv_x1, short pred_mv_y1, short pred_mv_x2, short pred_mv_y2,
+                                    short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                    int search_range, int min_mcost, int lambda_factor)
+{
+  int rec[REC_INTS] = {0};
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  int cost;
+  dump_current_if_needed();
+  rec[0] = REC_BI_FULL; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->opix_x; rec[4] = img->opix_y;
+  rec[5] = list; rec[6] = ref; rec[7] = blocktype; rec[8] = pic_pix_x; rec[9] = pic_pix_y;
+  rec[10] = pred_mv_x1; rec[11] = pred_mv_y1; rec[12] = pred_mv_x2; rec[13] = pred_mv_y2;
+  rec[14] = min_mcost; rec[15] = lambda_factor; rec[16] = search_range;
+  rec[17] = *mv_x; rec[18] = *mv_y; rec[19] = *s_mv_x; rec[20] = *s_mv_y;
+  rec[21] = ref_id_of(listX[list + list_offset][ref]);          /* picture read at the fixed vector s_mv */
+  rec[22] = ref_id_of(listX[(list ^ 1) + list_offset][0]);      /* picture read at the searched candidate */
+  cost = __real_FullPelBlockMotionBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
+                                         pred_mv_x1, pred_mv_y1, pred_mv_x2, pred_mv_y2,
+                                         mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
+  rec[23] = *mv_x; rec[24] = *mv_y; rec[25] = cost;
+  put(rec);
+  return cost;
+}
+
+/* ---------------------------------------------------------------- bi-predictive sub-pel refinement */
+int __real_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                   int blocktype, short pred_mv_x, short pred_mv_y,
+                                   short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                   int search_pos2, int search_pos4, int min_mcost, int *lambda_factor);
+int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                   int blocktype, short pred_mv_x, short pred_mv_y,
+                                   short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                   int search_pos2, int search_pos4, int min_mcost, int *lambda_factor)
+{
+  int rec[REC_INTS] = {0};
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  int cost;
+  dump_current_if_needed();
+  rec[0] = REC_BI_SUB; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->opix_x; rec[4] = img->opix_y;
+  rec[5] = list; rec[6] = ref; rec[7] = blocktype; rec[8] = pic_pix_x; rec[9] = pic_pix_y;
+  rec[10] = pred_mv_x; rec[11] = pred_mv_y;
+  rec[12] = *mv_x; rec[13] = *mv_y; rec[14] = *s_mv_x; rec[15] = *s_mv_y;
+  rec[16] = min_mcost; rec[17] = lambda_factor[0]; rec[18] = lambda_factor[1]; rec[19] = lambda_factor[2];
+  rec[21] = ref_id_of(listX[list + list_offset][ref]);
+  rec[22] = ref_id_of(listX[(list ^ 1) + list_offset][0]);
+  rec[26] = test8x8transform; rec[27] = start_me_refinement_hp; rec[28] = start_me_refinement_qp;
+  cost = __real_SubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                        mv_x, mv_y, s_mv_x, s_mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+  rec[23] = *mv_x; rec[24] = *mv_y; rec[25] = cost;
+  put(rec);
+  return cost;
+}
