@@ -1,0 +1,668 @@
+// me_cuda_host.cu -- host side of libme_cuda.so: the C ABI of include/me_cuda.h.
+//
+// Owns the device mirrors of the encoder's pictures (current picture = pCurImg, reference pictures = the imgY_sub
+// plane sets of StorablePicture), the per-macroblock fast-full-search state that lives in the static arrays of
+// the reference's me_fullfast.c:41-46 (search_setup_done / search_center_x/y / BlockSAD), and the launch sequences.
+// There is no CPU fallback in here: every entry point needs a working CUDA device.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "me_common.cuh"
+
+// ---- kernel launchers (planes.cu, ffs_basic.cu, ffs_tuned.cu, subpel.cu) ----
+struct MeSubpelArgs {
+  int pic_pix_x, pic_pix_y, blocktype;
+  int pmv_x, pmv_y, mv_x, mv_y, s_mv_x, s_mv_y;
+  int search_pos2, search_pos4, min_mcost;
+  int lambda[3];
+  int check0;
+  int bi;
+};
+struct MeBiFullArgs {
+  int pic_pix_x, pic_pix_y, blocktype;
+  int pmv_x1, pmv_y1, pmv_x2, pmv_y2;
+  int mv_x, mv_y, s_mv_x, s_mv_y;
+  int search_range, min_mcost, lambda;
+};
+extern "C" {
+void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t *planes, int pitch, size_t plane_stride,
+                      uint8_t *search, int spad, int spitch, cudaStream_t st);
+void me_launch_narrow(const uint16_t *src, int n, uint8_t *dst, cudaStream_t st);
+void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp, uint16_t *dst, cudaStream_t st);
+void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
+                               const MeCfgDev *cfg, MeResultInt *out, cudaStream_t st);
+int  me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
+                               const MeCfgDev *cfg, MeResultInt *out, cudaStream_t st);   // returns kernels launched, 0 = not applicable
+void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y, int cx, int cy,
+                            int R, int sse, int32_t *surf, cudaStream_t st);
+void me_launch_ffs_block(const int32_t *surf_p, int setup_range, int offx, int offy, int pmv_x, int pmv_y, int search_range,
+                         int min_mcost, int lambda, int rdopt, int *result, cudaStream_t st);
+void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
+                            const MeCfgDev *cfg, const MeResultInt *in_int, MeResult *out, cudaStream_t st);
+void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
+                             const MeSubpelArgs *a, int *result, cudaStream_t st);
+void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
+                           const MeBiFullArgs *a, int *result, cudaStream_t st);
+}
+
+namespace {
+
+struct RefPic {
+  bool used = false;
+  uint8_t *planes = nullptr, *search = nullptr;
+  MeRefDev dev{};
+};
+
+struct State {
+  bool inited = false;
+  me_cuda_params p{};
+  MeCfgDev cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<RefPic> refs;
+  // current picture
+  uint8_t *d_cur = nullptr;
+  int cur_pitch = 0;
+  // staging
+  uint8_t *h_pin = nullptr; size_t h_pin_bytes = 0;
+  uint16_t *d_wide = nullptr; uint16_t *h_wide = nullptr; size_t wide_elems = 0;
+  // reference lists
+  MeRefDev h_table[2 * ME_MAX_REFS];
+  MeRefDev *d_table = nullptr;
+  me_ref_handle list[2][ME_MAX_REFS];
+  int list_n[2] = {0, 0};
+  bool table_dirty = true;
+  int slice_type = ME_P_SLICE;
+  // per-macroblock fast full search state
+  int opix_x = 0, opix_y = 0;
+  int setup_done[2][ME_MAX_REFS];
+  int centre_x[2][ME_MAX_REFS], centre_y[2][ME_MAX_REFS], setup_range[2][ME_MAX_REFS];
+  int32_t *d_surf[2][ME_MAX_REFS];
+  int *d_result = nullptr, *h_result = nullptr;
+  // batch scratch
+  MeJob *d_jobs = nullptr; MeResult *d_out = nullptr; MeResultInt *d_out_int = nullptr; int batch_cap = 0;
+  MeResultInt *d_int_scratch = nullptr; int int_scratch_cap = 0;
+  long long launches = 0;
+  // optional per-kernel-class timing (bench.py): event pairs around every launch of a class
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 planes, 1 integer-pel search, 2 sub-pel
+};
+
+State g;
+char g_err[512] = "";
+me_cuda_error_fn g_handler = nullptr;
+
+int fail(int code, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// drop-in search calls return a cost, so they report through the handler
+void fatal(const char *what)
+{
+  if (g_handler) { g_handler(g_err[0] ? g_err : what, 500); return; }
+  fprintf(stderr, "libme_cuda: fatal: %s\n", g_err[0] ? g_err : what);
+  abort();
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+struct ScopedTimer {
+  int which; cudaStream_t st; cudaEvent_t e1 = nullptr; bool on;
+  ScopedTimer(int w, cudaStream_t s) : which(w), st(s), on(g.timing) {
+    if (!on) return;
+    cudaEvent_t e0;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    g.ev[which].push_back({e0, e1});
+  }
+  ~ScopedTimer() { if (on) cudaEventRecord(e1, st); }
+};
+
+RefPic *ref_of(me_ref_handle h)
+{
+  if (h <= 0 || (size_t)h > g.refs.size() || !g.refs[h - 1].used) return nullptr;
+  return &g.refs[h - 1];
+}
+
+int ensure_pin(size_t bytes)
+{
+  if (g.h_pin_bytes >= bytes) return 0;
+  if (g.h_pin) cudaFreeHost(g.h_pin);
+  g.h_pin = nullptr; g.h_pin_bytes = 0;
+  CK(cudaMallocHost((void **)&g.h_pin, bytes));
+  g.h_pin_bytes = bytes;
+  return 0;
+}
+
+int upload_table()
+{
+  if (!g.table_dirty) return 0;
+  memset(g.h_table, 0, sizeof g.h_table);
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < g.list_n[l]; i++) {
+      RefPic *r = ref_of(g.list[l][i]);
+      if (!r) return fail(3, "reference list %d entry %d holds an invalid handle", l, i);
+      g.h_table[l * ME_MAX_REFS + i] = r->dev;
+    }
+  CK(cudaMemcpyAsync(g.d_table, g.h_table, sizeof g.h_table, cudaMemcpyHostToDevice, g.stream));
+  // h_table is pageable: the copy above is staged synchronously by the runtime, safe to reuse
+  g.table_dirty = false;
+  return 0;
+}
+
+int ensure_batch(int n)
+{
+  if (n <= g.batch_cap) return 0;
+  if (g.d_jobs) cudaFree(g.d_jobs);
+  if (g.d_out) cudaFree(g.d_out);
+  if (g.d_out_int) cudaFree(g.d_out_int);
+  g.d_jobs = nullptr; g.d_out = nullptr; g.d_out_int = nullptr; g.batch_cap = 0;
+  CK(cudaMalloc((void **)&g.d_jobs, sizeof(MeJob) * (size_t)n));
+  CK(cudaMalloc((void **)&g.d_out, sizeof(MeResult) * (size_t)n));
+  CK(cudaMalloc((void **)&g.d_out_int, sizeof(MeResultInt) * (size_t)n));
+  g.batch_cap = n;
+  return 0;
+}
+
+int setup_range_of(int ref)
+{
+  return (g.cfg.full_search == 2 || ref == 0) ? g.cfg.search_range : g.cfg.search_range / 2;
+}
+
+int create_ref_common(const uint8_t *d_luma, int stride, int w, int h, cudaStream_t st, me_ref_handle *out)
+{
+  // find a free slot
+  size_t slot = 0;
+  for (; slot < g.refs.size(); slot++) if (!g.refs[slot].used) break;
+  if (slot == g.refs.size()) g.refs.emplace_back();
+  RefPic &r = g.refs[slot];
+  MeRefDev &d = r.dev;
+  d.w = w; d.h = h; d.wp = w + 2 * ME_PAD; d.hp = h + 2 * ME_PAD;
+  d.pitch = align_up(d.wp, 128);
+  d.plane_stride = (size_t)d.pitch * d.hp;
+  d.spad = g.cfg.search_range + 32;
+  d.sw = w + 2 * d.spad; d.sh = h + 2 * d.spad;
+  d.spitch = align_up(d.sw, 128);
+  CK(cudaMalloc((void **)&r.planes, d.plane_stride * 16));
+  CK(cudaMalloc((void **)&r.search, (size_t)d.spitch * d.sh));
+  d.planes = r.planes; d.search = r.search;
+  { ScopedTimer t(0, st); me_launch_planes(d_luma, stride, w, h, r.planes, d.pitch, d.plane_stride, r.search, d.spad, d.spitch, st); }
+  g.launches += 2;
+  CK(cudaGetLastError());
+  r.used = true;
+  *out = (me_ref_handle)(slot + 1);
+  return 0;
+}
+
+// regenerate the planes of an existing picture slot in place (a DPB frame store being reused)
+int update_ref_common(me_ref_handle h, const uint8_t *d_luma, int stride, cudaStream_t st)
+{
+  RefPic *r = ref_of(h);
+  if (!r) return fail(3, "me_cuda_ref_update: invalid handle %d", (int)h);
+  MeRefDev &d = r->dev;
+  { ScopedTimer t(0, st); me_launch_planes(d_luma, stride, d.w, d.h, r->planes, d.pitch, d.plane_stride, r->search, d.spad, d.spitch, st); }
+  g.launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// staging buffer for pictures on the device (u8, pitch = w)
+uint8_t *g_d_stage = nullptr; size_t g_d_stage_bytes = 0;
+int ensure_stage(size_t bytes)
+{
+  if (g_d_stage_bytes >= bytes) return 0;
+  if (g_d_stage) cudaFree(g_d_stage);
+  g_d_stage = nullptr; g_d_stage_bytes = 0;
+  CK(cudaMalloc((void **)&g_d_stage, bytes));
+  g_d_stage_bytes = bytes;
+  return 0;
+}
+
+int check_size(int w, int h)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (w != g.p.width || h != g.p.height) return fail(1, "picture size %dx%d differs from the initialised %dx%d", w, h, g.p.width, g.p.height);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void me_cuda_set_error_handler(me_cuda_error_fn fn) { g_handler = fn; }
+const char *me_cuda_last_error(void) { return g_err; }
+
+int me_cuda_init(const me_cuda_params *p)
+{
+  if (!p) return fail(1, "me_cuda_init: null parameters");
+  if (p->abi_version != ME_CUDA_ABI_VERSION) return fail(1, "ABI version %d, library is %d", p->abi_version, ME_CUDA_ABI_VERSION);
+  if (g.inited) me_cuda_shutdown();
+  if (p->bit_depth != 8) return fail(1, "bit depth %d not supported (8-bit content only)", p->bit_depth);
+  if (p->chroma_me_enable) return fail(1, "ChromaMEEnable is not supported by the CUDA path");
+  if (p->weighted_me) return fail(1, "weighted-prediction ME is not supported by the CUDA path");
+  if (p->width <= 0 || p->height <= 0 || (p->width & 15) || (p->height & 15)) return fail(1, "picture size %dx%d must be positive multiples of 16", p->width, p->height);
+  if (p->search_range < 1 || p->search_range > 64) return fail(1, "search range %d outside 1..64", p->search_range);
+  if (p->max_num_references < 1 || p->max_num_references > ME_MAX_REFS) return fail(1, "max_num_references %d outside 1..%d", p->max_num_references, ME_MAX_REFS);
+  int dev = p->device;
+  if (dev < 0) { const char *e = getenv("ME_CUDA_DEVICE"); dev = e ? atoi(e) : 0; }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(2, "no CUDA device available (%s); libme_cuda has no CPU path", cudaGetErrorString(e));
+  if (dev >= count) return fail(2, "CUDA device %d requested, %d present", dev, count);
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) return fail(2, "device %s is sm_%d%d; libme_cuda is built for sm_100a only", prop.name, prop.major, prop.minor);
+  g = State();
+  g.p = *p; g.device = dev;
+  g.cfg.search_range = p->search_range; g.cfg.rdopt = p->rdopt; g.cfg.full_search = p->full_search;
+  for (int i = 0; i < 3; i++) g.cfg.metric[i] = p->me_metric[i];
+  g.cfg.transform8x8 = p->transform8x8 != 0;
+  g.cfg.mv_limit_min_y = p->mv_limit_min_y; g.cfg.mv_limit_max_y = p->mv_limit_max_y;
+  g.cfg.start_hp = (p->me_metric[0] != p->me_metric[1]) ? 0 : 1;      // mv-search.c:396 with ChromaMEEnable == 0
+  g.cfg.start_qp = (p->me_metric[1] != p->me_metric[2]) ? 0 : 1;      // mv-search.c:397
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  g.cur_pitch = align_up(p->width, 128);
+  CK(cudaMalloc((void **)&g.d_cur, (size_t)g.cur_pitch * p->height));
+  CK(cudaMalloc((void **)&g.d_table, sizeof g.h_table));
+  CK(cudaMalloc((void **)&g.d_result, 64));
+  CK(cudaMallocHost((void **)&g.h_result, 64));
+  memset(g.d_surf, 0, sizeof g.d_surf);
+  memset(g.setup_done, 0, sizeof g.setup_done);
+  g_err[0] = 0;
+  g.inited = true;
+  return 0;
+}
+
+void me_cuda_shutdown(void)
+{
+  if (!g.inited) return;
+  cudaSetDevice(g.device);
+  cudaStreamSynchronize(g.stream);
+  for (auto &r : g.refs) if (r.used) { cudaFree(r.planes); cudaFree(r.search); }
+  g.refs.clear();
+  for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) if (g.d_surf[l][i]) cudaFree(g.d_surf[l][i]);
+  cudaFree(g.d_cur); cudaFree(g.d_table); cudaFree(g.d_result); cudaFreeHost(g.h_result);
+  if (g.h_pin) cudaFreeHost(g.h_pin);
+  if (g.d_wide) cudaFree(g.d_wide);
+  if (g.h_wide) cudaFreeHost(g.h_wide);
+  if (g.d_jobs) cudaFree(g.d_jobs);
+  if (g.d_out) cudaFree(g.d_out);
+  if (g.d_out_int) cudaFree(g.d_out_int);
+  if (g.d_int_scratch) cudaFree(g.d_int_scratch);
+  if (g_d_stage) { cudaFree(g_d_stage); g_d_stage = nullptr; g_d_stage_bytes = 0; }
+  cudaStreamDestroy(g.stream);
+  g = State();
+}
+
+void *me_cuda_stream(void) { return (void *)g.stream; }
+int me_cuda_sync(void) { CK(cudaStreamSynchronize(g.stream)); return 0; }
+int64_t me_cuda_launch_count(void) { return g.launches; }
+
+// ------------------------------------------------------------------------------------------------ pictures
+int me_cuda_ref_create_device(const void *d_luma, int stride, int w, int h, void *stream, me_ref_handle *out)
+{
+  if (int rc = check_size(w, h)) return rc;
+  return create_ref_common((const uint8_t *)d_luma, stride, w, h, stream ? (cudaStream_t)stream : g.stream, out);
+}
+
+int me_cuda_ref_create_u8(const uint8_t *luma, int stride, int w, int h, me_ref_handle *out)
+{
+  if (int rc = check_size(w, h)) return rc;
+  size_t bytes = (size_t)w * h;
+  if (int rc = ensure_pin(bytes)) return rc;
+  if (int rc = ensure_stage(bytes)) return rc;
+  CK(cudaStreamSynchronize(g.stream));               // the pinned staging buffer may still be in flight
+  for (int y = 0; y < h; y++) memcpy(g.h_pin + (size_t)y * w, luma + (size_t)y * stride, w);
+  CK(cudaMemcpyAsync(g_d_stage, g.h_pin, bytes, cudaMemcpyHostToDevice, g.stream));
+  return create_ref_common(g_d_stage, w, w, h, g.stream, out);
+}
+
+int me_cuda_ref_create(const me_imgpel *const *rows, int w, int h, me_imgpel ****host_sub, me_ref_handle *out)
+{
+  if (int rc = check_size(w, h)) return rc;
+  size_t bytes = (size_t)w * h;
+  if (int rc = ensure_pin(bytes)) return rc;
+  if (int rc = ensure_stage(bytes)) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  for (int y = 0; y < h; y++) {
+    const me_imgpel *s = rows[y];
+    uint8_t *d = g.h_pin + (size_t)y * w;
+    for (int x = 0; x < w; x++) d[x] = (uint8_t)s[x];
+  }
+  CK(cudaMemcpyAsync(g_d_stage, g.h_pin, bytes, cudaMemcpyHostToDevice, g.stream));
+  if (int rc = create_ref_common(g_d_stage, w, w, h, g.stream, out)) return rc;
+  if (host_sub) {
+    // the encoder's motion compensation still reads imgY_sub on the host (macroblock.c:816): hand the planes back
+    RefPic *r = ref_of(*out);
+    int wp = r->dev.wp, hp = r->dev.hp;
+    size_t n = (size_t)16 * wp * hp;
+    if (g.wide_elems < n) {
+      if (g.d_wide) cudaFree(g.d_wide);
+      if (g.h_wide) cudaFreeHost(g.h_wide);
+      g.d_wide = nullptr; g.h_wide = nullptr; g.wide_elems = 0;
+      CK(cudaMalloc((void **)&g.d_wide, n * sizeof(uint16_t)));
+      CK(cudaMallocHost((void **)&g.h_wide, n * sizeof(uint16_t)));
+      g.wide_elems = n;
+    }
+    me_launch_widen_planes(r->planes, r->dev.pitch, r->dev.plane_stride, wp, hp, g.d_wide, g.stream);
+    g.launches++;
+    CK(cudaMemcpyAsync(g.h_wide, g.d_wide, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (int fy = 0; fy < 4; fy++)
+      for (int fx = 0; fx < 4; fx++)
+        for (int y = 0; y < hp; y++)
+          memcpy(host_sub[fy][fx][y], g.h_wide + ((size_t)(fy * 4 + fx) * hp + y) * wp, (size_t)wp * sizeof(uint16_t));
+  }
+  return 0;
+}
+
+int me_cuda_ref_destroy(me_ref_handle h)
+{
+  RefPic *r = ref_of(h);
+  if (!r) return fail(3, "me_cuda_ref_destroy: invalid handle %d", (int)h);
+  CK(cudaStreamSynchronize(g.stream));
+  cudaFree(r->planes); cudaFree(r->search);
+  *r = RefPic();
+  for (int l = 0; l < 2; l++) for (int i = 0; i < g.list_n[l]; i++) if (g.list[l][i] == h) { g.list[l][i] = 0; g.table_dirty = true; }
+  return 0;
+}
+
+int me_cuda_ref_download_plane(me_ref_handle h, int fy, int fx, uint8_t *dst, int dst_stride)
+{
+  RefPic *r = ref_of(h);
+  if (!r) return fail(3, "me_cuda_ref_download_plane: invalid handle %d", (int)h);
+  if (fy < 0 || fy > 3 || fx < 0 || fx > 3) return fail(1, "plane index out of range");
+  CK(cudaMemcpy2DAsync(dst, dst_stride, r->planes + (size_t)(fy * 4 + fx) * r->dev.plane_stride, r->dev.pitch,
+                       r->dev.wp, r->dev.hp, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int me_cuda_ref_update_device(me_ref_handle hd, const void *d_luma, int stride, int w, int h, void *stream)
+{
+  if (int rc = check_size(w, h)) return rc;
+  return update_ref_common(hd, (const uint8_t *)d_luma, stride, stream ? (cudaStream_t)stream : g.stream);
+}
+
+int me_cuda_ref_update_u8(me_ref_handle hd, const uint8_t *luma, int stride, int w, int h)
+{
+  if (int rc = check_size(w, h)) return rc;
+  size_t bytes = (size_t)w * h;
+  if (int rc = ensure_stage(bytes)) return rc;
+  // straight from the caller's buffer (pinned memory makes this an asynchronous DMA)
+  CK(cudaMemcpy2DAsync(g_d_stage, w, luma, stride, w, h, cudaMemcpyHostToDevice, g.stream));
+  return update_ref_common(hd, g_d_stage, w, g.stream);
+}
+
+int me_cuda_set_timing(int on)
+{
+  for (int k = 0; k < 3; k++) {
+    for (auto &p : g.ev[k]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    g.ev[k].clear();
+  }
+  g.timing = on != 0;
+  return 0;
+}
+
+int me_cuda_kernel_time_ms(int which, double *total_ms, int *n_launches)
+{
+  if (which < 0 || which > 2) return fail(1, "me_cuda_kernel_time_ms: class %d out of range", which);
+  double tot = 0;
+  for (auto &p : g.ev[which]) {
+    CK(cudaEventSynchronize(p.second));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, p.first, p.second));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *n_launches = (int)g.ev[which].size();
+  return 0;
+}
+
+int me_cuda_set_current_device(const void *d_luma, int stride, int w, int h, void *stream)
+{
+  if (int rc = check_size(w, h)) return rc;
+  CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, d_luma, stride, w, h, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : g.stream));
+  return 0;
+}
+
+int me_cuda_set_current_u8(const uint8_t *luma, int stride, int w, int h)
+{
+  if (int rc = check_size(w, h)) return rc;
+  CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, luma, stride, w, h, cudaMemcpyHostToDevice, g.stream));
+  return 0;
+}
+
+int me_cuda_set_current(const me_imgpel *const *rows, int w, int h)
+{
+  if (int rc = check_size(w, h)) return rc;
+  size_t bytes = (size_t)w * h;
+  if (int rc = ensure_pin(bytes)) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  for (int y = 0; y < h; y++) {
+    const me_imgpel *s = rows[y];
+    uint8_t *d = g.h_pin + (size_t)y * w;
+    for (int x = 0; x < w; x++) d[x] = (uint8_t)s[x];
+  }
+  CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, g.h_pin, w, w, h, cudaMemcpyHostToDevice, g.stream));
+  return 0;
+}
+
+int me_cuda_set_ref_list(int list, int n, const me_ref_handle *handles)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (list < 0 || list > 1 || n < 0 || n > ME_MAX_REFS) return fail(1, "me_cuda_set_ref_list: list %d / count %d out of range", list, n);
+  for (int i = 0; i < n; i++) if (!ref_of(handles[i])) return fail(3, "me_cuda_set_ref_list: invalid handle %d at %d", (int)handles[i], i);
+  bool same = g.list_n[list] == n;
+  for (int i = 0; same && i < n; i++) same = g.list[list][i] == handles[i];
+  if (same) return 0;
+  g.list_n[list] = n;
+  for (int i = 0; i < n; i++) g.list[list][i] = handles[i];
+  g.table_dirty = true;
+  return 0;
+}
+
+int me_cuda_set_slice_type(int t) { g.slice_type = t; return 0; }
+
+// ------------------------------------------------------------------------------------------------ drop-in calls
+int me_cuda_mb_begin(int opix_x, int opix_y)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  g.opix_x = opix_x; g.opix_y = opix_y;
+  memset(g.setup_done, 0, sizeof g.setup_done);
+  return 0;
+}
+
+int me_cuda_ffs_is_set_up(int list, int ref) { return g.setup_done[list][ref]; }
+
+int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (list < 0 || list > 1 || ref < 0 || ref >= g.list_n[list]) return fail(1, "me_cuda_ffs_setup: (list %d, ref %d) not in the reference lists", list, ref);
+  RefPic *r = ref_of(g.list[list][ref]);
+  if (!r) return fail(3, "me_cuda_ffs_setup: stale reference handle");
+  int R = setup_range_of(ref);
+  int cx = pmv16_x / 4, cy = pmv16_y / 4;                                          // me_fullfast.c:552-553
+  if (!g.cfg.rdopt) { cx = me_clamp(cx, -R, R); cy = me_clamp(cy, -R, R); }       // :555-560
+  cx = me_clamp(cx, -2047 + R, 2047 - R);                                         // :562
+  cy = me_clamp(cy, g.cfg.mv_limit_min_y + R, g.cfg.mv_limit_max_y - R);           // :563
+  cx += g.opix_x; cy += g.opix_y;
+  int P = (2 * g.cfg.search_range + 1) * (2 * g.cfg.search_range + 1);
+  if (!g.d_surf[list][ref]) CK(cudaMalloc((void **)&g.d_surf[list][ref], sizeof(int32_t) * (size_t)ME_NUM_PARTITIONS * P));
+  me_launch_ffs_surfaces(&r->dev, g.d_cur, g.cur_pitch, g.opix_x, g.opix_y, cx, cy, R, g.cfg.metric[0] != 0, g.d_surf[list][ref], g.stream);
+  g.launches++;
+  CK(cudaGetLastError());
+  g.centre_x[list][ref] = cx; g.centre_y[list][ref] = cy; g.setup_range[list][ref] = R;
+  g.setup_done[list][ref] = 1;
+  return 0;
+}
+
+static int fetch_result(int *mvx, int *mvy, int *cost)
+{
+  CK(cudaMemcpyAsync(g.h_result, g.d_result, 3 * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  *mvx = g.h_result[0]; *mvy = g.h_result[1]; *cost = g.h_result[2];
+  return 0;
+}
+
+int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                         short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                         int search_range, int min_mcost, int lambda_factor)
+{
+  if (!g.inited || list < 0 || list > 1 || ref < 0 || ref >= ME_MAX_REFS || !g.setup_done[list][ref]) {
+    fail(1, "me_cuda_FastFullPelBlockMotionSearch: me_cuda_ffs_setup(list %d, ref %d) has not run for this macroblock", list, (int)ref);
+    fatal("ffs"); return ME_INT_MAX;
+  }
+  int blk = (pic_pix_y - g.opix_y) + ((pic_pix_x - g.opix_x) >> 2);                 // me_fullfast.c:854
+  int p = me_part_index(blocktype, blk);
+  if (p < 0) { fail(1, "block (%d,%d) is not a type-%d partition origin", pic_pix_x, pic_pix_y, blocktype); fatal("ffs"); return ME_INT_MAX; }
+  int R = g.setup_range[list][ref], P = (2 * R + 1) * (2 * R + 1);
+  me_launch_ffs_block(g.d_surf[list][ref] + (size_t)p * P, R, g.centre_x[list][ref] - g.opix_x, g.centre_y[list][ref] - g.opix_y,
+                      pred_mv_x, pred_mv_y, search_range, min_mcost, lambda_factor, g.cfg.rdopt, g.d_result, g.stream);
+  g.launches++;
+  int mx, my, cost;
+  if (fetch_result(&mx, &my, &cost)) { fatal("ffs"); return ME_INT_MAX; }
+  *mv_x = (short)mx; *mv_y = (short)my;
+  return cost;
+}
+
+int me_cuda_SubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                    short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                    int search_pos2, int search_pos4, int min_mcost, const int *lambda)
+{
+  RefPic *r = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
+  if (!r) { fail(1, "me_cuda_SubPelBlockMotionSearch: (list %d, ref %d) not in the reference lists", list, (int)ref); fatal("subpel"); return ME_INT_MAX; }
+  MeSubpelArgs a{};
+  a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
+  a.pmv_x = pred_mv_x; a.pmv_y = pred_mv_y; a.mv_x = *mv_x; a.mv_y = *mv_y;
+  a.search_pos2 = search_pos2; a.search_pos4 = search_pos4; a.min_mcost = min_mcost;
+  for (int i = 0; i < 3; i++) a.lambda[i] = lambda[i];
+  a.check0 = (!g.cfg.rdopt && g.slice_type != ME_B_SLICE && ref == 0 && blocktype == 1 && *mv_x == 0 && *mv_y == 0);   // me_fullsearch.c:361
+  a.bi = 0;
+  me_launch_subpel_single(&r->dev, nullptr, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, g.stream);
+  g.launches++;
+  int mx, my, cost;
+  if (fetch_result(&mx, &my, &cost)) { fatal("subpel"); return ME_INT_MAX; }
+  *mv_x = (short)mx; *mv_y = (short)my;
+  return cost;
+}
+
+int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                     short pred_mv_x1, short pred_mv_y1, short pred_mv_x2, short pred_mv_y2,
+                                     short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                     int search_range, int min_mcost, int lambda_factor)
+{
+  RefPic *r1 = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
+  RefPic *r2 = (g.inited && g.list_n[list ^ 1] > 0) ? ref_of(g.list[list ^ 1][0]) : nullptr;
+  if (!r1 || !r2) { fail(1, "me_cuda_FullPelBlockMotionBiPred: reference lists incomplete"); fatal("bipred"); return ME_INT_MAX; }
+  if (g.cfg.metric[0] == 2) { fail(1, "bi-predictive integer search with a Hadamard metric is not implemented"); fatal("bipred"); return ME_INT_MAX; }
+  if (search_range > 64) { fail(1, "bi-pred search range %d too large", search_range); fatal("bipred"); return ME_INT_MAX; }
+  MeBiFullArgs a{};
+  a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
+  a.pmv_x1 = pred_mv_x1; a.pmv_y1 = pred_mv_y1; a.pmv_x2 = pred_mv_x2; a.pmv_y2 = pred_mv_y2;
+  a.mv_x = *mv_x; a.mv_y = *mv_y; a.s_mv_x = *s_mv_x; a.s_mv_y = *s_mv_y;
+  a.search_range = search_range; a.min_mcost = min_mcost; a.lambda = lambda_factor;
+  me_launch_bipred_full(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, g.stream);
+  g.launches++;
+  int mx, my, cost;
+  if (fetch_result(&mx, &my, &cost)) { fatal("bipred"); return ME_INT_MAX; }
+  *mv_x = (short)mx; *mv_y = (short)my;
+  return cost;
+}
+
+int me_cuda_SubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                    short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                    int search_pos2, int search_pos4, int min_mcost, const int *lambda)
+{
+  RefPic *r1 = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
+  RefPic *r2 = (g.inited && g.list_n[list ^ 1] > 0) ? ref_of(g.list[list ^ 1][0]) : nullptr;
+  if (!r1 || !r2) { fail(1, "me_cuda_SubPelBlockSearchBiPred: reference lists incomplete"); fatal("bipred"); return ME_INT_MAX; }
+  MeSubpelArgs a{};
+  a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
+  a.pmv_x = pred_mv_x; a.pmv_y = pred_mv_y; a.mv_x = *mv_x; a.mv_y = *mv_y; a.s_mv_x = *s_mv_x; a.s_mv_y = *s_mv_y;
+  a.search_pos2 = search_pos2; a.search_pos4 = search_pos4; a.min_mcost = min_mcost;
+  for (int i = 0; i < 3; i++) a.lambda[i] = lambda[i];
+  a.check0 = 0; a.bi = 1;
+  me_launch_subpel_single(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, g.stream);
+  g.launches++;
+  int mx, my, cost;
+  if (fetch_result(&mx, &my, &cost)) { fatal("bipred"); return ME_INT_MAX; }
+  *mv_x = (short)mx; *mv_y = (short)my;
+  return cost;
+}
+
+// ------------------------------------------------------------------------------------------------ frame batch
+static int use_basic_only()
+{
+  const char *e = getenv("ME_CUDA_FFS_KERNEL");
+  return e && !strcmp(e, "basic");
+}
+
+int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, void *d_out_int, void *stream)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (n_jobs <= 0) return 0;
+  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  if (g.table_dirty) {
+    // the table upload runs on the library stream; make the caller's stream wait for it
+    if (int rc = upload_table()) return rc;
+    CK(cudaStreamSynchronize(g.stream));
+  }
+  MeResultInt *di = (MeResultInt *)d_out_int;
+  if (!di) {
+    if (g.int_scratch_cap < n_jobs) {
+      if (g.d_int_scratch) cudaFree(g.d_int_scratch);
+      g.d_int_scratch = nullptr; g.int_scratch_cap = 0;
+      CK(cudaMalloc((void **)&g.d_int_scratch, sizeof(MeResultInt) * (size_t)n_jobs));
+      g.int_scratch_cap = n_jobs;
+    }
+    di = g.d_int_scratch;
+  }
+  int launched = 0;
+  {
+    ScopedTimer t(1, st);
+    if (!use_basic_only()) launched = me_launch_ffs_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, st);
+    if (!launched) { me_launch_ffs_batch_basic((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, st); launched = 1; }
+  }
+  { ScopedTimer t(2, st); me_launch_subpel_batch((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, (MeResult *)d_out, st); }
+  g.launches += launched + 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, me_mb_result_int *out_int)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (n_jobs <= 0) return 0;
+  for (int i = 0; i < n_jobs; i++) {
+    const me_mb_job &j = jobs[i];
+    if (j.list < 0 || j.list > 1 || j.ref < 0 || j.ref >= g.list_n[j.list])
+      return fail(1, "job %d: (list %d, ref %d) not in the reference lists", i, (int)j.list, (int)j.ref);
+    if (j.opix_x < 0 || j.opix_y < 0 || j.opix_x + 16 > g.p.width || j.opix_y + 16 > g.p.height || (j.opix_x & 15) || (j.opix_y & 15))
+      return fail(1, "job %d: macroblock origin (%d,%d) invalid", i, (int)j.opix_x, (int)j.opix_y);
+  }
+  if (int rc = ensure_batch(n_jobs)) return rc;
+  CK(cudaMemcpyAsync(g.d_jobs, jobs, sizeof(MeJob) * (size_t)n_jobs, cudaMemcpyHostToDevice, g.stream));
+  if (int rc = me_cuda_frame_search_device(g.d_jobs, n_jobs, g.d_out, g.d_out_int, g.stream)) return rc;
+  CK(cudaMemcpyAsync(out, g.d_out, sizeof(MeResult) * (size_t)n_jobs, cudaMemcpyDeviceToHost, g.stream));
+  if (out_int) CK(cudaMemcpyAsync(out_int, g.d_out_int, sizeof(MeResultInt) * (size_t)n_jobs, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+}  // extern "C"

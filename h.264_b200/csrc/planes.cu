@@ -1,0 +1,151 @@
+// planes.cu -- quarter-pel reference plane generation on the device.
+//
+// Replaces getSubImagesLuma and its helpers (reference lencod/src/img_luma.c:45-639, called from
+// UnifiedOneForthPix, lencod/src/image.c:1601-1661): from one reconstructed luma picture S (w x h) build the 16
+// planes P[fy][fx] of size (h+40) x (w+40):
+//   G = P[0][0](y,x) = S(clamp(y-20,0,h-1), clamp(x-20,0,w-1))                                   img_luma.c:120
+//   t(y,x)  = 20*(G(x)+G(x+1)) - 5*(G(x-1)+G(x+2)) + (G(x-2)+G(x+3))   columns clamped to [0,wp-1]  img_luma.c:181
+//   b = P[0][2] = clip255((t+16)>>5)
+//   h = P[2][0] = clip255((same 6 taps vertically on G, rows clamped to [0,hp-1], +16)>>5)        img_luma.c:293
+//   j = P[2][2] = clip255((6 taps vertically on t, +512)>>10)                                      img_luma.c:390
+//   twelve quarter positions = (p+q+1)>>1 of two of {G,b,h,j} at the same / right / lower sample    img_luma.c:483-639
+// All arithmetic is 32-bit integer.  One kernel computes all 16 planes of a 64x16 tile from a shared-memory copy of
+// the tile plus halo; a second tiny kernel writes the wide-border search copy of the integer plane (me_common.cuh).
+//
+// Roofline: HBM-bound.  Algorithmic bytes per reference picture = w*h (read) + 16*(w+40)*(h+40) (write).
+#include "me_common.cuh"
+
+#define TW 64
+#define TH 16
+#define GW (TW + 7)   // columns x0-2 .. x0+TW+4
+#define GH (TH + 7)   // rows    y0-2 .. y0+TH+4
+#define TMW (TW + 1)  // t / b / j for columns x0 .. x0+TW
+
+__device__ __forceinline__ int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+__global__ void __launch_bounds__(256)
+me_planes_kernel(const uint8_t *__restrict__ src, int src_stride, int w, int h,
+                 uint8_t *__restrict__ planes, int pitch, size_t plane_stride)
+{
+  __shared__ uint8_t Gs[GH][GW + 1];
+  __shared__ int     Ts[GH][TMW];        // unrounded horizontal sums t for rows y0-2..y0+TH+4, columns x0..x0+TW
+  __shared__ uint8_t Bs[TH + 1][TMW];    // b for rows y0..y0+TH
+  __shared__ uint8_t Hs[TH + 1][TMW];    // h
+  __shared__ uint8_t Js[TH + 1][TMW];    // j
+  const int wp = w + 2 * ME_PAD, hp = h + 2 * ME_PAD;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int tid = threadIdx.x;
+
+  // integer samples with both clamps (padded-plane clamp of the filters, then picture clamp of the border)
+  for (int i = tid; i < GH * GW; i += blockDim.x) {
+    int ly = i / GW, lx = i - ly * GW;
+    int y = me_clamp(y0 - 2 + ly, 0, hp - 1), x = me_clamp(x0 - 2 + lx, 0, wp - 1);
+    Gs[ly][lx] = src[(size_t)me_clamp(y - ME_PAD, 0, h - 1) * src_stride + me_clamp(x - ME_PAD, 0, w - 1)];
+  }
+  __syncthreads();
+  // horizontal six-tap sums.  Local column lx of Ts is plane column x0+lx; its taps are Gs columns lx .. lx+5.
+  // The plane-edge clamp of the taps is already in Gs for every column except when x0+lx itself is past wp-1
+  // (only the +1 neighbour column of the last tile), where the value is never used unclamped (see idx1 below).
+  for (int i = tid; i < GH * TMW; i += blockDim.x) {
+    int ly = i / TMW, lx = i - ly * TMW;
+    const uint8_t *g = &Gs[ly][lx];
+    Ts[ly][lx] = 20 * (g[2] + g[3]) - 5 * (g[1] + g[4]) + (g[0] + g[5]);
+  }
+  __syncthreads();
+  for (int i = tid; i < (TH + 1) * TMW; i += blockDim.x) {
+    int ly = i / TMW, lx = i - ly * TMW;        // plane row y0+ly, column x0+lx
+    Bs[ly][lx] = (uint8_t)clip255((Ts[ly + 2][lx] + 16) >> 5);
+    int v = 20 * (Gs[ly + 2][lx + 2] + Gs[ly + 3][lx + 2]) - 5 * (Gs[ly + 1][lx + 2] + Gs[ly + 4][lx + 2])
+            + (Gs[ly][lx + 2] + Gs[ly + 5][lx + 2]);
+    Hs[ly][lx] = (uint8_t)clip255((v + 16) >> 5);
+    int u = 20 * (Ts[ly + 2][lx] + Ts[ly + 3][lx]) - 5 * (Ts[ly + 1][lx] + Ts[ly + 4][lx]) + (Ts[ly][lx] + Ts[ly + 5][lx]);
+    Js[ly][lx] = (uint8_t)clip255((u + 512) >> 10);
+  }
+  __syncthreads();
+  // write the 16 planes; one thread per output pixel of the tile, 4 rows per pass
+  for (int i = tid; i < TH * TW; i += blockDim.x) {
+    int ly = i / TW, lx = i - ly * TW;
+    int y = y0 + ly, x = x0 + lx;
+    if (y >= hp || x >= wp) continue;
+    int lx1 = (x + 1 > wp - 1) ? lx : lx + 1;   // right neighbour, clamped at the plane edge
+    int ly1 = (y + 1 > hp - 1) ? ly : ly + 1;   // lower neighbour
+    int g = Gs[ly + 2][lx + 2], b = Bs[ly][lx], hv = Hs[ly][lx], j = Js[ly][lx];
+    int g_r = Gs[ly + 2][lx1 + 2], h_r = Hs[ly][lx1];
+    int g_d = Gs[ly1 + 2][lx + 2], b_d = Bs[ly1][lx];
+    size_t o = (size_t)y * pitch + x;
+    uint8_t *P = planes + o;
+    P[0 * plane_stride]  = (uint8_t)g;
+    P[1 * plane_stride]  = (uint8_t)((g + b + 1) >> 1);
+    P[2 * plane_stride]  = (uint8_t)b;
+    P[3 * plane_stride]  = (uint8_t)((b + g_r + 1) >> 1);
+    P[4 * plane_stride]  = (uint8_t)((g + hv + 1) >> 1);
+    P[5 * plane_stride]  = (uint8_t)((b + hv + 1) >> 1);
+    P[6 * plane_stride]  = (uint8_t)((b + j + 1) >> 1);
+    P[7 * plane_stride]  = (uint8_t)((b + h_r + 1) >> 1);
+    P[8 * plane_stride]  = (uint8_t)hv;
+    P[9 * plane_stride]  = (uint8_t)((hv + j + 1) >> 1);
+    P[10 * plane_stride] = (uint8_t)j;
+    P[11 * plane_stride] = (uint8_t)((j + h_r + 1) >> 1);
+    P[12 * plane_stride] = (uint8_t)((hv + g_d + 1) >> 1);
+    P[13 * plane_stride] = (uint8_t)((hv + b_d + 1) >> 1);
+    P[14 * plane_stride] = (uint8_t)((j + b_d + 1) >> 1);
+    P[15 * plane_stride] = (uint8_t)((b_d + h_r + 1) >> 1);
+  }
+}
+
+// wide-border integer plane for the search-window tiles
+__global__ void __launch_bounds__(256)
+me_search_plane_kernel(const uint8_t *__restrict__ src, int src_stride, int w, int h,
+                       uint8_t *__restrict__ dst, int spad, int spitch, int sw, int sh)
+{
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (x >= sw || y >= sh) return;
+  dst[(size_t)y * spitch + x] = src[(size_t)me_clamp(y - spad, 0, h - 1) * src_stride + me_clamp(x - spad, 0, w - 1)];
+}
+
+// JM hands pictures over as 16-bit samples (imgpel = unsigned short); narrow to the 8-bit device layout
+__global__ void __launch_bounds__(256)
+me_narrow_u16_kernel(const uint16_t *__restrict__ src, int n, uint8_t *__restrict__ dst)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (uint8_t)src[i];
+}
+
+// widen one plane row block back to imgpel for the host copy of imgY_sub
+__global__ void __launch_bounds__(256)
+me_widen_planes_kernel(const uint8_t *__restrict__ planes, int pitch, size_t plane_stride, int wp, int hp,
+                       uint16_t *__restrict__ dst)
+{
+  // dst: [16][hp][wp] contiguous
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)16 * hp * wp;
+  if (i >= n) return;
+  int x = (int)(i % wp);
+  size_t t = i / wp;
+  int y = (int)(t % hp), pl = (int)(t / hp);
+  dst[i] = planes[(size_t)pl * plane_stride + (size_t)y * pitch + x];
+}
+
+extern "C" void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t *planes, int pitch,
+                                 size_t plane_stride, uint8_t *search, int spad, int spitch, cudaStream_t st)
+{
+  int wp = w + 2 * ME_PAD, hp = h + 2 * ME_PAD;
+  dim3 grid((wp + TW - 1) / TW, (hp + TH - 1) / TH);
+  me_planes_kernel<<<grid, 256, 0, st>>>(src, src_stride, w, h, planes, pitch, plane_stride);
+  int sw = w + 2 * spad, sh = h + 2 * spad;
+  dim3 g2((sw + 255) / 256, sh);
+  me_search_plane_kernel<<<g2, 256, 0, st>>>(src, src_stride, w, h, search, spad, spitch, sw, sh);
+}
+
+extern "C" void me_launch_narrow(const uint16_t *src, int n, uint8_t *dst, cudaStream_t st)
+{
+  me_narrow_u16_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, n, dst);
+}
+
+extern "C" void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp,
+                                       uint16_t *dst, cudaStream_t st)
+{
+  size_t n = (size_t)16 * hp * wp;
+  me_widen_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(planes, pitch, plane_stride, wp, hp, dst);
+}

@@ -1,0 +1,335 @@
+// subpel.cu -- half / quarter-pel refinement (uni- and bi-predictive) and the bi-predictive integer search.
+//
+// Replaces SubPelBlockMotionSearch (reference lencod/src/me_fullsearch.c:341-511), SubPelBlockSearchBiPred (:520-754),
+// FullPelBlockMotionBiPred (:164-332) and the distortion functions they call: computeSAD / computeSATD /
+// computeBiPredSAD1 / computeBiPredSATD1 with HadamardSAD4x4 / HadamardSAD8x8 (lencod/src/me_distortion.c:351,657,482,
+// 824,182,272).  Reference samples come from the 16 quarter-pel planes with JM's origin clamp (refbuf.c:37), applied per
+// transform tile for SATD and per block for SAD exactly as the reference does.
+//
+// Work decomposition: a refinement stage scores 9 (or 8) candidates of every partition; the unit of work is one
+// transform tile (4x4, or 8x8 when Transform8x8Mode && blocktype <= 4, mv-search.c:640) of one candidate.  Tiles
+// accumulate into a per-(partition, candidate) cost in shared memory; one thread per partition then replays the
+// reference's sequential "first strict minimum" scan (me_fullsearch.c:423-449, 482-502).  The reference's early exits
+// (mcost >= min_mcost -> continue; partial sums > min_mcost -> return) never change the outcome and are dropped.
+#include "me_common.cuh"
+
+// spiral entries 0..8 (mv-search.c:366-393 with range 1)
+__constant__ int8_t c_sp_x[9] = { 0, 0, 0, -1, 1, -1, 1, -1, 1 };
+__constant__ int8_t c_sp_y[9] = { 0, -1, 1, -1, -1, 0, 0, 1, 1 };
+
+__device__ __forceinline__ int hadamard4(const int d[16])
+{
+  int t[16], s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int a = d[4 * i], b = d[4 * i + 1], c = d[4 * i + 2], e = d[4 * i + 3];
+    int p = a + e, q = b + c, u = a - e, v = b - c;
+    t[4 * i] = p + q; t[4 * i + 1] = p - q; t[4 * i + 2] = u + v; t[4 * i + 3] = u - v;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int a = t[i], b = t[4 + i], c = t[8 + i], e = t[12 + i];
+    int p = a + e, q = b + c, u = a - e, v = b - c;
+    s += abs(p + q) + abs(p - q) + abs(u + v) + abs(u - v);
+  }
+  return (s + 1) >> 1;                                   // me_distortion.c:263
+}
+
+__device__ __forceinline__ void wht8(int v[8])
+{
+#pragma unroll
+  for (int stage = 4; stage >= 1; stage >>= 1)
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (!(k & stage)) { int a = v[k], b = v[k + stage]; v[k] = a + b; v[k + stage] = a - b; }
+}
+
+__device__ __noinline__ int hadamard8(int d[64])
+{
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) wht8(&d[8 * i]);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int col[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) col[k] = d[8 * k + i];
+    wht8(col);
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += abs(col[k]);
+  }
+  return (s + 2) >> 2;                                   // me_distortion.c:342
+}
+
+// distortion of one N x N tile.  metric: 0 SAD, 1 SSE, 2 SATD.  r2 != nullptr: bi-prediction (p1 + p2 + 1) >> 1.
+template <int N>
+__device__ __forceinline__ int tile_dist(int metric, const uint8_t *__restrict__ src, int src_pitch,
+                                         const uint8_t *__restrict__ p1, int pitch1,
+                                         const uint8_t *__restrict__ p2, int pitch2)
+{
+  int d[N * N];
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int x = 0; x < N; x++) {
+      int pred = p1[y * pitch1 + x];
+      if (p2) pred = (pred + p2[y * pitch2 + x] + 1) >> 1;
+      d[y * N + x] = (int)src[y * src_pitch + x] - pred;
+    }
+  if (metric == 2) {
+    if (N == 4) return hadamard4(d);
+    return hadamard8(d);
+  }
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < N * N; i++) s += metric ? d[i] * d[i] : abs(d[i]);
+  return s;
+}
+
+// The reference fetches SAD blocks with one origin clamp per block and SATD tiles with one per tile; both are served by
+// this helper: (bx,by) = tile offset inside the block, `per_tile` selects where the clamp applies.
+__device__ __forceinline__ const uint8_t *tile_ptr(const MeRefDev &r, int x4, int y4, int bx, int by, bool per_tile)
+{
+  if (per_tile) return me_umv_ptr(r, y4 + (by << 2), x4 + (bx << 2));
+  return me_umv_ptr(r, y4, x4) + (size_t)by * r.pitch + bx;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// batch: one CTA per (macroblock, list, ref) job, all 41 partitions
+__global__ void __launch_bounds__(256)
+me_subpel_batch_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
+                       const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                       const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out)
+{
+  __shared__ int cost_s[ME_NUM_PARTITIONS][9];
+  __shared__ int mv_s[ME_NUM_PARTITIONS][2];
+  __shared__ int min_s[ME_NUM_PARTITIONS];
+  __shared__ uint8_t cur_s[16][16];
+  const int job_id = blockIdx.x;
+  if (job_id >= n_jobs) return;
+  const MeJob &job = jobs[job_id];
+  const MeRefDev ref = ref_table[job.list * ME_MAX_REFS + job.ref];
+  const int tid = threadIdx.x;
+
+  cur_s[tid >> 4][tid & 15] = cur[(size_t)(job.opix_y + (tid >> 4)) * cur_pitch + job.opix_x + (tid & 15)];
+  if (tid < ME_NUM_PARTITIONS) {
+    mv_s[tid][0] = in_int[job_id].mv[tid][0] << 2;          // mv-search.c:770-774
+    mv_s[tid][1] = in_int[job_id].mv[tid][1] << 2;
+    min_s[tid] = cfg.start_hp ? in_int[job_id].cost[tid] : ME_INT_MAX;   // mv-search.c:785-788
+  }
+  __syncthreads();
+
+  for (int stage = 0; stage < 2; stage++) {               // 0: half-pel (step 2), 1: quarter-pel (step 1)
+    const int step = stage == 0 ? 2 : 1;
+    const int level = stage == 0 ? 1 : 2;
+    const int metric = cfg.metric[level];
+    const int lam = job.lambda[level];
+    const int first = stage == 0 ? cfg.start_hp : cfg.start_qp;
+    if (stage == 1 && !cfg.start_qp && tid < ME_NUM_PARTITIONS) min_s[tid] = ME_INT_MAX;   // me_fullsearch.c:456-457
+    for (int i = tid; i < ME_NUM_PARTITIONS * 9; i += blockDim.x) {
+      int p = i / 9, c = i - 9 * p;
+      cost_s[p][c] = me_mv_cost(lam, mv_s[p][0] + step * c_sp_x[c], mv_s[p][1] + step * c_sp_y[c], job.pmv[p][0], job.pmv[p][1]);
+    }
+    __syncthreads();
+    // tiles: for every block type the macroblock is covered by 16 4x4 tiles (or 4 8x8 tiles)
+    for (int i = tid; i < 7 * 16 * 9; i += blockDim.x) {
+      int c = i % 9, rest = i / 9;
+      int tile = rest & 15, t = (rest >> 4) + 1;
+      if (c < first) continue;
+      bool use8 = cfg.transform8x8 && t <= 4 && metric == 2;
+      int tx = tile & 3, ty = tile >> 2;                  // tile position in 4-pel units inside the macroblock
+      if (use8 && ((tx | ty) & 1)) continue;
+      int bw = me_bsx(t) >> 2, bh = me_bsy(t) >> 2;       // block size in 4-pel units
+      int px = tx / bw * bw, py = ty / bh * bh;           // origin of the partition that contains the tile
+      int p = me_part_index(t, py * 4 + px);
+      int x4 = ((job.opix_x + 4 * px + ME_PAD) << 2) + mv_s[p][0] + step * c_sp_x[c];
+      int y4 = ((job.opix_y + 4 * py + ME_PAD) << 2) + mv_s[p][1] + step * c_sp_y[c];
+      int bx = 4 * (tx - px), by = 4 * (ty - py);
+      const uint8_t *rp = tile_ptr(ref, x4, y4, bx, by, metric == 2);
+      const uint8_t *sp = &cur_s[4 * ty][4 * tx];
+      int d = use8 ? tile_dist<8>(metric, sp, 16, rp, ref.pitch, nullptr, 0)
+                   : tile_dist<4>(metric, sp, 16, rp, ref.pitch, nullptr, 0);
+      atomicAdd(&cost_s[p][c], d);
+    }
+    __syncthreads();
+    if (tid < ME_NUM_PARTITIONS) {
+      int p = tid, best = 0, mn = min_s[p];
+      for (int c = first; c < 9; c++) {
+        int mc = cost_s[p][c];
+        if (stage == 0 && c == 0 && !cfg.rdopt && job.slice_type != ME_B_SLICE && job.ref == 0 && p == 0 &&
+            mv_s[p][0] == 0 && mv_s[p][1] == 0)
+          mc -= (lam * 16) >> 16;                         // check_position0, me_fullsearch.c:361,439-442
+        if (mc < mn) { mn = mc; best = c; }
+      }
+      min_s[p] = mn;
+      mv_s[p][0] += step * c_sp_x[best];
+      mv_s[p][1] += step * c_sp_y[best];
+    }
+    __syncthreads();
+  }
+  if (tid < ME_NUM_PARTITIONS) {
+    out[job_id].mv[tid][0] = (int16_t)mv_s[tid][0];
+    out[job_id].mv[tid][1] = (int16_t)mv_s[tid][1];
+    out[job_id].cost[tid] = min_s[tid];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// single block, uni- or bi-predictive (drop-in calls).  One CTA.
+//   bi == 0: SubPelBlockMotionSearch.  bi == 1: SubPelBlockSearchBiPred with r1 read at the fixed vector (s_mv).
+struct MeSubpelArgs {
+  int pic_pix_x, pic_pix_y, blocktype;
+  int pmv_x, pmv_y, mv_x, mv_y, s_mv_x, s_mv_y;
+  int search_pos2, search_pos4, min_mcost;
+  int lambda[3];
+  int check0;           // check_position0 already evaluated by the host side (needs slice type / ref)
+  int bi;
+};
+
+__global__ void __launch_bounds__(128)
+me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                        MeSubpelArgs a, int *__restrict__ result /* mvx, mvy, cost */)
+{
+  __shared__ int cost_s[9];
+  __shared__ int mv_s[2], min_sh;
+  const int tid = threadIdx.x;
+  const int t = a.blocktype, bsx = me_bsx(t), bsy = me_bsy(t);
+  if (tid == 0) { mv_s[0] = a.mv_x; mv_s[1] = a.mv_y; min_sh = a.min_mcost; }
+  __syncthreads();
+  for (int stage = 0; stage < 2; stage++) {
+    const int step = stage == 0 ? 2 : 1, level = stage == 0 ? 1 : 2;
+    const int metric = cfg.metric[level], lam = a.lambda[level];
+    const int first = stage == 0 ? cfg.start_hp : cfg.start_qp;
+    int npos = stage == 0 ? a.search_pos2 : a.search_pos4;
+    if (stage == 0 && !cfg.start_hp && npos < 1) npos = 1;   // max_pos2, me_fullsearch.c:366
+    if (npos > 9) npos = 9;
+    if (tid == 0 && stage == 1 && !cfg.start_qp) min_sh = ME_INT_MAX;
+    if (tid < 9) cost_s[tid] = me_mv_cost(lam, mv_s[0] + step * c_sp_x[tid], mv_s[1] + step * c_sp_y[tid], a.pmv_x, a.pmv_y);
+    __syncthreads();
+    bool use8 = cfg.transform8x8 && t <= 4 && metric == 2;
+    int n = use8 ? 8 : 4, tw = bsx / n, th = bsy / n;
+    for (int i = tid; i < tw * th * 9; i += blockDim.x) {
+      int c = i % 9, tile = i / 9;
+      if (c < first || c >= npos) continue;
+      int bx = (tile % tw) * n, by = (tile / tw) * n;
+      int x4 = ((a.pic_pix_x + ME_PAD) << 2) + mv_s[0] + step * c_sp_x[c];
+      int y4 = ((a.pic_pix_y + ME_PAD) << 2) + mv_s[1] + step * c_sp_y[c];
+      const uint8_t *sp = cur + (size_t)(a.pic_pix_y + by) * cur_pitch + a.pic_pix_x + bx;
+      int d;
+      if (!a.bi) {
+        const uint8_t *rp = tile_ptr(r1, x4, y4, bx, by, metric == 2);
+        d = use8 ? tile_dist<8>(metric, sp, cur_pitch, rp, r1.pitch, nullptr, 0)
+                 : tile_dist<4>(metric, sp, cur_pitch, rp, r1.pitch, nullptr, 0);
+      } else {
+        int fx4 = ((a.pic_pix_x + ME_PAD) << 2) + a.s_mv_x, fy4 = ((a.pic_pix_y + ME_PAD) << 2) + a.s_mv_y;
+        const uint8_t *p1 = tile_ptr(r1, fx4, fy4, bx, by, metric == 2);
+        const uint8_t *p2 = tile_ptr(r2, x4, y4, bx, by, metric == 2);
+        d = use8 ? tile_dist<8>(metric, sp, cur_pitch, p1, r1.pitch, p2, r2.pitch)
+                 : tile_dist<4>(metric, sp, cur_pitch, p1, r1.pitch, p2, r2.pitch);
+      }
+      atomicAdd(&cost_s[c], d);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int best = 0, mn = min_sh;
+      for (int c = first; c < npos; c++) {
+        int mc = cost_s[c];
+        if (stage == 0 && c == 0 && a.check0) mc -= (lam * 16) >> 16;
+        if (mc < mn) { mn = mc; best = c; }
+      }
+      min_sh = mn;
+      mv_s[0] += step * c_sp_x[best];
+      mv_s[1] += step * c_sp_y[best];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { result[0] = mv_s[0]; result[1] = mv_s[1]; result[2] = min_sh; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// FullPelBlockMotionBiPred (me_fullsearch.c:164-332): r1 at the fixed integer vector, r2 searched over (2r+1)^2
+struct MeBiFullArgs {
+  int pic_pix_x, pic_pix_y, blocktype;
+  int pmv_x1, pmv_y1, pmv_x2, pmv_y2;
+  int mv_x, mv_y, s_mv_x, s_mv_y;
+  int search_range, min_mcost, lambda;
+};
+
+__device__ __forceinline__ void spiral_xy_dev(int s, int &dx, int &dy)
+{
+  if (s == 0) { dx = 0; dy = 0; return; }
+  int l = (int)((sqrtf((float)s) + 1.0f) * 0.5f);
+  while ((2 * l - 1) * (2 * l - 1) > s) l--;
+  while ((2 * l + 1) * (2 * l + 1) <= s) l++;
+  int k = s - (2 * l - 1) * (2 * l - 1);
+  if (k < 2 * (2 * l - 1)) { dx = (k >> 1) - l + 1; dy = (k & 1) ? l : -l; }
+  else { k -= 2 * (2 * l - 1); dy = (k >> 1) - l; dx = (k & 1) ? l : -l; }
+}
+
+__global__ void __launch_bounds__(256)
+me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                      MeBiFullArgs a, int *__restrict__ result)
+{
+  __shared__ unsigned long long red[8];
+  const int P = (2 * a.search_range + 1) * (2 * a.search_range + 1);
+  const int bsx = me_bsx(a.blocktype), bsy = me_bsy(a.blocktype);
+  const int metric = cfg.metric[0];
+  // the reference keeps these centres in `short` (me_fullsearch.c:196-199)
+  const int c2x = (short)(a.pic_pix_x + a.mv_x), c2y = (short)(a.pic_pix_y + a.mv_y);
+  const int c1x = (short)(a.pic_pix_x + a.s_mv_x), c1y = (short)(a.pic_pix_y + a.s_mv_y);
+  const int px1 = (a.pic_pix_x << 2) + a.pmv_x1, py1 = (a.pic_pix_y << 2) + a.pmv_y1;
+  const int px2 = (a.pic_pix_x << 2) + a.pmv_x2, py2 = (a.pic_pix_y << 2) + a.pmv_y2;
+  const uint8_t *p1 = me_umv_ptr(r1, (c1y << 2) + 4 * ME_PAD, (c1x << 2) + 4 * ME_PAD);
+  const int fixed_cost = me_mv_cost(a.lambda, c1x << 2, c1y << 2, px1, py1);
+  unsigned long long best = ~0ull;
+  for (int s = threadIdx.x; s < P; s += blockDim.x) {
+    int dx, dy;
+    spiral_xy_dev(s, dx, dy);
+    int cx = (c2x + dx) << 2, cy = (c2y + dy) << 2;
+    int mc = fixed_cost + me_mv_cost(a.lambda, cx, cy, px2, py2);
+    const uint8_t *p2 = me_umv_ptr(r2, cy + 4 * ME_PAD, cx + 4 * ME_PAD);
+    int d = 0;
+    for (int y = 0; y < bsy; y++)
+      for (int x = 0; x < bsx; x++) {
+        int e = (int)cur[(size_t)(a.pic_pix_y + y) * cur_pitch + a.pic_pix_x + x]
+                - (((int)p1[(size_t)y * r1.pitch + x] + (int)p2[(size_t)y * r2.pitch + x] + 1) >> 1);
+        d += metric ? e * e : abs(e);                      // computeBiPred1[F_PEL]: SAD, SSE, (SATD -> see host)
+      }
+    mc += d;
+    unsigned long long key = ((unsigned long long)(unsigned)mc << 32) | (unsigned)s;
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other < best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); i++) best = red[i] < best ? red[i] : best;
+    int cost = (int)(unsigned)(best >> 32), pos = (int)(unsigned)(best & 0xffffffffu);
+    int dx = 0, dy = 0;
+    if (cost < a.min_mcost) spiral_xy_dev(pos, dx, dy); else cost = a.min_mcost;
+    result[0] = a.mv_x + dx; result[1] = a.mv_y + dy; result[2] = cost;
+  }
+}
+
+extern "C" void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur,
+                                       int cur_pitch, const MeCfgDev *cfg, const MeResultInt *in_int, MeResult *out,
+                                       cudaStream_t st)
+{
+  me_subpel_batch_kernel<<<n_jobs, 256, 0, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, in_int, out);
+}
+
+extern "C" void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
+                                        const MeCfgDev *cfg, const MeSubpelArgs *a, int *result, cudaStream_t st)
+{
+  me_subpel_single_kernel<<<1, 128, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, result);
+}
+
+extern "C" void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
+                                      const MeCfgDev *cfg, const MeBiFullArgs *a, int *result, cudaStream_t st)
+{
+  me_bipred_full_kernel<<<1, 256, 0, st>>>(*r1, *r2, cur, cur_pitch, *cfg, *a, result);
+}

@@ -1,0 +1,269 @@
+"""ctypes binding of libme_cuda.so (include/me_cuda.h).  Host-side mirror of the reference interface: method names
+follow the reference functions they replace (FastFullPelBlockMotionSearch, SubPelBlockMotionSearch, ...), same
+argument meaning, same return value; failures raise MeCudaError.  No CPU fallback: loading fails loudly when the
+library is missing, and init fails when there is no CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libme_cuda.so")
+
+NUM_PART = 41
+PART_TYPE = [1, 2, 2, 3, 3, 4, 4, 4, 4] + [5] * 8 + [6] * 8 + [7] * 16
+PART_BLK = [0, 0, 8, 0, 2, 0, 2, 8, 10, 0, 2, 4, 6, 8, 10, 12, 14, 0, 1, 2, 3, 8, 9, 10, 11] + list(range(16))
+P_SLICE, B_SLICE = 0, 1
+
+JOB_DTYPE = np.dtype([("opix_x", "<i2"), ("opix_y", "<i2"), ("list", "i1"), ("ref", "i1"), ("slice_type", "i1"),
+                      ("reserved", "i1"), ("pmv16", "<i2", (2,)), ("pmv", "<i2", (NUM_PART, 2)),
+                      ("lambda", "<i4", (3,))])
+RESULT_DTYPE = np.dtype([("mv", "<i2", (NUM_PART, 2)), ("cost", "<i4", (NUM_PART,))])
+assert JOB_DTYPE.itemsize == 188 and RESULT_DTYPE.itemsize == 328
+
+# every symbol include/me_cuda.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "me_cuda_set_error_handler", "me_cuda_last_error", "me_cuda_init", "me_cuda_shutdown",
+    "me_cuda_ref_create", "me_cuda_ref_create_u8", "me_cuda_ref_destroy", "me_cuda_ref_download_plane",
+    "me_cuda_set_current", "me_cuda_set_current_u8", "me_cuda_set_ref_list", "me_cuda_set_slice_type",
+    "me_cuda_mb_begin", "me_cuda_ffs_setup", "me_cuda_ffs_is_set_up",
+    "me_cuda_FastFullPelBlockMotionSearch", "me_cuda_SubPelBlockMotionSearch",
+    "me_cuda_FullPelBlockMotionBiPred", "me_cuda_SubPelBlockSearchBiPred",
+    "me_cuda_frame_search", "me_cuda_frame_search_device", "me_cuda_ref_create_device",
+    "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count",
+    "me_cuda_measure_int_peak", "me_cuda_ref_update_u8", "me_cuda_ref_update_device", "me_cuda_set_timing",
+    "me_cuda_kernel_time_ms",
+]
+
+
+class MeCudaError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32),
+                ("search_range", C.c_int32), ("max_num_references", C.c_int32), ("rdopt", C.c_int32),
+                ("full_search", C.c_int32), ("me_metric", C.c_int32 * 3), ("transform8x8", C.c_int32),
+                ("mv_limit_min_y", C.c_int32), ("mv_limit_max_y", C.c_int32), ("chroma_me_enable", C.c_int32),
+                ("weighted_me", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 8)]
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise MeCudaError("libme_cuda.so not built (%s): run __graft_entry__.build(); there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    vp, sp, ip = C.c_void_p, C.POINTER(C.c_short), C.POINTER(C.c_int)
+    L.me_cuda_last_error.restype = C.c_char_p
+    L.me_cuda_init.argtypes = [C.POINTER(Params)]
+    L.me_cuda_ref_create_u8.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    L.me_cuda_ref_create.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(C.c_int32)]
+    L.me_cuda_ref_create_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_int32)]
+    L.me_cuda_ref_destroy.argtypes = [C.c_int32]
+    L.me_cuda_ref_download_plane.argtypes = [C.c_int32, C.c_int, C.c_int, vp, C.c_int]
+    L.me_cuda_set_current_u8.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.me_cuda_set_current.argtypes = [vp, C.c_int, C.c_int]
+    L.me_cuda_set_current_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.me_cuda_set_ref_list.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    L.me_cuda_set_slice_type.argtypes = [C.c_int]
+    L.me_cuda_mb_begin.argtypes = [C.c_int, C.c_int]
+    L.me_cuda_ffs_setup.argtypes = [C.c_int] * 4
+    L.me_cuda_ffs_is_set_up.argtypes = [C.c_int] * 2
+    L.me_cuda_FastFullPelBlockMotionSearch.argtypes = ([C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, C.c_short, C.c_short,
+                                                        sp, sp, C.c_int, C.c_int, C.c_int])
+    L.me_cuda_SubPelBlockMotionSearch.argtypes = ([C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, C.c_short, C.c_short,
+                                                   sp, sp, C.c_int, C.c_int, C.c_int, ip])
+    L.me_cuda_FullPelBlockMotionBiPred.argtypes = ([C.c_short, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_short] * 4
+                                                   + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int])
+    L.me_cuda_SubPelBlockSearchBiPred.argtypes = ([C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, C.c_short, C.c_short,
+                                                   sp, sp, sp, sp, C.c_int, C.c_int, C.c_int, ip])
+    L.me_cuda_frame_search.argtypes = [vp, C.c_int, vp, vp]
+    L.me_cuda_frame_search_device.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.me_cuda_stream.restype = vp
+    L.me_cuda_launch_count.restype = C.c_int64
+    L.me_cuda_measure_int_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.me_cuda_ref_update_u8.argtypes = [C.c_int32, vp, C.c_int, C.c_int, C.c_int]
+    L.me_cuda_ref_update_device.argtypes = [C.c_int32, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.me_cuda_set_timing.argtypes = [C.c_int]
+    L.me_cuda_kernel_time_ms.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    return L
+
+
+class MeCuda:
+    """One initialised libme_cuda context (the library keeps global state like the reference does)."""
+
+    def __init__(self, width, height, search_range=32, max_num_references=5, rdopt=1, full_search=2,
+                 me_metric=(0, 2, 2), transform8x8=0, mv_limits=(-511, 511), device=-1, lib_path=LIB_PATH):
+        self.L = load_library(lib_path)
+        p = Params()
+        p.abi_version = 1
+        p.width, p.height, p.bit_depth = width, height, 8
+        p.search_range, p.max_num_references, p.rdopt, p.full_search = search_range, max_num_references, rdopt, full_search
+        for i in range(3):
+            p.me_metric[i] = me_metric[i]
+        p.transform8x8 = transform8x8
+        p.mv_limit_min_y, p.mv_limit_max_y = mv_limits
+        p.device = device
+        self.width, self.height = width, height
+        self._check(self.L.me_cuda_init(C.byref(p)))
+        self.open = True
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MeCudaError(self.L.me_cuda_last_error().decode())
+
+    def close(self):
+        if getattr(self, "open", False):
+            self.L.me_cuda_shutdown()
+            self.open = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- pictures
+    def ref_create(self, luma):
+        luma = np.ascontiguousarray(luma, np.uint8)
+        h = C.c_int32(0)
+        self._check(self.L.me_cuda_ref_create_u8(luma.ctypes.data, luma.strides[0], luma.shape[1], luma.shape[0], C.byref(h)))
+        return h.value
+
+    def ref_create_device(self, ptr, stride, stream=None):
+        h = C.c_int32(0)
+        self._check(self.L.me_cuda_ref_create_device(ptr, stride, self.width, self.height, stream, C.byref(h)))
+        return h.value
+
+    def ref_create_imgpel(self, luma_u16, want_planes=False):
+        """JM-style entry: 16-bit rows in, optionally the 16 planes back as imgY_sub[4][4][h+40][w+40] (u16)."""
+        luma_u16 = np.ascontiguousarray(luma_u16, np.uint16)
+        hgt, wid = luma_u16.shape
+        rows = (C.c_void_p * hgt)(*[luma_u16.ctypes.data + y * luma_u16.strides[0] for y in range(hgt)])
+        h = C.c_int32(0)
+        sub = None
+        if want_planes:
+            hp, wp = hgt + 40, wid + 40
+            sub = np.zeros((4, 4, hp, wp), np.uint16)
+            # imgpel**** : [4] -> [4] -> [hp] row pointers
+            self._rowptr = [[(C.c_void_p * hp)(*[sub[fy, fx].ctypes.data + y * sub.strides[2] for y in range(hp)])
+                             for fx in range(4)] for fy in range(4)]
+            self._lvl2 = [(C.c_void_p * 4)(*[C.cast(self._rowptr[fy][fx], C.c_void_p).value for fx in range(4)]) for fy in range(4)]
+            self._lvl1 = (C.c_void_p * 4)(*[C.cast(self._lvl2[fy], C.c_void_p).value for fy in range(4)])
+            self._check(self.L.me_cuda_ref_create(rows, wid, hgt, self._lvl1, C.byref(h)))
+        else:
+            self._check(self.L.me_cuda_ref_create(rows, wid, hgt, None, C.byref(h)))
+        return h.value, sub
+
+    def ref_update(self, h, luma):
+        """luma: uint8 ndarray (pinned memory makes the upload asynchronous) or (ptr, stride) of host memory"""
+        if isinstance(luma, tuple):
+            ptr, stride = luma
+        else:
+            luma = np.ascontiguousarray(luma, np.uint8)
+            ptr, stride = luma.ctypes.data, luma.strides[0]
+        self._check(self.L.me_cuda_ref_update_u8(h, ptr, stride, self.width, self.height))
+
+    def ref_update_device(self, h, ptr, stride, stream=None):
+        self._check(self.L.me_cuda_ref_update_device(h, ptr, stride, self.width, self.height, stream))
+
+    def set_timing(self, on):
+        self._check(self.L.me_cuda_set_timing(1 if on else 0))
+
+    def kernel_time_ms(self, which):
+        ms, n = C.c_double(0), C.c_int(0)
+        self._check(self.L.me_cuda_kernel_time_ms(which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def ref_destroy(self, h):
+        self._check(self.L.me_cuda_ref_destroy(h))
+
+    def ref_plane(self, h, fy, fx):
+        out = np.zeros((self.height + 40, self.width + 40), np.uint8)
+        self._check(self.L.me_cuda_ref_download_plane(h, fy, fx, out.ctypes.data, out.strides[0]))
+        return out
+
+    def ref_planes(self, h):
+        return np.stack([np.stack([self.ref_plane(h, fy, fx) for fx in range(4)]) for fy in range(4)])
+
+    def set_current(self, luma):
+        luma = np.ascontiguousarray(luma, np.uint8)
+        self._check(self.L.me_cuda_set_current_u8(luma.ctypes.data, luma.strides[0], luma.shape[1], luma.shape[0]))
+
+    def set_ref_list(self, lst, handles):
+        arr = (C.c_int32 * max(1, len(handles)))(*handles)
+        self._check(self.L.me_cuda_set_ref_list(lst, len(handles), arr))
+
+    def set_slice_type(self, t):
+        self._check(self.L.me_cuda_set_slice_type(t))
+
+    # ---- drop-in sequence
+    def mb_begin(self, opix_x, opix_y):
+        self._check(self.L.me_cuda_mb_begin(opix_x, opix_y))
+
+    def ffs_setup(self, lst, ref, pmv16_x, pmv16_y):
+        self._check(self.L.me_cuda_ffs_setup(lst, ref, pmv16_x, pmv16_y))
+
+    def FastFullPelBlockMotionSearch(self, ref, lst, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                     search_range, min_mcost, lambda_factor):
+        mx, my = C.c_short(0), C.c_short(0)
+        cost = self.L.me_cuda_FastFullPelBlockMotionSearch(ref, lst, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                                           C.byref(mx), C.byref(my), search_range, min_mcost, lambda_factor)
+        return mx.value, my.value, cost
+
+    def SubPelBlockMotionSearch(self, ref, lst, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y,
+                                search_pos2, search_pos4, min_mcost, lambda_factor):
+        mx, my = C.c_short(mv_x), C.c_short(mv_y)
+        lam = (C.c_int * 3)(*lambda_factor)
+        cost = self.L.me_cuda_SubPelBlockMotionSearch(ref, lst, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                                      C.byref(mx), C.byref(my), search_pos2, search_pos4, min_mcost, lam)
+        return mx.value, my.value, cost
+
+    def FullPelBlockMotionBiPred(self, ref, lst, pic_pix_x, pic_pix_y, blocktype, pmv1, pmv2, mv, s_mv, search_range,
+                                 min_mcost, lambda_factor):
+        mx, my, sx, sy = C.c_short(mv[0]), C.c_short(mv[1]), C.c_short(s_mv[0]), C.c_short(s_mv[1])
+        cost = self.L.me_cuda_FullPelBlockMotionBiPred(ref, lst, pic_pix_x, pic_pix_y, blocktype, pmv1[0], pmv1[1], pmv2[0], pmv2[1],
+                                                       C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy), search_range,
+                                                       min_mcost, lambda_factor)
+        return mx.value, my.value, cost
+
+    def SubPelBlockSearchBiPred(self, ref, lst, pic_pix_x, pic_pix_y, blocktype, pmv, mv, s_mv, search_pos2, search_pos4,
+                                min_mcost, lambda_factor):
+        mx, my, sx, sy = C.c_short(mv[0]), C.c_short(mv[1]), C.c_short(s_mv[0]), C.c_short(s_mv[1])
+        lam = (C.c_int * 3)(*lambda_factor)
+        cost = self.L.me_cuda_SubPelBlockSearchBiPred(ref, lst, pic_pix_x, pic_pix_y, blocktype, pmv[0], pmv[1],
+                                                      C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy),
+                                                      search_pos2, search_pos4, min_mcost, lam)
+        return mx.value, my.value, cost
+
+    # ---- frame batch
+    def frame_search(self, jobs, want_int=False):
+        jobs = np.ascontiguousarray(jobs)
+        assert jobs.dtype == JOB_DTYPE
+        out = np.zeros(len(jobs), RESULT_DTYPE)
+        out_int = np.zeros(len(jobs), RESULT_DTYPE) if want_int else None
+        self._check(self.L.me_cuda_frame_search(jobs.ctypes.data, len(jobs), out.ctypes.data,
+                                                out_int.ctypes.data if want_int else None))
+        return (out, out_int) if want_int else out
+
+    def frame_search_device(self, d_jobs, n, d_out, d_out_int=None, stream=None):
+        self._check(self.L.me_cuda_frame_search_device(d_jobs, n, d_out, d_out_int, stream))
+
+    def set_current_device(self, ptr, stride, stream=None):
+        self._check(self.L.me_cuda_set_current_device(ptr, stride, self.width, self.height, stream))
+
+    def stream(self):
+        return self.L.me_cuda_stream()
+
+    def sync(self):
+        self._check(self.L.me_cuda_sync())
+
+    def launch_count(self):
+        return int(self.L.me_cuda_launch_count())
+
+    def measure_int_peak(self, kind):
+        v = C.c_double(0)
+        rc = self.L.me_cuda_measure_int_peak(kind, C.byref(v))
+        if rc:
+            raise MeCudaError("me_cuda_measure_int_peak(%d) failed: %d" % (kind, rc))
+        return v.value

@@ -85,6 +85,8 @@ int me_cuda_ref_create(const me_imgpel *const *imgY_rows, int w, int h, me_imgpe
 int me_cuda_ref_create_u8(const uint8_t *luma, int stride, int w, int h, me_ref_handle *out);
 /* free_storable_picture (mbuffer.c:556-600) */
 int me_cuda_ref_destroy(me_ref_handle h);
+/* rebuild the planes of an existing handle from a new picture, in place (a decoded-picture-buffer frame store being reused) */
+int me_cuda_ref_update_u8(me_ref_handle h, const uint8_t *luma, int stride, int w, int hgt);
 /* copy one of the 16 planes back: dst[(h+40)][dst_stride], plane index as Pic[fy][fx] (refbuf.c:27) */
 int me_cuda_ref_download_plane(me_ref_handle h, int fy, int fx, uint8_t *dst, int dst_stride);
 
@@ -156,11 +158,20 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
  * cudaStream_t passed as void* (NULL = the library's own stream).  Asynchronous. ---- */
 int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, void *d_out_int, void *stream);
 int me_cuda_ref_create_device(const void *d_luma_u8, int stride, int w, int h, void *stream, me_ref_handle *out);
+int me_cuda_ref_update_device(me_ref_handle hd, const void *d_luma_u8, int stride, int w, int h, void *stream);
 int me_cuda_set_current_device(const void *d_luma_u8, int stride, int w, int h, void *stream);
+/* per-kernel-class device timing (CUDA events around every launch; class 0 plane generation, 1 integer-pel search,
+ * 2 sub-pel refinement).  me_cuda_set_timing(1) starts / resets collection, (0) stops it. */
+int me_cuda_set_timing(int on);
+int me_cuda_kernel_time_ms(int which, double *total_ms, int *n_launches);
 void *me_cuda_stream(void);                 /* the library's stream (cudaStream_t) */
 int   me_cuda_sync(void);                   /* cudaStreamSynchronize on it */
 /* number of kernels this library has launched since init (bench.py reports it as gpu_launches) */
 int64_t me_cuda_launch_count(void);
+/* diagnostics: measured issue rate (lane-operations per second, whole GPU) of the integer instructions the search
+ * kernels are bound by; kind 0 VABSDIFF4, 1 IADD3, 2 IMAD, 3 VIADDMNMX, 4 LOP3, 5 SHF, 6 VABSDIFF4+IMAD, 7 VABSDIFF4+IADD3.
+ * This is the denominator of bench.py's INT-ALU roofline (MEASURED_PEAKS.json has no integer figure). */
+int me_cuda_measure_int_peak(int kind, double *lane_ops_per_s);
 
 #ifdef __cplusplus
 }

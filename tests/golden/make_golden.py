@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures from the UNMODIFIED reference encoder.
+
+Runs oracle/_ref/lencod_trace (reference objects + the --wrap call tracer oracle/trace_wrap.c; built by
+`make -C oracle ref` in a container that has /root/reference) and stores, per case, a compact .npz:
+  recs            traced calls of the hot-path functions (arguments and results; layout in oracle/trace_wrap.c)
+  cur_<n>, ref_<i> original / reconstructed luma pictures the calls operated on
+plus planes_crc.json: CRC32 of each of the 16 quarter-pel planes the reference built for every reference picture.
+
+Cases
+  kat        bin/encoder.cfg as shipped (the run behind the committed bin/test.264): QCIF I-B-P, SR 32, 5 refs, RDO on,
+             8x8 transform, bi-pred ME.  Every 4th macroblock is kept.
+  rdopt0     encoder_baseline.cfg, RDOptimization=0, RestrictSearchRange=0, SR 16, 2 refs, synthetic QCIF IPPP --
+             pins the !rdopt zero-vector rules and the reduced search ranges.  Every 5th macroblock is kept.
+Usage: python tests/golden/make_golden.py            (rewrites tests/golden/*.npz, planes_crc.json, bitstream_md5.json)
+"""
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from trace_util import Trace, REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB  # noqa: E402
+import h264_b200_pkg  # noqa: E402,F401
+from h264_b200 import synth  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def run_trace(workdir, args, planes=True, binary="lencod_trace"):
+    for f in os.listdir(os.path.join(REF, "fixtures")):
+        if f.endswith(".cfg"):
+            shutil.copy(os.path.join(REF, "fixtures", f), workdir)
+    env = dict(os.environ, ME_TRACE_DIR=workdir, ME_TRACE_PLANES="1" if planes else "0")
+    r = subprocess.run([os.path.join(REF, binary)] + args, cwd=workdir, env=env, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout[-2000:] + r.stderr[-2000:])
+    return r.stdout
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+def keep_mask(tr, step):
+    recs = tr.recs
+    mb_w = tr.size[("cur", tr.cur_ids()[0])][1] // 16
+    mb = (recs[:, 4] // 16) * mb_w + recs[:, 3] // 16
+    is_call = np.isin(recs[:, 0], [REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB])
+    return ~is_call | (mb % step == 0)
+
+
+def planes_crc(tr, workdir):
+    out = {}
+    for i in tr.ref_ids():
+        sub = tr.ref_sub(i)
+        out[str(i)] = [[int(zlib.crc32(sub[fy, fx].tobytes())) for fx in range(4)] for fy in range(4)]
+    return out
+
+
+def main():
+    crc, md5s = {}, {}
+    # ---- kat
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(os.path.join(REF, "fixtures", "foreman_part_qcif.yuv"), d)
+        run_trace(d, ["-d", "encoder.cfg"])
+        md5s["kat"] = {"test.264": md5(os.path.join(d, "test.264")), "test_rec.yuv": md5(os.path.join(d, "test_rec.yuv"))}
+        assert md5s["kat"]["test.264"] == md5(os.path.join(REF, "fixtures", "golden_test.264"))
+        tr = Trace(d)
+        tr.save_npz(os.path.join(HERE, "kat.npz"), keep_mask(tr, 4))
+        crc["kat"] = planes_crc(tr, d)
+    # ---- rdopt0
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_yuv420(os.path.join(d, "syn_qcif.yuv"), 176, 144, 4)
+        args = ["-d", "encoder_baseline.cfg", "-p", "InputFile=syn_qcif.yuv", "-p", "FramesToBeEncoded=4",
+                "-p", "RDOptimization=0", "-p", "RestrictSearchRange=0", "-p", "SearchRange=16",
+                "-p", "NumberReferenceFrames=2", "-p", "FrameSkip=0"]
+        run_trace(d, args)
+        md5s["rdopt0"] = {"test.264": md5(os.path.join(d, "test.264"))}
+        tr = Trace(d)
+        tr.save_npz(os.path.join(HERE, "rdopt0.npz"), keep_mask(tr, 5))
+        crc["rdopt0"] = planes_crc(tr, d)
+    json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
+    json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+"""Replay of reference call traces through an implementation under test.
+
+An adapter exposes the reference's call sequence (mb_begin / ffs_setup / FastFullPelBlockMotionSearch / ...).
+OracleAdapter drives oracle/liboracle_me.so (CPU restatement); CudaAdapter drives libme_cuda.so through its C ABI.
+replay() walks a Trace in call order and returns the mismatching records per function.
+"""
+import numpy as np
+
+from trace_util import REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_CURPIC, REC_REFPIC
+
+
+def picture_lists(trace, pic):
+    """reference lists of coded picture `pic` as {list: [ref picture id by index]} recovered from the records"""
+    lists = {0: {}, 1: {}}
+    recs = trace.recs[(trace.recs[:, 1] == pic)]
+    for r in recs:
+        t = int(r[0])
+        if t in (REC_FFS, REC_SUBPEL):
+            lists[int(r[5])][int(r[6])] = int(r[21])
+        elif t in (REC_BI_FULL, REC_BI_SUB):
+            lists[int(r[5])][int(r[6])] = int(r[21])
+            lists[int(r[5]) ^ 1][0] = int(r[22])
+    out = {}
+    for l in (0, 1):
+        if lists[l]:
+            n = max(lists[l]) + 1
+            # indices never used by a traced call get any valid picture
+            anyid = next(iter(lists[l].values()))
+            out[l] = [lists[l].get(i, anyid) for i in range(n)]
+        else:
+            out[l] = []
+    return out
+
+
+class OracleAdapter:
+    def __init__(self, trace, cfgkw):
+        from oracle import binding as ob
+        self.ob = ob
+        self.cfg = ob.make_cfg(**cfgkw)
+        self.refs = {i: ob.Ref(trace.ref(i)) for i in trace.ref_ids()}
+        self.surf = {}
+
+    def begin_picture(self, cur, slice_type, lists):
+        self.cur, self.slice_type, self.lists = np.ascontiguousarray(cur), slice_type, lists
+
+    def mb_begin(self, ox, oy):
+        self.ox, self.oy = ox, oy
+        self.surf = {}
+
+    def ffs_setup(self, lst, ref, pmvx, pmvy):
+        ob = self.ob
+        cx, cy = ob.search_centre(self.cfg, ref, self.ox, self.oy, pmvx, pmvy)
+        rng = ob.lib().ora_setup_range(self.cfg, ref)
+        s = ob.ffs_surfaces(self.cfg, self.cur, self.refs[self.lists[lst][ref]], self.ox, self.oy, cx, cy, rng)
+        self.surf[(lst, ref)] = (s, cx, cy, rng)
+        return cx, cy, rng
+
+    def ffs_block(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, search_range, min_mcost, lam):
+        s, cx, cy, rng = self.surf[(lst, ref)]
+        p = self.ob.part_index(bt, (ppy - self.oy) + ((ppx - self.ox) >> 2))
+        return self.ob.ffs_block(self.cfg, s[p], rng, self.ox, self.oy, cx, cy, pmvx, pmvy, search_range, min_mcost, lam)
+
+    def subpel(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, sp2, sp4, min_mcost, lam3):
+        return self.ob.subpel(self.cfg, self.cur, self.refs[self.lists[lst][ref]], ppx, ppy, bt, ref, self.slice_type,
+                              pmvx, pmvy, mvx, mvy, min_mcost, lam3, sp2, sp4)
+
+    def bipred_full(self, ref, lst, ppx, ppy, bt, pmv1, pmv2, mv, smv, sr, min_mcost, lam):
+        r1, r2 = self.refs[self.lists[lst][ref]], self.refs[self.lists[lst ^ 1][0]]
+        return self.ob.bipred_fullpel(self.cfg, self.cur, r1, r2, ppx, ppy, bt, pmv1, pmv2, mv, smv, sr, min_mcost, lam)
+
+    def bipred_sub(self, ref, lst, ppx, ppy, bt, pmv, mv, smv, sp2, sp4, min_mcost, lam3):
+        r1, r2 = self.refs[self.lists[lst][ref]], self.refs[self.lists[lst ^ 1][0]]
+        return self.ob.bipred_subpel(self.cfg, self.cur, r1, r2, ppx, ppy, bt, pmv, mv, smv, min_mcost, lam3, sp2, sp4)
+
+    def close(self):
+        for r in self.refs.values():
+            r.close()
+
+
+class CudaAdapter:
+    """the drop-in call sequence of include/me_cuda.h"""
+
+    def __init__(self, trace, cfgkw, max_refs=5):
+        import h264_b200_pkg  # noqa: F401
+        from h264_b200 import MeCuda
+        h, w = trace.size[("cur", trace.cur_ids()[0])]
+        self.me = MeCuda(w, h, search_range=cfgkw["search_range"], max_num_references=max_refs, rdopt=cfgkw["rdopt"],
+                         full_search=cfgkw["full_search"], me_metric=cfgkw["metric"], transform8x8=cfgkw["transform8x8"],
+                         mv_limits=(cfgkw["mv_limit_min_y"], cfgkw["mv_limit_max_y"]))
+        self.handles = {i: self.me.ref_create(trace.ref(i)) for i in trace.ref_ids()}
+
+    def begin_picture(self, cur, slice_type, lists):
+        self.me.set_current(cur)
+        self.me.set_slice_type(slice_type)
+        for l in (0, 1):
+            self.me.set_ref_list(l, [self.handles[i] for i in lists[l]])
+
+    def mb_begin(self, ox, oy):
+        self.me.mb_begin(ox, oy)
+
+    def ffs_setup(self, lst, ref, pmvx, pmvy):
+        self.me.ffs_setup(lst, ref, pmvx, pmvy)
+        return None
+
+    def ffs_block(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, search_range, min_mcost, lam):
+        return self.me.FastFullPelBlockMotionSearch(ref, lst, ppx, ppy, bt, pmvx, pmvy, search_range, min_mcost, lam)
+
+    def subpel(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, sp2, sp4, min_mcost, lam3):
+        return self.me.SubPelBlockMotionSearch(ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, sp2, sp4, min_mcost, lam3)
+
+    def bipred_full(self, ref, lst, ppx, ppy, bt, pmv1, pmv2, mv, smv, sr, min_mcost, lam):
+        return self.me.FullPelBlockMotionBiPred(ref, lst, ppx, ppy, bt, pmv1, pmv2, mv, smv, sr, min_mcost, lam)
+
+    def bipred_sub(self, ref, lst, ppx, ppy, bt, pmv, mv, smv, sp2, sp4, min_mcost, lam3):
+        return self.me.SubPelBlockSearchBiPred(ref, lst, ppx, ppy, bt, pmv, mv, smv, sp2, sp4, min_mcost, lam3)
+
+    def close(self):
+        self.me.close()
+
+
+def replay(trace, impl, max_calls=None):
+    """returns {name: (n_calls, [mismatch descriptions])}"""
+    res = {"ffs": [0, []], "centre": [0, []], "subpel": [0, []], "bi_full": [0, []], "bi_sub": [0, []]}
+    cur_pic, cur_mb = None, None
+    slice_of = {int(r[1]): int(r[2]) for r in trace.of_type(REC_CURPIC)}
+    n = 0
+    for r in trace.recs:
+        t = int(r[0])
+        if t in (REC_REFPIC, REC_CURPIC):
+            continue
+        pic, ox, oy = int(r[1]), int(r[3]), int(r[4])
+        if pic != cur_pic:
+            impl.begin_picture(trace.cur(pic), slice_of.get(pic, int(r[2])), picture_lists(trace, pic))
+            cur_pic, cur_mb = pic, None
+        if (ox, oy) != cur_mb:
+            impl.mb_begin(ox, oy)
+            cur_mb = (ox, oy)
+        lst, ref, bt, ppx, ppy = int(r[5]), int(r[6]), int(r[7]), int(r[8]), int(r[9])
+        if t == REC_FFS:
+            if r[22]:
+                c = impl.ffs_setup(lst, ref, int(r[23]), int(r[24]))
+                if c is not None:
+                    res["centre"][0] += 1
+                    if c != (int(r[15]), int(r[16]), int(r[17])):
+                        res["centre"][1].append((r[:26].tolist(), c))
+            got = impl.ffs_block(ref, lst, ppx, ppy, bt, int(r[10]), int(r[11]), int(r[12]), int(r[14]), int(r[13]))
+            exp = (int(r[18]), int(r[19]), int(r[20]))
+            key = "ffs"
+        elif t == REC_SUBPEL:
+            got = impl.subpel(ref, lst, ppx, ppy, bt, int(r[10]), int(r[11]), int(r[12]), int(r[13]), int(r[26]), int(r[27]),
+                              int(r[14]), [int(r[15]), int(r[16]), int(r[17])])
+            exp = (int(r[18]), int(r[19]), int(r[20]))
+            key = "subpel"
+        elif t == REC_BI_FULL:
+            got = impl.bipred_full(ref, lst, ppx, ppy, bt, (int(r[10]), int(r[11])), (int(r[12]), int(r[13])),
+                                   (int(r[17]), int(r[18])), (int(r[19]), int(r[20])), int(r[16]), int(r[14]), int(r[15]))
+            exp = (int(r[23]), int(r[24]), int(r[25]))
+            key = "bi_full"
+        else:
+            got = impl.bipred_sub(ref, lst, ppx, ppy, bt, (int(r[10]), int(r[11])), (int(r[12]), int(r[13])),
+                                  (int(r[14]), int(r[15])), 9, 9, int(r[16]),
+                                  [int(r[17]), int(r[18]), int(r[19])])
+            exp = (int(r[23]), int(r[24]), int(r[25]))
+            key = "bi_sub"
+        res[key][0] += 1
+        if tuple(got) != exp:
+            res[key][1].append((r[:29].tolist(), tuple(got)))
+        n += 1
+        if max_calls and n >= max_calls:
+            break
+    return {k: (v[0], v[1]) for k, v in res.items()}

@@ -1,0 +1,251 @@
+"""GPU parity tests: libme_cuda.so through its C ABI against the oracle and the reference-derived golden vectors.
+Bit-exact everywhere (integer / byte work): identical planes, motion vectors and costs."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, golden_trace
+from replay import CudaAdapter, replay
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg(me_lib_path):
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import h264_b200_pkg  # noqa: F401
+    import h264_b200
+    return h264_b200
+
+
+def _cfg(ob, **kw):
+    d = dict(search_range=32, rdopt=1, full_search=2, metric=(0, 2, 2), transform8x8=0, mv_limit_min_y=-511, mv_limit_max_y=511)
+    d.update(kw)
+    return d, ob.make_cfg(**d)
+
+
+def _open(pkg, w, h, d, max_refs=5):
+    return pkg.MeCuda(w, h, search_range=d["search_range"], max_num_references=max_refs, rdopt=d["rdopt"],
+                      full_search=d["full_search"], me_metric=d["metric"], transform8x8=d["transform8x8"],
+                      mv_limits=(d["mv_limit_min_y"], d["mv_limit_max_y"]))
+
+
+# ------------------------------------------------------------------------------------------------ planes
+@pytest.mark.parametrize("kind", ["pan", "noise", "flat", "extremes"])
+def test_planes_bit_exact(pkg, oracle_lib, kind):
+    from h264_b200 import synth
+    w, h = 352, 288
+    rng = np.random.default_rng(5)
+    if kind == "pan":
+        luma = synth.luma_frames(w, h, 2)[1]
+    elif kind == "noise":
+        luma = rng.integers(0, 256, (h, w)).astype(np.uint8)
+    elif kind == "flat":
+        luma = np.full((h, w), 200, np.uint8)
+    else:   # 0/255 checkerboards drive the six-tap filter into both clip limits
+        luma = (((np.arange(h)[:, None] // 3 + np.arange(w)[None, :] // 2) % 2) * 255).astype(np.uint8)
+    d, _ = _cfg(oracle_lib)
+    with _open(pkg, w, h, d) as me:
+        hd = me.ref_create(luma)
+        got = me.ref_planes(hd)
+        ref = oracle_lib.Ref(luma)
+        exp = ref.planes()
+        assert got.shape == exp.shape
+        bad = np.argwhere(got != exp)
+        assert len(bad) == 0, (kind, bad[:5])
+        # JM-style entry: 16-bit samples in, imgY_sub[4][4][h+40][w+40] filled on the host
+        hd2, sub = me.ref_create_imgpel(luma.astype(np.uint16), want_planes=True)
+        assert np.array_equal(sub, exp.astype(np.uint16))
+        me.ref_destroy(hd); me.ref_destroy(hd2)
+        ref.close()
+
+
+def test_planes_golden_reference_pictures(pkg, oracle_lib):
+    """the reference's own reconstructed pictures from the known-answer run"""
+    import json, zlib
+    from conftest import GOLDEN
+    crc = json.load(open(os.path.join(GOLDEN, "planes_crc.json")))
+    for case in sorted(GOLDEN_CASES):
+        tr, cfgkw = golden_trace(case)
+        h, w = tr.size[("cur", tr.cur_ids()[0])]
+        with _open(pkg, w, h, cfgkw) as me:
+            for i in tr.ref_ids():
+                hd = me.ref_create(tr.ref(i))
+                for fy in range(4):
+                    for fx in range(4):
+                        assert zlib.crc32(me.ref_plane(hd, fy, fx).tobytes()) == crc[case][str(i)][fy][fx], (case, i, fy, fx)
+
+
+# ------------------------------------------------------------------------------------------------ drop-in calls
+@pytest.mark.parametrize("case", sorted(GOLDEN_CASES))
+def test_dropin_calls_match_reference_trace(pkg, case):
+    """every traced call of the unmodified reference encoder, replayed through the drop-in C ABI"""
+    tr, cfgkw = golden_trace(case)
+    impl = CudaAdapter(tr, cfgkw)
+    try:
+        res = replay(tr, impl)
+    finally:
+        impl.close()
+    for name, (n, bad) in res.items():
+        assert not bad, (case, name, n, len(bad), bad[:3])
+    assert res["ffs"][0] > 1000 and res["subpel"][0] > 1000
+
+
+# ------------------------------------------------------------------------------------------------ frame batch
+def _batch_case(pkg, ob, w, h, frames, n_refs, d, cfg, jobs, sample=None, seed=0):
+    from h264_b200 import synth  # noqa: F401
+    cur = frames[-1]
+    with _open(pkg, w, h, d, max_refs=max(1, n_refs)) as me:
+        handles = [me.ref_create(frames[-2 - r]) for r in range(n_refs)]
+        me.set_ref_list(0, handles)
+        me.set_current(cur)
+        out, out_int = me.frame_search(jobs, want_int=True)
+    idx = np.arange(len(jobs))
+    if sample is not None and sample < len(jobs):
+        idx = np.sort(np.random.default_rng(seed).choice(len(jobs), sample, replace=False))
+    refs = [ob.Ref(frames[-2 - r]) for r in range(n_refs)]
+    bad = []
+    for r in range(n_refs):
+        sel = idx[jobs["ref"][idx] == r]
+        if not len(sel):
+            continue
+        exp, exp_int = ob.mb_search(cfg, np.ascontiguousarray(cur), refs[r], jobs[sel])
+        for k, j in enumerate(sel):
+            if not (np.array_equal(out_int["mv"][j], exp_int["mv"][k]) and np.array_equal(out_int["cost"][j], exp_int["cost"][k])):
+                p = int(np.argmax((out_int["mv"][j] != exp_int["mv"][k]).any(axis=1) | (out_int["cost"][j] != exp_int["cost"][k])))
+                bad.append(("int", int(j), p, out_int["mv"][j][p].tolist(), int(out_int["cost"][j][p]), exp_int["mv"][k][p].tolist(), int(exp_int["cost"][k][p])))
+            elif not (np.array_equal(out["mv"][j], exp["mv"][k]) and np.array_equal(out["cost"][j], exp["cost"][k])):
+                p = int(np.argmax((out["mv"][j] != exp["mv"][k]).any(axis=1) | (out["cost"][j] != exp["cost"][k])))
+                bad.append(("sub", int(j), p, out["mv"][j][p].tolist(), int(out["cost"][j][p]), exp["mv"][k][p].tolist(), int(exp["cost"][k][p])))
+    for r in refs:
+        r.close()
+    return bad, len(idx)
+
+
+@pytest.mark.parametrize("variant", ["default", "t8x8", "rdopt0", "restrict0_sr16", "sse_fpel", "sad_subpel", "qcif_sr32"])
+def test_batch_matches_oracle(pkg, oracle_lib, variant):
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h, n_refs, kw = 352, 288, 3, {}
+    if variant == "t8x8":
+        kw = dict(transform8x8=1)
+    elif variant == "rdopt0":
+        kw = dict(rdopt=0)
+    elif variant == "restrict0_sr16":
+        kw = dict(full_search=0, search_range=16)
+    elif variant == "sse_fpel":
+        kw = dict(metric=(1, 2, 2))
+    elif variant == "sad_subpel":
+        kw = dict(metric=(0, 0, 0))
+    elif variant == "qcif_sr32":
+        w, h, n_refs = 176, 144, 2          # most windows leave the picture
+    d, cfg = _cfg(ob, **kw)
+    frames = synth.luma_frames(w, h, n_refs + 1)
+    jobs = synth.synthetic_jobs(w, h, n_refs, (334459, 334459, 334459), seed=11, max_pmv=40)
+    bad, n = _batch_case(pkg, ob, w, h, frames, n_refs, d, cfg, jobs, sample=260)
+    assert not bad, (variant, len(bad), n, bad[:4])
+
+
+@pytest.mark.parametrize("kind", ["flat", "stripes"])
+def test_batch_ties_follow_spiral_order(pkg, oracle_lib, kind):
+    """flat / periodic content: thousands of equal costs, the winner must be the first one in JM's spiral order"""
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h, n_refs = 176, 144, 2
+    d, cfg = _cfg(ob, transform8x8=1)
+    frames = synth.luma_frames(w, h, n_refs + 1, kind=kind)
+    jobs = synth.synthetic_jobs(w, h, n_refs, (334459, 334459, 334459), seed=3, max_pmv=60)
+    jobs["lambda"][::2] = (0, 0, 0)            # lambda 0: every position ties
+    bad, n = _batch_case(pkg, ob, w, h, frames, n_refs, d, cfg, jobs, sample=None)
+    assert not bad, (kind, len(bad), n, bad[:4])
+
+
+def test_batch_extreme_predictors(pkg, oracle_lib):
+    """predictors far outside the picture: centre clipping (me_fullfast.c:555-563) and fully clamped windows"""
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h, n_refs = 176, 144, 1
+    d, cfg = _cfg(ob)
+    frames = synth.luma_frames(w, h, 2)
+    jobs = synth.synthetic_jobs(w, h, n_refs, (200000, 150000, 100000), seed=5)
+    rng = np.random.default_rng(9)
+    ext = np.array([[-8191, -8191], [8188, 8188], [-8191, 2044], [300, -2047], [-257, 511], [1023, -1023], [3, -3], [0, 0]])
+    for i in range(len(jobs)):
+        jobs["pmv16"][i] = ext[rng.integers(len(ext))]
+        jobs["pmv"][i] = jobs["pmv16"][i][None, :] + rng.integers(-300, 301, size=(41, 2))
+    bad, n = _batch_case(pkg, ob, w, h, frames, n_refs, d, cfg, jobs, sample=None)
+    assert not bad, (len(bad), n, bad[:4])
+
+
+def test_full_size_1080p_properties(pkg, oracle_lib):
+    """BASELINE headline size: 1920x1088, SR 32, 5 refs.  Size-independent checks on the whole frame, oracle on a sample."""
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h, n_refs = 1920, 1088, 5
+    d, cfg = _cfg(ob)
+    frames = synth.luma_frames(w, h, n_refs + 1)
+    lam = (334459, 334459, 334459)
+    jobs = synth.synthetic_jobs(w, h, n_refs, lam, seed=21)
+    cur = frames[-1]
+    with _open(pkg, w, h, d) as me:
+        handles = [me.ref_create(frames[-2 - r]) for r in range(n_refs)]
+        me.set_ref_list(0, handles)
+        me.set_current(cur)
+        out1, int1 = me.frame_search(jobs, want_int=True)
+        out2, int2 = me.frame_search(jobs, want_int=True)
+        # known answer: search the current picture in itself with zero predictors -> zero vector, cost = rate of (0,0)
+        hs = me.ref_create(cur)
+        me.set_ref_list(0, [hs])
+        selfjobs = jobs[: (w // 16) * (h // 16)].copy()
+        selfjobs["ref"] = 0
+        selfjobs["pmv16"] = 0
+        selfjobs["pmv"] = 0
+        so, si = me.frame_search(selfjobs, want_int=True)
+    assert np.array_equal(out1, out2) and np.array_equal(int1, int2)          # deterministic
+    assert (si["mv"] == 0).all() and (so["mv"] == 0).all()
+    zero_rate = (lam[0] * 2) >> 16
+    assert (si["cost"] == zero_rate).all() and (so["cost"] == zero_rate).all()
+    # integer-pel cost is an upper bound only within the same metric; vectors stay inside centre +- range
+    mvx = int1["mv"][..., 0].astype(np.int32)
+    cx = (jobs["pmv16"][:, 0].astype(np.int32) / 4).astype(np.int32)         # C truncation
+    assert (np.abs(mvx - cx[:, None]) <= 32).all()
+    # the sub-pel result moves at most 3 quarter pels from the integer result
+    assert (np.abs(out1["mv"].astype(np.int32) - 4 * int1["mv"].astype(np.int32)) <= 3).all()
+    # oracle on a sample of jobs
+    refs = [ob.Ref(frames[-2 - r]) for r in range(n_refs)]
+    rng = np.random.default_rng(2)
+    sel = np.sort(rng.choice(len(jobs), 100, replace=False))
+    curc = np.ascontiguousarray(cur)
+    for r in range(n_refs):
+        s = sel[jobs["ref"][sel] == r]
+        if len(s):
+            exp, exp_int = ob.mb_search(cfg, curc, refs[r], jobs[s])
+            assert np.array_equal(int1[s], exp_int), r
+            assert np.array_equal(out1[s], exp), r
+    for r in refs:
+        r.close()
+
+
+def test_tuned_and_basic_kernels_agree(pkg, oracle_lib):
+    """the tuned search kernel against the straightforward one on a whole CIF frame (env switch in the library)"""
+    from h264_b200 import synth
+    w, h, n_refs = 352, 288, 2
+    d, _ = _cfg(oracle_lib)
+    frames = synth.luma_frames(w, h, n_refs + 1)
+    jobs = synth.synthetic_jobs(w, h, n_refs, (334459, 334459, 334459), seed=4, max_pmv=50)
+    res = []
+    for mode in ("basic", ""):
+        os.environ["ME_CUDA_FFS_KERNEL"] = mode
+        try:
+            with _open(pkg, w, h, d) as me:
+                me.set_ref_list(0, [me.ref_create(frames[-2 - r]) for r in range(n_refs)])
+                me.set_current(frames[-1])
+                res.append(me.frame_search(jobs, want_int=True))
+        finally:
+            os.environ.pop("ME_CUDA_FFS_KERNEL", None)
+    assert np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][0], res[1][0])
+EOF
+echo written
