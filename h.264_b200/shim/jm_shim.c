@@ -1,0 +1,295 @@
+/*
+ * jm_shim.c -- the reference-side binding of libme_cuda.so for the JM 12.4 encoder (lencod).
+ *
+ * This is what a maintainer adds to lencod to route its motion-estimation hot path through the GPU library.  It is
+ * written as a link-time interposer: the UNMODIFIED reference objects are linked with
+ *     -Wl,--wrap=FastFullPelBlockMotionSearch,--wrap=SubPelBlockMotionSearch,--wrap=FullPelBlockMotionBiPred,
+ *         --wrap=SubPelBlockSearchBiPred,--wrap=ResetFastFullIntegerSearch,--wrap=getSubImagesLuma,
+ *         --wrap=encode_one_frame,--wrap=Init_Motion_Search_Module,--wrap=Clear_Motion_Search_Module,
+ *         --wrap=free_storable_picture
+ * so every call site the SearchMode dispatch of mv-search.c reaches (mv-search.c:745, :823, :960, :998, :1018), the
+ * per-macroblock reset (macroblock.c:509), the plane generation (image.c:1642) and the module init / clear
+ * (lencod.c:255, :387) land here.  Everything else -- predictors (SetMotionVectorPredictor, mv-search.c:87), mode
+ * decision, transforms, entropy coding -- stays the reference's host C.  (INTEGRATION.md shows the same binding as a
+ * source patch.)  The library is loaded with dlopen, so the encoder binary has no link-time CUDA dependency; it is
+ * compiled against the reference's own headers by oracle/Makefile (target _ref/lencod_cuda).
+ *
+ * Environment: ME_CUDA_LIB = path of libme_cuda.so (default: <dir of executable>/../../h.264_b200/libme_cuda.so),
+ *              ME_CUDA_DISABLE=1 turns the interposer into a pass-through (pure reference behaviour).
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "global.h"
+#include "image.h"
+#include "mbuffer.h"
+#include "me_distortion.h"
+
+#include "me_cuda.h"
+
+extern const int LEVELMVLIMIT[17][6];
+extern void SetMotionVectorPredictor (short pmv[2], char **refPic, short ***tmp_mv, short ref_frame,
+                                      int list, int block_x, int block_y, int blockshape_x, int blockshape_y);
+
+/* ---- the library, resolved at run time ---- */
+static struct {
+  void *dl;
+  int  (*init)(const me_cuda_params *);
+  void (*shutdown)(void);
+  void (*set_error_handler)(me_cuda_error_fn);
+  const char *(*last_error)(void);
+  int  (*ref_create)(const me_imgpel *const *, int, int, me_imgpel ****, me_ref_handle *);
+  int  (*ref_destroy)(me_ref_handle);
+  int  (*set_current)(const me_imgpel *const *, int, int);
+  int  (*set_ref_list)(int, int, const me_ref_handle *);
+  int  (*set_slice_type)(int);
+  int  (*mb_begin)(int, int);
+  int  (*ffs_setup)(int, int, int, int);
+  int  (*ffs_is_set_up)(int, int);
+  int  (*ffs)(short, int, int, int, int, short, short, short *, short *, int, int, int);
+  int  (*subpel)(short, int, int, int, int, short, short, short *, short *, int, int, int, const int *);
+  int  (*bi_full)(short, int, int, int, int, short, short, short, short, short *, short *, short *, short *, int, int, int);
+  int  (*bi_sub)(short, int, int, int, int, short, short, short *, short *, short *, short *, int, int, int, const int *);
+} L;
+
+static int active = 0;          /* GPU path in use for this run */
+static int pic_counter = 0, pic_uploaded = -1;
+
+#define MAX_MAP 64
+static struct { StorablePicture *p; me_ref_handle h; } map[MAX_MAP];
+static int n_map = 0;
+
+static void die(const char *what)
+{
+  static char msg[600];
+  snprintf(msg, sizeof msg, "me_cuda shim: %s: %s", what, L.last_error ? L.last_error() : "");
+  error(msg, 500);                                      /* filehandle.c:38: prints, flushes the DPB, exits */
+}
+static void on_library_error(const char *text, int code)
+{
+  static char msg[600];
+  snprintf(msg, sizeof msg, "me_cuda: %s", text);
+  error(msg, code);
+}
+
+static void *sym(const char *name)
+{
+  void *p = dlsym(L.dl, name);
+  if (!p) { fprintf(stderr, "me_cuda shim: symbol %s missing in libme_cuda.so\n", name); exit(501); }
+  return p;
+}
+
+static void load_library(void)
+{
+  char path[PATH_MAX];
+  const char *e = getenv("ME_CUDA_LIB");
+  if (e && *e) snprintf(path, sizeof path, "%s", e);
+  else {
+    char exe[PATH_MAX];
+    ssize_t n = readlink("/proc/self/exe", exe, sizeof exe - 1);
+    char *slash;
+    if (n <= 0) { fprintf(stderr, "me_cuda shim: cannot locate the executable\n"); exit(501); }
+    exe[n] = 0;
+    slash = strrchr(exe, '/');
+    if (slash) *slash = 0;
+    snprintf(path, sizeof path, "%s/../../h.264_b200/libme_cuda.so", exe);
+  }
+  L.dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!L.dl) { fprintf(stderr, "me_cuda shim: cannot load %s: %s (no CPU fallback: set ME_CUDA_DISABLE=1 for the pure reference)\n", path, dlerror()); exit(501); }
+  L.init = sym("me_cuda_init"); L.shutdown = sym("me_cuda_shutdown");
+  L.set_error_handler = sym("me_cuda_set_error_handler"); L.last_error = sym("me_cuda_last_error");
+  L.ref_create = sym("me_cuda_ref_create"); L.ref_destroy = sym("me_cuda_ref_destroy");
+  L.set_current = sym("me_cuda_set_current"); L.set_ref_list = sym("me_cuda_set_ref_list");
+  L.set_slice_type = sym("me_cuda_set_slice_type"); L.mb_begin = sym("me_cuda_mb_begin");
+  L.ffs_setup = sym("me_cuda_ffs_setup"); L.ffs_is_set_up = sym("me_cuda_ffs_is_set_up");
+  L.ffs = sym("me_cuda_FastFullPelBlockMotionSearch"); L.subpel = sym("me_cuda_SubPelBlockMotionSearch");
+  L.bi_full = sym("me_cuda_FullPelBlockMotionBiPred"); L.bi_sub = sym("me_cuda_SubPelBlockSearchBiPred");
+}
+
+static me_ref_handle handle_of(StorablePicture *p)
+{
+  int i;
+  for (i = n_map - 1; i >= 0; i--) if (map[i].p == p) return map[i].h;
+  return 0;
+}
+
+static void unmap_index(int i)
+{
+  if (L.ref_destroy(map[i].h)) die("me_cuda_ref_destroy");
+  memmove(&map[i], &map[i + 1], sizeof(map[0]) * (size_t)(n_map - 1 - i));
+  n_map--;
+}
+
+static int in_dpb(StorablePicture *p)
+{
+  unsigned i;
+  for (i = 0; i < dpb.used_size; i++)
+    if (dpb.fs[i] && (dpb.fs[i]->frame == p || dpb.fs[i]->top_field == p || dpb.fs[i]->bottom_field == p)) return 1;
+  return 0;
+}
+
+/* ---------------------------------------------------------------- module init / clear (mv-search.c:290, :443) */
+void __real_Init_Motion_Search_Module(void);
+void __wrap_Init_Motion_Search_Module(void)
+{
+  const char *dis = getenv("ME_CUDA_DISABLE");
+  __real_Init_Motion_Search_Module();
+  active = 0;
+  if (dis && atoi(dis)) return;
+  if (input->SearchMode != FAST_FULL_SEARCH) return;   /* the library implements the SearchMode=0 path */
+  {
+    me_cuda_params p;
+    int apply_wp = (input->WeightedPrediction || input->WeightedBiprediction) && input->UseWeightedReferenceME;
+    memset(&p, 0, sizeof p);
+    load_library();
+    L.set_error_handler(on_library_error);
+    p.abi_version = ME_CUDA_ABI_VERSION;
+    p.width = img->width; p.height = img->height;
+    p.bit_depth = (img->max_imgpel_value == 255) ? 8 : 16;
+    p.search_range = input->search_range;
+    p.max_num_references = img->max_num_references;
+    p.rdopt = input->rdopt;
+    p.full_search = input->full_search;
+    p.me_metric[0] = input->MEErrorMetric[F_PEL]; p.me_metric[1] = input->MEErrorMetric[H_PEL]; p.me_metric[2] = input->MEErrorMetric[Q_PEL];
+    p.transform8x8 = input->Transform8x8Mode != 0;
+    p.mv_limit_min_y = LEVELMVLIMIT[img->LevelIndex][0];
+    p.mv_limit_max_y = LEVELMVLIMIT[img->LevelIndex][1];
+    p.chroma_me_enable = input->ChromaMEEnable;
+    p.weighted_me = apply_wp;
+    p.device = -1;
+    if (L.init(&p)) die("me_cuda_init");
+    active = 1;
+  }
+}
+
+void __real_Clear_Motion_Search_Module(void);
+void __wrap_Clear_Motion_Search_Module(void)
+{
+  if (active) { L.shutdown(); active = 0; n_map = 0; }
+  __real_Clear_Motion_Search_Module();
+}
+
+/* ---------------------------------------------------------------- pictures */
+int __real_encode_one_frame(void);
+int __wrap_encode_one_frame(void)
+{
+  pic_counter++;
+  return __real_encode_one_frame();
+}
+
+void __real_getSubImagesLuma(StorablePicture *s);
+void __wrap_getSubImagesLuma(StorablePicture *s)
+{
+  me_ref_handle h = 0;
+  int i;
+  /* 4:4:4 runs this routine on the U and V planes too; those (host motion compensation only) stay on the CPU */
+  if (!active || s->p_curr_img != s->imgY) { __real_getSubImagesLuma(s); return; }
+  /* a picture structure can be reallocated at the same address: drop a stale mapping, and forget pictures that
+   * left the decoded picture buffer through a call path that bypasses the wrapped free (same translation unit) */
+  for (i = n_map - 1; i >= 0; i--)
+    if (map[i].p == s || !in_dpb(map[i].p)) unmap_index(i);
+  /* the 16 planes are computed on the device and copied into imgY_sub for the encoder's host-side consumers */
+  if (L.ref_create((const me_imgpel *const *)s->imgY, s->size_x, s->size_y, (me_imgpel ****)s->imgY_sub, &h)) die("me_cuda_ref_create");
+  if (n_map == MAX_MAP) unmap_index(0);
+  map[n_map].p = s; map[n_map].h = h; n_map++;
+}
+
+void __real_free_storable_picture(StorablePicture *p);
+void __wrap_free_storable_picture(StorablePicture *p)
+{
+  int i;
+  if (active && p)
+    for (i = n_map - 1; i >= 0; i--)
+      if (map[i].p == p) unmap_index(i);
+  __real_free_storable_picture(p);
+}
+
+/* ---------------------------------------------------------------- per macroblock (macroblock.c:509) */
+void __real_ResetFastFullIntegerSearch(void);
+void __wrap_ResetFastFullIntegerSearch(void)
+{
+  __real_ResetFastFullIntegerSearch();
+  if (!active) return;
+  if (pic_uploaded != pic_counter) {
+    if (L.set_current((const me_imgpel *const *)pCurImg, img->width, img->height)) die("me_cuda_set_current");
+    pic_uploaded = pic_counter;
+  }
+  {
+    int list_offset = img->mb_data[img->current_mb_nr].list_offset, l, i;
+    int nlists = (img->type == B_SLICE) ? 2 : 1;
+    me_ref_handle hs[32];
+    for (l = 0; l < 2; l++) {
+      int n = (l < nlists) ? listXsize[l + list_offset] : 0;
+      if (n > 32) n = 32;
+      for (i = 0; i < n; i++) {
+        hs[i] = handle_of(listX[l + list_offset][i]);
+        if (!hs[i]) { n = i; break; }                   /* no planes on the device (never happens for frame coding) */
+      }
+      if (L.set_ref_list(l, n, hs)) die("me_cuda_set_ref_list");
+    }
+    L.set_slice_type(img->type == B_SLICE ? ME_B_SLICE : ME_P_SLICE);
+    if (L.mb_begin(img->opix_x, img->opix_y)) die("me_cuda_mb_begin");
+  }
+}
+
+/* ---------------------------------------------------------------- block searches */
+int __real_FastFullPelBlockMotionSearch(imgpel *, short, int, int, int, int, short, short, short *, short *, int, int, int);
+int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                        short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                        int search_range, int min_mcost, int lambda_factor)
+{
+  if (!active)
+    return __real_FastFullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                               mv_x, mv_y, search_range, min_mcost, lambda_factor);
+  if (!L.ffs_is_set_up(list, ref)) {
+    /* SetupFastFullPelSearch (me_fullfast.c:550): the search centre is the 16x16 predictor, computed by host code */
+    short pmv[2];
+    SetMotionVectorPredictor(pmv, enc_picture->ref_idx[list], enc_picture->mv[list], ref, list, 0, 0, 16, 16);
+    if (L.ffs_setup(list, ref, pmv[0], pmv[1])) die("me_cuda_ffs_setup");
+  }
+  return L.ffs(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
+}
+
+int __real_SubPelBlockMotionSearch(imgpel *, short, int, int, int, int, short, short, short *, short *, int, int, int, int *);
+int __wrap_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                   short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                   int search_pos2, int search_pos4, int min_mcost, int *lambda_factor)
+{
+  if (!active)
+    return __real_SubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                          mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+  return L.subpel(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2, search_pos4,
+                  min_mcost, lambda_factor);
+}
+
+int __real_FullPelBlockMotionBiPred(imgpel *, short, int, int, int, int, short, short, short, short,
+                                    short *, short *, short *, short *, int, int, int);
+int __wrap_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                    short pred_mv_x1, short pred_mv_y1, short pred_mv_x2, short pred_mv_y2,
+                                    short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                    int search_range, int min_mcost, int lambda_factor)
+{
+  if (!active)
+    return __real_FullPelBlockMotionBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x1, pred_mv_y1,
+                                           pred_mv_x2, pred_mv_y2, mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
+  return L.bi_full(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x1, pred_mv_y1, pred_mv_x2, pred_mv_y2,
+                   mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
+}
+
+int __real_SubPelBlockSearchBiPred(imgpel *, short, int, int, int, int, short, short, short *, short *, short *, short *,
+                                   int, int, int, int *);
+int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                   short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
+                                   int search_pos2, int search_pos4, int min_mcost, int *lambda_factor)
+{
+  if (!active)
+    return __real_SubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                          mv_x, mv_y, s_mv_x, s_mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+  return L.bi_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, s_mv_x, s_mv_y,
+                  search_pos2, search_pos4, min_mcost, lambda_factor);
+}

@@ -247,5 +247,3 @@ def test_tuned_and_basic_kernels_agree(pkg, oracle_lib):
             os.environ.pop("ME_CUDA_FFS_KERNEL", None)
     assert np.array_equal(res[0][1], res[1][1])
     assert np.array_equal(res[0][0], res[1][0])
-EOF
-echo written

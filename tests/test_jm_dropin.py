@@ -1,0 +1,80 @@
+"""GPU: the unmodified reference encoder with its hot path routed through libme_cuda.so (oracle/_ref/lencod_cuda, the
+--wrap shim of h.264_b200/shim/jm_shim.c) must write byte-identical bitstreams and reconstructions."""
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, REF_DIR, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _md5(p):
+    return hashlib.md5(open(p, "rb").read()).hexdigest()
+
+
+def _have():
+    return os.path.exists(os.path.join(REF_DIR, "lencod_cuda")) and os.path.exists(os.path.join(REF_DIR, "fixtures", "encoder.cfg"))
+
+
+def _prep(tmp):
+    fx = os.path.join(REF_DIR, "fixtures")
+    for f in os.listdir(fx):
+        if f.endswith(".cfg") or f.endswith(".yuv"):
+            shutil.copy(os.path.join(fx, f), tmp)
+
+
+def _run(exe, args, cwd, env=None):
+    e = dict(os.environ)
+    e["ME_CUDA_LIB"] = os.path.join(ROOT, "h.264_b200", "libme_cuda.so")
+    if env:
+        e.update(env)
+    r = subprocess.run([os.path.join(REF_DIR, exe)] + args, cwd=cwd, env=e, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    return r.stdout
+
+
+@pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built (needs the reference tree at build time)")
+def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
+    """bin/encoder.cfg: the run behind the reference's committed bin/test.264 / bin/test_rec.yuv"""
+    _prep(str(tmp_path))
+    _run("lencod_cuda", ["-d", "encoder.cfg"], str(tmp_path))
+    md5 = json.load(open(os.path.join(GOLDEN, "bitstream_md5.json")))["kat"]
+    assert _md5(str(tmp_path / "test.264")) == md5["test.264"] == _md5(os.path.join(REF_DIR, "fixtures", "golden_test.264"))
+    assert _md5(str(tmp_path / "test_rec.yuv")) == md5["test_rec.yuv"] == _md5(os.path.join(REF_DIR, "fixtures", "golden_test_rec.yuv"))
+
+
+@pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
+@pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0"])
+def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
+    """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
+    import sys
+    sys.path.insert(0, ROOT)
+    import h264_b200_pkg  # noqa: F401
+    from h264_b200 import synth
+    a, b = tmp_path / "gpu", tmp_path / "cpu"
+    a.mkdir(); b.mkdir()
+    if case == "baseline_sr16_1ref":
+        args = ["-d", "encoder_baseline.cfg", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=1"]
+    elif case == "main_cif_5ref":
+        args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=352", "-p", "SourceHeight=288",
+                "-p", "FramesToBeEncoded=4", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=32",
+                "-p", "NumberReferenceFrames=5", "-p", "LevelIDC=51"]
+    else:
+        args = ["-d", "encoder_baseline.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
+                "-p", "FramesToBeEncoded=3", "-p", "FrameSkip=0", "-p", "RDOptimization=0", "-p", "RestrictSearchRange=0",
+                "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+    for d in (a, b):
+        _prep(str(d))
+        if "InputFile=syn.yuv" in args:
+            wdt = 352 if "SourceWidth=352" in args else 176
+            hgt = 288 if wdt == 352 else 144
+            synth.write_yuv420(str(d / "syn.yuv"), wdt, hgt, 4)
+    _run("lencod_cuda", args, str(a))
+    _run("lencod", args, str(b))
+    assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
+    assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))

@@ -1,0 +1,47 @@
+"""CPU: the oracle against LIVE traces of the unmodified reference encoder (oracle/_ref/lencod_trace), when that binary
+is present (it is built from /root/reference by `make -C oracle ref`; it travels to the GPU box but cannot be rebuilt there)."""
+import hashlib
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import REF_DIR, has_ref_binaries
+from replay import OracleAdapter, replay
+from trace_util import Trace, cfg_from_trace
+
+pytestmark = pytest.mark.skipif(not has_ref_binaries(), reason="oracle/_ref not built")
+
+
+def _trace(tmp, args, yuv=None):
+    fx = os.path.join(REF_DIR, "fixtures")
+    for f in os.listdir(fx):
+        if f.endswith(".cfg") or f.endswith(".yuv"):
+            shutil.copy(os.path.join(fx, f), tmp)
+    env = dict(os.environ, ME_TRACE_DIR=tmp, ME_TRACE_PLANES="1")
+    r = subprocess.run([os.path.join(REF_DIR, "lencod_trace")] + args, cwd=tmp, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-1000:]
+    return Trace(tmp)
+
+
+def test_tracer_does_not_change_the_bitstream(tmp_path):
+    _trace(str(tmp_path), ["-d", "encoder.cfg"])
+    got = hashlib.md5(open(tmp_path / "test.264", "rb").read()).hexdigest()
+    exp = hashlib.md5(open(os.path.join(REF_DIR, "fixtures", "golden_test.264"), "rb").read()).hexdigest()
+    assert got == exp == "92402ba469c35bc09f97017a3903bdf9"
+
+
+def test_oracle_reproduces_every_call_of_the_known_answer_run(tmp_path, oracle_lib):
+    tr = _trace(str(tmp_path), ["-d", "encoder.cfg"])
+    for i in tr.ref_ids():                       # all 16 planes of both reference pictures, pixel exact
+        ref = oracle_lib.Ref(tr.ref(i))
+        assert (ref.planes() == tr.ref_sub(i)).all()
+        ref.close()
+    # every 3rd record group keeps the CPU suite short; the golden test covers a different subset
+    cfgkw = cfg_from_trace(tr, search_range=32, full_search=2)
+    impl = OracleAdapter(tr, cfgkw)
+    res = replay(tr, impl, max_calls=12000)
+    impl.close()
+    for name, (n, bad) in res.items():
+        assert not bad, (name, n, bad[:3])
