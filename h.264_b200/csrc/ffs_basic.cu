@@ -124,9 +124,12 @@ me_ffs_batch_basic_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRe
   __shared__ uint32_t curw[64];
   __shared__ unsigned long long red[8][ME_NUM_PARTITIONS];
   __shared__ int16_t pmv_s[ME_NUM_PARTITIONS][2];
+  __shared__ MeJob sjob;
   const int job_id = blockIdx.x;
   if (job_id >= n_jobs) return;
-  const MeJob &job = jobs[job_id];
+  me_load_job(&sjob, jobs + job_id);
+  __syncthreads();
+  const MeJob &job = sjob;
   const MeRefDev ref = ref_table[job.list * ME_MAX_REFS + job.ref];
   const int R = me_setup_range(cfg, job.ref);
   const int n = 2 * R + 16, tp = (n + 3) & ~3, side = 2 * R + 1;

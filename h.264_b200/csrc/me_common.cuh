@@ -101,3 +101,15 @@ __device__ __forceinline__ const uint8_t *me_umv_ptr(const MeRefDev &r, int y4, 
 typedef me_mb_job MeJob;
 typedef me_mb_result MeResult;
 typedef me_mb_result_int MeResultInt;
+
+// Stage one job descriptor in shared memory with whole-word loads (the caller synchronises afterwards).
+// Reading the 16-bit fields of me_mb_job straight from global memory made ptxas 12.9 (sm_100a) pair the two halves of
+// pmv16 into one 32-bit load and then take the high half from the wrong register -- observed as a search centre that
+// depended on stale register contents; word loads + shared-memory field reads avoid that code path.
+__device__ __forceinline__ void me_load_job(MeJob *dst, const MeJob *src)
+{
+  static_assert(sizeof(MeJob) % 4 == 0, "me_mb_job must be a whole number of words");
+  const unsigned words = sizeof(MeJob) / 4;
+  if (threadIdx.x < words)
+    reinterpret_cast<volatile uint32_t *>(dst)[threadIdx.x] = reinterpret_cast<const uint32_t *>(src)[threadIdx.x];
+}

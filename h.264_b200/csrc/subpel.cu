@@ -105,16 +105,21 @@ me_subpel_batch_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDe
   __shared__ int mv_s[ME_NUM_PARTITIONS][2];
   __shared__ int min_s[ME_NUM_PARTITIONS];
   __shared__ uint8_t cur_s[16][16];
+  __shared__ MeJob sjob;
   const int job_id = blockIdx.x;
   if (job_id >= n_jobs) return;
-  const MeJob &job = jobs[job_id];
+  me_load_job(&sjob, jobs + job_id);
+  __syncthreads();
+  const MeJob &job = sjob;
   const MeRefDev ref = ref_table[job.list * ME_MAX_REFS + job.ref];
   const int tid = threadIdx.x;
 
   cur_s[tid >> 4][tid & 15] = cur[(size_t)(job.opix_y + (tid >> 4)) * cur_pitch + job.opix_x + (tid & 15)];
   if (tid < ME_NUM_PARTITIONS) {
-    mv_s[tid][0] = in_int[job_id].mv[tid][0] << 2;          // mv-search.c:770-774
-    mv_s[tid][1] = in_int[job_id].mv[tid][1] << 2;
+    // one word = (mv_x, mv_y); explicit word load + split (see me_load_job for why 16-bit global loads are avoided)
+    uint32_t w = reinterpret_cast<const uint32_t *>(in_int[job_id].mv)[tid];
+    mv_s[tid][0] = (int)(int16_t)(w & 0xffffu) * 4;        // mv <<= 2, mv-search.c:770-774
+    mv_s[tid][1] = (int)(int16_t)(w >> 16) * 4;
     min_s[tid] = cfg.start_hp ? in_int[job_id].cost[tid] : ME_INT_MAX;   // mv-search.c:785-788
   }
   __syncthreads();

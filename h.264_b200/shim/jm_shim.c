@@ -14,7 +14,8 @@
  * source patch.)  The library is loaded with dlopen, so the encoder binary has no link-time CUDA dependency; it is
  * compiled against the reference's own headers by oracle/Makefile (target _ref/lencod_cuda).
  *
- * Environment: ME_CUDA_LIB = path of libme_cuda.so (default: <dir of executable>/../../h.264_b200/libme_cuda.so),
+ * Environment: ME_CUDA_VERIFY=1 runs the reference function next to every GPU call and reports differences (diagnostic),
+ *              ME_CUDA_LIB = path of libme_cuda.so (default: <dir of executable>/../../h.264_b200/libme_cuda.so),
  *              ME_CUDA_DISABLE=1 turns the interposer into a pass-through (pure reference behaviour).
  */
 #define _GNU_SOURCE
@@ -29,6 +30,7 @@
 #include "image.h"
 #include "mbuffer.h"
 #include "me_distortion.h"
+#include "refbuf.h"
 
 #include "me_cuda.h"
 
@@ -58,6 +60,8 @@ static struct {
 } L;
 
 static int active = 0;          /* GPU path in use for this run */
+static int verify = 0;          /* ME_CUDA_VERIFY=1: run the reference function too, report any difference, keep the reference result */
+static long n_checked = 0, n_mismatch = 0;
 static int pic_counter = 0, pic_uploaded = -1;
 
 #define MAX_MAP 64
@@ -164,12 +168,14 @@ void __wrap_Init_Motion_Search_Module(void)
     p.device = -1;
     if (L.init(&p)) die("me_cuda_init");
     active = 1;
+    verify = getenv("ME_CUDA_VERIFY") && atoi(getenv("ME_CUDA_VERIFY"));
   }
 }
 
 void __real_Clear_Motion_Search_Module(void);
 void __wrap_Clear_Motion_Search_Module(void)
 {
+  if (active && verify) fprintf(stderr, "me_cuda shim: verify mode: %ld calls checked, %ld mismatches\n", n_checked, n_mismatch);
   if (active) { L.shutdown(); active = 0; n_map = 0; }
   __real_Clear_Motion_Search_Module();
 }
@@ -237,6 +243,22 @@ void __wrap_ResetFastFullIntegerSearch(void)
   }
 }
 
+/* The reference search functions leave values in the globals of refbuf.h / me_distortion.c that later host code relies
+ * on: OneComponentLumaPrediction (macroblock.c:816-819) calls UMVLine4X BEFORE it assigns width_pad / height_pad, so its
+ * first clamp uses whatever the last motion search stored there (me_fullfast.c:524-525, me_fullsearch.c:380-381,
+ * :215-216, :570-571).  A drop-in replacement has to keep those side effects or the very first prediction of a run is
+ * fetched with a clamp range of 0 and one mode decision changes. */
+static void keep_reference_side_effects(int list, short ref)
+{
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  StorablePicture *rp = listX[list + list_offset][ref];
+  ref_pic_sub.luma = rp->p_curr_img_sub;
+  img_width  = rp->size_x;
+  img_height = rp->size_y;
+  width_pad  = rp->size_x_pad;
+  height_pad = rp->size_y_pad;
+}
+
 /* ---------------------------------------------------------------- block searches */
 int __real_FastFullPelBlockMotionSearch(imgpel *, short, int, int, int, int, short, short, short *, short *, int, int, int);
 int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
@@ -249,8 +271,23 @@ int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, i
   if (!L.ffs_is_set_up(list, ref)) {
     /* SetupFastFullPelSearch (me_fullfast.c:550): the search centre is the 16x16 predictor, computed by host code */
     short pmv[2];
+    keep_reference_side_effects(list, ref);
     SetMotionVectorPredictor(pmv, enc_picture->ref_idx[list], enc_picture->mv[list], ref, list, 0, 0, 16, 16);
     if (L.ffs_setup(list, ref, pmv[0], pmv[1])) die("me_cuda_ffs_setup");
+  }
+  if (verify) {
+    short gx = *mv_x, gy = *mv_y;
+    int gc = L.ffs(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, &gx, &gy, search_range, min_mcost, lambda_factor);
+    int rc = __real_FastFullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                                 mv_x, mv_y, search_range, min_mcost, lambda_factor);
+    n_checked++;
+    if (gc != rc || gx != *mv_x || gy != *mv_y) {
+      n_mismatch++;
+      fprintf(stderr, "VERIFY ffs pic %d mb (%d,%d) list %d ref %d bt %d blk (%d,%d) pmv (%d,%d) sr %d lam %d: gpu (%d,%d,%d) ref (%d,%d,%d)\n",
+              pic_counter, img->opix_x, img->opix_y, list, ref, blocktype, pic_pix_x, pic_pix_y, pred_mv_x, pred_mv_y, search_range,
+              lambda_factor, gx, gy, gc, *mv_x, *mv_y, rc);
+    }
+    return rc;
   }
   return L.ffs(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
 }
@@ -263,6 +300,21 @@ int __wrap_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pi
   if (!active)
     return __real_SubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                           mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+  keep_reference_side_effects(list, ref);
+  if (verify) {
+    short ix = *mv_x, iy = *mv_y, gx = *mv_x, gy = *mv_y;
+    int gc = L.subpel(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, &gx, &gy, search_pos2, search_pos4, min_mcost, lambda_factor);
+    int rc = __real_SubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                            mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+    n_checked++;
+    if (gc != rc || gx != *mv_x || gy != *mv_y) {
+      n_mismatch++;
+      fprintf(stderr, "VERIFY subpel pic %d mb (%d,%d) list %d ref %d bt %d blk (%d,%d) pmv (%d,%d) in (%d,%d) min %d: gpu (%d,%d,%d) ref (%d,%d,%d)\n",
+              pic_counter, img->opix_x, img->opix_y, list, ref, blocktype, pic_pix_x, pic_pix_y, pred_mv_x, pred_mv_y, ix, iy, min_mcost,
+              gx, gy, gc, *mv_x, *mv_y, rc);
+    }
+    return rc;
+  }
   return L.subpel(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2, search_pos4,
                   min_mcost, lambda_factor);
 }
@@ -277,6 +329,7 @@ int __wrap_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int p
   if (!active)
     return __real_FullPelBlockMotionBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x1, pred_mv_y1,
                                            pred_mv_x2, pred_mv_y2, mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
+  keep_reference_side_effects(list, ref);
   return L.bi_full(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x1, pred_mv_y1, pred_mv_x2, pred_mv_y2,
                    mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
 }
@@ -290,6 +343,7 @@ int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pi
   if (!active)
     return __real_SubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                           mv_x, mv_y, s_mv_x, s_mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+  keep_reference_side_effects(list, ref);
   return L.bi_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, s_mv_x, s_mv_y,
                   search_pos2, search_pos4, min_mcost, lambda_factor);
 }

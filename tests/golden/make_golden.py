@@ -10,6 +10,7 @@ plus planes_crc.json: CRC32 of each of the 16 quarter-pel planes the reference b
 Cases
   kat        bin/encoder.cfg as shipped (the run behind the committed bin/test.264): QCIF I-B-P, SR 32, 5 refs, RDO on,
              8x8 transform, bi-pred ME.  Every 4th macroblock is kept.
+  baseline16 encoder_baseline.cfg with SearchRange=16, NumberReferenceFrames=1 (BASELINE.json config 1), every 3rd macroblock.
   rdopt0     encoder_baseline.cfg, RDOptimization=0, RestrictSearchRange=0, SR 16, 2 refs, synthetic QCIF IPPP --
              pins the !rdopt zero-vector rules and the reduced search ranges.  Every 5th macroblock is kept.
 Usage: python tests/golden/make_golden.py            (rewrites tests/golden/*.npz, planes_crc.json, bitstream_md5.json)
@@ -89,6 +90,14 @@ def main():
         tr = Trace(d)
         tr.save_npz(os.path.join(HERE, "rdopt0.npz"), keep_mask(tr, 5))
         crc["rdopt0"] = planes_crc(tr, d)
+    # ---- baseline16: BASELINE.json config 1 (encoder_baseline.cfg, SR 16, 1 reference, real QCIF clip, IPP)
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(os.path.join(REF, "fixtures", "foreman_part_qcif.yuv"), d)
+        run_trace(d, ["-d", "encoder_baseline.cfg", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=1"])
+        md5s["baseline16"] = {"test.264": md5(os.path.join(d, "test.264")), "test_rec.yuv": md5(os.path.join(d, "test_rec.yuv"))}
+        tr = Trace(d)
+        tr.save_npz(os.path.join(HERE, "baseline16.npz"), keep_mask(tr, 3))
+        crc["baseline16"] = planes_crc(tr, d)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
     for f in sorted(os.listdir(HERE)):

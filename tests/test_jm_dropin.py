@@ -78,3 +78,23 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     _run("lencod", args, str(b))
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
     assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
+
+
+@pytest.mark.skipif(not _have(), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("case", ["kat", "baseline16"])
+def test_live_full_trace_replays_through_the_c_abi(tmp_path, me_lib_path, case):
+    """every call of a fresh run of the traced reference encoder (all macroblocks), replayed through the drop-in ABI"""
+    from replay import CudaAdapter, replay
+    from trace_util import Trace, cfg_from_trace
+    _prep(str(tmp_path))
+    args = ["-d", "encoder.cfg"] if case == "kat" else ["-d", "encoder_baseline.cfg", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=1"]
+    _run("lencod_trace", args, str(tmp_path), env={"ME_TRACE_DIR": str(tmp_path), "ME_TRACE_PLANES": "0"})
+    tr = Trace(str(tmp_path))
+    cfgkw = cfg_from_trace(tr, search_range=32 if case == "kat" else 16, full_search=2)
+    impl = CudaAdapter(tr, cfgkw)
+    try:
+        res = replay(tr, impl)
+    finally:
+        impl.close()
+    for name, (n, bad) in res.items():
+        assert not bad, (case, name, n, len(bad), bad[:4])
