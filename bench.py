@@ -349,15 +349,18 @@ def main():
     # sanity: the end-to-end results equal the device-resident ones for the same inputs (same code path)
     checksum = int(torch.from_numpy(h_out.numpy().view(np.int32)).sum().item())
 
-    # ---- roofline of the dominant kernel (integer-pel search): measured INT-pipe issue rate as the denominator
+    # ---- roofline of the dominant kernel (integer-pel search).  The bound is integer issue, not HBM and not tensor:
+    # denominator = the two 16-lane integer pipes of every SM sub-partition, each measured alone on this GPU
+    # (VABSDIFF4 on the ALU pipe + IMAD on the FMA pipe; MEASURED_PEAKS.json carries no integer figure).
     peaks = {}
     if rank == 0:
-        names = {0: "vabsdiff4", 1: "iadd3", 2: "imad", 3: "viaddmnmx", 4: "lop3", 5: "shf", 6: "vabsdiff4+imad", 7: "vabsdiff4+iadd3"}
+        names = {0: "vabsdiff4", 2: "imad", 3: "viaddmnmx", 5: "shf", 9: "vabsdiff4+imad", 10: "vabsdiff4+viaddmnmx",
+                 15: "vabsdiff4+lds"}
         for k, nm in names.items():
             peaks[nm] = me.measure_int_peak(k) / 1e9
     ffs_avg_ms = ffs_ms / max(1, ffs_n)
     achieved = LANE_OPS_PER_JOB * n_jobs / (ffs_avg_ms * 1e-3) / 1e9 if ffs_n else None
-    peak = max(peaks.values()) if peaks else None
+    peak = (peaks["vabsdiff4"] + peaks["imad"]) if peaks else None
     mp = {}
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -366,9 +369,13 @@ def main():
     alg_bytes = n_jobs * ((2 * SEARCH_RANGE + 16) ** 2 + 256 + JOB_DTYPE.itemsize + RESULT_DTYPE.itemsize)
     roofline = {"bound": "int_alu", "kernel": "integer-pel fast full search (me_ffs_*)", "achieved": achieved, "peak": peak,
                 "unit": "Glaneop/s", "frac": (achieved / peak) if (achieved and peak) else None,
-                "peak_source": "measured on this GPU by me_cuda_measure_int_peak (max over instruction kinds); MEASURED_PEAKS.json has no integer figure",
-                "algorithmic_laneops_per_launch": LANE_OPS_PER_JOB * n_jobs, "kernel_ms": ffs_avg_ms,
-                "sad_only_frac": (SAD_OPS_PER_JOB * n_jobs / (ffs_avg_ms * 1e-3) / 1e9 / peaks["vabsdiff4"]) if (ffs_n and peaks) else None,
+                "peak_source": "measured on this GPU by me_cuda_measure_int_peak: VABSDIFF4 alone (ALU pipe) + IMAD alone (FMA pipe), "
+                               "the two integer pipes; MEASURED_PEAKS.json has no integer figure",
+                "algorithmic_laneops_per_launch": LANE_OPS_PER_JOB * n_jobs,
+                "algorithmic_laneops_per_job": "212 * (2R+1)^2 = 64 SAD + 25 larger-block adds + 3*41 cost ops per position (SURVEY.md 8d)",
+                "kernel_ms": ffs_avg_ms,
+                "frac_of_alu_pipe_alone": (achieved / peaks["vabsdiff4"]) if (achieved and peaks) else None,
+                "sad_only_frac_of_alu_pipe": (SAD_OPS_PER_JOB * n_jobs / (ffs_avg_ms * 1e-3) / 1e9 / peaks["vabsdiff4"]) if (ffs_n and peaks) else None,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (ffs_avg_ms * 1e-3) / 1e9 if ffs_n else None,
                         "peak_gbs": mp.get("hbm_gbs", 6650.0), "peak_source": "MEASURED_PEAKS.json" if mp else "fallback"},
                 "traffic": None, "int_peaks_glaneops": peaks,

@@ -1,50 +1,63 @@
 // int_peak.cu -- on-device measurement of the integer-pipe issue rates the motion search is bounded by.
 //
 // the roofline of the search kernel is the INT-ALU pipe, and MEASURED_PEAKS.json carries no integer
-// figure, so the denominator is measured here with dependency-free chains of the instructions the kernels use:
-//   kind 0  VABSDIFF4.U8.ACC   (__vsadu4 with accumulate)        -- 4 pixel |a-b| + add per lane-op
-//   kind 1  IADD3              (a + b + c)
-//   kind 2  IMAD               (a * b + c)
-//   kind 3  VIADDMNMX          (min(a + b, c), __viaddmin_u32)
-//   kind 4  LOP3               ((a & b) ^ c)
-//   kind 5  SHF (funnel shift)
-//   kind 6  VABSDIFF4 and IMAD interleaved 1:1 (do the two pipes dual-issue?)
-//   kind 7  VABSDIFF4 and IADD3 interleaved 1:1 (same pipe?)
-// Result: lane-operations per second over the whole GPU (warp instructions * 32).
+// figure, so the denominator is measured here with dependency-free chains of the instructions the kernels use.
+// Every operation is an `asm volatile` so that the compiler can neither fold nor reorder it away; 8 independent
+// chains per thread hide the 4-cycle ALU latency.  Result: lane-operations per second over the whole GPU
+// (warp instructions * 32).  Kinds:
+//   0 VABSDIFF4 (+acc)   1 IADD3 (add)        2 IMAD (mad.lo)        3 VIADDMNMX (add+min, DPX)
+//   4 LOP3 (xor/and)     5 SHF (funnel shift) 6 VIMNMX (min)         7 PRMT (byte permute)
+//   8..14: the same as 1..7 interleaved 1:1 with VABSDIFF4 (do the two instructions issue on different pipes?)
+//   15 LDS.32 (shared-memory load, conflict-free) interleaved 1:1 with VABSDIFF4
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #define CHAINS 8
 
+template <int OP>
+__device__ __forceinline__ void one_op(uint32_t &a, uint32_t x, uint32_t b)
+{
+  if (OP == 0) asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(a) : "r"(x), "r"(b));
+  else if (OP == 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(a) : "r"(x));
+  else if (OP == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a) : "r"(b), "r"(x));
+  else if (OP == 3) asm volatile("{.reg .u32 t; add.u32 t, %0, %1; min.u32 %0, t, %2;}" : "+r"(a) : "r"(b), "r"(x));
+  else if (OP == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(x), "r"(b));
+  else if (OP == 5) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(a) : "r"(x), "r"(b));
+  else if (OP == 6) asm volatile("min.u32 %0, %0, %1;" : "+r"(a) : "r"(x));
+  else if (OP == 7) asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(a) : "r"(x), "r"(b));
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256)
 int_peak_kernel(uint32_t *out, int iters, uint32_t s1, uint32_t s2)
 {
+  __shared__ uint32_t sm[256 * 2];
   uint32_t a[CHAINS], x[CHAINS];
 #pragma unroll
   for (int k = 0; k < CHAINS; k++) { a[k] = threadIdx.x * 2654435761u + k * 40503u + s1; x[k] = a[k] ^ (s2 * (k + 1)); }
-  uint32_t b = s1 | 1u, c = s2;
-#pragma unroll 4
+  sm[threadIdx.x] = a[0]; sm[threadIdx.x + 256] = x[0];
+  __syncthreads();
+  uint32_t b = s1 | 1u;
+  const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(&sm[threadIdx.x]);
+#pragma unroll 2
   for (int i = 0; i < iters; i++) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
 #pragma unroll
       for (int k = 0; k < CHAINS; k++) {
-        if (KIND == 0) a[k] = __vsadu4(x[k], a[k]) + a[k];
-        else if (KIND == 1) a[k] = a[k] + b + x[k];
-        else if (KIND == 2) a[k] = a[k] * b + x[k];
-        else if (KIND == 3) a[k] = __viaddmin_u32(a[k], b, x[k]);
-        else if (KIND == 4) a[k] = (a[k] & b) ^ x[k];
-        else if (KIND == 5) a[k] = __funnelshift_r(a[k], x[k], b);
-        else if (KIND == 6) { if (k & 1) a[k] = a[k] * b + x[k]; else a[k] = __vsadu4(x[k], a[k]) + a[k]; }
-        else if (KIND == 7) { if (k & 1) a[k] = a[k] + b + x[k]; else a[k] = __vsadu4(x[k], a[k]) + a[k]; }
+        if (KIND < 8) one_op<KIND>(a[k], x[k], b);
+        else if (KIND < 15) { if (k & 1) one_op<KIND - 7>(a[k], x[k], b); else one_op<0>(a[k], x[k], b); }
+        else {
+          if (k & 1) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr + ((k & 2) ? 1024u : 0u))); x[k] ^= v; }
+          else one_op<0>(a[k], x[k], b);
+        }
       }
     }
   }
   uint32_t s = 0;
 #pragma unroll
   for (int k = 0; k < CHAINS; k++) s += a[k] + x[k];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = s + c;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 template <int KIND>
@@ -60,7 +73,8 @@ static double run_kind(uint32_t *d_out, int blocks, int iters)
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  double ops = (double)blocks * 256.0 * (double)iters * 4.0 * CHAINS;
+  double per_op = (KIND == 3 || KIND == 10) ? 1.0 : 1.0;   // add+min is counted as ONE operation (it fuses to VIADDMNMX when it can)
+  double ops = (double)blocks * 256.0 * (double)iters * 4.0 * CHAINS * per_op;
   return ops / (ms * 1e-3);
 }
 
@@ -69,19 +83,14 @@ extern "C" int me_cuda_measure_int_peak(int kind, double *lane_ops_per_s)
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 2;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int blocks = sms * 8, iters = 4096;
+  int blocks = sms * 8, iters = 2048;
   uint32_t *d_out = nullptr;
   if (cudaMalloc((void **)&d_out, (size_t)blocks * 256 * sizeof(uint32_t)) != cudaSuccess) return 2;
   double r = 0;
   switch (kind) {
-    case 0: r = run_kind<0>(d_out, blocks, iters); break;
-    case 1: r = run_kind<1>(d_out, blocks, iters); break;
-    case 2: r = run_kind<2>(d_out, blocks, iters); break;
-    case 3: r = run_kind<3>(d_out, blocks, iters); break;
-    case 4: r = run_kind<4>(d_out, blocks, iters); break;
-    case 5: r = run_kind<5>(d_out, blocks, iters); break;
-    case 6: r = run_kind<6>(d_out, blocks, iters); break;
-    case 7: r = run_kind<7>(d_out, blocks, iters); break;
+#define K(n) case n: r = run_kind<n>(d_out, blocks, iters); break;
+    K(0) K(1) K(2) K(3) K(4) K(5) K(6) K(7) K(8) K(9) K(10) K(11) K(12) K(13) K(14) K(15)
+#undef K
     default: cudaFree(d_out); return 1;
   }
   cudaError_t e = cudaDeviceSynchronize();
