@@ -118,15 +118,18 @@ template <bool SSE>
 __global__ void __launch_bounds__(256)
 me_ffs_batch_basic_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                           const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
-                          MeResultInt *__restrict__ out)
+                          MeResultInt *__restrict__ out, const int *__restrict__ job_list)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t curw[64];
   __shared__ unsigned long long red[8][ME_NUM_PARTITIONS];
   __shared__ int16_t pmv_s[ME_NUM_PARTITIONS][2];
   __shared__ MeJob sjob;
-  const int job_id = blockIdx.x;
-  if (job_id >= n_jobs) return;
+  // job_list == nullptr: CTA b takes job b.  Otherwise job_list[0] jobs, ids in job_list[1..] (the jobs the tuned
+  // kernel of ffs_tuned.cu handed back), walked with a grid stride.
+  const int total = job_list ? job_list[0] : n_jobs;
+  for (int ji = blockIdx.x; ji < total; ji += gridDim.x) {
+  const int job_id = job_list ? job_list[1 + ji] : ji;
   me_load_job(&sjob, jobs + job_id);
   __syncthreads();
   const MeJob &job = sjob;
@@ -199,6 +202,8 @@ me_ffs_batch_basic_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRe
     out[job_id].mv[p][0] = (int16_t)(offx + dx);
     out[job_id].mv[p][1] = (int16_t)(offy + dy);
     out[job_id].cost[p] = cost;
+  }
+  __syncthreads();
   }
 }
 
@@ -274,15 +279,18 @@ me_ffs_block_kernel(const int32_t *__restrict__ surf_p, int setup_range, int off
   }
 }
 
+// job_list == nullptr: all n_jobs jobs; else the device-side list {count, ids...} with a fixed small grid
 extern "C" void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur,
-                                          int cur_pitch, const MeCfgDev *cfg, MeResultInt *out, cudaStream_t st)
+                                          int cur_pitch, const MeCfgDev *cfg, MeResultInt *out, const int *job_list,
+                                          cudaStream_t st)
 {
   int R = cfg->search_range, n = 2 * R + 16, tp = (n + 3) & ~3;
   size_t smem = (size_t)(n + 1) * tp + 16;
+  int grid = job_list ? (n_jobs < 296 ? n_jobs : 296) : n_jobs;
   if (cfg->metric[0])
-    me_ffs_batch_basic_kernel<true><<<n_jobs, 256, smem, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, out);
+    me_ffs_batch_basic_kernel<true><<<grid, 256, smem, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, out, job_list);
   else
-    me_ffs_batch_basic_kernel<false><<<n_jobs, 256, smem, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, out);
+    me_ffs_batch_basic_kernel<false><<<grid, 256, smem, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, out, job_list);
 }
 
 extern "C" void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y,

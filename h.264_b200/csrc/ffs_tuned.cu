@@ -1,7 +1,602 @@
-// ffs_tuned.cu -- placeholder until the tuned search kernel lands (returns 0 = "not applicable": caller uses ffs_basic).
+// ffs_tuned.cu -- integer-pel fast full search, the throughput kernel (SAD metric, RDO on, same range for every reference).
+//
+// Same results as ffs_basic.cu, i.e. as SetupFastFullPelSearch / SetupLargerBlocks / FastFullPelBlockMotionSearch of the
+// reference (lencod/src/me_fullfast.c:491, :210, :833), with the work laid out for the B200 integer pipes.
+//
+//  * Persistent CTAs (3 per SM), each walking the (macroblock, list, ref) jobs blockIdx.x, +gridDim.x, ...  A CTA has
+//    4R threads: thread (dx, h) owns ONE horizontal displacement dx in [0, 2R) and ONE 8-pixel column pair h of the
+//    macroblock and streams down the (2R+16)-row search window.  Its 32 current-picture words (16 rows x 2 columns) stay
+//    in registers; one window row costs 3 shared-memory words + 2 funnel shifts and feeds 32 VABSDIFF4.U8.ACC -- the 16
+//    vertical displacements that overlap the row are in flight at once, in 16 rotating accumulator pairs whose indices
+//    are compile-time constants (the row loop is unrolled 16x, with specialised first / last groups so that no SAD
+//    instruction is spent outside the (2R+1)^2 positions).
+//  * The larger-block SADs are never materialised: key(sum) = a*K + key(b) folds every SetupLargerBlocks add into the
+//    IMAD that builds the comparison key (FMA pipe); only the 8x8 sums and the two 16-wide sums (one warp shuffle each
+//    between the lanes h = 0 / 1) exist as plain integers.
+//  * Cost: key = (SAD + mvcost) * K + spiral_index with K = (2R+1)^2 > any spiral index, so ONE unsigned minimum per
+//    (partition, position) reproduces JM's "first strict minimum in spiral order" (me_fullfast.c:879-897).
+//    K * (lambda * (bits_x + bits_y) >> 16) comes from a 36-entry shared table indexed by the sum of the Exp-Golomb length
+//    classes of the two vector components: the x class is a per-thread constant (fixed dx), the y class is uniform and
+//    read from a per-job table.  Per (partition, position): IMAD (key) + IMAD (table address) + LDS + VIADDMNMX.
+//  * The window column dx = 2R (the 65th of 65) does not fit the 2R-lane layout: thread pair i scores position (2R, i)
+//    with the same key encoding after the sweep.
+//  * Search windows (2R+16)^2 and the 16x16 current macroblock arrive by TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) from
+//    the wide-border search plane / the current picture, double-buffered one job ahead on two mbarriers; a window whose
+//    box leaves the wide border (predictor drift beyond the 32-pixel guard) is loaded with clamped element reads instead.
+//
+// ALU-pipe work per search position (both lanes): 64 VABSDIFF4 + 42 VIADDMNMX + 4 SHF + ~10 adds/selects.
+#include <cuda.h>
+#include <cstdio>
+#include <cstring>
+#include <utility>
 #include "me_common.cuh"
-extern "C" int me_launch_ffs_batch_tuned(const MeJob *, int, const MeRefDev *, const uint8_t *, int, const MeCfgDev *,
-                                         MeResultInt *, cudaStream_t)
+
+namespace {
+
+constexpr int CYW = 28;            // words per (dy, h) row of the y-class table: band groups at words 0, 4, 12, 16
+constexpr int LUT_STRIDE_B = 12;   // bytes between table entries: odd word stride -> conflict-free and the address is an IMAD
+constexpr int LUT_ENTRIES = 36;    // class sums 0..35 (classes up to 17 per component: |d| < 2^17)
+constexpr int NSLOT = 21;          // partitions scored by one thread
+
+template <int R> struct Geo {
+  static constexpr int N = 2 * R + 16;            // window side
+  static constexpr int SIDE = 2 * R + 1;
+  static constexpr int NT = 4 * R;                // threads per CTA
+  static constexpr int NW = NT / 32;
+  static constexpr int GROUPS = R / 8 + 1;        // 16-row groups of the window
+  static constexpr unsigned KMUL = SIDE * SIDE;   // key = cost * KMUL + spiral index
+};
+
+// partition (ABI order, include/me_cuda.h) scored in slot e by the lanes of column pair h
+__constant__ int8_t c_slot_part[2][NSLOT] = {
+  { 25, 26,  9, 29, 30, 11, 17, 18, 5, 33, 34, 13, 37, 38, 15, 21, 22, 7, 3, 1, 0 },
+  { 27, 28, 10, 31, 32, 12, 19, 20, 6, 35, 36, 14, 39, 40, 16, 23, 24, 8, 4, 2, 0 } };
+
+__host__ __device__ constexpr int slot_cyword(int e) { return e < 3 ? e : e < 9 ? e + 1 : e < 12 ? e + 3 : e + 4; }
+
+template <int R> struct __align__(128) Smem {
+  uint8_t  win[2][Geo<R>::N * Geo<R>::N];       // search windows, row pitch N (TMA box, dense)
+  uint32_t cur[2][64];                          // current macroblocks, 16 rows x 4 words
+  uint32_t cyt[Geo<R>::SIDE][2][CYW];           // y length class per (dy, h, slot)
+  uint32_t lut[LUT_ENTRIES * 3];                // K * mvcost(class sum), entry stride 12 bytes
+  uint32_t lutA_last[2][NSLOT];                 // shared address of the table row of column 2R per (h, slot)
+  uint32_t red[Geo<R>::NW][2][NSLOT];
+  uint32_t job[3][48];                          // me_mb_job ring (188 bytes each)
+  uint16_t sptab[Geo<R>::SIDE * Geo<R>::SIDE];  // spiral index of (dy, dx)
+  MeRefDev refs[2 * ME_MAX_REFS];               // copy of the reference table
+  unsigned long long mbar[2];
+  int lut_lambda, lut_valid;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// shared-memory loads at [address register + compile-time offset]: the unrolled sweep addresses everything relative to three
+// per-group base registers, so no address arithmetic is issued inside it
+template <int OFF = 0> __device__ __forceinline__ unsigned lds32(unsigned a)
 {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF = 0> __device__ __forceinline__ unsigned lds16(unsigned a)
+{
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF = 0> __device__ __forceinline__ uint4 lds128(unsigned a)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(OFF));
+  return v;
+}
+// sum of the four byte |a - b| plus c: one VABSDIFF4.U8.ACC (the intrinsic __vsadu4 leaves the accumulate to a separate add)
+__device__ __forceinline__ unsigned vsad(unsigned a, unsigned b, unsigned c)
+{
+  unsigned d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// a * m + c on the FMA pipe
+__device__ __forceinline__ unsigned imad(unsigned a, unsigned m, unsigned c)
+{
+  unsigned d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int len_class(int d)   // (mvbits(d) - 1) / 2: 0 for 0, floor(log2|d|) + 1 otherwise (mv-search.c:333-341)
+{
+  return 32 - __clz(d < 0 ? -d : d);
+}
+
+// ---- mbarrier / TMA ----
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+  // bounded: a transfer that never completes (bad tensor map) traps instead of hanging the GPU
+  for (unsigned spin = 0; spin < (1u << 24); spin++) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int x, int y, unsigned bar)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+
+struct Regs {
+  unsigned accL[16], accR[16];      // 16 vertical displacements in flight, left / right 4-pixel column of the pair
+  unsigned curL[16], curR[16];      // current-picture words of the 16 rows
+  unsigned h0L[4], h0R[4];          // band-0 4x4 SADs waiting for band 1
+  unsigned h2L[4], h2R[4];          // band-2 4x4 SADs waiting for band 3
+  unsigned hT[8];                   // top 8x8 SAD waiting for the bottom one
+  unsigned best[NSLOT];             // running minima of the keys
+  unsigned lutA[NSLOT];             // shared address of lut[x class of this thread's dx] per slot
+};
+
+struct Thr {
+  unsigned sp_addr;     // shared address of sptab[0][dx]
+  unsigned cy_addr;     // shared address of cyt[0][h][0]
+  unsigned shift;       // (dx & 3) * 8
+  int h;
+};
+
+template <int E>
+__device__ __forceinline__ void eval(Regs &rg, unsigned key, unsigned cy)
+{
+  const unsigned m = lds32(imad(cy, LUT_STRIDE_B, rg.lutA[E]));
+  rg.best[E] = __viaddmin_u32(key, m, rg.best[E]);
+}
+
+// per 16-row group: shared addresses every load of the group is an immediate offset from
+struct GroupBase {
+  unsigned win;     // window row r0, this thread's first word
+  unsigned sp;      // sptab[r0][dx]
+  unsigned cy;      // cyt[r0][h][0]
+};
+
+// Band B (rows 4B..4B+3 of the macroblock) of vertical displacement dy = r0 + DYO has just been accumulated: L / Rr are
+// the two 4x4 SADs.
+template <int R, int B, int DYO>
+__device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBase &g, unsigned L, unsigned Rr)
+{
+  constexpr unsigned K = Geo<R>::KMUL;
+  constexpr int q4 = DYO & 3, q8 = DYO & 7;                     // two's complement: right for negative DYO too
+  constexpr int SPO = DYO * Geo<R>::SIDE * 2, CYO = DYO * 2 * CYW * 4;
+  const unsigned sp = lds16<SPO>(g.sp);
+  const unsigned kL = imad(L, K, sp), kR = imad(Rr, K, sp);
+  if (B == 0 || B == 2) {
+    constexpr int E0 = (B == 0) ? 0 : 9;
+    const uint4 c = lds128<CYO + (B == 0 ? 0 : 48)>(g.cy);
+    eval<E0>(rg, kL, c.x);
+    eval<E0 + 1>(rg, kR, c.y);
+    eval<E0 + 2>(rg, imad(L, K, kR), c.z);
+    if (B == 0) { rg.h0L[q4] = L; rg.h0R[q4] = Rr; } else { rg.h2L[q4] = L; rg.h2R[q4] = Rr; }
+  } else {
+    constexpr int E0 = (B == 1) ? 3 : 12;
+    constexpr int CB = CYO + (B == 1 ? 16 : 64);
+    const uint4 c0 = lds128<CB>(g.cy), c1 = lds128<CB + 16>(g.cy);
+    const unsigned hL = (B == 1) ? rg.h0L[q4] : rg.h2L[q4], hR = (B == 1) ? rg.h0R[q4] : rg.h2R[q4];
+    eval<E0>(rg, kL, c0.x);
+    eval<E0 + 1>(rg, kR, c0.y);
+    eval<E0 + 2>(rg, imad(L, K, kR), c0.z);
+    const unsigned k48R = imad(hR, K, kR);
+    eval<E0 + 3>(rg, imad(hL, K, kL), c0.w);
+    eval<E0 + 4>(rg, k48R, c1.x);
+    const unsigned PL = L + hL;
+    eval<E0 + 5>(rg, imad(PL, K, k48R), c1.y);          // 8x8
+    const unsigned S8 = PL + Rr + hR;
+    if (B == 1) {
+      rg.hT[q8] = S8;
+    } else {
+      const unsigned c2 = lds32<CB + 32>(g.cy);
+      const unsigned T = rg.hT[q8], V = T + S8;          // 8x16 of this column pair
+      const unsigned kV = imad(V, K, sp);
+      eval<18>(rg, kV, c1.z);
+      const unsigned X = t.h ? T : S8;                   // what the other lane needs for its 16x8
+      const unsigned Y = __shfl_xor_sync(0xffffffffu, X, 1);
+      const unsigned Vo = __shfl_xor_sync(0xffffffffu, V, 1);
+      eval<19>(rg, imad(V - X + Y, K, sp), c1.w);        // h = 0: 16x8 top, h = 1: 16x8 bottom
+      eval<20>(rg, imad(Vo, K, kV), c2);                 // 16x16 (both lanes, same key)
+    }
+  }
+}
+
+template <int R, int MODE, int U, int B>
+__device__ __forceinline__ void band_if(Regs &rg, const Thr &t, const GroupBase &g)
+{
+  constexpr int k = 4 * B + 3;
+  constexpr bool valid = (MODE == 0) ? (U >= k) : (MODE == 2) ? (U <= k) : true;
+  if constexpr (valid) {
+    constexpr int s = (U - k) & 15;
+    band_done<R, B, U - k>(rg, t, g, rg.accL[s], rg.accR[s]);
+  }
+}
+
+// One window row.  MODE 0: first group (rows 0..15, displacements dy < 0 do not exist), 1: interior, 2: last group
+// (rows 2R..2R+15, displacements dy > 2R do not exist).
+template <int R, int MODE, int U>
+__device__ __forceinline__ void sweep_row(Regs &rg, const Thr &t, const GroupBase &g)
+{
+  constexpr int N = Geo<R>::N;
+  const unsigned w0 = lds32<U * N>(g.win), w1 = lds32<U * N + 4>(g.win), w2 = lds32<U * N + 8>(g.win);
+  const unsigned refL = __funnelshift_r(w0, w1, t.shift), refR = __funnelshift_r(w1, w2, t.shift);
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const bool valid = (MODE == 0) ? (k <= U) : (MODE == 2) ? (k >= U) : true;
+    if (valid) {
+      const int s = (U - k) & 15;
+      rg.accL[s] = vsad(refL, rg.curL[k], (k & 3) ? rg.accL[s] : 0u);
+      rg.accR[s] = vsad(refR, rg.curR[k], (k & 3) ? rg.accR[s] : 0u);
+    }
+  }
+  // bands in descending order: bands 3 / 1 read the hold registers that bands 2 / 1 / 0 of a later displacement overwrite
+  band_if<R, MODE, U, 3>(rg, t, g);
+  band_if<R, MODE, U, 2>(rg, t, g);
+  band_if<R, MODE, U, 1>(rg, t, g);
+  band_if<R, MODE, U, 0>(rg, t, g);
+}
+
+template <int R, int MODE, int... U>
+__device__ __forceinline__ void sweep_rows(Regs &rg, const Thr &t, const GroupBase &g, std::integer_sequence<int, U...>)
+{
+  (sweep_row<R, MODE, U>(rg, t, g), ...);
+}
+
+// 16 window rows starting at row r0 (a multiple of 16)
+template <int R, int MODE>
+__device__ __forceinline__ void sweep16(Regs &rg, const Thr &t, unsigned row0_addr, int r0)
+{
+  GroupBase g;
+  g.win = row0_addr + (unsigned)r0 * Geo<R>::N;
+  g.sp = t.sp_addr + (unsigned)r0 * (Geo<R>::SIDE * 2);
+  g.cy = t.cy_addr + (unsigned)r0 * (2 * CYW * 4);
+  sweep_rows<R, MODE>(rg, t, g, std::make_integer_sequence<int, 16>{});
+}
+
+// slot e with the table row address taken from shared memory (column 2R, same for all threads of one h)
+template <int E>
+__device__ __forceinline__ void eval_at(Regs &rg, unsigned key, unsigned cyrow, unsigned lutA_addr)
+{
+  const unsigned cy = lds32(cyrow + slot_cyword(E) * 4);
+  const unsigned la = lds32(lutA_addr + E * 4);
+  const unsigned m = lds32(imad(cy, LUT_STRIDE_B, la));
+  rg.best[E] = __viaddmin_u32(key, m, rg.best[E]);
+}
+
+// one whole position of the last window column (dx = 2R, word-aligned: no funnel shift), all 21 slots of this lane
+template <int R>
+__device__ __forceinline__ void last_column(Regs &rg, const Thr &t, unsigned win_addr, unsigned cyt_h_addr, unsigned lutA_addr,
+                                            unsigned sptab_addr, int dy)
+{
+  constexpr unsigned K = Geo<R>::KMUL;
+  constexpr int N = Geo<R>::N, SIDE = Geo<R>::SIDE;
+  unsigned L[4] = { 0, 0, 0, 0 }, Q[4] = { 0, 0, 0, 0 };
+  const unsigned a0 = win_addr + (unsigned)dy * N + (2 * R) + 8 * t.h;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const unsigned w0 = lds32(a0 + k * N), w1 = lds32(a0 + k * N + 4);
+    L[k >> 2] = vsad(w0, rg.curL[k], L[k >> 2]);
+    Q[k >> 2] = vsad(w1, rg.curR[k], Q[k >> 2]);
+  }
+  const unsigned sp = lds16(sptab_addr + (unsigned)(dy * SIDE + 2 * R) * 2);
+  const unsigned cyrow = cyt_h_addr + (unsigned)dy * (2 * CYW * 4);
+#define KEY(v) imad((v), K, sp)
+  eval_at<0>(rg, KEY(L[0]), cyrow, lutA_addr);  eval_at<1>(rg, KEY(Q[0]), cyrow, lutA_addr);  eval_at<2>(rg, KEY(L[0] + Q[0]), cyrow, lutA_addr);
+  eval_at<3>(rg, KEY(L[1]), cyrow, lutA_addr);  eval_at<4>(rg, KEY(Q[1]), cyrow, lutA_addr);  eval_at<5>(rg, KEY(L[1] + Q[1]), cyrow, lutA_addr);
+  eval_at<6>(rg, KEY(L[0] + L[1]), cyrow, lutA_addr);  eval_at<7>(rg, KEY(Q[0] + Q[1]), cyrow, lutA_addr);
+  const unsigned T = L[0] + L[1] + Q[0] + Q[1];
+  eval_at<8>(rg, KEY(T), cyrow, lutA_addr);
+  eval_at<9>(rg, KEY(L[2]), cyrow, lutA_addr);  eval_at<10>(rg, KEY(Q[2]), cyrow, lutA_addr); eval_at<11>(rg, KEY(L[2] + Q[2]), cyrow, lutA_addr);
+  eval_at<12>(rg, KEY(L[3]), cyrow, lutA_addr); eval_at<13>(rg, KEY(Q[3]), cyrow, lutA_addr); eval_at<14>(rg, KEY(L[3] + Q[3]), cyrow, lutA_addr);
+  eval_at<15>(rg, KEY(L[2] + L[3]), cyrow, lutA_addr); eval_at<16>(rg, KEY(Q[2] + Q[3]), cyrow, lutA_addr);
+  const unsigned S8 = L[2] + L[3] + Q[2] + Q[3];
+  eval_at<17>(rg, KEY(S8), cyrow, lutA_addr);
+  const unsigned V = T + S8;
+  eval_at<18>(rg, KEY(V), cyrow, lutA_addr);
+  const unsigned X = t.h ? T : S8;
+  const unsigned Y = __shfl_xor_sync(0xffffffffu, X, 1);
+  const unsigned Vo = __shfl_xor_sync(0xffffffffu, V, 1);
+  eval_at<19>(rg, KEY(V - X + Y), cyrow, lutA_addr);
+  eval_at<20>(rg, KEY(V + Vo), cyrow, lutA_addr);
+#undef KEY
+}
+
+// inverse of me_spiral_index (mv-search.c:366-393)
+__device__ __forceinline__ void spiral_xy(int s, int &dx, int &dy)
+{
+  if (s == 0) { dx = 0; dy = 0; return; }
+  int l = (int)((sqrtf((float)s) + 1.0f) * 0.5f);
+  while ((2 * l - 1) * (2 * l - 1) > s) l--;
+  while ((2 * l + 1) * (2 * l + 1) <= s) l++;
+  int k = s - (2 * l - 1) * (2 * l - 1);
+  if (k < 2 * (2 * l - 1)) { dx = (k >> 1) - l + 1; dy = (k & 1) ? l : -l; }
+  else { k -= 2 * (2 * l - 1); dy = (k >> 1) - l; dx = (k & 1) ? l : -l; }
+}
+
+struct JobView {            // fields of me_mb_job read from its shared-memory word image
+  int opix_x, opix_y, list, ref, pmv16_x, pmv16_y, lambda;
+};
+__device__ __forceinline__ JobView job_view(const uint32_t *w)
+{
+  JobView v;
+  v.opix_x = (int)(int16_t)(w[0] & 0xffffu); v.opix_y = (int)(int16_t)(w[0] >> 16);
+  v.list = (int)(int8_t)(w[1] & 0xffu); v.ref = (int)(int8_t)((w[1] >> 8) & 0xffu);
+  v.pmv16_x = (int)(int16_t)(w[2] & 0xffffu); v.pmv16_y = (int)(int16_t)(w[2] >> 16);
+  v.lambda = (int)w[44];                          // lambda[0]: byte offset 176
+  return v;
+}
+// pmv[p] = word 3 + p
+__device__ __forceinline__ int job_pmvx(const uint32_t *w, int p) { return (int)(int16_t)(w[3 + p] & 0xffffu); }
+__device__ __forceinline__ int job_pmvy(const uint32_t *w, int p) { return (int)(int16_t)(w[3 + p] >> 16); }
+
+// search centre (me_fullfast.c:550-566), RDO on
+__device__ __forceinline__ void search_centre(const MeCfgDev &c, int R, const JobView &j, int &offx, int &offy)
+{
+  int x = j.pmv16_x / 4, y = j.pmv16_y / 4;
+  x = me_clamp(x, -2047 + R, 2047 - R);
+  y = me_clamp(y, c.mv_limit_min_y + R, c.mv_limit_max_y - R);
+  offx = x; offy = y;
+}
+
+template <int R>
+__global__ void __launch_bounds__(Geo<R>::NT, (R == 32) ? 3 : (R == 16) ? 6 : 1)
+me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
+                    const CUtensorMap *__restrict__ win_maps, const __grid_constant__ CUtensorMap cur_map,
+                    MeCfgDev cfg, MeResultInt *__restrict__ out, int *__restrict__ deferred /* [0] count, [1..] job ids */)
+{
+  using G = Geo<R>;
+  constexpr int N = G::N, SIDE = G::SIDE, NT = G::NT;
+  constexpr unsigned K = G::KMUL;
+  constexpr int JW = sizeof(MeJob) / 4;   // 47 words
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Smem<R> &sm = *reinterpret_cast<Smem<R> *>(smem_raw);
+
+  const int tid = threadIdx.x, dx = tid >> 1, lane = tid & 31, warp = tid >> 5;
+  Thr t;
+  t.h = tid & 1;
+  t.shift = (dx & 3) * 8;
+  t.sp_addr = smem_u32(&sm.sptab[dx]);
+  t.cy_addr = smem_u32(&sm.cyt[0][t.h][0]);
+  const unsigned win_off = (dx >> 2) * 4 + 8 * t.h;
+  const unsigned lut_addr = smem_u32(sm.lut);
+  const int n_mine = (n_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (n_mine <= 0) return;
+
+  // ---- once per CTA: spiral table, barriers, first two job descriptors, first window
+  for (int i = tid; i < SIDE * SIDE; i += NT) {
+    int y = i / SIDE, x = i - y * SIDE;
+    sm.sptab[i] = (uint16_t)me_spiral_index(x - R, y - R);
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&sm.mbar[0]), 1);
+    mbar_init(smem_u32(&sm.mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sm.lut_valid = 0;
+  }
+  for (int i = tid; i < (int)(sizeof(sm.refs) / 4); i += NT)
+    reinterpret_cast<uint32_t *>(sm.refs)[i] = reinterpret_cast<const uint32_t *>(ref_table)[i];
+  if (tid < JW) {
+    sm.job[0][tid] = jobs[(size_t)blockIdx.x * JW + tid];
+    if (n_mine > 1) sm.job[1][tid] = jobs[((size_t)blockIdx.x + gridDim.x) * JW + tid];
+  }
+  __syncthreads();
+
+  // window origin in search-plane coordinates; true when the whole box lies inside the plane (TMA path)
+  auto window_origin = [&](const JobView &jv, const MeRefDev &rf, int &X0, int &Y0) -> bool {
+    int offx, offy;
+    search_centre(cfg, R, jv, offx, offy);
+    X0 = jv.opix_x + offx - R + rf.spad;
+    Y0 = jv.opix_y + offy - R + rf.spad;
+    return X0 >= 0 && Y0 >= 0 && X0 + N <= rf.sw && Y0 + N <= rf.sh;
+  };
+  auto issue_loads = [&](int slot, int buf) {      // thread 0 only
+    const JobView jv = job_view(sm.job[slot]);
+    const int ri = jv.list * ME_MAX_REFS + jv.ref;
+    const MeRefDev &rf = sm.refs[ri];
+    int X0, Y0;
+    const bool tma_ok = window_origin(jv, rf, X0, Y0);
+    const unsigned bar = smem_u32(&sm.mbar[buf]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, 256u + (tma_ok ? (unsigned)(N * N) : 0u));
+    tma_load_2d(smem_u32(sm.cur[buf]), &cur_map, jv.opix_x, jv.opix_y, bar);
+    if (tma_ok) tma_load_2d(smem_u32(sm.win[buf]), &win_maps[ri], X0, Y0, bar);
+  };
+  if (tid == 0) issue_loads(0, 0);
+
+  for (int it = 0; it < n_mine; it++) {
+    const int buf = it & 1, slot = it % 3;
+    const int job_id = (int)blockIdx.x + it * (int)gridDim.x;
+    const uint32_t *jw = sm.job[slot];
+    // prefetch: window + macroblock of the next job (TMA), descriptor of the one after (registers -> shared at the end)
+    if (tid == 0 && it + 1 < n_mine) issue_loads((it + 1) % 3, buf ^ 1);
+    uint32_t pf = 0;
+    if (tid < JW && it + 2 < n_mine) pf = jobs[((size_t)job_id + 2 * (size_t)gridDim.x) * JW + tid];
+
+    const JobView jv = job_view(jw);
+    if ((unsigned)jv.lambda > (1u << 24)) {
+      // lambda too large for 32-bit keys (never the case for H.264 quantisers): leave the job to the kernel of ffs_basic.cu
+      if (tid == 0) deferred[1 + atomicAdd(&deferred[0], 1)] = job_id;
+      mbar_wait(smem_u32(&sm.mbar[buf]), (unsigned)((it >> 1) & 1));
+      if (tid < JW && it + 2 < n_mine) sm.job[(it + 2) % 3][tid] = pf;
+      __syncthreads();
+      continue;
+    }
+    const MeRefDev &rf = sm.refs[jv.list * ME_MAX_REFS + jv.ref];
+    int offx, offy, X0, Y0;
+    search_centre(cfg, R, jv, offx, offy);
+    const bool tma_ok = window_origin(jv, rf, X0, Y0);
+
+    // ---- per-job tables
+    if (!sm.lut_valid || sm.lut_lambda != jv.lambda) {       // uniform: K * ((lambda * bits) >> 16), bits = 2 * class sum + 2
+      __syncthreads();
+      if (tid < LUT_ENTRIES) sm.lut[tid * 3] = K * (unsigned)((jv.lambda * (2 * tid + 2)) >> 16);
+      if (tid == 0) { sm.lut_lambda = jv.lambda; sm.lut_valid = 1; }
+    }
+    if (NT >= 3 * 2 * NSLOT) {
+      if (tid < 3 * 2 * NSLOT) {
+        // y length classes: thread (q, third) fills dy = third, third + 3, ... of slot q = (h, e)
+        const int q = tid / 3, third = tid - 3 * q, hh = q / NSLOT, e = q - hh * NSLOT;
+        const int pmvy = job_pmvy(jw, c_slot_part[hh][e]);
+        uint32_t *dst = &sm.cyt[third][hh][slot_cyword(e)];
+        int d = 4 * (offy + third - R) - pmvy;
+        for (int dy = third; dy < SIDE; dy += 3) {
+          *dst = (uint32_t)len_class(d);
+          d += 12; dst += 3 * 2 * CYW;
+        }
+      }
+    } else if (tid < 2 * NSLOT) {   // R = 16: 64 threads -> one thread per slot, all dy
+      const int hh = tid / NSLOT, e = tid - hh * NSLOT;
+      const int pmvy = job_pmvy(jw, c_slot_part[hh][e]);
+      for (int dy = 0; dy < SIDE; dy++) sm.cyt[dy][hh][slot_cyword(e)] = (uint32_t)len_class(4 * (offy + dy - R) - pmvy);
+    }
+    if (tid < 2 * NSLOT) {
+      const int hh = tid / NSLOT, e = tid - hh * NSLOT;
+      sm.lutA_last[hh][e] = lut_addr + LUT_STRIDE_B * len_class(4 * (offx + R) - job_pmvx(jw, c_slot_part[hh][e]));
+    }
+    Regs rg;
+#pragma unroll
+    for (int e = 0; e < NSLOT; e++) {
+      rg.best[e] = 0xffffffffu;
+      rg.lutA[e] = lut_addr + LUT_STRIDE_B * len_class(4 * (offx + dx - R) - job_pmvx(jw, c_slot_part[t.h][e]));
+    }
+
+    // ---- wait for this job's macroblock + window
+    mbar_wait(smem_u32(&sm.mbar[buf]), (unsigned)((it >> 1) & 1));
+    if (!tma_ok) {
+      for (int i = tid; i < N * N; i += NT) {
+        int y = i / N, x = i - y * N;
+        int sy = me_clamp(Y0 + y, 0, rf.sh - 1), sx = me_clamp(X0 + x, 0, rf.sw - 1);
+        sm.win[buf][i] = rf.search[(size_t)sy * rf.spitch + sx];
+      }
+    }
+    __syncthreads();          // tables + manual window visible
+#pragma unroll
+    for (int k = 0; k < 16; k++) { rg.curL[k] = sm.cur[buf][4 * k + 2 * t.h]; rg.curR[k] = sm.cur[buf][4 * k + 2 * t.h + 1]; }
+
+    // ---- the sweep
+    const unsigned wbase = smem_u32(sm.win[buf]);
+    const unsigned row0 = wbase + win_off;
+    sweep16<R, 0>(rg, t, row0, 0);
+#pragma unroll 1
+    for (int g = 1; g < G::GROUPS - 1; g++) sweep16<R, 1>(rg, t, row0, 16 * g);
+    sweep16<R, 2>(rg, t, row0, 16 * (G::GROUPS - 1));
+
+    // ---- last window column: pair i scores (2R, i); (2R, 2R) is scored by warp 0
+    {
+      const unsigned cyh = smem_u32(&sm.cyt[0][t.h][0]), la = smem_u32(&sm.lutA_last[t.h][0]), spa = smem_u32(sm.sptab);
+      last_column<R>(rg, t, wbase, cyh, la, spa, dx);
+      if (warp == 0) last_column<R>(rg, t, wbase, cyh, la, spa, 2 * R);
+    }
+
+    // ---- minima over the CTA
+#pragma unroll
+    for (int e = 0; e < NSLOT; e++) {
+      const unsigned m0 = __reduce_min_sync(0xffffffffu, t.h ? 0xffffffffu : rg.best[e]);
+      const unsigned m1 = __reduce_min_sync(0xffffffffu, t.h ? rg.best[e] : 0xffffffffu);
+      if (lane < 2) sm.red[warp][lane][e] = lane ? m1 : m0;
+    }
+    __syncthreads();
+    if (tid < 2 * NSLOT - 1) {            // (h = 1, slot 20) duplicates (h = 0, slot 20)
+      const int hh = tid / NSLOT, e = tid - hh * NSLOT;
+      unsigned kmin = sm.red[0][hh][e];
+#pragma unroll
+      for (int w = 1; w < G::NW; w++) kmin = min(kmin, sm.red[w][hh][e]);
+      const unsigned cost = kmin / K, sp = kmin - cost * K;
+      int sx, sy;
+      spiral_xy((int)sp, sx, sy);
+      const int p = c_slot_part[hh][e];
+      const unsigned mvw = ((unsigned)(offx + sx) & 0xffffu) | ((unsigned)(offy + sy) << 16);
+      reinterpret_cast<uint32_t *>(out[job_id].mv)[p] = mvw;
+      out[job_id].cost[p] = (int)cost;
+    }
+    if (tid < JW && it + 2 < n_mine) sm.job[(it + 2) % 3][tid] = pf;
+    __syncthreads();          // window / tables / red free for the next job
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+template <int R>
+int launch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps, const void *cur_map,
+           const MeCfgDev *cfg, MeResultInt *out, int *deferred, cudaStream_t st)
+{
+  static int sms = 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(me_ffs_tuned_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<R>));
+    attr_done = true;
+  }
+  const int per_sm = (R == 32) ? 3 : (R == 16) ? 6 : 1;
+  int grid = sms * per_sm;
+  if (grid > n_jobs) grid = n_jobs;
+  CUtensorMap cm;
+  memcpy(&cm, cur_map, sizeof cm);
+  me_ffs_tuned_kernel<R><<<grid, Geo<R>::NT, sizeof(Smem<R>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table,
+                                                                    reinterpret_cast<const CUtensorMap *>(win_maps), cm, *cfg, out, deferred);
+  return 1;
+}
+
+}  // namespace
+
+// A 2-D byte tensor map (row pitch `pitch`, box bw x bh, no swizzle) for cp.async.bulk.tensor; out = 128 bytes, 64-aligned.
+extern "C" int me_make_tensor_map_2d(void *out, const void *base, int w, int h, int pitch, int bw, int bh)
+{
+  if (!g_encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return 1;
+    g_encode = (EncodeTiledFn)fn;
+  }
+  CUtensorMap m;
+  cuuint64_t dims[2] = { (cuuint64_t)w, (cuuint64_t)h };
+  cuuint64_t strides[1] = { (cuuint64_t)pitch };
+  cuuint32_t box[2] = { (cuuint32_t)bw, (cuuint32_t)bh };
+  cuuint32_t estr[2] = { 1, 1 };
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 2;
+  memcpy(out, &m, sizeof m);
   return 0;
+}
+
+// window side of the tuned kernel for a search range, 0 when the range has no tuned kernel
+extern "C" int me_ffs_tuned_window(int search_range)
+{
+  return (search_range == 16 || search_range == 32 || search_range == 64) ? 2 * search_range + 16 : 0;
+}
+
+// Returns the number of kernels launched; 0 = configuration not covered (the caller runs the kernel of ffs_basic.cu on
+// every job).  Jobs the kernel cannot take (lambda factor above 2^24) are appended to deferred[1..], count in deferred[0]
+// (zeroed by the caller); the caller then runs the kernel of ffs_basic.cu on that list.
+extern "C" int me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps,
+                                         const void *cur_map, const MeCfgDev *cfg, MeResultInt *out, int *deferred,
+                                         cudaStream_t st)
+{
+  if (!win_maps || !cur_map || !deferred) return 0;
+  if (cfg->metric[0] != 0 || !cfg->rdopt || cfg->full_search != 2) return 0;
+  switch (cfg->search_range) {
+    case 16: return launch<16>(jobs, n_jobs, ref_table, win_maps, cur_map, cfg, out, deferred, st);
+    case 32: return launch<32>(jobs, n_jobs, ref_table, win_maps, cur_map, cfg, out, deferred, st);
+    case 64: return launch<64>(jobs, n_jobs, ref_table, win_maps, cur_map, cfg, out, deferred, st);
+    default: return 0;
+  }
 }

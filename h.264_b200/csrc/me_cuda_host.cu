@@ -33,9 +33,11 @@ void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t 
 void me_launch_narrow(const uint16_t *src, int n, uint8_t *dst, cudaStream_t st);
 void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp, uint16_t *dst, cudaStream_t st);
 void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
-                               const MeCfgDev *cfg, MeResultInt *out, cudaStream_t st);
-int  me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
-                               const MeCfgDev *cfg, MeResultInt *out, cudaStream_t st);   // returns kernels launched, 0 = not applicable
+                               const MeCfgDev *cfg, MeResultInt *out, const int *job_list, cudaStream_t st);
+int  me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps, const void *cur_map,
+                               const MeCfgDev *cfg, MeResultInt *out, int *deferred, cudaStream_t st);   // kernels launched, 0 = not applicable
+int  me_make_tensor_map_2d(void *out, const void *base, int w, int h, int pitch, int bw, int bh);
+int  me_ffs_tuned_window(int search_range);
 void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y, int cx, int cy,
                             int R, int sse, int32_t *surf, cudaStream_t st);
 void me_launch_ffs_block(const int32_t *surf_p, int setup_range, int offx, int offy, int pmv_x, int pmv_y, int search_range,
@@ -50,10 +52,14 @@ void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t
 
 namespace {
 
+struct TensorMap { alignas(64) unsigned char bytes[128]; };   // CUtensorMap
+
 struct RefPic {
   bool used = false;
   uint8_t *planes = nullptr, *search = nullptr;
   MeRefDev dev{};
+  bool has_map = false;
+  TensorMap win_map{};          // search plane, box = one search window of the tuned kernel
 };
 
 struct State {
@@ -72,6 +78,11 @@ struct State {
   // reference lists
   MeRefDev h_table[2 * ME_MAX_REFS];
   MeRefDev *d_table = nullptr;
+  TensorMap h_maps[2 * ME_MAX_REFS];
+  TensorMap *d_maps = nullptr;
+  bool maps_ok = false;         // every listed reference has a window tensor map
+  TensorMap cur_map{}; bool has_cur_map = false;   // current picture, box 16 x 16
+  int *d_deferred = nullptr; int deferred_cap = 0;  // jobs the tuned search kernel hands back: {count, ids...}
   me_ref_handle list[2][ME_MAX_REFS];
   int list_n[2] = {0, 0};
   bool table_dirty = true;
@@ -152,13 +163,18 @@ int upload_table()
 {
   if (!g.table_dirty) return 0;
   memset(g.h_table, 0, sizeof g.h_table);
+  memset(g.h_maps, 0, sizeof g.h_maps);
+  g.maps_ok = true;
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < g.list_n[l]; i++) {
       RefPic *r = ref_of(g.list[l][i]);
       if (!r) return fail(3, "reference list %d entry %d holds an invalid handle", l, i);
       g.h_table[l * ME_MAX_REFS + i] = r->dev;
+      g.h_maps[l * ME_MAX_REFS + i] = r->win_map;
+      g.maps_ok = g.maps_ok && r->has_map;
     }
   CK(cudaMemcpyAsync(g.d_table, g.h_table, sizeof g.h_table, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(g.d_maps, g.h_maps, sizeof g.h_maps, cudaMemcpyHostToDevice, g.stream));
   // h_table is pageable: the copy above is staged synchronously by the runtime, safe to reuse
   g.table_dirty = false;
   return 0;
@@ -200,6 +216,8 @@ int create_ref_common(const uint8_t *d_luma, int stride, int w, int h, cudaStrea
   CK(cudaMalloc((void **)&r.planes, d.plane_stride * 16));
   CK(cudaMalloc((void **)&r.search, (size_t)d.spitch * d.sh));
   d.planes = r.planes; d.search = r.search;
+  if (int n = me_ffs_tuned_window(g.cfg.search_range))
+    r.has_map = me_make_tensor_map_2d(r.win_map.bytes, r.search, d.sw, d.sh, d.spitch, n, n) == 0;
   { ScopedTimer t(0, st); me_launch_planes(d_luma, stride, w, h, r.planes, d.pitch, d.plane_stride, r.search, d.spad, d.spitch, st); }
   g.launches += 2;
   CK(cudaGetLastError());
@@ -279,6 +297,8 @@ int me_cuda_init(const me_cuda_params *p)
   g.cur_pitch = align_up(p->width, 128);
   CK(cudaMalloc((void **)&g.d_cur, (size_t)g.cur_pitch * p->height));
   CK(cudaMalloc((void **)&g.d_table, sizeof g.h_table));
+  CK(cudaMalloc((void **)&g.d_maps, sizeof g.h_maps));
+  g.has_cur_map = me_make_tensor_map_2d(g.cur_map.bytes, g.d_cur, p->width, p->height, g.cur_pitch, 16, 16) == 0;
   CK(cudaMalloc((void **)&g.d_result, 64));
   CK(cudaMallocHost((void **)&g.h_result, 64));
   memset(g.d_surf, 0, sizeof g.d_surf);
@@ -296,7 +316,8 @@ void me_cuda_shutdown(void)
   for (auto &r : g.refs) if (r.used) { cudaFree(r.planes); cudaFree(r.search); }
   g.refs.clear();
   for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) if (g.d_surf[l][i]) cudaFree(g.d_surf[l][i]);
-  cudaFree(g.d_cur); cudaFree(g.d_table); cudaFree(g.d_result); cudaFreeHost(g.h_result);
+  cudaFree(g.d_cur); cudaFree(g.d_table); cudaFree(g.d_maps); cudaFree(g.d_result); cudaFreeHost(g.h_result);
+  if (g.d_deferred) cudaFree(g.d_deferred);
   if (g.h_pin) cudaFreeHost(g.h_pin);
   if (g.d_wide) cudaFree(g.d_wide);
   if (g.h_wide) cudaFreeHost(g.h_wide);
@@ -633,11 +654,22 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
     }
     di = g.d_int_scratch;
   }
+  if (g.deferred_cap < n_jobs) {
+    if (g.d_deferred) cudaFree(g.d_deferred);
+    g.d_deferred = nullptr; g.deferred_cap = 0;
+    CK(cudaMalloc((void **)&g.d_deferred, sizeof(int) * ((size_t)n_jobs + 1)));
+    g.deferred_cap = n_jobs;
+  }
   int launched = 0;
   {
     ScopedTimer t(1, st);
-    if (!use_basic_only()) launched = me_launch_ffs_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, st);
-    if (!launched) { me_launch_ffs_batch_basic((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, st); launched = 1; }
+    if (!use_basic_only() && g.maps_ok && g.has_cur_map) {
+      CK(cudaMemsetAsync(g.d_deferred, 0, sizeof(int), st));
+      launched = me_launch_ffs_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_maps, g.cur_map.bytes, &g.cfg, di, g.d_deferred, st);
+      // the jobs the tuned kernel handed back (lambda factors beyond its 32-bit keys; normally none: the launch finds an empty list)
+      if (launched) { me_launch_ffs_batch_basic((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, g.d_deferred, st); launched++; }
+    }
+    if (!launched) { me_launch_ffs_batch_basic((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, nullptr, st); launched = 1; }
   }
   { ScopedTimer t(2, st); me_launch_subpel_batch((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, (MeResult *)d_out, st); }
   g.launches += launched + 1;

@@ -148,6 +148,33 @@ def test_batch_matches_oracle(pkg, oracle_lib, variant):
     assert not bad, (variant, len(bad), n, bad[:4])
 
 
+@pytest.mark.parametrize("sr,w,h", [(16, 176, 144), (64, 352, 288)])
+def test_batch_tuned_kernel_other_ranges(pkg, oracle_lib, sr, w, h):
+    """the tuned search kernel exists for search ranges 16, 32 and 64 (config 1 / headline / config 5)"""
+    from h264_b200 import synth
+    ob = oracle_lib
+    n_refs = 2
+    d, cfg = _cfg(ob, search_range=sr)
+    frames = synth.luma_frames(w, h, n_refs + 1)
+    jobs = synth.synthetic_jobs(w, h, n_refs, (334459, 334459, 334459), seed=13, max_pmv=4 * sr)
+    bad, n = _batch_case(pkg, ob, w, h, frames, n_refs, d, cfg, jobs, sample=80 if sr == 64 else 200)
+    assert not bad, (sr, len(bad), n, bad[:4])
+
+
+def test_batch_huge_lambda_jobs_are_handed_to_the_general_kernel(pkg, oracle_lib):
+    """lambda factors beyond the 32-bit key range of the tuned kernel (> 2^24) go through the general kernel, job by job"""
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h, n_refs = 176, 144, 2
+    d, cfg = _cfg(ob)
+    frames = synth.luma_frames(w, h, n_refs + 1)
+    jobs = synth.synthetic_jobs(w, h, n_refs, (334459, 334459, 334459), seed=17, max_pmv=30)
+    jobs["lambda"][::3] = ((1 << 24) + 12345, 334459, 334459)
+    jobs["lambda"][1::7] = (1 << 24, 334459, 334459)           # the largest factor the tuned kernel accepts
+    bad, n = _batch_case(pkg, ob, w, h, frames, n_refs, d, cfg, jobs, sample=None)
+    assert not bad, (len(bad), n, bad[:4])
+
+
 @pytest.mark.parametrize("kind", ["flat", "stripes"])
 def test_batch_ties_follow_spiral_order(pkg, oracle_lib, kind):
     """flat / periodic content: thousands of equal costs, the winner must be the first one in JM's spiral order"""
