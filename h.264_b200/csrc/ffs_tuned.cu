@@ -23,10 +23,14 @@
 //  * Search windows (2R+16)^2 and the 16x16 current macroblock arrive by TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) from
 //    the wide-border search plane / the current picture, double-buffered one job ahead on two mbarriers; a window whose
 //    box leaves the wide border (predictor drift beyond the 32-pixel guard) is loaded with clamped element reads instead.
+//    TMA needs the first byte of a box row 16-byte aligned in global memory (measured on B200: any other start column of a
+//    byte tensor raises an illegal-instruction fault), so the box is 16 bytes wider than the window and starts at
+//    X0 & ~15; the residue X0 & 15 goes into each thread's word offset and funnel-shift count.
 //
 // ALU-pipe work per search position (both lanes): 64 VABSDIFF4 + 42 VIADDMNMX + 4 SHF + ~10 adds/selects.
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 #include "me_common.cuh"
@@ -40,6 +44,7 @@ constexpr int NSLOT = 21;          // partitions scored by one thread
 
 template <int R> struct Geo {
   static constexpr int N = 2 * R + 16;            // window side
+  static constexpr int NP = N + 16;               // row pitch in shared memory: the TMA box starts at a 16-byte aligned column
   static constexpr int SIDE = 2 * R + 1;
   static constexpr int NT = 4 * R;                // threads per CTA
   static constexpr int NW = NT / 32;
@@ -55,7 +60,7 @@ __constant__ int8_t c_slot_part[2][NSLOT] = {
 __host__ __device__ constexpr int slot_cyword(int e) { return e < 3 ? e : e < 9 ? e + 1 : e < 12 ? e + 3 : e + 4; }
 
 template <int R> struct __align__(128) Smem {
-  uint8_t  win[2][Geo<R>::N * Geo<R>::N];       // search windows, row pitch N (TMA box, dense)
+  uint8_t  win[2][Geo<R>::NP * Geo<R>::N];      // search windows, N rows of NP bytes (TMA box, dense); the window starts at byte X0 & 15
   uint32_t cur[2][64];                          // current macroblocks, 16 rows x 4 words
   uint32_t cyt[Geo<R>::SIDE][2][CYW];           // y length class per (dy, h, slot)
   uint32_t lut[LUT_ENTRIES * 3];                // K * mvcost(class sum), entry stride 12 bytes
@@ -229,8 +234,8 @@ __device__ __forceinline__ void band_if(Regs &rg, const Thr &t, const GroupBase 
 template <int R, int MODE, int U>
 __device__ __forceinline__ void sweep_row(Regs &rg, const Thr &t, const GroupBase &g)
 {
-  constexpr int N = Geo<R>::N;
-  const unsigned w0 = lds32<U * N>(g.win), w1 = lds32<U * N + 4>(g.win), w2 = lds32<U * N + 8>(g.win);
+  constexpr int NP = Geo<R>::NP;
+  const unsigned w0 = lds32<U * NP>(g.win), w1 = lds32<U * NP + 4>(g.win), w2 = lds32<U * NP + 8>(g.win);
   const unsigned refL = __funnelshift_r(w0, w1, t.shift), refR = __funnelshift_r(w1, w2, t.shift);
 #pragma unroll
   for (int k = 0; k < 16; k++) {
@@ -259,7 +264,7 @@ template <int R, int MODE>
 __device__ __forceinline__ void sweep16(Regs &rg, const Thr &t, unsigned row0_addr, int r0)
 {
   GroupBase g;
-  g.win = row0_addr + (unsigned)r0 * Geo<R>::N;
+  g.win = row0_addr + (unsigned)r0 * Geo<R>::NP;
   g.sp = t.sp_addr + (unsigned)r0 * (Geo<R>::SIDE * 2);
   g.cy = t.cy_addr + (unsigned)r0 * (2 * CYW * 4);
   sweep_rows<R, MODE>(rg, t, g, std::make_integer_sequence<int, 16>{});
@@ -275,20 +280,21 @@ __device__ __forceinline__ void eval_at(Regs &rg, unsigned key, unsigned cyrow, 
   rg.best[E] = __viaddmin_u32(key, m, rg.best[E]);
 }
 
-// one whole position of the last window column (dx = 2R, word-aligned: no funnel shift), all 21 slots of this lane
+// one whole position of the last window column (dx = 2R), all 21 slots of this lane.  col_addr: shared address of the first
+// word of window row 0 that holds column 2R + 8h; shift: byte residue of the window start, as a funnel-shift count
 template <int R>
-__device__ __forceinline__ void last_column(Regs &rg, const Thr &t, unsigned win_addr, unsigned cyt_h_addr, unsigned lutA_addr,
-                                            unsigned sptab_addr, int dy)
+__device__ __forceinline__ void last_column(Regs &rg, const Thr &t, unsigned col_addr, unsigned shift, unsigned cyt_h_addr,
+                                            unsigned lutA_addr, unsigned sptab_addr, int dy)
 {
   constexpr unsigned K = Geo<R>::KMUL;
-  constexpr int N = Geo<R>::N, SIDE = Geo<R>::SIDE;
+  constexpr int NP = Geo<R>::NP, SIDE = Geo<R>::SIDE;
   unsigned L[4] = { 0, 0, 0, 0 }, Q[4] = { 0, 0, 0, 0 };
-  const unsigned a0 = win_addr + (unsigned)dy * N + (2 * R) + 8 * t.h;
+  const unsigned a0 = col_addr + (unsigned)dy * NP;
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    const unsigned w0 = lds32(a0 + k * N), w1 = lds32(a0 + k * N + 4);
-    L[k >> 2] = vsad(w0, rg.curL[k], L[k >> 2]);
-    Q[k >> 2] = vsad(w1, rg.curR[k], Q[k >> 2]);
+    const unsigned w0 = lds32(a0 + k * NP), w1 = lds32(a0 + k * NP + 4), w2 = lds32(a0 + k * NP + 8);
+    L[k >> 2] = vsad(__funnelshift_r(w0, w1, shift), rg.curL[k], L[k >> 2]);
+    Q[k >> 2] = vsad(__funnelshift_r(w1, w2, shift), rg.curR[k], Q[k >> 2]);
   }
   const unsigned sp = lds16(sptab_addr + (unsigned)(dy * SIDE + 2 * R) * 2);
   const unsigned cyrow = cyt_h_addr + (unsigned)dy * (2 * CYW * 4);
@@ -325,6 +331,10 @@ __device__ __forceinline__ void spiral_xy(int s, int &dx, int &dy)
   else { k -= 2 * (2 * l - 1); dy = (k >> 1) - l; dx = (k & 1) ? l : -l; }
 }
 
+// window tensor maps travel as a kernel parameter (constant bank): (list, ref) -> list * TUNED_MAX_REFS + ref
+constexpr int TUNED_MAX_REFS = 8;
+struct WinMaps { CUtensorMap m[2 * TUNED_MAX_REFS]; };
+
 struct JobView {            // fields of me_mb_job read from its shared-memory word image
   int opix_x, opix_y, list, ref, pmv16_x, pmv16_y, lambda;
 };
@@ -353,11 +363,12 @@ __device__ __forceinline__ void search_centre(const MeCfgDev &c, int R, const Jo
 template <int R>
 __global__ void __launch_bounds__(Geo<R>::NT, (R == 32) ? 3 : (R == 16) ? 6 : 1)
 me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
-                    const CUtensorMap *__restrict__ win_maps, const __grid_constant__ CUtensorMap cur_map,
+                    const __grid_constant__ WinMaps win_maps, const __grid_constant__ CUtensorMap cur_map,
+                    const uint8_t *__restrict__ cur_pic, int cur_pitch, int use_tma,
                     MeCfgDev cfg, MeResultInt *__restrict__ out, int *__restrict__ deferred /* [0] count, [1..] job ids */)
 {
   using G = Geo<R>;
-  constexpr int N = G::N, SIDE = G::SIDE, NT = G::NT;
+  constexpr int N = G::N, NP = G::NP, SIDE = G::SIDE, NT = G::NT;
   constexpr unsigned K = G::KMUL;
   constexpr int JW = sizeof(MeJob) / 4;   // 47 words
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -366,10 +377,8 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
   const int tid = threadIdx.x, dx = tid >> 1, lane = tid & 31, warp = tid >> 5;
   Thr t;
   t.h = tid & 1;
-  t.shift = (dx & 3) * 8;
   t.sp_addr = smem_u32(&sm.sptab[dx]);
   t.cy_addr = smem_u32(&sm.cyt[0][t.h][0]);
-  const unsigned win_off = (dx >> 2) * 4 + 8 * t.h;
   const unsigned lut_addr = smem_u32(sm.lut);
   const int n_mine = (n_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (n_mine <= 0) return;
@@ -399,7 +408,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     search_centre(cfg, R, jv, offx, offy);
     X0 = jv.opix_x + offx - R + rf.spad;
     Y0 = jv.opix_y + offy - R + rf.spad;
-    return X0 >= 0 && Y0 >= 0 && X0 + N <= rf.sw && Y0 + N <= rf.sh;
+    return use_tma && X0 >= 0 && Y0 >= 0 && X0 + N <= rf.sw && Y0 + N <= rf.sh;
   };
   auto issue_loads = [&](int slot, int buf) {      // thread 0 only
     const JobView jv = job_view(sm.job[slot]);
@@ -409,18 +418,18 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     const bool tma_ok = window_origin(jv, rf, X0, Y0);
     const unsigned bar = smem_u32(&sm.mbar[buf]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(bar, 256u + (tma_ok ? (unsigned)(N * N) : 0u));
+    mbar_expect_tx(bar, 256u + (tma_ok ? (unsigned)(NP * N) : 0u));
     tma_load_2d(smem_u32(sm.cur[buf]), &cur_map, jv.opix_x, jv.opix_y, bar);
-    if (tma_ok) tma_load_2d(smem_u32(sm.win[buf]), &win_maps[ri], X0, Y0, bar);
+    if (tma_ok) tma_load_2d(smem_u32(sm.win[buf]), &win_maps.m[jv.list * TUNED_MAX_REFS + jv.ref], X0 & ~15, Y0, bar);
   };
-  if (tid == 0) issue_loads(0, 0);
+  if (tid == 0 && use_tma) issue_loads(0, 0);
 
   for (int it = 0; it < n_mine; it++) {
     const int buf = it & 1, slot = it % 3;
     const int job_id = (int)blockIdx.x + it * (int)gridDim.x;
     const uint32_t *jw = sm.job[slot];
     // prefetch: window + macroblock of the next job (TMA), descriptor of the one after (registers -> shared at the end)
-    if (tid == 0 && it + 1 < n_mine) issue_loads((it + 1) % 3, buf ^ 1);
+    if (tid == 0 && use_tma && it + 1 < n_mine) issue_loads((it + 1) % 3, buf ^ 1);
     uint32_t pf = 0;
     if (tid < JW && it + 2 < n_mine) pf = jobs[((size_t)job_id + 2 * (size_t)gridDim.x) * JW + tid];
 
@@ -428,7 +437,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     if ((unsigned)jv.lambda > (1u << 24)) {
       // lambda too large for 32-bit keys (never the case for H.264 quantisers): leave the job to the kernel of ffs_basic.cu
       if (tid == 0) deferred[1 + atomicAdd(&deferred[0], 1)] = job_id;
-      mbar_wait(smem_u32(&sm.mbar[buf]), (unsigned)((it >> 1) & 1));
+      if (use_tma) mbar_wait(smem_u32(&sm.mbar[buf]), (unsigned)((it >> 1) & 1));
       if (tid < JW && it + 2 < n_mine) sm.job[(it + 2) % 3][tid] = pf;
       __syncthreads();
       continue;
@@ -437,6 +446,8 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     int offx, offy, X0, Y0;
     search_centre(cfg, R, jv, offx, offy);
     const bool tma_ok = window_origin(jv, rf, X0, Y0);
+    const int mis = X0 & 15;                                 // window column 0 sits at byte `mis` of every shared row
+    t.shift = ((dx + mis) & 3) * 8;
 
     // ---- per-job tables
     if (!sm.lut_valid || sm.lut_lambda != jv.lambda) {       // uniform: K * ((lambda * bits) >> 16), bits = 2 * class sum + 2
@@ -473,11 +484,13 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     }
 
     // ---- wait for this job's macroblock + window
-    mbar_wait(smem_u32(&sm.mbar[buf]), (unsigned)((it >> 1) & 1));
+    if (use_tma) mbar_wait(smem_u32(&sm.mbar[buf]), (unsigned)((it >> 1) & 1));
+    else if (tid < 64)       // diagnostic mode without TMA: plain loads of the current macroblock
+      sm.cur[buf][tid] = *reinterpret_cast<const uint32_t *>(cur_pic + (size_t)(jv.opix_y + (tid >> 2)) * cur_pitch + jv.opix_x + 4 * (tid & 3));
     if (!tma_ok) {
-      for (int i = tid; i < N * N; i += NT) {
-        int y = i / N, x = i - y * N;
-        int sy = me_clamp(Y0 + y, 0, rf.sh - 1), sx = me_clamp(X0 + x, 0, rf.sw - 1);
+      for (int i = tid; i < NP * N; i += NT) {
+        int y = i / NP, x = i - y * NP;
+        int sy = me_clamp(Y0 + y, 0, rf.sh - 1), sx = me_clamp(X0 - mis + x, 0, rf.sw - 1);
         sm.win[buf][i] = rf.search[(size_t)sy * rf.spitch + sx];
       }
     }
@@ -487,7 +500,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
 
     // ---- the sweep
     const unsigned wbase = smem_u32(sm.win[buf]);
-    const unsigned row0 = wbase + win_off;
+    const unsigned row0 = wbase + (unsigned)((dx + mis) >> 2) * 4 + 8 * t.h;
     sweep16<R, 0>(rg, t, row0, 0);
 #pragma unroll 1
     for (int g = 1; g < G::GROUPS - 1; g++) sweep16<R, 1>(rg, t, row0, 16 * g);
@@ -496,8 +509,9 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     // ---- last window column: pair i scores (2R, i); (2R, 2R) is scored by warp 0
     {
       const unsigned cyh = smem_u32(&sm.cyt[0][t.h][0]), la = smem_u32(&sm.lutA_last[t.h][0]), spa = smem_u32(sm.sptab);
-      last_column<R>(rg, t, wbase, cyh, la, spa, dx);
-      if (warp == 0) last_column<R>(rg, t, wbase, cyh, la, spa, 2 * R);
+      const unsigned col = wbase + (unsigned)((2 * R + mis) >> 2) * 4 + 8 * t.h, sh_last = (mis & 3) * 8;
+      last_column<R>(rg, t, col, sh_last, cyh, la, spa, dx);
+      if (warp == 0) last_column<R>(rg, t, col, sh_last, cyh, la, spa, 2 * R);
     }
 
     // ---- minima over the CTA
@@ -533,7 +547,7 @@ EncodeTiledFn g_encode = nullptr;
 
 template <int R>
 int launch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps, const void *cur_map,
-           const MeCfgDev *cfg, MeResultInt *out, int *deferred, cudaStream_t st)
+           const uint8_t *cur_pic, int cur_pitch, const MeCfgDev *cfg, MeResultInt *out, int *deferred, cudaStream_t st)
 {
   static int sms = 0;
   static bool attr_done = false;
@@ -549,8 +563,14 @@ int launch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void 
   if (grid > n_jobs) grid = n_jobs;
   CUtensorMap cm;
   memcpy(&cm, cur_map, sizeof cm);
-  me_ffs_tuned_kernel<R><<<grid, Geo<R>::NT, sizeof(Smem<R>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table,
-                                                                    reinterpret_cast<const CUtensorMap *>(win_maps), cm, *cfg, out, deferred);
+  // host table: [2][ME_MAX_REFS] maps of 128 bytes -> kernel parameter [2][TUNED_MAX_REFS]
+  WinMaps wm;
+  for (int l = 0; l < 2; l++)
+    memcpy(&wm.m[l * TUNED_MAX_REFS], (const unsigned char *)win_maps + (size_t)l * ME_MAX_REFS * 128, sizeof(CUtensorMap) * TUNED_MAX_REFS);
+  static int use_tma = -1;
+  if (use_tma < 0) { const char *e = getenv("ME_CUDA_FFS_TMA"); use_tma = !(e && e[0] == '0'); }
+  me_ffs_tuned_kernel<R><<<grid, Geo<R>::NT, sizeof(Smem<R>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, wm, cm,
+                                                                    cur_pic, cur_pitch, use_tma, *cfg, out, deferred);
   return 1;
 }
 
@@ -578,25 +598,28 @@ extern "C" int me_make_tensor_map_2d(void *out, const void *base, int w, int h, 
   return 0;
 }
 
-// window side of the tuned kernel for a search range, 0 when the range has no tuned kernel
+// window height of the tuned kernel for a search range (the TMA box is that many rows of height + 16 bytes), 0 when the
+// range has no tuned kernel
 extern "C" int me_ffs_tuned_window(int search_range)
 {
   return (search_range == 16 || search_range == 32 || search_range == 64) ? 2 * search_range + 16 : 0;
 }
 
 // Returns the number of kernels launched; 0 = configuration not covered (the caller runs the kernel of ffs_basic.cu on
-// every job).  Jobs the kernel cannot take (lambda factor above 2^24) are appended to deferred[1..], count in deferred[0]
-// (zeroed by the caller); the caller then runs the kernel of ffs_basic.cu on that list.
+// every job).  win_maps: host array [2][ME_MAX_REFS] of 128-byte tensor maps of the listed references' search planes;
+// n_refs0 / n_refs1: list sizes.  Jobs the kernel cannot take (lambda factor above 2^24) are appended to deferred[1..],
+// count in deferred[0] (zeroed by the caller); the caller then runs the kernel of ffs_basic.cu on that list.
 extern "C" int me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps,
-                                         const void *cur_map, const MeCfgDev *cfg, MeResultInt *out, int *deferred,
-                                         cudaStream_t st)
+                                         int n_refs0, int n_refs1, const void *cur_map, const uint8_t *cur_pic, int cur_pitch,
+                                         const MeCfgDev *cfg, MeResultInt *out, int *deferred, cudaStream_t st)
 {
   if (!win_maps || !cur_map || !deferred) return 0;
+  if (n_refs0 > TUNED_MAX_REFS || n_refs1 > TUNED_MAX_REFS) return 0;
   if (cfg->metric[0] != 0 || !cfg->rdopt || cfg->full_search != 2) return 0;
   switch (cfg->search_range) {
-    case 16: return launch<16>(jobs, n_jobs, ref_table, win_maps, cur_map, cfg, out, deferred, st);
-    case 32: return launch<32>(jobs, n_jobs, ref_table, win_maps, cur_map, cfg, out, deferred, st);
-    case 64: return launch<64>(jobs, n_jobs, ref_table, win_maps, cur_map, cfg, out, deferred, st);
+    case 16: return launch<16>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, st);
+    case 32: return launch<32>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, st);
+    case 64: return launch<64>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, st);
     default: return 0;
   }
 }

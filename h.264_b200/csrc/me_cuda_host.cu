@@ -34,8 +34,9 @@ void me_launch_narrow(const uint16_t *src, int n, uint8_t *dst, cudaStream_t st)
 void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp, uint16_t *dst, cudaStream_t st);
 void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
                                const MeCfgDev *cfg, MeResultInt *out, const int *job_list, cudaStream_t st);
-int  me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps, const void *cur_map,
-                               const MeCfgDev *cfg, MeResultInt *out, int *deferred, cudaStream_t st);   // kernels launched, 0 = not applicable
+int  me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps, int n_refs0, int n_refs1,
+                               const void *cur_map, const uint8_t *cur_pic, int cur_pitch, const MeCfgDev *cfg, MeResultInt *out,
+                               int *deferred, cudaStream_t st);   // kernels launched, 0 = not applicable
 int  me_make_tensor_map_2d(void *out, const void *base, int w, int h, int pitch, int bw, int bh);
 int  me_ffs_tuned_window(int search_range);
 void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y, int cx, int cy,
@@ -79,7 +80,6 @@ struct State {
   MeRefDev h_table[2 * ME_MAX_REFS];
   MeRefDev *d_table = nullptr;
   TensorMap h_maps[2 * ME_MAX_REFS];
-  TensorMap *d_maps = nullptr;
   bool maps_ok = false;         // every listed reference has a window tensor map
   TensorMap cur_map{}; bool has_cur_map = false;   // current picture, box 16 x 16
   int *d_deferred = nullptr; int deferred_cap = 0;  // jobs the tuned search kernel hands back: {count, ids...}
@@ -174,7 +174,6 @@ int upload_table()
       g.maps_ok = g.maps_ok && r->has_map;
     }
   CK(cudaMemcpyAsync(g.d_table, g.h_table, sizeof g.h_table, cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(g.d_maps, g.h_maps, sizeof g.h_maps, cudaMemcpyHostToDevice, g.stream));
   // h_table is pageable: the copy above is staged synchronously by the runtime, safe to reuse
   g.table_dirty = false;
   return 0;
@@ -217,7 +216,7 @@ int create_ref_common(const uint8_t *d_luma, int stride, int w, int h, cudaStrea
   CK(cudaMalloc((void **)&r.search, (size_t)d.spitch * d.sh));
   d.planes = r.planes; d.search = r.search;
   if (int n = me_ffs_tuned_window(g.cfg.search_range))
-    r.has_map = me_make_tensor_map_2d(r.win_map.bytes, r.search, d.sw, d.sh, d.spitch, n, n) == 0;
+    r.has_map = me_make_tensor_map_2d(r.win_map.bytes, r.search, d.sw, d.sh, d.spitch, n + 16, n) == 0;
   { ScopedTimer t(0, st); me_launch_planes(d_luma, stride, w, h, r.planes, d.pitch, d.plane_stride, r.search, d.spad, d.spitch, st); }
   g.launches += 2;
   CK(cudaGetLastError());
@@ -297,7 +296,6 @@ int me_cuda_init(const me_cuda_params *p)
   g.cur_pitch = align_up(p->width, 128);
   CK(cudaMalloc((void **)&g.d_cur, (size_t)g.cur_pitch * p->height));
   CK(cudaMalloc((void **)&g.d_table, sizeof g.h_table));
-  CK(cudaMalloc((void **)&g.d_maps, sizeof g.h_maps));
   g.has_cur_map = me_make_tensor_map_2d(g.cur_map.bytes, g.d_cur, p->width, p->height, g.cur_pitch, 16, 16) == 0;
   CK(cudaMalloc((void **)&g.d_result, 64));
   CK(cudaMallocHost((void **)&g.h_result, 64));
@@ -316,7 +314,7 @@ void me_cuda_shutdown(void)
   for (auto &r : g.refs) if (r.used) { cudaFree(r.planes); cudaFree(r.search); }
   g.refs.clear();
   for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) if (g.d_surf[l][i]) cudaFree(g.d_surf[l][i]);
-  cudaFree(g.d_cur); cudaFree(g.d_table); cudaFree(g.d_maps); cudaFree(g.d_result); cudaFreeHost(g.h_result);
+  cudaFree(g.d_cur); cudaFree(g.d_table); cudaFree(g.d_result); cudaFreeHost(g.h_result);
   if (g.d_deferred) cudaFree(g.d_deferred);
   if (g.h_pin) cudaFreeHost(g.h_pin);
   if (g.d_wide) cudaFree(g.d_wide);
@@ -665,7 +663,8 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
     ScopedTimer t(1, st);
     if (!use_basic_only() && g.maps_ok && g.has_cur_map) {
       CK(cudaMemsetAsync(g.d_deferred, 0, sizeof(int), st));
-      launched = me_launch_ffs_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_maps, g.cur_map.bytes, &g.cfg, di, g.d_deferred, st);
+      launched = me_launch_ffs_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.h_maps, g.list_n[0], g.list_n[1], g.cur_map.bytes,
+                                           g.d_cur, g.cur_pitch, &g.cfg, di, g.d_deferred, st);
       // the jobs the tuned kernel handed back (lambda factors beyond its 32-bit keys; normally none: the launch finds an empty list)
       if (launched) { me_launch_ffs_batch_basic((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, g.d_deferred, st); launched++; }
     }
