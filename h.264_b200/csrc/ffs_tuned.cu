@@ -48,7 +48,6 @@ template <int R> struct Geo {
   static constexpr int SIDE = 2 * R + 1;
   static constexpr int NT = 4 * R;                // threads per CTA
   static constexpr int NW = NT / 32;
-  static constexpr int GROUPS = R / 8 + 1;        // 16-row groups of the window
   static constexpr unsigned KMUL = SIDE * SIDE;   // key = cost * KMUL + spiral index
 };
 
@@ -122,6 +121,7 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
   // bounded: a transfer that never completes (bad tensor map) traps instead of hanging the GPU
+#pragma unroll 1
   for (unsigned spin = 0; spin < (1u << 24); spin++) {
     unsigned done;
     asm volatile(
@@ -141,11 +141,11 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int 
 }
 
 struct Regs {
-  unsigned accL[16], accR[16];      // 16 vertical displacements in flight, left / right 4-pixel column of the pair
+  unsigned accL[4][4], accR[4][4];  // [band b][dy & 3]: 4x4 SAD in progress, left / right 4-pixel column of the pair
   unsigned curL[16], curR[16];      // current-picture words of the 16 rows
-  unsigned h0L[4], h0R[4];          // band-0 4x4 SADs waiting for band 1
+  unsigned h0L[4], h0R[4];          // band-0 4x4 SADs waiting for band 1, by dy & 3
   unsigned h2L[4], h2R[4];          // band-2 4x4 SADs waiting for band 3
-  unsigned hT[8];                   // top 8x8 SAD waiting for the bottom one
+  unsigned hT1[4], hT2[4];          // top 8x8 SAD waiting 8 rows for the bottom one: two-stage queue per dy & 3
   unsigned best[NSLOT];             // running minima of the keys
   unsigned lutA[NSLOT];             // shared address of lut[x class of this thread's dx] per slot
 };
@@ -164,7 +164,7 @@ __device__ __forceinline__ void eval(Regs &rg, unsigned key, unsigned cy)
   rg.best[E] = __viaddmin_u32(key, m, rg.best[E]);
 }
 
-// per 16-row group: shared addresses every load of the group is an immediate offset from
+// per 4-row group: shared addresses every load of the group is an immediate offset from
 struct GroupBase {
   unsigned win;     // window row r0, this thread's first word
   unsigned sp;      // sptab[r0][dx]
@@ -172,12 +172,11 @@ struct GroupBase {
 };
 
 // Band B (rows 4B..4B+3 of the macroblock) of vertical displacement dy = r0 + DYO has just been accumulated: L / Rr are
-// the two 4x4 SADs.
-template <int R, int B, int DYO>
+// the two 4x4 SADs, J = dy & 3.
+template <int R, int B, int DYO, int J>
 __device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBase &g, unsigned L, unsigned Rr)
 {
   constexpr unsigned K = Geo<R>::KMUL;
-  constexpr int q4 = DYO & 3, q8 = DYO & 7;                     // two's complement: right for negative DYO too
   constexpr int SPO = DYO * Geo<R>::SIDE * 2, CYO = DYO * 2 * CYW * 4;
   const unsigned sp = lds16<SPO>(g.sp);
   const unsigned kL = imad(L, K, sp), kR = imad(Rr, K, sp);
@@ -187,12 +186,12 @@ __device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBas
     eval<E0>(rg, kL, c.x);
     eval<E0 + 1>(rg, kR, c.y);
     eval<E0 + 2>(rg, imad(L, K, kR), c.z);
-    if (B == 0) { rg.h0L[q4] = L; rg.h0R[q4] = Rr; } else { rg.h2L[q4] = L; rg.h2R[q4] = Rr; }
+    if (B == 0) { rg.h0L[J] = L; rg.h0R[J] = Rr; } else { rg.h2L[J] = L; rg.h2R[J] = Rr; }
   } else {
     constexpr int E0 = (B == 1) ? 3 : 12;
     constexpr int CB = CYO + (B == 1 ? 16 : 64);
     const uint4 c0 = lds128<CB>(g.cy), c1 = lds128<CB + 16>(g.cy);
-    const unsigned hL = (B == 1) ? rg.h0L[q4] : rg.h2L[q4], hR = (B == 1) ? rg.h0R[q4] : rg.h2R[q4];
+    const unsigned hL = (B == 1) ? rg.h0L[J] : rg.h2L[J], hR = (B == 1) ? rg.h0R[J] : rg.h2R[J];
     eval<E0>(rg, kL, c0.x);
     eval<E0 + 1>(rg, kR, c0.y);
     eval<E0 + 2>(rg, imad(L, K, kR), c0.z);
@@ -203,10 +202,10 @@ __device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBas
     eval<E0 + 5>(rg, imad(PL, K, k48R), c1.y);          // 8x8
     const unsigned S8 = PL + Rr + hR;
     if (B == 1) {
-      rg.hT[q8] = S8;
+      rg.hT1[J] = S8;
     } else {
       const unsigned c2 = lds32<CB + 32>(g.cy);
-      const unsigned T = rg.hT[q8], V = T + S8;          // 8x16 of this column pair
+      const unsigned T = rg.hT2[J], V = T + S8;          // 8x16 of this column pair
       const unsigned kV = imad(V, K, sp);
       eval<18>(rg, kV, c1.z);
       const unsigned X = t.h ? T : S8;                   // what the other lane needs for its 16x8
@@ -218,56 +217,48 @@ __device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBas
   }
 }
 
-template <int R, int MODE, int U, int B>
-__device__ __forceinline__ void band_if(Regs &rg, const Thr &t, const GroupBase &g)
-{
-  constexpr int k = 4 * B + 3;
-  constexpr bool valid = (MODE == 0) ? (U >= k) : (MODE == 2) ? (U <= k) : true;
-  if constexpr (valid) {
-    constexpr int s = (U - k) & 15;
-    band_done<R, B, U - k>(rg, t, g, rg.accL[s], rg.accR[s]);
-  }
-}
-
-// One window row.  MODE 0: first group (rows 0..15, displacements dy < 0 do not exist), 1: interior, 2: last group
-// (rows 2R..2R+15, displacements dy > 2R do not exist).
-template <int R, int MODE, int U>
-__device__ __forceinline__ void sweep_row(Regs &rg, const Thr &t, const GroupBase &g)
+// One window row r = r0 + U (r0 a multiple of 4).  Row r is row k = 4b + i of the macroblock for the displacement
+// dy = r - k; with J = dy & 3 the phase is i = (U - J) & 3, so the 32 accumulators are addressed by compile-time (b, J)
+// although the loop is unrolled over four rows only (the whole sweep body stays within the instruction caches).
+// CHECK: rows 0..15 and 2R..2R+15, where some displacements fall outside [0, 2R]: their SADs are computed into
+// accumulators nobody reads, their evaluation is skipped.
+template <int R, bool CHECK, int U>
+__device__ __forceinline__ void sweep_row(Regs &rg, const Thr &t, const GroupBase &g, int r0)
 {
   constexpr int NP = Geo<R>::NP;
   const unsigned w0 = lds32<U * NP>(g.win), w1 = lds32<U * NP + 4>(g.win), w2 = lds32<U * NP + 8>(g.win);
   const unsigned refL = __funnelshift_r(w0, w1, t.shift), refR = __funnelshift_r(w1, w2, t.shift);
 #pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const bool valid = (MODE == 0) ? (k <= U) : (MODE == 2) ? (k >= U) : true;
-    if (valid) {
-      const int s = (U - k) & 15;
-      rg.accL[s] = vsad(refL, rg.curL[k], (k & 3) ? rg.accL[s] : 0u);
-      rg.accR[s] = vsad(refR, rg.curR[k], (k & 3) ? rg.accR[s] : 0u);
+  for (int b = 0; b < 4; b++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int i = (U - j) & 3, k = 4 * b + i;
+      rg.accL[b][j] = vsad(refL, rg.curL[k], i ? rg.accL[b][j] : 0u);
+      rg.accR[b][j] = vsad(refR, rg.curR[k], i ? rg.accR[b][j] : 0u);
     }
-  }
-  // bands in descending order: bands 3 / 1 read the hold registers that bands 2 / 1 / 0 of a later displacement overwrite
-  band_if<R, MODE, U, 3>(rg, t, g);
-  band_if<R, MODE, U, 2>(rg, t, g);
-  band_if<R, MODE, U, 1>(rg, t, g);
-  band_if<R, MODE, U, 0>(rg, t, g);
+  // the displacements whose band completes in this row have dy & 3 == J; bands in descending order: bands 3 / 1 read the
+  // hold registers that bands 2 / 1 / 0 of a later displacement overwrite
+  constexpr int J = (U + 1) & 3;
+  const unsigned lim = 2 * R;
+  if (!CHECK || (unsigned)(r0 + U - 15) <= lim) band_done<R, 3, U - 15, J>(rg, t, g, rg.accL[3][J], rg.accR[3][J]);
+  if (!CHECK || (unsigned)(r0 + U - 11) <= lim) band_done<R, 2, U - 11, J>(rg, t, g, rg.accL[2][J], rg.accR[2][J]);
+  rg.hT2[J] = rg.hT1[J];
+  if (!CHECK || (unsigned)(r0 + U - 7) <= lim) band_done<R, 1, U - 7, J>(rg, t, g, rg.accL[1][J], rg.accR[1][J]);
+  if (!CHECK || (unsigned)(r0 + U - 3) <= lim) band_done<R, 0, U - 3, J>(rg, t, g, rg.accL[0][J], rg.accR[0][J]);
 }
 
-template <int R, int MODE, int... U>
-__device__ __forceinline__ void sweep_rows(Regs &rg, const Thr &t, const GroupBase &g, std::integer_sequence<int, U...>)
-{
-  (sweep_row<R, MODE, U>(rg, t, g), ...);
-}
-
-// 16 window rows starting at row r0 (a multiple of 16)
-template <int R, int MODE>
-__device__ __forceinline__ void sweep16(Regs &rg, const Thr &t, unsigned row0_addr, int r0)
+// four window rows starting at row r0 (a multiple of 4)
+template <int R, bool CHECK>
+__device__ __forceinline__ void sweep4(Regs &rg, const Thr &t, unsigned row0_addr, int r0)
 {
   GroupBase g;
   g.win = row0_addr + (unsigned)r0 * Geo<R>::NP;
   g.sp = t.sp_addr + (unsigned)r0 * (Geo<R>::SIDE * 2);
   g.cy = t.cy_addr + (unsigned)r0 * (2 * CYW * 4);
-  sweep_rows<R, MODE>(rg, t, g, std::make_integer_sequence<int, 16>{});
+  sweep_row<R, CHECK, 0>(rg, t, g, r0);
+  sweep_row<R, CHECK, 1>(rg, t, g, r0);
+  sweep_row<R, CHECK, 2>(rg, t, g, r0);
+  sweep_row<R, CHECK, 3>(rg, t, g, r0);
 }
 
 // slot e with the table row address taken from shared memory (column 2R, same for all threads of one h)
@@ -501,10 +492,11 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     // ---- the sweep
     const unsigned wbase = smem_u32(sm.win[buf]);
     const unsigned row0 = wbase + (unsigned)((dx + mis) >> 2) * 4 + 8 * t.h;
-    sweep16<R, 0>(rg, t, row0, 0);
 #pragma unroll 1
-    for (int g = 1; g < G::GROUPS - 1; g++) sweep16<R, 1>(rg, t, row0, 16 * g);
-    sweep16<R, 2>(rg, t, row0, 16 * (G::GROUPS - 1));
+    for (int r0 = 0; r0 < N; r0 += 4) {
+      if (r0 < 16 || r0 >= 2 * R) sweep4<R, true>(rg, t, row0, r0);
+      else sweep4<R, false>(rg, t, row0, r0);
+    }
 
     // ---- last window column: pair i scores (2R, i); (2R, 2R) is scored by warp 0
     {
