@@ -38,6 +38,10 @@ int  me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *re
                                const void *cur_map, const uint8_t *cur_pic, int cur_pitch, const MeCfgDev *cfg, MeResultInt *out,
                                int *deferred, cudaStream_t st);   // kernels launched, 0 = not applicable
 int  me_make_tensor_map_2d(void *out, const void *base, int w, int h, int pitch, int bw, int bh);
+int  me_make_planes_tensor_map(void *out, const void *planes, int pitch, int hp, size_t plane_stride);
+int  me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *plane_maps, int n_refs0, int n_refs1,
+                                  const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg, const MeResultInt *in_int, MeResult *out,
+                                  cudaStream_t st);   // 1 = launched, 0 = not applicable
 int  me_ffs_tuned_window(int search_range);
 void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y, int cx, int cy,
                             int R, int sse, int32_t *surf, cudaStream_t st);
@@ -61,6 +65,8 @@ struct RefPic {
   MeRefDev dev{};
   bool has_map = false;
   TensorMap win_map{};          // search plane, box = one search window of the tuned kernel
+  bool has_pmap = false;
+  TensorMap planes_map{};       // the 16 planes as a 3-D tensor, box = one sub-pel region of the tuned kernel
 };
 
 struct State {
@@ -80,6 +86,8 @@ struct State {
   MeRefDev h_table[2 * ME_MAX_REFS];
   MeRefDev *d_table = nullptr;
   TensorMap h_maps[2 * ME_MAX_REFS];
+  TensorMap h_pmaps[2 * ME_MAX_REFS];
+  bool pmaps_ok = false;
   bool maps_ok = false;         // every listed reference has a window tensor map
   TensorMap cur_map{}; bool has_cur_map = false;   // current picture, box 16 x 16
   int *d_deferred = nullptr; int deferred_cap = 0;  // jobs the tuned search kernel hands back: {count, ids...}
@@ -164,7 +172,8 @@ int upload_table()
   if (!g.table_dirty) return 0;
   memset(g.h_table, 0, sizeof g.h_table);
   memset(g.h_maps, 0, sizeof g.h_maps);
-  g.maps_ok = true;
+  memset(g.h_pmaps, 0, sizeof g.h_pmaps);
+  g.maps_ok = true; g.pmaps_ok = true;
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < g.list_n[l]; i++) {
       RefPic *r = ref_of(g.list[l][i]);
@@ -172,6 +181,8 @@ int upload_table()
       g.h_table[l * ME_MAX_REFS + i] = r->dev;
       g.h_maps[l * ME_MAX_REFS + i] = r->win_map;
       g.maps_ok = g.maps_ok && r->has_map;
+      g.h_pmaps[l * ME_MAX_REFS + i] = r->planes_map;
+      g.pmaps_ok = g.pmaps_ok && r->has_pmap;
     }
   CK(cudaMemcpyAsync(g.d_table, g.h_table, sizeof g.h_table, cudaMemcpyHostToDevice, g.stream));
   // h_table is pageable: the copy above is staged synchronously by the runtime, safe to reuse
@@ -217,6 +228,7 @@ int create_ref_common(const uint8_t *d_luma, int stride, int w, int h, cudaStrea
   d.planes = r.planes; d.search = r.search;
   if (int n = me_ffs_tuned_window(g.cfg.search_range))
     r.has_map = me_make_tensor_map_2d(r.win_map.bytes, r.search, d.sw, d.sh, d.spitch, n + 16, n) == 0;
+  r.has_pmap = me_make_planes_tensor_map(r.planes_map.bytes, r.planes, d.pitch, d.hp, d.plane_stride) == 0;
   { ScopedTimer t(0, st); me_launch_planes(d_luma, stride, w, h, r.planes, d.pitch, d.plane_stride, r.search, d.spad, d.spitch, st); }
   g.launches += 2;
   CK(cudaGetLastError());
@@ -670,7 +682,14 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
     }
     if (!launched) { me_launch_ffs_batch_basic((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, nullptr, st); launched = 1; }
   }
-  { ScopedTimer t(2, st); me_launch_subpel_batch((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, (MeResult *)d_out, st); }
+  {
+    ScopedTimer t(2, st);
+    int done = 0;
+    if (!use_basic_only() && g.pmaps_ok)
+      done = me_launch_subpel_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.h_pmaps, g.list_n[0], g.list_n[1], g.d_cur, g.cur_pitch,
+                                          &g.cfg, di, (MeResult *)d_out, st);
+    if (!done) me_launch_subpel_batch((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, (MeResult *)d_out, st);
+  }
   g.launches += launched + 1;
   CK(cudaGetLastError());
   return 0;

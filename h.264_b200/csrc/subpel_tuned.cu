@@ -1,0 +1,336 @@
+// subpel_tuned.cu -- half / quarter-pel refinement, the throughput kernel (Hadamard SATD 4x4 at both sub-pel levels).
+//
+// Same results as me_subpel_batch_kernel (subpel.cu), i.e. as SubPelBlockMotionSearch (reference
+// lencod/src/me_fullsearch.c:341-511) with computeSATD / HadamardSAD4x4 (lencod/src/me_distortion.c:657, :182), for
+// MEDistortionHPel = MEDistortionQPel = 2 and Transform8x8Mode = 0.  Everything else goes through subpel.cu.
+//
+//  * Persistent CTAs of 128 threads (4 per SM), one (macroblock, list, ref) job at a time.
+//  * The reference samples of a job come from ONE TMA box: a 48 x 33 pixel region of all 16 quarter-pel planes
+//    (3-D tensor map x, y, plane; cp.async.bulk.tensor.3d, 25 KB) around the macroblock displaced by the integer vector of
+//    its 16x16 partition.  It covers every candidate of every partition whose integer vector lies within +-8 pixels of
+//    that vector and whose 4x4 tiles are not touched by the origin clamp of UMVLine4X (refbuf.c:37); a job for which this
+//    does not hold (checked exactly, per partition) reads its tiles from global memory with the clamp instead.  The
+//    region of the next job is requested as soon as the last tile of the current one has been read.
+//  * Work unit: one 4x4 transform tile of one candidate of one block type: 7 x 16 x 9 (8) units per half (quarter) pel
+//    stage, 128 per round.  Lanes are ordered (type, candidate, tile) with the tiles of one partition adjacent, so a
+//    partition's SATD is a segmented butterfly sum over 1..16 lanes -- no atomics -- and the lane that ends up with the sum
+//    adds the motion-vector rate and stores the cost; one thread per partition then replays the reference's sequential
+//    first-strict-minimum scan (me_fullsearch.c:423-449, :482-502).
+//  * The Hadamard transform runs on pairs of 16-bit lanes: pixels (0,2) / (1,3) of a row share a register, every value
+//    carries a bias of 4096 so that lanes never go negative and plain 32-bit IADD3 (with a negated operand and the bias
+//    as immediate) is an exact two-lane add / subtract.  Rows first (lane-parallel), the last, lane-crossing stage is
+//    folded into the absolute sum: |u+v| + |u-v| with two VABSDIFF-accumulate per register.
+#include <cuda.h>
+#include <cstring>
+#include "me_common.cuh"
+
+namespace {
+
+constexpr int RD = 8;                       // integer vectors within +-RD of the 16x16 vector use the staged region
+constexpr int RW = 48;                      // region row pitch (bytes): 2*RD + 17 pixels + up to 15 bytes of alignment
+constexpr int RH = 2 * RD + 17;             // region rows
+constexpr int REGION_BYTES = RW * RH * 16;  // all 16 planes
+constexpr int NT = 128;
+constexpr unsigned BIAS = 0x1000u, BIAS2 = 0x10001000u;
+
+// slot q of a (type, candidate) group of 16 lanes -> raster tile 4*ty+tx / partition number (ABI order); the tiles of a
+// partition are adjacent and aligned to the partition's tile count
+__constant__ uint8_t c_tile[7][16] = {
+  {  0,  1,  2,  3,  4,  5,  6,  7,  8,  9, 10, 11, 12, 13, 14, 15 },
+  {  0,  1,  2,  3,  4,  5,  6,  7,  8,  9, 10, 11, 12, 13, 14, 15 },
+  {  0,  1,  4,  5,  8,  9, 12, 13,  2,  3,  6,  7, 10, 11, 14, 15 },
+  {  0,  1,  4,  5,  2,  3,  6,  7,  8,  9, 12, 13, 10, 11, 14, 15 },
+  {  0,  1,  2,  3,  4,  5,  6,  7,  8,  9, 10, 11, 12, 13, 14, 15 },
+  {  0,  4,  1,  5,  2,  6,  3,  7,  8, 12,  9, 13, 10, 14, 11, 15 },
+  {  0,  1,  2,  3,  4,  5,  6,  7,  8,  9, 10, 11, 12, 13, 14, 15 } };
+__constant__ uint8_t c_part[7][16] = {
+  {  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0 },
+  {  1,  1,  1,  1,  1,  1,  1,  1,  2,  2,  2,  2,  2,  2,  2,  2 },
+  {  3,  3,  3,  3,  3,  3,  3,  3,  4,  4,  4,  4,  4,  4,  4,  4 },
+  {  5,  5,  5,  5,  6,  6,  6,  6,  7,  7,  7,  7,  8,  8,  8,  8 },
+  {  9,  9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16 },
+  { 17, 17, 18, 18, 19, 19, 20, 20, 21, 21, 22, 22, 23, 23, 24, 24 },
+  { 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40 } };
+__constant__ uint8_t c_group[7] = { 16, 8, 8, 4, 2, 2, 1 };     // tiles per partition
+// spiral entries 0..8 (mv-search.c:366-393 with range 1)
+__constant__ int8_t c_spx[9] = { 0, 0, 0, -1, 1, -1, 1, -1, 1 };
+__constant__ int8_t c_spy[9] = { 0, -1, 1, -1, -1, 0, 0, 1, 1 };
+
+struct __align__(128) Smem {
+  uint8_t  region[REGION_BYTES + 128];      // [plane][RH][RW]
+  uint32_t curpk[16][8];                    // per tile: rows 0..3 x {pixels (0,2), pixels (1,3)} as biased 16-bit lanes
+  uint32_t job[48];                         // me_mb_job
+  int      cost[ME_NUM_PARTITIONS][9];
+  int      mv[ME_NUM_PARTITIONS][2];        // current best vector, quarter pel
+  int      mn[ME_NUM_PARTITIONS];           // its cost
+  unsigned long long mbar;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+#pragma unroll 1
+  for (unsigned spin = 0; spin < (1u << 24); spin++) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const void *tmap, int x, int y, int z, unsigned bar)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+// two-lane (16-bit, biased) add / subtract: one IADD3 each
+__device__ __forceinline__ unsigned padd(unsigned a, unsigned b) { return a + b - BIAS2; }
+__device__ __forceinline__ unsigned psub(unsigned a, unsigned b) { return a - b + BIAS2; }
+
+// SATD of one 4x4 tile (HadamardSAD4x4, me_distortion.c:182-264): ref rows r[y] (4 bytes each), cur rows as biased lane pairs
+__device__ __forceinline__ int satd4x4(const unsigned r[4], const uint4 c01, const uint4 c23)
+{
+  const unsigned ce[4] = { c01.x, c01.z, c23.x, c23.z }, co[4] = { c01.y, c01.w, c23.y, c23.w };
+  unsigned s[4], t[4];
+#pragma unroll
+  for (int y = 0; y < 4; y++) {
+    const unsigned de = ce[y] - __byte_perm(r[y], 0, 0x4240);      // (c0 - r0 + B | c2 - r2 + B)
+    const unsigned dd = co[y] - __byte_perm(r[y], 0, 0x4341);      // (c1 - r1 + B | c3 - r3 + B)
+    s[y] = padd(de, dd);                                           // (d0 + d1 | d2 + d3)
+    t[y] = psub(de, dd);                                           // (d0 - d1 | d2 - d3)
+  }
+  unsigned acc = 0;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const unsigned *x = k ? t : s;
+    const unsigned a = padd(x[0], x[1]), b = psub(x[0], x[1]), c = padd(x[2], x[3]), d = psub(x[2], x[3]);
+    const unsigned y4[4] = { padd(a, c), psub(a, c), padd(b, d), psub(b, d) };
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const unsigned lo = y4[i] & 0xffffu, hi = y4[i] >> 16;       // u + B, v + B
+      acc = __usad(lo, hi, acc);                                   // |u - v|
+      acc = __usad(lo + hi, 2 * BIAS, acc);                        // |u + v|
+    }
+  }
+  return (int)((acc + 1) >> 1);
+}
+
+struct JobView { int opix_x, opix_y, list, ref, slice_type; };
+__device__ __forceinline__ JobView job_view(const uint32_t *w)
+{
+  JobView v;
+  v.opix_x = (int)(int16_t)(w[0] & 0xffffu); v.opix_y = (int)(int16_t)(w[0] >> 16);
+  v.list = (int)(int8_t)(w[1] & 0xffu); v.ref = (int)(int8_t)((w[1] >> 8) & 0xffu); v.slice_type = (int)(int8_t)((w[1] >> 16) & 0xffu);
+  return v;
+}
+
+constexpr int TUNED_MAX_REFS = 8;
+struct PlaneMaps { CUtensorMap m[2 * TUNED_MAX_REFS]; };
+
+__global__ void __launch_bounds__(NT, 4)
+me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
+                       const __grid_constant__ PlaneMaps maps, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                       const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out)
+{
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+  constexpr int JW = sizeof(MeJob) / 4;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n_mine = (n_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (n_mine <= 0) return;
+  const unsigned bar = smem_u32(&sm.mbar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // region origin of a job: its 16x16 partition's integer vector, minus the margin, x aligned down to 16 bytes (TMA)
+  auto region_origin = [&](uint32_t job_w0, uint32_t mv0_w, int &Xr, int &Yr) {
+    const int ox = (int)(int16_t)(job_w0 & 0xffffu), oy = (int)(int16_t)(job_w0 >> 16);
+    const int mx = (int)(int16_t)(mv0_w & 0xffffu), my = (int)(int16_t)(mv0_w >> 16);
+    Xr = (ox + ME_PAD + mx - RD - 1) & ~15;
+    Yr = oy + ME_PAD + my - RD - 1;
+  };
+  auto issue_region = [&](int job_id) {             // thread 0
+    const uint32_t w0 = jobs[(size_t)job_id * JW], w1 = jobs[(size_t)job_id * JW + 1];
+    const uint32_t mv0 = reinterpret_cast<const uint32_t *>(in_int[job_id].mv)[0];
+    int Xr, Yr;
+    region_origin(w0, mv0, Xr, Yr);
+    const int list = (int)(int8_t)(w1 & 0xffu), ref = (int)(int8_t)((w1 >> 8) & 0xffu);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, REGION_BYTES);
+    tma_load_3d(smem_u32(sm.region), &maps.m[list * TUNED_MAX_REFS + ref], Xr, Yr, 0, bar);
+  };
+  if (tid == 0) issue_region((int)blockIdx.x);
+
+  for (int it = 0; it < n_mine; it++) {
+    const int job_id = (int)blockIdx.x + it * (int)gridDim.x;
+    // ---- job set-up
+    if (tid < JW) sm.job[tid] = jobs[(size_t)job_id * JW + tid];
+    if (tid < ME_NUM_PARTITIONS) {
+      const uint32_t w = reinterpret_cast<const uint32_t *>(in_int[job_id].mv)[tid];
+      sm.mv[tid][0] = (int)(int16_t)(w & 0xffffu) * 4;                       // mv <<= 2, mv-search.c:770-774
+      sm.mv[tid][1] = (int)(int16_t)(w >> 16) * 4;
+      sm.mn[tid] = cfg.start_hp ? in_int[job_id].cost[tid] : ME_INT_MAX;     // mv-search.c:785-788
+    }
+    __syncthreads();
+    const JobView jv = job_view(sm.job);
+    const MeRefDev ref = ref_table[jv.list * ME_MAX_REFS + jv.ref];
+    {
+      // current macroblock as biased lane pairs: thread -> (tile, row, even/odd)
+      const int tile = tid >> 3, k = tid & 7, y = k >> 1, odd = k & 1;
+      const uint8_t *p = cur + (size_t)(jv.opix_y + 4 * (tile >> 2) + y) * cur_pitch + jv.opix_x + 4 * (tile & 3) + odd;
+      sm.curpk[tile][k] = ((unsigned)p[0] | ((unsigned)p[2] << 16)) + BIAS2;
+    }
+    int Xr, Yr;
+    region_origin(sm.job[0], ((unsigned)(sm.mv[0][0] >> 2) & 0xffffu) | ((unsigned)(sm.mv[0][1] >> 2) << 16), Xr, Yr);
+    // does the staged region serve every tile of every candidate of this job?  Per partition: integer vector within
+    // +-RD of the 16x16 one, and no tile origin outside [0, size_pad] (the clamp of UMVLine4X would move it)
+    int ok = 1;
+    if (tid < ME_NUM_PARTITIONS) {
+      const int t = me_part_type(tid), blk = me_part_blk(tid);
+      const int mix = sm.mv[tid][0] >> 2, miy = sm.mv[tid][1] >> 2, m0x = sm.mv[0][0] >> 2, m0y = sm.mv[0][1] >> 2;
+      const int x0 = jv.opix_x + ME_PAD + 4 * (blk & 3) + mix, y0 = jv.opix_y + ME_PAD + 4 * (blk >> 2) + miy;   // first tile, centre
+      const int x1 = x0 + me_bsx(t) - 4, y1 = y0 + me_bsy(t) - 4;                                                // last tile
+      ok = abs(mix - m0x) <= RD && abs(miy - m0y) <= RD &&
+           x0 - 1 >= 0 && y0 - 1 >= 0 && x1 <= ref.w + 2 * ME_PAD - 1 - 16 && y1 <= ref.h + 2 * ME_PAD - 1 - 16;
+    }
+    const int fast = __syncthreads_and(ok);          // also publishes curpk
+    mbar_wait(bar, (unsigned)(it & 1));
+
+    for (int stage = 0; stage < 2; stage++) {                // 0: half pel (step 2), 1: quarter pel (step 1)
+      const int step = stage == 0 ? 2 : 1;
+      const int lam = (int)sm.job[44 + 1 + stage];          // lambda[H_PEL], lambda[Q_PEL]
+      const int first = stage == 0 ? cfg.start_hp : cfg.start_qp;
+      const int nc = 9 - first;
+      if (stage == 1 && !cfg.start_qp && tid < ME_NUM_PARTITIONS) sm.mn[tid] = ME_INT_MAX;   // me_fullsearch.c:456-457
+      const int total = 7 * 16 * nc;
+      for (int base = 0; base < total; base += NT) {
+        const int i = base + tid;
+        const bool active = i < total;
+        const int ii = active ? i : 0;
+        const int q = ii & 15, gi = ii >> 4, ti = gi / nc, c = gi - ti * nc + first;     // ti = block type - 1
+        const int p = c_part[ti][q], tile = c_tile[ti][q], g = c_group[ti];
+        const int mvx = sm.mv[p][0] + step * c_spx[c], mvy = sm.mv[p][1] + step * c_spy[c];
+        const int x4 = ((jv.opix_x + 4 * (tile & 3) + ME_PAD) << 2) + mvx, y4 = ((jv.opix_y + 4 * (tile >> 2) + ME_PAD) << 2) + mvy;
+        unsigned r[4];
+        if (fast) {
+          const unsigned a = smem_u32(sm.region) + (unsigned)((((y4 & 3) << 2) | (x4 & 3)) * (RW * RH) + ((y4 >> 2) - Yr) * RW + ((x4 >> 2) - Xr));
+          const unsigned a4 = a & ~3u, sh = (a & 3u) * 8;
+#pragma unroll
+          for (int y = 0; y < 4; y++) {
+            unsigned w0, w1;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a4 + y * RW));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(a4 + y * RW + 4));
+            r[y] = __funnelshift_r(w0, w1, sh);
+          }
+        } else {
+          const uint8_t *rp = me_umv_ptr(ref, y4, x4);     // per-tile origin clamp, as computeSATD does (me_distortion.c:657)
+#pragma unroll
+          for (int y = 0; y < 4; y++) {
+            const uint8_t *b = rp + (size_t)y * ref.pitch;
+            r[y] = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
+          }
+        }
+        const uint4 c01 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][0]), c23 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][4]);
+        int v = satd4x4(r, c01, c23);
+        // segmented sum over the g lanes of the partition
+#pragma unroll
+        for (int s = 1; s < 16; s <<= 1) {
+          const int o = __shfl_xor_sync(0xffffffffu, v, s);
+          if (s < g) v += o;
+        }
+        if (active && (q & (g - 1)) == 0)
+          sm.cost[p][c] = v + me_mv_cost(lam, mvx, mvy, (int)(int16_t)(sm.job[3 + p] & 0xffffu), (int)(int16_t)(sm.job[3 + p] >> 16));
+      }
+      __syncthreads();
+      // the region is free once the quarter-pel tiles are read: request the next job's
+      if (stage == 1 && tid == 0 && it + 1 < n_mine) issue_region(job_id + (int)gridDim.x);
+      if (tid < ME_NUM_PARTITIONS) {
+        const int p = tid;
+        int best = 0, mn = sm.mn[p];
+        for (int c = first; c < 9; c++) {
+          int mc = sm.cost[p][c];
+          if (stage == 0 && c == 0 && !cfg.rdopt && jv.slice_type != ME_B_SLICE && jv.ref == 0 && p == 0 &&
+              sm.mv[p][0] == 0 && sm.mv[p][1] == 0)
+            mc -= (lam * 16) >> 16;                          // check_position0, me_fullsearch.c:361,439-442
+          if (mc < mn) { mn = mc; best = c; }
+        }
+        sm.mn[p] = mn;
+        sm.mv[p][0] += step * c_spx[best];
+        sm.mv[p][1] += step * c_spy[best];
+      }
+      __syncthreads();
+    }
+    if (tid < ME_NUM_PARTITIONS) {
+      reinterpret_cast<uint32_t *>(out[job_id].mv)[tid] = ((unsigned)sm.mv[tid][0] & 0xffffu) | ((unsigned)sm.mv[tid][1] << 16);
+      out[job_id].cost[tid] = sm.mn[tid];
+    }
+    __syncthreads();
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+}  // namespace
+
+// 3-D byte tensor map over the 16 quarter-pel planes of a reference picture (x, y, plane), box = one sub-pel region
+extern "C" int me_make_planes_tensor_map(void *out, const void *planes, int pitch, int hp, size_t plane_stride)
+{
+  if (!g_encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return 1;
+    g_encode = (EncodeTiledFn)fn;
+  }
+  CUtensorMap m;
+  cuuint64_t dims[3] = { (cuuint64_t)pitch, (cuuint64_t)hp, 16 };
+  cuuint64_t strides[2] = { (cuuint64_t)pitch, (cuuint64_t)plane_stride };
+  cuuint32_t box[3] = { RW, RH, 16 };
+  cuuint32_t estr[3] = { 1, 1, 1 };
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(planes), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 2;
+  memcpy(out, &m, sizeof m);
+  return 0;
+}
+
+// Returns 1 when the kernel was launched, 0 when the configuration is not covered (the caller runs subpel.cu).
+// plane_maps: host array [2][ME_MAX_REFS] of 128-byte tensor maps of the listed references' plane sets.
+extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *plane_maps,
+                                            int n_refs0, int n_refs1, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
+                                            const MeResultInt *in_int, MeResult *out, cudaStream_t st)
+{
+  if (!plane_maps || n_refs0 > TUNED_MAX_REFS || n_refs1 > TUNED_MAX_REFS) return 0;
+  if (cfg->metric[1] != 2 || cfg->metric[2] != 2 || cfg->transform8x8) return 0;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(me_subpel_tuned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  }
+  PlaneMaps pm;
+  for (int l = 0; l < 2; l++)
+    memcpy(&pm.m[l * TUNED_MAX_REFS], (const unsigned char *)plane_maps + (size_t)l * ME_MAX_REFS * 128, sizeof(CUtensorMap) * TUNED_MAX_REFS);
+  int grid = sms * 4;
+  if (grid > n_jobs) grid = n_jobs;
+  me_subpel_tuned_kernel<<<grid, NT, sizeof(Smem), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
+                                                         *cfg, in_int, out);
+  return 1;
+}
