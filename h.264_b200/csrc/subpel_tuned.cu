@@ -4,12 +4,12 @@
 // lencod/src/me_fullsearch.c:341-511) with computeSATD / HadamardSAD4x4 (lencod/src/me_distortion.c:657, :182), for
 // MEDistortionHPel = MEDistortionQPel = 2 and Transform8x8Mode = 0.  Everything else goes through subpel.cu.
 //
-//  * Persistent CTAs of 128 threads (4 per SM), one (macroblock, list, ref) job at a time.
+//  * Persistent CTAs of 128 threads (6 per SM), one (macroblock, list, ref) job at a time.
 //  * The reference samples of a job come from ONE TMA box: a 48 x 33 pixel region of all 16 quarter-pel planes
 //    (3-D tensor map x, y, plane; cp.async.bulk.tensor.3d, 25 KB) around the macroblock displaced by the integer vector of
 //    its 16x16 partition.  It covers every candidate of every partition whose integer vector lies within +-8 pixels of
-//    that vector and whose 4x4 tiles are not touched by the origin clamp of UMVLine4X (refbuf.c:37); a job for which this
-//    does not hold (checked exactly, per partition) reads its tiles from global memory with the clamp instead.  The
+//    that vector and whose 4x4 tiles are not touched by the origin clamp of UMVLine4X (refbuf.c:37); a partition for
+//    which this does not hold (checked exactly) reads its tiles from global memory with the clamp instead.  The
 //    region of the next job is requested as soon as the last tile of the current one has been read.
 //  * Work unit: one 4x4 transform tile of one candidate of one block type: 7 x 16 x 9 (8) units per half (quarter) pel
 //    stage, 128 per round.  Lanes are ordered (type, candidate, tile) with the tiles of one partition adjacent, so a
@@ -63,6 +63,7 @@ struct __align__(128) Smem {
   int      cost[ME_NUM_PARTITIONS][9];
   int      mv[ME_NUM_PARTITIONS][2];        // current best vector, quarter pel
   int      mn[ME_NUM_PARTITIONS];           // its cost
+  int      okp[ME_NUM_PARTITIONS];          // partition served by the staged region (else: global reads with the clamp)
   unsigned long long mbar;
 };
 
@@ -137,7 +138,7 @@ __device__ __forceinline__ JobView job_view(const uint32_t *w)
 constexpr int TUNED_MAX_REFS = 8;
 struct PlaneMaps { CUtensorMap m[2 * TUNED_MAX_REFS]; };
 
-__global__ void __launch_bounds__(NT, 4)
+__global__ void __launch_bounds__(NT, 6)
 me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                        const __grid_constant__ PlaneMaps maps, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                        const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out)
@@ -195,18 +196,17 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     }
     int Xr, Yr;
     region_origin(sm.job[0], ((unsigned)(sm.mv[0][0] >> 2) & 0xffffu) | ((unsigned)(sm.mv[0][1] >> 2) << 16), Xr, Yr);
-    // does the staged region serve every tile of every candidate of this job?  Per partition: integer vector within
+    // does the staged region serve every tile of every candidate of a partition?  Its integer vector must lie within
     // +-RD of the 16x16 one, and no tile origin outside [0, size_pad] (the clamp of UMVLine4X would move it)
-    int ok = 1;
     if (tid < ME_NUM_PARTITIONS) {
       const int t = me_part_type(tid), blk = me_part_blk(tid);
       const int mix = sm.mv[tid][0] >> 2, miy = sm.mv[tid][1] >> 2, m0x = sm.mv[0][0] >> 2, m0y = sm.mv[0][1] >> 2;
       const int x0 = jv.opix_x + ME_PAD + 4 * (blk & 3) + mix, y0 = jv.opix_y + ME_PAD + 4 * (blk >> 2) + miy;   // first tile, centre
       const int x1 = x0 + me_bsx(t) - 4, y1 = y0 + me_bsy(t) - 4;                                                // last tile
-      ok = abs(mix - m0x) <= RD && abs(miy - m0y) <= RD &&
-           x0 - 1 >= 0 && y0 - 1 >= 0 && x1 <= ref.w + 2 * ME_PAD - 1 - 16 && y1 <= ref.h + 2 * ME_PAD - 1 - 16;
+      sm.okp[tid] = abs(mix - m0x) <= RD && abs(miy - m0y) <= RD &&
+                    x0 - 1 >= 0 && y0 - 1 >= 0 && x1 <= ref.w + 2 * ME_PAD - 1 - 16 && y1 <= ref.h + 2 * ME_PAD - 1 - 16;
     }
-    const int fast = __syncthreads_and(ok);          // also publishes curpk
+    __syncthreads();                                 // publishes okp and curpk
     mbar_wait(bar, (unsigned)(it & 1));
 
     for (int stage = 0; stage < 2; stage++) {                // 0: half pel (step 2), 1: quarter pel (step 1)
@@ -225,7 +225,7 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
         const int mvx = sm.mv[p][0] + step * c_spx[c], mvy = sm.mv[p][1] + step * c_spy[c];
         const int x4 = ((jv.opix_x + 4 * (tile & 3) + ME_PAD) << 2) + mvx, y4 = ((jv.opix_y + 4 * (tile >> 2) + ME_PAD) << 2) + mvy;
         unsigned r[4];
-        if (fast) {
+        if (sm.okp[p]) {
           const unsigned a = smem_u32(sm.region) + (unsigned)((((y4 & 3) << 2) | (x4 & 3)) * (RW * RH) + ((y4 >> 2) - Yr) * RW + ((x4 >> 2) - Xr));
           const unsigned a4 = a & ~3u, sh = (a & 3u) * 8;
 #pragma unroll
@@ -328,7 +328,7 @@ extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const
   PlaneMaps pm;
   for (int l = 0; l < 2; l++)
     memcpy(&pm.m[l * TUNED_MAX_REFS], (const unsigned char *)plane_maps + (size_t)l * ME_MAX_REFS * 128, sizeof(CUtensorMap) * TUNED_MAX_REFS);
-  int grid = sms * 4;
+  int grid = sms * 6;
   if (grid > n_jobs) grid = n_jobs;
   me_subpel_tuned_kernel<<<grid, NT, sizeof(Smem), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
                                                          *cfg, in_int, out);
