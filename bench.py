@@ -221,7 +221,7 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -293,13 +293,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
-    for s in range(args.warmup):
-        device_step(s)
-    me.sync()
+    # ---- device-resident timing.  The clock sampler (nvidia-smi every 100 ms) runs from the first warm-up step to the end of the
+    # timed region: same load throughout, and a timed region of a few hundred ms alone would yield too few samples.
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    t_warm = time.perf_counter()
+    s = 0
+    while s < args.warmup or time.perf_counter() - t_warm < 0.5:     # at least W steps and half a second of load
+        device_step(s)
+        s += 1
+        if s % 8 == 0:
+            me.sync()
+    n_warm = s
+    me.sync()
+    barrier()
     launches0 = me.launch_count()
     me.set_timing(True)
     step_ms = []
@@ -309,7 +316,7 @@ def main():
             flush.fill_(s & 255)                                      # evict L2 between timed iterations (not timed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            device_step(args.warmup + s)
+            device_step(n_warm + s)
             e1.record(stream)
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))

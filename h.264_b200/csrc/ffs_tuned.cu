@@ -174,7 +174,7 @@ struct GroupBase {
 // Band B (rows 4B..4B+3 of the macroblock) of vertical displacement dy = r0 + DYO has just been accumulated: L / Rr are
 // the two 4x4 SADs, J = dy & 3.
 template <int R, int B, int DYO, int J>
-__device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBase &g, unsigned L, unsigned Rr)
+__device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBase &g, unsigned L, unsigned Rr, unsigned hL, unsigned hR)
 {
   constexpr unsigned K = Geo<R>::KMUL;
   constexpr int SPO = DYO * Geo<R>::SIDE * 2, CYO = DYO * 2 * CYW * 4;
@@ -186,12 +186,10 @@ __device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBas
     eval<E0>(rg, kL, c.x);
     eval<E0 + 1>(rg, kR, c.y);
     eval<E0 + 2>(rg, imad(L, K, kR), c.z);
-    if (B == 0) { rg.h0L[J] = L; rg.h0R[J] = Rr; } else { rg.h2L[J] = L; rg.h2R[J] = Rr; }
   } else {
     constexpr int E0 = (B == 1) ? 3 : 12;
     constexpr int CB = CYO + (B == 1 ? 16 : 64);
     const uint4 c0 = lds128<CB>(g.cy), c1 = lds128<CB + 16>(g.cy);
-    const unsigned hL = (B == 1) ? rg.h0L[J] : rg.h2L[J], hR = (B == 1) ? rg.h0R[J] : rg.h2R[J];
     eval<E0>(rg, kL, c0.x);
     eval<E0 + 1>(rg, kR, c0.y);
     eval<E0 + 2>(rg, imad(L, K, kR), c0.z);
@@ -220,31 +218,35 @@ __device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBas
 // One window row r = r0 + U (r0 a multiple of 4).  Row r is row k = 4b + i of the macroblock for the displacement
 // dy = r - k; with J = dy & 3 the phase is i = (U - J) & 3, so the 32 accumulators are addressed by compile-time (b, J)
 // although the loop is unrolled over four rows only (the whole sweep body stays within the instruction caches).
+// The last accumulate of bands 0 / 2 writes the hold register the next band reads four rows later (h0 / h2).
 // CHECK: rows 0..15 and 2R..2R+15, where some displacements fall outside [0, 2R]: their SADs are computed into
 // accumulators nobody reads, their evaluation is skipped.
 template <int R, bool CHECK, int U>
 __device__ __forceinline__ void sweep_row(Regs &rg, const Thr &t, const GroupBase &g, int r0)
 {
   constexpr int NP = Geo<R>::NP;
+  constexpr int J = (U + 1) & 3;      // dy & 3 of the displacements whose bands complete in this row
   const unsigned w0 = lds32<U * NP>(g.win), w1 = lds32<U * NP + 4>(g.win), w2 = lds32<U * NP + 8>(g.win);
   const unsigned refL = __funnelshift_r(w0, w1, t.shift), refR = __funnelshift_r(w1, w2, t.shift);
+  // holds of the displacement four rows older, read before this row's completions replace them
+  const unsigned h0L = rg.h0L[J], h0R = rg.h0R[J], h2L = rg.h2L[J], h2R = rg.h2R[J];
 #pragma unroll
   for (int b = 0; b < 4; b++)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int i = (U - j) & 3, k = 4 * b + i;
-      rg.accL[b][j] = vsad(refL, rg.curL[k], i ? rg.accL[b][j] : 0u);
-      rg.accR[b][j] = vsad(refR, rg.curR[k], i ? rg.accR[b][j] : 0u);
+      const unsigned vL = vsad(refL, rg.curL[k], i ? rg.accL[b][j] : 0u), vR = vsad(refR, rg.curR[k], i ? rg.accR[b][j] : 0u);
+      if (i == 3 && b == 0) { rg.h0L[j] = vL; rg.h0R[j] = vR; }
+      else if (i == 3 && b == 2) { rg.h2L[j] = vL; rg.h2R[j] = vR; }
+      else { rg.accL[b][j] = vL; rg.accR[b][j] = vR; }
     }
-  // the displacements whose band completes in this row have dy & 3 == J; bands in descending order: bands 3 / 1 read the
-  // hold registers that bands 2 / 1 / 0 of a later displacement overwrite
-  constexpr int J = (U + 1) & 3;
+  // bands in descending order (band 3 reads the 8x8 queue that band 1 of a later displacement advances)
   const unsigned lim = 2 * R;
-  if (!CHECK || (unsigned)(r0 + U - 15) <= lim) band_done<R, 3, U - 15, J>(rg, t, g, rg.accL[3][J], rg.accR[3][J]);
-  if (!CHECK || (unsigned)(r0 + U - 11) <= lim) band_done<R, 2, U - 11, J>(rg, t, g, rg.accL[2][J], rg.accR[2][J]);
+  if (!CHECK || (unsigned)(r0 + U - 15) <= lim) band_done<R, 3, U - 15, J>(rg, t, g, rg.accL[3][J], rg.accR[3][J], h2L, h2R);
+  if (!CHECK || (unsigned)(r0 + U - 11) <= lim) band_done<R, 2, U - 11, J>(rg, t, g, rg.h2L[J], rg.h2R[J], 0u, 0u);
   rg.hT2[J] = rg.hT1[J];
-  if (!CHECK || (unsigned)(r0 + U - 7) <= lim) band_done<R, 1, U - 7, J>(rg, t, g, rg.accL[1][J], rg.accR[1][J]);
-  if (!CHECK || (unsigned)(r0 + U - 3) <= lim) band_done<R, 0, U - 3, J>(rg, t, g, rg.accL[0][J], rg.accR[0][J]);
+  if (!CHECK || (unsigned)(r0 + U - 7) <= lim) band_done<R, 1, U - 7, J>(rg, t, g, rg.accL[1][J], rg.accR[1][J], h0L, h0R);
+  if (!CHECK || (unsigned)(r0 + U - 3) <= lim) band_done<R, 0, U - 3, J>(rg, t, g, rg.h0L[J], rg.h0R[J], 0u, 0u);
 }
 
 // four window rows starting at row r0 (a multiple of 4)

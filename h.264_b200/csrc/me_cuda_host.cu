@@ -57,6 +57,8 @@ void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t
 
 namespace {
 
+constexpr int ME_PIPE_CHUNKS = 4;
+
 struct TensorMap { alignas(64) unsigned char bytes[128]; };   // CUtensorMap
 
 struct RefPic {
@@ -91,6 +93,8 @@ struct State {
   bool maps_ok = false;         // every listed reference has a window tensor map
   TensorMap cur_map{}; bool has_cur_map = false;   // current picture, box 16 x 16
   int *d_deferred = nullptr; int deferred_cap = 0;  // jobs the tuned search kernel hands back: {count, ids...}
+  cudaStream_t s_in = nullptr, s_out = nullptr;     // host <-> device pipeline of me_cuda_frame_search
+  cudaEvent_t ev_in[ME_PIPE_CHUNKS] = {}, ev_done[ME_PIPE_CHUNKS] = {};
   me_ref_handle list[2][ME_MAX_REFS];
   int list_n[2] = {0, 0};
   bool table_dirty = true;
@@ -328,6 +332,11 @@ void me_cuda_shutdown(void)
   for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) if (g.d_surf[l][i]) cudaFree(g.d_surf[l][i]);
   cudaFree(g.d_cur); cudaFree(g.d_table); cudaFree(g.d_result); cudaFreeHost(g.h_result);
   if (g.d_deferred) cudaFree(g.d_deferred);
+  if (g.s_in) {
+    cudaStreamSynchronize(g.s_in); cudaStreamSynchronize(g.s_out);
+    for (int c = 0; c < ME_PIPE_CHUNKS; c++) { cudaEventDestroy(g.ev_in[c]); cudaEventDestroy(g.ev_done[c]); }
+    cudaStreamDestroy(g.s_in); cudaStreamDestroy(g.s_out);
+  }
   if (g.h_pin) cudaFreeHost(g.h_pin);
   if (g.d_wide) cudaFree(g.d_wide);
   if (g.h_wide) cudaFreeHost(g.h_wide);
@@ -707,10 +716,36 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
       return fail(1, "job %d: macroblock origin (%d,%d) invalid", i, (int)j.opix_x, (int)j.opix_y);
   }
   if (int rc = ensure_batch(n_jobs)) return rc;
-  CK(cudaMemcpyAsync(g.d_jobs, jobs, sizeof(MeJob) * (size_t)n_jobs, cudaMemcpyHostToDevice, g.stream));
-  if (int rc = me_cuda_frame_search_device(g.d_jobs, n_jobs, g.d_out, g.d_out_int, g.stream)) return rc;
-  CK(cudaMemcpyAsync(out, g.d_out, sizeof(MeResult) * (size_t)n_jobs, cudaMemcpyDeviceToHost, g.stream));
-  if (out_int) CK(cudaMemcpyAsync(out_int, g.d_out_int, sizeof(MeResultInt) * (size_t)n_jobs, cudaMemcpyDeviceToHost, g.stream));
+  // Large batches are cut into chunks that move through three streams -- jobs in (H2D engine), search (library stream),
+  // results out (D2H engine) -- so that with pinned caller buffers only the first upload and the last download are exposed.
+  const int n_chunks = n_jobs >= 8192 ? ME_PIPE_CHUNKS : 1;
+  if (!g.s_in) {
+    CK(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.s_out, cudaStreamNonBlocking));
+    for (int c = 0; c < ME_PIPE_CHUNKS; c++) {
+      CK(cudaEventCreateWithFlags(&g.ev_in[c], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&g.ev_done[c], cudaEventDisableTiming));
+    }
+  }
+  if (int rc = upload_table()) return rc;                      // on the library stream, before any chunk's kernels
+  const int per = (n_jobs + n_chunks - 1) / n_chunks;
+  for (int c = 0; c < n_chunks; c++) {
+    const int off = c * per, n = (off + per <= n_jobs) ? per : n_jobs - off;
+    if (n <= 0) break;
+    CK(cudaMemcpyAsync(g.d_jobs + off, jobs + off, sizeof(MeJob) * (size_t)n, cudaMemcpyHostToDevice, g.s_in));
+    CK(cudaEventRecord(g.ev_in[c], g.s_in));
+  }
+  for (int c = 0; c < n_chunks; c++) {
+    const int off = c * per, n = (off + per <= n_jobs) ? per : n_jobs - off;
+    if (n <= 0) break;
+    CK(cudaStreamWaitEvent(g.stream, g.ev_in[c], 0));
+    if (int rc = me_cuda_frame_search_device(g.d_jobs + off, n, g.d_out + off, g.d_out_int + off, g.stream)) return rc;
+    CK(cudaEventRecord(g.ev_done[c], g.stream));
+    CK(cudaStreamWaitEvent(g.s_out, g.ev_done[c], 0));
+    CK(cudaMemcpyAsync(out + off, g.d_out + off, sizeof(MeResult) * (size_t)n, cudaMemcpyDeviceToHost, g.s_out));
+    if (out_int) CK(cudaMemcpyAsync(out_int + off, g.d_out_int + off, sizeof(MeResultInt) * (size_t)n, cudaMemcpyDeviceToHost, g.s_out));
+  }
+  CK(cudaStreamSynchronize(g.s_out));
   CK(cudaStreamSynchronize(g.stream));
   return 0;
 }
