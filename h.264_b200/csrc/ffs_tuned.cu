@@ -15,9 +15,10 @@
 //    between the lanes h = 0 / 1) exist as plain integers.
 //  * Cost: key = (SAD + mvcost) * K + spiral_index with K = (2R+1)^2 > any spiral index, so ONE unsigned minimum per
 //    (partition, position) reproduces JM's "first strict minimum in spiral order" (me_fullfast.c:879-897).
-//    K * (lambda * (bits_x + bits_y) >> 16) comes from a 36-entry shared table indexed by the sum of the Exp-Golomb length
-//    classes of the two vector components: the x class is a per-thread constant (fixed dx), the y class is uniform and
-//    read from a per-job table.  Per (partition, position): IMAD (key) + IMAD (table address) + LDS + VIADDMNMX.
+//    K * (lambda * (bits_x + bits_y) >> 16) comes from a shared table indexed by the sum of the Exp-Golomb length classes
+//    of the two vector components: the x class is a per-thread constant (fixed dx), the y class is uniform and read
+//    from a per-job table.  Slots of the same band are looked up in PAIRS: a 36 x 36 table of {value(s0), value(s1)}
+//    gives both with one IMAD (address) + one LDS.64.  Per (partition, position): IMAD (key) + VIADDMNMX + half a lookup.
 //  * The window column dx = 2R (the 65th of 65) does not fit the 2R-lane layout: thread pair i scores position (2R, i)
 //    with the same key encoding after the sweep.
 //  * Search windows (2R+16)^2 and the 16x16 current macroblock arrive by TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) from
@@ -37,10 +38,19 @@
 
 namespace {
 
-constexpr int CYW = 28;            // words per (dy, h) row of the y-class table: band groups at words 0, 4, 12, 16
+constexpr int CYW = 20;            // words per (dy, h) row of the y-class table: band groups at words 0, 4, 8, 12
 constexpr int LUT_STRIDE_B = 12;   // bytes between table entries: odd word stride -> conflict-free and the address is an IMAD
 constexpr int LUT_ENTRIES = 36;    // class sums 0..35 (classes up to 17 per component: |d| < 2^17)
 constexpr int NSLOT = 21;          // partitions scored by one thread
+// The 21 slots are looked up in 12 units: 9 PAIRS of slots of the same band share one 64-bit load from a table indexed by
+// both class sums (36 x 36 entries of {K*mvcost(s0), K*mvcost(s1)}), 3 single slots use the 36-entry table.
+constexpr int NUNIT = 12;
+__host__ __device__ constexpr int unit_a(int u) { constexpr int t[NUNIT] = { 0, 2, 3, 5, 7, 9, 11, 12, 14, 16, 18, 20 }; return t[u]; }
+__host__ __device__ constexpr int unit_b(int u) { constexpr int t[NUNIT] = { 1, -1, 4, 6, 8, 10, -1, 13, 15, 17, 19, -1 }; return t[u]; }
+__host__ __device__ constexpr int unit_word(int u) { constexpr int t[NUNIT] = { 0, 1, 4, 5, 6, 8, 9, 12, 13, 14, 15, 16 }; return t[u]; }
+__constant__ int8_t c_unit_a[NUNIT] = { 0, 2, 3, 5, 7, 9, 11, 12, 14, 16, 18, 20 };
+__constant__ int8_t c_unit_b[NUNIT] = { 1, -1, 4, 6, 8, 10, -1, 13, 15, 17, 19, -1 };
+__constant__ int8_t c_unit_word[NUNIT] = { 0, 1, 4, 5, 6, 8, 9, 12, 13, 14, 15, 16 };
 
 template <int R> struct Geo {
   static constexpr int N = 2 * R + 16;            // window side
@@ -56,14 +66,13 @@ __constant__ int8_t c_slot_part[2][NSLOT] = {
   { 25, 26,  9, 29, 30, 11, 17, 18, 5, 33, 34, 13, 37, 38, 15, 21, 22, 7, 3, 1, 0 },
   { 27, 28, 10, 31, 32, 12, 19, 20, 6, 35, 36, 14, 39, 40, 16, 23, 24, 8, 4, 2, 0 } };
 
-__host__ __device__ constexpr int slot_cyword(int e) { return e < 3 ? e : e < 9 ? e + 1 : e < 12 ? e + 3 : e + 4; }
-
 template <int R> struct __align__(128) Smem {
   uint8_t  win[2][Geo<R>::NP * Geo<R>::N];      // search windows, N rows of NP bytes (TMA box, dense); the window starts at byte X0 & 15
   uint32_t cur[2][64];                          // current macroblocks, 16 rows x 4 words
-  uint32_t cyt[Geo<R>::SIDE][2][CYW];           // y length class per (dy, h, slot)
+  uint32_t cyt[Geo<R>::SIDE][2][CYW];           // per (dy, h, unit): y class of a single slot, 36 * class_a + class_b of a pair
+  uint2    lut2[LUT_ENTRIES * LUT_ENTRIES];     // {K * mvcost(s0), K * mvcost(s1)} at index 36 * s0 + s1
   uint32_t lut[LUT_ENTRIES * 3];                // K * mvcost(class sum), entry stride 12 bytes
-  uint32_t lutA_last[2][NSLOT];                 // shared address of the table row of column 2R per (h, slot)
+  uint32_t ua_last[2][NUNIT];                   // unit table addresses of column 2R per (h, unit)
   uint32_t red[Geo<R>::NW][2][NSLOT];
   uint32_t job[3][48];                          // me_mb_job ring (188 bytes each)
   uint16_t sptab[Geo<R>::SIDE * Geo<R>::SIDE];  // spiral index of (dy, dx)
@@ -85,6 +94,12 @@ template <int OFF = 0> __device__ __forceinline__ unsigned lds16(unsigned a)
 {
   unsigned short v;
   asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF = 0> __device__ __forceinline__ uint2 lds64(unsigned a)
+{
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(a), "n"(OFF));
   return v;
 }
 template <int OFF = 0> __device__ __forceinline__ uint4 lds128(unsigned a)
@@ -147,21 +162,31 @@ struct Regs {
   unsigned h2L[4], h2R[4];          // band-2 4x4 SADs waiting for band 3
   unsigned hT1[4], hT2[4];          // top 8x8 SAD waiting 8 rows for the bottom one: two-stage queue per dy & 3
   unsigned best[NSLOT];             // running minima of the keys
-  unsigned lutA[NSLOT];             // shared address of lut[x class of this thread's dx] per slot
+  unsigned ua[NUNIT];               // per unit: shared address of the table entry of this thread's x class(es), y class 0
 };
 
 struct Thr {
   unsigned sp_addr;     // shared address of sptab[0][dx]
   unsigned cy_addr;     // shared address of cyt[0][h][0]
   unsigned shift;       // (dx & 3) * 8
+  unsigned k8;          // 8, as a run-time value: keeps the pair-table address an IMAD (FMA pipe) instead of an ALU-pipe LEA
   int h;
 };
 
-template <int E>
-__device__ __forceinline__ void eval(Regs &rg, unsigned key, unsigned cy)
+// single slot E of unit U: one 32-bit lookup
+template <int U, int E>
+__device__ __forceinline__ void eval1(Regs &rg, unsigned key, unsigned cy)
 {
-  const unsigned m = lds32(imad(cy, LUT_STRIDE_B, rg.lutA[E]));
+  const unsigned m = lds32(imad(cy, LUT_STRIDE_B, rg.ua[U]));
   rg.best[E] = __viaddmin_u32(key, m, rg.best[E]);
+}
+// slots EA, EB of pair unit U: one 64-bit lookup
+template <int U, int EA, int EB>
+__device__ __forceinline__ void eval2(Regs &rg, const Thr &t, unsigned keyA, unsigned keyB, unsigned cyp)
+{
+  const uint2 m = lds64(imad(cyp, t.k8, rg.ua[U]));
+  rg.best[EA] = __viaddmin_u32(keyA, m.x, rg.best[EA]);
+  rg.best[EB] = __viaddmin_u32(keyB, m.y, rg.best[EB]);
 }
 
 // per 4-row group: shared addresses every load of the group is an immediate offset from
@@ -180,37 +205,34 @@ __device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBas
   constexpr int SPO = DYO * Geo<R>::SIDE * 2, CYO = DYO * 2 * CYW * 4;
   const unsigned sp = lds16<SPO>(g.sp);
   const unsigned kL = imad(L, K, sp), kR = imad(Rr, K, sp);
+  const unsigned k84 = imad(L, K, kR);                  // 8x4
   if (B == 0 || B == 2) {
-    constexpr int E0 = (B == 0) ? 0 : 9;
-    const uint4 c = lds128<CYO + (B == 0 ? 0 : 48)>(g.cy);
-    eval<E0>(rg, kL, c.x);
-    eval<E0 + 1>(rg, kR, c.y);
-    eval<E0 + 2>(rg, imad(L, K, kR), c.z);
+    const uint2 c = lds64<CYO + (B == 0 ? 0 : 32)>(g.cy);
+    if (B == 0) { eval2<0, 0, 1>(rg, t, kL, kR, c.x); eval1<1, 2>(rg, k84, c.y); }
+    else        { eval2<5, 9, 10>(rg, t, kL, kR, c.x); eval1<6, 11>(rg, k84, c.y); }
   } else {
-    constexpr int E0 = (B == 1) ? 3 : 12;
-    constexpr int CB = CYO + (B == 1 ? 16 : 64);
-    const uint4 c0 = lds128<CB>(g.cy), c1 = lds128<CB + 16>(g.cy);
-    eval<E0>(rg, kL, c0.x);
-    eval<E0 + 1>(rg, kR, c0.y);
-    eval<E0 + 2>(rg, imad(L, K, kR), c0.z);
-    const unsigned k48R = imad(hR, K, kR);
-    eval<E0 + 3>(rg, imad(hL, K, kL), c0.w);
-    eval<E0 + 4>(rg, k48R, c1.x);
+    const uint4 c = lds128<CYO + (B == 1 ? 16 : 48)>(g.cy);
+    const unsigned k48L = imad(hL, K, kL), k48R = imad(hR, K, kR);
     const unsigned PL = L + hL;
-    eval<E0 + 5>(rg, imad(PL, K, k48R), c1.y);          // 8x8
+    const unsigned k88 = imad(PL, K, k48R);             // 8x8
     const unsigned S8 = PL + Rr + hR;
     if (B == 1) {
+      eval2<2, 3, 4>(rg, t, kL, kR, c.x);
+      eval2<3, 5, 6>(rg, t, k84, k48L, c.y);
+      eval2<4, 7, 8>(rg, t, k48R, k88, c.z);
       rg.hT1[J] = S8;
     } else {
-      const unsigned c2 = lds32<CB + 32>(g.cy);
+      const unsigned c20 = lds32<CYO + 64>(g.cy);
+      eval2<7, 12, 13>(rg, t, kL, kR, c.x);
+      eval2<8, 14, 15>(rg, t, k84, k48L, c.y);
+      eval2<9, 16, 17>(rg, t, k48R, k88, c.z);
       const unsigned T = rg.hT2[J], V = T + S8;          // 8x16 of this column pair
       const unsigned kV = imad(V, K, sp);
-      eval<18>(rg, kV, c1.z);
       const unsigned X = t.h ? T : S8;                   // what the other lane needs for its 16x8
       const unsigned Y = __shfl_xor_sync(0xffffffffu, X, 1);
       const unsigned Vo = __shfl_xor_sync(0xffffffffu, V, 1);
-      eval<19>(rg, imad(V - X + Y, K, sp), c1.w);        // h = 0: 16x8 top, h = 1: 16x8 bottom
-      eval<20>(rg, imad(Vo, K, kV), c2);                 // 16x16 (both lanes, same key)
+      eval2<10, 18, 19>(rg, t, kV, imad(V - X + Y, K, sp), c.w);   // 8x16; 16x8 top (h = 0) / bottom (h = 1)
+      eval1<11, 20>(rg, imad(Vo, K, kV), c20);                     // 16x16 (both lanes, same key)
     }
   }
 }
@@ -263,21 +285,27 @@ __device__ __forceinline__ void sweep4(Regs &rg, const Thr &t, unsigned row0_add
   sweep_row<R, CHECK, 3>(rg, t, g, r0);
 }
 
-// slot e with the table row address taken from shared memory (column 2R, same for all threads of one h)
-template <int E>
-__device__ __forceinline__ void eval_at(Regs &rg, unsigned key, unsigned cyrow, unsigned lutA_addr)
+// unit U with its table address taken from shared memory (column 2R: the same for all threads of one h)
+template <int U>
+__device__ __forceinline__ void eval_unit_at(Regs &rg, const Thr &t, unsigned keyA, unsigned keyB, unsigned cyrow, unsigned ua_addr)
 {
-  const unsigned cy = lds32(cyrow + slot_cyword(E) * 4);
-  const unsigned la = lds32(lutA_addr + E * 4);
-  const unsigned m = lds32(imad(cy, LUT_STRIDE_B, la));
-  rg.best[E] = __viaddmin_u32(key, m, rg.best[E]);
+  const unsigned w = lds32(cyrow + unit_word(U) * 4);
+  const unsigned ua = lds32(ua_addr + U * 4);
+  if (unit_b(U) >= 0) {
+    const uint2 m = lds64(imad(w, t.k8, ua));
+    rg.best[unit_a(U)] = __viaddmin_u32(keyA, m.x, rg.best[unit_a(U)]);
+    rg.best[unit_b(U) >= 0 ? unit_b(U) : 0] = __viaddmin_u32(keyB, m.y, rg.best[unit_b(U) >= 0 ? unit_b(U) : 0]);
+  } else {
+    const unsigned m = lds32(imad(w, LUT_STRIDE_B, ua));
+    rg.best[unit_a(U)] = __viaddmin_u32(keyA, m, rg.best[unit_a(U)]);
+  }
 }
 
 // one whole position of the last window column (dx = 2R), all 21 slots of this lane.  col_addr: shared address of the first
 // word of window row 0 that holds column 2R + 8h; shift: byte residue of the window start, as a funnel-shift count
 template <int R>
 __device__ __forceinline__ void last_column(Regs &rg, const Thr &t, unsigned col_addr, unsigned shift, unsigned cyt_h_addr,
-                                            unsigned lutA_addr, unsigned sptab_addr, int dy)
+                                            unsigned ua_addr, unsigned sptab_addr, int dy)
 {
   constexpr unsigned K = Geo<R>::KMUL;
   constexpr int NP = Geo<R>::NP, SIDE = Geo<R>::SIDE;
@@ -292,23 +320,22 @@ __device__ __forceinline__ void last_column(Regs &rg, const Thr &t, unsigned col
   const unsigned sp = lds16(sptab_addr + (unsigned)(dy * SIDE + 2 * R) * 2);
   const unsigned cyrow = cyt_h_addr + (unsigned)dy * (2 * CYW * 4);
 #define KEY(v) imad((v), K, sp)
-  eval_at<0>(rg, KEY(L[0]), cyrow, lutA_addr);  eval_at<1>(rg, KEY(Q[0]), cyrow, lutA_addr);  eval_at<2>(rg, KEY(L[0] + Q[0]), cyrow, lutA_addr);
-  eval_at<3>(rg, KEY(L[1]), cyrow, lutA_addr);  eval_at<4>(rg, KEY(Q[1]), cyrow, lutA_addr);  eval_at<5>(rg, KEY(L[1] + Q[1]), cyrow, lutA_addr);
-  eval_at<6>(rg, KEY(L[0] + L[1]), cyrow, lutA_addr);  eval_at<7>(rg, KEY(Q[0] + Q[1]), cyrow, lutA_addr);
-  const unsigned T = L[0] + L[1] + Q[0] + Q[1];
-  eval_at<8>(rg, KEY(T), cyrow, lutA_addr);
-  eval_at<9>(rg, KEY(L[2]), cyrow, lutA_addr);  eval_at<10>(rg, KEY(Q[2]), cyrow, lutA_addr); eval_at<11>(rg, KEY(L[2] + Q[2]), cyrow, lutA_addr);
-  eval_at<12>(rg, KEY(L[3]), cyrow, lutA_addr); eval_at<13>(rg, KEY(Q[3]), cyrow, lutA_addr); eval_at<14>(rg, KEY(L[3] + Q[3]), cyrow, lutA_addr);
-  eval_at<15>(rg, KEY(L[2] + L[3]), cyrow, lutA_addr); eval_at<16>(rg, KEY(Q[2] + Q[3]), cyrow, lutA_addr);
-  const unsigned S8 = L[2] + L[3] + Q[2] + Q[3];
-  eval_at<17>(rg, KEY(S8), cyrow, lutA_addr);
-  const unsigned V = T + S8;
-  eval_at<18>(rg, KEY(V), cyrow, lutA_addr);
+  const unsigned T = L[0] + L[1] + Q[0] + Q[1], S8 = L[2] + L[3] + Q[2] + Q[3], V = T + S8;
   const unsigned X = t.h ? T : S8;
   const unsigned Y = __shfl_xor_sync(0xffffffffu, X, 1);
   const unsigned Vo = __shfl_xor_sync(0xffffffffu, V, 1);
-  eval_at<19>(rg, KEY(V - X + Y), cyrow, lutA_addr);
-  eval_at<20>(rg, KEY(V + Vo), cyrow, lutA_addr);
+  eval_unit_at<0>(rg, t, KEY(L[0]), KEY(Q[0]), cyrow, ua_addr);
+  eval_unit_at<1>(rg, t, KEY(L[0] + Q[0]), 0u, cyrow, ua_addr);
+  eval_unit_at<2>(rg, t, KEY(L[1]), KEY(Q[1]), cyrow, ua_addr);
+  eval_unit_at<3>(rg, t, KEY(L[1] + Q[1]), KEY(L[0] + L[1]), cyrow, ua_addr);
+  eval_unit_at<4>(rg, t, KEY(Q[0] + Q[1]), KEY(T), cyrow, ua_addr);
+  eval_unit_at<5>(rg, t, KEY(L[2]), KEY(Q[2]), cyrow, ua_addr);
+  eval_unit_at<6>(rg, t, KEY(L[2] + Q[2]), 0u, cyrow, ua_addr);
+  eval_unit_at<7>(rg, t, KEY(L[3]), KEY(Q[3]), cyrow, ua_addr);
+  eval_unit_at<8>(rg, t, KEY(L[3] + Q[3]), KEY(L[2] + L[3]), cyrow, ua_addr);
+  eval_unit_at<9>(rg, t, KEY(Q[2] + Q[3]), KEY(S8), cyrow, ua_addr);
+  eval_unit_at<10>(rg, t, KEY(V), KEY(V - X + Y), cyrow, ua_addr);
+  eval_unit_at<11>(rg, t, KEY(V + Vo), 0u, cyrow, ua_addr);
 #undef KEY
 }
 
@@ -370,6 +397,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
   const int tid = threadIdx.x, dx = tid >> 1, lane = tid & 31, warp = tid >> 5;
   Thr t;
   t.h = tid & 1;
+  t.k8 = (unsigned)cfg.search_range / (R / 8);     // = 8
   t.sp_addr = smem_u32(&sm.sptab[dx]);
   t.cy_addr = smem_u32(&sm.cyt[0][t.h][0]);
   const unsigned lut_addr = smem_u32(sm.lut);
@@ -446,34 +474,47 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     if (!sm.lut_valid || sm.lut_lambda != jv.lambda) {       // uniform: K * ((lambda * bits) >> 16), bits = 2 * class sum + 2
       __syncthreads();
       if (tid < LUT_ENTRIES) sm.lut[tid * 3] = K * (unsigned)((jv.lambda * (2 * tid + 2)) >> 16);
+      for (int i = tid; i < LUT_ENTRIES * LUT_ENTRIES; i += NT) {
+        const int s0 = i / LUT_ENTRIES, s1 = i - s0 * LUT_ENTRIES;
+        sm.lut2[i] = make_uint2(K * (unsigned)((jv.lambda * (2 * s0 + 2)) >> 16), K * (unsigned)((jv.lambda * (2 * s1 + 2)) >> 16));
+      }
       if (tid == 0) { sm.lut_lambda = jv.lambda; sm.lut_valid = 1; }
     }
-    if (NT >= 3 * 2 * NSLOT) {
-      if (tid < 3 * 2 * NSLOT) {
-        // y length classes: thread (q, third) fills dy = third, third + 3, ... of slot q = (h, e)
-        const int q = tid / 3, third = tid - 3 * q, hh = q / NSLOT, e = q - hh * NSLOT;
-        const int pmvy = job_pmvy(jw, c_slot_part[hh][e]);
-        uint32_t *dst = &sm.cyt[third][hh][slot_cyword(e)];
-        int d = 4 * (offy + third - R) - pmvy;
-        for (int dy = third; dy < SIDE; dy += 3) {
-          *dst = (uint32_t)len_class(d);
-          d += 12; dst += 3 * 2 * CYW;
+    {
+      // y classes: PER threads per (h, unit) column, interleaved over dy
+      constexpr int PER = NT / (2 * NUNIT);
+      if (tid < 2 * NUNIT * PER) {
+        const int col = tid / PER, first = tid - col * PER, hh = col / NUNIT, u = col - hh * NUNIT;
+        const int ea = c_unit_a[u], eb = c_unit_b[u];
+        const int pya = job_pmvy(jw, c_slot_part[hh][ea]), pyb = job_pmvy(jw, c_slot_part[hh][eb < 0 ? ea : eb]);
+        uint32_t *dst = &sm.cyt[first][hh][c_unit_word[u]];
+        int d = 4 * (offy + first - R);
+        for (int dy = first; dy < SIDE; dy += PER) {
+          const int ca = len_class(d - pya), cb = len_class(d - pyb);
+          *dst = (uint32_t)(eb < 0 ? ca : LUT_ENTRIES * ca + cb);
+          d += 4 * PER; dst += PER * 2 * CYW;
         }
       }
-    } else if (tid < 2 * NSLOT) {   // R = 16: 64 threads -> one thread per slot, all dy
-      const int hh = tid / NSLOT, e = tid - hh * NSLOT;
-      const int pmvy = job_pmvy(jw, c_slot_part[hh][e]);
-      for (int dy = 0; dy < SIDE; dy++) sm.cyt[dy][hh][slot_cyword(e)] = (uint32_t)len_class(4 * (offy + dy - R) - pmvy);
     }
-    if (tid < 2 * NSLOT) {
-      const int hh = tid / NSLOT, e = tid - hh * NSLOT;
-      sm.lutA_last[hh][e] = lut_addr + LUT_STRIDE_B * len_class(4 * (offx + R) - job_pmvx(jw, c_slot_part[hh][e]));
+    const unsigned lut2_addr = smem_u32(sm.lut2);
+    if (tid < 2 * NUNIT) {
+      const int hh = tid / NUNIT, u = tid - hh * NUNIT, ea = c_unit_a[u], eb = c_unit_b[u];
+      const int ca = len_class(4 * (offx + R) - job_pmvx(jw, c_slot_part[hh][ea]));
+      const int cb = len_class(4 * (offx + R) - job_pmvx(jw, c_slot_part[hh][eb < 0 ? ea : eb]));
+      sm.ua_last[hh][u] = eb < 0 ? lut_addr + LUT_STRIDE_B * ca : lut2_addr + 8 * (LUT_ENTRIES * ca + cb);
     }
     Regs rg;
 #pragma unroll
-    for (int e = 0; e < NSLOT; e++) {
-      rg.best[e] = 0xffffffffu;
-      rg.lutA[e] = lut_addr + LUT_STRIDE_B * len_class(4 * (offx + dx - R) - job_pmvx(jw, c_slot_part[t.h][e]));
+    for (int e = 0; e < NSLOT; e++) rg.best[e] = 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < NUNIT; u++) {
+      const int ca = len_class(4 * (offx + dx - R) - job_pmvx(jw, c_slot_part[t.h][unit_a(u)]));
+      if (unit_b(u) >= 0) {
+        const int cb = len_class(4 * (offx + dx - R) - job_pmvx(jw, c_slot_part[t.h][unit_b(u) >= 0 ? unit_b(u) : 0]));
+        rg.ua[u] = lut2_addr + 8 * (LUT_ENTRIES * ca + cb);
+      } else {
+        rg.ua[u] = lut_addr + LUT_STRIDE_B * ca;
+      }
     }
 
     // ---- wait for this job's macroblock + window
@@ -502,7 +543,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
 
     // ---- last window column: pair i scores (2R, i); (2R, 2R) is scored by warp 0
     {
-      const unsigned cyh = smem_u32(&sm.cyt[0][t.h][0]), la = smem_u32(&sm.lutA_last[t.h][0]), spa = smem_u32(sm.sptab);
+      const unsigned cyh = smem_u32(&sm.cyt[0][t.h][0]), la = smem_u32(&sm.ua_last[t.h][0]), spa = smem_u32(sm.sptab);
       const unsigned col = wbase + (unsigned)((2 * R + mis) >> 2) * 4 + 8 * t.h, sh_last = (mis & 3) * 8;
       last_column<R>(rg, t, col, sh_last, cyh, la, spa, dx);
       if (warp == 0) last_column<R>(rg, t, col, sh_last, cyh, la, spa, 2 * R);
