@@ -239,12 +239,36 @@ __device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBas
 
 // One window row r = r0 + U (r0 a multiple of 4).  Row r is row k = 4b + i of the macroblock for the displacement
 // dy = r - k; with J = dy & 3 the phase is i = (U - J) & 3, so the 32 accumulators are addressed by compile-time (b, J)
-// although the loop is unrolled over four rows only (the whole sweep body stays within the instruction caches).
+// although the loop is unrolled over four rows only (the sweep body stays within the instruction caches).
 // The last accumulate of bands 0 / 2 writes the hold register the next band reads four rows later (h0 / h2).
-// CHECK: rows 0..15 and 2R..2R+15, where some displacements fall outside [0, 2R]: their SADs are computed into
-// accumulators nobody reads, their evaluation is skipped.
-template <int R, bool CHECK, int U>
-__device__ __forceinline__ void sweep_row(Regs &rg, const Thr &t, const GroupBase &g, int r0)
+// MODE 0: interior rows 16 .. 2R-1, every displacement exists.  MODE 1: rows 4G .. 4G+3 of the first sixteen, displacements
+// dy < 0 do not exist.  MODE 2: rows 2R+4G .. 2R+4G+3 of the last sixteen, displacements dy > 2R do not exist.  The first and
+// last groups are specialised at compile time (no SAD and no evaluation is issued for a displacement outside [0, 2R]).
+template <int MODE, int G, int U, int B, int I>
+__host__ __device__ constexpr bool sad_valid()      // accumulate row k = 4B + I in this row?
+{
+  return MODE == 0 ? true : MODE == 1 ? (B < G || (B == G && I <= U)) : (B > G || (B == G && I >= U));
+}
+template <int MODE, int G, int U, int B>
+__host__ __device__ constexpr bool band_valid()     // does band B of an existing displacement complete in this row?
+{
+  return MODE == 0 ? true : MODE == 1 ? (B < G || (B == G && U == 3)) : (B >= G);
+}
+
+template <int R, int MODE, int G, int U, int B, int J>
+__device__ __forceinline__ void sad_step(Regs &rg, unsigned refL, unsigned refR)
+{
+  constexpr int i = (U - J) & 3, k = 4 * B + i;
+  if constexpr (sad_valid<MODE, G, U, B, i>()) {
+    const unsigned vL = vsad(refL, rg.curL[k], i ? rg.accL[B][J] : 0u), vR = vsad(refR, rg.curR[k], i ? rg.accR[B][J] : 0u);
+    if (i == 3 && B == 0) { rg.h0L[J] = vL; rg.h0R[J] = vR; }
+    else if (i == 3 && B == 2) { rg.h2L[J] = vL; rg.h2R[J] = vR; }
+    else { rg.accL[B][J] = vL; rg.accR[B][J] = vR; }
+  }
+}
+
+template <int R, int MODE, int G, int U>
+__device__ __forceinline__ void sweep_row(Regs &rg, const Thr &t, const GroupBase &g)
 {
   constexpr int NP = Geo<R>::NP;
   constexpr int J = (U + 1) & 3;      // dy & 3 of the displacements whose bands complete in this row
@@ -252,37 +276,30 @@ __device__ __forceinline__ void sweep_row(Regs &rg, const Thr &t, const GroupBas
   const unsigned refL = __funnelshift_r(w0, w1, t.shift), refR = __funnelshift_r(w1, w2, t.shift);
   // holds of the displacement four rows older, read before this row's completions replace them
   const unsigned h0L = rg.h0L[J], h0R = rg.h0R[J], h2L = rg.h2L[J], h2R = rg.h2R[J];
-#pragma unroll
-  for (int b = 0; b < 4; b++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int i = (U - j) & 3, k = 4 * b + i;
-      const unsigned vL = vsad(refL, rg.curL[k], i ? rg.accL[b][j] : 0u), vR = vsad(refR, rg.curR[k], i ? rg.accR[b][j] : 0u);
-      if (i == 3 && b == 0) { rg.h0L[j] = vL; rg.h0R[j] = vR; }
-      else if (i == 3 && b == 2) { rg.h2L[j] = vL; rg.h2R[j] = vR; }
-      else { rg.accL[b][j] = vL; rg.accR[b][j] = vR; }
-    }
+#define ME_SAD_BAND(B) sad_step<R, MODE, G, U, B, 0>(rg, refL, refR); sad_step<R, MODE, G, U, B, 1>(rg, refL, refR); \
+                       sad_step<R, MODE, G, U, B, 2>(rg, refL, refR); sad_step<R, MODE, G, U, B, 3>(rg, refL, refR);
+  ME_SAD_BAND(0) ME_SAD_BAND(1) ME_SAD_BAND(2) ME_SAD_BAND(3)
+#undef ME_SAD_BAND
   // bands in descending order (band 3 reads the 8x8 queue that band 1 of a later displacement advances)
-  const unsigned lim = 2 * R;
-  if (!CHECK || (unsigned)(r0 + U - 15) <= lim) band_done<R, 3, U - 15, J>(rg, t, g, rg.accL[3][J], rg.accR[3][J], h2L, h2R);
-  if (!CHECK || (unsigned)(r0 + U - 11) <= lim) band_done<R, 2, U - 11, J>(rg, t, g, rg.h2L[J], rg.h2R[J], 0u, 0u);
+  if constexpr (band_valid<MODE, G, U, 3>()) band_done<R, 3, U - 15, J>(rg, t, g, rg.accL[3][J], rg.accR[3][J], h2L, h2R);
+  if constexpr (band_valid<MODE, G, U, 2>()) band_done<R, 2, U - 11, J>(rg, t, g, rg.h2L[J], rg.h2R[J], 0u, 0u);
   rg.hT2[J] = rg.hT1[J];
-  if (!CHECK || (unsigned)(r0 + U - 7) <= lim) band_done<R, 1, U - 7, J>(rg, t, g, rg.accL[1][J], rg.accR[1][J], h0L, h0R);
-  if (!CHECK || (unsigned)(r0 + U - 3) <= lim) band_done<R, 0, U - 3, J>(rg, t, g, rg.h0L[J], rg.h0R[J], 0u, 0u);
+  if constexpr (band_valid<MODE, G, U, 1>()) band_done<R, 1, U - 7, J>(rg, t, g, rg.accL[1][J], rg.accR[1][J], h0L, h0R);
+  if constexpr (band_valid<MODE, G, U, 0>()) band_done<R, 0, U - 3, J>(rg, t, g, rg.h0L[J], rg.h0R[J], 0u, 0u);
 }
 
 // four window rows starting at row r0 (a multiple of 4)
-template <int R, bool CHECK>
+template <int R, int MODE, int G>
 __device__ __forceinline__ void sweep4(Regs &rg, const Thr &t, unsigned row0_addr, int r0)
 {
   GroupBase g;
   g.win = row0_addr + (unsigned)r0 * Geo<R>::NP;
   g.sp = t.sp_addr + (unsigned)r0 * (Geo<R>::SIDE * 2);
   g.cy = t.cy_addr + (unsigned)r0 * (2 * CYW * 4);
-  sweep_row<R, CHECK, 0>(rg, t, g, r0);
-  sweep_row<R, CHECK, 1>(rg, t, g, r0);
-  sweep_row<R, CHECK, 2>(rg, t, g, r0);
-  sweep_row<R, CHECK, 3>(rg, t, g, r0);
+  sweep_row<R, MODE, G, 0>(rg, t, g);
+  sweep_row<R, MODE, G, 1>(rg, t, g);
+  sweep_row<R, MODE, G, 2>(rg, t, g);
+  sweep_row<R, MODE, G, 3>(rg, t, g);
 }
 
 // unit U with its table address taken from shared memory (column 2R: the same for all threads of one h)
@@ -535,11 +552,16 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     // ---- the sweep
     const unsigned wbase = smem_u32(sm.win[buf]);
     const unsigned row0 = wbase + (unsigned)((dx + mis) >> 2) * 4 + 8 * t.h;
+    sweep4<R, 1, 0>(rg, t, row0, 0);
+    sweep4<R, 1, 1>(rg, t, row0, 4);
+    sweep4<R, 1, 2>(rg, t, row0, 8);
+    sweep4<R, 1, 3>(rg, t, row0, 12);
 #pragma unroll 1
-    for (int r0 = 0; r0 < N; r0 += 4) {
-      if (r0 < 16 || r0 >= 2 * R) sweep4<R, true>(rg, t, row0, r0);
-      else sweep4<R, false>(rg, t, row0, r0);
-    }
+    for (int r0 = 16; r0 < 2 * R; r0 += 4) sweep4<R, 0, 0>(rg, t, row0, r0);
+    sweep4<R, 2, 0>(rg, t, row0, 2 * R);
+    sweep4<R, 2, 1>(rg, t, row0, 2 * R + 4);
+    sweep4<R, 2, 2>(rg, t, row0, 2 * R + 8);
+    sweep4<R, 2, 3>(rg, t, row0, 2 * R + 12);
 
     // ---- last window column: pair i scores (2R, i); (2R, 2R) is scored by warp 0
     {
