@@ -38,7 +38,7 @@
 
 namespace {
 
-constexpr int CYW = 20;            // words per (dy, h) row of the y-class table: band groups at words 0, 4, 8, 12
+constexpr int CYW = 12;            // words per (window row, h) of the y-class table: one per lookup unit
 constexpr int LUT_STRIDE_B = 12;   // bytes between table entries: odd word stride -> conflict-free and the address is an IMAD
 constexpr int LUT_ENTRIES = 36;    // class sums 0..35 (classes up to 17 per component: |d| < 2^17)
 constexpr int NSLOT = 21;          // partitions scored by one thread
@@ -47,10 +47,11 @@ constexpr int NSLOT = 21;          // partitions scored by one thread
 constexpr int NUNIT = 12;
 __host__ __device__ constexpr int unit_a(int u) { constexpr int t[NUNIT] = { 0, 2, 3, 5, 7, 9, 11, 12, 14, 16, 18, 20 }; return t[u]; }
 __host__ __device__ constexpr int unit_b(int u) { constexpr int t[NUNIT] = { 1, -1, 4, 6, 8, 10, -1, 13, 15, 17, 19, -1 }; return t[u]; }
-__host__ __device__ constexpr int unit_word(int u) { constexpr int t[NUNIT] = { 0, 1, 4, 5, 6, 8, 9, 12, 13, 14, 15, 16 }; return t[u]; }
+// the band whose completion evaluates the unit; its displacement is dy = window row - (4 * band + 3)
+__host__ __device__ constexpr int unit_lag(int u) { return u < 2 ? 3 : u < 5 ? 7 : u < 7 ? 11 : 15; }
 __constant__ int8_t c_unit_a[NUNIT] = { 0, 2, 3, 5, 7, 9, 11, 12, 14, 16, 18, 20 };
 __constant__ int8_t c_unit_b[NUNIT] = { 1, -1, 4, 6, 8, 10, -1, 13, 15, 17, 19, -1 };
-__constant__ int8_t c_unit_word[NUNIT] = { 0, 1, 4, 5, 6, 8, 9, 12, 13, 14, 15, 16 };
+__constant__ int8_t c_unit_lag[NUNIT] = { 3, 3, 7, 7, 7, 11, 11, 15, 15, 15, 15, 15 };
 
 template <int R> struct Geo {
   static constexpr int N = 2 * R + 16;            // window side
@@ -69,7 +70,8 @@ __constant__ int8_t c_slot_part[2][NSLOT] = {
 template <int R> struct __align__(128) Smem {
   uint8_t  win[2][Geo<R>::NP * Geo<R>::N];      // search windows, N rows of NP bytes (TMA box, dense); the window starts at byte X0 & 15
   uint32_t cur[2][64];                          // current macroblocks, 16 rows x 4 words
-  uint32_t cyt[Geo<R>::SIDE][2][CYW];           // per (dy, h, unit): y class of a single slot, 36 * class_a + class_b of a pair
+  uint32_t cyt[Geo<R>::N][2][CYW];              // per (window row r, h, unit): y class word (single: class, pair: 36 * class_a +
+                                                // class_b) of the displacement dy = r - lag(unit) the unit is evaluated for in row r
   uint2    lut2[LUT_ENTRIES * LUT_ENTRIES];     // {K * mvcost(s0), K * mvcost(s1)} at index 36 * s0 + s1
   uint32_t lut[LUT_ENTRIES * 3];                // K * mvcost(class sum), entry stride 12 bytes
   uint32_t ua_last[2][NUNIT];                   // unit table addresses of column 2R per (h, unit)
@@ -197,42 +199,39 @@ struct GroupBase {
 };
 
 // Band B (rows 4B..4B+3 of the macroblock) of vertical displacement dy = r0 + DYO has just been accumulated: L / Rr are
-// the two 4x4 SADs, J = dy & 3.
+// the two 4x4 SADs, J = dy & 3, hL / hR the 4x4 SADs of the band above (bands 1, 3).  cA, cB, cC: this row's y-class words.
 template <int R, int B, int DYO, int J>
-__device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBase &g, unsigned L, unsigned Rr, unsigned hL, unsigned hR)
+__device__ __forceinline__ void band_done(Regs &rg, const Thr &t, const GroupBase &g, unsigned L, unsigned Rr, unsigned hL, unsigned hR,
+                                          const uint4 &cA, const uint4 &cB, const uint4 &cC)
 {
   constexpr unsigned K = Geo<R>::KMUL;
-  constexpr int SPO = DYO * Geo<R>::SIDE * 2, CYO = DYO * 2 * CYW * 4;
+  constexpr int SPO = DYO * Geo<R>::SIDE * 2;
   const unsigned sp = lds16<SPO>(g.sp);
   const unsigned kL = imad(L, K, sp), kR = imad(Rr, K, sp);
   const unsigned k84 = imad(L, K, kR);                  // 8x4
-  if (B == 0 || B == 2) {
-    const uint2 c = lds64<CYO + (B == 0 ? 0 : 32)>(g.cy);
-    if (B == 0) { eval2<0, 0, 1>(rg, t, kL, kR, c.x); eval1<1, 2>(rg, k84, c.y); }
-    else        { eval2<5, 9, 10>(rg, t, kL, kR, c.x); eval1<6, 11>(rg, k84, c.y); }
-  } else {
-    const uint4 c = lds128<CYO + (B == 1 ? 16 : 48)>(g.cy);
+  if (B == 0) { eval2<0, 0, 1>(rg, t, kL, kR, cA.x); eval1<1, 2>(rg, k84, cA.y); }
+  else if (B == 2) { eval2<5, 9, 10>(rg, t, kL, kR, cB.y); eval1<6, 11>(rg, k84, cB.z); }
+  else {
     const unsigned k48L = imad(hL, K, kL), k48R = imad(hR, K, kR);
     const unsigned PL = L + hL;
     const unsigned k88 = imad(PL, K, k48R);             // 8x8
     const unsigned S8 = PL + Rr + hR;
     if (B == 1) {
-      eval2<2, 3, 4>(rg, t, kL, kR, c.x);
-      eval2<3, 5, 6>(rg, t, k84, k48L, c.y);
-      eval2<4, 7, 8>(rg, t, k48R, k88, c.z);
+      eval2<2, 3, 4>(rg, t, kL, kR, cA.z);
+      eval2<3, 5, 6>(rg, t, k84, k48L, cA.w);
+      eval2<4, 7, 8>(rg, t, k48R, k88, cB.x);
       rg.hT1[J] = S8;
     } else {
-      const unsigned c20 = lds32<CYO + 64>(g.cy);
-      eval2<7, 12, 13>(rg, t, kL, kR, c.x);
-      eval2<8, 14, 15>(rg, t, k84, k48L, c.y);
-      eval2<9, 16, 17>(rg, t, k48R, k88, c.z);
+      eval2<7, 12, 13>(rg, t, kL, kR, cB.w);
+      eval2<8, 14, 15>(rg, t, k84, k48L, cC.x);
+      eval2<9, 16, 17>(rg, t, k48R, k88, cC.y);
       const unsigned T = rg.hT2[J], V = T + S8;          // 8x16 of this column pair
       const unsigned kV = imad(V, K, sp);
       const unsigned X = t.h ? T : S8;                   // what the other lane needs for its 16x8
       const unsigned Y = __shfl_xor_sync(0xffffffffu, X, 1);
       const unsigned Vo = __shfl_xor_sync(0xffffffffu, V, 1);
-      eval2<10, 18, 19>(rg, t, kV, imad(V - X + Y, K, sp), c.w);   // 8x16; 16x8 top (h = 0) / bottom (h = 1)
-      eval1<11, 20>(rg, imad(Vo, K, kV), c20);                     // 16x16 (both lanes, same key)
+      eval2<10, 18, 19>(rg, t, kV, imad(V - X + Y, K, sp), cC.z);   // 8x16; 16x8 top (h = 0) / bottom (h = 1)
+      eval1<11, 20>(rg, imad(Vo, K, kV), cC.w);                     // 16x16 (both lanes, same key)
     }
   }
 }
@@ -280,12 +279,18 @@ __device__ __forceinline__ void sweep_row(Regs &rg, const Thr &t, const GroupBas
                        sad_step<R, MODE, G, U, B, 2>(rg, refL, refR); sad_step<R, MODE, G, U, B, 3>(rg, refL, refR);
   ME_SAD_BAND(0) ME_SAD_BAND(1) ME_SAD_BAND(2) ME_SAD_BAND(3)
 #undef ME_SAD_BAND
+  // this row's twelve y-class words (already shifted by each band's lag when the table was built)
+  constexpr int CYO = U * 2 * CYW * 4;
+  uint4 cA = make_uint4(0, 0, 0, 0), cB = cA, cC = cA;
+  if constexpr (band_valid<MODE, G, U, 0>() || band_valid<MODE, G, U, 1>()) cA = lds128<CYO>(g.cy);
+  if constexpr (band_valid<MODE, G, U, 1>() || band_valid<MODE, G, U, 2>() || band_valid<MODE, G, U, 3>()) cB = lds128<CYO + 16>(g.cy);
+  if constexpr (band_valid<MODE, G, U, 3>()) cC = lds128<CYO + 32>(g.cy);
   // bands in descending order (band 3 reads the 8x8 queue that band 1 of a later displacement advances)
-  if constexpr (band_valid<MODE, G, U, 3>()) band_done<R, 3, U - 15, J>(rg, t, g, rg.accL[3][J], rg.accR[3][J], h2L, h2R);
-  if constexpr (band_valid<MODE, G, U, 2>()) band_done<R, 2, U - 11, J>(rg, t, g, rg.h2L[J], rg.h2R[J], 0u, 0u);
+  if constexpr (band_valid<MODE, G, U, 3>()) band_done<R, 3, U - 15, J>(rg, t, g, rg.accL[3][J], rg.accR[3][J], h2L, h2R, cA, cB, cC);
+  if constexpr (band_valid<MODE, G, U, 2>()) band_done<R, 2, U - 11, J>(rg, t, g, rg.h2L[J], rg.h2R[J], 0u, 0u, cA, cB, cC);
   rg.hT2[J] = rg.hT1[J];
-  if constexpr (band_valid<MODE, G, U, 1>()) band_done<R, 1, U - 7, J>(rg, t, g, rg.accL[1][J], rg.accR[1][J], h0L, h0R);
-  if constexpr (band_valid<MODE, G, U, 0>()) band_done<R, 0, U - 3, J>(rg, t, g, rg.h0L[J], rg.h0R[J], 0u, 0u);
+  if constexpr (band_valid<MODE, G, U, 1>()) band_done<R, 1, U - 7, J>(rg, t, g, rg.accL[1][J], rg.accR[1][J], h0L, h0R, cA, cB, cC);
+  if constexpr (band_valid<MODE, G, U, 0>()) band_done<R, 0, U - 3, J>(rg, t, g, rg.h0L[J], rg.h0R[J], 0u, 0u, cA, cB, cC);
 }
 
 // four window rows starting at row r0 (a multiple of 4)
@@ -306,7 +311,7 @@ __device__ __forceinline__ void sweep4(Regs &rg, const Thr &t, unsigned row0_add
 template <int U>
 __device__ __forceinline__ void eval_unit_at(Regs &rg, const Thr &t, unsigned keyA, unsigned keyB, unsigned cyrow, unsigned ua_addr)
 {
-  const unsigned w = lds32(cyrow + unit_word(U) * 4);
+  const unsigned w = lds32(cyrow + unit_lag(U) * (2 * CYW * 4) + U * 4);
   const unsigned ua = lds32(ua_addr + U * 4);
   if (unit_b(U) >= 0) {
     const uint2 m = lds64(imad(w, t.k8, ua));
@@ -504,7 +509,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
         const int col = tid / PER, first = tid - col * PER, hh = col / NUNIT, u = col - hh * NUNIT;
         const int ea = c_unit_a[u], eb = c_unit_b[u];
         const int pya = job_pmvy(jw, c_slot_part[hh][ea]), pyb = job_pmvy(jw, c_slot_part[hh][eb < 0 ? ea : eb]);
-        uint32_t *dst = &sm.cyt[first][hh][c_unit_word[u]];
+        uint32_t *dst = &sm.cyt[first + c_unit_lag[u]][hh][u];          // row r = dy + lag
         int d = 4 * (offy + first - R);
         for (int dy = first; dy < SIDE; dy += PER) {
           const int ca = len_class(d - pya), cb = len_class(d - pyb);
