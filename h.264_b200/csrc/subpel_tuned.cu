@@ -65,6 +65,7 @@ struct __align__(128) Smem {
   int      mv[ME_NUM_PARTITIONS][2];        // current best vector, quarter pel
   int      mn[ME_NUM_PARTITIONS];           // its cost
   int      okp[ME_NUM_PARTITIONS];          // partition served by the staged region (else: global reads with the clamp)
+  uint32_t itab[2][7 * 16 * 9];             // per stage, work unit -> partition | tile << 8 | candidate << 12 | (tiles per partition - 1) << 16
   unsigned long long mbar;
 };
 
@@ -155,6 +156,14 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // work-unit tables (depend on the configuration only): lanes ordered (type, candidate, tile slot)
+  for (int stage = 0; stage < 2; stage++) {
+    const int first = stage == 0 ? cfg.start_hp : cfg.start_qp, nc = 9 - first;
+    for (int i = tid; i < 7 * 16 * nc; i += NT) {
+      const int q = i & 15, gi = i >> 4, ti = gi / nc, c = gi - ti * nc + first;      // ti = block type - 1
+      sm.itab[stage][i] = (uint32_t)c_part[ti][q] | ((uint32_t)c_tile[ti][q] << 8) | ((uint32_t)c << 12) | ((uint32_t)(c_group[ti] - 1) << 16);
+    }
+  }
   __syncthreads();
 
   // region origin of a job: its 16x16 partition's integer vector, minus the margin, x aligned down to 16 bytes (TMA)
@@ -227,10 +236,9 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
           const int i = base + k * NT + tid;
           u.active = i < total;
           const int ii = u.active ? i : 0;
-          const int gi = ii >> 4, ti = gi / nc;                                      // ti = block type - 1
-          u.q = ii & 15; u.c = gi - ti * nc + first;
-          u.p = c_part[ti][u.q]; u.g = c_group[ti];
-          const int tile = c_tile[ti][u.q];
+          const uint32_t e = sm.itab[stage][ii];
+          u.q = ii & 15; u.p = (int)(e & 0xffu); u.c = (int)((e >> 12) & 0xfu); u.g = (int)(e >> 16) + 1;
+          const int tile = (int)((e >> 8) & 0xfu);
           u.mvx = sm.mv[u.p][0] + step * c_spx[u.c]; u.mvy = sm.mv[u.p][1] + step * c_spy[u.c];
           const int x4 = ((jv.opix_x + 4 * (tile & 3) + ME_PAD) << 2) + u.mvx, y4 = ((jv.opix_y + 4 * (tile >> 2) + ME_PAD) << 2) + u.mvy;
           // tiles of the lower macroblock half take their rows in the order 2, 3, 0, 1 (the Hadamard sum does not change under a
