@@ -374,6 +374,12 @@ def main():
     except Exception:
         pass
     alg_bytes = n_jobs * ((2 * SEARCH_RANGE + 16) ** 2 + 256 + JOB_DTYPE.itemsize + RESULT_DTYPE.itemsize)
+    traffic = None          # DRAM bytes per launch of the search kernel, from the committed ncu capture (not measurable in-process)
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["me_ffs_tuned_kernel"]
+        traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "int_alu", "kernel": "integer-pel fast full search (me_ffs_*)", "achieved": achieved, "peak": peak,
                 "unit": "Glaneop/s", "frac": (achieved / peak) if (achieved and peak) else None,
                 "peak_source": "measured on this GPU by me_cuda_measure_int_peak: VABSDIFF4 alone (ALU pipe) + IMAD alone (FMA pipe), "
@@ -385,7 +391,9 @@ def main():
                 "sad_only_frac_of_alu_pipe": (SAD_OPS_PER_JOB * n_jobs / (ffs_avg_ms * 1e-3) / 1e9 / peaks["vabsdiff4"]) if (ffs_n and peaks) else None,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (ffs_avg_ms * 1e-3) / 1e9 if ffs_n else None,
                         "peak_gbs": mp.get("hbm_gbs", 6650.0), "peak_source": "MEASURED_PEAKS.json" if mp else "fallback"},
-                "traffic": None, "int_peaks_glaneops": peaks,
+                "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full, same workload); windows are re-read from L2, "
+                                                      "DRAM sees each reference plane once",
+                "int_peaks_glaneops": peaks,
                 "share_of_step": {"planes_ms": pl_ms / max(1, args.steps), "ffs_ms": ffs_ms / max(1, args.steps),
                                   "subpel_ms": sub_ms / max(1, args.steps)}}
 
