@@ -238,7 +238,7 @@ me_ffs_surfaces_kernel(MeRefDev ref, const uint8_t *__restrict__ cur, int cur_pi
 // ... then one argmin per block search (FastFullPelBlockMotionSearch, me_fullfast.c:833-903)
 __global__ void __launch_bounds__(256)
 me_ffs_block_kernel(const int32_t *__restrict__ surf_p, int setup_range, int offx, int offy, int pmv_x, int pmv_y,
-                    int search_range, int min_mcost, int lambda, int rdopt, int *__restrict__ result /* mvx, mvy, cost */)
+                    int search_range, int min_mcost, int lambda, int rdopt, int *result /* mvx, mvy, cost, ticket */, int ticket)
 {
   __shared__ unsigned long long red[8];
   const int Pset = (2 * setup_range + 1) * (2 * setup_range + 1);
@@ -276,6 +276,8 @@ me_ffs_block_kernel(const int32_t *__restrict__ surf_p, int setup_range, int off
     int dx, dy;
     me_spiral_xy(bestpos, dx, dy);
     result[0] = offx + dx; result[1] = offy + dy; result[2] = cost;
+    __threadfence_system();                              // `result` is mapped host memory: the host spins on the ticket
+    *(volatile int *)&result[3] = ticket;
   }
 }
 
@@ -303,8 +305,8 @@ extern "C" void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, 
 }
 
 extern "C" void me_launch_ffs_block(const int32_t *surf_p, int setup_range, int offx, int offy, int pmv_x, int pmv_y,
-                                    int search_range, int min_mcost, int lambda, int rdopt, int *result, cudaStream_t st)
+                                    int search_range, int min_mcost, int lambda, int rdopt, int *result, int ticket, cudaStream_t st)
 {
   me_ffs_block_kernel<<<1, 256, 0, st>>>(surf_p, setup_range, offx, offy, pmv_x, pmv_y, search_range, min_mcost, lambda,
-                                         rdopt, result);
+                                         rdopt, result, ticket);
 }

@@ -46,13 +46,13 @@ int  me_ffs_tuned_window(int search_range);
 void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y, int cx, int cy,
                             int R, int sse, int32_t *surf, cudaStream_t st);
 void me_launch_ffs_block(const int32_t *surf_p, int setup_range, int offx, int offy, int pmv_x, int pmv_y, int search_range,
-                         int min_mcost, int lambda, int rdopt, int *result, cudaStream_t st);
+                         int min_mcost, int lambda, int rdopt, int *result, int ticket, cudaStream_t st);
 void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
                             const MeCfgDev *cfg, const MeResultInt *in_int, MeResult *out, cudaStream_t st);
 void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
-                             const MeSubpelArgs *a, int *result, cudaStream_t st);
+                             const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st);
 void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
-                           const MeBiFullArgs *a, int *result, cudaStream_t st);
+                           const MeBiFullArgs *a, int *result, int ticket, cudaStream_t st);
 }
 
 namespace {
@@ -104,7 +104,8 @@ struct State {
   int setup_done[2][ME_MAX_REFS];
   int centre_x[2][ME_MAX_REFS], centre_y[2][ME_MAX_REFS], setup_range[2][ME_MAX_REFS];
   int32_t *d_surf[2][ME_MAX_REFS];
-  int *d_result = nullptr, *h_result = nullptr;
+  int *d_result = nullptr, *h_result = nullptr;   // one mapped pinned buffer: the drop-in kernels write {mvx, mvy, cost, ticket}
+  int ticket = 0;                                 // straight into host memory and the host spins on the ticket (no copy, no sync)
   // batch scratch
   MeJob *d_jobs = nullptr; MeResult *d_out = nullptr; MeResultInt *d_out_int = nullptr; int batch_cap = 0;
   MeResultInt *d_int_scratch = nullptr; int int_scratch_cap = 0;
@@ -313,8 +314,9 @@ int me_cuda_init(const me_cuda_params *p)
   CK(cudaMalloc((void **)&g.d_cur, (size_t)g.cur_pitch * p->height));
   CK(cudaMalloc((void **)&g.d_table, sizeof g.h_table));
   g.has_cur_map = me_make_tensor_map_2d(g.cur_map.bytes, g.d_cur, p->width, p->height, g.cur_pitch, 16, 16) == 0;
-  CK(cudaMalloc((void **)&g.d_result, 64));
-  CK(cudaMallocHost((void **)&g.h_result, 64));
+  CK(cudaHostAlloc((void **)&g.h_result, 64, cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer((void **)&g.d_result, g.h_result, 0));
+  memset(g.h_result, 0, 64);
   memset(g.d_surf, 0, sizeof g.d_surf);
   memset(g.setup_done, 0, sizeof g.setup_done);
   g_err[0] = 0;
@@ -330,7 +332,7 @@ void me_cuda_shutdown(void)
   for (auto &r : g.refs) if (r.used) { cudaFree(r.planes); cudaFree(r.search); }
   g.refs.clear();
   for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) if (g.d_surf[l][i]) cudaFree(g.d_surf[l][i]);
-  cudaFree(g.d_cur); cudaFree(g.d_table); cudaFree(g.d_result); cudaFreeHost(g.h_result);
+  cudaFree(g.d_cur); cudaFree(g.d_table); cudaFreeHost(g.h_result);
   if (g.d_deferred) cudaFree(g.d_deferred);
   if (g.s_in) {
     cudaStreamSynchronize(g.s_in); cudaStreamSynchronize(g.s_out);
@@ -554,9 +556,21 @@ int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
 
 static int fetch_result(int *mvx, int *mvy, int *cost)
 {
-  CK(cudaMemcpyAsync(g.h_result, g.d_result, 3 * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
-  *mvx = g.h_result[0]; *mvy = g.h_result[1]; *cost = g.h_result[2];
+  // the kernel launched with g.ticket writes its three results and then the ticket into mapped host memory
+  volatile int *r = g.h_result;
+  for (unsigned spin = 0;; spin++) {
+    if (r[3] == g.ticket) break;
+    if ((spin & 0x3fff) == 0x3fff) {
+      // the stream has drained without the ticket arriving: the kernel failed
+      cudaError_t e = cudaStreamQuery(g.stream);
+      if (e != cudaErrorNotReady && r[3] != g.ticket) {
+        if (e == cudaSuccess) e = cudaGetLastError();
+        return fail(2, "drop-in search kernel did not deliver its result: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  __sync_synchronize();
+  *mvx = r[0]; *mvy = r[1]; *cost = r[2];
   return 0;
 }
 
@@ -573,7 +587,7 @@ int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int
   if (p < 0) { fail(1, "block (%d,%d) is not a type-%d partition origin", pic_pix_x, pic_pix_y, blocktype); fatal("ffs"); return ME_INT_MAX; }
   int R = g.setup_range[list][ref], P = (2 * R + 1) * (2 * R + 1);
   me_launch_ffs_block(g.d_surf[list][ref] + (size_t)p * P, R, g.centre_x[list][ref] - g.opix_x, g.centre_y[list][ref] - g.opix_y,
-                      pred_mv_x, pred_mv_y, search_range, min_mcost, lambda_factor, g.cfg.rdopt, g.d_result, g.stream);
+                      pred_mv_x, pred_mv_y, search_range, min_mcost, lambda_factor, g.cfg.rdopt, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("ffs"); return ME_INT_MAX; }
@@ -594,7 +608,7 @@ int me_cuda_SubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_
   for (int i = 0; i < 3; i++) a.lambda[i] = lambda[i];
   a.check0 = (!g.cfg.rdopt && g.slice_type != ME_B_SLICE && ref == 0 && blocktype == 1 && *mv_x == 0 && *mv_y == 0);   // me_fullsearch.c:361
   a.bi = 0;
-  me_launch_subpel_single(&r->dev, nullptr, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, g.stream);
+  me_launch_subpel_single(&r->dev, nullptr, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("subpel"); return ME_INT_MAX; }
@@ -617,7 +631,7 @@ int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic
   a.pmv_x1 = pred_mv_x1; a.pmv_y1 = pred_mv_y1; a.pmv_x2 = pred_mv_x2; a.pmv_y2 = pred_mv_y2;
   a.mv_x = *mv_x; a.mv_y = *mv_y; a.s_mv_x = *s_mv_x; a.s_mv_y = *s_mv_y;
   a.search_range = search_range; a.min_mcost = min_mcost; a.lambda = lambda_factor;
-  me_launch_bipred_full(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, g.stream);
+  me_launch_bipred_full(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("bipred"); return ME_INT_MAX; }
@@ -638,7 +652,7 @@ int me_cuda_SubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_
   a.search_pos2 = search_pos2; a.search_pos4 = search_pos4; a.min_mcost = min_mcost;
   for (int i = 0; i < 3; i++) a.lambda[i] = lambda[i];
   a.check0 = 0; a.bi = 1;
-  me_launch_subpel_single(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, g.stream);
+  me_launch_subpel_single(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("bipred"); return ME_INT_MAX; }

@@ -193,7 +193,7 @@ struct MeSubpelArgs {
 
 __global__ void __launch_bounds__(128)
 me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
-                        MeSubpelArgs a, int *__restrict__ result /* mvx, mvy, cost */)
+                        MeSubpelArgs a, int *result /* mvx, mvy, cost, ticket */, int ticket)
 {
   __shared__ int cost_s[9];
   __shared__ int mv_s[2], min_sh;
@@ -248,7 +248,11 @@ me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cu
     }
     __syncthreads();
   }
-  if (tid == 0) { result[0] = mv_s[0]; result[1] = mv_s[1]; result[2] = min_sh; }
+  if (tid == 0) {
+    result[0] = mv_s[0]; result[1] = mv_s[1]; result[2] = min_sh;
+    __threadfence_system();                              // `result` is mapped host memory: the host spins on the ticket
+    *(volatile int *)&result[3] = ticket;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -273,7 +277,7 @@ __device__ __forceinline__ void spiral_xy_dev(int s, int &dx, int &dy)
 
 __global__ void __launch_bounds__(256)
 me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
-                      MeBiFullArgs a, int *__restrict__ result)
+                      MeBiFullArgs a, int *result, int ticket)
 {
   __shared__ unsigned long long red[8];
   const int P = (2 * a.search_range + 1) * (2 * a.search_range + 1);
@@ -317,6 +321,8 @@ me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur,
     int dx = 0, dy = 0;
     if (cost < a.min_mcost) spiral_xy_dev(pos, dx, dy); else cost = a.min_mcost;
     result[0] = a.mv_x + dx; result[1] = a.mv_y + dy; result[2] = cost;
+    __threadfence_system();
+    *(volatile int *)&result[3] = ticket;
   }
 }
 
@@ -328,13 +334,13 @@ extern "C" void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRe
 }
 
 extern "C" void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
-                                        const MeCfgDev *cfg, const MeSubpelArgs *a, int *result, cudaStream_t st)
+                                        const MeCfgDev *cfg, const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st)
 {
-  me_subpel_single_kernel<<<1, 128, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, result);
+  me_subpel_single_kernel<<<1, 128, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, result, ticket);
 }
 
 extern "C" void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
-                                      const MeCfgDev *cfg, const MeBiFullArgs *a, int *result, cudaStream_t st)
+                                      const MeCfgDev *cfg, const MeBiFullArgs *a, int *result, int ticket, cudaStream_t st)
 {
-  me_bipred_full_kernel<<<1, 256, 0, st>>>(*r1, *r2, cur, cur_pitch, *cfg, *a, result);
+  me_bipred_full_kernel<<<1, 256, 0, st>>>(*r1, *r2, cur, cur_pitch, *cfg, *a, result, ticket);
 }

@@ -175,6 +175,41 @@ def test_batch_huge_lambda_jobs_are_handed_to_the_general_kernel(pkg, oracle_lib
     assert not bad, (len(bad), n, bad[:4])
 
 
+def test_batch_two_reference_lists(pkg, oracle_lib):
+    """B-slice style batch: jobs against list 0 and list 1 (different pictures) in one call"""
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h = 352, 288
+    d, cfg = _cfg(ob)
+    frames = synth.luma_frames(w, h, 5)
+    cur = frames[2]
+    l0, l1 = [frames[1], frames[0]], [frames[3], frames[4]]            # past pictures / future pictures
+    jobs0 = synth.synthetic_jobs(w, h, 2, (334459, 334459, 334459), seed=23, max_pmv=30, slice_type=1)
+    jobs1 = synth.synthetic_jobs(w, h, 2, (334459, 334459, 334459), seed=29, max_pmv=30, slice_type=1)
+    jobs1["list"] = 1
+    jobs1["pmv16"] = -jobs1["pmv16"]; jobs1["pmv"] = -jobs1["pmv"]  # the pan runs the other way for future pictures
+    jobs = np.concatenate([jobs0, jobs1])
+    rng = np.random.default_rng(31)
+    jobs = jobs[rng.permutation(len(jobs))]                            # lists and references interleaved
+    with _open(pkg, w, h, d, max_refs=4) as me:
+        me.set_ref_list(0, [me.ref_create(f) for f in l0])
+        me.set_ref_list(1, [me.ref_create(f) for f in l1])
+        me.set_current(cur)
+        out, out_int = me.frame_search(jobs, want_int=True)
+    curc = np.ascontiguousarray(cur)
+    sel = np.sort(rng.choice(len(jobs), 240, replace=False))
+    for lst, pics in ((0, l0), (1, l1)):
+        for r, pic in enumerate(pics):
+            s_ = sel[(jobs["list"][sel] == lst) & (jobs["ref"][sel] == r)]
+            if not len(s_):
+                continue
+            ref = ob.Ref(pic)
+            exp, exp_int = ob.mb_search(cfg, curc, ref, jobs[s_])
+            assert np.array_equal(out_int[s_], exp_int), (lst, r)
+            assert np.array_equal(out[s_], exp), (lst, r)
+            ref.close()
+
+
 @pytest.mark.parametrize("kind", ["flat", "stripes"])
 def test_batch_ties_follow_spiral_order(pkg, oracle_lib, kind):
     """flat / periodic content: thousands of equal costs, the winner must be the first one in JM's spiral order"""
