@@ -30,13 +30,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, N_REFS, SEARCH_RANGE = 1920, 1088, 5, 32
+W, H, N_REFS, SEARCH_RANGE = 1920, 1088, 5, 32   # the headline workload (BASELINE.json configs[2])
+if os.environ.get("ME_BENCH_WORKLOAD", "") == "4k":   # side measurement of configs[4] (not the bench contract): 3840x2176, SR 64
+    W, H, N_REFS, SEARCH_RANGE = 3840, 2176, 5, 64
 MBS = (W // 16) * (H // 16)                      # 8160
 LAMBDA = (334459, 334459, 334459)               # QP 28 P-slice lambda factors of the reference run (trace of bin/encoder.cfg)
 P_POS = (2 * SEARCH_RANGE + 1) ** 2              # 4225 search positions
 LANE_OPS_PER_JOB = 212 * P_POS                   # 64 VABSDIFF4 + 25 adds + 3*41 cost ops per position
 SAD_OPS_PER_JOB = 64 * P_POS
 METRIC = "1080p FS-ME+QPel macroblocks/s (SR32, 5 refs)"
+WORKLOAD = "1080p_sr32_5ref_allpartitions_qpel" if SEARCH_RANGE == 32 else "4k_sr64_5ref_allpartitions_qpel (side measurement)"
 UNIT = "MB/s"
 
 
@@ -207,7 +210,7 @@ def reference_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "1080p_sr32_5ref_allpartitions_qpel", "width": W, "height": H, "search_range": SEARCH_RANGE,
+            "config": {"workload": WORKLOAD, "width": W, "height": H, "search_range": SEARCH_RANGE,
                        "refs": N_REFS, "note": "per step every host core runs the unmodified lencod on I+P (1 reference); "
                                                "MB/s = cores * 8160 (MB,ref) / 5 refs / mean ME seconds (encoder's own ME timer)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
@@ -408,7 +411,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
-                "config": {"workload": "1080p_sr32_5ref_allpartitions_qpel", "width": W, "height": H, "search_range": SEARCH_RANGE,
+                "config": {"workload": WORKLOAD, "width": W, "height": H, "search_range": SEARCH_RANGE,
                            "refs": N_REFS, "macroblocks_per_step": MBS, "jobs_per_step": n_jobs, "partitions": 41,
                            "metrics": "SAD fpel / SATD hpel,qpel", "parallelism": "gop-sharded x%d, no collective" % world,
                            "l2": "256 MB write between timed steps (L2 flush) and ~250 MB working set per step",
