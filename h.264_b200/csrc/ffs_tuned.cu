@@ -474,7 +474,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     const int job_id = (int)blockIdx.x + it * (int)gridDim.x;
     const uint32_t *jw = sm.job[slot];
     // prefetch: window + macroblock of the next job (TMA), descriptor of the one after (registers -> shared at the end)
-    if (tid == 0 && use_tma && it + 1 < n_mine) issue_loads((it + 1) % 3, buf ^ 1);
+    if (tid == 32 * (it & (G::NW - 1)) && use_tma && it + 1 < n_mine) issue_loads((it + 1) % 3, buf ^ 1);   // rotating warp
     uint32_t pf = 0;
     if (tid < JW && it + 2 < n_mine) pf = jobs[((size_t)job_id + 2 * (size_t)gridDim.x) * JW + tid];
 
@@ -570,12 +570,12 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     sweep4<R, 2, 2>(rg, t, row0, 2 * R + 8);
     sweep4<R, 2, 3>(rg, t, row0, 2 * R + 12);
 
-    // ---- last window column: pair i scores (2R, i); (2R, 2R) is scored by warp 0
+    // ---- last window column: pair i scores (2R, i); (2R, 2R) is scored by one warp (all its pairs, same result)
     {
       const unsigned cyh = smem_u32(&sm.cyt[0][t.h][0]), la = smem_u32(&sm.ua_last[t.h][0]), spa = smem_u32(sm.sptab);
       const unsigned col = wbase + (unsigned)((2 * R + mis) >> 2) * 4 + 8 * t.h, sh_last = (mis & 3) * 8;
       last_column<R>(rg, t, col, sh_last, cyh, la, spa, dx);
-      if (warp == 0) last_column<R>(rg, t, col, sh_last, cyh, la, spa, 2 * R);
+      if (warp == (it & (G::NW - 1))) last_column<R>(rg, t, col, sh_last, cyh, la, spa, 2 * R);   // rotates over the sub-partitions
     }
 
     // ---- minima over the CTA

@@ -49,7 +49,7 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
 
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
-@pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0"])
+@pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0", "yuv444_3ref_bframes", "sr64_2ref"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -64,6 +64,15 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=352", "-p", "SourceHeight=288",
                 "-p", "FramesToBeEncoded=4", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=32",
                 "-p", "NumberReferenceFrames=5", "-p", "LevelIDC=51"]
+    elif case == "yuv444_3ref_bframes":
+        # BASELINE config 4 on the reference's own 4:4:4 fixture: High 4:4:4, I-B-P with bi-predictive ME, 3 references
+        args = ["-d", "encoder.cfg", "-p", "InputFile=foreman_part_qcif_444.yuv", "-p", "YUVFormat=3", "-p", "ProfileIDC=244",
+                "-p", "NumberReferenceFrames=3"]
+    elif case == "sr64_2ref":
+        # the search range of BASELINE config 5 (4K), on a QCIF clip so that the CPU side finishes in seconds
+        args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
+                "-p", "FramesToBeEncoded=3", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=64",
+                "-p", "NumberReferenceFrames=2", "-p", "LevelIDC=51"]
     else:
         args = ["-d", "encoder_baseline.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
                 "-p", "FramesToBeEncoded=3", "-p", "FrameSkip=0", "-p", "RDOptimization=0", "-p", "RestrictSearchRange=0",
