@@ -2,7 +2,8 @@
 //
 // Same results as me_subpel_batch_kernel (subpel.cu), i.e. as SubPelBlockMotionSearch (reference
 // lencod/src/me_fullsearch.c:341-511) with computeSATD / HadamardSAD4x4 (lencod/src/me_distortion.c:657, :182), for
-// MEDistortionHPel = MEDistortionQPel = 2 and Transform8x8Mode = 0.  Everything else goes through subpel.cu.
+// MEDistortionHPel = MEDistortionQPel = 2; with Transform8x8Mode the block types 1..4 use HadamardSAD8x8 (me_distortion.c:272,
+// test8x8transform, mv-search.c:640).  SAD / SSE sub-pel metrics go through subpel.cu.
 //
 //  * Persistent CTAs of 128 threads (6 per SM), one (macroblock, list, ref) job at a time.
 //  * The reference samples of a job come from ONE TMA box: a 48 x 33 pixel region of all 16 quarter-pel planes
@@ -11,8 +12,8 @@
 //    that vector and whose 4x4 tiles are not touched by the origin clamp of UMVLine4X (refbuf.c:37); a partition for
 //    which this does not hold (checked exactly) reads its tiles from global memory with the clamp instead.  The
 //    region of the next job is requested as soon as the last tile of the current one has been read.
-//  * Work unit: one 4x4 transform tile of one candidate of one block type: 7 x 16 x 9 (8) units per half (quarter) pel
-//    stage, 128 per round.  Lanes are ordered (type, candidate, tile) with the tiles of one partition adjacent, so a
+//  * Work unit: one transform tile (4x4, or 8x8 for block types 1..4 with Transform8x8Mode) of one candidate of one block
+//    type: 7 x 16 x 9 (8) 4x4 units per half (quarter) pel stage, 128 per round.  Lanes are ordered (type, candidate, tile) with the tiles of one partition adjacent, so a
 //    partition's SATD is a segmented butterfly sum over 1..16 lanes -- no atomics -- and the lane that ends up with the sum
 //    adds the motion-vector rate and stores the cost; one thread per partition then replays the reference's sequential
 //    first-strict-minimum scan (me_fullsearch.c:423-449, :482-502).
@@ -31,8 +32,8 @@ constexpr int RW = 48;                      // region row pitch (bytes): 2*RD + 
 constexpr int RH = 2 * RD + 17;             // region rows
 constexpr int REGION_BYTES = RW * RH * 16;  // all 16 planes
 constexpr int NT = 128;
-constexpr int UNITS = 1;                    // work units per thread and round (2 measured slower: 0.92 vs 0.88 ms per 1080p picture)
-constexpr unsigned BIAS = 0x1000u, BIAS2 = 0x10001000u;
+constexpr unsigned BIAS = 0x1000u, BIAS2 = 0x10001000u;       // 4x4 Hadamard: |coefficient| <= 16 * 255 < 4096
+constexpr unsigned BIAS8 = 0x4000u, BIAS82 = 0x40004000u;     // 8x8 Hadamard: |coefficient before the last stage| <= 32 * 255 < 16384
 
 // slot q of a (type, candidate) group of 16 lanes -> raster tile 4*ty+tx / partition number (ABI order); the tiles of a
 // partition are adjacent and aligned to the partition's tile count
@@ -53,6 +54,10 @@ __constant__ uint8_t c_part[7][16] = {
   { 17, 17, 18, 18, 19, 19, 20, 20, 21, 21, 22, 22, 23, 23, 24, 24 },
   { 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40 } };
 __constant__ uint8_t c_group[7] = { 16, 8, 8, 4, 2, 2, 1 };     // tiles per partition
+// the same for the 8x8 tiles (quadrants 2*qy+qx) of block types 1..4
+__constant__ uint8_t c_quad[4][4] = { { 0, 1, 2, 3 }, { 0, 1, 2, 3 }, { 0, 2, 1, 3 }, { 0, 1, 2, 3 } };
+__constant__ uint8_t c_part8[4][4] = { { 0, 0, 0, 0 }, { 1, 1, 2, 2 }, { 3, 3, 4, 4 }, { 5, 6, 7, 8 } };
+__constant__ uint8_t c_group8[4] = { 4, 2, 2, 1 };
 // spiral entries 0..8 (mv-search.c:366-393 with range 1)
 __constant__ int8_t c_spx[9] = { 0, 0, 0, -1, 1, -1, 1, -1, 1 };
 __constant__ int8_t c_spy[9] = { 0, -1, 1, -1, -1, 0, 0, 1, 1 };
@@ -60,12 +65,14 @@ __constant__ int8_t c_spy[9] = { 0, -1, 1, -1, -1, 0, 0, 1, 1 };
 struct __align__(128) Smem {
   uint8_t  region[REGION_BYTES + 128];      // [plane][RH][RW]
   uint32_t curpk[16][8];                    // per tile: rows 0..3 x {pixels (0,2), pixels (1,3)} as biased 16-bit lanes
+  uint32_t cur8[4][8][4];                   // per 8x8 quadrant and row: pixels (0,2), (1,3), (4,6), (5,7), bias BIAS8
   uint32_t job[48];                         // me_mb_job
   int      cost[ME_NUM_PARTITIONS][9];
   int      mv[ME_NUM_PARTITIONS][2];        // current best vector, quarter pel
   int      mn[ME_NUM_PARTITIONS];           // its cost
   int      okp[ME_NUM_PARTITIONS];          // partition served by the staged region (else: global reads with the clamp)
-  uint32_t itab[2][7 * 16 * 9];             // per stage, work unit -> partition | tile << 8 | candidate << 12 | (tiles per partition - 1) << 16
+  uint32_t itab[2][7 * 16 * 9];             // per stage, work unit -> partition | tile << 8 | candidate << 12 | (tiles per partition - 1) << 16;
+                                            // with the 8x8 transform: the 4x4 units of types 5..7 first, then the 8x8 units of types 1..4
   unsigned long long mbar;
 };
 
@@ -128,6 +135,44 @@ __device__ __forceinline__ int satd4x4(const unsigned r[4], const uint4 c01, con
   return (int)((acc + 1) >> 1);
 }
 
+__device__ __forceinline__ unsigned padd8(unsigned a, unsigned b) { return a + b - BIAS82; }
+__device__ __forceinline__ unsigned psub8(unsigned a, unsigned b) { return a - b + BIAS82; }
+
+// SATD of one 8x8 tile (HadamardSAD8x8, me_distortion.c:272-343): ref rows as two words (pixels 0..3, 4..7), cur rows from
+// shared memory as four biased lane pairs (0,2) (1,3) (4,6) (5,7).  Index bits 0 and 2 of the row transform pair whole
+// registers, bit 1 pairs the two lanes of a register and is folded into the absolute sum like in the 4x4 case.
+__device__ __forceinline__ int satd8x8(const unsigned rl[8], const unsigned rr[8], const uint32_t *curp)
+{
+  unsigned x[8][4];
+#pragma unroll
+  for (int y = 0; y < 8; y++) {
+    const uint4 c = *reinterpret_cast<const uint4 *>(curp + 4 * y);
+    const unsigned el = c.x - __byte_perm(rl[y], 0, 0x4240), ol = c.y - __byte_perm(rl[y], 0, 0x4341);
+    const unsigned er = c.z - __byte_perm(rr[y], 0, 0x4240), orr = c.w - __byte_perm(rr[y], 0, 0x4341);
+    const unsigned a0 = padd8(el, ol), a1 = psub8(el, ol), a2 = padd8(er, orr), a3 = psub8(er, orr);
+    x[y][0] = padd8(a0, a2); x[y][1] = psub8(a0, a2); x[y][2] = padd8(a1, a3); x[y][3] = psub8(a1, a3);
+  }
+  unsigned acc = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    unsigned v[8];
+#pragma unroll
+    for (int y = 0; y < 8; y++) v[y] = x[y][j];
+#pragma unroll
+    for (int st = 1; st < 8; st <<= 1)
+#pragma unroll
+      for (int y = 0; y < 8; y++)
+        if (!(y & st)) { const unsigned a = v[y], b = v[y + st]; v[y] = padd8(a, b); v[y + st] = psub8(a, b); }
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+      const unsigned lo = v[y] & 0xffffu, hi = v[y] >> 16;         // u + B, v + B
+      acc = __usad(lo, hi, acc);                                   // |u - v|
+      acc = __usad(lo + hi, 2 * BIAS8, acc);                       // |u + v|
+    }
+  }
+  return (int)((acc + 2) >> 2);
+}
+
 struct JobView { int opix_x, opix_y, list, ref, slice_type; };
 __device__ __forceinline__ JobView job_view(const uint32_t *w)
 {
@@ -140,7 +185,8 @@ __device__ __forceinline__ JobView job_view(const uint32_t *w)
 constexpr int TUNED_MAX_REFS = 8;
 struct PlaneMaps { CUtensorMap m[2 * TUNED_MAX_REFS]; };
 
-__global__ void __launch_bounds__(NT, 6)
+template <bool T8>     // T8: Transform8x8Mode (block types 1..4 scored with the 8x8 Hadamard transform)
+__global__ void __launch_bounds__(NT, T8 ? 4 : 6)
 me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                        const __grid_constant__ PlaneMaps maps, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                        const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out)
@@ -148,7 +194,7 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
   constexpr int JW = sizeof(MeJob) / 4;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int n_mine = (n_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (n_mine <= 0) return;
   const unsigned bar = smem_u32(&sm.mbar);
@@ -159,10 +205,17 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
   // work-unit tables (depend on the configuration only): lanes ordered (type, candidate, tile slot)
   for (int stage = 0; stage < 2; stage++) {
     const int first = stage == 0 ? cfg.start_hp : cfg.start_qp, nc = 9 - first;
-    for (int i = tid; i < 7 * 16 * nc; i += NT) {
-      const int q = i & 15, gi = i >> 4, ti = gi / nc, c = gi - ti * nc + first;      // ti = block type - 1
+    const int t0 = T8 ? 4 : 0;                                   // first block type (minus 1) scored with 4x4 tiles
+    const int n4 = (7 - t0) * 16 * nc;
+    for (int i = tid; i < n4; i += NT) {
+      const int q = i & 15, gi = i >> 4, ti = t0 + gi / nc, c = gi % nc + first;      // ti = block type - 1
       sm.itab[stage][i] = (uint32_t)c_part[ti][q] | ((uint32_t)c_tile[ti][q] << 8) | ((uint32_t)c << 12) | ((uint32_t)(c_group[ti] - 1) << 16);
     }
+    if (T8)
+      for (int i = tid; i < 4 * 4 * nc; i += NT) {
+        const int q = i & 3, gi = i >> 2, ti = gi / nc, c = gi % nc + first;
+        sm.itab[stage][n4 + i] = (uint32_t)c_part8[ti][q] | ((uint32_t)c_quad[ti][q] << 8) | ((uint32_t)c << 12) | ((uint32_t)(c_group8[ti] - 1) << 16);
+      }
   }
   __syncthreads();
 
@@ -203,6 +256,12 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
       const int tile = tid >> 3, k = tid & 7, y = k >> 1, odd = k & 1;
       const uint8_t *p = cur + (size_t)(jv.opix_y + 4 * (tile >> 2) + y) * cur_pitch + jv.opix_x + 4 * (tile & 3) + odd;
       sm.curpk[tile][k] = ((unsigned)p[0] | ((unsigned)p[2] << 16)) + BIAS2;
+      if (T8) {
+        // 8x8 quadrants: thread -> (quadrant, row, lane pair)
+        const int quad = tid >> 5, y8 = (tid >> 2) & 7, j = tid & 3;
+        const uint8_t *p8 = cur + (size_t)(jv.opix_y + 8 * (quad >> 1) + y8) * cur_pitch + jv.opix_x + 8 * (quad & 1) + 4 * (j >> 1) + (j & 1);
+        sm.cur8[quad][y8][j] = ((unsigned)p8[0] | ((unsigned)p8[2] << 16)) + BIAS82;
+      }
     }
     int Xr, Yr;
     region_origin(sm.job[0], ((unsigned)(sm.mv[0][0] >> 2) & 0xffffu) | ((unsigned)(sm.mv[0][1] >> 2) << 16), Xr, Yr);
@@ -225,61 +284,90 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
       const int first = stage == 0 ? cfg.start_hp : cfg.start_qp;
       const int nc = 9 - first;
       if (stage == 1 && !cfg.start_qp && tid < ME_NUM_PARTITIONS) sm.mn[tid] = ME_INT_MAX;   // me_fullsearch.c:456-457
-      const int total = 7 * 16 * nc;
-      for (int base = 0; base < total; base += UNITS * NT) {
-        struct Unit { bool active; int p, c, g, q, mvx, mvy; unsigned r[4]; uint4 c01, c23; } un[UNITS];
-        const bool two = UNITS == 2 && base + NT < total;            // uniform: the last round may hold one unit per thread only
+      const int total = (T8 ? 3 : 7) * 16 * nc;              // 4x4 units
+      for (int base = 0; base < total; base += NT) {
+        const int i = base + tid;
+        const bool active = i < total;
+        const int ii = active ? i : 0;
+        const uint32_t e = sm.itab[stage][ii];
+        const int q = ii & 15, p = (int)(e & 0xffu), c = (int)((e >> 12) & 0xfu), g = (int)(e >> 16) + 1, tile = (int)((e >> 8) & 0xfu);
+        const int mvx = sm.mv[p][0] + step * c_spx[c], mvy = sm.mv[p][1] + step * c_spy[c];
+        const int x4 = ((jv.opix_x + 4 * (tile & 3) + ME_PAD) << 2) + mvx, y4 = ((jv.opix_y + 4 * (tile >> 2) + ME_PAD) << 2) + mvy;
+        // tiles of the lower macroblock half take their rows in the order 2, 3, 0, 1 (the Hadamard sum does not change under a
+        // cyclic row shift): the lanes of a partition then hit four different bank groups instead of two
+        const int rot = (tile >> 2) & 2;
+        unsigned r[4];
+        if (sm.okp[p]) {
+          const unsigned a = smem_u32(sm.region) + (unsigned)((((y4 & 3) << 2) | (x4 & 3)) * (RW * RH) + ((y4 >> 2) - Yr) * RW + ((x4 >> 2) - Xr));
+          const unsigned a4 = a & ~3u, sh = (a & 3u) * 8;
+          const unsigned bA = a4 + rot * RW, bB = a4 + (2 - rot) * RW;
 #pragma unroll
-        for (int k = 0; k < UNITS; k++) {
-          Unit &u = un[k];
-          if (k == 1 && !two) break;
-          const int i = base + k * NT + tid;
-          u.active = i < total;
-          const int ii = u.active ? i : 0;
-          const uint32_t e = sm.itab[stage][ii];
-          u.q = ii & 15; u.p = (int)(e & 0xffu); u.c = (int)((e >> 12) & 0xfu); u.g = (int)(e >> 16) + 1;
-          const int tile = (int)((e >> 8) & 0xfu);
-          u.mvx = sm.mv[u.p][0] + step * c_spx[u.c]; u.mvy = sm.mv[u.p][1] + step * c_spy[u.c];
-          const int x4 = ((jv.opix_x + 4 * (tile & 3) + ME_PAD) << 2) + u.mvx, y4 = ((jv.opix_y + 4 * (tile >> 2) + ME_PAD) << 2) + u.mvy;
-          // tiles of the lower macroblock half take their rows in the order 2, 3, 0, 1 (the Hadamard sum does not change under a
-          // cyclic row shift): the lanes of a partition then hit four different bank groups instead of two
-          const int rot = (tile >> 2) & 2;
-          if (sm.okp[u.p]) {
+          for (int y = 0; y < 4; y++) {
+            const unsigned ra = (y < 2 ? bA : bB) + (y & 1) * RW;
+            unsigned w0, w1;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(ra + 4));
+            r[y] = __funnelshift_r(w0, w1, sh);
+          }
+        } else {
+          const uint8_t *rp = me_umv_ptr(ref, y4, x4);     // per-tile origin clamp, as computeSATD does (me_distortion.c:657)
+#pragma unroll
+          for (int y = 0; y < 4; y++) {
+            const uint8_t *b = rp + (size_t)((y + rot) & 3) * ref.pitch;
+            r[y] = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
+          }
+        }
+        const uint4 c01 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][rot ? 4 : 0]);
+        const uint4 c23 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][rot ? 0 : 4]);
+        int v = satd4x4(r, c01, c23);
+        // segmented sum over the g lanes of the partition
+#pragma unroll
+        for (int sft = 1; sft < 16; sft <<= 1) {
+          const int o = __shfl_xor_sync(0xffffffffu, v, sft);
+          if (sft < g) v += o;
+        }
+        if (active && (q & (g - 1)) == 0)
+          sm.cost[p][c] = v + me_mv_cost(lam, mvx, mvy, (int)(int16_t)(sm.job[3 + p] & 0xffffu), (int)(int16_t)(sm.job[3 + p] >> 16));
+      }
+      if (T8) {
+        const int total8 = 4 * 4 * nc;                         // 8x8 units of block types 1..4
+        for (int base = 0; base < total8; base += NT) {
+          const int i = base + tid;
+          const bool active = i < total8;
+          const int ii = active ? i : 0;
+          const uint32_t e = sm.itab[stage][total + ii];
+          const int q = ii & 3, p = (int)(e & 0xffu), c = (int)((e >> 12) & 0xfu), g = (int)(e >> 16) + 1, quad = (int)((e >> 8) & 0xfu);
+          const int mvx = sm.mv[p][0] + step * c_spx[c], mvy = sm.mv[p][1] + step * c_spy[c];
+          const int x4 = ((jv.opix_x + 8 * (quad & 1) + ME_PAD) << 2) + mvx, y4 = ((jv.opix_y + 8 * (quad >> 1) + ME_PAD) << 2) + mvy;
+          unsigned rl[8], rr[8];
+          if (sm.okp[p]) {
             const unsigned a = smem_u32(sm.region) + (unsigned)((((y4 & 3) << 2) | (x4 & 3)) * (RW * RH) + ((y4 >> 2) - Yr) * RW + ((x4 >> 2) - Xr));
             const unsigned a4 = a & ~3u, sh = (a & 3u) * 8;
-            const unsigned bA = a4 + rot * RW, bB = a4 + (2 - rot) * RW;
 #pragma unroll
-            for (int y = 0; y < 4; y++) {
-              const unsigned ra = (y < 2 ? bA : bB) + (y & 1) * RW;
-              unsigned w0, w1;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(ra + 4));
-              u.r[y] = __funnelshift_r(w0, w1, sh);
+            for (int y = 0; y < 8; y++) {
+              unsigned w0, w1, w2;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a4 + y * RW));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(a4 + y * RW + 4));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(a4 + y * RW + 8));
+              rl[y] = __funnelshift_r(w0, w1, sh); rr[y] = __funnelshift_r(w1, w2, sh);
             }
           } else {
-            const uint8_t *rp = me_umv_ptr(ref, y4, x4);   // per-tile origin clamp, as computeSATD does (me_distortion.c:657)
+            const uint8_t *rp = me_umv_ptr(ref, y4, x4);   // per-tile (8x8) origin clamp
 #pragma unroll
-            for (int y = 0; y < 4; y++) {
-              const uint8_t *b = rp + (size_t)((y + rot) & 3) * ref.pitch;
-              u.r[y] = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
+            for (int y = 0; y < 8; y++) {
+              const uint8_t *b = rp + (size_t)y * ref.pitch;
+              rl[y] = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
+              rr[y] = (unsigned)b[4] | ((unsigned)b[5] << 8) | ((unsigned)b[6] << 16) | ((unsigned)b[7] << 24);
             }
           }
-          u.c01 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][rot ? 4 : 0]);
-          u.c23 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][rot ? 0 : 4]);
-        }
+          int v = satd8x8(rl, rr, &sm.cur8[quad][0][0]);
 #pragma unroll
-        for (int k = 0; k < UNITS; k++) {
-          Unit &u = un[k];
-          if (k == 1 && !two) break;
-          int v = satd4x4(u.r, u.c01, u.c23);
-          // segmented sum over the g lanes of the partition
-#pragma unroll
-          for (int sft = 1; sft < 16; sft <<= 1) {
+          for (int sft = 1; sft < 4; sft <<= 1) {
             const int o = __shfl_xor_sync(0xffffffffu, v, sft);
-            if (sft < u.g) v += o;
+            if (sft < g) v += o;
           }
-          if (u.active && (u.q & (u.g - 1)) == 0)
-            sm.cost[u.p][u.c] = v + me_mv_cost(lam, u.mvx, u.mvy, (int)(int16_t)(sm.job[3 + u.p] & 0xffffu), (int)(int16_t)(sm.job[3 + u.p] >> 16));
+          if (active && (q & (g - 1)) == 0)
+            sm.cost[p][c] = v + me_mv_cost(lam, mvx, mvy, (int)(int16_t)(sm.job[3 + p] & 0xffffu), (int)(int16_t)(sm.job[3 + p] >> 16));
         }
       }
       __syncthreads();
@@ -345,20 +433,25 @@ extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const
                                             const MeResultInt *in_int, MeResult *out, cudaStream_t st)
 {
   if (!plane_maps || n_refs0 > TUNED_MAX_REFS || n_refs1 > TUNED_MAX_REFS) return 0;
-  if (cfg->metric[1] != 2 || cfg->metric[2] != 2 || cfg->transform8x8) return 0;
+  if (cfg->metric[1] != 2 || cfg->metric[2] != 2) return 0;
   static int sms = 0;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(me_subpel_tuned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaFuncSetAttribute(me_subpel_tuned_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaFuncSetAttribute(me_subpel_tuned_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   }
   PlaneMaps pm;
   for (int l = 0; l < 2; l++)
     memcpy(&pm.m[l * TUNED_MAX_REFS], (const unsigned char *)plane_maps + (size_t)l * ME_MAX_REFS * 128, sizeof(CUtensorMap) * TUNED_MAX_REFS);
-  int grid = sms * 6;
+  int grid = sms * (cfg->transform8x8 ? 4 : 6);
   if (grid > n_jobs) grid = n_jobs;
-  me_subpel_tuned_kernel<<<grid, NT, sizeof(Smem), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
-                                                         *cfg, in_int, out);
+  if (cfg->transform8x8)
+    me_subpel_tuned_kernel<true><<<grid, NT, sizeof(Smem), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
+                                                                 *cfg, in_int, out);
+  else
+    me_subpel_tuned_kernel<false><<<grid, NT, sizeof(Smem), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
+                                                                  *cfg, in_int, out);
   return 1;
 }
