@@ -251,7 +251,9 @@ def main():
     frames = synth.luma_frames(W, H, n_frames, seed=1234 + 17 * rank)
     jobs_np = synth.synthetic_jobs(W, H, N_REFS, LAMBDA, seed=21 + rank)
     n_jobs = len(jobs_np)
-    me = MeCuda(W, H, search_range=SEARCH_RANGE, max_num_references=N_REFS, device=local)
+    # ME_BENCH_T8=1: side measurement with Transform8x8Mode (High profile: 8x8 Hadamard for block types 1..4)
+    me = MeCuda(W, H, search_range=SEARCH_RANGE, max_num_references=N_REFS, device=local,
+                transform8x8=1 if os.environ.get("ME_BENCH_T8", "") == "1" else 0)
     stream = torch.cuda.ExternalStream(me.stream(), device=dev)
 
     # device-resident inputs

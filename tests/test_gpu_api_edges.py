@@ -1,0 +1,102 @@
+"""GPU: error behaviour and edge cases of the C ABI (the reference's failure mode is error(text, code): loud, never silent)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg(me_lib_path):
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import h264_b200_pkg  # noqa: F401
+    import h264_b200
+    return h264_b200
+
+
+def test_init_rejects_unsupported_configurations(pkg):
+    from h264_b200 import MeCuda, MeCudaError
+    for kw in (dict(width=180, height=144), dict(width=176, height=150), dict(width=0, height=144)):
+        with pytest.raises(MeCudaError):
+            MeCuda(kw["width"], kw["height"])
+    with pytest.raises(MeCudaError):
+        MeCuda(176, 144, search_range=65)
+    with pytest.raises(MeCudaError):
+        MeCuda(176, 144, max_num_references=33)
+    with pytest.raises(MeCudaError):
+        MeCuda(176, 144, device=99)
+
+
+def test_calls_before_init_and_bad_arguments_fail_loudly(pkg):
+    from h264_b200 import MeCuda, MeCudaError, synth
+    w, h = 176, 144
+    frames = synth.luma_frames(w, h, 2)
+    with MeCuda(w, h, max_num_references=2) as me:
+        hd = me.ref_create(frames[0])
+        with pytest.raises(MeCudaError):
+            me.ref_create(frames[0][:, :160])                    # picture size differs from the initialised one
+        with pytest.raises(MeCudaError):
+            me.set_ref_list(0, [hd, 12345])                      # unknown handle
+        me.set_ref_list(0, [hd])
+        me.set_current(frames[1])
+        jobs = synth.synthetic_jobs(w, h, 1, (334459,) * 3, seed=1)
+        bad = jobs.copy(); bad["ref"][5] = 1                     # reference index beyond the list
+        with pytest.raises(MeCudaError):
+            me.frame_search(bad)
+        bad = jobs.copy(); bad["opix_x"][3] = 8                  # not a macroblock origin
+        with pytest.raises(MeCudaError):
+            me.frame_search(bad)
+        bad = jobs.copy(); bad["opix_y"][7] = h                  # outside the picture
+        with pytest.raises(MeCudaError):
+            me.frame_search(bad)
+        out = me.frame_search(jobs[:0])                          # empty batch: nothing to do, no error
+        assert len(out) == 0
+        me.ref_destroy(hd)
+        with pytest.raises(MeCudaError):
+            me.ref_destroy(hd)                                   # double free
+        with pytest.raises(MeCudaError):
+            me.frame_search(jobs)                                # the list now holds a destroyed picture
+    me.close()                                                   # idempotent
+    with pytest.raises(MeCudaError):
+        me.set_current(frames[1])                                # after shutdown
+
+
+def test_single_job_and_ragged_batches(pkg, oracle_lib):
+    """batches of 1, 2, 3, 127, 129 jobs (fewer jobs than CTAs, odd tails of the persistent kernels)"""
+    from h264_b200 import MeCuda, synth
+    ob = oracle_lib
+    w, h = 352, 288
+    frames = synth.luma_frames(w, h, 2)
+    cfg = ob.make_cfg()
+    jobs = synth.synthetic_jobs(w, h, 1, (334459,) * 3, seed=9, max_pmv=30)
+    ref = ob.Ref(frames[0])
+    cur = np.ascontiguousarray(frames[1])
+    with MeCuda(w, h, max_num_references=1) as me:
+        me.set_ref_list(0, [me.ref_create(frames[0])])
+        me.set_current(frames[1])
+        for n in (1, 2, 3, 127, 129):
+            sel = jobs[200:200 + n]
+            out, out_int = me.frame_search(sel, want_int=True)
+            exp, exp_int = ob.mb_search(cfg, cur, ref, sel)
+            assert np.array_equal(out_int, exp_int), n
+            assert np.array_equal(out, exp), n
+    ref.close()
+
+
+def test_reference_slot_reuse_and_in_place_update(pkg, oracle_lib):
+    """a decoded-picture-buffer style life cycle: create, destroy, re-create in the freed slot, update in place"""
+    from h264_b200 import MeCuda, synth
+    ob = oracle_lib
+    w, h = 176, 144
+    frames = synth.luma_frames(w, h, 4)
+    with MeCuda(w, h, max_num_references=2) as me:
+        a = me.ref_create(frames[0]); b = me.ref_create(frames[1])
+        me.ref_destroy(a)
+        c = me.ref_create(frames[2])
+        assert c == a                                            # the freed slot is reused
+        r2 = ob.Ref(frames[2])
+        assert np.array_equal(me.ref_planes(c), r2.planes())
+        me.ref_update(b, frames[3])
+        r3 = ob.Ref(frames[3])
+        assert np.array_equal(me.ref_planes(b), r3.planes())
+        r2.close(); r3.close()
