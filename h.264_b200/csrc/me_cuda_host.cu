@@ -225,7 +225,7 @@ int create_ref_common(const uint8_t *d_luma, int stride, int w, int h, cudaStrea
   d.w = w; d.h = h; d.wp = w + 2 * ME_PAD; d.hp = h + 2 * ME_PAD;
   d.pitch = align_up(d.wp, 128);
   d.plane_stride = (size_t)d.pitch * d.hp;
-  d.spad = g.cfg.search_range + 32;
+  d.spad = (g.cfg.search_range + 32 + 1) & ~1;      // even: the search plane is written four bytes at a time
   d.sw = w + 2 * d.spad; d.sh = h + 2 * d.spad;
   d.spitch = align_up(d.sw, 128);
   CK(cudaMalloc((void **)&r.planes, d.plane_stride * 16));

@@ -62,46 +62,60 @@ me_planes_kernel(const uint8_t *__restrict__ src, int src_stride, int w, int h,
     Js[ly][lx] = (uint8_t)clip255((u + 512) >> 10);
   }
   __syncthreads();
-  // write the 16 planes; one thread per output pixel of the tile, 4 rows per pass
-  for (int i = tid; i < TH * TW; i += blockDim.x) {
-    int ly = i / TW, lx = i - ly * TW;
-    int y = y0 + ly, x = x0 + lx;
+  // write the 16 planes: one thread per 4 consecutive pixels, one 32-bit store per plane (wp is a multiple of 4 and the
+  // plane pitch a multiple of 128, so a group never straddles the plane edge and every store is aligned)
+  for (int i = tid; i < TH * (TW / 4); i += blockDim.x) {
+    int ly = i / (TW / 4), lx0 = (i - ly * (TW / 4)) * 4;
+    int y = y0 + ly, x = x0 + lx0;
     if (y >= hp || x >= wp) continue;
-    int lx1 = (x + 1 > wp - 1) ? lx : lx + 1;   // right neighbour, clamped at the plane edge
-    int ly1 = (y + 1 > hp - 1) ? ly : ly + 1;   // lower neighbour
-    int g = Gs[ly + 2][lx + 2], b = Bs[ly][lx], hv = Hs[ly][lx], j = Js[ly][lx];
-    int g_r = Gs[ly + 2][lx1 + 2], h_r = Hs[ly][lx1];
-    int g_d = Gs[ly1 + 2][lx + 2], b_d = Bs[ly1][lx];
-    size_t o = (size_t)y * pitch + x;
-    uint8_t *P = planes + o;
-    P[0 * plane_stride]  = (uint8_t)g;
-    P[1 * plane_stride]  = (uint8_t)((g + b + 1) >> 1);
-    P[2 * plane_stride]  = (uint8_t)b;
-    P[3 * plane_stride]  = (uint8_t)((b + g_r + 1) >> 1);
-    P[4 * plane_stride]  = (uint8_t)((g + hv + 1) >> 1);
-    P[5 * plane_stride]  = (uint8_t)((b + hv + 1) >> 1);
-    P[6 * plane_stride]  = (uint8_t)((b + j + 1) >> 1);
-    P[7 * plane_stride]  = (uint8_t)((b + h_r + 1) >> 1);
-    P[8 * plane_stride]  = (uint8_t)hv;
-    P[9 * plane_stride]  = (uint8_t)((hv + j + 1) >> 1);
-    P[10 * plane_stride] = (uint8_t)j;
-    P[11 * plane_stride] = (uint8_t)((j + h_r + 1) >> 1);
-    P[12 * plane_stride] = (uint8_t)((hv + g_d + 1) >> 1);
-    P[13 * plane_stride] = (uint8_t)((hv + b_d + 1) >> 1);
-    P[14 * plane_stride] = (uint8_t)((j + b_d + 1) >> 1);
-    P[15 * plane_stride] = (uint8_t)((b_d + h_r + 1) >> 1);
+    int ly1 = (y + 1 > hp - 1) ? ly : ly + 1;   // lower neighbour, clamped at the plane edge
+    uint32_t o[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) o[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int lx = lx0 + k;
+      int lx1 = (x + k + 1 > wp - 1) ? lx : lx + 1;   // right neighbour, clamped at the plane edge
+      int g = Gs[ly + 2][lx + 2], b = Bs[ly][lx], hv = Hs[ly][lx], j = Js[ly][lx];
+      int g_r = Gs[ly + 2][lx1 + 2], h_r = Hs[ly][lx1];
+      int g_d = Gs[ly1 + 2][lx + 2], b_d = Bs[ly1][lx];
+      const int sh = 8 * k;
+      o[0]  |= (uint32_t)g << sh;
+      o[1]  |= (uint32_t)((g + b + 1) >> 1) << sh;
+      o[2]  |= (uint32_t)b << sh;
+      o[3]  |= (uint32_t)((b + g_r + 1) >> 1) << sh;
+      o[4]  |= (uint32_t)((g + hv + 1) >> 1) << sh;
+      o[5]  |= (uint32_t)((b + hv + 1) >> 1) << sh;
+      o[6]  |= (uint32_t)((b + j + 1) >> 1) << sh;
+      o[7]  |= (uint32_t)((b + h_r + 1) >> 1) << sh;
+      o[8]  |= (uint32_t)hv << sh;
+      o[9]  |= (uint32_t)((hv + j + 1) >> 1) << sh;
+      o[10] |= (uint32_t)j << sh;
+      o[11] |= (uint32_t)((j + h_r + 1) >> 1) << sh;
+      o[12] |= (uint32_t)((hv + g_d + 1) >> 1) << sh;
+      o[13] |= (uint32_t)((hv + b_d + 1) >> 1) << sh;
+      o[14] |= (uint32_t)((j + b_d + 1) >> 1) << sh;
+      o[15] |= (uint32_t)((b_d + h_r + 1) >> 1) << sh;
+    }
+    uint8_t *P = planes + (size_t)y * pitch + x;
+#pragma unroll
+    for (int k = 0; k < 16; k++) *reinterpret_cast<uint32_t *>(P + (size_t)k * plane_stride) = o[k];
   }
 }
 
-// wide-border integer plane for the search-window tiles
+// wide-border integer plane for the search-window tiles: one thread per 4 consecutive bytes (sw is a multiple of 4)
 __global__ void __launch_bounds__(256)
 me_search_plane_kernel(const uint8_t *__restrict__ src, int src_stride, int w, int h,
                        uint8_t *__restrict__ dst, int spad, int spitch, int sw, int sh)
 {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   int y = blockIdx.y;
   if (x >= sw || y >= sh) return;
-  dst[(size_t)y * spitch + x] = src[(size_t)me_clamp(y - spad, 0, h - 1) * src_stride + me_clamp(x - spad, 0, w - 1)];
+  const uint8_t *row = src + (size_t)me_clamp(y - spad, 0, h - 1) * src_stride;
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) v |= (uint32_t)row[me_clamp(x + k - spad, 0, w - 1)] << (8 * k);
+  *reinterpret_cast<uint32_t *>(dst + (size_t)y * spitch + x) = v;
 }
 
 // JM hands pictures over as 16-bit samples (imgpel = unsigned short); narrow to the 8-bit device layout
@@ -134,7 +148,7 @@ extern "C" void me_launch_planes(const uint8_t *src, int src_stride, int w, int 
   dim3 grid((wp + TW - 1) / TW, (hp + TH - 1) / TH);
   me_planes_kernel<<<grid, 256, 0, st>>>(src, src_stride, w, h, planes, pitch, plane_stride);
   int sw = w + 2 * spad, sh = h + 2 * spad;
-  dim3 g2((sw + 255) / 256, sh);
+  dim3 g2((sw / 4 + 255) / 256, sh);
   me_search_plane_kernel<<<g2, 256, 0, st>>>(src, src_stride, w, h, search, spad, spitch, sw, sh);
 }
 
