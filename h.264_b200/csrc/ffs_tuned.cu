@@ -32,11 +32,11 @@
 //    X0 & ~15; the residue X0 & 15 goes into each thread's word offset and funnel-shift count.
 //
 // ALU-pipe work per search position (both lanes): 64 VABSDIFF4 + 42 VIADDMNMX + 4 SHF + ~10 adds/selects.
-#include <cuda.h>
 #include <cstdlib>
 #include <cstring>
 #include <utility>
 #include "me_common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -85,7 +85,6 @@ template <int R> struct __align__(128) Smem {
   int lut_lambda, lut_valid;
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 // shared-memory loads at [address register + compile-time offset]: the unrolled sweep addresses everything relative to three
 // per-group base registers, so no address arithmetic is issued inside it
 template <int OFF = 0> __device__ __forceinline__ unsigned lds32(unsigned a)
@@ -129,34 +128,6 @@ __device__ __forceinline__ unsigned imad(unsigned a, unsigned m, unsigned c)
 __device__ __forceinline__ int len_class(int d)   // (mvbits(d) - 1) / 2: 0 for 0, floor(log2|d|) + 1 otherwise (mv-search.c:333-341)
 {
   return 32 - __clz(d < 0 ? -d : d);
-}
-
-// ---- mbarrier / TMA ----
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
-{
-  // bounded: a transfer that never completes (bad tensor map) traps instead of hanging the GPU
-#pragma unroll 1
-  for (unsigned spin = 0; spin < (1u << 24); spin++) {
-    unsigned done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int x, int y, unsigned bar)
-{
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
 }
 
 struct Regs {
@@ -436,7 +407,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
   if (tid == 0) {
     mbar_init(smem_u32(&sm.mbar[0]), 1);
     mbar_init(smem_u32(&sm.mbar[1]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_init_fence();
     sm.lut_valid = 0;
   }
   for (int i = tid; i < (int)(sizeof(sm.refs) / 4); i += NT)
@@ -462,7 +433,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     int X0, Y0;
     const bool tma_ok = window_origin(jv, rf, X0, Y0);
     const unsigned bar = smem_u32(&sm.mbar[buf]);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    proxy_fence();
     mbar_expect_tx(bar, 256u + (tma_ok ? (unsigned)(NP * N) : 0u));
     tma_load_2d(smem_u32(sm.cur[buf]), &cur_map, jv.opix_x, jv.opix_y, bar);
     if (tma_ok) tma_load_2d(smem_u32(sm.win[buf]), &win_maps.m[jv.list * TUNED_MAX_REFS + jv.ref], X0 & ~15, Y0, bar);
@@ -604,11 +575,6 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-
 template <int R>
 int launch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps, const void *cur_map,
            const uint8_t *cur_pic, int cur_pitch, const MeCfgDev *cfg, MeResultInt *out, int *deferred, cudaStream_t st)
@@ -643,23 +609,9 @@ int launch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void 
 // A 2-D byte tensor map (row pitch `pitch`, box bw x bh, no swizzle) for cp.async.bulk.tensor; out = 128 bytes, 64-aligned.
 extern "C" int me_make_tensor_map_2d(void *out, const void *base, int w, int h, int pitch, int bw, int bh)
 {
-  if (!g_encode) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return 1;
-    g_encode = (EncodeTiledFn)fn;
-  }
-  CUtensorMap m;
-  cuuint64_t dims[2] = { (cuuint64_t)w, (cuuint64_t)h };
-  cuuint64_t strides[1] = { (cuuint64_t)pitch };
-  cuuint32_t box[2] = { (cuuint32_t)bw, (cuuint32_t)bh };
-  cuuint32_t estr[2] = { 1, 1 };
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return 2;
-  memcpy(out, &m, sizeof m);
-  return 0;
+  const cuuint64_t dims[2] = { (cuuint64_t)w, (cuuint64_t)h }, strides[1] = { (cuuint64_t)pitch };
+  const cuuint32_t box[2] = { (cuuint32_t)bw, (cuuint32_t)bh };
+  return me_encode_tensor_map(out, base, 2, dims, strides, box);
 }
 
 // window height of the tuned kernel for a search range (the TMA box is that many rows of height + 16 bytes), 0 when the

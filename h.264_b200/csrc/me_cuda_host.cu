@@ -30,7 +30,6 @@ struct MeBiFullArgs {
 extern "C" {
 void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t *planes, int pitch, size_t plane_stride,
                       uint8_t *search, int spad, int spitch, cudaStream_t st);
-void me_launch_narrow(const uint16_t *src, int n, uint8_t *dst, cudaStream_t st);
 void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp, uint16_t *dst, cudaStream_t st);
 void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
                                const MeCfgDev *cfg, MeResultInt *out, const int *job_list, cudaStream_t st);

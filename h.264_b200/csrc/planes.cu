@@ -118,14 +118,6 @@ me_search_plane_kernel(const uint8_t *__restrict__ src, int src_stride, int w, i
   *reinterpret_cast<uint32_t *>(dst + (size_t)y * spitch + x) = v;
 }
 
-// JM hands pictures over as 16-bit samples (imgpel = unsigned short); narrow to the 8-bit device layout
-__global__ void __launch_bounds__(256)
-me_narrow_u16_kernel(const uint16_t *__restrict__ src, int n, uint8_t *__restrict__ dst)
-{
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = (uint8_t)src[i];
-}
-
 // widen one plane row block back to imgpel for the host copy of imgY_sub
 __global__ void __launch_bounds__(256)
 me_widen_planes_kernel(const uint8_t *__restrict__ planes, int pitch, size_t plane_stride, int wp, int hp,
@@ -150,11 +142,6 @@ extern "C" void me_launch_planes(const uint8_t *src, int src_stride, int w, int 
   int sw = w + 2 * spad, sh = h + 2 * spad;
   dim3 g2((sw / 4 + 255) / 256, sh);
   me_search_plane_kernel<<<g2, 256, 0, st>>>(src, src_stride, w, h, search, spad, spitch, sw, sh);
-}
-
-extern "C" void me_launch_narrow(const uint16_t *src, int n, uint8_t *dst, cudaStream_t st)
-{
-  me_narrow_u16_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, n, dst);
 }
 
 extern "C" void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp,

@@ -21,9 +21,9 @@
 //    carries a bias of 4096 so that lanes never go negative and plain 32-bit IADD3 (with a negated operand and the bias
 //    as immediate) is an exact two-lane add / subtract.  Rows first (lane-parallel), the last, lane-crossing stage is
 //    folded into the absolute sum: |u+v| + |u-v| with two VABSDIFF-accumulate per register.
-#include <cuda.h>
 #include <cstring>
 #include "me_common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -75,33 +75,6 @@ struct __align__(128) Smem {
                                             // with the 8x8 transform: the 4x4 units of types 5..7 first, then the 8x8 units of types 1..4
   unsigned long long mbar;
 };
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
-{
-#pragma unroll 1
-  for (unsigned spin = 0; spin < (1u << 24); spin++) {
-    unsigned done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tma_load_3d(unsigned dst, const void *tmap, int x, int y, int z, unsigned bar)
-{
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
-}
 
 // two-lane (16-bit, biased) add / subtract: one IADD3 each
 __device__ __forceinline__ unsigned padd(unsigned a, unsigned b) { return a + b - BIAS2; }
@@ -200,7 +173,7 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
   const unsigned bar = smem_u32(&sm.mbar);
   if (tid == 0) {
     mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_init_fence();
   }
   // work-unit tables (depend on the configuration only): lanes ordered (type, candidate, tile slot)
   for (int stage = 0; stage < 2; stage++) {
@@ -232,7 +205,7 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     int Xr, Yr;
     region_origin(w0, mv0, Xr, Yr);
     const int list = (int)(int8_t)(w1 & 0xffu), ref = (int)(int8_t)((w1 >> 8) & 0xffu);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    proxy_fence();
     mbar_expect_tx(bar, REGION_BYTES);
     tma_load_3d(smem_u32(sm.region), &maps.m[list * TUNED_MAX_REFS + ref], Xr, Yr, 0, bar);
   };
@@ -397,33 +370,14 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-
 }  // namespace
 
 // 3-D byte tensor map over the 16 quarter-pel planes of a reference picture (x, y, plane), box = one sub-pel region
 extern "C" int me_make_planes_tensor_map(void *out, const void *planes, int pitch, int hp, size_t plane_stride)
 {
-  if (!g_encode) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return 1;
-    g_encode = (EncodeTiledFn)fn;
-  }
-  CUtensorMap m;
-  cuuint64_t dims[3] = { (cuuint64_t)pitch, (cuuint64_t)hp, 16 };
-  cuuint64_t strides[2] = { (cuuint64_t)pitch, (cuuint64_t)plane_stride };
-  cuuint32_t box[3] = { RW, RH, 16 };
-  cuuint32_t estr[3] = { 1, 1, 1 };
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(planes), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return 2;
-  memcpy(out, &m, sizeof m);
-  return 0;
+  const cuuint64_t dims[3] = { (cuuint64_t)pitch, (cuuint64_t)hp, 16 }, strides[2] = { (cuuint64_t)pitch, (cuuint64_t)plane_stride };
+  const cuuint32_t box[3] = { RW, RH, 16 };
+  return me_encode_tensor_map(out, planes, 3, dims, strides, box);
 }
 
 // Returns 1 when the kernel was launched, 0 when the configuration is not covered (the caller runs subpel.cu).
