@@ -5,15 +5,16 @@
 // MEDistortionHPel = MEDistortionQPel = 2; with Transform8x8Mode the block types 1..4 use HadamardSAD8x8 (me_distortion.c:272,
 // test8x8transform, mv-search.c:640).  SAD / SSE sub-pel metrics go through subpel.cu.
 //
-//  * Persistent CTAs of 128 threads (6 per SM), one (macroblock, list, ref) job at a time.
+//  * Persistent CTAs of 128 threads (7 per SM), one (macroblock, list, ref) job at a time.
 //  * The reference samples of a job come from ONE TMA box: a 48 x 33 pixel region of all 16 quarter-pel planes
 //    (3-D tensor map x, y, plane; cp.async.bulk.tensor.3d, 25 KB) around the macroblock displaced by the integer vector of
 //    its 16x16 partition.  It covers every candidate of every partition whose integer vector lies within +-8 pixels of
 //    that vector and whose 4x4 tiles are not touched by the origin clamp of UMVLine4X (refbuf.c:37); a partition for
 //    which this does not hold (checked exactly) reads its tiles from global memory with the clamp instead.  The
 //    region of the next job is requested as soon as the last tile of the current one has been read.
-//  * Work unit: one transform tile (4x4, or 8x8 for block types 1..4 with Transform8x8Mode) of one candidate of one block
-//    type: 7 x 16 x 9 (8) 4x4 units per half (quarter) pel stage, 128 per round.  Lanes are ordered (type, candidate, tile) with the tiles of one partition adjacent, so a
+//  * A thread owns one transform tile (4x4, or 8x8 for block types 1..4 with Transform8x8Mode) of one block type for the
+//    whole job -- its current-picture lanes stay in registers -- and scores it candidate after candidate (9 half-pel, 8
+//    quarter-pel).  Lanes are ordered (type, tile) with the tiles of one partition adjacent, so a
 //    partition's SATD is a segmented butterfly sum over 1..16 lanes -- no atomics -- and the lane that ends up with the sum
 //    adds the motion-vector rate and stores the cost; one thread per partition then replays the reference's sequential
 //    first-strict-minimum scan (me_fullsearch.c:423-449, :482-502).
@@ -62,17 +63,16 @@ __constant__ uint8_t c_group8[4] = { 4, 2, 2, 1 };
 __constant__ int8_t c_spx[9] = { 0, 0, 0, -1, 1, -1, 1, -1, 1 };
 __constant__ int8_t c_spy[9] = { 0, -1, 1, -1, -1, 0, 0, 1, 1 };
 
-struct __align__(128) Smem {
+template <bool T8> struct __align__(128) Smem {
   uint8_t  region[REGION_BYTES + 128];      // [plane][RH][RW]
   uint32_t curpk[16][8];                    // per tile: rows 0..3 x {pixels (0,2), pixels (1,3)} as biased 16-bit lanes
-  uint32_t cur8[4][8][4];                   // per 8x8 quadrant and row: pixels (0,2), (1,3), (4,6), (5,7), bias BIAS8
+  uint32_t cur8[T8 ? 4 : 1][8][4];          // per 8x8 quadrant and row: pixels (0,2), (1,3), (4,6), (5,7), bias BIAS8
   uint32_t job[48];                         // me_mb_job
-  int      cost[ME_NUM_PARTITIONS][9];
+  int      cost[T8 ? 9 : 1][9];             // 8x8-transform partitions (block types 1..4): cost per candidate
   int      mv[ME_NUM_PARTITIONS][2];        // current best vector, quarter pel
   int      mn[ME_NUM_PARTITIONS];           // its cost
   int      okp[ME_NUM_PARTITIONS];          // partition served by the staged region (else: global reads with the clamp)
-  uint32_t itab[2][7 * 16 * 9];             // per stage, work unit -> partition | tile << 8 | candidate << 12 | (tiles per partition - 1) << 16;
-                                            // with the 8x8 transform: the 4x4 units of types 5..7 first, then the 8x8 units of types 1..4
+  int      mvc[T8 ? 9 : 1][9];              // their motion-vector rate per candidate
   unsigned long long mbar;
 };
 
@@ -159,13 +159,13 @@ constexpr int TUNED_MAX_REFS = 8;
 struct PlaneMaps { CUtensorMap m[2 * TUNED_MAX_REFS]; };
 
 template <bool T8>     // T8: Transform8x8Mode (block types 1..4 scored with the 8x8 Hadamard transform)
-__global__ void __launch_bounds__(NT, T8 ? 4 : 6)
+__global__ void __launch_bounds__(NT, T8 ? 4 : 7)      // measured: 6 CTAs 0.775 ms, 7 CTAs 0.736 ms, 8 CTAs (64 registers) 0.777 ms
 me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                        const __grid_constant__ PlaneMaps maps, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                        const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out)
 {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+  Smem<T8> &sm = *reinterpret_cast<Smem<T8> *>(smem_raw);
   constexpr int JW = sizeof(MeJob) / 4;
   const int tid = threadIdx.x;
   const int n_mine = (n_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -174,21 +174,6 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_init_fence();
-  }
-  // work-unit tables (depend on the configuration only): lanes ordered (type, candidate, tile slot)
-  for (int stage = 0; stage < 2; stage++) {
-    const int first = stage == 0 ? cfg.start_hp : cfg.start_qp, nc = 9 - first;
-    const int t0 = T8 ? 4 : 0;                                   // first block type (minus 1) scored with 4x4 tiles
-    const int n4 = (7 - t0) * 16 * nc;
-    for (int i = tid; i < n4; i += NT) {
-      const int q = i & 15, gi = i >> 4, ti = t0 + gi / nc, c = gi % nc + first;      // ti = block type - 1
-      sm.itab[stage][i] = (uint32_t)c_part[ti][q] | ((uint32_t)c_tile[ti][q] << 8) | ((uint32_t)c << 12) | ((uint32_t)(c_group[ti] - 1) << 16);
-    }
-    if (T8)
-      for (int i = tid; i < 4 * 4 * nc; i += NT) {
-        const int q = i & 3, gi = i >> 2, ti = gi / nc, c = gi % nc + first;
-        sm.itab[stage][n4 + i] = (uint32_t)c_part8[ti][q] | ((uint32_t)c_quad[ti][q] << 8) | ((uint32_t)c << 12) | ((uint32_t)(c_group8[ti] - 1) << 16);
-      }
   }
   __syncthreads();
 
@@ -249,72 +234,110 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
                     x0 - 1 >= 0 && y0 - 1 >= 0 && x1 <= ref.w + 2 * ME_PAD - 1 - 16 && y1 <= ref.h + 2 * ME_PAD - 1 - 16;
     }
     __syncthreads();                                 // publishes okp and curpk
+    // ---- this thread's tile for the whole job.  4x4: slot = (block type, tile slot), 16 lanes per type, the tiles of a
+    // partition adjacent (c_tile / c_part).  With the 8x8 transform only the types 5..7 have 4x4 tiles (threads 0..47 of the
+    // first two warps) and the last two warps hold the 8x8 tiles of types 1..4 (c_quad / c_part8), four lane groups of 16.
+    struct Slot4 { int p, g, x4, y4, rot; bool ok, leader; uint4 c01, c23; } s4;
+    struct Slot8 { int p, g, x4, y4, quad, grp; bool ok, leader; } s8;
+    {
+      const int nslot = T8 ? 3 * 16 : 7 * 16;
+      const int slot = tid < nslot ? tid : 0, ti = (T8 ? 4 : 0) + (slot >> 4), q = slot & 15, tile = c_tile[ti][q];
+      s4.p = c_part[ti][q]; s4.g = c_group[ti];
+      s4.leader = tid < nslot && (q & (s4.g - 1)) == 0;
+      s4.ok = sm.okp[s4.p] != 0;
+      s4.x4 = (jv.opix_x + 4 * (tile & 3) + ME_PAD) << 2; s4.y4 = (jv.opix_y + 4 * (tile >> 2) + ME_PAD) << 2;
+      // tiles of the lower macroblock half take their rows in the order 2, 3, 0, 1 (the Hadamard sum does not change under a
+      // cyclic row shift): the lanes of a partition then hit four different bank groups instead of two
+      s4.rot = (tile >> 2) & 2;
+      s4.c01 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][s4.rot ? 4 : 0]);
+      s4.c23 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][s4.rot ? 0 : 4]);
+      const int l8 = (tid - 64) & 63, q16 = l8 & 15, t8 = q16 >> 2, qs = q16 & 3;
+      s8.grp = l8 >> 4; s8.p = c_part8[t8][qs]; s8.g = c_group8[t8]; s8.quad = c_quad[t8][qs];
+      s8.leader = (qs & (s8.g - 1)) == 0;
+      s8.ok = sm.okp[s8.p] != 0;
+      s8.x4 = (jv.opix_x + 8 * (s8.quad & 1) + ME_PAD) << 2; s8.y4 = (jv.opix_y + 8 * (s8.quad >> 1) + ME_PAD) << 2;
+    }
+    const unsigned region_addr = smem_u32(sm.region);
     mbar_wait(bar, (unsigned)(it & 1));
 
     for (int stage = 0; stage < 2; stage++) {                // 0: half pel (step 2), 1: quarter pel (step 1)
       const int step = stage == 0 ? 2 : 1;
       const int lam = (int)sm.job[44 + 1 + stage];          // lambda[H_PEL], lambda[Q_PEL]
       const int first = stage == 0 ? cfg.start_hp : cfg.start_qp;
-      const int nc = 9 - first;
-      if (stage == 1 && !cfg.start_qp && tid < ME_NUM_PARTITIONS) sm.mn[tid] = ME_INT_MAX;   // me_fullsearch.c:456-457
-      const int total = (T8 ? 3 : 7) * 16 * nc;              // 4x4 units
-      for (int base = 0; base < total; base += NT) {
-        const int i = base + tid;
-        const bool active = i < total;
-        const int ii = active ? i : 0;
-        const uint32_t e = sm.itab[stage][ii];
-        const int q = ii & 15, p = (int)(e & 0xffu), c = (int)((e >> 12) & 0xfu), g = (int)(e >> 16) + 1, tile = (int)((e >> 8) & 0xfu);
-        const int mvx = sm.mv[p][0] + step * c_spx[c], mvy = sm.mv[p][1] + step * c_spy[c];
-        const int x4 = ((jv.opix_x + 4 * (tile & 3) + ME_PAD) << 2) + mvx, y4 = ((jv.opix_y + 4 * (tile >> 2) + ME_PAD) << 2) + mvy;
-        // tiles of the lower macroblock half take their rows in the order 2, 3, 0, 1 (the Hadamard sum does not change under a
-        // cyclic row shift): the lanes of a partition then hit four different bank groups instead of two
-        const int rot = (tile >> 2) & 2;
-        unsigned r[4];
-        if (sm.okp[p]) {
-          const unsigned a = smem_u32(sm.region) + (unsigned)((((y4 & 3) << 2) | (x4 & 3)) * (RW * RH) + ((y4 >> 2) - Yr) * RW + ((x4 >> 2) - Xr));
-          const unsigned a4 = a & ~3u, sh = (a & 3u) * 8;
-          const unsigned bA = a4 + rot * RW, bB = a4 + (2 - rot) * RW;
-#pragma unroll
-          for (int y = 0; y < 4; y++) {
-            const unsigned ra = (y < 2 ? bA : bB) + (y & 1) * RW;
-            unsigned w0, w1;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(ra + 4));
-            r[y] = __funnelshift_r(w0, w1, sh);
-          }
-        } else {
-          const uint8_t *rp = me_umv_ptr(ref, y4, x4);     // per-tile origin clamp, as computeSATD does (me_distortion.c:657)
-#pragma unroll
-          for (int y = 0; y < 4; y++) {
-            const uint8_t *b = rp + (size_t)((y + rot) & 3) * ref.pitch;
-            r[y] = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
-          }
-        }
-        const uint4 c01 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][rot ? 4 : 0]);
-        const uint4 c23 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][rot ? 0 : 4]);
-        int v = satd4x4(r, c01, c23);
-        // segmented sum over the g lanes of the partition
-#pragma unroll
-        for (int sft = 1; sft < 16; sft <<= 1) {
-          const int o = __shfl_xor_sync(0xffffffffu, v, sft);
-          if (sft < g) v += o;
-        }
-        if (active && (q & (g - 1)) == 0)
-          sm.cost[p][c] = v + me_mv_cost(lam, mvx, mvy, (int)(int16_t)(sm.job[3 + p] & 0xffffu), (int)(int16_t)(sm.job[3 + p] >> 16));
-      }
       if (T8) {
-        const int total8 = 4 * 4 * nc;                         // 8x8 units of block types 1..4
-        for (int base = 0; base < total8; base += NT) {
-          const int i = base + tid;
-          const bool active = i < total8;
-          const int ii = active ? i : 0;
-          const uint32_t e = sm.itab[stage][total + ii];
-          const int q = ii & 3, p = (int)(e & 0xffu), c = (int)((e >> 12) & 0xfu), g = (int)(e >> 16) + 1, quad = (int)((e >> 8) & 0xfu);
-          const int mvx = sm.mv[p][0] + step * c_spx[c], mvy = sm.mv[p][1] + step * c_spy[c];
-          const int x4 = ((jv.opix_x + 8 * (quad & 1) + ME_PAD) << 2) + mvx, y4 = ((jv.opix_y + 8 * (quad >> 1) + ME_PAD) << 2) + mvy;
+        // motion-vector rate of every candidate of the 8x8-transform partitions (block types 1..4), scored across lane groups
+        for (int i = tid; i < 9 * 9; i += NT) {
+          const int p = i / 9, c = i - 9 * p;
+          sm.mvc[p][c] = me_mv_cost(lam, sm.mv[p][0] + step * c_spx[c], sm.mv[p][1] + step * c_spy[c],
+                                    (int)(int16_t)(sm.job[3 + p] & 0xffffu), (int)(int16_t)(sm.job[3 + p] >> 16));
+        }
+        __syncthreads();
+      }
+      if (!T8 || tid < 64) {
+        // ---- 4x4 tiles: this thread's tile, candidate after candidate
+        // The lane that ends up with a partition's SATD also replays the reference's sequential scan over the candidates
+        // (first strict minimum, me_fullsearch.c:423-449, :482-502) as they come, in order.
+        const int mvpx = sm.mv[s4.p][0], mvpy = sm.mv[s4.p][1];
+        const int pmx = (int)(int16_t)(sm.job[3 + s4.p] & 0xffffu), pmy = (int)(int16_t)(sm.job[3 + s4.p] >> 16);
+        // length of the three possible differences per component: candidate offset -step, 0, +step (MV_COST_SMP, defines.h:126)
+        const int bx0 = me_mvbits(mvpx - pmx), bxm = me_mvbits(mvpx - step - pmx), bxp = me_mvbits(mvpx + step - pmx);
+        const int by0 = me_mvbits(mvpy - pmy), bym = me_mvbits(mvpy - step - pmy), byp = me_mvbits(mvpy + step - pmy);
+        int mn = (stage == 1 && !cfg.start_qp) ? ME_INT_MAX : sm.mn[s4.p];       // me_fullsearch.c:456-457
+        int best = 0;
+        const bool check0 = stage == 0 && !cfg.rdopt && jv.slice_type != ME_B_SLICE && jv.ref == 0 && s4.p == 0 && mvpx == 0 && mvpy == 0;
+#pragma unroll 3
+        for (int c = first; c < 9; c++) {
+          const int sx = c_spx[c], sy = c_spy[c];
+          const int x4 = s4.x4 + mvpx + step * sx, y4 = s4.y4 + mvpy + step * sy;
+          unsigned r[4];
+          if (s4.ok) {
+            const unsigned a = region_addr + (unsigned)((((y4 & 3) << 2) | (x4 & 3)) * (RW * RH) + ((y4 >> 2) - Yr) * RW + ((x4 >> 2) - Xr));
+            const unsigned a4 = a & ~3u, sh = (a & 3u) * 8;
+            const unsigned bA = a4 + s4.rot * RW, bB = a4 + (2 - s4.rot) * RW;
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+              const unsigned ra = (y < 2 ? bA : bB) + (y & 1) * RW;
+              unsigned w0, w1;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(ra + 4));
+              r[y] = __funnelshift_r(w0, w1, sh);
+            }
+          } else {
+            const uint8_t *rp = me_umv_ptr(ref, y4, x4);   // per-tile origin clamp, as computeSATD does (me_distortion.c:657)
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+              const uint8_t *b = rp + (size_t)((y + s4.rot) & 3) * ref.pitch;
+              r[y] = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
+            }
+          }
+          int v = satd4x4(r, s4.c01, s4.c23);
+          // segmented sum over the g lanes of the partition
+#pragma unroll
+          for (int sft = 1; sft < 16; sft <<= 1) {
+            const int o = __shfl_xor_sync(0xffffffffu, v, sft);
+            if (sft < s4.g) v += o;
+          }
+          int mc = v + ((lam * ((sx < 0 ? bxm : sx > 0 ? bxp : bx0) + (sy < 0 ? bym : sy > 0 ? byp : by0))) >> 16);
+          if (check0 && c == 0) mc -= (lam * 16) >> 16;    // check_position0, me_fullsearch.c:361,439-442
+          if (mc < mn) { mn = mc; best = c; }
+        }
+        if (s4.leader) {
+          sm.mn[s4.p] = mn;
+          sm.mv[s4.p][0] = mvpx + step * c_spx[best];
+          sm.mv[s4.p][1] = mvpy + step * c_spy[best];
+        }
+      } else {
+        // ---- 8x8 tiles (block types 1..4): 16 lanes per (type, quadrant), four lane groups share the candidates
+        const int mvpx = sm.mv[s8.p][0], mvpy = sm.mv[s8.p][1];
+        // the same trip count for every lane (the shuffles below need the whole warp); a lane group without a candidate
+        // left re-scores candidate 8 and does not store
+#pragma unroll 1
+        for (int k = 0; k < (9 - first + 3) / 4; k++) {
+          const int cc = first + s8.grp + 4 * k, c = cc < 9 ? cc : 8;
+          const int x4 = s8.x4 + mvpx + step * c_spx[c], y4 = s8.y4 + mvpy + step * c_spy[c];
           unsigned rl[8], rr[8];
-          if (sm.okp[p]) {
-            const unsigned a = smem_u32(sm.region) + (unsigned)((((y4 & 3) << 2) | (x4 & 3)) * (RW * RH) + ((y4 >> 2) - Yr) * RW + ((x4 >> 2) - Xr));
+          if (s8.ok) {
+            const unsigned a = region_addr + (unsigned)((((y4 & 3) << 2) | (x4 & 3)) * (RW * RH) + ((y4 >> 2) - Yr) * RW + ((x4 >> 2) - Xr));
             const unsigned a4 = a & ~3u, sh = (a & 3u) * 8;
 #pragma unroll
             for (int y = 0; y < 8; y++) {
@@ -333,34 +356,36 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
               rr[y] = (unsigned)b[4] | ((unsigned)b[5] << 8) | ((unsigned)b[6] << 16) | ((unsigned)b[7] << 24);
             }
           }
-          int v = satd8x8(rl, rr, &sm.cur8[quad][0][0]);
+          int v = satd8x8(rl, rr, &sm.cur8[s8.quad][0][0]);
 #pragma unroll
           for (int sft = 1; sft < 4; sft <<= 1) {
             const int o = __shfl_xor_sync(0xffffffffu, v, sft);
-            if (sft < g) v += o;
+            if (sft < s8.g) v += o;
           }
-          if (active && (q & (g - 1)) == 0)
-            sm.cost[p][c] = v + me_mv_cost(lam, mvx, mvy, (int)(int16_t)(sm.job[3 + p] & 0xffffu), (int)(int16_t)(sm.job[3 + p] >> 16));
+          if (s8.leader && cc < 9) sm.cost[s8.p][c] = v + sm.mvc[s8.p][c];
         }
       }
       __syncthreads();
       // the region is free once the quarter-pel tiles are read: request the next job's
       if (stage == 1 && tid == 0 && it + 1 < n_mine) issue_region(job_id + (int)gridDim.x);
-      if (tid < ME_NUM_PARTITIONS) {
-        const int p = tid;
-        int best = 0, mn = sm.mn[p];
-        for (int c = first; c < 9; c++) {
-          int mc = sm.cost[p][c];
-          if (stage == 0 && c == 0 && !cfg.rdopt && jv.slice_type != ME_B_SLICE && jv.ref == 0 && p == 0 &&
-              sm.mv[p][0] == 0 && sm.mv[p][1] == 0)
-            mc -= (lam * 16) >> 16;                          // check_position0, me_fullsearch.c:361,439-442
-          if (mc < mn) { mn = mc; best = c; }
+      if (T8) {
+        // partitions of block types 1..4: their candidates were scored by four lane groups, scan them here
+        if (tid < 9) {
+          const int p = tid;
+          int best = 0, mn = (stage == 1 && !cfg.start_qp) ? ME_INT_MAX : sm.mn[p];
+          for (int c = first; c < 9; c++) {
+            int mc = sm.cost[p][c];
+            if (stage == 0 && c == 0 && !cfg.rdopt && jv.slice_type != ME_B_SLICE && jv.ref == 0 && p == 0 &&
+                sm.mv[p][0] == 0 && sm.mv[p][1] == 0)
+              mc -= (lam * 16) >> 16;                        // check_position0, me_fullsearch.c:361,439-442
+            if (mc < mn) { mn = mc; best = c; }
+          }
+          sm.mn[p] = mn;
+          sm.mv[p][0] += step * c_spx[best];
+          sm.mv[p][1] += step * c_spy[best];
         }
-        sm.mn[p] = mn;
-        sm.mv[p][0] += step * c_spx[best];
-        sm.mv[p][1] += step * c_spy[best];
+        __syncthreads();
       }
-      __syncthreads();
     }
     if (tid < ME_NUM_PARTITIONS) {
       reinterpret_cast<uint32_t *>(out[job_id].mv)[tid] = ((unsigned)sm.mv[tid][0] & 0xffffu) | ((unsigned)sm.mv[tid][1] << 16);
@@ -393,19 +418,19 @@ extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(me_subpel_tuned_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    cudaFuncSetAttribute(me_subpel_tuned_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaFuncSetAttribute(me_subpel_tuned_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>));
+    cudaFuncSetAttribute(me_subpel_tuned_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<true>));
   }
   PlaneMaps pm;
   for (int l = 0; l < 2; l++)
     memcpy(&pm.m[l * TUNED_MAX_REFS], (const unsigned char *)plane_maps + (size_t)l * ME_MAX_REFS * 128, sizeof(CUtensorMap) * TUNED_MAX_REFS);
-  int grid = sms * (cfg->transform8x8 ? 4 : 6);
+  int grid = sms * (cfg->transform8x8 ? 4 : 7);
   if (grid > n_jobs) grid = n_jobs;
   if (cfg->transform8x8)
-    me_subpel_tuned_kernel<true><<<grid, NT, sizeof(Smem), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
+    me_subpel_tuned_kernel<true><<<grid, NT, sizeof(Smem<true>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
                                                                  *cfg, in_int, out);
   else
-    me_subpel_tuned_kernel<false><<<grid, NT, sizeof(Smem), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
+    me_subpel_tuned_kernel<false><<<grid, NT, sizeof(Smem<false>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
                                                                   *cfg, in_int, out);
   return 1;
 }
