@@ -375,6 +375,7 @@ __device__ __forceinline__ void search_centre(const MeCfgDev &c, int R, const Jo
   offx = x; offy = y;
 }
 
+// 3 CTAs per SM at R = 32 (168 registers); 4 CTAs (128 registers, 43 spill stores) measured slower: 2.20 vs 2.01 ms
 template <int R>
 __global__ void __launch_bounds__(Geo<R>::NT, (R == 32) ? 3 : (R == 16) ? 6 : 1)
 me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
