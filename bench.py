@@ -105,10 +105,10 @@ def reference_cfg_args(yuv, frames, refs=N_REFS, sr=SEARCH_RANGE, w=W, h=H):
             "-p", "LevelIDC=51", "-p", "QPISlice=28", "-p", "QPPSlice=28", "-p", "OutputFile=out.264", "-p", "ReconFile=rec.yuv"]
 
 
-def run_lencod(workdir, frames, yuv="clip.yuv"):
+def run_lencod(workdir, frames, yuv="clip.yuv", h=H):
     """runs the unmodified reference encoder; returns (ME seconds, (macroblock, ref) units searched)"""
     exe = os.path.join(ROOT, "oracle", "_ref", "lencod")
-    r = subprocess.run([exe] + reference_cfg_args(yuv, frames), cwd=workdir, capture_output=True, text=True)
+    r = subprocess.run([exe] + reference_cfg_args(yuv, frames, h=h), cwd=workdir, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("lencod failed: " + r.stdout[-1500:] + r.stderr[-500:])
     me_s = None
@@ -116,11 +116,11 @@ def run_lencod(workdir, frames, yuv="clip.yuv"):
         if "Total ME time for sequence" in ln:
             me_s = float(ln.split(":")[1].split("sec")[0])
     # IPPP: P picture k (k = 1..frames-1) searches min(k, N_REFS) references
-    units = MBS * sum(min(k, N_REFS) for k in range(1, frames))
+    units = (W // 16) * (h // 16) * sum(min(k, N_REFS) for k in range(1, frames))
     return me_s, units
 
 
-def prepare_reference_dir(frames):
+def prepare_reference_dir(frames, h=H):
     import shutil
     import h264_b200_pkg  # noqa: F401
     from h264_b200 import synth
@@ -129,7 +129,7 @@ def prepare_reference_dir(frames):
     for f in os.listdir(fx):
         if f.endswith(".cfg"):
             shutil.copy(os.path.join(fx, f), d)
-    synth.write_yuv420(os.path.join(d, "clip.yuv"), W, H, frames)
+    synth.write_yuv420(os.path.join(d, "clip.yuv"), W, h, frames)
     return d
 
 
@@ -171,32 +171,46 @@ def reference_arm(args):
         # the oracle port, one process per core
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lencod not built on this box"}))
         return 0
-    d = prepare_reference_dir(2)
-    workdirs = []
+    # Bounded sample: per step every core encodes I + P of a full-width strip of the 1080p clip.  A calibration step on an
+    # 8-row strip measures this box; the strip then gets as many macroblock rows (8 .. 68 = the whole picture) as K + W steps
+    # can afford in about 150 s.  The per-macroblock work does not depend on the picture height.
     import shutil
-    for c in range(cores):
-        wd = os.path.join(d, "p%d" % c)
-        os.makedirs(wd)
-        for f in os.listdir(d):
-            if f.endswith(".cfg"):
-                shutil.copy(os.path.join(d, f), wd)
-        os.symlink(os.path.join(d, "clip.yuv"), os.path.join(wd, "clip.yuv"))
-        workdirs.append(wd)
     exe = os.path.join(ROOT, "oracle", "_ref", "lencod")
 
-    def one_step():
-        # every core encodes I + P (1 reference): 8160 (MB,ref) searches per process
+    def make_workdirs(hs):
+        d = prepare_reference_dir(2, h=hs)
+        wds = []
+        for c in range(cores):
+            wd = os.path.join(d, "p%d" % c)
+            os.makedirs(wd)
+            for f in os.listdir(d):
+                if f.endswith(".cfg"):
+                    shutil.copy(os.path.join(d, f), wd)
+            os.symlink(os.path.join(d, "clip.yuv"), os.path.join(wd, "clip.yuv"))
+            wds.append(wd)
+        return wds
+
+    def run_step(wds, hs):
         t0 = time.perf_counter()
-        procs = [subprocess.Popen([exe] + reference_cfg_args("clip.yuv", 2), cwd=wd, stdout=subprocess.PIPE,
-                                  stderr=subprocess.DEVNULL, text=True) for wd in workdirs]
+        procs = [subprocess.Popen([exe] + reference_cfg_args("clip.yuv", 2, h=hs), cwd=wd, stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL, text=True) for wd in wds]
         me = []
         for p in procs:
             out = p.communicate()[0]
             for ln in out.splitlines():
                 if "Total ME time for sequence" in ln:
                     me.append(float(ln.split(":")[1].split("sec")[0]))
-        wall = time.perf_counter() - t0
-        return wall, me
+        return time.perf_counter() - t0, me
+
+    cal_s, _ = run_step(make_workdirs(16 * 8), 16 * 8)
+    rows = int(8 * 150.0 / (max(1, args.steps + args.warmup) * cal_s))
+    rows = max(8, min(H // 16, rows))
+    hs = 16 * rows
+    mbs = (W // 16) * rows
+    workdirs = make_workdirs(hs)
+
+    def one_step():
+        return run_step(workdirs, hs)
 
     for _ in range(args.warmup):
         one_step()
@@ -206,15 +220,16 @@ def reference_arm(args):
         walls.append(wall); mes.append(float(np.mean(me)))
     # throughput of the hot path: every process searched MBS (MB,ref) units in its ME seconds, all processes concurrently
     me_mean = float(np.mean(mes))
-    value = cores * MBS / N_REFS / me_mean
+    value = cores * mbs / N_REFS / me_mean
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "search_range": SEARCH_RANGE,
-                       "refs": N_REFS, "note": "per step every host core runs the unmodified lencod on I+P (1 reference); "
-                                               "MB/s = cores * 8160 (MB,ref) / 5 refs / mean ME seconds (encoder's own ME timer)"},
+                       "refs": N_REFS, "note": "per step every host core runs the unmodified lencod on I+P (1 reference) of a "
+                                               "%dx%d strip of the clip (%d macroblocks); MB/s = cores * %d (MB,ref) / 5 refs / mean ME "
+                                               "seconds (encoder's own ME timer)" % (W, hs, mbs, mbs)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                             "sample": "%d concurrent lencod processes, 2 pictures each, per step" % cores},
+                             "sample": "%d concurrent lencod processes, I+P of a %dx%d strip each, per step" % (cores, W, hs)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0

@@ -56,7 +56,7 @@ void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t
 
 namespace {
 
-constexpr int ME_PIPE_CHUNKS = 4;
+constexpr int ME_PIPE_CHUNKS = 8;       // most chunks a batch is cut into (events are created for this many)
 
 struct TensorMap { alignas(64) unsigned char bytes[128]; };   // CUtensorMap
 
@@ -731,7 +731,9 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
   if (int rc = ensure_batch(n_jobs)) return rc;
   // Large batches are cut into chunks that move through three streams -- jobs in (H2D engine), search (library stream),
   // results out (D2H engine) -- so that with pinned caller buffers only the first upload and the last download are exposed.
-  const int n_chunks = n_jobs >= 8192 ? ME_PIPE_CHUNKS : 1;
+  static int want_chunks = 0;
+  if (!want_chunks) { const char *e = getenv("ME_CUDA_PIPE_CHUNKS"); want_chunks = e ? atoi(e) : 6; if (want_chunks < 1 || want_chunks > ME_PIPE_CHUNKS) want_chunks = 6; }
+  const int n_chunks = n_jobs >= 8192 ? want_chunks : 1;
   if (!g.s_in) {
     CK(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.s_out, cudaStreamNonBlocking));

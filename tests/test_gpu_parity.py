@@ -175,6 +175,18 @@ def test_batch_huge_lambda_jobs_are_handed_to_the_general_kernel(pkg, oracle_lib
     assert not bad, (len(bad), n, bad[:4])
 
 
+def test_batch_more_references_than_the_tuned_kernels_take(pkg, oracle_lib):
+    """nine references in one list: beyond the eight tensor maps the tuned kernels carry, so the general kernels run"""
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h, n_refs = 176, 144, 9
+    d, cfg = _cfg(ob)
+    frames = synth.luma_frames(w, h, n_refs + 1)
+    jobs = synth.synthetic_jobs(w, h, n_refs, (334459, 334459, 334459), seed=37, max_pmv=30)
+    bad, n = _batch_case(pkg, ob, w, h, frames, n_refs, d, cfg, jobs, sample=180)
+    assert not bad, (len(bad), n, bad[:4])
+
+
 def test_batch_two_reference_lists(pkg, oracle_lib):
     """B-slice style batch: jobs against list 0 and list 1 (different pictures) in one call"""
     from h264_b200 import synth
