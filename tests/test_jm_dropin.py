@@ -49,7 +49,8 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
 
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
-@pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0", "yuv444_3ref_bframes", "sr64_2ref"])
+@pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0", "yuv444_3ref_bframes", "sr64_2ref",
+                                  "hd1080_sr32_ip"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -68,6 +69,11 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         # BASELINE config 4 on the reference's own 4:4:4 fixture: High 4:4:4, I-B-P with bi-predictive ME, 3 references
         args = ["-d", "encoder.cfg", "-p", "InputFile=foreman_part_qcif_444.yuv", "-p", "YUVFormat=3", "-p", "ProfileIDC=244",
                 "-p", "NumberReferenceFrames=3"]
+    elif case == "hd1080_sr32_ip":
+        # the headline picture size and search range (BASELINE config 3), one I and one P picture
+        args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=1920", "-p", "SourceHeight=1088",
+                "-p", "FramesToBeEncoded=2", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=32",
+                "-p", "NumberReferenceFrames=5", "-p", "LevelIDC=51"]
     elif case == "sr64_2ref":
         # the search range of BASELINE config 5 (4K), on a QCIF clip so that the CPU side finishes in seconds
         args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
@@ -80,9 +86,9 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     for d in (a, b):
         _prep(str(d))
         if "InputFile=syn.yuv" in args:
-            wdt = 352 if "SourceWidth=352" in args else 176
-            hgt = 288 if wdt == 352 else 144
-            synth.write_yuv420(str(d / "syn.yuv"), wdt, hgt, 4)
+            wdt = int([a for a in args if a.startswith("SourceWidth=")][0].split("=")[1])
+            hgt = int([a for a in args if a.startswith("SourceHeight=")][0].split("=")[1])
+            synth.write_yuv420(str(d / "syn.yuv"), wdt, hgt, 2 if wdt == 1920 else 4)
     _run("lencod_cuda", args, str(a))
     _run("lencod", args, str(b))
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
