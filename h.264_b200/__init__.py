@@ -10,4 +10,5 @@ registers this package as module `h264_b200`.
   build.py   nvcc build of libme_cuda.so
 """
 from . import build as _build  # noqa: F401
-from .me_cuda import MeCuda, MeCudaError, JOB_DTYPE, RESULT_DTYPE, NUM_PART, PART_TYPE, PART_BLK  # noqa: F401
+from .me_cuda import (MeCuda, MeCudaError, JOB_DTYPE, RESULT_DTYPE, BIPRED_JOB_DTYPE, BIPRED_RESULT_DTYPE,  # noqa: F401
+                      NUM_PART, PART_TYPE, PART_BLK)

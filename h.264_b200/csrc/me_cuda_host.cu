@@ -50,6 +50,8 @@ void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_t
                             const MeCfgDev *cfg, const MeResultInt *in_int, MeResult *out, cudaStream_t st);
 void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                              const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st);
+void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
+                            const MeCfgDev *cfg, int refinements, int search_range, int subpel, me_bipred_result *out, cudaStream_t st);
 void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                            const MeBiFullArgs *a, int *result, int ticket, cudaStream_t st);
 }
@@ -108,6 +110,7 @@ struct State {
   // batch scratch
   MeJob *d_jobs = nullptr; MeResult *d_out = nullptr; MeResultInt *d_out_int = nullptr; int batch_cap = 0;
   MeResultInt *d_int_scratch = nullptr; int int_scratch_cap = 0;
+  me_bipred_job *d_bi_jobs = nullptr; me_bipred_result *d_bi_out = nullptr; int bi_cap = 0;
   long long launches = 0;
   // optional per-kernel-class timing (bench.py): event pairs around every launch of a class
   bool timing = false;
@@ -345,6 +348,8 @@ void me_cuda_shutdown(void)
   if (g.d_out) cudaFree(g.d_out);
   if (g.d_out_int) cudaFree(g.d_out_int);
   if (g.d_int_scratch) cudaFree(g.d_int_scratch);
+  if (g.d_bi_jobs) cudaFree(g.d_bi_jobs);
+  if (g.d_bi_out) cudaFree(g.d_bi_out);
   if (g_d_stage) { cudaFree(g_d_stage); g_d_stage = nullptr; g_d_stage_bytes = 0; }
   cudaStreamDestroy(g.stream);
   g = State();
@@ -761,6 +766,38 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
     if (out_int) CK(cudaMemcpyAsync(out_int + off, g.d_out_int + off, sizeof(MeResultInt) * (size_t)n, cudaMemcpyDeviceToHost, g.s_out));
   }
   CK(cudaStreamSynchronize(g.s_out));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements, int search_range, int subpel, me_bipred_result *out)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (n_jobs <= 0) return 0;
+  if (g.list_n[0] < 1 || g.list_n[1] < 1) return fail(1, "me_cuda_frame_bipred needs a reference picture in both lists");
+  if (refinements < 0 || refinements > 16 || search_range < 0 || search_range > 64 || subpel < 0 || subpel > 2)
+    return fail(1, "me_cuda_frame_bipred: refinements %d / search range %d / sub-pel levels %d out of range", refinements, search_range, subpel);
+  if (g.cfg.metric[0] == 2) return fail(1, "bi-predictive integer search with a Hadamard metric is not implemented");
+  for (int i = 0; i < n_jobs; i++) {
+    const me_bipred_job &j = jobs[i];
+    if (j.list < 0 || j.list > 1) return fail(1, "bi-pred job %d: list %d", i, (int)j.list);
+    if (j.opix_x < 0 || j.opix_y < 0 || j.opix_x + 16 > g.p.width || j.opix_y + 16 > g.p.height || (j.opix_x & 15) || (j.opix_y & 15))
+      return fail(1, "bi-pred job %d: macroblock origin (%d,%d) invalid", i, (int)j.opix_x, (int)j.opix_y);
+  }
+  if (g.bi_cap < n_jobs) {
+    if (g.d_bi_jobs) cudaFree(g.d_bi_jobs);
+    if (g.d_bi_out) cudaFree(g.d_bi_out);
+    g.d_bi_jobs = nullptr; g.d_bi_out = nullptr; g.bi_cap = 0;
+    CK(cudaMalloc((void **)&g.d_bi_jobs, sizeof(me_bipred_job) * (size_t)n_jobs));
+    CK(cudaMalloc((void **)&g.d_bi_out, sizeof(me_bipred_result) * (size_t)n_jobs));
+    g.bi_cap = n_jobs;
+  }
+  if (int rc = upload_table()) return rc;
+  CK(cudaMemcpyAsync(g.d_bi_jobs, jobs, sizeof(me_bipred_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, g.stream));
+  me_launch_bipred_batch(g.d_bi_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, refinements, search_range, subpel, g.d_bi_out, g.stream);
+  g.launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, g.d_bi_out, sizeof(me_bipred_result) * (size_t)n_jobs, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   return 0;
 }

@@ -191,15 +191,22 @@ struct MeSubpelArgs {
   int bi;
 };
 
-__global__ void __launch_bounds__(128)
-me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
-                        MeSubpelArgs a, int *result /* mvx, mvy, cost, ticket */, int ticket)
+// scratch of the block-level device functions below (one per CTA)
+struct BlockScratch {
+  unsigned long long red[8];
+  int cost_s[9];
+  int mv_s[2], min_sh;
+};
+
+// One block, both sub-pel levels.  bi == 0: SubPelBlockMotionSearch (r1 searched).  bi == 1: SubPelBlockSearchBiPred, r1 read at
+// the fixed vector (s_mv), r2 at the candidate.  Called by all threads of the CTA; returns the result to all of them.
+__device__ void subpel_block(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch,
+                             const MeCfgDev &cfg, const MeSubpelArgs &a, BlockScratch &sc, int &out_mvx, int &out_mvy, int &out_cost)
 {
-  __shared__ int cost_s[9];
-  __shared__ int mv_s[2], min_sh;
   const int tid = threadIdx.x;
   const int t = a.blocktype, bsx = me_bsx(t), bsy = me_bsy(t);
-  if (tid == 0) { mv_s[0] = a.mv_x; mv_s[1] = a.mv_y; min_sh = a.min_mcost; }
+  __syncthreads();                      // the scratch may still be read from a previous call
+  if (tid == 0) { sc.mv_s[0] = a.mv_x; sc.mv_s[1] = a.mv_y; sc.min_sh = a.min_mcost; }
   __syncthreads();
   for (int stage = 0; stage < 2; stage++) {
     const int step = stage == 0 ? 2 : 1, level = stage == 0 ? 1 : 2;
@@ -208,8 +215,8 @@ me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cu
     int npos = stage == 0 ? a.search_pos2 : a.search_pos4;
     if (stage == 0 && !cfg.start_hp && npos < 1) npos = 1;   // max_pos2, me_fullsearch.c:366
     if (npos > 9) npos = 9;
-    if (tid == 0 && stage == 1 && !cfg.start_qp) min_sh = ME_INT_MAX;
-    if (tid < 9) cost_s[tid] = me_mv_cost(lam, mv_s[0] + step * c_sp_x[tid], mv_s[1] + step * c_sp_y[tid], a.pmv_x, a.pmv_y);
+    if (tid == 0 && stage == 1 && !cfg.start_qp) sc.min_sh = ME_INT_MAX;
+    if (tid < 9) sc.cost_s[tid] = me_mv_cost(lam, sc.mv_s[0] + step * c_sp_x[tid], sc.mv_s[1] + step * c_sp_y[tid], a.pmv_x, a.pmv_y);
     __syncthreads();
     bool use8 = cfg.transform8x8 && t <= 4 && metric == 2;
     int n = use8 ? 8 : 4, tw = bsx / n, th = bsy / n;
@@ -217,8 +224,8 @@ me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cu
       int c = i % 9, tile = i / 9;
       if (c < first || c >= npos) continue;
       int bx = (tile % tw) * n, by = (tile / tw) * n;
-      int x4 = ((a.pic_pix_x + ME_PAD) << 2) + mv_s[0] + step * c_sp_x[c];
-      int y4 = ((a.pic_pix_y + ME_PAD) << 2) + mv_s[1] + step * c_sp_y[c];
+      int x4 = ((a.pic_pix_x + ME_PAD) << 2) + sc.mv_s[0] + step * c_sp_x[c];
+      int y4 = ((a.pic_pix_y + ME_PAD) << 2) + sc.mv_s[1] + step * c_sp_y[c];
       const uint8_t *sp = cur + (size_t)(a.pic_pix_y + by) * cur_pitch + a.pic_pix_x + bx;
       int d;
       if (!a.bi) {
@@ -232,24 +239,34 @@ me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cu
         d = use8 ? tile_dist<8>(metric, sp, cur_pitch, p1, r1.pitch, p2, r2.pitch)
                  : tile_dist<4>(metric, sp, cur_pitch, p1, r1.pitch, p2, r2.pitch);
       }
-      atomicAdd(&cost_s[c], d);
+      atomicAdd(&sc.cost_s[c], d);
     }
     __syncthreads();
     if (tid == 0) {
-      int best = 0, mn = min_sh;
+      int best = 0, mn = sc.min_sh;
       for (int c = first; c < npos; c++) {
-        int mc = cost_s[c];
+        int mc = sc.cost_s[c];
         if (stage == 0 && c == 0 && a.check0) mc -= (lam * 16) >> 16;
         if (mc < mn) { mn = mc; best = c; }
       }
-      min_sh = mn;
-      mv_s[0] += step * c_sp_x[best];
-      mv_s[1] += step * c_sp_y[best];
+      sc.min_sh = mn;
+      sc.mv_s[0] += step * c_sp_x[best];
+      sc.mv_s[1] += step * c_sp_y[best];
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    result[0] = mv_s[0]; result[1] = mv_s[1]; result[2] = min_sh;
+  out_mvx = sc.mv_s[0]; out_mvy = sc.mv_s[1]; out_cost = sc.min_sh;
+}
+
+__global__ void __launch_bounds__(128)
+me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                        MeSubpelArgs a, int *result /* mvx, mvy, cost, ticket */, int ticket)
+{
+  __shared__ BlockScratch sc;
+  int mvx, mvy, cost;
+  subpel_block(r1, r2, cur, cur_pitch, cfg, a, sc, mvx, mvy, cost);
+  if (threadIdx.x == 0) {
+    result[0] = mvx; result[1] = mvy; result[2] = cost;
     __threadfence_system();                              // `result` is mapped host memory: the host spins on the ticket
     *(volatile int *)&result[3] = ticket;
   }
@@ -275,11 +292,10 @@ __device__ __forceinline__ void spiral_xy_dev(int s, int &dx, int &dy)
   else { k -= 2 * (2 * l - 1); dy = (k >> 1) - l; dx = (k & 1) ? l : -l; }
 }
 
-__global__ void __launch_bounds__(256)
-me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
-                      MeBiFullArgs a, int *result, int ticket)
+// one bi-predictive integer-pel search; called by all threads of the CTA, returns the result to all of them
+__device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch,
+                                  const MeCfgDev &cfg, const MeBiFullArgs &a, BlockScratch &sc, int &out_mvx, int &out_mvy, int &out_cost)
 {
-  __shared__ unsigned long long red[8];
   const int P = (2 * a.search_range + 1) * (2 * a.search_range + 1);
   const int bsx = me_bsx(a.blocktype), bsy = me_bsy(a.blocktype);
   const int metric = cfg.metric[0];
@@ -313,16 +329,112 @@ me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur,
     unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
     best = other < best ? other : best;
   }
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();                      // the scratch may still be read from a previous call
+  if ((threadIdx.x & 31) == 0) sc.red[threadIdx.x >> 5] = best;
   __syncthreads();
+  best = sc.red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); i++) best = sc.red[i] < best ? sc.red[i] : best;
+  int cost = (int)(unsigned)(best >> 32), pos = (int)(unsigned)(best & 0xffffffffu);
+  int dx = 0, dy = 0;
+  if (cost < a.min_mcost) spiral_xy_dev(pos, dx, dy); else cost = a.min_mcost;
+  out_mvx = a.mv_x + dx; out_mvy = a.mv_y + dy; out_cost = cost;
+}
+
+__global__ void __launch_bounds__(256)
+me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                      MeBiFullArgs a, int *result, int ticket)
+{
+  __shared__ BlockScratch sc;
+  int mvx, mvy, cost;
+  bipred_full_block(r1, r2, cur, cur_pitch, cfg, a, sc, mvx, mvy, cost);
   if (threadIdx.x == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); i++) best = red[i] < best ? red[i] : best;
-    int cost = (int)(unsigned)(best >> 32), pos = (int)(unsigned)(best & 0xffffffffu);
-    int dx = 0, dy = 0;
-    if (cost < a.min_mcost) spiral_xy_dev(pos, dx, dy); else cost = a.min_mcost;
-    result[0] = a.mv_x + dx; result[1] = a.mv_y + dy; result[2] = cost;
+    result[0] = mvx; result[1] = mvy; result[2] = cost;
     __threadfence_system();
     *(volatile int *)&result[3] = ticket;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Frame batch of the bi-predictive refinement: one CTA per (macroblock, list) job runs the whole block of
+// BlockMotionSearch at mv-search.c:864-1034 (block type 1, reference 0): vectors to integer pel ((mv + 2) >> 2, :884-885);
+// 1 + refinements integer-pel searches in which the two lists take turns, cost carried over, range halved each time
+// (:889-975); back to quarter pel (:976-982); sub-pel refinement of bimv with mv fixed (:984-1001) and, for
+// BiPredMESubPel == 2, of mv with bimv fixed (:1004-1021).  Every thread keeps the same copy of the (short) vectors.
+__global__ void __launch_bounds__(256)
+me_bipred_batch_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
+                       const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg, int refinements, int search_range,
+                       int subpel, me_bipred_result *__restrict__ out)
+{
+  __shared__ BlockScratch sc;
+  __shared__ uint32_t jw[8];
+  const int job_id = blockIdx.x;
+  if (job_id >= n_jobs) return;
+  if (threadIdx.x < 8) jw[threadIdx.x] = jobs[(size_t)job_id * 8 + threadIdx.x];    // whole-word loads (see me_load_job)
+  __syncthreads();
+  const int opix_x = (int)(int16_t)(jw[0] & 0xffffu), opix_y = (int)(int16_t)(jw[0] >> 16);
+  const int list = (int)(int8_t)(jw[1] & 0xffu);
+  const int pred_mv[2] = { (int)(int16_t)(jw[2] & 0xffffu), (int)(int16_t)(jw[2] >> 16) };
+  const int pred_mv_bi[2] = { (int)(int16_t)(jw[3] & 0xffffu), (int)(int16_t)(jw[3] >> 16) };
+  short mv[2] = { (short)(jw[4] & 0xffffu), (short)(jw[4] >> 16) }, bimv[2] = { 0, 0 }, tempmv[2] = { 0, 0 };
+  const int lambda[3] = { (int)jw[5], (int)jw[6], (int)jw[7] };
+  const MeRefDev refs[2] = { ref_table[0 * ME_MAX_REFS + 0], ref_table[1 * ME_MAX_REFS + 0] };
+  const int *pred_mv1 = pred_mv, *pred_mv2 = pred_mv_bi;
+  int min_mcostbi = ME_INT_MAX, iterlist = list;
+  mv[0] = (short)((mv[0] + 2) >> 2);
+  mv[1] = (short)((mv[1] + 2) >> 2);
+  for (int i = 0; i <= refinements; i++) {
+    if (i & 1) {
+      pred_mv2 = pred_mv; pred_mv1 = pred_mv_bi;
+      tempmv[0] = bimv[0]; tempmv[1] = bimv[1];
+      bimv[0] = mv[0]; bimv[1] = mv[1];
+      iterlist = list ^ 1;
+    } else {
+      pred_mv1 = pred_mv; pred_mv2 = pred_mv_bi;
+      if (i != 0) {
+        tempmv[0] = bimv[0]; tempmv[1] = bimv[1];
+        bimv[0] = mv[0]; bimv[1] = mv[1];
+      } else {
+        tempmv[0] = mv[0]; tempmv[1] = mv[1];
+        bimv[0] = (short)((pred_mv2[0] + 2) >> 2);
+        bimv[1] = (short)((pred_mv2[1] + 2) >> 2);
+      }
+      iterlist = list;
+    }
+    mv[0] = bimv[0]; mv[1] = bimv[1];
+    MeBiFullArgs a;
+    a.pic_pix_x = opix_x; a.pic_pix_y = opix_y; a.blocktype = 1;
+    a.pmv_x1 = pred_mv1[0]; a.pmv_y1 = pred_mv1[1]; a.pmv_x2 = pred_mv2[0]; a.pmv_y2 = pred_mv2[1];
+    a.mv_x = bimv[0]; a.mv_y = bimv[1]; a.s_mv_x = tempmv[0]; a.s_mv_y = tempmv[1];
+    a.search_range = search_range >> i; a.min_mcost = min_mcostbi; a.lambda = lambda[0];
+    int mx, my;
+    bipred_full_block(refs[iterlist], refs[iterlist ^ 1], cur, cur_pitch, cfg, a, sc, mx, my, min_mcostbi);
+    bimv[0] = (short)mx; bimv[1] = (short)my;
+    mv[0] = tempmv[0]; mv[1] = tempmv[1];
+  }
+  mv[0] = (short)(tempmv[0] << 2); mv[1] = (short)(tempmv[1] << 2);
+  bimv[0] = (short)(bimv[0] << 2); bimv[1] = (short)(bimv[1] << 2);
+  for (int pass = 0; pass < subpel && pass < 2; pass++) {
+    // pass 0 refines bimv (list iterlist ^ 1) with mv fixed; pass 1 refines mv (list iterlist) with bimv fixed
+    if (pass == 0 ? !cfg.start_hp : (!cfg.start_hp || !cfg.start_qp)) min_mcostbi = ME_INT_MAX;
+    MeSubpelArgs a;
+    a.pic_pix_x = opix_x; a.pic_pix_y = opix_y; a.blocktype = 1;
+    a.pmv_x = pass == 0 ? pred_mv2[0] : pred_mv1[0]; a.pmv_y = pass == 0 ? pred_mv2[1] : pred_mv1[1];
+    a.mv_x = pass == 0 ? bimv[0] : mv[0]; a.mv_y = pass == 0 ? bimv[1] : mv[1];
+    a.s_mv_x = pass == 0 ? mv[0] : bimv[0]; a.s_mv_y = pass == 0 ? mv[1] : bimv[1];
+    a.search_pos2 = 9; a.search_pos4 = 9; a.min_mcost = min_mcostbi;
+    a.lambda[0] = lambda[0]; a.lambda[1] = lambda[1]; a.lambda[2] = lambda[2];
+    a.check0 = 0; a.bi = 1;
+    const int l1 = pass == 0 ? iterlist : iterlist ^ 1;            // the `list` argument of SubPelBlockSearchBiPred: r1 = its reference 0
+    int mx, my;
+    subpel_block(refs[l1], refs[l1 ^ 1], cur, cur_pitch, cfg, a, sc, mx, my, min_mcostbi);
+    if (pass == 0) { bimv[0] = (short)mx; bimv[1] = (short)my; } else { mv[0] = (short)mx; mv[1] = (short)my; }
+  }
+  if (threadIdx.x == 0) {
+    uint32_t *o = reinterpret_cast<uint32_t *>(&out[job_id]);
+    o[0] = ((unsigned)(unsigned short)mv[0]) | ((unsigned)(unsigned short)mv[1] << 16);
+    o[1] = ((unsigned)(unsigned short)bimv[0]) | ((unsigned)(unsigned short)bimv[1] << 16);
+    o[2] = (uint32_t)min_mcostbi;
+    o[3] = (uint32_t)iterlist;
   }
 }
 
@@ -331,6 +443,15 @@ extern "C" void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRe
                                        cudaStream_t st)
 {
   me_subpel_batch_kernel<<<n_jobs, 256, 0, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, in_int, out);
+}
+
+extern "C" void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur,
+                                       int cur_pitch, const MeCfgDev *cfg, int refinements, int search_range, int subpel,
+                                       me_bipred_result *out, cudaStream_t st)
+{
+  static_assert(sizeof(me_bipred_job) == 32 && sizeof(me_bipred_result) == 16, "ABI struct sizes");
+  me_bipred_batch_kernel<<<n_jobs, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, cur, cur_pitch, *cfg,
+                                                 refinements, search_range, subpel, out);
 }
 
 extern "C" void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,

@@ -20,7 +20,11 @@ JOB_DTYPE = np.dtype([("opix_x", "<i2"), ("opix_y", "<i2"), ("list", "i1"), ("re
                       ("reserved", "i1"), ("pmv16", "<i2", (2,)), ("pmv", "<i2", (NUM_PART, 2)),
                       ("lambda", "<i4", (3,))])
 RESULT_DTYPE = np.dtype([("mv", "<i2", (NUM_PART, 2)), ("cost", "<i4", (NUM_PART,))])
+BIPRED_JOB_DTYPE = np.dtype([("opix_x", "<i2"), ("opix_y", "<i2"), ("list", "i1"), ("reserved", "i1", (3,)), ("pmv", "<i2", (2,)),
+                             ("pmv_bi", "<i2", (2,)), ("mv", "<i2", (2,)), ("lambda", "<i4", (3,))])
+BIPRED_RESULT_DTYPE = np.dtype([("mv", "<i2", (2,)), ("bimv", "<i2", (2,)), ("cost", "<i4"), ("iterlist", "<i4")])
 assert JOB_DTYPE.itemsize == 188 and RESULT_DTYPE.itemsize == 328
+assert BIPRED_JOB_DTYPE.itemsize == 32 and BIPRED_RESULT_DTYPE.itemsize == 16
 
 # every symbol include/me_cuda.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
@@ -30,7 +34,7 @@ ABI_SYMBOLS = [
     "me_cuda_mb_begin", "me_cuda_ffs_setup", "me_cuda_ffs_is_set_up",
     "me_cuda_FastFullPelBlockMotionSearch", "me_cuda_SubPelBlockMotionSearch",
     "me_cuda_FullPelBlockMotionBiPred", "me_cuda_SubPelBlockSearchBiPred",
-    "me_cuda_frame_search", "me_cuda_frame_search_device", "me_cuda_ref_create_device",
+    "me_cuda_frame_search", "me_cuda_frame_search_device", "me_cuda_frame_bipred", "me_cuda_ref_create_device",
     "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count",
     "me_cuda_measure_int_peak", "me_cuda_ref_update_u8", "me_cuda_ref_update_device", "me_cuda_set_timing",
     "me_cuda_kernel_time_ms",
@@ -79,6 +83,7 @@ def load_library(path=LIB_PATH):
                                                    sp, sp, sp, sp, C.c_int, C.c_int, C.c_int, ip])
     L.me_cuda_frame_search.argtypes = [vp, C.c_int, vp, vp]
     L.me_cuda_frame_search_device.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.me_cuda_frame_bipred.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.me_cuda_stream.restype = vp
     L.me_cuda_launch_count.restype = C.c_int64
     L.me_cuda_measure_int_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -245,6 +250,14 @@ class MeCuda:
         self._check(self.L.me_cuda_frame_search(jobs.ctypes.data, len(jobs), out.ctypes.data,
                                                 out_int.ctypes.data if want_int else None))
         return (out, out_int) if want_int else out
+
+    def frame_bipred(self, jobs, refinements, search_range, subpel):
+        """bi-predictive refinement of B-slice macroblocks (mv-search.c:864-1034): jobs of BIPRED_JOB_DTYPE"""
+        jobs = np.ascontiguousarray(jobs)
+        assert jobs.dtype == BIPRED_JOB_DTYPE
+        out = np.zeros(len(jobs), BIPRED_RESULT_DTYPE)
+        self._check(self.L.me_cuda_frame_bipred(jobs.ctypes.data, len(jobs), refinements, search_range, subpel, out.ctypes.data))
+        return out
 
     def frame_search_device(self, d_jobs, n, d_out, d_out_int=None, stream=None):
         self._check(self.L.me_cuda_frame_search_device(d_jobs, n, d_out, d_out_int, stream))

@@ -154,6 +154,33 @@ typedef struct me_mb_result_int {       /* optional: the integer-pel stage on it
 /* host buffers in, host buffers out; synchronous.  out_int may be NULL. */
 int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, me_mb_result_int *out_int);
 
+/* ---- frame batch, bi-predictive refinement of B slices: the block of BlockMotionSearch (mv-search.c:864-1034) that follows
+ * the uni-predictive search of block type 1 against reference 0 of `list` -- (1 + refinements) integer-pel searches
+ * (FullPelBlockMotionBiPred, me_fullsearch.c:164) with the range halved each time and the two lists taking turns, then up
+ * to two sub-pel refinements (SubPelBlockSearchBiPred, me_fullsearch.c:520).  One job per (macroblock, list); the pictures
+ * are reference 0 of both lists as set by me_cuda_set_ref_list. */
+typedef struct me_bipred_job {
+  int16_t opix_x, opix_y;               /* macroblock origin */
+  int8_t  list;                         /* the list whose 16x16 / reference-0 search has just finished */
+  int8_t  reserved[3];
+  int16_t pmv[2];                       /* pred_mv: predictor of `list`, reference 0 (quarter pel) */
+  int16_t pmv_bi[2];                    /* pred_mv_bi: predictor of the other list, reference 0 (mv-search.c:880) */
+  int16_t mv[2];                        /* quarter-pel vector that uni-predictive search returned (mv-search.c:855) */
+  int32_t lambda[3];                    /* lambda_factor[F_PEL,H_PEL,Q_PEL] */
+} me_bipred_job;                        /* 32 bytes */
+
+typedef struct me_bipred_result {
+  int16_t mv[2];                        /* bipred_mv[..][iterlist][0][1]     (mv-search.c:1028-1029), quarter pel */
+  int16_t bimv[2];                      /* bipred_mv[..][iterlist ^ 1][0][1] (mv-search.c:1030-1031) */
+  int32_t cost;                         /* min_mcostbi after the last stage */
+  int32_t iterlist;                     /* list ^ (refinements & 1) */
+} me_bipred_result;                     /* 16 bytes */
+
+/* refinements = input->BiPredMERefinements, search_range = input->BiPredMESearchRange (<= 64), subpel = input->BiPredMESubPel
+ * (0, 1 or 2).  Host buffers in, host buffers out; synchronous. */
+int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements, int search_range, int subpel,
+                         me_bipred_result *out);
+
 /* ---- device-resident variants for measurement (bench.py): pointers are CUDA device pointers, `stream` is a
  * cudaStream_t passed as void* (NULL = the library's own stream).  Asynchronous. ---- */
 int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, void *d_out_int, void *stream);

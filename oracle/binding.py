@@ -91,6 +91,7 @@ def lib():
         L.ora_bipred_subpel.argtypes = ([C.POINTER(OraCfg), vp, C.c_int, vp, vp] + [C.c_int] * 5
                                         + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int, ip])
         L.ora_mb_search.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, vp]
+        L.ora_mb_bipred.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         _lib = L
     return _lib
 
@@ -197,6 +198,24 @@ def bipred_subpel(cfg, cur, ref1, ref2, pic_pix_x, pic_pix_y, blocktype, pmv, mv
                                    C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy), search_pos2, search_pos4,
                                    min_mcost, lam3)
     return mx.value, my.value, cost
+
+
+BIPRED_JOB_DTYPE = np.dtype([("opix_x", "<i2"), ("opix_y", "<i2"), ("list", "i1"), ("reserved", "i1", (3,)), ("pmv", "<i2", (2,)),
+                             ("pmv_bi", "<i2", (2,)), ("mv", "<i2", (2,)), ("lambda", "<i4", (3,))])
+BIPRED_RESULT_DTYPE = np.dtype([("mv", "<i2", (2,)), ("bimv", "<i2", (2,)), ("cost", "<i4"), ("iterlist", "<i4")])
+assert BIPRED_JOB_DTYPE.itemsize == 32 and BIPRED_RESULT_DTYPE.itemsize == 16
+
+
+def mb_bipred(cfg, cur, ref_l0, ref_l1, jobs, refinements, search_range, subpel):
+    """jobs: numpy array of BIPRED_JOB_DTYPE; ref_l0 / ref_l1 = reference 0 of the two lists."""
+    jobs = np.ascontiguousarray(jobs)
+    out = np.zeros(len(jobs), BIPRED_RESULT_DTYPE)
+    L = lib()
+    for i in range(len(jobs)):
+        L.ora_mb_bipred(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref_l0.ptr, ref_l1.ptr,
+                        jobs.ctypes.data + i * BIPRED_JOB_DTYPE.itemsize, refinements, search_range, subpel,
+                        out.ctypes.data + i * BIPRED_RESULT_DTYPE.itemsize)
+    return out
 
 
 def mb_search(cfg, cur, ref, jobs):

@@ -527,3 +527,61 @@ void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const o
   }
   free(surf);
 }
+
+/* The bi-predictive refinement that BlockMotionSearch runs for block type 1 / reference 0 of a B slice
+ * (mv-search.c:864-1034, SearchMode 0): vectors back to integer pel ((mv + 2) >> 2, :884-885); 1 + refinements
+ * integer-pel searches in which the two lists take turns (:889-975: odd passes search the vector of `list` with the
+ * other one fixed, the cost carries over, the range is BiPredMESearchRange >> i); back to quarter pel (:976-982); one
+ * sub-pel refinement of bimv with mv fixed (:984-1001) and, for BiPredMESubPel == 2, one of mv with bimv fixed
+ * (:1004-1021).  The vectors are kept in `short` like the reference does. */
+void ora_mb_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *l0, const ora_ref *l1,
+                   const me_bipred_job *job, int refinements, int search_range, int subpel, me_bipred_result *out)
+{
+  const ora_ref *refs[2] = { l0, l1 };
+  const int list = job->list;
+  short mv[2] = { job->mv[0], job->mv[1] }, bimv[2] = { 0, 0 }, tempmv[2] = { 0, 0 };
+  const int16_t *pred_mv = job->pmv, *pred_mv_bi = job->pmv_bi, *pred_mv1 = NULL, *pred_mv2 = NULL;
+  int min_mcostbi = INT_MAX, iterlist = list, i;
+  mv[0] = (short)((mv[0] + 2) >> 2);
+  mv[1] = (short)((mv[1] + 2) >> 2);
+  for (i = 0; i <= refinements; i++) {
+    if (i & 1) {
+      pred_mv2 = pred_mv; pred_mv1 = pred_mv_bi;
+      tempmv[0] = bimv[0]; tempmv[1] = bimv[1];
+      bimv[0] = mv[0]; bimv[1] = mv[1];
+      iterlist = list ^ 1;
+    } else {
+      pred_mv1 = pred_mv; pred_mv2 = pred_mv_bi;
+      if (i != 0) {
+        tempmv[0] = bimv[0]; tempmv[1] = bimv[1];
+        bimv[0] = mv[0]; bimv[1] = mv[1];
+      } else {
+        tempmv[0] = mv[0]; tempmv[1] = mv[1];
+        bimv[0] = (short)((pred_mv2[0] + 2) >> 2);
+        bimv[1] = (short)((pred_mv2[1] + 2) >> 2);
+      }
+      iterlist = list;
+    }
+    mv[0] = bimv[0]; mv[1] = bimv[1];
+    min_mcostbi = ora_bipred_fullpel(c, cur, cur_stride, refs[iterlist], refs[iterlist ^ 1], job->opix_x, job->opix_y, 1,
+                                     pred_mv1[0], pred_mv1[1], pred_mv2[0], pred_mv2[1],
+                                     &bimv[0], &bimv[1], &tempmv[0], &tempmv[1], search_range >> i, min_mcostbi, job->lambda[0]);
+    mv[0] = tempmv[0]; mv[1] = tempmv[1];
+  }
+  mv[0] = (short)(tempmv[0] << 2); mv[1] = (short)(tempmv[1] << 2);
+  bimv[0] = (short)(bimv[0] << 2); bimv[1] = (short)(bimv[1] << 2);
+  if (subpel) {
+    if (!start_hp(c)) min_mcostbi = INT_MAX;
+    min_mcostbi = ora_bipred_subpel(c, cur, cur_stride, refs[iterlist], refs[iterlist ^ 1], job->opix_x, job->opix_y, 1,
+                                    pred_mv2[0], pred_mv2[1], &bimv[0], &bimv[1], &mv[0], &mv[1], 9, 9, min_mcostbi, job->lambda);
+  }
+  if (subpel == 2) {
+    if (!start_hp(c) || !start_qp(c)) min_mcostbi = INT_MAX;
+    min_mcostbi = ora_bipred_subpel(c, cur, cur_stride, refs[iterlist ^ 1], refs[iterlist], job->opix_x, job->opix_y, 1,
+                                    pred_mv1[0], pred_mv1[1], &mv[0], &mv[1], &bimv[0], &bimv[1], 9, 9, min_mcostbi, job->lambda);
+  }
+  out->mv[0] = mv[0]; out->mv[1] = mv[1];
+  out->bimv[0] = bimv[0]; out->bimv[1] = bimv[1];
+  out->cost = min_mcostbi;
+  out->iterlist = iterlist;
+}

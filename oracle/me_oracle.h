@@ -88,6 +88,11 @@ int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
 void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
                    const me_mb_job *job, me_mb_result *out, me_mb_result_int *out_int);
 
+/* one bi-predictive batch job = the block of BlockMotionSearch at mv-search.c:864-1034 (block type 1, reference 0):
+ * l0 / l1 = reference 0 of list 0 / list 1 */
+void ora_mb_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *l0, const ora_ref *l1,
+                   const me_bipred_job *job, int refinements, int search_range, int subpel, me_bipred_result *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -321,3 +321,57 @@ def test_tuned_and_basic_kernels_agree(pkg, oracle_lib):
             os.environ.pop("ME_CUDA_FFS_KERNEL", None)
     assert np.array_equal(res[0][1], res[1][1])
     assert np.array_equal(res[0][0], res[1][0])
+
+
+# ------------------------------------------------------------------------------------------------ bi-predictive batch
+def test_bipred_batch_matches_reference_chains(pkg):
+    """me_cuda_frame_bipred against the chains of bi-predictive calls the unmodified reference made (known-answer run, B picture)"""
+    from test_oracle_bipred import kat_chain_jobs
+    from oracle import binding as ob
+    tr, cfgkw = golden_trace("kat")
+    chains, jobs = kat_chain_jobs(ob, tr)
+    h, w = tr.size[("cur", chains[0]["pic"])]
+    with _open(pkg, w, h, cfgkw) as me:
+        # all chains of the B picture use the same two pictures: reference 0 of list 0 and of list 1
+        c0 = chains[0]
+        ids = {c0["list"]: c0["ref_l"][0], c0["list"] ^ 1: c0["ref_l"][1]}
+        assert all({c["list"]: c["ref_l"][0], c["list"] ^ 1: c["ref_l"][1]} == ids and c["pic"] == c0["pic"] for c in chains)
+        me.set_ref_list(0, [me.ref_create(tr.ref(ids[0]))])
+        me.set_ref_list(1, [me.ref_create(tr.ref(ids[1]))])
+        me.set_current(tr.cur(c0["pic"]))
+        out = me.frame_bipred(jobs.view(pkg.BIPRED_JOB_DTYPE), 3, 16, 2)
+    for k, c in enumerate(chains):
+        assert tuple(out["mv"][k]) == c["exp_mv"] and tuple(out["bimv"][k]) == c["exp_bimv"], (k, out[k], c["exp_mv"], c["exp_bimv"])
+        assert int(out["cost"][k]) == c["exp_cost"] and int(out["iterlist"][k]) == c["list"] ^ 1, (k, out[k], c["exp_cost"])
+
+
+@pytest.mark.parametrize("refinements,subpel,t8", [(3, 2, 0), (0, 1, 0), (2, 0, 0), (1, 2, 1)])
+def test_bipred_batch_matches_oracle(pkg, oracle_lib, refinements, subpel, t8):
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h = 352, 288
+    d, cfg = _cfg(ob, transform8x8=t8)
+    frames = synth.luma_frames(w, h, 3)
+    cur, past, future = frames[1], frames[0], frames[2]
+    rng = np.random.default_rng(41 + refinements)
+    mbs = [(16 * x, 16 * y) for y in range(h // 16) for x in range(w // 16)]
+    sel = [mbs[i] for i in rng.choice(len(mbs), 60, replace=False)]
+    jobs = np.zeros(2 * len(sel), pkg.BIPRED_JOB_DTYPE)
+    for k, (x, y) in enumerate(sel):
+        for lst in (0, 1):
+            j = jobs[2 * k + lst]
+            j["opix_x"], j["opix_y"], j["list"] = x, y, lst
+            sign = 1 if lst == 0 else -1                      # the pan runs the other way for the future picture
+            j["pmv"] = (sign * 12 + rng.integers(-6, 7), sign * 8 + rng.integers(-6, 7))
+            j["pmv_bi"] = (-sign * 12 + rng.integers(-6, 7), -sign * 8 + rng.integers(-6, 7))
+            j["mv"] = (sign * 12 + rng.integers(-9, 10), sign * 8 + rng.integers(-9, 10))
+            j["lambda"] = (334459, 334459, 334459)
+    with _open(pkg, w, h, d, max_refs=1) as me:
+        me.set_ref_list(0, [me.ref_create(past)])
+        me.set_ref_list(1, [me.ref_create(future)])
+        me.set_current(cur)
+        out = me.frame_bipred(jobs, refinements, 16, subpel)
+    r0, r1 = ob.Ref(past), ob.Ref(future)
+    exp = ob.mb_bipred(cfg, np.ascontiguousarray(cur), r0, r1, jobs.view(ob.BIPRED_JOB_DTYPE), refinements, 16, subpel)
+    r0.close(); r1.close()
+    assert np.array_equal(out.view(ob.BIPRED_RESULT_DTYPE), exp), np.nonzero(out.view(ob.BIPRED_RESULT_DTYPE) != exp)[0][:5]

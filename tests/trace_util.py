@@ -80,3 +80,30 @@ def cfg_from_trace(trace, search_range=32, full_search=2, metric=(0, 2, 2), mv_l
     t8 = int(sub[:, 22].max()) if len(sub) else 0
     return dict(search_range=search_range, rdopt=rdopt, full_search=full_search, metric=metric,
                 transform8x8=t8, mv_limit_min_y=mv_limits[0], mv_limit_max_y=mv_limits[1])
+
+
+def bipred_chains(trace, refinements=3, subpel=2):
+    """Groups the bi-predictive records of a trace into the per-(macroblock, list) chains BlockMotionSearch runs
+    (mv-search.c:864-1034): 1 + refinements REC_BI_FULL records followed by `subpel` REC_BI_SUB records.
+    Returns a list of dicts: job fields recovered from the first record, the records themselves, and the expected result."""
+    recs = trace.recs[(trace.recs[:, 0] == REC_BI_FULL) | (trace.recs[:, 0] == REC_BI_SUB)]
+    n = 1 + refinements + subpel
+    chains = []
+    i = 0
+    while i + n <= len(recs):
+        grp = recs[i:i + n]
+        assert (grp[:1 + refinements, 0] == REC_BI_FULL).all() and (grp[1 + refinements:, 0] == REC_BI_SUB).all(), i
+        assert len(set(map(tuple, grp[:, [1, 3, 4]]))) == 1, i         # same picture, same macroblock
+        f0 = grp[0]
+        last_sub = grp[-1]
+        first_sub = grp[1 + refinements]
+        chains.append(dict(
+            pic=int(f0[1]), opix=(int(f0[3]), int(f0[4])), list=int(f0[5]),
+            pmv=(int(f0[10]), int(f0[11])), pmv_bi=(int(f0[12]), int(f0[13])),
+            mv_int=(int(f0[19]), int(f0[20])),                       # the fixed vector of pass 0 = the uni-predictive result
+            lam=(int(last_sub[17]), int(last_sub[18]), int(last_sub[19])), search_range=int(f0[16]),
+            ref_l=(int(f0[21]), int(f0[22])),                        # picture ids: reference 0 of `list`, of the other list
+            exp_mv=(int(last_sub[23]), int(last_sub[24])) if subpel == 2 else (int(first_sub[14]), int(first_sub[15])),
+            exp_bimv=(int(first_sub[23]), int(first_sub[24])), exp_cost=int(last_sub[25]), recs=grp))
+        i += n
+    return chains
