@@ -340,13 +340,83 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
   out_mvx = a.mv_x + dx; out_mvy = a.mv_y + dy; out_cost = cost;
 }
 
+// The same search for the SAD metric with the data staged in shared memory and four pixels per instruction: the fixed block
+// (r1), the current block and the (2r+16)^2 window of r2 around the searched vector come from the wide-border integer
+// planes (pure edge replication, equal to the reference's origin clamp, refbuf.c:37, for whole blocks); per position and
+// row: 5 LDS + 4 funnel shifts for the window words, byte-wise rounded average with the fixed block ((p1 + p2 + 1) >> 1,
+// me_distortion.c:502) and one VABSDIFF4 per word.  win: (2 * BI_FAST_RANGE + 16 + 1) rows of BI_WIN_PITCH bytes.
+constexpr int BI_FAST_RANGE = 32;
+constexpr int BI_WIN_PITCH = 2 * BI_FAST_RANGE + 16 + 8;
+struct BiFastScratch {
+  uint32_t curw[64], p1w[64];
+  uint8_t  win[(2 * BI_FAST_RANGE + 16 + 1) * BI_WIN_PITCH];
+};
+
+__device__ void bipred_full_block_sad(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch,
+                                      const MeBiFullArgs &a, BlockScratch &sc, BiFastScratch &fs, int &out_mvx, int &out_mvy, int &out_cost)
+{
+  const int R = a.search_range, P = (2 * R + 1) * (2 * R + 1), n = 2 * R + 16;
+  const int c2x = (short)(a.pic_pix_x + a.mv_x), c2y = (short)(a.pic_pix_y + a.mv_y);
+  const int c1x = (short)(a.pic_pix_x + a.s_mv_x), c1y = (short)(a.pic_pix_y + a.s_mv_y);
+  const int px1 = (a.pic_pix_x << 2) + a.pmv_x1, py1 = (a.pic_pix_y << 2) + a.pmv_y1;
+  const int px2 = (a.pic_pix_x << 2) + a.pmv_x2, py2 = (a.pic_pix_y << 2) + a.pmv_y2;
+  __syncthreads();                      // the scratch may still be read from a previous call
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+    int y = i / n, x = i - y * n;
+    int sy = me_clamp(c2y - R + y + r2.spad, 0, r2.sh - 1), sx = me_clamp(c2x - R + x + r2.spad, 0, r2.sw - 1);
+    fs.win[y * BI_WIN_PITCH + x] = r2.search[(size_t)sy * r2.spitch + sx];
+  }
+  {
+    // 256 threads: one pixel each of the fixed block and of the current block
+    int y = threadIdx.x >> 4, x = threadIdx.x & 15;
+    int sy = me_clamp(c1y + y + r1.spad, 0, r1.sh - 1), sx = me_clamp(c1x + x + r1.spad, 0, r1.sw - 1);
+    reinterpret_cast<uint8_t *>(fs.p1w)[threadIdx.x] = r1.search[(size_t)sy * r1.spitch + sx];
+    reinterpret_cast<uint8_t *>(fs.curw)[threadIdx.x] = cur[(size_t)(a.pic_pix_y + y) * cur_pitch + a.pic_pix_x + x];
+  }
+  __syncthreads();
+  const int fixed_cost = me_mv_cost(a.lambda, c1x << 2, c1y << 2, px1, py1);
+  unsigned long long best = ~0ull;
+  for (int s = threadIdx.x; s < P; s += blockDim.x) {
+    int dx, dy;
+    spiral_xy_dev(s, dx, dy);
+    const int wx = dx + R, wy = dy + R, sh = (wx & 3) * 8;
+    unsigned sad = 0;
+#pragma unroll 4
+    for (int y = 0; y < 16; y++) {
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(fs.win + (wy + y) * BI_WIN_PITCH + (wx & ~3));
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+      const uint32_t q[4] = { __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh) };
+#pragma unroll
+      for (int c = 0; c < 4; c++) sad = __vsadu4(__vavgu4(fs.p1w[4 * y + c], q[c]), fs.curw[4 * y + c]) + sad;
+    }
+    const int mc = fixed_cost + me_mv_cost(a.lambda, (c2x + dx) << 2, (c2y + dy) << 2, px2, py2) + (int)sad;
+    const unsigned long long key = ((unsigned long long)(unsigned)mc << 32) | (unsigned)s;
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other < best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0) sc.red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  best = sc.red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); i++) best = sc.red[i] < best ? sc.red[i] : best;
+  int cost = (int)(unsigned)(best >> 32), pos = (int)(unsigned)(best & 0xffffffffu);
+  int dx = 0, dy = 0;
+  if (cost < a.min_mcost) spiral_xy_dev(pos, dx, dy); else cost = a.min_mcost;
+  out_mvx = a.mv_x + dx; out_mvy = a.mv_y + dy; out_cost = cost;
+}
+
 __global__ void __launch_bounds__(256)
 me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                       MeBiFullArgs a, int *result, int ticket)
 {
   __shared__ BlockScratch sc;
+  __shared__ BiFastScratch fs;
   int mvx, mvy, cost;
-  bipred_full_block(r1, r2, cur, cur_pitch, cfg, a, sc, mvx, mvy, cost);
+  if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE) bipred_full_block_sad(r1, r2, cur, cur_pitch, a, sc, fs, mvx, mvy, cost);
+  else bipred_full_block(r1, r2, cur, cur_pitch, cfg, a, sc, mvx, mvy, cost);
   if (threadIdx.x == 0) {
     result[0] = mvx; result[1] = mvy; result[2] = cost;
     __threadfence_system();
@@ -366,6 +436,7 @@ me_bipred_batch_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
                        int subpel, me_bipred_result *__restrict__ out)
 {
   __shared__ BlockScratch sc;
+  __shared__ BiFastScratch fs;
   __shared__ uint32_t jw[8];
   const int job_id = blockIdx.x;
   if (job_id >= n_jobs) return;
@@ -407,7 +478,10 @@ me_bipred_batch_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     a.mv_x = bimv[0]; a.mv_y = bimv[1]; a.s_mv_x = tempmv[0]; a.s_mv_y = tempmv[1];
     a.search_range = search_range >> i; a.min_mcost = min_mcostbi; a.lambda = lambda[0];
     int mx, my;
-    bipred_full_block(refs[iterlist], refs[iterlist ^ 1], cur, cur_pitch, cfg, a, sc, mx, my, min_mcostbi);
+    if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE)
+      bipred_full_block_sad(refs[iterlist], refs[iterlist ^ 1], cur, cur_pitch, a, sc, fs, mx, my, min_mcostbi);
+    else
+      bipred_full_block(refs[iterlist], refs[iterlist ^ 1], cur, cur_pitch, cfg, a, sc, mx, my, min_mcostbi);
     bimv[0] = (short)mx; bimv[1] = (short)my;
     mv[0] = tempmv[0]; mv[1] = tempmv[1];
   }
