@@ -13,18 +13,6 @@
 //    sequence of the encoder (setup once per (macroblock, list, ref), then one argmin per block search).
 #include "me_common.cuh"
 
-// inverse of me_spiral_index
-__device__ __forceinline__ void me_spiral_xy(int s, int &dx, int &dy)
-{
-  if (s == 0) { dx = 0; dy = 0; return; }
-  int l = (int)((sqrtf((float)s) + 1.0f) * 0.5f);
-  while ((2 * l - 1) * (2 * l - 1) > s) l--;
-  while ((2 * l + 1) * (2 * l + 1) <= s) l++;
-  int k = s - (2 * l - 1) * (2 * l - 1);
-  if (k < 2 * (2 * l - 1)) { dx = (k >> 1) - l + 1; dy = (k & 1) ? l : -l; }
-  else { k -= 2 * (2 * l - 1); dy = (k >> 1) - l; dx = (k & 1) ? l : -l; }
-}
-
 // search centre (me_fullfast.c:550-566)
 __device__ __forceinline__ void me_search_centre(const MeCfgDev &c, int range, int opix_x, int opix_y,
                                                  int pmv16_x, int pmv16_y, int &cx, int &cy)
@@ -241,47 +229,15 @@ me_ffs_block_kernel(const int32_t *__restrict__ surf_p, int setup_range, int off
                     int search_range, int min_mcost, int lambda, int rdopt, int *result /* mvx, mvy, cost, ticket */, int ticket)
 {
   __shared__ unsigned long long red[8];
-  const int Pset = (2 * setup_range + 1) * (2 * setup_range + 1);
-  int P = (2 * search_range + 1) * (2 * search_range + 1);
-  if (P > Pset) P = Pset;
-  unsigned long long best = ~0ull;
-  int pos00 = -1;
-  if (!rdopt && abs(offx) <= setup_range && abs(offy) <= setup_range) pos00 = me_spiral_index(-offx, -offy);
-  for (int s = threadIdx.x; s < P; s += blockDim.x) {
-    int dx, dy;
-    me_spiral_xy(s, dx, dy);
-    int mc = surf_p[s] + me_mv_cost(lambda, (offx + dx) << 2, (offy + dy) << 2, pmv_x, pmv_y);
-    unsigned long long key = ((unsigned long long)(unsigned)mc << 32) | (unsigned)(s + 1);
-    best = key < best ? key : best;
-  }
-  if (threadIdx.x == 0 && pos00 >= 0) {
-    int mc = surf_p[pos00] + me_mv_cost(lambda, 0, 0, pmv_x, pmv_y);
-    unsigned long long key = ((unsigned long long)(unsigned)mc << 32);
-    best = key < best ? key : best;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-    best = other < best ? other : best;
-  }
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
-  __syncthreads();
+  int mvx, mvy, cost;
+  me_ffs_block_argmin(surf_p, setup_range, offx, offy, pmv_x, pmv_y, search_range, min_mcost, lambda, rdopt, red, mvx, mvy, cost);
   if (threadIdx.x == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); i++) best = red[i] < best ? red[i] : best;
-    int cost = (int)(unsigned)(best >> 32);
-    unsigned tie = (unsigned)(best & 0xffffffffu);
-    int bestpos = 0;
-    // min_mcost from the caller: a candidate only wins when strictly below it (me_fullfast.c:871,891)
-    if (cost < min_mcost) { bestpos = tie == 0 ? pos00 : (int)tie - 1; } else cost = min_mcost;
-    int dx, dy;
-    me_spiral_xy(bestpos, dx, dy);
-    result[0] = offx + dx; result[1] = offy + dy; result[2] = cost;
+    result[0] = mvx; result[1] = mvy; result[2] = cost;
     __threadfence_system();                              // `result` is mapped host memory: the host spins on the ticket
     *(volatile int *)&result[3] = ticket;
   }
 }
 
-// job_list == nullptr: all n_jobs jobs; else the device-side list {count, ids...} with a fixed small grid
 extern "C" void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur,
                                           int cur_pitch, const MeCfgDev *cfg, MeResultInt *out, const int *job_list,
                                           cudaStream_t st)

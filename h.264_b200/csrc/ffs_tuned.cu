@@ -334,18 +334,6 @@ __device__ __forceinline__ void last_column(Regs &rg, const Thr &t, unsigned col
 #undef KEY
 }
 
-// inverse of me_spiral_index (mv-search.c:366-393)
-__device__ __forceinline__ void spiral_xy(int s, int &dx, int &dy)
-{
-  if (s == 0) { dx = 0; dy = 0; return; }
-  int l = (int)((sqrtf((float)s) + 1.0f) * 0.5f);
-  while ((2 * l - 1) * (2 * l - 1) > s) l--;
-  while ((2 * l + 1) * (2 * l + 1) <= s) l++;
-  int k = s - (2 * l - 1) * (2 * l - 1);
-  if (k < 2 * (2 * l - 1)) { dx = (k >> 1) - l + 1; dy = (k & 1) ? l : -l; }
-  else { k -= 2 * (2 * l - 1); dy = (k >> 1) - l; dx = (k & 1) ? l : -l; }
-}
-
 // window tensor maps travel as a kernel parameter (constant bank): (list, ref) -> list * TUNED_MAX_REFS + ref
 constexpr int TUNED_MAX_REFS = 8;
 struct WinMaps { CUtensorMap m[2 * TUNED_MAX_REFS]; };
@@ -565,7 +553,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
       for (int w = 1; w < G::NW; w++) kmin = min(kmin, sm.red[w][hh][e]);
       const unsigned cost = kmin / K, sp = kmin - cost * K;
       int sx, sy;
-      spiral_xy((int)sp, sx, sy);
+      me_spiral_xy((int)sp, sx, sy);
       const int p = c_slot_part[hh][e];
       const unsigned mvw = ((unsigned)(offx + sx) & 0xffffu) | ((unsigned)(offy + sy) << 16);
       reinterpret_cast<uint32_t *>(out[job_id].mv)[p] = mvw;

@@ -89,6 +89,18 @@ __host__ __device__ __forceinline__ int me_spiral_index(int dx, int dy)
   return base + 2 * (2 * l - 1) + 2 * (dy + l) + (dx > 0 ? 1 : 0);
 }
 
+// inverse of me_spiral_index
+__device__ __forceinline__ void me_spiral_xy(int s, int &dx, int &dy)
+{
+  if (s == 0) { dx = 0; dy = 0; return; }
+  int l = (int)((sqrtf((float)s) + 1.0f) * 0.5f);
+  while ((2 * l - 1) * (2 * l - 1) > s) l--;
+  while ((2 * l + 1) * (2 * l + 1) <= s) l++;
+  int k = s - (2 * l - 1) * (2 * l - 1);
+  if (k < 2 * (2 * l - 1)) { dx = (k >> 1) - l + 1; dy = (k & 1) ? l : -l; }
+  else { k -= 2 * (2 * l - 1); dy = (k >> 1) - l; dx = (k & 1) ? l : -l; }
+}
+
 // UMVLine4X (refbuf.c:37): byte offset into the plane set for padded quarter-pel coordinates
 __device__ __forceinline__ const uint8_t *me_umv_ptr(const MeRefDev &r, int y4, int x4)
 {
@@ -112,4 +124,49 @@ __device__ __forceinline__ void me_load_job(MeJob *dst, const MeJob *src)
   const unsigned words = sizeof(MeJob) / 4;
   if (threadIdx.x < words)
     reinterpret_cast<volatile uint32_t *>(dst)[threadIdx.x] = reinterpret_cast<const uint32_t *>(src)[threadIdx.x];
+}
+
+// One block search over a stored surface (FastFullPelBlockMotionSearch, me_fullfast.c:833-903): first strict minimum of
+// SAD + motion-vector rate in spiral order; with !rdopt the zero vector is scored first (:867-876).  Called by all threads
+// of the CTA, returns the result to all of them.  red: 8 words of shared memory.
+__device__ __forceinline__ void me_ffs_block_argmin(const int32_t *__restrict__ surf_p, int setup_range, int offx, int offy,
+                                                    int pmv_x, int pmv_y, int search_range, int min_mcost, int lambda, int rdopt,
+                                                    unsigned long long *red, int &out_mvx, int &out_mvy, int &out_cost)
+{
+  const int Pset = (2 * setup_range + 1) * (2 * setup_range + 1);
+  int P = (2 * search_range + 1) * (2 * search_range + 1);
+  if (P > Pset) P = Pset;
+  unsigned long long best = ~0ull;
+  int pos00 = -1;
+  if (!rdopt && abs(offx) <= setup_range && abs(offy) <= setup_range) pos00 = me_spiral_index(-offx, -offy);
+  for (int s = threadIdx.x; s < P; s += blockDim.x) {
+    int dx, dy;
+    me_spiral_xy(s, dx, dy);
+    int mc = surf_p[s] + me_mv_cost(lambda, (offx + dx) << 2, (offy + dy) << 2, pmv_x, pmv_y);
+    unsigned long long key = ((unsigned long long)(unsigned)mc << 32) | (unsigned)(s + 1);
+    best = key < best ? key : best;
+  }
+  if (threadIdx.x == 0 && pos00 >= 0) {
+    int mc = surf_p[pos00] + me_mv_cost(lambda, 0, 0, pmv_x, pmv_y);
+    unsigned long long key = ((unsigned long long)(unsigned)mc << 32);
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other < best ? other : best;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  best = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); i++) best = red[i] < best ? red[i] : best;
+  int cost = (int)(unsigned)(best >> 32);
+  unsigned tie = (unsigned)(best & 0xffffffffu);
+  int bestpos = 0;
+  // min_mcost from the caller: a candidate only wins when strictly below it (me_fullfast.c:871,891)
+  if (cost < min_mcost) { bestpos = tie == 0 ? pos00 : (int)tie - 1; } else cost = min_mcost;
+  int dx, dy;
+  me_spiral_xy(bestpos, dx, dy);
+  out_mvx = offx + dx; out_mvy = offy + dy; out_cost = cost;
 }

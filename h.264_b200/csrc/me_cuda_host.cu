@@ -48,6 +48,9 @@ void me_launch_ffs_block(const int32_t *surf_p, int setup_range, int offx, int o
                          int min_mcost, int lambda, int rdopt, int *result, int ticket, cudaStream_t st);
 void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
                             const MeCfgDev *cfg, const MeResultInt *in_int, MeResult *out, cudaStream_t st);
+void me_launch_ffs_block_subpel(const int32_t *surf_p, int setup_range, int offx, int offy, int search_range, int min_mcost, int rdopt,
+                                const MeRefDev *r1, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg, const MeSubpelArgs *a,
+                                int *result, int ticket, cudaStream_t st);
 void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                              const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st);
 void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
@@ -107,11 +110,18 @@ struct State {
   int32_t *d_surf[2][ME_MAX_REFS];
   int *d_result = nullptr, *h_result = nullptr;   // one mapped pinned buffer: the drop-in kernels write {mvx, mvy, cost, ticket}
   int ticket = 0;                                 // straight into host memory and the host spins on the ticket (no copy, no sync)
+  // The reference follows every integer-pel block search with the sub-pel refinement of the same block (mv-search.c:745 ->
+  // :823).  Once a sub-pel call has shown the lambda factors and position counts in use, the block search kernel also
+  // computes that refinement; the result is handed out when the sub-pel call arrives with exactly the predicted arguments.
+  struct { bool seen = false; int lambda[3] = {0, 0, 0}, pos2 = 9, pos4 = 9; } sub_params;
+  struct { bool valid = false; int list, ref, ppx, ppy, bt, pmvx, pmvy, mv_in_x, mv_in_y, min_in, lambda[3], pos2, pos4;
+           int mvx, mvy, cost; } spec;
   // batch scratch
   MeJob *d_jobs = nullptr; MeResult *d_out = nullptr; MeResultInt *d_out_int = nullptr; int batch_cap = 0;
   MeResultInt *d_int_scratch = nullptr; int int_scratch_cap = 0;
   me_bipred_job *d_bi_jobs = nullptr; me_bipred_result *d_bi_out = nullptr; int bi_cap = 0;
   long long launches = 0;
+  long long spec_hits = 0;                        // sub-pel calls answered from the fused block-search kernel
   // optional per-kernel-class timing (bench.py): event pairs around every launch of a class
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 planes, 1 integer-pel search, 2 sub-pel
@@ -362,12 +372,14 @@ int64_t me_cuda_launch_count(void) { return g.launches; }
 // ------------------------------------------------------------------------------------------------ pictures
 int me_cuda_ref_create_device(const void *d_luma, int stride, int w, int h, void *stream, me_ref_handle *out)
 {
+  g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   return create_ref_common((const uint8_t *)d_luma, stride, w, h, stream ? (cudaStream_t)stream : g.stream, out);
 }
 
 int me_cuda_ref_create_u8(const uint8_t *luma, int stride, int w, int h, me_ref_handle *out)
 {
+  g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   size_t bytes = (size_t)w * h;
   if (int rc = ensure_pin(bytes)) return rc;
@@ -380,6 +392,7 @@ int me_cuda_ref_create_u8(const uint8_t *luma, int stride, int w, int h, me_ref_
 
 int me_cuda_ref_create(const me_imgpel *const *rows, int w, int h, me_imgpel ****host_sub, me_ref_handle *out)
 {
+  g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   size_t bytes = (size_t)w * h;
   if (int rc = ensure_pin(bytes)) return rc;
@@ -419,6 +432,7 @@ int me_cuda_ref_create(const me_imgpel *const *rows, int w, int h, me_imgpel ***
 
 int me_cuda_ref_destroy(me_ref_handle h)
 {
+  g.spec.valid = false;
   RefPic *r = ref_of(h);
   if (!r) return fail(3, "me_cuda_ref_destroy: invalid handle %d", (int)h);
   CK(cudaStreamSynchronize(g.stream));
@@ -441,12 +455,14 @@ int me_cuda_ref_download_plane(me_ref_handle h, int fy, int fx, uint8_t *dst, in
 
 int me_cuda_ref_update_device(me_ref_handle hd, const void *d_luma, int stride, int w, int h, void *stream)
 {
+  g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   return update_ref_common(hd, (const uint8_t *)d_luma, stride, stream ? (cudaStream_t)stream : g.stream);
 }
 
 int me_cuda_ref_update_u8(me_ref_handle hd, const uint8_t *luma, int stride, int w, int h)
 {
+  g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   size_t bytes = (size_t)w * h;
   if (int rc = ensure_stage(bytes)) return rc;
@@ -482,6 +498,7 @@ int me_cuda_kernel_time_ms(int which, double *total_ms, int *n_launches)
 
 int me_cuda_set_current_device(const void *d_luma, int stride, int w, int h, void *stream)
 {
+  g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, d_luma, stride, w, h, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : g.stream));
   return 0;
@@ -489,6 +506,7 @@ int me_cuda_set_current_device(const void *d_luma, int stride, int w, int h, voi
 
 int me_cuda_set_current_u8(const uint8_t *luma, int stride, int w, int h)
 {
+  g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, luma, stride, w, h, cudaMemcpyHostToDevice, g.stream));
   return 0;
@@ -496,6 +514,7 @@ int me_cuda_set_current_u8(const uint8_t *luma, int stride, int w, int h)
 
 int me_cuda_set_current(const me_imgpel *const *rows, int w, int h)
 {
+  g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   size_t bytes = (size_t)w * h;
   if (int rc = ensure_pin(bytes)) return rc;
@@ -511,6 +530,7 @@ int me_cuda_set_current(const me_imgpel *const *rows, int w, int h)
 
 int me_cuda_set_ref_list(int list, int n, const me_ref_handle *handles)
 {
+  g.spec.valid = false;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (list < 0 || list > 1 || n < 0 || n > ME_MAX_REFS) return fail(1, "me_cuda_set_ref_list: list %d / count %d out of range", list, n);
   for (int i = 0; i < n; i++) if (!ref_of(handles[i])) return fail(3, "me_cuda_set_ref_list: invalid handle %d at %d", (int)handles[i], i);
@@ -523,13 +543,14 @@ int me_cuda_set_ref_list(int list, int n, const me_ref_handle *handles)
   return 0;
 }
 
-int me_cuda_set_slice_type(int t) { g.slice_type = t; return 0; }
+int me_cuda_set_slice_type(int t) { g.slice_type = t; g.spec.valid = false; return 0; }
 
 // ------------------------------------------------------------------------------------------------ drop-in calls
 int me_cuda_mb_begin(int opix_x, int opix_y)
 {
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   g.opix_x = opix_x; g.opix_y = opix_y;
+  g.spec.valid = false;
   memset(g.setup_done, 0, sizeof g.setup_done);
   return 0;
 }
@@ -538,6 +559,7 @@ int me_cuda_ffs_is_set_up(int list, int ref) { return g.setup_done[list][ref]; }
 
 int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
 {
+  g.spec.valid = false;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (list < 0 || list > 1 || ref < 0 || ref >= g.list_n[list]) return fail(1, "me_cuda_ffs_setup: (list %d, ref %d) not in the reference lists", list, ref);
   RefPic *r = ref_of(g.list[list][ref]);
@@ -590,12 +612,38 @@ int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int
   int p = me_part_index(blocktype, blk);
   if (p < 0) { fail(1, "block (%d,%d) is not a type-%d partition origin", pic_pix_x, pic_pix_y, blocktype); fatal("ffs"); return ME_INT_MAX; }
   int R = g.setup_range[list][ref], P = (2 * R + 1) * (2 * R + 1);
-  me_launch_ffs_block(g.d_surf[list][ref] + (size_t)p * P, R, g.centre_x[list][ref] - g.opix_x, g.centre_y[list][ref] - g.opix_y,
-                      pred_mv_x, pred_mv_y, search_range, min_mcost, lambda_factor, g.cfg.rdopt, g.d_result, ++g.ticket, g.stream);
+  const int offx = g.centre_x[list][ref] - g.opix_x, offy = g.centre_y[list][ref] - g.opix_y;
+  RefPic *rp = ref < g.list_n[list] ? ref_of(g.list[list][ref]) : nullptr;
+  g.spec.valid = false;
+  const bool speculate = g.sub_params.seen && g.sub_params.lambda[0] == lambda_factor && rp != nullptr;
+  if (speculate) {
+    MeSubpelArgs a{};
+    a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
+    a.pmv_x = pred_mv_x; a.pmv_y = pred_mv_y;
+    a.search_pos2 = g.sub_params.pos2; a.search_pos4 = g.sub_params.pos4;
+    for (int i = 0; i < 3; i++) a.lambda[i] = g.sub_params.lambda[i];
+    a.check0 = (!g.cfg.rdopt && g.slice_type != ME_B_SLICE && ref == 0 && blocktype == 1);   // and mv == 0: decided on the device
+    a.bi = 0;
+    me_launch_ffs_block_subpel(g.d_surf[list][ref] + (size_t)p * P, R, offx, offy, search_range, min_mcost, g.cfg.rdopt, &rp->dev,
+                               g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
+  } else {
+    me_launch_ffs_block(g.d_surf[list][ref] + (size_t)p * P, R, offx, offy, pred_mv_x, pred_mv_y, search_range, min_mcost,
+                        lambda_factor, g.cfg.rdopt, g.d_result, ++g.ticket, g.stream);
+  }
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("ffs"); return ME_INT_MAX; }
   *mv_x = (short)mx; *mv_y = (short)my;
+  if (speculate) {
+    auto &sp = g.spec;
+    sp.valid = true; sp.list = list; sp.ref = ref; sp.ppx = pic_pix_x; sp.ppy = pic_pix_y; sp.bt = blocktype;
+    sp.pmvx = pred_mv_x; sp.pmvy = pred_mv_y;
+    sp.mv_in_x = (short)(mx * 4); sp.mv_in_y = (short)(my * 4);
+    sp.min_in = g.cfg.start_hp ? cost : ME_INT_MAX;
+    for (int i = 0; i < 3; i++) sp.lambda[i] = g.sub_params.lambda[i];
+    sp.pos2 = g.sub_params.pos2; sp.pos4 = g.sub_params.pos4;
+    sp.mvx = g.h_result[4]; sp.mvy = g.h_result[5]; sp.cost = g.h_result[6];
+  }
   return cost;
 }
 
@@ -605,6 +653,18 @@ int me_cuda_SubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_
 {
   RefPic *r = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
   if (!r) { fail(1, "me_cuda_SubPelBlockMotionSearch: (list %d, ref %d) not in the reference lists", list, (int)ref); fatal("subpel"); return ME_INT_MAX; }
+  g.sub_params.seen = true;
+  for (int i = 0; i < 3; i++) g.sub_params.lambda[i] = lambda[i];
+  g.sub_params.pos2 = search_pos2; g.sub_params.pos4 = search_pos4;
+  if (g.spec.valid) {
+    const auto &sp = g.spec;
+    const bool hit = sp.list == list && sp.ref == ref && sp.ppx == pic_pix_x && sp.ppy == pic_pix_y && sp.bt == blocktype &&
+                     sp.pmvx == pred_mv_x && sp.pmvy == pred_mv_y && sp.mv_in_x == *mv_x && sp.mv_in_y == *mv_y &&
+                     sp.min_in == min_mcost && sp.pos2 == search_pos2 && sp.pos4 == search_pos4 &&
+                     sp.lambda[0] == lambda[0] && sp.lambda[1] == lambda[1] && sp.lambda[2] == lambda[2];
+    g.spec.valid = false;
+    if (hit) { *mv_x = (short)sp.mvx; *mv_y = (short)sp.mvy; g.spec_hits++; return sp.cost; }
+  }
   MeSubpelArgs a{};
   a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
   a.pmv_x = pred_mv_x; a.pmv_y = pred_mv_y; a.mv_x = *mv_x; a.mv_y = *mv_y;
@@ -625,6 +685,7 @@ int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic
                                      short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
                                      int search_range, int min_mcost, int lambda_factor)
 {
+  g.spec.valid = false;
   RefPic *r1 = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
   RefPic *r2 = (g.inited && g.list_n[list ^ 1] > 0) ? ref_of(g.list[list ^ 1][0]) : nullptr;
   if (!r1 || !r2) { fail(1, "me_cuda_FullPelBlockMotionBiPred: reference lists incomplete"); fatal("bipred"); return ME_INT_MAX; }
@@ -647,6 +708,7 @@ int me_cuda_SubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_
                                     short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y, short *s_mv_x, short *s_mv_y,
                                     int search_pos2, int search_pos4, int min_mcost, const int *lambda)
 {
+  g.spec.valid = false;
   RefPic *r1 = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
   RefPic *r2 = (g.inited && g.list_n[list ^ 1] > 0) ? ref_of(g.list[list ^ 1][0]) : nullptr;
   if (!r1 || !r2) { fail(1, "me_cuda_SubPelBlockSearchBiPred: reference lists incomplete"); fatal("bipred"); return ME_INT_MAX; }

@@ -272,6 +272,31 @@ me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cu
   }
 }
 
+// The block search over the stored surface followed at once by the sub-pel refinement BlockMotionSearch will ask for next
+// (mv-search.c:745 -> :770-774 mv <<= 2 -> :785-788 -> :823): one launch and one host wake-up instead of two.  The host
+// hands the second result out when the reference's SubPelBlockMotionSearch call arrives with exactly the predicted
+// arguments, and runs the plain kernel otherwise.  result: {mvx, mvy, cost, ticket, sub mvx, sub mvy, sub cost}.
+__global__ void __launch_bounds__(256)
+me_ffs_block_subpel_kernel(const int32_t *__restrict__ surf_p, int setup_range, int offx, int offy, int search_range, int min_mcost,
+                           int rdopt, MeRefDev r1, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                           MeSubpelArgs a /* block, predictor, lambda[3], check0 = everything but mv == 0 */, int *result, int ticket)
+{
+  __shared__ BlockScratch sc;
+  int mvx, mvy, cost;
+  me_ffs_block_argmin(surf_p, setup_range, offx, offy, a.pmv_x, a.pmv_y, search_range, min_mcost, a.lambda[0], rdopt, sc.red, mvx, mvy, cost);
+  a.mv_x = mvx * 4; a.mv_y = mvy * 4;                                   // mv <<= 2 on shorts, mv-search.c:770-774
+  a.min_mcost = cfg.start_hp ? cost : ME_INT_MAX;                       // mv-search.c:785-788
+  a.check0 = a.check0 && a.mv_x == 0 && a.mv_y == 0;                    // me_fullsearch.c:361
+  int smx, smy, scost;
+  subpel_block(r1, r1, cur, cur_pitch, cfg, a, sc, smx, smy, scost);
+  if (threadIdx.x == 0) {
+    result[0] = mvx; result[1] = mvy; result[2] = cost;
+    result[4] = smx; result[5] = smy; result[6] = scost;
+    __threadfence_system();
+    *(volatile int *)&result[3] = ticket;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // FullPelBlockMotionBiPred (me_fullsearch.c:164-332): r1 at the fixed integer vector, r2 searched over (2r+1)^2
 struct MeBiFullArgs {
@@ -280,17 +305,6 @@ struct MeBiFullArgs {
   int mv_x, mv_y, s_mv_x, s_mv_y;
   int search_range, min_mcost, lambda;
 };
-
-__device__ __forceinline__ void spiral_xy_dev(int s, int &dx, int &dy)
-{
-  if (s == 0) { dx = 0; dy = 0; return; }
-  int l = (int)((sqrtf((float)s) + 1.0f) * 0.5f);
-  while ((2 * l - 1) * (2 * l - 1) > s) l--;
-  while ((2 * l + 1) * (2 * l + 1) <= s) l++;
-  int k = s - (2 * l - 1) * (2 * l - 1);
-  if (k < 2 * (2 * l - 1)) { dx = (k >> 1) - l + 1; dy = (k & 1) ? l : -l; }
-  else { k -= 2 * (2 * l - 1); dy = (k >> 1) - l; dx = (k & 1) ? l : -l; }
-}
 
 // one bi-predictive integer-pel search; called by all threads of the CTA, returns the result to all of them
 __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch,
@@ -309,7 +323,7 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
   unsigned long long best = ~0ull;
   for (int s = threadIdx.x; s < P; s += blockDim.x) {
     int dx, dy;
-    spiral_xy_dev(s, dx, dy);
+    me_spiral_xy(s, dx, dy);
     int cx = (c2x + dx) << 2, cy = (c2y + dy) << 2;
     int mc = fixed_cost + me_mv_cost(a.lambda, cx, cy, px2, py2);
     const uint8_t *p2 = me_umv_ptr(r2, cy + 4 * ME_PAD, cx + 4 * ME_PAD);
@@ -336,7 +350,7 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
   for (int i = 1; i < (int)(blockDim.x >> 5); i++) best = sc.red[i] < best ? sc.red[i] : best;
   int cost = (int)(unsigned)(best >> 32), pos = (int)(unsigned)(best & 0xffffffffu);
   int dx = 0, dy = 0;
-  if (cost < a.min_mcost) spiral_xy_dev(pos, dx, dy); else cost = a.min_mcost;
+  if (cost < a.min_mcost) me_spiral_xy(pos, dx, dy); else cost = a.min_mcost;
   out_mvx = a.mv_x + dx; out_mvy = a.mv_y + dy; out_cost = cost;
 }
 
@@ -378,7 +392,7 @@ __device__ void bipred_full_block_sad(const MeRefDev &r1, const MeRefDev &r2, co
   unsigned long long best = ~0ull;
   for (int s = threadIdx.x; s < P; s += blockDim.x) {
     int dx, dy;
-    spiral_xy_dev(s, dx, dy);
+    me_spiral_xy(s, dx, dy);
     const int wx = dx + R, wy = dy + R, sh = (wx & 3) * 8;
     unsigned sad = 0;
 #pragma unroll 4
@@ -404,7 +418,7 @@ __device__ void bipred_full_block_sad(const MeRefDev &r1, const MeRefDev &r2, co
   for (int i = 1; i < (int)(blockDim.x >> 5); i++) best = sc.red[i] < best ? sc.red[i] : best;
   int cost = (int)(unsigned)(best >> 32), pos = (int)(unsigned)(best & 0xffffffffu);
   int dx = 0, dy = 0;
-  if (cost < a.min_mcost) spiral_xy_dev(pos, dx, dy); else cost = a.min_mcost;
+  if (cost < a.min_mcost) me_spiral_xy(pos, dx, dy); else cost = a.min_mcost;
   out_mvx = a.mv_x + dx; out_mvy = a.mv_y + dy; out_cost = cost;
 }
 
@@ -526,6 +540,14 @@ extern "C" void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, co
   static_assert(sizeof(me_bipred_job) == 32 && sizeof(me_bipred_result) == 16, "ABI struct sizes");
   me_bipred_batch_kernel<<<n_jobs, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, cur, cur_pitch, *cfg,
                                                  refinements, search_range, subpel, out);
+}
+
+extern "C" void me_launch_ffs_block_subpel(const int32_t *surf_p, int setup_range, int offx, int offy, int search_range, int min_mcost,
+                                           int rdopt, const MeRefDev *r1, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
+                                           const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st)
+{
+  me_ffs_block_subpel_kernel<<<1, 256, 0, st>>>(surf_p, setup_range, offx, offy, search_range, min_mcost, rdopt, *r1, cur, cur_pitch,
+                                                *cfg, *a, result, ticket);
 }
 
 extern "C" void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
