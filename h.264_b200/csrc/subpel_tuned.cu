@@ -322,10 +322,15 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
           if (mc < mn) { mn = mc; best = c; }
         }
         if (s4.leader) {
-          sm.mn[s4.p] = mn;
-          sm.mv[s4.p][0] = mvpx + step * c_spx[best];
-          sm.mv[s4.p][1] = mvpy + step * c_spy[best];
+          const int fx = mvpx + step * c_spx[best], fy = mvpy + step * c_spy[best];
+          sm.mn[s4.p] = mn; sm.mv[s4.p][0] = fx; sm.mv[s4.p][1] = fy;
+          if (!T8 && stage == 1) {
+            // the partition's lanes all sit in this warp, so its result is final here: straight to global memory
+            reinterpret_cast<uint32_t *>(out[job_id].mv)[s4.p] = ((unsigned)fx & 0xffffu) | ((unsigned)fy << 16);
+            out[job_id].cost[s4.p] = mn;
+          }
         }
+        if (!T8) __syncwarp();       // the half-pel result is read by the lanes of the same warp only: no CTA-wide barrier
       } else {
         // ---- 8x8 tiles (block types 1..4): 16 lanes per (type, quadrant), four lane groups share the candidates
         const int mvpx = sm.mv[s8.p][0], mvpy = sm.mv[s8.p][1];
@@ -365,10 +370,11 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
           if (s8.leader && cc < 9) sm.cost[s8.p][c] = v + sm.mvc[s8.p][c];
         }
       }
+      if (!T8) continue;
       __syncthreads();
       // the region is free once the quarter-pel tiles are read: request the next job's
       if (stage == 1 && tid == 0 && it + 1 < n_mine) issue_region(job_id + (int)gridDim.x);
-      if (T8) {
+      {
         // partitions of block types 1..4: their candidates were scored by four lane groups, scan them here
         if (tid < 9) {
           const int p = tid;
@@ -387,11 +393,18 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
         __syncthreads();
       }
     }
-    if (tid < ME_NUM_PARTITIONS) {
-      reinterpret_cast<uint32_t *>(out[job_id].mv)[tid] = ((unsigned)sm.mv[tid][0] & 0xffffu) | ((unsigned)sm.mv[tid][1] << 16);
-      out[job_id].cost[tid] = sm.mn[tid];
+    if (T8) {
+      if (tid < ME_NUM_PARTITIONS) {
+        reinterpret_cast<uint32_t *>(out[job_id].mv)[tid] = ((unsigned)sm.mv[tid][0] & 0xffffu) | ((unsigned)sm.mv[tid][1] << 16);
+        out[job_id].cost[tid] = sm.mn[tid];
+      }
+      __syncthreads();
+    } else {
+      // without the 8x8 transform every partition lives inside one warp: the warps ran both stages without meeting; they meet
+      // once per job, before the region and the job data are replaced
+      __syncthreads();
+      if (tid == 0 && it + 1 < n_mine) issue_region(job_id + (int)gridDim.x);
     }
-    __syncthreads();
   }
 }
 
