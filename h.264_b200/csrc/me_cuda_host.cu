@@ -31,6 +31,7 @@ extern "C" {
 void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t *planes, int pitch, size_t plane_stride,
                       uint8_t *search, int spad, int spitch, cudaStream_t st);
 void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp, uint16_t *dst, cudaStream_t st);
+void me_launch_weight_planes(const uint8_t *src, uint8_t *dst, size_t bytes, int weight, int offset, int log_denom, cudaStream_t st);
 void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
                                const MeCfgDev *cfg, MeResultInt *out, const int *job_list, cudaStream_t st);
 int  me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps, int n_refs0, int n_refs1,
@@ -67,12 +68,29 @@ struct TensorMap { alignas(64) unsigned char bytes[128]; };   // CUtensorMap
 
 struct RefPic {
   bool used = false;
+  unsigned long long gen = 0;   // changes whenever the planes are (re)generated: weighted copies made from them go stale
   uint8_t *planes = nullptr, *search = nullptr;
   MeRefDev dev{};
   bool has_map = false;
   TensorMap win_map{};          // search plane, box = one search window of the tuned kernel
   bool has_pmap = false;
   TensorMap planes_map{};       // the 16 planes as a 3-D tensor, box = one sub-pel region of the tuned kernel
+};
+
+// Weighted-prediction ME: the weights of one reference-list entry (wp_weight / wp_offset [list][ref][0], luma_log_weight_denom)
+struct WeightSet {
+  int apply = 0, weight = 32, offset = 0, denom = 5;
+  bool identity() const { return !apply || (weight == (1 << denom) && offset == 0); }
+  bool operator==(const WeightSet &o) const { return apply == o.apply && weight == o.weight && offset == o.offset && denom == o.denom; }
+};
+// ... and the weighted copy of that entry's planes the uni-predictive searches read instead (planes.cu: me_weight_planes_kernel)
+struct Twin {
+  uint8_t *planes = nullptr, *search = nullptr;
+  size_t planes_bytes = 0, search_bytes = 0;
+  MeRefDev dev{};
+  bool has_map = false, has_pmap = false;
+  TensorMap win_map{}, planes_map{};
+  me_ref_handle src = 0; unsigned long long src_gen = 0; WeightSet w; bool valid = false;
 };
 
 struct State {
@@ -82,6 +100,9 @@ struct State {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::vector<RefPic> refs;
+  unsigned long long gen_counter = 0;
+  WeightSet wp[2][ME_MAX_REFS];
+  Twin twin[2][ME_MAX_REFS];
   // current picture
   uint8_t *d_cur = nullptr;
   int cur_pitch = 0;
@@ -184,6 +205,49 @@ int ensure_pin(size_t bytes)
   return 0;
 }
 
+// The planes a uni-predictive search of reference-list entry (list, idx) reads: the picture's own, or -- under weighted-
+// prediction ME with non-trivial weights -- their weighted copy, (re)built here when the picture or the weights changed.
+int search_planes(int list, int idx, RefPic *r, const MeRefDev **dev, const TensorMap **win_map, bool *has_map,
+                  const TensorMap **planes_map, bool *has_pmap)
+{
+  const WeightSet &w = g.wp[list][idx];
+  if (w.identity()) {
+    *dev = &r->dev;
+    if (win_map) { *win_map = &r->win_map; *has_map = r->has_map; *planes_map = &r->planes_map; *has_pmap = r->has_pmap; }
+    return 0;
+  }
+  Twin &t = g.twin[list][idx];
+  const me_ref_handle h = g.list[list][idx];
+  if (!(t.valid && t.src == h && t.src_gen == r->gen && t.w == w)) {
+    const MeRefDev &d = r->dev;
+    const size_t pb = d.plane_stride * 16, sb = (size_t)d.spitch * d.sh;
+    t.valid = false;
+    if (t.planes_bytes != pb || t.search_bytes != sb) {
+      CK(cudaStreamSynchronize(g.stream));
+      if (t.planes) cudaFree(t.planes);
+      if (t.search) cudaFree(t.search);
+      t.planes = t.search = nullptr; t.planes_bytes = t.search_bytes = 0;
+      CK(cudaMalloc((void **)&t.planes, pb));
+      CK(cudaMalloc((void **)&t.search, sb));
+      t.planes_bytes = pb; t.search_bytes = sb;
+      t.dev = d; t.dev.planes = t.planes; t.dev.search = t.search;
+      t.has_map = false;
+      if (int n = me_ffs_tuned_window(g.cfg.search_range))
+        t.has_map = me_make_tensor_map_2d(t.win_map.bytes, t.search, d.sw, d.sh, d.spitch, n + 16, n) == 0;
+      t.has_pmap = me_make_planes_tensor_map(t.planes_map.bytes, t.planes, d.pitch, d.hp, d.plane_stride) == 0;
+    }
+    { ScopedTimer tm(0, g.stream);
+      me_launch_weight_planes(r->planes, t.planes, pb, w.weight, w.offset, w.denom, g.stream);
+      me_launch_weight_planes(r->search, t.search, sb, w.weight, w.offset, w.denom, g.stream); }
+    g.launches += 2;
+    CK(cudaGetLastError());
+    t.src = h; t.src_gen = r->gen; t.w = w; t.valid = true;
+  }
+  *dev = &t.dev;
+  if (win_map) { *win_map = &t.win_map; *has_map = t.has_map; *planes_map = &t.planes_map; *has_pmap = t.has_pmap; }
+  return 0;
+}
+
 int upload_table()
 {
   if (!g.table_dirty) return 0;
@@ -195,11 +259,13 @@ int upload_table()
     for (int i = 0; i < g.list_n[l]; i++) {
       RefPic *r = ref_of(g.list[l][i]);
       if (!r) return fail(3, "reference list %d entry %d holds an invalid handle", l, i);
-      g.h_table[l * ME_MAX_REFS + i] = r->dev;
-      g.h_maps[l * ME_MAX_REFS + i] = r->win_map;
-      g.maps_ok = g.maps_ok && r->has_map;
-      g.h_pmaps[l * ME_MAX_REFS + i] = r->planes_map;
-      g.pmaps_ok = g.pmaps_ok && r->has_pmap;
+      const MeRefDev *dev; const TensorMap *wm, *pm; bool hm, hp;
+      if (int rc = search_planes(l, i, r, &dev, &wm, &hm, &pm, &hp)) return rc;
+      g.h_table[l * ME_MAX_REFS + i] = *dev;
+      g.h_maps[l * ME_MAX_REFS + i] = *wm;
+      g.maps_ok = g.maps_ok && hm;
+      g.h_pmaps[l * ME_MAX_REFS + i] = *pm;
+      g.pmaps_ok = g.pmaps_ok && hp;
     }
   CK(cudaMemcpyAsync(g.d_table, g.h_table, sizeof g.h_table, cudaMemcpyHostToDevice, g.stream));
   // h_table is pageable: the copy above is staged synchronously by the runtime, safe to reuse
@@ -250,6 +316,7 @@ int create_ref_common(const uint8_t *d_luma, int stride, int w, int h, cudaStrea
   g.launches += 2;
   CK(cudaGetLastError());
   r.used = true;
+  r.gen = ++g.gen_counter;
   *out = (me_ref_handle)(slot + 1);
   return 0;
 }
@@ -263,6 +330,9 @@ int update_ref_common(me_ref_handle h, const uint8_t *d_luma, int stride, cudaSt
   { ScopedTimer t(0, st); me_launch_planes(d_luma, stride, d.w, d.h, r->planes, d.pitch, d.plane_stride, r->search, d.spad, d.spitch, st); }
   g.launches += 2;
   CK(cudaGetLastError());
+  r->gen = ++g.gen_counter;
+  for (int l = 0; l < 2; l++)    // weighted copies of these planes are rebuilt with the next table
+    for (int i = 0; i < g.list_n[l]; i++) if (g.twin[l][i].valid && g.twin[l][i].src == h) g.table_dirty = true;
   return 0;
 }
 
@@ -299,7 +369,6 @@ int me_cuda_init(const me_cuda_params *p)
   if (g.inited) me_cuda_shutdown();
   if (p->bit_depth != 8) return fail(1, "bit depth %d not supported (8-bit content only)", p->bit_depth);
   if (p->chroma_me_enable) return fail(1, "ChromaMEEnable is not supported by the CUDA path");
-  if (p->weighted_me) return fail(1, "weighted-prediction ME is not supported by the CUDA path");
   if (p->width <= 0 || p->height <= 0 || (p->width & 15) || (p->height & 15)) return fail(1, "picture size %dx%d must be positive multiples of 16", p->width, p->height);
   if (p->search_range < 1 || p->search_range > 64) return fail(1, "search range %d outside 1..64", p->search_range);
   if (p->max_num_references < 1 || p->max_num_references > ME_MAX_REFS) return fail(1, "max_num_references %d outside 1..%d", p->max_num_references, ME_MAX_REFS);
@@ -343,6 +412,7 @@ void me_cuda_shutdown(void)
   cudaStreamSynchronize(g.stream);
   for (auto &r : g.refs) if (r.used) { cudaFree(r.planes); cudaFree(r.search); }
   g.refs.clear();
+  for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) { if (g.twin[l][i].planes) cudaFree(g.twin[l][i].planes); if (g.twin[l][i].search) cudaFree(g.twin[l][i].search); }
   for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) if (g.d_surf[l][i]) cudaFree(g.d_surf[l][i]);
   cudaFree(g.d_cur); cudaFree(g.d_table); cudaFreeHost(g.h_result);
   if (g.d_deferred) cudaFree(g.d_deferred);
@@ -545,6 +615,24 @@ int me_cuda_set_ref_list(int list, int n, const me_ref_handle *handles)
 
 int me_cuda_set_slice_type(int t) { g.slice_type = t; g.spec.valid = false; return 0; }
 
+int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset, int log_denom)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (list < 0 || list > 1 || ref < 0 || ref >= ME_MAX_REFS) return fail(1, "me_cuda_set_ref_weights: (list %d, ref %d) out of range", list, ref);
+  WeightSet w;
+  w.apply = apply != 0;
+  if (w.apply) {
+    if (weight < -128 || weight > 127 || offset < -128 || offset > 127 || log_denom < 0 || log_denom > 7)
+      return fail(1, "me_cuda_set_ref_weights: weight %d / offset %d / log denominator %d out of range", weight, offset, log_denom);
+    w.weight = weight; w.offset = offset; w.denom = log_denom;
+  }
+  if (g.wp[list][ref] == w) return 0;
+  g.wp[list][ref] = w;
+  g.table_dirty = true;
+  g.spec.valid = false;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ drop-in calls
 int me_cuda_mb_begin(int opix_x, int opix_y)
 {
@@ -572,7 +660,9 @@ int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
   cx += g.opix_x; cy += g.opix_y;
   int P = (2 * g.cfg.search_range + 1) * (2 * g.cfg.search_range + 1);
   if (!g.d_surf[list][ref]) CK(cudaMalloc((void **)&g.d_surf[list][ref], sizeof(int32_t) * (size_t)ME_NUM_PARTITIONS * P));
-  me_launch_ffs_surfaces(&r->dev, g.d_cur, g.cur_pitch, g.opix_x, g.opix_y, cx, cy, R, g.cfg.metric[0] != 0, g.d_surf[list][ref], g.stream);
+  const MeRefDev *dev;
+  if (int rc = search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) return rc;
+  me_launch_ffs_surfaces(dev, g.d_cur, g.cur_pitch, g.opix_x, g.opix_y, cx, cy, R, g.cfg.metric[0] != 0, g.d_surf[list][ref], g.stream);
   g.launches++;
   CK(cudaGetLastError());
   g.centre_x[list][ref] = cx; g.centre_y[list][ref] = cy; g.setup_range[list][ref] = R;
@@ -615,6 +705,8 @@ int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int
   const int offx = g.centre_x[list][ref] - g.opix_x, offy = g.centre_y[list][ref] - g.opix_y;
   RefPic *rp = ref < g.list_n[list] ? ref_of(g.list[list][ref]) : nullptr;
   g.spec.valid = false;
+  const MeRefDev *rdev = nullptr;
+  if (rp && search_planes(list, ref, rp, &rdev, nullptr, nullptr, nullptr, nullptr)) { fatal("ffs"); return ME_INT_MAX; }
   const bool speculate = g.sub_params.seen && g.sub_params.lambda[0] == lambda_factor && rp != nullptr;
   if (speculate) {
     MeSubpelArgs a{};
@@ -624,7 +716,7 @@ int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int
     for (int i = 0; i < 3; i++) a.lambda[i] = g.sub_params.lambda[i];
     a.check0 = (!g.cfg.rdopt && g.slice_type != ME_B_SLICE && ref == 0 && blocktype == 1);   // and mv == 0: decided on the device
     a.bi = 0;
-    me_launch_ffs_block_subpel(g.d_surf[list][ref] + (size_t)p * P, R, offx, offy, search_range, min_mcost, g.cfg.rdopt, &rp->dev,
+    me_launch_ffs_block_subpel(g.d_surf[list][ref] + (size_t)p * P, R, offx, offy, search_range, min_mcost, g.cfg.rdopt, rdev,
                                g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   } else {
     me_launch_ffs_block(g.d_surf[list][ref] + (size_t)p * P, R, offx, offy, pred_mv_x, pred_mv_y, search_range, min_mcost,
@@ -672,7 +764,9 @@ int me_cuda_SubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_
   for (int i = 0; i < 3; i++) a.lambda[i] = lambda[i];
   a.check0 = (!g.cfg.rdopt && g.slice_type != ME_B_SLICE && ref == 0 && blocktype == 1 && *mv_x == 0 && *mv_y == 0);   // me_fullsearch.c:361
   a.bi = 0;
-  me_launch_subpel_single(&r->dev, nullptr, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
+  const MeRefDev *dev;
+  if (search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) { fatal("subpel"); return ME_INT_MAX; }
+  me_launch_subpel_single(dev, nullptr, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("subpel"); return ME_INT_MAX; }
@@ -840,6 +934,8 @@ int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements,
   if (refinements < 0 || refinements > 16 || search_range < 0 || search_range > 64 || subpel < 0 || subpel > 2)
     return fail(1, "me_cuda_frame_bipred: refinements %d / search range %d / sub-pel levels %d out of range", refinements, search_range, subpel);
   if (g.cfg.metric[0] == 2) return fail(1, "bi-predictive integer search with a Hadamard metric is not implemented");
+  if (!g.wp[0][0].identity() || !g.wp[1][0].identity())
+    return fail(1, "me_cuda_frame_bipred: weighted bi-prediction (computeBiPred*2) is not implemented; clear the weights of reference 0");
   for (int i = 0; i < n_jobs; i++) {
     const me_bipred_job &j = jobs[i];
     if (j.list < 0 || j.list > 1) return fail(1, "bi-pred job %d: list %d", i, (int)j.list);

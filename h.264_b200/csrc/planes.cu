@@ -150,3 +150,44 @@ extern "C" void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t 
   size_t n = (size_t)16 * hp * wp;
   me_widen_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(planes, pitch, plane_stride, wp, hp, dst);
 }
+
+// Weighted-prediction ME (UseWeightedReferenceME): every reference sample a uni-predictive distortion reads is replaced by
+//   weighted_pel = iClip1(255, ((weight * p + round) >> log_denom) + offset),  round = 1 << (log_denom - 1)
+// (me_fullfast.c:653, computeSADWP me_distortion.c:413, computeSATDWP :734, weighted_prediction.c:50).  That is a function of
+// the sample alone, and JM's origin clamp moves coordinates, not values -- so the searches run unchanged on a second copy
+// of the picture's planes with the 256-entry table applied once per (picture, weights).  HBM-bound: one read and one
+// write of the plane set (2 x 40 MB at 1080p); 16 bytes per thread, table in shared memory.
+__global__ void __launch_bounds__(256)
+me_weight_planes_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16, int weight, int offset, int log_denom)
+{
+  __shared__ uint8_t lut[256];
+  {
+    const int p = threadIdx.x, round = log_denom ? 1 << (log_denom - 1) : 0;
+    lut[p] = (uint8_t)me_clamp(((weight * p + round) >> log_denom) + offset, 0, 255);
+  }
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = src[i];
+    uint4 o;
+    const uint32_t in[4] = { v.x, v.y, v.z, v.w };
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      out[k] = (uint32_t)lut[in[k] & 0xffu] | ((uint32_t)lut[(in[k] >> 8) & 0xffu] << 8) |
+               ((uint32_t)lut[(in[k] >> 16) & 0xffu] << 16) | ((uint32_t)lut[in[k] >> 24] << 24);
+    o.x = out[0]; o.y = out[1]; o.z = out[2]; o.w = out[3];
+    dst[i] = o;
+  }
+}
+
+// bytes: multiple of 16 (plane sets and search planes have 128-byte pitches)
+extern "C" void me_launch_weight_planes(const uint8_t *src, uint8_t *dst, size_t bytes, int weight, int offset, int log_denom,
+                                        cudaStream_t st)
+{
+  const size_t n16 = bytes / 16;
+  size_t blocks = (n16 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks == 0) return;
+  me_weight_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), n16,
+                                                            weight, offset, log_denom);
+}

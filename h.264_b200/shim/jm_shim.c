@@ -50,6 +50,7 @@ static struct {
   int  (*set_current)(const me_imgpel *const *, int, int);
   int  (*set_ref_list)(int, int, const me_ref_handle *);
   int  (*set_slice_type)(int);
+  int  (*set_ref_weights)(int, int, int, int, int, int);
   int  (*mb_begin)(int, int);
   int  (*ffs_setup)(int, int, int, int);
   int  (*ffs_is_set_up)(int, int);
@@ -110,6 +111,7 @@ static void load_library(void)
   L.ref_create = sym("me_cuda_ref_create"); L.ref_destroy = sym("me_cuda_ref_destroy");
   L.set_current = sym("me_cuda_set_current"); L.set_ref_list = sym("me_cuda_set_ref_list");
   L.set_slice_type = sym("me_cuda_set_slice_type"); L.mb_begin = sym("me_cuda_mb_begin");
+  L.set_ref_weights = sym("me_cuda_set_ref_weights");
   L.ffs_setup = sym("me_cuda_ffs_setup"); L.ffs_is_set_up = sym("me_cuda_ffs_is_set_up");
   L.ffs = sym("me_cuda_FastFullPelBlockMotionSearch"); L.subpel = sym("me_cuda_SubPelBlockMotionSearch");
   L.bi_full = sym("me_cuda_FullPelBlockMotionBiPred"); L.bi_sub = sym("me_cuda_SubPelBlockSearchBiPred");
@@ -146,6 +148,11 @@ void __wrap_Init_Motion_Search_Module(void)
   active = 0;
   if (dis && atoi(dis)) return;
   if (input->SearchMode != FAST_FULL_SEARCH) return;   /* the library implements the SearchMode=0 path */
+  if (input->WeightedBiprediction && input->BiPredMotionEstimation) {
+    fprintf(stderr, "me_cuda shim: weighted bi-predictive ME (computeBiPred*2) is not implemented on the GPU path; "
+                    "set ME_CUDA_DISABLE=1 for the pure reference\n");
+    exit(502);
+  }
   {
     me_cuda_params p;
     int apply_wp = (input->WeightedPrediction || input->WeightedBiprediction) && input->UseWeightedReferenceME;
@@ -259,6 +266,18 @@ static void keep_reference_side_effects(int list, short ref)
   height_pad = rp->size_y_pad;
 }
 
+/* Weighted-prediction ME: what SetupFastFullPelSearch (me_fullfast.c:507-508, :530-534) and SubPelBlockMotionSearch
+ * (me_fullsearch.c:368-388) read from the picture parameter set and the wp_* tables before a uni-predictive search. */
+static void pass_weights(int list, short ref)
+{
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  int apply = ((active_pps->weighted_pred_flag && (img->type == P_SLICE || img->type == SP_SLICE)) ||
+               (active_pps->weighted_bipred_idc && (img->type == B_SLICE))) && input->UseWeightedReferenceME;
+  if (L.set_ref_weights(list, ref, apply, apply ? wp_weight[list + list_offset][ref][0] : 0,
+                        apply ? wp_offset[list + list_offset][ref][0] : 0, apply ? luma_log_weight_denom : 0))
+    die("me_cuda_set_ref_weights");
+}
+
 /* ---------------------------------------------------------------- block searches */
 int __real_FastFullPelBlockMotionSearch(imgpel *, short, int, int, int, int, short, short, short *, short *, int, int, int);
 int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
@@ -272,6 +291,7 @@ int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, i
     /* SetupFastFullPelSearch (me_fullfast.c:550): the search centre is the 16x16 predictor, computed by host code */
     short pmv[2];
     keep_reference_side_effects(list, ref);
+    pass_weights(list, ref);
     SetMotionVectorPredictor(pmv, enc_picture->ref_idx[list], enc_picture->mv[list], ref, list, 0, 0, 16, 16);
     if (L.ffs_setup(list, ref, pmv[0], pmv[1])) die("me_cuda_ffs_setup");
   }
@@ -301,6 +321,7 @@ int __wrap_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pi
     return __real_SubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                           mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
   keep_reference_side_effects(list, ref);
+  pass_weights(list, ref);
   if (verify) {
     short ix = *mv_x, iy = *mv_y, gx = *mv_x, gy = *mv_y;
     int gc = L.subpel(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, &gx, &gy, search_pos2, search_pos4, min_mcost, lambda_factor);

@@ -38,6 +38,8 @@ def luma_frames(width, height, n_frames, seed=1234, kind="pan"):
         px = (width // 2 - 32 - 5 * t) % max(1, width - 64)
         f[py:py + 64, px:px + 64] = patch[:min(64, height - py), :min(64, width - px)]
         f = f + rng.normal(0.0, 1.5, f.shape)
+        if kind == "fade":          # brightness ramps down and a pedestal comes in: weighted prediction gets real weights
+            f = f * (1.0 - 0.06 * t) + 3.0 * t
         out.append(np.clip(np.rint(f), 0, 255).astype(np.uint8))
     return out
 

@@ -61,7 +61,7 @@ typedef struct me_cuda_params {
   int32_t mv_limit_min_y;       /* LEVELMVLIMIT[img->LevelIndex][0], mv-search.h:36 */
   int32_t mv_limit_max_y;       /* LEVELMVLIMIT[img->LevelIndex][1] */
   int32_t chroma_me_enable;     /* input->ChromaMEEnable: must be 0 (chroma ME not implemented) */
-  int32_t weighted_me;          /* weighted-prediction ME active: must be 0 */
+  int32_t weighted_me;          /* informational: weighted-prediction ME in use (weights arrive through me_cuda_set_ref_weights) */
   int32_t device;               /* CUDA device ordinal; -1: env ME_CUDA_DEVICE, else 0 */
   int32_t reserved[8];
 } me_cuda_params;
@@ -98,6 +98,16 @@ int me_cuda_set_current_u8(const uint8_t *luma, int stride, int w, int h);
 int me_cuda_set_ref_list(int list, int n, const me_ref_handle *handles);
 /* img->type of the slice being coded (ME_P_SLICE / ME_B_SLICE); only the !rdopt zero-vector bonus depends on it */
 int me_cuda_set_slice_type(int slice_type);
+
+/* ---- weighted-prediction ME (cfg UseWeightedReferenceME with WeightedPrediction / WeightedBiprediction): the reference's
+ * uni-predictive searches replace every reference sample p of list entry (list, ref) by
+ *     iClip1(255, ((weight * p + (1 << (log_denom - 1))) >> log_denom) + offset)
+ * with weight = wp_weight[list][ref][0], offset = wp_offset[list][ref][0], log_denom = luma_log_weight_denom
+ * (me_fullfast.c:507-508,530-534,640-737; me_fullsearch.c:368-388; computeSADWP / computeSSEWP / computeSATDWP,
+ * me_distortion.c:413,1107,734; weighted_prediction.c:50).  apply = 0 switches the entry back to plain samples.  The weights
+ * stay with the list entry until changed; set them after me_cuda_set_ref_list, before the searches of the slice.
+ * Bi-predictive searches with weights (computeBiPred*2) are not implemented: their calls fail when weights are set. ---- */
+int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset, int log_denom);
 
 /* ---- per macroblock: ResetFastFullIntegerSearch (me_fullfast.c:197, called macroblock.c:509) ---- */
 int me_cuda_mb_begin(int opix_x, int opix_y);

@@ -73,6 +73,7 @@ def lib():
         L.ora_ref_destroy.argtypes = [vp]
         L.ora_ref_plane.restype = vp
         L.ora_ref_plane.argtypes = [vp, C.c_int, C.c_int]
+        L.ora_ref_set_weights.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.ora_spiral.argtypes = [C.c_int, vp, vp]
         L.ora_mvbits.argtypes = [C.c_int]
         L.ora_mv_cost.argtypes = [C.c_int] * 5
@@ -131,6 +132,10 @@ class Ref:
 
     def planes(self):
         return np.stack([np.stack([self.plane(fy, fx) for fx in range(4)]) for fy in range(4)])
+
+    def set_weights(self, apply, weight=32, offset=0, log_denom=5):
+        """weighted-prediction ME: the weights of the (list, ref) entry this picture is about to be searched as"""
+        lib().ora_ref_set_weights(self.ptr, int(apply), int(weight), int(offset), int(log_denom))
 
     def close(self):
         if self.ptr:

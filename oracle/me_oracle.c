@@ -151,6 +151,20 @@ void ora_ref_destroy(ora_ref *r)
 
 const uint8_t *ora_ref_plane(const ora_ref *r, int fy, int fx) { return r->plane[fy][fx]; }
 
+void ora_ref_set_weights(ora_ref *r, int apply, int weight, int offset, int log_denom)
+{
+  r->wp_apply = apply; r->wp_weight = weight; r->wp_offset = offset; r->wp_denom = log_denom;
+}
+
+/* the reference sample a uni-predictive distortion sees: as stored, or weighted_pel of me_fullfast.c:653 /
+ * computeSADWP (me_distortion.c:413) / computeSATDWP (:734) with wp_luma_round = 1 << (denom - 1)
+ * (weighted_prediction.c:50) and iClip1(255, .) */
+static inline int refpel(const ora_ref *r, int v)
+{
+  if (!r->wp_apply) return v;
+  return clampi(((r->wp_weight * v + (r->wp_denom ? 1 << (r->wp_denom - 1) : 0)) >> r->wp_denom) + r->wp_offset, 0, 255);
+}
+
 /* UMVLine4X (refbuf.c:37-43) with size_x_pad = w + 2*20 - 1 - 16 (mbuffer.c:421-422).  FastLine4X (refbuf.c:25)
  * yields the same pixels whenever the reference chooses it: it is only chosen where the clamp is a no-op or where
  * both addresses lie in the edge-replicated region in which every plane is constant along the row / column. */
@@ -205,7 +219,7 @@ void ora_ffs_surfaces(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
     memset(leaf, 0, sizeof leaf);
     for (y = 0; y < 16; y++)
       for (x = 0; x < 16; x++) {
-        int d = (int)rp[(size_t)y * r->wp + x] - (int)cur[(size_t)(opix_y + y) * cur_stride + opix_x + x];
+        int d = refpel(r, rp[(size_t)y * r->wp + x]) - (int)cur[(size_t)(opix_y + y) * cur_stride + opix_x + x];
         leaf[(y >> 2) * 4 + (x >> 2)] += c->metric[0] ? d * d : iabs_(d);
       }
     for (p = 0; p < ME_NUM_PARTITIONS; p++) {
@@ -302,7 +316,7 @@ int ora_sad_block(const uint8_t *src, int src_stride, int bsx, int bsy, const or
   const uint8_t *rp = ora_umv_line(r, y4, x4);
   int x, y, s = 0;
   for (y = 0; y < bsy; y++)
-    for (x = 0; x < bsx; x++) s += iabs_((int)src[(size_t)y * src_stride + x] - (int)rp[(size_t)y * r->wp + x]);
+    for (x = 0; x < bsx; x++) s += iabs_((int)src[(size_t)y * src_stride + x] - refpel(r, rp[(size_t)y * r->wp + x]));
   return s;
 }
 
@@ -312,7 +326,7 @@ static int sse_block(const uint8_t *src, int src_stride, int bsx, int bsy, const
   int x, y, s = 0;
   for (y = 0; y < bsy; y++)
     for (x = 0; x < bsx; x++) {
-      int d = (int)src[(size_t)y * src_stride + x] - (int)rp[(size_t)y * r->wp + x];
+      int d = (int)src[(size_t)y * src_stride + x] - refpel(r, rp[(size_t)y * r->wp + x]);
       s += d * d;
     }
   return s;
@@ -328,7 +342,7 @@ int ora_satd_block(const uint8_t *src, int src_stride, int bsx, int bsy, const o
       const uint8_t *rp = ora_umv_line(r, y4 + (by << 2), x4 + (bx << 2));
       for (y = 0; y < n; y++)
         for (x = 0; x < n; x++)
-          d[y * n + x] = (int)src[(size_t)(by + y) * src_stride + bx + x] - (int)rp[(size_t)y * r->wp + x];
+          d[y * n + x] = (int)src[(size_t)(by + y) * src_stride + bx + x] - refpel(r, rp[(size_t)y * r->wp + x]);
       s += use8x8 ? ora_hadamard8x8(d) : ora_hadamard4x4(d);
     }
   return s;

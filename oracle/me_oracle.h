@@ -29,6 +29,9 @@ typedef struct ora_cfg {
 typedef struct ora_ref {
   int w, h, wp, hp;        /* picture and padded (+40) sizes */
   uint8_t *plane[4][4];    /* [vertical fraction][horizontal fraction], hp rows of wp bytes */
+  /* weighted-prediction ME (UseWeightedReferenceME): every reference sample of a UNI-predictive distortion becomes
+   * clip1(((wp_weight * p + wp_round) >> wp_denom) + wp_offset) (me_fullfast.c:653, me_distortion.c:413-480, :734-822) */
+  int wp_apply, wp_weight, wp_offset, wp_denom;
 } ora_ref;
 
 /* tables */
@@ -44,6 +47,8 @@ void ora_block_size(int blocktype, int *bsx, int *bsy);
 ora_ref *ora_ref_create(const uint8_t *luma, int stride, int w, int h);
 void     ora_ref_destroy(ora_ref *r);
 const uint8_t *ora_ref_plane(const ora_ref *r, int fy, int fx);
+/* weights of the (list, ref) entry this picture is searched as: wp_weight / wp_offset [list][ref][0], luma_log_weight_denom */
+void     ora_ref_set_weights(ora_ref *r, int apply, int weight, int offset, int log_denom);
 
 /* plane access with JM's origin clamp (UMVLine4X, refbuf.c:37): pointer to the first pixel of a block row */
 const uint8_t *ora_umv_line(const ora_ref *r, int y4, int x4);

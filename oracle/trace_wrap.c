@@ -166,6 +166,20 @@ void __wrap_ResetFastFullIntegerSearch(void)
 
 static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 
+/* weighted-prediction state of a uni-predictive search as the reference derives it (me_fullfast.c:507-508,530-534;
+ * me_fullsearch.c:368-388): rec[28] apply_weights, rec[29] weight, rec[30] offset, rec[31] luma_log_weight_denom */
+static void put_weights(int *rec, int list, int list_offset, int ref)
+{
+  int apply = ((active_pps->weighted_pred_flag && (img->type == P_SLICE || img->type == SP_SLICE)) ||
+               (active_pps->weighted_bipred_idc && (img->type == B_SLICE))) && input->UseWeightedReferenceME;
+  rec[28] = apply;
+  if (apply) {
+    rec[29] = wp_weight[list + list_offset][ref][0];
+    rec[30] = wp_offset[list + list_offset][ref][0];
+    rec[31] = luma_log_weight_denom;
+  }
+}
+
 /* ---------------------------------------------------------------- integer-pel fast full search */
 int __real_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
                                         int blocktype, short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
@@ -201,6 +215,7 @@ int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, i
   rec[15] = centre_x[list][ref]; rec[16] = centre_y[list][ref]; rec[17] = setup_range[list][ref];
   rec[21] = ref_id_of(listX[list + list_offset][ref]);
   rec[25] = input->rdopt;
+  put_weights(rec, list, list_offset, ref);
   cost = __real_FastFullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
                                              pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
   rec[18] = *mv_x; rec[19] = *mv_y; rec[20] = cost;
@@ -227,6 +242,7 @@ int __wrap_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pi
   rec[21] = ref_id_of(listX[list + list_offset][ref]);
   rec[22] = test8x8transform; rec[23] = start_me_refinement_hp; rec[24] = start_me_refinement_qp;
   rec[25] = input->rdopt; rec[26] = search_pos2; rec[27] = search_pos4;
+  put_weights(rec, list, list_offset, ref);
   cost = __real_SubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
                                         pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
   rec[18] = *mv_x; rec[19] = *mv_y; rec[20] = cost;

@@ -13,6 +13,9 @@ Cases
   baseline16 encoder_baseline.cfg with SearchRange=16, NumberReferenceFrames=1 (BASELINE.json config 1), every 3rd macroblock.
   rdopt0     encoder_baseline.cfg, RDOptimization=0, RestrictSearchRange=0, SR 16, 2 refs, synthetic QCIF IPPP --
              pins the !rdopt zero-vector rules and the reduced search ranges.  Every 5th macroblock is kept.
+  wp         encoder_main.cfg, WeightedPrediction=1 + UseWeightedReferenceME=1 on a synthetic QCIF clip that fades
+             (h264_b200.synth kind="fade"), IPPP, SR 16, 3 references: the encoder estimates weights 28..31 / 32 and the
+             searches run on weighted reference samples (computeSADWP / SATDWP).  Every 4th macroblock is kept.
 Usage: python tests/golden/make_golden.py            (rewrites tests/golden/*.npz, planes_crc.json, bitstream_md5.json)
 """
 import hashlib
@@ -98,6 +101,18 @@ def main():
         tr = Trace(d)
         tr.save_npz(os.path.join(HERE, "baseline16.npz"), keep_mask(tr, 3))
         crc["baseline16"] = planes_crc(tr, d)
+    # ---- wp: weighted-prediction ME (records carry apply / weight / offset / denominator in fields 28..31)
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_yuv420(os.path.join(d, "syn.yuv"), 176, 144, 4, kind="fade")
+        args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
+                "-p", "FramesToBeEncoded=4", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=16",
+                "-p", "NumberReferenceFrames=3", "-p", "WeightedPrediction=1", "-p", "UseWeightedReferenceME=1"]
+        run_trace(d, args)
+        md5s["wp"] = {"test.264": md5(os.path.join(d, "test.264"))}
+        tr = Trace(d)
+        assert set(np.unique(tr.of_type(REC_FFS)[:, 29])) - {32}, "the fade clip must produce non-default weights"
+        tr.save_npz(os.path.join(HERE, "wp.npz"), keep_mask(tr, 4))
+        crc["wp"] = planes_crc(tr, d)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
     for f in sorted(os.listdir(HERE)):

@@ -39,9 +39,20 @@ class OracleAdapter:
         self.cfg = ob.make_cfg(**cfgkw)
         self.refs = {i: ob.Ref(trace.ref(i)) for i in trace.ref_ids()}
         self.surf = {}
+        self.wp = {}
+
+    def set_weights(self, lst, ref, apply, weight, offset, denom):
+        self.wp[(lst, ref)] = (apply, weight, offset, denom)
+
+    def _ref(self, lst, ref):
+        """the picture at (list, ref) carrying that entry's weights (uni-predictive searches)"""
+        r = self.refs[self.lists[lst][ref]]
+        r.set_weights(*self.wp.get((lst, ref), (0, 32, 0, 5)))
+        return r
 
     def begin_picture(self, cur, slice_type, lists):
         self.cur, self.slice_type, self.lists = np.ascontiguousarray(cur), slice_type, lists
+        self.wp = {}
 
     def mb_begin(self, ox, oy):
         self.ox, self.oy = ox, oy
@@ -51,7 +62,7 @@ class OracleAdapter:
         ob = self.ob
         cx, cy = ob.search_centre(self.cfg, ref, self.ox, self.oy, pmvx, pmvy)
         rng = ob.lib().ora_setup_range(self.cfg, ref)
-        s = ob.ffs_surfaces(self.cfg, self.cur, self.refs[self.lists[lst][ref]], self.ox, self.oy, cx, cy, rng)
+        s = ob.ffs_surfaces(self.cfg, self.cur, self._ref(lst, ref), self.ox, self.oy, cx, cy, rng)
         self.surf[(lst, ref)] = (s, cx, cy, rng)
         return cx, cy, rng
 
@@ -61,7 +72,7 @@ class OracleAdapter:
         return self.ob.ffs_block(self.cfg, s[p], rng, self.ox, self.oy, cx, cy, pmvx, pmvy, search_range, min_mcost, lam)
 
     def subpel(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, sp2, sp4, min_mcost, lam3):
-        return self.ob.subpel(self.cfg, self.cur, self.refs[self.lists[lst][ref]], ppx, ppy, bt, ref, self.slice_type,
+        return self.ob.subpel(self.cfg, self.cur, self._ref(lst, ref), ppx, ppy, bt, ref, self.slice_type,
                               pmvx, pmvy, mvx, mvy, min_mcost, lam3, sp2, sp4)
 
     def bipred_full(self, ref, lst, ppx, ppy, bt, pmv1, pmv2, mv, smv, sr, min_mcost, lam):
@@ -94,6 +105,9 @@ class CudaAdapter:
         self.me.set_slice_type(slice_type)
         for l in (0, 1):
             self.me.set_ref_list(l, [self.handles[i] for i in lists[l]])
+
+    def set_weights(self, lst, ref, apply, weight, offset, denom):
+        self.me.set_ref_weights(lst, ref, apply, weight, offset, denom)
 
     def mb_begin(self, ox, oy):
         self.me.mb_begin(ox, oy)
@@ -136,6 +150,9 @@ def replay(trace, impl, max_calls=None):
             impl.mb_begin(ox, oy)
             cur_mb = (ox, oy)
         lst, ref, bt, ppx, ppy = int(r[5]), int(r[6]), int(r[7]), int(r[8]), int(r[9])
+        if t in (REC_FFS, REC_SUBPEL):
+            # weighted-prediction ME: the weights the reference derived for this (list, ref) (0 = off in older fixtures)
+            impl.set_weights(lst, ref, int(r[28]), int(r[29]), int(r[30]), int(r[31]))
         if t == REC_FFS:
             if r[22]:
                 c = impl.ffs_setup(lst, ref, int(r[23]), int(r[24]))

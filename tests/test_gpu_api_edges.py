@@ -100,3 +100,27 @@ def test_reference_slot_reuse_and_in_place_update(pkg, oracle_lib):
         r3 = ob.Ref(frames[3])
         assert np.array_equal(me.ref_planes(b), r3.planes())
         r2.close(); r3.close()
+
+
+def test_weight_arguments_are_checked_and_weighted_bipred_is_refused(pkg):
+    """me_cuda_set_ref_weights: ranges of the slice header syntax (weights / offsets -128..127, log denominator 0..7); the
+    bi-predictive batch has no weighted form (computeBiPred*2) and must say so instead of searching weighted copies"""
+    from h264_b200 import MeCuda, MeCudaError, synth
+    from h264_b200.me_cuda import BIPRED_JOB_DTYPE
+    w, h = 176, 144
+    frames = synth.luma_frames(w, h, 3)
+    with MeCuda(w, h, max_num_references=2) as me:
+        me.set_ref_list(0, [me.ref_create(frames[0])])
+        me.set_ref_list(1, [me.ref_create(frames[2])])
+        me.set_current(frames[1])
+        for bad in ((0, 0, 1, 128, 0, 5), (0, 0, 1, 32, -129, 5), (0, 0, 1, 32, 0, 8), (2, 0, 1, 32, 0, 5), (0, 32, 1, 32, 0, 5)):
+            with pytest.raises(MeCudaError):
+                me.set_ref_weights(*bad)
+        jobs = np.zeros(1, BIPRED_JOB_DTYPE)
+        jobs["lambda"] = 334459
+        me.frame_bipred(jobs, 3, 16, 2)
+        me.set_ref_weights(1, 0, 1, 30, 2, 5)
+        with pytest.raises(MeCudaError):
+            me.frame_bipred(jobs, 3, 16, 2)
+        me.set_ref_weights(1, 0, 0)
+        me.frame_bipred(jobs, 3, 16, 2)

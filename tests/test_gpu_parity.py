@@ -222,6 +222,44 @@ def test_batch_two_reference_lists(pkg, oracle_lib):
             ref.close()
 
 
+@pytest.mark.parametrize("t8", [0, 1])
+def test_batch_weighted_prediction(pkg, oracle_lib, t8):
+    """weighted-prediction ME (UseWeightedReferenceME): every list entry with its own weight / offset / denominator, including
+    negative offsets, clipping at both ends, a negative weight, identity weights, and weights that change between two calls
+    and after the planes of a picture are regenerated in place"""
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h, n_refs = 352, 288, 4
+    d, cfg = _cfg(ob, transform8x8=t8)
+    frames = synth.luma_frames(w, h, n_refs + 2, kind="fade")
+    cur = np.ascontiguousarray(frames[-1])
+    jobs = synth.synthetic_jobs(w, h, n_refs, (334459, 334459, 334459), seed=41, max_pmv=40)
+    rng = np.random.default_rng(43)
+    sel = np.sort(rng.choice(len(jobs), 200, replace=False))
+    sets = [[(1, 29, 3, 5), (1, 40, -20, 5), (1, 32, 0, 5), (0, 0, 0, 0)],          # (apply, weight, offset, log_denom) per ref
+            [(1, 127, 100, 6), (1, -3, 127, 2), (1, 17, -128, 4), (1, 1, 0, 0)]]
+    with _open(pkg, w, h, d, max_refs=n_refs) as me:
+        handles = [me.ref_create(frames[-2 - r]) for r in range(n_refs)]
+        me.set_ref_list(0, handles)
+        me.set_current(cur)
+        pics = [frames[-2 - r] for r in range(n_refs)]
+        for rnd, ws in enumerate(sets + [sets[0]]):
+            if rnd == 2:                                    # a frame store reused: the weighted copy must follow the new planes
+                pics[1] = frames[0]
+                me.ref_update(handles[1], frames[0])
+            for r, wt in enumerate(ws):
+                me.set_ref_weights(0, r, *wt)
+            out, out_int = me.frame_search(jobs, want_int=True)
+            for r in range(n_refs):
+                s_ = sel[jobs["ref"][sel] == r]
+                ref = ob.Ref(pics[r])
+                ref.set_weights(*ws[r])
+                exp, exp_int = ob.mb_search(cfg, cur, ref, jobs[s_])
+                assert np.array_equal(out_int[s_], exp_int), (rnd, r)
+                assert np.array_equal(out[s_], exp), (rnd, r)
+                ref.close()
+
+
 @pytest.mark.parametrize("kind", ["flat", "stripes"])
 def test_batch_ties_follow_spiral_order(pkg, oracle_lib, kind):
     """flat / periodic content: thousands of equal costs, the winner must be the first one in JM's spiral order"""
