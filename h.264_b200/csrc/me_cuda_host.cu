@@ -13,6 +13,7 @@
 #include "me_common.cuh"
 
 // ---- kernel launchers (planes.cu, ffs_basic.cu, ffs_tuned.cu, subpel.cu) ----
+struct MeBiW { int apply, w1, w2, obi, denom; };   // weighted bi-prediction of one `list` argument (subpel.cu)
 struct MeSubpelArgs {
   int pic_pix_x, pic_pix_y, blocktype;
   int pmv_x, pmv_y, mv_x, mv_y, s_mv_x, s_mv_y;
@@ -20,12 +21,14 @@ struct MeSubpelArgs {
   int lambda[3];
   int check0;
   int bi;
+  MeBiW bw;
 };
 struct MeBiFullArgs {
   int pic_pix_x, pic_pix_y, blocktype;
   int pmv_x1, pmv_y1, pmv_x2, pmv_y2;
   int mv_x, mv_y, s_mv_x, s_mv_y;
   int search_range, min_mcost, lambda;
+  MeBiW bw;
 };
 extern "C" {
 void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t *planes, int pitch, size_t plane_stride,
@@ -55,7 +58,8 @@ void me_launch_ffs_block_subpel(const int32_t *surf_p, int setup_range, int offx
 void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                              const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st);
 void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
-                            const MeCfgDev *cfg, int refinements, int search_range, int subpel, me_bipred_result *out, cudaStream_t st);
+                            const MeCfgDev *cfg, int refinements, int search_range, int subpel, const MeBiW *bw, me_bipred_result *out,
+                            cudaStream_t st);
 void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                            const MeBiFullArgs *a, int *result, int ticket, cudaStream_t st);
 }
@@ -103,6 +107,7 @@ struct State {
   unsigned long long gen_counter = 0;
   WeightSet wp[2][ME_MAX_REFS];
   Twin twin[2][ME_MAX_REFS];
+  MeBiW bw[2] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};   // weighted bi-prediction per `list` argument of the bi-predictive searches
   // current picture
   uint8_t *d_cur = nullptr;
   int cur_pitch = 0;
@@ -141,6 +146,7 @@ struct State {
   MeJob *d_jobs = nullptr; MeResult *d_out = nullptr; MeResultInt *d_out_int = nullptr; int batch_cap = 0;
   MeResultInt *d_int_scratch = nullptr; int int_scratch_cap = 0;
   me_bipred_job *d_bi_jobs = nullptr; me_bipred_result *d_bi_out = nullptr; int bi_cap = 0;
+  MeRefDev *d_bi_table = nullptr;
   long long launches = 0;
   long long spec_hits = 0;                        // sub-pel calls answered from the fused block-search kernel
   // optional per-kernel-class timing (bench.py): event pairs around every launch of a class
@@ -430,6 +436,7 @@ void me_cuda_shutdown(void)
   if (g.d_int_scratch) cudaFree(g.d_int_scratch);
   if (g.d_bi_jobs) cudaFree(g.d_bi_jobs);
   if (g.d_bi_out) cudaFree(g.d_bi_out);
+  if (g.d_bi_table) cudaFree(g.d_bi_table);
   if (g_d_stage) { cudaFree(g_d_stage); g_d_stage = nullptr; g_d_stage_bytes = 0; }
   cudaStreamDestroy(g.stream);
   g = State();
@@ -615,6 +622,21 @@ int me_cuda_set_ref_list(int list, int n, const me_ref_handle *handles)
 
 int me_cuda_set_slice_type(int t) { g.slice_type = t; g.spec.valid = false; return 0; }
 
+int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (list < 0 || list > 1) return fail(1, "me_cuda_set_bipred_weights: list %d out of range", list);
+  MeBiW w = {0, 0, 0, 0, 0};
+  if (apply) {
+    if (weight1 < -128 || weight1 > 127 || weight2 < -128 || weight2 > 127 || offset_bi < -128 || offset_bi > 127 || log_denom < 0 || log_denom > 7)
+      return fail(1, "me_cuda_set_bipred_weights: weights %d, %d / offset %d / log denominator %d out of range", weight1, weight2, offset_bi, log_denom);
+    w.apply = 1; w.w1 = weight1; w.w2 = weight2; w.obi = offset_bi; w.denom = log_denom;
+  }
+  g.bw[list] = w;
+  g.spec.valid = false;
+  return 0;
+}
+
 int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset, int log_denom)
 {
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
@@ -790,6 +812,7 @@ int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic
   a.pmv_x1 = pred_mv_x1; a.pmv_y1 = pred_mv_y1; a.pmv_x2 = pred_mv_x2; a.pmv_y2 = pred_mv_y2;
   a.mv_x = *mv_x; a.mv_y = *mv_y; a.s_mv_x = *s_mv_x; a.s_mv_y = *s_mv_y;
   a.search_range = search_range; a.min_mcost = min_mcost; a.lambda = lambda_factor;
+  a.bw = g.bw[list];
   me_launch_bipred_full(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
@@ -812,6 +835,7 @@ int me_cuda_SubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_
   a.search_pos2 = search_pos2; a.search_pos4 = search_pos4; a.min_mcost = min_mcost;
   for (int i = 0; i < 3; i++) a.lambda[i] = lambda[i];
   a.check0 = 0; a.bi = 1;
+  a.bw = g.bw[list];
   me_launch_subpel_single(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
@@ -934,8 +958,6 @@ int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements,
   if (refinements < 0 || refinements > 16 || search_range < 0 || search_range > 64 || subpel < 0 || subpel > 2)
     return fail(1, "me_cuda_frame_bipred: refinements %d / search range %d / sub-pel levels %d out of range", refinements, search_range, subpel);
   if (g.cfg.metric[0] == 2) return fail(1, "bi-predictive integer search with a Hadamard metric is not implemented");
-  if (!g.wp[0][0].identity() || !g.wp[1][0].identity())
-    return fail(1, "me_cuda_frame_bipred: weighted bi-prediction (computeBiPred*2) is not implemented; clear the weights of reference 0");
   for (int i = 0; i < n_jobs; i++) {
     const me_bipred_job &j = jobs[i];
     if (j.list < 0 || j.list > 1) return fail(1, "bi-pred job %d: list %d", i, (int)j.list);
@@ -950,9 +972,18 @@ int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements,
     CK(cudaMalloc((void **)&g.d_bi_out, sizeof(me_bipred_result) * (size_t)n_jobs));
     g.bi_cap = n_jobs;
   }
-  if (int rc = upload_table()) return rc;
+  if (!ref_of(g.list[0][0]) || !ref_of(g.list[1][0])) return fail(3, "me_cuda_frame_bipred: stale reference handle in a list");
   CK(cudaMemcpyAsync(g.d_bi_jobs, jobs, sizeof(me_bipred_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, g.stream));
-  me_launch_bipred_batch(g.d_bi_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, refinements, search_range, subpel, g.d_bi_out, g.stream);
+  // the bi-predictive distortions read the pictures' own planes (their weights are applied to the pair of samples), never the
+  // weighted copies the uni-predictive searches of the same list entries may be using: a two-entry table of its own
+  {
+    MeRefDev pair[2 * ME_MAX_REFS];
+    memset(pair, 0, sizeof pair);
+    pair[0] = ref_of(g.list[0][0])->dev; pair[ME_MAX_REFS] = ref_of(g.list[1][0])->dev;
+    if (!g.d_bi_table) CK(cudaMalloc((void **)&g.d_bi_table, sizeof pair));
+    CK(cudaMemcpyAsync(g.d_bi_table, pair, sizeof pair, cudaMemcpyHostToDevice, g.stream));
+  }
+  me_launch_bipred_batch(g.d_bi_jobs, n_jobs, g.d_bi_table, g.d_cur, g.cur_pitch, &g.cfg, refinements, search_range, subpel, g.bw, g.d_bi_out, g.stream);
   g.launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, g.d_bi_out, sizeof(me_bipred_result) * (size_t)n_jobs, cudaMemcpyDeviceToHost, g.stream));

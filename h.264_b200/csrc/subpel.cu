@@ -61,20 +61,41 @@ __device__ __noinline__ int hadamard8(int d[64])
   return (s + 2) >> 2;                                   // me_distortion.c:342
 }
 
-// distortion of one N x N tile.  metric: 0 SAD, 1 SSE, 2 SATD.  r2 != nullptr: bi-prediction (p1 + p2 + 1) >> 1.
+// Weighted bi-prediction (computeBiPred*2, me_distortion.c:556, :907, :1254): what FullPelBlockMotionBiPred /
+// SubPelBlockSearchBiPred derive from their `list` argument (me_fullsearch.c:202-234, :538-590).  Same layout in me_cuda_host.cu.
+struct MeBiW { int apply, w1, w2, obi, denom; };
+
+// prediction sample of a bi-predictive distortion: (p1 + p2 + 1) >> 1 (me_distortion.c:502), or with weights
+// iClip1(255, ((weight1 * p1 + weight2 * p2 + 2 * wp_luma_round) >> (denom + 1)) + offsetBi)
+__device__ __forceinline__ int bipred_pel(int p1, int p2, const MeBiW &w)
+{
+  if (!w.apply) return (p1 + p2 + 1) >> 1;
+  return me_clamp(((w.w1 * p1 + w.w2 * p2 + (w.denom ? 1 << w.denom : 0)) >> (w.denom + 1)) + w.obi, 0, 255);
+}
+
+// distortion of one N x N tile.  metric: 0 SAD, 1 SSE, 2 SATD.  p2 != nullptr: bi-prediction.
+// blk / bsx / bx / by: origin of the block in the current picture, its width, the tile's offset inside it.  They matter for one
+// case only: the 8x8 branch of computeBiPredSATD2 reads the eighth sample of every row without advancing its source pointer
+// (me_distortion.c:1015), so each row of the ORIGINAL block starts one sample further left than the row above -- linear
+// index by*bsx + bx + y*(bsx-1) + x into the bsx-wide copy of the block (mv-search.c:607-611).  Reproduced as is.
 template <int N>
-__device__ __forceinline__ int tile_dist(int metric, const uint8_t *__restrict__ src, int src_pitch,
+__device__ __forceinline__ int tile_dist(int metric, const uint8_t *__restrict__ blk, int src_pitch, int bsx, int bx, int by,
                                          const uint8_t *__restrict__ p1, int pitch1,
-                                         const uint8_t *__restrict__ p2, int pitch2)
+                                         const uint8_t *__restrict__ p2, int pitch2, const MeBiW &bw)
 {
   int d[N * N];
+  const uint8_t *src = blk + by * src_pitch + bx;
+  const bool skew = N == 8 && metric == 2 && p2 && bw.apply;
 #pragma unroll
   for (int y = 0; y < N; y++)
 #pragma unroll
     for (int x = 0; x < N; x++) {
       int pred = p1[y * pitch1 + x];
-      if (p2) pred = (pred + p2[y * pitch2 + x] + 1) >> 1;
-      d[y * N + x] = (int)src[y * src_pitch + x] - pred;
+      if (p2) pred = bipred_pel(pred, p2[y * pitch2 + x], bw);
+      int s;
+      if (skew) { const int L = by * bsx + bx + y * (bsx - 1) + x; s = blk[(L / bsx) * src_pitch + (L % bsx)]; }
+      else s = src[y * src_pitch + x];
+      d[y * N + x] = s - pred;
     }
   if (metric == 2) {
     if (N == 4) return hadamard4(d);
@@ -152,8 +173,9 @@ me_subpel_batch_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDe
       int bx = 4 * (tx - px), by = 4 * (ty - py);
       const uint8_t *rp = tile_ptr(ref, x4, y4, bx, by, metric == 2);
       const uint8_t *sp = &cur_s[4 * ty][4 * tx];
-      int d = use8 ? tile_dist<8>(metric, sp, 16, rp, ref.pitch, nullptr, 0)
-                   : tile_dist<4>(metric, sp, 16, rp, ref.pitch, nullptr, 0);
+      const MeBiW nobw = { 0, 0, 0, 0, 0 };
+      int d = use8 ? tile_dist<8>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw)
+                   : tile_dist<4>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw);
       atomicAdd(&cost_s[p][c], d);
     }
     __syncthreads();
@@ -189,6 +211,7 @@ struct MeSubpelArgs {
   int lambda[3];
   int check0;           // check_position0 already evaluated by the host side (needs slice type / ref)
   int bi;
+  MeBiW bw;             // bi == 1: weights of this call's `list`
 };
 
 // scratch of the block-level device functions below (one per CTA)
@@ -226,18 +249,18 @@ __device__ void subpel_block(const MeRefDev &r1, const MeRefDev &r2, const uint8
       int bx = (tile % tw) * n, by = (tile / tw) * n;
       int x4 = ((a.pic_pix_x + ME_PAD) << 2) + sc.mv_s[0] + step * c_sp_x[c];
       int y4 = ((a.pic_pix_y + ME_PAD) << 2) + sc.mv_s[1] + step * c_sp_y[c];
-      const uint8_t *sp = cur + (size_t)(a.pic_pix_y + by) * cur_pitch + a.pic_pix_x + bx;
+      const uint8_t *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
       int d;
       if (!a.bi) {
         const uint8_t *rp = tile_ptr(r1, x4, y4, bx, by, metric == 2);
-        d = use8 ? tile_dist<8>(metric, sp, cur_pitch, rp, r1.pitch, nullptr, 0)
-                 : tile_dist<4>(metric, sp, cur_pitch, rp, r1.pitch, nullptr, 0);
+        d = use8 ? tile_dist<8>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw)
+                 : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw);
       } else {
         int fx4 = ((a.pic_pix_x + ME_PAD) << 2) + a.s_mv_x, fy4 = ((a.pic_pix_y + ME_PAD) << 2) + a.s_mv_y;
         const uint8_t *p1 = tile_ptr(r1, fx4, fy4, bx, by, metric == 2);
         const uint8_t *p2 = tile_ptr(r2, x4, y4, bx, by, metric == 2);
-        d = use8 ? tile_dist<8>(metric, sp, cur_pitch, p1, r1.pitch, p2, r2.pitch)
-                 : tile_dist<4>(metric, sp, cur_pitch, p1, r1.pitch, p2, r2.pitch);
+        d = use8 ? tile_dist<8>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw)
+                 : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
       }
       atomicAdd(&sc.cost_s[c], d);
     }
@@ -304,6 +327,7 @@ struct MeBiFullArgs {
   int pmv_x1, pmv_y1, pmv_x2, pmv_y2;
   int mv_x, mv_y, s_mv_x, s_mv_y;
   int search_range, min_mcost, lambda;
+  MeBiW bw;
 };
 
 // one bi-predictive integer-pel search; called by all threads of the CTA, returns the result to all of them
@@ -331,7 +355,7 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
     for (int y = 0; y < bsy; y++)
       for (int x = 0; x < bsx; x++) {
         int e = (int)cur[(size_t)(a.pic_pix_y + y) * cur_pitch + a.pic_pix_x + x]
-                - (((int)p1[(size_t)y * r1.pitch + x] + (int)p2[(size_t)y * r2.pitch + x] + 1) >> 1);
+                - bipred_pel(p1[(size_t)y * r1.pitch + x], p2[(size_t)y * r2.pitch + x], a.bw);
         d += metric ? e * e : abs(e);                      // computeBiPred1[F_PEL]: SAD, SSE, (SATD -> see host)
       }
     mc += d;
@@ -429,7 +453,7 @@ me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur,
   __shared__ BlockScratch sc;
   __shared__ BiFastScratch fs;
   int mvx, mvy, cost;
-  if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE) bipred_full_block_sad(r1, r2, cur, cur_pitch, a, sc, fs, mvx, mvy, cost);
+  if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE && !a.bw.apply) bipred_full_block_sad(r1, r2, cur, cur_pitch, a, sc, fs, mvx, mvy, cost);
   else bipred_full_block(r1, r2, cur, cur_pitch, cfg, a, sc, mvx, mvy, cost);
   if (threadIdx.x == 0) {
     result[0] = mvx; result[1] = mvy; result[2] = cost;
@@ -447,7 +471,7 @@ me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur,
 __global__ void __launch_bounds__(256)
 me_bipred_batch_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                        const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg, int refinements, int search_range,
-                       int subpel, me_bipred_result *__restrict__ out)
+                       int subpel, MeBiW bw0, MeBiW bw1 /* weights of calls with list argument 0 / 1 */, me_bipred_result *__restrict__ out)
 {
   __shared__ BlockScratch sc;
   __shared__ BiFastScratch fs;
@@ -492,7 +516,8 @@ me_bipred_batch_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     a.mv_x = bimv[0]; a.mv_y = bimv[1]; a.s_mv_x = tempmv[0]; a.s_mv_y = tempmv[1];
     a.search_range = search_range >> i; a.min_mcost = min_mcostbi; a.lambda = lambda[0];
     int mx, my;
-    if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE)
+    a.bw = iterlist ? bw1 : bw0;
+    if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE && !a.bw.apply)
       bipred_full_block_sad(refs[iterlist], refs[iterlist ^ 1], cur, cur_pitch, a, sc, fs, mx, my, min_mcostbi);
     else
       bipred_full_block(refs[iterlist], refs[iterlist ^ 1], cur, cur_pitch, cfg, a, sc, mx, my, min_mcostbi);
@@ -513,6 +538,7 @@ me_bipred_batch_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     a.lambda[0] = lambda[0]; a.lambda[1] = lambda[1]; a.lambda[2] = lambda[2];
     a.check0 = 0; a.bi = 1;
     const int l1 = pass == 0 ? iterlist : iterlist ^ 1;            // the `list` argument of SubPelBlockSearchBiPred: r1 = its reference 0
+    a.bw = l1 ? bw1 : bw0;
     int mx, my;
     subpel_block(refs[l1], refs[l1 ^ 1], cur, cur_pitch, cfg, a, sc, mx, my, min_mcostbi);
     if (pass == 0) { bimv[0] = (short)mx; bimv[1] = (short)my; } else { mv[0] = (short)mx; mv[1] = (short)my; }
@@ -535,11 +561,11 @@ extern "C" void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRe
 
 extern "C" void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur,
                                        int cur_pitch, const MeCfgDev *cfg, int refinements, int search_range, int subpel,
-                                       me_bipred_result *out, cudaStream_t st)
+                                       const MeBiW *bw /* [2] */, me_bipred_result *out, cudaStream_t st)
 {
   static_assert(sizeof(me_bipred_job) == 32 && sizeof(me_bipred_result) == 16, "ABI struct sizes");
   me_bipred_batch_kernel<<<n_jobs, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, cur, cur_pitch, *cfg,
-                                                 refinements, search_range, subpel, out);
+                                                 refinements, search_range, subpel, bw[0], bw[1], out);
 }
 
 extern "C" void me_launch_ffs_block_subpel(const int32_t *surf_p, int setup_range, int offx, int offy, int search_range, int min_mcost,

@@ -51,6 +51,7 @@ static struct {
   int  (*set_ref_list)(int, int, const me_ref_handle *);
   int  (*set_slice_type)(int);
   int  (*set_ref_weights)(int, int, int, int, int, int);
+  int  (*set_bipred_weights)(int, int, int, int, int, int);
   int  (*mb_begin)(int, int);
   int  (*ffs_setup)(int, int, int, int);
   int  (*ffs_is_set_up)(int, int);
@@ -111,7 +112,7 @@ static void load_library(void)
   L.ref_create = sym("me_cuda_ref_create"); L.ref_destroy = sym("me_cuda_ref_destroy");
   L.set_current = sym("me_cuda_set_current"); L.set_ref_list = sym("me_cuda_set_ref_list");
   L.set_slice_type = sym("me_cuda_set_slice_type"); L.mb_begin = sym("me_cuda_mb_begin");
-  L.set_ref_weights = sym("me_cuda_set_ref_weights");
+  L.set_ref_weights = sym("me_cuda_set_ref_weights"); L.set_bipred_weights = sym("me_cuda_set_bipred_weights");
   L.ffs_setup = sym("me_cuda_ffs_setup"); L.ffs_is_set_up = sym("me_cuda_ffs_is_set_up");
   L.ffs = sym("me_cuda_FastFullPelBlockMotionSearch"); L.subpel = sym("me_cuda_SubPelBlockMotionSearch");
   L.bi_full = sym("me_cuda_FullPelBlockMotionBiPred"); L.bi_sub = sym("me_cuda_SubPelBlockSearchBiPred");
@@ -148,11 +149,6 @@ void __wrap_Init_Motion_Search_Module(void)
   active = 0;
   if (dis && atoi(dis)) return;
   if (input->SearchMode != FAST_FULL_SEARCH) return;   /* the library implements the SearchMode=0 path */
-  if (input->WeightedBiprediction && input->BiPredMotionEstimation) {
-    fprintf(stderr, "me_cuda shim: weighted bi-predictive ME (computeBiPred*2) is not implemented on the GPU path; "
-                    "set ME_CUDA_DISABLE=1 for the pure reference\n");
-    exit(502);
-  }
   {
     me_cuda_params p;
     int apply_wp = (input->WeightedPrediction || input->WeightedBiprediction) && input->UseWeightedReferenceME;
@@ -278,6 +274,26 @@ static void pass_weights(int list, short ref)
     die("me_cuda_set_ref_weights");
 }
 
+/* Weighted bi-prediction: the weights the two bi-predictive searches derive from their arguments -- FullPelBlockMotionBiPred
+ * at me_fullsearch.c:202-227, SubPelBlockSearchBiPred at :541-582 (their wp_offset index expressions differ for list 1). */
+static void pass_bipred_weights(int list, short ref, int subpel)
+{
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  if (active_pps->weighted_bipred_idc > 0) {
+    int o1, o2, w1, w2;
+    if (subpel) {
+      o1 = list == 0 ? wp_offset[list_offset][ref][0] : wp_offset[list_offset + 1][0][0];
+      o2 = list == 0 ? wp_offset[list_offset + 1][ref][0] : wp_offset[list_offset][0][0];
+    } else {
+      o1 = list == 0 ? wp_offset[list_offset][ref][0] : wp_offset[list_offset + 1][0][ref];
+      o2 = list == 0 ? wp_offset[list_offset + 1][ref][0] : wp_offset[list_offset][0][ref];
+    }
+    w1 = list == 0 ? wbp_weight[list_offset][ref][0][0] : wbp_weight[list_offset + LIST_1][0][ref][0];
+    w2 = list == 0 ? wbp_weight[list_offset + LIST_1][ref][0][0] : wbp_weight[list_offset][0][ref][0];
+    if (L.set_bipred_weights(list, 1, w1, w2, (o1 + o2 + 1) >> 1, luma_log_weight_denom)) die("me_cuda_set_bipred_weights");
+  } else if (L.set_bipred_weights(list, 0, 0, 0, 0, 0)) die("me_cuda_set_bipred_weights");
+}
+
 /* ---------------------------------------------------------------- block searches */
 int __real_FastFullPelBlockMotionSearch(imgpel *, short, int, int, int, int, short, short, short *, short *, int, int, int);
 int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
@@ -351,6 +367,7 @@ int __wrap_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int p
     return __real_FullPelBlockMotionBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x1, pred_mv_y1,
                                            pred_mv_x2, pred_mv_y2, mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
   keep_reference_side_effects(list, ref);
+  pass_bipred_weights(list, ref, 0);
   return L.bi_full(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x1, pred_mv_y1, pred_mv_x2, pred_mv_y2,
                    mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
 }
@@ -365,6 +382,7 @@ int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pi
     return __real_SubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                           mv_x, mv_y, s_mv_x, s_mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
   keep_reference_side_effects(list, ref);
+  pass_bipred_weights(list, ref, 1);
   return L.bi_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, s_mv_x, s_mv_y,
                   search_pos2, search_pos4, min_mcost, lambda_factor);
 }

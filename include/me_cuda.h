@@ -106,8 +106,16 @@ int me_cuda_set_slice_type(int slice_type);
  * (me_fullfast.c:507-508,530-534,640-737; me_fullsearch.c:368-388; computeSADWP / computeSSEWP / computeSATDWP,
  * me_distortion.c:413,1107,734; weighted_prediction.c:50).  apply = 0 switches the entry back to plain samples.  The weights
  * stay with the list entry until changed; set them after me_cuda_set_ref_list, before the searches of the slice.
- * Bi-predictive searches with weights (computeBiPred*2) are not implemented: their calls fail when weights are set. ---- */
+ * The bi-predictive searches never read these weighted samples (see me_cuda_set_bipred_weights). ---- */
 int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset, int log_denom);
+/* Weighted bi-prediction (active_pps->weighted_bipred_idc > 0): FullPelBlockMotionBiPred / SubPelBlockSearchBiPred called with
+ * list argument `list` predict iClip1(255, ((weight1 * p1 + weight2 * p2 + 2 * round) >> (log_denom + 1)) + offset_bi), p1 = sample
+ * of reference 0 of `list` at the fixed vector, p2 = sample of reference 0 of the other list at the candidate, with the values
+ * those functions derive at me_fullsearch.c:202-227 / :541-582 (wbp_weight, wp_offset, luma_log_weight_denom), distortion =
+ * computeBiPredSAD2 / SSE2 / SATD2 (me_distortion.c:556, :1254, :907 -- including the source-pointer slip of the 8x8 branch
+ * of computeBiPredSATD2, :1015, which the encoder's results depend on).  apply = 0: plain (p1 + p2 + 1) >> 1.  Used by the
+ * drop-in calls and by me_cuda_frame_bipred. */
+int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom);
 
 /* ---- per macroblock: ResetFastFullIntegerSearch (me_fullfast.c:197, called macroblock.c:509) ---- */
 int me_cuda_mb_begin(int opix_x, int opix_y);

@@ -74,6 +74,8 @@ def lib():
         L.ora_ref_plane.restype = vp
         L.ora_ref_plane.argtypes = [vp, C.c_int, C.c_int]
         L.ora_ref_set_weights.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ora_set_bipred_weights.argtypes = [C.c_int] * 6
+        L.ora_select_bipred_list.argtypes = [C.c_int]
         L.ora_spiral.argtypes = [C.c_int, vp, vp]
         L.ora_mvbits.argtypes = [C.c_int]
         L.ora_mv_cost.argtypes = [C.c_int] * 5
@@ -147,6 +149,15 @@ class Ref:
             self.close()
         except Exception:
             pass
+
+
+def set_bipred_weights(lst, apply, w1=32, w2=32, offset_bi=0, log_denom=5):
+    """weight set of bi-predictive searches called with list argument `lst` (weighted bi-prediction, computeBiPred*2)"""
+    lib().ora_set_bipred_weights(lst, int(apply), int(w1), int(w2), int(offset_bi), int(log_denom))
+
+
+def select_bipred_list(lst):
+    lib().ora_select_bipred_list(lst)
 
 
 def _shorts(*vals):

@@ -414,6 +414,29 @@ int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_r
 
 /* ------------------------------------------------------------------------------------------------ bi-pred */
 
+/* Weighted bi-prediction: the state FullPelBlockMotionBiPred / SubPelBlockSearchBiPred derive per call from their `list`
+ * argument (me_fullsearch.c:202-234, :538-590) -- weight1 (picture of `list`, read at the fixed vector), weight2 (reference 0
+ * of the other list, read at the candidates), offsetBi, luma_log_weight_denom.  One set per value of `list`; the set in
+ * use is selected before a call (the composite of mv-search.c:864-1034 switches it as the lists take turns). */
+static struct { int apply, w1, w2, obi, denom; } g_bw[2], g_bw_cur;
+
+void ora_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom)
+{
+  g_bw[list & 1].apply = apply; g_bw[list & 1].w1 = weight1; g_bw[list & 1].w2 = weight2;
+  g_bw[list & 1].obi = offset_bi; g_bw[list & 1].denom = log_denom;
+}
+void ora_select_bipred_list(int list) { g_bw_cur = g_bw[list & 1]; }
+
+/* prediction sample: (p1 + p2 + 1) >> 1 (computeBiPredSAD1, me_distortion.c:502), or with weights
+ * iClip1(255, ((weight1 * p1 + weight2 * p2 + 2 * wp_luma_round) >> (denom + 1)) + offsetBi) (computeBiPredSAD2 :556-640,
+ * computeBiPredSATD2 :907) */
+static inline int bipel(int p1, int p2)
+{
+  if (!g_bw_cur.apply) return (p1 + p2 + 1) >> 1;
+  return clampi(((g_bw_cur.w1 * p1 + g_bw_cur.w2 * p2 + 2 * (g_bw_cur.denom ? 1 << (g_bw_cur.denom - 1) : 0)) >> (g_bw_cur.denom + 1))
+                + g_bw_cur.obi, 0, 255);
+}
+
 /* computeBiPredSAD1 / computeBiPredSATD1 (me_distortion.c:482-548, 824-899): prediction = (p1 + p2 + 1) >> 1.
  * SAD fetches each picture once per block; SATD once per transform tile. */
 static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stride, int bsx, int bsy,
@@ -424,7 +447,7 @@ static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stri
     const uint8_t *a = ora_umv_line(r1, y41, x41), *b = ora_umv_line(r2, y42, x42);
     for (y = 0; y < bsy; y++)
       for (x = 0; x < bsx; x++) {
-        int e = (int)src[(size_t)y * stride + x] - (((int)a[(size_t)y * r1->wp + x] + (int)b[(size_t)y * r2->wp + x] + 1) >> 1);
+        int e = (int)src[(size_t)y * stride + x] - bipel(a[(size_t)y * r1->wp + x], b[(size_t)y * r2->wp + x]);
         s += metric ? e * e : iabs_(e);
       }
     return s;
@@ -436,8 +459,14 @@ static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stri
         const uint8_t *b = ora_umv_line(r2, y42 + (by << 2), x42 + (bx << 2));
         for (y = 0; y < n; y++)
           for (x = 0; x < n; x++)
-            d[y * n + x] = (int)src[(size_t)(by + y) * stride + bx + x]
-                           - (((int)a[(size_t)y * r1->wp + x] + (int)b[(size_t)y * r2->wp + x] + 1) >> 1);
+            if (use8x8 && g_bw_cur.apply) {
+              /* computeBiPredSATD2, 8x8 branch (me_distortion.c:966-1023): the eighth sample of a row is read without
+               * advancing src_line (:1015), so every row of the ORIGINAL block starts one sample further left than the one
+               * above it: linear index by*bsx + bx + y*(bsx-1) + x into the bsx-wide copy of the block (mv-search.c:607-611) */
+              int L = by * bsx + bx + y * (bsx - 1) + x;
+              d[y * n + x] = (int)src[(size_t)(L / bsx) * stride + (L % bsx)] - bipel(a[(size_t)y * r1->wp + x], b[(size_t)y * r2->wp + x]);
+            } else
+            d[y * n + x] = (int)src[(size_t)(by + y) * stride + bx + x] - bipel(a[(size_t)y * r1->wp + x], b[(size_t)y * r2->wp + x]);
         s += use8x8 ? ora_hadamard8x8(d) : ora_hadamard4x4(d);
       }
     return s;
@@ -577,6 +606,7 @@ void ora_mb_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const o
       iterlist = list;
     }
     mv[0] = bimv[0]; mv[1] = bimv[1];
+    ora_select_bipred_list(iterlist);
     min_mcostbi = ora_bipred_fullpel(c, cur, cur_stride, refs[iterlist], refs[iterlist ^ 1], job->opix_x, job->opix_y, 1,
                                      pred_mv1[0], pred_mv1[1], pred_mv2[0], pred_mv2[1],
                                      &bimv[0], &bimv[1], &tempmv[0], &tempmv[1], search_range >> i, min_mcostbi, job->lambda[0]);
@@ -586,11 +616,13 @@ void ora_mb_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const o
   bimv[0] = (short)(bimv[0] << 2); bimv[1] = (short)(bimv[1] << 2);
   if (subpel) {
     if (!start_hp(c)) min_mcostbi = INT_MAX;
+    ora_select_bipred_list(iterlist);
     min_mcostbi = ora_bipred_subpel(c, cur, cur_stride, refs[iterlist], refs[iterlist ^ 1], job->opix_x, job->opix_y, 1,
                                     pred_mv2[0], pred_mv2[1], &bimv[0], &bimv[1], &mv[0], &mv[1], 9, 9, min_mcostbi, job->lambda);
   }
   if (subpel == 2) {
     if (!start_hp(c) || !start_qp(c)) min_mcostbi = INT_MAX;
+    ora_select_bipred_list(iterlist ^ 1);
     min_mcostbi = ora_bipred_subpel(c, cur, cur_stride, refs[iterlist ^ 1], refs[iterlist], job->opix_x, job->opix_y, 1,
                                     pred_mv1[0], pred_mv1[1], &mv[0], &mv[1], &bimv[0], &bimv[1], 9, 9, min_mcostbi, job->lambda);
   }

@@ -271,6 +271,15 @@ int __wrap_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int p
   rec[17] = *mv_x; rec[18] = *mv_y; rec[19] = *s_mv_x; rec[20] = *s_mv_y;
   rec[21] = ref_id_of(listX[list + list_offset][ref]);          /* picture read at the fixed vector s_mv */
   rec[22] = ref_id_of(listX[(list ^ 1) + list_offset][0]);      /* picture read at the searched candidate */
+  if (active_pps->weighted_bipred_idc > 0) {
+    /* what the function is about to derive (me_fullsearch.c:202-227): rec[29] = 1 + log denominator (0 = no weights),
+     * rec[30] = weight1 | weight2 << 16, rec[31] = offsetBi */
+    int o1 = list == 0 ? wp_offset[list_offset][ref][0] : wp_offset[list_offset + 1][0][ref];
+    int o2 = list == 0 ? wp_offset[list_offset + 1][ref][0] : wp_offset[list_offset][0][ref];
+    int w1 = list == 0 ? wbp_weight[list_offset][ref][0][0] : wbp_weight[list_offset + LIST_1][0][ref][0];
+    int w2 = list == 0 ? wbp_weight[list_offset + LIST_1][ref][0][0] : wbp_weight[list_offset][0][ref][0];
+    rec[29] = 1 + luma_log_weight_denom; rec[30] = (w1 & 0xffff) | (w2 << 16); rec[31] = (o1 + o2 + 1) >> 1;
+  }
   cost = __real_FullPelBlockMotionBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
                                          pred_mv_x1, pred_mv_y1, pred_mv_x2, pred_mv_y2,
                                          mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
@@ -301,6 +310,14 @@ int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pi
   rec[21] = ref_id_of(listX[list + list_offset][ref]);
   rec[22] = ref_id_of(listX[(list ^ 1) + list_offset][0]);
   rec[26] = test8x8transform; rec[27] = start_me_refinement_hp; rec[28] = start_me_refinement_qp;
+  if (active_pps->weighted_bipred_idc > 0) {
+    /* me_fullsearch.c:541-542, :574-582; same packing as in the integer-pel record */
+    int o1 = list == 0 ? wp_offset[list_offset][ref][0] : wp_offset[list_offset + 1][0][0];
+    int o2 = list == 0 ? wp_offset[list_offset + 1][ref][0] : wp_offset[list_offset][0][0];
+    int w1 = list == 0 ? wbp_weight[list_offset][ref][0][0] : wbp_weight[list_offset + LIST_1][0][ref][0];
+    int w2 = list == 0 ? wbp_weight[list_offset + LIST_1][ref][0][0] : wbp_weight[list_offset][0][ref][0];
+    rec[29] = 1 + luma_log_weight_denom; rec[30] = (w1 & 0xffff) | (w2 << 16); rec[31] = (o1 + o2 + 1) >> 1;
+  }
   cost = __real_SubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                         mv_x, mv_y, s_mv_x, s_mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
   rec[23] = *mv_x; rec[24] = *mv_y; rec[25] = cost;

@@ -16,6 +16,9 @@ Cases
   wp         encoder_main.cfg, WeightedPrediction=1 + UseWeightedReferenceME=1 on a synthetic QCIF clip that fades
              (h264_b200.synth kind="fade"), IPPP, SR 16, 3 references: the encoder estimates weights 28..31 / 32 and the
              searches run on weighted reference samples (computeSADWP / SATDWP).  Every 4th macroblock is kept.
+  wpb        encoder.cfg (High profile, I-B-P, bi-predictive ME, 8x8 transform) with WeightedBiprediction=1 and
+             WeightedPrediction=1 on the fading clip, SR 16, 2 references: weighted bi-predictive searches
+             (computeBiPredSAD2 / SATD2, including the 8x8 branch's source-pointer slip).  Every 6th macroblock is kept.
 Usage: python tests/golden/make_golden.py            (rewrites tests/golden/*.npz, planes_crc.json, bitstream_md5.json)
 """
 import hashlib
@@ -113,6 +116,17 @@ def main():
         assert set(np.unique(tr.of_type(REC_FFS)[:, 29])) - {32}, "the fade clip must produce non-default weights"
         tr.save_npz(os.path.join(HERE, "wp.npz"), keep_mask(tr, 4))
         crc["wp"] = planes_crc(tr, d)
+    # ---- wpb: weighted bi-prediction (bi-predictive records carry the weights in fields 29..31), High profile, 8x8 transform
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_yuv420(os.path.join(d, "syn.yuv"), 176, 144, 5, kind="fade")
+        args = ["-d", "encoder.cfg", "-p", "InputFile=syn.yuv", "-p", "FramesToBeEncoded=3", "-p", "WeightedBiprediction=1",
+                "-p", "WeightedPrediction=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+        run_trace(d, args)
+        md5s["wpb"] = {"test.264": md5(os.path.join(d, "test.264"))}
+        tr = Trace(d)
+        assert (tr.of_type(REC_BI_SUB)[:, 29] > 0).all() and (tr.of_type(REC_BI_SUB)[:, 26] == 1).all()
+        tr.save_npz(os.path.join(HERE, "wpb.npz"), keep_mask(tr, 6))
+        crc["wpb"] = planes_crc(tr, d)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
     for f in sorted(os.listdir(HERE)):

@@ -75,12 +75,17 @@ class OracleAdapter:
         return self.ob.subpel(self.cfg, self.cur, self._ref(lst, ref), ppx, ppy, bt, ref, self.slice_type,
                               pmvx, pmvy, mvx, mvy, min_mcost, lam3, sp2, sp4)
 
+    def set_bipred_weights(self, lst, apply, w1, w2, obi, denom):
+        self.ob.set_bipred_weights(lst, apply, w1, w2, obi, denom)
+
     def bipred_full(self, ref, lst, ppx, ppy, bt, pmv1, pmv2, mv, smv, sr, min_mcost, lam):
         r1, r2 = self.refs[self.lists[lst][ref]], self.refs[self.lists[lst ^ 1][0]]
+        self.ob.select_bipred_list(lst)
         return self.ob.bipred_fullpel(self.cfg, self.cur, r1, r2, ppx, ppy, bt, pmv1, pmv2, mv, smv, sr, min_mcost, lam)
 
     def bipred_sub(self, ref, lst, ppx, ppy, bt, pmv, mv, smv, sp2, sp4, min_mcost, lam3):
         r1, r2 = self.refs[self.lists[lst][ref]], self.refs[self.lists[lst ^ 1][0]]
+        self.ob.select_bipred_list(lst)
         return self.ob.bipred_subpel(self.cfg, self.cur, r1, r2, ppx, ppy, bt, pmv, mv, smv, min_mcost, lam3, sp2, sp4)
 
     def close(self):
@@ -108,6 +113,9 @@ class CudaAdapter:
 
     def set_weights(self, lst, ref, apply, weight, offset, denom):
         self.me.set_ref_weights(lst, ref, apply, weight, offset, denom)
+
+    def set_bipred_weights(self, lst, apply, w1, w2, obi, denom):
+        self.me.set_bipred_weights(lst, apply, w1, w2, obi, denom)
 
     def mb_begin(self, ox, oy):
         self.me.mb_begin(ox, oy)
@@ -153,6 +161,10 @@ def replay(trace, impl, max_calls=None):
         if t in (REC_FFS, REC_SUBPEL):
             # weighted-prediction ME: the weights the reference derived for this (list, ref) (0 = off in older fixtures)
             impl.set_weights(lst, ref, int(r[28]), int(r[29]), int(r[30]), int(r[31]))
+        if t in (REC_BI_FULL, REC_BI_SUB):
+            # weighted bi-prediction: 1 + log denominator (0 = off), weight1 | weight2 << 16, offsetBi
+            w = int(r[30])
+            impl.set_bipred_weights(lst, int(r[29]) > 0, (w << 16 >> 16) if w & 0x8000 else w & 0xffff, w >> 16, int(r[31]), max(0, int(r[29]) - 1))
         if t == REC_FFS:
             if r[22]:
                 c = impl.ffs_setup(lst, ref, int(r[23]), int(r[24]))

@@ -102,9 +102,9 @@ def test_reference_slot_reuse_and_in_place_update(pkg, oracle_lib):
         r2.close(); r3.close()
 
 
-def test_weight_arguments_are_checked_and_weighted_bipred_is_refused(pkg):
-    """me_cuda_set_ref_weights: ranges of the slice header syntax (weights / offsets -128..127, log denominator 0..7); the
-    bi-predictive batch has no weighted form (computeBiPred*2) and must say so instead of searching weighted copies"""
+def test_weight_arguments_are_checked(pkg):
+    """me_cuda_set_ref_weights / me_cuda_set_bipred_weights: ranges of the slice header syntax (weights / offsets -128..127,
+    log denominator 0..7); the bi-predictive batch reads the pictures' own planes whatever the list entries' weights are"""
     from h264_b200 import MeCuda, MeCudaError, synth
     from h264_b200.me_cuda import BIPRED_JOB_DTYPE
     w, h = 176, 144
@@ -118,9 +118,9 @@ def test_weight_arguments_are_checked_and_weighted_bipred_is_refused(pkg):
                 me.set_ref_weights(*bad)
         jobs = np.zeros(1, BIPRED_JOB_DTYPE)
         jobs["lambda"] = 334459
-        me.frame_bipred(jobs, 3, 16, 2)
-        me.set_ref_weights(1, 0, 1, 30, 2, 5)
-        with pytest.raises(MeCudaError):
-            me.frame_bipred(jobs, 3, 16, 2)
-        me.set_ref_weights(1, 0, 0)
-        me.frame_bipred(jobs, 3, 16, 2)
+        for bad in ((2, 1, 32, 32, 0, 5), (0, 1, 128, 32, 0, 5), (0, 1, 32, -129, 0, 5), (1, 1, 32, 32, 128, 5), (1, 1, 32, 32, 0, 8)):
+            with pytest.raises(MeCudaError):
+                me.set_bipred_weights(*bad)
+        plain = me.frame_bipred(jobs, 3, 16, 2)
+        me.set_ref_weights(1, 0, 1, 30, 2, 5)                 # uni-predictive weights of the same list entry: no effect here
+        assert np.array_equal(me.frame_bipred(jobs, 3, 16, 2), plain)

@@ -383,13 +383,18 @@ def test_bipred_batch_matches_reference_chains(pkg):
         assert int(out["cost"][k]) == c["exp_cost"] and int(out["iterlist"][k]) == c["list"] ^ 1, (k, out[k], c["exp_cost"])
 
 
-@pytest.mark.parametrize("refinements,subpel,t8", [(3, 2, 0), (0, 1, 0), (2, 0, 0), (1, 2, 1)])
-def test_bipred_batch_matches_oracle(pkg, oracle_lib, refinements, subpel, t8):
+# weights: per list argument (apply, weight1, weight2, offsetBi, log denominator) of weighted bi-prediction, or None
+@pytest.mark.parametrize("refinements,subpel,t8,weights", [
+    (3, 2, 0, None), (0, 1, 0, None), (2, 0, 0, None), (1, 2, 1, None),
+    (3, 2, 0, ((1, 31, 33, 0, 5), (1, 33, 31, 0, 5))),          # explicit weights as the reference estimates them for a fade
+    (1, 2, 1, ((1, 20, 45, -7, 5), (1, 45, 20, -7, 5))),        # 8x8 transform: the source-pointer slip of computeBiPredSATD2
+    (2, 2, 1, ((1, -10, 74, 12, 6), (0, 0, 0, 0, 0)))])         # negative weight, clipping; list 1 calls unweighted
+def test_bipred_batch_matches_oracle(pkg, oracle_lib, refinements, subpel, t8, weights):
     from h264_b200 import synth
     ob = oracle_lib
     w, h = 352, 288
     d, cfg = _cfg(ob, transform8x8=t8)
-    frames = synth.luma_frames(w, h, 3)
+    frames = synth.luma_frames(w, h, 3, kind="fade" if weights else "pan")
     cur, past, future = frames[1], frames[0], frames[2]
     rng = np.random.default_rng(41 + refinements)
     mbs = [(16 * x, 16 * y) for y in range(h // 16) for x in range(w // 16)]
@@ -408,8 +413,14 @@ def test_bipred_batch_matches_oracle(pkg, oracle_lib, refinements, subpel, t8):
         me.set_ref_list(0, [me.ref_create(past)])
         me.set_ref_list(1, [me.ref_create(future)])
         me.set_current(cur)
+        for lst in (0, 1):
+            wt = weights[lst] if weights else (0, 0, 0, 0, 0)
+            me.set_bipred_weights(lst, *wt)
+            ob.set_bipred_weights(lst, *wt)
         out = me.frame_bipred(jobs, refinements, 16, subpel)
     r0, r1 = ob.Ref(past), ob.Ref(future)
     exp = ob.mb_bipred(cfg, np.ascontiguousarray(cur), r0, r1, jobs.view(ob.BIPRED_JOB_DTYPE), refinements, 16, subpel)
     r0.close(); r1.close()
+    for lst in (0, 1):
+        ob.set_bipred_weights(lst, 0)
     assert np.array_equal(out.view(ob.BIPRED_RESULT_DTYPE), exp), np.nonzero(out.view(ob.BIPRED_RESULT_DTYPE) != exp)[0][:5]

@@ -50,7 +50,7 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
 @pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0", "yuv444_3ref_bframes", "sr64_2ref",
-                                  "hd1080_sr32_ip", "weighted_pred_fade"])
+                                  "hd1080_sr32_ip", "weighted_pred_fade", "weighted_bipred_fade"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -79,6 +79,11 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
                 "-p", "FramesToBeEncoded=4", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=16",
                 "-p", "NumberReferenceFrames=3", "-p", "WeightedPrediction=1", "-p", "UseWeightedReferenceME=1"]
+    elif case == "weighted_bipred_fade":
+        # I-B-P with explicit weighted bi-prediction and bi-predictive ME (computeBiPred*2), High profile with the 8x8 transform
+        args = ["-d", "encoder.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
+                "-p", "FramesToBeEncoded=3", "-p", "WeightedBiprediction=1", "-p", "WeightedPrediction=1", "-p", "SearchRange=16",
+                "-p", "NumberReferenceFrames=2"]
     elif case == "sr64_2ref":
         # the search range of BASELINE config 5 (4K), on a QCIF clip so that the CPU side finishes in seconds
         args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
@@ -93,7 +98,7 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         if "InputFile=syn.yuv" in args:
             wdt = int([a for a in args if a.startswith("SourceWidth=")][0].split("=")[1])
             hgt = int([a for a in args if a.startswith("SourceHeight=")][0].split("=")[1])
-            synth.write_yuv420(str(d / "syn.yuv"), wdt, hgt, 2 if wdt == 1920 else 4, kind="fade" if case == "weighted_pred_fade" else "pan")
+            synth.write_yuv420(str(d / "syn.yuv"), wdt, hgt, 2 if wdt == 1920 else 5, kind="fade" if "fade" in case else "pan")
     _run("lencod_cuda", args, str(a))
     _run("lencod", args, str(b))
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
