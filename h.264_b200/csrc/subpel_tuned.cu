@@ -279,30 +279,55 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
         // (first strict minimum, me_fullsearch.c:423-449, :482-502) as they come, in order.
         const int mvpx = sm.mv[s4.p][0], mvpy = sm.mv[s4.p][1];
         const int pmx = (int)(int16_t)(sm.job[3 + s4.p] & 0xffffu), pmy = (int)(int16_t)(sm.job[3 + s4.p] >> 16);
-        // length of the three possible differences per component: candidate offset -step, 0, +step (MV_COST_SMP, defines.h:126)
-        const int bx0 = me_mvbits(mvpx - pmx), bxm = me_mvbits(mvpx - step - pmx), bxp = me_mvbits(mvpx + step - pmx);
-        const int by0 = me_mvbits(mvpy - pmy), bym = me_mvbits(mvpy - step - pmy), byp = me_mvbits(mvpy + step - pmy);
+        // The nine candidates are a 3 x 3 grid (offsets -step, 0, +step per component): everything that depends on one
+        // component only is computed three times per stage, not nine -- lambda * code length (MV_COST_SMP, defines.h:126),
+        // and the two halves of the region address.  Address of sample (x4, y4) of the staged region:
+        //   region + [(x4 & 3) * RW*RH + (x4 >> 2) - Xr] + [(y4 & 3) * 4 * RW*RH + ((y4 >> 2) - Yr) * RW]
+        // and the second bracket is a multiple of 4, so the word address and the funnel-shift count come from x alone.
+        int lbx[3], lby[3];
+        unsigned axw[3], shx[3], ayr[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const int ox = (k - 1) * step;
+          lbx[k] = lam * me_mvbits(mvpx + ox - pmx);
+          lby[k] = lam * me_mvbits(mvpy + ox - pmy);
+          const int x4 = s4.x4 + mvpx + ox, y4 = s4.y4 + mvpy + ox;
+          const unsigned ax = (unsigned)((x4 & 3) * (RW * RH) + ((x4 >> 2) - Xr));
+          axw[k] = region_addr + (ax & ~3u); shx[k] = (ax & 3u) * 8;
+          ayr[k] = (unsigned)((y4 & 3) * (4 * RW * RH) + ((y4 >> 2) - Yr + s4.rot) * RW);
+        }
+        const int half_delta = (2 - 2 * s4.rot) * RW;       // rows 2, 3 of the (rotated) tile relative to rows 0, 1
         int mn = (stage == 1 && !cfg.start_qp) ? ME_INT_MAX : sm.mn[s4.p];       // me_fullsearch.c:456-457
         int best = 0;
         const bool check0 = stage == 0 && !cfg.rdopt && jv.slice_type != ME_B_SLICE && jv.ref == 0 && s4.p == 0 && mvpx == 0 && mvpy == 0;
-#pragma unroll 3
-        for (int c = first; c < 9; c++) {
-          const int sx = c_spx[c], sy = c_spy[c];
-          const int x4 = s4.x4 + mvpx + step * sx, y4 = s4.y4 + mvpy + step * sy;
+        const int gmax = __shfl_sync(0xffffffffu, s4.g, 0);   // largest partition (in tiles) among this warp's two block types
+        // does this lane's partition take part in the butterfly stage with distance 1, 2, 4, 8?  As 0 / 1 factors: the add becomes
+        // one multiply-add on the FMA pipe instead of a compare and a select on the (busier) ALU pipe
+        const int gk[4] = { 1 < s4.g, 2 < s4.g, 4 < s4.g, 8 < s4.g };
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+          if (c == 0 && first) continue;                      // start_me_refinement_hp / qp = 1: the centre keeps its cost
+          // spiral entries 0..8 (c_spx / c_spy) as compile-time grid indices
+          constexpr int SX[9] = { 1, 1, 1, 0, 2, 0, 2, 0, 2 }, SY[9] = { 1, 0, 2, 0, 0, 1, 1, 2, 2 };
+          const int kx = SX[c], ky = SY[c];
           unsigned r[4];
           if (s4.ok) {
-            const unsigned a = region_addr + (unsigned)((((y4 & 3) << 2) | (x4 & 3)) * (RW * RH) + ((y4 >> 2) - Yr) * RW + ((x4 >> 2) - Xr));
-            const unsigned a4 = a & ~3u, sh = (a & 3u) * 8;
-            const unsigned bA = a4 + s4.rot * RW, bB = a4 + (2 - s4.rot) * RW;
-#pragma unroll
-            for (int y = 0; y < 4; y++) {
-              const unsigned ra = (y < 2 ? bA : bB) + (y & 1) * RW;
-              unsigned w0, w1;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(ra));
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(ra + 4));
-              r[y] = __funnelshift_r(w0, w1, sh);
-            }
+            const unsigned bA = axw[kx] + ayr[ky], bB = bA + half_delta, sh = shx[kx];
+            unsigned w0, w1;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(bA));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(bA));
+            r[0] = __funnelshift_r(w0, w1, sh);
+            asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w0) : "r"(bA), "n"(RW));
+            asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w1) : "r"(bA), "n"(RW + 4));
+            r[1] = __funnelshift_r(w0, w1, sh);
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(bB));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(bB));
+            r[2] = __funnelshift_r(w0, w1, sh);
+            asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w0) : "r"(bB), "n"(RW));
+            asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w1) : "r"(bB), "n"(RW + 4));
+            r[3] = __funnelshift_r(w0, w1, sh);
           } else {
+            const int x4 = s4.x4 + mvpx + (kx - 1) * step, y4 = s4.y4 + mvpy + (ky - 1) * step;
             const uint8_t *rp = me_umv_ptr(ref, y4, x4);   // per-tile origin clamp, as computeSATD does (me_distortion.c:657)
 #pragma unroll
             for (int y = 0; y < 4; y++) {
@@ -311,14 +336,16 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
             }
           }
           int v = satd4x4(r, s4.c01, s4.c23);
-          // segmented sum over the g lanes of the partition
+          // segmented sum over the g lanes of the partition (stages no partition of this warp needs are skipped: uniform)
 #pragma unroll
-          for (int sft = 1; sft < 16; sft <<= 1) {
-            const int o = __shfl_xor_sync(0xffffffffu, v, sft);
-            if (sft < s4.g) v += o;
+          for (int st = 0; st < 4; st++) {
+            if ((1 << st) < gmax) {
+              const int o = __shfl_xor_sync(0xffffffffu, v, 1 << st);
+              asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(v) : "r"(o), "r"(gk[st]));
+            }
           }
-          int mc = v + ((lam * ((sx < 0 ? bxm : sx > 0 ? bxp : bx0) + (sy < 0 ? bym : sy > 0 ? byp : by0))) >> 16);
-          if (check0 && c == 0) mc -= (lam * 16) >> 16;    // check_position0, me_fullsearch.c:361,439-442
+          int mc = v + ((lbx[kx] + lby[ky]) >> 16);
+          if (c == 0 && check0) mc -= (lam * 16) >> 16;    // check_position0, me_fullsearch.c:361,439-442
           if (mc < mn) { mn = mc; best = c; }
         }
         if (s4.leader) {
