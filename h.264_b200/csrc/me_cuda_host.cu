@@ -30,6 +30,12 @@ struct MeBiFullArgs {
   int search_range, min_mcost, lambda;
   MeBiW bw;
 };
+struct MeFullPelArgs {
+  int pic_pix_x, pic_pix_y, blocktype;
+  int pmv_x, pmv_y, mv_x, mv_y;
+  int search_range, min_mcost, lambda;
+  int check00;
+};
 extern "C" {
 void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t *planes, int pitch, size_t plane_stride,
                       uint8_t *search, int spad, int spitch, cudaStream_t st);
@@ -62,6 +68,8 @@ void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, const MeRefDe
                             cudaStream_t st);
 void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                            const MeBiFullArgs *a, int *result, int ticket, cudaStream_t st);
+void me_launch_fullpel_block(const MeRefDev *r, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg, const MeFullPelArgs *a,
+                             int *result, int ticket, cudaStream_t st);
 }
 
 namespace {
@@ -758,6 +766,31 @@ int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int
     sp.pos2 = g.sub_params.pos2; sp.pos4 = g.sub_params.pos4;
     sp.mvx = g.h_result[4]; sp.mvy = g.h_result[5]; sp.cost = g.h_result[6];
   }
+  return cost;
+}
+
+int me_cuda_FullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                     short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                     int search_range, int min_mcost, int lambda_factor)
+{
+  g.spec.valid = false;
+  RefPic *r = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
+  if (!r) { fail(1, "me_cuda_FullPelBlockMotionSearch: (list %d, ref %d) not in the reference lists", list, (int)ref); fatal("fullpel"); return ME_INT_MAX; }
+  if (blocktype < 1 || blocktype > 7 || search_range < 0 || search_range > 64) {
+    fail(1, "me_cuda_FullPelBlockMotionSearch: block type %d / search range %d out of range", blocktype, search_range); fatal("fullpel"); return ME_INT_MAX;
+  }
+  const MeRefDev *dev;
+  if (search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) { fatal("fullpel"); return ME_INT_MAX; }
+  MeFullPelArgs a{};
+  a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
+  a.pmv_x = pred_mv_x; a.pmv_y = pred_mv_y; a.mv_x = *mv_x; a.mv_y = *mv_y;
+  a.search_range = search_range; a.min_mcost = min_mcost; a.lambda = lambda_factor;
+  a.check00 = (blocktype == 1 && !g.cfg.rdopt && g.slice_type != ME_B_SLICE && ref == 0);       // me_fullsearch.c:72
+  me_launch_fullpel_block(dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
+  g.launches++;
+  int mx, my, cost;
+  if (fetch_result(&mx, &my, &cost)) { fatal("fullpel"); return ME_INT_MAX; }
+  *mv_x = (short)mx; *mv_y = (short)my;
   return cost;
 }
 

@@ -321,6 +321,93 @@ me_ffs_block_subpel_kernel(const int32_t *__restrict__ surf_p, int setup_range, 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// FullPelBlockMotionSearch (me_fullsearch.c:47-155): the per-block spiral full search of SearchMode = -1.  One CTA; a thread
+// scores every 256th spiral position with the whole-block distortion computeUniPred[F_PEL] (SAD / SSE: one origin clamp per
+// block; SATD: one per transform tile), the first strict minimum in spiral order wins.
+struct MeFullPelArgs {
+  int pic_pix_x, pic_pix_y, blocktype;
+  int pmv_x, pmv_y, mv_x, mv_y;
+  int search_range, min_mcost, lambda;
+  int check00;          // blocktype == 1 && !rdopt && slice != B && ref == 0 (me_fullsearch.c:72)
+};
+
+// whole-block distortion; thr / use_thr: the reference's early exits (after a row of SAD / SSE when the sum has reached the
+// threshold, after a tile of SATD when it exceeds it), needed for the one position where they change the result (below)
+__device__ int fullpel_dist(const MeRefDev &r, const uint8_t *__restrict__ cur, int cur_pitch, const MeCfgDev &cfg, const MeFullPelArgs &a,
+                            int x4, int y4, bool use_thr, int thr)
+{
+  const int metric = cfg.metric[0], bsx = me_bsx(a.blocktype), bsy = me_bsy(a.blocktype);
+  const uint8_t *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
+  const MeBiW nobw = { 0, 0, 0, 0, 0 };
+  int m = 0;
+  if (metric == 2) {
+    const bool use8 = cfg.transform8x8 && a.blocktype <= 4;
+    const int n = use8 ? 8 : 4;
+    for (int by = 0; by < bsy; by += n)
+      for (int bx = 0; bx < bsx; bx += n) {
+        const uint8_t *rp = me_umv_ptr(r, y4 + (by << 2), x4 + (bx << 2));
+        m += use8 ? tile_dist<8>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw)
+                  : tile_dist<4>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw);
+        if (use_thr && m > thr) return m;
+      }
+    return m;
+  }
+  const uint8_t *rp = me_umv_ptr(r, y4, x4);
+  for (int y = 0; y < bsy; y++) {
+    for (int x = 0; x < bsx; x++) {
+      const int d = (int)blk[(size_t)y * cur_pitch + x] - (int)rp[(size_t)y * r.pitch + x];
+      m += metric ? d * d : abs(d);
+    }
+    if (use_thr && m >= thr) return m;
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(256)
+me_fullpel_block_kernel(MeRefDev r, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg, MeFullPelArgs a, int *result, int ticket)
+{
+  __shared__ unsigned long long red[8];
+  const int P = (2 * a.search_range + 1) * (2 * a.search_range + 1);
+  const int pred_x = (a.pic_pix_x << 2) + a.pmv_x, pred_y = (a.pic_pix_y << 2) + a.pmv_y;
+  const int center_x = a.pic_pix_x + a.mv_x, center_y = a.pic_pix_y + a.mv_y;
+  unsigned long long best = ~0ull;
+  for (int s = threadIdx.x; s < P; s += blockDim.x) {
+    int dx, dy;
+    me_spiral_xy(s, dx, dy);
+    const int cand_x = (center_x + dx) << 2, cand_y = (center_y + dy) << 2;
+    int mcost = me_mv_cost(a.lambda, cand_x, cand_y, pred_x, pred_y);
+    // the zero-vector bonus: a quarter-pel candidate compared with integer-pel block coordinates (me_fullsearch.c:129), as is
+    if (a.check00 && cand_x == a.pic_pix_x && cand_y == a.pic_pix_y) mcost -= (a.lambda * 16) >> 16;
+    // Position 0 is scored against the caller's min_mcost with the early exits in force: the bonus is subtracted before the
+    // distortion call and its threshold min_mcost - mcost (me_fullsearch.c:138) wraps negative for min_mcost = INT_MAX, mcost < 0
+    // -- the distortion function then leaves after one row / tile and the candidate is accepted with that partial sum.
+    // For every later position the running minimum is finite and a partial sum can only reject what the full sum rejects.
+    const bool first = s == 0;
+    if (first && mcost >= a.min_mcost) continue;
+    const int thr = (int)((unsigned)a.min_mcost - (unsigned)mcost);
+    mcost += fullpel_dist(r, cur, cur_pitch, cfg, a, cand_x + 4 * ME_PAD, cand_y + 4 * ME_PAD, first, thr);
+    const unsigned long long key = ((unsigned long long)(unsigned)(mcost ^ 0x80000000) << 32) | (unsigned)s;   // costs can be negative
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other < best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) best = red[i] < best ? red[i] : best;
+    int cost = (int)((unsigned)(best >> 32) ^ 0x80000000u), pos = (int)(unsigned)(best & 0xffffffffu);
+    int dx = 0, dy = 0;
+    if (best != ~0ull && cost < a.min_mcost) me_spiral_xy(pos, dx, dy); else cost = a.min_mcost;
+    result[0] = a.mv_x + dx; result[1] = a.mv_y + dy; result[2] = cost;
+    __threadfence_system();
+    *(volatile int *)&result[3] = ticket;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // FullPelBlockMotionBiPred (me_fullsearch.c:164-332): r1 at the fixed integer vector, r2 searched over (2r+1)^2
 struct MeBiFullArgs {
   int pic_pix_x, pic_pix_y, blocktype;
@@ -580,6 +667,12 @@ extern "C" void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, 
                                         const MeCfgDev *cfg, const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st)
 {
   me_subpel_single_kernel<<<1, 128, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, result, ticket);
+}
+
+extern "C" void me_launch_fullpel_block(const MeRefDev *r, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
+                                        const MeFullPelArgs *a, int *result, int ticket, cudaStream_t st)
+{
+  me_fullpel_block_kernel<<<1, 256, 0, st>>>(*r, cur, cur_pitch, *cfg, *a, result, ticket);
 }
 
 extern "C" void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "me_cuda_ref_create", "me_cuda_ref_create_u8", "me_cuda_ref_destroy", "me_cuda_ref_download_plane",
     "me_cuda_set_current", "me_cuda_set_current_u8", "me_cuda_set_ref_list", "me_cuda_set_slice_type",
     "me_cuda_mb_begin", "me_cuda_ffs_setup", "me_cuda_ffs_is_set_up",
-    "me_cuda_FastFullPelBlockMotionSearch", "me_cuda_SubPelBlockMotionSearch",
+    "me_cuda_FastFullPelBlockMotionSearch", "me_cuda_FullPelBlockMotionSearch", "me_cuda_SubPelBlockMotionSearch",
     "me_cuda_FullPelBlockMotionBiPred", "me_cuda_SubPelBlockSearchBiPred",
     "me_cuda_frame_search", "me_cuda_frame_search_device", "me_cuda_frame_bipred", "me_cuda_ref_create_device",
     "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count",
@@ -77,6 +77,7 @@ def load_library(path=LIB_PATH):
     L.me_cuda_ffs_is_set_up.argtypes = [C.c_int] * 2
     L.me_cuda_FastFullPelBlockMotionSearch.argtypes = ([C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, C.c_short, C.c_short,
                                                         sp, sp, C.c_int, C.c_int, C.c_int])
+    L.me_cuda_FullPelBlockMotionSearch.argtypes = L.me_cuda_FastFullPelBlockMotionSearch.argtypes
     L.me_cuda_SubPelBlockMotionSearch.argtypes = ([C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, C.c_short, C.c_short,
                                                    sp, sp, C.c_int, C.c_int, C.c_int, ip])
     L.me_cuda_FullPelBlockMotionBiPred.argtypes = ([C.c_short, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_short] * 4
@@ -224,6 +225,14 @@ class MeCuda:
         mx, my = C.c_short(0), C.c_short(0)
         cost = self.L.me_cuda_FastFullPelBlockMotionSearch(ref, lst, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                                            C.byref(mx), C.byref(my), search_range, min_mcost, lambda_factor)
+        return mx.value, my.value, cost
+
+    def FullPelBlockMotionSearch(self, ref, lst, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y,
+                                 search_range, min_mcost, lambda_factor):
+        """SearchMode = -1: mv_x / mv_y in = search centre (integer pel); returns (mv_x, mv_y, cost)"""
+        mx, my = C.c_short(mv_x), C.c_short(mv_y)
+        cost = self.L.me_cuda_FullPelBlockMotionSearch(ref, lst, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                                       C.byref(mx), C.byref(my), search_range, min_mcost, lambda_factor)
         return mx.value, my.value, cost
 
     def SubPelBlockMotionSearch(self, ref, lst, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y,

@@ -3,7 +3,7 @@
  *
  * This is what a maintainer adds to lencod to route its motion-estimation hot path through the GPU library.  It is
  * written as a link-time interposer: the UNMODIFIED reference objects are linked with
- *     -Wl,--wrap=FastFullPelBlockMotionSearch,--wrap=SubPelBlockMotionSearch,--wrap=FullPelBlockMotionBiPred,
+ *     -Wl,--wrap=FastFullPelBlockMotionSearch,--wrap=FullPelBlockMotionSearch,--wrap=SubPelBlockMotionSearch,--wrap=FullPelBlockMotionBiPred,
  *         --wrap=SubPelBlockSearchBiPred,--wrap=ResetFastFullIntegerSearch,--wrap=getSubImagesLuma,
  *         --wrap=encode_one_frame,--wrap=Init_Motion_Search_Module,--wrap=Clear_Motion_Search_Module,
  *         --wrap=free_storable_picture
@@ -56,6 +56,7 @@ static struct {
   int  (*ffs_setup)(int, int, int, int);
   int  (*ffs_is_set_up)(int, int);
   int  (*ffs)(short, int, int, int, int, short, short, short *, short *, int, int, int);
+  int  (*fullpel)(short, int, int, int, int, short, short, short *, short *, int, int, int);
   int  (*subpel)(short, int, int, int, int, short, short, short *, short *, int, int, int, const int *);
   int  (*bi_full)(short, int, int, int, int, short, short, short, short, short *, short *, short *, short *, int, int, int);
   int  (*bi_sub)(short, int, int, int, int, short, short, short *, short *, short *, short *, int, int, int, const int *);
@@ -114,6 +115,7 @@ static void load_library(void)
   L.set_slice_type = sym("me_cuda_set_slice_type"); L.mb_begin = sym("me_cuda_mb_begin");
   L.set_ref_weights = sym("me_cuda_set_ref_weights"); L.set_bipred_weights = sym("me_cuda_set_bipred_weights");
   L.ffs_setup = sym("me_cuda_ffs_setup"); L.ffs_is_set_up = sym("me_cuda_ffs_is_set_up");
+  L.fullpel = sym("me_cuda_FullPelBlockMotionSearch");
   L.ffs = sym("me_cuda_FastFullPelBlockMotionSearch"); L.subpel = sym("me_cuda_SubPelBlockMotionSearch");
   L.bi_full = sym("me_cuda_FullPelBlockMotionBiPred"); L.bi_sub = sym("me_cuda_SubPelBlockSearchBiPred");
 }
@@ -148,7 +150,8 @@ void __wrap_Init_Motion_Search_Module(void)
   __real_Init_Motion_Search_Module();
   active = 0;
   if (dis && atoi(dis)) return;
-  if (input->SearchMode != FAST_FULL_SEARCH) return;   /* the library implements the SearchMode=0 path */
+  /* the library implements SearchMode 0 (fast full search) and -1 (per-block full search) */
+  if (input->SearchMode != FAST_FULL_SEARCH && input->SearchMode != FULL_SEARCH) return;
   {
     me_cuda_params p;
     int apply_wp = (input->WeightedPrediction || input->WeightedBiprediction) && input->UseWeightedReferenceME;
@@ -219,11 +222,14 @@ void __wrap_free_storable_picture(StorablePicture *p)
 }
 
 /* ---------------------------------------------------------------- per macroblock (macroblock.c:509) */
-void __real_ResetFastFullIntegerSearch(void);
-void __wrap_ResetFastFullIntegerSearch(void)
+/* Once per macroblock, before its first search: current picture (first macroblock of a picture), reference lists, slice type,
+ * macroblock origin.  With SearchMode = 0 the reference's own per-macroblock reset (macroblock.c:509) triggers it; with
+ * SearchMode = -1 there is no such call and the first search of the macroblock does. */
+static int mb_synced_pic = -1, mb_synced_mb = -1;
+static void mb_sync(void)
 {
-  __real_ResetFastFullIntegerSearch();
-  if (!active) return;
+  if (mb_synced_pic == pic_counter && mb_synced_mb == img->current_mb_nr) return;
+  mb_synced_pic = pic_counter; mb_synced_mb = img->current_mb_nr;
   if (pic_uploaded != pic_counter) {
     if (L.set_current((const me_imgpel *const *)pCurImg, img->width, img->height)) die("me_cuda_set_current");
     pic_uploaded = pic_counter;
@@ -244,6 +250,15 @@ void __wrap_ResetFastFullIntegerSearch(void)
     L.set_slice_type(img->type == B_SLICE ? ME_B_SLICE : ME_P_SLICE);
     if (L.mb_begin(img->opix_x, img->opix_y)) die("me_cuda_mb_begin");
   }
+}
+
+void __real_ResetFastFullIntegerSearch(void);
+void __wrap_ResetFastFullIntegerSearch(void)
+{
+  __real_ResetFastFullIntegerSearch();
+  if (!active) return;
+  mb_synced_mb = -1;                                     /* a macroblock coded twice (e.g. rate control) is set up twice */
+  mb_sync();
 }
 
 /* The reference search functions leave values in the globals of refbuf.h / me_distortion.c that later host code relies
@@ -328,6 +343,34 @@ int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, i
   return L.ffs(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
 }
 
+int __real_FullPelBlockMotionSearch(imgpel *, short, int, int, int, int, short, short, short *, short *, int, int, int);
+int __wrap_FullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                    short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                    int search_range, int min_mcost, int lambda_factor)
+{
+  if (!active)
+    return __real_FullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                           mv_x, mv_y, search_range, min_mcost, lambda_factor);
+  mb_sync();
+  keep_reference_side_effects(list, ref);
+  pass_weights(list, ref);
+  if (verify) {
+    short gx = *mv_x, gy = *mv_y;
+    int gc = L.fullpel(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, &gx, &gy, search_range, min_mcost, lambda_factor);
+    int rc = __real_FullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                                             mv_x, mv_y, search_range, min_mcost, lambda_factor);
+    n_checked++;
+    if (gc != rc || gx != *mv_x || gy != *mv_y) {
+      n_mismatch++;
+      fprintf(stderr, "VERIFY fullpel pic %d mb (%d,%d) list %d ref %d bt %d blk (%d,%d) pmv (%d,%d) sr %d min %d: gpu (%d,%d,%d) ref (%d,%d,%d)\n",
+              pic_counter, img->opix_x, img->opix_y, list, ref, blocktype, pic_pix_x, pic_pix_y, pred_mv_x, pred_mv_y, search_range,
+              min_mcost, gx, gy, gc, *mv_x, *mv_y, rc);
+    }
+    return rc;
+  }
+  return L.fullpel(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
+}
+
 int __real_SubPelBlockMotionSearch(imgpel *, short, int, int, int, int, short, short, short *, short *, int, int, int, int *);
 int __wrap_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
                                    short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
@@ -336,6 +379,7 @@ int __wrap_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pi
   if (!active)
     return __real_SubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                           mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+  mb_sync();
   keep_reference_side_effects(list, ref);
   pass_weights(list, ref);
   if (verify) {
@@ -366,6 +410,7 @@ int __wrap_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int p
   if (!active)
     return __real_FullPelBlockMotionBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x1, pred_mv_y1,
                                            pred_mv_x2, pred_mv_y2, mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
+  mb_sync();
   keep_reference_side_effects(list, ref);
   pass_bipred_weights(list, ref, 0);
   return L.bi_full(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x1, pred_mv_y1, pred_mv_x2, pred_mv_y2,
@@ -381,6 +426,7 @@ int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pi
   if (!active)
     return __real_SubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                           mv_x, mv_y, s_mv_x, s_mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+  mb_sync();
   keep_reference_side_effects(list, ref);
   pass_bipred_weights(list, ref, 1);
   return L.bi_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, s_mv_x, s_mv_y,

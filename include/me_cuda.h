@@ -6,6 +6,7 @@
  *   - integer-pel fast full search      lencod/src/me_fullfast.c:491 (SetupFastFullPelSearch), :210 (SetupLargerBlocks),
  *                                       :833 (FastFullPelBlockMotionSearch)
  *   - quarter-pel plane generation      lencod/src/img_luma.c:45 (getSubImagesLuma), lencod/src/image.c:1601
+ *   - per-block full search             lencod/src/me_fullsearch.c:47 (FullPelBlockMotionSearch, SearchMode = -1)
  *   - sub-pel refinement (SAD / SATD)   lencod/src/me_fullsearch.c:341 (SubPelBlockMotionSearch),
  *                                       lencod/src/me_distortion.c:351,657,182,272
  *   - bi-predictive search              lencod/src/me_fullsearch.c:164 (FullPelBlockMotionBiPred), :520 (SubPelBlockSearchBiPred),
@@ -130,6 +131,11 @@ int me_cuda_ffs_is_set_up(int list, int ref);
 int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
                                          short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
                                          int search_range, int min_mcost, int lambda_factor);   /* me_fullfast.h:21 */
+/* the per-block spiral full search of SearchMode = -1 (and of the `else` branch of the dispatch, mv-search.c:749-768); mv in:
+ * search centre in integer pel as set at mv-search.c:751-762.  Needs no me_cuda_ffs_setup. */
+int me_cuda_FullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                     short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                     int search_range, int min_mcost, int lambda_factor);       /* me_fullsearch.h:21, me_fullsearch.c:47 */
 int me_cuda_SubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
                                     short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
                                     int search_pos2, int search_pos4, int min_mcost,

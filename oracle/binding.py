@@ -89,6 +89,7 @@ def lib():
         L.ora_hadamard4x4.argtypes = [vp]
         L.ora_hadamard8x8.argtypes = [vp]
         L.ora_subpel.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp] + [C.c_int] * 7 + [sp, sp, C.c_int, C.c_int, C.c_int, ip]
+        L.ora_fullpel_block.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp] + [C.c_int] * 7 + [sp, sp, C.c_int, C.c_int, C.c_int]
         L.ora_bipred_fullpel.argtypes = ([C.POINTER(OraCfg), vp, C.c_int, vp, vp] + [C.c_int] * 7
                                          + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int])
         L.ora_bipred_subpel.argtypes = ([C.POINTER(OraCfg), vp, C.c_int, vp, vp] + [C.c_int] * 5
@@ -149,6 +150,14 @@ class Ref:
             self.close()
         except Exception:
             pass
+
+
+def fullpel_block(cfg, cur, ref, ppx, ppy, bt, ref_idx, slice_type, pmvx, pmvy, mvx, mvy, search_range, min_mcost, lam):
+    """FullPelBlockMotionSearch (SearchMode = -1): returns (mv_x, mv_y, cost), vectors in integer pel"""
+    mx, my = C.c_short(mvx), C.c_short(mvy)
+    cost = lib().ora_fullpel_block(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr, ppx, ppy, bt, ref_idx, slice_type,
+                                   pmvx, pmvy, C.byref(mx), C.byref(my), search_range, min_mcost, lam)
+    return mx.value, my.value, cost
 
 
 def set_bipred_weights(lst, apply, w1=32, w2=32, offset_bi=0, log_denom=5):

@@ -412,6 +412,70 @@ int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_r
   return min_mcost;
 }
 
+/* The block distortions with the reference's early exits (computeSAD / SSE: after every row when the sum has reached the
+ * threshold, me_distortion.c:366,1066; computeSATD: after every tile when the sum exceeds it, :689).  For a threshold below
+ * the full distortion the partial sum comes back.  Everywhere else on this path the caller discards such a candidate, so
+ * the full sum is equivalent; FullPelBlockMotionSearch is the exception (see below). */
+static int unipred_exit(const ora_cfg *c, const uint8_t *src, int stride, int bsx, int bsy, const ora_ref *r, int x4, int y4,
+                        int use8x8, int thr)
+{
+  int metric = c->metric[0], m = 0, x, y;
+  if (metric == 2) {
+    int n = use8x8 ? 8 : 4, bx, by;
+    for (by = 0; by < bsy; by += n)
+      for (bx = 0; bx < bsx; bx += n) {
+        m += ora_satd_block(src + (size_t)by * stride + bx, stride, n, n, r, x4 + (bx << 2), y4 + (by << 2), use8x8);
+        if (m > thr) return m;
+      }
+    return m;
+  } else {
+    const uint8_t *rp = ora_umv_line(r, y4, x4);
+    for (y = 0; y < bsy; y++) {
+      for (x = 0; x < bsx; x++) {
+        int d = (int)src[(size_t)y * stride + x] - refpel(r, rp[(size_t)y * r->wp + x]);
+        m += metric ? d * d : iabs_(d);
+      }
+      if (m >= thr) return m;
+    }
+    return m;
+  }
+}
+
+/* FullPelBlockMotionSearch (me_fullsearch.c:47-155): the per-block spiral full search of SearchMode = -1 (and of every
+ * SearchMode value the dispatch of mv-search.c:629-768 does not know).  mv in: search centre (integer pel, set by the caller at
+ * mv-search.c:751-762), out: best vector.  Distortion = computeUniPred[F_PEL (+3 with weights)]: SAD, SSE or SATD of the whole
+ * block.  The zero-vector bonus compares a quarter-pel candidate with integer-pel block coordinates (:129) -- kept as is.
+ * The bonus is subtracted BEFORE the distortion call, whose early-exit threshold is min_mcost - mcost (:138): with the
+ * caller's min_mcost = INT_MAX and a negative mcost that difference wraps to a negative int, the distortion function leaves
+ * after its first row (first tile for SATD) and the candidate is accepted with that partial sum.  This happens for the first
+ * spiral position of blocks at picture origin under !rdopt, and the encoder's decisions depend on it -- reproduced. */
+int ora_fullpel_block(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                      int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type,
+                      int pmv_x, int pmv_y, short *mv_x, short *mv_y, int search_range, int min_mcost, int lambda_factor)
+{
+  int P = ora_num_positions(search_range), pos, best = 0, bsx, bsy;
+  int16_t *sx = (int16_t *)malloc(sizeof(int16_t) * P), *sy = (int16_t *)malloc(sizeof(int16_t) * P);
+  int pred_x = (pic_pix_x << 2) + pmv_x, pred_y = (pic_pix_y << 2) + pmv_y;
+  int center_x = pic_pix_x + *mv_x, center_y = pic_pix_y + *mv_y;
+  int check_for_00 = (blocktype == 1 && !c->rdopt && slice_type != ME_B_SLICE && ref == 0);
+  int use8x8 = c->transform8x8 && blocktype <= 4;
+  const uint8_t *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
+  ora_block_size(blocktype, &bsx, &bsy);
+  ora_spiral(search_range, sx, sy);
+  for (pos = 0; pos < P; pos++) {
+    int cand_x = (center_x + sx[pos]) << 2, cand_y = (center_y + sy[pos]) << 2;
+    int mcost = ora_mv_cost(lambda_factor, cand_x, cand_y, pred_x, pred_y);
+    if (check_for_00 && cand_x == pic_pix_x && cand_y == pic_pix_y) mcost -= (lambda_factor * 16) >> 16;
+    if (mcost >= min_mcost) continue;
+    mcost += unipred_exit(c, src, cur_stride, bsx, bsy, r, cand_x + 4 * PAD, cand_y + 4 * PAD, use8x8,
+                          (int)((unsigned)min_mcost - (unsigned)mcost));
+    if (mcost < min_mcost) { best = pos; min_mcost = mcost; }
+  }
+  if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }
+  free(sx); free(sy);
+  return min_mcost;
+}
+
 /* ------------------------------------------------------------------------------------------------ bi-pred */
 
 /* Weighted bi-prediction: the state FullPelBlockMotionBiPred / SubPelBlockSearchBiPred derive per call from their `list`

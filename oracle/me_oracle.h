@@ -78,6 +78,11 @@ int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_r
                int pmv_x, int pmv_y, short *mv_x, short *mv_y, int search_pos2, int search_pos4,
                int min_mcost, const int *lambda);
 
+/* per-block full search (FullPelBlockMotionSearch, me_fullsearch.c:47): SearchMode = -1 */
+int ora_fullpel_block(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                      int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type,
+                      int pmv_x, int pmv_y, short *mv_x, short *mv_y, int search_range, int min_mcost, int lambda_factor);
+
 /* weighted bi-prediction (computeBiPred*2): one weight set per value of the searches' `list` argument; ora_bipred_fullpel /
  * ora_bipred_subpel use the set chosen by ora_select_bipred_list, ora_mb_bipred switches between the two as the reference does */
 void ora_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom);

@@ -12,6 +12,7 @@
  * Functions intercepted (reference file:line of the definition):
  *   FastFullPelBlockMotionSearch   lencod/src/me_fullfast.c:833   (called mv-search.c:745)
  *   SubPelBlockMotionSearch        lencod/src/me_fullsearch.c:341 (called mv-search.c:799,823)
+ *   FullPelBlockMotionSearch       lencod/src/me_fullsearch.c:47  (called mv-search.c:765; SearchMode = -1)
  *   FullPelBlockMotionBiPred       lencod/src/me_fullsearch.c:164 (called mv-search.c:960)
  *   SubPelBlockSearchBiPred        lencod/src/me_fullsearch.c:520 (called mv-search.c:998,1018)
  *   ResetFastFullIntegerSearch     lencod/src/me_fullfast.c:197   (called macroblock.c:509)
@@ -35,7 +36,7 @@
 #include "me_distortion.h"
 
 #define REC_INTS 32
-enum { REC_FFS = 1, REC_SUBPEL = 2, REC_BI_FULL = 3, REC_BI_SUB = 4, REC_REFPIC = 5, REC_CURPIC = 6 };
+enum { REC_FFS = 1, REC_SUBPEL = 2, REC_BI_FULL = 3, REC_BI_SUB = 4, REC_REFPIC = 5, REC_CURPIC = 6, REC_FULLPEL = 7 };
 
 extern const int LEVELMVLIMIT[17][6];
 extern void SetMotionVectorPredictor (short pmv[2], char **refPic, short ***tmp_mv, short ref_frame,
@@ -218,6 +219,32 @@ int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, i
   put_weights(rec, list, list_offset, ref);
   cost = __real_FastFullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
                                              pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
+  rec[18] = *mv_x; rec[19] = *mv_y; rec[20] = cost;
+  put(rec);
+  return cost;
+}
+
+/* ---------------------------------------------------------------- per-block full search (SearchMode = -1) */
+int __real_FullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                    int blocktype, short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                    int search_range, int min_mcost, int lambda_factor);
+int __wrap_FullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y,
+                                    int blocktype, short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                    int search_range, int min_mcost, int lambda_factor)
+{
+  int rec[REC_INTS] = {0};
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  int cost;
+  dump_current_if_needed();
+  rec[0] = REC_FULLPEL; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->opix_x; rec[4] = img->opix_y;
+  rec[5] = list; rec[6] = ref; rec[7] = blocktype; rec[8] = pic_pix_x; rec[9] = pic_pix_y;
+  rec[10] = pred_mv_x; rec[11] = pred_mv_y; rec[12] = search_range; rec[13] = lambda_factor; rec[14] = min_mcost;
+  rec[15] = *mv_x; rec[16] = *mv_y;                              /* search centre, integer pel */
+  rec[21] = ref_id_of(listX[list + list_offset][ref]);
+  rec[22] = test8x8transform; rec[25] = input->rdopt;
+  put_weights(rec, list, list_offset, ref);
+  cost = __real_FullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
+                                         pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
   rec[18] = *mv_x; rec[19] = *mv_y; rec[20] = cost;
   put(rec);
   return cost;

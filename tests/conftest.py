@@ -41,6 +41,7 @@ GOLDEN_CASES = {
     "baseline16": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),
     "rdopt0": dict(search_range=16, full_search=0, metric=(0, 2, 2), mv_limits=(-511, 511)),
     "wp": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),     # weighted-prediction ME
+    "fullsearch": dict(search_range=8, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),   # SearchMode = -1
     "wpb": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),    # + weighted bi-prediction
 }
 

@@ -16,6 +16,9 @@ Cases
   wp         encoder_main.cfg, WeightedPrediction=1 + UseWeightedReferenceME=1 on a synthetic QCIF clip that fades
              (h264_b200.synth kind="fade"), IPPP, SR 16, 3 references: the encoder estimates weights 28..31 / 32 and the
              searches run on weighted reference samples (computeSADWP / SATDWP).  Every 4th macroblock is kept.
+  fullsearch encoder_baseline.cfg with SearchMode=-1 (FullPelBlockMotionSearch, me_fullsearch.c:47, for every block), SR 8,
+             2 references, RDOptimization=0 on the synthetic QCIF clip: includes the blocks at picture origin whose first
+             candidate is accepted with a one-row SAD (early-exit threshold wrap, me_fullsearch.c:129-138).  Every 3rd MB.
   wpb        encoder.cfg (High profile, I-B-P, bi-predictive ME, 8x8 transform) with WeightedBiprediction=1 and
              WeightedPrediction=1 on the fading clip, SR 16, 2 references: weighted bi-predictive searches
              (computeBiPredSAD2 / SATD2, including the 8x8 branch's source-pointer slip).  Every 6th macroblock is kept.
@@ -36,7 +39,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from trace_util import Trace, REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB  # noqa: E402
+from trace_util import Trace, REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_FULLPEL  # noqa: E402
 import h264_b200_pkg  # noqa: E402,F401
 from h264_b200 import synth  # noqa: E402
 
@@ -62,7 +65,7 @@ def keep_mask(tr, step):
     recs = tr.recs
     mb_w = tr.size[("cur", tr.cur_ids()[0])][1] // 16
     mb = (recs[:, 4] // 16) * mb_w + recs[:, 3] // 16
-    is_call = np.isin(recs[:, 0], [REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB])
+    is_call = np.isin(recs[:, 0], [REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_FULLPEL])
     return ~is_call | (mb % step == 0)
 
 
@@ -127,6 +130,18 @@ def main():
         assert (tr.of_type(REC_BI_SUB)[:, 29] > 0).all() and (tr.of_type(REC_BI_SUB)[:, 26] == 1).all()
         tr.save_npz(os.path.join(HERE, "wpb.npz"), keep_mask(tr, 6))
         crc["wpb"] = planes_crc(tr, d)
+    # ---- fullsearch: SearchMode = -1, FullPelBlockMotionSearch for every block (records of type 7)
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_yuv420(os.path.join(d, "syn.yuv"), 176, 144, 3)
+        args = ["-d", "encoder_baseline.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
+                "-p", "FramesToBeEncoded=3", "-p", "FrameSkip=0", "-p", "SearchMode=-1", "-p", "SearchRange=8",
+                "-p", "NumberReferenceFrames=2", "-p", "RDOptimization=0"]
+        run_trace(d, args)
+        md5s["fullsearch"] = {"test.264": md5(os.path.join(d, "test.264"))}
+        tr = Trace(d)
+        assert len(tr.of_type(REC_FULLPEL)) > 10000 and not len(tr.of_type(REC_FFS))
+        tr.save_npz(os.path.join(HERE, "fullsearch.npz"), keep_mask(tr, 3))
+        crc["fullsearch"] = planes_crc(tr, d)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
     for f in sorted(os.listdir(HERE)):

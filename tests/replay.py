@@ -6,7 +6,7 @@ replay() walks a Trace in call order and returns the mismatching records per fun
 """
 import numpy as np
 
-from trace_util import REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_CURPIC, REC_REFPIC
+from trace_util import REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_CURPIC, REC_REFPIC, REC_FULLPEL
 
 
 def picture_lists(trace, pic):
@@ -15,7 +15,7 @@ def picture_lists(trace, pic):
     recs = trace.recs[(trace.recs[:, 1] == pic)]
     for r in recs:
         t = int(r[0])
-        if t in (REC_FFS, REC_SUBPEL):
+        if t in (REC_FFS, REC_SUBPEL, REC_FULLPEL):
             lists[int(r[5])][int(r[6])] = int(r[21])
         elif t in (REC_BI_FULL, REC_BI_SUB):
             lists[int(r[5])][int(r[6])] = int(r[21])
@@ -70,6 +70,10 @@ class OracleAdapter:
         s, cx, cy, rng = self.surf[(lst, ref)]
         p = self.ob.part_index(bt, (ppy - self.oy) + ((ppx - self.ox) >> 2))
         return self.ob.ffs_block(self.cfg, s[p], rng, self.ox, self.oy, cx, cy, pmvx, pmvy, search_range, min_mcost, lam)
+
+    def fullpel(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, search_range, min_mcost, lam):
+        return self.ob.fullpel_block(self.cfg, self.cur, self._ref(lst, ref), ppx, ppy, bt, ref, self.slice_type, pmvx, pmvy,
+                                     mvx, mvy, search_range, min_mcost, lam)
 
     def subpel(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, sp2, sp4, min_mcost, lam3):
         return self.ob.subpel(self.cfg, self.cur, self._ref(lst, ref), ppx, ppy, bt, ref, self.slice_type,
@@ -127,6 +131,9 @@ class CudaAdapter:
     def ffs_block(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, search_range, min_mcost, lam):
         return self.me.FastFullPelBlockMotionSearch(ref, lst, ppx, ppy, bt, pmvx, pmvy, search_range, min_mcost, lam)
 
+    def fullpel(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, search_range, min_mcost, lam):
+        return self.me.FullPelBlockMotionSearch(ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, search_range, min_mcost, lam)
+
     def subpel(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, sp2, sp4, min_mcost, lam3):
         return self.me.SubPelBlockMotionSearch(ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, sp2, sp4, min_mcost, lam3)
 
@@ -142,7 +149,7 @@ class CudaAdapter:
 
 def replay(trace, impl, max_calls=None):
     """returns {name: (n_calls, [mismatch descriptions])}"""
-    res = {"ffs": [0, []], "centre": [0, []], "subpel": [0, []], "bi_full": [0, []], "bi_sub": [0, []]}
+    res = {"ffs": [0, []], "centre": [0, []], "subpel": [0, []], "bi_full": [0, []], "bi_sub": [0, []], "fullpel": [0, []]}
     cur_pic, cur_mb = None, None
     slice_of = {int(r[1]): int(r[2]) for r in trace.of_type(REC_CURPIC)}
     n = 0
@@ -158,7 +165,7 @@ def replay(trace, impl, max_calls=None):
             impl.mb_begin(ox, oy)
             cur_mb = (ox, oy)
         lst, ref, bt, ppx, ppy = int(r[5]), int(r[6]), int(r[7]), int(r[8]), int(r[9])
-        if t in (REC_FFS, REC_SUBPEL):
+        if t in (REC_FFS, REC_SUBPEL, REC_FULLPEL):
             # weighted-prediction ME: the weights the reference derived for this (list, ref) (0 = off in older fixtures)
             impl.set_weights(lst, ref, int(r[28]), int(r[29]), int(r[30]), int(r[31]))
         if t in (REC_BI_FULL, REC_BI_SUB):
@@ -175,6 +182,10 @@ def replay(trace, impl, max_calls=None):
             got = impl.ffs_block(ref, lst, ppx, ppy, bt, int(r[10]), int(r[11]), int(r[12]), int(r[14]), int(r[13]))
             exp = (int(r[18]), int(r[19]), int(r[20]))
             key = "ffs"
+        elif t == REC_FULLPEL:
+            got = impl.fullpel(ref, lst, ppx, ppy, bt, int(r[10]), int(r[11]), int(r[15]), int(r[16]), int(r[12]), int(r[14]), int(r[13]))
+            exp = (int(r[18]), int(r[19]), int(r[20]))
+            key = "fullpel"
         elif t == REC_SUBPEL:
             got = impl.subpel(ref, lst, ppx, ppy, bt, int(r[10]), int(r[11]), int(r[12]), int(r[13]), int(r[26]), int(r[27]),
                               int(r[14]), [int(r[15]), int(r[16]), int(r[17])])

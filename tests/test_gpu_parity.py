@@ -90,7 +90,7 @@ def test_dropin_calls_match_reference_trace(pkg, case):
         impl.close()
     for name, (n, bad) in res.items():
         assert not bad, (case, name, n, len(bad), bad[:3])
-    assert res["ffs"][0] > 1000 and res["subpel"][0] > 1000
+    assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000) and res["subpel"][0] > 1000
 
 
 # ------------------------------------------------------------------------------------------------ frame batch

@@ -50,7 +50,8 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
 @pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0", "yuv444_3ref_bframes", "sr64_2ref",
-                                  "hd1080_sr32_ip", "weighted_pred_fade", "weighted_bipred_fade"])
+                                  "hd1080_sr32_ip", "weighted_pred_fade", "weighted_bipred_fade", "full_search_mode_rdopt0",
+                                  "full_search_mode_satd"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -84,6 +85,13 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         args = ["-d", "encoder.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
                 "-p", "FramesToBeEncoded=3", "-p", "WeightedBiprediction=1", "-p", "WeightedPrediction=1", "-p", "SearchRange=16",
                 "-p", "NumberReferenceFrames=2"]
+    elif case in ("full_search_mode_rdopt0", "full_search_mode_satd"):
+        # SearchMode = -1: FullPelBlockMotionSearch (me_fullsearch.c:47) for every block; without RDO the zero-vector bonus and the
+        # early-exit wrap at picture origin are in play; with MEDistortionFPel = 2 the integer-pel metric is the Hadamard SAD
+        args = ["-d", "encoder_baseline.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
+                "-p", "FramesToBeEncoded=3", "-p", "FrameSkip=0", "-p", "SearchMode=-1", "-p", "SearchRange=8",
+                "-p", "NumberReferenceFrames=2"]
+        args += ["-p", "RDOptimization=0"] if case.endswith("rdopt0") else ["-p", "MEDistortionFPel=2"]
     elif case == "sr64_2ref":
         # the search range of BASELINE config 5 (4K), on a QCIF clip so that the CPU side finishes in seconds
         args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",

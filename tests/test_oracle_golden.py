@@ -30,7 +30,7 @@ def test_calls_match_reference_trace(oracle_lib, case):
     impl.close()
     for name, (n, bad) in res.items():
         assert not bad, (case, name, n, bad[:3])
-    assert res["ffs"][0] > 1000 and res["subpel"][0] > 1000
+    assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000) and res["subpel"][0] > 1000
     if case == "kat":
         assert res["bi_full"][0] > 100 and res["bi_sub"][0] > 50
 

@@ -7,7 +7,7 @@ import os
 
 import numpy as np
 
-REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_REFPIC, REC_CURPIC = 1, 2, 3, 4, 5, 6
+REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_REFPIC, REC_CURPIC, REC_FULLPEL = 1, 2, 3, 4, 5, 6, 7
 
 
 class Trace:
@@ -76,6 +76,8 @@ def cfg_from_trace(trace, search_range=32, full_search=2, metric=(0, 2, 2), mv_l
     """Encoder-wide parameters recoverable from the records themselves."""
     sub = trace.of_type(REC_SUBPEL)
     ffs = trace.of_type(REC_FFS)
+    if not len(ffs):
+        ffs = trace.of_type(REC_FULLPEL)
     rdopt = int(ffs[0][25]) if len(ffs) else 1
     t8 = int(sub[:, 22].max()) if len(sub) else 0
     return dict(search_range=search_range, rdopt=rdopt, full_search=full_search, metric=metric,
