@@ -65,10 +65,10 @@ static struct {
 static int active = 0;          /* GPU path in use for this run */
 static int verify = 0;          /* ME_CUDA_VERIFY=1: run the reference function too, report any difference, keep the reference result */
 static long n_checked = 0, n_mismatch = 0;
-static int pic_counter = 0, pic_uploaded = -1;
+static int pic_counter = 0, pic_uploaded = -1, plane_uploaded = -1;
 
 #define MAX_MAP 64
-static struct { StorablePicture *p; me_ref_handle h; } map[MAX_MAP];
+static struct { StorablePicture *p; int plane; me_ref_handle h; } map[MAX_MAP];   /* plane: 0, or the colour plane in 4:4:4 independent mode */
 static int n_map = 0;
 
 static void die(const char *what)
@@ -120,10 +120,15 @@ static void load_library(void)
   L.bi_full = sym("me_cuda_FullPelBlockMotionBiPred"); L.bi_sub = sym("me_cuda_SubPelBlockSearchBiPred");
 }
 
+/* 4:4:4 independent mode (SeparateColourPlane = 1, IS_INDEPENDENT, defines.h:224): the three colour planes are coded one after
+ * the other as luma pictures; every reference picture has three sets of quarter-pel planes (UnifiedOneForthPix_JV,
+ * image.c:1672-1711, p_img_sub[0..2]) and the searches of plane img->colour_plane_id read the set of that plane. */
+static int current_plane(void) { return IS_INDEPENDENT(input) ? img->colour_plane_id : 0; }
+
 static me_ref_handle handle_of(StorablePicture *p)
 {
-  int i;
-  for (i = n_map - 1; i >= 0; i--) if (map[i].p == p) return map[i].h;
+  int i, plane = current_plane();
+  for (i = n_map - 1; i >= 0; i--) if (map[i].p == p && map[i].plane == plane) return map[i].h;
   return 0;
 }
 
@@ -198,17 +203,19 @@ void __real_getSubImagesLuma(StorablePicture *s);
 void __wrap_getSubImagesLuma(StorablePicture *s)
 {
   me_ref_handle h = 0;
-  int i;
-  /* 4:4:4 runs this routine on the U and V planes too; those (host motion compensation only) stay on the CPU */
-  if (!active || s->p_curr_img != s->imgY) { __real_getSubImagesLuma(s); return; }
+  int i, plane = 0;
+  if (!active) { __real_getSubImagesLuma(s); return; }
+  if (IS_INDEPENDENT(input)) plane = s->colour_plane_id;      /* set by UnifiedOneForthPix_JV (image.c:1706) right before this call */
+  /* 4:4:4 common mode runs this routine on the U and V planes too; those (host motion compensation only) stay on the CPU */
+  else if (s->p_curr_img != s->imgY) { __real_getSubImagesLuma(s); return; }
   /* a picture structure can be reallocated at the same address: drop a stale mapping, and forget pictures that
    * left the decoded picture buffer through a call path that bypasses the wrapped free (same translation unit) */
   for (i = n_map - 1; i >= 0; i--)
-    if (map[i].p == s || !in_dpb(map[i].p)) unmap_index(i);
-  /* the 16 planes are computed on the device and copied into imgY_sub for the encoder's host-side consumers */
-  if (L.ref_create((const me_imgpel *const *)s->imgY, s->size_x, s->size_y, (me_imgpel ****)s->imgY_sub, &h)) die("me_cuda_ref_create");
+    if (map[i].p == s ? map[i].plane == plane : !in_dpb(map[i].p)) unmap_index(i);   /* s itself enters the buffer after this call */
+  /* the 16 planes are computed on the device and copied into the picture's plane set for the encoder's host-side consumers */
+  if (L.ref_create((const me_imgpel *const *)s->p_curr_img, s->size_x, s->size_y, (me_imgpel ****)s->p_curr_img_sub, &h)) die("me_cuda_ref_create");
   if (n_map == MAX_MAP) unmap_index(0);
-  map[n_map].p = s; map[n_map].h = h; n_map++;
+  map[n_map].p = s; map[n_map].plane = plane; map[n_map].h = h; n_map++;
 }
 
 void __real_free_storable_picture(StorablePicture *p);
@@ -230,9 +237,9 @@ static void mb_sync(void)
 {
   if (mb_synced_pic == pic_counter && mb_synced_mb == img->current_mb_nr) return;
   mb_synced_pic = pic_counter; mb_synced_mb = img->current_mb_nr;
-  if (pic_uploaded != pic_counter) {
+  if (pic_uploaded != pic_counter || plane_uploaded != current_plane()) {
     if (L.set_current((const me_imgpel *const *)pCurImg, img->width, img->height)) die("me_cuda_set_current");
-    pic_uploaded = pic_counter;
+    pic_uploaded = pic_counter; plane_uploaded = current_plane();
   }
   {
     int list_offset = img->mb_data[img->current_mb_nr].list_offset, l, i;
