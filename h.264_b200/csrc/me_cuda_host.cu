@@ -935,23 +935,35 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
   return 0;
 }
 
-int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, me_mb_result_int *out_int)
+// job fields the kernels index with: checked on the host, chunk by chunk, while the chunk's upload is already in flight
+static int check_jobs(const me_mb_job *jobs, int first, int n)
 {
-  if (!g.inited) return fail(1, "me_cuda_init has not been called");
-  if (n_jobs <= 0) return 0;
-  for (int i = 0; i < n_jobs; i++) {
+  for (int i = first; i < first + n; i++) {
     const me_mb_job &j = jobs[i];
     if (j.list < 0 || j.list > 1 || j.ref < 0 || j.ref >= g.list_n[j.list])
       return fail(1, "job %d: (list %d, ref %d) not in the reference lists", i, (int)j.list, (int)j.ref);
     if (j.opix_x < 0 || j.opix_y < 0 || j.opix_x + 16 > g.p.width || j.opix_y + 16 > g.p.height || (j.opix_x & 15) || (j.opix_y & 15))
       return fail(1, "job %d: macroblock origin (%d,%d) invalid", i, (int)j.opix_x, (int)j.opix_y);
   }
+  return 0;
+}
+
+int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, me_mb_result_int *out_int)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (n_jobs <= 0) return 0;
   if (int rc = ensure_batch(n_jobs)) return rc;
   // Large batches are cut into chunks that move through three streams -- jobs in (H2D engine), search (library stream),
   // results out (D2H engine) -- so that with pinned caller buffers only the first upload and the last download are exposed.
-  static int want_chunks = 0;
-  if (!want_chunks) { const char *e = getenv("ME_CUDA_PIPE_CHUNKS"); want_chunks = e ? atoi(e) : 6; if (want_chunks < 1 || want_chunks > ME_PIPE_CHUNKS) want_chunks = 6; }
-  const int n_chunks = n_jobs >= 8192 ? want_chunks : 1;
+  // chunk sizes in twentieths of the batch: a small first chunk starts the kernels early, a small last one keeps the exposed
+  // download short (ME_CUDA_PIPE_WEIGHTS="a,b,..." overrides; measured on B200, 1080p x 5 references)
+  static int weights[ME_PIPE_CHUNKS], n_weights = 0;
+  if (!n_weights) {
+    const char *e = getenv("ME_CUDA_PIPE_WEIGHTS");
+    if (e) for (const char *q = e; *q && n_weights < ME_PIPE_CHUNKS; ) { int v = atoi(q); if (v > 0) weights[n_weights++] = v; while (*q && *q != ',') q++; if (*q) q++; }
+    if (!n_weights) { const int def[4] = { 5, 5, 5, 5 }; for (int i = 0; i < 4; i++) weights[n_weights++] = def[i]; }
+  }
+  const int n_chunks = n_jobs >= 8192 ? n_weights : 1;
   if (!g.s_in) {
     CK(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.s_out, cudaStreamNonBlocking));
@@ -960,27 +972,36 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
       CK(cudaEventCreateWithFlags(&g.ev_done[c], cudaEventDisableTiming));
     }
   }
-  if (int rc = upload_table()) return rc;                      // on the library stream, before any chunk's kernels
-  const int per = (n_jobs + n_chunks - 1) / n_chunks;
+  int c_off[ME_PIPE_CHUNKS + 1];
+  {
+    int wsum = 0, acc = 0;
+    for (int c = 0; c < n_chunks; c++) wsum += weights[c];
+    c_off[0] = 0;
+    for (int c = 0; c < n_chunks; c++) { acc += weights[c]; c_off[c + 1] = n_chunks == 1 ? n_jobs : (int)((long long)n_jobs * acc / wsum); }
+  }
   for (int c = 0; c < n_chunks; c++) {
-    const int off = c * per, n = (off + per <= n_jobs) ? per : n_jobs - off;
-    if (n <= 0) break;
+    const int off = c_off[c], n = c_off[c + 1] - off;
+    if (n <= 0) continue;
     CK(cudaMemcpyAsync(g.d_jobs + off, jobs + off, sizeof(MeJob) * (size_t)n, cudaMemcpyHostToDevice, g.s_in));
     CK(cudaEventRecord(g.ev_in[c], g.s_in));
   }
-  for (int c = 0; c < n_chunks; c++) {
-    const int off = c * per, n = (off + per <= n_jobs) ? per : n_jobs - off;
-    if (n <= 0) break;
+  int rc = upload_table();                                     // on the library stream, before any chunk's kernels
+  for (int c = 0; c < n_chunks && !rc; c++) {
+    const int off = c_off[c], n = c_off[c + 1] - off;
+    if (n <= 0) continue;
+    if ((rc = check_jobs(jobs, off, n)) != 0) break;           // host work hidden behind the uploads / the previous chunk's kernels
     CK(cudaStreamWaitEvent(g.stream, g.ev_in[c], 0));
-    if (int rc = me_cuda_frame_search_device(g.d_jobs + off, n, g.d_out + off, g.d_out_int + off, g.stream)) return rc;
+    if ((rc = me_cuda_frame_search_device(g.d_jobs + off, n, g.d_out + off, g.d_out_int + off, g.stream)) != 0) break;
     CK(cudaEventRecord(g.ev_done[c], g.stream));
     CK(cudaStreamWaitEvent(g.s_out, g.ev_done[c], 0));
     CK(cudaMemcpyAsync(out + off, g.d_out + off, sizeof(MeResult) * (size_t)n, cudaMemcpyDeviceToHost, g.s_out));
     if (out_int) CK(cudaMemcpyAsync(out_int + off, g.d_out_int + off, sizeof(MeResultInt) * (size_t)n, cudaMemcpyDeviceToHost, g.s_out));
   }
+  // also on the error path: nothing may still be reading the caller's job array or writing its result arrays on return
+  cudaStreamSynchronize(g.s_in);
   CK(cudaStreamSynchronize(g.s_out));
   CK(cudaStreamSynchronize(g.stream));
-  return 0;
+  return rc;
 }
 
 int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements, int search_range, int subpel, me_bipred_result *out)
