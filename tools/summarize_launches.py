@@ -23,6 +23,13 @@ def main(path):
     print("%-60s %8s %12s %12s %7s" % ("kernel", "launches", "total_ms", "mean_us", "share"))
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("%-60s %8d %12.3f %12.1f %6.1f%%" % (k[-60:], n, t / 1e6, t / n / 1e3, 100 * t / total))
+    # the kernels of a step only (bench.py also launches its integer-peak micro-benchmarks and the L2 flush fill)
+    step = {k: v for k, v in agg.items() if "me_" in k}
+    st = sum(t for _, t in step.values())
+    if st and st != total:
+        print("\nshare of the step kernels only (me_*):")
+        for k, (n, t) in sorted(step.items(), key=lambda kv: -kv[1][1]):
+            print("%-60s %8d %12.3f %12.1f %6.1f%%" % (k[-60:], n, t / 1e6, t / n / 1e3, 100 * t / st))
 
 
 if __name__ == "__main__":
