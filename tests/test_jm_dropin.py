@@ -118,6 +118,23 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
 
 
+@pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
+@pytest.mark.parametrize("cfg", ["encoder_baseline.cfg", "encoder_main.cfg", "encoder_extended.cfg", "encoder_yuv422.cfg"])
+def test_shipped_configurations_as_they_are(tmp_path, me_lib_path, cfg):
+    """the reference's own cfg files, unchanged, on its own QCIF fixtures (Baseline / Main / Extended with B pictures / High 4:2:2):
+    SR 32, 5 references"""
+    if cfg == "encoder_yuv422.cfg" and not os.path.exists(os.path.join(REF_DIR, "fixtures", "foreman_part_qcif_422.yuv")):
+        pytest.skip("4:2:2 fixture not in oracle/_ref/fixtures (rebuild with make -C oracle ref)")
+    a, b = tmp_path / "gpu", tmp_path / "cpu"
+    a.mkdir(); b.mkdir()
+    for d in (a, b):
+        _prep(str(d))
+    _run("lencod_cuda", ["-d", cfg], str(a))
+    _run("lencod", ["-d", cfg], str(b))
+    assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
+    assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
+
+
 @pytest.mark.skipif(not _have(), reason="oracle/_ref binaries not built")
 @pytest.mark.parametrize("case", ["kat", "baseline16"])
 def test_live_full_trace_replays_through_the_c_abi(tmp_path, me_lib_path, case):
