@@ -78,6 +78,7 @@ template <int R> struct __align__(128) Smem {
   uint32_t lut[LUT_ENTRIES * 3];                // K * mvcost(class sum), entry stride 12 bytes
   uint32_t ua_last[2][NUNIT];                   // unit table addresses of column 2R per (h, unit)
   uint32_t red[Geo<R>::NW][2][NSLOT];
+  uint32_t pslot[2][24];                        // per (h, slot): predictor word (x | y << 16) of the job about to be searched, 21 used
   uint32_t job[3][48];                          // me_mb_job ring (188 bytes each)
   uint16_t sptab[Geo<R>::SIDE * Geo<R>::SIDE];  // spiral index of (dy, dx)
   MeRefDev refs[2 * ME_MAX_REFS];               // copy of the reference table
@@ -406,6 +407,12 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     if (n_mine > 1) sm.job[1][tid] = jobs[((size_t)blockIdx.x + gridDim.x) * JW + tid];
   }
   __syncthreads();
+  // predictors in slot order (read with vector loads when a thread derives its table addresses)
+  auto fill_pslot = [&](const uint32_t *jwn) {
+    if (tid < 2 * NSLOT) { const int hh = tid / NSLOT, e = tid - hh * NSLOT; sm.pslot[hh][e] = jwn[3 + c_slot_part[hh][e]]; }
+  };
+  fill_pslot(sm.job[0]);
+  __syncthreads();
 
   // window origin in search-plane coordinates; true when the whole box lies inside the plane (TMA path)
   auto window_origin = [&](const JobView &jv, const MeRefDev &rf, int &X0, int &Y0) -> bool {
@@ -444,6 +451,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
       if (tid == 0) deferred[1 + atomicAdd(&deferred[0], 1)] = job_id;
       if (use_tma) mbar_wait(smem_u32(&sm.mbar[buf]), (unsigned)((it >> 1) & 1));
       if (tid < JW && it + 2 < n_mine) sm.job[(it + 2) % 3][tid] = pf;
+      if (it + 1 < n_mine) fill_pslot(sm.job[(it + 1) % 3]);
       __syncthreads();
       continue;
     }
@@ -490,14 +498,21 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     Regs rg;
 #pragma unroll
     for (int e = 0; e < NSLOT; e++) rg.best[e] = 0xffffffffu;
+    {
+      const uint4 *ps = reinterpret_cast<const uint4 *>(sm.pslot[t.h]);
+      uint32_t pw[24];
 #pragma unroll
-    for (int u = 0; u < NUNIT; u++) {
-      const int ca = len_class(4 * (offx + dx - R) - job_pmvx(jw, c_slot_part[t.h][unit_a(u)]));
-      if (unit_b(u) >= 0) {
-        const int cb = len_class(4 * (offx + dx - R) - job_pmvx(jw, c_slot_part[t.h][unit_b(u) >= 0 ? unit_b(u) : 0]));
-        rg.ua[u] = lut2_addr + 8 * (LUT_ENTRIES * ca + cb);
-      } else {
-        rg.ua[u] = lut_addr + LUT_STRIDE_B * ca;
+      for (int q = 0; q < 6; q++) { const uint4 v = ps[q]; pw[4 * q] = v.x; pw[4 * q + 1] = v.y; pw[4 * q + 2] = v.z; pw[4 * q + 3] = v.w; }
+      const int xq = 4 * (offx + dx - R);
+#pragma unroll
+      for (int u = 0; u < NUNIT; u++) {
+        const int ca = len_class(xq - (int)(int16_t)(pw[unit_a(u)] & 0xffffu));
+        if (unit_b(u) >= 0) {
+          const int cb = len_class(xq - (int)(int16_t)(pw[unit_b(u) >= 0 ? unit_b(u) : 0] & 0xffffu));
+          rg.ua[u] = lut2_addr + 8 * (LUT_ENTRIES * ca + cb);
+        } else {
+          rg.ua[u] = lut_addr + LUT_STRIDE_B * ca;
+        }
       }
     }
 
@@ -534,16 +549,25 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     {
       const unsigned cyh = smem_u32(&sm.cyt[0][t.h][0]), la = smem_u32(&sm.ua_last[t.h][0]), spa = smem_u32(sm.sptab);
       const unsigned col = wbase + (unsigned)((2 * R + mis) >> 2) * 4 + 8 * t.h, sh_last = (mis & 3) * 8;
-      last_column<R>(rg, t, col, sh_last, cyh, la, spa, dx);
-      if (warp == (it & (G::NW - 1))) last_column<R>(rg, t, col, sh_last, cyh, la, spa, 2 * R);   // rotates over the sub-partitions
+      const int reps = (warp == (it & (G::NW - 1))) ? 2 : 1;      // the corner rotates over the sub-partitions
+#pragma unroll 1                                                 // one copy of the code (the kernel is instruction-fetch sensitive)
+      for (int rep = 0; rep < reps; rep++) last_column<R>(rg, t, col, sh_last, cyh, la, spa, rep ? 2 * R : dx);
     }
 
-    // ---- minima over the CTA
+    // ---- minima over the CTA: even lanes hold the slots of column pair 0, odd lanes those of column pair 1 -- each half
+    // reduces among itself (redux.sync with its own member mask)
+    if (t.h) {
 #pragma unroll
-    for (int e = 0; e < NSLOT; e++) {
-      const unsigned m0 = __reduce_min_sync(0xffffffffu, t.h ? 0xffffffffu : rg.best[e]);
-      const unsigned m1 = __reduce_min_sync(0xffffffffu, t.h ? rg.best[e] : 0xffffffffu);
-      if (lane < 2) sm.red[warp][lane][e] = lane ? m1 : m0;
+      for (int e = 0; e < NSLOT - 1; e++) {               // (h = 1, slot 20) duplicates (h = 0, slot 20)
+        const unsigned m = __reduce_min_sync(0xaaaaaaaau, rg.best[e]);
+        if (lane == 1) sm.red[warp][1][e] = m;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NSLOT; e++) {
+        const unsigned m = __reduce_min_sync(0x55555555u, rg.best[e]);
+        if (lane == 0) sm.red[warp][0][e] = m;
+      }
     }
     __syncthreads();
     if (tid < 2 * NSLOT - 1) {            // (h = 1, slot 20) duplicates (h = 0, slot 20)
@@ -560,6 +584,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
       out[job_id].cost[p] = (int)cost;
     }
     if (tid < JW && it + 2 < n_mine) sm.job[(it + 2) % 3][tid] = pf;
+    if (it + 1 < n_mine) fill_pslot(sm.job[(it + 1) % 3]);
     __syncthreads();          // window / tables / red free for the next job
   }
 }
