@@ -30,7 +30,7 @@ def part_index(blocktype, blk):
 class OraCfg(C.Structure):
     _fields_ = [("search_range", C.c_int), ("rdopt", C.c_int), ("full_search", C.c_int),
                 ("metric", C.c_int * 3), ("transform8x8", C.c_int),
-                ("mv_limit_min_y", C.c_int), ("mv_limit_max_y", C.c_int)]
+                ("mv_limit_min_y", C.c_int), ("mv_limit_max_y", C.c_int), ("chroma_me", C.c_int)]
 
 
 class MbJob(C.Structure):
@@ -74,6 +74,8 @@ def lib():
         L.ora_ref_plane.restype = vp
         L.ora_ref_plane.argtypes = [vp, C.c_int, C.c_int]
         L.ora_ref_set_weights.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ora_ref_set_chroma.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
+        L.ora_set_chroma.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int]
         L.ora_set_bipred_weights.argtypes = [C.c_int] * 6
         L.ora_select_bipred_list.argtypes = [C.c_int]
         L.ora_spiral.argtypes = [C.c_int, vp, vp]
@@ -101,8 +103,9 @@ def lib():
 
 
 def make_cfg(search_range=32, rdopt=1, full_search=2, metric=(0, 2, 2), transform8x8=0,
-             mv_limit_min_y=-511, mv_limit_max_y=511):
+             mv_limit_min_y=-511, mv_limit_max_y=511, chroma_me=0):
     c = OraCfg()
+    c.chroma_me = chroma_me
     c.search_range, c.rdopt, c.full_search = search_range, rdopt, full_search
     c.metric[0], c.metric[1], c.metric[2] = metric
     c.transform8x8 = transform8x8
@@ -136,6 +139,11 @@ class Ref:
     def planes(self):
         return np.stack([np.stack([self.plane(fy, fx) for fx in range(4)]) for fy in range(4)])
 
+    def set_chroma(self, u, v):
+        """ChromaMEEnable: the picture's reconstructed chroma planes (uint8, same shape)"""
+        u, v = np.ascontiguousarray(u, np.uint8), np.ascontiguousarray(v, np.uint8)
+        lib().ora_ref_set_chroma(self.ptr, u.ctypes.data, v.ctypes.data, u.strides[0], u.shape[1], u.shape[0])
+
     def set_weights(self, apply, weight=32, offset=0, log_denom=5):
         """weighted-prediction ME: the weights of the (list, ref) entry this picture is about to be searched as"""
         lib().ora_ref_set_weights(self.ptr, int(apply), int(weight), int(offset), int(log_denom))
@@ -158,6 +166,20 @@ def fullpel_block(cfg, cur, ref, ppx, ppy, bt, ref_idx, slice_type, pmvx, pmvy, 
     cost = lib().ora_fullpel_block(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr, ppx, ppy, bt, ref_idx, slice_type,
                                    pmvx, pmvy, C.byref(mx), C.byref(my), search_range, min_mcost, lam)
     return mx.value, my.value, cost
+
+
+_chroma_keep = []
+
+
+def set_chroma(enable, weight=0, cur_u=None, cur_v=None, shift=(3, 3)):
+    """chroma state of the next search calls: the global ChromaMEEnable they see, ChromaMEWeight, original chroma planes,
+    (chroma_shift_x, chroma_shift_y)"""
+    if not enable or cur_u is None:
+        lib().ora_set_chroma(0, 0, None, None, 0, shift[0], shift[1])
+        return
+    cur_u, cur_v = np.ascontiguousarray(cur_u, np.uint8), np.ascontiguousarray(cur_v, np.uint8)
+    _chroma_keep[:] = [cur_u, cur_v]
+    lib().ora_set_chroma(int(enable), int(weight), cur_u.ctypes.data, cur_v.ctypes.data, cur_u.strides[0], shift[0], shift[1])
 
 
 def set_bipred_weights(lst, apply, w1=32, w2=32, offset_bi=0, log_denom=5):

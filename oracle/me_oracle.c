@@ -146,6 +146,7 @@ void ora_ref_destroy(ora_ref *r)
   if (!r) return;
   for (fy = 0; fy < 4; fy++)
     for (fx = 0; fx < 4; fx++) free(r->plane[fy][fx]);
+  free(r->crec[0]); free(r->crec[1]);
   free(r);
 }
 
@@ -173,6 +174,86 @@ const uint8_t *ora_umv_line(const ora_ref *r, int y4, int x4)
   int xp = clampi(x4 >> 2, 0, r->w + 2 * PAD - 1 - 16);
   int yp = clampi(y4 >> 2, 0, r->h + 2 * PAD - 1 - 16);
   return r->plane[y4 & 3][x4 & 3] + (size_t)yp * r->wp + xp;
+}
+
+/* ------------------------------------------------------------------------------------------------ chroma (ChromaMEEnable) */
+
+static struct {
+  int enable, weight, stride, shift_x, shift_y;
+  const uint8_t *cur[2];
+} g_cr;
+
+void ora_set_chroma(int enable, int weight, const uint8_t *cur_u, const uint8_t *cur_v, int stride, int shift_x, int shift_y)
+{
+  g_cr.enable = enable; g_cr.weight = weight; g_cr.cur[0] = cur_u; g_cr.cur[1] = cur_v; g_cr.stride = stride;
+  g_cr.shift_x = shift_x; g_cr.shift_y = shift_y;
+}
+
+void ora_ref_set_chroma(ora_ref *r, const uint8_t *u, const uint8_t *v, int stride, int cw, int ch)
+{
+  int k, y;
+  for (k = 0; k < 2; k++) {
+    const uint8_t *src = k ? v : u;
+    free(r->crec[k]);
+    r->crec[k] = (uint8_t *)malloc((size_t)cw * ch);
+    for (y = 0; y < ch; y++) memcpy(r->crec[k] + (size_t)y * cw, src + (size_t)y * stride, cw);
+  }
+  r->cw = cw; r->ch = ch;
+}
+
+/* geometry of the chroma sub-images: padding = luma padding in chroma samples (img_pad_size_uv_x/y, lencod.c:2856-2879), macroblock
+ * size in chroma samples (mb_cr_size_x/y, lencod.c:622-623) */
+static inline int cr_pad_x(void) { return (4 * PAD) >> g_cr.shift_x; }
+static inline int cr_pad_y(void) { return (4 * PAD) >> g_cr.shift_y; }
+static inline int cr_mb_x(void) { return 64 >> g_cr.shift_x; }
+static inline int cr_mb_y(void) { return 64 >> g_cr.shift_y; }
+
+/* One sample of sub-image (sy, sx) at padded-plane position (ypos, xpos) of component k: getSubImagesChroma (img_chroma.c:374-440) blends
+ * the four neighbours with eighth-sample weights, rshift_rnd_sf(., 6), over the edge-replicated reconstruction
+ * (generateChroma00/01/10/XX, img_chroma.c:34-372: the padding rows / columns repeat the first / last row / column). */
+static int cr_pel(const ora_ref *r, int k, int ypos, int xpos, int sy, int sx)
+{
+  int jy = ypos - cr_pad_y(), ix = xpos - cr_pad_x();
+  int y0 = clampi(jy, 0, r->ch - 1), y1 = clampi(jy + 1, 0, r->ch - 1), x0 = clampi(ix, 0, r->cw - 1), x1 = clampi(ix + 1, 0, r->cw - 1);
+  int kk = sy << (3 - g_cr.shift_y), ll = sx << (3 - g_cr.shift_x);          /* vertical / horizontal offset in eighths */
+  int w01 = (8 - kk) * ll, w00 = ((8 - kk) << 3) - w01, w11 = kk * ll, w10 = (kk << 3) - w11;
+  const uint8_t *p = r->crec[k];
+  return (w00 * p[(size_t)y0 * r->cw + x0] + w01 * p[(size_t)y0 * r->cw + x1] +
+          w10 * p[(size_t)y1 * r->cw + x0] + w11 * p[(size_t)y1 * r->cw + x1] + 32) >> 6;
+}
+
+/* UMVLine8X_chroma (refbuf.c:53-59): sub-image from the fraction bits, position clamped to [0, size_cr - 1 + 2 * pad - mb_cr_size]
+ * (mbuffer.c:425-426).  y, x: luma quarter-pel coordinates including the luma padding, as for ora_umv_line. */
+static void cr_line(const ora_ref *r, int y, int x, int *ypos, int *xpos, int *sy, int *sx)
+{
+  *xpos = clampi(x >> g_cr.shift_x, 0, r->cw - 1 + 2 * cr_pad_x() - cr_mb_x());
+  *ypos = clampi(y >> g_cr.shift_y, 0, r->ch - 1 + 2 * cr_pad_y() - cr_mb_y());
+  *sy = y & ((1 << g_cr.shift_y) - 1);
+  *sx = x & ((1 << g_cr.shift_x) - 1);
+}
+
+/* chroma part of computeSAD / computeSSE (me_distortion.c:376-402, :1069-1091) for the luma block of bsx x bsy at (pic_pix_x,
+ * pic_pix_y): per component the SAD / SSE of the co-located chroma block, each multiplied by ChromaMEWeight.  r2 != NULL:
+ * bi-prediction (p1 + p2 + 1) >> 1 (computeBiPredSAD1 :516-543). */
+static int cr_block_dist(int sse, int pic_pix_x, int pic_pix_y, int bsx, int bsy, const ora_ref *r1, int x41, int y41,
+                         const ora_ref *r2, int x42, int y42)
+{
+  int scx = g_cr.shift_x - 2, scy = g_cr.shift_y - 2;                        /* shift_cr_x/y, lencod.c:2881-2882 */
+  int bx = bsx >> scx, by = bsy >> scy, cx0 = pic_pix_x >> scx, cy0 = pic_pix_y >> scy, k, x, y, total = 0;
+  for (k = 0; k < 2; k++) {
+    int yp1, xp1, sy1, sx1, yp2 = 0, xp2 = 0, sy2 = 0, sx2 = 0, m = 0;
+    cr_line(r1, y41, x41, &yp1, &xp1, &sy1, &sx1);
+    if (r2) cr_line(r2, y42, x42, &yp2, &xp2, &sy2, &sx2);
+    for (y = 0; y < by; y++)
+      for (x = 0; x < bx; x++) {
+        int p = cr_pel(r1, k, yp1 + y, xp1 + x, sy1, sx1), d;
+        if (r2) p = (p + cr_pel(r2, k, yp2 + y, xp2 + x, sy2, sx2) + 1) >> 1;
+        d = (int)g_cr.cur[k][(size_t)(cy0 + y) * g_cr.stride + cx0 + x] - p;
+        m += sse ? d * d : iabs_(d);
+      }
+    total += g_cr.weight * m;
+  }
+  return total;
 }
 
 /* ------------------------------------------------------------------------------------------------ integer pel */
@@ -222,6 +303,19 @@ void ora_ffs_surfaces(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
         int d = refpel(r, rp[(size_t)y * r->wp + x]) - (int)cur[(size_t)(opix_y + y) * cur_stride + opix_x + x];
         leaf[(y >> 2) * 4 + (x >> 2)] += c->metric[0] ? d * d : iabs_(d);
       }
+    if (g_cr.enable && r->crec[0]) {
+      /* me_fullfast.c:776-814: the co-located chroma block of every 4x4 luma block, both components, added as it is
+       * (no ChromaMEWeight here) */
+      int k, yp, xp, sy_, sx_, cy, cx, mbx = cr_mb_x(), mby = cr_mb_y();
+      int ocx = (mbx * opix_x) >> 4, ocy = (mby * opix_y) >> 4;            /* img->opix_c_x/y, macroblock.c:206-207 */
+      cr_line(r, (centre_y + sy[pos] + PAD) << 2, (centre_x + sx[pos] + PAD) << 2, &yp, &xp, &sy_, &sx_);
+      for (k = 0; k < 2; k++)
+        for (cy = 0; cy < mby; cy++)
+          for (cx = 0; cx < mbx; cx++) {
+            int d = cr_pel(r, k, yp + cy, xp + cx, sy_, sx_) - (int)g_cr.cur[k][(size_t)(ocy + cy) * g_cr.stride + ocx + cx];
+            leaf[(cy / (mby / 4)) * 4 + cx / (mbx / 4)] += c->metric[0] ? d * d : iabs_(d);
+          }
+    }
     for (p = 0; p < ME_NUM_PARTITIONS; p++) {
       int bsx, bsy, s = 0, b = ora_part_blk[p];
       ora_block_size(ora_part_type[p], &bsx, &bsy);
@@ -370,8 +464,9 @@ static void first_spiral(int n, int16_t *sx, int16_t *sy)
 }
 
 /* start_me_refinement_hp/qp (mv-search.c:396-397) with ChromaMEEnable == 0 */
-static int start_hp(const ora_cfg *c) { return c->metric[0] != c->metric[1] ? 0 : 1; }
-static int start_qp(const ora_cfg *c) { return c->metric[1] != c->metric[2] ? 0 : 1; }
+/* start_me_refinement_hp / qp (mv-search.c:396-397) */
+static int start_hp(const ora_cfg *c) { return (c->chroma_me == 1 || c->metric[0] != c->metric[1]) ? 0 : 1; }
+static int start_qp(const ora_cfg *c) { return (c->chroma_me == 1 || c->metric[1] != c->metric[2]) ? 0 : 1; }
 
 /* SubPelBlockMotionSearch (me_fullsearch.c:341-511) */
 int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
@@ -417,7 +512,7 @@ int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_r
  * the full distortion the partial sum comes back.  Everywhere else on this path the caller discards such a candidate, so
  * the full sum is equivalent; FullPelBlockMotionSearch is the exception (see below). */
 static int unipred_exit(const ora_cfg *c, const uint8_t *src, int stride, int bsx, int bsy, const ora_ref *r, int x4, int y4,
-                        int use8x8, int thr)
+                        int use8x8, int thr, int pic_pix_x, int pic_pix_y)
 {
   int metric = c->metric[0], m = 0, x, y;
   if (metric == 2) {
@@ -436,6 +531,22 @@ static int unipred_exit(const ora_cfg *c, const uint8_t *src, int stride, int bs
         m += metric ? d * d : iabs_(d);
       }
       if (m >= thr) return m;
+    }
+    if (g_cr.enable && r->crec[0]) {
+      /* chroma terms (me_distortion.c:376-402): one component after the other, each followed by the same early exit */
+      int scx = g_cr.shift_x - 2, scy = g_cr.shift_y - 2, k;
+      int bx = bsx >> scx, by = bsy >> scy, cx0 = pic_pix_x >> scx, cy0 = pic_pix_y >> scy;
+      for (k = 0; k < 2; k++) {
+        int yp, xp, sy_, sx_, mc = 0;
+        cr_line(r, y4, x4, &yp, &xp, &sy_, &sx_);
+        for (y = 0; y < by; y++)
+          for (x = 0; x < bx; x++) {
+            int d = (int)g_cr.cur[k][(size_t)(cy0 + y) * g_cr.stride + cx0 + x] - cr_pel(r, k, yp + y, xp + x, sy_, sx_);
+            mc += metric ? d * d : iabs_(d);
+          }
+        m += g_cr.weight * mc;
+        if (m >= thr) return m;
+      }
     }
     return m;
   }
@@ -468,7 +579,7 @@ int ora_fullpel_block(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
     if (check_for_00 && cand_x == pic_pix_x && cand_y == pic_pix_y) mcost -= (lambda_factor * 16) >> 16;
     if (mcost >= min_mcost) continue;
     mcost += unipred_exit(c, src, cur_stride, bsx, bsy, r, cand_x + 4 * PAD, cand_y + 4 * PAD, use8x8,
-                          (int)((unsigned)min_mcost - (unsigned)mcost));
+                          (int)((unsigned)min_mcost - (unsigned)mcost), pic_pix_x, pic_pix_y);
     if (mcost < min_mcost) { best = pos; min_mcost = mcost; }
   }
   if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }
@@ -504,7 +615,8 @@ static inline int bipel(int p1, int p2)
 /* computeBiPredSAD1 / computeBiPredSATD1 (me_distortion.c:482-548, 824-899): prediction = (p1 + p2 + 1) >> 1.
  * SAD fetches each picture once per block; SATD once per transform tile. */
 static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stride, int bsx, int bsy,
-                       const ora_ref *r1, int x41, int y41, const ora_ref *r2, int x42, int y42, int use8x8)
+                       const ora_ref *r1, int x41, int y41, const ora_ref *r2, int x42, int y42, int use8x8,
+                       int pic_pix_x, int pic_pix_y)
 {
   int metric = c->metric[level], s = 0, x, y, bx, by, d[64];
   if (metric == 0 || metric == 1) {
@@ -514,6 +626,8 @@ static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stri
         int e = (int)src[(size_t)y * stride + x] - bipel(a[(size_t)y * r1->wp + x], b[(size_t)y * r2->wp + x]);
         s += metric ? e * e : iabs_(e);
       }
+    if (g_cr.enable && r1->crec[0] && r2->crec[0])     /* computeBiPredSAD1 :516-543 (weighted chroma is not restated) */
+      s += cr_block_dist(metric, pic_pix_x, pic_pix_y, bsx, bsy, r1, x41, y41, r2, x42, y42);
     return s;
   } else {
     int n = use8x8 ? 8 : 4;
@@ -560,7 +674,7 @@ int ora_bipred_fullpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, con
     int mcost = ora_mv_cost(lambda_factor, fx0 << 2, fy0 << 2, px1, py1) + ora_mv_cost(lambda_factor, cx, cy, px2, py2);
     if (mcost >= min_mcost) continue;
     mcost += bipred_dist(c, 0, src, cur_stride, bsx, bsy, r1, (fx0 << 2) + 4 * PAD, (fy0 << 2) + 4 * PAD,
-                         r2, cx + 4 * PAD, cy + 4 * PAD, 0);
+                         r2, cx + 4 * PAD, cy + 4 * PAD, 0, pic_pix_x, pic_pix_y);
     if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
   }
   if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }
@@ -590,7 +704,7 @@ int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
     cx = *mv_x + 2 * sx[pos]; cy = *mv_y + 2 * sy[pos];
     mcost = ora_mv_cost(lambda[1], cx, cy, pmv_x, pmv_y);
     if (mcost >= min_mcost) continue;
-    mcost += bipred_dist(c, 1, src, cur_stride, bsx, bsy, r1, smx, smy, r2, cx + p4x, cy + p4y, use8x8);
+    mcost += bipred_dist(c, 1, src, cur_stride, bsx, bsy, r1, smx, smy, r2, cx + p4x, cy + p4y, use8x8, pic_pix_x, pic_pix_y);
     if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
   }
   if (best) { *mv_x += 2 * sx[best]; *mv_y += 2 * sy[best]; }
@@ -599,7 +713,7 @@ int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
     cx = *mv_x + sx[pos]; cy = *mv_y + sy[pos];
     mcost = ora_mv_cost(lambda[2], cx, cy, pmv_x, pmv_y);
     if (mcost >= min_mcost) continue;
-    mcost += bipred_dist(c, 2, src, cur_stride, bsx, bsy, r1, smx, smy, r2, cx + p4x, cy + p4y, use8x8);
+    mcost += bipred_dist(c, 2, src, cur_stride, bsx, bsy, r1, smx, smy, r2, cx + p4x, cy + p4y, use8x8, pic_pix_x, pic_pix_y);
     if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
   }
   if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }

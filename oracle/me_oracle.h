@@ -24,6 +24,7 @@ typedef struct ora_cfg {
   int metric[3];           /* input->MEErrorMetric[] */
   int transform8x8;        /* input->Transform8x8Mode */
   int mv_limit_min_y, mv_limit_max_y;  /* LEVELMVLIMIT[LevelIndex][0..1] */
+  int chroma_me;           /* input->ChromaMEEnable (0, 1 = integer pel only, 2 = also sub-pel): enters start_me_refinement_hp/qp */
 } ora_cfg;
 
 typedef struct ora_ref {
@@ -32,6 +33,9 @@ typedef struct ora_ref {
   /* weighted-prediction ME (UseWeightedReferenceME): every reference sample of a UNI-predictive distortion becomes
    * clip1(((wp_weight * p + wp_round) >> wp_denom) + wp_offset) (me_fullfast.c:653, me_distortion.c:413-480, :734-822) */
   int wp_apply, wp_weight, wp_offset, wp_denom;
+  /* reconstructed chroma (StorablePicture::imgUV), for ChromaMEEnable; NULL when not set */
+  uint8_t *crec[2];
+  int cw, ch;
 } ora_ref;
 
 /* tables */
@@ -49,6 +53,13 @@ void     ora_ref_destroy(ora_ref *r);
 const uint8_t *ora_ref_plane(const ora_ref *r, int fy, int fx);
 /* weights of the (list, ref) entry this picture is searched as: wp_weight / wp_offset [list][ref][0], luma_log_weight_denom */
 void     ora_ref_set_weights(ora_ref *r, int apply, int weight, int offset, int log_denom);
+
+/* ChromaMEEnable: reconstructed chroma planes of a reference picture (copied) */
+void ora_ref_set_chroma(ora_ref *r, const uint8_t *u, const uint8_t *v, int stride, int cw, int ch);
+/* chroma state of the NEXT search call: the global ChromaMEEnable as that call sees it (me_distortion.c:56; mv-search.c:612, :779),
+ * input->ChromaMEWeight, the original chroma planes (imgUV_org) and chroma_shift_x / chroma_shift_y (lencod.c:2856-2879:
+ * 3,3 for 4:2:0; 3,2 for 4:2:2) */
+void ora_set_chroma(int enable, int weight, const uint8_t *cur_u, const uint8_t *cur_v, int stride, int shift_x, int shift_y);
 
 /* plane access with JM's origin clamp (UMVLine4X, refbuf.c:37): pointer to the first pixel of a block row */
 const uint8_t *ora_umv_line(const ora_ref *r, int y4, int x4);

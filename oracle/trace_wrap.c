@@ -21,8 +21,8 @@
  *
  * Output (directory named by env ME_TRACE_DIR, default "."):
  *   trace.bin          fixed-size records, 32 little-endian int32 each (layout: REC_* below)
- *   cur_<n>.y          original luma of coded picture n (8-bit, W*H bytes)
- *   ref_<id>.y         reconstructed luma a set of quarter-pel planes was built from
+ *   cur_<n>.y          original luma of coded picture n (8-bit, W*H bytes); with ChromaMEEnable also cur_<n>.u / .v
+ *   ref_<id>.y         reconstructed luma a set of quarter-pel planes was built from; with ChromaMEEnable also ref_<id>.u / .v
  *   ref_<id>.sub       the 16 planes as the reference produced them, [4][4][H+40][W+40] bytes
  *                      (only when ME_TRACE_PLANES=1)
  */
@@ -104,8 +104,13 @@ static void dump_current_if_needed(void)
   cur_dumped_for = coded_pic_no;
   snprintf(name, sizeof name, "cur_%d.y", coded_pic_no);
   dump_luma(name, pCurImg, img->width, img->height);
+  if (input->ChromaMEEnable) {
+    snprintf(name, sizeof name, "cur_%d.u", coded_pic_no); dump_luma(name, imgUV_org[0], img->width_cr, img->height_cr);
+    snprintf(name, sizeof name, "cur_%d.v", coded_pic_no); dump_luma(name, imgUV_org[1], img->width_cr, img->height_cr);
+  }
   rec[0] = REC_CURPIC; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->width; rec[4] = img->height;
   rec[5] = img->framepoc; rec[6] = img->qp;
+  rec[7] = input->ChromaMEEnable; rec[8] = input->ChromaMEWeight; rec[9] = img->yuv_format; rec[10] = img->width_cr; rec[11] = img->height_cr;
   put(rec);
 }
 
@@ -134,6 +139,10 @@ void __wrap_getSubImagesLuma(StorablePicture *s)
   tracked[n_tracked].p = s; tracked[n_tracked].id = id; n_tracked++;
   snprintf(name, sizeof name, "ref_%d.y", id);
   dump_luma(name, s->imgY, s->size_x, s->size_y);
+  if (input->ChromaMEEnable) {
+    snprintf(name, sizeof name, "ref_%d.u", id); dump_luma(name, s->imgUV[0], s->size_x_cr, s->size_y_cr);
+    snprintf(name, sizeof name, "ref_%d.v", id); dump_luma(name, s->imgUV[1], s->size_x_cr, s->size_y_cr);
+  }
   if (dump_planes) {
     char path[1024];
     FILE *f;
@@ -216,6 +225,7 @@ int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, i
   rec[15] = centre_x[list][ref]; rec[16] = centre_y[list][ref]; rec[17] = setup_range[list][ref];
   rec[21] = ref_id_of(listX[list + list_offset][ref]);
   rec[25] = input->rdopt;
+  rec[27] = ChromaMEEnable;                    /* the global of me_distortion.c:56 as this call sees it */
   put_weights(rec, list, list_offset, ref);
   cost = __real_FastFullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
                                              pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
@@ -241,7 +251,7 @@ int __wrap_FullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int p
   rec[10] = pred_mv_x; rec[11] = pred_mv_y; rec[12] = search_range; rec[13] = lambda_factor; rec[14] = min_mcost;
   rec[15] = *mv_x; rec[16] = *mv_y;                              /* search centre, integer pel */
   rec[21] = ref_id_of(listX[list + list_offset][ref]);
-  rec[22] = test8x8transform; rec[25] = input->rdopt;
+  rec[22] = test8x8transform; rec[25] = input->rdopt; rec[26] = ChromaMEEnable;
   put_weights(rec, list, list_offset, ref);
   cost = __real_FullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
                                          pred_mv_x, pred_mv_y, mv_x, mv_y, search_range, min_mcost, lambda_factor);
@@ -298,6 +308,7 @@ int __wrap_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int p
   rec[17] = *mv_x; rec[18] = *mv_y; rec[19] = *s_mv_x; rec[20] = *s_mv_y;
   rec[21] = ref_id_of(listX[list + list_offset][ref]);          /* picture read at the fixed vector s_mv */
   rec[22] = ref_id_of(listX[(list ^ 1) + list_offset][0]);      /* picture read at the searched candidate */
+  rec[26] = ChromaMEEnable;
   if (active_pps->weighted_bipred_idc > 0) {
     /* what the function is about to derive (me_fullsearch.c:202-227): rec[29] = 1 + log denominator (0 = no weights),
      * rec[30] = weight1 | weight2 << 16, rec[31] = offsetBi */

@@ -40,6 +40,19 @@ class OracleAdapter:
         self.refs = {i: ob.Ref(trace.ref(i)) for i in trace.ref_ids()}
         self.surf = {}
         self.wp = {}
+        self.ci = trace.chroma_info()
+        if self.ci:
+            for i, r in self.refs.items():
+                r.set_chroma(*trace.chroma("ref", i))
+        self.trace = trace
+
+    def set_chroma_state(self, pic, enable):
+        """the global ChromaMEEnable the next call sees (0 / 1 / 2: any non-zero value switches the chroma terms on)"""
+        if not self.ci:
+            return
+        u, v = self.trace.chroma("cur", pic)
+        shift = (3, 3) if self.ci["yuv_format"] == 1 else (3, 2)
+        self.ob.set_chroma(enable, self.ci["weight"], u, v, shift)
 
     def set_weights(self, lst, ref, apply, weight, offset, denom):
         self.wp[(lst, ref)] = (apply, weight, offset, denom)
@@ -118,6 +131,10 @@ class CudaAdapter:
     def set_weights(self, lst, ref, apply, weight, offset, denom):
         self.me.set_ref_weights(lst, ref, apply, weight, offset, denom)
 
+    def set_chroma_state(self, pic, enable):
+        if self.ci:
+            self.me.set_chroma_state(enable)
+
     def set_bipred_weights(self, lst, apply, w1, w2, obi, denom):
         self.me.set_bipred_weights(lst, apply, w1, w2, obi, denom)
 
@@ -168,6 +185,9 @@ def replay(trace, impl, max_calls=None):
         if t in (REC_FFS, REC_SUBPEL, REC_FULLPEL):
             # weighted-prediction ME: the weights the reference derived for this (list, ref) (0 = off in older fixtures)
             impl.set_weights(lst, ref, int(r[28]), int(r[29]), int(r[30]), int(r[31]))
+        # ChromaMEEnable as the call sees it (the reference resets the global between the stages of BlockMotionSearch); the
+        # sub-pel calls of these runs use SATD, which has no chroma term
+        impl.set_chroma_state(pic, int(r[27]) if t == REC_FFS else int(r[26]) if t in (REC_FULLPEL, REC_BI_FULL) else 0)
         if t in (REC_BI_FULL, REC_BI_SUB):
             # weighted bi-prediction: 1 + log denominator (0 = off), weight1 | weight2 << 16, offsetBi
             w = int(r[30])

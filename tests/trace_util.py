@@ -11,13 +11,14 @@ REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_REFPIC, REC_CURPIC, REC_FULLPE
 
 
 class Trace:
-    def __init__(self, directory=None, recs=None, cur=None, ref=None):
+    def __init__(self, directory=None, recs=None, cur=None, ref=None, chroma=None):
         self.dir = directory
         if recs is None:
             recs = np.fromfile(os.path.join(directory, "trace.bin"), dtype="<i4").reshape(-1, 32)
         self.recs = recs
         self._cur = dict(cur or {})
         self._ref = dict(ref or {})
+        self._chroma = dict(chroma or {})
         self.size = {}
         for r in recs[recs[:, 0] == REC_CURPIC]:
             self.size[("cur", int(r[1]))] = (int(r[4]), int(r[3]))
@@ -39,6 +40,23 @@ class Trace:
             self._ref[i] = np.fromfile(os.path.join(self.dir, "ref_%d.y" % i), np.uint8).reshape(h, w)
         return self._ref[i]
 
+    # ChromaMEEnable runs: original / reconstructed chroma planes (REC_CURPIC fields 7..11: ChromaMEEnable, ChromaMEWeight,
+    # yuv_format, chroma width, chroma height)
+    def chroma_info(self):
+        r = self.of_type(REC_CURPIC)
+        if not len(r) or not int(r[0][7]):
+            return None
+        return dict(enable=int(r[0][7]), weight=int(r[0][8]), yuv_format=int(r[0][9]), cw=int(r[0][10]), ch=int(r[0][11]))
+
+    def chroma(self, kind, n):
+        """(U, V) of 'cur' picture n or 'ref' picture n"""
+        key = (kind, n)
+        if key not in self._chroma:
+            ci = self.chroma_info()
+            self._chroma[key] = tuple(np.fromfile(os.path.join(self.dir, "%s_%d.%s" % (kind, n, c)), np.uint8).reshape(ci["ch"], ci["cw"])
+                                      for c in "uv")
+        return self._chroma[key]
+
     def ref_sub(self, i):
         h, w = self.size[("ref", i)]
         return np.fromfile(os.path.join(self.dir, "ref_%d.sub" % i), np.uint8).reshape(4, 4, h + 40, w + 40)
@@ -57,6 +75,12 @@ class Trace:
             d["cur_%d" % n] = self.cur(n)
         for i in self.ref_ids():
             d["ref_%d" % i] = self.ref(i)
+        if self.chroma_info():
+            for kind, ids in (("cur", self.cur_ids()), ("ref", self.ref_ids())):
+                for n in ids:
+                    u, v = self.chroma(kind, n)
+                    d["%su_%d" % (kind, n)] = u
+                    d["%sv_%d" % (kind, n)] = v
         np.savez_compressed(path, **d)
 
     @staticmethod
@@ -64,7 +88,12 @@ class Trace:
         z = np.load(path)
         cur = {int(k[4:]): z[k] for k in z.files if k.startswith("cur_")}
         ref = {int(k[4:]): z[k] for k in z.files if k.startswith("ref_")}
-        t = Trace(None, z["recs"], cur, ref)
+        chroma = {}
+        for k in z.files:
+            if k.startswith(("curu_", "refu_")):
+                kind, n = k[:3], int(k[5:])
+                chroma[(kind, n)] = (z[k], z[kind + "v_%d" % n])
+        t = Trace(None, z["recs"], cur, ref, chroma)
         for n, a in cur.items():
             t.size[("cur", n)] = a.shape
         for i, a in ref.items():
@@ -80,8 +109,9 @@ def cfg_from_trace(trace, search_range=32, full_search=2, metric=(0, 2, 2), mv_l
         ffs = trace.of_type(REC_FULLPEL)
     rdopt = int(ffs[0][25]) if len(ffs) else 1
     t8 = int(sub[:, 22].max()) if len(sub) else 0
+    ci = trace.chroma_info()
     return dict(search_range=search_range, rdopt=rdopt, full_search=full_search, metric=metric,
-                transform8x8=t8, mv_limit_min_y=mv_limits[0], mv_limit_max_y=mv_limits[1])
+                transform8x8=t8, mv_limit_min_y=mv_limits[0], mv_limit_max_y=mv_limits[1], chroma_me=ci["enable"] if ci else 0)
 
 
 def bipred_chains(trace, refinements=3, subpel=2):
