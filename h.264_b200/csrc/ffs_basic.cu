@@ -148,6 +148,7 @@ me_ffs_batch_basic_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRe
     int dy = idx / side, dx = idx - dy * side;
     int leaf[16], part[ME_NUM_PARTITIONS];
     me_leaf16<SSE>(tile, tp, curw, dx, dy, leaf);
+    if (cfg.chroma.on && ref.chroma[0]) me_leaf_chroma(ref, cfg.chroma, SSE, job.opix_x, job.opix_y, cx - R + dx, cy - R + dy, leaf);
     me_aggregate(leaf, part);
     int sidx = me_spiral_index(dx - R, dy - R);
     bool is00 = (!cfg.rdopt) && dx == dx00 && dy == dy00;
@@ -200,7 +201,7 @@ me_ffs_batch_basic_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRe
 template <bool SSE>
 __global__ void __launch_bounds__(128)
 me_ffs_surfaces_kernel(MeRefDev ref, const uint8_t *__restrict__ cur, int cur_pitch, int opix_x, int opix_y,
-                       int cx, int cy, int R, int32_t *__restrict__ surf /* [41][P] in spiral order */)
+                       int cx, int cy, int R, MeChromaDev chroma, int32_t *__restrict__ surf /* [41][P] in spiral order */)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t curw[64];
@@ -217,6 +218,7 @@ me_ffs_surfaces_kernel(MeRefDev ref, const uint8_t *__restrict__ cur, int cur_pi
   int dy = idx / side, dx = idx - dy * side;
   int leaf[16], part[ME_NUM_PARTITIONS];
   me_leaf16<SSE>(smem, tp, curw, dx, dy, leaf);
+  if (chroma.on && ref.chroma[0]) me_leaf_chroma(ref, chroma, SSE, opix_x, opix_y, cx - R + dx, cy - R + dy, leaf);
   me_aggregate(leaf, part);
   int s = me_spiral_index(dx - R, dy - R);
 #pragma unroll
@@ -252,12 +254,12 @@ extern "C" void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const M
 }
 
 extern "C" void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y,
-                                       int cx, int cy, int R, int sse, int32_t *surf, cudaStream_t st)
+                                       int cx, int cy, int R, int sse, const MeChromaDev *chroma, int32_t *surf, cudaStream_t st)
 {
   int n = 2 * R + 16, tp = (n + 3) & ~3, P = (2 * R + 1) * (2 * R + 1);
   size_t smem = (size_t)(n + 1) * tp + 16;
-  if (sse) me_ffs_surfaces_kernel<true><<<(P + 127) / 128, 128, smem, st>>>(*ref, cur, cur_pitch, opix_x, opix_y, cx, cy, R, surf);
-  else     me_ffs_surfaces_kernel<false><<<(P + 127) / 128, 128, smem, st>>>(*ref, cur, cur_pitch, opix_x, opix_y, cx, cy, R, surf);
+  if (sse) me_ffs_surfaces_kernel<true><<<(P + 127) / 128, 128, smem, st>>>(*ref, cur, cur_pitch, opix_x, opix_y, cx, cy, R, *chroma, surf);
+  else     me_ffs_surfaces_kernel<false><<<(P + 127) / 128, 128, smem, st>>>(*ref, cur, cur_pitch, opix_x, opix_y, cx, cy, R, *chroma, surf);
 }
 
 extern "C" void me_launch_ffs_block(const int32_t *surf_p, int setup_range, int offx, int offy, int pmv_x, int pmv_y,

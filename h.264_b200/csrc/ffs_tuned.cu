@@ -646,6 +646,7 @@ extern "C" int me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const Me
   if (!win_maps || !cur_map || !deferred) return 0;
   if (n_refs0 > TUNED_MAX_REFS || n_refs1 > TUNED_MAX_REFS) return 0;
   if (cfg->metric[0] != 0 || !cfg->rdopt || cfg->full_search != 2) return 0;
+  if (cfg->chroma.on) return 0;                 // chroma terms (ChromaMEEnable): the general kernel
   switch (cfg->search_range) {
     case 16: return launch<16>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, st);
     case 32: return launch<32>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, st);

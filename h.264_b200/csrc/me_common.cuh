@@ -21,6 +21,19 @@ struct MeRefDev {
   int w, h, wp, hp, pitch;
   size_t plane_stride;
   int spad, spitch, sw, sh;     // search plane: border, pitch, width (w+2*spad), height (h+2*spad)
+  // ChromaMEEnable: the picture's reconstructed chroma planes (StorablePicture::imgUV), u8, cw x ch samples, rows of cpitch
+  // bytes; nullptr when the caller has not supplied them
+  const uint8_t *chroma[2];
+  int cw, ch, cpitch;
+};
+
+// Chroma terms of the integer-pel searches (ChromaMEEnable; me_fullfast.c:776-814, me_distortion.c:376-402, :516-543).
+struct MeChromaDev {
+  int on;                       // the global ChromaMEEnable as the next call sees it (me_distortion.c:56; mv-search.c:612, :779)
+  int weight;                   // input->ChromaMEWeight
+  int shift_x, shift_y;         // chroma_shift_x / chroma_shift_y (lencod.c:2856-2879): 3,3 for 4:2:0; 3,2 for 4:2:2
+  int cur_pitch;
+  const uint8_t *cur[2];        // original chroma planes (imgUV_org)
 };
 
 struct MeCfgDev {
@@ -29,6 +42,7 @@ struct MeCfgDev {
   int transform8x8;
   int mv_limit_min_y, mv_limit_max_y;
   int start_hp, start_qp;       // start_me_refinement_hp/qp (mv-search.c:396-397)
+  MeChromaDev chroma;
 };
 
 // partition tables (order documented in include/me_cuda.h)
@@ -107,6 +121,66 @@ __device__ __forceinline__ const uint8_t *me_umv_ptr(const MeRefDev &r, int y4, 
   int xp = me_clamp(x4 >> 2, 0, r.w + 2 * ME_PAD - 1 - 16);
   int yp = me_clamp(y4 >> 2, 0, r.h + 2 * ME_PAD - 1 - 16);
   return r.planes + (size_t)(((y4 & 3) << 2) | (x4 & 3)) * r.plane_stride + (size_t)yp * r.pitch + xp;
+}
+
+// ---- chroma sub-images (getSubImagesChroma, img_chroma.c:374-440) evaluated on the fly: sub-image (sy, sx) at padded-plane
+// position (ypos, xpos) is the blend of four neighbours of the edge-replicated reconstruction with eighth-sample weights,
+// rshift_rnd_sf(., 6) (generateChroma00/01/10/XX, img_chroma.c:34-372)
+__device__ __forceinline__ int me_cr_pel(const MeRefDev &r, const MeChromaDev &c, int k, int ypos, int xpos, int sy, int sx)
+{
+  const int jy = ypos - ((4 * ME_PAD) >> c.shift_y), ix = xpos - ((4 * ME_PAD) >> c.shift_x);
+  const int y0 = me_clamp(jy, 0, r.ch - 1), y1 = me_clamp(jy + 1, 0, r.ch - 1), x0 = me_clamp(ix, 0, r.cw - 1), x1 = me_clamp(ix + 1, 0, r.cw - 1);
+  const int kk = sy << (3 - c.shift_y), ll = sx << (3 - c.shift_x);
+  const int w01 = (8 - kk) * ll, w00 = ((8 - kk) << 3) - w01, w11 = kk * ll, w10 = (kk << 3) - w11;
+  const uint8_t *p = r.chroma[k];
+  return (w00 * p[(size_t)y0 * r.cpitch + x0] + w01 * p[(size_t)y0 * r.cpitch + x1] +
+          w10 * p[(size_t)y1 * r.cpitch + x0] + w11 * p[(size_t)y1 * r.cpitch + x1] + 32) >> 6;
+}
+// UMVLine8X_chroma (refbuf.c:53-59): y, x = luma quarter-pel coordinates including the luma padding
+__device__ __forceinline__ void me_cr_line(const MeRefDev &r, const MeChromaDev &c, int y, int x, int &ypos, int &xpos, int &sy, int &sx)
+{
+  xpos = me_clamp(x >> c.shift_x, 0, r.cw - 1 + 2 * ((4 * ME_PAD) >> c.shift_x) - (64 >> c.shift_x));    // size_x_cr_pad, mbuffer.c:425
+  ypos = me_clamp(y >> c.shift_y, 0, r.ch - 1 + 2 * ((4 * ME_PAD) >> c.shift_y) - (64 >> c.shift_y));
+  sy = y & ((1 << c.shift_y) - 1);
+  sx = x & ((1 << c.shift_x) - 1);
+}
+// chroma part of computeSAD / SSE (me_distortion.c:376-402, :1069-1091) or of computeBiPredSAD1 (:516-543, r2 != nullptr) for the
+// luma block bsx x bsy at (pic_pix_x, pic_pix_y): distortion of the co-located block of component k, NOT yet weighted
+__device__ __forceinline__ int me_cr_block(const MeChromaDev &c, int sse, int k, int pic_pix_x, int pic_pix_y, int bsx, int bsy,
+                                           const MeRefDev &r1, int x41, int y41, const MeRefDev *r2, int x42, int y42)
+{
+  const int scx = c.shift_x - 2, scy = c.shift_y - 2;
+  const int bx = bsx >> scx, by = bsy >> scy, cx0 = pic_pix_x >> scx, cy0 = pic_pix_y >> scy;
+  int yp1, xp1, sy1, sx1, yp2 = 0, xp2 = 0, sy2 = 0, sx2 = 0, m = 0;
+  me_cr_line(r1, c, y41, x41, yp1, xp1, sy1, sx1);
+  if (r2) me_cr_line(*r2, c, y42, x42, yp2, xp2, sy2, sx2);
+  for (int y = 0; y < by; y++)
+    for (int x = 0; x < bx; x++) {
+      int p = me_cr_pel(r1, c, k, yp1 + y, xp1 + x, sy1, sx1);
+      if (r2) p = (p + me_cr_pel(*r2, c, k, yp2 + y, xp2 + x, sy2, sx2) + 1) >> 1;
+      const int d = (int)c.cur[k][(size_t)(cy0 + y) * c.cur_pitch + cx0 + x] - p;
+      m += sse ? d * d : abs(d);
+    }
+  return m;
+}
+// chroma term of the fast full search (me_fullfast.c:776-814): the co-located chroma block of every 4x4 luma block, both
+// components, added to the 16 leaves as it is (no ChromaMEWeight).  abs_x / abs_y: the candidate's position in the picture.
+__device__ __forceinline__ void me_leaf_chroma(const MeRefDev &r, const MeChromaDev &c, int sse, int opix_x, int opix_y, int abs_x, int abs_y,
+                                               int leaf[16])
+{
+  const int mbx = 64 >> c.shift_x, mby = 64 >> c.shift_y;
+  const int ocx = (mbx * opix_x) >> 4, ocy = (mby * opix_y) >> 4;      // img->opix_c_x/y, macroblock.c:206-207
+  int yp, xp, sy, sx;
+  me_cr_line(r, c, (abs_y + ME_PAD) << 2, (abs_x + ME_PAD) << 2, yp, xp, sy, sx);
+  for (int k = 0; k < 2; k++)
+    for (int cy = 0; cy < mby; cy++)
+      for (int cx = 0; cx < mbx; cx++) {
+        const int d = me_cr_pel(r, c, k, yp + cy, xp + cx, sy, sx) - (int)c.cur[k][(size_t)(ocy + cy) * c.cur_pitch + ocx + cx];
+        const int b = (cy / (mby >> 2)) * 4 + cx / (mbx >> 2);
+        // leaf[] is indexed with compile-time constants everywhere else: keep it in registers
+#pragma unroll
+        for (int q = 0; q < 16; q++) if (q == b) leaf[q] += sse ? d * d : abs(d);
+      }
 }
 
 // device-side job/result layouts = the ABI structs

@@ -53,7 +53,7 @@ int  me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev 
                                   cudaStream_t st);   // 1 = launched, 0 = not applicable
 int  me_ffs_tuned_window(int search_range);
 void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y, int cx, int cy,
-                            int R, int sse, int32_t *surf, cudaStream_t st);
+                            int R, int sse, const MeChromaDev *chroma, int32_t *surf, cudaStream_t st);
 void me_launch_ffs_block(const int32_t *surf_p, int setup_range, int offx, int offy, int pmv_x, int pmv_y, int search_range,
                          int min_mcost, int lambda, int rdopt, int *result, int ticket, cudaStream_t st);
 void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
@@ -80,6 +80,7 @@ struct TensorMap { alignas(64) unsigned char bytes[128]; };   // CUtensorMap
 
 struct RefPic {
   bool used = false;
+  uint8_t *chroma = nullptr;    // ChromaMEEnable: both reconstructed chroma planes, one allocation (U then V)
   unsigned long long gen = 0;   // changes whenever the planes are (re)generated: weighted copies made from them go stale
   uint8_t *planes = nullptr, *search = nullptr;
   MeRefDev dev{};
@@ -119,6 +120,8 @@ struct State {
   // current picture
   uint8_t *d_cur = nullptr;
   int cur_pitch = 0;
+  uint8_t *d_cur_c = nullptr;   // ChromaMEEnable: original chroma planes (U then V), rows of cfg.chroma.cur_pitch bytes
+  int chroma_w = 0, chroma_h = 0;
   // staging
   uint8_t *h_pin = nullptr; size_t h_pin_bytes = 0;
   uint16_t *d_wide = nullptr; uint16_t *h_wide = nullptr; size_t wide_elems = 0;
@@ -274,6 +277,8 @@ int upload_table()
       RefPic *r = ref_of(g.list[l][i]);
       if (!r) return fail(3, "reference list %d entry %d holds an invalid handle", l, i);
       const MeRefDev *dev; const TensorMap *wm, *pm; bool hm, hp;
+      if (g.p.chroma_me_enable && !r->chroma)
+        return fail(3, "reference list %d entry %d has no chroma planes (ChromaMEEnable: call me_cuda_ref_set_chroma after creating the picture)", l, i);
       if (int rc = search_planes(l, i, r, &dev, &wm, &hm, &pm, &hp)) return rc;
       g.h_table[l * ME_MAX_REFS + i] = *dev;
       g.h_maps[l * ME_MAX_REFS + i] = *wm;
@@ -382,7 +387,14 @@ int me_cuda_init(const me_cuda_params *p)
   if (p->abi_version != ME_CUDA_ABI_VERSION) return fail(1, "ABI version %d, library is %d", p->abi_version, ME_CUDA_ABI_VERSION);
   if (g.inited) me_cuda_shutdown();
   if (p->bit_depth != 8) return fail(1, "bit depth %d not supported (8-bit content only)", p->bit_depth);
-  if (p->chroma_me_enable) return fail(1, "ChromaMEEnable is not supported by the CUDA path");
+  if (p->chroma_me_enable < 0 || p->chroma_me_enable > 2) return fail(1, "ChromaMEEnable %d outside 0..2", p->chroma_me_enable);
+  if (p->chroma_me_enable) {
+    if (p->yuv_format != 1 && p->yuv_format != 2)
+      return fail(1, "ChromaMEEnable needs yuv_format 1 (4:2:0) or 2 (4:2:2); the 4:4:4 chroma sub-images are not implemented");
+    if (p->me_metric[0] == 2 || p->me_metric[1] != 2 || p->me_metric[2] != 2)
+      return fail(1, "ChromaMEEnable is implemented for SAD / SSE integer-pel and Hadamard sub-pel metrics only");
+    if (p->weighted_me) return fail(1, "ChromaMEEnable together with weighted-prediction ME is not implemented");
+  }
   if (p->width <= 0 || p->height <= 0 || (p->width & 15) || (p->height & 15)) return fail(1, "picture size %dx%d must be positive multiples of 16", p->width, p->height);
   if (p->search_range < 1 || p->search_range > 64) return fail(1, "search range %d outside 1..64", p->search_range);
   if (p->max_num_references < 1 || p->max_num_references > ME_MAX_REFS) return fail(1, "max_num_references %d outside 1..%d", p->max_num_references, ME_MAX_REFS);
@@ -402,8 +414,19 @@ int me_cuda_init(const me_cuda_params *p)
   for (int i = 0; i < 3; i++) g.cfg.metric[i] = p->me_metric[i];
   g.cfg.transform8x8 = p->transform8x8 != 0;
   g.cfg.mv_limit_min_y = p->mv_limit_min_y; g.cfg.mv_limit_max_y = p->mv_limit_max_y;
-  g.cfg.start_hp = (p->me_metric[0] != p->me_metric[1]) ? 0 : 1;      // mv-search.c:396 with ChromaMEEnable == 0
-  g.cfg.start_qp = (p->me_metric[1] != p->me_metric[2]) ? 0 : 1;      // mv-search.c:397
+  g.cfg.start_hp = (p->chroma_me_enable == 1 || p->me_metric[0] != p->me_metric[1]) ? 0 : 1;      // mv-search.c:396
+  g.cfg.start_qp = (p->chroma_me_enable == 1 || p->me_metric[1] != p->me_metric[2]) ? 0 : 1;      // mv-search.c:397
+  memset(&g.cfg.chroma, 0, sizeof g.cfg.chroma);
+  if (p->chroma_me_enable) {
+    g.cfg.chroma.on = p->chroma_me_enable;                             // until me_cuda_set_chroma_state says otherwise
+    g.cfg.chroma.weight = p->chroma_me_weight;
+    g.cfg.chroma.shift_x = 3; g.cfg.chroma.shift_y = p->yuv_format == 1 ? 3 : 2;       // lencod.c:2856-2870
+    g.chroma_w = p->width >> 1; g.chroma_h = p->yuv_format == 1 ? p->height >> 1 : p->height;
+    g.cfg.chroma.cur_pitch = align_up(g.chroma_w, 16);
+    CK(cudaMalloc((void **)&g.d_cur_c, (size_t)2 * g.cfg.chroma.cur_pitch * g.chroma_h));
+    CK(cudaMemset(g.d_cur_c, 128, (size_t)2 * g.cfg.chroma.cur_pitch * g.chroma_h));
+    g.cfg.chroma.cur[0] = g.d_cur_c; g.cfg.chroma.cur[1] = g.d_cur_c + (size_t)g.cfg.chroma.cur_pitch * g.chroma_h;
+  }
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   g.cur_pitch = align_up(p->width, 128);
   CK(cudaMalloc((void **)&g.d_cur, (size_t)g.cur_pitch * p->height));
@@ -424,8 +447,9 @@ void me_cuda_shutdown(void)
   if (!g.inited) return;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
-  for (auto &r : g.refs) if (r.used) { cudaFree(r.planes); cudaFree(r.search); }
+  for (auto &r : g.refs) if (r.used) { cudaFree(r.planes); cudaFree(r.search); if (r.chroma) cudaFree(r.chroma); }
   g.refs.clear();
+  if (g.d_cur_c) cudaFree(g.d_cur_c);
   for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) { if (g.twin[l][i].planes) cudaFree(g.twin[l][i].planes); if (g.twin[l][i].search) cudaFree(g.twin[l][i].search); }
   for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) if (g.d_surf[l][i]) cudaFree(g.d_surf[l][i]);
   cudaFree(g.d_cur); cudaFree(g.d_table); cudaFreeHost(g.h_result);
@@ -522,6 +546,7 @@ int me_cuda_ref_destroy(me_ref_handle h)
   if (!r) return fail(3, "me_cuda_ref_destroy: invalid handle %d", (int)h);
   CK(cudaStreamSynchronize(g.stream));
   cudaFree(r->planes); cudaFree(r->search);
+  if (r->chroma) cudaFree(r->chroma);
   *r = RefPic();
   for (int l = 0; l < 2; l++) for (int i = 0; i < g.list_n[l]; i++) if (g.list[l][i] == h) { g.list[l][i] = 0; g.table_dirty = true; }
   return 0;
@@ -613,6 +638,74 @@ int me_cuda_set_current(const me_imgpel *const *rows, int w, int h)
   return 0;
 }
 
+// ---- chroma (ChromaMEEnable)
+static int chroma_check(const char *who, int cw, int ch)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (!g.p.chroma_me_enable) return fail(1, "%s: the library was initialised with chroma_me_enable = 0", who);
+  if (cw != g.chroma_w || ch != g.chroma_h) return fail(1, "%s: chroma size %dx%d differs from the expected %dx%d", who, cw, ch, g.chroma_w, g.chroma_h);
+  return 0;
+}
+// both planes through the pinned staging buffer into a device allocation of 2 * pitch * ch bytes
+static int upload_chroma(uint8_t *d_dst, int pitch, const uint8_t *u, const uint8_t *v, int stride, const me_imgpel *const *ur,
+                         const me_imgpel *const *vr, int cw, int ch)
+{
+  const size_t bytes = (size_t)2 * cw * ch;
+  if (int rc = ensure_pin(bytes)) return rc;
+  CK(cudaStreamSynchronize(g.stream));               // the pinned staging buffer may still be in flight
+  for (int k = 0; k < 2; k++)
+    for (int y = 0; y < ch; y++) {
+      uint8_t *d = g.h_pin + ((size_t)k * ch + y) * cw;
+      if (ur) { const me_imgpel *s = (k ? vr : ur)[y]; for (int x = 0; x < cw; x++) d[x] = (uint8_t)s[x]; }
+      else memcpy(d, (k ? v : u) + (size_t)y * stride, cw);
+    }
+  CK(cudaMemcpy2DAsync(d_dst, pitch, g.h_pin, cw, cw, (size_t)2 * ch, cudaMemcpyHostToDevice, g.stream));
+  return 0;
+}
+static int ref_set_chroma_common(me_ref_handle h, const uint8_t *u, const uint8_t *v, int stride, const me_imgpel *const *ur,
+                                 const me_imgpel *const *vr, int cw, int ch)
+{
+  g.spec.valid = false;
+  if (int rc = chroma_check("me_cuda_ref_set_chroma", cw, ch)) return rc;
+  RefPic *r = ref_of(h);
+  if (!r) return fail(3, "me_cuda_ref_set_chroma: invalid handle %d", (int)h);
+  const int pitch = align_up(cw, 16);
+  if (!r->chroma) CK(cudaMalloc((void **)&r->chroma, (size_t)2 * pitch * ch));
+  if (int rc = upload_chroma(r->chroma, pitch, u, v, stride, ur, vr, cw, ch)) return rc;
+  r->dev.chroma[0] = r->chroma; r->dev.chroma[1] = r->chroma + (size_t)pitch * ch;
+  r->dev.cw = cw; r->dev.ch = ch; r->dev.cpitch = pitch;
+  g.table_dirty = true;
+  return 0;
+}
+int me_cuda_ref_set_chroma(me_ref_handle h, const me_imgpel *const *u_rows, const me_imgpel *const *v_rows, int cw, int ch)
+{
+  return ref_set_chroma_common(h, nullptr, nullptr, 0, u_rows, v_rows, cw, ch);
+}
+int me_cuda_ref_set_chroma_u8(me_ref_handle h, const uint8_t *u, const uint8_t *v, int stride, int cw, int ch)
+{
+  return ref_set_chroma_common(h, u, v, stride, nullptr, nullptr, cw, ch);
+}
+int me_cuda_set_current_chroma(const me_imgpel *const *u_rows, const me_imgpel *const *v_rows, int cw, int ch)
+{
+  g.spec.valid = false;
+  if (int rc = chroma_check("me_cuda_set_current_chroma", cw, ch)) return rc;
+  return upload_chroma(g.d_cur_c, g.cfg.chroma.cur_pitch, nullptr, nullptr, 0, u_rows, v_rows, cw, ch);
+}
+int me_cuda_set_current_chroma_u8(const uint8_t *u, const uint8_t *v, int stride, int cw, int ch)
+{
+  g.spec.valid = false;
+  if (int rc = chroma_check("me_cuda_set_current_chroma_u8", cw, ch)) return rc;
+  return upload_chroma(g.d_cur_c, g.cfg.chroma.cur_pitch, u, v, stride, nullptr, nullptr, cw, ch);
+}
+int me_cuda_set_chroma_state(int enable)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (enable && !g.p.chroma_me_enable) return fail(1, "me_cuda_set_chroma_state: the library was initialised with chroma_me_enable = 0");
+  g.cfg.chroma.on = enable;
+  g.spec.valid = false;
+  return 0;
+}
+
 int me_cuda_set_ref_list(int list, int n, const me_ref_handle *handles)
 {
   g.spec.valid = false;
@@ -651,6 +744,8 @@ int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset
   if (list < 0 || list > 1 || ref < 0 || ref >= ME_MAX_REFS) return fail(1, "me_cuda_set_ref_weights: (list %d, ref %d) out of range", list, ref);
   WeightSet w;
   w.apply = apply != 0;
+  if (w.apply && g.p.chroma_me_enable && !(weight == (1 << log_denom) && offset == 0))
+    return fail(1, "me_cuda_set_ref_weights: weighted-prediction ME together with ChromaMEEnable is not implemented");
   if (w.apply) {
     if (weight < -128 || weight > 127 || offset < -128 || offset > 127 || log_denom < 0 || log_denom > 7)
       return fail(1, "me_cuda_set_ref_weights: weight %d / offset %d / log denominator %d out of range", weight, offset, log_denom);
@@ -682,6 +777,7 @@ int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
   if (list < 0 || list > 1 || ref < 0 || ref >= g.list_n[list]) return fail(1, "me_cuda_ffs_setup: (list %d, ref %d) not in the reference lists", list, ref);
   RefPic *r = ref_of(g.list[list][ref]);
   if (!r) return fail(3, "me_cuda_ffs_setup: stale reference handle");
+  if (g.cfg.chroma.on && !r->chroma) return fail(3, "me_cuda_ffs_setup: (list %d, ref %d) has no chroma planes (me_cuda_ref_set_chroma)", list, ref);
   int R = setup_range_of(ref);
   int cx = pmv16_x / 4, cy = pmv16_y / 4;                                          // me_fullfast.c:552-553
   if (!g.cfg.rdopt) { cx = me_clamp(cx, -R, R); cy = me_clamp(cy, -R, R); }       // :555-560
@@ -692,7 +788,7 @@ int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
   if (!g.d_surf[list][ref]) CK(cudaMalloc((void **)&g.d_surf[list][ref], sizeof(int32_t) * (size_t)ME_NUM_PARTITIONS * P));
   const MeRefDev *dev;
   if (int rc = search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) return rc;
-  me_launch_ffs_surfaces(dev, g.d_cur, g.cur_pitch, g.opix_x, g.opix_y, cx, cy, R, g.cfg.metric[0] != 0, g.d_surf[list][ref], g.stream);
+  me_launch_ffs_surfaces(dev, g.d_cur, g.cur_pitch, g.opix_x, g.opix_y, cx, cy, R, g.cfg.metric[0] != 0, &g.cfg.chroma, g.d_surf[list][ref], g.stream);
   g.launches++;
   CK(cudaGetLastError());
   g.centre_x[list][ref] = cx; g.centre_y[list][ref] = cy; g.setup_range[list][ref] = R;
@@ -779,6 +875,7 @@ int me_cuda_FullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic
   if (blocktype < 1 || blocktype > 7 || search_range < 0 || search_range > 64) {
     fail(1, "me_cuda_FullPelBlockMotionSearch: block type %d / search range %d out of range", blocktype, search_range); fatal("fullpel"); return ME_INT_MAX;
   }
+  if (g.cfg.chroma.on && !r->chroma) { fail(3, "me_cuda_FullPelBlockMotionSearch: reference without chroma planes (me_cuda_ref_set_chroma)"); fatal("fullpel"); return ME_INT_MAX; }
   const MeRefDev *dev;
   if (search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) { fatal("fullpel"); return ME_INT_MAX; }
   MeFullPelArgs a{};
@@ -840,6 +937,8 @@ int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic
   if (!r1 || !r2) { fail(1, "me_cuda_FullPelBlockMotionBiPred: reference lists incomplete"); fatal("bipred"); return ME_INT_MAX; }
   if (g.cfg.metric[0] == 2) { fail(1, "bi-predictive integer search with a Hadamard metric is not implemented"); fatal("bipred"); return ME_INT_MAX; }
   if (search_range > 64) { fail(1, "bi-pred search range %d too large", search_range); fatal("bipred"); return ME_INT_MAX; }
+  if (g.cfg.chroma.on && (!r1->chroma || !r2->chroma)) { fail(3, "me_cuda_FullPelBlockMotionBiPred: reference without chroma planes (me_cuda_ref_set_chroma)"); fatal("bipred"); return ME_INT_MAX; }
+  if (g.cfg.chroma.on && g.bw[list].apply) { fail(1, "weighted bi-prediction together with ChromaMEEnable is not implemented"); fatal("bipred"); return ME_INT_MAX; }
   MeBiFullArgs a{};
   a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
   a.pmv_x1 = pred_mv_x1; a.pmv_y1 = pred_mv_y1; a.pmv_x2 = pred_mv_x2; a.pmv_y2 = pred_mv_y2;

@@ -360,6 +360,11 @@ __device__ int fullpel_dist(const MeRefDev &r, const uint8_t *__restrict__ cur, 
     }
     if (use_thr && m >= thr) return m;
   }
+  if (cfg.chroma.on && r.chroma[0])
+    for (int k = 0; k < 2; k++) {               // me_distortion.c:376-402: one component after the other, same early exit
+      m += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r, x4, y4, nullptr, 0, 0);
+      if (use_thr && m >= thr) return m;
+    }
   return m;
 }
 
@@ -445,6 +450,10 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
                 - bipred_pel(p1[(size_t)y * r1.pitch + x], p2[(size_t)y * r2.pitch + x], a.bw);
         d += metric ? e * e : abs(e);                      // computeBiPred1[F_PEL]: SAD, SSE, (SATD -> see host)
       }
+    if (cfg.chroma.on && r1.chroma[0] && r2.chroma[0])     // computeBiPredSAD1, me_distortion.c:516-543
+      for (int k = 0; k < 2; k++)
+        d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, (c1x << 2) + 4 * ME_PAD,
+                                             (c1y << 2) + 4 * ME_PAD, &r2, cx + 4 * ME_PAD, cy + 4 * ME_PAD);
     mc += d;
     unsigned long long key = ((unsigned long long)(unsigned)mc << 32) | (unsigned)s;
     best = key < best ? key : best;
@@ -540,7 +549,7 @@ me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur,
   __shared__ BlockScratch sc;
   __shared__ BiFastScratch fs;
   int mvx, mvy, cost;
-  if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE && !a.bw.apply) bipred_full_block_sad(r1, r2, cur, cur_pitch, a, sc, fs, mvx, mvy, cost);
+  if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE && !a.bw.apply && !cfg.chroma.on) bipred_full_block_sad(r1, r2, cur, cur_pitch, a, sc, fs, mvx, mvy, cost);
   else bipred_full_block(r1, r2, cur, cur_pitch, cfg, a, sc, mvx, mvy, cost);
   if (threadIdx.x == 0) {
     result[0] = mvx; result[1] = mvy; result[2] = cost;
@@ -604,7 +613,7 @@ me_bipred_batch_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     a.search_range = search_range >> i; a.min_mcost = min_mcostbi; a.lambda = lambda[0];
     int mx, my;
     a.bw = iterlist ? bw1 : bw0;
-    if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE && !a.bw.apply)
+    if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE && !a.bw.apply && !cfg.chroma.on)
       bipred_full_block_sad(refs[iterlist], refs[iterlist ^ 1], cur, cur_pitch, a, sc, fs, mx, my, min_mcostbi);
     else
       bipred_full_block(refs[iterlist], refs[iterlist ^ 1], cur, cur_pitch, cfg, a, sc, mx, my, min_mcostbi);

@@ -38,6 +38,8 @@ ABI_SYMBOLS = [
     "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count",
     "me_cuda_measure_int_peak", "me_cuda_ref_update_u8", "me_cuda_ref_update_device", "me_cuda_set_timing",
     "me_cuda_kernel_time_ms", "me_cuda_set_ref_weights", "me_cuda_set_bipred_weights",
+    "me_cuda_set_current_chroma", "me_cuda_set_current_chroma_u8", "me_cuda_ref_set_chroma", "me_cuda_ref_set_chroma_u8",
+    "me_cuda_set_chroma_state",
 ]
 
 
@@ -50,7 +52,8 @@ class Params(C.Structure):
                 ("search_range", C.c_int32), ("max_num_references", C.c_int32), ("rdopt", C.c_int32),
                 ("full_search", C.c_int32), ("me_metric", C.c_int32 * 3), ("transform8x8", C.c_int32),
                 ("mv_limit_min_y", C.c_int32), ("mv_limit_max_y", C.c_int32), ("chroma_me_enable", C.c_int32),
-                ("weighted_me", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("weighted_me", C.c_int32), ("device", C.c_int32), ("chroma_me_weight", C.c_int32), ("yuv_format", C.c_int32),
+                ("reserved", C.c_int32 * 6)]
 
 
 def load_library(path=LIB_PATH):
@@ -71,6 +74,9 @@ def load_library(path=LIB_PATH):
     L.me_cuda_set_ref_list.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)]
     L.me_cuda_set_slice_type.argtypes = [C.c_int]
     L.me_cuda_set_ref_weights.argtypes = [C.c_int] * 6
+    L.me_cuda_set_current_chroma_u8.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.me_cuda_ref_set_chroma_u8.argtypes = [C.c_int32, vp, vp, C.c_int, C.c_int, C.c_int]
+    L.me_cuda_set_chroma_state.argtypes = [C.c_int]
     L.me_cuda_set_bipred_weights.argtypes = [C.c_int] * 6
     L.me_cuda_mb_begin.argtypes = [C.c_int, C.c_int]
     L.me_cuda_ffs_setup.argtypes = [C.c_int] * 4
@@ -101,7 +107,8 @@ class MeCuda:
     """One initialised libme_cuda context (the library keeps global state like the reference does)."""
 
     def __init__(self, width, height, search_range=32, max_num_references=5, rdopt=1, full_search=2,
-                 me_metric=(0, 2, 2), transform8x8=0, mv_limits=(-511, 511), device=-1, lib_path=LIB_PATH):
+                 me_metric=(0, 2, 2), transform8x8=0, mv_limits=(-511, 511), device=-1, lib_path=LIB_PATH,
+                 chroma_me=0, chroma_me_weight=1, yuv_format=1):
         self.L = load_library(lib_path)
         p = Params()
         p.abi_version = 1
@@ -112,6 +119,7 @@ class MeCuda:
         p.transform8x8 = transform8x8
         p.mv_limit_min_y, p.mv_limit_max_y = mv_limits
         p.device = device
+        p.chroma_me_enable, p.chroma_me_weight, p.yuv_format = chroma_me, chroma_me_weight, yuv_format
         self.width, self.height = width, height
         self._check(self.L.me_cuda_init(C.byref(p)))
         self.open = True
@@ -208,6 +216,19 @@ class MeCuda:
     def set_ref_weights(self, lst, ref, apply, weight=32, offset=0, log_denom=5):
         """weighted-prediction ME: wp_weight / wp_offset [list][ref][0] and luma_log_weight_denom of a list entry"""
         self._check(self.L.me_cuda_set_ref_weights(lst, ref, int(apply), int(weight), int(offset), int(log_denom)))
+
+    # ---- chroma terms of the integer-pel searches (ChromaMEEnable)
+    def set_current_chroma(self, u, v):
+        u, v = np.ascontiguousarray(u, np.uint8), np.ascontiguousarray(v, np.uint8)
+        self._check(self.L.me_cuda_set_current_chroma_u8(u.ctypes.data, v.ctypes.data, u.strides[0], u.shape[1], u.shape[0]))
+
+    def ref_set_chroma(self, h, u, v):
+        u, v = np.ascontiguousarray(u, np.uint8), np.ascontiguousarray(v, np.uint8)
+        self._check(self.L.me_cuda_ref_set_chroma_u8(h, u.ctypes.data, v.ctypes.data, u.strides[0], u.shape[1], u.shape[0]))
+
+    def set_chroma_state(self, enable):
+        """the global ChromaMEEnable as the next search call sees it (mv-search.c:612, :779)"""
+        self._check(self.L.me_cuda_set_chroma_state(int(enable)))
 
     def set_bipred_weights(self, lst, apply, w1=32, w2=32, offset_bi=0, log_denom=5):
         """weighted bi-prediction for bi-predictive searches called with list argument `lst` (me_fullsearch.c:202-227)"""

@@ -52,6 +52,9 @@ static struct {
   int  (*set_slice_type)(int);
   int  (*set_ref_weights)(int, int, int, int, int, int);
   int  (*set_bipred_weights)(int, int, int, int, int, int);
+  int  (*set_current_chroma)(const me_imgpel *const *, const me_imgpel *const *, int, int);
+  int  (*ref_set_chroma)(me_ref_handle, const me_imgpel *const *, const me_imgpel *const *, int, int);
+  int  (*set_chroma_state)(int);
   int  (*mb_begin)(int, int);
   int  (*ffs_setup)(int, int, int, int);
   int  (*ffs_is_set_up)(int, int);
@@ -114,6 +117,8 @@ static void load_library(void)
   L.set_current = sym("me_cuda_set_current"); L.set_ref_list = sym("me_cuda_set_ref_list");
   L.set_slice_type = sym("me_cuda_set_slice_type"); L.mb_begin = sym("me_cuda_mb_begin");
   L.set_ref_weights = sym("me_cuda_set_ref_weights"); L.set_bipred_weights = sym("me_cuda_set_bipred_weights");
+  L.set_current_chroma = sym("me_cuda_set_current_chroma"); L.ref_set_chroma = sym("me_cuda_ref_set_chroma");
+  L.set_chroma_state = sym("me_cuda_set_chroma_state");
   L.ffs_setup = sym("me_cuda_ffs_setup"); L.ffs_is_set_up = sym("me_cuda_ffs_is_set_up");
   L.fullpel = sym("me_cuda_FullPelBlockMotionSearch");
   L.ffs = sym("me_cuda_FastFullPelBlockMotionSearch"); L.subpel = sym("me_cuda_SubPelBlockMotionSearch");
@@ -175,6 +180,8 @@ void __wrap_Init_Motion_Search_Module(void)
     p.mv_limit_min_y = LEVELMVLIMIT[img->LevelIndex][0];
     p.mv_limit_max_y = LEVELMVLIMIT[img->LevelIndex][1];
     p.chroma_me_enable = input->ChromaMEEnable;
+    p.chroma_me_weight = input->ChromaMEWeight;
+    p.yuv_format = img->yuv_format;
     p.weighted_me = apply_wp;
     p.device = -1;
     if (L.init(&p)) die("me_cuda_init");
@@ -216,6 +223,11 @@ void __wrap_getSubImagesLuma(StorablePicture *s)
   if (L.ref_create((const me_imgpel *const *)s->p_curr_img, s->size_x, s->size_y, (me_imgpel ****)s->p_curr_img_sub, &h)) die("me_cuda_ref_create");
   if (n_map == MAX_MAP) unmap_index(0);
   map[n_map].p = s; map[n_map].plane = plane; map[n_map].h = h; n_map++;
+  /* ChromaMEEnable: the searches read the chroma sub-images of this picture (getSubImagesChroma, image.c:1659, still runs on the
+   * host for motion compensation); the library evaluates them from the reconstructed chroma planes */
+  if (input->ChromaMEEnable &&
+      L.ref_set_chroma(h, (const me_imgpel *const *)s->imgUV[0], (const me_imgpel *const *)s->imgUV[1], s->size_x_cr, s->size_y_cr))
+    die("me_cuda_ref_set_chroma");
 }
 
 void __real_free_storable_picture(StorablePicture *p);
@@ -239,6 +251,9 @@ static void mb_sync(void)
   mb_synced_pic = pic_counter; mb_synced_mb = img->current_mb_nr;
   if (pic_uploaded != pic_counter || plane_uploaded != current_plane()) {
     if (L.set_current((const me_imgpel *const *)pCurImg, img->width, img->height)) die("me_cuda_set_current");
+    if (input->ChromaMEEnable &&
+        L.set_current_chroma((const me_imgpel *const *)imgUV_org[0], (const me_imgpel *const *)imgUV_org[1], img->width_cr, img->height_cr))
+      die("me_cuda_set_current_chroma");
     pic_uploaded = pic_counter; plane_uploaded = current_plane();
   }
   {
@@ -282,6 +297,9 @@ static void keep_reference_side_effects(int list, short ref)
   img_height = rp->size_y;
   width_pad  = rp->size_x_pad;
   height_pad = rp->size_y_pad;
+  /* the global ChromaMEEnable (me_distortion.c:56) as the reference function about to be replaced would see it:
+   * BlockMotionSearch changes it between the integer-pel and the later stages (mv-search.c:612, :779) */
+  if (input->ChromaMEEnable && L.set_chroma_state(ChromaMEEnable)) die("me_cuda_set_chroma_state");
 }
 
 /* Weighted-prediction ME: what SetupFastFullPelSearch (me_fullfast.c:507-508, :530-534) and SubPelBlockMotionSearch

@@ -61,10 +61,12 @@ typedef struct me_cuda_params {
   int32_t transform8x8;         /* input->Transform8x8Mode != 0 */
   int32_t mv_limit_min_y;       /* LEVELMVLIMIT[img->LevelIndex][0], mv-search.h:36 */
   int32_t mv_limit_max_y;       /* LEVELMVLIMIT[img->LevelIndex][1] */
-  int32_t chroma_me_enable;     /* input->ChromaMEEnable: must be 0 (chroma ME not implemented) */
+  int32_t chroma_me_enable;     /* input->ChromaMEEnable: 0, 1 (chroma in the integer-pel searches) or 2 (also later stages); see below */
   int32_t weighted_me;          /* informational: weighted-prediction ME in use (weights arrive through me_cuda_set_ref_weights) */
   int32_t device;               /* CUDA device ordinal; -1: env ME_CUDA_DEVICE, else 0 */
-  int32_t reserved[8];
+  int32_t chroma_me_weight;     /* input->ChromaMEWeight (used when chroma_me_enable != 0) */
+  int32_t yuv_format;           /* img->yuv_format: 1 = 4:2:0, 2 = 4:2:2 (chroma_me_enable != 0 needs one of these); 0 = not given */
+  int32_t reserved[6];
 } me_cuda_params;
 
 /* error handling: the drop-in search calls return a cost like the reference functions do, so failures are reported
@@ -117,6 +119,25 @@ int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset
  * of computeBiPredSATD2, :1015, which the encoder's results depend on).  apply = 0: plain (p1 + p2 + 1) >> 1.  Used by the
  * drop-in calls and by me_cuda_frame_bipred. */
 int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom);
+
+/* ---- chroma terms of the integer-pel searches (cfg ChromaMEEnable = 1 or 2, 4:2:0 and 4:2:2): the fast full search adds the
+ * distortion of the co-located chroma block of every 4x4 (me_fullfast.c:776-814), computeSAD / computeSSE and their
+ * bi-predictive forms add ChromaMEWeight times the chroma block distortion of each component (me_distortion.c:376-402,
+ * :516-543, :1069-1091); the Hadamard functions have no chroma term.  Reference samples are the 1/8-sample sub-images of
+ * getSubImagesChroma (img_chroma.c:374), read through UMVLine8X_chroma (refbuf.c:53); the library evaluates them on the fly
+ * from the reconstructed chroma planes.  Supported with the shipped metrics (SAD or SSE integer pel, Hadamard sub-pel) and
+ * without weighted prediction; me_cuda_init fails otherwise.
+ *   me_cuda_set_current_chroma : imgUV_org[0..1] of the picture being coded (cw x ch samples each)
+ *   me_cuda_ref_set_chroma     : StorablePicture::imgUV[0..1] of a reference picture, after me_cuda_ref_create
+ *   me_cuda_set_chroma_state   : the value of the global ChromaMEEnable (me_distortion.c:56) the NEXT search call sees -- the
+ *                                reference sets it to input->ChromaMEEnable before the integer-pel search (mv-search.c:612)
+ *                                and to (input->ChromaMEEnable == 2) from the sub-pel stage on (mv-search.c:779), which is
+ *                                what the bi-predictive searches of the same BlockMotionSearch call run with ---- */
+int me_cuda_set_current_chroma(const me_imgpel *const *u_rows, const me_imgpel *const *v_rows, int cw, int ch);
+int me_cuda_set_current_chroma_u8(const uint8_t *u, const uint8_t *v, int stride, int cw, int ch);
+int me_cuda_ref_set_chroma(me_ref_handle h, const me_imgpel *const *u_rows, const me_imgpel *const *v_rows, int cw, int ch);
+int me_cuda_ref_set_chroma_u8(me_ref_handle h, const uint8_t *u, const uint8_t *v, int stride, int cw, int ch);
+int me_cuda_set_chroma_state(int enable);
 
 /* ---- per macroblock: ResetFastFullIntegerSearch (me_fullfast.c:197, called macroblock.c:509) ---- */
 int me_cuda_mb_begin(int opix_x, int opix_y);

@@ -19,6 +19,10 @@ Cases
   fullsearch encoder_baseline.cfg with SearchMode=-1 (FullPelBlockMotionSearch, me_fullsearch.c:47, for every block), SR 8,
              2 references, RDOptimization=0 on the synthetic QCIF clip: includes the blocks at picture origin whose first
              candidate is accepted with a one-row SAD (early-exit threshold wrap, me_fullsearch.c:129-138).  Every 3rd MB.
+  chroma     encoder.cfg with ChromaMEEnable=2, SR 16, 2 references (I-B-P, 8x8 transform): chroma terms in the fast full search
+             and in the bi-predictive integer-pel search.  chroma_fs: encoder_main.cfg with ChromaMEEnable=1, SearchMode=-1,
+             RDOptimization=0: chroma terms of computeSAD in the per-block full search.  Every 6th macroblock; the fixtures
+             carry the original and reconstructed chroma planes.
   wpb        encoder.cfg (High profile, I-B-P, bi-predictive ME, 8x8 transform) with WeightedBiprediction=1 and
              WeightedPrediction=1 on the fading clip, SR 16, 2 references: weighted bi-predictive searches
              (computeBiPredSAD2 / SATD2, including the 8x8 branch's source-pointer slip).  Every 6th macroblock is kept.
@@ -142,6 +146,26 @@ def main():
         assert len(tr.of_type(REC_FULLPEL)) > 10000 and not len(tr.of_type(REC_FFS))
         tr.save_npz(os.path.join(HERE, "fullsearch.npz"), keep_mask(tr, 3))
         crc["fullsearch"] = planes_crc(tr, d)
+    # ---- chroma: ChromaMEEnable = 2 (chroma terms in the fast full search and in the bi-predictive integer-pel search); the
+    # fixtures also hold the original / reconstructed chroma planes
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(os.path.join(REF, "fixtures", "foreman_part_qcif.yuv"), d)
+        run_trace(d, ["-d", "encoder.cfg", "-p", "ChromaMEEnable=2", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"])
+        md5s["chroma"] = {"test.264": md5(os.path.join(d, "test.264"))}
+        tr = Trace(d)
+        assert tr.chroma_info()["enable"] == 2 and (tr.of_type(REC_BI_FULL)[:, 26] == 1).all()
+        tr.save_npz(os.path.join(HERE, "chroma.npz"), keep_mask(tr, 6))
+        crc["chroma"] = planes_crc(tr, d)
+    # ---- chroma_fs: ChromaMEEnable = 1 with SearchMode = -1 (chroma terms of computeSAD in the per-block full search), no RDO
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(os.path.join(REF, "fixtures", "foreman_part_qcif.yuv"), d)
+        run_trace(d, ["-d", "encoder_main.cfg", "-p", "ChromaMEEnable=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2",
+                      "-p", "SearchMode=-1", "-p", "RDOptimization=0"])
+        md5s["chroma_fs"] = {"test.264": md5(os.path.join(d, "test.264"))}
+        tr = Trace(d)
+        assert tr.chroma_info()["enable"] == 1 and len(tr.of_type(REC_FULLPEL)) > 10000
+        tr.save_npz(os.path.join(HERE, "chroma_fs.npz"), keep_mask(tr, 6))
+        crc["chroma_fs"] = planes_crc(tr, d)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
     for f in sorted(os.listdir(HERE)):

@@ -63,7 +63,7 @@ class OracleAdapter:
         r.set_weights(*self.wp.get((lst, ref), (0, 32, 0, 5)))
         return r
 
-    def begin_picture(self, cur, slice_type, lists):
+    def begin_picture(self, cur, slice_type, lists, pic=None):
         self.cur, self.slice_type, self.lists = np.ascontiguousarray(cur), slice_type, lists
         self.wp = {}
 
@@ -117,13 +117,21 @@ class CudaAdapter:
         import h264_b200_pkg  # noqa: F401
         from h264_b200 import MeCuda
         h, w = trace.size[("cur", trace.cur_ids()[0])]
+        self.ci = trace.chroma_info()
+        self.trace = trace
+        ckw = dict(chroma_me=self.ci["enable"], chroma_me_weight=self.ci["weight"], yuv_format=self.ci["yuv_format"]) if self.ci else {}
         self.me = MeCuda(w, h, search_range=cfgkw["search_range"], max_num_references=max_refs, rdopt=cfgkw["rdopt"],
                          full_search=cfgkw["full_search"], me_metric=cfgkw["metric"], transform8x8=cfgkw["transform8x8"],
-                         mv_limits=(cfgkw["mv_limit_min_y"], cfgkw["mv_limit_max_y"]))
+                         mv_limits=(cfgkw["mv_limit_min_y"], cfgkw["mv_limit_max_y"]), **ckw)
         self.handles = {i: self.me.ref_create(trace.ref(i)) for i in trace.ref_ids()}
+        if self.ci:
+            for i, hd in self.handles.items():
+                self.me.ref_set_chroma(hd, *trace.chroma("ref", i))
 
-    def begin_picture(self, cur, slice_type, lists):
+    def begin_picture(self, cur, slice_type, lists, pic=None):
         self.me.set_current(cur)
+        if self.ci:
+            self.me.set_current_chroma(*self.trace.chroma("cur", pic))
         self.me.set_slice_type(slice_type)
         for l in (0, 1):
             self.me.set_ref_list(l, [self.handles[i] for i in lists[l]])
@@ -176,7 +184,7 @@ def replay(trace, impl, max_calls=None):
             continue
         pic, ox, oy = int(r[1]), int(r[3]), int(r[4])
         if pic != cur_pic:
-            impl.begin_picture(trace.cur(pic), slice_of.get(pic, int(r[2])), picture_lists(trace, pic))
+            impl.begin_picture(trace.cur(pic), slice_of.get(pic, int(r[2])), picture_lists(trace, pic), pic)
             cur_pic, cur_mb = pic, None
         if (ox, oy) != cur_mb:
             impl.mb_begin(ox, oy)

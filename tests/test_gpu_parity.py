@@ -26,10 +26,10 @@ def _cfg(ob, **kw):
     return d, ob.make_cfg(**d)
 
 
-def _open(pkg, w, h, d, max_refs=5):
+def _open(pkg, w, h, d, max_refs=5, **extra):
     return pkg.MeCuda(w, h, search_range=d["search_range"], max_num_references=max_refs, rdopt=d["rdopt"],
                       full_search=d["full_search"], me_metric=d["metric"], transform8x8=d["transform8x8"],
-                      mv_limits=(d["mv_limit_min_y"], d["mv_limit_max_y"]))
+                      mv_limits=(d["mv_limit_min_y"], d["mv_limit_max_y"]), chroma_me=d.get("chroma_me", 0), **extra)
 
 
 # ------------------------------------------------------------------------------------------------ planes
@@ -258,6 +258,47 @@ def test_batch_weighted_prediction(pkg, oracle_lib, t8):
                 assert np.array_equal(out_int[s_], exp_int), (rnd, r)
                 assert np.array_equal(out[s_], exp), (rnd, r)
                 ref.close()
+
+
+@pytest.mark.parametrize("chroma_me,sse", [(1, 0), (2, 0), (1, 1)])
+def test_batch_chroma_terms(pkg, oracle_lib, chroma_me, sse):
+    """ChromaMEEnable: the fast full search adds the distortion of the co-located chroma block of every 4x4 (me_fullfast.c:776-814);
+    the frame batch takes the general search kernel then.  4:2:0 pictures with real chroma, predictors that push windows out of
+    the picture (chroma origin clamp), SAD and squared error"""
+    from h264_b200 import synth
+    ob = oracle_lib
+    w, h, n_refs = 176, 144, 2
+    d, cfg = _cfg(ob, chroma_me=chroma_me, metric=(sse, 2, 2), search_range=16)
+    yuv = synth.yuv420_frames(w, h, n_refs + 1)
+    rng = np.random.default_rng(71)
+    yuv = [(y, np.clip(u.astype(int) + rng.integers(-20, 21, u.shape), 0, 255).astype(np.uint8),
+            np.clip(v.astype(int) + rng.integers(-20, 21, v.shape), 0, 255).astype(np.uint8)) for y, u, v in yuv]
+    cur = yuv[-1]
+    jobs = synth.synthetic_jobs(w, h, n_refs, (334459, 334459, 334459), seed=73, max_pmv=64)
+    with _open(pkg, w, h, d, max_refs=n_refs, chroma_me_weight=4, yuv_format=1) as me:
+        handles = []
+        for r in range(n_refs):
+            hd = me.ref_create(yuv[-2 - r][0])
+            me.ref_set_chroma(hd, yuv[-2 - r][1], yuv[-2 - r][2])
+            handles.append(hd)
+        me.set_ref_list(0, handles)
+        me.set_current(cur[0])
+        me.set_current_chroma(cur[1], cur[2])
+        me.set_chroma_state(chroma_me)
+        out, out_int = me.frame_search(jobs, want_int=True)
+    ob.set_chroma(chroma_me, 4, cur[1], cur[2], (3, 3))
+    try:
+        sel = np.sort(rng.choice(len(jobs), 120, replace=False))
+        for r in range(n_refs):
+            s_ = sel[jobs["ref"][sel] == r]
+            ref = ob.Ref(yuv[-2 - r][0])
+            ref.set_chroma(yuv[-2 - r][1], yuv[-2 - r][2])
+            exp, exp_int = ob.mb_search(cfg, np.ascontiguousarray(cur[0]), ref, jobs[s_])
+            assert np.array_equal(out_int[s_], exp_int), r
+            assert np.array_equal(out[s_], exp), r
+            ref.close()
+    finally:
+        ob.set_chroma(0)
 
 
 @pytest.mark.parametrize("kind", ["flat", "stripes"])

@@ -51,7 +51,8 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
 @pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0", "yuv444_3ref_bframes", "sr64_2ref",
                                   "hd1080_sr32_ip", "weighted_pred_fade", "weighted_bipred_fade", "full_search_mode_rdopt0",
-                                  "full_search_mode_satd", "yuv444_independent_planes"])
+                                  "full_search_mode_satd", "yuv444_independent_planes", "chroma_me_2_bframes",
+                                  "chroma_me_1_full_search_rdopt0", "chroma_me_1_yuv422"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -75,6 +76,14 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         # quarter-pel plane set per reference picture (UnifiedOneForthPix_JV, image.c:1672) and its own original plane
         args = ["-d", "encoder.cfg", "-p", "InputFile=foreman_part_qcif_444.yuv", "-p", "YUVFormat=3", "-p", "ProfileIDC=244",
                 "-p", "SeparateColourPlane=1", "-p", "NumberReferenceFrames=2", "-p", "SearchRange=16"]
+    elif case == "chroma_me_2_bframes":
+        # SURVEY.md 8(f) row 1, chroma half: chroma terms in the fast full search and the bi-predictive integer-pel search
+        args = ["-d", "encoder.cfg", "-p", "ChromaMEEnable=2", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+    elif case == "chroma_me_1_full_search_rdopt0":
+        args = ["-d", "encoder_main.cfg", "-p", "ChromaMEEnable=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2",
+                "-p", "SearchMode=-1", "-p", "RDOptimization=0"]
+    elif case == "chroma_me_1_yuv422":
+        args = ["-d", "encoder_yuv422.cfg", "-p", "ChromaMEEnable=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
     elif case == "hd1080_sr32_ip":
         # the headline picture size and search range (BASELINE config 3), one I and one P picture
         args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=1920", "-p", "SourceHeight=1088",
