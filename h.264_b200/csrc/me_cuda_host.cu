@@ -391,8 +391,8 @@ int me_cuda_init(const me_cuda_params *p)
   if (p->chroma_me_enable) {
     if (p->yuv_format != 1 && p->yuv_format != 2)
       return fail(1, "ChromaMEEnable needs yuv_format 1 (4:2:0) or 2 (4:2:2); the 4:4:4 chroma sub-images are not implemented");
-    if (p->me_metric[0] == 2 || p->me_metric[1] != 2 || p->me_metric[2] != 2)
-      return fail(1, "ChromaMEEnable is implemented for SAD / SSE integer-pel and Hadamard sub-pel metrics only");
+    if (p->me_metric[0] == 2)
+      return fail(1, "ChromaMEEnable with a Hadamard integer-pel metric is not implemented");
     if (p->weighted_me) return fail(1, "ChromaMEEnable together with weighted-prediction ME is not implemented");
   }
   if (p->width <= 0 || p->height <= 0 || (p->width & 15) || (p->height & 15)) return fail(1, "picture size %dx%d must be positive multiples of 16", p->width, p->height);
@@ -833,7 +833,8 @@ int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int
   g.spec.valid = false;
   const MeRefDev *rdev = nullptr;
   if (rp && search_planes(list, ref, rp, &rdev, nullptr, nullptr, nullptr, nullptr)) { fatal("ffs"); return ME_INT_MAX; }
-  const bool speculate = g.sub_params.seen && g.sub_params.lambda[0] == lambda_factor && rp != nullptr;
+  // (with ChromaMEEnable the sub-pel stage runs under a different chroma state than this call: no speculation)
+  const bool speculate = g.sub_params.seen && g.sub_params.lambda[0] == lambda_factor && rp != nullptr && !g.p.chroma_me_enable;
   if (speculate) {
     MeSubpelArgs a{};
     a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
@@ -1023,11 +1024,14 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
   }
   {
     ScopedTimer t(2, st);
+    // the sub-pel stage of BlockMotionSearch runs with ChromaMEEnable = (input->ChromaMEEnable == 2) (mv-search.c:779)
+    MeCfgDev sub_cfg = g.cfg;
+    sub_cfg.chroma.on = (g.cfg.chroma.on && g.p.chroma_me_enable == 2) ? 1 : 0;
     int done = 0;
     if (!use_basic_only() && g.pmaps_ok)
       done = me_launch_subpel_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.h_pmaps, g.list_n[0], g.list_n[1], g.d_cur, g.cur_pitch,
-                                          &g.cfg, di, (MeResult *)d_out, st);
-    if (!done) me_launch_subpel_batch((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, (MeResult *)d_out, st);
+                                          &sub_cfg, di, (MeResult *)d_out, st);
+    if (!done) me_launch_subpel_batch((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &sub_cfg, di, (MeResult *)d_out, st);
   }
   g.launches += launched + 1;
   CK(cudaGetLastError());

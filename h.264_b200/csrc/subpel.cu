@@ -176,6 +176,11 @@ me_subpel_batch_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDe
       const MeBiW nobw = { 0, 0, 0, 0, 0 };
       int d = use8 ? tile_dist<8>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw)
                    : tile_dist<4>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw);
+      // chroma terms of computeSAD / computeSSE (me_distortion.c:376-402, :1069-1091): once per block, by the lane of its first tile
+      if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && ref.chroma[0])
+        for (int k = 0; k < 2; k++)
+          d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, job.opix_x + 4 * px, job.opix_y + 4 * py, me_bsx(t), me_bsy(t),
+                                               ref, x4, y4, nullptr, 0, 0);
       atomicAdd(&cost_s[p][c], d);
     }
     __syncthreads();
@@ -261,7 +266,13 @@ __device__ void subpel_block(const MeRefDev &r1, const MeRefDev &r2, const uint8
         const uint8_t *p2 = tile_ptr(r2, x4, y4, bx, by, metric == 2);
         d = use8 ? tile_dist<8>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw)
                  : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
+        if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0] && r2.chroma[0])      // computeBiPredSAD1 :516-543
+          for (int k = 0; k < 2; k++)
+            d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, fx4, fy4, &r2, x4, y4);
       }
+      if (!a.bi && cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0])                // computeSAD / SSE :376-402
+        for (int k = 0; k < 2; k++)
+          d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, x4, y4, nullptr, 0, 0);
       atomicAdd(&sc.cost_s[c], d);
     }
     __syncthreads();

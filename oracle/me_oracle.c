@@ -442,12 +442,19 @@ int ora_satd_block(const uint8_t *src, int src_stride, int bsx, int bsy, const o
   return s;
 }
 
+static int cr_block_dist(int sse, int pic_pix_x, int pic_pix_y, int bsx, int bsy, const ora_ref *r1, int x41, int y41,
+                         const ora_ref *r2, int x42, int y42);
+
+/* pic_pix_x / y: position of the block in the picture (for the chroma terms of computeSAD / computeSSE, me_distortion.c:376-402,
+ * :1069-1091, when the global ChromaMEEnable is set; computeSATD has none) */
 static int unipred(const ora_cfg *c, int level, const uint8_t *src, int stride, int bsx, int bsy,
-                   const ora_ref *r, int x4, int y4, int use8x8)
+                   const ora_ref *r, int x4, int y4, int use8x8, int pic_pix_x, int pic_pix_y)
 {
+  int chroma = (g_cr.enable && r->crec[0] && c->metric[level] != 2)
+               ? cr_block_dist(c->metric[level], pic_pix_x, pic_pix_y, bsx, bsy, r, x4, y4, NULL, 0, 0) : 0;
   switch (c->metric[level]) {       /* computeUniPred[] set-up, mv-search.c:400-424 */
-    case 0:  return ora_sad_block(src, stride, bsx, bsy, r, x4, y4);
-    case 1:  return sse_block(src, stride, bsx, bsy, r, x4, y4);
+    case 0:  return ora_sad_block(src, stride, bsx, bsy, r, x4, y4) + chroma;
+    case 1:  return sse_block(src, stride, bsx, bsy, r, x4, y4) + chroma;
     default: return ora_satd_block(src, stride, bsx, bsy, r, x4, y4, use8x8);
   }
 }
@@ -489,7 +496,7 @@ int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_r
     cx = *mv_x + 2 * sx[pos]; cy = *mv_y + 2 * sy[pos];
     mcost = ora_mv_cost(lambda[1], cx, cy, pmv_x, pmv_y);
     if (mcost >= min_mcost) continue;
-    mcost += unipred(c, 1, src, cur_stride, bsx, bsy, r, cx + p4x, cy + p4y, use8x8);
+    mcost += unipred(c, 1, src, cur_stride, bsx, bsy, r, cx + p4x, cy + p4y, use8x8, pic_pix_x, pic_pix_y);
     if (pos == 0 && check0) mcost -= (lambda[1] * 16) >> 16;      /* WEIGHTED_COST(lambda, 16), :439-442 */
     if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
   }
@@ -500,7 +507,7 @@ int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_r
     cx = *mv_x + sx[pos]; cy = *mv_y + sy[pos];
     mcost = ora_mv_cost(lambda[2], cx, cy, pmv_x, pmv_y);
     if (mcost >= min_mcost) continue;
-    mcost += unipred(c, 2, src, cur_stride, bsx, bsy, r, cx + p4x, cy + p4y, use8x8);
+    mcost += unipred(c, 2, src, cur_stride, bsx, bsy, r, cx + p4x, cy + p4y, use8x8, pic_pix_x, pic_pix_y);
     if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
   }
   if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }
@@ -742,8 +749,14 @@ void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const o
     if (out_int) { out_int->mv[p][0] = mx; out_int->mv[p][1] = my; out_int->cost[p] = cost; }
     mx = (short)(mx << 2); my = (short)(my << 2);
     if (!start_hp(c)) cost = INT_MAX;
-    cost = ora_subpel(c, cur, cur_stride, r, ppx, ppy, t, job->ref, job->slice_type,
-                      job->pmv[p][0], job->pmv[p][1], &mx, &my, 9, 9, cost, job->lambda);
+    {
+      /* from the sub-pel stage on BlockMotionSearch runs with ChromaMEEnable = (input->ChromaMEEnable == 2) (mv-search.c:779) */
+      int chroma_int = g_cr.enable;
+      g_cr.enable = chroma_int && c->chroma_me == 2;
+      cost = ora_subpel(c, cur, cur_stride, r, ppx, ppy, t, job->ref, job->slice_type,
+                        job->pmv[p][0], job->pmv[p][1], &mx, &my, 9, 9, cost, job->lambda);
+      g_cr.enable = chroma_int;
+    }
     out->mv[p][0] = mx; out->mv[p][1] = my; out->cost[p] = cost;
   }
   free(surf);

@@ -272,7 +272,7 @@ int __wrap_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pi
   int list_offset = img->mb_data[img->current_mb_nr].list_offset;
   int cost;
   dump_current_if_needed();
-  rec[0] = REC_SUBPEL; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->opix_x; rec[4] = img->opix_y;
+  rec[0] = REC_SUBPEL; rec[1] = coded_pic_no; rec[2] = img->type | (ChromaMEEnable << 8);   /* bits 8..: the global ChromaMEEnable */ rec[3] = img->opix_x; rec[4] = img->opix_y;
   rec[5] = list; rec[6] = ref; rec[7] = blocktype; rec[8] = pic_pix_x; rec[9] = pic_pix_y;
   rec[10] = pred_mv_x; rec[11] = pred_mv_y; rec[12] = *mv_x; rec[13] = *mv_y; rec[14] = min_mcost;
   rec[15] = lambda_factor[0]; rec[16] = lambda_factor[1]; rec[17] = lambda_factor[2];
@@ -340,7 +340,7 @@ int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pi
   int list_offset = img->mb_data[img->current_mb_nr].list_offset;
   int cost;
   dump_current_if_needed();
-  rec[0] = REC_BI_SUB; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->opix_x; rec[4] = img->opix_y;
+  rec[0] = REC_BI_SUB; rec[1] = coded_pic_no; rec[2] = img->type | (ChromaMEEnable << 8); rec[3] = img->opix_x; rec[4] = img->opix_y;
   rec[5] = list; rec[6] = ref; rec[7] = blocktype; rec[8] = pic_pix_x; rec[9] = pic_pix_y;
   rec[10] = pred_mv_x; rec[11] = pred_mv_y;
   rec[12] = *mv_x; rec[13] = *mv_y; rec[14] = *s_mv_x; rec[15] = *s_mv_y;

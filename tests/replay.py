@@ -184,7 +184,7 @@ def replay(trace, impl, max_calls=None):
             continue
         pic, ox, oy = int(r[1]), int(r[3]), int(r[4])
         if pic != cur_pic:
-            impl.begin_picture(trace.cur(pic), slice_of.get(pic, int(r[2])), picture_lists(trace, pic), pic)
+            impl.begin_picture(trace.cur(pic), slice_of.get(pic, int(r[2]) & 255), picture_lists(trace, pic), pic)
             cur_pic, cur_mb = pic, None
         if (ox, oy) != cur_mb:
             impl.mb_begin(ox, oy)
@@ -193,9 +193,8 @@ def replay(trace, impl, max_calls=None):
         if t in (REC_FFS, REC_SUBPEL, REC_FULLPEL):
             # weighted-prediction ME: the weights the reference derived for this (list, ref) (0 = off in older fixtures)
             impl.set_weights(lst, ref, int(r[28]), int(r[29]), int(r[30]), int(r[31]))
-        # ChromaMEEnable as the call sees it (the reference resets the global between the stages of BlockMotionSearch); the
-        # sub-pel calls of these runs use SATD, which has no chroma term
-        impl.set_chroma_state(pic, int(r[27]) if t == REC_FFS else int(r[26]) if t in (REC_FULLPEL, REC_BI_FULL) else 0)
+        # ChromaMEEnable as the call sees it (the reference resets the global between the stages of BlockMotionSearch)
+        impl.set_chroma_state(pic, int(r[27]) if t == REC_FFS else int(r[26]) if t in (REC_FULLPEL, REC_BI_FULL) else int(r[2]) >> 8)
         if t in (REC_BI_FULL, REC_BI_SUB):
             # weighted bi-prediction: 1 + log denominator (0 = off), weight1 | weight2 << 16, offsetBi
             w = int(r[30])

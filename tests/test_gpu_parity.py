@@ -260,15 +260,15 @@ def test_batch_weighted_prediction(pkg, oracle_lib, t8):
                 ref.close()
 
 
-@pytest.mark.parametrize("chroma_me,sse", [(1, 0), (2, 0), (1, 1)])
-def test_batch_chroma_terms(pkg, oracle_lib, chroma_me, sse):
+@pytest.mark.parametrize("chroma_me,sse,sub", [(1, 0, (2, 2)), (2, 0, (2, 2)), (1, 1, (2, 2)), (2, 0, (0, 1)), (1, 0, (0, 0))])
+def test_batch_chroma_terms(pkg, oracle_lib, chroma_me, sse, sub):
     """ChromaMEEnable: the fast full search adds the distortion of the co-located chroma block of every 4x4 (me_fullfast.c:776-814);
     the frame batch takes the general search kernel then.  4:2:0 pictures with real chroma, predictors that push windows out of
     the picture (chroma origin clamp), SAD and squared error"""
     from h264_b200 import synth
     ob = oracle_lib
     w, h, n_refs = 176, 144, 2
-    d, cfg = _cfg(ob, chroma_me=chroma_me, metric=(sse, 2, 2), search_range=16)
+    d, cfg = _cfg(ob, chroma_me=chroma_me, metric=(sse,) + sub, search_range=16)
     yuv = synth.yuv420_frames(w, h, n_refs + 1)
     rng = np.random.default_rng(71)
     yuv = [(y, np.clip(u.astype(int) + rng.integers(-20, 21, u.shape), 0, 255).astype(np.uint8),
@@ -286,13 +286,14 @@ def test_batch_chroma_terms(pkg, oracle_lib, chroma_me, sse):
         me.set_current_chroma(cur[1], cur[2])
         me.set_chroma_state(chroma_me)
         out, out_int = me.frame_search(jobs, want_int=True)
-    ob.set_chroma(chroma_me, 4, cur[1], cur[2], (3, 3))
+    # integer-pel stage: chroma on; sub-pel stage: on only for value 2 (mv-search.c:612, :779) -- the oracle's composite does the same
     try:
         sel = np.sort(rng.choice(len(jobs), 120, replace=False))
         for r in range(n_refs):
             s_ = sel[jobs["ref"][sel] == r]
             ref = ob.Ref(yuv[-2 - r][0])
             ref.set_chroma(yuv[-2 - r][1], yuv[-2 - r][2])
+            ob.set_chroma(chroma_me, 4, cur[1], cur[2], (3, 3))
             exp, exp_int = ob.mb_search(cfg, np.ascontiguousarray(cur[0]), ref, jobs[s_])
             assert np.array_equal(out_int[s_], exp_int), r
             assert np.array_equal(out[s_], exp), r

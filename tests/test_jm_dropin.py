@@ -52,7 +52,8 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
 @pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0", "yuv444_3ref_bframes", "sr64_2ref",
                                   "hd1080_sr32_ip", "weighted_pred_fade", "weighted_bipred_fade", "full_search_mode_rdopt0",
                                   "full_search_mode_satd", "yuv444_independent_planes", "chroma_me_2_bframes",
-                                  "chroma_me_1_full_search_rdopt0", "chroma_me_1_yuv422"])
+                                  "chroma_me_1_full_search_rdopt0", "chroma_me_1_yuv422", "chroma_me_2_sad_sse_subpel",
+                                  "chroma_me_1_sad_subpel"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -82,6 +83,14 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     elif case == "chroma_me_1_full_search_rdopt0":
         args = ["-d", "encoder_main.cfg", "-p", "ChromaMEEnable=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2",
                 "-p", "SearchMode=-1", "-p", "RDOptimization=0"]
+    elif case == "chroma_me_2_sad_sse_subpel":
+        # chroma terms also in the sub-pel stages (SAD half-pel, SSE quarter-pel) and in the bi-predictive sub-pel refinement
+        args = ["-d", "encoder.cfg", "-p", "ChromaMEEnable=2", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2",
+                "-p", "MEDistortionHPel=0", "-p", "MEDistortionQPel=1"]
+    elif case == "chroma_me_1_sad_subpel":
+        # value 1: the sub-pel stages run WITHOUT chroma although their metric would carry the term
+        args = ["-d", "encoder_main.cfg", "-p", "ChromaMEEnable=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2",
+                "-p", "MEDistortionHPel=0", "-p", "MEDistortionQPel=0"]
     elif case == "chroma_me_1_yuv422":
         args = ["-d", "encoder_yuv422.cfg", "-p", "ChromaMEEnable=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
     elif case == "hd1080_sr32_ip":
