@@ -25,6 +25,9 @@ struct MeRefDev {
   // bytes; nullptr when the caller has not supplied them
   const uint8_t *chroma[2];
   int cw, ch, cpitch;
+  // 4:4:4: chroma[k] is instead the 16-plane set built from the U / V plane by the luma interpolator (image.c:1647-1657),
+  // cplane_stride bytes per plane (0 for 4:2:0 / 4:2:2)
+  size_t cplane_stride;
 };
 
 // Chroma terms of the integer-pel searches (ChromaMEEnable; me_fullfast.c:776-814, me_distortion.c:376-402, :516-543).
@@ -128,6 +131,8 @@ __device__ __forceinline__ const uint8_t *me_umv_ptr(const MeRefDev &r, int y4, 
 // rshift_rnd_sf(., 6) (generateChroma00/01/10/XX, img_chroma.c:34-372)
 __device__ __forceinline__ int me_cr_pel(const MeRefDev &r, const MeChromaDev &c, int k, int ypos, int xpos, int sy, int sx)
 {
+  if (r.cplane_stride)      // 4:4:4: a stored quarter-pel plane set, addressed like luma (refbuf.c:53 with shift 2, mask 3)
+    return r.chroma[k][(size_t)((sy << 2) | sx) * r.cplane_stride + (size_t)ypos * r.cpitch + xpos];
   const int jy = ypos - ((4 * ME_PAD) >> c.shift_y), ix = xpos - ((4 * ME_PAD) >> c.shift_x);
   const int y0 = me_clamp(jy, 0, r.ch - 1), y1 = me_clamp(jy + 1, 0, r.ch - 1), x0 = me_clamp(ix, 0, r.cw - 1), x1 = me_clamp(ix + 1, 0, r.cw - 1);
   const int kk = sy << (3 - c.shift_y), ll = sx << (3 - c.shift_x);

@@ -81,7 +81,10 @@ struct TensorMap { alignas(64) unsigned char bytes[128]; };   // CUtensorMap
 struct RefPic {
   bool used = false;
   uint8_t *chroma = nullptr;    // ChromaMEEnable: both reconstructed chroma planes, one allocation (U then V)
+  me_ref_handle chroma444[2] = {0, 0};   // 4:4:4: the pictures made from the U / V planes (their plane sets are the chroma sub-images)
+  bool has_chroma() const { return chroma != nullptr || chroma444[0] != 0; }
   unsigned long long gen = 0;   // changes whenever the planes are (re)generated: weighted copies made from them go stale
+  cudaStream_t written_on = nullptr;   // stream of the last plane generation (a caller's stream in the *_device calls)
   uint8_t *planes = nullptr, *search = nullptr;
   MeRefDev dev{};
   bool has_map = false;
@@ -253,6 +256,8 @@ int search_planes(int list, int idx, RefPic *r, const MeRefDev **dev, const Tens
         t.has_map = me_make_tensor_map_2d(t.win_map.bytes, t.search, d.sw, d.sh, d.spitch, n + 16, n) == 0;
       t.has_pmap = me_make_planes_tensor_map(t.planes_map.bytes, t.planes, d.pitch, d.hp, d.plane_stride) == 0;
     }
+    // the planes may have been generated on a caller's stream (me_cuda_ref_create_device / me_cuda_ref_update_device)
+    if (r->written_on && r->written_on != g.stream) CK(cudaStreamSynchronize(r->written_on));
     { ScopedTimer tm(0, g.stream);
       me_launch_weight_planes(r->planes, t.planes, pb, w.weight, w.offset, w.denom, g.stream);
       me_launch_weight_planes(r->search, t.search, sb, w.weight, w.offset, w.denom, g.stream); }
@@ -277,7 +282,7 @@ int upload_table()
       RefPic *r = ref_of(g.list[l][i]);
       if (!r) return fail(3, "reference list %d entry %d holds an invalid handle", l, i);
       const MeRefDev *dev; const TensorMap *wm, *pm; bool hm, hp;
-      if (g.p.chroma_me_enable && !r->chroma)
+      if (g.p.chroma_me_enable && !r->has_chroma())
         return fail(3, "reference list %d entry %d has no chroma planes (ChromaMEEnable: call me_cuda_ref_set_chroma after creating the picture)", l, i);
       if (int rc = search_planes(l, i, r, &dev, &wm, &hm, &pm, &hp)) return rc;
       g.h_table[l * ME_MAX_REFS + i] = *dev;
@@ -335,6 +340,7 @@ int create_ref_common(const uint8_t *d_luma, int stride, int w, int h, cudaStrea
   g.launches += 2;
   CK(cudaGetLastError());
   r.used = true;
+  r.written_on = st;
   r.gen = ++g.gen_counter;
   *out = (me_ref_handle)(slot + 1);
   return 0;
@@ -350,6 +356,7 @@ int update_ref_common(me_ref_handle h, const uint8_t *d_luma, int stride, cudaSt
   g.launches += 2;
   CK(cudaGetLastError());
   r->gen = ++g.gen_counter;
+  r->written_on = st;
   for (int l = 0; l < 2; l++)    // weighted copies of these planes are rebuilt with the next table
     for (int i = 0; i < g.list_n[l]; i++) if (g.twin[l][i].valid && g.twin[l][i].src == h) g.table_dirty = true;
   return 0;
@@ -389,8 +396,8 @@ int me_cuda_init(const me_cuda_params *p)
   if (p->bit_depth != 8) return fail(1, "bit depth %d not supported (8-bit content only)", p->bit_depth);
   if (p->chroma_me_enable < 0 || p->chroma_me_enable > 2) return fail(1, "ChromaMEEnable %d outside 0..2", p->chroma_me_enable);
   if (p->chroma_me_enable) {
-    if (p->yuv_format != 1 && p->yuv_format != 2)
-      return fail(1, "ChromaMEEnable needs yuv_format 1 (4:2:0) or 2 (4:2:2); the 4:4:4 chroma sub-images are not implemented");
+    if (p->yuv_format < 1 || p->yuv_format > 3)
+      return fail(1, "ChromaMEEnable needs yuv_format 1 (4:2:0), 2 (4:2:2) or 3 (4:4:4)");
     if (p->me_metric[0] == 2)
       return fail(1, "ChromaMEEnable with a Hadamard integer-pel metric is not implemented");
     if (p->weighted_me) return fail(1, "ChromaMEEnable together with weighted-prediction ME is not implemented");
@@ -420,8 +427,8 @@ int me_cuda_init(const me_cuda_params *p)
   if (p->chroma_me_enable) {
     g.cfg.chroma.on = p->chroma_me_enable;                             // until me_cuda_set_chroma_state says otherwise
     g.cfg.chroma.weight = p->chroma_me_weight;
-    g.cfg.chroma.shift_x = 3; g.cfg.chroma.shift_y = p->yuv_format == 1 ? 3 : 2;       // lencod.c:2856-2870
-    g.chroma_w = p->width >> 1; g.chroma_h = p->yuv_format == 1 ? p->height >> 1 : p->height;
+    g.cfg.chroma.shift_x = p->yuv_format == 3 ? 2 : 3; g.cfg.chroma.shift_y = p->yuv_format == 1 ? 3 : 2;       // lencod.c:2856-2879
+    g.chroma_w = p->yuv_format == 3 ? p->width : p->width >> 1; g.chroma_h = p->yuv_format == 1 ? p->height >> 1 : p->height;
     g.cfg.chroma.cur_pitch = align_up(g.chroma_w, 16);
     CK(cudaMalloc((void **)&g.d_cur_c, (size_t)2 * g.cfg.chroma.cur_pitch * g.chroma_h));
     CK(cudaMemset(g.d_cur_c, 128, (size_t)2 * g.cfg.chroma.cur_pitch * g.chroma_h));
@@ -667,6 +674,7 @@ static int ref_set_chroma_common(me_ref_handle h, const uint8_t *u, const uint8_
 {
   g.spec.valid = false;
   if (int rc = chroma_check("me_cuda_ref_set_chroma", cw, ch)) return rc;
+  if (g.p.yuv_format == 3) return fail(1, "me_cuda_ref_set_chroma: in 4:4:4 the chroma sub-images are plane sets (me_cuda_ref_set_chroma_planes)");
   RefPic *r = ref_of(h);
   if (!r) return fail(3, "me_cuda_ref_set_chroma: invalid handle %d", (int)h);
   const int pitch = align_up(cw, 16);
@@ -684,6 +692,19 @@ int me_cuda_ref_set_chroma(me_ref_handle h, const me_imgpel *const *u_rows, cons
 int me_cuda_ref_set_chroma_u8(me_ref_handle h, const uint8_t *u, const uint8_t *v, int stride, int cw, int ch)
 {
   return ref_set_chroma_common(h, u, v, stride, nullptr, nullptr, cw, ch);
+}
+int me_cuda_ref_set_chroma_planes(me_ref_handle h, me_ref_handle hu, me_ref_handle hv)
+{
+  g.spec.valid = false;
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (!g.p.chroma_me_enable || g.p.yuv_format != 3) return fail(1, "me_cuda_ref_set_chroma_planes is for ChromaMEEnable in 4:4:4");
+  RefPic *r = ref_of(h), *ru = ref_of(hu), *rv = ref_of(hv);
+  if (!r || !ru || !rv) return fail(3, "me_cuda_ref_set_chroma_planes: invalid handle (%d, %d, %d)", (int)h, (int)hu, (int)hv);
+  r->chroma444[0] = hu; r->chroma444[1] = hv;
+  r->dev.chroma[0] = ru->planes; r->dev.chroma[1] = rv->planes;
+  r->dev.cw = ru->dev.w; r->dev.ch = ru->dev.h; r->dev.cpitch = ru->dev.pitch; r->dev.cplane_stride = ru->dev.plane_stride;
+  g.table_dirty = true;
+  return 0;
 }
 int me_cuda_set_current_chroma(const me_imgpel *const *u_rows, const me_imgpel *const *v_rows, int cw, int ch)
 {
@@ -777,7 +798,7 @@ int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
   if (list < 0 || list > 1 || ref < 0 || ref >= g.list_n[list]) return fail(1, "me_cuda_ffs_setup: (list %d, ref %d) not in the reference lists", list, ref);
   RefPic *r = ref_of(g.list[list][ref]);
   if (!r) return fail(3, "me_cuda_ffs_setup: stale reference handle");
-  if (g.cfg.chroma.on && !r->chroma) return fail(3, "me_cuda_ffs_setup: (list %d, ref %d) has no chroma planes (me_cuda_ref_set_chroma)", list, ref);
+  if (g.cfg.chroma.on && !r->has_chroma()) return fail(3, "me_cuda_ffs_setup: (list %d, ref %d) has no chroma planes (me_cuda_ref_set_chroma)", list, ref);
   int R = setup_range_of(ref);
   int cx = pmv16_x / 4, cy = pmv16_y / 4;                                          // me_fullfast.c:552-553
   if (!g.cfg.rdopt) { cx = me_clamp(cx, -R, R); cy = me_clamp(cy, -R, R); }       // :555-560
@@ -876,7 +897,7 @@ int me_cuda_FullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic
   if (blocktype < 1 || blocktype > 7 || search_range < 0 || search_range > 64) {
     fail(1, "me_cuda_FullPelBlockMotionSearch: block type %d / search range %d out of range", blocktype, search_range); fatal("fullpel"); return ME_INT_MAX;
   }
-  if (g.cfg.chroma.on && !r->chroma) { fail(3, "me_cuda_FullPelBlockMotionSearch: reference without chroma planes (me_cuda_ref_set_chroma)"); fatal("fullpel"); return ME_INT_MAX; }
+  if (g.cfg.chroma.on && !r->has_chroma()) { fail(3, "me_cuda_FullPelBlockMotionSearch: reference without chroma planes (me_cuda_ref_set_chroma)"); fatal("fullpel"); return ME_INT_MAX; }
   const MeRefDev *dev;
   if (search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) { fatal("fullpel"); return ME_INT_MAX; }
   MeFullPelArgs a{};
@@ -938,7 +959,7 @@ int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic
   if (!r1 || !r2) { fail(1, "me_cuda_FullPelBlockMotionBiPred: reference lists incomplete"); fatal("bipred"); return ME_INT_MAX; }
   if (g.cfg.metric[0] == 2) { fail(1, "bi-predictive integer search with a Hadamard metric is not implemented"); fatal("bipred"); return ME_INT_MAX; }
   if (search_range > 64) { fail(1, "bi-pred search range %d too large", search_range); fatal("bipred"); return ME_INT_MAX; }
-  if (g.cfg.chroma.on && (!r1->chroma || !r2->chroma)) { fail(3, "me_cuda_FullPelBlockMotionBiPred: reference without chroma planes (me_cuda_ref_set_chroma)"); fatal("bipred"); return ME_INT_MAX; }
+  if (g.cfg.chroma.on && (!r1->has_chroma() || !r2->has_chroma())) { fail(3, "me_cuda_FullPelBlockMotionBiPred: reference without chroma planes (me_cuda_ref_set_chroma)"); fatal("bipred"); return ME_INT_MAX; }
   if (g.cfg.chroma.on && g.bw[list].apply) { fail(1, "weighted bi-prediction together with ChromaMEEnable is not implemented"); fatal("bipred"); return ME_INT_MAX; }
   MeBiFullArgs a{};
   a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "me_cuda_measure_int_peak", "me_cuda_ref_update_u8", "me_cuda_ref_update_device", "me_cuda_set_timing",
     "me_cuda_kernel_time_ms", "me_cuda_set_ref_weights", "me_cuda_set_bipred_weights",
     "me_cuda_set_current_chroma", "me_cuda_set_current_chroma_u8", "me_cuda_ref_set_chroma", "me_cuda_ref_set_chroma_u8",
-    "me_cuda_set_chroma_state",
+    "me_cuda_set_chroma_state", "me_cuda_ref_set_chroma_planes",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library(path=LIB_PATH):
     L.me_cuda_set_current_chroma_u8.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.me_cuda_ref_set_chroma_u8.argtypes = [C.c_int32, vp, vp, C.c_int, C.c_int, C.c_int]
     L.me_cuda_set_chroma_state.argtypes = [C.c_int]
+    L.me_cuda_ref_set_chroma_planes.argtypes = [C.c_int32] * 3
     L.me_cuda_set_bipred_weights.argtypes = [C.c_int] * 6
     L.me_cuda_mb_begin.argtypes = [C.c_int, C.c_int]
     L.me_cuda_ffs_setup.argtypes = [C.c_int] * 4
@@ -225,6 +226,10 @@ class MeCuda:
     def ref_set_chroma(self, h, u, v):
         u, v = np.ascontiguousarray(u, np.uint8), np.ascontiguousarray(v, np.uint8)
         self._check(self.L.me_cuda_ref_set_chroma_u8(h, u.ctypes.data, v.ctypes.data, u.strides[0], u.shape[1], u.shape[0]))
+
+    def ref_set_chroma_planes(self, h, h_u, h_v):
+        """4:4:4: attach the pictures made from the U and V planes (their quarter-pel plane sets are the chroma sub-images)"""
+        self._check(self.L.me_cuda_ref_set_chroma_planes(h, h_u, h_v))
 
     def set_chroma_state(self, enable):
         """the global ChromaMEEnable as the next search call sees it (mv-search.c:612, :779)"""

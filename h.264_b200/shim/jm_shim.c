@@ -55,6 +55,7 @@ static struct {
   int  (*set_current_chroma)(const me_imgpel *const *, const me_imgpel *const *, int, int);
   int  (*ref_set_chroma)(me_ref_handle, const me_imgpel *const *, const me_imgpel *const *, int, int);
   int  (*set_chroma_state)(int);
+  int  (*ref_set_chroma_planes)(me_ref_handle, me_ref_handle, me_ref_handle);
   int  (*mb_begin)(int, int);
   int  (*ffs_setup)(int, int, int, int);
   int  (*ffs_is_set_up)(int, int);
@@ -118,7 +119,7 @@ static void load_library(void)
   L.set_slice_type = sym("me_cuda_set_slice_type"); L.mb_begin = sym("me_cuda_mb_begin");
   L.set_ref_weights = sym("me_cuda_set_ref_weights"); L.set_bipred_weights = sym("me_cuda_set_bipred_weights");
   L.set_current_chroma = sym("me_cuda_set_current_chroma"); L.ref_set_chroma = sym("me_cuda_ref_set_chroma");
-  L.set_chroma_state = sym("me_cuda_set_chroma_state");
+  L.set_chroma_state = sym("me_cuda_set_chroma_state"); L.ref_set_chroma_planes = sym("me_cuda_ref_set_chroma_planes");
   L.ffs_setup = sym("me_cuda_ffs_setup"); L.ffs_is_set_up = sym("me_cuda_ffs_is_set_up");
   L.fullpel = sym("me_cuda_FullPelBlockMotionSearch");
   L.ffs = sym("me_cuda_FastFullPelBlockMotionSearch"); L.subpel = sym("me_cuda_SubPelBlockMotionSearch");
@@ -213,8 +214,12 @@ void __wrap_getSubImagesLuma(StorablePicture *s)
   int i, plane = 0;
   if (!active) { __real_getSubImagesLuma(s); return; }
   if (IS_INDEPENDENT(input)) plane = s->colour_plane_id;      /* set by UnifiedOneForthPix_JV (image.c:1706) right before this call */
-  /* 4:4:4 common mode runs this routine on the U and V planes too; those (host motion compensation only) stay on the CPU */
-  else if (s->p_curr_img != s->imgY) { __real_getSubImagesLuma(s); return; }
+  /* 4:4:4 common mode runs this routine on the U and V planes too (image.c:1647-1657).  Those plane sets are the chroma sub-images
+   * of ChromaMEEnable; without it they only serve the host's motion compensation and stay on the CPU */
+  else if (s->p_curr_img != s->imgY) {
+    if (!input->ChromaMEEnable) { __real_getSubImagesLuma(s); return; }
+    plane = (s->p_curr_img == s->imgUV[0]) ? 1 : 2;
+  }
   /* a picture structure can be reallocated at the same address: drop a stale mapping, and forget pictures that
    * left the decoded picture buffer through a call path that bypasses the wrapped free (same translation unit) */
   for (i = n_map - 1; i >= 0; i--)
@@ -225,9 +230,14 @@ void __wrap_getSubImagesLuma(StorablePicture *s)
   map[n_map].p = s; map[n_map].plane = plane; map[n_map].h = h; n_map++;
   /* ChromaMEEnable: the searches read the chroma sub-images of this picture (getSubImagesChroma, image.c:1659, still runs on the
    * host for motion compensation); the library evaluates them from the reconstructed chroma planes */
-  if (input->ChromaMEEnable &&
+  if (input->ChromaMEEnable && img->yuv_format != YUV444 &&
       L.ref_set_chroma(h, (const me_imgpel *const *)s->imgUV[0], (const me_imgpel *const *)s->imgUV[1], s->size_x_cr, s->size_y_cr))
     die("me_cuda_ref_set_chroma");
+  if (input->ChromaMEEnable && img->yuv_format == YUV444 && !IS_INDEPENDENT(input) && plane == 2) {
+    me_ref_handle hy = 0, hu = 0;
+    for (i = 0; i < n_map; i++) if (map[i].p == s) { if (map[i].plane == 0) hy = map[i].h; else if (map[i].plane == 1) hu = map[i].h; }
+    if (!hy || !hu || L.ref_set_chroma_planes(hy, hu, h)) die("me_cuda_ref_set_chroma_planes");
+  }
 }
 
 void __real_free_storable_picture(StorablePicture *p);

@@ -65,7 +65,7 @@ typedef struct me_cuda_params {
   int32_t weighted_me;          /* informational: weighted-prediction ME in use (weights arrive through me_cuda_set_ref_weights) */
   int32_t device;               /* CUDA device ordinal; -1: env ME_CUDA_DEVICE, else 0 */
   int32_t chroma_me_weight;     /* input->ChromaMEWeight (used when chroma_me_enable != 0) */
-  int32_t yuv_format;           /* img->yuv_format: 1 = 4:2:0, 2 = 4:2:2 (chroma_me_enable != 0 needs one of these); 0 = not given */
+  int32_t yuv_format;           /* img->yuv_format: 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (needed when chroma_me_enable != 0); 0 = not given */
   int32_t reserved[6];
 } me_cuda_params;
 
@@ -120,12 +120,12 @@ int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset
  * drop-in calls and by me_cuda_frame_bipred. */
 int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom);
 
-/* ---- chroma terms of the integer-pel searches (cfg ChromaMEEnable = 1 or 2, 4:2:0 and 4:2:2): the fast full search adds the
+/* ---- chroma terms of the searches (cfg ChromaMEEnable = 1 or 2): the fast full search adds the
  * distortion of the co-located chroma block of every 4x4 (me_fullfast.c:776-814), computeSAD / computeSSE and their
  * bi-predictive forms add ChromaMEWeight times the chroma block distortion of each component (me_distortion.c:376-402,
  * :516-543, :1069-1091); the Hadamard functions have no chroma term.  Reference samples are the 1/8-sample sub-images of
  * getSubImagesChroma (img_chroma.c:374), read through UMVLine8X_chroma (refbuf.c:53); the library evaluates them on the fly
- * from the reconstructed chroma planes.  Supported with SAD or SSE as the integer-pel metric, any sub-pel metric, and
+ * from the reconstructed chroma planes (4:2:0, 4:2:2; for 4:4:4 see me_cuda_ref_set_chroma_planes).  Supported with SAD or SSE as the integer-pel metric, any sub-pel metric, and
  * without weighted prediction; me_cuda_init fails otherwise.
  *   me_cuda_set_current_chroma : imgUV_org[0..1] of the picture being coded (cw x ch samples each)
  *   me_cuda_ref_set_chroma     : StorablePicture::imgUV[0..1] of a reference picture, after me_cuda_ref_create
@@ -137,6 +137,10 @@ int me_cuda_set_current_chroma(const me_imgpel *const *u_rows, const me_imgpel *
 int me_cuda_set_current_chroma_u8(const uint8_t *u, const uint8_t *v, int stride, int cw, int ch);
 int me_cuda_ref_set_chroma(me_ref_handle h, const me_imgpel *const *u_rows, const me_imgpel *const *v_rows, int cw, int ch);
 int me_cuda_ref_set_chroma_u8(me_ref_handle h, const uint8_t *u, const uint8_t *v, int stride, int cw, int ch);
+/* 4:4:4 (common mode): the chroma sub-images are made by the luma interpolator from the U and V planes (image.c:1647-1657), so
+ * they are ordinary pictures of this library: create them with me_cuda_ref_create from StorablePicture::imgUV[0] / [1] and
+ * attach them to the luma picture.  The three handles are destroyed separately. */
+int me_cuda_ref_set_chroma_planes(me_ref_handle h, me_ref_handle h_u, me_ref_handle h_v);
 int me_cuda_set_chroma_state(int enable);
 
 /* ---- per macroblock: ResetFastFullIntegerSearch (me_fullfast.c:197, called macroblock.c:509) ---- */

@@ -75,6 +75,7 @@ def lib():
         L.ora_ref_plane.argtypes = [vp, C.c_int, C.c_int]
         L.ora_ref_set_weights.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.ora_ref_set_chroma.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
+        L.ora_ref_set_chroma444.argtypes = [vp, vp, vp]
         L.ora_set_chroma.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int]
         L.ora_set_bipred_weights.argtypes = [C.c_int] * 6
         L.ora_select_bipred_list.argtypes = [C.c_int]
@@ -143,6 +144,11 @@ class Ref:
         """ChromaMEEnable: the picture's reconstructed chroma planes (uint8, same shape)"""
         u, v = np.ascontiguousarray(u, np.uint8), np.ascontiguousarray(v, np.uint8)
         lib().ora_ref_set_chroma(self.ptr, u.ctypes.data, v.ctypes.data, u.strides[0], u.shape[1], u.shape[0])
+
+    def set_chroma444(self, ref_u, ref_v):
+        """4:4:4: the plane sets (Ref objects, kept alive by the caller) built from the picture's U and V planes"""
+        self._c444 = (ref_u, ref_v)
+        lib().ora_ref_set_chroma444(self.ptr, ref_u.ptr, ref_v.ptr)
 
     def set_weights(self, apply, weight=32, offset=0, log_denom=5):
         """weighted-prediction ME: the weights of the (list, ref) entry this picture is about to be searched as"""

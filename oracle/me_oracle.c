@@ -201,6 +201,13 @@ void ora_ref_set_chroma(ora_ref *r, const uint8_t *u, const uint8_t *v, int stri
   r->cw = cw; r->ch = ch;
 }
 
+void ora_ref_set_chroma444(ora_ref *r, const ora_ref *u, const ora_ref *v)
+{
+  r->c444[0] = u; r->c444[1] = v;
+  r->cw = r->w; r->ch = r->h;
+}
+static inline int has_chroma(const ora_ref *r) { return r->crec[0] != NULL || r->c444[0] != NULL; }
+
 /* geometry of the chroma sub-images: padding = luma padding in chroma samples (img_pad_size_uv_x/y, lencod.c:2856-2879), macroblock
  * size in chroma samples (mb_cr_size_x/y, lencod.c:622-623) */
 static inline int cr_pad_x(void) { return (4 * PAD) >> g_cr.shift_x; }
@@ -213,6 +220,7 @@ static inline int cr_mb_y(void) { return 64 >> g_cr.shift_y; }
  * (generateChroma00/01/10/XX, img_chroma.c:34-372: the padding rows / columns repeat the first / last row / column). */
 static int cr_pel(const ora_ref *r, int k, int ypos, int xpos, int sy, int sx)
 {
+  if (r->c444[k]) return r->c444[k]->plane[sy][sx][(size_t)ypos * r->c444[k]->wp + xpos];     /* 4:4:4: a luma-style plane set */
   int jy = ypos - cr_pad_y(), ix = xpos - cr_pad_x();
   int y0 = clampi(jy, 0, r->ch - 1), y1 = clampi(jy + 1, 0, r->ch - 1), x0 = clampi(ix, 0, r->cw - 1), x1 = clampi(ix + 1, 0, r->cw - 1);
   int kk = sy << (3 - g_cr.shift_y), ll = sx << (3 - g_cr.shift_x);          /* vertical / horizontal offset in eighths */
@@ -303,7 +311,7 @@ void ora_ffs_surfaces(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
         int d = refpel(r, rp[(size_t)y * r->wp + x]) - (int)cur[(size_t)(opix_y + y) * cur_stride + opix_x + x];
         leaf[(y >> 2) * 4 + (x >> 2)] += c->metric[0] ? d * d : iabs_(d);
       }
-    if (g_cr.enable && r->crec[0]) {
+    if (g_cr.enable && has_chroma(r)) {
       /* me_fullfast.c:776-814: the co-located chroma block of every 4x4 luma block, both components, added as it is
        * (no ChromaMEWeight here) */
       int k, yp, xp, sy_, sx_, cy, cx, mbx = cr_mb_x(), mby = cr_mb_y();
@@ -450,7 +458,7 @@ static int cr_block_dist(int sse, int pic_pix_x, int pic_pix_y, int bsx, int bsy
 static int unipred(const ora_cfg *c, int level, const uint8_t *src, int stride, int bsx, int bsy,
                    const ora_ref *r, int x4, int y4, int use8x8, int pic_pix_x, int pic_pix_y)
 {
-  int chroma = (g_cr.enable && r->crec[0] && c->metric[level] != 2)
+  int chroma = (g_cr.enable && has_chroma(r) && c->metric[level] != 2)
                ? cr_block_dist(c->metric[level], pic_pix_x, pic_pix_y, bsx, bsy, r, x4, y4, NULL, 0, 0) : 0;
   switch (c->metric[level]) {       /* computeUniPred[] set-up, mv-search.c:400-424 */
     case 0:  return ora_sad_block(src, stride, bsx, bsy, r, x4, y4) + chroma;
@@ -539,7 +547,7 @@ static int unipred_exit(const ora_cfg *c, const uint8_t *src, int stride, int bs
       }
       if (m >= thr) return m;
     }
-    if (g_cr.enable && r->crec[0]) {
+    if (g_cr.enable && has_chroma(r)) {
       /* chroma terms (me_distortion.c:376-402): one component after the other, each followed by the same early exit */
       int scx = g_cr.shift_x - 2, scy = g_cr.shift_y - 2, k;
       int bx = bsx >> scx, by = bsy >> scy, cx0 = pic_pix_x >> scx, cy0 = pic_pix_y >> scy;
@@ -633,7 +641,7 @@ static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stri
         int e = (int)src[(size_t)y * stride + x] - bipel(a[(size_t)y * r1->wp + x], b[(size_t)y * r2->wp + x]);
         s += metric ? e * e : iabs_(e);
       }
-    if (g_cr.enable && r1->crec[0] && r2->crec[0])     /* computeBiPredSAD1 :516-543 (weighted chroma is not restated) */
+    if (g_cr.enable && has_chroma(r1) && has_chroma(r2))     /* computeBiPredSAD1 :516-543 (weighted chroma is not restated) */
       s += cr_block_dist(metric, pic_pix_x, pic_pix_y, bsx, bsy, r1, x41, y41, r2, x42, y42);
     return s;
   } else {

@@ -36,6 +36,8 @@ typedef struct ora_ref {
   /* reconstructed chroma (StorablePicture::imgUV), for ChromaMEEnable; NULL when not set */
   uint8_t *crec[2];
   int cw, ch;
+  /* 4:4:4: the chroma sub-images are made by the luma interpolator (image.c:1647-1657): the plane sets of U and V (not owned) */
+  const struct ora_ref *c444[2];
 } ora_ref;
 
 /* tables */
@@ -56,6 +58,8 @@ void     ora_ref_set_weights(ora_ref *r, int apply, int weight, int offset, int 
 
 /* ChromaMEEnable: reconstructed chroma planes of a reference picture (copied) */
 void ora_ref_set_chroma(ora_ref *r, const uint8_t *u, const uint8_t *v, int stride, int cw, int ch);
+/* 4:4:4 (chroma_shift 2, 2): the quarter-pel plane sets built from the picture's U and V planes */
+void ora_ref_set_chroma444(ora_ref *r, const ora_ref *u, const ora_ref *v);
 /* chroma state of the NEXT search call: the global ChromaMEEnable as that call sees it (me_distortion.c:56; mv-search.c:612, :779),
  * input->ChromaMEWeight, the original chroma planes (imgUV_org) and chroma_shift_x / chroma_shift_y (lencod.c:2856-2879:
  * 3,3 for 4:2:0; 3,2 for 4:2:2) */

@@ -41,9 +41,16 @@ class OracleAdapter:
         self.surf = {}
         self.wp = {}
         self.ci = trace.chroma_info()
+        self.crefs = []
         if self.ci:
             for i, r in self.refs.items():
-                r.set_chroma(*trace.chroma("ref", i))
+                u, v = trace.chroma("ref", i)
+                if self.ci["yuv_format"] == 3:            # 4:4:4: chroma sub-images = quarter-pel plane sets of U and V
+                    ru, rv = ob.Ref(u), ob.Ref(v)
+                    self.crefs += [ru, rv]
+                    r.set_chroma444(ru, rv)
+                else:
+                    r.set_chroma(u, v)
         self.trace = trace
 
     def set_chroma_state(self, pic, enable):
@@ -51,7 +58,7 @@ class OracleAdapter:
         if not self.ci:
             return
         u, v = self.trace.chroma("cur", pic)
-        shift = (3, 3) if self.ci["yuv_format"] == 1 else (3, 2)
+        shift = {1: (3, 3), 2: (3, 2), 3: (2, 2)}[self.ci["yuv_format"]]
         self.ob.set_chroma(enable, self.ci["weight"], u, v, shift)
 
     def set_weights(self, lst, ref, apply, weight, offset, denom):
@@ -106,7 +113,7 @@ class OracleAdapter:
         return self.ob.bipred_subpel(self.cfg, self.cur, r1, r2, ppx, ppy, bt, pmv, mv, smv, min_mcost, lam3, sp2, sp4)
 
     def close(self):
-        for r in self.refs.values():
+        for r in list(self.refs.values()) + self.crefs:
             r.close()
 
 
@@ -125,8 +132,12 @@ class CudaAdapter:
                          mv_limits=(cfgkw["mv_limit_min_y"], cfgkw["mv_limit_max_y"]), **ckw)
         self.handles = {i: self.me.ref_create(trace.ref(i)) for i in trace.ref_ids()}
         if self.ci:
-            for i, hd in self.handles.items():
-                self.me.ref_set_chroma(hd, *trace.chroma("ref", i))
+            for i, hd in list(self.handles.items()):
+                u, v = trace.chroma("ref", i)
+                if self.ci["yuv_format"] == 3:
+                    self.me.ref_set_chroma_planes(hd, self.me.ref_create(u), self.me.ref_create(v))
+                else:
+                    self.me.ref_set_chroma(hd, u, v)
 
     def begin_picture(self, cur, slice_type, lists, pic=None):
         self.me.set_current(cur)

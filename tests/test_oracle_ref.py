@@ -45,3 +45,17 @@ def test_oracle_reproduces_every_call_of_the_known_answer_run(tmp_path, oracle_l
     impl.close()
     for name, (n, bad) in res.items():
         assert not bad, (name, n, bad[:3])
+
+
+def test_oracle_reproduces_chroma_me_in_444(tmp_path, oracle_lib):
+    """ChromaMEEnable = 2 in 4:4:4 common mode: the chroma sub-images are plane sets made by the luma interpolator; every traced call
+    (fast full search and bi-predictive integer-pel search carry chroma terms)"""
+    tr = _trace(str(tmp_path), ["-d", "encoder.cfg", "-p", "InputFile=foreman_part_qcif_444.yuv", "-p", "YUVFormat=3", "-p", "ProfileIDC=244",
+                                "-p", "NumberReferenceFrames=2", "-p", "SearchRange=16", "-p", "ChromaMEEnable=2"])
+    assert tr.chroma_info() == dict(enable=2, weight=4, yuv_format=3, cw=176, ch=144)
+    impl = OracleAdapter(tr, cfg_from_trace(tr, search_range=16, full_search=2))
+    res = replay(tr, impl, max_calls=9000)
+    impl.close()
+    for name, (n, bad) in res.items():
+        assert not bad, (name, n, bad[:3])
+    assert res["ffs"][0] > 3000
