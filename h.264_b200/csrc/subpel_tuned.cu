@@ -34,6 +34,7 @@ constexpr int RW = 48;                      // region row pitch (bytes): 2*RD + 
 constexpr int RH = 2 * RD + 17;             // region rows
 constexpr int REGION_BYTES = RW * RH * 16;  // all 16 planes
 constexpr int NT = 128;
+constexpr int T4_CTAS = 7;                  // CTAs per SM of the 4x4-transform variant (72 registers); 8 CTAs at 64 registers measured 0.65 ms instead of 0.60
 constexpr int T8_CTAS = 7;                  // CTAs per SM of the 8x8-transform variant (72 registers, no spills; measured 4: 1.11, 5: 1.01, 6: 0.95 ms)
 constexpr unsigned BIAS = 0x1000u, BIAS2 = 0x10001000u;       // 4x4 Hadamard: |coefficient| <= 16 * 255 < 4096
 constexpr unsigned BIAS8 = 0x4000u, BIAS82 = 0x40004000u;     // 8x8 Hadamard: |coefficient before the last stage| <= 32 * 255 < 16384
@@ -161,7 +162,7 @@ constexpr int TUNED_MAX_REFS = 8;
 struct PlaneMaps { CUtensorMap m[2 * TUNED_MAX_REFS]; };
 
 template <bool T8>     // T8: Transform8x8Mode (block types 1..4 scored with the 8x8 Hadamard transform)
-__global__ void __launch_bounds__(NT, T8 ? T8_CTAS : 7)      // measured (4x4 transform): 6 CTAs 0.775 ms, 7 CTAs 0.736 ms, 8 CTAs (64 registers) 0.777 ms
+__global__ void __launch_bounds__(NT, T8 ? T8_CTAS : T4_CTAS)      // measured (4x4 transform): 6 CTAs 0.775 ms, 7 CTAs 0.736 ms, 8 CTAs (64 registers) 0.777 ms
 me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                        const __grid_constant__ PlaneMaps maps, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                        const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out)
@@ -468,7 +469,9 @@ extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const
     memcpy(&pm.m[l * TUNED_MAX_REFS], (const unsigned char *)plane_maps + (size_t)l * ME_MAX_REFS * 128, sizeof(CUtensorMap) * TUNED_MAX_REFS);
   static int t8_ctas = 0;
   if (!t8_ctas) { const char *e = getenv("ME_CUDA_SUBPEL_T8_CTAS"); t8_ctas = e ? atoi(e) : T8_CTAS; if (t8_ctas < 1 || t8_ctas > T8_CTAS) t8_ctas = T8_CTAS; }
-  int grid = sms * (cfg->transform8x8 ? t8_ctas : 7);
+  static int t4_ctas = 0;
+  if (!t4_ctas) { const char *e = getenv("ME_CUDA_SUBPEL_CTAS"); t4_ctas = e ? atoi(e) : T4_CTAS; if (t4_ctas < 1 || t4_ctas > T4_CTAS) t4_ctas = T4_CTAS; }
+  int grid = sms * (cfg->transform8x8 ? t8_ctas : t4_ctas);
   if (grid > n_jobs) grid = n_jobs;
   if (cfg->transform8x8)
     me_subpel_tuned_kernel<true><<<grid, NT, sizeof(Smem<true>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
