@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Randomised parity soak (not part of the test suite): frame batches on random clips, sizes, ranges, predictors, lambda factors
+and weights against the oracle on a sample of the jobs.  usage: soak.py [rounds] [seed]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import h264_b200_pkg  # noqa: E402,F401
+from h264_b200 import MeCuda, synth  # noqa: E402
+from oracle import binding as ob  # noqa: E402
+
+rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 12345)
+ob.build()
+bad = 0
+for it in range(rounds):
+    w, h = [(176, 144), (352, 288), (320, 240), (640, 368)][rng.integers(4)]
+    sr = int([16, 32, 64, 24][rng.integers(4)])
+    n_refs = int(rng.integers(1, 4))
+    t8 = int(rng.integers(2))
+    rdopt = int(rng.integers(4) > 0)
+    metric = [(0, 2, 2), (0, 2, 2), (1, 2, 2), (0, 0, 0), (0, 1, 2)][rng.integers(5)]
+    lam = int([334459, 65536, 1200000, 20000000, 3][rng.integers(5)])
+    kind = ["pan", "fade", "stripes", "pan"][rng.integers(4)]
+    d = dict(search_range=sr, rdopt=rdopt, full_search=2, metric=metric, transform8x8=t8, mv_limit_min_y=-511, mv_limit_max_y=511)
+    cfg = ob.make_cfg(**d)
+    frames = synth.luma_frames(w, h, n_refs + 1, seed=int(rng.integers(1 << 30)), kind=kind)
+    if kind == "stripes":
+        frames = [np.roll(f, int(rng.integers(8)), axis=1) for f in frames]
+    cur = np.ascontiguousarray(frames[-1])
+    jobs = synth.synthetic_jobs(w, h, n_refs, (lam, lam, lam), seed=int(rng.integers(1 << 30)), max_pmv=int(rng.integers(4, 4 * sr + 200)), rdopt=rdopt)
+    weights = [(int(rng.integers(2)), int(rng.integers(-20, 90)), int(rng.integers(-40, 40)), int(rng.integers(0, 7))) for _ in range(n_refs)]
+    with MeCuda(w, h, search_range=sr, max_num_references=n_refs, rdopt=rdopt, me_metric=metric, transform8x8=t8) as me:
+        me.set_ref_list(0, [me.ref_create(frames[-2 - r]) for r in range(n_refs)])
+        me.set_current(cur)
+        for r, wt in enumerate(weights):
+            me.set_ref_weights(0, r, *wt)
+        out, out_int = me.frame_search(jobs, want_int=True)
+    sel = np.sort(rng.choice(len(jobs), min(len(jobs), 60), replace=False))
+    ok = True
+    for r in range(n_refs):
+        s_ = sel[jobs["ref"][sel] == r]
+        if not len(s_):
+            continue
+        ref = ob.Ref(frames[-2 - r])
+        ref.set_weights(*weights[r])
+        exp, exp_int = ob.mb_search(cfg, cur, ref, jobs[s_])
+        ok = ok and np.array_equal(out_int[s_], exp_int) and np.array_equal(out[s_], exp)
+        ref.close()
+    print("round %2d %s: %dx%d sr %d refs %d t8 %d rdopt %d metric %s lambda %d %s weights %s" %
+          (it, "ok " if ok else "MISMATCH", w, h, sr, n_refs, t8, rdopt, metric, lam, kind, weights), flush=True)
+    bad += not ok
+print("soak: %d rounds, %d mismatching" % (rounds, bad))
+sys.exit(1 if bad else 0)
