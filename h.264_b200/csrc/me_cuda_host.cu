@@ -398,8 +398,6 @@ int me_cuda_init(const me_cuda_params *p)
   if (p->chroma_me_enable) {
     if (p->yuv_format < 1 || p->yuv_format > 3)
       return fail(1, "ChromaMEEnable needs yuv_format 1 (4:2:0), 2 (4:2:2) or 3 (4:4:4)");
-    if (p->me_metric[0] == 2)
-      return fail(1, "ChromaMEEnable with a Hadamard integer-pel metric is not implemented");
     if (p->weighted_me) return fail(1, "ChromaMEEnable together with weighted-prediction ME is not implemented");
   }
   if (p->width <= 0 || p->height <= 0 || (p->width & 15) || (p->height & 15)) return fail(1, "picture size %dx%d must be positive multiples of 16", p->width, p->height);
@@ -957,7 +955,6 @@ int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic
   RefPic *r1 = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
   RefPic *r2 = (g.inited && g.list_n[list ^ 1] > 0) ? ref_of(g.list[list ^ 1][0]) : nullptr;
   if (!r1 || !r2) { fail(1, "me_cuda_FullPelBlockMotionBiPred: reference lists incomplete"); fatal("bipred"); return ME_INT_MAX; }
-  if (g.cfg.metric[0] == 2) { fail(1, "bi-predictive integer search with a Hadamard metric is not implemented"); fatal("bipred"); return ME_INT_MAX; }
   if (search_range > 64) { fail(1, "bi-pred search range %d too large", search_range); fatal("bipred"); return ME_INT_MAX; }
   if (g.cfg.chroma.on && (!r1->has_chroma() || !r2->has_chroma())) { fail(3, "me_cuda_FullPelBlockMotionBiPred: reference without chroma planes (me_cuda_ref_set_chroma)"); fatal("bipred"); return ME_INT_MAX; }
   if (g.cfg.chroma.on && g.bw[list].apply) { fail(1, "weighted bi-prediction together with ChromaMEEnable is not implemented"); fatal("bipred"); return ME_INT_MAX; }
@@ -1135,7 +1132,6 @@ int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements,
   if (g.list_n[0] < 1 || g.list_n[1] < 1) return fail(1, "me_cuda_frame_bipred needs a reference picture in both lists");
   if (refinements < 0 || refinements > 16 || search_range < 0 || search_range > 64 || subpel < 0 || subpel > 2)
     return fail(1, "me_cuda_frame_bipred: refinements %d / search range %d / sub-pel levels %d out of range", refinements, search_range, subpel);
-  if (g.cfg.metric[0] == 2) return fail(1, "bi-predictive integer search with a Hadamard metric is not implemented");
   for (int i = 0; i < n_jobs; i++) {
     const me_bipred_job &j = jobs[i];
     if (j.list < 0 || j.list > 1) return fail(1, "bi-pred job %d: list %d", i, (int)j.list);

@@ -455,13 +455,26 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
     int mc = fixed_cost + me_mv_cost(a.lambda, cx, cy, px2, py2);
     const uint8_t *p2 = me_umv_ptr(r2, cy + 4 * ME_PAD, cx + 4 * ME_PAD);
     int d = 0;
+    if (metric == 2) {
+      // computeBiPredSATD1 / SATD2 (me_distortion.c:824, :907): Hadamard SAD tile by tile, each tile with its own origin clamp
+      const bool use8 = cfg.transform8x8 && a.blocktype <= 4;
+      const int n = use8 ? 8 : 4;
+      const uint8_t *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
+      for (int by = 0; by < bsy; by += n)
+        for (int bx = 0; bx < bsx; bx += n) {
+          const uint8_t *t1 = me_umv_ptr(r1, (c1y << 2) + 4 * ME_PAD + (by << 2), (c1x << 2) + 4 * ME_PAD + (bx << 2));
+          const uint8_t *t2 = me_umv_ptr(r2, cy + 4 * ME_PAD + (by << 2), cx + 4 * ME_PAD + (bx << 2));
+          d += use8 ? tile_dist<8>(2, blk, cur_pitch, bsx, bx, by, t1, r1.pitch, t2, r2.pitch, a.bw)
+                    : tile_dist<4>(2, blk, cur_pitch, bsx, bx, by, t1, r1.pitch, t2, r2.pitch, a.bw);
+        }
+    } else
     for (int y = 0; y < bsy; y++)
       for (int x = 0; x < bsx; x++) {
         int e = (int)cur[(size_t)(a.pic_pix_y + y) * cur_pitch + a.pic_pix_x + x]
                 - bipred_pel(p1[(size_t)y * r1.pitch + x], p2[(size_t)y * r2.pitch + x], a.bw);
-        d += metric ? e * e : abs(e);                      // computeBiPred1[F_PEL]: SAD, SSE, (SATD -> see host)
+        d += metric ? e * e : abs(e);                      // computeBiPred1[F_PEL] / computeBiPred2[F_PEL]: SAD, SSE
       }
-    if (cfg.chroma.on && r1.chroma[0] && r2.chroma[0])     // computeBiPredSAD1, me_distortion.c:516-543
+    if (cfg.chroma.on && metric != 2 && r1.chroma[0] && r2.chroma[0])     // computeBiPredSAD1, me_distortion.c:516-543
       for (int k = 0; k < 2; k++)
         d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, (c1x << 2) + 4 * ME_PAD,
                                              (c1y << 2) + 4 * ME_PAD, &r2, cx + 4 * ME_PAD, cy + 4 * ME_PAD);

@@ -125,8 +125,8 @@ int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, in
  * bi-predictive forms add ChromaMEWeight times the chroma block distortion of each component (me_distortion.c:376-402,
  * :516-543, :1069-1091); the Hadamard functions have no chroma term.  Reference samples are the 1/8-sample sub-images of
  * getSubImagesChroma (img_chroma.c:374), read through UMVLine8X_chroma (refbuf.c:53); the library evaluates them on the fly
- * from the reconstructed chroma planes (4:2:0, 4:2:2; for 4:4:4 see me_cuda_ref_set_chroma_planes).  Supported with SAD or SSE as the integer-pel metric, any sub-pel metric, and
- * without weighted prediction; me_cuda_init fails otherwise.
+ * from the reconstructed chroma planes (4:2:0, 4:2:2; for 4:4:4 see me_cuda_ref_set_chroma_planes).  Supported with every metric combination, but not
+ * together with weighted prediction (me_cuda_init / me_cuda_set_ref_weights fail).
  *   me_cuda_set_current_chroma : imgUV_org[0..1] of the picture being coded (cw x ch samples each)
  *   me_cuda_ref_set_chroma     : StorablePicture::imgUV[0..1] of a reference picture, after me_cuda_ref_create
  *   me_cuda_set_chroma_state   : the value of the global ChromaMEEnable (me_distortion.c:56) the NEXT search call sees -- the

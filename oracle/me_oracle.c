@@ -689,7 +689,8 @@ int ora_bipred_fullpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, con
     int mcost = ora_mv_cost(lambda_factor, fx0 << 2, fy0 << 2, px1, py1) + ora_mv_cost(lambda_factor, cx, cy, px2, py2);
     if (mcost >= min_mcost) continue;
     mcost += bipred_dist(c, 0, src, cur_stride, bsx, bsy, r1, (fx0 << 2) + 4 * PAD, (fy0 << 2) + 4 * PAD,
-                         r2, cx + 4 * PAD, cy + 4 * PAD, 0, pic_pix_x, pic_pix_y);
+                         r2, cx + 4 * PAD, cy + 4 * PAD, c->transform8x8 && blocktype <= 4 /* test8x8transform, mv-search.c:640 */,
+                         pic_pix_x, pic_pix_y);
     if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
   }
   if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }

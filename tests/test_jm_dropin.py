@@ -53,7 +53,8 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
                                   "hd1080_sr32_ip", "weighted_pred_fade", "weighted_bipred_fade", "full_search_mode_rdopt0",
                                   "full_search_mode_satd", "yuv444_independent_planes", "chroma_me_2_bframes",
                                   "chroma_me_1_full_search_rdopt0", "chroma_me_1_yuv422", "chroma_me_2_sad_sse_subpel",
-                                  "chroma_me_1_sad_subpel", "chroma_me_2_yuv444"])
+                                  "chroma_me_1_sad_subpel", "chroma_me_2_yuv444", "hadamard_fpel_bframes",
+                                  "hadamard_fpel_chroma_me_1"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -95,6 +96,12 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         # 4:4:4 common mode: the chroma sub-images are the quarter-pel plane sets of U and V (luma interpolator, image.c:1647-1657)
         args = ["-d", "encoder.cfg", "-p", "InputFile=foreman_part_qcif_444.yuv", "-p", "YUVFormat=3", "-p", "ProfileIDC=244",
                 "-p", "NumberReferenceFrames=2", "-p", "SearchRange=16", "-p", "ChromaMEEnable=2"]
+    elif case in ("hadamard_fpel_bframes", "hadamard_fpel_chroma_me_1"):
+        # MEDistortionFPel = 2: squared error in the fast full search (me_fullfast.c:512), Hadamard SAD (8x8 transform) in the
+        # bi-predictive integer-pel search (computeBiPredSATD1, me_distortion.c:824)
+        args = ["-d", "encoder.cfg", "-p", "MEDistortionFPel=2", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+        if case.endswith("chroma_me_1"):
+            args += ["-p", "ChromaMEEnable=1"]
     elif case == "chroma_me_1_yuv422":
         args = ["-d", "encoder_yuv422.cfg", "-p", "ChromaMEEnable=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
     elif case == "hd1080_sr32_ip":
