@@ -151,8 +151,11 @@ __device__ __forceinline__ void me_cr_line(const MeRefDev &r, const MeChromaDev 
 }
 // chroma part of computeSAD / SSE (me_distortion.c:376-402, :1069-1091) or of computeBiPredSAD1 (:516-543, r2 != nullptr) for the
 // luma block bsx x bsy at (pic_pix_x, pic_pix_y): distortion of the co-located block of component k, NOT yet weighted
+// bw_*: weighted bi-prediction of the chroma samples (computeBiPredSAD2, me_distortion.c:608-643: weight1_cr / weight2_cr /
+// offsetBi_cr with the LUMA denominator and rounding of the function, :565-566 -- kept as it is)
 __device__ __forceinline__ int me_cr_block(const MeChromaDev &c, int sse, int k, int pic_pix_x, int pic_pix_y, int bsx, int bsy,
-                                           const MeRefDev &r1, int x41, int y41, const MeRefDev *r2, int x42, int y42)
+                                           const MeRefDev &r1, int x41, int y41, const MeRefDev *r2, int x42, int y42,
+                                           int bw_apply = 0, int bw_w1 = 0, int bw_w2 = 0, int bw_obi = 0, int bw_denom = 0)
 {
   const int scx = c.shift_x - 2, scy = c.shift_y - 2;
   const int bx = bsx >> scx, by = bsy >> scy, cx0 = pic_pix_x >> scx, cy0 = pic_pix_y >> scy;
@@ -162,7 +165,10 @@ __device__ __forceinline__ int me_cr_block(const MeChromaDev &c, int sse, int k,
   for (int y = 0; y < by; y++)
     for (int x = 0; x < bx; x++) {
       int p = me_cr_pel(r1, c, k, yp1 + y, xp1 + x, sy1, sx1);
-      if (r2) p = (p + me_cr_pel(*r2, c, k, yp2 + y, xp2 + x, sy2, sx2) + 1) >> 1;
+      if (r2) {
+        const int q = me_cr_pel(*r2, c, k, yp2 + y, xp2 + x, sy2, sx2);
+        p = bw_apply ? me_clamp(((bw_w1 * p + bw_w2 * q + (bw_denom ? 1 << bw_denom : 0)) >> (bw_denom + 1)) + bw_obi, 0, 255) : (p + q + 1) >> 1;
+      }
       const int d = (int)c.cur[k][(size_t)(cy0 + y) * c.cur_pitch + cx0 + x] - p;
       m += sse ? d * d : abs(d);
     }

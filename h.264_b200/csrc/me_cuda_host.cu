@@ -13,7 +13,7 @@
 #include "me_common.cuh"
 
 // ---- kernel launchers (planes.cu, ffs_basic.cu, ffs_tuned.cu, subpel.cu) ----
-struct MeBiW { int apply, w1, w2, obi, denom; };   // weighted bi-prediction of one `list` argument (subpel.cu)
+struct MeBiW { int apply, w1, w2, obi, denom; int cw1[2], cw2[2], cobi[2]; };   // weighted bi-prediction of one `list` argument (subpel.cu)
 struct MeSubpelArgs {
   int pic_pix_x, pic_pix_y, blocktype;
   int pmv_x, pmv_y, mv_x, mv_y, s_mv_x, s_mv_y;
@@ -119,7 +119,7 @@ struct State {
   unsigned long long gen_counter = 0;
   WeightSet wp[2][ME_MAX_REFS];
   Twin twin[2][ME_MAX_REFS];
-  MeBiW bw[2] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};   // weighted bi-prediction per `list` argument of the bi-predictive searches
+  MeBiW bw[2] = {};   // weighted bi-prediction per `list` argument of the bi-predictive searches
   // current picture
   uint8_t *d_cur = nullptr;
   int cur_pitch = 0;
@@ -250,12 +250,13 @@ int search_planes(int list, int idx, RefPic *r, const MeRefDev **dev, const Tens
       CK(cudaMalloc((void **)&t.planes, pb));
       CK(cudaMalloc((void **)&t.search, sb));
       t.planes_bytes = pb; t.search_bytes = sb;
-      t.dev = d; t.dev.planes = t.planes; t.dev.search = t.search;
       t.has_map = false;
       if (int n = me_ffs_tuned_window(g.cfg.search_range))
         t.has_map = me_make_tensor_map_2d(t.win_map.bytes, t.search, d.sw, d.sh, d.spitch, n + 16, n) == 0;
       t.has_pmap = me_make_planes_tensor_map(t.planes_map.bytes, t.planes, d.pitch, d.hp, d.plane_stride) == 0;
     }
+    // everything but the luma planes (geometry, chroma planes) is the picture's own: taken afresh, the slot may have served another picture
+    t.dev = d; t.dev.planes = t.planes; t.dev.search = t.search;
     // the planes may have been generated on a caller's stream (me_cuda_ref_create_device / me_cuda_ref_update_device)
     if (r->written_on && r->written_on != g.stream) CK(cudaStreamSynchronize(r->written_on));
     { ScopedTimer tm(0, g.stream);
@@ -398,7 +399,6 @@ int me_cuda_init(const me_cuda_params *p)
   if (p->chroma_me_enable) {
     if (p->yuv_format < 1 || p->yuv_format > 3)
       return fail(1, "ChromaMEEnable needs yuv_format 1 (4:2:0), 2 (4:2:2) or 3 (4:4:4)");
-    if (p->weighted_me) return fail(1, "ChromaMEEnable together with weighted-prediction ME is not implemented");
   }
   if (p->width <= 0 || p->height <= 0 || (p->width & 15) || (p->height & 15)) return fail(1, "picture size %dx%d must be positive multiples of 16", p->width, p->height);
   if (p->search_range < 1 || p->search_range > 64) return fail(1, "search range %d outside 1..64", p->search_range);
@@ -644,6 +644,12 @@ int me_cuda_set_current(const me_imgpel *const *rows, int w, int h)
 }
 
 // ---- chroma (ChromaMEEnable)
+// the weighted copies of a picture carry a copy of its descriptor (chroma pointers included): rebuilt after a change
+static void invalidate_twins(me_ref_handle h)
+{
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < ME_MAX_REFS; i++) if (g.twin[l][i].src == h) g.twin[l][i].valid = false;
+}
 static int chroma_check(const char *who, int cw, int ch)
 {
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
@@ -680,6 +686,7 @@ static int ref_set_chroma_common(me_ref_handle h, const uint8_t *u, const uint8_
   if (int rc = upload_chroma(r->chroma, pitch, u, v, stride, ur, vr, cw, ch)) return rc;
   r->dev.chroma[0] = r->chroma; r->dev.chroma[1] = r->chroma + (size_t)pitch * ch;
   r->dev.cw = cw; r->dev.ch = ch; r->dev.cpitch = pitch;
+  invalidate_twins(h);
   g.table_dirty = true;
   return 0;
 }
@@ -701,6 +708,7 @@ int me_cuda_ref_set_chroma_planes(me_ref_handle h, me_ref_handle hu, me_ref_hand
   r->chroma444[0] = hu; r->chroma444[1] = hv;
   r->dev.chroma[0] = ru->planes; r->dev.chroma[1] = rv->planes;
   r->dev.cw = ru->dev.w; r->dev.ch = ru->dev.h; r->dev.cpitch = ru->dev.pitch; r->dev.cplane_stride = ru->dev.plane_stride;
+  invalidate_twins(h);
   g.table_dirty = true;
   return 0;
 }
@@ -746,13 +754,28 @@ int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, in
 {
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (list < 0 || list > 1) return fail(1, "me_cuda_set_bipred_weights: list %d out of range", list);
-  MeBiW w = {0, 0, 0, 0, 0};
+  MeBiW w = {};
   if (apply) {
     if (weight1 < -128 || weight1 > 127 || weight2 < -128 || weight2 > 127 || offset_bi < -128 || offset_bi > 127 || log_denom < 0 || log_denom > 7)
       return fail(1, "me_cuda_set_bipred_weights: weights %d, %d / offset %d / log denominator %d out of range", weight1, weight2, offset_bi, log_denom);
     w.apply = 1; w.w1 = weight1; w.w2 = weight2; w.obi = offset_bi; w.denom = log_denom;
+    // chroma: like luma until me_cuda_set_bipred_chroma_weights says otherwise (explicit mode leaves chroma at the default
+    // weights, i.e. the plain average; implicit mode gives chroma the luma weights, weighted_prediction.c:243-252)
+    for (int k = 0; k < 2; k++) { w.cw1[k] = 1 << log_denom; w.cw2[k] = 1 << log_denom; w.cobi[k] = 0; }
   }
   g.bw[list] = w;
+  g.spec.valid = false;
+  return 0;
+}
+
+int me_cuda_set_bipred_chroma_weights(int list, int component, int weight1, int weight2, int offset_bi)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (list < 0 || list > 1 || component < 0 || component > 1) return fail(1, "me_cuda_set_bipred_chroma_weights: list %d / component %d out of range", list, component);
+  if (weight1 < -128 || weight1 > 127 || weight2 < -128 || weight2 > 127 || offset_bi < -128 || offset_bi > 127)
+    return fail(1, "me_cuda_set_bipred_chroma_weights: weights %d, %d / offset %d out of range", weight1, weight2, offset_bi);
+  if (!g.bw[list].apply) return fail(1, "me_cuda_set_bipred_chroma_weights: call me_cuda_set_bipred_weights(list %d, apply = 1, ...) first", list);
+  g.bw[list].cw1[component] = weight1; g.bw[list].cw2[component] = weight2; g.bw[list].cobi[component] = offset_bi;
   g.spec.valid = false;
   return 0;
 }
@@ -763,8 +786,6 @@ int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset
   if (list < 0 || list > 1 || ref < 0 || ref >= ME_MAX_REFS) return fail(1, "me_cuda_set_ref_weights: (list %d, ref %d) out of range", list, ref);
   WeightSet w;
   w.apply = apply != 0;
-  if (w.apply && g.p.chroma_me_enable && !(weight == (1 << log_denom) && offset == 0))
-    return fail(1, "me_cuda_set_ref_weights: weighted-prediction ME together with ChromaMEEnable is not implemented");
   if (w.apply) {
     if (weight < -128 || weight > 127 || offset < -128 || offset > 127 || log_denom < 0 || log_denom > 7)
       return fail(1, "me_cuda_set_ref_weights: weight %d / offset %d / log denominator %d out of range", weight, offset, log_denom);
@@ -957,7 +978,6 @@ int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic
   if (!r1 || !r2) { fail(1, "me_cuda_FullPelBlockMotionBiPred: reference lists incomplete"); fatal("bipred"); return ME_INT_MAX; }
   if (search_range > 64) { fail(1, "bi-pred search range %d too large", search_range); fatal("bipred"); return ME_INT_MAX; }
   if (g.cfg.chroma.on && (!r1->has_chroma() || !r2->has_chroma())) { fail(3, "me_cuda_FullPelBlockMotionBiPred: reference without chroma planes (me_cuda_ref_set_chroma)"); fatal("bipred"); return ME_INT_MAX; }
-  if (g.cfg.chroma.on && g.bw[list].apply) { fail(1, "weighted bi-prediction together with ChromaMEEnable is not implemented"); fatal("bipred"); return ME_INT_MAX; }
   MeBiFullArgs a{};
   a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
   a.pmv_x1 = pred_mv_x1; a.pmv_y1 = pred_mv_y1; a.pmv_x2 = pred_mv_x2; a.pmv_y2 = pred_mv_y2;

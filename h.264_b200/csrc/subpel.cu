@@ -63,7 +63,7 @@ __device__ __noinline__ int hadamard8(int d[64])
 
 // Weighted bi-prediction (computeBiPred*2, me_distortion.c:556, :907, :1254): what FullPelBlockMotionBiPred /
 // SubPelBlockSearchBiPred derive from their `list` argument (me_fullsearch.c:202-234, :538-590).  Same layout in me_cuda_host.cu.
-struct MeBiW { int apply, w1, w2, obi, denom; };
+struct MeBiW { int apply, w1, w2, obi, denom; int cw1[2], cw2[2], cobi[2]; };   // c*: the same for the two chroma components
 
 // prediction sample of a bi-predictive distortion: (p1 + p2 + 1) >> 1 (me_distortion.c:502), or with weights
 // iClip1(255, ((weight1 * p1 + weight2 * p2 + 2 * wp_luma_round) >> (denom + 1)) + offsetBi)
@@ -173,7 +173,7 @@ me_subpel_batch_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDe
       int bx = 4 * (tx - px), by = 4 * (ty - py);
       const uint8_t *rp = tile_ptr(ref, x4, y4, bx, by, metric == 2);
       const uint8_t *sp = &cur_s[4 * ty][4 * tx];
-      const MeBiW nobw = { 0, 0, 0, 0, 0 };
+      const MeBiW nobw = { 0, 0, 0, 0, 0, { 0, 0 }, { 0, 0 }, { 0, 0 } };
       int d = use8 ? tile_dist<8>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw)
                    : tile_dist<4>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw);
       // chroma terms of computeSAD / computeSSE (me_distortion.c:376-402, :1069-1091): once per block, by the lane of its first tile
@@ -268,7 +268,8 @@ __device__ void subpel_block(const MeRefDev &r1, const MeRefDev &r2, const uint8
                  : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
         if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0] && r2.chroma[0])      // computeBiPredSAD1 :516-543
           for (int k = 0; k < 2; k++)
-            d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, fx4, fy4, &r2, x4, y4);
+            d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, fx4, fy4, &r2, x4, y4,
+                                                 a.bw.apply, a.bw.cw1[k], a.bw.cw2[k], a.bw.cobi[k], a.bw.denom);
       }
       if (!a.bi && cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0])                // computeSAD / SSE :376-402
         for (int k = 0; k < 2; k++)
@@ -349,7 +350,7 @@ __device__ int fullpel_dist(const MeRefDev &r, const uint8_t *__restrict__ cur, 
 {
   const int metric = cfg.metric[0], bsx = me_bsx(a.blocktype), bsy = me_bsy(a.blocktype);
   const uint8_t *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
-  const MeBiW nobw = { 0, 0, 0, 0, 0 };
+  const MeBiW nobw = { 0, 0, 0, 0, 0, { 0, 0 }, { 0, 0 }, { 0, 0 } };
   int m = 0;
   if (metric == 2) {
     const bool use8 = cfg.transform8x8 && a.blocktype <= 4;
@@ -477,7 +478,8 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
     if (cfg.chroma.on && metric != 2 && r1.chroma[0] && r2.chroma[0])     // computeBiPredSAD1, me_distortion.c:516-543
       for (int k = 0; k < 2; k++)
         d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, (c1x << 2) + 4 * ME_PAD,
-                                             (c1y << 2) + 4 * ME_PAD, &r2, cx + 4 * ME_PAD, cy + 4 * ME_PAD);
+                                             (c1y << 2) + 4 * ME_PAD, &r2, cx + 4 * ME_PAD, cy + 4 * ME_PAD,
+                                             a.bw.apply, a.bw.cw1[k], a.bw.cw2[k], a.bw.cobi[k], a.bw.denom);
     mc += d;
     unsigned long long key = ((unsigned long long)(unsigned)mc << 32) | (unsigned)s;
     best = key < best ? key : best;

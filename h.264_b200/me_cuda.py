@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "me_cuda_frame_search", "me_cuda_frame_search_device", "me_cuda_frame_bipred", "me_cuda_ref_create_device",
     "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count",
     "me_cuda_measure_int_peak", "me_cuda_ref_update_u8", "me_cuda_ref_update_device", "me_cuda_set_timing",
-    "me_cuda_kernel_time_ms", "me_cuda_set_ref_weights", "me_cuda_set_bipred_weights",
+    "me_cuda_kernel_time_ms", "me_cuda_set_ref_weights", "me_cuda_set_bipred_weights", "me_cuda_set_bipred_chroma_weights",
     "me_cuda_set_current_chroma", "me_cuda_set_current_chroma_u8", "me_cuda_ref_set_chroma", "me_cuda_ref_set_chroma_u8",
     "me_cuda_set_chroma_state", "me_cuda_ref_set_chroma_planes",
 ]
@@ -74,6 +74,7 @@ def load_library(path=LIB_PATH):
     L.me_cuda_set_ref_list.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)]
     L.me_cuda_set_slice_type.argtypes = [C.c_int]
     L.me_cuda_set_ref_weights.argtypes = [C.c_int] * 6
+    L.me_cuda_set_bipred_chroma_weights.argtypes = [C.c_int] * 5
     L.me_cuda_set_current_chroma_u8.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.me_cuda_ref_set_chroma_u8.argtypes = [C.c_int32, vp, vp, C.c_int, C.c_int, C.c_int]
     L.me_cuda_set_chroma_state.argtypes = [C.c_int]
@@ -217,6 +218,9 @@ class MeCuda:
     def set_ref_weights(self, lst, ref, apply, weight=32, offset=0, log_denom=5):
         """weighted-prediction ME: wp_weight / wp_offset [list][ref][0] and luma_log_weight_denom of a list entry"""
         self._check(self.L.me_cuda_set_ref_weights(lst, ref, int(apply), int(weight), int(offset), int(log_denom)))
+
+    def set_bipred_chroma_weights(self, lst, component, w1, w2, offset_bi=0):
+        self._check(self.L.me_cuda_set_bipred_chroma_weights(lst, component, int(w1), int(w2), int(offset_bi)))
 
     # ---- chroma terms of the integer-pel searches (ChromaMEEnable)
     def set_current_chroma(self, u, v):

@@ -52,6 +52,7 @@ static struct {
   int  (*set_slice_type)(int);
   int  (*set_ref_weights)(int, int, int, int, int, int);
   int  (*set_bipred_weights)(int, int, int, int, int, int);
+  int  (*set_bipred_chroma_weights)(int, int, int, int, int);
   int  (*set_current_chroma)(const me_imgpel *const *, const me_imgpel *const *, int, int);
   int  (*ref_set_chroma)(me_ref_handle, const me_imgpel *const *, const me_imgpel *const *, int, int);
   int  (*set_chroma_state)(int);
@@ -118,6 +119,7 @@ static void load_library(void)
   L.set_current = sym("me_cuda_set_current"); L.set_ref_list = sym("me_cuda_set_ref_list");
   L.set_slice_type = sym("me_cuda_set_slice_type"); L.mb_begin = sym("me_cuda_mb_begin");
   L.set_ref_weights = sym("me_cuda_set_ref_weights"); L.set_bipred_weights = sym("me_cuda_set_bipred_weights");
+  L.set_bipred_chroma_weights = sym("me_cuda_set_bipred_chroma_weights");
   L.set_current_chroma = sym("me_cuda_set_current_chroma"); L.ref_set_chroma = sym("me_cuda_ref_set_chroma");
   L.set_chroma_state = sym("me_cuda_set_chroma_state"); L.ref_set_chroma_planes = sym("me_cuda_ref_set_chroma_planes");
   L.ffs_setup = sym("me_cuda_ffs_setup"); L.ffs_is_set_up = sym("me_cuda_ffs_is_set_up");
@@ -319,6 +321,12 @@ static void pass_weights(int list, short ref)
   int list_offset = img->mb_data[img->current_mb_nr].list_offset;
   int apply = ((active_pps->weighted_pred_flag && (img->type == P_SLICE || img->type == SP_SLICE)) ||
                (active_pps->weighted_bipred_idc && (img->type == B_SLICE))) && input->UseWeightedReferenceME;
+  /* the library does not weight the chroma samples of uni-predictive searches: the encoder's estimators never produce
+   * chroma weights other than the default (weighted_prediction.c:98-103, 308-313); anything else is refused loudly */
+  if (apply && input->ChromaMEEnable &&
+      (wp_weight[list + list_offset][ref][1] != (1 << chroma_log_weight_denom) || wp_weight[list + list_offset][ref][2] != (1 << chroma_log_weight_denom) ||
+       wp_offset[list + list_offset][ref][1] || wp_offset[list + list_offset][ref][2]))
+    die("weighted chroma samples in a uni-predictive search (ChromaMEEnable with non-default weight_cr / offset_cr) are not implemented");
   if (L.set_ref_weights(list, ref, apply, apply ? wp_weight[list + list_offset][ref][0] : 0,
                         apply ? wp_offset[list + list_offset][ref][0] : 0, apply ? luma_log_weight_denom : 0))
     die("me_cuda_set_ref_weights");
@@ -341,6 +349,17 @@ static void pass_bipred_weights(int list, short ref, int subpel)
     w1 = list == 0 ? wbp_weight[list_offset][ref][0][0] : wbp_weight[list_offset + LIST_1][0][ref][0];
     w2 = list == 0 ? wbp_weight[list_offset + LIST_1][ref][0][0] : wbp_weight[list_offset][0][ref][0];
     if (L.set_bipred_weights(list, 1, w1, w2, (o1 + o2 + 1) >> 1, luma_log_weight_denom)) die("me_cuda_set_bipred_weights");
+    if (input->ChromaMEEnable) {
+      /* weight1_cr / weight2_cr / offsetBi_cr, me_fullsearch.c:245-262 (the same expressions in both functions) */
+      int k;
+      for (k = 0; k < 2; k++) {
+        int c1 = list == 0 ? wbp_weight[list_offset][ref][0][k + 1] : wbp_weight[list_offset + LIST_1][0][ref][k + 1];
+        int c2 = list == 0 ? wbp_weight[list_offset + LIST_1][ref][0][k + 1] : wbp_weight[list_offset][0][ref][k + 1];
+        int ob = list == 0 ? (wp_offset[list_offset][ref][k + 1] + wp_offset[list_offset + LIST_1][ref][k + 1] + 1) >> 1
+                           : (wp_offset[list_offset + LIST_1][0][k + 1] + wp_offset[list_offset][0][k + 1] + 1) >> 1;
+        if (L.set_bipred_chroma_weights(list, k, c1, c2, ob)) die("me_cuda_set_bipred_chroma_weights");
+      }
+    }
   } else if (L.set_bipred_weights(list, 0, 0, 0, 0, 0)) die("me_cuda_set_bipred_weights");
 }
 

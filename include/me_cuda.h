@@ -119,14 +119,20 @@ int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset
  * of computeBiPredSATD2, :1015, which the encoder's results depend on).  apply = 0: plain (p1 + p2 + 1) >> 1.  Used by the
  * drop-in calls and by me_cuda_frame_bipred. */
 int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom);
+/* the same for chroma component 0 / 1 when ChromaMEEnable puts chroma terms into the bi-predictive distortions: weight1_cr[k],
+ * weight2_cr[k], offsetBi_cr[k] (me_fullsearch.c:245-262; the reference applies them with the luma denominator,
+ * me_distortion.c:565-566, 634).  After me_cuda_set_bipred_weights(list, 1, ...), which resets chroma to the default weights.
+ * Chroma samples of the UNI-predictive searches are never weighted here: the reference's estimators leave weight_cr / offset_cr
+ * at their defaults (weighted_prediction.c:98-103, 308-313); a caller with other values must not use the chroma terms. */
+int me_cuda_set_bipred_chroma_weights(int list, int component, int weight1, int weight2, int offset_bi);
 
 /* ---- chroma terms of the searches (cfg ChromaMEEnable = 1 or 2): the fast full search adds the
  * distortion of the co-located chroma block of every 4x4 (me_fullfast.c:776-814), computeSAD / computeSSE and their
  * bi-predictive forms add ChromaMEWeight times the chroma block distortion of each component (me_distortion.c:376-402,
  * :516-543, :1069-1091); the Hadamard functions have no chroma term.  Reference samples are the 1/8-sample sub-images of
  * getSubImagesChroma (img_chroma.c:374), read through UMVLine8X_chroma (refbuf.c:53); the library evaluates them on the fly
- * from the reconstructed chroma planes (4:2:0, 4:2:2; for 4:4:4 see me_cuda_ref_set_chroma_planes).  Supported with every metric combination, but not
- * together with weighted prediction (me_cuda_init / me_cuda_set_ref_weights fail).
+ * from the reconstructed chroma planes (4:2:0, 4:2:2; for 4:4:4 see me_cuda_ref_set_chroma_planes).  Supported with every metric combination and together
+ * with weighted prediction (see me_cuda_set_bipred_chroma_weights for what is weighted).
  *   me_cuda_set_current_chroma : imgUV_org[0..1] of the picture being coded (cw x ch samples each)
  *   me_cuda_ref_set_chroma     : StorablePicture::imgUV[0..1] of a reference picture, after me_cuda_ref_create
  *   me_cuda_set_chroma_state   : the value of the global ChromaMEEnable (me_distortion.c:56) the NEXT search call sees -- the

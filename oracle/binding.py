@@ -79,6 +79,7 @@ def lib():
         L.ora_set_chroma.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int]
         L.ora_set_bipred_weights.argtypes = [C.c_int] * 6
         L.ora_select_bipred_list.argtypes = [C.c_int]
+        L.ora_set_bipred_chroma_weights.argtypes = [C.c_int] * 5
         L.ora_spiral.argtypes = [C.c_int, vp, vp]
         L.ora_mvbits.argtypes = [C.c_int]
         L.ora_mv_cost.argtypes = [C.c_int] * 5
@@ -191,6 +192,10 @@ def set_chroma(enable, weight=0, cur_u=None, cur_v=None, shift=(3, 3)):
 def set_bipred_weights(lst, apply, w1=32, w2=32, offset_bi=0, log_denom=5):
     """weight set of bi-predictive searches called with list argument `lst` (weighted bi-prediction, computeBiPred*2)"""
     lib().ora_set_bipred_weights(lst, int(apply), int(w1), int(w2), int(offset_bi), int(log_denom))
+
+
+def set_bipred_chroma_weights(lst, component, w1, w2, offset_bi=0):
+    lib().ora_set_bipred_chroma_weights(lst, component, int(w1), int(w2), int(offset_bi))
 
 
 def select_bipred_list(lst):

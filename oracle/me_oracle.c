@@ -182,6 +182,8 @@ static struct {
   int enable, weight, stride, shift_x, shift_y;
   const uint8_t *cur[2];
 } g_cr;
+/* weighted bi-prediction state (see ora_set_bipred_weights below); c*: the two chroma components */
+static struct { int apply, w1, w2, obi, denom, cw1[2], cw2[2], cobi[2]; } g_bw[2], g_bw_cur;
 
 void ora_set_chroma(int enable, int weight, const uint8_t *cur_u, const uint8_t *cur_v, int stride, int shift_x, int shift_y)
 {
@@ -255,7 +257,14 @@ static int cr_block_dist(int sse, int pic_pix_x, int pic_pix_y, int bsx, int bsy
     for (y = 0; y < by; y++)
       for (x = 0; x < bx; x++) {
         int p = cr_pel(r1, k, yp1 + y, xp1 + x, sy1, sx1), d;
-        if (r2) p = (p + cr_pel(r2, k, yp2 + y, xp2 + x, sy2, sx2) + 1) >> 1;
+        if (r2) {
+          int q = cr_pel(r2, k, yp2 + y, xp2 + x, sy2, sx2);
+          /* computeBiPredSAD2 chroma (me_distortion.c:608-643): weight1_cr / weight2_cr / offsetBi_cr with the function's LUMA
+           * denominator and rounding (:565-566) */
+          p = g_bw_cur.apply ? clampi(((g_bw_cur.cw1[k] * p + g_bw_cur.cw2[k] * q + (g_bw_cur.denom ? 1 << g_bw_cur.denom : 0))
+                                       >> (g_bw_cur.denom + 1)) + g_bw_cur.cobi[k], 0, 255)
+                             : (p + q + 1) >> 1;
+        }
         d = (int)g_cr.cur[k][(size_t)(cy0 + y) * g_cr.stride + cx0 + x] - p;
         m += sse ? d * d : iabs_(d);
       }
@@ -608,12 +617,20 @@ int ora_fullpel_block(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
  * argument (me_fullsearch.c:202-234, :538-590) -- weight1 (picture of `list`, read at the fixed vector), weight2 (reference 0
  * of the other list, read at the candidates), offsetBi, luma_log_weight_denom.  One set per value of `list`; the set in
  * use is selected before a call (the composite of mv-search.c:864-1034 switches it as the lists take turns). */
-static struct { int apply, w1, w2, obi, denom; } g_bw[2], g_bw_cur;
+/* (g_bw, g_bw_cur: defined with the chroma state above) */
 
 void ora_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom)
 {
   g_bw[list & 1].apply = apply; g_bw[list & 1].w1 = weight1; g_bw[list & 1].w2 = weight2;
   g_bw[list & 1].obi = offset_bi; g_bw[list & 1].denom = log_denom;
+  /* chroma: the default weights (plain average) until ora_set_bipred_chroma_weights */
+  g_bw[list & 1].cw1[0] = g_bw[list & 1].cw1[1] = g_bw[list & 1].cw2[0] = g_bw[list & 1].cw2[1] = 1 << log_denom;
+  g_bw[list & 1].cobi[0] = g_bw[list & 1].cobi[1] = 0;
+}
+/* weight1_cr[k], weight2_cr[k], offsetBi_cr[k] of me_fullsearch.c:245-262 */
+void ora_set_bipred_chroma_weights(int list, int k, int weight1, int weight2, int offset_bi)
+{
+  g_bw[list & 1].cw1[k & 1] = weight1; g_bw[list & 1].cw2[k & 1] = weight2; g_bw[list & 1].cobi[k & 1] = offset_bi;
 }
 void ora_select_bipred_list(int list) { g_bw_cur = g_bw[list & 1]; }
 

@@ -102,6 +102,7 @@ int ora_fullpel_block(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
  * ora_bipred_subpel use the set chosen by ora_select_bipred_list, ora_mb_bipred switches between the two as the reference does */
 void ora_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom);
 void ora_select_bipred_list(int list);
+void ora_set_bipred_chroma_weights(int list, int component, int weight1, int weight2, int offset_bi);   /* after ora_set_bipred_weights */
 
 /* bi-predictive searches (me_fullsearch.c:164, :520): r1 is read at the fixed vector, r2 at the candidate */
 int ora_bipred_fullpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,

@@ -317,6 +317,18 @@ int __wrap_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int p
     int w1 = list == 0 ? wbp_weight[list_offset][ref][0][0] : wbp_weight[list_offset + LIST_1][0][ref][0];
     int w2 = list == 0 ? wbp_weight[list_offset + LIST_1][ref][0][0] : wbp_weight[list_offset][0][ref][0];
     rec[29] = 1 + luma_log_weight_denom; rec[30] = (w1 & 0xffff) | (w2 << 16); rec[31] = (o1 + o2 + 1) >> 1;
+    if (ChromaMEEnable) {
+      /* weight1_cr / weight2_cr / offsetBi_cr (me_fullsearch.c:245-262), 8 bits each:
+       * rec[27] = w1_cb | w2_cb << 8 | obi_cb << 16 | 1 << 24 (present), rec[28] = w1_cr | w2_cr << 8 | obi_cr << 16 */
+      int k;
+      for (k = 0; k < 2; k++) {
+        int c1 = list == 0 ? wbp_weight[list_offset][ref][0][k + 1] : wbp_weight[list_offset + LIST_1][0][ref][k + 1];
+        int c2 = list == 0 ? wbp_weight[list_offset + LIST_1][ref][0][k + 1] : wbp_weight[list_offset][0][ref][k + 1];
+        int ob = list == 0 ? (wp_offset[list_offset][ref][k + 1] + wp_offset[list_offset + LIST_1][ref][k + 1] + 1) >> 1
+                           : (wp_offset[list_offset + LIST_1][0][k + 1] + wp_offset[list_offset][0][k + 1] + 1) >> 1;
+        rec[27 + k] = (c1 & 0xff) | ((c2 & 0xff) << 8) | ((ob & 0xff) << 16) | ((k == 0) << 24);
+      }
+    }
   }
   cost = __real_FullPelBlockMotionBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype,
                                          pred_mv_x1, pred_mv_y1, pred_mv_x2, pred_mv_y2,

@@ -23,6 +23,9 @@ Cases
              and in the bi-predictive integer-pel search.  chroma_fs: encoder_main.cfg with ChromaMEEnable=1, SearchMode=-1,
              RDOptimization=0: chroma terms of computeSAD in the per-block full search.  Every 6th macroblock; the fixtures
              carry the original and reconstructed chroma planes.
+  wpbc       encoder.cfg with two B pictures between references, WeightedBiprediction=2 (implicit weights 43 / 21),
+             WeightedPrediction=1 and ChromaMEEnable=2 on the fading clip: weighted chroma samples in the bi-predictive
+             integer-pel search, explicit luma weights + chroma terms in the P pictures.  Every 12th macroblock.
   wpb        encoder.cfg (High profile, I-B-P, bi-predictive ME, 8x8 transform) with WeightedBiprediction=1 and
              WeightedPrediction=1 on the fading clip, SR 16, 2 references: weighted bi-predictive searches
              (computeBiPredSAD2 / SATD2, including the 8x8 branch's source-pointer slip).  Every 6th macroblock is kept.
@@ -166,6 +169,19 @@ def main():
         assert tr.chroma_info()["enable"] == 1 and len(tr.of_type(REC_FULLPEL)) > 10000
         tr.save_npz(os.path.join(HERE, "chroma_fs.npz"), keep_mask(tr, 6))
         crc["chroma_fs"] = planes_crc(tr, d)
+    # ---- wpbc: implicit weighted bi-prediction (two B pictures between references: weights 43 / 21) with ChromaMEEnable = 2 --
+    # weighted chroma samples in the bi-predictive integer-pel search; explicit weights + chroma terms in the P pictures
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_yuv420(os.path.join(d, "syn.yuv"), 176, 144, 7, kind="fade")
+        run_trace(d, ["-d", "encoder.cfg", "-p", "InputFile=syn.yuv", "-p", "FramesToBeEncoded=3", "-p", "FrameSkip=2", "-p", "NumberBFrames=2",
+                      "-p", "WeightedBiprediction=2", "-p", "WeightedPrediction=1", "-p", "ChromaMEEnable=2", "-p", "SearchRange=16",
+                      "-p", "NumberReferenceFrames=2"])
+        md5s["wpbc"] = {"test.264": md5(os.path.join(d, "test.264"))}
+        tr = Trace(d)
+        bf = tr.of_type(REC_BI_FULL)
+        assert (bf[:, 29] > 0).all() and ((bf[:, 27] >> 24) & 1).all() and len(set(bf[:, 30].tolist())) > 1
+        tr.save_npz(os.path.join(HERE, "wpbc.npz"), keep_mask(tr, 12))
+        crc["wpbc"] = planes_crc(tr, d)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
     for f in sorted(os.listdir(HERE)):

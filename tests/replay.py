@@ -102,6 +102,9 @@ class OracleAdapter:
     def set_bipred_weights(self, lst, apply, w1, w2, obi, denom):
         self.ob.set_bipred_weights(lst, apply, w1, w2, obi, denom)
 
+    def set_bipred_chroma_weights(self, lst, k, w1, w2, obi):
+        self.ob.set_bipred_chroma_weights(lst, k, w1, w2, obi)
+
     def bipred_full(self, ref, lst, ppx, ppy, bt, pmv1, pmv2, mv, smv, sr, min_mcost, lam):
         r1, r2 = self.refs[self.lists[lst][ref]], self.refs[self.lists[lst ^ 1][0]]
         self.ob.select_bipred_list(lst)
@@ -157,6 +160,9 @@ class CudaAdapter:
     def set_bipred_weights(self, lst, apply, w1, w2, obi, denom):
         self.me.set_bipred_weights(lst, apply, w1, w2, obi, denom)
 
+    def set_bipred_chroma_weights(self, lst, k, w1, w2, obi):
+        self.me.set_bipred_chroma_weights(lst, k, w1, w2, obi)
+
     def mb_begin(self, ox, oy):
         self.me.mb_begin(ox, oy)
 
@@ -187,6 +193,7 @@ def replay(trace, impl, max_calls=None):
     """returns {name: (n_calls, [mismatch descriptions])}"""
     res = {"ffs": [0, []], "centre": [0, []], "subpel": [0, []], "bi_full": [0, []], "bi_sub": [0, []], "fullpel": [0, []]}
     cur_pic, cur_mb = None, None
+    bi_chroma = {}
     slice_of = {int(r[1]): int(r[2]) for r in trace.of_type(REC_CURPIC)}
     n = 0
     for r in trace.recs:
@@ -210,6 +217,13 @@ def replay(trace, impl, max_calls=None):
             # weighted bi-prediction: 1 + log denominator (0 = off), weight1 | weight2 << 16, offsetBi
             w = int(r[30])
             impl.set_bipred_weights(lst, int(r[29]) > 0, (w << 16 >> 16) if w & 0x8000 else w & 0xffff, w >> 16, int(r[31]), max(0, int(r[29]) - 1))
+            # chroma weights: recorded with the integer-pel search (8 bits each), valid for the sub-pel calls of the same list
+            if t == REC_BI_FULL and int(r[29]) > 0 and (int(r[27]) >> 24) & 1:
+                s8 = lambda v: (v & 0xff) - 256 if v & 0x80 else v & 0xff   # noqa: E731
+                bi_chroma[(pic, lst)] = [(s8(int(r[27 + k])), s8(int(r[27 + k]) >> 8), s8(int(r[27 + k]) >> 16)) for k in (0, 1)]
+            if int(r[29]) > 0 and (pic, lst) in bi_chroma:
+                for k, (c1, c2, ob_) in enumerate(bi_chroma[(pic, lst)]):
+                    impl.set_bipred_chroma_weights(lst, k, c1, c2, ob_)
         if t == REC_FFS:
             if r[22]:
                 c = impl.ffs_setup(lst, ref, int(r[23]), int(r[24]))

@@ -54,7 +54,8 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
                                   "full_search_mode_satd", "yuv444_independent_planes", "chroma_me_2_bframes",
                                   "chroma_me_1_full_search_rdopt0", "chroma_me_1_yuv422", "chroma_me_2_sad_sse_subpel",
                                   "chroma_me_1_sad_subpel", "chroma_me_2_yuv444", "hadamard_fpel_bframes",
-                                  "hadamard_fpel_chroma_me_1"])
+                                  "hadamard_fpel_chroma_me_1", "weighted_implicit_bipred_chroma_me_2",
+                                  "weighted_pred_chroma_me_1"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -102,6 +103,15 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         args = ["-d", "encoder.cfg", "-p", "MEDistortionFPel=2", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
         if case.endswith("chroma_me_1"):
             args += ["-p", "ChromaMEEnable=1"]
+    elif case == "weighted_implicit_bipred_chroma_me_2":
+        # two B pictures between references: implicit weights 43 / 21 for luma AND chroma in the bi-predictive searches
+        args = ["-d", "encoder.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
+                "-p", "FramesToBeEncoded=3", "-p", "FrameSkip=2", "-p", "NumberBFrames=2", "-p", "WeightedBiprediction=2",
+                "-p", "WeightedPrediction=1", "-p", "ChromaMEEnable=2", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+    elif case == "weighted_pred_chroma_me_1":
+        args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
+                "-p", "FramesToBeEncoded=4", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=16",
+                "-p", "NumberReferenceFrames=3", "-p", "WeightedPrediction=1", "-p", "ChromaMEEnable=1"]
     elif case == "chroma_me_1_yuv422":
         args = ["-d", "encoder_yuv422.cfg", "-p", "ChromaMEEnable=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
     elif case == "hd1080_sr32_ip":
@@ -140,7 +150,7 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         if "InputFile=syn.yuv" in args:
             wdt = int([a for a in args if a.startswith("SourceWidth=")][0].split("=")[1])
             hgt = int([a for a in args if a.startswith("SourceHeight=")][0].split("=")[1])
-            synth.write_yuv420(str(d / "syn.yuv"), wdt, hgt, 2 if wdt == 1920 else 5, kind="fade" if "fade" in case else "pan")
+            synth.write_yuv420(str(d / "syn.yuv"), wdt, hgt, 2 if wdt == 1920 else 7, kind="fade" if ("fade" in case or "weighted" in case) else "pan")
     _run("lencod_cuda", args, str(a))
     _run("lencod", args, str(b))
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
