@@ -54,5 +54,43 @@ for it in range(rounds):
     print("round %2d %s: %dx%d sr %d refs %d t8 %d rdopt %d metric %s lambda %d %s weights %s" %
           (it, "ok " if ok else "MISMATCH", w, h, sr, n_refs, t8, rdopt, metric, lam, kind, weights), flush=True)
     bad += not ok
+# ---- bi-predictive batch: random predictors, vectors, refinements, ranges, sub-pel levels, weights
+from h264_b200 import BIPRED_JOB_DTYPE  # noqa: E402
+for it in range(max(1, rounds // 3)):
+    w, h = [(176, 144), (352, 288)][rng.integers(2)]
+    t8 = int(rng.integers(2))
+    metric = [(0, 2, 2), (1, 2, 2), (2, 2, 2), (0, 0, 1)][rng.integers(4)]
+    refinements, srange, subpel = int(rng.integers(0, 4)), int([4, 8, 16, 32][rng.integers(4)]), int(rng.integers(0, 3))
+    d = dict(search_range=32, rdopt=1, full_search=2, metric=metric, transform8x8=t8, mv_limit_min_y=-511, mv_limit_max_y=511)
+    cfg = ob.make_cfg(**d)
+    frames = synth.luma_frames(w, h, 3, seed=int(rng.integers(1 << 30)), kind=["pan", "fade"][rng.integers(2)])
+    cur, past, future = np.ascontiguousarray(frames[1]), frames[0], frames[2]
+    mbs = [(16 * x, 16 * y) for y in range(h // 16) for x in range(w // 16)]
+    pick = [mbs[i] for i in rng.choice(len(mbs), 24, replace=False)]
+    jobs = np.zeros(2 * len(pick), BIPRED_JOB_DTYPE)
+    for k, (x, y) in enumerate(pick):
+        for lst in (0, 1):
+            j = jobs[2 * k + lst]
+            j["opix_x"], j["opix_y"], j["list"] = x, y, lst
+            j["pmv"] = rng.integers(-60, 61, 2); j["pmv_bi"] = rng.integers(-60, 61, 2); j["mv"] = rng.integers(-80, 81, 2)
+            j["lambda"] = int([334459, 65536, 3000000][rng.integers(3)])
+    bw = [(int(rng.integers(2)), int(rng.integers(-10, 70)), int(rng.integers(-10, 70)), int(rng.integers(-20, 20)), int(rng.integers(3, 7))) for _ in (0, 1)]
+    with MeCuda(w, h, search_range=32, max_num_references=1, me_metric=metric, transform8x8=t8) as me:
+        me.set_ref_list(0, [me.ref_create(past)])
+        me.set_ref_list(1, [me.ref_create(future)])
+        me.set_current(cur)
+        for lst in (0, 1):
+            me.set_bipred_weights(lst, *bw[lst])
+            ob.set_bipred_weights(lst, *bw[lst])
+        out = me.frame_bipred(jobs, refinements, srange, subpel)
+    r0, r1 = ob.Ref(past), ob.Ref(future)
+    exp = ob.mb_bipred(cfg, cur, r0, r1, jobs.view(ob.BIPRED_JOB_DTYPE), refinements, srange, subpel)
+    r0.close(); r1.close()
+    for lst in (0, 1):
+        ob.set_bipred_weights(lst, 0)
+    ok = np.array_equal(out.view(ob.BIPRED_RESULT_DTYPE), exp)
+    print("bipred %2d %s: %dx%d t8 %d metric %s refinements %d range %d subpel %d weights %s" %
+          (it, "ok " if ok else "MISMATCH", w, h, t8, metric, refinements, srange, subpel, bw), flush=True)
+    bad += not ok
 print("soak: %d rounds, %d mismatching" % (rounds, bad))
 sys.exit(1 if bad else 0)
