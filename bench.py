@@ -267,7 +267,10 @@ def main():
     jobs_np = synth.synthetic_jobs(W, H, N_REFS, LAMBDA, seed=21 + rank)
     n_jobs = len(jobs_np)
     # ME_BENCH_T8=1: side measurement with Transform8x8Mode (High profile: 8x8 Hadamard for block types 1..4)
+    # ME_BENCH_SUBPEL_METRIC=0|1: side measurement with SAD / SSE as the sub-pel metric (MEDistortionHPel / QPel)
+    sub_metric = env_int("ME_BENCH_SUBPEL_METRIC", 2)
     me = MeCuda(W, H, search_range=SEARCH_RANGE, max_num_references=N_REFS, device=local,
+                me_metric=(0, sub_metric, sub_metric),
                 transform8x8=1 if os.environ.get("ME_BENCH_T8", "") == "1" else 0)
     stream = torch.cuda.ExternalStream(me.stream(), device=dev)
 
@@ -430,7 +433,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "width": W, "height": H, "search_range": SEARCH_RANGE,
                            "refs": N_REFS, "macroblocks_per_step": MBS, "jobs_per_step": n_jobs, "partitions": 41,
-                           "metrics": "SAD fpel / SATD hpel,qpel", "parallelism": "gop-sharded x%d, no collective" % world,
+                           "metrics": "SAD fpel / %s hpel,qpel" % ("SAD", "SSE", "SATD")[sub_metric],
+                           "parallelism": "gop-sharded x%d, no collective" % world,
                            "l2": "256 MB write between timed steps (L2 flush) and ~250 MB working set per step",
                            "predictors": "synthetic per-partition predictors (pan + jitter), seed 21"},
                 "clocks": clocks, "gpu_launches": int(launches),

@@ -1,9 +1,11 @@
-// subpel_tuned.cu -- half / quarter-pel refinement, the throughput kernel (Hadamard SATD 4x4 at both sub-pel levels).
+// subpel_tuned.cu -- half / quarter-pel refinement, the throughput kernel (Hadamard SATD 4x4 / 8x8, SAD, SSE).
 //
 // Same results as me_subpel_batch_kernel (subpel.cu), i.e. as SubPelBlockMotionSearch (reference
 // lencod/src/me_fullsearch.c:341-511) with computeSATD / HadamardSAD4x4 (lencod/src/me_distortion.c:657, :182), for
 // MEDistortionHPel = MEDistortionQPel = 2; with Transform8x8Mode the block types 1..4 use HadamardSAD8x8 (me_distortion.c:272,
-// test8x8transform, mv-search.c:640).  SAD / SSE sub-pel metrics go through subpel.cu.
+// test8x8transform, mv-search.c:640).  MEDistortionHPel / QPel = 0 / 1 (computeSAD me_distortion.c:351, computeSSE :500)
+// run in a second instantiation (HAD = false) on the same lanes, so that the Hadamard instantiation keeps its compile-time
+// metric; the sub-pel chroma terms of those two metrics stay in subpel.cu.
 //
 //  * Persistent CTAs of 128 threads (7 per SM), one (macroblock, list, ref) job at a time.
 //  * The reference samples of a job come from ONE TMA box: a 48 x 33 pixel region of all 16 quarter-pel planes
@@ -111,6 +113,24 @@ __device__ __forceinline__ int satd4x4(const unsigned r[4], const uint4 c01, con
   return (int)((acc + 1) >> 1);
 }
 
+// SAD / squared error of one 4x4 tile (the tile's share of computeSAD / computeSSE, me_distortion.c:351, :1042): the current rows
+// come back from their biased lane pairs as plain byte words
+__device__ __forceinline__ int sadsse4x4(const unsigned r[4], const uint4 c01, const uint4 c23, int sse)
+{
+  const unsigned ce[4] = { c01.x, c01.z, c23.x, c23.z }, co[4] = { c01.y, c01.w, c23.y, c23.w };
+  int acc = 0;
+#pragma unroll
+  for (int y = 0; y < 4; y++) {
+    const unsigned cw = __byte_perm(ce[y] - BIAS2, co[y] - BIAS2, 0x6240);      // c0 | c1 << 8 | c2 << 16 | c3 << 24
+    if (!sse) acc = (int)__vsadu4(r[y], cw) + acc;
+    else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const int d = (int)((r[y] >> (8 * k)) & 255u) - (int)((cw >> (8 * k)) & 255u); acc += d * d; }
+    }
+  }
+  return acc;
+}
+
 __device__ __forceinline__ unsigned padd8(unsigned a, unsigned b) { return a + b - BIAS82; }
 __device__ __forceinline__ unsigned psub8(unsigned a, unsigned b) { return a - b + BIAS82; }
 
@@ -161,7 +181,9 @@ __device__ __forceinline__ JobView job_view(const uint32_t *w)
 constexpr int TUNED_MAX_REFS = 8;
 struct PlaneMaps { CUtensorMap m[2 * TUNED_MAX_REFS]; };
 
-template <bool T8>     // T8: Transform8x8Mode (block types 1..4 scored with the 8x8 Hadamard transform)
+// T8: Transform8x8Mode (block types 1..4 scored with the 8x8 Hadamard transform).  HAD: both sub-pel metrics are the Hadamard SAD
+// (the shipped configurations; the metric is then a compile-time constant and the SAD / SSE code does not exist)
+template <bool T8, bool HAD>
 __global__ void __launch_bounds__(NT, T8 ? T8_CTAS : T4_CTAS)      // measured (4x4 transform): 6 CTAs 0.775 ms, 7 CTAs 0.736 ms, 8 CTAs (64 registers) 0.777 ms
 me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                        const __grid_constant__ PlaneMaps maps, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
@@ -240,7 +262,7 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     // ---- this thread's tile for the whole job.  4x4: slot = (block type, tile slot), 16 lanes per type, the tiles of a
     // partition adjacent (c_tile / c_part).  With the 8x8 transform only the types 5..7 have 4x4 tiles (threads 0..47 of the
     // first two warps) and the last two warps hold the 8x8 tiles of types 1..4 (c_quad / c_part8), four lane groups of 16.
-    struct Slot4 { int p, g, x4, y4, rot; bool ok, leader; uint4 c01, c23; } s4;
+    struct Slot4 { int p, g, x4, y4, rot, bx, by; bool ok, leader; uint4 c01, c23; } s4;
     struct Slot8 { int p, g, x4, y4, quad, grp; bool ok, leader; } s8;
     {
       const int nslot = T8 ? 3 * 16 : 7 * 16;
@@ -251,6 +273,8 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
       s4.x4 = (jv.opix_x + 4 * (tile & 3) + ME_PAD) << 2; s4.y4 = (jv.opix_y + 4 * (tile >> 2) + ME_PAD) << 2;
       // tiles of the lower macroblock half take their rows in the order 2, 3, 0, 1 (the Hadamard sum does not change under a
       // cyclic row shift): the lanes of a partition then hit four different bank groups instead of two
+      // offset of the tile inside its partition: SAD / SSE blocks are clamped at the block origin, not per tile (me_distortion.c:365)
+      s4.bx = 4 * ((tile & 3) - (me_part_blk(s4.p) & 3)); s4.by = 4 * ((tile >> 2) - (me_part_blk(s4.p) >> 2));
       s4.rot = (tile >> 2) & 2;
       s4.c01 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][s4.rot ? 4 : 0]);
       s4.c23 = *reinterpret_cast<const uint4 *>(&sm.curpk[tile][s4.rot ? 0 : 4]);
@@ -266,6 +290,7 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     for (int stage = 0; stage < 2; stage++) {                // 0: half pel (step 2), 1: quarter pel (step 1)
       const int step = stage == 0 ? 2 : 1;
       const int lam = (int)sm.job[44 + 1 + stage];          // lambda[H_PEL], lambda[Q_PEL]
+      const int metric = HAD ? 2 : (stage == 0 ? cfg.metric[1] : cfg.metric[2]);      // 2 Hadamard SAD, 0 SAD, 1 squared error (uniform)
       const int first = stage == 0 ? cfg.start_hp : cfg.start_qp;
       if (T8) {
         // motion-vector rate of every candidate of the 8x8-transform partitions (block types 1..4), scored across lane groups
@@ -331,14 +356,16 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
             r[3] = __funnelshift_r(w0, w1, sh);
           } else {
             const int x4 = s4.x4 + mvpx + (kx - 1) * step, y4 = s4.y4 + mvpy + (ky - 1) * step;
-            const uint8_t *rp = me_umv_ptr(ref, y4, x4);   // per-tile origin clamp, as computeSATD does (me_distortion.c:657)
+            // origin clamp per tile as computeSATD does (me_distortion.c:657), per block for SAD / SSE (:365, :1056)
+            const uint8_t *rp = metric == 2 ? me_umv_ptr(ref, y4, x4)
+                                            : me_umv_ptr(ref, y4 - (s4.by << 2), x4 - (s4.bx << 2)) + (size_t)s4.by * ref.pitch + s4.bx;
 #pragma unroll
             for (int y = 0; y < 4; y++) {
               const uint8_t *b = rp + (size_t)((y + s4.rot) & 3) * ref.pitch;
               r[y] = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
             }
           }
-          int v = satd4x4(r, s4.c01, s4.c23);
+          int v = metric == 2 ? satd4x4(r, s4.c01, s4.c23) : sadsse4x4(r, s4.c01, s4.c23, metric);
           // segmented sum over the g lanes of the partition (stages no partition of this warp needs are skipped: uniform)
 #pragma unroll
           for (int st = 0; st < 4; st++) {
@@ -455,14 +482,23 @@ extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const
                                             const MeResultInt *in_int, MeResult *out, cudaStream_t st)
 {
   if (!plane_maps || n_refs0 > TUNED_MAX_REFS || n_refs1 > TUNED_MAX_REFS) return 0;
-  if (cfg->metric[1] != 2 || cfg->metric[2] != 2) return 0;
+  // 8x8 transform tiles exist for the Hadamard metric only: with Transform8x8Mode either both sub-pel metrics are Hadamard (8x8
+  // variant) or neither (4x4 variant, the transform size does not matter); a mix goes to the general kernel
+  const bool had1 = cfg->metric[1] == 2, had2 = cfg->metric[2] == 2;
+  if (cfg->transform8x8 && had1 != had2) return 0;
+  if (cfg->chroma.on && !(had1 && had2)) return 0;          // chroma terms of computeSAD / SSE at sub-pel positions: general kernel
+  const bool use_t8 = cfg->transform8x8 && had1;
+  static int general_sad = -1;                               // measurement switch: SAD / SSE sub-pel metrics through subpel.cu
+  if (general_sad < 0) { const char *e = getenv("ME_CUDA_SUBPEL_SAD_GENERAL"); general_sad = e && atoi(e) ? 1 : 0; }
+  if (general_sad && !(had1 && had2)) return 0;
   static int sms = 0;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(me_subpel_tuned_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>));
-    cudaFuncSetAttribute(me_subpel_tuned_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<true>));
+    cudaFuncSetAttribute(me_subpel_tuned_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>));
+    cudaFuncSetAttribute(me_subpel_tuned_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>));
+    cudaFuncSetAttribute(me_subpel_tuned_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<true>));
   }
   PlaneMaps pm;
   for (int l = 0; l < 2; l++)
@@ -471,13 +507,16 @@ extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const
   if (!t8_ctas) { const char *e = getenv("ME_CUDA_SUBPEL_T8_CTAS"); t8_ctas = e ? atoi(e) : T8_CTAS; if (t8_ctas < 1 || t8_ctas > T8_CTAS) t8_ctas = T8_CTAS; }
   static int t4_ctas = 0;
   if (!t4_ctas) { const char *e = getenv("ME_CUDA_SUBPEL_CTAS"); t4_ctas = e ? atoi(e) : T4_CTAS; if (t4_ctas < 1 || t4_ctas > T4_CTAS) t4_ctas = T4_CTAS; }
-  int grid = sms * (cfg->transform8x8 ? t8_ctas : t4_ctas);
+  int grid = sms * (use_t8 ? t8_ctas : t4_ctas);
   if (grid > n_jobs) grid = n_jobs;
-  if (cfg->transform8x8)
-    me_subpel_tuned_kernel<true><<<grid, NT, sizeof(Smem<true>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
-                                                                 *cfg, in_int, out);
+  if (use_t8)
+    me_subpel_tuned_kernel<true, true><<<grid, NT, sizeof(Smem<true>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur,
+                                                                       cur_pitch, *cfg, in_int, out);
+  else if (had1 && had2)
+    me_subpel_tuned_kernel<false, true><<<grid, NT, sizeof(Smem<false>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur,
+                                                                         cur_pitch, *cfg, in_int, out);
   else
-    me_subpel_tuned_kernel<false><<<grid, NT, sizeof(Smem<false>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur, cur_pitch,
-                                                                  *cfg, in_int, out);
+    me_subpel_tuned_kernel<false, false><<<grid, NT, sizeof(Smem<false>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur,
+                                                                          cur_pitch, *cfg, in_int, out);
   return 1;
 }
