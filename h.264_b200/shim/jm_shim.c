@@ -163,8 +163,11 @@ void __wrap_Init_Motion_Search_Module(void)
   __real_Init_Motion_Search_Module();
   active = 0;
   if (dis && atoi(dis)) return;
-  /* the library implements SearchMode 0 (fast full search) and -1 (per-block full search) */
-  if (input->SearchMode != FAST_FULL_SEARCH && input->SearchMode != FULL_SEARCH) return;
+  /* SearchMode 0 (fast full search) and -1 (per-block full search) run every stage on the device.  With the pattern searches
+   * (1 UMHexagonS, 2 simplified UMHexagonS, 3 EPZS) the integer-pel stage and the modes' own sub-pel patterns stay the reference's
+   * host code -- data-dependent walks of a few positions -- and the device serves what the dispatch still sends to the plain
+   * routines: the plane sets, SubPelBlockMotionSearch (UMHexagonS block types 1..3, mv-search.c:799; EPZS without EPZSSubPelME,
+   * :823) and SubPelBlockSearchBiPred (:1018, unless EPZSSubPelMEBiPred) */
   {
     me_cuda_params p;
     int apply_wp = (input->WeightedPrediction || input->WeightedBiprediction) && input->UseWeightedReferenceME;

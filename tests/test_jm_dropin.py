@@ -55,7 +55,8 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
                                   "chroma_me_1_full_search_rdopt0", "chroma_me_1_yuv422", "chroma_me_2_sad_sse_subpel",
                                   "chroma_me_1_sad_subpel", "chroma_me_2_yuv444", "hadamard_fpel_bframes",
                                   "hadamard_fpel_chroma_me_1", "weighted_implicit_bipred_chroma_me_2",
-                                  "weighted_pred_chroma_me_1"])
+                                  "weighted_pred_chroma_me_1", "umhex_plain_subpel", "umhex_simple_bipred_subpel",
+                                  "epzs_plain_subpel", "epzs_subpel_grid_plain_subpel"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -136,6 +137,16 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
                 "-p", "FramesToBeEncoded=3", "-p", "FrameSkip=0", "-p", "SearchMode=-1", "-p", "SearchRange=8",
                 "-p", "NumberReferenceFrames=2"]
         args += ["-p", "RDOptimization=0"] if case.endswith("rdopt0") else ["-p", "MEDistortionFPel=2"]
+    elif case in ("umhex_plain_subpel", "umhex_simple_bipred_subpel", "epzs_plain_subpel", "epzs_subpel_grid_plain_subpel"):
+        # SURVEY.md 8(f) row 4, first half: the pattern searches keep their integer-pel stage (and their own sub-pel patterns) on the
+        # host; the plain sub-pel routines their dispatch still calls (mv-search.c:799, :823, :1018) and the plane sets are the
+        # library's.  With EPZSSubPelGrid the integer stage hands over vectors that are not multiples of four.
+        args = ["-d", "encoder.cfg", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+        args += {"umhex_plain_subpel": ["-p", "SearchMode=1"],
+                 "umhex_simple_bipred_subpel": ["-p", "SearchMode=2"],
+                 "epzs_plain_subpel": ["-p", "SearchMode=3", "-p", "EPZSSubPelME=0", "-p", "EPZSSubPelMEBiPred=0", "-p", "EPZSSubPelGrid=0"],
+                 "epzs_subpel_grid_plain_subpel": ["-p", "SearchMode=3", "-p", "EPZSSubPelME=0", "-p", "EPZSSubPelMEBiPred=0",
+                                                   "-p", "EPZSSubPelGrid=1"]}[case]
     elif case == "sr64_2ref":
         # the search range of BASELINE config 5 (4K), on a QCIF clip so that the CPU side finishes in seconds
         args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
@@ -155,6 +166,14 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     _run("lencod", args, str(b))
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
     assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
+    if "plain_subpel" in case:
+        # the device did serve these modes: verify mode counts the SubPelBlockMotionSearch calls it answered (and compares each)
+        import re
+        r = subprocess.run([os.path.join(REF_DIR, "lencod_cuda")] + args, cwd=str(a), capture_output=True, text=True, timeout=1500,
+                           env=dict(os.environ, ME_CUDA_LIB=os.path.join(ROOT, "h.264_b200", "libme_cuda.so"), ME_CUDA_VERIFY="1"))
+        m = re.search(r"verify mode: (\d+) calls checked, (\d+) mismatches", r.stderr)
+        assert r.returncode == 0 and m, r.stderr[-1500:]
+        assert int(m.group(1)) > 0 and int(m.group(2)) == 0, m.group(0)
 
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
