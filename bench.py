@@ -258,7 +258,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the motion-estimation path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner to STDOUT when the communicator comes up; stdout carries the one JSON line only, so
+        # file descriptor 1 points at stderr while the group is created and used for the first time
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     dev = torch.device("cuda", local)
 
     # ---- workload: this rank's GOP (its own clip)
