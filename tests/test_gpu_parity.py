@@ -124,7 +124,8 @@ def _batch_case(pkg, ob, w, h, frames, n_refs, d, cfg, jobs, sample=None, seed=0
     return bad, len(idx)
 
 
-@pytest.mark.parametrize("variant", ["default", "t8x8", "rdopt0", "restrict0_sr16", "sse_fpel", "sad_subpel", "qcif_sr32"])
+@pytest.mark.parametrize("variant", ["default", "t8x8", "rdopt0", "restrict0_sr16", "sse_fpel", "sad_subpel", "sse_subpel",
+                                     "sad_hpel_satd_qpel", "satd_hpel_sse_qpel_qcif", "sad_subpel_t8x8", "qcif_sr32"])
 def test_batch_matches_oracle(pkg, oracle_lib, variant):
     from h264_b200 import synth
     ob = oracle_lib
@@ -139,6 +140,15 @@ def test_batch_matches_oracle(pkg, oracle_lib, variant):
         kw = dict(metric=(1, 2, 2))
     elif variant == "sad_subpel":
         kw = dict(metric=(0, 0, 0))
+    elif variant == "sse_subpel":
+        kw = dict(metric=(0, 1, 1))
+    elif variant == "sad_hpel_satd_qpel":
+        kw = dict(metric=(0, 0, 2))          # the stages of one launch run different metrics
+    elif variant == "satd_hpel_sse_qpel_qcif":
+        kw = dict(metric=(0, 2, 1))
+        w, h, n_refs = 176, 144, 2          # block-origin clamp of SAD / SSE on the global-memory path
+    elif variant == "sad_subpel_t8x8":
+        kw = dict(metric=(0, 0, 0), transform8x8=1)       # the transform size does not matter without the Hadamard metric
     elif variant == "qcif_sr32":
         w, h, n_refs = 176, 144, 2          # most windows leave the picture
     d, cfg = _cfg(ob, **kw)
