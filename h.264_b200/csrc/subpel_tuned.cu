@@ -70,7 +70,7 @@ __constant__ int8_t c_spy[9] = { 0, -1, 1, -1, -1, 0, 0, 1, 1 };
 
 template <bool T8> struct __align__(128) Smem {
   uint8_t  region[REGION_BYTES + 128];      // [plane][RH][RW]
-  uint32_t curpk[16][8];                    // per tile: rows 0..3 x {pixels (0,2), pixels (1,3)} as biased 16-bit lanes
+  uint32_t curpk[16][8];                    // per tile: rows 0..3 x {(c0 + c1 | c2 + c3), (c0 - c1 | c2 - c3)} as biased 16-bit lanes
   uint32_t cur8[T8 ? 4 : 1][8][4];          // per 8x8 quadrant and row: pixels (0,2), (1,3), (4,6), (5,7), bias BIAS8
   uint32_t job[48];                         // me_mb_job
   int      cost[T8 ? 9 : 1][9];             // 8x8-transform partitions (block types 1..4): cost per candidate
@@ -85,43 +85,46 @@ template <bool T8> struct __align__(128) Smem {
 __device__ __forceinline__ unsigned padd(unsigned a, unsigned b) { return a + b - BIAS2; }
 __device__ __forceinline__ unsigned psub(unsigned a, unsigned b) { return a - b + BIAS2; }
 
-// SATD of one 4x4 tile (HadamardSAD4x4, me_distortion.c:182-264): ref rows r[y] (4 bytes each), cur rows as biased lane pairs
+// SATD of one 4x4 tile (HadamardSAD4x4, me_distortion.c:182-264): ref rows r[y] (4 bytes each); the current rows arrive with
+// the first horizontal stage already applied (job-invariant): cs = (c0 + c1 | c2 + c3), ct = (c0 - c1 | c2 - c3), biased lanes
 __device__ __forceinline__ int satd4x4(const unsigned r[4], const uint4 c01, const uint4 c23)
 {
-  const unsigned ce[4] = { c01.x, c01.z, c23.x, c23.z }, co[4] = { c01.y, c01.w, c23.y, c23.w };
+  const unsigned cs[4] = { c01.x, c01.z, c23.x, c23.z }, ct[4] = { c01.y, c01.w, c23.y, c23.w };
   unsigned s[4], t[4];
 #pragma unroll
   for (int y = 0; y < 4; y++) {
-    const unsigned de = ce[y] - __byte_perm(r[y], 0, 0x4240);      // (c0 - r0 + B | c2 - r2 + B)
-    const unsigned dd = co[y] - __byte_perm(r[y], 0, 0x4341);      // (c1 - r1 + B | c3 - r3 + B)
-    s[y] = padd(de, dd);                                           // (d0 + d1 | d2 + d3)
-    t[y] = psub(de, dd);                                           // (d0 - d1 | d2 - d3)
+    const unsigned re = __byte_perm(r[y], 0, 0x4240), ro = __byte_perm(r[y], 0, 0x4341);      // (r0 | r2), (r1 | r3)
+    s[y] = cs[y] - re - ro;                                        // (d0 + d1 | d2 + d3), d = c - r, bias B
+    t[y] = ct[y] - re + ro;                                        // (d0 - d1 | d2 - d3)
   }
-  unsigned acc = 0;
+  // after the vertical stages a register holds (u + B | v + B) and the last stage would give u + v and u - v:
+  // |u + v| + |u - v| = 2 max(|u|, |v|), so the SATD ((sum + 1) >> 1) is the sum of max(|u|, |v|) over the eight registers --
+  // packed 16-bit maxima (VIMNMX.U16x2): B + |x| = max(x + B, B - x), then the two lanes of a register against each other
+  unsigned accp = 0;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
     const unsigned *x = k ? t : s;
     const unsigned a = padd(x[0], x[1]), b = psub(x[0], x[1]), c = padd(x[2], x[3]), d = psub(x[2], x[3]);
     const unsigned y4[4] = { padd(a, c), psub(a, c), padd(b, d), psub(b, d) };
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const unsigned lo = y4[i] & 0xffffu, hi = y4[i] >> 16;       // u + B, v + B
-      acc = __usad(lo, hi, acc);                                   // |u - v|
-      acc = __usad(lo + hi, 2 * BIAS, acc);                        // |u + v|
+    for (int i = 0; i < 4; i += 2) {
+      const unsigned mi = __vmaxu2(y4[i], 2 * BIAS2 - y4[i]), mj = __vmaxu2(y4[i + 1], 2 * BIAS2 - y4[i + 1]);
+      accp += __vmaxu2(__byte_perm(mi, mj, 0x5410), __byte_perm(mi, mj, 0x7632));       // (B + max_i | B + max_j)
     }
   }
-  return (int)((acc + 1) >> 1);
+  return (int)((accp & 0xffffu) + (accp >> 16)) - 8 * (int)BIAS;   // four values per lane: <= 4 * (4096 + 4080) < 65536
 }
 
 // SAD / squared error of one 4x4 tile (the tile's share of computeSAD / computeSSE, me_distortion.c:351, :1042): the current rows
-// come back from their biased lane pairs as plain byte words
+// come back from cs / ct as plain byte words (cs + ct = twice the even pixels, cs - ct = twice the odd ones)
 __device__ __forceinline__ int sadsse4x4(const unsigned r[4], const uint4 c01, const uint4 c23, int sse)
 {
-  const unsigned ce[4] = { c01.x, c01.z, c23.x, c23.z }, co[4] = { c01.y, c01.w, c23.y, c23.w };
+  const unsigned cs[4] = { c01.x, c01.z, c23.x, c23.z }, ct[4] = { c01.y, c01.w, c23.y, c23.w };
   int acc = 0;
 #pragma unroll
   for (int y = 0; y < 4; y++) {
-    const unsigned cw = __byte_perm(ce[y] - BIAS2, co[y] - BIAS2, 0x6240);      // c0 | c1 << 8 | c2 << 16 | c3 << 24
+    const unsigned ce = (cs[y] + ct[y] - 2 * BIAS2) >> 1, co = (cs[y] - ct[y]) >> 1;      // (c0 | c2), (c1 | c3): the doubled lanes are even
+    const unsigned cw = __byte_perm(ce, co, 0x6240);                            // c0 | c1 << 8 | c2 << 16 | c3 << 24
     if (!sse) acc = (int)__vsadu4(r[y], cw) + acc;
     else {
 #pragma unroll
@@ -237,8 +240,9 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     {
       // current macroblock as biased lane pairs: thread -> (tile, row, even/odd)
       const int tile = tid >> 3, k = tid & 7, y = k >> 1, odd = k & 1;
-      const uint8_t *p = cur + (size_t)(jv.opix_y + 4 * (tile >> 2) + y) * cur_pitch + jv.opix_x + 4 * (tile & 3) + odd;
-      sm.curpk[tile][k] = ((unsigned)p[0] | ((unsigned)p[2] << 16)) + BIAS2;
+      const uint8_t *p = cur + (size_t)(jv.opix_y + 4 * (tile >> 2) + y) * cur_pitch + jv.opix_x + 4 * (tile & 3);
+      const unsigned ce = (unsigned)p[0] | ((unsigned)p[2] << 16), co = (unsigned)p[1] | ((unsigned)p[3] << 16);
+      sm.curpk[tile][k] = (odd ? ce - co : ce + co) + BIAS2;       // cs / ct of satd4x4
       if (T8) {
         // 8x8 quadrants: thread -> (quadrant, row, lane pair)
         const int quad = tid >> 5, y8 = (tid >> 2) & 7, j = tid & 3;
