@@ -39,7 +39,7 @@ constexpr int NT = 128;
 constexpr int T4_CTAS = 7;                  // CTAs per SM of the 4x4-transform variant (72 registers); 8 CTAs at 64 registers measured 0.65 ms instead of 0.60
 constexpr int T8_CTAS = 7;                  // CTAs per SM of the 8x8-transform variant (72 registers, no spills; measured 4: 1.11, 5: 1.01, 6: 0.95 ms)
 constexpr unsigned BIAS = 0x1000u, BIAS2 = 0x10001000u;       // 4x4 Hadamard: |coefficient| <= 16 * 255 < 4096
-constexpr unsigned BIAS8 = 0x4000u, BIAS82 = 0x40004000u;     // 8x8 Hadamard: |coefficient before the last stage| <= 32 * 255 < 16384
+constexpr unsigned BIAS82 = 0x40004000u;                      // 8x8 Hadamard: bias 0x4000 per lane, |coefficient before the last stage| <= 32 * 255 < 16384
 
 // slot q of a (type, candidate) group of 16 lanes -> raster tile 4*ty+tx / partition number (ABI order); the tiles of a
 // partition are adjacent and aligned to the partition's tile count
@@ -71,7 +71,7 @@ __constant__ int8_t c_spy[9] = { 0, -1, 1, -1, -1, 0, 0, 1, 1 };
 template <bool T8> struct __align__(128) Smem {
   uint8_t  region[REGION_BYTES + 128];      // [plane][RH][RW]
   uint32_t curpk[16][8];                    // per tile: rows 0..3 x {(c0 + c1 | c2 + c3), (c0 - c1 | c2 - c3)} as biased 16-bit lanes
-  uint32_t cur8[T8 ? 4 : 1][8][4];          // per 8x8 quadrant and row: pixels (0,2), (1,3), (4,6), (5,7), bias BIAS8
+  uint32_t cur8[T8 ? 4 : 1][8][4];          // per 8x8 quadrant and row: (c0+c1 | c2+c3), (c0-c1 | c2-c3), (c4+c5 | c6+c7), (c4-c5 | c6-c7), bias BIAS8
   uint32_t job[48];                         // me_mb_job
   int      cost[T8 ? 9 : 1][9];             // 8x8-transform partitions (block types 1..4): cost per candidate
   int      mv[ME_NUM_PARTITIONS][2];        // current best vector, quarter pel
@@ -137,18 +137,19 @@ __device__ __forceinline__ int sadsse4x4(const unsigned r[4], const uint4 c01, c
 __device__ __forceinline__ unsigned padd8(unsigned a, unsigned b) { return a + b - BIAS82; }
 __device__ __forceinline__ unsigned psub8(unsigned a, unsigned b) { return a - b + BIAS82; }
 
-// SATD of one 8x8 tile (HadamardSAD8x8, me_distortion.c:272-343): ref rows as two words (pixels 0..3, 4..7), cur rows from
-// shared memory as four biased lane pairs (0,2) (1,3) (4,6) (5,7).  Index bits 0 and 2 of the row transform pair whole
-// registers, bit 1 pairs the two lanes of a register and is folded into the absolute sum like in the 4x4 case.
+// SATD of one 8x8 tile (HadamardSAD8x8, me_distortion.c:272-343): ref rows as two words (pixels 0..3, 4..7); the current rows
+// come from shared memory with the first horizontal stage applied, four biased lane pairs per row: (c0 + c1 | c2 + c3),
+// (c0 - c1 | c2 - c3), (c4 + c5 | c6 + c7), (c4 - c5 | c6 - c7).  Index bits 0 and 2 of the row transform pair whole registers,
+// bit 1 pairs the two lanes of a register and is folded into the absolute sum like in the 4x4 case (packed maxima).
 __device__ __forceinline__ int satd8x8(const unsigned rl[8], const unsigned rr[8], const uint32_t *curp)
 {
   unsigned x[8][4];
 #pragma unroll
   for (int y = 0; y < 8; y++) {
     const uint4 c = *reinterpret_cast<const uint4 *>(curp + 4 * y);
-    const unsigned el = c.x - __byte_perm(rl[y], 0, 0x4240), ol = c.y - __byte_perm(rl[y], 0, 0x4341);
-    const unsigned er = c.z - __byte_perm(rr[y], 0, 0x4240), orr = c.w - __byte_perm(rr[y], 0, 0x4341);
-    const unsigned a0 = padd8(el, ol), a1 = psub8(el, ol), a2 = padd8(er, orr), a3 = psub8(er, orr);
+    const unsigned le = __byte_perm(rl[y], 0, 0x4240), lo = __byte_perm(rl[y], 0, 0x4341);
+    const unsigned re = __byte_perm(rr[y], 0, 0x4240), ro = __byte_perm(rr[y], 0, 0x4341);
+    const unsigned a0 = c.x - le - lo, a1 = c.y - le + lo, a2 = c.z - re - ro, a3 = c.w - re + ro;
     x[y][0] = padd8(a0, a2); x[y][1] = psub8(a0, a2); x[y][2] = padd8(a1, a3); x[y][3] = psub8(a1, a3);
   }
   unsigned acc = 0;
@@ -162,14 +163,16 @@ __device__ __forceinline__ int satd8x8(const unsigned rl[8], const unsigned rr[8
 #pragma unroll
       for (int y = 0; y < 8; y++)
         if (!(y & st)) { const unsigned a = v[y], b = v[y + st]; v[y] = padd8(a, b); v[y + st] = psub8(a, b); }
+    // |u + v| + |u - v| = 2 max(|u|, |v|) per register (u + B8 | v + B8): B8 + |x| = max(x + B8, B8 - x), then lane against lane
+    unsigned accp = 0;                                             // four values <= 16320 per lane
 #pragma unroll
-    for (int y = 0; y < 8; y++) {
-      const unsigned lo = v[y] & 0xffffu, hi = v[y] >> 16;         // u + B, v + B
-      acc = __usad(lo, hi, acc);                                   // |u - v|
-      acc = __usad(lo + hi, 2 * BIAS8, acc);                       // |u + v|
+    for (int y = 0; y < 8; y += 2) {
+      const unsigned mi = __vmaxu2(v[y], 2 * BIAS82 - v[y]), mj = __vmaxu2(v[y + 1], 2 * BIAS82 - v[y + 1]);
+      accp += __vmaxu2(__byte_perm(mi, mj, 0x5410), __byte_perm(mi, mj, 0x7632)) - BIAS82;
     }
+    acc += (accp & 0xffffu) + (accp >> 16);
   }
-  return (int)((acc + 2) >> 2);
+  return (int)((2 * acc + 2) >> 2);                                // acc = half the reference's sum of absolute values
 }
 
 struct JobView { int opix_x, opix_y, list, ref, slice_type; };
@@ -246,8 +249,9 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
       if (T8) {
         // 8x8 quadrants: thread -> (quadrant, row, lane pair)
         const int quad = tid >> 5, y8 = (tid >> 2) & 7, j = tid & 3;
-        const uint8_t *p8 = cur + (size_t)(jv.opix_y + 8 * (quad >> 1) + y8) * cur_pitch + jv.opix_x + 8 * (quad & 1) + 4 * (j >> 1) + (j & 1);
-        sm.cur8[quad][y8][j] = ((unsigned)p8[0] | ((unsigned)p8[2] << 16)) + BIAS82;
+        const uint8_t *p8 = cur + (size_t)(jv.opix_y + 8 * (quad >> 1) + y8) * cur_pitch + jv.opix_x + 8 * (quad & 1) + 4 * (j >> 1);
+        const unsigned e8 = (unsigned)p8[0] | ((unsigned)p8[2] << 16), o8 = (unsigned)p8[1] | ((unsigned)p8[3] << 16);
+        sm.cur8[quad][y8][j] = ((j & 1) ? e8 - o8 : e8 + o8) + BIAS82;      // first horizontal stage, see satd8x8
       }
     }
     int Xr, Yr;
