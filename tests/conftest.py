@@ -46,6 +46,7 @@ GOLDEN_CASES = {
     "chroma_fs": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),    # ChromaMEEnable = 1, SearchMode = -1
     "wpbc": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),      # implicit weighted bi-prediction + chroma
     "wpb": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),    # + weighted bi-prediction
+    "epzs": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),   # plain sub-pel calls under SearchMode = 3
 }
 
 

@@ -182,11 +182,35 @@ def main():
         assert (bf[:, 29] > 0).all() and ((bf[:, 27] >> 24) & 1).all() and len(set(bf[:, 30].tolist())) > 1
         tr.save_npz(os.path.join(HERE, "wpbc.npz"), keep_mask(tr, 12))
         crc["wpbc"] = planes_crc(tr, d)
+    epzs(crc, md5s)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
+def epzs(crc, md5s):
+    """epzs: encoder.cfg with SearchMode=3 (EPZS), EPZSSubPelGrid=1, EPZSSubPelME=0, EPZSSubPelMEBiPred=0 -- the integer-pel stage is
+    the reference's own pattern search (not traced, not on the path); what reaches the traced functions are the plain sub-pel
+    routines it still calls (mv-search.c:823, :1018), with start vectors that are not multiples of four.  Every 3rd macroblock."""
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(os.path.join(REF, "fixtures", "foreman_part_qcif.yuv"), d)
+        run_trace(d, ["-d", "encoder.cfg", "-p", "SearchMode=3", "-p", "EPZSSubPelME=0", "-p", "EPZSSubPelMEBiPred=0",
+                      "-p", "EPZSSubPelGrid=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"])
+        md5s["epzs"] = {"test.264": md5(os.path.join(d, "test.264"))}
+        tr = Trace(d)
+        sp = tr.of_type(REC_SUBPEL)
+        assert len(sp) > 1000 and not len(tr.of_type(REC_FFS)) and ((sp[:, 12] & 3) != 0).any() and len(tr.of_type(REC_BI_SUB))
+        tr.save_npz(os.path.join(HERE, "epzs.npz"), keep_mask(tr, 3))
+        crc["epzs"] = planes_crc(tr, d)
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["epzs"]:                  # add this case without rewriting the other fixtures
+        crc = json.load(open(os.path.join(HERE, "planes_crc.json")))
+        md5s = json.load(open(os.path.join(HERE, "bitstream_md5.json")))
+        epzs(crc, md5s)
+        json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
+        json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
+    else:
+        main()

@@ -90,7 +90,8 @@ def test_dropin_calls_match_reference_trace(pkg, case):
         impl.close()
     for name, (n, bad) in res.items():
         assert not bad, (case, name, n, len(bad), bad[:3])
-    assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000) and res["subpel"][0] > 1000
+    # the pattern-search trace (epzs) holds no integer-pel calls of the path: that stage stays the reference's own
+    assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000 or case == "epzs") and res["subpel"][0] > 1000
 
 
 # ------------------------------------------------------------------------------------------------ frame batch

@@ -30,7 +30,8 @@ def test_calls_match_reference_trace(oracle_lib, case):
     impl.close()
     for name, (n, bad) in res.items():
         assert not bad, (case, name, n, bad[:3])
-    assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000) and res["subpel"][0] > 1000
+    # the pattern-search trace (epzs) holds no integer-pel calls of the path: that stage stays the reference's own
+    assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000 or case == "epzs") and res["subpel"][0] > 1000
     if case == "kat":
         assert res["bi_full"][0] > 100 and res["bi_sub"][0] > 50
 
