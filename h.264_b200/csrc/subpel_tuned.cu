@@ -36,7 +36,7 @@ constexpr int RW = 48;                      // region row pitch (bytes): 2*RD + 
 constexpr int RH = 2 * RD + 17;             // region rows
 constexpr int REGION_BYTES = RW * RH * 16;  // all 16 planes
 constexpr int NT = 128;
-constexpr int T4_CTAS = 7;                  // CTAs per SM of the 4x4-transform variant (72 registers); 8 CTAs at 64 registers (no spills) measured 0.685 ms instead of 0.584
+constexpr int T4_CTAS = 7;                  // CTAs per SM of the 4x4-transform variant (72 registers); 8 CTAs at 64 registers (no spills) measured 0.685 ms, 6 CTAs at 80 registers 0.607 ms, instead of 0.584
 constexpr int T8_CTAS = 7;                  // CTAs per SM of the 8x8-transform variant (72 registers, no spills; measured 4: 1.11, 5: 1.01, 6: 0.95 ms)
 constexpr unsigned BIAS = 0x1000u, BIAS2 = 0x10001000u;       // 4x4 Hadamard: |coefficient| <= 16 * 255 < 4096
 constexpr unsigned BIAS82 = 0x40004000u;                      // 8x8 Hadamard: bias 0x4000 per lane, |coefficient before the last stage| <= 32 * 255 < 16384
