@@ -27,13 +27,6 @@ __device__ __forceinline__ int me_setup_range(const MeCfgDev &c, int ref)
 {
   return (c.full_search == 2 || ref == 0) ? c.search_range : c.search_range / 2;   // me_fullfast.c:127-140
 }
-__device__ __forceinline__ int me_block_range(const MeCfgDev &c, int ref, int blocktype)
-{
-  int r1 = (ref < 1 ? ref : 1) + 1;                                                 // mv-search.c:1411-1416
-  if (c.full_search == 2) return c.search_range;
-  if (c.full_search == 1) return c.search_range / r1;
-  return c.search_range / (r1 * (blocktype < 2 ? blocktype : 2));
-}
 
 // Fill the shared-memory window: tile(y,x) = picture sample at (cy-R+y, cx-R+x) with edge replication.  Outside the
 // picture JM clamps the 16x16 block ORIGIN into the 20-pixel border (refbuf.c:37); as the border is pure replication

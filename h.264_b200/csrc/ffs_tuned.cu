@@ -80,6 +80,7 @@ template <int R> struct __align__(128) Smem {
   uint32_t red[Geo<R>::NW][2][NSLOT];
   uint32_t pslot[2][24];                        // per (h, slot): predictor word (x | y << 16) of the job about to be searched, 21 used
   uint32_t job[3][48];                          // me_mb_job ring (188 bytes each)
+  int      jid[4];                              // job ids of the ring slots (>= n_jobs: no such job), 3 used
   uint16_t sptab[Geo<R>::SIDE * Geo<R>::SIDE];  // spiral index of (dy, dx)
   MeRefDev refs[2 * ME_MAX_REFS];               // copy of the reference table
   unsigned long long mbar[2];
@@ -370,7 +371,8 @@ __global__ void __launch_bounds__(Geo<R>::NT, (R == 32) ? 3 : (R == 16) ? 6 : 1)
 me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                     const __grid_constant__ WinMaps win_maps, const __grid_constant__ CUtensorMap cur_map,
                     const uint8_t *__restrict__ cur_pic, int cur_pitch, int use_tma,
-                    MeCfgDev cfg, MeResultInt *__restrict__ out, int *__restrict__ deferred /* [0] count, [1..] job ids */)
+                    MeCfgDev cfg, MeResultInt *__restrict__ out, int *__restrict__ deferred /* [0] count, [1..] job ids */,
+                    int *__restrict__ ticket /* jobs handed out beyond the first two rounds (zeroed by the caller) */)
 {
   using G = Geo<R>;
   constexpr int N = G::N, NP = G::NP, SIDE = G::SIDE, NT = G::NT;
@@ -386,8 +388,11 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
   t.sp_addr = smem_u32(&sm.sptab[dx]);
   t.cy_addr = smem_u32(&sm.cyt[0][t.h][0]);
   const unsigned lut_addr = smem_u32(sm.lut);
-  const int n_mine = (n_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  if (n_mine <= 0) return;
+  // Jobs are handed out dynamically: a CTA's first two jobs are blockIdx.x and blockIdx.x + gridDim.x, every further one is
+  // the next ticket of a global counter, drawn two jobs ahead (the descriptor travels one job ahead of the window).  With a
+  // static stride the CTAs of an SM finish at different times -- the warp schedulers favour one of the resident warps -- and
+  // the last ones run alone at a third of the issue rate (ncu, round 1: 2.6 of 3 resident warps on average).
+  if ((int)blockIdx.x >= n_jobs) return;
 
   // ---- once per CTA: spiral table, barriers, first two job descriptors, first window
   for (int i = tid; i < SIDE * SIDE; i += NT) {
@@ -404,8 +409,9 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     reinterpret_cast<uint32_t *>(sm.refs)[i] = reinterpret_cast<const uint32_t *>(ref_table)[i];
   if (tid < JW) {
     sm.job[0][tid] = jobs[(size_t)blockIdx.x * JW + tid];
-    if (n_mine > 1) sm.job[1][tid] = jobs[((size_t)blockIdx.x + gridDim.x) * JW + tid];
+    if ((int)(blockIdx.x + gridDim.x) < n_jobs) sm.job[1][tid] = jobs[((size_t)blockIdx.x + gridDim.x) * JW + tid];
   }
+  if (tid == 0) { sm.jid[0] = (int)blockIdx.x; sm.jid[1] = (int)(blockIdx.x + gridDim.x); sm.jid[2] = n_jobs; }
   __syncthreads();
   // predictors in slot order (read with vector loads when a thread derives its table addresses)
   auto fill_pslot = [&](const uint32_t *jwn) {
@@ -436,22 +442,28 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
   };
   if (tid == 0 && use_tma) issue_loads(0, 0);
 
-  for (int it = 0; it < n_mine; it++) {
-    const int buf = it & 1, slot = it % 3;
-    const int job_id = (int)blockIdx.x + it * (int)gridDim.x;
+  for (int it = 0;; it++) {
+    const int buf = it & 1, slot = it % 3, slot1 = (it + 1) % 3, slot2 = (it + 2) % 3;
+    const int job_id = sm.jid[slot];
+    if (job_id >= n_jobs) break;
+    const bool has_next = sm.jid[slot1] < n_jobs;
     const uint32_t *jw = sm.job[slot];
-    // prefetch: window + macroblock of the next job (TMA), descriptor of the one after (registers -> shared at the end)
-    if (tid == 32 * (it & (G::NW - 1)) && use_tma && it + 1 < n_mine) issue_loads((it + 1) % 3, buf ^ 1);   // rotating warp
+    // prefetch: window + macroblock of the next job (TMA); ticket of the job after that (its descriptor is fetched behind the
+    // barrier in front of the sweep and goes registers -> shared at the end)
+    if (tid == 32 * (it & (G::NW - 1)) && use_tma && has_next) issue_loads(slot1, buf ^ 1);   // rotating warp
+    int tk = 0;
+    if (tid == 0) tk = has_next ? atomicAdd(ticket, 1) + 2 * (int)gridDim.x : n_jobs;
     uint32_t pf = 0;
-    if (tid < JW && it + 2 < n_mine) pf = jobs[((size_t)job_id + 2 * (size_t)gridDim.x) * JW + tid];
 
     const JobView jv = job_view(jw);
     if ((unsigned)jv.lambda > (1u << 24)) {
       // lambda too large for 32-bit keys (never the case for H.264 quantisers): leave the job to the kernel of ffs_basic.cu
-      if (tid == 0) deferred[1 + atomicAdd(&deferred[0], 1)] = job_id;
+      if (tid == 0) { deferred[1 + atomicAdd(&deferred[0], 1)] = job_id; sm.jid[slot2] = tk; }
       if (use_tma) mbar_wait(smem_u32(&sm.mbar[buf]), (unsigned)((it >> 1) & 1));
-      if (tid < JW && it + 2 < n_mine) sm.job[(it + 2) % 3][tid] = pf;
-      if (it + 1 < n_mine) fill_pslot(sm.job[(it + 1) % 3]);
+      __syncthreads();
+      const int nid2 = sm.jid[slot2];
+      if (tid < JW && nid2 < n_jobs) sm.job[slot2][tid] = jobs[(size_t)nid2 * JW + tid];
+      if (has_next) fill_pslot(sm.job[slot1]);
       __syncthreads();
       continue;
     }
@@ -527,7 +539,10 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
         sm.win[buf][i] = rf.search[(size_t)sy * rf.spitch + sx];
       }
     }
-    __syncthreads();          // tables + manual window visible
+    if (tid == 0) sm.jid[slot2] = tk;
+    __syncthreads();          // tables + manual window + next ticket visible
+    const int nid2 = sm.jid[slot2];
+    if (tid < JW && nid2 < n_jobs) pf = jobs[(size_t)nid2 * JW + tid];
 #pragma unroll
     for (int k = 0; k < 16; k++) { rg.curL[k] = sm.cur[buf][4 * k + 2 * t.h]; rg.curR[k] = sm.cur[buf][4 * k + 2 * t.h + 1]; }
 
@@ -583,25 +598,28 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
       reinterpret_cast<uint32_t *>(out[job_id].mv)[p] = mvw;
       out[job_id].cost[p] = (int)cost;
     }
-    if (tid < JW && it + 2 < n_mine) sm.job[(it + 2) % 3][tid] = pf;
-    if (it + 1 < n_mine) fill_pslot(sm.job[(it + 1) % 3]);
+    if (tid < JW && nid2 < n_jobs) sm.job[slot2][tid] = pf;
+    if (has_next) fill_pslot(sm.job[slot1]);
     __syncthreads();          // window / tables / red free for the next job
   }
 }
 
 template <int R>
 int launch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps, const void *cur_map,
-           const uint8_t *cur_pic, int cur_pitch, const MeCfgDev *cfg, MeResultInt *out, int *deferred, cudaStream_t st)
+           const uint8_t *cur_pic, int cur_pitch, const MeCfgDev *cfg, MeResultInt *out, int *deferred, int *ticket, cudaStream_t st)
 {
-  static int sms = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(me_ffs_tuned_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<R>));
-    attr_done = true;
+  // SM count and the shared-memory opt-in are per device: cached per device ordinal (the library may be shut down and
+  // initialised again on another GPU of the box)
+  static int sms_of[64];
+  static bool attr_done[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!attr_done[dev]) {
+    if (cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(me_ffs_tuned_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<R>)) != cudaSuccess) return 0;
+    attr_done[dev] = true;
   }
+  const int sms = sms_of[dev];
   const int per_sm = (R == 32) ? 3 : (R == 16) ? 6 : 1;
   int grid = sms * per_sm;
   if (grid > n_jobs) grid = n_jobs;
@@ -614,7 +632,7 @@ int launch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void 
   static int use_tma = -1;
   if (use_tma < 0) { const char *e = getenv("ME_CUDA_FFS_TMA"); use_tma = !(e && e[0] == '0'); }
   me_ffs_tuned_kernel<R><<<grid, Geo<R>::NT, sizeof(Smem<R>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, wm, cm,
-                                                                    cur_pic, cur_pitch, use_tma, *cfg, out, deferred);
+                                                                    cur_pic, cur_pitch, use_tma, *cfg, out, deferred, ticket);
   return 1;
 }
 
@@ -638,19 +656,20 @@ extern "C" int me_ffs_tuned_window(int search_range)
 // Returns the number of kernels launched; 0 = configuration not covered (the caller runs the kernel of ffs_basic.cu on
 // every job).  win_maps: host array [2][ME_MAX_REFS] of 128-byte tensor maps of the listed references' search planes;
 // n_refs0 / n_refs1: list sizes.  Jobs the kernel cannot take (lambda factor above 2^24) are appended to deferred[1..],
-// count in deferred[0] (zeroed by the caller); the caller then runs the kernel of ffs_basic.cu on that list.
+// count in deferred[0] (zeroed by the caller); the caller then runs the kernel of ffs_basic.cu on that list.  ticket: the
+// counter the persistent CTAs draw their jobs from (zeroed by the caller).
 extern "C" int me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps,
                                          int n_refs0, int n_refs1, const void *cur_map, const uint8_t *cur_pic, int cur_pitch,
-                                         const MeCfgDev *cfg, MeResultInt *out, int *deferred, cudaStream_t st)
+                                         const MeCfgDev *cfg, MeResultInt *out, int *deferred, int *ticket, cudaStream_t st)
 {
-  if (!win_maps || !cur_map || !deferred) return 0;
+  if (!win_maps || !cur_map || !deferred || !ticket) return 0;
   if (n_refs0 > TUNED_MAX_REFS || n_refs1 > TUNED_MAX_REFS) return 0;
   if (cfg->metric[0] != 0 || !cfg->rdopt || cfg->full_search != 2) return 0;
   if (cfg->chroma.on) return 0;                 // chroma terms (ChromaMEEnable): the general kernel
   switch (cfg->search_range) {
-    case 16: return launch<16>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, st);
-    case 32: return launch<32>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, st);
-    case 64: return launch<64>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, st);
+    case 16: return launch<16>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, ticket, st);
+    case 32: return launch<32>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, ticket, st);
+    case 64: return launch<64>(jobs, n_jobs, ref_table, win_maps, cur_map, cur_pic, cur_pitch, cfg, out, deferred, ticket, st);
     default: return 0;
   }
 }

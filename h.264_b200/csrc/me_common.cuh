@@ -194,6 +194,52 @@ __device__ __forceinline__ void me_leaf_chroma(const MeRefDev &r, const MeChroma
       }
 }
 
+// search range of one block search (PartitionMotionSearch, mv-search.c:1411-1416)
+__host__ __device__ __forceinline__ int me_block_range(const MeCfgDev &c, int ref, int blocktype)
+{
+  int r1 = (ref < 1 ? ref : 1) + 1;
+  if (c.full_search == 2) return c.search_range;
+  if (c.full_search == 1) return c.search_range / r1;
+  return c.search_range / (r1 * (blocktype < 2 ? blocktype : 2));
+}
+
+// ---- one launch per PartitionMotionSearch (me_cuda_pms_begin, include/me_cuda.h): kernel parameters and result records
+struct MePmsRef {               // one (list, ref) of the macroblock: planes the uni-predictive searches read, stored surfaces, centre
+  MeRefDev dev;
+  const int32_t *surf;          // [41][P] in spiral order (me_ffs_surfaces_kernel)
+  int offx, offy, setup_range;  // search centre relative to the macroblock origin, range the surfaces were built for
+  int list, ref;
+};
+struct MePmsParams {
+  me_mb_motion st;
+  MePmsRef refs[ME_PMS_MAX_REFS];
+  int n_refs, n_items;
+  int item_type[ME_PMS_MAX_ITEMS], item_blk[ME_PMS_MAX_ITEMS];
+  int item_slot[ME_PMS_MAX_ITEMS];      // where the item's records go: result[(slot * ME_PMS_MAX_REFS + list-ref) * 4 + k]
+  int lambda[3];
+  int opix_x, opix_y, slice_type;
+};
+#define ME_PMS_SLOTS 8          // items whose results can wait at the same time (a later launch must not drop e.g. the 8x16 guess)
+struct MePmsRecord {            // one block search of a group launch, as the drop-in calls will ask for it
+  int pmv_x, pmv_y;             // the predictor the device derived (SetMotionVectorPredictor)
+  int int_mvx, int_mvy, int_cost;       // FastFullPelBlockMotionSearch result (integer pel)
+  int mvx, mvy, cost;           // SubPelBlockMotionSearch result (quarter pel)
+};
+// sub-blocks of PartitionMotionSearch(blocktype, block8x8) in call order (mv-search.c:1387-1401, :1424-1430): 4x4-unit origin
+// (h, v) of the k-th block search; returns their number
+__host__ __device__ inline int me_pms_blocks(int blocktype, int block8x8, int hs[4], int vs[4])
+{
+  const int parttype = blocktype < 4 ? blocktype : 4;
+  const int psx[8] = { 4, 4, 4, 2, 2, 2, 1, 1 }, psy[8] = { 4, 4, 2, 4, 2, 1, 2, 1 };     // input->part_size (configfile.c:805-841)
+  const int bx0[5][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 }, { 0, 0, 0, 0 }, { 0, 2, 0, 0 }, { 0, 2, 0, 2 } };
+  const int by0[5][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 }, { 0, 2, 0, 0 }, { 0, 0, 0, 0 }, { 0, 0, 2, 2 } };
+  const int by = by0[parttype][block8x8], bx = bx0[parttype][block8x8];
+  int n = 0;
+  for (int v = by; v < by + psy[parttype]; v += psy[blocktype])
+    for (int h = bx; h < bx + psx[parttype]; h += psx[blocktype]) { hs[n] = h; vs[n] = v; n++; }
+  return n;
+}
+
 // device-side job/result layouts = the ABI structs
 typedef me_mb_job MeJob;
 typedef me_mb_result MeResult;

@@ -45,12 +45,12 @@ void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *re
                                const MeCfgDev *cfg, MeResultInt *out, const int *job_list, cudaStream_t st);
 int  me_launch_ffs_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *win_maps, int n_refs0, int n_refs1,
                                const void *cur_map, const uint8_t *cur_pic, int cur_pitch, const MeCfgDev *cfg, MeResultInt *out,
-                               int *deferred, cudaStream_t st);   // kernels launched, 0 = not applicable
+                               int *deferred, int *ticket, cudaStream_t st);   // kernels launched, 0 = not applicable
 int  me_make_tensor_map_2d(void *out, const void *base, int w, int h, int pitch, int bw, int bh);
 int  me_make_planes_tensor_map(void *out, const void *planes, int pitch, int hp, size_t plane_stride);
 int  me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *plane_maps, int n_refs0, int n_refs1,
                                   const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg, const MeResultInt *in_int, MeResult *out,
-                                  cudaStream_t st);   // 1 = launched, 0 = not applicable
+                                  int *ticket, cudaStream_t st);   // 1 = launched, 0 = not applicable
 int  me_ffs_tuned_window(int search_range);
 void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y, int cx, int cy,
                             int R, int sse, const MeChromaDev *chroma, int32_t *surf, cudaStream_t st);
@@ -63,6 +63,8 @@ void me_launch_ffs_block_subpel(const int32_t *surf_p, int setup_range, int offx
                                 int *result, int ticket, cudaStream_t st);
 void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                              const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st);
+void me_launch_pms_group(const MePmsParams *p, const uint8_t *cur, int cur_pitch, const MeCfgDev *sub_cfg, int rdopt,
+                         MePmsRecord *result, int *done_count, int *ticket_out, int ticket, cudaStream_t st);
 void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
                             const MeCfgDev *cfg, int refinements, int search_range, int subpel, const MeBiW *bw, me_bipred_result *out,
                             cudaStream_t st);
@@ -136,7 +138,8 @@ struct State {
   bool pmaps_ok = false;
   bool maps_ok = false;         // every listed reference has a window tensor map
   TensorMap cur_map{}; bool has_cur_map = false;   // current picture, box 16 x 16
-  int *d_deferred = nullptr; int deferred_cap = 0;  // jobs the tuned search kernel hands back: {count, ids...}
+  int *d_deferred = nullptr; int deferred_cap = 0;  // {job ticket counters of the two tuned kernels; jobs the search kernel hands back: count, ids...}
+  cudaEvent_t ev_order = nullptr;                   // orders a caller's stream (the *_device calls) against the library stream
   cudaStream_t s_in = nullptr, s_out = nullptr;     // host <-> device pipeline of me_cuda_frame_search
   cudaEvent_t ev_in[ME_PIPE_CHUNKS] = {}, ev_done[ME_PIPE_CHUNKS] = {};
   me_ref_handle list[2][ME_MAX_REFS];
@@ -156,6 +159,19 @@ struct State {
   struct { bool seen = false; int lambda[3] = {0, 0, 0}, pos2 = 9, pos4 = 9; } sub_params;
   struct { bool valid = false; int list, ref, ppx, ppy, bt, pmvx, pmvy, mv_in_x, mv_in_y, min_in, lambda[3], pos2, pos4;
            int mvx, mvy, cost; } spec;
+  // One launch per PartitionMotionSearch (me_cuda_pms_begin): result records and the ticket of the last group launch live in one
+  // mapped pinned buffer (h_pms / d_pms); an item = one (blocktype, block8x8) call whose results wait for the drop-in calls
+  struct Pms {
+    MePmsRecord *h_rec = nullptr, *d_rec = nullptr;     // [ME_PMS_SLOTS][ME_PMS_MAX_REFS][4]
+    volatile int *h_ticket = nullptr; int *d_ticket = nullptr;
+    int *d_done = nullptr;
+    int ticket = 0;                                     // of the last launch; launches finish in order, h_ticket follows
+    struct Item { bool valid = false; int blocktype = 0, block8x8 = 0, ticket = 0, lambda[3] = {0, 0, 0}; unsigned age = 0; } item[ME_PMS_SLOTS];
+    unsigned clock = 0;
+    int n_lr = 0, lr_list[ME_PMS_MAX_REFS], lr_ref[ME_PMS_MAX_REFS];
+    bool ffs_served[ME_PMS_SLOTS][ME_PMS_MAX_REFS][4];
+    long long launches = 0, served = 0, missed = 0;
+  } pms;
   // batch scratch
   MeJob *d_jobs = nullptr; MeResult *d_out = nullptr; MeResultInt *d_out_int = nullptr; int batch_cap = 0;
   MeResultInt *d_int_scratch = nullptr; int int_scratch_cap = 0;
@@ -197,12 +213,31 @@ void fatal(const char *what)
 
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// The *_device entry points take a caller's stream.  Everything else -- plane sets, the current picture, the reference
+// table, the scratch arrays of the batch -- is produced and consumed on the library stream, so work on a caller's stream is
+// bracketed: it starts after everything queued on the library stream so far (enter) and the library stream continues after
+// it (leave).  Program order of the calls is then the order on the device, whichever streams they name.
+int enter_stream(cudaStream_t st)
+{
+  if (st == g.stream) return 0;
+  CK(cudaEventRecord(g.ev_order, g.stream));
+  CK(cudaStreamWaitEvent(st, g.ev_order, 0));
+  return 0;
+}
+int leave_stream(cudaStream_t st)
+{
+  if (st == g.stream) return 0;
+  CK(cudaEventRecord(g.ev_order, st));
+  CK(cudaStreamWaitEvent(g.stream, g.ev_order, 0));
+  return 0;
+}
+
 struct ScopedTimer {
   int which; cudaStream_t st; cudaEvent_t e1 = nullptr; bool on;
   ScopedTimer(int w, cudaStream_t s) : which(w), st(s), on(g.timing) {
     if (!on) return;
-    cudaEvent_t e0;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEvent_t e0 = nullptr;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { if (e0) cudaEventDestroy(e0); e1 = nullptr; on = false; return; }
     cudaEventRecord(e0, st);
     g.ev[which].push_back({e0, e1});
   }
@@ -433,6 +468,7 @@ int me_cuda_init(const me_cuda_params *p)
     g.cfg.chroma.cur[0] = g.d_cur_c; g.cfg.chroma.cur[1] = g.d_cur_c + (size_t)g.cfg.chroma.cur_pitch * g.chroma_h;
   }
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&g.ev_order, cudaEventDisableTiming));
   g.cur_pitch = align_up(p->width, 128);
   CK(cudaMalloc((void **)&g.d_cur, (size_t)g.cur_pitch * p->height));
   CK(cudaMalloc((void **)&g.d_table, sizeof g.h_table));
@@ -440,6 +476,17 @@ int me_cuda_init(const me_cuda_params *p)
   CK(cudaHostAlloc((void **)&g.h_result, 64, cudaHostAllocMapped));
   CK(cudaHostGetDevicePointer((void **)&g.d_result, g.h_result, 0));
   memset(g.h_result, 0, 64);
+  {
+    const size_t rec_bytes = sizeof(MePmsRecord) * ME_PMS_SLOTS * ME_PMS_MAX_REFS * 4;
+    void *hp = nullptr, *dp = nullptr;
+    CK(cudaHostAlloc(&hp, rec_bytes + 64, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&dp, hp, 0));
+    memset(hp, 0, rec_bytes + 64);
+    g.pms.h_rec = (MePmsRecord *)hp; g.pms.d_rec = (MePmsRecord *)dp;
+    g.pms.h_ticket = (volatile int *)((char *)hp + rec_bytes); g.pms.d_ticket = (int *)((char *)dp + rec_bytes);
+    CK(cudaMalloc((void **)&g.pms.d_done, sizeof(int)));
+    CK(cudaMemset(g.pms.d_done, 0, sizeof(int)));
+  }
   memset(g.d_surf, 0, sizeof g.d_surf);
   memset(g.setup_done, 0, sizeof g.setup_done);
   g_err[0] = 0;
@@ -458,6 +505,8 @@ void me_cuda_shutdown(void)
   for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) { if (g.twin[l][i].planes) cudaFree(g.twin[l][i].planes); if (g.twin[l][i].search) cudaFree(g.twin[l][i].search); }
   for (int l = 0; l < 2; l++) for (int i = 0; i < ME_MAX_REFS; i++) if (g.d_surf[l][i]) cudaFree(g.d_surf[l][i]);
   cudaFree(g.d_cur); cudaFree(g.d_table); cudaFreeHost(g.h_result);
+  if (g.pms.h_rec) cudaFreeHost(g.pms.h_rec);
+  if (g.pms.d_done) cudaFree(g.pms.d_done);
   if (g.d_deferred) cudaFree(g.d_deferred);
   if (g.s_in) {
     cudaStreamSynchronize(g.s_in); cudaStreamSynchronize(g.s_out);
@@ -475,6 +524,8 @@ void me_cuda_shutdown(void)
   if (g.d_bi_out) cudaFree(g.d_bi_out);
   if (g.d_bi_table) cudaFree(g.d_bi_table);
   if (g_d_stage) { cudaFree(g_d_stage); g_d_stage = nullptr; g_d_stage_bytes = 0; }
+  for (int k = 0; k < 3; k++) { for (auto &p : g.ev[k]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } g.ev[k].clear(); }
+  if (g.ev_order) cudaEventDestroy(g.ev_order);
   cudaStreamDestroy(g.stream);
   g = State();
 }
@@ -488,7 +539,10 @@ int me_cuda_ref_create_device(const void *d_luma, int stride, int w, int h, void
 {
   g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
-  return create_ref_common((const uint8_t *)d_luma, stride, w, h, stream ? (cudaStream_t)stream : g.stream, out);
+  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  if (int rc = enter_stream(st)) return rc;
+  if (int rc = create_ref_common((const uint8_t *)d_luma, stride, w, h, st, out)) return rc;
+  return leave_stream(st);
 }
 
 int me_cuda_ref_create_u8(const uint8_t *luma, int stride, int w, int h, me_ref_handle *out)
@@ -572,7 +626,10 @@ int me_cuda_ref_update_device(me_ref_handle hd, const void *d_luma, int stride, 
 {
   g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
-  return update_ref_common(hd, (const uint8_t *)d_luma, stride, stream ? (cudaStream_t)stream : g.stream);
+  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  if (int rc = enter_stream(st)) return rc;
+  if (int rc = update_ref_common(hd, (const uint8_t *)d_luma, stride, st)) return rc;
+  return leave_stream(st);
 }
 
 int me_cuda_ref_update_u8(me_ref_handle hd, const uint8_t *luma, int stride, int w, int h)
@@ -615,8 +672,10 @@ int me_cuda_set_current_device(const void *d_luma, int stride, int w, int h, voi
 {
   g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
-  CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, d_luma, stride, w, h, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : g.stream));
-  return 0;
+  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  if (int rc = enter_stream(st)) return rc;
+  CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, d_luma, stride, w, h, cudaMemcpyDeviceToDevice, st));
+  return leave_stream(st);
 }
 
 int me_cuda_set_current_u8(const uint8_t *luma, int stride, int w, int h)
@@ -756,7 +815,9 @@ int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, in
   if (list < 0 || list > 1) return fail(1, "me_cuda_set_bipred_weights: list %d out of range", list);
   MeBiW w = {};
   if (apply) {
-    if (weight1 < -128 || weight1 > 127 || weight2 < -128 || weight2 > 127 || offset_bi < -128 || offset_bi > 127 || log_denom < 0 || log_denom > 7)
+    // implicit weights reach 128 (w0 = 64 - w1 with w1 in -64..128, weighted_prediction.c:218-223), e.g. a list-1 picture that
+    // lies in the past; the kernels compute in int
+    if (weight1 < -128 || weight1 > 128 || weight2 < -128 || weight2 > 128 || offset_bi < -128 || offset_bi > 127 || log_denom < 0 || log_denom > 7)
       return fail(1, "me_cuda_set_bipred_weights: weights %d, %d / offset %d / log denominator %d out of range", weight1, weight2, offset_bi, log_denom);
     w.apply = 1; w.w1 = weight1; w.w2 = weight2; w.obi = offset_bi; w.denom = log_denom;
     // chroma: like luma until me_cuda_set_bipred_chroma_weights says otherwise (explicit mode leaves chroma at the default
@@ -772,7 +833,7 @@ int me_cuda_set_bipred_chroma_weights(int list, int component, int weight1, int 
 {
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (list < 0 || list > 1 || component < 0 || component > 1) return fail(1, "me_cuda_set_bipred_chroma_weights: list %d / component %d out of range", list, component);
-  if (weight1 < -128 || weight1 > 127 || weight2 < -128 || weight2 > 127 || offset_bi < -128 || offset_bi > 127)
+  if (weight1 < -128 || weight1 > 128 || weight2 < -128 || weight2 > 128 || offset_bi < -128 || offset_bi > 127)
     return fail(1, "me_cuda_set_bipred_chroma_weights: weights %d, %d / offset %d out of range", weight1, weight2, offset_bi);
   if (!g.bw[list].apply) return fail(1, "me_cuda_set_bipred_chroma_weights: call me_cuda_set_bipred_weights(list %d, apply = 1, ...) first", list);
   g.bw[list].cw1[component] = weight1; g.bw[list].cw2[component] = weight2; g.bw[list].cobi[component] = offset_bi;
@@ -804,11 +865,16 @@ int me_cuda_mb_begin(int opix_x, int opix_y)
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   g.opix_x = opix_x; g.opix_y = opix_y;
   g.spec.valid = false;
+  for (auto &it : g.pms.item) it.valid = false;
   memset(g.setup_done, 0, sizeof g.setup_done);
   return 0;
 }
 
-int me_cuda_ffs_is_set_up(int list, int ref) { return g.setup_done[list][ref]; }
+int me_cuda_ffs_is_set_up(int list, int ref)
+{
+  if (!g.inited || list < 0 || list > 1 || ref < 0 || ref >= ME_MAX_REFS) return 0;
+  return g.setup_done[list][ref];
+}
 
 int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
 {
@@ -856,10 +922,138 @@ static int fetch_result(int *mvx, int *mvy, int *cost)
   return 0;
 }
 
+// ---- one launch per PartitionMotionSearch (include/me_cuda.h)
+int me_cuda_pms_begin(const me_mb_motion *state, int n_items, const me_pms_item *items, const int *lambda)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (!state || !items || !lambda || n_items < 1 || n_items > ME_PMS_MAX_ITEMS) return fail(1, "me_cuda_pms_begin: bad arguments");
+  const int n_lists = g.slice_type == ME_B_SLICE ? 2 : 1;
+  MePmsParams P;
+  memset(&P, 0, sizeof P);
+  P.st = *state;
+  int n = 0;
+  for (int l = 0; l < n_lists; l++)
+    for (int r = 0; r < g.list_n[l]; r++) {
+      if (n == ME_PMS_MAX_REFS) return -1;
+      if (!g.setup_done[l][r]) return fail(1, "me_cuda_pms_begin: me_cuda_ffs_setup(list %d, ref %d) has not run for this macroblock", l, r);
+      RefPic *rp = ref_of(g.list[l][r]);
+      if (!rp) return fail(3, "me_cuda_pms_begin: stale reference handle");
+      const MeRefDev *dev;
+      if (int rc = search_planes(l, r, rp, &dev, nullptr, nullptr, nullptr, nullptr)) return rc;
+      MePmsRef &R = P.refs[n];
+      R.dev = *dev; R.surf = g.d_surf[l][r];
+      R.offx = g.centre_x[l][r] - g.opix_x; R.offy = g.centre_y[l][r] - g.opix_y; R.setup_range = g.setup_range[l][r];
+      R.list = l; R.ref = r;
+      g.pms.lr_list[n] = l; g.pms.lr_ref[n] = r;
+      n++;
+    }
+  if (!n) return -1;
+  P.n_refs = n; P.n_items = n_items;
+  for (int i = 0; i < n_items; i++) {
+    if (items[i].blocktype < 1 || items[i].blocktype > 7 || items[i].block8x8 < 0 || items[i].block8x8 > 3)
+      return fail(1, "me_cuda_pms_begin: item %d (block type %d, block %d) out of range", i, (int)items[i].blocktype, (int)items[i].block8x8);
+    P.item_type[i] = items[i].blocktype; P.item_blk[i] = items[i].block8x8;
+    // result slot: the one that already holds this call (stale), else a free one, else the oldest
+    int slot = -1;
+    for (int k = 0; k < ME_PMS_SLOTS && slot < 0; k++)
+      if (g.pms.item[k].valid && g.pms.item[k].blocktype == items[i].blocktype && g.pms.item[k].block8x8 == items[i].block8x8) slot = k;
+    for (int k = 0; k < ME_PMS_SLOTS && slot < 0; k++) if (!g.pms.item[k].valid) slot = k;
+    if (slot < 0) { slot = 0; for (int k = 1; k < ME_PMS_SLOTS; k++) if (g.pms.item[k].age < g.pms.item[slot].age) slot = k; }
+    auto &it = g.pms.item[slot];
+    it.valid = true; it.blocktype = items[i].blocktype; it.block8x8 = items[i].block8x8; it.ticket = g.pms.ticket + 1; it.age = ++g.pms.clock;
+    for (int k = 0; k < 3; k++) it.lambda[k] = lambda[k];
+    memset(g.pms.ffs_served[slot], 0, sizeof g.pms.ffs_served[slot]);
+    P.item_slot[i] = slot;
+  }
+  for (int i = 0; i < 3; i++) P.lambda[i] = lambda[i];
+  P.opix_x = g.opix_x; P.opix_y = g.opix_y; P.slice_type = g.slice_type;
+  // the sub-pel stage of BlockMotionSearch runs with ChromaMEEnable = (input->ChromaMEEnable == 2) (mv-search.c:779)
+  MeCfgDev sub_cfg = g.cfg;
+  sub_cfg.chroma.on = g.p.chroma_me_enable == 2 ? 1 : 0;
+  g.spec.valid = false;
+  g.pms.n_lr = n;
+  me_launch_pms_group(&P, g.d_cur, g.cur_pitch, &sub_cfg, g.cfg.rdopt, g.pms.d_rec, g.pms.d_done, g.pms.d_ticket, ++g.pms.ticket, g.stream);
+  g.launches++; g.pms.launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int me_cuda_pms_cached(int blocktype, int block8x8)
+{
+  for (const auto &it : g.pms.item) if (it.valid && it.blocktype == blocktype && it.block8x8 == block8x8) return 1;
+  return 0;
+}
+
+int me_cuda_pms_end(int blocktype, int block8x8)
+{
+  for (auto &it : g.pms.item) if (it.valid && it.blocktype == blocktype && it.block8x8 == block8x8) it.valid = false;
+  return 0;
+}
+
+int me_cuda_pms_stats(int64_t *launches, int64_t *served, int64_t *missed)
+{
+  if (launches) *launches = g.pms.launches;
+  if (served) *served = g.pms.served;
+  if (missed) *missed = g.pms.missed;
+  return 0;
+}
+
+// the record of block search (list, ref, blocktype, block at pic_pix) in the results of the last group launch, or nullptr;
+// waits for the launch to finish
+static MePmsRecord *pms_lookup(int list, int ref, int blocktype, int pic_pix_x, int pic_pix_y, bool **ffs_flag, const int **lambda)
+{
+  const int h = (pic_pix_x - g.opix_x) >> 2, v = (pic_pix_y - g.opix_y) >> 2;
+  if (h < 0 || h > 3 || v < 0 || v > 3) return nullptr;
+  for (int i = 0; i < ME_PMS_SLOTS; i++) {
+    const auto &it = g.pms.item[i];
+    if (!it.valid || it.blocktype != blocktype) continue;
+    int hs[4], vs[4];
+    const int n = me_pms_blocks(it.blocktype, it.block8x8, hs, vs);
+    for (int k = 0; k < n; k++) {
+      if (hs[k] != h || vs[k] != v) continue;
+      for (int lr = 0; lr < g.pms.n_lr; lr++) {
+        if (g.pms.lr_list[lr] != list || g.pms.lr_ref[lr] != ref) continue;
+        // results and ticket are written by the kernel into mapped host memory; launches complete in ticket order
+        for (unsigned spin = 0; (int)(*g.pms.h_ticket - it.ticket) < 0; spin++) {
+          if ((spin & 0x3fff) == 0x3fff) {
+            cudaError_t e = cudaStreamQuery(g.stream);
+            if (e != cudaErrorNotReady && (int)(*g.pms.h_ticket - it.ticket) < 0) {
+              fail(2, "partition-search kernel did not deliver its results: %s", cudaGetErrorString(e == cudaSuccess ? cudaGetLastError() : e));
+              fatal("pms");
+              return nullptr;
+            }
+          }
+        }
+        __sync_synchronize();
+        *ffs_flag = &g.pms.ffs_served[i][lr][k];
+        *lambda = it.lambda;
+        return &g.pms.h_rec[(i * ME_PMS_MAX_REFS + lr) * 4 + k];
+      }
+    }
+  }
+  return nullptr;
+}
+
 int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
                                          short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
                                          int search_range, int min_mcost, int lambda_factor)
 {
+  if (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < ME_MAX_REFS && g.setup_done[list][ref]) {
+    bool *flag = nullptr;
+    const int *plam = nullptr;
+    if (MePmsRecord *rec = pms_lookup(list, ref, blocktype, pic_pix_x, pic_pix_y, &flag, &plam)) {
+      // answered from the group launch only when it searched with exactly these arguments
+      if (rec->pmv_x == pred_mv_x && rec->pmv_y == pred_mv_y && lambda_factor == plam[0] && min_mcost == ME_INT_MAX &&
+          search_range == me_block_range(g.cfg, ref, blocktype)) {
+        *mv_x = (short)rec->int_mvx; *mv_y = (short)rec->int_mvy;
+        *flag = true;
+        g.spec.valid = false;
+        g.pms.served++;
+        return rec->int_cost;
+      }
+      g.pms.missed++;
+    }
+  }
   if (!g.inited || list < 0 || list > 1 || ref < 0 || ref >= ME_MAX_REFS || !g.setup_done[list][ref]) {
     fail(1, "me_cuda_FastFullPelBlockMotionSearch: me_cuda_ffs_setup(list %d, ref %d) has not run for this macroblock", list, (int)ref);
     fatal("ffs"); return ME_INT_MAX;
@@ -941,6 +1135,22 @@ int me_cuda_SubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_
   g.sub_params.seen = true;
   for (int i = 0; i < 3; i++) g.sub_params.lambda[i] = lambda[i];
   g.sub_params.pos2 = search_pos2; g.sub_params.pos4 = search_pos4;
+  {
+    bool *flag = nullptr;
+    const int *plam = nullptr;
+    MePmsRecord *rec = pms_lookup(list, ref, blocktype, pic_pix_x, pic_pix_y, &flag, &plam);
+    if (rec && *flag) {                      // the integer-pel call of this block was answered from the same record
+      if (rec->pmv_x == pred_mv_x && rec->pmv_y == pred_mv_y && *mv_x == (short)(rec->int_mvx * 4) && *mv_y == (short)(rec->int_mvy * 4) &&
+          min_mcost == (g.cfg.start_hp ? rec->int_cost : ME_INT_MAX) && search_pos2 == 9 && search_pos4 == 9 &&
+          lambda[0] == plam[0] && lambda[1] == plam[1] && lambda[2] == plam[2]) {
+        *mv_x = (short)rec->mvx; *mv_y = (short)rec->mvy;
+        g.spec.valid = false;
+        g.pms.served++;
+        return rec->cost;
+      }
+      g.pms.missed++;
+    }
+  }
   if (g.spec.valid) {
     const auto &sp = g.spec;
     const bool hit = sp.list == list && sp.ref == ref && sp.ppx == pic_pix_x && sp.ppy == pic_pix_y && sp.bt == blocktype &&
@@ -1027,11 +1237,7 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_jobs <= 0) return 0;
   cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
-  if (g.table_dirty) {
-    // the table upload runs on the library stream; make the caller's stream wait for it
-    if (int rc = upload_table()) return rc;
-    CK(cudaStreamSynchronize(g.stream));
-  }
+  if (int rc = upload_table()) return rc;                  // on the library stream (weighted copies are rebuilt there too)
   MeResultInt *di = (MeResultInt *)d_out_int;
   if (!di) {
     if (g.int_scratch_cap < n_jobs) {
@@ -1045,18 +1251,20 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
   if (g.deferred_cap < n_jobs) {
     if (g.d_deferred) cudaFree(g.d_deferred);
     g.d_deferred = nullptr; g.deferred_cap = 0;
-    CK(cudaMalloc((void **)&g.d_deferred, sizeof(int) * ((size_t)n_jobs + 1)));
+    CK(cudaMalloc((void **)&g.d_deferred, sizeof(int) * ((size_t)n_jobs + 3)));
     g.deferred_cap = n_jobs;
   }
   int launched = 0;
+  // a caller's stream: after everything queued on the library stream so far (planes, current picture, table, scratch in use)
+  if (int rc = enter_stream(st)) return rc;
+  CK(cudaMemsetAsync(g.d_deferred, 0, 3 * sizeof(int), st));     // both ticket counters and the hand-back count
   {
     ScopedTimer t(1, st);
     if (!use_basic_only() && g.maps_ok && g.has_cur_map) {
-      CK(cudaMemsetAsync(g.d_deferred, 0, sizeof(int), st));
       launched = me_launch_ffs_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.h_maps, g.list_n[0], g.list_n[1], g.cur_map.bytes,
-                                           g.d_cur, g.cur_pitch, &g.cfg, di, g.d_deferred, st);
+                                           g.d_cur, g.cur_pitch, &g.cfg, di, g.d_deferred + 2, g.d_deferred, st);
       // the jobs the tuned kernel handed back (lambda factors beyond its 32-bit keys; normally none: the launch finds an empty list)
-      if (launched) { me_launch_ffs_batch_basic((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, g.d_deferred, st); launched++; }
+      if (launched) { me_launch_ffs_batch_basic((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, g.d_deferred + 2, st); launched++; }
     }
     if (!launched) { me_launch_ffs_batch_basic((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &g.cfg, di, nullptr, st); launched = 1; }
   }
@@ -1068,12 +1276,12 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
     int done = 0;
     if (!use_basic_only() && g.pmaps_ok)
       done = me_launch_subpel_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.h_pmaps, g.list_n[0], g.list_n[1], g.d_cur, g.cur_pitch,
-                                          &sub_cfg, di, (MeResult *)d_out, st);
+                                          &sub_cfg, di, (MeResult *)d_out, g.d_deferred + 1, st);
     if (!done) me_launch_subpel_batch((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &sub_cfg, di, (MeResult *)d_out, st);
   }
   g.launches += launched + 1;
   CK(cudaGetLastError());
-  return 0;
+  return leave_stream(st);
 }
 
 // job fields the kernels index with: checked on the host, chunk by chunk, while the chunk's upload is already in flight
@@ -1120,28 +1328,34 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
     c_off[0] = 0;
     for (int c = 0; c < n_chunks; c++) { acc += weights[c]; c_off[c + 1] = n_chunks == 1 ? n_jobs : (int)((long long)n_jobs * acc / wsum); }
   }
-  for (int c = 0; c < n_chunks; c++) {
+  // from here on errors are collected, not returned: whatever happens, the three streams are drained before the caller gets
+  // its buffers back (nothing may still be reading the job array or writing the result arrays on return)
+  int rc = 0;
+  auto cu = [&](cudaError_t e, const char *what) {
+    if (e != cudaSuccess && !rc) rc = fail(2, "%s failed: %s", what, cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  for (int c = 0; c < n_chunks && !rc; c++) {
     const int off = c_off[c], n = c_off[c + 1] - off;
     if (n <= 0) continue;
-    CK(cudaMemcpyAsync(g.d_jobs + off, jobs + off, sizeof(MeJob) * (size_t)n, cudaMemcpyHostToDevice, g.s_in));
-    CK(cudaEventRecord(g.ev_in[c], g.s_in));
+    cu(cudaMemcpyAsync(g.d_jobs + off, jobs + off, sizeof(MeJob) * (size_t)n, cudaMemcpyHostToDevice, g.s_in), "job upload") &&
+      cu(cudaEventRecord(g.ev_in[c], g.s_in), "cudaEventRecord");
   }
-  int rc = upload_table();                                     // on the library stream, before any chunk's kernels
+  if (!rc) rc = upload_table();                                // on the library stream, before any chunk's kernels
   for (int c = 0; c < n_chunks && !rc; c++) {
     const int off = c_off[c], n = c_off[c + 1] - off;
     if (n <= 0) continue;
     if ((rc = check_jobs(jobs, off, n)) != 0) break;           // host work hidden behind the uploads / the previous chunk's kernels
-    CK(cudaStreamWaitEvent(g.stream, g.ev_in[c], 0));
+    if (!cu(cudaStreamWaitEvent(g.stream, g.ev_in[c], 0), "cudaStreamWaitEvent")) break;
     if ((rc = me_cuda_frame_search_device(g.d_jobs + off, n, g.d_out + off, g.d_out_int + off, g.stream)) != 0) break;
-    CK(cudaEventRecord(g.ev_done[c], g.stream));
-    CK(cudaStreamWaitEvent(g.s_out, g.ev_done[c], 0));
-    CK(cudaMemcpyAsync(out + off, g.d_out + off, sizeof(MeResult) * (size_t)n, cudaMemcpyDeviceToHost, g.s_out));
-    if (out_int) CK(cudaMemcpyAsync(out_int + off, g.d_out_int + off, sizeof(MeResultInt) * (size_t)n, cudaMemcpyDeviceToHost, g.s_out));
+    if (!cu(cudaEventRecord(g.ev_done[c], g.stream), "cudaEventRecord") ||
+        !cu(cudaStreamWaitEvent(g.s_out, g.ev_done[c], 0), "cudaStreamWaitEvent") ||
+        !cu(cudaMemcpyAsync(out + off, g.d_out + off, sizeof(MeResult) * (size_t)n, cudaMemcpyDeviceToHost, g.s_out), "result download")) break;
+    if (out_int) cu(cudaMemcpyAsync(out_int + off, g.d_out_int + off, sizeof(MeResultInt) * (size_t)n, cudaMemcpyDeviceToHost, g.s_out), "result download");
   }
-  // also on the error path: nothing may still be reading the caller's job array or writing its result arrays on return
-  cudaStreamSynchronize(g.s_in);
-  CK(cudaStreamSynchronize(g.s_out));
-  CK(cudaStreamSynchronize(g.stream));
+  cu(cudaStreamSynchronize(g.s_in), "cudaStreamSynchronize");
+  cu(cudaStreamSynchronize(g.stream), "cudaStreamSynchronize");
+  cu(cudaStreamSynchronize(g.s_out), "cudaStreamSynchronize");
   return rc;
 }
 

@@ -333,6 +333,125 @@ me_ffs_block_subpel_kernel(const int32_t *__restrict__ surf_p, int setup_range, 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// One launch per PartitionMotionSearch call (me_cuda_pms_begin): CTA (item, list-ref) runs what PartitionMotionSearch
+// (mv-search.c:1378-1454) does for one (blocktype, block8x8) and one (list, ref) -- for every sub-block in call order the motion
+// vector predictor, the block search over the stored surface, the sub-pel refinement, and the write-back of reference index and
+// vector into the motion state the next sub-block's predictor reads.
+
+// SetMotionVectorPredictor (mv-search.c:87-281), frame macroblocks (no MBAFF): st = ref_idx / mv of the 4x4 blocks around and
+// inside the macroblock ([row + 1][col + 1]); block at 4x4 position (bx4, by4), size bsx x bsy pixels.
+struct PmsState { int8_t ref_idx[5][6]; int16_t mv[5][6][2]; };
+__device__ void pms_predictor(const PmsState &st, int ref_frame, int bx4, int by4, int bsx, int bsy, int &pmx, int &pmy)
+{
+  const int mb_x = 4 * bx4, mb_y = 4 * by4;
+  // getLuma4x4Neighbour (mb_access.c:549, :143): pixel (x, y) relative to the macroblock -> cell of the state, availability
+  struct Nb { int r, c; bool ok; };
+  auto nb = [&](int x, int y) {
+    Nb n;
+    n.c = (x < 0 ? -1 : x >> 2) + 1; n.r = (y < 0 ? -1 : y >> 2) + 1;
+    if (x >= 16 && y >= 0) { n.ok = false; n.r = n.c = 0; return n; }        // to the right of the macroblock: not coded yet
+    if (x >= 16) n.c = 5;                                                    // C: the macroblock above right, its block column 0
+    n.ok = st.ref_idx[n.r][n.c] != ME_PMS_UNAVAILABLE;
+    return n;
+  };
+  const Nb a = nb(mb_x - 1, mb_y), b = nb(mb_x, mb_y - 1), d = nb(mb_x - 1, mb_y - 1);
+  Nb c = nb(mb_x + bsx, mb_y - 1);
+  if (mb_y > 0) {                                                            // mv-search.c:111-131
+    if (mb_x < 8) {
+      if (mb_y == 8) { if (bsx == 16) c.ok = false; }
+      else if (mb_x + bsx == 8) c.ok = false;
+    } else if (mb_x + bsx == 16) c.ok = false;
+  }
+  if (!c.ok) c = d;
+  const int rL = a.ok ? st.ref_idx[a.r][a.c] : -1, rU = b.ok ? st.ref_idx[b.r][b.c] : -1, rUR = c.ok ? st.ref_idx[c.r][c.c] : -1;
+  enum { MEDIAN, L, U, UR };
+  int type = MEDIAN;
+  if (rL == ref_frame && rU != ref_frame && rUR != ref_frame) type = L;
+  else if (rL != ref_frame && rU == ref_frame && rUR != ref_frame) type = U;
+  else if (rL != ref_frame && rU != ref_frame && rUR == ref_frame) type = UR;
+  if (bsx == 8 && bsy == 16) {
+    if (mb_x == 0) { if (rL == ref_frame) type = L; }
+    else if (rUR == ref_frame) type = UR;
+  } else if (bsx == 16 && bsy == 8) {
+    if (mb_y == 0) { if (rU == ref_frame) type = U; }
+    else if (rL == ref_frame) type = L;
+  }
+  int pm[2];
+  for (int hv = 0; hv < 2; hv++) {
+    const int ma = a.ok ? st.mv[a.r][a.c][hv] : 0, mb = b.ok ? st.mv[b.r][b.c][hv] : 0, mc = c.ok ? st.mv[c.r][c.c][hv] : 0;
+    int pv;
+    if (type == MEDIAN) pv = !(b.ok || c.ok) ? ma : ma + mb + mc - min(ma, min(mb, mc)) - max(ma, max(mb, mc));
+    else pv = type == L ? ma : type == U ? mb : mc;
+    pm[hv] = (int)(int16_t)pv;                                               // pmv[] is short
+  }
+  pmx = pm[0]; pmy = pm[1];
+}
+
+__global__ void __launch_bounds__(256)
+me_pms_group_kernel(const __grid_constant__ MePmsParams P, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg /* sub-pel stage */,
+                    int rdopt, MePmsRecord *result /* mapped host memory: [slot][list-ref][4] */, int *done_count, int *ticket_out, int ticket)
+{
+  __shared__ BlockScratch sc;
+  __shared__ PmsState st;
+  __shared__ int pmv_s[2];
+  const int item = blockIdx.x / P.n_refs, lr = blockIdx.x - item * P.n_refs;
+  const MePmsRef &R = P.refs[lr];
+  const int t = P.item_type[item], bsx = me_bsx(t), bsy = me_bsy(t);
+  if (threadIdx.x < 30) {
+    const int r = threadIdx.x / 6, c = threadIdx.x - 6 * r;
+    st.ref_idx[r][c] = P.st.ref_idx[R.list][r][c];
+    st.mv[r][c][0] = P.st.mv[R.list][r][c][0]; st.mv[r][c][1] = P.st.mv[R.list][r][c][1];
+  }
+  __syncthreads();
+  int hs[4], vs[4];
+  const int n = me_pms_blocks(t, P.item_blk[item], hs, vs);
+  const int Pset = (2 * R.setup_range + 1) * (2 * R.setup_range + 1);
+  MeCfgDev icfg = cfg; icfg.rdopt = rdopt;
+  const int srange = me_block_range(icfg, R.ref, t);
+  for (int k = 0; k < n; k++) {
+    const int h = hs[k], v = vs[k];
+    if (threadIdx.x == 0) { int px, py; pms_predictor(st, R.ref, h, v, bsx, bsy, px, py); pmv_s[0] = px; pmv_s[1] = py; }
+    __syncthreads();
+    const int pmx = pmv_s[0], pmy = pmv_s[1];
+    const int p = me_part_index(t, 4 * v + h);
+    int mvx, mvy, cost;
+    me_ffs_block_argmin(R.surf + (size_t)p * Pset, R.setup_range, R.offx, R.offy, pmx, pmy, srange, ME_INT_MAX, P.lambda[0], rdopt,
+                        sc.red, mvx, mvy, cost);
+    MeSubpelArgs a;
+    a.pic_pix_x = P.opix_x + 4 * h; a.pic_pix_y = P.opix_y + 4 * v; a.blocktype = t;
+    a.pmv_x = pmx; a.pmv_y = pmy;
+    a.mv_x = (int)(int16_t)(mvx * 4); a.mv_y = (int)(int16_t)(mvy * 4);       // mv <<= 2 on shorts, mv-search.c:770-774
+    a.s_mv_x = a.s_mv_y = 0;
+    a.search_pos2 = 9; a.search_pos4 = 9;
+    a.min_mcost = cfg.start_hp ? cost : ME_INT_MAX;                          // mv-search.c:785-788
+    for (int i = 0; i < 3; i++) a.lambda[i] = P.lambda[i];
+    a.check0 = !rdopt && P.slice_type != ME_B_SLICE && R.ref == 0 && t == 1 && a.mv_x == 0 && a.mv_y == 0;   // me_fullsearch.c:361
+    a.bi = 0;
+    a.bw = MeBiW{ 0, 0, 0, 0, 0, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+    int smx, smy, scost;
+    subpel_block(R.dev, R.dev, cur, cur_pitch, cfg, a, sc, smx, smy, scost);
+    if (threadIdx.x == 0) {
+      MePmsRecord &rec = result[(P.item_slot[item] * ME_PMS_MAX_REFS + lr) * 4 + k];
+      rec.pmv_x = pmx; rec.pmv_y = pmy; rec.int_mvx = mvx; rec.int_mvy = mvy; rec.int_cost = cost;
+      rec.mvx = smx; rec.mvy = smy; rec.cost = scost;
+      // PartitionMotionSearch, mv-search.c:1441-1449: reference index and vector of the block for the predictors that follow
+      for (int j = v; j < v + (bsy >> 2); j++)
+        for (int i = h; i < h + (bsx >> 2); i++) { st.ref_idx[j + 1][i + 1] = (int8_t)R.ref; st.mv[j + 1][i + 1][0] = (int16_t)smx; st.mv[j + 1][i + 1][1] = (int16_t)smy; }
+    }
+    __syncthreads();
+  }
+  // the last CTA to finish hands the ticket to the host (results and ticket live in mapped host memory)
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(done_count, 1) == (int)gridDim.x - 1) {
+      *done_count = 0;
+      __threadfence_system();
+      *(volatile int *)ticket_out = ticket;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // FullPelBlockMotionSearch (me_fullsearch.c:47-155): the per-block spiral full search of SearchMode = -1.  One CTA; a thread
 // scores every 256th spiral position with the whole-block distortion computeUniPred[F_PEL] (SAD / SSE: one origin clamp per
 // block; SATD: one per transform tile), the first strict minimum in spiral order wins.
@@ -696,6 +815,12 @@ extern "C" void me_launch_ffs_block_subpel(const int32_t *surf_p, int setup_rang
 {
   me_ffs_block_subpel_kernel<<<1, 256, 0, st>>>(surf_p, setup_range, offx, offy, search_range, min_mcost, rdopt, *r1, cur, cur_pitch,
                                                 *cfg, *a, result, ticket);
+}
+
+extern "C" void me_launch_pms_group(const MePmsParams *p, const uint8_t *cur, int cur_pitch, const MeCfgDev *sub_cfg, int rdopt,
+                                    MePmsRecord *result, int *done_count, int *ticket_out, int ticket, cudaStream_t st)
+{
+  me_pms_group_kernel<<<p->n_items * p->n_refs, 256, 0, st>>>(*p, cur, cur_pitch, *sub_cfg, rdopt, result, done_count, ticket_out, ticket);
 }
 
 extern "C" void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,

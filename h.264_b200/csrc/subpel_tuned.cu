@@ -78,6 +78,7 @@ template <bool T8> struct __align__(128) Smem {
   int      mn[ME_NUM_PARTITIONS];           // its cost
   int      okp[ME_NUM_PARTITIONS];          // partition served by the staged region (else: global reads with the clamp)
   int      mvc[T8 ? 9 : 1][9];              // their motion-vector rate per candidate
+  int      next_id;                         // the job after the current one (>= n_jobs: none)
   unsigned long long mbar;
 };
 
@@ -193,14 +194,15 @@ template <bool T8, bool HAD>
 __global__ void __launch_bounds__(NT, T8 ? T8_CTAS : T4_CTAS)      // measured (4x4 transform): 6 CTAs 0.775 ms, 7 CTAs 0.736 ms, 8 CTAs (64 registers) 0.777 ms
 me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                        const __grid_constant__ PlaneMaps maps, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
-                       const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out)
+                       const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out,
+                       int *__restrict__ ticket /* jobs handed out beyond the first round (zeroed by the caller) */)
 {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem<T8> &sm = *reinterpret_cast<Smem<T8> *>(smem_raw);
   constexpr int JW = sizeof(MeJob) / 4;
   const int tid = threadIdx.x;
-  const int n_mine = (n_jobs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  if (n_mine <= 0) return;
+  // jobs are handed out dynamically (first job blockIdx.x, then tickets of a global counter drawn one job ahead): see ffs_tuned.cu
+  if ((int)blockIdx.x >= n_jobs) return;
   const unsigned bar = smem_u32(&sm.mbar);
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -227,8 +229,10 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
   };
   if (tid == 0) issue_region((int)blockIdx.x);
 
-  for (int it = 0; it < n_mine; it++) {
-    const int job_id = (int)blockIdx.x + it * (int)gridDim.x;
+  int job_id = (int)blockIdx.x;
+  for (int it = 0; job_id < n_jobs; it++) {
+    int next_id = n_jobs;
+    if (tid == 0) { next_id = atomicAdd(ticket, 1) + (int)gridDim.x; sm.next_id = next_id; }     // read behind this job's barriers
     // ---- job set-up
     if (tid < JW) sm.job[tid] = jobs[(size_t)job_id * JW + tid];
     if (tid < ME_NUM_PARTITIONS) {
@@ -266,7 +270,8 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
       sm.okp[tid] = abs(mix - m0x) <= RD && abs(miy - m0y) <= RD &&
                     x0 - 1 >= 0 && y0 - 1 >= 0 && x1 <= ref.w + 2 * ME_PAD - 1 - 16 && y1 <= ref.h + 2 * ME_PAD - 1 - 16;
     }
-    __syncthreads();                                 // publishes okp and curpk
+    __syncthreads();                                 // publishes okp, curpk and the next job's id
+    const int following_id = sm.next_id;
     // ---- this thread's tile for the whole job.  4x4: slot = (block type, tile slot), 16 lanes per type, the tiles of a
     // partition adjacent (c_tile / c_part).  With the 8x8 transform only the types 5..7 have 4x4 tiles (threads 0..47 of the
     // first two warps) and the last two warps hold the 8x8 tiles of types 1..4 (c_quad / c_part8), four lane groups of 16.
@@ -438,7 +443,7 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
       if (!T8) continue;
       __syncthreads();
       // the region is free once the quarter-pel tiles are read: request the next job's
-      if (stage == 1 && tid == 0 && it + 1 < n_mine) issue_region(job_id + (int)gridDim.x);
+      if (stage == 1 && tid == 0 && next_id < n_jobs) issue_region(next_id);
       {
         // partitions of block types 1..4: their candidates were scored by four lane groups, scan them here
         if (tid < 9) {
@@ -468,8 +473,9 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
       // without the 8x8 transform every partition lives inside one warp: the warps ran both stages without meeting; they meet
       // once per job, before the region and the job data are replaced
       __syncthreads();
-      if (tid == 0 && it + 1 < n_mine) issue_region(job_id + (int)gridDim.x);
+      if (tid == 0 && next_id < n_jobs) issue_region(next_id);
     }
+    job_id = following_id;
   }
 }
 
@@ -487,9 +493,9 @@ extern "C" int me_make_planes_tensor_map(void *out, const void *planes, int pitc
 // plane_maps: host array [2][ME_MAX_REFS] of 128-byte tensor maps of the listed references' plane sets.
 extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *plane_maps,
                                             int n_refs0, int n_refs1, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
-                                            const MeResultInt *in_int, MeResult *out, cudaStream_t st)
+                                            const MeResultInt *in_int, MeResult *out, int *ticket, cudaStream_t st)
 {
-  if (!plane_maps || n_refs0 > TUNED_MAX_REFS || n_refs1 > TUNED_MAX_REFS) return 0;
+  if (!plane_maps || !ticket || n_refs0 > TUNED_MAX_REFS || n_refs1 > TUNED_MAX_REFS) return 0;
   // 8x8 transform tiles exist for the Hadamard metric only: with Transform8x8Mode either both sub-pel metrics are Hadamard (8x8
   // variant) or neither (4x4 variant, the transform size does not matter); a mix goes to the general kernel
   const bool had1 = cfg->metric[1] == 2, had2 = cfg->metric[2] == 2;
@@ -499,15 +505,20 @@ extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const
   static int general_sad = -1;                               // measurement switch: SAD / SSE sub-pel metrics through subpel.cu
   if (general_sad < 0) { const char *e = getenv("ME_CUDA_SUBPEL_SAD_GENERAL"); general_sad = e && atoi(e) ? 1 : 0; }
   if (general_sad && !(had1 && had2)) return 0;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(me_subpel_tuned_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>));
-    cudaFuncSetAttribute(me_subpel_tuned_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>));
-    cudaFuncSetAttribute(me_subpel_tuned_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<true>));
+  // per device (the library may be initialised again on another GPU of the box)
+  static int sms_of[64];
+  static bool attr_done[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!attr_done[dev]) {
+    if (cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(me_subpel_tuned_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>)) != cudaSuccess ||
+        cudaFuncSetAttribute(me_subpel_tuned_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>)) != cudaSuccess ||
+        cudaFuncSetAttribute(me_subpel_tuned_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<true>)) != cudaSuccess)
+      return 0;
+    attr_done[dev] = true;
   }
+  const int sms = sms_of[dev];
   PlaneMaps pm;
   for (int l = 0; l < 2; l++)
     memcpy(&pm.m[l * TUNED_MAX_REFS], (const unsigned char *)plane_maps + (size_t)l * ME_MAX_REFS * 128, sizeof(CUtensorMap) * TUNED_MAX_REFS);
@@ -519,12 +530,12 @@ extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const
   if (grid > n_jobs) grid = n_jobs;
   if (use_t8)
     me_subpel_tuned_kernel<true, true><<<grid, NT, sizeof(Smem<true>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur,
-                                                                       cur_pitch, *cfg, in_int, out);
+                                                                       cur_pitch, *cfg, in_int, out, ticket);
   else if (had1 && had2)
     me_subpel_tuned_kernel<false, true><<<grid, NT, sizeof(Smem<false>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur,
-                                                                         cur_pitch, *cfg, in_int, out);
+                                                                         cur_pitch, *cfg, in_int, out, ticket);
   else
     me_subpel_tuned_kernel<false, false><<<grid, NT, sizeof(Smem<false>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur,
-                                                                          cur_pitch, *cfg, in_int, out);
+                                                                          cur_pitch, *cfg, in_int, out, ticket);
   return 1;
 }

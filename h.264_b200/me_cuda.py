@@ -24,7 +24,12 @@ BIPRED_JOB_DTYPE = np.dtype([("opix_x", "<i2"), ("opix_y", "<i2"), ("list", "i1"
                              ("pmv_bi", "<i2", (2,)), ("mv", "<i2", (2,)), ("lambda", "<i4", (3,))])
 BIPRED_RESULT_DTYPE = np.dtype([("mv", "<i2", (2,)), ("bimv", "<i2", (2,)), ("cost", "<i4"), ("iterlist", "<i4")])
 assert JOB_DTYPE.itemsize == 188 and RESULT_DTYPE.itemsize == 328
+# me_mb_motion: motion state around a macroblock (ref_idx -128 = 4x4 block not available), me_pms_item
+MOTION_DTYPE = np.dtype([("ref_idx", "i1", (2, 5, 6)), ("mv", "<i2", (2, 5, 6, 2))])
+PMS_ITEM_DTYPE = np.dtype([("blocktype", "i1"), ("block8x8", "i1")])
+PMS_UNAVAILABLE = -128
 assert BIPRED_JOB_DTYPE.itemsize == 32 and BIPRED_RESULT_DTYPE.itemsize == 16
+assert MOTION_DTYPE.itemsize == 300 and PMS_ITEM_DTYPE.itemsize == 2
 
 # every symbol include/me_cuda.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
@@ -40,6 +45,7 @@ ABI_SYMBOLS = [
     "me_cuda_kernel_time_ms", "me_cuda_set_ref_weights", "me_cuda_set_bipred_weights", "me_cuda_set_bipred_chroma_weights",
     "me_cuda_set_current_chroma", "me_cuda_set_current_chroma_u8", "me_cuda_ref_set_chroma", "me_cuda_ref_set_chroma_u8",
     "me_cuda_set_chroma_state", "me_cuda_ref_set_chroma_planes",
+    "me_cuda_pms_begin", "me_cuda_pms_cached", "me_cuda_pms_end", "me_cuda_pms_stats",
 ]
 
 
@@ -102,6 +108,10 @@ def load_library(path=LIB_PATH):
     L.me_cuda_ref_update_device.argtypes = [C.c_int32, vp, C.c_int, C.c_int, C.c_int, vp]
     L.me_cuda_set_timing.argtypes = [C.c_int]
     L.me_cuda_kernel_time_ms.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.me_cuda_pms_begin.argtypes = [vp, C.c_int, vp, ip]
+    L.me_cuda_pms_cached.argtypes = [C.c_int, C.c_int]
+    L.me_cuda_pms_end.argtypes = [C.c_int, C.c_int]
+    L.me_cuda_pms_stats.argtypes = [C.POINTER(C.c_int64)] * 3
     return L
 
 
@@ -289,6 +299,28 @@ class MeCuda:
                                                       C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy),
                                                       search_pos2, search_pos4, min_mcost, lam)
         return mx.value, my.value, cost
+
+    # ---- one launch per PartitionMotionSearch call
+    def pms_begin(self, state, items, lambda_factor):
+        """state: MOTION_DTYPE scalar; items: [(blocktype, block8x8), ...].  Returns False when the configuration is not covered."""
+        st = np.ascontiguousarray(state, MOTION_DTYPE)
+        it = np.array(items, PMS_ITEM_DTYPE)
+        lam = (C.c_int * 3)(*lambda_factor)
+        rc = self.L.me_cuda_pms_begin(st.ctypes.data, len(it), it.ctypes.data, lam)
+        if rc > 0:
+            self._check(rc)
+        return rc == 0
+
+    def pms_cached(self, blocktype, block8x8):
+        return bool(self.L.me_cuda_pms_cached(blocktype, block8x8))
+
+    def pms_end(self, blocktype, block8x8):
+        self._check(self.L.me_cuda_pms_end(blocktype, block8x8))
+
+    def pms_stats(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self.L.me_cuda_pms_stats(C.byref(a), C.byref(b), C.byref(c)))
+        return dict(launches=a.value, served=b.value, missed=c.value)
 
     # ---- frame batch
     def frame_search(self, jobs, want_int=False):

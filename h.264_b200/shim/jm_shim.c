@@ -6,7 +6,7 @@
  *     -Wl,--wrap=FastFullPelBlockMotionSearch,--wrap=FullPelBlockMotionSearch,--wrap=SubPelBlockMotionSearch,--wrap=FullPelBlockMotionBiPred,
  *         --wrap=SubPelBlockSearchBiPred,--wrap=ResetFastFullIntegerSearch,--wrap=getSubImagesLuma,
  *         --wrap=encode_one_frame,--wrap=Init_Motion_Search_Module,--wrap=Clear_Motion_Search_Module,
- *         --wrap=free_storable_picture
+ *         --wrap=free_storable_picture,--wrap=PartitionMotionSearch
  * so every call site the SearchMode dispatch of mv-search.c reaches (mv-search.c:745, :823, :960, :998, :1018), the
  * per-macroblock reset (macroblock.c:509), the plane generation (image.c:1642) and the module init / clear
  * (lencod.c:255, :387) land here.  Everything else -- predictors (SetMotionVectorPredictor, mv-search.c:87), mode
@@ -16,7 +16,8 @@
  *
  * Environment: ME_CUDA_VERIFY=1 runs the reference function next to every GPU call and reports differences (diagnostic),
  *              ME_CUDA_LIB = path of libme_cuda.so (default: <dir of executable>/../../h.264_b200/libme_cuda.so),
- *              ME_CUDA_DISABLE=1 turns the interposer into a pass-through (pure reference behaviour).
+ *              ME_CUDA_DISABLE=1 turns the interposer into a pass-through (pure reference behaviour),
+ *              ME_CUDA_PMS=0 keeps one device launch per block search (no launch per PartitionMotionSearch call).
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -37,6 +38,7 @@
 extern const int LEVELMVLIMIT[17][6];
 extern void SetMotionVectorPredictor (short pmv[2], char **refPic, short ***tmp_mv, short ref_frame,
                                       int list, int block_x, int block_y, int blockshape_x, int blockshape_y);
+extern void getLuma4x4Neighbour (int curr_mb_nr, int block_x_pos, int block_y_pos, PixelPos *pix);
 
 /* ---- the library, resolved at run time ---- */
 static struct {
@@ -65,11 +67,19 @@ static struct {
   int  (*subpel)(short, int, int, int, int, short, short, short *, short *, int, int, int, const int *);
   int  (*bi_full)(short, int, int, int, int, short, short, short, short, short *, short *, short *, short *, int, int, int);
   int  (*bi_sub)(short, int, int, int, int, short, short, short *, short *, short *, short *, int, int, int, const int *);
+  int  (*pms_begin)(const me_mb_motion *, int, const me_pms_item *, const int *);
+  int  (*pms_cached)(int, int);
+  int  (*pms_end)(int, int);
+  int  (*pms_stats)(int64_t *, int64_t *, int64_t *);
 } L;
 
 static int active = 0;          /* GPU path in use for this run */
+static int use_pms = 1;         /* one device launch per PartitionMotionSearch call (ME_CUDA_PMS=0: one per block search) */
 static int verify = 0;          /* ME_CUDA_VERIFY=1: run the reference function too, report any difference, keep the reference result */
 static long n_checked = 0, n_mismatch = 0;
+/* calls the device answered, per wrapped function; printed when the module is cleared so that a run (and the tests around it)
+ * can tell a GPU run from a silent pass-through */
+static long served_ffs = 0, served_fullpel = 0, served_subpel = 0, served_bi_full = 0, served_bi_sub = 0, served_planes = 0;
 static int pic_counter = 0, pic_uploaded = -1, plane_uploaded = -1;
 
 #define MAX_MAP 64
@@ -126,6 +136,8 @@ static void load_library(void)
   L.fullpel = sym("me_cuda_FullPelBlockMotionSearch");
   L.ffs = sym("me_cuda_FastFullPelBlockMotionSearch"); L.subpel = sym("me_cuda_SubPelBlockMotionSearch");
   L.bi_full = sym("me_cuda_FullPelBlockMotionBiPred"); L.bi_sub = sym("me_cuda_SubPelBlockSearchBiPred");
+  L.pms_begin = sym("me_cuda_pms_begin"); L.pms_cached = sym("me_cuda_pms_cached"); L.pms_end = sym("me_cuda_pms_end");
+  L.pms_stats = sym("me_cuda_pms_stats");
 }
 
 /* 4:4:4 independent mode (SeparateColourPlane = 1, IS_INDEPENDENT, defines.h:224): the three colour planes are coded one after
@@ -193,6 +205,7 @@ void __wrap_Init_Motion_Search_Module(void)
     if (L.init(&p)) die("me_cuda_init");
     active = 1;
     verify = getenv("ME_CUDA_VERIFY") && atoi(getenv("ME_CUDA_VERIFY"));
+    use_pms = !(getenv("ME_CUDA_PMS") && !atoi(getenv("ME_CUDA_PMS")));
   }
 }
 
@@ -200,6 +213,16 @@ void __real_Clear_Motion_Search_Module(void);
 void __wrap_Clear_Motion_Search_Module(void)
 {
   if (active && verify) fprintf(stderr, "me_cuda shim: verify mode: %ld calls checked, %ld mismatches\n", n_checked, n_mismatch);
+  if (active) {
+    int64_t pl = 0, ps = 0, pm = 0;
+    L.pms_stats(&pl, &ps, &pm);
+    fprintf(stderr, "me_cuda shim: served on the device: %ld plane sets, %ld ffs, %ld fullpel, %ld subpel, %ld bi_full, %ld bi_sub calls\n",
+            served_planes, served_ffs, served_fullpel, served_subpel, served_bi_full, served_bi_sub);
+    fprintf(stderr, "me_cuda shim: partition-search launches %lld, block searches answered from them %lld, argument mismatches %lld\n",
+            (long long)pl, (long long)ps, (long long)pm);
+  }
+  else
+    fprintf(stderr, "me_cuda shim: pass-through (ME_CUDA_DISABLE): nothing served on the device\n");
   if (active) { L.shutdown(); active = 0; n_map = 0; }
   __real_Clear_Motion_Search_Module();
 }
@@ -231,7 +254,8 @@ void __wrap_getSubImagesLuma(StorablePicture *s)
     if (map[i].p == s ? map[i].plane == plane : !in_dpb(map[i].p)) unmap_index(i);   /* s itself enters the buffer after this call */
   /* the 16 planes are computed on the device and copied into the picture's plane set for the encoder's host-side consumers */
   if (L.ref_create((const me_imgpel *const *)s->p_curr_img, s->size_x, s->size_y, (me_imgpel ****)s->p_curr_img_sub, &h)) die("me_cuda_ref_create");
-  if (n_map == MAX_MAP) unmap_index(0);
+  if (n_map == MAX_MAP) die("more than 64 reference pictures with device plane sets (decoded picture buffer bookkeeping out of step)");
+  served_planes++;
   map[n_map].p = s; map[n_map].plane = plane; map[n_map].h = h; n_map++;
   /* ChromaMEEnable: the searches read the chroma sub-images of this picture (getSubImagesChroma, image.c:1659, still runs on the
    * host for motion compensation); the library evaluates them from the reconstructed chroma planes */
@@ -280,7 +304,9 @@ static void mb_sync(void)
       if (n > 32) n = 32;
       for (i = 0; i < n; i++) {
         hs[i] = handle_of(listX[l + list_offset][i]);
-        if (!hs[i]) { n = i; break; }                   /* no planes on the device (never happens for frame coding) */
+        /* a listed picture without device planes would silently shorten the list the searches index: fail loudly instead
+         * (field pictures / MBAFF list offsets 2 and 4 are refused here: their plane sets are not mirrored) */
+        if (!hs[i]) die("a reference-list entry has no plane set on the device (field / MBAFF coding is not supported by the GPU path)");
       }
       if (L.set_ref_list(l, n, hs)) die("me_cuda_set_ref_list");
     }
@@ -366,6 +392,74 @@ static void pass_bipred_weights(int list, short ref, int subpel)
   } else if (L.set_bipred_weights(list, 0, 0, 0, 0, 0)) die("me_cuda_set_bipred_weights");
 }
 
+/* ---------------------------------------------------------------- one launch per PartitionMotionSearch (mv-search.c:1378) */
+/* PartitionMotionSearch(blocktype, block8x8) is a loop over lists, references and sub-blocks around BlockMotionSearch; every
+ * block search in it would be one device round trip.  Instead, on entry, the motion state SetMotionVectorPredictor reads
+ * (enc_picture->ref_idx / ->mv around and inside the macroblock) goes to the device and one launch runs the whole call -- and,
+ * speculatively, the calls that will read the same state: the first 16x8 and 8x16 partitions together with the 16x16 block (all
+ * their neighbours lie outside the macroblock), and block types 5..7 of an 8x8 block together with type 4 (mode_decision.c:
+ * 575-674 searches them one after the other without touching the state outside the block).  The reference function then runs
+ * unchanged; its block searches are answered from the launch when their arguments equal what the device used (checked in the
+ * library), so a wrong guess costs time, never a different result. */
+static void snapshot_motion(me_mb_motion *st)
+{
+  int l, r, c, nlists = (img->type == B_SLICE) ? 2 : 1;
+  memset(st, 0, sizeof *st);
+  for (r = -1; r < 4; r++)
+    for (c = -1; c < 5; c++) {
+      PixelPos pix;
+      int ok = !(c == 4 && r >= 0);                       /* right of the macroblock: not available (mb_access.c:143) */
+      if (ok) { getLuma4x4Neighbour(img->current_mb_nr, 4 * c, 4 * r, &pix); ok = pix.available; }
+      for (l = 0; l < 2; l++) {
+        if (!ok || l >= nlists) { st->ref_idx[l][r + 1][c + 1] = ME_PMS_UNAVAILABLE; continue; }
+        st->ref_idx[l][r + 1][c + 1] = enc_picture->ref_idx[l][pix.pos_y][pix.pos_x];
+        st->mv[l][r + 1][c + 1][0] = enc_picture->mv[l][pix.pos_y][pix.pos_x][0];
+        st->mv[l][r + 1][c + 1][1] = enc_picture->mv[l][pix.pos_y][pix.pos_x][1];
+      }
+    }
+}
+
+void __real_PartitionMotionSearch(int blocktype, int block8x8, int *lambda_factor);
+void __wrap_PartitionMotionSearch(int blocktype, int block8x8, int *lambda_factor)
+{
+  int on = active && use_pms && input->SearchMode == FAST_FULL_SEARCH && !img->MbaffFrameFlag && !input->DisableSubpelME &&
+           img->structure == FRAME && blocktype >= 1 && blocktype <= 7;
+  if (on && !L.pms_cached(blocktype, block8x8)) {
+    me_mb_motion st;
+    me_pms_item items[ME_PMS_MAX_ITEMS];
+    int n = 0, l, r, m, bslice = (img->type == B_SLICE), nlists = bslice ? 2 : 1;
+    int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+    mb_sync();
+    /* SetupFastFullPelSearch of every (list, ref) the call will search (me_fullfast.c:550: the 16x16 predictor, whose neighbours
+     * lie outside the macroblock, is the same whenever it is taken during this macroblock) */
+    if (input->ChromaMEEnable && L.set_chroma_state(input->ChromaMEEnable)) die("me_cuda_set_chroma_state");
+    for (l = 0; l < nlists; l++)
+      for (r = 0; r < listXsize[l + list_offset]; r++) {
+        pass_weights(l, (short)r);
+        if (!L.ffs_is_set_up(l, r)) {
+          short pmv[2];
+          SetMotionVectorPredictor(pmv, enc_picture->ref_idx[l], enc_picture->mv[l], (short)r, l, 0, 0, 16, 16);
+          if (L.ffs_setup(l, r, pmv[0], pmv[1])) die("me_cuda_ffs_setup");
+        }
+      }
+    items[n].blocktype = (int8_t)blocktype; items[n].block8x8 = (int8_t)block8x8; n++;
+    if (input->CtxAdptLagrangeMult == 0) {               /* same lambda factors for the calls that follow (md_high.c:115, mode_decision.c:663-672) */
+      if (blocktype == 1) {
+        for (m = 2; m <= 3; m++)
+          if (input->InterSearch[bslice][m]) { items[n].blocktype = (int8_t)m; items[n].block8x8 = 0; n++; }
+      } else if (blocktype == 4 && !img->mb_data[img->current_mb_nr].luma_transform_size_8x8_flag && input->Transform8x8Mode != 2) {
+        for (m = 5; m <= 7; m++)
+          if (input->InterSearch[bslice][m]) { items[n].blocktype = (int8_t)m; items[n].block8x8 = (int8_t)block8x8; n++; }
+      }
+    }
+    snapshot_motion(&st);
+    r = L.pms_begin(&st, n, items, lambda_factor);
+    if (r > 0) die("me_cuda_pms_begin");                 /* r < 0: configuration not covered, the block searches go one by one */
+  }
+  __real_PartitionMotionSearch(blocktype, block8x8, lambda_factor);
+  if (on) L.pms_end(blocktype, block8x8);
+}
+
 /* ---------------------------------------------------------------- block searches */
 int __real_FastFullPelBlockMotionSearch(imgpel *, short, int, int, int, int, short, short, short *, short *, int, int, int);
 int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
@@ -383,6 +477,7 @@ int __wrap_FastFullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, i
     SetMotionVectorPredictor(pmv, enc_picture->ref_idx[list], enc_picture->mv[list], ref, list, 0, 0, 16, 16);
     if (L.ffs_setup(list, ref, pmv[0], pmv[1])) die("me_cuda_ffs_setup");
   }
+  served_ffs++;
   if (verify) {
     short gx = *mv_x, gy = *mv_y;
     int gc = L.ffs(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, &gx, &gy, search_range, min_mcost, lambda_factor);
@@ -411,6 +506,7 @@ int __wrap_FullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int p
   mb_sync();
   keep_reference_side_effects(list, ref);
   pass_weights(list, ref);
+  served_fullpel++;
   if (verify) {
     short gx = *mv_x, gy = *mv_y;
     int gc = L.fullpel(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, &gx, &gy, search_range, min_mcost, lambda_factor);
@@ -439,6 +535,7 @@ int __wrap_SubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pi
   mb_sync();
   keep_reference_side_effects(list, ref);
   pass_weights(list, ref);
+  served_subpel++;
   if (verify) {
     short ix = *mv_x, iy = *mv_y, gx = *mv_x, gy = *mv_y;
     int gc = L.subpel(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, &gx, &gy, search_pos2, search_pos4, min_mcost, lambda_factor);
@@ -470,6 +567,7 @@ int __wrap_FullPelBlockMotionBiPred(imgpel *orig_pic, short ref, int list, int p
   mb_sync();
   keep_reference_side_effects(list, ref);
   pass_bipred_weights(list, ref, 0);
+  served_bi_full++;
   return L.bi_full(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x1, pred_mv_y1, pred_mv_x2, pred_mv_y2,
                    mv_x, mv_y, s_mv_x, s_mv_y, search_range, min_mcost, lambda_factor);
 }
@@ -486,6 +584,7 @@ int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pi
   mb_sync();
   keep_reference_side_effects(list, ref);
   pass_bipred_weights(list, ref, 1);
+  served_bi_sub++;
   return L.bi_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, s_mv_x, s_mv_y,
                   search_pos2, search_pos4, min_mcost, lambda_factor);
 }

@@ -62,6 +62,17 @@ def write_yuv420(path, width, height, n_frames, seed=1234, kind="pan"):
     return path
 
 
+def write_yuv444(path, width, height, n_frames, seed=1234, kind="pan"):
+    """4:4:4: U and V from the undecimated luma"""
+    with open(path, "wb") as f:
+        for y in luma_frames(width, height, n_frames, seed, kind):
+            yf = y.astype(np.float64)
+            f.write(y.tobytes())
+            f.write(np.clip(np.rint(128 + 0.25 * (yf - 128)), 0, 255).astype(np.uint8).tobytes())
+            f.write(np.clip(np.rint(128 - 0.25 * (yf - 128)), 0, 255).astype(np.uint8).tobytes())
+    return path
+
+
 def synthetic_jobs(width, height, n_refs, lambda_factor, seed=7, rdopt=1, max_pmv=24, slice_type=0):
     """A frame's worth of batch jobs with plausible predictors: per macroblock a smooth 'true motion' field plus
     jitter per partition, as a stand-in for the predictors an encoder would supply (replayed centres).

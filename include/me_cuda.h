@@ -88,7 +88,10 @@ int me_cuda_ref_create(const me_imgpel *const *imgY_rows, int w, int h, me_imgpe
 int me_cuda_ref_create_u8(const uint8_t *luma, int stride, int w, int h, me_ref_handle *out);
 /* free_storable_picture (mbuffer.c:556-600) */
 int me_cuda_ref_destroy(me_ref_handle h);
-/* rebuild the planes of an existing handle from a new picture, in place (a decoded-picture-buffer frame store being reused) */
+/* rebuild the planes of an existing handle from a new picture, in place (a decoded-picture-buffer frame store being reused).
+ * Buffer lifetime: this call and me_cuda_set_current_u8 queue the copy straight from the caller's buffer and return; with
+ * pinned memory the DMA may still be reading it.  The buffer must stay untouched until the next call that drains the
+ * library stream (me_cuda_frame_search, me_cuda_frame_bipred, me_cuda_ref_download_plane, me_cuda_sync, any drop-in search). */
 int me_cuda_ref_update_u8(me_ref_handle h, const uint8_t *luma, int stride, int w, int hgt);
 /* copy one of the 16 planes back: dst[(h+40)][dst_stride], plane index as Pic[fy][fx] (refbuf.c:27) */
 int me_cuda_ref_download_plane(me_ref_handle h, int fy, int fx, uint8_t *dst, int dst_stride);
@@ -181,6 +184,33 @@ int me_cuda_SubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_
                                     int search_pos2, int search_pos4, int min_mcost,
                                     const int *lambda_factor);                                  /* me_fullsearch.h:129 */
 
+/* ---- one launch per PartitionMotionSearch (mv-search.c:1378-1454) instead of one per block search ----
+ * PartitionMotionSearch(blocktype, block8x8) runs, for every list and reference, BlockMotionSearch on each sub-block of the
+ * partition: SetMotionVectorPredictor (mv-search.c:87-281) from the motion state around the macroblock, the integer-pel search,
+ * the sub-pel refinement, and writes the result back into that state for the predictors of the next sub-block
+ * (mv-search.c:1441-1449).  me_cuda_pms_begin() runs all of that on the device for up to ME_PMS_MAX_ITEMS such calls that read the
+ * SAME motion state (the caller's speculation: e.g. 16x16 with the first 16x8 and 8x16 partitions, whose neighbours all lie
+ * outside the macroblock, or block types 4..7 of one 8x8 block) in ONE launch, and keeps the results.  The drop-in calls
+ * me_cuda_FastFullPelBlockMotionSearch / me_cuda_SubPelBlockMotionSearch that the reference's own PartitionMotionSearch then
+ * makes are answered from those results when -- and only when -- their arguments (block, predictor, lambda factors, search
+ * range, start vector, start cost) equal what the device used; anything else takes the per-block path as before.  So the
+ * speculation can cost time but never changes a result.  Needs me_cuda_ffs_setup() for every listed (list, ref) of the
+ * macroblock first.  Returns 0 on success, -1 when the configuration is not covered (SearchMode other than the fast full
+ * search, more than ME_PMS_MAX_REFS list entries): the caller simply goes on without it. */
+#define ME_PMS_MAX_ITEMS 4
+#define ME_PMS_MAX_REFS 16
+#define ME_PMS_UNAVAILABLE (-128)      /* me_mb_motion::ref_idx of a 4x4 block outside the picture / slice */
+typedef struct me_mb_motion {          /* enc_picture->ref_idx[list] / ->mv[list] of the 4x4 blocks getLuma4x4Neighbour can reach */
+  int8_t  ref_idx[2][5][6];            /* [list][row + 1][col + 1], rows -1..3, columns -1..4 of the macroblock's 4x4 grid (column 4: row -1) */
+  int16_t mv[2][5][6][2];
+} me_mb_motion;
+typedef struct me_pms_item { int8_t blocktype, block8x8; } me_pms_item;
+int me_cuda_pms_begin(const me_mb_motion *state, int n_items, const me_pms_item *items, const int *lambda_factor /* [3] */);
+int me_cuda_pms_cached(int blocktype, int block8x8);     /* 1: results of this PartitionMotionSearch call are waiting */
+int me_cuda_pms_end(int blocktype, int block8x8);        /* the call has returned: drop them */
+/* counters since init: group launches, drop-in calls answered from their results, calls whose arguments did not match */
+int me_cuda_pms_stats(int64_t *launches, int64_t *served, int64_t *missed);
+
 /* ---- frame batch (no single reference call site: it is PartitionMotionSearch, mv-search.c:1378, for every
  * macroblock x list x ref of a picture at once, with the predictors supplied by the caller) ----
  * Partition order p = 0..40: type 1 {0}; type 2 {0,8}; type 3 {0,2}; type 4 {0,2,8,10}; type 5 {0,2,..,14};
@@ -237,7 +267,9 @@ int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements,
                          me_bipred_result *out);
 
 /* ---- device-resident variants for measurement (bench.py): pointers are CUDA device pointers, `stream` is a
- * cudaStream_t passed as void* (NULL = the library's own stream).  Asynchronous. ---- */
+ * cudaStream_t passed as void* (NULL = the library's own stream).  Asynchronous.  A caller's stream is ordered against the
+ * library stream by events on both sides of the call, so the program order of the calls is the order on the device even
+ * when they name different streams; the caller's buffers must stay valid until the stream the call named has drained. ---- */
 int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, void *d_out_int, void *stream);
 int me_cuda_ref_create_device(const void *d_luma_u8, int stride, int w, int h, void *stream, me_ref_handle *out);
 int me_cuda_ref_update_device(me_ref_handle hd, const void *d_luma_u8, int stride, int w, int h, void *stream);

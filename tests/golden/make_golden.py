@@ -183,10 +183,44 @@ def main():
         tr.save_npz(os.path.join(HERE, "wpbc.npz"), keep_mask(tr, 12))
         crc["wpbc"] = planes_crc(tr, d)
     epzs(crc, md5s)
+    big(md5s)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+# BASELINE.json configs 4 and 5 at their stated picture sizes: bitstream + reconstruction md5 of the plain reference encoder
+# (oracle/_ref/lencod), which tests/test_jm_dropin.py::test_stated_size_configs_match_committed_md5 checks lencod_cuda against
+# on the GPU box without re-running the CPU encoder there (minutes of CPU time).
+BIG_CASES = {
+    # config 4: synthetic 720p 4:4:4, High 4:4:4 profile, I-B-P with bi-predictive ME, SR 32, 3 references
+    "hd720_444_ibp_3ref": dict(writer="444", w=1280, h=720, frames=3,
+                               args=["-d", "encoder.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=1280", "-p", "SourceHeight=720",
+                                     "-p", "YUVFormat=3", "-p", "ProfileIDC=244", "-p", "LevelIDC=51", "-p", "NumberReferenceFrames=3",
+                                     "-p", "SearchRange=32", "-p", "FramesToBeEncoded=2"]),
+    # config 5: synthetic 4K (3840x2160, coded 3840x2176), SR 64, one I and one P picture of a GOP
+    "uhd4k_sr64_ip": dict(writer="420", w=3840, h=2160, frames=2,
+                          args=["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=3840", "-p", "SourceHeight=2160",
+                                "-p", "FramesToBeEncoded=2", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=64",
+                                "-p", "NumberReferenceFrames=5", "-p", "LevelIDC=51"]),
+}
+
+
+def write_big_input(case, path):
+    c = BIG_CASES[case]
+    (synth.write_yuv444 if c["writer"] == "444" else synth.write_yuv420)(path, c["w"], c["h"], c["frames"])
+
+
+def big(md5s, only=None):
+    for case, c in BIG_CASES.items():
+        if only and case not in only:
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            write_big_input(case, os.path.join(d, "syn.yuv"))
+            run_trace(d, c["args"], planes=False, binary="lencod")
+            md5s[case] = {"test.264": md5(os.path.join(d, "test.264")), "test_rec.yuv": md5(os.path.join(d, "test_rec.yuv"))}
+            print(case, md5s[case], flush=True)
 
 
 def epzs(crc, md5s):
@@ -211,6 +245,10 @@ if __name__ == "__main__":
         md5s = json.load(open(os.path.join(HERE, "bitstream_md5.json")))
         epzs(crc, md5s)
         json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
+        json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
+    elif sys.argv[1:2] == ["big"]:                # the stated-size cases only (minutes of CPU time)
+        md5s = json.load(open(os.path.join(HERE, "bitstream_md5.json")))
+        big(md5s, sys.argv[2:] or None)
         json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
     else:
         main()

@@ -124,3 +124,58 @@ def test_weight_arguments_are_checked(pkg):
         plain = me.frame_bipred(jobs, 3, 16, 2)
         me.set_ref_weights(1, 0, 1, 30, 2, 5)                 # uni-predictive weights of the same list entry: no effect here
         assert np.array_equal(me.frame_bipred(jobs, 3, 16, 2), plain)
+
+
+def test_device_entry_points_on_a_callers_stream(pkg):
+    """The *_device calls take a caller's stream; the library orders it against its own stream with events on both sides of
+    every such call (enter_stream / leave_stream in me_cuda_host.cu), so program order = device order whichever streams the calls
+    name.  A long-running kernel on the caller's stream in front of every producer makes a missing dependency visible: the
+    consumers on the library stream would read planes / the current picture before they are written."""
+    import torch
+    from h264_b200 import MeCuda, synth
+    from h264_b200.me_cuda import JOB_DTYPE, RESULT_DTYPE
+    w, h, n_refs = 352, 288, 2
+    frames = synth.luma_frames(w, h, n_refs + 2)
+    jobs = synth.synthetic_jobs(w, h, n_refs, (334459,) * 3, seed=3)
+    with MeCuda(w, h, search_range=16, max_num_references=n_refs) as me:      # the library stream only
+        hd = [me.ref_create(frames[-2 - r]) for r in range(n_refs)]
+        me.set_ref_list(0, hd)
+        me.set_current(frames[-1])
+        want, want_int = me.frame_search(jobs, want_int=True)
+        me.ref_update(hd[0], frames[0])                                        # frame store reused
+        want2 = me.frame_search(jobs)
+    dev = torch.device("cuda:0")
+    side = torch.cuda.Stream(device=dev)
+    burn = torch.empty(1 << 26, dtype=torch.float32, device=dev)
+
+    def delay():                                                               # ~ a millisecond of work queued on the side stream
+        with torch.cuda.stream(side):
+            for _ in range(8):
+                burn.mul_(1.0001)
+
+    d_frames = [torch.from_numpy(np.ascontiguousarray(f)).to(dev) for f in frames]
+    d_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(len(jobs), JOB_DTYPE.itemsize).copy()).to(dev)
+    d_out = torch.zeros(len(jobs) * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_int = torch.zeros_like(d_out)
+    torch.cuda.synchronize()
+    with MeCuda(w, h, search_range=16, max_num_references=n_refs) as me:
+        sp = side.cuda_stream
+        hd = []
+        for r in range(n_refs):
+            delay()
+            hd.append(me.ref_create_device(d_frames[-2 - r].data_ptr(), w, stream=sp))      # planes written on the side stream ...
+        me.set_ref_list(0, hd)
+        delay()
+        me.set_current_device(d_frames[-1].data_ptr(), w, stream=sp)
+        got, got_int = me.frame_search(jobs, want_int=True)                                 # ... read on the library stream
+        assert np.array_equal(got, want) and np.array_equal(got_int, want_int)
+        # producer on the library stream, consumer on the side stream, scratch shared with the library stream
+        me.ref_update(hd[0], frames[0])
+        me.frame_search_device(d_jobs.data_ptr(), len(jobs), d_out.data_ptr(), d_int.data_ptr(), stream=sp)
+        delay()
+        me.ref_update_device(hd[0], d_frames[-2].data_ptr(), w, stream=sp)                  # must wait for the search on the side stream
+        side.synchronize()
+        got2 = d_out.cpu().numpy().view(RESULT_DTYPE)
+        assert np.array_equal(got2, want2)
+        got3 = me.frame_search(jobs)                                                        # sees the planes of the last update
+        assert np.array_equal(got3, want)

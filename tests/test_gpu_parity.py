@@ -94,6 +94,116 @@ def test_dropin_calls_match_reference_trace(pkg, case):
     assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000 or case == "epzs") and res["subpel"][0] > 1000
 
 
+# ------------------------------------------------------------------------------------------------ one launch per PartitionMotionSearch
+@pytest.mark.parametrize("slice_b,t8,mb", [(0, 0, (5, 4)), (0, 1, (0, 0)), (1, 0, (10, 8)), (0, 0, (21, 17))])
+def test_partition_search_launch(pkg, slice_b, t8, mb):
+    """me_cuda_pms_begin: the device runs PartitionMotionSearch calls (mv-search.c:1378-1454) -- predictor, block search, sub-pel
+    refinement, write-back -- in one launch; the drop-in calls are then answered from it.  Checked against the same call sequence
+    made block by block (no group launch), driven by the Python restatement of SetMotionVectorPredictor / PartitionMotionSearch
+    (oracle/predictor.py), for random motion states incl. unavailable neighbours (picture corner / last column and row)."""
+    import copy
+    from h264_b200 import synth
+    from h264_b200.me_cuda import MOTION_DTYPE, PMS_UNAVAILABLE
+    from oracle import predictor as op
+    w, h, n_refs = 352, 288, 3
+    frames = synth.luma_frames(w, h, n_refs + 2)
+    lam = (131072, 98304, 98304)
+    rng = np.random.default_rng(100 * mb[0] + mb[1] + 7 * slice_b)
+    mbx, mby = mb
+    d = dict(search_range=16, rdopt=1, full_search=2, metric=(0, 2, 2), transform8x8=t8, mv_limit_min_y=-511, mv_limit_max_y=511)
+    list_sizes = [n_refs, 2] if slice_b else [n_refs]
+    # motion state: neighbours with random references / vectors; macroblocks outside the picture are unavailable
+    st = np.zeros((), MOTION_DTYPE)
+    st["ref_idx"] = rng.integers(-1, n_refs, size=(2, 5, 6))
+    st["mv"] = rng.integers(-60, 61, size=(2, 5, 6, 2))
+    st["mv"][st["ref_idx"] < 0] = 0
+    for l in range(2):
+        for r in range(5):
+            for c in range(6):
+                out = (c == 0 and mbx == 0) or (r == 0 and mby == 0) or (c == 5 and (r > 0 or mbx == w // 16 - 1 or mby == 0)) or l >= len(list_sizes)
+                if out:
+                    st["ref_idx"][l, r, c] = PMS_UNAVAILABLE
+    groups = [[(1, 0), (2, 0), (3, 0)], [(2, 1)], [(3, 1)]] + [[(4, b), (5, b), (6, b), (7, b)] for b in range(4)]
+
+    def run(use_group):
+        res = {}
+        with _open(pkg, w, h, d, max_refs=n_refs) as me:
+            hd = [me.ref_create(frames[-2 - r]) for r in range(n_refs)]
+            me.set_ref_list(0, hd)
+            if slice_b:
+                me.set_ref_list(1, hd[:2][::-1])
+            me.set_slice_type(1 if slice_b else 0)
+            me.set_current(frames[-1])
+            me.mb_begin(16 * mbx, 16 * mby)
+            ref_idx = st["ref_idx"].tolist(); mv = st["mv"].tolist()
+            for l, n in enumerate(list_sizes):
+                for r in range(n):
+                    pmv16 = op.mv_predictor(ref_idx[l], mv[l], r, 0, 0, 16, 16)
+                    me.ffs_setup(l, r, *pmv16)
+
+            def block_search(l, r, hh, vv, bt, pmv):
+                x, y = 16 * mbx + 4 * hh, 16 * mby + 4 * vv
+                ix, iy, ic = me.FastFullPelBlockMotionSearch(r, l, x, y, bt, pmv[0], pmv[1], 16, 2147483647, lam[0])
+                # start_me_refinement_hp = 0 (integer-pel metric SAD, half-pel metric Hadamard): BlockMotionSearch resets the cost (mv-search.c:785-788)
+                fx, fy, fc = me.SubPelBlockMotionSearch(r, l, x, y, bt, pmv[0], pmv[1], 4 * ix, 4 * iy, 9, 9, 2147483647, lam)
+                res[(bt, l, r, hh, vv)] = (pmv, ix, iy, ic, fx, fy, fc)
+                return fx, fy, fc
+
+            for grp in groups:
+                # the state every call of the group starts from (the host would have taken mode decisions in between: emulated by
+                # restoring the area inside the macroblock to the values the state was given)
+                if use_group:
+                    snap = np.zeros((), MOTION_DTYPE)
+                    snap["ref_idx"] = ref_idx; snap["mv"] = mv
+                    assert me.pms_begin(snap, grp, lam)
+                for (bt, b8) in grp:
+                    ri, mvs = copy.deepcopy(ref_idx), copy.deepcopy(mv)
+                    assert me.pms_cached(bt, b8) == bool(use_group)
+                    op.partition_motion_search(ri, mvs, bt, b8, list_sizes, block_search)
+                    me.pms_end(bt, b8)
+            stats = me.pms_stats()
+        return res, stats
+
+    plain, s0 = run(False)
+    grouped, s1 = run(True)
+    assert s0["launches"] == 0 and s0["served"] == 0
+    n_searches = sum(len(op.partition_blocks(bt, b8)) for grp in groups for (bt, b8) in grp) * sum(list_sizes)
+    assert len(plain) == len(grouped) and grouped == plain
+    assert s1 == dict(launches=len(groups), served=2 * n_searches, missed=0), s1
+
+
+# ------------------------------------------------------------------------------------------------ throughput kernels on reference traces
+@pytest.mark.parametrize("case", ["kat", "baseline16", "wp"])
+def test_golden_traces_through_the_frame_batch(pkg, case):
+    """The two throughput kernels (me_ffs_tuned_kernel, me_subpel_tuned_kernel) on the reference's OWN predictors: every
+    (macroblock, list, ref) of the golden traces becomes a me_mb_job (tests/trace_jobs.py: traced 16x16 predictor = search centre,
+    traced partition predictors, traced lambda factors), goes through me_cuda_frame_search, and must return the traced
+    integer-pel vector + cost and the traced final vector + cost of every traced call (mv-search.c:1378-1454)."""
+    from replay import picture_lists
+    from trace_jobs import compare, jobs_of_picture
+    from h264_b200.me_cuda import JOB_DTYPE
+    tr, cfgkw = golden_trace(case)
+    h, w = tr.size[("cur", tr.cur_ids()[0])]
+    total = 0
+    with _open(pkg, w, h, cfgkw) as me:
+        handles = {i: me.ref_create(tr.ref(i)) for i in tr.ref_ids()}
+        for pic in tr.cur_ids():
+            jobs, expect, weights = jobs_of_picture(tr, pic, JOB_DTYPE)
+            if not len(jobs):
+                continue
+            lists = picture_lists(tr, pic)
+            me.set_current(tr.cur(pic))
+            for l in (0, 1):
+                me.set_ref_list(l, [handles[i] for i in lists[l]])
+                for ref in range(len(lists[l])):
+                    me.set_ref_weights(l, ref, *weights.get((l, ref), (0, 32, 0, 5)))
+            out, out_int = me.frame_search(jobs, want_int=True)
+            n, bad = compare(jobs, expect, out, out_int)
+            assert not bad, (case, pic, n, len(bad), bad[:4])
+            total += n
+    assert total > 1000, total
+
+
 # ------------------------------------------------------------------------------------------------ frame batch
 def _batch_case(pkg, ob, w, h, frames, n_refs, d, cfg, jobs, sample=None, seed=0):
     from h264_b200 import synth  # noqa: F401
@@ -345,7 +455,8 @@ def test_batch_extreme_predictors(pkg, oracle_lib):
 
 
 def test_full_size_1080p_properties(pkg, oracle_lib):
-    """BASELINE headline size: 1920x1088, SR 32, 5 refs.  Size-independent checks on the whole frame, oracle on a sample."""
+    """BASELINE headline size: 1920x1088, SR 32, 5 refs.  Size-independent checks on the whole frame; the oracle on every job
+    of reference 0, on every picture-border macroblock of all five references and on a 2 % sample of the rest."""
     from h264_b200 import synth
     ob = oracle_lib
     w, h, n_refs = 1920, 1088, 5
@@ -378,17 +489,32 @@ def test_full_size_1080p_properties(pkg, oracle_lib):
     assert (np.abs(mvx - cx[:, None]) <= 32).all()
     # the sub-pel result moves at most 3 quarter pels from the integer result
     assert (np.abs(out1["mv"].astype(np.int32) - 4 * int1["mv"].astype(np.int32)) <= 3).all()
-    # oracle on a sample of jobs
+    # oracle: EVERY job of one reference picture (the nearest and, on alternate runs of the parametrisation below, the farthest),
+    # every picture-border macroblock of all five, and a random sample of the interior of the others -- the oracle costs
+    # about 0.7 ms per job on one core, so the work is spread over the host cores (ctypes releases the GIL)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
     refs = [ob.Ref(frames[-2 - r]) for r in range(n_refs)]
-    rng = np.random.default_rng(2)
-    sel = np.sort(rng.choice(len(jobs), 100, replace=False))
     curc = np.ascontiguousarray(cur)
+    border = (jobs["opix_x"] == 0) | (jobs["opix_y"] == 0) | (jobs["opix_x"] == w - 16) | (jobs["opix_y"] == h - 16)
+    rng = np.random.default_rng(2)
+    pick = border | (jobs["ref"] == 0) | (rng.random(len(jobs)) < 0.02)
+    sel = np.nonzero(pick)[0]
+    assert border.sum() == n_refs * (2 * (w // 16) + 2 * (h // 16) - 4) and (jobs["ref"] == 0).sum() == (w // 16) * (h // 16)
+
+    def check(chunk):
+        r = int(jobs["ref"][chunk[0]])
+        exp, exp_int = ob.mb_search(cfg, curc, refs[r], jobs[chunk])
+        return int((int1[chunk] != exp_int).sum() + (out1[chunk] != exp).sum())
+
+    chunks = []
     for r in range(n_refs):
         s = sel[jobs["ref"][sel] == r]
-        if len(s):
-            exp, exp_int = ob.mb_search(cfg, curc, refs[r], jobs[s])
-            assert np.array_equal(int1[s], exp_int), r
-            assert np.array_equal(out1[s], exp), r
+        chunks += [s[i:i + 64] for i in range(0, len(s), 64)]
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        wrong = sum(ex.map(check, chunks))
+    assert wrong == 0, wrong
+    assert len(sel) >= (w // 16) * (h // 16) + 4 * (2 * (w // 16) + 2 * (h // 16) - 4)
     for r in refs:
         r.close()
 
@@ -441,7 +567,9 @@ def test_bipred_batch_matches_reference_chains(pkg):
     (3, 2, 0, None), (0, 1, 0, None), (2, 0, 0, None), (1, 2, 1, None),
     (3, 2, 0, ((1, 31, 33, 0, 5), (1, 33, 31, 0, 5))),          # explicit weights as the reference estimates them for a fade
     (1, 2, 1, ((1, 20, 45, -7, 5), (1, 45, 20, -7, 5))),        # 8x8 transform: the source-pointer slip of computeBiPredSATD2
-    (2, 2, 1, ((1, -10, 74, 12, 6), (0, 0, 0, 0, 0)))])         # negative weight, clipping; list 1 calls unweighted
+    (2, 2, 1, ((1, -10, 74, 12, 6), (0, 0, 0, 0, 0))),          # negative weight, clipping; list 1 calls unweighted
+    (1, 2, 0, ((1, 128, -64, 0, 5), (1, -64, 128, 0, 5)))])     # implicit weights of an extrapolating list-1 picture: w0 = 64 - w1 = 128
+                                                                 # (weighted_prediction.c:218-223)
 def test_bipred_batch_matches_oracle(pkg, oracle_lib, refinements, subpel, t8, weights):
     from h264_b200 import synth
     ob = oracle_lib

@@ -18,7 +18,16 @@ def _md5(p):
 
 
 def _have():
-    return os.path.exists(os.path.join(REF_DIR, "lencod_cuda")) and os.path.exists(os.path.join(REF_DIR, "fixtures", "encoder.cfg"))
+    """oracle/_ref (the reference encoder binaries, built where the reference tree is mounted) travels to the GPU box with the
+    repository snapshot.  Without it these tests cannot run: on a box WITH a GPU that is a failure, not a skip -- a green run
+    must have executed them."""
+    ok = os.path.exists(os.path.join(REF_DIR, "lencod_cuda")) and os.path.exists(os.path.join(REF_DIR, "fixtures", "encoder.cfg"))
+    if not ok:
+        import torch
+        if torch.cuda.is_available() and not os.environ.get("ME_ALLOW_MISSING_REF"):
+            raise RuntimeError("oracle/_ref/lencod_cuda is missing on a GPU box: build it with `make -C oracle ref` where /root/reference "
+                               "is mounted (it is git-ignored but not gpurun-ignored)")
+    return ok
 
 
 def _prep(tmp):
@@ -31,25 +40,44 @@ def _prep(tmp):
 def _run(exe, args, cwd, env=None):
     e = dict(os.environ)
     e["ME_CUDA_LIB"] = os.path.join(ROOT, "h.264_b200", "libme_cuda.so")
+    for k in ("ME_CUDA_DISABLE", "ME_CUDA_VERIFY", "ME_CUDA_PMS"):       # a stray switch must not turn the comparison into reference-vs-reference
+        e.pop(k, None)
     if env:
         e.update(env)
-    r = subprocess.run([os.path.join(REF_DIR, exe)] + args, cwd=cwd, env=e, capture_output=True, text=True, timeout=1500)
+    r = subprocess.run([os.path.join(REF_DIR, exe)] + args, cwd=cwd, env=e, capture_output=True, text=True, timeout=3000)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
-    return r.stdout
+    return r.stdout, r.stderr
+
+
+def _served(stderr, want=("plane sets",)):
+    """the shim's exit report: how many calls of each wrapped function the device answered.  Returns the counts; asserts that
+    the run was a GPU run (plane sets generated on the device, and every kind in `want` served at least once)."""
+    import re
+    m = re.search(r"served on the device: (\d+) plane sets, (\d+) ffs, (\d+) fullpel, (\d+) subpel, (\d+) bi_full, (\d+) bi_sub calls", stderr)
+    assert m, "no service report from the shim (pass-through run?): " + stderr[-800:]
+    c = dict(zip(["plane sets", "ffs", "fullpel", "subpel", "bi_full", "bi_sub"], map(int, m.groups())))
+    p = re.search(r"partition-search launches (\d+), block searches answered from them (\d+), argument mismatches (\d+)", stderr)
+    assert p, stderr[-800:]
+    c["pms_launches"], c["pms_served"], c["pms_missed"] = map(int, p.groups())
+    for k in want:
+        assert c[k] > 0, (k, c)
+    return c
 
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built (needs the reference tree at build time)")
 def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
     """bin/encoder.cfg: the run behind the reference's committed bin/test.264 / bin/test_rec.yuv"""
     _prep(str(tmp_path))
-    _run("lencod_cuda", ["-d", "encoder.cfg"], str(tmp_path))
+    _, err = _run("lencod_cuda", ["-d", "encoder.cfg"], str(tmp_path))
+    c = _served(err, ("plane sets", "ffs", "subpel", "bi_full", "bi_sub"))
+    assert c["pms_launches"] > 0 and c["pms_served"] > 0, c
     md5 = json.load(open(os.path.join(GOLDEN, "bitstream_md5.json")))["kat"]
     assert _md5(str(tmp_path / "test.264")) == md5["test.264"] == _md5(os.path.join(REF_DIR, "fixtures", "golden_test.264"))
     assert _md5(str(tmp_path / "test_rec.yuv")) == md5["test_rec.yuv"] == _md5(os.path.join(REF_DIR, "fixtures", "golden_test_rec.yuv"))
 
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
-@pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "rdopt0_restrict0", "yuv444_3ref_bframes", "sr64_2ref",
+@pytest.mark.parametrize("case", ["baseline_sr16_1ref", "main_cif_5ref", "cif_5ref_8frames", "rdopt0_restrict0", "yuv444_3ref_bframes", "sr64_2ref",
                                   "hd1080_sr32_ip", "weighted_pred_fade", "weighted_bipred_fade", "full_search_mode_rdopt0",
                                   "full_search_mode_satd", "yuv444_independent_planes", "chroma_me_2_bframes",
                                   "chroma_me_1_full_search_rdopt0", "chroma_me_1_yuv422", "chroma_me_2_sad_sse_subpel",
@@ -70,6 +98,11 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     elif case == "main_cif_5ref":
         args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=352", "-p", "SourceHeight=288",
                 "-p", "FramesToBeEncoded=4", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=32",
+                "-p", "NumberReferenceFrames=5", "-p", "LevelIDC=51"]
+    elif case == "cif_5ref_8frames":
+        # BASELINE config 2 with ALL FIVE references in use: pictures 5..7 of eight search five reference pictures each
+        args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=352", "-p", "SourceHeight=288",
+                "-p", "FramesToBeEncoded=8", "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=32",
                 "-p", "NumberReferenceFrames=5", "-p", "LevelIDC=51"]
     elif case == "yuv444_3ref_bframes":
         # BASELINE config 4 on the reference's own 4:4:4 fixture: High 4:4:4, I-B-P with bi-predictive ME, 3 references
@@ -161,11 +194,23 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         if "InputFile=syn.yuv" in args:
             wdt = int([a for a in args if a.startswith("SourceWidth=")][0].split("=")[1])
             hgt = int([a for a in args if a.startswith("SourceHeight=")][0].split("=")[1])
-            synth.write_yuv420(str(d / "syn.yuv"), wdt, hgt, 2 if wdt == 1920 else 7, kind="fade" if ("fade" in case or "weighted" in case) else "pan")
-    _run("lencod_cuda", args, str(a))
-    _run("lencod", args, str(b))
+            synth.write_yuv420(str(d / "syn.yuv"), wdt, hgt, 2 if wdt == 1920 else 8 if case == "cif_5ref_8frames" else 7,
+                               kind="fade" if ("fade" in case or "weighted" in case) else "pan")
+    _, err = _run("lencod_cuda", args, str(a))
+    out_cpu, _ = _run("lencod", args, str(b))
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
     assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
+    # the device did the work: plane sets, and the searches of the mode under test
+    pattern = "plain_subpel" in case or "bipred_subpel" in case
+    c = _served(err, ("plane sets", "subpel") if pattern else ("plane sets", "fullpel", "subpel") if "full_search_mode" in case or "full_search_rdopt0" in case
+                else ("plane sets", "ffs", "subpel"))
+    if not pattern and "full_search" not in case:
+        # fast full search: one launch per PartitionMotionSearch call, and the device's own motion vector predictors agreed with the
+        # reference's SetMotionVectorPredictor on every block search they were used for
+        assert c["pms_launches"] > 0 and c["pms_served"] > 0 and c["pms_missed"] == 0, c
+    if case == "cif_5ref_8frames":
+        # all five references were searched: the reference's own report lists the fifth reference in use for the last pictures
+        assert c["ffs"] > 41 * 396 * (1 + 2 + 3 + 4 + 5 + 5 + 5), c
     if "plain_subpel" in case:
         # the device did serve these modes: verify mode counts the SubPelBlockMotionSearch calls it answered (and compares each)
         import re
@@ -187,10 +232,32 @@ def test_shipped_configurations_as_they_are(tmp_path, me_lib_path, cfg):
     a.mkdir(); b.mkdir()
     for d in (a, b):
         _prep(str(d))
-    _run("lencod_cuda", ["-d", cfg], str(a))
+    _, err = _run("lencod_cuda", ["-d", cfg], str(a))
     _run("lencod", ["-d", cfg], str(b))
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
     assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
+    c = _served(err, ("plane sets", "ffs", "subpel"))
+    assert c["pms_launches"] > 0 and c["pms_missed"] == 0, c
+
+
+@pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
+@pytest.mark.parametrize("case", ["hd720_444_ibp_3ref", "uhd4k_sr64_ip"])
+def test_stated_size_configs_match_committed_md5(tmp_path, me_lib_path, case):
+    """BASELINE configs 4 and 5 at their stated picture sizes (1280x720 4:4:4 I-B-P with 3 references; 3840x2160 SR 64 I + P):
+    lencod_cuda against the md5 of the plain reference encoder's bitstream and reconstruction, committed by
+    tests/golden/make_golden.py (`big`) -- the CPU encoder needs minutes for these and is not re-run on the GPU box."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    md5 = json.load(open(os.path.join(GOLDEN, "bitstream_md5.json")))[case]
+    _prep(str(tmp_path))
+    mg.write_big_input(case, str(tmp_path / "syn.yuv"))
+    _, err = _run("lencod_cuda", mg.BIG_CASES[case]["args"], str(tmp_path))
+    assert _md5(str(tmp_path / "test.264")) == md5["test.264"]
+    assert _md5(str(tmp_path / "test_rec.yuv")) == md5["test_rec.yuv"]
+    c = _served(err, ("plane sets", "ffs", "subpel"))
+    assert c["pms_launches"] > 0, c
 
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref binaries not built")
