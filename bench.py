@@ -43,6 +43,16 @@ WORKLOAD = "1080p_sr32_5ref_allpartitions_qpel" if SEARCH_RANGE == 32 else "4k_s
 UNIT = "MB/s"
 
 
+def bench_config(world, sub_metric=2):
+    """the `config` object of the JSON line: the same for both arms (the reference arm runs this workload on the host cores)"""
+    return {"workload": WORKLOAD, "width": W, "height": H, "search_range": SEARCH_RANGE, "refs": N_REFS,
+            "macroblocks_per_step": MBS, "jobs_per_step": MBS * N_REFS, "partitions": 41,
+            "metrics": "SAD fpel / %s hpel,qpel" % ("SAD", "SSE", "SATD")[sub_metric],
+            "parallelism": "gop-sharded x%d, no collective" % world,
+            "l2": "256 MB write between timed steps (L2 flush) and ~250 MB working set per step",
+            "predictors": "synthetic per-partition predictors (pan + jitter), seed 21"}
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -56,7 +66,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.lines, self.proc = gpu_index, [], None
+        self.idx, self.lines, self.stamps, self.proc = gpu_index, [], [], None
 
     def start(self):
         try:
@@ -71,8 +81,10 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+            self.stamps.append(time.perf_counter())
 
-    def stop(self):
+    def stop(self, timed=None):
+        """timed = (t0, t1) perf_counter bounds of the timed steps: the record says how many samples fall inside them"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -80,8 +92,8 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        sm, mx, reasons, power, inside = [], [], set(), [], 0
+        for ln, ts in zip(self.lines, self.stamps):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -89,11 +101,15 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
             except ValueError:
                 continue
+            if timed and timed[0] <= ts <= timed[1]:
+                inside += 1
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "samples_in_timed_steps": inside,
+                "sampled_over": "the warm-up loop (same step, same load, >= 2.5 s) and the timed steps; nvidia-smi every 100 ms",
+                "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
@@ -202,6 +218,17 @@ def reference_arm(args):
                     me.append(float(ln.split(":")[1].split("sec")[0]))
         return time.perf_counter() - t0, me
 
+    # Beside the stepped sample: ONE encoder process on the stated configuration itself -- the whole 1920x1088 picture, 8 pictures
+    # IPPP, so that pictures 5..7 search all five references -- started now on one core and collected at the
+    # end; the stepped strips use the remaining cores.  It pins the per-core figure the strips extrapolate.
+    full = None
+    strip_cores = cores
+    if cores >= 4 and os.environ.get("ME_BENCH_REF_FULL", "1") != "0":
+        full_dir = prepare_reference_dir(8)
+        full = (subprocess.Popen([exe] + reference_cfg_args("clip.yuv", 8), cwd=full_dir, stdout=subprocess.PIPE,
+                                 stderr=subprocess.DEVNULL, text=True), time.perf_counter())
+        strip_cores = cores - 1
+    cores_all, cores = cores, strip_cores
     cal_s, _ = run_step(make_workdirs(16 * 8), 16 * 8)
     rows = int(8 * 150.0 / (max(1, args.steps + args.warmup) * cal_s))
     rows = max(8, min(H // 16, rows))
@@ -220,16 +247,36 @@ def reference_arm(args):
         walls.append(wall); mes.append(float(np.mean(me)))
     # throughput of the hot path: every process searched MBS (MB,ref) units in its ME seconds, all processes concurrently
     me_mean = float(np.mean(mes))
-    value = cores * mbs / N_REFS / me_mean
+    per_core = mbs / N_REFS / me_mean
+    full_note = None
+    if full:
+        out = full[0].communicate()[0]
+        me_full = None
+        for ln in out.splitlines():
+            if "Total ME time for sequence" in ln:
+                me_full = float(ln.split(":")[1].split("sec")[0])
+        units_full = MBS * sum(min(k, N_REFS) for k in range(1, 8))           # 25 (picture, ref) searches of 8160 macroblocks
+        if full[0].returncode == 0 and me_full:
+            full_note = {"what": "one lencod process, 1920x1088, 8 pictures IPPP, SR 32, 5 references: pictures 5..7 search five references",
+                         "me_seconds": me_full, "mb_ref_searches": units_full, "mb_per_s_one_core": units_full / N_REFS / me_full,
+                         "strip_sample_mb_per_s_one_core": per_core, "strip_over_full": per_core / (units_full / N_REFS / me_full),
+                         "wall_s": time.perf_counter() - full[1], "ran": "concurrently with the stepped strips, on its own core"}
+            # the stated configuration, measured directly, is the per-core figure; the strips confirm it step by step
+            per_core = units_full / N_REFS / me_full
+    cores = cores_all
+    value = cores * per_core
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "width": W, "height": H, "search_range": SEARCH_RANGE,
-                       "refs": N_REFS, "note": "per step every host core runs the unmodified lencod on I+P (1 reference) of a "
-                                               "%dx%d strip of the clip (%d macroblocks); MB/s = cores * %d (MB,ref) / 5 refs / mean ME "
-                                               "seconds (encoder's own ME timer)" % (W, hs, mbs, mbs)},
+            "config": bench_config(args.gpus),
+            "reference_sample": {"stepped": "per step %d host cores each run the unmodified lencod on I+P (1 reference) of a %dx%d strip of the clip "
+                                            "(%d macroblocks); per-core MB/s = %d (MB,ref) / 5 refs / mean ME seconds (encoder's own ME timer) = %.1f"
+                                            % (strip_cores, W, hs, mbs, mbs, mbs / N_REFS / me_mean),
+                                 "full_config": full_note,
+                                 "value": "host cores (%d) x per-core MB/s of the %s" % (cores, "full-configuration run" if full_note else "strips")},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                             "sample": "%d concurrent lencod processes, I+P of a %dx%d strip each, per step" % (cores, W, hs)},
+                             "sample": "%d concurrent lencod processes per step on I+P strips of %dx%d%s" %
+                                       (strip_cores, W, hs, "; one process on the full 1920x1088 x 8-picture, 5-reference configuration" if full_note else "")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -334,7 +381,7 @@ def main():
     sampler.start()
     t_warm = time.perf_counter()
     s = 0
-    while s < args.warmup or time.perf_counter() - t_warm < 0.5:     # at least W steps and half a second of load
+    while s < args.warmup or time.perf_counter() - t_warm < 2.5:     # at least W steps and 2.5 s of load (>= 20 clock samples)
         device_step(s)
         s += 1
         if s % 8 == 0:
@@ -362,7 +409,7 @@ def main():
     sub_ms, sub_n = me.kernel_time_ms(2)
     pl_ms, pl_n = me.kernel_time_ms(0)
     me.set_timing(False)
-    clocks = sampler.stop()
+    clocks = sampler.stop((t_wall0, t_wall0 + wall_s))
     total_ms = float(sum(step_ms))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -443,12 +490,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "width": W, "height": H, "search_range": SEARCH_RANGE,
-                           "refs": N_REFS, "macroblocks_per_step": MBS, "jobs_per_step": n_jobs, "partitions": 41,
-                           "metrics": "SAD fpel / %s hpel,qpel" % ("SAD", "SSE", "SATD")[sub_metric],
-                           "parallelism": "gop-sharded x%d, no collective" % world,
-                           "l2": "256 MB write between timed steps (L2 flush) and ~250 MB working set per step",
-                           "predictors": "synthetic per-partition predictors (pan + jitter), seed 21"},
+                "config": bench_config(world, sub_metric),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": 1e3 * e2e_s / args.steps, "result_checksum": checksum},

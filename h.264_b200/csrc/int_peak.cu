@@ -9,6 +9,11 @@
 //   4 LOP3 (xor/and)     5 SHF (funnel shift) 6 VIMNMX (min)         7 PRMT (byte permute)
 //   8..14: the same as 1..7 interleaved 1:1 with VABSDIFF4 (do the two instructions issue on different pipes?)
 //   15 LDS.32 (shared-memory load, conflict-free) interleaved 1:1 with VABSDIFF4
+//   16 VABSDIFF4 + IMAD 1:1 with the operand pattern of the search kernel's sweep: every VABSDIFF4 of a group reads the SAME
+//      reference word (operand-reuse cache) and the IMAD has an immediate multiplier, so an instruction fetches at most two
+//      registers from the register file -- kind 9 fetches three per instruction (two distinct per chain + a shared one) and is
+//      bound by the two register-file banks, not by the pipes (see profiles/r02_int_peak.md)
+//   17 the same with VIADDMNMX in place of the IMAD (both on the ALU pipe)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -60,21 +65,51 @@ int_peak_kernel(uint32_t *out, int iters, uint32_t s1, uint32_t s2)
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// kinds 16 / 17: 8 accumulators fed by one shared reference word per group (like refL / refR of the sweep), 8 keys
+template <int KIND>
+__global__ void __launch_bounds__(256)
+int_peak_reuse_kernel(uint32_t *out, int iters, uint32_t s1, uint32_t s2)
+{
+  uint32_t acc[CHAINS], cur[CHAINS], key[CHAINS];
+#pragma unroll
+  for (int k = 0; k < CHAINS; k++) { acc[k] = 0; cur[k] = threadIdx.x * 2654435761u + k * 40503u + s1; key[k] = cur[k] ^ s2; }
+  uint32_t ref = s1 ^ threadIdx.x, best = 0xffffffffu;
+#pragma unroll 2
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int k = 0; k < CHAINS; k++) {
+        asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(ref), "r"(cur[k]));
+        if (KIND == 16) asm volatile("mad.lo.u32 %0, %0, 4225, %1;" : "+r"(key[k]) : "r"(ref));
+        else asm volatile("{.reg .u32 t; add.u32 t, %0, %1; min.u32 %0, t, %2;}" : "+r"(key[k]) : "r"(ref), "r"(best));
+      }
+      ref += 0x01010101u * (u + 1);
+    }
+  }
+  uint32_t s = best;
+#pragma unroll
+  for (int k = 0; k < CHAINS; k++) s += acc[k] + key[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <int KIND>
 static double run_kind(uint32_t *d_out, int blocks, int iters)
 {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  int_peak_kernel<KIND><<<blocks, 256>>>(d_out, iters / 8, 12345u, 777u);   // warm-up
+  if (KIND >= 16) int_peak_reuse_kernel<KIND><<<blocks, 256>>>(d_out, iters / 8, 12345u, 777u);
+  else int_peak_kernel<KIND><<<blocks, 256>>>(d_out, iters / 8, 12345u, 777u);   // warm-up
   cudaEventRecord(e0);
-  int_peak_kernel<KIND><<<blocks, 256>>>(d_out, iters, 12345u, 777u);
+  if (KIND >= 16) int_peak_reuse_kernel<KIND><<<blocks, 256>>>(d_out, iters, 12345u, 777u);
+  else int_peak_kernel<KIND><<<blocks, 256>>>(d_out, iters, 12345u, 777u);
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   double per_op = (KIND == 3 || KIND == 10) ? 1.0 : 1.0;   // add+min is counted as ONE operation (it fuses to VIADDMNMX when it can)
-  double ops = (double)blocks * 256.0 * (double)iters * 4.0 * CHAINS * per_op;
+  double ops = (double)blocks * 256.0 * (double)iters * 4.0 * CHAINS * per_op * (KIND >= 16 ? 2.0 : 1.0);   // kinds 16 / 17: two instructions per chain step
   return ops / (ms * 1e-3);
 }
 
@@ -89,7 +124,7 @@ extern "C" int me_cuda_measure_int_peak(int kind, double *lane_ops_per_s)
   double r = 0;
   switch (kind) {
 #define K(n) case n: r = run_kind<n>(d_out, blocks, iters); break;
-    K(0) K(1) K(2) K(3) K(4) K(5) K(6) K(7) K(8) K(9) K(10) K(11) K(12) K(13) K(14) K(15)
+    K(0) K(1) K(2) K(3) K(4) K(5) K(6) K(7) K(8) K(9) K(10) K(11) K(12) K(13) K(14) K(15) K(16) K(17)
 #undef K
     default: cudaFree(d_out); return 1;
   }

@@ -283,7 +283,9 @@ int   me_cuda_sync(void);                   /* cudaStreamSynchronize on it */
 /* number of kernels this library has launched since init (bench.py reports it as gpu_launches) */
 int64_t me_cuda_launch_count(void);
 /* diagnostics: measured issue rate (lane-operations per second, whole GPU) of the integer instructions the search
- * kernels are bound by; kind 0 VABSDIFF4, 1 IADD3, 2 IMAD, 3 VIADDMNMX, 4 LOP3, 5 SHF, 6 VABSDIFF4+IMAD, 7 VABSDIFF4+IADD3.
+ * kernels are bound by; kind 0 VABSDIFF4, 1 IADD3, 2 IMAD, 3 VIADDMNMX, 4 LOP3, 5 SHF, 6 VIMNMX, 7 PRMT, 8..14 the kinds 1..7
+ * interleaved 1:1 with VABSDIFF4, 15 LDS + VABSDIFF4, 16 / 17 VABSDIFF4 + IMAD / VIADDMNMX with the operand pattern of the search
+ * kernel (one shared reference word per group, immediate multiplier: at most two register-file reads per instruction).
  * This is the denominator of bench.py's INT-ALU roofline (MEASURED_PEAKS.json has no integer figure). */
 int me_cuda_measure_int_peak(int kind, double *lane_ops_per_s);
 

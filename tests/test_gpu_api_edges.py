@@ -104,7 +104,7 @@ def test_reference_slot_reuse_and_in_place_update(pkg, oracle_lib):
 
 def test_weight_arguments_are_checked(pkg):
     """me_cuda_set_ref_weights / me_cuda_set_bipred_weights: ranges of the slice header syntax (weights / offsets -128..127,
-    log denominator 0..7); the bi-predictive batch reads the pictures' own planes whatever the list entries' weights are"""
+    log denominator 0..7; bi-predictive weights -128..128, the range implicit weighting produces, weighted_prediction.c:218-223); the bi-predictive batch reads the pictures' own planes whatever the list entries' weights are"""
     from h264_b200 import MeCuda, MeCudaError, synth
     from h264_b200.me_cuda import BIPRED_JOB_DTYPE
     w, h = 176, 144
@@ -118,9 +118,11 @@ def test_weight_arguments_are_checked(pkg):
                 me.set_ref_weights(*bad)
         jobs = np.zeros(1, BIPRED_JOB_DTYPE)
         jobs["lambda"] = 334459
-        for bad in ((2, 1, 32, 32, 0, 5), (0, 1, 128, 32, 0, 5), (0, 1, 32, -129, 0, 5), (1, 1, 32, 32, 128, 5), (1, 1, 32, 32, 0, 8)):
+        for bad in ((2, 1, 32, 32, 0, 5), (0, 1, 129, 32, 0, 5), (0, 1, 32, -129, 0, 5), (1, 1, 32, 32, 128, 5), (1, 1, 32, 32, 0, 8)):
             with pytest.raises(MeCudaError):
                 me.set_bipred_weights(*bad)
+        me.set_bipred_weights(0, 1, 128, -64, 0, 5)          # w0 = 128, w1 = -64: an extrapolating implicit pair is accepted
+        me.set_bipred_weights(0, 0, 32, 32, 0, 5)
         plain = me.frame_bipred(jobs, 3, 16, 2)
         me.set_ref_weights(1, 0, 1, 30, 2, 5)                 # uni-predictive weights of the same list entry: no effect here
         assert np.array_equal(me.frame_bipred(jobs, 3, 16, 2), plain)
