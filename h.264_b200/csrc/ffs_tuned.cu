@@ -366,8 +366,11 @@ __device__ __forceinline__ void search_centre(const MeCfgDev &c, int R, const Jo
 }
 
 // 3 CTAs per SM at R = 32 (168 registers); 4 CTAs (128 registers, 43 spill stores) measured slower: 2.20 vs 2.01 ms
+#ifndef ME_FFS_R32_CTAS
+#define ME_FFS_R32_CTAS 3
+#endif
 template <int R>
-__global__ void __launch_bounds__(Geo<R>::NT, (R == 32) ? 3 : (R == 16) ? 6 : 1)
+__global__ void __launch_bounds__(Geo<R>::NT, (R == 32) ? ME_FFS_R32_CTAS : (R == 16) ? 6 : 1)
 me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                     const __grid_constant__ WinMaps win_maps, const __grid_constant__ CUtensorMap cur_map,
                     const uint8_t *__restrict__ cur_pic, int cur_pitch, int use_tma,
@@ -553,6 +556,12 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
     sweep4<R, 1, 1>(rg, t, row0, 4);
     sweep4<R, 1, 2>(rg, t, row0, 8);
     sweep4<R, 1, 3>(rg, t, row0, 12);
+#ifdef ME_FFS_INTERIOR_REPEAT   // timing experiment only (results invalid): the interior rows N times, to read the steady-state rate of the sweep
+#pragma unroll 1
+    for (int rep = 1; rep < ME_FFS_INTERIOR_REPEAT; rep++)
+#pragma unroll 1
+      for (int r0 = 16; r0 < 2 * R; r0 += 4) sweep4<R, 0, 0>(rg, t, row0, r0);
+#endif
 #pragma unroll 1        // four rows per iteration: eight measured slower (2.14 vs 2.02 ms per 1080p picture, instruction cache)
     for (int r0 = 16; r0 < 2 * R; r0 += 4) sweep4<R, 0, 0>(rg, t, row0, r0);
     sweep4<R, 2, 0>(rg, t, row0, 2 * R);
@@ -620,7 +629,16 @@ int launch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void 
     attr_done[dev] = true;
   }
   const int sms = sms_of[dev];
-  const int per_sm = (R == 32) ? 3 : (R == 16) ? 6 : 1;
+  int per_sm = (R == 32) ? ME_FFS_R32_CTAS : (R == 16) ? 6 : 1;
+  // timing experiments (profiles/r02_ffs_occupancy.md): fewer resident CTAs per SM, enforced with a larger shared-memory request
+  static int cta_limit = -1;
+  if (cta_limit < 0) { const char *e = getenv("ME_CUDA_FFS_CTAS"); cta_limit = e ? atoi(e) : 0; }
+  size_t smem_bytes = sizeof(Smem<R>);
+  if (cta_limit > 0 && cta_limit < per_sm) {
+    per_sm = cta_limit;
+    smem_bytes = (size_t)(220 * 1024 / cta_limit) & ~(size_t)1023;
+    if (cudaFuncSetAttribute(me_ffs_tuned_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return 0;
+  }
   int grid = sms * per_sm;
   if (grid > n_jobs) grid = n_jobs;
   CUtensorMap cm;
@@ -631,7 +649,7 @@ int launch(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void 
     memcpy(&wm.m[l * TUNED_MAX_REFS], (const unsigned char *)win_maps + (size_t)l * ME_MAX_REFS * 128, sizeof(CUtensorMap) * TUNED_MAX_REFS);
   static int use_tma = -1;
   if (use_tma < 0) { const char *e = getenv("ME_CUDA_FFS_TMA"); use_tma = !(e && e[0] == '0'); }
-  me_ffs_tuned_kernel<R><<<grid, Geo<R>::NT, sizeof(Smem<R>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, wm, cm,
+  me_ffs_tuned_kernel<R><<<grid, Geo<R>::NT, smem_bytes, st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, wm, cm,
                                                                     cur_pic, cur_pitch, use_tma, *cfg, out, deferred, ticket);
   return 1;
 }
