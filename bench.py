@@ -410,6 +410,12 @@ def main():
     pl_ms, pl_n = me.kernel_time_ms(0)
     me.set_timing(False)
     clocks = sampler.stop((t_wall0, t_wall0 + wall_s))
+    # share of the partitions the sub-pel kernel reads from its TMA-staged region (the rest: clamped reads from global memory); one
+    # more step outside the timed region with the counters on
+    me.subpel_region_stats(True)
+    device_step(n_warm + args.steps)
+    me.sync()
+    region_served, region_total = me.subpel_region_stats(False)
     total_ms = float(sum(step_ms))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -477,7 +483,8 @@ def main():
                                                       "DRAM sees each reference plane once",
                 "int_peaks_glaneops": peaks,
                 "share_of_step": {"planes_ms": pl_ms / max(1, args.steps), "ffs_ms": ffs_ms / max(1, args.steps),
-                                  "subpel_ms": sub_ms / max(1, args.steps)}}
+                                  "subpel_ms": sub_ms / max(1, args.steps)},
+                "subpel_region_share": (region_served / region_total) if region_total else None}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -50,7 +50,7 @@ int  me_make_tensor_map_2d(void *out, const void *base, int w, int h, int pitch,
 int  me_make_planes_tensor_map(void *out, const void *planes, int pitch, int hp, size_t plane_stride);
 int  me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *plane_maps, int n_refs0, int n_refs1,
                                   const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg, const MeResultInt *in_int, MeResult *out,
-                                  int *ticket, cudaStream_t st);   // 1 = launched, 0 = not applicable
+                                  int *ticket, unsigned long long *stats, cudaStream_t st);   // 1 = launched, 0 = not applicable
 int  me_ffs_tuned_window(int search_range);
 void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y, int cx, int cy,
                             int R, int sse, const MeChromaDev *chroma, int32_t *surf, cudaStream_t st);
@@ -138,6 +138,7 @@ struct State {
   bool pmaps_ok = false;
   bool maps_ok = false;         // every listed reference has a window tensor map
   TensorMap cur_map{}; bool has_cur_map = false;   // current picture, box 16 x 16
+  unsigned long long *d_subpel_stats = nullptr;      // {partitions the sub-pel kernel served from its staged region, all partitions}, while enabled
   int *d_deferred = nullptr; int deferred_cap = 0;  // {job ticket counters of the two tuned kernels; jobs the search kernel hands back: count, ids...}
   cudaEvent_t ev_order = nullptr;                   // orders a caller's stream (the *_device calls) against the library stream
   cudaStream_t s_in = nullptr, s_out = nullptr;     // host <-> device pipeline of me_cuda_frame_search
@@ -508,6 +509,7 @@ void me_cuda_shutdown(void)
   if (g.pms.h_rec) cudaFreeHost(g.pms.h_rec);
   if (g.pms.d_done) cudaFree(g.pms.d_done);
   if (g.d_deferred) cudaFree(g.d_deferred);
+  if (g.d_subpel_stats) cudaFree(g.d_subpel_stats);
   if (g.s_in) {
     cudaStreamSynchronize(g.s_in); cudaStreamSynchronize(g.s_out);
     for (int c = 0; c < ME_PIPE_CHUNKS; c++) { cudaEventDestroy(g.ev_in[c]); cudaEventDestroy(g.ev_done[c]); }
@@ -533,6 +535,31 @@ void me_cuda_shutdown(void)
 void *me_cuda_stream(void) { return (void *)g.stream; }
 int me_cuda_sync(void) { CK(cudaStreamSynchronize(g.stream)); return 0; }
 int64_t me_cuda_launch_count(void) { return g.launches; }
+
+// Share of the partitions the throughput sub-pel kernel reads from its staged region (the others take the clamped reads from
+// global memory).  enable != 0 starts (and zeroes) the count, 0 stops it; served / total may be null.
+int me_cuda_subpel_region_stats(int enable, int64_t *served, int64_t *total)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  CK(cudaStreamSynchronize(g.stream));
+  if (g.d_subpel_stats && (served || total)) {
+    unsigned long long h[2] = { 0, 0 };
+    CK(cudaMemcpy(h, g.d_subpel_stats, sizeof h, cudaMemcpyDeviceToHost));
+    if (served) *served = (int64_t)h[0];
+    if (total) *total = (int64_t)h[1];
+  } else {
+    if (served) *served = 0;
+    if (total) *total = 0;
+  }
+  if (enable) {
+    if (!g.d_subpel_stats) CK(cudaMalloc((void **)&g.d_subpel_stats, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(g.d_subpel_stats, 0, 2 * sizeof(unsigned long long)));
+  } else if (g.d_subpel_stats) {
+    cudaFree(g.d_subpel_stats);
+    g.d_subpel_stats = nullptr;
+  }
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ pictures
 int me_cuda_ref_create_device(const void *d_luma, int stride, int w, int h, void *stream, me_ref_handle *out)
@@ -1276,7 +1303,7 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
     int done = 0;
     if (!use_basic_only() && g.pmaps_ok)
       done = me_launch_subpel_batch_tuned((const MeJob *)d_jobs, n_jobs, g.d_table, g.h_pmaps, g.list_n[0], g.list_n[1], g.d_cur, g.cur_pitch,
-                                          &sub_cfg, di, (MeResult *)d_out, g.d_deferred + 1, st);
+                                          &sub_cfg, di, (MeResult *)d_out, g.d_deferred + 1, g.d_subpel_stats, st);
     if (!done) me_launch_subpel_batch((const MeJob *)d_jobs, n_jobs, g.d_table, g.d_cur, g.cur_pitch, &sub_cfg, di, (MeResult *)d_out, st);
   }
   g.launches += launched + 1;

@@ -78,9 +78,22 @@ template <bool T8> struct __align__(128) Smem {
   int      mn[ME_NUM_PARTITIONS];           // its cost
   int      okp[ME_NUM_PARTITIONS];          // partition served by the staged region (else: global reads with the clamp)
   int      mvc[T8 ? 9 : 1][9];              // their motion-vector rate per candidate
-  int      next_id;                         // the job after the current one (>= n_jobs: none)
+  int      next_id;                         // the job after the next one (>= n_jobs: none)
   unsigned long long mbar;
+  // the NEXT job, copied in with cp.async while the current one is scored (no global-memory latency between two jobs)
+  uint32_t stg_job[48];                     // its descriptor
+  uint32_t stg_mv[ME_NUM_PARTITIONS];       // integer-pel vectors of its partitions
+  int      stg_cost[ME_NUM_PARTITIONS];     // and their costs
+  uint32_t stg_cur[NT];                     // its macroblock, one word per (tile, row, even / odd) thread
+  uint32_t stg_cur8[T8 ? NT : 1];           // and per (quadrant, row, lane pair) thread
+  MeRefDev refs[2 * 8];                     // copy of the reference table, [list][ref < TUNED_MAX_REFS]
 };
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // two-lane (16-bit, biased) add / subtract: one IADD3 each
 __device__ __forceinline__ unsigned padd(unsigned a, unsigned b) { return a + b - BIAS2; }
@@ -195,20 +208,29 @@ __global__ void __launch_bounds__(NT, T8 ? T8_CTAS : T4_CTAS)      // measured (
 me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
                        const __grid_constant__ PlaneMaps maps, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                        const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out,
-                       int *__restrict__ ticket /* jobs handed out beyond the first round (zeroed by the caller) */)
+                       int *__restrict__ ticket /* jobs handed out beyond the first round (zeroed by the caller) */,
+                       unsigned long long *__restrict__ stats /* [0] partitions served by the staged region, [1] all partitions; may be null */)
 {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem<T8> &sm = *reinterpret_cast<Smem<T8> *>(smem_raw);
   constexpr int JW = sizeof(MeJob) / 4;
   const int tid = threadIdx.x;
-  // jobs are handed out dynamically (first job blockIdx.x, then tickets of a global counter drawn one job ahead): see ffs_tuned.cu
+  // Jobs are handed out dynamically (first job blockIdx.x, then tickets of a global counter, see ffs_tuned.cu), drawn TWO jobs
+  // ahead: while job n is scored, the descriptor, integer-pel results and macroblock of job n + 1 travel into a staging area
+  // with cp.async, so that between two jobs there is no global-memory round trip -- one barrier, the region request (TMA),
+  // the staging area unpacked into the working arrays, a second barrier.
   if ((int)blockIdx.x >= n_jobs) return;
   const unsigned bar = smem_u32(&sm.mbar);
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_init_fence();
+    sm.next_id = atomicAdd(ticket, 1) + (int)gridDim.x;
   }
-  __syncthreads();
+  for (int i = tid; i < 2 * TUNED_MAX_REFS * (int)(sizeof(MeRefDev) / 4); i += NT) {
+    const int e = i / (int)(sizeof(MeRefDev) / 4), w = i - e * (int)(sizeof(MeRefDev) / 4);
+    reinterpret_cast<uint32_t *>(&sm.refs[e])[w] =
+        reinterpret_cast<const uint32_t *>(&ref_table[(e / TUNED_MAX_REFS) * ME_MAX_REFS + (e % TUNED_MAX_REFS)])[w];
+  }
 
   // region origin of a job: its 16x16 partition's integer vector, minus the margin, x aligned down to 16 bytes (TMA)
   auto region_origin = [&](uint32_t job_w0, uint32_t mv0_w, int &Xr, int &Yr) {
@@ -217,61 +239,98 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
     Xr = (ox + ME_PAD + mx - RD - 1) & ~15;
     Yr = oy + ME_PAD + my - RD - 1;
   };
-  auto issue_region = [&](int job_id) {             // thread 0
-    const uint32_t w0 = jobs[(size_t)job_id * JW], w1 = jobs[(size_t)job_id * JW + 1];
-    const uint32_t mv0 = reinterpret_cast<const uint32_t *>(in_int[job_id].mv)[0];
+  // asynchronous copies of a job into the staging area.  Part A needs the job's number only; part B (the macroblock's
+  // pixels) its origin, word 0 of the descriptor
+  auto stage_a = [&](int id) {
+    if (tid < JW) cp_async4(&sm.stg_job[tid], jobs + (size_t)id * JW + tid);
+    if (tid < ME_NUM_PARTITIONS) {
+      cp_async4(&sm.stg_mv[tid], reinterpret_cast<const uint32_t *>(in_int[id].mv) + tid);
+      cp_async4(&sm.stg_cost[tid], in_int[id].cost + tid);
+    }
+  };
+  auto stage_b = [&](uint32_t w0) {
+    const int ox = (int)(int16_t)(w0 & 0xffffu), oy = (int)(int16_t)(w0 >> 16);
+    const int tile = tid >> 3, y = (tid & 7) >> 1;          // thread -> (tile, row, even / odd): both threads of a row copy its word
+    cp_async4(&sm.stg_cur[tid], cur + (size_t)(oy + 4 * (tile >> 2) + y) * cur_pitch + ox + 4 * (tile & 3));
+    if (T8) {
+      const int quad = tid >> 5, y8 = (tid >> 2) & 7, j = tid & 3;      // thread -> (quadrant, row, lane pair)
+      cp_async4(&sm.stg_cur8[tid], cur + (size_t)(oy + 8 * (quad >> 1) + y8) * cur_pitch + ox + 8 * (quad & 1) + 4 * (j >> 1));
+    }
+  };
+  // thread 0, behind the barrier that ends a job: the staged job's region
+  auto issue_region = [&]() {
+    const uint32_t w1 = sm.stg_job[1];
     int Xr, Yr;
-    region_origin(w0, mv0, Xr, Yr);
+    region_origin(sm.stg_job[0], sm.stg_mv[0], Xr, Yr);
     const int list = (int)(int8_t)(w1 & 0xffu), ref = (int)(int8_t)((w1 >> 8) & 0xffu);
     proxy_fence();
     mbar_expect_tx(bar, REGION_BYTES);
     tma_load_3d(smem_u32(sm.region), &maps.m[list * TUNED_MAX_REFS + ref], Xr, Yr, 0, bar);
   };
-  if (tid == 0) issue_region((int)blockIdx.x);
-
-  int job_id = (int)blockIdx.x;
-  for (int it = 0; job_id < n_jobs; it++) {
-    int next_id = n_jobs;
-    if (tid == 0) { next_id = atomicAdd(ticket, 1) + (int)gridDim.x; sm.next_id = next_id; }     // read behind this job's barriers
-    // ---- job set-up
-    if (tid < JW) sm.job[tid] = jobs[(size_t)job_id * JW + tid];
+  // staging area -> working arrays (every thread unpacks what the job set-up used to fetch from global memory)
+  auto commit = [&]() {
+    if (tid < JW) sm.job[tid] = sm.stg_job[tid];
+    const int ox = (int)(int16_t)(sm.stg_job[0] & 0xffffu), oy = (int)(int16_t)(sm.stg_job[0] >> 16);
     if (tid < ME_NUM_PARTITIONS) {
-      const uint32_t w = reinterpret_cast<const uint32_t *>(in_int[job_id].mv)[tid];
-      sm.mv[tid][0] = (int)(int16_t)(w & 0xffffu) * 4;                       // mv <<= 2, mv-search.c:770-774
-      sm.mv[tid][1] = (int)(int16_t)(w >> 16) * 4;
-      sm.mn[tid] = cfg.start_hp ? in_int[job_id].cost[tid] : ME_INT_MAX;     // mv-search.c:785-788
+      const uint32_t w = sm.stg_mv[tid], w0 = sm.stg_mv[0], w1 = sm.stg_job[1];
+      const int mix = (int)(int16_t)(w & 0xffffu), miy = (int)(int16_t)(w >> 16);
+      const int m0x = (int)(int16_t)(w0 & 0xffffu), m0y = (int)(int16_t)(w0 >> 16);
+      sm.mv[tid][0] = mix * 4;                                                 // mv <<= 2, mv-search.c:770-774
+      sm.mv[tid][1] = miy * 4;
+      sm.mn[tid] = cfg.start_hp ? sm.stg_cost[tid] : ME_INT_MAX;               // mv-search.c:785-788
+      // does the staged region serve every tile of every candidate of the partition?  Its integer vector must lie within
+      // +-RD of the 16x16 one, and no tile origin outside [0, size_pad] (the clamp of UMVLine4X would move it)
+      const MeRefDev &rf = sm.refs[(int)(int8_t)(w1 & 0xffu) * TUNED_MAX_REFS + (int)(int8_t)((w1 >> 8) & 0xffu)];
+      const int t = me_part_type(tid), blk = me_part_blk(tid);
+      const int x0 = ox + ME_PAD + 4 * (blk & 3) + mix, y0 = oy + ME_PAD + 4 * (blk >> 2) + miy;   // first tile, centre
+      const int x1 = x0 + me_bsx(t) - 4, y1 = y0 + me_bsy(t) - 4;                                  // last tile
+      const int ok = abs(mix - m0x) <= RD && abs(miy - m0y) <= RD &&
+                     x0 - 1 >= 0 && y0 - 1 >= 0 && x1 <= rf.w + 2 * ME_PAD - 1 - 16 && y1 <= rf.h + 2 * ME_PAD - 1 - 16;
+      sm.okp[tid] = ok;
+      if (stats) {                                   // share of the partitions the staged region serves (bench.py reports it)
+        const unsigned b = __ballot_sync(__activemask(), ok);
+        if ((tid & 31) == 0) { atomicAdd(&stats[0], (unsigned long long)__popc(b)); if (tid == 0) atomicAdd(&stats[1], (unsigned long long)ME_NUM_PARTITIONS); }
+      }
     }
-    __syncthreads();
-    const JobView jv = job_view(sm.job);
-    const MeRefDev ref = ref_table[jv.list * ME_MAX_REFS + jv.ref];
     {
       // current macroblock as biased lane pairs: thread -> (tile, row, even/odd)
-      const int tile = tid >> 3, k = tid & 7, y = k >> 1, odd = k & 1;
-      const uint8_t *p = cur + (size_t)(jv.opix_y + 4 * (tile >> 2) + y) * cur_pitch + jv.opix_x + 4 * (tile & 3);
-      const unsigned ce = (unsigned)p[0] | ((unsigned)p[2] << 16), co = (unsigned)p[1] | ((unsigned)p[3] << 16);
+      const int tile = tid >> 3, k = tid & 7, odd = k & 1;
+      const uint32_t w = sm.stg_cur[tid];
+      const unsigned ce = w & 0x00ff00ffu, co = (w >> 8) & 0x00ff00ffu;                   // (c0 | c2 << 16), (c1 | c3 << 16)
       sm.curpk[tile][k] = (odd ? ce - co : ce + co) + BIAS2;       // cs / ct of satd4x4
       if (T8) {
-        // 8x8 quadrants: thread -> (quadrant, row, lane pair)
         const int quad = tid >> 5, y8 = (tid >> 2) & 7, j = tid & 3;
-        const uint8_t *p8 = cur + (size_t)(jv.opix_y + 8 * (quad >> 1) + y8) * cur_pitch + jv.opix_x + 8 * (quad & 1) + 4 * (j >> 1);
-        const unsigned e8 = (unsigned)p8[0] | ((unsigned)p8[2] << 16), o8 = (unsigned)p8[1] | ((unsigned)p8[3] << 16);
+        const uint32_t w8 = sm.stg_cur8[T8 ? tid : 0];
+        const unsigned e8 = w8 & 0x00ff00ffu, o8 = (w8 >> 8) & 0x00ff00ffu;
         sm.cur8[quad][y8][j] = ((j & 1) ? e8 - o8 : e8 + o8) + BIAS82;      // first horizontal stage, see satd8x8
       }
     }
+  };
+
+  // ---- the first job arrives the same way, synchronously
+  int job_id = (int)blockIdx.x;
+  stage_a(job_id);
+  stage_b(jobs[(size_t)job_id * JW]);
+  cp_async_wait_all();
+  __syncthreads();
+  if (tid == 0) issue_region();
+  commit();
+  __syncthreads();
+  int next_id = sm.next_id;
+
+  for (int it = 0; job_id < n_jobs; it++) {
+    // the job after the next one (ticket), and the next one on its way into the staging area
+    int tk = n_jobs;
+    uint32_t w0n = 0;
+    if (next_id < n_jobs) {
+      if (tid == 0) tk = atomicAdd(ticket, 1) + (int)gridDim.x;
+      stage_a(next_id);
+      w0n = jobs[(size_t)next_id * JW];
+    }
+    const JobView jv = job_view(sm.job);
+    const MeRefDev &ref = sm.refs[jv.list * TUNED_MAX_REFS + jv.ref];
     int Xr, Yr;
     region_origin(sm.job[0], ((unsigned)(sm.mv[0][0] >> 2) & 0xffffu) | ((unsigned)(sm.mv[0][1] >> 2) << 16), Xr, Yr);
-    // does the staged region serve every tile of every candidate of a partition?  Its integer vector must lie within
-    // +-RD of the 16x16 one, and no tile origin outside [0, size_pad] (the clamp of UMVLine4X would move it)
-    if (tid < ME_NUM_PARTITIONS) {
-      const int t = me_part_type(tid), blk = me_part_blk(tid);
-      const int mix = sm.mv[tid][0] >> 2, miy = sm.mv[tid][1] >> 2, m0x = sm.mv[0][0] >> 2, m0y = sm.mv[0][1] >> 2;
-      const int x0 = jv.opix_x + ME_PAD + 4 * (blk & 3) + mix, y0 = jv.opix_y + ME_PAD + 4 * (blk >> 2) + miy;   // first tile, centre
-      const int x1 = x0 + me_bsx(t) - 4, y1 = y0 + me_bsy(t) - 4;                                                // last tile
-      sm.okp[tid] = abs(mix - m0x) <= RD && abs(miy - m0y) <= RD &&
-                    x0 - 1 >= 0 && y0 - 1 >= 0 && x1 <= ref.w + 2 * ME_PAD - 1 - 16 && y1 <= ref.h + 2 * ME_PAD - 1 - 16;
-    }
-    __syncthreads();                                 // publishes okp, curpk and the next job's id
-    const int following_id = sm.next_id;
     // ---- this thread's tile for the whole job.  4x4: slot = (block type, tile slot), 16 lanes per type, the tiles of a
     // partition adjacent (c_tile / c_part).  With the 8x8 transform only the types 5..7 have 4x4 tiles (threads 0..47 of the
     // first two warps) and the last two warps hold the 8x8 tiles of types 1..4 (c_quad / c_part8), four lane groups of 16.
@@ -440,10 +499,9 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
           if (s8.leader && cc < 9) sm.cost[s8.p][c] = v + sm.mvc[s8.p][c];
         }
       }
+      if (stage == 0 && next_id < n_jobs) stage_b(w0n);   // the next macroblock's pixels: word 0 of its descriptor has arrived by now
       if (!T8) continue;
       __syncthreads();
-      // the region is free once the quarter-pel tiles are read: request the next job's
-      if (stage == 1 && tid == 0 && next_id < n_jobs) issue_region(next_id);
       {
         // partitions of block types 1..4: their candidates were scored by four lane groups, scan them here
         if (tid < 9) {
@@ -463,19 +521,20 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
         __syncthreads();
       }
     }
-    if (T8) {
-      if (tid < ME_NUM_PARTITIONS) {
-        reinterpret_cast<uint32_t *>(out[job_id].mv)[tid] = ((unsigned)sm.mv[tid][0] & 0xffffu) | ((unsigned)sm.mv[tid][1] << 16);
-        out[job_id].cost[tid] = sm.mn[tid];
-      }
-      __syncthreads();
-    } else {
-      // without the 8x8 transform every partition lives inside one warp: the warps ran both stages without meeting; they meet
-      // once per job, before the region and the job data are replaced
-      __syncthreads();
-      if (tid == 0 && next_id < n_jobs) issue_region(next_id);
+    if (T8 && tid < ME_NUM_PARTITIONS) {
+      reinterpret_cast<uint32_t *>(out[job_id].mv)[tid] = ((unsigned)sm.mv[tid][0] & 0xffffu) | ((unsigned)sm.mv[tid][1] << 16);
+      out[job_id].cost[tid] = sm.mn[tid];
     }
-    job_id = following_id;
+    // Without the 8x8 transform every partition lives inside one warp and the warps ran both stages without meeting.  They meet
+    // here: the region and the working arrays are free, the staged copies of the next job have landed (every thread waited
+    // for its own, the barrier publishes them)
+    cp_async_wait_all();
+    __syncthreads();
+    if (tid == 0) { if (next_id < n_jobs) issue_region(); sm.next_id = tk; }
+    if (next_id < n_jobs) commit();
+    __syncthreads();
+    job_id = next_id;
+    next_id = sm.next_id;
   }
 }
 
@@ -493,7 +552,7 @@ extern "C" int me_make_planes_tensor_map(void *out, const void *planes, int pitc
 // plane_maps: host array [2][ME_MAX_REFS] of 128-byte tensor maps of the listed references' plane sets.
 extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const void *plane_maps,
                                             int n_refs0, int n_refs1, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
-                                            const MeResultInt *in_int, MeResult *out, int *ticket, cudaStream_t st)
+                                            const MeResultInt *in_int, MeResult *out, int *ticket, unsigned long long *stats, cudaStream_t st)
 {
   if (!plane_maps || !ticket || n_refs0 > TUNED_MAX_REFS || n_refs1 > TUNED_MAX_REFS) return 0;
   // 8x8 transform tiles exist for the Hadamard metric only: with Transform8x8Mode either both sub-pel metrics are Hadamard (8x8
@@ -530,12 +589,12 @@ extern "C" int me_launch_subpel_batch_tuned(const MeJob *jobs, int n_jobs, const
   if (grid > n_jobs) grid = n_jobs;
   if (use_t8)
     me_subpel_tuned_kernel<true, true><<<grid, NT, sizeof(Smem<true>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur,
-                                                                       cur_pitch, *cfg, in_int, out, ticket);
+                                                                       cur_pitch, *cfg, in_int, out, ticket, stats);
   else if (had1 && had2)
     me_subpel_tuned_kernel<false, true><<<grid, NT, sizeof(Smem<false>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur,
-                                                                         cur_pitch, *cfg, in_int, out, ticket);
+                                                                         cur_pitch, *cfg, in_int, out, ticket, stats);
   else
     me_subpel_tuned_kernel<false, false><<<grid, NT, sizeof(Smem<false>), st>>>(reinterpret_cast<const uint32_t *>(jobs), n_jobs, ref_table, pm, cur,
-                                                                          cur_pitch, *cfg, in_int, out, ticket);
+                                                                          cur_pitch, *cfg, in_int, out, ticket, stats);
   return 1;
 }

@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "me_cuda_FastFullPelBlockMotionSearch", "me_cuda_FullPelBlockMotionSearch", "me_cuda_SubPelBlockMotionSearch",
     "me_cuda_FullPelBlockMotionBiPred", "me_cuda_SubPelBlockSearchBiPred",
     "me_cuda_frame_search", "me_cuda_frame_search_device", "me_cuda_frame_bipred", "me_cuda_ref_create_device",
-    "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count",
+    "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count", "me_cuda_subpel_region_stats",
     "me_cuda_measure_int_peak", "me_cuda_ref_update_u8", "me_cuda_ref_update_device", "me_cuda_set_timing",
     "me_cuda_kernel_time_ms", "me_cuda_set_ref_weights", "me_cuda_set_bipred_weights", "me_cuda_set_bipred_chroma_weights",
     "me_cuda_set_current_chroma", "me_cuda_set_current_chroma_u8", "me_cuda_ref_set_chroma", "me_cuda_ref_set_chroma_u8",
@@ -354,6 +354,13 @@ class MeCuda:
 
     def launch_count(self):
         return int(self.L.me_cuda_launch_count())
+
+    def subpel_region_stats(self, enable):
+        """(partitions served from the staged region, all partitions) of the throughput sub-pel kernel since the count was enabled;
+        enable=True restarts the count, False stops it"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.L.me_cuda_subpel_region_stats(1 if enable else 0, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def measure_int_peak(self, kind):
         v = C.c_double(0)

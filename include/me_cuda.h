@@ -282,6 +282,10 @@ void *me_cuda_stream(void);                 /* the library's stream (cudaStream_
 int   me_cuda_sync(void);                   /* cudaStreamSynchronize on it */
 /* number of kernels this library has launched since init (bench.py reports it as gpu_launches) */
 int64_t me_cuda_launch_count(void);
+/* diagnostics: share of the partitions the throughput sub-pel kernel serves from its TMA-staged 48 x 33 x 16-plane region (the
+ * others read their tiles from global memory with the clamp of UMVLine4X, refbuf.c:37).  enable != 0 starts and zeroes the
+ * count, 0 stops it; the counts so far go to served / total (may be null). */
+int me_cuda_subpel_region_stats(int enable, int64_t *served, int64_t *total);
 /* diagnostics: measured issue rate (lane-operations per second, whole GPU) of the integer instructions the search
  * kernels are bound by; kind 0 VABSDIFF4, 1 IADD3, 2 IMAD, 3 VIADDMNMX, 4 LOP3, 5 SHF, 6 VIMNMX, 7 PRMT, 8..14 the kinds 1..7
  * interleaved 1:1 with VABSDIFF4, 15 LDS + VABSDIFF4, 16 / 17 VABSDIFF4 + IMAD / VIADDMNMX with the operand pattern of the search

@@ -25,6 +25,8 @@
  *   ref_<id>.y         reconstructed luma a set of quarter-pel planes was built from; with ChromaMEEnable also ref_<id>.u / .v
  *   ref_<id>.sub       the 16 planes as the reference produced them, [4][4][H+40][W+40] bytes
  *                      (only when ME_TRACE_PLANES=1)
+ * ME_TRACE_FROM_PIC=n keeps the search records of coded pictures >= n only (picture records and dumps are always written):
+ * a 1080p run is traced for its last picture without gigabytes of records of the pictures that only build up the reference list.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -45,6 +47,7 @@ extern void SetMotionVectorPredictor (short pmv[2], char **refPic, short ***tmp_
 static FILE *trace_fp = NULL;
 static const char *trace_dir = ".";
 static int dump_planes = 0;
+static int from_pic = 0;
 static int coded_pic_no = -1;      /* incremented per encode_one_frame */
 static int cur_dumped_for = -2;
 
@@ -65,12 +68,18 @@ static void trace_open(void)
   d = getenv("ME_TRACE_DIR");
   if (d && *d) trace_dir = d;
   dump_planes = getenv("ME_TRACE_PLANES") && atoi(getenv("ME_TRACE_PLANES"));
+  if (getenv("ME_TRACE_FROM_PIC")) from_pic = atoi(getenv("ME_TRACE_FROM_PIC"));
   snprintf(path, sizeof path, "%s/trace.bin", trace_dir);
   trace_fp = fopen(path, "wb");
   if (!trace_fp) { perror(path); exit(97); }
 }
 
-static void put(const int *rec) { trace_open(); fwrite(rec, sizeof(int), REC_INTS, trace_fp); }
+static void put(const int *rec)
+{
+  trace_open();
+  if (rec[0] != REC_REFPIC && rec[0] != REC_CURPIC && rec[1] < from_pic) return;
+  fwrite(rec, sizeof(int), REC_INTS, trace_fp);
+}
 
 static int ref_id_of(StorablePicture *p)
 {

@@ -104,3 +104,59 @@ def compare(jobs, expect, out, out_int):
             if got != e:
                 bad.append((k, p, got, e))
     return n, bad
+
+
+def jobs_of_picture_fast(recs, pic, job_dtype):
+    """Vectorised jobs_of_picture for a picture in which every partition of a (macroblock, list, ref) is searched exactly once, each
+    FastFullPelBlockMotionSearch call directly followed by its SubPelBlockMotionSearch call (P pictures, Transform8x8Mode off,
+    mv-search.c:745-826) -- full-size traces hold millions of records.  -> (jobs, exp) with exp = dict(mask [n, 41],
+    int_mv [n, 41, 2], int_cost [n, 41], mv [n, 41, 2], cost [n, 41], ref_ids {(list, ref): picture id})."""
+    f = recs[(recs[:, 0] == REC_FFS) & (recs[:, 1] == pic)]
+    s = recs[(recs[:, 0] == REC_SUBPEL) & (recs[:, 1] == pic)]
+    assert len(f) and len(f) == len(s), (len(f), len(s))
+    for c in (3, 4, 5, 6, 7, 8, 9, 10, 11):                        # same block, same predictor, call by call
+        assert np.array_equal(f[:, c], s[:, c]), c
+    assert np.array_equal(4 * f[:, 18], s[:, 12]) and np.array_equal(4 * f[:, 19], s[:, 13])     # sub-pel starts at the integer result << 2
+    assert np.array_equal(f[:, 13], s[:, 15])                                                    # lambda[F_PEL]
+    key = f[:, 3].astype(np.int64) | (f[:, 4].astype(np.int64) << 16) | (f[:, 5].astype(np.int64) << 32) | (f[:, 6].astype(np.int64) << 40)
+    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    order = np.argsort(first)                                      # jobs in the order the encoder reached them
+    rank = np.empty(len(uniq), np.int64)
+    rank[order] = np.arange(len(uniq))
+    ji = rank[inv]
+    lut = np.full(8 * 16, -1, np.int64)
+    for p, (t, b) in enumerate(zip(PART_TYPE, PART_BLK)):
+        lut[t * 16 + b] = p
+    blk = (f[:, 9] - f[:, 4]) + ((f[:, 8] - f[:, 3]) >> 2)
+    p = lut[f[:, 7] * 16 + blk]
+    assert (p >= 0).all()
+    n = len(uniq)
+    mask = np.zeros((n, 41), bool)
+    assert not mask[ji, p].any()
+    mask[ji, p] = True
+    assert len(np.unique(ji * 41 + p)) == len(f), "a partition searched twice: use jobs_of_picture"
+    jobs = np.zeros(n, job_dtype)
+    jobs["opix_x"][ji] = f[:, 3]; jobs["opix_y"][ji] = f[:, 4]; jobs["list"][ji] = f[:, 5]; jobs["ref"][ji] = f[:, 6]
+    jobs["slice_type"][ji] = np.where((f[:, 2] & 255) == 1, 1, 0)
+    jobs["pmv"][ji, p, 0] = f[:, 10]; jobs["pmv"][ji, p, 1] = f[:, 11]
+    su = f[f[:, 22] != 0]                                           # the call that ran SetupFastFullPelSearch: its predictor is the centre's
+    sji = rank[np.searchsorted(uniq, su[:, 3].astype(np.int64) | (su[:, 4].astype(np.int64) << 16) | (su[:, 5].astype(np.int64) << 32) | (su[:, 6].astype(np.int64) << 40))]
+    got = np.zeros(n, bool); got[sji] = True
+    assert got.all(), "a (macroblock, list, ref) without its set-up call"
+    jobs["pmv16"][sji, 0] = su[:, 23]; jobs["pmv16"][sji, 1] = su[:, 24]
+    jobs["lambda"][ji, 0] = s[:, 15]; jobs["lambda"][ji, 1] = s[:, 16]; jobs["lambda"][ji, 2] = s[:, 17]
+    exp = dict(mask=mask, int_mv=np.zeros((n, 41, 2), np.int64), int_cost=np.zeros((n, 41), np.int64),
+               mv=np.zeros((n, 41, 2), np.int64), cost=np.zeros((n, 41), np.int64), ref_ids={})
+    exp["int_mv"][ji, p, 0] = f[:, 18]; exp["int_mv"][ji, p, 1] = f[:, 19]; exp["int_cost"][ji, p] = f[:, 20]
+    exp["mv"][ji, p, 0] = s[:, 18]; exp["mv"][ji, p, 1] = s[:, 19]; exp["cost"][ji, p] = s[:, 20]
+    for l, r, i in set(map(tuple, f[:, [5, 6, 21]].tolist())):
+        exp["ref_ids"][(int(l), int(r))] = int(i)
+    return jobs, exp
+
+
+def compare_fast(exp, out, out_int):
+    """-> (number of traced partition results, indices [job, partition] of the mismatches)"""
+    m = exp["mask"]
+    bad = m & ((out_int["mv"].astype(np.int64) != exp["int_mv"]).any(axis=2) | (out_int["cost"].astype(np.int64) != exp["int_cost"]) |
+               (out["mv"].astype(np.int64) != exp["mv"]).any(axis=2) | (out["cost"].astype(np.int64) != exp["cost"]))
+    return int(m.sum()), np.argwhere(bad)
