@@ -8,6 +8,7 @@ registers this package as module `h264_b200`.
   me_cuda.py ctypes binding of the C ABI (tests, bench)
   synth.py   deterministic synthetic YUV clips
   build.py   nvcc build of libme_cuda.so
+  mc.py      GetSkipCostMB / GetDirectCost8x8 / BIDPartitionCost on the library's prediction primitives
   gop_shard.py GOP sharding across GPUs: the assignment rule and the one-encoder-process-per-GOP driver
 """
 from . import build as _build  # noqa: F401

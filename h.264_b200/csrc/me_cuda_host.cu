@@ -40,6 +40,10 @@ extern "C" {
 void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t *planes, int pitch, size_t plane_stride,
                       uint8_t *search, int spad, int spitch, cudaStream_t st);
 void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp, uint16_t *dst, cudaStream_t st);
+void me_launch_luma_prediction(const void *blocks, int n, int bsx, int bsy, const MeRefDev *table, uint8_t *pred, cudaStream_t st);
+void me_launch_pred_cost8x8(const void *blocks, int n_regions, int metric, const MeRefDev *table, const uint8_t *cur, int cur_pitch,
+                            int32_t *cost4, int32_t *cost8, cudaStream_t st);
+void me_launch_widen_region(const uint8_t *plane, int pitch, int x0, int y0, int w, int h, uint16_t *dst, cudaStream_t st);
 void me_launch_weight_planes(const uint8_t *src, uint8_t *dst, size_t bytes, int weight, int offset, int log_denom, cudaStream_t st);
 void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
                                const MeCfgDev *cfg, MeResultInt *out, const int *job_list, cudaStream_t st);
@@ -178,6 +182,11 @@ struct State {
   MeResultInt *d_int_scratch = nullptr; int int_scratch_cap = 0;
   me_bipred_job *d_bi_jobs = nullptr; me_bipred_result *d_bi_out = nullptr; int bi_cap = 0;
   MeRefDev *d_bi_table = nullptr;
+  // motion-compensated prediction / mode-decision costs (mc.cu): the listed pictures' own planes, and a staging area that is
+  // mapped pinned memory up to MC_MAPPED bytes (one launch + one wait per call, no copies) and device memory beyond
+  MeRefDev *d_mc_table = nullptr; MeRefDev h_mc_table[2 * ME_MAX_REFS]; bool mc_table_valid = false;
+  uint8_t *h_mc = nullptr, *d_mc_mapped = nullptr;        // mapped pinned
+  uint8_t *d_mc = nullptr; size_t d_mc_bytes = 0;         // device
   long long launches = 0;
   long long spec_hits = 0;                        // sub-pel calls answered from the fused block-search kernel
   // optional per-kernel-class timing (bench.py): event pairs around every launch of a class
@@ -525,6 +534,9 @@ void me_cuda_shutdown(void)
   if (g.d_bi_jobs) cudaFree(g.d_bi_jobs);
   if (g.d_bi_out) cudaFree(g.d_bi_out);
   if (g.d_bi_table) cudaFree(g.d_bi_table);
+  if (g.d_mc_table) cudaFree(g.d_mc_table);
+  if (g.h_mc) cudaFreeHost(g.h_mc);
+  if (g.d_mc) cudaFree(g.d_mc);
   if (g_d_stage) { cudaFree(g_d_stage); g_d_stage = nullptr; g_d_stage_bytes = 0; }
   for (int k = 0; k < 3; k++) { for (auto &p : g.ev[k]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } g.ev[k].clear(); }
   if (g.ev_order) cudaEventDestroy(g.ev_order);
@@ -1328,6 +1340,27 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
 {
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_jobs <= 0) return 0;
+  // Pinned (page-locked) caller buffers are visible to the device under unified addressing: the kernels then read the job array and
+  // write the result arrays in place -- descriptors are fetched two jobs / one job ahead of their use, results leave as contiguous
+  // 164-byte runs -- and the whole batch is one search launch and one sub-pel launch with no copy in front or behind.
+  // (ME_CUDA_ZEROCOPY=0: always the chunked copies below.)
+  {
+    static int zero_copy = -1;
+    if (zero_copy < 0) { const char *e = getenv("ME_CUDA_ZEROCOPY"); zero_copy = !(e && e[0] == '0'); }
+    auto dev_ptr = [](const void *p) -> void * {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+    };
+    void *dj = zero_copy ? dev_ptr(jobs) : nullptr, *dout = dj ? dev_ptr(out) : nullptr, *dint = (dout && out_int) ? dev_ptr(out_int) : nullptr;
+    if (dj && dout && (!out_int || dint)) {
+      if (int rc = check_jobs(jobs, 0, n_jobs)) return rc;
+      int rc = me_cuda_frame_search_device(dj, n_jobs, dout, dint, g.stream);
+      cudaError_t e = cudaStreamSynchronize(g.stream);               // whatever happened, nothing touches the caller's buffers after return
+      if (!rc && e != cudaSuccess) rc = fail(2, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+      return rc;
+    }
+  }
   if (int rc = ensure_batch(n_jobs)) return rc;
   // Large batches are cut into chunks that move through three streams -- jobs in (H2D engine), search (library stream),
   // results out (D2H engine) -- so that with pinned caller buffers only the first upload and the last download are exposed.
@@ -1384,6 +1417,145 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
   cu(cudaStreamSynchronize(g.stream), "cudaStreamSynchronize");
   cu(cudaStreamSynchronize(g.s_out), "cudaStreamSynchronize");
   return rc;
+}
+
+
+// ------------------------------------------------------------------------------------------------ prediction and mode-decision costs
+static const size_t MC_MAPPED = 64 * 1024;
+
+// table of the listed pictures' own plane sets (never the weighted copies of the searches), uploaded when the lists changed
+static int mc_table()
+{
+  MeRefDev t[2 * ME_MAX_REFS];
+  memset(t, 0, sizeof t);
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < g.list_n[l]; i++) {
+      RefPic *r = ref_of(g.list[l][i]);
+      if (!r) return fail(3, "reference list %d entry %d holds an invalid handle", l, i);
+      if (r->written_on && r->written_on != g.stream) CK(cudaStreamSynchronize(r->written_on));
+      t[l * ME_MAX_REFS + i] = r->dev;
+    }
+  if (!g.d_mc_table) CK(cudaMalloc((void **)&g.d_mc_table, sizeof t));
+  if (!g.mc_table_valid || memcmp(t, g.h_mc_table, sizeof t)) {
+    CK(cudaStreamSynchronize(g.stream));                  // a kernel may still be reading the old table
+    memcpy(g.h_mc_table, t, sizeof t);
+    CK(cudaMemcpyAsync(g.d_mc_table, g.h_mc_table, sizeof t, cudaMemcpyHostToDevice, g.stream));
+    g.mc_table_valid = true;
+  }
+  return 0;
+}
+
+static int mc_check_blocks(const me_pred_block *b, int n, int bsx, int bsy, const char *who)
+{
+  for (int i = 0; i < n; i++) {
+    if (b[i].p_dir > 2) return fail(1, "%s: block %d: p_dir %d", who, i, (int)b[i].p_dir);
+    if (b[i].p_dir < 0) continue;
+    for (int l = 0; l < 2; l++)
+      if ((b[i].p_dir == l || b[i].p_dir == 2) && (b[i].ref[l] < 0 || b[i].ref[l] >= g.list_n[l]))
+        return fail(1, "%s: block %d: reference %d not in list %d", who, i, (int)b[i].ref[l], l);
+    if (b[i].pix_x < 0 || b[i].pix_y < 0 || b[i].pix_x + bsx > g.p.width || b[i].pix_y + bsy > g.p.height)
+      return fail(1, "%s: block %d at (%d,%d) outside the picture", who, i, (int)b[i].pix_x, (int)b[i].pix_y);
+    if (b[i].apply_weights && (b[i].log_denom < 0 || b[i].log_denom > 7))
+      return fail(1, "%s: block %d: log weight denominator %d", who, i, (int)b[i].log_denom);
+  }
+  return 0;
+}
+
+// staging for `in` bytes of requests and `out` bytes of results: *d_in / *d_out device addresses, *h_out where the results
+// appear on the host (nullptr: copy them from *d_out)
+static int mc_stage(const void *src, size_t in, size_t out, uint8_t **d_in, uint8_t **d_out, uint8_t **h_out)
+{
+  const size_t in_al = (in + 255) & ~(size_t)255;
+  if (in_al + out <= MC_MAPPED) {
+    if (!g.h_mc) {
+      CK(cudaHostAlloc((void **)&g.h_mc, MC_MAPPED, cudaHostAllocMapped));
+      CK(cudaHostGetDevicePointer((void **)&g.d_mc_mapped, g.h_mc, 0));
+    }
+    memcpy(g.h_mc, src, in);
+    *d_in = g.d_mc_mapped; *d_out = g.d_mc_mapped + in_al; *h_out = g.h_mc + in_al;
+    return 0;
+  }
+  if (g.d_mc_bytes < in_al + out) {
+    CK(cudaStreamSynchronize(g.stream));
+    if (g.d_mc) cudaFree(g.d_mc);
+    g.d_mc = nullptr; g.d_mc_bytes = 0;
+    CK(cudaMalloc((void **)&g.d_mc, in_al + out));
+    g.d_mc_bytes = in_al + out;
+  }
+  CK(cudaMemcpyAsync(g.d_mc, src, in, cudaMemcpyHostToDevice, g.stream));
+  *d_in = g.d_mc; *d_out = g.d_mc + in_al; *h_out = nullptr;
+  return 0;
+}
+
+int me_cuda_luma_prediction(const me_pred_block *blocks, int n, int bsx, int bsy, uint8_t *pred)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (n <= 0) return 0;
+  if ((bsx != 4 && bsx != 8 && bsx != 16) || (bsy != 4 && bsy != 8 && bsy != 16)) return fail(1, "me_cuda_luma_prediction: block size %d x %d", bsx, bsy);
+  if (int rc = mc_check_blocks(blocks, n, bsx, bsy, "me_cuda_luma_prediction")) return rc;
+  if (int rc = mc_table()) return rc;
+  const size_t in = sizeof(me_pred_block) * (size_t)n, out = (size_t)n * bsx * bsy;
+  uint8_t *d_in, *d_out, *h_out;
+  if (int rc = mc_stage(blocks, in, out, &d_in, &d_out, &h_out)) return rc;
+  me_launch_luma_prediction(d_in, n, bsx, bsy, g.d_mc_table, d_out, g.stream);
+  g.launches++;
+  CK(cudaGetLastError());
+  if (!h_out) CK(cudaMemcpyAsync(pred, d_out, out, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  if (h_out) memcpy(pred, h_out, out);
+  return 0;
+}
+
+int me_cuda_pred_cost8x8(const me_pred_block *blocks, int n_regions, int metric, int32_t *cost4, int32_t *cost8)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (n_regions <= 0) return 0;
+  if (metric < 0 || metric > 2) return fail(1, "me_cuda_pred_cost8x8: metric %d", metric);
+  if (int rc = mc_check_blocks(blocks, 4 * n_regions, 4, 4, "me_cuda_pred_cost8x8")) return rc;
+  if (int rc = mc_table()) return rc;
+  const size_t in = sizeof(me_pred_block) * 4 * (size_t)n_regions, out = 2 * sizeof(int32_t) * (size_t)n_regions;
+  uint8_t *d_in, *d_out, *h_out;
+  if (int rc = mc_stage(blocks, in, out, &d_in, &d_out, &h_out)) return rc;
+  int32_t *d4 = (int32_t *)d_out, *d8 = d4 + n_regions;
+  me_launch_pred_cost8x8(d_in, n_regions, metric, g.d_mc_table, g.d_cur, g.cur_pitch, d4, d8, g.stream);
+  g.launches++;
+  CK(cudaGetLastError());
+  if (!h_out) {
+    CK(cudaMemcpyAsync(cost4, d4, sizeof(int32_t) * (size_t)n_regions, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(cost8, d8, sizeof(int32_t) * (size_t)n_regions, cudaMemcpyDeviceToHost, g.stream));
+  }
+  CK(cudaStreamSynchronize(g.stream));
+  if (h_out) {
+    memcpy(cost4, h_out, sizeof(int32_t) * (size_t)n_regions);
+    memcpy(cost8, h_out + sizeof(int32_t) * (size_t)n_regions, sizeof(int32_t) * (size_t)n_regions);
+  }
+  return 0;
+}
+
+int me_cuda_ref_download_region(me_ref_handle h, int fy, int fx, int x0, int y0, int w, int hgt, me_imgpel *dst, int dst_stride)
+{
+  RefPic *r = ref_of(h);
+  if (!r) return fail(3, "me_cuda_ref_download_region: invalid handle %d", (int)h);
+  if (fy < 0 || fy > 3 || fx < 0 || fx > 3) return fail(1, "plane index out of range");
+  if (x0 < 0 || y0 < 0 || w <= 0 || hgt <= 0 || x0 + w > r->dev.wp || y0 + hgt > r->dev.hp)
+    return fail(1, "me_cuda_ref_download_region: rectangle (%d,%d) %d x %d outside the %d x %d plane", x0, y0, w, hgt, r->dev.wp, r->dev.hp);
+  const size_t bytes = (size_t)w * hgt * sizeof(uint16_t);
+  uint8_t *d_in, *d_out, *h_out;
+  uint32_t dummy = 0;
+  if (r->written_on && r->written_on != g.stream) CK(cudaStreamSynchronize(r->written_on));
+  if (int rc = mc_stage(&dummy, sizeof dummy, bytes, &d_in, &d_out, &h_out)) return rc;
+  me_launch_widen_region(r->planes + (size_t)(fy * 4 + fx) * r->dev.plane_stride, r->dev.pitch, x0, y0, w, hgt, (uint16_t *)d_out, g.stream);
+  g.launches++;
+  CK(cudaGetLastError());
+  if (!h_out) {
+    CK(cudaMemcpy2DAsync(dst, (size_t)dst_stride * sizeof(uint16_t), d_out, (size_t)w * sizeof(uint16_t), (size_t)w * sizeof(uint16_t), hgt,
+                         cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+  }
+  CK(cudaStreamSynchronize(g.stream));
+  for (int y = 0; y < hgt; y++) memcpy(dst + (size_t)y * dst_stride, h_out + (size_t)y * w * sizeof(uint16_t), (size_t)w * sizeof(uint16_t));
+  return 0;
 }
 
 int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements, int search_range, int subpel, me_bipred_result *out)

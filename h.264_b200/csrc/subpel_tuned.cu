@@ -453,11 +453,6 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
         if (s4.leader) {
           const int fx = mvpx + step * c_spx[best], fy = mvpy + step * c_spy[best];
           sm.mn[s4.p] = mn; sm.mv[s4.p][0] = fx; sm.mv[s4.p][1] = fy;
-          if (!T8 && stage == 1) {
-            // the partition's lanes all sit in this warp, so its result is final here: straight to global memory
-            reinterpret_cast<uint32_t *>(out[job_id].mv)[s4.p] = ((unsigned)fx & 0xffffu) | ((unsigned)fy << 16);
-            out[job_id].cost[s4.p] = mn;
-          }
         }
         if (!T8) __syncwarp();       // the half-pel result is read by the lanes of the same warp only: no CTA-wide barrier
       } else {
@@ -521,15 +516,17 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
         __syncthreads();
       }
     }
-    if (T8 && tid < ME_NUM_PARTITIONS) {
-      reinterpret_cast<uint32_t *>(out[job_id].mv)[tid] = ((unsigned)sm.mv[tid][0] & 0xffffu) | ((unsigned)sm.mv[tid][1] << 16);
-      out[job_id].cost[tid] = sm.mn[tid];
-    }
     // Without the 8x8 transform every partition lives inside one warp and the warps ran both stages without meeting.  They meet
     // here: the region and the working arrays are free, the staged copies of the next job have landed (every thread waited
     // for its own, the barrier publishes them)
     cp_async_wait_all();
     __syncthreads();
+    // the job's results leave as two contiguous runs of 41 words (the result array may be pinned host memory the kernel writes
+    // across PCIe: me_cuda_frame_search hands such buffers through without a copy)
+    if (tid < ME_NUM_PARTITIONS) {
+      reinterpret_cast<uint32_t *>(out[job_id].mv)[tid] = ((unsigned)sm.mv[tid][0] & 0xffffu) | ((unsigned)sm.mv[tid][1] << 16);
+      out[job_id].cost[tid] = sm.mn[tid];
+    }
     if (tid == 0) { if (next_id < n_jobs) issue_region(); sm.next_id = tk; }
     if (next_id < n_jobs) commit();
     __syncthreads();

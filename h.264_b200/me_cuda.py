@@ -41,6 +41,7 @@ ABI_SYMBOLS = [
     "me_cuda_FullPelBlockMotionBiPred", "me_cuda_SubPelBlockSearchBiPred",
     "me_cuda_frame_search", "me_cuda_frame_search_device", "me_cuda_frame_bipred", "me_cuda_ref_create_device",
     "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count", "me_cuda_subpel_region_stats",
+    "me_cuda_luma_prediction", "me_cuda_pred_cost8x8", "me_cuda_ref_download_region",
     "me_cuda_measure_int_peak", "me_cuda_ref_update_u8", "me_cuda_ref_update_device", "me_cuda_set_timing",
     "me_cuda_kernel_time_ms", "me_cuda_set_ref_weights", "me_cuda_set_bipred_weights", "me_cuda_set_bipred_chroma_weights",
     "me_cuda_set_current_chroma", "me_cuda_set_current_chroma_u8", "me_cuda_ref_set_chroma", "me_cuda_ref_set_chroma_u8",
@@ -112,6 +113,9 @@ def load_library(path=LIB_PATH):
     L.me_cuda_pms_cached.argtypes = [C.c_int, C.c_int]
     L.me_cuda_pms_end.argtypes = [C.c_int, C.c_int]
     L.me_cuda_pms_stats.argtypes = [C.POINTER(C.c_int64)] * 3
+    L.me_cuda_luma_prediction.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.me_cuda_pred_cost8x8.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.me_cuda_ref_download_region.argtypes = [C.c_int32] + [C.c_int] * 6 + [vp, C.c_int]
     return L
 
 
@@ -338,6 +342,31 @@ class MeCuda:
         assert jobs.dtype == BIPRED_JOB_DTYPE
         out = np.zeros(len(jobs), BIPRED_RESULT_DTYPE)
         self._check(self.L.me_cuda_frame_bipred(jobs.ctypes.data, len(jobs), refinements, search_range, subpel, out.ctypes.data))
+        return out
+
+    def luma_prediction(self, blocks, bsx, bsy):
+        """LumaPrediction (macroblock.c:832) of blocks (mc.PRED_BLOCK_DTYPE) of bsx x bsy samples -> uint8 [n, bsy, bsx]"""
+        from .mc import PRED_BLOCK_DTYPE
+        blocks = np.ascontiguousarray(blocks)
+        assert blocks.dtype == PRED_BLOCK_DTYPE
+        out = np.zeros((len(blocks), bsy, bsx), np.uint8)
+        self._check(self.L.me_cuda_luma_prediction(blocks.ctypes.data, len(blocks), bsx, bsy, out.ctypes.data))
+        return out
+
+    def pred_cost8x8(self, blocks, metric=2):
+        """per 8x8 region (four PRED_BLOCK records, raster order): (sum of distortion4x4, distortion8x8) of original - prediction"""
+        from .mc import PRED_BLOCK_DTYPE
+        blocks = np.ascontiguousarray(blocks)
+        assert blocks.dtype == PRED_BLOCK_DTYPE and len(blocks) % 4 == 0
+        n = len(blocks) // 4
+        c4, c8 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(self.L.me_cuda_pred_cost8x8(blocks.ctypes.data, n, metric, c4.ctypes.data, c8.ctypes.data))
+        return c4, c8
+
+    def ref_region(self, h, fy, fx, x0, y0, w, hgt):
+        """a rectangle of plane Pic[fy][fx] as imgpel (uint16) rows"""
+        out = np.zeros((hgt, w), np.uint16)
+        self._check(self.L.me_cuda_ref_download_region(h, fy, fx, x0, y0, w, hgt, out.ctypes.data, w))
         return out
 
     def frame_search_device(self, d_jobs, n, d_out, d_out_int=None, stream=None):

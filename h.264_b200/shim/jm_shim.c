@@ -6,7 +6,8 @@
  *     -Wl,--wrap=FastFullPelBlockMotionSearch,--wrap=FullPelBlockMotionSearch,--wrap=SubPelBlockMotionSearch,--wrap=FullPelBlockMotionBiPred,
  *         --wrap=SubPelBlockSearchBiPred,--wrap=ResetFastFullIntegerSearch,--wrap=getSubImagesLuma,
  *         --wrap=encode_one_frame,--wrap=Init_Motion_Search_Module,--wrap=Clear_Motion_Search_Module,
- *         --wrap=free_storable_picture,--wrap=PartitionMotionSearch
+ *         --wrap=free_storable_picture,--wrap=PartitionMotionSearch,--wrap=BIDPartitionCost,--wrap=GetDirectCost8x8,
+ *         --wrap=UMVLine4X,--wrap=FastLine4X
  * so every call site the SearchMode dispatch of mv-search.c reaches (mv-search.c:745, :823, :960, :998, :1018), the
  * per-macroblock reset (macroblock.c:509), the plane generation (image.c:1642) and the module init / clear
  * (lencod.c:255, :387) land here.  Everything else -- predictors (SetMotionVectorPredictor, mv-search.c:87), mode
@@ -17,7 +18,11 @@
  * Environment: ME_CUDA_VERIFY=1 runs the reference function next to every GPU call and reports differences (diagnostic),
  *              ME_CUDA_LIB = path of libme_cuda.so (default: <dir of executable>/../../h.264_b200/libme_cuda.so),
  *              ME_CUDA_DISABLE=1 turns the interposer into a pass-through (pure reference behaviour),
- *              ME_CUDA_PMS=0 keeps one device launch per block search (no launch per PartitionMotionSearch call).
+ *              ME_CUDA_PMS=0 keeps one device launch per block search (no launch per PartitionMotionSearch call),
+ *              ME_CUDA_MC=0 leaves BIDPartitionCost / GetDirectCost8x8 (mv-search.c:1052, :1273) to the reference's host code,
+ *              ME_CUDA_HOST_PLANES=1 copies all 16 planes of every reference picture back into imgY_sub (70 MB per 1080p picture)
+ *              instead of paging in what the host code touches, ME_CUDA_POISON_PLANES=1 fills imgY_sub with a pattern first
+ *              (test aid: a host read that bypasses the paging then changes the bitstream).
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -71,6 +76,8 @@ static struct {
   int  (*pms_cached)(int, int);
   int  (*pms_end)(int, int);
   int  (*pms_stats)(int64_t *, int64_t *, int64_t *);
+  int  (*pred_cost8x8)(const me_pred_block *, int, int, int32_t *, int32_t *);
+  int  (*ref_download_region)(me_ref_handle, int, int, int, int, int, int, me_imgpel *, int);
 } L;
 
 static int active = 0;          /* GPU path in use for this run */
@@ -80,10 +87,18 @@ static long n_checked = 0, n_mismatch = 0;
 /* calls the device answered, per wrapped function; printed when the module is cleared so that a run (and the tests around it)
  * can tell a GPU run from a silent pass-through */
 static long served_ffs = 0, served_fullpel = 0, served_subpel = 0, served_bi_full = 0, served_bi_sub = 0, served_planes = 0;
+static long served_bid_cost = 0, served_direct_cost = 0, paged_tiles = 0, paged_bytes = 0;
+static int use_mc = 1;          /* BIDPartitionCost / GetDirectCost8x8 on the device (ME_CUDA_MC=0: the reference's host code) */
+static int lazy_planes = 1;     /* imgY_sub paged in on demand (ME_CUDA_HOST_PLANES=1: all planes copied back at creation) */
+static int poison_planes = 0;
 static int pic_counter = 0, pic_uploaded = -1, plane_uploaded = -1;
 
 #define MAX_MAP 64
-static struct { StorablePicture *p; int plane; me_ref_handle h; } map[MAX_MAP];   /* plane: 0, or the colour plane in 4:4:4 independent mode */
+/* plane: 0, or the colour plane in 4:4:4 independent mode.  sub: the picture's host plane set (StorablePicture::p_curr_img_sub at
+ * creation); valid: one flag per (plane, tile of TILE_W x TILE_H samples) -- has the tile been paged in from the device? */
+#define TILE_W 64
+#define TILE_H 32
+static struct { StorablePicture *p; int plane; me_ref_handle h; imgpel ****sub; unsigned char *valid; int ntx, nty, wp, hp; } map[MAX_MAP];
 static int n_map = 0;
 
 static void die(const char *what)
@@ -138,6 +153,7 @@ static void load_library(void)
   L.bi_full = sym("me_cuda_FullPelBlockMotionBiPred"); L.bi_sub = sym("me_cuda_SubPelBlockSearchBiPred");
   L.pms_begin = sym("me_cuda_pms_begin"); L.pms_cached = sym("me_cuda_pms_cached"); L.pms_end = sym("me_cuda_pms_end");
   L.pms_stats = sym("me_cuda_pms_stats");
+  L.pred_cost8x8 = sym("me_cuda_pred_cost8x8"); L.ref_download_region = sym("me_cuda_ref_download_region");
 }
 
 /* 4:4:4 independent mode (SeparateColourPlane = 1, IS_INDEPENDENT, defines.h:224): the three colour planes are coded one after
@@ -155,6 +171,7 @@ static me_ref_handle handle_of(StorablePicture *p)
 static void unmap_index(int i)
 {
   if (L.ref_destroy(map[i].h)) die("me_cuda_ref_destroy");
+  free(map[i].valid);
   memmove(&map[i], &map[i + 1], sizeof(map[0]) * (size_t)(n_map - 1 - i));
   n_map--;
 }
@@ -206,6 +223,9 @@ void __wrap_Init_Motion_Search_Module(void)
     active = 1;
     verify = getenv("ME_CUDA_VERIFY") && atoi(getenv("ME_CUDA_VERIFY"));
     use_pms = !(getenv("ME_CUDA_PMS") && !atoi(getenv("ME_CUDA_PMS")));
+    use_mc = !(getenv("ME_CUDA_MC") && !atoi(getenv("ME_CUDA_MC")));
+    lazy_planes = !(getenv("ME_CUDA_HOST_PLANES") && atoi(getenv("ME_CUDA_HOST_PLANES")));
+    poison_planes = getenv("ME_CUDA_POISON_PLANES") && atoi(getenv("ME_CUDA_POISON_PLANES"));
   }
 }
 
@@ -220,6 +240,8 @@ void __wrap_Clear_Motion_Search_Module(void)
             served_planes, served_ffs, served_fullpel, served_subpel, served_bi_full, served_bi_sub);
     fprintf(stderr, "me_cuda shim: partition-search launches %lld, block searches answered from them %lld, argument mismatches %lld\n",
             (long long)pl, (long long)ps, (long long)pm);
+    fprintf(stderr, "me_cuda shim: mode-decision costs on the device: %ld BIDPartitionCost, %ld GetDirectCost8x8 calls; plane tiles paged to the host: %ld (%ld bytes%s)\n",
+            served_bid_cost, served_direct_cost, paged_tiles, paged_bytes, lazy_planes ? "" : "; all planes copied back at creation");
   }
   else
     fprintf(stderr, "me_cuda shim: pass-through (ME_CUDA_DISABLE): nothing served on the device\n");
@@ -253,10 +275,34 @@ void __wrap_getSubImagesLuma(StorablePicture *s)
   for (i = n_map - 1; i >= 0; i--)
     if (map[i].p == s ? map[i].plane == plane : !in_dpb(map[i].p)) unmap_index(i);   /* s itself enters the buffer after this call */
   /* the 16 planes are computed on the device and copied into the picture's plane set for the encoder's host-side consumers */
-  if (L.ref_create((const me_imgpel *const *)s->p_curr_img, s->size_x, s->size_y, (me_imgpel ****)s->p_curr_img_sub, &h)) die("me_cuda_ref_create");
+  /* the 16 planes stay on the device; the host's own consumers (OneComponentLumaPrediction, macroblock.c:816, and whatever host
+   * search code a SearchMode keeps) reach them through UMVLine4X / FastLine4X, which page in the tiles they are about to read */
+  if (L.ref_create((const me_imgpel *const *)s->p_curr_img, s->size_x, s->size_y, lazy_planes ? NULL : (me_imgpel ****)s->p_curr_img_sub, &h)) die("me_cuda_ref_create");
   if (n_map == MAX_MAP) die("more than 64 reference pictures with device plane sets (decoded picture buffer bookkeeping out of step)");
   served_planes++;
-  map[n_map].p = s; map[n_map].plane = plane; map[n_map].h = h; n_map++;
+  map[n_map].p = s; map[n_map].plane = plane; map[n_map].h = h; map[n_map].sub = s->p_curr_img_sub;
+  map[n_map].wp = s->size_x + 2 * IMG_PAD_SIZE; map[n_map].hp = s->size_y + 2 * IMG_PAD_SIZE;
+  map[n_map].ntx = (map[n_map].wp + TILE_W - 1) / TILE_W; map[n_map].nty = (map[n_map].hp + TILE_H - 1) / TILE_H;
+  map[n_map].valid = NULL;
+  if (lazy_planes) {
+    map[n_map].valid = calloc((size_t)16 * map[n_map].ntx * map[n_map].nty, 1);
+    if (!map[n_map].valid) die("out of memory (tile flags)");
+    if (poison_planes) {
+      int fy, fx, y;
+      for (fy = 0; fy < 4; fy++) for (fx = 0; fx < 4; fx++) for (y = 0; y < map[n_map].hp; y++)
+        memset(s->p_curr_img_sub[fy][fx][y], 0xa5, (size_t)map[n_map].wp * sizeof(imgpel));
+    }
+    /* the weight estimators read the integer plane of every listed picture directly, not through the line accessors
+     * (weighted_prediction.c:84, :280, :427, :623: p_curr_img_sub[0][0]): with weighted prediction that plane comes over whole */
+    if (input->WeightedPrediction || input->WeightedBiprediction) {
+      if (L.ref_download_region(h, 0, 0, 0, 0, map[n_map].wp, map[n_map].hp, (me_imgpel *)&s->p_curr_img_sub[0][0][0][0],
+                                (int)(s->p_curr_img_sub[0][0][1] - s->p_curr_img_sub[0][0][0])))
+        die("me_cuda_ref_download_region");
+      memset(map[n_map].valid, 1, (size_t)map[n_map].ntx * map[n_map].nty);
+      paged_tiles += (long)map[n_map].ntx * map[n_map].nty; paged_bytes += (long)map[n_map].wp * map[n_map].hp * (long)sizeof(imgpel);
+    }
+  }
+  n_map++;
   /* ChromaMEEnable: the searches read the chroma sub-images of this picture (getSubImagesChroma, image.c:1659, still runs on the
    * host for motion compensation); the library evaluates them from the reconstructed chroma planes */
   if (input->ChromaMEEnable && img->yuv_format != YUV444 &&
@@ -587,4 +633,165 @@ int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pi
   served_bi_sub++;
   return L.bi_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, s_mv_x, s_mv_y,
                   search_pos2, search_pos4, min_mcost, lambda_factor);
+}
+
+/* ---------------------------------------------------------------- the host's reads of the quarter-pel planes (refbuf.c:25, :37) */
+/* FastLine4X / UMVLine4X return a pointer into plane Pic[y & 3][x & 3]; every caller then reads at most 16 rows of at most 16
+ * samples from it (OneComponentLumaPrediction, macroblock.c:821-826; the distortion functions of me_distortion.c).  The planes
+ * live on the device: the tiles that rectangle touches are copied into the picture's host plane set first, once. */
+static void page_in(imgpel ****Pic, int fy, int fx, int ypos, int xpos)
+{
+  int i, tx, ty, x1, y1;
+  if (!active || !lazy_planes) return;
+  for (i = n_map - 1; i >= 0; i--) if (map[i].sub == Pic) break;
+  if (i < 0) return;                                   /* a plane set the host built itself (4:4:4 chroma without ChromaMEEnable) */
+  if (xpos < 0) xpos = 0;
+  if (ypos < 0) ypos = 0;
+  x1 = xpos + 15 < map[i].wp - 1 ? xpos + 15 : map[i].wp - 1;
+  y1 = ypos + 15 < map[i].hp - 1 ? ypos + 15 : map[i].hp - 1;
+  for (ty = ypos / TILE_H; ty <= y1 / TILE_H; ty++)
+    for (tx = xpos / TILE_W; tx <= x1 / TILE_W; tx++) {
+      unsigned char *v = &map[i].valid[((size_t)(fy * 4 + fx) * map[i].nty + ty) * map[i].ntx + tx];
+      int x0 = tx * TILE_W, y0 = ty * TILE_H, w, h;
+      if (*v) continue;
+      w = map[i].wp - x0 < TILE_W ? map[i].wp - x0 : TILE_W;
+      h = map[i].hp - y0 < TILE_H ? map[i].hp - y0 : TILE_H;
+      /* rows of a plane are contiguous (get_mem2Dpel, memalloc.c:69-82): row pitch = padded width */
+      if (L.ref_download_region(map[i].h, fy, fx, x0, y0, w, h, (me_imgpel *)&Pic[fy][fx][y0][x0], (int)(Pic[fy][fx][1] - Pic[fy][fx][0])))
+        die("me_cuda_ref_download_region");
+      *v = 1;
+      paged_tiles++; paged_bytes += (long)w * h * (long)sizeof(imgpel);
+    }
+}
+
+imgpel *__real_FastLine4X(imgpel ****Pic, int y, int x);
+imgpel *__wrap_FastLine4X(imgpel ****Pic, int y, int x)
+{
+  page_in(Pic, y & 3, x & 3, y >> 2, x >> 2);
+  return __real_FastLine4X(Pic, y, x);
+}
+
+imgpel *__real_UMVLine4X(imgpel ****Pic, int y, int x);
+imgpel *__wrap_UMVLine4X(imgpel ****Pic, int y, int x)
+{
+  page_in(Pic, y & 3, x & 3, iClip3(0, height_pad, y >> 2), iClip3(0, width_pad, x >> 2));     /* the clamp of refbuf.c:39-40 */
+  return __real_UMVLine4X(Pic, y, x);
+}
+
+/* ---------------------------------------------------------------- mode-decision costs (mv-search.c:1052, :1273) */
+/* What LumaPrediction (macroblock.c:832-930) would do for the 4x4 block (h, v) of the macroblock, as a record of the library:
+ * direction, references, the vectors it picks (all_mv, or the bi-predictive search results when currMB->bi_pred_me selects
+ * them, macroblock.c:863-864) and the weights of macroblock.c:876-913. */
+static void fill_pred_block(me_pred_block *b, Macroblock *currMB, int h, int v, int p_dir, int l0_mode, int l1_mode, short l0_ref, short l1_ref)
+{
+  short ****mv_array = img->all_mv[v][h];
+  int apply = ((active_pps->weighted_pred_flag && (img->type == P_SLICE || img->type == SP_SLICE)) ||
+               (active_pps->weighted_bipred_idc && (img->type == B_SLICE)));
+  memset(b, 0, sizeof *b);
+  b->pix_x = (int16_t)(img->opix_x + 4 * h); b->pix_y = (int16_t)(img->opix_y + 4 * v);
+  b->p_dir = (int8_t)p_dir;
+  if (p_dir < 0) return;
+  if (currMB->bi_pred_me && l0_ref == 0 && l1_ref == 0 && p_dir == 2 && l0_mode == 1 && l1_mode == 1)
+    mv_array = currMB->bi_pred_me == 1 ? img->bipred_mv1[v][h] : img->bipred_mv2[v][h];
+  b->ref[0] = (int8_t)l0_ref; b->ref[1] = (int8_t)l1_ref;
+  if (p_dir == 0 || p_dir == 2) { b->mv[0][0] = mv_array[LIST_0][l0_ref][l0_mode][0]; b->mv[0][1] = mv_array[LIST_0][l0_ref][l0_mode][1]; }
+  if (p_dir == 1 || p_dir == 2) { b->mv[1][0] = mv_array[LIST_1][l1_ref][l1_mode][0]; b->mv[1][1] = mv_array[LIST_1][l1_ref][l1_mode][1]; }
+  b->apply_weights = (int8_t)apply;
+  if (apply) {
+    b->log_denom = (int16_t)luma_log_weight_denom;
+    if (p_dir == 2) {
+      b->weight[0] = (int16_t)wbp_weight[0][l0_ref][l1_ref][0]; b->weight[1] = (int16_t)wbp_weight[1][l0_ref][l1_ref][0];
+      b->offset = (int16_t)((wp_offset[0][l0_ref][0] + wp_offset[1][l1_ref][0] + 1) >> 1);
+    } else if (p_dir == 0) { b->weight[0] = (int16_t)wp_weight[0][l0_ref][0]; b->offset = (int16_t)wp_offset[0][l0_ref][0]; }
+    else { b->weight[0] = (int16_t)wp_weight[1][l1_ref][0]; b->offset = (int16_t)wp_offset[1][l1_ref][0]; }
+  }
+}
+
+/* OneComponentLumaPrediction leaves the clamp range of the last picture it read in width_pad / height_pad (macroblock.c:818-819) */
+static void keep_prediction_side_effects(Macroblock *currMB, int p_dir, short l0_ref, short l1_ref)
+{
+  StorablePicture *rp = NULL;
+  if (p_dir == 0 || p_dir == 2) rp = listX[0 + currMB->list_offset][l0_ref];
+  if (p_dir == 1 || p_dir == 2) rp = listX[1 + currMB->list_offset][l1_ref];
+  if (rp) { width_pad = rp->size_x_pad; height_pad = rp->size_y_pad; }
+}
+
+extern int *mvbits;
+
+int __real_BIDPartitionCost(Macroblock *currMB, int blocktype, int block8x8, short ref_l0, short ref_l1, int lambda_factor);
+int __wrap_BIDPartitionCost(Macroblock *currMB, int blocktype, int block8x8, short ref_l0, short ref_l1, int lambda_factor)
+{
+  static const int bx0[5][4] = {{0,0,0,0}, {0,0,0,0}, {0,0,0,0}, {0,2,0,0}, {0,2,0,2}};
+  static const int by0[5][4] = {{0,0,0,0}, {0,0,0,0}, {0,2,0,0}, {0,0,0,0}, {0,0,2,2}};
+  me_pred_block blocks[16];
+  int32_t c4[4], c8[4];
+  int parttype = blocktype < 4 ? blocktype : 4;
+  int step_h0 = input->part_size[parttype][0], step_v0 = input->part_size[parttype][1];
+  int step_h = input->part_size[blocktype][0], step_v = input->part_size[blocktype][1];
+  int bx = bx0[parttype][block8x8], by = by0[parttype][block8x8];
+  int v, h, rx, ry, k, n = 0, mvd_bits = 0, mcost, use8 = input->Transform8x8Mode && blocktype <= 4;
+  if (!active || !use_mc) return __real_BIDPartitionCost(currMB, blocktype, block8x8, ref_l0, ref_l1, lambda_factor);
+  mb_sync();
+  /* motion-vector rate (mv-search.c:1083-1096): host arithmetic on the encoder's own arrays */
+  for (v = by; v < by + step_v0; v += step_v)
+    for (h = bx; h < bx + step_h0; h += step_h) {
+      mvd_bits += mvbits[img->all_mv[v][h][LIST_0][ref_l0][blocktype][0] - img->pred_mv[v][h][LIST_0][ref_l0][blocktype][0]];
+      mvd_bits += mvbits[img->all_mv[v][h][LIST_0][ref_l0][blocktype][1] - img->pred_mv[v][h][LIST_0][ref_l0][blocktype][1]];
+      mvd_bits += mvbits[img->all_mv[v][h][LIST_1][ref_l1][blocktype][0] - img->pred_mv[v][h][LIST_1][ref_l1][blocktype][0]];
+      mvd_bits += mvbits[img->all_mv[v][h][LIST_1][ref_l1][blocktype][1] - img->pred_mv[v][h][LIST_1][ref_l1][blocktype][1]];
+    }
+  mcost = WEIGHTED_COST(lambda_factor, mvd_bits);
+  /* residual (mv-search.c:1100-1127): the partition's 8x8 regions, four 4x4 predictions each */
+  for (ry = by; ry < by + step_v0; ry += 2)
+    for (rx = bx; rx < bx + step_h0; rx += 2, n++)
+      for (k = 0; k < 4; k++) fill_pred_block(&blocks[4 * n + k], currMB, rx + (k & 1), ry + (k >> 1), 2, blocktype, blocktype, ref_l0, ref_l1);
+  if (L.pred_cost8x8(blocks, n, input->ModeDecisionMetric, c4, c8)) die("me_cuda_pred_cost8x8");
+  for (k = 0; k < n; k++) mcost += use8 ? c8[k] : c4[k];
+  keep_prediction_side_effects(currMB, 2, ref_l0, ref_l1);
+  served_bid_cost++;
+  if (verify) {
+    int rc = __real_BIDPartitionCost(currMB, blocktype, block8x8, ref_l0, ref_l1, lambda_factor);
+    n_checked++;
+    if (rc != mcost) {
+      n_mismatch++;
+      fprintf(stderr, "VERIFY BIDPartitionCost pic %d mb %d bt %d blk %d refs (%d,%d): gpu %d ref %d\n", pic_counter, img->current_mb_nr, blocktype, block8x8,
+              (int)ref_l0, (int)ref_l1, mcost, rc);
+    }
+    return rc;
+  }
+  return mcost;
+}
+
+int __real_GetDirectCost8x8(Macroblock *currMB, int block, int *cost8x8);
+int __wrap_GetDirectCost8x8(Macroblock *currMB, int block, int *cost8x8)
+{
+  me_pred_block blocks[4];
+  int32_t c4, c8;
+  int k, bx = (block % 2) * 2, by = (block / 2) * 2, cost, in8 = *cost8x8;
+  if (!active || !use_mc) return __real_GetDirectCost8x8(currMB, block, cost8x8);
+  mb_sync();
+  for (k = 0; k < 4; k++) {
+    int h = bx + (k & 1), v = by + (k >> 1);
+    int py = (img->opix_y >> 2) + v, px = (img->opix_x >> 2) + h;                    /* pic_pix_y >> 2, pic_pix_x >> 2 (mv-search.c:1290) */
+    fill_pred_block(&blocks[k], currMB, h, v, direct_pdir[py][px], 0, 0, direct_ref_idx[LIST_0][py][px], direct_ref_idx[LIST_1][py][px]);
+  }
+  if (L.pred_cost8x8(blocks, 1, input->ModeDecisionMetric, &c4, &c8)) die("me_cuda_pred_cost8x8");
+  if (c4 == INT_MAX) { *cost8x8 = INT_MAX; cost = INT_MAX; }                          /* mode not allowed (mv-search.c:1290-1294) */
+  else {
+    cost = c4;
+    if ((input->rdopt == 0) && input->Transform8x8Mode) *cost8x8 += c8;
+    keep_prediction_side_effects(currMB, blocks[3].p_dir, blocks[3].ref[0], blocks[3].ref[1]);
+  }
+  served_direct_cost++;
+  if (verify) {
+    int r8 = in8, rc = __real_GetDirectCost8x8(currMB, block, &r8);
+    n_checked++;
+    if (rc != cost || r8 != *cost8x8) {
+      n_mismatch++;
+      fprintf(stderr, "VERIFY GetDirectCost8x8 pic %d mb %d block %d: gpu (%d,%d) ref (%d,%d)\n", pic_counter, img->current_mb_nr, block, cost, *cost8x8, rc, r8);
+    }
+    *cost8x8 = r8;
+    return rc;
+  }
+  return cost;
 }

@@ -266,6 +266,44 @@ typedef struct me_bipred_result {
 int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements, int search_range, int subpel,
                          me_bipred_result *out);
 
+/* ---- motion-compensated luma prediction and the mode-decision costs built on it: the host consumers
+ * of the quarter-pel planes other than the searches.  With these served by the library the planes need not be copied back into
+ * StorablePicture::imgY_sub (me_cuda_ref_create with host_sub = NULL). ----
+ *
+ * LumaPrediction (macroblock.c:832-930) of one block: p_dir 0 / 1 fetch the block from the plane set of one list entry with
+ * OneComponentLumaPrediction (macroblock.c:807-827: UMVLine4X on the block origin, refbuf.c:37, then plain rows), p_dir 2 from
+ * both and average ((l0 + l1 + 1) >> 1); with apply_weights the explicit / implicit weighted forms of macroblock.c:876-909. */
+typedef struct me_pred_block {
+  int16_t pix_x, pix_y;                 /* top-left sample of the block in the picture (img->opix_x + block_x, img->opix_y + block_y) */
+  int8_t  p_dir;                        /* 0: list 0, 1: list 1, 2: both; < 0: no prediction (GetDirectCost8x8: mode not allowed) */
+  int8_t  ref[2];                       /* l0_ref_idx, l1_ref_idx: indices into the lists of me_cuda_set_ref_list */
+  int8_t  apply_weights;                /* active_pps->weighted_pred_flag (P) / weighted_bipred_idc (B) */
+  int16_t mv[2][2];                     /* quarter-pel vectors, [list][x, y] (all_mv / bipred_mv of the block) */
+  int16_t weight[2];                    /* p_dir 0 / 1: wp_weight[list][ref][0] in weight[0]; p_dir 2: wbp_weight[0 / 1][l0][l1][0] */
+  int16_t offset;                       /* p_dir 0 / 1: wp_offset[list][ref][0]; 2: (wp_offset[0][l0][0] + wp_offset[1][l1][0] + 1) >> 1 */
+  int16_t log_denom;                    /* luma_log_weight_denom */
+} me_pred_block;                        /* 24 bytes */
+
+/* n blocks of bsx x bsy samples (4, 8 or 16 each way): pred receives n * bsx * bsy bytes, every block row by row -- the rows
+ * img->mpr[block_y ..][block_x ..] LumaPrediction writes.  Synchronous. */
+int me_cuda_luma_prediction(const me_pred_block *blocks, int n, int bsx, int bsy, uint8_t *pred);
+
+/* The residual cost all three mode-decision functions are made of, per 8x8 luma region: blocks[4 * r + k], k = 0..3 in raster
+ * order, are the 4x4 blocks of region r, each predicted by itself (LumaPrediction with block size 4x4, as the reference does);
+ * cost4[r] = sum over the four blocks of distortion4x4(original - prediction) (me_distortion.c:76), cost8[r] = distortion8x8
+ * of the whole region (me_distortion.c:110).  metric = input->ModeDecisionMetric: 0 SAD, 1 squared error, 2 Hadamard SAD.
+ * A region with a block whose p_dir < 0 gets cost4 = cost8 = INT_MAX.
+ *   GetSkipCostMB    (mv-search.c:1136-1181): four regions, cost4 each -- or cost8 each when rdopt == 0 with Transform8x8Mode
+ *   GetDirectCost8x8 (mv-search.c:1273-1325): one region, returns cost4; *cost8x8 += cost8 when rdopt == 0 with Transform8x8Mode
+ *   BIDPartitionCost (mv-search.c:1052-1128): the regions of the partition (p_dir 2), cost4 -- or cost8 with Transform8x8Mode
+ *                    and blocktype <= 4 -- plus the motion-vector rate
+ * Original samples: the picture of me_cuda_set_current.  Synchronous. */
+int me_cuda_pred_cost8x8(const me_pred_block *blocks, int n_regions, int metric, int32_t *cost4, int32_t *cost8);
+
+/* a rectangle of one of the 16 planes as imgpel rows: dst[y * dst_stride + x] = Pic[fy][fx][y0 + y][x0 + x] (refbuf.c:27);
+ * the binding pages the planes into StorablePicture::imgY_sub on demand with it instead of copying them all back */
+int me_cuda_ref_download_region(me_ref_handle h, int fy, int fx, int x0, int y0, int w, int hgt, me_imgpel *dst, int dst_stride);
+
 /* ---- device-resident variants for measurement (bench.py): pointers are CUDA device pointers, `stream` is a
  * cudaStream_t passed as void* (NULL = the library's own stream).  Asynchronous.  A caller's stream is ordered against the
  * library stream by events on both sides of the call, so the program order of the calls is the order on the device even

@@ -100,6 +100,10 @@ def lib():
                                         + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int, ip])
         L.ora_mb_search.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, vp]
         L.ora_mb_bipred.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.ora_luma_prediction.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+        L.ora_get_skip_cost_mb.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
+        L.ora_get_direct_cost8x8.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, ip]
+        L.ora_bid_partition_cost.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -288,3 +292,51 @@ def mb_search(cfg, cur, ref, jobs):
                         out.ctypes.data + i * RESULT_DTYPE.itemsize,
                         out_int.ctypes.data + i * RESULT_DTYPE.itemsize)
     return out, out_int
+
+
+# ---- motion-compensated prediction / mode-decision costs (me_oracle.c: ora_luma_prediction, ora_get_skip_cost_mb, ...)
+PRED_BLOCK_DTYPE = np.dtype([("pix_x", "<i2"), ("pix_y", "<i2"), ("p_dir", "i1"), ("ref", "i1", (2,)), ("apply_weights", "i1"),
+                             ("mv", "<i2", (2, 2)), ("weight", "<i2", (2,)), ("offset", "<i2"), ("log_denom", "<i2")])
+assert PRED_BLOCK_DTYPE.itemsize == 24
+
+
+def _ref_array(refs):
+    arr = (C.c_void_p * max(1, len(refs)))()
+    for i, r in enumerate(refs):
+        arr[i] = r.ptr
+    return arr
+
+
+def luma_prediction(list0, list1, block, bsx, bsy):
+    """LumaPrediction (macroblock.c:832) of one block (a PRED_BLOCK_DTYPE record) -> uint8 [bsy, bsx]"""
+    b = np.ascontiguousarray(np.array(block, PRED_BLOCK_DTYPE).reshape(1))
+    out = np.zeros((bsy, bsx), np.uint8)
+    a0, a1 = _ref_array(list0), _ref_array(list1)
+    lib().ora_luma_prediction(a0, a1, b.ctypes.data, bsx, bsy, out.ctypes.data)
+    return out
+
+
+def get_skip_cost_mb(cur, list0, list1, blocks16, rdopt, transform8x8, metric=2):
+    cur = np.ascontiguousarray(cur, np.uint8)
+    b = np.ascontiguousarray(blocks16, PRED_BLOCK_DTYPE)
+    a0, a1 = _ref_array(list0), _ref_array(list1)
+    return lib().ora_get_skip_cost_mb(cur.ctypes.data, cur.strides[0], a0, a1, b.ctypes.data, rdopt, transform8x8, metric)
+
+
+def get_direct_cost8x8(cur, list0, list1, blocks16, block, rdopt, transform8x8, metric=2, cost8x8=0):
+    cur = np.ascontiguousarray(cur, np.uint8)
+    b = np.ascontiguousarray(blocks16, PRED_BLOCK_DTYPE)
+    a0, a1 = _ref_array(list0), _ref_array(list1)
+    c8 = C.c_int(cost8x8)
+    c = lib().ora_get_direct_cost8x8(cur.ctypes.data, cur.strides[0], a0, a1, b.ctypes.data, block, rdopt, transform8x8, metric, C.byref(c8))
+    return c, c8.value
+
+
+def bid_partition_cost(cur, list0, list1, blocks16, pmv16, blocktype, block8x8, lambda_factor, transform8x8, metric=2):
+    cur = np.ascontiguousarray(cur, np.uint8)
+    b = np.ascontiguousarray(blocks16, PRED_BLOCK_DTYPE)
+    pm = np.ascontiguousarray(pmv16, np.int16)
+    assert pm.shape == (16, 2, 2)
+    a0, a1 = _ref_array(list0), _ref_array(list1)
+    return lib().ora_bid_partition_cost(cur.ctypes.data, cur.strides[0], a0, a1, b.ctypes.data, pm.ctypes.data, blocktype, block8x8,
+                                        lambda_factor, transform8x8, metric)

@@ -848,3 +848,146 @@ void ora_mb_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const o
   out->cost = min_mcostbi;
   out->iterlist = iterlist;
 }
+
+/* ------------------------------------------------------------------------------------------------ prediction / mode-decision costs */
+
+/* OneComponentLumaPrediction (macroblock.c:807-827): the block's rows start at UMVLine4X(plane set, y, x) (refbuf.c:37) and follow
+ * at the padded pitch.  The picture's own samples: the weighted-ME copy (refpel) plays no part in motion compensation. */
+static void one_component_luma_prediction(uint8_t *mpred, int pic_pix_x, int pic_pix_y, int bsx, int bsy, const ora_ref *r)
+{
+  const uint8_t *line = ora_umv_line(r, pic_pix_y, pic_pix_x);
+  int j;
+  for (j = 0; j < bsy; j++) { memcpy(mpred, line, (size_t)bsx); line += r->wp; mpred += bsx; }
+}
+
+/* LumaPrediction (macroblock.c:832-930), block of bsx x bsy at b->pix_x / pix_y; pred: bsy rows of bsx samples (img->mpr) */
+void ora_luma_prediction(const ora_ref *const *list0, const ora_ref *const *list1, const me_pred_block *b, int bsx, int bsy, uint8_t *pred)
+{
+  uint8_t l0[256], l1[256];
+  const int pic_opix_x = ((b->pix_x) << 2) + 4 * PAD, pic_opix_y = ((b->pix_y) << 2) + 4 * PAD;      /* macroblock.c:850-851 */
+  int k, n = bsx * bsy;
+  memset(l0, 0, sizeof l0); memset(l1, 0, sizeof l1);
+  if (b->p_dir == 0 || b->p_dir == 2)
+    one_component_luma_prediction(l0, pic_opix_x + b->mv[0][0], pic_opix_y + b->mv[0][1], bsx, bsy, list0[b->ref[0]]);
+  if (b->p_dir == 1 || b->p_dir == 2)
+    one_component_luma_prediction(l1, pic_opix_x + b->mv[1][0], pic_opix_y + b->mv[1][1], bsx, bsy, list1[b->ref[1]]);
+  if (b->apply_weights) {
+    const int wp_luma_round = 1 << (b->log_denom - 1);                       /* weighted_prediction.c:50 (denominators >= 1) */
+    if (b->p_dir == 2) {                                                     /* macroblock.c:884-895 */
+      const int wp_round = 2 * wp_luma_round, weight_denom = b->log_denom + 1;
+      for (k = 0; k < n; k++) pred[k] = (uint8_t)clampi(((b->weight[0] * l0[k] + b->weight[1] * l1[k] + wp_round) >> weight_denom) + b->offset, 0, 255);
+    } else {                                                                 /* :897-913 */
+      const uint8_t *l = b->p_dir ? l1 : l0;
+      for (k = 0; k < n; k++) pred[k] = (uint8_t)clampi(((b->weight[0] * l[k] + wp_luma_round) >> b->log_denom) + b->offset, 0, 255);
+    }
+  } else if (b->p_dir == 2) {                                                /* :917-922 */
+    for (k = 0; k < n; k++) pred[k] = (uint8_t)((l0[k] + l1[k] + 1) >> 1);
+  } else memcpy(pred, b->p_dir ? l1 : l0, (size_t)n);
+}
+
+/* distortion4x4 / distortion8x8 (me_distortion.c:76-103, :110-137): metric = input->ModeDecisionMetric */
+int ora_distortion4x4(int metric, const int *diff)
+{
+  int k, s = 0;
+  if (metric == 2) return ora_hadamard4x4(diff);
+  for (k = 0; k < 16; k++) s += metric == 0 ? iabs_(diff[k]) : diff[k] * diff[k];
+  return s;
+}
+int ora_distortion8x8(int metric, const int *diff)
+{
+  int k, s = 0;
+  if (metric == 2) return ora_hadamard8x8(diff);
+  for (k = 0; k < 64; k++) s += metric == 0 ? iabs_(diff[k]) : diff[k] * diff[k];
+  return s;
+}
+
+/* the state the three cost functions read from the encoder's globals, as plain arrays: blocks[4 * by + bx] describes what
+ * LumaPrediction does for the 4x4 block (bx, by) of the macroblock (mode's vectors, direction, references, weights) */
+static void diff4x4(const uint8_t *cur, int cur_stride, const ora_ref *const *l0, const ora_ref *const *l1, const me_pred_block *b, int *d /*16*/)
+{
+  uint8_t mpr[16];
+  int i, j;
+  ora_luma_prediction(l0, l1, b, 4, 4, mpr);
+  for (j = 0; j < 4; j++)
+    for (i = 0; i < 4; i++) d[4 * j + i] = (int)cur[(size_t)(b->pix_y + j) * cur_stride + b->pix_x + i] - mpr[4 * j + i];
+}
+
+/* GetSkipCostMB (mv-search.c:1136-1181) */
+int ora_get_skip_cost_mb(const uint8_t *cur, int cur_stride, const ora_ref *const *l0, const ora_ref *const *l1,
+                         const me_pred_block *blocks /* 16 */, int rdopt, int transform8x8, int metric)
+{
+  int block, block_y, block_x, i, j, cost = 0, d[16], curr_diff[8][8], diff64[64];
+  for (block = 0; block < 4; block++) {
+    const int mb_y = (block >> 1) << 3, mb_x = (block & 1) << 3;
+    for (block_y = mb_y; block_y < mb_y + 8; block_y += 4)
+      for (block_x = mb_x; block_x < mb_x + 8; block_x += 4) {
+        diff4x4(cur, cur_stride, l0, l1, &blocks[(block_y >> 2) * 4 + (block_x >> 2)], d);
+        for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) curr_diff[block_y - mb_y + j][block_x - mb_x + i] = d[4 * j + i];
+        if (!((rdopt == 0) && transform8x8)) cost += ora_distortion4x4(metric, d);
+      }
+    if ((rdopt == 0) && transform8x8) {
+      for (j = 0; j < 8; j++) memcpy(&diff64[8 * j], curr_diff[j], 8 * sizeof(int));
+      cost += ora_distortion8x8(metric, diff64);
+    }
+  }
+  return cost;
+}
+
+/* GetDirectCost8x8 (mv-search.c:1273-1325); a block with p_dir < 0 is direct_pdir < 0 (mode not allowed) */
+int ora_get_direct_cost8x8(const uint8_t *cur, int cur_stride, const ora_ref *const *l0, const ora_ref *const *l1,
+                           const me_pred_block *blocks /* 16 */, int block, int rdopt, int transform8x8, int metric, int *cost8x8)
+{
+  const int mb_y = (block / 2) << 3, mb_x = (block % 2) << 3;
+  int block_y, block_x, i, j, cost = 0, d[16], curr_diff[8][8], diff64[64];
+  for (block_y = mb_y; block_y < mb_y + 8; block_y += 4)
+    for (block_x = mb_x; block_x < mb_x + 8; block_x += 4) {
+      const me_pred_block *b = &blocks[(block_y >> 2) * 4 + (block_x >> 2)];
+      if (b->p_dir < 0) { *cost8x8 = 2147483647; return 2147483647; }
+      diff4x4(cur, cur_stride, l0, l1, b, d);
+      for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) curr_diff[block_y - mb_y + j][block_x - mb_x + i] = d[4 * j + i];
+      cost += ora_distortion4x4(metric, d);
+    }
+  if ((rdopt == 0) && transform8x8) {
+    for (j = 0; j < 8; j++) memcpy(&diff64[8 * j], curr_diff[j], 8 * sizeof(int));
+    *cost8x8 += ora_distortion8x8(metric, diff64);
+  }
+  return cost;
+}
+
+/* BIDPartitionCost (mv-search.c:1052-1128): blocks[] carry p_dir 2 and the vectors all_mv[v][h][list][ref][blocktype];
+ * pmv[4 * v + h][list] = img->pred_mv[v][h][list][ref][blocktype] */
+int ora_bid_partition_cost(const uint8_t *cur, int cur_stride, const ora_ref *const *l0, const ora_ref *const *l1,
+                           const me_pred_block *blocks /* 16 */, const int16_t (*pmv)[2][2] /* 16 */, int blocktype, int block8x8,
+                           int lambda_factor, int transform8x8, int metric)
+{
+  static const int bx0[5][4] = { {0,0,0,0}, {0,0,0,0}, {0,0,0,0}, {0,2,0,0}, {0,2,0,2} };
+  static const int by0[5][4] = { {0,0,0,0}, {0,0,0,0}, {0,2,0,0}, {0,0,0,0}, {0,0,2,2} };
+  static const int blc_size[8][2] = { {0,0}, {16,16}, {16,8}, {8,16}, {8,8}, {8,4}, {4,8}, {4,4} };        /* configfile.c:805-841 */
+  int curr_blk[16][16], diff64[64], d[16];
+  const int bsx = blc_size[blocktype][0] < 8 ? blc_size[blocktype][0] : 8, bsy = blc_size[blocktype][1] < 8 ? blc_size[blocktype][1] : 8;
+  const int parttype = blocktype < 4 ? blocktype : 4;
+  const int step_h0 = blc_size[parttype][0] >> 2, step_v0 = blc_size[parttype][1] >> 2;                     /* input->part_size */
+  const int step_h = blc_size[blocktype][0] >> 2, step_v = blc_size[blocktype][1] >> 2;
+  const int bx = bx0[parttype][block8x8], by = by0[parttype][block8x8];
+  int v, h, i, j, k, bxx, byy, mvd_bits = 0, mcost;
+  for (v = by; v < by + step_v0; v += step_v)
+    for (h = bx; h < bx + step_h0; h += step_h) {
+      const me_pred_block *b = &blocks[4 * v + h];
+      mvd_bits += ora_mvbits(b->mv[0][0] - pmv[4 * v + h][0][0]) + ora_mvbits(b->mv[0][1] - pmv[4 * v + h][0][1]);
+      mvd_bits += ora_mvbits(b->mv[1][0] - pmv[4 * v + h][1][0]) + ora_mvbits(b->mv[1][1] - pmv[4 * v + h][1][1]);
+    }
+  mcost = (lambda_factor * mvd_bits) >> 16;                                                                 /* WEIGHTED_COST, defines.h:125 */
+  for (byy = 0, v = by; v < by + step_v0; byy += 4, v++)
+    for (bxx = 0, h = bx; h < bx + step_h0; bxx += 4, h++) {
+      diff4x4(cur, cur_stride, l0, l1, &blocks[4 * v + h], d);
+      for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) curr_blk[byy + j][bxx + i] = d[4 * j + i];
+      if (!transform8x8 || blocktype > 4) mcost += ora_distortion4x4(metric, d);
+    }
+  if (transform8x8 && blocktype <= 4)
+    for (byy = 0; byy < blc_size[parttype][1]; byy += bsy)
+      for (bxx = 0; bxx < blc_size[parttype][0]; bxx += bsx) {
+        for (k = 0, j = byy; j < byy + 8; j++, k += 8) memcpy(&diff64[k], &curr_blk[j][bxx], 8 * sizeof(int));
+        mcost += ora_distortion8x8(metric, diff64);
+      }
+  return mcost;
+}

@@ -124,6 +124,20 @@ void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const o
 void ora_mb_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *l0, const ora_ref *l1,
                    const me_bipred_job *job, int refinements, int search_range, int subpel, me_bipred_result *out);
 
+/* ---- motion-compensated prediction and the mode-decision costs built on it (include/me_cuda.h: me_pred_block).
+ * list0 / list1: the reference lists as arrays of pictures; blocks[4 * by + bx]: what LumaPrediction does for the 4x4 block
+ * (bx, by) of the macroblock.  Reference: macroblock.c:807-930, me_distortion.c:76-137, mv-search.c:1052-1128, :1136-1181, :1273-1325 */
+void ora_luma_prediction(const ora_ref *const *list0, const ora_ref *const *list1, const me_pred_block *b, int bsx, int bsy, uint8_t *pred);
+int  ora_distortion4x4(int metric, const int *diff);
+int  ora_distortion8x8(int metric, const int *diff);
+int  ora_get_skip_cost_mb(const uint8_t *cur, int cur_stride, const ora_ref *const *l0, const ora_ref *const *l1,
+                          const me_pred_block *blocks, int rdopt, int transform8x8, int metric);
+int  ora_get_direct_cost8x8(const uint8_t *cur, int cur_stride, const ora_ref *const *l0, const ora_ref *const *l1,
+                            const me_pred_block *blocks, int block, int rdopt, int transform8x8, int metric, int *cost8x8);
+int  ora_bid_partition_cost(const uint8_t *cur, int cur_stride, const ora_ref *const *l0, const ora_ref *const *l1,
+                            const me_pred_block *blocks, const int16_t (*pmv)[2][2], int blocktype, int block8x8,
+                            int lambda_factor, int transform8x8, int metric);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,7 @@ def _prep(tmp):
 def _run(exe, args, cwd, env=None):
     e = dict(os.environ)
     e["ME_CUDA_LIB"] = os.path.join(ROOT, "h.264_b200", "libme_cuda.so")
-    for k in ("ME_CUDA_DISABLE", "ME_CUDA_VERIFY", "ME_CUDA_PMS"):       # a stray switch must not turn the comparison into reference-vs-reference
+    for k in ("ME_CUDA_DISABLE", "ME_CUDA_VERIFY", "ME_CUDA_PMS", "ME_CUDA_MC", "ME_CUDA_HOST_PLANES", "ME_CUDA_POISON_PLANES"):       # a stray switch must not turn the comparison into reference-vs-reference
         e.pop(k, None)
     if env:
         e.update(env)
@@ -59,6 +59,9 @@ def _served(stderr, want=("plane sets",)):
     p = re.search(r"partition-search launches (\d+), block searches answered from them (\d+), argument mismatches (\d+)", stderr)
     assert p, stderr[-800:]
     c["pms_launches"], c["pms_served"], c["pms_missed"] = map(int, p.groups())
+    q = re.search(r"mode-decision costs on the device: (\d+) BIDPartitionCost, (\d+) GetDirectCost8x8 calls; plane tiles paged to the host: (\d+) \((\d+) bytes", stderr)
+    assert q, stderr[-800:]
+    c["bid_cost"], c["direct_cost"], c["paged_tiles"], c["paged_bytes"] = map(int, q.groups())
     for k in want:
         assert c[k] > 0, (k, c)
     return c
@@ -69,11 +72,45 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
     """bin/encoder.cfg: the run behind the reference's committed bin/test.264 / bin/test_rec.yuv"""
     _prep(str(tmp_path))
     _, err = _run("lencod_cuda", ["-d", "encoder.cfg"], str(tmp_path))
-    c = _served(err, ("plane sets", "ffs", "subpel", "bi_full", "bi_sub"))
+    c = _served(err, ("plane sets", "ffs", "subpel", "bi_full", "bi_sub", "bid_cost", "paged_tiles"))
     assert c["pms_launches"] > 0 and c["pms_served"] > 0, c
+    # the planes stayed on the device: the host paged in what it read, tile by tile, never more than the 16 x 216 x 184 samples x 2 bytes
+    # per reference picture a copy-back would have moved (on this QCIF clip most tiles are touched; at 1080p a small share is)
+    assert 0 < c["paged_bytes"] <= c["plane sets"] * 16 * 216 * 184 * 2, c
     md5 = json.load(open(os.path.join(GOLDEN, "bitstream_md5.json")))["kat"]
     assert _md5(str(tmp_path / "test.264")) == md5["test.264"] == _md5(os.path.join(REF_DIR, "fixtures", "golden_test.264"))
     assert _md5(str(tmp_path / "test_rec.yuv")) == md5["test_rec.yuv"] == _md5(os.path.join(REF_DIR, "fixtures", "golden_test_rec.yuv"))
+
+
+@pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
+@pytest.mark.parametrize("args,want", [
+    (["-d", "encoder.cfg"], "bid_cost"),                                                       # B pictures, Transform8x8Mode = 1, RDO
+    (["-d", "encoder.cfg", "-p", "RDOptimization=0", "-p", "SearchRange=16"], "direct_cost"),    # rdopt = 0: GetDirectCost8x8 with the 8x8 costs
+    (["-d", "encoder_main.cfg", "-p", "RDOptimization=0", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2", "-p", "WeightedBiprediction=1"],
+     "direct_cost")])                                                                            # explicit weights in the predictions
+def test_mode_decision_costs_and_paged_planes(tmp_path, me_lib_path, args, want):
+    """SURVEY.md 8(f) row 2.  BIDPartitionCost / GetDirectCost8x8 (mv-search.c:1052, :1273) served by the library, the planes paged into
+    imgY_sub on demand instead of copied back: (1) byte-identical output with the host plane sets poisoned first -- a host read
+    that bypassed the paging would change the bitstream; (2) verify mode: the reference function runs next to every device call of the two
+    cost functions (and of the searches) and every result is compared."""
+    import re
+    a, b = tmp_path / "gpu", tmp_path / "cpu"
+    for d in (a, b):
+        d.mkdir()
+        _prep(str(d))
+    _, err = _run("lencod_cuda", args, str(a), env={"ME_CUDA_POISON_PLANES": "1"})
+    _run("lencod", args, str(b))
+    assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
+    assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
+    c = _served(err, ("plane sets", "paged_tiles", want))
+    _, err = _run("lencod_cuda", args, str(a), env={"ME_CUDA_VERIFY": "1"})
+    m = re.search(r"verify mode: (\d+) calls checked, (\d+) mismatches", err)
+    assert m and int(m.group(1)) > c["bid_cost"] + c["direct_cost"] and int(m.group(2)) == 0, err[-1500:]
+    # the same run with the two switches off: reference host code for the costs, all planes copied back -- same output
+    _, err = _run("lencod_cuda", args, str(a), env={"ME_CUDA_MC": "0", "ME_CUDA_HOST_PLANES": "1"})
+    assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
+    c0 = _served(err, ("plane sets",))
+    assert c0["bid_cost"] == 0 and c0["direct_cost"] == 0 and c0["paged_tiles"] == 0, c0
 
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
