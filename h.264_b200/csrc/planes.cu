@@ -9,112 +9,151 @@
 //   h = P[2][0] = clip255((same 6 taps vertically on G, rows clamped to [0,hp-1], +16)>>5)        img_luma.c:293
 //   j = P[2][2] = clip255((6 taps vertically on t, +512)>>10)                                      img_luma.c:390
 //   twelve quarter positions = (p+q+1)>>1 of two of {G,b,h,j} at the same / right / lower sample    img_luma.c:483-639
-// All arithmetic is 32-bit integer.  One kernel computes all 16 planes of a 64x16 tile from a shared-memory copy of
-// the tile plus halo; a second tiny kernel writes the wide-border search copy of the integer plane (me_common.cuh).
+// All arithmetic is integer.  One kernel computes all 16 planes of a 128x16 tile from a shared-memory copy of the tile plus halo,
+// four samples per 32-bit word throughout (byte-SIMD averages, 16-bit lane pairs for the six-tap sums); a second tiny kernel
+// writes the wide-border search copy of the integer plane (me_common.cuh).
 //
 // Roofline: HBM-bound.  Algorithmic bytes per reference picture = w*h (read) + 16*(w+40)*(h+40) (write).
 #include "me_common.cuh"
 
-#define TW 64
+#define TW 128                 // tile: 128 x 16 plane samples per CTA
 #define TH 16
-#define GW (TW + 7)   // columns x0-2 .. x0+TW+4
-#define GH (TH + 7)   // rows    y0-2 .. y0+TH+4
-#define TMW (TW + 1)  // t / b / j for columns x0 .. x0+TW
+#define GROWS (TH + 5)         // plane rows y0-2 .. y0+TH+2: what the vertical filters and the lower neighbours of the tile read
+#define GWORDS (TW / 4 + 2)    // plane columns x0-4 .. x0+TW+3 as 32-bit words (x0 is a multiple of 128: word loads stay aligned)
+#define BIASP 0x0A000A00u      // 2560 in both 16-bit lanes: keeps the six-tap sums (-2550 .. 10710) non-negative; a multiple of 32
 
-__device__ __forceinline__ int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+// Everything below works on words of four samples.  Two samples share a register as 16-bit lanes for the six-tap sums (the
+// biased sums stay below 2^14, so plain 32-bit adds and multiplies never carry between the lanes); the vertical filter of the
+// unrounded horizontal sums (plane j) needs 19 bits and runs per sample.  Rounding with the bias in place: the bias is a multiple
+// of 32 and the tap weights sum to 32, so ((t + bias) + 16) >> 5 = ((t + 16) >> 5) + 80 and (sum of weighted (t + bias) + 512) >> 10
+// = ((sum + 512) >> 10) + 80: clip255(v) = clamp(v + 80, 80, 335) - 80.
+__device__ __forceinline__ unsigned pair_lo(unsigned w) { return __byte_perm(w, 0, 0x4140); }      // (b0 | b1 << 16)
+__device__ __forceinline__ unsigned pair_hi(unsigned w) { return __byte_perm(w, 0, 0x4342); }      // (b2 | b3 << 16)
+__device__ __forceinline__ unsigned pair_mid(unsigned w) { return __byte_perm(w, 0, 0x4241); }     // (b1 | b2 << 16)
+// 20 * (a + b) - 5 * (c + d) + (e + f) + bias on lane pairs
+__device__ __forceinline__ unsigned six_tap_pairs(unsigned a, unsigned b, unsigned c, unsigned d, unsigned e, unsigned f)
+{
+  return (a + b) * 20u + (e + f + BIASP) - (c + d) * 5u;
+}
+// two biased six-tap sums -> clip255((t + 16) >> 5) in both lanes
+__device__ __forceinline__ unsigned round5_pairs(unsigned t)
+{
+  const unsigned v = ((t + 0x00100010u) >> 5) & 0x07ff07ffu;
+  return __vmins2(__vmaxs2(v, 0x00500050u), 0x014f014fu) - 0x00500050u;
+}
+__device__ __forceinline__ unsigned pack_pairs(unsigned p01, unsigned p23) { return __byte_perm(p01, p23, 0x6420); }
 
 __global__ void __launch_bounds__(256)
 me_planes_kernel(const uint8_t *__restrict__ src, int src_stride, int w, int h,
-                 uint8_t *__restrict__ planes, int pitch, size_t plane_stride)
+                 uint8_t *__restrict__ planes, int pitch, size_t plane_stride, int src_words_ok)
 {
-  __shared__ uint8_t Gs[GH][GW + 1];
-  __shared__ int     Ts[GH][TMW];        // unrounded horizontal sums t for rows y0-2..y0+TH+4, columns x0..x0+TW
-  __shared__ uint8_t Bs[TH + 1][TMW];    // b for rows y0..y0+TH
-  __shared__ uint8_t Hs[TH + 1][TMW];    // h
-  __shared__ uint8_t Js[TH + 1][TMW];    // j
+  __shared__ uint32_t Gw[GROWS][GWORDS];        // integer samples, rows y0-2.., columns x0-4..
+  __shared__ uint32_t Tw[GROWS][TW / 2];        // biased horizontal six-tap sums as lane pairs, rows y0-2.., columns x0..x0+TW-1
+  __shared__ uint32_t Bw[TH + 1][TW / 4];       // b, rows y0..y0+TH
+  __shared__ uint32_t Hw[TH][TW / 4 + 1];       // h, rows y0..y0+TH-1, columns x0..x0+TW+3
+  __shared__ uint32_t Jw[TH][TW / 4];           // j
   const int wp = w + 2 * ME_PAD, hp = h + 2 * ME_PAD;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int tid = threadIdx.x;
 
-  // integer samples with both clamps (padded-plane clamp of the filters, then picture clamp of the border)
-  for (int i = tid; i < GH * GW; i += blockDim.x) {
-    int ly = i / GW, lx = i - ly * GW;
-    int y = me_clamp(y0 - 2 + ly, 0, hp - 1), x = me_clamp(x0 - 2 + lx, 0, wp - 1);
-    Gs[ly][lx] = src[(size_t)me_clamp(y - ME_PAD, 0, h - 1) * src_stride + me_clamp(x - ME_PAD, 0, w - 1)];
+  // ---- integer samples.  G(y, x) = S(clamp(y - 20, 0, h - 1), clamp(x - 20, 0, w - 1)) for every y, x: the plane-edge clamp of
+  // the filters (img_luma.c:181, :293) lands in the replicated border, where it changes nothing
+  for (int i = tid; i < GROWS * GWORDS; i += 256) {
+    const int ly = i / GWORDS, wi = i - ly * GWORDS;
+    const int sy = me_clamp(y0 - 2 + ly - ME_PAD, 0, h - 1), sx = x0 - 4 + 4 * wi - ME_PAD;
+    const uint8_t *row = src + (size_t)sy * src_stride;
+    uint32_t v;
+    if (src_words_ok && sx >= 0 && sx + 3 <= w - 1) v = *reinterpret_cast<const uint32_t *>(row + sx);
+    else
+      v = (uint32_t)row[me_clamp(sx, 0, w - 1)] | ((uint32_t)row[me_clamp(sx + 1, 0, w - 1)] << 8) |
+          ((uint32_t)row[me_clamp(sx + 2, 0, w - 1)] << 16) | ((uint32_t)row[me_clamp(sx + 3, 0, w - 1)] << 24);
+    Gw[ly][wi] = v;
   }
   __syncthreads();
-  // horizontal six-tap sums.  Local column lx of Ts is plane column x0+lx; its taps are Gs columns lx .. lx+5.
-  // The plane-edge clamp of the taps is already in Gs for every column except when x0+lx itself is past wp-1
-  // (only the +1 neighbour column of the last tile), where the value is never used unclamped (see idx1 below).
-  for (int i = tid; i < GH * TMW; i += blockDim.x) {
-    int ly = i / TMW, lx = i - ly * TMW;
-    const uint8_t *g = &Gs[ly][lx];
-    Ts[ly][lx] = 20 * (g[2] + g[3]) - 5 * (g[1] + g[4]) + (g[0] + g[5]);
+  // ---- horizontal sums t (img_luma.c:181-190), four columns per thread: samples g0..g11 = three words starting at column c - 4
+  for (int i = tid; i < GROWS * (TW / 4); i += 256) {
+    const int ly = i / (TW / 4), wq = i - ly * (TW / 4);
+    const unsigned W0 = Gw[ly][wq], W1 = Gw[ly][wq + 1], W2 = Gw[ly][wq + 2];
+    const unsigned V1 = __funnelshift_r(W0, W1, 24), V2 = __funnelshift_r(W1, W2, 24);    // (g3 g4 g5 g6), (g7 g8 g9 g10)
+    const unsigned g23 = pair_hi(W0), g45 = pair_lo(W1), g67 = pair_hi(W1), g89 = pair_lo(W2);
+    const unsigned g34 = pair_lo(V1), g56 = pair_mid(W1), g78 = pair_lo(V2), g9a = pair_hi(V2);
+    // columns c, c + 1 (samples g4, g5) and c + 2, c + 3 (g6, g7)
+    uint2 t;
+    t.x = six_tap_pairs(g45, g56, g34, g67, g23, g78);
+    t.y = six_tap_pairs(g67, g78, g56, g89, g45, g9a);
+    *reinterpret_cast<uint2 *>(&Tw[ly][2 * wq]) = t;
   }
   __syncthreads();
-  for (int i = tid; i < (TH + 1) * TMW; i += blockDim.x) {
-    int ly = i / TMW, lx = i - ly * TMW;        // plane row y0+ly, column x0+lx
-    Bs[ly][lx] = (uint8_t)clip255((Ts[ly + 2][lx] + 16) >> 5);
-    int v = 20 * (Gs[ly + 2][lx + 2] + Gs[ly + 3][lx + 2]) - 5 * (Gs[ly + 1][lx + 2] + Gs[ly + 4][lx + 2])
-            + (Gs[ly][lx + 2] + Gs[ly + 5][lx + 2]);
-    Hs[ly][lx] = (uint8_t)clip255((v + 16) >> 5);
-    int u = 20 * (Ts[ly + 2][lx] + Ts[ly + 3][lx]) - 5 * (Ts[ly + 1][lx] + Ts[ly + 4][lx]) + (Ts[ly][lx] + Ts[ly + 5][lx]);
-    Js[ly][lx] = (uint8_t)clip255((u + 512) >> 10);
+  // ---- b (rows y0..y0+TH), h (columns x0..x0+TW+3) and j
+  for (int i = tid; i < (TH + 1) * (TW / 4); i += 256) {
+    const int r = i / (TW / 4), wq = i - r * (TW / 4);
+    const uint2 t = *reinterpret_cast<const uint2 *>(&Tw[r + 2][2 * wq]);
+    Bw[r][wq] = pack_pairs(round5_pairs(t.x), round5_pairs(t.y));                         // img_luma.c:206
   }
-  __syncthreads();
-  // write the 16 planes: one thread per 4 consecutive pixels, one 32-bit store per plane (wp is a multiple of 4 and the
-  // plane pitch a multiple of 128, so a group never straddles the plane edge and every store is aligned)
-  for (int i = tid; i < TH * (TW / 4); i += blockDim.x) {
-    int ly = i / (TW / 4), lx0 = (i - ly * (TW / 4)) * 4;
-    int y = y0 + ly, x = x0 + lx0;
-    if (y >= hp || x >= wp) continue;
-    int ly1 = (y + 1 > hp - 1) ? ly : ly + 1;   // lower neighbour, clamped at the plane edge
-    uint32_t o[16];
+  for (int i = tid; i < TH * (TW / 4 + 1); i += 256) {
+    const int r = i / (TW / 4 + 1), wq = i - r * (TW / 4 + 1);
+    unsigned lo[6], hi[6];
 #pragma unroll
-    for (int k = 0; k < 16; k++) o[k] = 0;
+    for (int k = 0; k < 6; k++) { const unsigned W = Gw[r + k][wq + 1]; lo[k] = pair_lo(W); hi[k] = pair_hi(W); }
+    Hw[r][wq] = pack_pairs(round5_pairs(six_tap_pairs(lo[2], lo[3], lo[1], lo[4], lo[0], lo[5])),
+                           round5_pairs(six_tap_pairs(hi[2], hi[3], hi[1], hi[4], hi[0], hi[5])));      // img_luma.c:293-330
+  }
+  for (int i = tid; i < TH * (TW / 4); i += 256) {
+    const int r = i / (TW / 4), wq = i - r * (TW / 4);
+    uint2 t[6];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      int lx = lx0 + k;
-      int lx1 = (x + k + 1 > wp - 1) ? lx : lx + 1;   // right neighbour, clamped at the plane edge
-      int g = Gs[ly + 2][lx + 2], b = Bs[ly][lx], hv = Hs[ly][lx], j = Js[ly][lx];
-      int g_r = Gs[ly + 2][lx1 + 2], h_r = Hs[ly][lx1];
-      int g_d = Gs[ly1 + 2][lx + 2], b_d = Bs[ly1][lx];
-      const int sh = 8 * k;
-      o[0]  |= (uint32_t)g << sh;
-      o[1]  |= (uint32_t)((g + b + 1) >> 1) << sh;
-      o[2]  |= (uint32_t)b << sh;
-      o[3]  |= (uint32_t)((b + g_r + 1) >> 1) << sh;
-      o[4]  |= (uint32_t)((g + hv + 1) >> 1) << sh;
-      o[5]  |= (uint32_t)((b + hv + 1) >> 1) << sh;
-      o[6]  |= (uint32_t)((b + j + 1) >> 1) << sh;
-      o[7]  |= (uint32_t)((b + h_r + 1) >> 1) << sh;
-      o[8]  |= (uint32_t)hv << sh;
-      o[9]  |= (uint32_t)((hv + j + 1) >> 1) << sh;
-      o[10] |= (uint32_t)j << sh;
-      o[11] |= (uint32_t)((j + h_r + 1) >> 1) << sh;
-      o[12] |= (uint32_t)((hv + g_d + 1) >> 1) << sh;
-      o[13] |= (uint32_t)((hv + b_d + 1) >> 1) << sh;
-      o[14] |= (uint32_t)((j + b_d + 1) >> 1) << sh;
-      o[15] |= (uint32_t)((b_d + h_r + 1) >> 1) << sh;
+    for (int k = 0; k < 6; k++) t[k] = *reinterpret_cast<const uint2 *>(&Tw[r + k][2 * wq]);
+    // vertical six taps on the biased sums: the pair sums fit 16 bits, the weighted sum does not
+    unsigned out[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const unsigned s1 = q ? t[2].y + t[3].y : t[2].x + t[3].x, s2 = q ? t[1].y + t[4].y : t[1].x + t[4].x,
+                     s3 = q ? t[0].y + t[5].y : t[0].x + t[5].x;
+      int v0 = (int)((s1 & 0xffffu) * 20u + (s3 & 0xffffu)) - (int)((s2 & 0xffffu) * 5u);
+      int v1 = (int)((s1 >> 16) * 20u + (s3 >> 16)) - (int)((s2 >> 16) * 5u);
+      v0 = me_clamp((v0 + 512) >> 10, 80, 335) - 80;                                     // img_luma.c:390-420 with the bias (see above)
+      v1 = me_clamp((v1 + 512) >> 10, 80, 335) - 80;
+      out[q] = (unsigned)v0 | ((unsigned)v1 << 16);
     }
+    Jw[r][wq] = pack_pairs(out[0], out[1]);
+  }
+  __syncthreads();
+  // ---- the 16 planes (img_luma.c:483-639): one word of four samples per thread and plane, a warp writes one 128-byte line
+  for (int i = tid; i < TH * (TW / 4); i += 256) {
+    const int r = i / (TW / 4), wq = i - r * (TW / 4);
+    const int y = y0 + r, x = x0 + 4 * wq;
+    if (y >= hp || x >= wp) continue;
+    const unsigned g = Gw[r + 2][wq + 1], gn = Gw[r + 2][wq + 2], g_d = Gw[r + 3][wq + 1];
+    const unsigned b = Bw[r][wq], b_d = Bw[r + 1][wq];
+    const unsigned hv = Hw[r][wq], hn = Hw[r][wq + 1];
+    const unsigned j = Jw[r][wq];
+    const unsigned g_r = __funnelshift_r(g, gn, 8), h_r = __funnelshift_r(hv, hn, 8);     // right neighbours
     uint8_t *P = planes + (size_t)y * pitch + x;
-#pragma unroll
-    for (int k = 0; k < 16; k++) *reinterpret_cast<uint32_t *>(P + (size_t)k * plane_stride) = o[k];
+#define ME_PUT(k, v) *reinterpret_cast<uint32_t *>(P + (size_t)(k) * plane_stride) = (v)
+    ME_PUT(0, g);                    ME_PUT(1, __vavgu4(g, b));       ME_PUT(2, b);                    ME_PUT(3, __vavgu4(b, g_r));
+    ME_PUT(4, __vavgu4(g, hv));      ME_PUT(5, __vavgu4(b, hv));      ME_PUT(6, __vavgu4(b, j));       ME_PUT(7, __vavgu4(b, h_r));
+    ME_PUT(8, hv);                   ME_PUT(9, __vavgu4(hv, j));      ME_PUT(10, j);                   ME_PUT(11, __vavgu4(j, h_r));
+    ME_PUT(12, __vavgu4(hv, g_d));   ME_PUT(13, __vavgu4(hv, b_d));   ME_PUT(14, __vavgu4(j, b_d));    ME_PUT(15, __vavgu4(b_d, h_r));
+#undef ME_PUT
   }
 }
 
 // wide-border integer plane for the search-window tiles: one thread per 4 consecutive bytes (sw is a multiple of 4)
 __global__ void __launch_bounds__(256)
 me_search_plane_kernel(const uint8_t *__restrict__ src, int src_stride, int w, int h,
-                       uint8_t *__restrict__ dst, int spad, int spitch, int sw, int sh)
+                       uint8_t *__restrict__ dst, int spad, int spitch, int sw, int sh, int src_words_ok)
 {
   int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   int y = blockIdx.y;
   if (x >= sw || y >= sh) return;
   const uint8_t *row = src + (size_t)me_clamp(y - spad, 0, h - 1) * src_stride;
+  const int sx = x - spad;
   uint32_t v = 0;
+  if (src_words_ok && sx >= 0 && sx + 3 <= w - 1) v = *reinterpret_cast<const uint32_t *>(row + sx);      // inside the picture: one aligned word
+  else {
 #pragma unroll
-  for (int k = 0; k < 4; k++) v |= (uint32_t)row[me_clamp(x + k - spad, 0, w - 1)] << (8 * k);
+    for (int k = 0; k < 4; k++) v |= (uint32_t)row[me_clamp(sx + k, 0, w - 1)] << (8 * k);
+  }
   *reinterpret_cast<uint32_t *>(dst + (size_t)y * spitch + x) = v;
 }
 
@@ -138,10 +177,11 @@ extern "C" void me_launch_planes(const uint8_t *src, int src_stride, int w, int 
 {
   int wp = w + 2 * ME_PAD, hp = h + 2 * ME_PAD;
   dim3 grid((wp + TW - 1) / TW, (hp + TH - 1) / TH);
-  me_planes_kernel<<<grid, 256, 0, st>>>(src, src_stride, w, h, planes, pitch, plane_stride);
+  const int words_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_stride) & 3) == 0;      // aligned word loads of the source rows
+  me_planes_kernel<<<grid, 256, 0, st>>>(src, src_stride, w, h, planes, pitch, plane_stride, words_ok);
   int sw = w + 2 * spad, sh = h + 2 * spad;
   dim3 g2((sw / 4 + 255) / 256, sh);
-  me_search_plane_kernel<<<g2, 256, 0, st>>>(src, src_stride, w, h, search, spad, spitch, sw, sh);
+  me_search_plane_kernel<<<g2, 256, 0, st>>>(src, src_stride, w, h, search, spad, spitch, sw, sh, words_ok && (spad & 3) == 0);
 }
 
 extern "C" void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp,
