@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libme_cuda.so")
-SOURCES = ["me_cuda_host.cu", "planes.cu", "ffs_basic.cu", "ffs_tuned.cu", "subpel.cu", "subpel_tuned.cu", "mc.cu", "int_peak.cu"]
+SOURCES = ["me_cuda_host.cu", "planes.cu", "ffs_basic.cu", "ffs_tuned.cu", "subpel.cu", "subpel_tuned.cu", "mc.cu", "deblock.cu", "int_peak.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

@@ -44,6 +44,7 @@ void me_launch_luma_prediction(const void *blocks, int n, int bsx, int bsy, cons
 void me_launch_pred_cost8x8(const void *blocks, int n_regions, int metric, const MeRefDev *table, const uint8_t *cur, int cur_pitch,
                             int32_t *cost4, int32_t *cost8, cudaStream_t st);
 void me_launch_widen_region(const uint8_t *plane, int pitch, int x0, int y0, int w, int h, uint16_t *dst, cudaStream_t st);
+void me_launch_deblock(uint8_t *Y, int ypitch, uint8_t *U, uint8_t *V, int cpitch, int mbw, int mbh, const void *mbs, int *progress, cudaStream_t st);
 void me_launch_weight_planes(const uint8_t *src, uint8_t *dst, size_t bytes, int weight, int offset, int log_denom, cudaStream_t st);
 void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
                                const MeCfgDev *cfg, MeResultInt *out, const int *job_list, cudaStream_t st);
@@ -187,6 +188,8 @@ struct State {
   MeRefDev *d_mc_table = nullptr; MeRefDev h_mc_table[2 * ME_MAX_REFS]; bool mc_table_valid = false;
   uint8_t *h_mc = nullptr, *d_mc_mapped = nullptr;        // mapped pinned
   uint8_t *d_mc = nullptr; size_t d_mc_bytes = 0;         // device
+  // deblocking (deblock.cu): the picture being filtered (luma, then U, V), the macroblock records and the row progress counters
+  uint8_t *d_db = nullptr; size_t d_db_bytes = 0; int db_w = 0, db_h = 0; bool db_valid = false;
   long long launches = 0;
   long long spec_hits = 0;                        // sub-pel calls answered from the fused block-search kernel
   // optional per-kernel-class timing (bench.py): event pairs around every launch of a class
@@ -537,6 +540,7 @@ void me_cuda_shutdown(void)
   if (g.d_mc_table) cudaFree(g.d_mc_table);
   if (g.h_mc) cudaFreeHost(g.h_mc);
   if (g.d_mc) cudaFree(g.d_mc);
+  if (g.d_db) cudaFree(g.d_db);
   if (g_d_stage) { cudaFree(g_d_stage); g_d_stage = nullptr; g_d_stage_bytes = 0; }
   for (int k = 0; k < 3; k++) { for (auto &p : g.ev[k]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } g.ev[k].clear(); }
   if (g.ev_order) cudaEventDestroy(g.ev_order);
@@ -1556,6 +1560,61 @@ int me_cuda_ref_download_region(me_ref_handle h, int fy, int fx, int x0, int y0,
   CK(cudaStreamSynchronize(g.stream));
   for (int y = 0; y < hgt; y++) memcpy(dst + (size_t)y * dst_stride, h_out + (size_t)y * w * sizeof(uint16_t), (size_t)w * sizeof(uint16_t));
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ deblocking
+int me_cuda_deblock_frame(me_imgpel *const *y_rows, me_imgpel *const *u_rows, me_imgpel *const *v_rows, int w, int h, int cw, int ch,
+                          const me_deblock_mb *mbs)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (w <= 0 || h <= 0 || (w & 15) || (h & 15)) return fail(1, "me_cuda_deblock_frame: picture size %d x %d", w, h);
+  const bool chroma = u_rows && v_rows;
+  if (chroma && (cw != w / 2 || ch != h / 2)) return fail(1, "me_cuda_deblock_frame: chroma %d x %d is not 4:2:0 of %d x %d", cw, ch, w, h);
+  const int mbw = w / 16, mbh = h / 16;
+  if (mbh > 148 * 16) return fail(1, "me_cuda_deblock_frame: %d macroblock rows exceed what is resident at once", mbh);
+  const size_t ybytes = (size_t)w * h, cbytes = chroma ? (size_t)cw * ch : 0, pix = ybytes + 2 * cbytes;
+  const size_t mb_bytes = sizeof(me_deblock_mb) * (size_t)mbw * mbh, mb_off = (pix + 255) & ~(size_t)255;
+  const size_t prog_off = (mb_off + mb_bytes + 255) & ~(size_t)255, total = prog_off + sizeof(int) * (size_t)mbh;
+  if (int rc = ensure_pin(mb_off + mb_bytes)) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  g.db_valid = false;
+  if (g.d_db_bytes < total) {
+    if (g.d_db) cudaFree(g.d_db);
+    g.d_db = nullptr; g.d_db_bytes = 0;
+    CK(cudaMalloc((void **)&g.d_db, total));
+    g.d_db_bytes = total;
+  }
+  for (int y = 0; y < h; y++) { const me_imgpel *s = y_rows[y]; uint8_t *d = g.h_pin + (size_t)y * w; for (int x = 0; x < w; x++) d[x] = (uint8_t)s[x]; }
+  for (int k = 0; k < (chroma ? 2 : 0); k++)
+    for (int y = 0; y < ch; y++) {
+      const me_imgpel *s = (k ? v_rows : u_rows)[y]; uint8_t *d = g.h_pin + ybytes + (size_t)k * cbytes + (size_t)y * cw;
+      for (int x = 0; x < cw; x++) d[x] = (uint8_t)s[x];
+    }
+  memcpy(g.h_pin + mb_off, mbs, mb_bytes);
+  CK(cudaMemcpyAsync(g.d_db, g.h_pin, mb_off + mb_bytes, cudaMemcpyHostToDevice, g.stream));
+  me_launch_deblock(g.d_db, w, chroma ? g.d_db + ybytes : nullptr, chroma ? g.d_db + ybytes + cbytes : nullptr, cw, mbw, mbh,
+                    g.d_db + mb_off, (int *)(g.d_db + prog_off), g.stream);
+  g.launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(g.h_pin, g.d_db, pix, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  for (int y = 0; y < h; y++) { me_imgpel *d = y_rows[y]; const uint8_t *s = g.h_pin + (size_t)y * w; for (int x = 0; x < w; x++) d[x] = s[x]; }
+  for (int k = 0; k < (chroma ? 2 : 0); k++)
+    for (int y = 0; y < ch; y++) {
+      me_imgpel *d = (k ? v_rows : u_rows)[y]; const uint8_t *s = g.h_pin + ybytes + (size_t)k * cbytes + (size_t)y * cw;
+      for (int x = 0; x < cw; x++) d[x] = s[x];
+    }
+  g.db_w = w; g.db_h = h; g.db_valid = true;
+  return 0;
+}
+
+int me_cuda_ref_create_deblocked(int w, int h, me_imgpel ****host_sub, me_ref_handle *out)
+{
+  g.spec.valid = false;
+  if (int rc = check_size(w, h)) return rc;
+  if (!g.db_valid || g.db_w != w || g.db_h != h) return fail(1, "me_cuda_ref_create_deblocked: no deblocked %d x %d picture on the device", w, h);
+  if (host_sub) return fail(1, "me_cuda_ref_create_deblocked: the plane copy-back is not offered here (page the planes in with me_cuda_ref_download_region)");
+  return create_ref_common(g.d_db, w, w, h, g.stream, out);
 }
 
 int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements, int search_range, int subpel, me_bipred_result *out)

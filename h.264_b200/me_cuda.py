@@ -28,6 +28,9 @@ assert JOB_DTYPE.itemsize == 188 and RESULT_DTYPE.itemsize == 328
 MOTION_DTYPE = np.dtype([("ref_idx", "i1", (2, 5, 6)), ("mv", "<i2", (2, 5, 6, 2))])
 PMS_ITEM_DTYPE = np.dtype([("blocktype", "i1"), ("block8x8", "i1")])
 PMS_UNAVAILABLE = -128
+DEBLOCK_MB_DTYPE = np.dtype([("strength", "u1", (2, 4, 16)), ("qp", "i1"), ("qpc", "i1", (2,)), ("alpha_off", "i1"), ("beta_off", "i1"),
+                             ("luma_skip", "u1"), ("reserved", "u1", (10,))])
+assert DEBLOCK_MB_DTYPE.itemsize == 144
 assert BIPRED_JOB_DTYPE.itemsize == 32 and BIPRED_RESULT_DTYPE.itemsize == 16
 assert MOTION_DTYPE.itemsize == 300 and PMS_ITEM_DTYPE.itemsize == 2
 
@@ -41,7 +44,7 @@ ABI_SYMBOLS = [
     "me_cuda_FullPelBlockMotionBiPred", "me_cuda_SubPelBlockSearchBiPred",
     "me_cuda_frame_search", "me_cuda_frame_search_device", "me_cuda_frame_bipred", "me_cuda_ref_create_device",
     "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count", "me_cuda_subpel_region_stats",
-    "me_cuda_luma_prediction", "me_cuda_pred_cost8x8", "me_cuda_ref_download_region",
+    "me_cuda_luma_prediction", "me_cuda_pred_cost8x8", "me_cuda_ref_download_region", "me_cuda_deblock_frame", "me_cuda_ref_create_deblocked",
     "me_cuda_measure_int_peak", "me_cuda_ref_update_u8", "me_cuda_ref_update_device", "me_cuda_set_timing",
     "me_cuda_kernel_time_ms", "me_cuda_set_ref_weights", "me_cuda_set_bipred_weights", "me_cuda_set_bipred_chroma_weights",
     "me_cuda_set_current_chroma", "me_cuda_set_current_chroma_u8", "me_cuda_ref_set_chroma", "me_cuda_ref_set_chroma_u8",
@@ -116,6 +119,8 @@ def load_library(path=LIB_PATH):
     L.me_cuda_luma_prediction.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.me_cuda_pred_cost8x8.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.me_cuda_ref_download_region.argtypes = [C.c_int32] + [C.c_int] * 6 + [vp, C.c_int]
+    L.me_cuda_deblock_frame.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.me_cuda_ref_create_deblocked.argtypes = [C.c_int, C.c_int, vp, C.POINTER(C.c_int32)]
     return L
 
 
@@ -362,6 +367,26 @@ class MeCuda:
         c4, c8 = np.zeros(n, np.int32), np.zeros(n, np.int32)
         self._check(self.L.me_cuda_pred_cost8x8(blocks.ctypes.data, n, metric, c4.ctypes.data, c8.ctypes.data))
         return c4, c8
+
+    def deblock_frame(self, y, u, v, mbs):
+        """DeblockFrame (loopFilter.c:87): y, u, v uint16 (imgpel) planes filtered in place (u, v None: 4:0:0); mbs: DEBLOCK_MB_DTYPE"""
+        assert y.dtype == np.uint16 and y.flags.c_contiguous and mbs.dtype == DEBLOCK_MB_DTYPE and mbs.flags.c_contiguous
+
+        def rows(a):
+            arr = (C.c_void_p * a.shape[0])()
+            for i in range(a.shape[0]):
+                arr[i] = a.ctypes.data + i * a.strides[0]
+            return arr
+        ry = rows(y)
+        ru, rv = (rows(u), rows(v)) if u is not None else (None, None)
+        cw, ch = (u.shape[1], u.shape[0]) if u is not None else (0, 0)
+        self._check(self.L.me_cuda_deblock_frame(ry, ru, rv, y.shape[1], y.shape[0], cw, ch, mbs.ctypes.data))
+
+    def ref_create_deblocked(self):
+        """the plane set of the picture me_cuda_deblock_frame has just filtered, built from the copy that stayed on the device"""
+        h = C.c_int32(0)
+        self._check(self.L.me_cuda_ref_create_deblocked(self.width, self.height, None, C.byref(h)))
+        return h.value
 
     def ref_region(self, h, fy, fx, x0, y0, w, hgt):
         """a rectangle of plane Pic[fy][fx] as imgpel (uint16) rows"""

@@ -7,7 +7,7 @@
  *         --wrap=SubPelBlockSearchBiPred,--wrap=ResetFastFullIntegerSearch,--wrap=getSubImagesLuma,
  *         --wrap=encode_one_frame,--wrap=Init_Motion_Search_Module,--wrap=Clear_Motion_Search_Module,
  *         --wrap=free_storable_picture,--wrap=PartitionMotionSearch,--wrap=BIDPartitionCost,--wrap=GetDirectCost8x8,
- *         --wrap=UMVLine4X,--wrap=FastLine4X
+ *         --wrap=UMVLine4X,--wrap=FastLine4X,--wrap=DeblockFrame
  * so every call site the SearchMode dispatch of mv-search.c reaches (mv-search.c:745, :823, :960, :998, :1018), the
  * per-macroblock reset (macroblock.c:509), the plane generation (image.c:1642) and the module init / clear
  * (lencod.c:255, :387) land here.  Everything else -- predictors (SetMotionVectorPredictor, mv-search.c:87), mode
@@ -20,6 +20,7 @@
  *              ME_CUDA_DISABLE=1 turns the interposer into a pass-through (pure reference behaviour),
  *              ME_CUDA_PMS=0 keeps one device launch per block search (no launch per PartitionMotionSearch call),
  *              ME_CUDA_MC=0 leaves BIDPartitionCost / GetDirectCost8x8 (mv-search.c:1052, :1273) to the reference's host code,
+ *              ME_CUDA_DEBLOCK=0 leaves the in-loop deblocking filter (loopFilter.c:87) to the reference's host code,
  *              ME_CUDA_HOST_PLANES=1 copies all 16 planes of every reference picture back into imgY_sub (70 MB per 1080p picture)
  *              instead of paging in what the host code touches, ME_CUDA_POISON_PLANES=1 fills imgY_sub with a pattern first
  *              (test aid: a host read that bypasses the paging then changes the bitstream).
@@ -37,6 +38,7 @@
 #include "mbuffer.h"
 #include "me_distortion.h"
 #include "refbuf.h"
+#include "mb_access.h"
 
 #include "me_cuda.h"
 
@@ -78,6 +80,8 @@ static struct {
   int  (*pms_stats)(int64_t *, int64_t *, int64_t *);
   int  (*pred_cost8x8)(const me_pred_block *, int, int, int32_t *, int32_t *);
   int  (*ref_download_region)(me_ref_handle, int, int, int, int, int, int, me_imgpel *, int);
+  int  (*deblock_frame)(me_imgpel *const *, me_imgpel *const *, me_imgpel *const *, int, int, int, int, const me_deblock_mb *);
+  int  (*ref_create_deblocked)(int, int, me_imgpel ****, me_ref_handle *);
 } L;
 
 static int active = 0;          /* GPU path in use for this run */
@@ -91,6 +95,10 @@ static long served_bid_cost = 0, served_direct_cost = 0, paged_tiles = 0, paged_
 static int use_mc = 1;          /* BIDPartitionCost / GetDirectCost8x8 on the device (ME_CUDA_MC=0: the reference's host code) */
 static int lazy_planes = 1;     /* imgY_sub paged in on demand (ME_CUDA_HOST_PLANES=1: all planes copied back at creation) */
 static int poison_planes = 0;
+static int use_deblock = 1;     /* DeblockFrame on the device (ME_CUDA_DEBLOCK=0: the reference's host code) */
+static long served_deblock = 0, reused_deblocked = 0;
+static imgpel **deblocked_rows = NULL;   /* the luma rows the device filtered last and still holds */
+static int deblocked_pic = -1;           /* ... during this encode_one_frame call */
 static int pic_counter = 0, pic_uploaded = -1, plane_uploaded = -1;
 
 #define MAX_MAP 64
@@ -154,6 +162,7 @@ static void load_library(void)
   L.pms_begin = sym("me_cuda_pms_begin"); L.pms_cached = sym("me_cuda_pms_cached"); L.pms_end = sym("me_cuda_pms_end");
   L.pms_stats = sym("me_cuda_pms_stats");
   L.pred_cost8x8 = sym("me_cuda_pred_cost8x8"); L.ref_download_region = sym("me_cuda_ref_download_region");
+  L.deblock_frame = sym("me_cuda_deblock_frame"); L.ref_create_deblocked = sym("me_cuda_ref_create_deblocked");
 }
 
 /* 4:4:4 independent mode (SeparateColourPlane = 1, IS_INDEPENDENT, defines.h:224): the three colour planes are coded one after
@@ -226,6 +235,8 @@ void __wrap_Init_Motion_Search_Module(void)
     use_mc = !(getenv("ME_CUDA_MC") && !atoi(getenv("ME_CUDA_MC")));
     lazy_planes = !(getenv("ME_CUDA_HOST_PLANES") && atoi(getenv("ME_CUDA_HOST_PLANES")));
     poison_planes = getenv("ME_CUDA_POISON_PLANES") && atoi(getenv("ME_CUDA_POISON_PLANES"));
+    use_deblock = !(getenv("ME_CUDA_DEBLOCK") && !atoi(getenv("ME_CUDA_DEBLOCK")));
+    deblocked_rows = NULL;
   }
 }
 
@@ -242,6 +253,8 @@ void __wrap_Clear_Motion_Search_Module(void)
             (long long)pl, (long long)ps, (long long)pm);
     fprintf(stderr, "me_cuda shim: mode-decision costs on the device: %ld BIDPartitionCost, %ld GetDirectCost8x8 calls; plane tiles paged to the host: %ld (%ld bytes%s)\n",
             served_bid_cost, served_direct_cost, paged_tiles, paged_bytes, lazy_planes ? "" : "; all planes copied back at creation");
+    fprintf(stderr, "me_cuda shim: pictures deblocked on the device: %ld, reference plane sets built from them without an upload: %ld\n",
+            served_deblock, reused_deblocked);
   }
   else
     fprintf(stderr, "me_cuda shim: pass-through (ME_CUDA_DISABLE): nothing served on the device\n");
@@ -277,7 +290,14 @@ void __wrap_getSubImagesLuma(StorablePicture *s)
   /* the 16 planes are computed on the device and copied into the picture's plane set for the encoder's host-side consumers */
   /* the 16 planes stay on the device; the host's own consumers (OneComponentLumaPrediction, macroblock.c:816, and whatever host
    * search code a SearchMode keeps) reach them through UMVLine4X / FastLine4X, which page in the tiles they are about to read */
-  if (L.ref_create((const me_imgpel *const *)s->p_curr_img, s->size_x, s->size_y, lazy_planes ? NULL : (me_imgpel ****)s->p_curr_img_sub, &h)) die("me_cuda_ref_create");
+  if (lazy_planes && deblocked_rows && deblocked_pic == pic_counter && s->p_curr_img == deblocked_rows && plane == 0 && s->p_curr_img == s->imgY) {
+    /* this is the picture the device has just deblocked (image.c:331 -> store_picture_in_dpb -> UnifiedOneForthPix): its filtered luma
+     * is still there */
+    if (L.ref_create_deblocked(s->size_x, s->size_y, NULL, &h)) die("me_cuda_ref_create_deblocked");
+    reused_deblocked++;
+  }
+  else if (L.ref_create((const me_imgpel *const *)s->p_curr_img, s->size_x, s->size_y, lazy_planes ? NULL : (me_imgpel ****)s->p_curr_img_sub, &h)) die("me_cuda_ref_create");
+  deblocked_rows = NULL;
   if (n_map == MAX_MAP) die("more than 64 reference pictures with device plane sets (decoded picture buffer bookkeeping out of step)");
   served_planes++;
   map[n_map].p = s; map[n_map].plane = plane; map[n_map].h = h; map[n_map].sub = s->p_curr_img_sub;
@@ -794,4 +814,95 @@ int __wrap_GetDirectCost8x8(Macroblock *currMB, int block, int *cost8x8)
     return rc;
   }
   return cost;
+}
+
+/* ---------------------------------------------------------------- in-loop deblocking (loopFilter.c:87, called image.c:331) */
+/* The boundary strengths stay the reference's own: GetStrengthNormal (loopFilter.c:262) reads macroblock modes, coded-block flags,
+ * reference indices and vectors.  This wrapper walks the macroblocks exactly as DeblockFrame / DeblockMb do (loopFilter.c:87-253),
+ * records per macroblock which edges the reference would filter and with which strengths, and hands the edge loops
+ * (EdgeLoopLumaNormal :529, EdgeLoopChromaNormal :814) to the device.  Frame pictures without MBAFF, 8 bit, 4:0:0 / 4:2:0; anything
+ * else runs the reference's host filter. */
+extern void GetStrengthNormal(byte Strength[16], ImageParameters *img, int MbQAddr, int dir, int edge, int mvlimit);
+void __real_DeblockFrame(ImageParameters *p_img, imgpel **imgY, imgpel ***imgUV);
+void __wrap_DeblockFrame(ImageParameters *p_img, imgpel **imgY, imgpel ***imgUV)
+{
+  static me_deblock_mb *mbs = NULL;
+  static unsigned mbs_cap = 0;
+  unsigned i;
+  int chroma = imgUV != NULL && p_img->yuv_format == YUV420;
+  if (!active || !use_deblock || p_img->MbaffFrameFlag || p_img->structure != FRAME || p_img->max_imgpel_value != 255 ||
+      (p_img->yuv_format != YUV420 && p_img->yuv_format != YUV400) || (p_img->width & 15) || (p_img->height & 15)) {
+    __real_DeblockFrame(p_img, imgY, imgUV);
+    return;
+  }
+  if (mbs_cap < p_img->PicSizeInMbs) {
+    free(mbs);
+    mbs = malloc(sizeof(me_deblock_mb) * p_img->PicSizeInMbs);
+    if (!mbs) die("out of memory (deblocking records)");
+    mbs_cap = p_img->PicSizeInMbs;
+  }
+  memset(mbs, 0, sizeof(me_deblock_mb) * p_img->PicSizeInMbs);
+  for (i = 0; i < p_img->PicSizeInMbs; i++)                    /* loopFilter.c:105-113 */
+    if (p_img->mb_data[i].mb_type == IPCM) { p_img->mb_data[i].qp = 0; p_img->mb_data[i].qpc[0] = 0; p_img->mb_data[i].qpc[1] = 0; }
+  for (i = 0; i < p_img->PicSizeInMbs; i++) {                  /* DeblockMb, loopFilter.c:128-253, up to the edge loops */
+    Macroblock *MbQ = &p_img->mb_data[i];
+    me_deblock_mb *r = &mbs[i];
+    byte Strength[16];
+    int mb_x, mb_y, dir, edge, k, left, top, non8x8;
+    r->qp = (int8_t)MbQ->qp; r->qpc[0] = (int8_t)MbQ->qpc[0]; r->qpc[1] = (int8_t)MbQ->qpc[1];
+    r->alpha_off = (int8_t)MbQ->LFAlphaC0Offset; r->beta_off = (int8_t)MbQ->LFBetaOffset;
+    p_img->DeblockCall = 1;
+    get_mb_pos((int)i, &mb_x, &mb_y, IS_LUMA);
+    left = mb_x != 0; top = mb_y != 0;
+    non8x8 = !MbQ->luma_transform_size_8x8_flag;
+    if (MbQ->LFDisableIdc == 1) { p_img->DeblockCall = 0; continue; }
+    if (MbQ->LFDisableIdc == 2) { left = MbQ->mbAvailA; top = MbQ->mbAvailB; }
+    p_img->current_mb_nr = (int)i;
+    CheckAvailabilityOfNeighbors(MbQ);
+    for (dir = 0; dir < 2; dir++) {
+      int EdgeCondition = (dir && top) || (!dir && left);
+      for (edge = 0; edge < 4; edge++) {
+        int sum = 0;
+        if (!(edge || EdgeCondition)) continue;
+        GetStrengthNormal(Strength, p_img, (int)i, dir, edge << 2, 4);
+        for (k = 0; k < 16; k++) sum += Strength[k];
+        if (!sum) continue;
+        memcpy(r->strength[dir][edge], Strength, 16);
+        if ((edge & 1) && !non8x8) r->luma_skip |= (uint8_t)(1u << (4 * dir + edge));
+      }
+    }
+    p_img->DeblockCall = 0;
+  }
+  if (verify) {
+    /* the reference filter on copies, compared sample by sample with what the device returns; the reference result is kept */
+    int w = p_img->width, h = p_img->height, cw = p_img->width_cr, ch = p_img->height_cr, y, c, bad = 0;
+    imgpel *cy = malloc(sizeof(imgpel) * (size_t)w * h), *cc = chroma ? malloc(sizeof(imgpel) * (size_t)cw * ch * 2) : NULL;
+    if (!cy || (chroma && !cc)) die("out of memory (verify)");
+    for (y = 0; y < h; y++) memcpy(cy + (size_t)y * w, imgY[y], sizeof(imgpel) * (size_t)w);
+    for (c = 0; c < (chroma ? 2 : 0); c++) for (y = 0; y < ch; y++) memcpy(cc + ((size_t)c * ch + y) * cw, imgUV[c][y], sizeof(imgpel) * (size_t)cw);
+    __real_DeblockFrame(p_img, imgY, imgUV);
+    {
+      imgpel **ry = malloc(sizeof(imgpel *) * (size_t)h), **ru = NULL, **rv = NULL;
+      for (y = 0; y < h; y++) ry[y] = cy + (size_t)y * w;
+      if (chroma) {
+        ru = malloc(sizeof(imgpel *) * (size_t)ch); rv = malloc(sizeof(imgpel *) * (size_t)ch);
+        for (y = 0; y < ch; y++) { ru[y] = cc + (size_t)y * cw; rv[y] = cc + ((size_t)ch + y) * cw; }
+      }
+      if (L.deblock_frame((me_imgpel *const *)ry, (me_imgpel *const *)ru, (me_imgpel *const *)rv, w, h, cw, ch, mbs)) die("me_cuda_deblock_frame");
+      for (y = 0; y < h; y++) if (memcmp(ry[y], imgY[y], sizeof(imgpel) * (size_t)w)) bad++;
+      for (c = 0; c < (chroma ? 2 : 0); c++) for (y = 0; y < ch; y++) if (memcmp((c ? rv : ru)[y], imgUV[c][y], sizeof(imgpel) * (size_t)cw)) bad++;
+      free(ry); free(ru); free(rv);
+    }
+    n_checked++;
+    if (bad) { n_mismatch++; fprintf(stderr, "VERIFY DeblockFrame pic %d: %d sample rows differ\n", pic_counter, bad); }
+    free(cy); free(cc);
+    served_deblock++;
+    deblocked_rows = bad ? NULL : imgY; deblocked_pic = pic_counter;
+    return;
+  }
+  if (L.deblock_frame((me_imgpel *const *)imgY, chroma ? (me_imgpel *const *)imgUV[0] : NULL, chroma ? (me_imgpel *const *)imgUV[1] : NULL,
+                      p_img->width, p_img->height, p_img->width_cr, p_img->height_cr, mbs))
+    die("me_cuda_deblock_frame");
+  served_deblock++;
+  deblocked_rows = imgY; deblocked_pic = pic_counter;
 }

@@ -304,6 +304,26 @@ int me_cuda_pred_cost8x8(const me_pred_block *blocks, int n_regions, int metric,
  * the binding pages the planes into StorablePicture::imgY_sub on demand with it instead of copying them all back */
 int me_cuda_ref_download_region(me_ref_handle h, int fy, int fx, int x0, int y0, int w, int hgt, me_imgpel *dst, int dst_stride);
 
+/* ---- in-loop deblocking of the coded picture: DeblockFrame (loopFilter.c:87-253) for frame pictures
+ * without MBAFF, 8-bit, 4:0:0 / 4:2:0.  The boundary strengths are the encoder's own (GetStrength, loopFilter.c:262): per macroblock
+ * and (direction 0 = vertical edges / 1 = horizontal, edge 0..3) the 16 values DeblockMb got for the edges it filters, zeros for the
+ * edges it does not (picture / slice boundary, LFDisableIdc, all-zero strengths). ---- */
+typedef struct me_deblock_mb {
+  uint8_t strength[2][4][16];
+  int8_t  qp, qpc[2];                   /* Macroblock::qp, ::qpc[0..1] (0 for IPCM, loopFilter.c:105-113) */
+  int8_t  alpha_off, beta_off;          /* LFAlphaC0Offset, LFBetaOffset */
+  uint8_t luma_skip;                    /* bit 4 * dir + edge: the luma edge is not filtered (8x8 transform, filterNon8x8LumaEdgesFlag,
+                                           loopFilter.c:154-155) although the strengths are set for the chroma edge */
+  uint8_t reserved[10];
+} me_deblock_mb;                        /* 144 bytes */
+
+/* filters the picture in place (rows of imgpel; u_rows / v_rows NULL for 4:0:0): mbs holds (w / 16) * (h / 16) records in raster order.
+ * The filtered luma also stays on the device: me_cuda_ref_create_deblocked builds the plane set of the stored reference picture
+ * from it without another upload (the caller guarantees the picture has not changed in between).  Synchronous. */
+int me_cuda_deblock_frame(me_imgpel *const *y_rows, me_imgpel *const *u_rows, me_imgpel *const *v_rows, int w, int h, int cw, int ch,
+                          const me_deblock_mb *mbs);
+int me_cuda_ref_create_deblocked(int w, int h, me_imgpel ****host_sub, me_ref_handle *out);
+
 /* ---- device-resident variants for measurement (bench.py): pointers are CUDA device pointers, `stream` is a
  * cudaStream_t passed as void* (NULL = the library's own stream).  Asynchronous.  A caller's stream is ordered against the
  * library stream by events on both sides of the call, so the program order of the calls is the order on the device even

@@ -101,6 +101,7 @@ def lib():
         L.ora_mb_search.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, vp]
         L.ora_mb_bipred.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         L.ora_luma_prediction.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+        L.ora_deblock_frame.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         L.ora_get_skip_cost_mb.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
         L.ora_get_direct_cost8x8.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, ip]
         L.ora_bid_partition_cost.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -340,3 +341,23 @@ def bid_partition_cost(cur, list0, list1, blocks16, pmv16, blocktype, block8x8, 
     a0, a1 = _ref_array(list0), _ref_array(list1)
     return lib().ora_bid_partition_cost(cur.ctypes.data, cur.strides[0], a0, a1, b.ctypes.data, pm.ctypes.data, blocktype, block8x8,
                                         lambda_factor, transform8x8, metric)
+
+
+# ---- deblocking (me_oracle.c: ora_deblock_frame)
+DEBLOCK_MB_DTYPE = np.dtype([("strength", "u1", (2, 4, 16)), ("qp", "i1"), ("qpc", "i1", (2,)), ("alpha_off", "i1"), ("beta_off", "i1"),
+                             ("luma_skip", "u1"), ("reserved", "u1", (10,))])
+assert DEBLOCK_MB_DTYPE.itemsize == 144
+
+
+def deblock_frame(y, u, v, mbs):
+    """DeblockFrame (loopFilter.c:87) on copies of the planes (uint8); u, v None for 4:0:0 -> filtered (y, u, v)"""
+    y = np.array(y, np.uint8, order="C")
+    h, w = y.shape
+    mbs = np.ascontiguousarray(mbs, DEBLOCK_MB_DTYPE)
+    assert len(mbs) == (w // 16) * (h // 16)
+    if u is None:
+        lib().ora_deblock_frame(y.ctypes.data, y.strides[0], None, None, 0, w, h, mbs.ctypes.data)
+        return y, None, None
+    u, v = np.array(u, np.uint8, order="C"), np.array(v, np.uint8, order="C")
+    lib().ora_deblock_frame(y.ctypes.data, y.strides[0], u.ctypes.data, v.ctypes.data, u.strides[0], w, h, mbs.ctypes.data)
+    return y, u, v

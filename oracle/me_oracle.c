@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <stddef.h>
 #include "me_oracle.h"
 
 #define PAD ME_IMG_PAD
@@ -990,4 +991,113 @@ int ora_bid_partition_cost(const uint8_t *cur, int cur_stride, const ora_ref *co
         mcost += ora_distortion8x8(metric, diff64);
       }
   return mcost;
+}
+
+/* ------------------------------------------------------------------------------------------------ deblocking */
+
+static const uint8_t DB_ALPHA[52] = { 0,0,0,0,0,0,0,0,0,0,0,0, 0,0,0,0,4,4,5,6, 7,8,9,10,12,13,15,17, 20,22,25,28,32,36,40,45, 50,56,63,71,80,90,101,113,
+                                      127,144,162,182,203,226,255,255 };                                   /* loopFilter.c:42 */
+static const uint8_t DB_BETA[52] = { 0,0,0,0,0,0,0,0,0,0,0,0, 0,0,0,0,2,2,2,3, 3,3,3,4,4,4,6,6, 7,7,8,8,9,9,10,10, 11,11,12,12,13,13,14,14,
+                                     15,15,16,16,17,17,18,18 };                                            /* loopFilter.c:43 */
+static const uint8_t DB_CLIP[52][5] = {                                                                     /* loopFilter.c:44-53 */
+  {0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},
+  {0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},{0,0,0,0,0},
+  {0,0,0,0,0},{0,0,0,1,1},{0,0,0,1,1},{0,0,0,1,1},{0,0,0,1,1},{0,0,1,1,1},{0,0,1,1,1},{0,1,1,1,1},
+  {0,1,1,1,1},{0,1,1,1,1},{0,1,1,1,1},{0,1,1,2,2},{0,1,1,2,2},{0,1,1,2,2},{0,1,1,2,2},{0,1,2,3,3},
+  {0,1,2,3,3},{0,2,2,3,3},{0,2,2,4,4},{0,2,3,4,4},{0,2,3,4,4},{0,3,3,5,5},{0,3,4,6,6},{0,3,4,6,6},
+  {0,4,5,7,7},{0,4,5,8,8},{0,4,6,9,9},{0,5,7,10,10},{0,6,8,11,11},{0,6,8,13,13},{0,7,10,14,14},{0,8,11,16,16},
+  {0,9,12,18,18},{0,10,13,20,20},{0,11,15,23,23},{0,13,17,25,25} };
+
+/* EdgeLoopLumaNormal (loopFilter.c:529-672) for one edge of 16 lines: q0 = first sample on the Q side of line 0, `step` from line to
+ * line, `inc` across the edge (1 for a vertical edge, the pitch for a horizontal one) */
+static void edge_loop_luma(uint8_t *q0, ptrdiff_t step, ptrdiff_t inc, const uint8_t *strength, int qp_p, int qp_q, int alpha_off, int beta_off)
+{
+  const int QP = (qp_p + qp_q + 1) >> 1;
+  const int indexA = clampi(QP + alpha_off, 0, 51), indexB = clampi(QP + beta_off, 0, 51);
+  const int Alpha = DB_ALPHA[indexA], Beta = DB_BETA[indexB];
+  int pel;
+  for (pel = 0; pel < 16; pel++) {
+    uint8_t *Q = q0 + pel * step, *P = Q - inc;
+    const int Strng = strength[pel];
+    int L3, L2, L1, L0, R0, R1, R2, R3, Delta, AbsDelta, C0;
+    if (!Strng) continue;
+    L3 = P[-inc * 3]; L2 = P[-inc * 2]; L1 = P[-inc]; L0 = P[0]; R0 = Q[0]; R1 = Q[inc]; R2 = Q[inc * 2]; R3 = Q[inc * 3];
+    Delta = R0 - L0; AbsDelta = iabs_(Delta);
+    if (AbsDelta >= Alpha) continue;
+    C0 = DB_CLIP[indexA][Strng];
+    if (!(((iabs_(R0 - R1) - Beta) & (iabs_(L0 - L1) - Beta)) < 0)) continue;
+    if (Strng == 4) {
+      const int RL0 = L0 + R0, small_gap = AbsDelta < ((Alpha >> 2) + 2);
+      const int aq = (iabs_(R0 - R2) < Beta) & small_gap, ap = (iabs_(L0 - L2) < Beta) & small_gap;
+      if (ap) { P[-inc * 2] = (uint8_t)((((L3 + L2) << 1) + L2 + L1 + RL0 + 4) >> 3); P[-inc] = (uint8_t)((L2 + L1 + L0 + R0 + 2) >> 2);
+                P[0] = (uint8_t)((R1 + ((L1 + RL0) << 1) + L2 + 4) >> 3); }
+      else P[0] = (uint8_t)(((L1 << 1) + L0 + R1 + 2) >> 2);
+      if (aq) { Q[0] = (uint8_t)((L1 + ((R1 + RL0) << 1) + R2 + 4) >> 3); Q[inc] = (uint8_t)((R2 + R0 + R1 + L0 + 2) >> 2);
+                Q[inc * 2] = (uint8_t)((((R3 + R2) << 1) + R2 + R1 + RL0 + 4) >> 3); }
+      else Q[0] = (uint8_t)(((R1 << 1) + R0 + L1 + 2) >> 2);
+    } else {
+      const int RL0 = (L0 + R0 + 1) >> 1, aq = iabs_(R0 - R2) < Beta, ap = iabs_(L0 - L2) < Beta;
+      const int c0 = C0 + ap + aq, dif = clampi(((Delta << 2) + (L1 - R1) + 4) >> 3, -c0, c0);
+      if (ap) P[-inc] = (uint8_t)(L1 + clampi((L2 + RL0 - (L1 << 1)) >> 1, -C0, C0));
+      P[0] = (uint8_t)clampi(L0 + dif, 0, 255);
+      Q[0] = (uint8_t)clampi(R0 - dif, 0, 255);
+      if (aq) Q[inc] = (uint8_t)(R1 + clampi((R2 + RL0 - (R1 << 1)) >> 1, -C0, C0));
+    }
+  }
+}
+
+/* EdgeLoopChromaNormal (loopFilter.c:814-921), 4:2:0: eight lines, strength index ((pel >> 1) << 2) + (pel & 1) */
+static void edge_loop_chroma(uint8_t *q0, ptrdiff_t step, ptrdiff_t inc, const uint8_t *strength, int qpc_p, int qpc_q, int alpha_off, int beta_off)
+{
+  const int QP = (qpc_p + qpc_q + 1) >> 1;
+  const int indexA = clampi(QP + alpha_off, 0, 51), indexB = clampi(QP + beta_off, 0, 51);
+  const int Alpha = DB_ALPHA[indexA], Beta = DB_BETA[indexB];
+  int pel;
+  for (pel = 0; pel < 8; pel++) {
+    uint8_t *Q = q0 + pel * step, *P = Q - inc;
+    const int Strng = strength[((pel >> 1) << 2) + (pel & 1)];
+    int L1, L0, R0, R1, Delta;
+    if (!Strng) continue;
+    L1 = P[-inc]; L0 = P[0]; R0 = Q[0]; R1 = Q[inc];
+    Delta = R0 - L0;
+    if (iabs_(Delta) >= Alpha) continue;
+    if (!(((iabs_(R0 - R1) - Beta) & (iabs_(L0 - L1) - Beta)) < 0)) continue;
+    if (Strng == 4) { Q[0] = (uint8_t)(((R1 << 1) + R0 + L1 + 2) >> 2); P[0] = (uint8_t)(((L1 << 1) + L0 + R1 + 2) >> 2); }
+    else {
+      const int c0 = DB_CLIP[indexA][Strng] + 1, dif = clampi(((Delta << 2) + (L1 - R1) + 4) >> 3, -c0, c0);
+      P[0] = (uint8_t)clampi(L0 + dif, 0, 255);
+      Q[0] = (uint8_t)clampi(R0 - dif, 0, 255);
+    }
+  }
+}
+
+/* DeblockFrame / DeblockMb (loopFilter.c:87-253) with the boundary strengths given (me_deblock_mb): macroblocks in raster order,
+ * vertical edges then horizontal ones, luma then the two chroma components per edge.  u, v NULL: 4:0:0 */
+void ora_deblock_frame(uint8_t *y, int ystride, uint8_t *u, uint8_t *v, int cstride, int w, int h, const me_deblock_mb *mbs)
+{
+  const int mbw = w / 16, mbh = h / 16;
+  int my, mx, dir, e, k;
+  for (my = 0; my < mbh; my++)
+    for (mx = 0; mx < mbw; mx++) {
+      const me_deblock_mb *Q = &mbs[my * mbw + mx];
+      for (dir = 0; dir < 2; dir++)
+        for (e = 0; e < 4; e++) {
+          const uint8_t *s = Q->strength[dir][e];
+          const me_deblock_mb *P = Q;
+          int sum = 0;
+          for (k = 0; k < 16; k++) sum += s[k];
+          if (!sum) continue;                                                       /* loopFilter.c:187-193 */
+          if (e == 0 && (dir ? my > 0 : mx > 0)) P = dir ? Q - mbw : Q - 1;           /* MbP: the neighbour across a macroblock edge */
+          if (!((Q->luma_skip >> (4 * dir + e)) & 1)) {
+            if (dir) edge_loop_luma(y + (size_t)(16 * my + 4 * e) * ystride + 16 * mx, 1, ystride, s, P->qp, Q->qp, Q->alpha_off, Q->beta_off);
+            else edge_loop_luma(y + (size_t)(16 * my) * ystride + 16 * mx + 4 * e, ystride, 1, s, P->qp, Q->qp, Q->alpha_off, Q->beta_off);
+          }
+          if (u && v && !(e & 1))                                                   /* chroma_edge[dir][edge][YUV420] = 0, -4, 4, -4 */
+            for (k = 0; k < 2; k++) {
+              uint8_t *c = k ? v : u;
+              if (dir) edge_loop_chroma(c + (size_t)(8 * my + 2 * e) * cstride + 8 * mx, 1, cstride, s, P->qpc[k], Q->qpc[k], Q->alpha_off, Q->beta_off);
+              else edge_loop_chroma(c + (size_t)(8 * my) * cstride + 8 * mx + 2 * e, cstride, 1, s, P->qpc[k], Q->qpc[k], Q->alpha_off, Q->beta_off);
+            }
+        }
+    }
 }

@@ -138,6 +138,10 @@ int  ora_bid_partition_cost(const uint8_t *cur, int cur_stride, const ora_ref *c
                             const me_pred_block *blocks, const int16_t (*pmv)[2][2], int blocktype, int block8x8,
                             int lambda_factor, int transform8x8, int metric);
 
+/* ---- DeblockFrame (loopFilter.c:87-253) with the boundary strengths given per macroblock (include/me_cuda.h: me_deblock_mb);
+ * frame pictures, no MBAFF, 8 bit, 4:2:0 (u, v non-NULL) or 4:0:0.  In place. */
+void ora_deblock_frame(uint8_t *y, int ystride, uint8_t *u, uint8_t *v, int cstride, int w, int h, const me_deblock_mb *mbs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,7 @@ def _prep(tmp):
 def _run(exe, args, cwd, env=None):
     e = dict(os.environ)
     e["ME_CUDA_LIB"] = os.path.join(ROOT, "h.264_b200", "libme_cuda.so")
-    for k in ("ME_CUDA_DISABLE", "ME_CUDA_VERIFY", "ME_CUDA_PMS", "ME_CUDA_MC", "ME_CUDA_HOST_PLANES", "ME_CUDA_POISON_PLANES"):       # a stray switch must not turn the comparison into reference-vs-reference
+    for k in ("ME_CUDA_DISABLE", "ME_CUDA_VERIFY", "ME_CUDA_PMS", "ME_CUDA_MC", "ME_CUDA_HOST_PLANES", "ME_CUDA_POISON_PLANES", "ME_CUDA_DEBLOCK"):       # a stray switch must not turn the comparison into reference-vs-reference
         e.pop(k, None)
     if env:
         e.update(env)
@@ -62,6 +62,9 @@ def _served(stderr, want=("plane sets",)):
     q = re.search(r"mode-decision costs on the device: (\d+) BIDPartitionCost, (\d+) GetDirectCost8x8 calls; plane tiles paged to the host: (\d+) \((\d+) bytes", stderr)
     assert q, stderr[-800:]
     c["bid_cost"], c["direct_cost"], c["paged_tiles"], c["paged_bytes"] = map(int, q.groups())
+    d = re.search(r"pictures deblocked on the device: (\d+), reference plane sets built from them without an upload: (\d+)", stderr)
+    assert d, stderr[-800:]
+    c["deblocked"], c["deblocked_reused"] = map(int, d.groups())
     for k in want:
         assert c[k] > 0, (k, c)
     return c
@@ -72,7 +75,7 @@ def test_known_answer_bitstream_is_byte_identical(tmp_path, me_lib_path):
     """bin/encoder.cfg: the run behind the reference's committed bin/test.264 / bin/test_rec.yuv"""
     _prep(str(tmp_path))
     _, err = _run("lencod_cuda", ["-d", "encoder.cfg"], str(tmp_path))
-    c = _served(err, ("plane sets", "ffs", "subpel", "bi_full", "bi_sub", "bid_cost", "paged_tiles"))
+    c = _served(err, ("plane sets", "ffs", "subpel", "bi_full", "bi_sub", "bid_cost", "paged_tiles", "deblocked", "deblocked_reused"))
     assert c["pms_launches"] > 0 and c["pms_served"] > 0, c
     # the planes stayed on the device: the host paged in what it read, tile by tile, never more than the 16 x 216 x 184 samples x 2 bytes
     # per reference picture a copy-back would have moved (on this QCIF clip most tiles are touched; at 1080p a small share is)
@@ -102,15 +105,15 @@ def test_mode_decision_costs_and_paged_planes(tmp_path, me_lib_path, args, want)
     _run("lencod", args, str(b))
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
     assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
-    c = _served(err, ("plane sets", "paged_tiles", want))
+    c = _served(err, ("plane sets", "paged_tiles", "deblocked", want))
     _, err = _run("lencod_cuda", args, str(a), env={"ME_CUDA_VERIFY": "1"})
     m = re.search(r"verify mode: (\d+) calls checked, (\d+) mismatches", err)
     assert m and int(m.group(1)) > c["bid_cost"] + c["direct_cost"] and int(m.group(2)) == 0, err[-1500:]
     # the same run with the two switches off: reference host code for the costs, all planes copied back -- same output
-    _, err = _run("lencod_cuda", args, str(a), env={"ME_CUDA_MC": "0", "ME_CUDA_HOST_PLANES": "1"})
+    _, err = _run("lencod_cuda", args, str(a), env={"ME_CUDA_MC": "0", "ME_CUDA_HOST_PLANES": "1", "ME_CUDA_DEBLOCK": "0"})
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
     c0 = _served(err, ("plane sets",))
-    assert c0["bid_cost"] == 0 and c0["direct_cost"] == 0 and c0["paged_tiles"] == 0, c0
+    assert c0["bid_cost"] == 0 and c0["direct_cost"] == 0 and c0["paged_tiles"] == 0 and c0["deblocked"] == 0, c0
 
 
 @pytest.mark.skipif(not _have(), reason="oracle/_ref/lencod_cuda not built")
