@@ -450,7 +450,7 @@ def main():
     peaks = {}
     if rank == 0:
         names = {0: "vabsdiff4", 2: "imad", 3: "viaddmnmx", 5: "shf", 9: "vabsdiff4+imad", 10: "vabsdiff4+viaddmnmx",
-                 15: "vabsdiff4+lds"}
+                 15: "vabsdiff4+lds", 18: "sweep_mix_32vabsdiff4_21addmin_33imad"}
         for k, nm in names.items():
             peaks[nm] = me.measure_int_peak(k) / 1e9
     ffs_avg_ms = ffs_ms / max(1, ffs_n)
@@ -476,6 +476,10 @@ def main():
                 "algorithmic_laneops_per_job": "212 * (2R+1)^2 = 64 SAD + 25 larger-block adds + 3*41 cost ops per position (SURVEY.md 8d)",
                 "kernel_ms": ffs_avg_ms,
                 "frac_of_alu_pipe_alone": (achieved / peaks["vabsdiff4"]) if (achieved and peaks) else None,
+                # what a dependency-free stream of the sweep's own arithmetic (32 VABSDIFF4 : 21 add+min : 33 IMAD per window row) issues on
+                # this GPU: the two pipes do not overlap fully (register-file reads, profiles/r02_ffs_ceiling.md) -- the practical ceiling
+                "sweep_mix_issue_ceiling_glaneops": peaks.get("sweep_mix_32vabsdiff4_21addmin_33imad") if peaks else None,
+                "frac_of_sweep_mix_ceiling": (achieved / peaks["sweep_mix_32vabsdiff4_21addmin_33imad"]) if (achieved and peaks) else None,
                 "sad_only_frac_of_alu_pipe": (SAD_OPS_PER_JOB * n_jobs / (ffs_avg_ms * 1e-3) / 1e9 / peaks["vabsdiff4"]) if (ffs_n and peaks) else None,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (ffs_avg_ms * 1e-3) / 1e9 if ffs_n else None,
                         "peak_gbs": mp.get("hbm_gbs", 6650.0), "peak_source": "MEASURED_PEAKS.json" if mp else "fallback"},

@@ -101,6 +101,7 @@ me_ffs_batch_basic_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRe
                           const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                           MeResultInt *__restrict__ out, const int *__restrict__ job_list)
 {
+  if (cfg.abort_flag && *cfg.abort_flag) return;
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t curw[64];
   __shared__ unsigned long long red[8][ME_NUM_PARTITIONS];
@@ -260,4 +261,27 @@ extern "C" void me_launch_ffs_block(const int32_t *surf_p, int setup_range, int 
 {
   me_ffs_block_kernel<<<1, 256, 0, st>>>(surf_p, setup_range, offx, offy, pmv_x, pmv_y, search_range, min_mcost, lambda,
                                          rdopt, result, ticket);
+}
+
+
+// Validation of a job array the host has not read (pinned caller memory handed straight to the kernels): the fields the search
+// kernels index with.  *bad = 1 + index of the first offending job (0: all fine).
+__global__ void __launch_bounds__(256)
+me_check_jobs_kernel(const MeJob *__restrict__ jobs, int n_jobs, int n_refs0, int n_refs1, int width, int height, int *bad)
+{
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_jobs; i += gridDim.x * blockDim.x) {
+    const uint32_t w0 = reinterpret_cast<const uint32_t *>(&jobs[i])[0], w1 = reinterpret_cast<const uint32_t *>(&jobs[i])[1];
+    const int ox = (int)(int16_t)(w0 & 0xffffu), oy = (int)(int16_t)(w0 >> 16);
+    const int list = (int)(int8_t)(w1 & 0xffu), ref = (int)(int8_t)((w1 >> 8) & 0xffu);
+    const bool ok = list >= 0 && list <= 1 && ref >= 0 && ref < (list ? n_refs1 : n_refs0) &&
+                    ox >= 0 && oy >= 0 && ox + 16 <= width && oy + 16 <= height && !(ox & 15) && !(oy & 15);
+    if (!ok) atomicCAS(bad, 0, i + 1);
+  }
+}
+
+extern "C" void me_launch_check_jobs(const MeJob *jobs, int n_jobs, int n_refs0, int n_refs1, int width, int height, int *bad, cudaStream_t st)
+{
+  int grid = (n_jobs + 255) / 256;
+  if (grid > 148 * 4) grid = 148 * 4;
+  me_check_jobs_kernel<<<grid, 256, 0, st>>>(jobs, n_jobs, n_refs0, n_refs1, width, height, bad);
 }

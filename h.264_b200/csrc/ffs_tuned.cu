@@ -396,6 +396,7 @@ me_ffs_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRefDe
   // static stride the CTAs of an SM finish at different times -- the warp schedulers favour one of the resident warps -- and
   // the last ones run alone at a third of the issue rate (ncu, round 1: 2.6 of 3 resident warps on average).
   if ((int)blockIdx.x >= n_jobs) return;
+  if (cfg.abort_flag && *cfg.abort_flag) return;          // a job failed validation (me_check_jobs_kernel): nothing is searched
 
   // ---- once per CTA: spiral table, barriers, first two job descriptors, first window
   for (int i = tid; i < SIDE * SIDE; i += NT) {

@@ -14,6 +14,9 @@
 //      registers from the register file -- kind 9 fetches three per instruction (two distinct per chain + a shared one) and is
 //      bound by the two register-file banks, not by the pipes (see profiles/r02_int_peak.md)
 //   17 the same with VIADDMNMX in place of the IMAD (both on the ALU pipe)
+//   18 the arithmetic of one window row of the search kernel's sweep, dependency-free: 32 VABSDIFF4.ACC : 21 add+min : 33 IMAD
+//      (immediate multiplier).  What this mix reaches (0.73 instructions per cycle and scheduler on B200, at any occupancy:
+//      register-file reads, profiles/r02_ffs_ceiling.md) is the practical ceiling of the sweep, below the sum of the two pipes
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -93,6 +96,45 @@ int_peak_reuse_kernel(uint32_t *out, int iters, uint32_t s1, uint32_t s2)
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// kind 18: one window row per step (tools/probe/pipe_probe.cu, mix 11)
+__global__ void __launch_bounds__(128)
+int_peak_sweep_mix_kernel(uint32_t *out, int iters, uint32_t s1, uint32_t s2)
+{
+  uint32_t acc[32], cur[8], key[21];
+#pragma unroll
+  for (int k = 0; k < 32; k++) acc[k] = k * s1;
+#pragma unroll
+  for (int k = 0; k < 8; k++) cur[k] = threadIdx.x * 2654435761u + k * 40503u + s1;
+#pragma unroll
+  for (int k = 0; k < 21; k++) key[k] = cur[k % 8] ^ (s2 + k);
+  uint32_t ref = s1 ^ threadIdx.x, best = 0xffffffffu;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(ref), "r"(cur[k % 8]));
+        asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc[16 + k]) : "r"(best), "r"(cur[k % 8]));
+      }
+#pragma unroll
+      for (int k = 0; k < 21; k++) {
+        asm volatile("mad.lo.u32 %0, %0, 4225, %1;" : "+r"(key[k]) : "r"(ref));
+        asm volatile("{.reg .u32 t; add.u32 t, %1, %2; min.u32 %0, t, %0;}" : "+r"(key[(k + 7) % 21]) : "r"(cur[k % 8]), "r"(ref));
+      }
+#pragma unroll
+      for (int k = 0; k < 12; k++) asm volatile("mad.lo.u32 %0, %0, 4225, %1;" : "+r"(key[(k + 3) % 21]) : "r"(best));
+      ref += 0x01010101u;
+    }
+  }
+  uint32_t s = best;
+#pragma unroll
+  for (int k = 0; k < 32; k++) s += acc[k];
+#pragma unroll
+  for (int k = 0; k < 21; k++) s += key[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <int KIND>
 static double run_kind(uint32_t *d_out, int blocks, int iters)
 {
@@ -126,6 +168,22 @@ extern "C" int me_cuda_measure_int_peak(int kind, double *lane_ops_per_s)
 #define K(n) case n: r = run_kind<n>(d_out, blocks, iters); break;
     K(0) K(1) K(2) K(3) K(4) K(5) K(6) K(7) K(8) K(9) K(10) K(11) K(12) K(13) K(14) K(15) K(16) K(17)
 #undef K
+    case 18: {
+      // three CTAs of 128 threads per SM like the search kernel; 86 instructions per step and thread, 4 steps per iteration
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      const int b = sms * 3, it = 2048;
+      int_peak_sweep_mix_kernel<<<b, 128>>>(d_out, it / 8, 12345u, 777u);
+      cudaEventRecord(e0);
+      int_peak_sweep_mix_kernel<<<b, 128>>>(d_out, it, 12345u, 777u);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      r = (double)b * 128.0 * (double)it * 4.0 * 86.0 / (ms * 1e-3);
+      break;
+    }
     default: cudaFree(d_out); return 1;
   }
   cudaError_t e = cudaDeviceSynchronize();

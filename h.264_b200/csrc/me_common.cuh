@@ -46,6 +46,9 @@ struct MeCfgDev {
   int mv_limit_min_y, mv_limit_max_y;
   int start_hp, start_qp;       // start_me_refinement_hp/qp (mv-search.c:396-397)
   MeChromaDev chroma;
+  // frame batch on caller memory the host has not read (pinned arrays handed through): a validation kernel in front of the searches
+  // stores 1 + the index of the first job with a field outside what the kernels index with; the batch kernels then return at once
+  const int *abort_flag;        // nullptr: jobs validated on the host
 };
 
 // partition tables (order documented in include/me_cuda.h)

@@ -40,6 +40,7 @@ extern "C" {
 void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t *planes, int pitch, size_t plane_stride,
                       uint8_t *search, int spad, int spitch, cudaStream_t st);
 void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp, uint16_t *dst, cudaStream_t st);
+void me_launch_check_jobs(const MeJob *jobs, int n_jobs, int n_refs0, int n_refs1, int width, int height, int *bad, cudaStream_t st);
 void me_launch_luma_prediction(const void *blocks, int n, int bsx, int bsy, const MeRefDev *table, uint8_t *pred, cudaStream_t st);
 void me_launch_pred_cost8x8(const void *blocks, int n_regions, int metric, const MeRefDev *table, const uint8_t *cur, int cur_pitch,
                             int32_t *cost4, int32_t *cost8, cudaStream_t st);
@@ -1358,10 +1359,21 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
     };
     void *dj = zero_copy ? dev_ptr(jobs) : nullptr, *dout = dj ? dev_ptr(out) : nullptr, *dint = (dout && out_int) ? dev_ptr(out_int) : nullptr;
     if (dj && dout && (!out_int || dint)) {
-      if (int rc = check_jobs(jobs, 0, n_jobs)) return rc;
+      // the host does not touch the job array either: a small kernel in front of the searches checks the fields they index with
+      // (the check_jobs() of the copying path) and the batch kernels return at once when it objects
+      volatile int *bad = g.h_result + 8;                              // mapped pinned, beside the drop-in result words
+      *bad = 0;
+      me_launch_check_jobs((const MeJob *)dj, n_jobs, g.list_n[0], g.list_n[1], g.p.width, g.p.height, g.d_result + 8, g.stream);
+      g.launches++;
+      g.cfg.abort_flag = g.d_result + 8;
       int rc = me_cuda_frame_search_device(dj, n_jobs, dout, dint, g.stream);
+      g.cfg.abort_flag = nullptr;
       cudaError_t e = cudaStreamSynchronize(g.stream);               // whatever happened, nothing touches the caller's buffers after return
       if (!rc && e != cudaSuccess) rc = fail(2, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+      if (!rc && *bad) {
+        const me_mb_job &j = jobs[*bad - 1];
+        rc = fail(1, "job %d: (list %d, ref %d) / macroblock origin (%d,%d) invalid", *bad - 1, (int)j.list, (int)j.ref, (int)j.opix_x, (int)j.opix_y);
+      }
       return rc;
     }
   }

@@ -122,6 +122,7 @@ me_subpel_batch_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDe
                        const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                        const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out)
 {
+  if (cfg.abort_flag && *cfg.abort_flag) return;
   __shared__ int cost_s[ME_NUM_PARTITIONS][9];
   __shared__ int mv_s[ME_NUM_PARTITIONS][2];
   __shared__ int min_s[ME_NUM_PARTITIONS];

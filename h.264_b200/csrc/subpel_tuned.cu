@@ -220,6 +220,7 @@ me_subpel_tuned_kernel(const uint32_t *__restrict__ jobs, int n_jobs, const MeRe
   // with cp.async, so that between two jobs there is no global-memory round trip -- one barrier, the region request (TMA),
   // the staging area unpacked into the working arrays, a second barrier.
   if ((int)blockIdx.x >= n_jobs) return;
+  if (cfg.abort_flag && *cfg.abort_flag) return;          // a job failed validation (me_check_jobs_kernel): nothing is searched
   const unsigned bar = smem_u32(&sm.mbar);
   if (tid == 0) {
     mbar_init(bar, 1);

@@ -347,7 +347,8 @@ int me_cuda_subpel_region_stats(int enable, int64_t *served, int64_t *total);
 /* diagnostics: measured issue rate (lane-operations per second, whole GPU) of the integer instructions the search
  * kernels are bound by; kind 0 VABSDIFF4, 1 IADD3, 2 IMAD, 3 VIADDMNMX, 4 LOP3, 5 SHF, 6 VIMNMX, 7 PRMT, 8..14 the kinds 1..7
  * interleaved 1:1 with VABSDIFF4, 15 LDS + VABSDIFF4, 16 / 17 VABSDIFF4 + IMAD / VIADDMNMX with the operand pattern of the search
- * kernel (one shared reference word per group, immediate multiplier: at most two register-file reads per instruction).
+ * kernel (one shared reference word per group, immediate multiplier: at most two register-file reads per instruction), 18 the
+ * arithmetic of one window row of the sweep (32 VABSDIFF4 : 21 add+min : 33 IMAD), dependency-free: the practical ceiling of that mix.
  * This is the denominator of bench.py's INT-ALU roofline (MEASURED_PEAKS.json has no integer figure). */
 int me_cuda_measure_int_peak(int kind, double *lane_ops_per_s);
 

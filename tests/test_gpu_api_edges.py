@@ -181,3 +181,38 @@ def test_device_entry_points_on_a_callers_stream(pkg):
         assert np.array_equal(got2, want2)
         got3 = me.frame_search(jobs)                                                        # sees the planes of the last update
         assert np.array_equal(got3, want)
+
+
+def test_pinned_buffers_are_searched_in_place(pkg, oracle_lib):
+    """me_cuda_frame_search with page-locked job / result arrays: the kernels read and write them in place (no copies, the job array is
+    validated by a kernel in front of the searches).  Same results as with pageable arrays; an invalid job is refused with the same
+    message and nothing is searched."""
+    import torch
+    from h264_b200 import MeCuda, MeCudaError, synth
+    from h264_b200.me_cuda import JOB_DTYPE, RESULT_DTYPE
+    w, h = 352, 288
+    frames = synth.luma_frames(w, h, 3)
+    jobs = synth.synthetic_jobs(w, h, 2, (334459,) * 3, seed=5)
+    with MeCuda(w, h, search_range=32, max_num_references=2) as me:
+        me.set_ref_list(0, [me.ref_create(frames[1]), me.ref_create(frames[0])])
+        me.set_current(frames[2])
+        ref_out, ref_int = me.frame_search(jobs, want_int=True)                      # pageable numpy arrays: the copying path
+        pj = torch.from_numpy(jobs.view(np.uint8).reshape(len(jobs), JOB_DTYPE.itemsize).copy()).pin_memory()
+        po = torch.zeros((len(jobs), RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+        pi = torch.zeros((len(jobs), RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+        launches = me.launch_count()
+        me._check(me.L.me_cuda_frame_search(pj.data_ptr(), len(jobs), po.data_ptr(), pi.data_ptr()))
+        assert me.launch_count() - launches <= 4                                       # check + search (+ hand-back) + sub-pel: one batch, no chunks
+        assert np.array_equal(po.numpy().reshape(-1).view(RESULT_DTYPE), ref_out)
+        assert np.array_equal(pi.numpy().reshape(-1).view(RESULT_DTYPE), ref_int)
+        # an invalid reference index in the middle of the array
+        bad = jobs.copy()
+        bad["ref"][len(bad) // 2] = 7
+        pb = torch.from_numpy(bad.view(np.uint8).reshape(len(bad), JOB_DTYPE.itemsize).copy()).pin_memory()
+        po.zero_()
+        with pytest.raises(MeCudaError, match="job %d" % (len(bad) // 2)):
+            me._check(me.L.me_cuda_frame_search(pb.data_ptr(), len(bad), po.data_ptr(), None))
+        assert not po.numpy().any()                                                    # nothing was written
+        # and the context still works
+        me._check(me.L.me_cuda_frame_search(pj.data_ptr(), len(jobs), po.data_ptr(), None))
+        assert np.array_equal(po.numpy().reshape(-1).view(RESULT_DTYPE), ref_out)
