@@ -23,6 +23,7 @@ struct MeSubpelArgs {
   int bi;
   MeBiW bw;
 };
+struct MePatArgs { int pattern, subthres, uplayer_x, uplayer_y, thr1, thr3, pmv2_x, pmv2_y; };   // subpel.cu
 struct MeBiFullArgs {
   int pic_pix_x, pic_pix_y, blocktype;
   int pmv_x1, pmv_y1, pmv_x2, pmv_y2;
@@ -69,6 +70,8 @@ void me_launch_ffs_block_subpel(const int32_t *surf_p, int setup_range, int offx
                                 int *result, int ticket, cudaStream_t st);
 void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                              const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st);
+void me_launch_subpel_pattern(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
+                              const MeSubpelArgs *a, const MePatArgs *pa, int *result, int ticket, cudaStream_t st);
 void me_launch_pms_group(const MePmsParams *p, const uint8_t *cur, int cur_pitch, const MeCfgDev *sub_cfg, int rdopt,
                          MePmsRecord *result, int *done_count, int *ticket_out, int ticket, cudaStream_t st);
 void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
@@ -1267,6 +1270,89 @@ int me_cuda_SubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_
   if (fetch_result(&mx, &my, &cost)) { fatal("bipred"); return ME_INT_MAX; }
   *mv_x = (short)mx; *mv_y = (short)my;
   return cost;
+}
+
+// ------------------------------------------------------------------------------------------------ sub-pel stages of the pattern searches
+// one launch per call (subpel.cu: me_subpel_pattern_kernel), result through mapped memory like the other drop-in calls
+static int subpel_pattern(const char *who, const MePatArgs &pa, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                          int pmv_x, int pmv_y, short *mv_x, short *mv_y, const short *s_mv, int search_pos2, int search_pos4,
+                          int min_mcost, int lam0, int lam1, int lam2, int check0)
+{
+  g.spec.valid = false;
+  if (blocktype < 1 || blocktype > 7) { fail(1, "%s: block type %d", who, blocktype); fatal(who); return ME_INT_MAX; }
+  MeSubpelArgs a{};
+  a.pic_pix_x = pic_pix_x; a.pic_pix_y = pic_pix_y; a.blocktype = blocktype;
+  a.pmv_x = pmv_x; a.pmv_y = pmv_y; a.mv_x = *mv_x; a.mv_y = *mv_y;
+  a.search_pos2 = search_pos2; a.search_pos4 = search_pos4; a.min_mcost = min_mcost;
+  a.lambda[0] = lam0; a.lambda[1] = lam1; a.lambda[2] = lam2;
+  a.check0 = check0;
+  if (s_mv) {
+    RefPic *r1 = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
+    RefPic *r2 = (g.inited && g.list_n[list ^ 1] > 0) ? ref_of(g.list[list ^ 1][0]) : nullptr;
+    if (!r1 || !r2) { fail(1, "%s: reference lists incomplete", who); fatal(who); return ME_INT_MAX; }
+    a.bi = 1; a.s_mv_x = s_mv[0]; a.s_mv_y = s_mv[1];
+    a.bw = g.bw[list];
+    me_launch_subpel_pattern(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, &pa, g.d_result, ++g.ticket, g.stream);
+  } else {
+    RefPic *r = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
+    if (!r) { fail(1, "%s: (list %d, ref %d) not in the reference lists", who, list, (int)ref); fatal(who); return ME_INT_MAX; }
+    const MeRefDev *dev;
+    if (search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) { fatal(who); return ME_INT_MAX; }
+    me_launch_subpel_pattern(dev, nullptr, g.d_cur, g.cur_pitch, &g.cfg, &a, &pa, g.d_result, ++g.ticket, g.stream);
+  }
+  g.launches++;
+  int mx, my, cost;
+  if (fetch_result(&mx, &my, &cost)) { fatal(who); return ME_INT_MAX; }
+  *mv_x = (short)mx; *mv_y = (short)my;
+  return cost;
+}
+
+static const int8_t smp_shift[8] = { 0, 0, 1, 1, 2, 3, 3, 1 };   // block_type_shift_factor, me_umhexsmp.c:46
+
+int me_cuda_EPZSSubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, const short pred_mv[2], short mv[2],
+                                        int search_pos2, int search_pos4, int min_mcost, const int *lambda, int subthres)
+{
+  MePatArgs pa{}; pa.pattern = 1; pa.subthres = subthres;
+  return subpel_pattern("me_cuda_EPZSSubPelBlockMotionSearch", pa, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv[0], pred_mv[1],
+                        &mv[0], &mv[1], nullptr, search_pos2, search_pos4, min_mcost, lambda[0], lambda[1], lambda[2], 0);
+}
+
+int me_cuda_EPZSSubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, const short *pred_mv1,
+                                        const short *pred_mv2, short mv[2], const short s_mv[2], int search_pos2, int search_pos4,
+                                        int min_mcost, const int *lambda)
+{
+  MePatArgs pa{}; pa.pattern = 1; pa.pmv2_x = pred_mv2[0]; pa.pmv2_y = pred_mv2[1];
+  return subpel_pattern("me_cuda_EPZSSubPelBlockSearchBiPred", pa, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv1[0], pred_mv1[1],
+                        &mv[0], &mv[1], s_mv, search_pos2, search_pos4, min_mcost, lambda[0], lambda[1], lambda[2], 0);
+}
+
+int me_cuda_UMHEXSubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, short pred_mv_x, short pred_mv_y,
+                                         short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor)
+{
+  MePatArgs pa{}; pa.pattern = 2;
+  return subpel_pattern("me_cuda_UMHEXSubPelBlockMotionSearch", pa, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                        mv_x, mv_y, nullptr, search_pos2, search_pos4, min_mcost, lambda_factor, lambda_factor, lambda_factor, 0);
+}
+
+int me_cuda_smpUMHEXSubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, short pred_mv_x, short pred_mv_y,
+                                            short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor,
+                                            int uplayer_x, int uplayer_y, int threshold1, int threshold3)
+{
+  MePatArgs pa{}; pa.pattern = 3; pa.uplayer_x = uplayer_x; pa.uplayer_y = uplayer_y;
+  pa.thr1 = threshold1 >> smp_shift[blocktype & 7]; pa.thr3 = threshold3 >> smp_shift[blocktype & 7];
+  return subpel_pattern("me_cuda_smpUMHEXSubPelBlockMotionSearch", pa, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                        mv_x, mv_y, nullptr, search_pos2, search_pos4, min_mcost, lambda_factor, lambda_factor, lambda_factor, 0);
+}
+
+int me_cuda_smpUMHEXFullSubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, short pred_mv_x, short pred_mv_y,
+                                                short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor,
+                                                int threshold1, int threshold3)
+{
+  MePatArgs pa{}; pa.pattern = 4;
+  pa.thr1 = threshold1 >> smp_shift[blocktype & 7]; pa.thr3 = threshold3 >> smp_shift[blocktype & 7];
+  const int check0 = (!g.cfg.rdopt && g.slice_type != ME_B_SLICE && ref == 0 && blocktype == 1 && *mv_x == 0 && *mv_y == 0);   // me_umhexsmp.c:442
+  return subpel_pattern("me_cuda_smpUMHEXFullSubPelBlockMotionSearch", pa, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
+                        mv_x, mv_y, nullptr, search_pos2, search_pos4, min_mcost, lambda_factor, lambda_factor, lambda_factor, check0);
 }
 
 // ------------------------------------------------------------------------------------------------ frame batch

@@ -225,6 +225,7 @@ struct BlockScratch {
   unsigned long long red[8];
   int cost_s[9];
   int mv_s[2], min_sh;
+  int grid[49], done;      // the pattern searches' candidate costs ((2E+1)^2 positions, E <= 3) and their early-return flag
 };
 
 // One block, both sub-pel levels.  bi == 0: SubPelBlockMotionSearch (r1 searched).  bi == 1: SubPelBlockSearchBiPred, r1 read at
@@ -292,6 +293,231 @@ __device__ void subpel_block(const MeRefDev &r1, const MeRefDev &r2, const uint8
     __syncthreads();
   }
   out_mvx = sc.mv_s[0]; out_mvy = sc.mv_s[1]; out_cost = sc.min_sh;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sub-pel stages of the pattern searches (SearchMode 1 UMHexagonS, 2 simplified UMHexagonS, 3 EPZS):
+// EPZSSubPelBlockMotionSearch (me_epzs.c:2390-2720), EPZSSubPelBlockSearchBiPred (:2728-3125), UMHEXSubPelBlockMotionSearch
+// (me_umhex.c:562-730), smpUMHEXSubPelBlockMotionSearch / smpUMHEXFullSubPelBlockMotionSearch (me_umhexsmp.c:616-812, :422-608).
+// The reference walks a few data-dependent positions one after the other; here every position the walk can reach is scored at
+// once (the 3 x 3 grid of a half- or quarter-pel level, the 7 x 7 quarter-pel grid of the UMHexagonS walks: one transform tile of
+// one candidate per thread, as above) and one thread then replays the walk over the table of costs.  Same outcome: the thresholds
+// the reference hands to its distortion functions on these paths only cut candidates that the comparison after the call rejects.
+struct MePatArgs {
+  int pattern;              // 1 EPZS, 2 UMHexagonS, 3 simplified UMHexagonS, 4 simplified UMHexagonS "full"
+  int subthres;             // EPZS: subthres[blocktype] (me_epzs.c:354)
+  int uplayer_x, uplayer_y; // simplified UMHexagonS: smpUMHEX_pred_MV_uplayer_X / _Y (me_umhexsmp.c:1203-1214)
+  int thr1, thr3;           // ... SubPelThreshold1 / 3 >> block_type_shift_factor[blocktype] (:106-107, :46)
+  int pmv2_x, pmv2_y;       // EPZS bi-predictive: predictor of the fixed vector (its rate is part of every candidate's cost)
+};
+
+// search_point_qp (me_epzs.c:44; search_point_hp, :43, is twice that); entry 9 repeats entry 5
+__constant__ int8_t c_epzs_x[10] = { 0, -1, 0, 1, 0, -1, 1, 1, -1, -1 };
+__constant__ int8_t c_epzs_y[10] = { 0, 0, 1, 0, -1, 1, 1, -1, -1, 1 };
+
+// costs (vector rate + distortion) of the (2E+1)^2 candidates centre + step * (dx, dy), |dx|, |dy| <= E, into sc.grid[(dy+E)*(2E+1) + dx+E].
+// Called by all threads; ends with a barrier.
+__device__ void pattern_grid(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch, const MeCfgDev &cfg,
+                             const MeSubpelArgs &a, const MePatArgs &pa, BlockScratch &sc, int level, int lam, int step, int E)
+{
+  const int tid = threadIdx.x, W = 2 * E + 1, ncand = W * W;
+  const int t = a.blocktype, bsx = me_bsx(t), bsy = me_bsy(t);
+  const int metric = cfg.metric[level];
+  const int cx0 = sc.mv_s[0], cy0 = sc.mv_s[1];
+  __syncthreads();                      // the grid may still be read by the walk of the previous level
+  for (int c = tid; c < ncand; c += blockDim.x) {
+    const int mx = cx0 + step * (c % W - E), my = cy0 + step * (c / W - E);
+    int m = me_mv_cost(lam, mx, my, a.pmv_x, a.pmv_y);
+    if (a.bi) m += me_mv_cost(lam, a.s_mv_x, a.s_mv_y, pa.pmv2_x, pa.pmv2_y);     // me_epzs.c:2867, :3021
+    sc.grid[c] = m;
+  }
+  __syncthreads();
+  const bool use8 = cfg.transform8x8 && t <= 4 && metric == 2;
+  const int n = use8 ? 8 : 4, tw = bsx / n, th = bsy / n;
+  const uint8_t *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
+  for (int i = tid; i < tw * th * ncand; i += blockDim.x) {
+    const int c = i % ncand, tile = i / ncand;
+    const int bx = (tile % tw) * n, by = (tile / tw) * n;
+    const int x4 = ((a.pic_pix_x + ME_PAD) << 2) + cx0 + step * (c % W - E);
+    const int y4 = ((a.pic_pix_y + ME_PAD) << 2) + cy0 + step * (c / W - E);
+    int d;
+    if (!a.bi) {
+      const uint8_t *rp = tile_ptr(r1, x4, y4, bx, by, metric == 2);
+      d = use8 ? tile_dist<8>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw)
+               : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw);
+      if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0])                        // computeSAD / SSE, me_distortion.c:376-402
+        for (int k = 0; k < 2; k++)
+          d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, x4, y4, nullptr, 0, 0);
+    } else {
+      const int fx4 = ((a.pic_pix_x + ME_PAD) << 2) + a.s_mv_x, fy4 = ((a.pic_pix_y + ME_PAD) << 2) + a.s_mv_y;
+      const uint8_t *p1 = tile_ptr(r1, fx4, fy4, bx, by, metric == 2);
+      const uint8_t *p2 = tile_ptr(r2, x4, y4, bx, by, metric == 2);
+      d = use8 ? tile_dist<8>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw)
+               : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
+      if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0] && r2.chroma[0])         // computeBiPredSAD1 :516-543
+        for (int k = 0; k < 2; k++)
+          d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, fx4, fy4, &r2, x4, y4,
+                                               a.bw.apply, a.bw.cw1[k], a.bw.cw2[k], a.bw.cobi[k], a.bw.denom);
+    }
+    atomicAdd(&sc.grid[c], d);
+  }
+  __syncthreads();
+}
+
+// one level of the EPZS refinements over the 3 x 3 table (one thread): the diamond points (and the centre from `first`), then the
+// corner(s) the best two point at (me_epzs.c:2470-2580, :2603-2712).  hp: the half-pel level, whose `case 0` evaluates nothing.
+// early_thr >= 0: the uni-predictive early return (:2496, :2629).  Returns true when that return was taken.
+__device__ bool epzs_level_walk(const int *grid, int step, bool hp, int first, int end_default, int early_thr, int pmv_x, int pmv_y,
+                                int &mvx, int &mvy, int &min_mcost)
+{
+  int best = 0, second = 0, second_cost = ME_INT_MAX, start = 5, end = end_default;
+  for (int pos = first; pos < 5; pos++) {
+    const int mc = grid[(c_epzs_y[pos] + 1) * 3 + c_epzs_x[pos] + 1];
+    if (mc < min_mcost) { second_cost = min_mcost; second = best; min_mcost = mc; best = pos; }
+    else if (mc < second_cost) { second_cost = mc; second = pos; }
+  }
+  if (early_thr >= 0 && best == 0 && pmv_x == mvx && pmv_y == mvy && min_mcost < early_thr) return true;
+  if (best != 0 && second != 0) {
+    switch (best ^ second) {
+      case 1: start = 6; end = 7; break;
+      case 3: start = 5; end = 6; break;
+      case 5: start = 8; end = 9; break;
+      case 7: start = 7; end = 8; break;
+      default: break;
+    }
+  } else {
+    switch (best + second) {
+      case 0: if (hp) { start = 5; end = 5; } break;
+      case 1: start = 8; end = 10; break;
+      case 2: start = 5; end = 7; break;
+      case 5: start = 6; end = 8; break;
+      case 7: start = 7; end = 9; break;
+      default: break;
+    }
+  }
+  if (end > 10) end = 10;
+  if (best != 0 || pmv_x != mvx || pmv_y != mvy)
+    for (int pos = start; pos < end; pos++) {
+      const int mc = grid[(c_epzs_y[pos] + 1) * 3 + c_epzs_x[pos] + 1];
+      if (mc < min_mcost) { min_mcost = mc; best = pos; }
+    }
+  mvx += step * c_epzs_x[best]; mvy += step * c_epzs_y[best];
+  return false;
+}
+
+// the quarter-pel diamond walks of the UMHexagonS searches over the 7 x 7 table (one thread; me_umhex.c:640-727, me_umhexsmp.c:700-811)
+__device__ void umhex_walk(const int *grid, bool smp, bool start_hp, const MePatArgs &pa, int pmv_x, int pmv_y, int &mvx, int &mvy, int &min_mcost)
+{
+  const int R = 3, mx0 = mvx, my0 = mvy;
+  unsigned long long seen = 1ull << (R * 7 + R);
+  int curx = 0, cury = 0;
+  const int fx = (pmv_x - mx0) % 4, fy = (pmv_y - my0) % 4;                      // C remainder: the sign of the dividend
+  const int ux = (pa.uplayer_x - mx0) % 4, uy = (pa.uplayer_y - my0) % 4;
+  if (!start_hp) {
+    const int mc = grid[R * 7 + R];
+    if (mc < min_mcost) { min_mcost = mc; curx = mx0; cury = my0; }               // otherwise the walk starts from the vector (0, 0), as in the reference
+  } else { curx = mx0; cury = my0; }
+  if (smp && mx0 == 0 && my0 == 0 && fx == 0 && ux == 0 && fy == 0 && uy == 0 && min_mcost < pa.thr1) { mvx = curx; mvy = cury; return; }
+  if (fx || fy) {
+    const int g = (fy + R) * 7 + fx + R, mc = grid[g];
+    seen |= 1ull << g;
+    if (mc < min_mcost) { min_mcost = mc; curx = mx0 + fx; cury = my0 + fy; }
+  }
+  for (int i = 0; i < R; i++) {
+    const int nx = curx, ny = cury;
+    bool abort_search = true;
+    for (int m = 0; m < 4; m++) {
+      // diamond order: (-1,0) (0,1) (1,0) (0,-1) in me_umhex.c:578-579, (-1,0) (1,0) (0,-1) (0,1) in me_umhexsmp.c:39-40
+      const int ddx = smp ? (m == 0 ? -1 : m == 1 ? 1 : 0) : (m == 0 ? -1 : m == 2 ? 1 : 0);
+      const int ddy = smp ? (m == 2 ? -1 : m == 3 ? 1 : 0) : (m == 1 ? 1 : m == 3 ? -1 : 0);
+      const int ox = nx + ddx - mx0, oy = ny + ddy - my0;
+      if (ox < -R || ox > R || oy < -R || oy > R) continue;
+      const int g = (oy + R) * 7 + ox + R;
+      if ((seen >> g) & 1) continue;
+      seen |= 1ull << g;
+      const int mc = grid[g];
+      if (mc < min_mcost) { min_mcost = mc; curx = nx + ddx; cury = ny + ddy; abort_search = false; }
+      if (smp && min_mcost < pa.thr3) { mvx = curx; mvy = cury; return; }
+    }
+    if (abort_search) break;
+  }
+  mvx = curx; mvy = cury;
+}
+
+// One block through the sub-pel stage of a pattern search.  Called by all threads of the CTA; returns the result to all of them.
+__device__ void pattern_block(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch, const MeCfgDev &cfg,
+                              const MeSubpelArgs &a, const MePatArgs &pa, BlockScratch &sc, int &out_mvx, int &out_mvy, int &out_cost)
+{
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid == 0) { sc.mv_s[0] = a.mv_x; sc.mv_s[1] = a.mv_y; sc.min_sh = a.min_mcost; sc.done = 0; }
+  __syncthreads();
+  if (pa.pattern == 2 || pa.pattern == 3) {
+    pattern_grid(r1, r2, cur, cur_pitch, cfg, a, pa, sc, 2, a.lambda[2], 1, 3);
+    if (tid == 0) {
+      int mvx = sc.mv_s[0], mvy = sc.mv_s[1], mn = sc.min_sh;
+      umhex_walk(sc.grid, pa.pattern == 3, cfg.start_hp != 0, pa, a.pmv_x, a.pmv_y, mvx, mvy, mn);
+      sc.mv_s[0] = (int16_t)mvx; sc.mv_s[1] = (int16_t)mvy; sc.min_sh = mn;       // *mv_x = (short) currmv_x
+    }
+  } else {
+    for (int stage = 0; stage < 2; stage++) {
+      const int level = pa.pattern == 4 ? 2 : stage + 1, lam = a.lambda[level], step = stage == 0 ? 2 : 1;
+      pattern_grid(r1, r2, cur, cur_pitch, cfg, a, pa, sc, level, lam, step, 1);
+      if (tid == 0) {
+        int mvx = sc.mv_s[0], mvy = sc.mv_s[1], mn = sc.min_sh;
+        if (pa.pattern == 1) {
+          // EPZSSubPelBlockMotionSearch / EPZSSubPelBlockSearchBiPred
+          int first, end_default;
+          if (stage == 0) {
+            first = a.bi ? (a.min_mcost == ME_INT_MAX ? 0 : cfg.start_hp) : cfg.start_hp;             // me_epzs.c:2760
+            end_default = ((!cfg.start_hp || !cfg.start_qp) && a.search_pos2 < 1) ? 1 : a.search_pos2; // :2411, :2761
+          } else {
+            if (!cfg.start_qp) mn = ME_INT_MAX;                                                        // :2581, :3008
+            first = cfg.start_qp; end_default = a.search_pos4;
+          }
+          if (epzs_level_walk(sc.grid, step, stage == 0, first, end_default, a.bi ? -1 : pa.subthres, a.pmv_x, a.pmv_y, mvx, mvy, mn)) sc.done = 1;
+          mvx = (int16_t)mvx; mvy = (int16_t)mvy;                                                      // the vector lives in shorts
+        } else {
+          // smpUMHEXFullSubPelBlockMotionSearch: the plain nine positions per level, quarter-pel metric and factor for both, each
+          // loop left as soon as the minimum is below SubPelThreshold3 (me_umhexsmp.c:504-540, :563-600)
+          const int first = stage == 0 ? cfg.start_hp : cfg.start_qp;
+          int npos = stage == 0 ? a.search_pos2 : a.search_pos4;
+          if (stage == 0 && !cfg.start_hp && npos < 1) npos = 1;
+          if (npos > 9) npos = 9;
+          if (stage == 1 && !cfg.start_qp) mn = ME_INT_MAX;
+          int best = 0;
+          for (int c = first; c < npos; c++) {
+            if (me_mv_cost(lam, mvx + step * c_sp_x[c], mvy + step * c_sp_y[c], a.pmv_x, a.pmv_y) >= mn) continue;   // skips the threshold test too (:519)
+            int mc = sc.grid[(c_sp_y[c] + 1) * 3 + c_sp_x[c] + 1];
+            if (stage == 0 && c == 0 && a.check0) mc -= (lam * 16) >> 16;
+            if (mc < mn) { mn = mc; best = c; }
+            if (mn < pa.thr3) break;
+          }
+          mvx = (int16_t)(mvx + step * c_sp_x[best]); mvy = (int16_t)(mvy + step * c_sp_y[best]);
+          if (stage == 0 && mvx == 0 && mvy == 0 && a.pmv_x == 0 && a.pmv_y == 0 && mn < pa.thr1) sc.done = 1;       // :546-551
+        }
+        sc.mv_s[0] = mvx; sc.mv_s[1] = mvy; sc.min_sh = mn;
+      }
+      __syncthreads();
+      if (sc.done) break;
+    }
+  }
+  __syncthreads();
+  out_mvx = sc.mv_s[0]; out_mvy = sc.mv_s[1]; out_cost = sc.min_sh;
+}
+
+__global__ void __launch_bounds__(256)
+me_subpel_pattern_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                         MeSubpelArgs a, MePatArgs pa, int *result /* mvx, mvy, cost, ticket */, int ticket)
+{
+  __shared__ BlockScratch sc;
+  int mvx, mvy, cost;
+  pattern_block(r1, r2, cur, cur_pitch, cfg, a, pa, sc, mvx, mvy, cost);
+  if (threadIdx.x == 0) {
+    result[0] = mvx; result[1] = mvy; result[2] = cost;
+    __threadfence_system();
+    *(volatile int *)&result[3] = ticket;
+  }
 }
 
 __global__ void __launch_bounds__(128)
@@ -828,6 +1054,12 @@ extern "C" void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, 
                                         const MeCfgDev *cfg, const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st)
 {
   me_subpel_single_kernel<<<1, 128, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, result, ticket);
+}
+
+extern "C" void me_launch_subpel_pattern(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
+                                         const MeCfgDev *cfg, const MeSubpelArgs *a, const MePatArgs *pa, int *result, int ticket, cudaStream_t st)
+{
+  me_subpel_pattern_kernel<<<1, 256, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, *pa, result, ticket);
 }
 
 extern "C" void me_launch_fullpel_block(const MeRefDev *r, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,

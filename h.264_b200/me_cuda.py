@@ -42,6 +42,8 @@ ABI_SYMBOLS = [
     "me_cuda_mb_begin", "me_cuda_ffs_setup", "me_cuda_ffs_is_set_up",
     "me_cuda_FastFullPelBlockMotionSearch", "me_cuda_FullPelBlockMotionSearch", "me_cuda_SubPelBlockMotionSearch",
     "me_cuda_FullPelBlockMotionBiPred", "me_cuda_SubPelBlockSearchBiPred",
+    "me_cuda_EPZSSubPelBlockMotionSearch", "me_cuda_EPZSSubPelBlockSearchBiPred", "me_cuda_UMHEXSubPelBlockMotionSearch",
+    "me_cuda_smpUMHEXSubPelBlockMotionSearch", "me_cuda_smpUMHEXFullSubPelBlockMotionSearch",
     "me_cuda_frame_search", "me_cuda_frame_search_device", "me_cuda_frame_bipred", "me_cuda_ref_create_device",
     "me_cuda_set_current_device", "me_cuda_stream", "me_cuda_sync", "me_cuda_launch_count", "me_cuda_subpel_region_stats",
     "me_cuda_luma_prediction", "me_cuda_pred_cost8x8", "me_cuda_ref_download_region", "me_cuda_deblock_frame", "me_cuda_ref_create_deblocked",
@@ -102,6 +104,13 @@ def load_library(path=LIB_PATH):
                                                    + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int])
     L.me_cuda_SubPelBlockSearchBiPred.argtypes = ([C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, C.c_short, C.c_short,
                                                    sp, sp, sp, sp, C.c_int, C.c_int, C.c_int, ip])
+    s2 = C.POINTER(C.c_short * 2)
+    L.me_cuda_EPZSSubPelBlockMotionSearch.argtypes = [C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, s2, s2, C.c_int, C.c_int, C.c_int, ip, C.c_int]
+    L.me_cuda_EPZSSubPelBlockSearchBiPred.argtypes = [C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, s2, s2, s2, s2, C.c_int, C.c_int, C.c_int, ip]
+    pat = [C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, C.c_short, C.c_short, sp, sp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.me_cuda_UMHEXSubPelBlockMotionSearch.argtypes = pat
+    L.me_cuda_smpUMHEXSubPelBlockMotionSearch.argtypes = pat + [C.c_int] * 4
+    L.me_cuda_smpUMHEXFullSubPelBlockMotionSearch.argtypes = pat + [C.c_int] * 2
     L.me_cuda_frame_search.argtypes = [vp, C.c_int, vp, vp]
     L.me_cuda_frame_search_device.argtypes = [vp, C.c_int, vp, vp, vp]
     L.me_cuda_frame_bipred.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
@@ -308,6 +317,35 @@ class MeCuda:
                                                       C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy),
                                                       search_pos2, search_pos4, min_mcost, lam)
         return mx.value, my.value, cost
+
+    # ---- sub-pel stages of the pattern searches (include/me_cuda.h): pattern 1 EPZSSubPelBlockMotionSearch, 2 UMHEXSubPelBlockMotionSearch,
+    # 3 smpUMHEXSubPelBlockMotionSearch, 4 smpUMHEXFullSubPelBlockMotionSearch (the UMHexagonS ones take the quarter-pel factor lam[2])
+    def SubPelPattern(self, pattern, ref, lst, pic_pix_x, pic_pix_y, blocktype, pmv, mv, search_pos2, search_pos4, min_mcost, lambda_factor,
+                      subthres=0, uplayer=(0, 0), thresholds=(1000, 400)):
+        lam = (C.c_int * 3)(*lambda_factor)
+        if pattern == 1:
+            pm, m = (C.c_short * 2)(*pmv), (C.c_short * 2)(*mv)
+            cost = self.L.me_cuda_EPZSSubPelBlockMotionSearch(ref, lst, pic_pix_x, pic_pix_y, blocktype, pm, m, search_pos2, search_pos4,
+                                                              min_mcost, lam, subthres)
+            return m[0], m[1], cost
+        mx, my = C.c_short(mv[0]), C.c_short(mv[1])
+        a = (ref, lst, pic_pix_x, pic_pix_y, blocktype, pmv[0], pmv[1], C.byref(mx), C.byref(my), search_pos2, search_pos4, min_mcost, lam[2])
+        if pattern == 2:
+            cost = self.L.me_cuda_UMHEXSubPelBlockMotionSearch(*a)
+        elif pattern == 3:
+            cost = self.L.me_cuda_smpUMHEXSubPelBlockMotionSearch(*a, uplayer[0], uplayer[1], thresholds[0], thresholds[1])
+        elif pattern == 4:
+            cost = self.L.me_cuda_smpUMHEXFullSubPelBlockMotionSearch(*a, thresholds[0], thresholds[1])
+        else:
+            raise ValueError(pattern)
+        return mx.value, my.value, cost
+
+    def EPZSSubPelBlockSearchBiPred(self, ref, lst, pic_pix_x, pic_pix_y, blocktype, pmv1, pmv2, mv, s_mv, search_pos2, search_pos4,
+                                    min_mcost, lambda_factor):
+        p1, p2, m, sm = (C.c_short * 2)(*pmv1), (C.c_short * 2)(*pmv2), (C.c_short * 2)(*mv), (C.c_short * 2)(*s_mv)
+        cost = self.L.me_cuda_EPZSSubPelBlockSearchBiPred(ref, lst, pic_pix_x, pic_pix_y, blocktype, p1, p2, m, sm, search_pos2, search_pos4,
+                                                          min_mcost, (C.c_int * 3)(*lambda_factor))
+        return m[0], m[1], cost
 
     # ---- one launch per PartitionMotionSearch call
     def pms_begin(self, state, items, lambda_factor):

@@ -39,6 +39,7 @@
 #include "me_distortion.h"
 #include "refbuf.h"
 #include "mb_access.h"
+#include "me_umhexsmp.h"
 
 #include "me_cuda.h"
 
@@ -74,6 +75,11 @@ static struct {
   int  (*subpel)(short, int, int, int, int, short, short, short *, short *, int, int, int, const int *);
   int  (*bi_full)(short, int, int, int, int, short, short, short, short, short *, short *, short *, short *, int, int, int);
   int  (*bi_sub)(short, int, int, int, int, short, short, short *, short *, short *, short *, int, int, int, const int *);
+  int  (*epzs_sub)(short, int, int, int, int, const short *, short *, int, int, int, const int *, int);
+  int  (*epzs_bi_sub)(short, int, int, int, int, const short *, const short *, short *, const short *, int, int, int, const int *);
+  int  (*umhex_sub)(short, int, int, int, int, short, short, short *, short *, int, int, int, int);
+  int  (*smp_sub)(short, int, int, int, int, short, short, short *, short *, int, int, int, int, int, int, int, int);
+  int  (*smp_full_sub)(short, int, int, int, int, short, short, short *, short *, int, int, int, int, int, int);
   int  (*pms_begin)(const me_mb_motion *, int, const me_pms_item *, const int *);
   int  (*pms_cached)(int, int);
   int  (*pms_end)(int, int);
@@ -91,6 +97,7 @@ static long n_checked = 0, n_mismatch = 0;
 /* calls the device answered, per wrapped function; printed when the module is cleared so that a run (and the tests around it)
  * can tell a GPU run from a silent pass-through */
 static long served_ffs = 0, served_fullpel = 0, served_subpel = 0, served_bi_full = 0, served_bi_sub = 0, served_planes = 0;
+static long served_pattern[5] = {0, 0, 0, 0, 0}, served_pattern_bi = 0;   /* sub-pel stages of the pattern searches, by pattern */
 static long served_bid_cost = 0, served_direct_cost = 0, paged_tiles = 0, paged_bytes = 0;
 static int use_mc = 1;          /* BIDPartitionCost / GetDirectCost8x8 on the device (ME_CUDA_MC=0: the reference's host code) */
 static int lazy_planes = 1;     /* imgY_sub paged in on demand (ME_CUDA_HOST_PLANES=1: all planes copied back at creation) */
@@ -159,6 +166,9 @@ static void load_library(void)
   L.fullpel = sym("me_cuda_FullPelBlockMotionSearch");
   L.ffs = sym("me_cuda_FastFullPelBlockMotionSearch"); L.subpel = sym("me_cuda_SubPelBlockMotionSearch");
   L.bi_full = sym("me_cuda_FullPelBlockMotionBiPred"); L.bi_sub = sym("me_cuda_SubPelBlockSearchBiPred");
+  L.epzs_sub = sym("me_cuda_EPZSSubPelBlockMotionSearch"); L.epzs_bi_sub = sym("me_cuda_EPZSSubPelBlockSearchBiPred");
+  L.umhex_sub = sym("me_cuda_UMHEXSubPelBlockMotionSearch"); L.smp_sub = sym("me_cuda_smpUMHEXSubPelBlockMotionSearch");
+  L.smp_full_sub = sym("me_cuda_smpUMHEXFullSubPelBlockMotionSearch");
   L.pms_begin = sym("me_cuda_pms_begin"); L.pms_cached = sym("me_cuda_pms_cached"); L.pms_end = sym("me_cuda_pms_end");
   L.pms_stats = sym("me_cuda_pms_stats");
   L.pred_cost8x8 = sym("me_cuda_pred_cost8x8"); L.ref_download_region = sym("me_cuda_ref_download_region");
@@ -202,10 +212,11 @@ void __wrap_Init_Motion_Search_Module(void)
   active = 0;
   if (dis && atoi(dis)) return;
   /* SearchMode 0 (fast full search) and -1 (per-block full search) run every stage on the device.  With the pattern searches
-   * (1 UMHexagonS, 2 simplified UMHexagonS, 3 EPZS) the integer-pel stage and the modes' own sub-pel patterns stay the reference's
-   * host code -- data-dependent walks of a few positions -- and the device serves what the dispatch still sends to the plain
-   * routines: the plane sets, SubPelBlockMotionSearch (UMHexagonS block types 1..3, mv-search.c:799; EPZS without EPZSSubPelME,
-   * :823) and SubPelBlockSearchBiPred (:1018, unless EPZSSubPelMEBiPred) */
+   * (1 UMHexagonS, 2 simplified UMHexagonS, 3 EPZS) the integer-pel stage stays the reference's host code -- a data-dependent walk
+   * of a few positions -- and the device serves everything the dispatch calls after it: the plane sets, SubPelBlockMotionSearch
+   * (UMHexagonS block types 1..3, mv-search.c:799; EPZS without EPZSSubPelME, :823), SubPelBlockSearchBiPred (:1018), and the
+   * modes' own sub-pel stages UMHEXSubPelBlockMotionSearch (:794), smpUMHEX[Full]SubPelBlockMotionSearch (:807, :812),
+   * EPZSSubPelBlockMotionSearch (:818) and EPZSSubPelBlockSearchBiPred (:993, :1013) */
   {
     me_cuda_params p;
     int apply_wp = (input->WeightedPrediction || input->WeightedBiprediction) && input->UseWeightedReferenceME;
@@ -249,6 +260,8 @@ void __wrap_Clear_Motion_Search_Module(void)
     L.pms_stats(&pl, &ps, &pm);
     fprintf(stderr, "me_cuda shim: served on the device: %ld plane sets, %ld ffs, %ld fullpel, %ld subpel, %ld bi_full, %ld bi_sub calls\n",
             served_planes, served_ffs, served_fullpel, served_subpel, served_bi_full, served_bi_sub);
+    fprintf(stderr, "me_cuda shim: sub-pel stages of the pattern searches served on the device: %ld EPZS, %ld EPZS bi-pred, %ld UMHEX, %ld smpUMHEX, %ld smpUMHEX full calls\n",
+            served_pattern[1], served_pattern_bi, served_pattern[2], served_pattern[3], served_pattern[4]);
     fprintf(stderr, "me_cuda shim: partition-search launches %lld, block searches answered from them %lld, argument mismatches %lld\n",
             (long long)pl, (long long)ps, (long long)pm);
     fprintf(stderr, "me_cuda shim: mode-decision costs on the device: %ld BIDPartitionCost, %ld GetDirectCost8x8 calls; plane tiles paged to the host: %ld (%ld bytes%s)\n",
@@ -654,6 +667,111 @@ int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pi
   return L.bi_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, s_mv_x, s_mv_y,
                   search_pos2, search_pos4, min_mcost, lambda_factor);
 }
+
+/* ---------------------------------------------------------------- sub-pel stages of the pattern searches (SearchMode 1, 2, 3) */
+/* subthres[blocktype] as EPZSInit derives it (me_epzs.c:335-354); the array itself is a file static of me_epzs.c */
+static int epzs_subthres(int blocktype)
+{
+  static const int medthres_base[8] = { 0, 256, 128, 128, 64, 32, 32, 16 };       /* me_epzs.c:41 */
+  int pel_error_me = 1 << (img->bitdepth_luma - 8), pel_error_me_cr = 1 << (img->bitdepth_chroma - 8);
+  double chroma_weight = input->ChromaMEEnable ? pel_error_me_cr * input->ChromaMEWeight * (double)(img->width_cr * img->height_cr) / (double)(img->width * img->height) : 0;
+  return input->EPZSSubPelThresScale * (medthres_base[blocktype] * pel_error_me + (int)(medthres_base[blocktype] * chroma_weight + 0.5));
+}
+
+static void pattern_verify(const char *what, int list, short ref, int blocktype, int pic_pix_x, int pic_pix_y, int ix, int iy, int min_mcost,
+                           int gx, int gy, int gc, int rx, int ry, int rc)
+{
+  n_checked++;
+  if (gc != rc || gx != rx || gy != ry) {
+    n_mismatch++;
+    fprintf(stderr, "VERIFY %s pic %d mb (%d,%d) list %d ref %d bt %d blk (%d,%d) in (%d,%d) min %d: gpu (%d,%d,%d) ref (%d,%d,%d)\n",
+            what, pic_counter, img->opix_x, img->opix_y, list, ref, blocktype, pic_pix_x, pic_pix_y, ix, iy, min_mcost, gx, gy, gc, rx, ry, rc);
+  }
+}
+
+int __real_EPZSSubPelBlockMotionSearch(imgpel *, short, int, int, int, int, short *, short *, int, int, int, int *);
+int __wrap_EPZSSubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                       short pred_mv[2], short mv[2], int search_pos2, int search_pos4, int min_mcost, int *lambda)
+{
+  if (!active)
+    return __real_EPZSSubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv, mv, search_pos2, search_pos4, min_mcost, lambda);
+  mb_sync();
+  keep_reference_side_effects(list, ref);
+  pass_weights(list, ref);
+  served_pattern[1]++;
+  if (verify) {
+    short g[2] = { mv[0], mv[1] }, in[2] = { mv[0], mv[1] };
+    int gc = L.epzs_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv, g, search_pos2, search_pos4, min_mcost, lambda, epzs_subthres(blocktype));
+    int rc = __real_EPZSSubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv, mv, search_pos2, search_pos4, min_mcost, lambda);
+    pattern_verify("epzs_subpel", list, ref, blocktype, pic_pix_x, pic_pix_y, in[0], in[1], min_mcost, g[0], g[1], gc, mv[0], mv[1], rc);
+    return rc;
+  }
+  return L.epzs_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv, mv, search_pos2, search_pos4, min_mcost, lambda, epzs_subthres(blocktype));
+}
+
+int __real_EPZSSubPelBlockSearchBiPred(imgpel *, short, int, int, int, int, short *, short *, short *, short *, int, int, int, int *);
+int __wrap_EPZSSubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                       short *pred_mv1, short *pred_mv2, short mv[2], short s_mv[2],
+                                       int search_pos2, int search_pos4, int min_mcost, int *lambda)
+{
+  if (!active)
+    return __real_EPZSSubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv1, pred_mv2, mv, s_mv,
+                                              search_pos2, search_pos4, min_mcost, lambda);
+  mb_sync();
+  keep_reference_side_effects(list, ref);
+  pass_bipred_weights(list, ref, 1);                      /* the index expressions of me_epzs.c:2746-2747 are those of SubPelBlockSearchBiPred */
+  served_pattern_bi++;
+  if (verify) {
+    short g[2] = { mv[0], mv[1] }, in[2] = { mv[0], mv[1] };
+    int gc = L.epzs_bi_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv1, pred_mv2, g, s_mv, search_pos2, search_pos4, min_mcost, lambda);
+    int rc = __real_EPZSSubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv1, pred_mv2, mv, s_mv,
+                                                search_pos2, search_pos4, min_mcost, lambda);
+    pattern_verify("epzs_bi_subpel", list, ref, blocktype, pic_pix_x, pic_pix_y, in[0], in[1], min_mcost, g[0], g[1], gc, mv[0], mv[1], rc);
+    return rc;
+  }
+  return L.epzs_bi_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv1, pred_mv2, mv, s_mv, search_pos2, search_pos4, min_mcost, lambda);
+}
+
+/* the three UMHexagonS sub-pel stages share a signature (me_umhex.h, me_umhexsmp.h); which = 2 UMHEX, 3 smpUMHEX, 4 smpUMHEX full */
+static int umhex_device(int which, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, short pred_mv_x, short pred_mv_y,
+                        short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor)
+{
+  if (which == 2)
+    return L.umhex_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
+  if (which == 3)
+    return L.smp_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor,
+                     smpUMHEX_pred_MV_uplayer_X, smpUMHEX_pred_MV_uplayer_Y, SubPelThreshold1, SubPelThreshold3);
+  return L.smp_full_sub(ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2, search_pos4, min_mcost, lambda_factor,
+                        SubPelThreshold1, SubPelThreshold3);
+}
+
+#define UMHEX_WRAP(NAME, WHICH, LABEL)                                                                                              \
+int __real_##NAME(imgpel *, short, int, int, int, int, short, short, short *, short *, int, int, int, int);                         \
+int __wrap_##NAME(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, short pred_mv_x, short pred_mv_y, \
+                  short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor)                     \
+{                                                                                                                                   \
+  if (!active)                                                                                                                      \
+    return __real_##NAME(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2,       \
+                         search_pos4, min_mcost, lambda_factor);                                                                    \
+  mb_sync();                                                                                                                        \
+  keep_reference_side_effects(list, ref);                                                                                           \
+  pass_weights(list, ref);                                                                                                          \
+  served_pattern[WHICH]++;                                                                                                          \
+  if (verify) {                                                                                                                     \
+    short ix = *mv_x, iy = *mv_y, gx = *mv_x, gy = *mv_y;                                                                           \
+    int gc = umhex_device(WHICH, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, &gx, &gy, search_pos2,           \
+                          search_pos4, min_mcost, lambda_factor);                                                                   \
+    int rc = __real_##NAME(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2,     \
+                           search_pos4, min_mcost, lambda_factor);                                                                  \
+    pattern_verify(LABEL, list, ref, blocktype, pic_pix_x, pic_pix_y, ix, iy, min_mcost, gx, gy, gc, *mv_x, *mv_y, rc);             \
+    return rc;                                                                                                                      \
+  }                                                                                                                                 \
+  return umhex_device(WHICH, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2,             \
+                      search_pos4, min_mcost, lambda_factor);                                                                       \
+}
+UMHEX_WRAP(UMHEXSubPelBlockMotionSearch, 2, "umhex_subpel")
+UMHEX_WRAP(smpUMHEXSubPelBlockMotionSearch, 3, "smpumhex_subpel")
+UMHEX_WRAP(smpUMHEXFullSubPelBlockMotionSearch, 4, "smpumhex_full_subpel")
 
 /* ---------------------------------------------------------------- the host's reads of the quarter-pel planes (refbuf.c:25, :37) */
 /* FastLine4X / UMVLine4X return a pointer into plane Pic[y & 3][x & 3]; every caller then reads at most 16 rows of at most 16

@@ -184,6 +184,31 @@ int me_cuda_SubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_
                                     int search_pos2, int search_pos4, int min_mcost,
                                     const int *lambda_factor);                                  /* me_fullsearch.h:129 */
 
+/* ---- sub-pel stages of the pattern searches (SearchMode 1 UMHexagonS, 2 simplified UMHexagonS, 3 EPZS).
+ * The integer-pel stages of these modes stay the reference's host code (data-dependent walks of a few positions); what the dispatch
+ * at mv-search.c:790-826 and :984-1022 calls afterwards is served here.  Arguments and return value as the reference functions minus
+ * orig_pic; state the reference keeps in file statics / globals of the mode arrives as trailing arguments:
+ *   subthres      subthres[blocktype] of EPZSInit (me_epzs.c:335-354; a file static there)
+ *   uplayer_x/y   smpUMHEX_pred_MV_uplayer_X / _Y (me_umhexsmp.h:44-45, set by smpUMHEX_setup, me_umhexsmp.c:1203-1214)
+ *   threshold1/3  SubPelThreshold1 / SubPelThreshold3 (me_umhexsmp.h:34-35, me_umhexsmp.c:106-107); shifted by the block type inside */
+int me_cuda_EPZSSubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                        const short pred_mv[2], short mv[2], int search_pos2, int search_pos4, int min_mcost,
+                                        const int *lambda, int subthres);                         /* me_epzs.h, me_epzs.c:2390 */
+int me_cuda_EPZSSubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                        const short *pred_mv1, const short *pred_mv2, short mv[2], const short s_mv[2],
+                                        int search_pos2, int search_pos4, int min_mcost, const int *lambda);   /* me_epzs.c:2728 */
+int me_cuda_UMHEXSubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                         short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                         int search_pos2, int search_pos4, int min_mcost, int lambda_factor);   /* me_umhex.c:562 */
+int me_cuda_smpUMHEXSubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                            short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                            int search_pos2, int search_pos4, int min_mcost, int lambda_factor,
+                                            int uplayer_x, int uplayer_y, int threshold1, int threshold3);       /* me_umhexsmp.c:616 */
+int me_cuda_smpUMHEXFullSubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                                short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
+                                                int search_pos2, int search_pos4, int min_mcost, int lambda_factor,
+                                                int threshold1, int threshold3);                                   /* me_umhexsmp.c:422 */
+
 /* ---- one launch per PartitionMotionSearch (mv-search.c:1378-1454) instead of one per block search ----
  * PartitionMotionSearch(blocktype, block8x8) runs, for every list and reference, BlockMotionSearch on each sub-block of the
  * partition: SetMotionVectorPredictor (mv-search.c:87-281) from the motion state around the macroblock, the integer-pel search,

@@ -98,6 +98,12 @@ def lib():
                                          + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int])
         L.ora_bipred_subpel.argtypes = ([C.POINTER(OraCfg), vp, C.c_int, vp, vp] + [C.c_int] * 5
                                         + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int, ip])
+        L.ora_epzs_subpel.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp] + [C.c_int] * 5 + [sp, sp, C.c_int, C.c_int, C.c_int, ip, C.c_int]
+        L.ora_epzs_subpel_bipred.argtypes = ([C.POINTER(OraCfg), vp, C.c_int, vp, vp] + [C.c_int] * 7
+                                             + [sp, sp, sp, sp, C.c_int, C.c_int, C.c_int, ip])
+        L.ora_umhex_subpel.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp] + [C.c_int] * 5 + [sp, sp, C.c_int, C.c_int]
+        L.ora_smpumhex_subpel.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp] + [C.c_int] * 5 + [sp, sp] + [C.c_int] * 6
+        L.ora_smpumhex_full_subpel.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp] + [C.c_int] * 7 + [sp, sp] + [C.c_int] * 6
         L.ora_mb_search.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, vp]
         L.ora_mb_bipred.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         L.ora_luma_prediction.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
@@ -260,6 +266,35 @@ def bipred_subpel(cfg, cur, ref1, ref2, pic_pix_x, pic_pix_y, blocktype, pmv, mv
                                    pic_pix_x, pic_pix_y, blocktype, pmv[0], pmv[1],
                                    C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy), search_pos2, search_pos4,
                                    min_mcost, lam3)
+    return mx.value, my.value, cost
+
+
+# sub-pel stages of the pattern searches: pattern 1 EPZSSubPelBlockMotionSearch, 2 UMHEXSubPelBlockMotionSearch,
+# 3 smpUMHEXSubPelBlockMotionSearch, 4 smpUMHEXFullSubPelBlockMotionSearch (lam: three factors; the UMHexagonS ones use lam[2])
+def subpel_pattern(cfg, cur, ref, pattern, pic_pix_x, pic_pix_y, blocktype, ref_idx, slice_type, pmv, mv, min_mcost, lam,
+                   search_pos2=9, search_pos4=9, subthres=0, uplayer=(0, 0), thresholds=(1000, 400)):
+    mx, my = _shorts(mv[0], mv[1])
+    L, a = lib(), (C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr, pic_pix_x, pic_pix_y, blocktype)
+    if pattern == 1:
+        cost = L.ora_epzs_subpel(*a, pmv[0], pmv[1], C.byref(mx), C.byref(my), search_pos2, search_pos4, min_mcost, (C.c_int * 3)(*lam), subthres)
+    elif pattern == 2:
+        cost = L.ora_umhex_subpel(*a, pmv[0], pmv[1], C.byref(mx), C.byref(my), min_mcost, lam[2])
+    elif pattern == 3:
+        cost = L.ora_smpumhex_subpel(*a, pmv[0], pmv[1], C.byref(mx), C.byref(my), min_mcost, lam[2], uplayer[0], uplayer[1], *thresholds)
+    elif pattern == 4:
+        cost = L.ora_smpumhex_full_subpel(*a, ref_idx, slice_type, pmv[0], pmv[1], C.byref(mx), C.byref(my), search_pos2, search_pos4,
+                                          min_mcost, lam[2], *thresholds)
+    else:
+        raise ValueError(pattern)
+    return mx.value, my.value, cost
+
+
+def epzs_subpel_bipred(cfg, cur, ref1, ref2, pic_pix_x, pic_pix_y, blocktype, pmv1, pmv2, mv, s_mv, min_mcost, lam,
+                       search_pos2=9, search_pos4=9):
+    mx, my, sx, sy = _shorts(mv[0], mv[1], s_mv[0], s_mv[1])
+    cost = lib().ora_epzs_subpel_bipred(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref1.ptr, ref2.ptr, pic_pix_x, pic_pix_y, blocktype,
+                                        pmv1[0], pmv1[1], pmv2[0], pmv2[1], C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy),
+                                        search_pos2, search_pos4, min_mcost, (C.c_int * 3)(*lam))
     return mx.value, my.value, cost
 
 

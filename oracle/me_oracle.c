@@ -1101,3 +1101,224 @@ void ora_deblock_frame(uint8_t *y, int ystride, uint8_t *u, uint8_t *v, int cstr
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------ sub-pel stages of the pattern searches
+ * (SURVEY.md 8f row 4).  Every candidate is scored with the FULL distortion: the thresholds the reference hands to computeUniPred /
+ * computeBiPred on these paths only ever cut a candidate that the comparison after the call rejects anyway (a partial sum above the
+ * threshold comes back, the full sum is at least as large), and position 0 with check_position0 is scored against INT_MAX
+ * (mv-search.c:785-788).  FAST_ACCESS / UMV_ACCESS: a centre inside the margin the reference tests keeps every candidate of the
+ * pattern inside the padded plane, where the clamp of UMVLine4X is the identity -- so the clamped access serves both. */
+
+typedef struct pat_ctx {
+  const ora_cfg *c; const uint8_t *src; int stride, bsx, bsy, use8x8, ppx, ppy, p4x, p4y;
+  const ora_ref *r1, *r2;      /* r2 != NULL: bi-predictive, r1 read at the fixed vector (smx, smy), r2 at the candidate */
+  int smx, smy, pmvx, pmvy, fixed_rate_lambda_level, s_mv_x, s_mv_y, pmv2x, pmv2y;
+} pat_ctx;
+
+/* motion-vector rate + distortion of the candidate (cx, cy) (quarter-pel vector) at sub-pel level `level` with factor `lam` */
+static int pat_cost(const pat_ctx *k, int level, int lam, int cx, int cy)
+{
+  int m = ora_mv_cost(lam, cx, cy, k->pmvx, k->pmvy);
+  if (k->r2) {
+    m += ora_mv_cost(lam, k->s_mv_x, k->s_mv_y, k->pmv2x, k->pmv2y);            /* me_epzs.c:2867, :3021: the fixed vector's rate too */
+    return m + bipred_dist(k->c, level, k->src, k->stride, k->bsx, k->bsy, k->r1, k->smx, k->smy, k->r2, cx + k->p4x, cy + k->p4y,
+                           k->use8x8, k->ppx, k->ppy);
+  }
+  return m + unipred(k->c, level, k->src, k->stride, k->bsx, k->bsy, k->r1, cx + k->p4x, cy + k->p4y, k->use8x8, k->ppx, k->ppy);
+}
+
+/* search_point_qp (me_epzs.c:44); search_point_hp (:43) is twice that.  Entry 9 repeats entry 5. */
+static const int8_t epzs_pt[10][2] = { {0, 0}, {-1, 0}, {0, 1}, {1, 0}, {0, -1}, {-1, 1}, {1, 1}, {1, -1}, {-1, -1}, {-1, 1} };
+
+/* One level of EPZSSubPelBlockMotionSearch / EPZSSubPelBlockSearchBiPred (me_epzs.c:2470-2580 = :2603-2712, :2858-2960 = :3014-3118):
+ * the four diamond points (and the centre from `first`), then the corner(s) the best two of them point at.
+ * hp: the half-pel level (its `case 0` of the second switch evaluates nothing; the quarter-pel level has that case commented out).
+ * early_thr >= 0: the uni-predictive early return (:2496, :2629); returns 1 when it was taken. */
+static int epzs_level(const pat_ctx *k, int level, int lam, int step, int hp, int first, int end_default, int early_thr,
+                      short *mv_x, short *mv_y, int *min_mcost)
+{
+  int pos, best = 0, second = 0, second_cost = INT_MAX, mcost, start = 5, end = end_default;
+  for (pos = first; pos < 5; pos++) {
+    mcost = pat_cost(k, level, lam, *mv_x + step * epzs_pt[pos][0], *mv_y + step * epzs_pt[pos][1]);
+    if (mcost < *min_mcost) { second_cost = *min_mcost; second = best; *min_mcost = mcost; best = pos; }
+    else if (mcost < second_cost) { second_cost = mcost; second = pos; }
+  }
+  if (early_thr >= 0 && best == 0 && k->pmvx == *mv_x && k->pmvy - *mv_y == 0 && *min_mcost < early_thr) return 1;
+  if (best != 0 && second != 0) {
+    switch (best ^ second) {
+      case 1: start = 6; end = 7; break;
+      case 3: start = 5; end = 6; break;
+      case 5: start = 8; end = 9; break;
+      case 7: start = 7; end = 8; break;
+      default: break;
+    }
+  } else {
+    switch (best + second) {
+      case 0: if (hp) { start = 5; end = 5; } break;
+      case 1: start = 8; end = 10; break;
+      case 2: start = 5; end = 7; break;
+      case 5: start = 6; end = 8; break;
+      case 7: start = 7; end = 9; break;
+      default: break;
+    }
+  }
+  if (best != 0 || (iabs_(k->pmvx - *mv_x) + iabs_(k->pmvy - *mv_y)))
+    for (pos = start; pos < end; pos++) {
+      mcost = pat_cost(k, level, lam, *mv_x + step * epzs_pt[pos][0], *mv_y + step * epzs_pt[pos][1]);
+      if (mcost < *min_mcost) { *min_mcost = mcost; best = pos; }
+    }
+  if (best) { *mv_x += step * epzs_pt[best][0]; *mv_y += step * epzs_pt[best][1]; }
+  return 0;
+}
+
+static void pat_init(pat_ctx *k, const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+                     int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y)
+{
+  memset(k, 0, sizeof *k);
+  k->c = c; k->stride = cur_stride; k->src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
+  ora_block_size(blocktype, &k->bsx, &k->bsy);
+  k->use8x8 = c->transform8x8 && blocktype <= 4;                 /* test8x8transform, mv-search.c:640 */
+  k->ppx = pic_pix_x; k->ppy = pic_pix_y; k->p4x = (pic_pix_x + PAD) << 2; k->p4y = (pic_pix_y + PAD) << 2;
+  k->r1 = r1; k->r2 = r2; k->pmvx = pmv_x; k->pmvy = pmv_y;
+}
+
+/* EPZSSubPelBlockMotionSearch (me_epzs.c:2390-2720).  subthres = subthres[blocktype] (:354) */
+int ora_epzs_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                    int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
+                    int search_pos2, int search_pos4, int min_mcost, const int *lambda, int subthres)
+{
+  pat_ctx k;
+  int shp = start_hp(c), sqp = start_qp(c);
+  int max_pos2 = ((!shp || !sqp) && search_pos2 < 1) ? 1 : search_pos2;          /* :2411 */
+  pat_init(&k, c, cur, cur_stride, r, NULL, pic_pix_x, pic_pix_y, blocktype, pmv_x, pmv_y);
+  if (epzs_level(&k, 1, lambda[1], 2, 1, shp, max_pos2, subthres, mv_x, mv_y, &min_mcost)) return min_mcost;
+  if (!sqp) min_mcost = INT_MAX;                                                  /* :2581 */
+  epzs_level(&k, 2, lambda[2], 1, 0, sqp, search_pos4, subthres, mv_x, mv_y, &min_mcost);
+  return min_mcost;
+}
+
+/* EPZSSubPelBlockSearchBiPred (me_epzs.c:2728-3125): r1 = listX[list][ref] read at the fixed vector s_mv, r2 = listX[list ^ 1][0] read
+ * at the candidate; both vectors carry a rate term; no early return (:2894 is commented out in the reference) */
+int ora_epzs_subpel_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+                           int pic_pix_x, int pic_pix_y, int blocktype, int pmv1_x, int pmv1_y, int pmv2_x, int pmv2_y,
+                           short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
+                           int search_pos2, int search_pos4, int min_mcost, const int *lambda)
+{
+  pat_ctx k;
+  int shp = (min_mcost == INT_MAX) ? 0 : start_hp(c), sqp = start_qp(c);         /* :2760 */
+  int max_pos2 = ((!start_hp(c) || !sqp) && search_pos2 < 1) ? 1 : search_pos2;   /* :2761 */
+  pat_init(&k, c, cur, cur_stride, r1, r2, pic_pix_x, pic_pix_y, blocktype, pmv1_x, pmv1_y);
+  k.smx = *s_mv_x + k.p4x; k.smy = *s_mv_y + k.p4y; k.s_mv_x = *s_mv_x; k.s_mv_y = *s_mv_y; k.pmv2x = pmv2_x; k.pmv2y = pmv2_y;
+  epzs_level(&k, 1, lambda[1], 2, 1, shp, max_pos2, -1, mv_x, mv_y, &min_mcost);
+  if (!sqp) min_mcost = INT_MAX;                                                  /* :3008 */
+  epzs_level(&k, 2, lambda[2], 1, 0, sqp, search_pos4, -1, mv_x, mv_y, &min_mcost);
+  return min_mcost;
+}
+
+/* The quarter-pel diamond walks of UMHEXSubPelBlockMotionSearch (me_umhex.c:562-730) and smpUMHEXSubPelBlockMotionSearch
+ * (me_umhexsmp.c:616-812): inside +-3 quarter pel of the start vector, every position scored at most once (SearchState), metric
+ * and factor of the quarter-pel level throughout.
+ * smp == 0: diamond order (-1,0) (0,1) (1,0) (0,-1); no thresholds.
+ * smp == 1: diamond order (-1,0) (1,0) (0,-1) (0,1); uplayer_x / y = smpUMHEX_pred_MV_uplayer_X / _Y (:1203-1214), thr1 / thr3 =
+ * SubPelThreshold1 / 3 >> block_type_shift_factor[blocktype] (:106-107, :46). */
+static int umhex_walk(const pat_ctx *k, int smp, int lam, int uplayer_x, int uplayer_y, int thr1, int thr3,
+                      short *mv_x, short *mv_y, int min_mcost)
+{
+  static const int8_t dia[2][4][2] = { { {-1, 0}, {0, 1}, {1, 0}, {0, -1} }, { {-1, 0}, {1, 0}, {0, -1}, {0, 1} } };
+  unsigned char seen[7][7];
+  const int R = 3, mx0 = *mv_x, my0 = *mv_y;
+  int cx, cy, mcost, curx = 0, cury = 0, i, m, abort_search;
+  int fx = (k->pmvx - mx0) % 4, fy = (k->pmvy - my0) % 4;                         /* C remainder: sign of the dividend */
+  int ux = (uplayer_x - mx0) % 4, uy = (uplayer_y - my0) % 4;
+  memset(seen, 0, sizeof seen);
+  seen[R][R] = 1;
+  if (!start_hp(k->c)) {
+    mcost = pat_cost(k, 2, lam, mx0, my0);
+    if (mcost < min_mcost) { min_mcost = mcost; curx = mx0; cury = my0; }         /* otherwise the walk starts from vector (0, 0), as in the reference */
+  } else { curx = mx0; cury = my0; }
+  if (smp && mx0 == 0 && my0 == 0 && fx == 0 && ux == 0 && fy == 0 && uy == 0 && min_mcost < thr1) {
+    *mv_x = (short)curx; *mv_y = (short)cury;
+    return min_mcost;
+  }
+  if (fx || fy) {
+    cx = mx0 + fx; cy = my0 + fy;
+    mcost = pat_cost(k, 2, lam, cx, cy);
+    seen[cy - my0 + R][cx - mx0 + R] = 1;
+    if (mcost < min_mcost) { min_mcost = mcost; curx = cx; cury = cy; }
+  }
+  for (i = 0; i < R; i++) {
+    int nx = curx, ny = cury;
+    abort_search = 1;
+    for (m = 0; m < 4; m++) {
+      cx = nx + dia[smp][m][0]; cy = ny + dia[smp][m][1];
+      if (iabs_(cx - mx0) <= R && iabs_(cy - my0) <= R && !seen[cy - my0 + R][cx - mx0 + R]) {
+        mcost = pat_cost(k, 2, lam, cx, cy);
+        seen[cy - my0 + R][cx - mx0 + R] = 1;
+        if (mcost < min_mcost) { min_mcost = mcost; curx = cx; cury = cy; abort_search = 0; }
+        if (smp && min_mcost < thr3) { *mv_x = (short)curx; *mv_y = (short)cury; return min_mcost; }
+      }
+    }
+    if (abort_search) break;
+  }
+  *mv_x = (short)curx; *mv_y = (short)cury;
+  return min_mcost;
+}
+
+int ora_umhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                     int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
+                     int min_mcost, int lambda_factor)
+{
+  pat_ctx k;
+  pat_init(&k, c, cur, cur_stride, r, NULL, pic_pix_x, pic_pix_y, blocktype, pmv_x, pmv_y);
+  return umhex_walk(&k, 0, lambda_factor, 0, 0, 0, 0, mv_x, mv_y, min_mcost);
+}
+
+static const int8_t smp_shift[8] = { 0, 0, 1, 1, 2, 3, 3, 1 };                    /* block_type_shift_factor, me_umhexsmp.c:46 */
+
+int ora_smpumhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                        int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
+                        int min_mcost, int lambda_factor, int uplayer_x, int uplayer_y, int threshold1, int threshold3)
+{
+  pat_ctx k;
+  pat_init(&k, c, cur, cur_stride, r, NULL, pic_pix_x, pic_pix_y, blocktype, pmv_x, pmv_y);
+  return umhex_walk(&k, 1, lambda_factor, uplayer_x, uplayer_y, threshold1 >> smp_shift[blocktype], threshold3 >> smp_shift[blocktype],
+                    mv_x, mv_y, min_mcost);
+}
+
+/* smpUMHEXFullSubPelBlockMotionSearch (me_umhexsmp.c:422-608): the nine half-pel and nine quarter-pel positions of the plain
+ * refinement, both scored with the quarter-pel metric and factor, each loop left as soon as the minimum is below SubPelThreshold3 */
+int ora_smpumhex_full_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                             int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type, int pmv_x, int pmv_y,
+                             short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor,
+                             int threshold1, int threshold3)
+{
+  pat_ctx k;
+  int pos, best, mcost, cx, cy;
+  int check0 = (!c->rdopt && slice_type != ME_B_SLICE && ref == 0 && blocktype == 1 && *mv_x == 0 && *mv_y == 0);
+  int shp = start_hp(c), sqp = start_qp(c);
+  int max_pos2 = (!shp && search_pos2 < 1) ? 1 : search_pos2;
+  int thr1 = threshold1 >> smp_shift[blocktype], thr3 = threshold3 >> smp_shift[blocktype];
+  int16_t sx[9], sy[9];
+  pat_init(&k, c, cur, cur_stride, r, NULL, pic_pix_x, pic_pix_y, blocktype, pmv_x, pmv_y);
+  first_spiral(9, sx, sy);
+  for (best = 0, pos = shp; pos < max_pos2; pos++) {
+    cx = *mv_x + 2 * sx[pos]; cy = *mv_y + 2 * sy[pos];
+    if (ora_mv_cost(lambda_factor, cx, cy, pmv_x, pmv_y) >= min_mcost) continue;  /* skips the threshold test below as well (:519) */
+    mcost = pat_cost(&k, 2, lambda_factor, cx, cy);
+    if (pos == 0 && check0) mcost -= (lambda_factor * 16) >> 16;
+    if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
+    if (min_mcost < thr3) break;
+  }
+  if (best) { *mv_x += 2 * sx[best]; *mv_y += 2 * sy[best]; }
+  if (*mv_x == 0 && *mv_y == 0 && pmv_x == 0 && pmv_y == 0 && min_mcost < thr1) return min_mcost;
+  if (!sqp) min_mcost = INT_MAX;
+  for (best = 0, pos = sqp; pos < search_pos4; pos++) {
+    cx = *mv_x + sx[pos]; cy = *mv_y + sy[pos];
+    if (ora_mv_cost(lambda_factor, cx, cy, pmv_x, pmv_y) >= min_mcost) continue;
+    mcost = pat_cost(&k, 2, lambda_factor, cx, cy);
+    if (mcost < min_mcost) { min_mcost = mcost; best = pos; }
+    if (min_mcost < thr3) break;
+  }
+  if (best) { *mv_x += sx[best]; *mv_y += sy[best]; }
+  return min_mcost;
+}

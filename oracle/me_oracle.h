@@ -115,6 +115,28 @@ int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
                       short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
                       int search_pos2, int search_pos4, int min_mcost, const int *lambda);
 
+/* ---- sub-pel stages of the pattern searches (SearchMode 1 UMHexagonS, 2 simplified UMHexagonS, 3 EPZS).
+ * Vectors are quarter pel.  State the reference keeps in file statics / globals arrives as arguments:
+ * subthres = subthres[blocktype] (me_epzs.c:354); uplayer_x / y = smpUMHEX_pred_MV_uplayer_X / _Y (me_umhexsmp.c:1203-1214);
+ * threshold1 / threshold3 = SubPelThreshold1 / SubPelThreshold3 (me_umhexsmp.c:106-107), shifted inside by the block type */
+int ora_epzs_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                    int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
+                    int search_pos2, int search_pos4, int min_mcost, const int *lambda, int subthres);
+int ora_epzs_subpel_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+                           int pic_pix_x, int pic_pix_y, int blocktype, int pmv1_x, int pmv1_y, int pmv2_x, int pmv2_y,
+                           short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
+                           int search_pos2, int search_pos4, int min_mcost, const int *lambda);
+int ora_umhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                     int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
+                     int min_mcost, int lambda_factor);
+int ora_smpumhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                        int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
+                        int min_mcost, int lambda_factor, int uplayer_x, int uplayer_y, int threshold1, int threshold3);
+int ora_smpumhex_full_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+                             int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type, int pmv_x, int pmv_y,
+                             short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor,
+                             int threshold1, int threshold3);
+
 /* one batch job = PartitionMotionSearch for all 41 partitions of one (macroblock, list, ref) */
 void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
                    const me_mb_job *job, me_mb_result *out, me_mb_result_int *out_int);

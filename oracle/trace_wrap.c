@@ -15,6 +15,10 @@
  *   FullPelBlockMotionSearch       lencod/src/me_fullsearch.c:47  (called mv-search.c:765; SearchMode = -1)
  *   FullPelBlockMotionBiPred       lencod/src/me_fullsearch.c:164 (called mv-search.c:960)
  *   SubPelBlockSearchBiPred        lencod/src/me_fullsearch.c:520 (called mv-search.c:998,1018)
+ *   EPZSSubPelBlockMotionSearch    lencod/src/me_epzs.c:2390      (called mv-search.c:818; SearchMode 3 with EPZSSubPelME)
+ *   EPZSSubPelBlockSearchBiPred    lencod/src/me_epzs.c:2728      (called mv-search.c:993,1013; EPZSSubPelMEBiPred)
+ *   UMHEXSubPelBlockMotionSearch   lencod/src/me_umhex.c:562      (called mv-search.c:794; SearchMode 1, block types 4..7)
+ *   smpUMHEXSubPelBlockMotionSearch / smpUMHEXFullSubPelBlockMotionSearch  lencod/src/me_umhexsmp.c:616, :422 (called mv-search.c:807,812; SearchMode 2)
  *   ResetFastFullIntegerSearch     lencod/src/me_fullfast.c:197   (called macroblock.c:509)
  *   getSubImagesLuma               lencod/src/img_luma.c:45       (called image.c:1642)
  *   encode_one_frame               lencod/src/image.c:346         (called lencod.c:341)
@@ -36,9 +40,11 @@
 #include "image.h"
 #include "mbuffer.h"
 #include "me_distortion.h"
+#include "me_umhexsmp.h"
 
 #define REC_INTS 32
-enum { REC_FFS = 1, REC_SUBPEL = 2, REC_BI_FULL = 3, REC_BI_SUB = 4, REC_REFPIC = 5, REC_CURPIC = 6, REC_FULLPEL = 7 };
+enum { REC_FFS = 1, REC_SUBPEL = 2, REC_BI_FULL = 3, REC_BI_SUB = 4, REC_REFPIC = 5, REC_CURPIC = 6, REC_FULLPEL = 7,
+       REC_SUBPEL_PAT = 8, REC_BI_SUB_PAT = 9 };
 
 extern const int LEVELMVLIMIT[17][6];
 extern void SetMotionVectorPredictor (short pmv[2], char **refPic, short ***tmp_mv, short ref_frame,
@@ -380,6 +386,108 @@ int __wrap_SubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pi
   cost = __real_SubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                         mv_x, mv_y, s_mv_x, s_mv_y, search_pos2, search_pos4, min_mcost, lambda_factor);
   rec[23] = *mv_x; rec[24] = *mv_y; rec[25] = cost;
+  put(rec);
+  return cost;
+}
+
+/* ---------------------------------------------------------------- sub-pel stages of the pattern searches (SearchMode 1, 2, 3)
+ * record REC_SUBPEL_PAT: fields 0..21 and 26..31 as REC_SUBPEL (a function with one factor has it in all of 15..17);
+ *   rec[22] = test8x8transform | start_me_refinement_hp << 1 | start_me_refinement_qp << 2 | rdopt << 3 | pattern << 4
+ *             (pattern: 1 EPZS, 2 UMHexagonS, 3 simplified UMHexagonS, 4 simplified UMHexagonS "full")
+ *   rec[23] = SubPelThreshold1 | SubPelThreshold3 << 16 (me_umhexsmp.c:106-107)
+ *   rec[24] = subthres[blocktype] as EPZSInit derives it (me_epzs.c:335-354; the array itself is a file static)
+ *   rec[25] = smpUMHEX_pred_MV_uplayer_X (low half) | smpUMHEX_pred_MV_uplayer_Y << 16 */
+static int epzs_subthres(int blocktype)
+{
+  static const int medthres_base[8] = { 0, 256, 128, 128, 64, 32, 32, 16 };       /* me_epzs.c:41 */
+  int pel_error_me = 1 << (img->bitdepth_luma - 8), pel_error_me_cr = 1 << (img->bitdepth_chroma - 8);
+  double chroma_weight = input->ChromaMEEnable ? pel_error_me_cr * input->ChromaMEWeight * (double)(img->width_cr * img->height_cr) / (double)(img->width * img->height) : 0;
+  return input->EPZSSubPelThresScale * (medthres_base[blocktype] * pel_error_me + (int)(medthres_base[blocktype] * chroma_weight + 0.5));
+}
+
+static void pat_head(int *rec, int pattern, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, int pmx, int pmy,
+                     int mvx, int mvy, int sp2, int sp4, int min_mcost, int l0, int l1, int l2)
+{
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  dump_current_if_needed();
+  rec[0] = REC_SUBPEL_PAT; rec[1] = coded_pic_no; rec[2] = img->type | (ChromaMEEnable << 8); rec[3] = img->opix_x; rec[4] = img->opix_y;
+  rec[5] = list; rec[6] = ref; rec[7] = blocktype; rec[8] = pic_pix_x; rec[9] = pic_pix_y;
+  rec[10] = pmx; rec[11] = pmy; rec[12] = mvx; rec[13] = mvy; rec[14] = min_mcost;
+  rec[15] = l0; rec[16] = l1; rec[17] = l2;
+  rec[21] = ref_id_of(listX[list + list_offset][ref]);
+  rec[22] = test8x8transform | (start_me_refinement_hp << 1) | (start_me_refinement_qp << 2) | ((input->rdopt != 0) << 3) | (pattern << 4);
+  rec[23] = SubPelThreshold1 | (SubPelThreshold3 << 16);
+  rec[24] = epzs_subthres(blocktype);
+  rec[25] = (smpUMHEX_pred_MV_uplayer_X & 0xffff) | (smpUMHEX_pred_MV_uplayer_Y << 16);
+  rec[26] = sp2; rec[27] = sp4;
+  put_weights(rec, list, list_offset, ref);
+}
+
+int __real_EPZSSubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                       short pred_mv[2], short mv[2], int search_pos2, int search_pos4, int min_mcost, int *lambda);
+int __wrap_EPZSSubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                       short pred_mv[2], short mv[2], int search_pos2, int search_pos4, int min_mcost, int *lambda)
+{
+  int rec[REC_INTS] = {0}, cost;
+  pat_head(rec, 1, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv[0], pred_mv[1], mv[0], mv[1], search_pos2, search_pos4, min_mcost,
+           lambda[0], lambda[1], lambda[2]);
+  cost = __real_EPZSSubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv, mv, search_pos2, search_pos4, min_mcost, lambda);
+  rec[18] = mv[0]; rec[19] = mv[1]; rec[20] = cost;
+  put(rec);
+  return cost;
+}
+
+#define PAT_WRAP(NAME, PATTERN)                                                                                                     \
+int __real_##NAME(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, short pred_mv_x, short pred_mv_y, \
+                  short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor);                    \
+int __wrap_##NAME(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, short pred_mv_x, short pred_mv_y, \
+                  short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor)                     \
+{                                                                                                                                   \
+  int rec[REC_INTS] = {0}, cost;                                                                                                    \
+  pat_head(rec, PATTERN, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, *mv_x, *mv_y, search_pos2, search_pos4,  \
+           min_mcost, lambda_factor, lambda_factor, lambda_factor);                                                                 \
+  cost = __real_##NAME(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2,         \
+                       search_pos4, min_mcost, lambda_factor);                                                                      \
+  rec[18] = *mv_x; rec[19] = *mv_y; rec[20] = cost;                                                                                 \
+  put(rec);                                                                                                                         \
+  return cost;                                                                                                                      \
+}
+PAT_WRAP(UMHEXSubPelBlockMotionSearch, 2)
+PAT_WRAP(smpUMHEXSubPelBlockMotionSearch, 3)
+PAT_WRAP(smpUMHEXFullSubPelBlockMotionSearch, 4)
+
+/* record REC_BI_SUB_PAT: as REC_BI_SUB, and rec[20] = second predictor, x (low half) | y << 16 */
+int __real_EPZSSubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                       short *pred_mv1, short *pred_mv2, short mv[2], short s_mv[2],
+                                       int search_pos2, int search_pos4, int min_mcost, int *lambda);
+int __wrap_EPZSSubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
+                                       short *pred_mv1, short *pred_mv2, short mv[2], short s_mv[2],
+                                       int search_pos2, int search_pos4, int min_mcost, int *lambda)
+{
+  int rec[REC_INTS] = {0};
+  int list_offset = img->mb_data[img->current_mb_nr].list_offset;
+  int cost;
+  dump_current_if_needed();
+  rec[0] = REC_BI_SUB_PAT; rec[1] = coded_pic_no; rec[2] = img->type | (ChromaMEEnable << 8); rec[3] = img->opix_x; rec[4] = img->opix_y;
+  rec[5] = list; rec[6] = ref; rec[7] = blocktype; rec[8] = pic_pix_x; rec[9] = pic_pix_y;
+  rec[10] = pred_mv1[0]; rec[11] = pred_mv1[1];
+  rec[12] = mv[0]; rec[13] = mv[1]; rec[14] = s_mv[0]; rec[15] = s_mv[1];
+  rec[16] = min_mcost; rec[17] = lambda[0]; rec[18] = lambda[1]; rec[19] = lambda[2];
+  rec[20] = (pred_mv2[0] & 0xffff) | (pred_mv2[1] << 16);
+  rec[21] = ref_id_of(listX[list + list_offset][ref]);
+  rec[22] = ref_id_of(listX[(list ^ 1) + list_offset][0]);
+  rec[26] = test8x8transform; rec[27] = start_me_refinement_hp; rec[28] = start_me_refinement_qp;
+  if (active_pps->weighted_bipred_idc > 0) {
+    /* me_epzs.c:2746-2747, :2783-2789; same packing as in the other bi-predictive records */
+    int o1 = list == 0 ? wp_offset[list_offset][ref][0] : wp_offset[list_offset + 1][0][0];
+    int o2 = list == 0 ? wp_offset[list_offset + 1][ref][0] : wp_offset[list_offset][0][0];
+    int w1 = list == 0 ? wbp_weight[list_offset][ref][0][0] : wbp_weight[list_offset + LIST_1][0][ref][0];
+    int w2 = list == 0 ? wbp_weight[list_offset + LIST_1][ref][0][0] : wbp_weight[list_offset][0][ref][0];
+    rec[29] = 1 + luma_log_weight_denom; rec[30] = (w1 & 0xffff) | (w2 << 16); rec[31] = (o1 + o2 + 1) >> 1;
+  }
+  cost = __real_EPZSSubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv1, pred_mv2, mv, s_mv,
+                                            search_pos2, search_pos4, min_mcost, lambda);
+  rec[23] = mv[0]; rec[24] = mv[1]; rec[25] = cost;
   put(rec);
   return cost;
 }

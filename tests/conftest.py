@@ -50,7 +50,17 @@ GOLDEN_CASES = {
 }
 
 
+# sub-pel stages of the pattern searches (SearchMode 1, 2, 3; records of type 8 / 9): EPZSSubPelBlockMotionSearch / ...BiPred,
+# UMHEXSubPelBlockMotionSearch, smpUMHEX[Full]SubPelBlockMotionSearch
+PATTERN_CASES = {
+    "epzs_sub": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),
+    "umhex_sub": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),
+    "smpumhex_sub": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),        # RDOptimization = 0
+    "epzs_chroma_sad": dict(search_range=16, full_search=2, metric=(0, 0, 0), mv_limits=(-511, 511)),     # ChromaMEEnable = 2, SAD sub-pel
+}
+
+
 def golden_trace(name):
     from trace_util import Trace, cfg_from_trace
     tr = Trace.load_npz(os.path.join(GOLDEN, name + ".npz"))
-    return tr, cfg_from_trace(tr, **GOLDEN_CASES[name])
+    return tr, cfg_from_trace(tr, **(GOLDEN_CASES.get(name) or PATTERN_CASES[name]))

@@ -46,7 +46,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from trace_util import Trace, REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_FULLPEL  # noqa: E402
+from trace_util import Trace, REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_FULLPEL, REC_SUBPEL_PAT, REC_BI_SUB_PAT  # noqa: E402
 import h264_b200_pkg  # noqa: E402,F401
 from h264_b200 import synth  # noqa: E402
 
@@ -72,7 +72,7 @@ def keep_mask(tr, step):
     recs = tr.recs
     mb_w = tr.size[("cur", tr.cur_ids()[0])][1] // 16
     mb = (recs[:, 4] // 16) * mb_w + recs[:, 3] // 16
-    is_call = np.isin(recs[:, 0], [REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_FULLPEL])
+    is_call = np.isin(recs[:, 0], [REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_FULLPEL, REC_SUBPEL_PAT, REC_BI_SUB_PAT])
     return ~is_call | (mb % step == 0)
 
 
@@ -183,6 +183,7 @@ def main():
         tr.save_npz(os.path.join(HERE, "wpbc.npz"), keep_mask(tr, 12))
         crc["wpbc"] = planes_crc(tr, d)
     epzs(crc, md5s)
+    patterns(crc, md5s)
     big(md5s)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
@@ -239,8 +240,52 @@ def epzs(crc, md5s):
         crc["epzs"] = planes_crc(tr, d)
 
 
+# Sub-pel stages of the pattern searches (records of type 8 / 9, oracle/trace_wrap.c)
+PATTERN_CASES = {
+    # EPZS as shipped in encoder.cfg (EPZSSubPelME = EPZSSubPelMEBiPred = EPZSSubPelGrid = 1): EPZSSubPelBlockMotionSearch and
+    # EPZSSubPelBlockSearchBiPred, SATD, 8x8 transform, I-B-P, start vectors off the integer grid
+    "epzs_sub": (["-d", "encoder.cfg", "-p", "SearchMode=3", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"], 4),
+    # UMHexagonS: UMHEXSubPelBlockMotionSearch for block types 4..7, the plain refinement for 1..3
+    "umhex_sub": (["-d", "encoder.cfg", "-p", "SearchMode=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"], 4),
+    # simplified UMHexagonS without RDO: smpUMHEXSubPelBlockMotionSearch / smpUMHEXFullSubPelBlockMotionSearch with the
+    # check_position0 bonus and the SubPelThreshold exits
+    "smpumhex_sub": (["-d", "encoder_baseline.cfg", "-p", "SearchMode=2", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2",
+                      "-p", "RDOptimization=0"], 3),
+    # EPZS with SAD at the sub-pel levels and ChromaMEEnable = 2: chroma terms in the pattern's candidates (uni- and bi-predictive)
+    "epzs_chroma_sad": (["-d", "encoder.cfg", "-p", "SearchMode=3", "-p", "ChromaMEEnable=2", "-p", "MEDistortionHPel=0",
+                         "-p", "MEDistortionQPel=0", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"], 8),
+}
+
+
+def patterns(crc, md5s, only=None):
+    for case, (args, step) in PATTERN_CASES.items():
+        if only and case not in only:
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            shutil.copy(os.path.join(REF, "fixtures", "foreman_part_qcif.yuv"), d)
+            run_trace(d, args)
+            md5s[case] = {"test.264": md5(os.path.join(d, "test.264"))}
+            tr = Trace(d)
+            pat = tr.of_type(REC_SUBPEL_PAT)
+            assert len(pat) > 5000 and not len(tr.of_type(REC_FFS))
+            if case.startswith("epzs"):
+                assert len(tr.of_type(REC_BI_SUB_PAT)) and ((pat[:, 22] >> 4) == 1).all() and ((pat[:, 12] & 3) != 0).any()
+            if case == "umhex_sub":
+                assert ((pat[:, 22] >> 4) == 2).all() and len(tr.of_type(REC_SUBPEL))
+            if case == "smpumhex_sub":
+                assert set((pat[:, 22] >> 4).tolist()) == {3, 4} and not ((pat[:, 22] >> 3) & 1).any()
+            tr.save_npz(os.path.join(HERE, case + ".npz"), keep_mask(tr, step))
+            crc[case] = planes_crc(tr, d)
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["epzs"]:                  # add this case without rewriting the other fixtures
+    if sys.argv[1:2] == ["patterns"]:               # add these cases without rewriting the other fixtures
+        crc = json.load(open(os.path.join(HERE, "planes_crc.json")))
+        md5s = json.load(open(os.path.join(HERE, "bitstream_md5.json")))
+        patterns(crc, md5s, sys.argv[2:] or None)
+        json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
+        json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
+    elif sys.argv[1:] == ["epzs"]:                  # add this case without rewriting the other fixtures
         crc = json.load(open(os.path.join(HERE, "planes_crc.json")))
         md5s = json.load(open(os.path.join(HERE, "bitstream_md5.json")))
         epzs(crc, md5s)

@@ -6,7 +6,7 @@ replay() walks a Trace in call order and returns the mismatching records per fun
 """
 import numpy as np
 
-from trace_util import REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_CURPIC, REC_REFPIC, REC_FULLPEL
+from trace_util import REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_CURPIC, REC_REFPIC, REC_FULLPEL, REC_SUBPEL_PAT, REC_BI_SUB_PAT
 
 
 def picture_lists(trace, pic):
@@ -15,9 +15,9 @@ def picture_lists(trace, pic):
     recs = trace.recs[(trace.recs[:, 1] == pic)]
     for r in recs:
         t = int(r[0])
-        if t in (REC_FFS, REC_SUBPEL, REC_FULLPEL):
+        if t in (REC_FFS, REC_SUBPEL, REC_FULLPEL, REC_SUBPEL_PAT):
             lists[int(r[5])][int(r[6])] = int(r[21])
-        elif t in (REC_BI_FULL, REC_BI_SUB):
+        elif t in (REC_BI_FULL, REC_BI_SUB, REC_BI_SUB_PAT):
             lists[int(r[5])][int(r[6])] = int(r[21])
             lists[int(r[5]) ^ 1][0] = int(r[22])
     out = {}
@@ -98,6 +98,15 @@ class OracleAdapter:
     def subpel(self, ref, lst, ppx, ppy, bt, pmvx, pmvy, mvx, mvy, sp2, sp4, min_mcost, lam3):
         return self.ob.subpel(self.cfg, self.cur, self._ref(lst, ref), ppx, ppy, bt, ref, self.slice_type,
                               pmvx, pmvy, mvx, mvy, min_mcost, lam3, sp2, sp4)
+
+    def subpel_pattern(self, pattern, ref, lst, ppx, ppy, bt, pmv, mv, sp2, sp4, min_mcost, lam3, subthres, uplayer, thresholds):
+        return self.ob.subpel_pattern(self.cfg, self.cur, self._ref(lst, ref), pattern, ppx, ppy, bt, ref, self.slice_type, pmv, mv,
+                                      min_mcost, lam3, sp2, sp4, subthres, uplayer, thresholds)
+
+    def bipred_sub_pattern(self, ref, lst, ppx, ppy, bt, pmv1, pmv2, mv, smv, sp2, sp4, min_mcost, lam3):
+        r1, r2 = self.refs[self.lists[lst][ref]], self.refs[self.lists[lst ^ 1][0]]
+        self.ob.select_bipred_list(lst)
+        return self.ob.epzs_subpel_bipred(self.cfg, self.cur, r1, r2, ppx, ppy, bt, pmv1, pmv2, mv, smv, min_mcost, lam3, sp2, sp4)
 
     def set_bipred_weights(self, lst, apply, w1, w2, obi, denom):
         self.ob.set_bipred_weights(lst, apply, w1, w2, obi, denom)
@@ -185,13 +194,20 @@ class CudaAdapter:
     def bipred_sub(self, ref, lst, ppx, ppy, bt, pmv, mv, smv, sp2, sp4, min_mcost, lam3):
         return self.me.SubPelBlockSearchBiPred(ref, lst, ppx, ppy, bt, pmv, mv, smv, sp2, sp4, min_mcost, lam3)
 
+    def subpel_pattern(self, pattern, ref, lst, ppx, ppy, bt, pmv, mv, sp2, sp4, min_mcost, lam3, subthres, uplayer, thresholds):
+        return self.me.SubPelPattern(pattern, ref, lst, ppx, ppy, bt, pmv, mv, sp2, sp4, min_mcost, lam3, subthres, uplayer, thresholds)
+
+    def bipred_sub_pattern(self, ref, lst, ppx, ppy, bt, pmv1, pmv2, mv, smv, sp2, sp4, min_mcost, lam3):
+        return self.me.EPZSSubPelBlockSearchBiPred(ref, lst, ppx, ppy, bt, pmv1, pmv2, mv, smv, sp2, sp4, min_mcost, lam3)
+
     def close(self):
         self.me.close()
 
 
 def replay(trace, impl, max_calls=None):
     """returns {name: (n_calls, [mismatch descriptions])}"""
-    res = {"ffs": [0, []], "centre": [0, []], "subpel": [0, []], "bi_full": [0, []], "bi_sub": [0, []], "fullpel": [0, []]}
+    res = {"ffs": [0, []], "centre": [0, []], "subpel": [0, []], "bi_full": [0, []], "bi_sub": [0, []], "fullpel": [0, []],
+           "subpel_pat": [0, []], "bi_sub_pat": [0, []]}
     cur_pic, cur_mb = None, None
     bi_chroma = {}
     slice_of = {int(r[1]): int(r[2]) for r in trace.of_type(REC_CURPIC)}
@@ -208,12 +224,12 @@ def replay(trace, impl, max_calls=None):
             impl.mb_begin(ox, oy)
             cur_mb = (ox, oy)
         lst, ref, bt, ppx, ppy = int(r[5]), int(r[6]), int(r[7]), int(r[8]), int(r[9])
-        if t in (REC_FFS, REC_SUBPEL, REC_FULLPEL):
+        if t in (REC_FFS, REC_SUBPEL, REC_FULLPEL, REC_SUBPEL_PAT):
             # weighted-prediction ME: the weights the reference derived for this (list, ref) (0 = off in older fixtures)
             impl.set_weights(lst, ref, int(r[28]), int(r[29]), int(r[30]), int(r[31]))
         # ChromaMEEnable as the call sees it (the reference resets the global between the stages of BlockMotionSearch)
         impl.set_chroma_state(pic, int(r[27]) if t == REC_FFS else int(r[26]) if t in (REC_FULLPEL, REC_BI_FULL) else int(r[2]) >> 8)
-        if t in (REC_BI_FULL, REC_BI_SUB):
+        if t in (REC_BI_FULL, REC_BI_SUB, REC_BI_SUB_PAT):
             # weighted bi-prediction: 1 + log denominator (0 = off), weight1 | weight2 << 16, offsetBi
             w = int(r[30])
             impl.set_bipred_weights(lst, int(r[29]) > 0, (w << 16 >> 16) if w & 0x8000 else w & 0xffff, w >> 16, int(r[31]), max(0, int(r[29]) - 1))
@@ -243,6 +259,20 @@ def replay(trace, impl, max_calls=None):
                               int(r[14]), [int(r[15]), int(r[16]), int(r[17])])
             exp = (int(r[18]), int(r[19]), int(r[20]))
             key = "subpel"
+        elif t == REC_SUBPEL_PAT:
+            s16 = lambda v: ((v & 0xffff) ^ 0x8000) - 0x8000   # noqa: E731
+            got = impl.subpel_pattern(int(r[22]) >> 4, ref, lst, ppx, ppy, bt, (int(r[10]), int(r[11])), (int(r[12]), int(r[13])),
+                                      int(r[26]), int(r[27]), int(r[14]), [int(r[15]), int(r[16]), int(r[17])], int(r[24]),
+                                      (s16(int(r[25])), int(r[25]) >> 16), (int(r[23]) & 0xffff, int(r[23]) >> 16))
+            exp = (int(r[18]), int(r[19]), int(r[20]))
+            key = "subpel_pat"
+        elif t == REC_BI_SUB_PAT:
+            s16 = lambda v: ((v & 0xffff) ^ 0x8000) - 0x8000   # noqa: E731
+            got = impl.bipred_sub_pattern(ref, lst, ppx, ppy, bt, (int(r[10]), int(r[11])), (s16(int(r[20])), int(r[20]) >> 16),
+                                          (int(r[12]), int(r[13])), (int(r[14]), int(r[15])), 9, 9, int(r[16]),
+                                          [int(r[17]), int(r[18]), int(r[19])])
+            exp = (int(r[23]), int(r[24]), int(r[25]))
+            key = "bi_sub_pat"
         elif t == REC_BI_FULL:
             got = impl.bipred_full(ref, lst, ppx, ppy, bt, (int(r[10]), int(r[11])), (int(r[12]), int(r[13])),
                                    (int(r[17]), int(r[18])), (int(r[19]), int(r[20])), int(r[16]), int(r[14]), int(r[15]))
@@ -261,3 +291,12 @@ def replay(trace, impl, max_calls=None):
         if max_calls and n >= max_calls:
             break
     return {k: (v[0], v[1]) for k, v in res.items()}
+
+
+def pattern_counts(case, res):
+    """what each pattern fixture must exercise (tests/golden/make_golden.py: PATTERN_CASES)"""
+    assert res["subpel_pat"][0] > 1500 and not res["ffs"][0]
+    if case.startswith("epzs"):
+        assert res["bi_sub_pat"][0] > 20
+    if case == "umhex_sub":
+        assert res["subpel"][0] > 300 and res["bi_sub"][0] > 20

@@ -5,8 +5,8 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, golden_trace
-from replay import CudaAdapter, replay
+from conftest import GOLDEN_CASES, PATTERN_CASES, golden_trace
+from replay import CudaAdapter, replay, pattern_counts
 
 pytestmark = pytest.mark.gpu
 
@@ -92,6 +92,22 @@ def test_dropin_calls_match_reference_trace(pkg, case):
         assert not bad, (case, name, n, len(bad), bad[:3])
     # the pattern-search trace (epzs) holds no integer-pel calls of the path: that stage stays the reference's own
     assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000 or case == "epzs") and res["subpel"][0] > 1000
+
+
+@pytest.mark.parametrize("case", sorted(PATTERN_CASES))
+def test_dropin_pattern_subpel_calls_match_reference_trace(pkg, case):
+    """sub-pel stages of the pattern searches (SearchMode 1 / 2 / 3) through me_cuda_EPZSSubPelBlockMotionSearch,
+    me_cuda_EPZSSubPelBlockSearchBiPred, me_cuda_UMHEXSubPelBlockMotionSearch, me_cuda_smpUMHEX[Full]SubPelBlockMotionSearch: every
+    kept call of the unmodified reference encoder, vectors and costs identical"""
+    tr, cfgkw = golden_trace(case)
+    impl = CudaAdapter(tr, cfgkw)
+    try:
+        res = replay(tr, impl)
+    finally:
+        impl.close()
+    for name, (n, bad) in res.items():
+        assert not bad, (case, name, n, len(bad), bad[:3])
+    pattern_counts(case, res)
 
 
 # ------------------------------------------------------------------------------------------------ one launch per PartitionMotionSearch

@@ -124,7 +124,9 @@ def test_mode_decision_costs_and_paged_planes(tmp_path, me_lib_path, args, want)
                                   "chroma_me_1_sad_subpel", "chroma_me_2_yuv444", "hadamard_fpel_bframes",
                                   "hadamard_fpel_chroma_me_1", "weighted_implicit_bipred_chroma_me_2",
                                   "weighted_pred_chroma_me_1", "umhex_plain_subpel", "umhex_simple_bipred_subpel",
-                                  "epzs_plain_subpel", "epzs_subpel_grid_plain_subpel"])
+                                  "epzs_plain_subpel", "epzs_subpel_grid_plain_subpel",
+                                  "epzs_pattern_subpel", "epzs_pattern_subpel_weighted", "umhex_pattern_subpel_chroma_sad",
+                                  "umhex_simple_pattern_subpel_rdopt0"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -220,6 +222,22 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
                  "epzs_plain_subpel": ["-p", "SearchMode=3", "-p", "EPZSSubPelME=0", "-p", "EPZSSubPelMEBiPred=0", "-p", "EPZSSubPelGrid=0"],
                  "epzs_subpel_grid_plain_subpel": ["-p", "SearchMode=3", "-p", "EPZSSubPelME=0", "-p", "EPZSSubPelMEBiPred=0",
                                                    "-p", "EPZSSubPelGrid=1"]}[case]
+    elif case == "epzs_pattern_subpel":
+        # SURVEY.md 8(f) row 4, second half: EPZS as shipped (EPZSSubPelME = EPZSSubPelMEBiPred = EPZSSubPelGrid = 1):
+        # EPZSSubPelBlockMotionSearch / EPZSSubPelBlockSearchBiPred (me_epzs.c:2390, :2728) on the device
+        args = ["-d", "encoder.cfg", "-p", "SearchMode=3", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+    elif case == "epzs_pattern_subpel_weighted":
+        # ... on weighted reference samples (explicit weights, fading clip) and with weighted bi-prediction in the B pictures
+        args = ["-d", "encoder.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144", "-p", "FramesToBeEncoded=3",
+                "-p", "WeightedBiprediction=1", "-p", "WeightedPrediction=1", "-p", "UseWeightedReferenceME=1", "-p", "SearchRange=16",
+                "-p", "NumberReferenceFrames=2", "-p", "SearchMode=3"]
+    elif case == "umhex_pattern_subpel_chroma_sad":
+        # UMHEXSubPelBlockMotionSearch (me_umhex.c:562) with SAD at the sub-pel levels and ChromaMEEnable = 2: chroma terms in the walk
+        args = ["-d", "encoder.cfg", "-p", "SearchMode=1", "-p", "ChromaMEEnable=2", "-p", "MEDistortionHPel=0", "-p", "MEDistortionQPel=0",
+                "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+    elif case == "umhex_simple_pattern_subpel_rdopt0":
+        # smpUMHEXSubPelBlockMotionSearch / smpUMHEXFullSubPelBlockMotionSearch (me_umhexsmp.c:616, :422) without RDO (check_position0)
+        args = ["-d", "encoder_baseline.cfg", "-p", "SearchMode=2", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2", "-p", "RDOptimization=0"]
     elif case == "sr64_2ref":
         # the search range of BASELINE config 5 (4K), on a QCIF clip so that the CPU side finishes in seconds
         args = ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144",
@@ -241,8 +259,8 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
     assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
     # the device did the work: plane sets, and the searches of the mode under test
-    pattern = "plain_subpel" in case or "bipred_subpel" in case
-    c = _served(err, ("plane sets", "bi_sub") if "bipred_subpel" in case else ("plane sets", "subpel") if pattern else ("plane sets", "fullpel", "subpel") if "full_search_mode" in case or "full_search_rdopt0" in case
+    pattern = "plain_subpel" in case or "bipred_subpel" in case or "pattern_subpel" in case
+    c = _served(err, ("plane sets", "bi_sub") if "bipred_subpel" in case else ("plane sets",) if "pattern_subpel" in case else ("plane sets", "subpel") if pattern else ("plane sets", "fullpel", "subpel") if "full_search_mode" in case or "full_search_rdopt0" in case
                 else ("plane sets", "ffs", "subpel"))
     if not pattern and "full_search" not in case:
         # fast full search: one launch per PartitionMotionSearch call, and the device's own motion vector predictors agreed with the
@@ -251,7 +269,20 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     if case == "cif_5ref_8frames":
         # all five references were searched: the reference's own report lists the fifth reference in use for the last pictures
         assert c["ffs"] >= 41 * 396 * (1 + 2 + 3 + 4 + 5 + 5 + 5), c
-    if "plain_subpel" in case:
+    if pattern:
+        # the modes' own sub-pel stages ran on the device (shim report: EPZS, EPZS bi-pred, UMHEX, smpUMHEX, smpUMHEX full)
+        import re
+        m = re.search(r"sub-pel stages of the pattern searches served on the device: (\d+) EPZS, (\d+) EPZS bi-pred, (\d+) UMHEX, (\d+) smpUMHEX, (\d+) smpUMHEX full", err)
+        assert m, err[-800:]
+        n_epzs, n_epzs_bi, n_umhex, n_smp, n_smp_full = map(int, m.groups())
+        mode = int([a for a in args if a.startswith("SearchMode=")][0].split("=")[1])
+        if mode == 1:
+            assert n_umhex > 1000 and c["subpel"] > 0, m.group(0)
+        elif mode == 2:
+            assert n_smp > 1000 and n_smp_full > 100, m.group(0)
+        elif "EPZSSubPelME=0" not in args:
+            assert n_epzs > 1000 and (n_epzs_bi > 0 or "baseline" in args[1]), m.group(0)
+    if pattern:
         # the device did serve these modes: verify mode counts the SubPelBlockMotionSearch calls it answered (and compares each)
         import re
         r = subprocess.run([os.path.join(REF_DIR, "lencod_cuda")] + args, cwd=str(a), capture_output=True, text=True, timeout=1500,

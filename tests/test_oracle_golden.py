@@ -6,11 +6,11 @@ import zlib
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, GOLDEN_CASES, golden_trace
-from replay import OracleAdapter, replay
+from conftest import GOLDEN, GOLDEN_CASES, PATTERN_CASES, golden_trace
+from replay import OracleAdapter, replay, pattern_counts
 
 
-@pytest.mark.parametrize("case", sorted(GOLDEN_CASES))
+@pytest.mark.parametrize("case", sorted(GOLDEN_CASES) + sorted(PATTERN_CASES))
 def test_planes_match_reference_crc(oracle_lib, case):
     tr, _ = golden_trace(case)
     crc = json.load(open(os.path.join(GOLDEN, "planes_crc.json")))[case]
@@ -34,6 +34,19 @@ def test_calls_match_reference_trace(oracle_lib, case):
     assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000 or case == "epzs") and res["subpel"][0] > 1000
     if case == "kat":
         assert res["bi_full"][0] > 100 and res["bi_sub"][0] > 50
+
+
+@pytest.mark.parametrize("case", sorted(PATTERN_CASES))
+def test_pattern_subpel_calls_match_reference_trace(oracle_lib, case):
+    """sub-pel stages of SearchMode 1 / 2 / 3 (EPZSSubPelBlockMotionSearch, EPZSSubPelBlockSearchBiPred, UMHEXSubPelBlockMotionSearch,
+    smpUMHEXSubPelBlockMotionSearch, smpUMHEXFullSubPelBlockMotionSearch): every kept call of the unmodified reference"""
+    tr, cfgkw = golden_trace(case)
+    impl = OracleAdapter(tr, cfgkw)
+    res = replay(tr, impl)
+    impl.close()
+    for name, (n, bad) in res.items():
+        assert not bad, (case, name, n, bad[:3])
+    pattern_counts(case, res)
 
 
 def test_spiral_and_mvbits(oracle_lib):

@@ -59,3 +59,32 @@ def test_oracle_reproduces_chroma_me_in_444(tmp_path, oracle_lib):
     for name, (n, bad) in res.items():
         assert not bad, (name, n, bad[:3])
     assert res["ffs"][0] > 3000
+
+
+@pytest.mark.parametrize("name,args,metric,clip", [
+    ("epzs_weighted", ["-d", "encoder_main.cfg", "-p", "InputFile=syn.yuv", "-p", "SourceWidth=176", "-p", "SourceHeight=144", "-p", "FramesToBeEncoded=4",
+                       "-p", "FrameSkip=0", "-p", "NumberBFrames=0", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=3", "-p", "WeightedPrediction=1",
+                       "-p", "UseWeightedReferenceME=1", "-p", "SearchMode=3"], (0, 2, 2), 4),
+    ("epzs_integer_grid", ["-d", "encoder.cfg", "-p", "SearchMode=3", "-p", "EPZSSubPelGrid=0", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"], (0, 2, 2), 0),
+    ("epzs_weighted_bipred", ["-d", "encoder.cfg", "-p", "InputFile=syn.yuv", "-p", "FramesToBeEncoded=3", "-p", "WeightedBiprediction=1", "-p", "WeightedPrediction=1",
+                              "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2", "-p", "SearchMode=3"], (0, 2, 2), 5),
+    ("umhex_chroma_me_1", ["-d", "encoder.cfg", "-p", "SearchMode=1", "-p", "ChromaMEEnable=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"], (0, 2, 2), 0),
+    ("umhex_simple_chroma_sse", ["-d", "encoder.cfg", "-p", "SearchMode=2", "-p", "ChromaMEEnable=2", "-p", "MEDistortionHPel=1", "-p", "MEDistortionQPel=1",
+                                 "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"], (0, 1, 1), 0),
+    ("umhex_sad", ["-d", "encoder_baseline.cfg", "-p", "SearchMode=1", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2", "-p", "MEDistortionHPel=0",
+                   "-p", "MEDistortionQPel=0", "-p", "RDOptimization=0"], (0, 0, 0), 0)])
+def test_oracle_reproduces_the_pattern_searches_subpel_stages(tmp_path, oracle_lib, name, args, metric, clip):
+    """SearchMode 1 / 2 / 3 of the live reference: every call of EPZSSubPelBlockMotionSearch, EPZSSubPelBlockSearchBiPred,
+    UMHEXSubPelBlockMotionSearch and smpUMHEX[Full]SubPelBlockMotionSearch (all macroblocks), with weighted reference samples, chroma
+    terms and the three metrics -- beyond what the committed fixtures (tests/golden: *_sub.npz) keep"""
+    import h264_b200_pkg  # noqa: F401
+    from h264_b200 import synth
+    if clip:
+        synth.write_yuv420(str(tmp_path / "syn.yuv"), 176, 144, clip, kind="fade")
+    tr = _trace(str(tmp_path), args)
+    impl = OracleAdapter(tr, cfg_from_trace(tr, search_range=16, full_search=2, metric=metric))
+    res = replay(tr, impl)
+    impl.close()
+    for key, (n, bad) in res.items():
+        assert not bad, (name, key, n, bad[:3])
+    assert res["subpel_pat"][0] > 10000 and (res["bi_sub_pat"][0] > 300 or "bipred" not in name)

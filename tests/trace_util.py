@@ -8,6 +8,7 @@ import os
 import numpy as np
 
 REC_FFS, REC_SUBPEL, REC_BI_FULL, REC_BI_SUB, REC_REFPIC, REC_CURPIC, REC_FULLPEL = 1, 2, 3, 4, 5, 6, 7
+REC_SUBPEL_PAT, REC_BI_SUB_PAT = 8, 9      # sub-pel stages of the pattern searches (SearchMode 1, 2, 3)
 
 
 class Trace:
@@ -104,10 +105,14 @@ class Trace:
 def cfg_from_trace(trace, search_range=32, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)):
     """Encoder-wide parameters recoverable from the records themselves."""
     sub = trace.of_type(REC_SUBPEL)
+    if not len(sub):
+        sub = trace.of_type(REC_SUBPEL_PAT)[:, :23].copy()
+        sub[:, 22] &= 1
     ffs = trace.of_type(REC_FFS)
     if not len(ffs):
         ffs = trace.of_type(REC_FULLPEL)
-    rdopt = int(ffs[0][25]) if len(ffs) else 1
+    pat = trace.of_type(REC_SUBPEL_PAT)
+    rdopt = int(ffs[0][25]) if len(ffs) else (int(pat[0][22]) >> 3) & 1 if len(pat) else 1
     t8 = int(sub[:, 22].max()) if len(sub) else 0
     ci = trace.chroma_info()
     return dict(search_range=search_range, rdopt=rdopt, full_search=full_search, metric=metric,
