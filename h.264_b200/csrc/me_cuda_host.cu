@@ -134,6 +134,11 @@ struct State {
   // current picture
   uint8_t *d_cur = nullptr;
   int cur_pitch = 0;
+  int cur_h = 0;                // rows of the picture last set (the initialised height, or half of it: a field picture)
+  // what the drop-in calls read as the current picture: the buffer itself, or one field of it (me_cuda_select_current_view)
+  int view = 0; const uint8_t *cur_view = nullptr; int cur_view_pitch = 0, cur_view_h = 0;
+  int chroma_base_pitch = 0;    // row pitch of d_cur_c (cfg.chroma.cur_pitch is that of the view)
+  int cur_ch = 0;               // rows of each original chroma plane last uploaded (V follows U after that many rows)
   uint8_t *d_cur_c = nullptr;   // ChromaMEEnable: original chroma planes (U then V), rows of cfg.chroma.cur_pitch bytes
   int chroma_w = 0, chroma_h = 0;
   // staging
@@ -427,12 +432,30 @@ int ensure_stage(size_t bytes)
   return 0;
 }
 
+// Pictures are frames of the initialised size or fields of such frames (half the rows; interlace: PicInterlace / MbInterlace,
+// dpb_split_field, mbuffer.c:2971): every reference picture carries its own size in its descriptor, the kernels take theirs from it
 int check_size(int w, int h)
 {
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
-  if (w != g.p.width || h != g.p.height) return fail(1, "picture size %dx%d differs from the initialised %dx%d", w, h, g.p.width, g.p.height);
+  const bool frame = w == g.p.width && h == g.p.height, field = w == g.p.width && 2 * h == g.p.height && !(h & 15);
+  if (!frame && !field) return fail(1, "picture size %dx%d is neither the initialised %dx%d nor a field of it", w, h, g.p.width, g.p.height);
   return 0;
 }
+
+// the current picture as the drop-in calls see it: view 0 the buffer as uploaded, 1 / 2 its top / bottom field (rows 2y / 2y + 1)
+void apply_view(int view)
+{
+  const int par = view == 2 ? 1 : 0, mul = view ? 2 : 1;
+  g.view = view;
+  g.cur_view = g.d_cur + (size_t)par * g.cur_pitch;
+  g.cur_view_pitch = g.cur_pitch * mul;
+  g.cur_view_h = g.cur_h / mul;
+  if (g.d_cur_c) {
+    g.cfg.chroma.cur_pitch = g.chroma_base_pitch * mul;
+    for (int k = 0; k < 2; k++) g.cfg.chroma.cur[k] = g.d_cur_c + (size_t)k * g.chroma_base_pitch * g.cur_ch + (size_t)par * g.chroma_base_pitch;
+  }
+}
+void picture_set(int h) { g.cur_h = h; apply_view(0); }
 
 }  // namespace
 
@@ -479,7 +502,8 @@ int me_cuda_init(const me_cuda_params *p)
     g.cfg.chroma.weight = p->chroma_me_weight;
     g.cfg.chroma.shift_x = p->yuv_format == 3 ? 2 : 3; g.cfg.chroma.shift_y = p->yuv_format == 1 ? 3 : 2;       // lencod.c:2856-2879
     g.chroma_w = p->yuv_format == 3 ? p->width : p->width >> 1; g.chroma_h = p->yuv_format == 1 ? p->height >> 1 : p->height;
-    g.cfg.chroma.cur_pitch = align_up(g.chroma_w, 16);
+    g.cfg.chroma.cur_pitch = g.chroma_base_pitch = align_up(g.chroma_w, 16);
+    g.cur_ch = g.chroma_h;
     CK(cudaMalloc((void **)&g.d_cur_c, (size_t)2 * g.cfg.chroma.cur_pitch * g.chroma_h));
     CK(cudaMemset(g.d_cur_c, 128, (size_t)2 * g.cfg.chroma.cur_pitch * g.chroma_h));
     g.cfg.chroma.cur[0] = g.d_cur_c; g.cfg.chroma.cur[1] = g.d_cur_c + (size_t)g.cfg.chroma.cur_pitch * g.chroma_h;
@@ -490,6 +514,7 @@ int me_cuda_init(const me_cuda_params *p)
   CK(cudaMalloc((void **)&g.d_cur, (size_t)g.cur_pitch * p->height));
   CK(cudaMalloc((void **)&g.d_table, sizeof g.h_table));
   g.has_cur_map = me_make_tensor_map_2d(g.cur_map.bytes, g.d_cur, p->width, p->height, g.cur_pitch, 16, 16) == 0;
+  picture_set(p->height);
   CK(cudaHostAlloc((void **)&g.h_result, 64, cudaHostAllocMapped));
   CK(cudaHostGetDevicePointer((void **)&g.d_result, g.h_result, 0));
   memset(g.h_result, 0, 64);
@@ -673,6 +698,7 @@ int me_cuda_ref_update_device(me_ref_handle hd, const void *d_luma, int stride, 
 {
   g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
+  if (RefPic *r = ref_of(hd)) if (r->dev.w != w || r->dev.h != h) return fail(1, "me_cuda_ref_update_device: a %dx%d picture into a %dx%d slot", w, h, r->dev.w, r->dev.h);
   cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
   if (int rc = enter_stream(st)) return rc;
   if (int rc = update_ref_common(hd, (const uint8_t *)d_luma, stride, st)) return rc;
@@ -683,6 +709,7 @@ int me_cuda_ref_update_u8(me_ref_handle hd, const uint8_t *luma, int stride, int
 {
   g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
+  if (RefPic *r = ref_of(hd)) if (r->dev.w != w || r->dev.h != h) return fail(1, "me_cuda_ref_update_u8: a %dx%d picture into a %dx%d slot", w, h, r->dev.w, r->dev.h);
   size_t bytes = (size_t)w * h;
   if (int rc = ensure_stage(bytes)) return rc;
   // straight from the caller's buffer (pinned memory makes this an asynchronous DMA)
@@ -722,6 +749,7 @@ int me_cuda_set_current_device(const void *d_luma, int stride, int w, int h, voi
   cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
   if (int rc = enter_stream(st)) return rc;
   CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, d_luma, stride, w, h, cudaMemcpyDeviceToDevice, st));
+  picture_set(h);
   return leave_stream(st);
 }
 
@@ -730,6 +758,7 @@ int me_cuda_set_current_u8(const uint8_t *luma, int stride, int w, int h)
   g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, luma, stride, w, h, cudaMemcpyHostToDevice, g.stream));
+  picture_set(h);
   return 0;
 }
 
@@ -746,6 +775,20 @@ int me_cuda_set_current(const me_imgpel *const *rows, int w, int h)
     for (int x = 0; x < w; x++) d[x] = (uint8_t)s[x];
   }
   CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, g.h_pin, w, w, h, cudaMemcpyHostToDevice, g.stream));
+  picture_set(h);
+  return 0;
+}
+
+// MBAFF / field coding of a frame whose original picture is on the device: the macroblock about to be searched is a frame
+// macroblock (view 0), or belongs to the top (1) / bottom (2) field -- pCurImg = imgY_org_frm / imgY_org_top / imgY_org_bot
+// (macroblock.c:165-190, image.c:2983, :3001; the field pictures are the even / odd rows of the frame, lencod.c:1970).  Applies to
+// the original chroma planes as well.  The drop-in calls and me_cuda_pred_cost8x8 read the view; the frame batch needs view 0.
+int me_cuda_select_current_view(int view)
+{
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
+  if (view < 0 || view > 2) return fail(1, "me_cuda_select_current_view: view %d", view);
+  if (view && (g.cur_h & 31)) return fail(1, "me_cuda_select_current_view: a picture of %d rows has no field views", g.cur_h);
+  if (view != g.view) { g.spec.valid = false; apply_view(view); }
   return 0;
 }
 
@@ -756,11 +799,13 @@ static void invalidate_twins(me_ref_handle h)
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < ME_MAX_REFS; i++) if (g.twin[l][i].src == h) g.twin[l][i].valid = false;
 }
-static int chroma_check(const char *who, int cw, int ch)
+// luma_h: rows of the luma picture the planes belong to (the initialised height, or half of it: a field)
+static int chroma_check(const char *who, int cw, int ch, int luma_h)
 {
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (!g.p.chroma_me_enable) return fail(1, "%s: the library was initialised with chroma_me_enable = 0", who);
-  if (cw != g.chroma_w || ch != g.chroma_h) return fail(1, "%s: chroma size %dx%d differs from the expected %dx%d", who, cw, ch, g.chroma_w, g.chroma_h);
+  const int want_h = luma_h == g.p.height ? g.chroma_h : g.chroma_h / 2;
+  if (cw != g.chroma_w || ch != want_h) return fail(1, "%s: chroma size %dx%d differs from the expected %dx%d", who, cw, ch, g.chroma_w, want_h);
   return 0;
 }
 // both planes through the pinned staging buffer into a device allocation of 2 * pitch * ch bytes
@@ -783,10 +828,11 @@ static int ref_set_chroma_common(me_ref_handle h, const uint8_t *u, const uint8_
                                  const me_imgpel *const *vr, int cw, int ch)
 {
   g.spec.valid = false;
-  if (int rc = chroma_check("me_cuda_ref_set_chroma", cw, ch)) return rc;
+  if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (g.p.yuv_format == 3) return fail(1, "me_cuda_ref_set_chroma: in 4:4:4 the chroma sub-images are plane sets (me_cuda_ref_set_chroma_planes)");
   RefPic *r = ref_of(h);
   if (!r) return fail(3, "me_cuda_ref_set_chroma: invalid handle %d", (int)h);
+  if (int rc = chroma_check("me_cuda_ref_set_chroma", cw, ch, r->dev.h)) return rc;
   const int pitch = align_up(cw, 16);
   if (!r->chroma) CK(cudaMalloc((void **)&r->chroma, (size_t)2 * pitch * ch));
   if (int rc = upload_chroma(r->chroma, pitch, u, v, stride, ur, vr, cw, ch)) return rc;
@@ -821,14 +867,16 @@ int me_cuda_ref_set_chroma_planes(me_ref_handle h, me_ref_handle hu, me_ref_hand
 int me_cuda_set_current_chroma(const me_imgpel *const *u_rows, const me_imgpel *const *v_rows, int cw, int ch)
 {
   g.spec.valid = false;
-  if (int rc = chroma_check("me_cuda_set_current_chroma", cw, ch)) return rc;
-  return upload_chroma(g.d_cur_c, g.cfg.chroma.cur_pitch, nullptr, nullptr, 0, u_rows, v_rows, cw, ch);
+  if (int rc = chroma_check("me_cuda_set_current_chroma", cw, ch, g.cur_h)) return rc;      // after me_cuda_set_current of the same picture
+  g.cur_ch = ch; apply_view(g.view);
+  return upload_chroma(g.d_cur_c, g.chroma_base_pitch, nullptr, nullptr, 0, u_rows, v_rows, cw, ch);
 }
 int me_cuda_set_current_chroma_u8(const uint8_t *u, const uint8_t *v, int stride, int cw, int ch)
 {
   g.spec.valid = false;
-  if (int rc = chroma_check("me_cuda_set_current_chroma_u8", cw, ch)) return rc;
-  return upload_chroma(g.d_cur_c, g.cfg.chroma.cur_pitch, u, v, stride, nullptr, nullptr, cw, ch);
+  if (int rc = chroma_check("me_cuda_set_current_chroma_u8", cw, ch, g.cur_h)) return rc;
+  g.cur_ch = ch; apply_view(g.view);
+  return upload_chroma(g.d_cur_c, g.chroma_base_pitch, u, v, stride, nullptr, nullptr, cw, ch);
 }
 int me_cuda_set_chroma_state(int enable)
 {
@@ -941,7 +989,7 @@ int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
   if (!g.d_surf[list][ref]) CK(cudaMalloc((void **)&g.d_surf[list][ref], sizeof(int32_t) * (size_t)ME_NUM_PARTITIONS * P));
   const MeRefDev *dev;
   if (int rc = search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) return rc;
-  me_launch_ffs_surfaces(dev, g.d_cur, g.cur_pitch, g.opix_x, g.opix_y, cx, cy, R, g.cfg.metric[0] != 0, &g.cfg.chroma, g.d_surf[list][ref], g.stream);
+  me_launch_ffs_surfaces(dev, g.cur_view, g.cur_view_pitch, g.opix_x, g.opix_y, cx, cy, R, g.cfg.metric[0] != 0, &g.cfg.chroma, g.d_surf[list][ref], g.stream);
   g.launches++;
   CK(cudaGetLastError());
   g.centre_x[list][ref] = cx; g.centre_y[list][ref] = cy; g.setup_range[list][ref] = R;
@@ -1019,7 +1067,7 @@ int me_cuda_pms_begin(const me_mb_motion *state, int n_items, const me_pms_item 
   sub_cfg.chroma.on = g.p.chroma_me_enable == 2 ? 1 : 0;
   g.spec.valid = false;
   g.pms.n_lr = n;
-  me_launch_pms_group(&P, g.d_cur, g.cur_pitch, &sub_cfg, g.cfg.rdopt, g.pms.d_rec, g.pms.d_done, g.pms.d_ticket, ++g.pms.ticket, g.stream);
+  me_launch_pms_group(&P, g.cur_view, g.cur_view_pitch, &sub_cfg, g.cfg.rdopt, g.pms.d_rec, g.pms.d_done, g.pms.d_ticket, ++g.pms.ticket, g.stream);
   g.launches++; g.pms.launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1125,7 +1173,7 @@ int me_cuda_FastFullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int
     a.check0 = (!g.cfg.rdopt && g.slice_type != ME_B_SLICE && ref == 0 && blocktype == 1);   // and mv == 0: decided on the device
     a.bi = 0;
     me_launch_ffs_block_subpel(g.d_surf[list][ref] + (size_t)p * P, R, offx, offy, search_range, min_mcost, g.cfg.rdopt, rdev,
-                               g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
+                               g.cur_view, g.cur_view_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   } else {
     me_launch_ffs_block(g.d_surf[list][ref] + (size_t)p * P, R, offx, offy, pred_mv_x, pred_mv_y, search_range, min_mcost,
                         lambda_factor, g.cfg.rdopt, g.d_result, ++g.ticket, g.stream);
@@ -1165,7 +1213,7 @@ int me_cuda_FullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic
   a.pmv_x = pred_mv_x; a.pmv_y = pred_mv_y; a.mv_x = *mv_x; a.mv_y = *mv_y;
   a.search_range = search_range; a.min_mcost = min_mcost; a.lambda = lambda_factor;
   a.check00 = (blocktype == 1 && !g.cfg.rdopt && g.slice_type != ME_B_SLICE && ref == 0);       // me_fullsearch.c:72
-  me_launch_fullpel_block(dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
+  me_launch_fullpel_block(dev, g.cur_view, g.cur_view_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("fullpel"); return ME_INT_MAX; }
@@ -1216,7 +1264,7 @@ int me_cuda_SubPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic_
   a.bi = 0;
   const MeRefDev *dev;
   if (search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) { fatal("subpel"); return ME_INT_MAX; }
-  me_launch_subpel_single(dev, nullptr, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
+  me_launch_subpel_single(dev, nullptr, g.cur_view, g.cur_view_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("subpel"); return ME_INT_MAX; }
@@ -1241,7 +1289,7 @@ int me_cuda_FullPelBlockMotionBiPred(short ref, int list, int pic_pix_x, int pic
   a.mv_x = *mv_x; a.mv_y = *mv_y; a.s_mv_x = *s_mv_x; a.s_mv_y = *s_mv_y;
   a.search_range = search_range; a.min_mcost = min_mcost; a.lambda = lambda_factor;
   a.bw = g.bw[list];
-  me_launch_bipred_full(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
+  me_launch_bipred_full(&r1->dev, &r2->dev, g.cur_view, g.cur_view_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("bipred"); return ME_INT_MAX; }
@@ -1264,7 +1312,7 @@ int me_cuda_SubPelBlockSearchBiPred(short ref, int list, int pic_pix_x, int pic_
   for (int i = 0; i < 3; i++) a.lambda[i] = lambda[i];
   a.check0 = 0; a.bi = 1;
   a.bw = g.bw[list];
-  me_launch_subpel_single(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
+  me_launch_subpel_single(&r1->dev, &r2->dev, g.cur_view, g.cur_view_pitch, &g.cfg, &a, g.d_result, ++g.ticket, g.stream);
   g.launches++;
   int mx, my, cost;
   if (fetch_result(&mx, &my, &cost)) { fatal("bipred"); return ME_INT_MAX; }
@@ -1292,13 +1340,13 @@ static int subpel_pattern(const char *who, const MePatArgs &pa, short ref, int l
     if (!r1 || !r2) { fail(1, "%s: reference lists incomplete", who); fatal(who); return ME_INT_MAX; }
     a.bi = 1; a.s_mv_x = s_mv[0]; a.s_mv_y = s_mv[1];
     a.bw = g.bw[list];
-    me_launch_subpel_pattern(&r1->dev, &r2->dev, g.d_cur, g.cur_pitch, &g.cfg, &a, &pa, g.d_result, ++g.ticket, g.stream);
+    me_launch_subpel_pattern(&r1->dev, &r2->dev, g.cur_view, g.cur_view_pitch, &g.cfg, &a, &pa, g.d_result, ++g.ticket, g.stream);
   } else {
     RefPic *r = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
     if (!r) { fail(1, "%s: (list %d, ref %d) not in the reference lists", who, list, (int)ref); fatal(who); return ME_INT_MAX; }
     const MeRefDev *dev;
     if (search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) { fatal(who); return ME_INT_MAX; }
-    me_launch_subpel_pattern(dev, nullptr, g.d_cur, g.cur_pitch, &g.cfg, &a, &pa, g.d_result, ++g.ticket, g.stream);
+    me_launch_subpel_pattern(dev, nullptr, g.cur_view, g.cur_view_pitch, &g.cfg, &a, &pa, g.d_result, ++g.ticket, g.stream);
   }
   g.launches++;
   int mx, my, cost;
@@ -1366,6 +1414,7 @@ int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, voi
 {
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_jobs <= 0) return 0;
+  if (g.view) return fail(1, "me_cuda_frame_search: a field view of the current picture is selected (the frame batch reads the picture as uploaded: upload the field itself)");
   cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
   if (int rc = upload_table()) return rc;                  // on the library stream (weighted copies are rebuilt there too)
   MeResultInt *di = (MeResultInt *)d_out_int;
@@ -1421,7 +1470,7 @@ static int check_jobs(const me_mb_job *jobs, int first, int n)
     const me_mb_job &j = jobs[i];
     if (j.list < 0 || j.list > 1 || j.ref < 0 || j.ref >= g.list_n[j.list])
       return fail(1, "job %d: (list %d, ref %d) not in the reference lists", i, (int)j.list, (int)j.ref);
-    if (j.opix_x < 0 || j.opix_y < 0 || j.opix_x + 16 > g.p.width || j.opix_y + 16 > g.p.height || (j.opix_x & 15) || (j.opix_y & 15))
+    if (j.opix_x < 0 || j.opix_y < 0 || j.opix_x + 16 > g.p.width || j.opix_y + 16 > g.cur_h || (j.opix_x & 15) || (j.opix_y & 15))
       return fail(1, "job %d: macroblock origin (%d,%d) invalid", i, (int)j.opix_x, (int)j.opix_y);
   }
   return 0;
@@ -1449,7 +1498,7 @@ int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, m
       // (the check_jobs() of the copying path) and the batch kernels return at once when it objects
       volatile int *bad = g.h_result + 8;                              // mapped pinned, beside the drop-in result words
       *bad = 0;
-      me_launch_check_jobs((const MeJob *)dj, n_jobs, g.list_n[0], g.list_n[1], g.p.width, g.p.height, g.d_result + 8, g.stream);
+      me_launch_check_jobs((const MeJob *)dj, n_jobs, g.list_n[0], g.list_n[1], g.p.width, g.cur_h, g.d_result + 8, g.stream);
       g.launches++;
       g.cfg.abort_flag = g.d_result + 8;
       int rc = me_cuda_frame_search_device(dj, n_jobs, dout, dint, g.stream);
@@ -1555,7 +1604,7 @@ static int mc_check_blocks(const me_pred_block *b, int n, int bsx, int bsy, cons
     for (int l = 0; l < 2; l++)
       if ((b[i].p_dir == l || b[i].p_dir == 2) && (b[i].ref[l] < 0 || b[i].ref[l] >= g.list_n[l]))
         return fail(1, "%s: block %d: reference %d not in list %d", who, i, (int)b[i].ref[l], l);
-    if (b[i].pix_x < 0 || b[i].pix_y < 0 || b[i].pix_x + bsx > g.p.width || b[i].pix_y + bsy > g.p.height)
+    if (b[i].pix_x < 0 || b[i].pix_y < 0 || b[i].pix_x + bsx > g.p.width || b[i].pix_y + bsy > g.cur_view_h)
       return fail(1, "%s: block %d at (%d,%d) outside the picture", who, i, (int)b[i].pix_x, (int)b[i].pix_y);
     if (b[i].apply_weights && (b[i].log_denom < 0 || b[i].log_denom > 7))
       return fail(1, "%s: block %d: log weight denominator %d", who, i, (int)b[i].log_denom);
@@ -1619,7 +1668,7 @@ int me_cuda_pred_cost8x8(const me_pred_block *blocks, int n_regions, int metric,
   uint8_t *d_in, *d_out, *h_out;
   if (int rc = mc_stage(blocks, in, out, &d_in, &d_out, &h_out)) return rc;
   int32_t *d4 = (int32_t *)d_out, *d8 = d4 + n_regions;
-  me_launch_pred_cost8x8(d_in, n_regions, metric, g.d_mc_table, g.d_cur, g.cur_pitch, d4, d8, g.stream);
+  me_launch_pred_cost8x8(d_in, n_regions, metric, g.d_mc_table, g.cur_view, g.cur_view_pitch, d4, d8, g.stream);
   g.launches++;
   CK(cudaGetLastError());
   if (!h_out) {
@@ -1720,12 +1769,13 @@ int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements,
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_jobs <= 0) return 0;
   if (g.list_n[0] < 1 || g.list_n[1] < 1) return fail(1, "me_cuda_frame_bipred needs a reference picture in both lists");
+  if (g.view) return fail(1, "me_cuda_frame_bipred: a field view of the current picture is selected (upload the field itself)");
   if (refinements < 0 || refinements > 16 || search_range < 0 || search_range > 64 || subpel < 0 || subpel > 2)
     return fail(1, "me_cuda_frame_bipred: refinements %d / search range %d / sub-pel levels %d out of range", refinements, search_range, subpel);
   for (int i = 0; i < n_jobs; i++) {
     const me_bipred_job &j = jobs[i];
     if (j.list < 0 || j.list > 1) return fail(1, "bi-pred job %d: list %d", i, (int)j.list);
-    if (j.opix_x < 0 || j.opix_y < 0 || j.opix_x + 16 > g.p.width || j.opix_y + 16 > g.p.height || (j.opix_x & 15) || (j.opix_y & 15))
+    if (j.opix_x < 0 || j.opix_y < 0 || j.opix_x + 16 > g.p.width || j.opix_y + 16 > g.cur_h || (j.opix_x & 15) || (j.opix_y & 15))
       return fail(1, "bi-pred job %d: macroblock origin (%d,%d) invalid", i, (int)j.opix_x, (int)j.opix_y);
   }
   if (g.bi_cap < n_jobs) {

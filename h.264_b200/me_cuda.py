@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "me_cuda_set_error_handler", "me_cuda_last_error", "me_cuda_init", "me_cuda_shutdown",
     "me_cuda_ref_create", "me_cuda_ref_create_u8", "me_cuda_ref_destroy", "me_cuda_ref_download_plane",
     "me_cuda_set_current", "me_cuda_set_current_u8", "me_cuda_set_ref_list", "me_cuda_set_slice_type",
-    "me_cuda_mb_begin", "me_cuda_ffs_setup", "me_cuda_ffs_is_set_up",
+    "me_cuda_select_current_view", "me_cuda_mb_begin", "me_cuda_ffs_setup", "me_cuda_ffs_is_set_up",
     "me_cuda_FastFullPelBlockMotionSearch", "me_cuda_FullPelBlockMotionSearch", "me_cuda_SubPelBlockMotionSearch",
     "me_cuda_FullPelBlockMotionBiPred", "me_cuda_SubPelBlockSearchBiPred",
     "me_cuda_EPZSSubPelBlockMotionSearch", "me_cuda_EPZSSubPelBlockSearchBiPred", "me_cuda_UMHEXSubPelBlockMotionSearch",
@@ -93,6 +93,7 @@ def load_library(path=LIB_PATH):
     L.me_cuda_ref_set_chroma_planes.argtypes = [C.c_int32] * 3
     L.me_cuda_set_bipred_weights.argtypes = [C.c_int] * 6
     L.me_cuda_mb_begin.argtypes = [C.c_int, C.c_int]
+    L.me_cuda_select_current_view.argtypes = [C.c_int]
     L.me_cuda_ffs_setup.argtypes = [C.c_int] * 4
     L.me_cuda_ffs_is_set_up.argtypes = [C.c_int] * 2
     L.me_cuda_FastFullPelBlockMotionSearch.argtypes = ([C.c_short, C.c_int, C.c_int, C.c_int, C.c_int, C.c_short, C.c_short,
@@ -203,12 +204,13 @@ class MeCuda:
 
     def ref_update(self, h, luma):
         """luma: uint8 ndarray (pinned memory makes the upload asynchronous) or (ptr, stride) of host memory"""
+        height = self.height
         if isinstance(luma, tuple):
             ptr, stride = luma
         else:
             luma = np.ascontiguousarray(luma, np.uint8)
-            ptr, stride = luma.ctypes.data, luma.strides[0]
-        self._check(self.L.me_cuda_ref_update_u8(h, ptr, stride, self.width, self.height))
+            ptr, stride, height = luma.ctypes.data, luma.strides[0], luma.shape[0]      # a frame, or a field of the frame size
+        self._check(self.L.me_cuda_ref_update_u8(h, ptr, stride, self.width, height))
 
     def ref_update_device(self, h, ptr, stride, stream=None):
         self._check(self.L.me_cuda_ref_update_device(h, ptr, stride, self.width, self.height, stream))
@@ -224,13 +226,14 @@ class MeCuda:
     def ref_destroy(self, h):
         self._check(self.L.me_cuda_ref_destroy(h))
 
-    def ref_plane(self, h, fy, fx):
-        out = np.zeros((self.height + 40, self.width + 40), np.uint8)
+    def ref_plane(self, h, fy, fx, height=None):
+        """height: rows of the picture behind the handle when it is a field (default: the initialised frame height)"""
+        out = np.zeros(((height or self.height) + 40, self.width + 40), np.uint8)
         self._check(self.L.me_cuda_ref_download_plane(h, fy, fx, out.ctypes.data, out.strides[0]))
         return out
 
-    def ref_planes(self, h):
-        return np.stack([np.stack([self.ref_plane(h, fy, fx) for fx in range(4)]) for fy in range(4)])
+    def ref_planes(self, h, height=None):
+        return np.stack([np.stack([self.ref_plane(h, fy, fx, height) for fx in range(4)]) for fy in range(4)])
 
     def set_current(self, luma):
         luma = np.ascontiguousarray(luma, np.uint8)
@@ -272,6 +275,10 @@ class MeCuda:
         self._check(self.L.me_cuda_set_bipred_weights(lst, int(apply), int(w1), int(w2), int(offset_bi), int(log_denom)))
 
     # ---- drop-in sequence
+    def select_current_view(self, view):
+        """0: the current picture as uploaded; 1 / 2: its top / bottom field (interlace: field pictures, MBAFF field macroblocks)"""
+        self._check(self.L.me_cuda_select_current_view(view))
+
     def mb_begin(self, opix_x, opix_y):
         self._check(self.L.me_cuda_mb_begin(opix_x, opix_y))
 

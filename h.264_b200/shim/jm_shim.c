@@ -68,6 +68,7 @@ static struct {
   int  (*set_chroma_state)(int);
   int  (*ref_set_chroma_planes)(me_ref_handle, me_ref_handle, me_ref_handle);
   int  (*mb_begin)(int, int);
+  int  (*select_view)(int);
   int  (*ffs_setup)(int, int, int, int);
   int  (*ffs_is_set_up)(int, int);
   int  (*ffs)(short, int, int, int, int, short, short, short *, short *, int, int, int);
@@ -97,6 +98,7 @@ static long n_checked = 0, n_mismatch = 0;
 /* calls the device answered, per wrapped function; printed when the module is cleared so that a run (and the tests around it)
  * can tell a GPU run from a silent pass-through */
 static long served_ffs = 0, served_fullpel = 0, served_subpel = 0, served_bi_full = 0, served_bi_sub = 0, served_planes = 0;
+static long served_field_mbs = 0, served_field_pictures_mbs = 0;   /* macroblocks searched on a field view: MBAFF field macroblocks, field pictures */
 static long served_pattern[5] = {0, 0, 0, 0, 0}, served_pattern_bi = 0;   /* sub-pel stages of the pattern searches, by pattern */
 static long served_bid_cost = 0, served_direct_cost = 0, paged_tiles = 0, paged_bytes = 0;
 static int use_mc = 1;          /* BIDPartitionCost / GetDirectCost8x8 on the device (ME_CUDA_MC=0: the reference's host code) */
@@ -158,6 +160,7 @@ static void load_library(void)
   L.ref_create = sym("me_cuda_ref_create"); L.ref_destroy = sym("me_cuda_ref_destroy");
   L.set_current = sym("me_cuda_set_current"); L.set_ref_list = sym("me_cuda_set_ref_list");
   L.set_slice_type = sym("me_cuda_set_slice_type"); L.mb_begin = sym("me_cuda_mb_begin");
+  L.select_view = sym("me_cuda_select_current_view");
   L.set_ref_weights = sym("me_cuda_set_ref_weights"); L.set_bipred_weights = sym("me_cuda_set_bipred_weights");
   L.set_bipred_chroma_weights = sym("me_cuda_set_bipred_chroma_weights");
   L.set_current_chroma = sym("me_cuda_set_current_chroma"); L.ref_set_chroma = sym("me_cuda_ref_set_chroma");
@@ -195,10 +198,12 @@ static void unmap_index(int i)
   n_map--;
 }
 
+/* the frame store at index used_size is the one being filled: insert_picture_in_dpb (mbuffer.c:2548) makes the plane sets of a frame
+ * and -- in a stream with field support -- of its two fields (dpb_split_field, :2971) before store_picture_in_dpb counts the store */
 static int in_dpb(StorablePicture *p)
 {
   unsigned i;
-  for (i = 0; i < dpb.used_size; i++)
+  for (i = 0; i <= dpb.used_size && i < dpb.size; i++)
     if (dpb.fs[i] && (dpb.fs[i]->frame == p || dpb.fs[i]->top_field == p || dpb.fs[i]->bottom_field == p)) return 1;
   return 0;
 }
@@ -262,6 +267,8 @@ void __wrap_Clear_Motion_Search_Module(void)
             served_planes, served_ffs, served_fullpel, served_subpel, served_bi_full, served_bi_sub);
     fprintf(stderr, "me_cuda shim: sub-pel stages of the pattern searches served on the device: %ld EPZS, %ld EPZS bi-pred, %ld UMHEX, %ld smpUMHEX, %ld smpUMHEX full calls\n",
             served_pattern[1], served_pattern_bi, served_pattern[2], served_pattern[3], served_pattern[4]);
+    fprintf(stderr, "me_cuda shim: interlace: %ld macroblock visits searched on a field view of an MBAFF frame, %ld on the fields of field pictures\n",
+            served_field_mbs, served_field_pictures_mbs);
     fprintf(stderr, "me_cuda shim: partition-search launches %lld, block searches answered from them %lld, argument mismatches %lld\n",
             (long long)pl, (long long)ps, (long long)pm);
     fprintf(stderr, "me_cuda shim: mode-decision costs on the device: %ld BIDPartitionCost, %ld GetDirectCost8x8 calls; plane tiles paged to the host: %ld (%ld bytes%s)\n",
@@ -363,16 +370,35 @@ void __wrap_free_storable_picture(StorablePicture *p)
  * macroblock origin.  With SearchMode = 0 the reference's own per-macroblock reset (macroblock.c:509) triggers it; with
  * SearchMode = -1 there is no such call and the first search of the macroblock does. */
 static int mb_synced_pic = -1, mb_synced_mb = -1;
+static imgpel **cur_uploaded_rows = NULL, **mb_synced_rows = NULL;   /* an MBAFF pair is visited as frame and as field macroblocks under the same numbers */
 static void mb_sync(void)
 {
-  if (mb_synced_pic == pic_counter && mb_synced_mb == img->current_mb_nr) return;
-  mb_synced_pic = pic_counter; mb_synced_mb = img->current_mb_nr;
-  if (pic_uploaded != pic_counter || plane_uploaded != current_plane()) {
+  /* Interlace: the macroblock's original samples are the frame (pCurImg == imgY_org_frm), or the top / bottom field -- row pointers
+   * into that frame (lencod.c:1970) -- for the two pictures of field coding (image.c:2983, :3001) and for field macroblocks of an MBAFF
+   * frame (macroblock.c:165-190).  The frame goes to the device once per coded picture; each macroblock selects its view. */
+  int view = (pCurImg == imgY_org_frm) ? 0 : (input->PicInterlace || input->MbInterlace) ? ((pCurImg == imgY_org_top) ? 1 : (pCurImg == imgY_org_bot) ? 2 : -1) : -1;
+  if (IS_INDEPENDENT(input)) view = -1;                  /* the colour planes are uploaded one by one (below) */
+  if (mb_synced_pic == pic_counter && mb_synced_mb == img->current_mb_nr && mb_synced_rows == pCurImg) return;
+  mb_synced_pic = pic_counter; mb_synced_mb = img->current_mb_nr; mb_synced_rows = pCurImg;
+  if (view >= 0) {
+    if (pic_uploaded != pic_counter || cur_uploaded_rows != imgY_org_frm) {
+      int frame_h = img->height << (img->structure != FRAME);
+      if (L.set_current((const me_imgpel *const *)imgY_org_frm, img->width, frame_h)) die("me_cuda_set_current");
+      if (input->ChromaMEEnable &&
+          L.set_current_chroma((const me_imgpel *const *)imgUV_org_frm[0], (const me_imgpel *const *)imgUV_org_frm[1], img->width_cr,
+                               img->height_cr << (img->structure != FRAME)))
+        die("me_cuda_set_current_chroma");
+      pic_uploaded = pic_counter; plane_uploaded = current_plane(); cur_uploaded_rows = imgY_org_frm;
+    }
+    if (L.select_view(view)) die("me_cuda_select_current_view");
+    if (view) { if (img->structure == FRAME) served_field_mbs++; else served_field_pictures_mbs++; }
+  }
+  else if (pic_uploaded != pic_counter || plane_uploaded != current_plane() || cur_uploaded_rows != pCurImg) {
     if (L.set_current((const me_imgpel *const *)pCurImg, img->width, img->height)) die("me_cuda_set_current");
     if (input->ChromaMEEnable &&
         L.set_current_chroma((const me_imgpel *const *)imgUV_org[0], (const me_imgpel *const *)imgUV_org[1], img->width_cr, img->height_cr))
       die("me_cuda_set_current_chroma");
-    pic_uploaded = pic_counter; plane_uploaded = current_plane();
+    pic_uploaded = pic_counter; plane_uploaded = current_plane(); cur_uploaded_rows = pCurImg;
   }
   {
     int list_offset = img->mb_data[img->current_mb_nr].list_offset, l, i;
@@ -384,8 +410,9 @@ static void mb_sync(void)
       for (i = 0; i < n; i++) {
         hs[i] = handle_of(listX[l + list_offset][i]);
         /* a listed picture without device planes would silently shorten the list the searches index: fail loudly instead
-         * (field pictures / MBAFF list offsets 2 and 4 are refused here: their plane sets are not mirrored) */
-        if (!hs[i]) die("a reference-list entry has no plane set on the device (field / MBAFF coding is not supported by the GPU path)");
+         * (the fields of a stored frame have their own plane sets, dpb_split_field; list offsets 2 / 4 of MBAFF field macroblocks
+         * select lists made of them) */
+        if (!hs[i]) die("a reference-list entry has no plane set on the device");
       }
       if (L.set_ref_list(l, n, hs)) die("me_cuda_set_ref_list");
     }
@@ -501,8 +528,10 @@ static void snapshot_motion(me_mb_motion *st)
 void __real_PartitionMotionSearch(int blocktype, int block8x8, int *lambda_factor);
 void __wrap_PartitionMotionSearch(int blocktype, int block8x8, int *lambda_factor)
 {
+  /* frame and field pictures; not the macroblocks of an MBAFF frame (SetMotionVectorPredictor scales the neighbours' vectors and
+   * reference indices between frame and field macroblocks there, mv-search.c:111-180: those block searches go one by one) */
   int on = active && use_pms && input->SearchMode == FAST_FULL_SEARCH && !img->MbaffFrameFlag && !input->DisableSubpelME &&
-           img->structure == FRAME && blocktype >= 1 && blocktype <= 7;
+           blocktype >= 1 && blocktype <= 7;
   if (on && !L.pms_cached(blocktype, block8x8)) {
     me_mb_motion st;
     me_pms_item items[ME_PMS_MAX_ITEMS];
@@ -868,7 +897,9 @@ int __wrap_BIDPartitionCost(Macroblock *currMB, int blocktype, int block8x8, sho
   int step_h = input->part_size[blocktype][0], step_v = input->part_size[blocktype][1];
   int bx = bx0[parttype][block8x8], by = by0[parttype][block8x8];
   int v, h, rx, ry, k, n = 0, mvd_bits = 0, mcost, use8 = input->Transform8x8Mode && blocktype <= 4;
-  if (!active || !use_mc) return __real_BIDPartitionCost(currMB, blocktype, block8x8, ref_l0, ref_l1, lambda_factor);
+  /* MBAFF frames: LumaPrediction indexes the weight tables through the field macroblock's list offset and halved reference indices
+   * (macroblock.c:846-860); left to the reference's host code, which reads the planes through the paging line accessors */
+  if (!active || !use_mc || img->MbaffFrameFlag) return __real_BIDPartitionCost(currMB, blocktype, block8x8, ref_l0, ref_l1, lambda_factor);
   mb_sync();
   /* motion-vector rate (mv-search.c:1083-1096): host arithmetic on the encoder's own arrays */
   for (v = by; v < by + step_v0; v += step_v)
@@ -906,7 +937,7 @@ int __wrap_GetDirectCost8x8(Macroblock *currMB, int block, int *cost8x8)
   me_pred_block blocks[4];
   int32_t c4, c8;
   int k, bx = (block % 2) * 2, by = (block / 2) * 2, cost, in8 = *cost8x8;
-  if (!active || !use_mc) return __real_GetDirectCost8x8(currMB, block, cost8x8);
+  if (!active || !use_mc || img->MbaffFrameFlag) return __real_GetDirectCost8x8(currMB, block, cost8x8);
   mb_sync();
   for (k = 0; k < 4; k++) {
     int h = bx + (k & 1), v = by + (k >> 1);

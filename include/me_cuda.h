@@ -152,6 +152,16 @@ int me_cuda_ref_set_chroma_u8(me_ref_handle h, const uint8_t *u, const uint8_t *
 int me_cuda_ref_set_chroma_planes(me_ref_handle h, me_ref_handle h_u, me_ref_handle h_v);
 int me_cuda_set_chroma_state(int enable);
 
+/* ---- interlace (PicInterlace / MbInterlace).  Reference pictures and the current picture may be frames of the
+ * initialised size or fields of such frames (same width, half the rows: dpb_split_field, mbuffer.c:2971-3024; field_picture,
+ * image.c:1015): me_cuda_ref_create* / me_cuda_set_current* accept both, every picture keeps its own size.  When the whole
+ * original frame is on the device, the field a macroblock belongs to need not be uploaded again: view 0 = the picture as uploaded,
+ * 1 / 2 = its top / bottom field (rows 2y / 2y + 1; imgY_org_top / imgY_org_bot are row pointers into imgY_org_frm, lencod.c:1970,
+ * memalloc.c:27), selected per macroblock as the reference sets pCurImg (macroblock.c:165-190 for MBAFF frames, image.c:2983, :3001
+ * for field pictures).  Covers the original chroma planes too.  Read by the drop-in block searches, me_cuda_pms_begin and
+ * me_cuda_pred_cost8x8; the frame batch wants view 0.  me_cuda_set_current* resets the view to 0. ---- */
+int me_cuda_select_current_view(int view);
+
 /* ---- per macroblock: ResetFastFullIntegerSearch (me_fullfast.c:197, called macroblock.c:509) ---- */
 int me_cuda_mb_begin(int opix_x, int opix_y);
 

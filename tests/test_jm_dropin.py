@@ -126,7 +126,9 @@ def test_mode_decision_costs_and_paged_planes(tmp_path, me_lib_path, args, want)
                                   "weighted_pred_chroma_me_1", "umhex_plain_subpel", "umhex_simple_bipred_subpel",
                                   "epzs_plain_subpel", "epzs_subpel_grid_plain_subpel",
                                   "epzs_pattern_subpel", "epzs_pattern_subpel_weighted", "umhex_pattern_subpel_chroma_sad",
-                                  "umhex_simple_pattern_subpel_rdopt0"])
+                                  "umhex_simple_pattern_subpel_rdopt0",
+                                  "interlace_field_pictures", "interlace_picture_adaptive", "interlace_mbaff_field_macroblocks",
+                                  "interlace_mbaff_adaptive", "interlace_picture_and_mbaff_adaptive_chroma_me", "interlace_field_pictures_epzs"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -222,6 +224,18 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
                  "epzs_plain_subpel": ["-p", "SearchMode=3", "-p", "EPZSSubPelME=0", "-p", "EPZSSubPelMEBiPred=0", "-p", "EPZSSubPelGrid=0"],
                  "epzs_subpel_grid_plain_subpel": ["-p", "SearchMode=3", "-p", "EPZSSubPelME=0", "-p", "EPZSSubPelMEBiPred=0",
                                                    "-p", "EPZSSubPelGrid=1"]}[case]
+    elif case.startswith("interlace_"):
+        # field pictures (PicInterlace 1: the two fields of every frame coded as pictures of half the rows with
+        # field references), picture-adaptive frame / field coding (2), MBAFF frames (MbInterlace 1: every pair as field macroblocks,
+        # 2: adaptive) whose field macroblocks search the top / bottom field of the frame with list offsets 2 / 4.  The reference
+        # refuses ReferenceReorder / PocMemoryManagement with interlace (configfile.c:1032-1043); 144 rows are padded to 160.
+        args = ["-d", "encoder.cfg", "-p", "ReferenceReorder=0", "-p", "PocMemoryManagement=0", "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+        args += {"interlace_field_pictures": ["-p", "PicInterlace=1"],
+                 "interlace_picture_adaptive": ["-p", "PicInterlace=2"],
+                 "interlace_mbaff_field_macroblocks": ["-p", "MbInterlace=1"],
+                 "interlace_mbaff_adaptive": ["-p", "MbInterlace=2"],
+                 "interlace_picture_and_mbaff_adaptive_chroma_me": ["-p", "PicInterlace=2", "-p", "MbInterlace=2", "-p", "ChromaMEEnable=2"],
+                 "interlace_field_pictures_epzs": ["-p", "PicInterlace=1", "-p", "SearchMode=3"]}[case]
     elif case == "epzs_pattern_subpel":
         # SURVEY.md 8(f) row 4, second half: EPZS as shipped (EPZSSubPelME = EPZSSubPelMEBiPred = EPZSSubPelGrid = 1):
         # EPZSSubPelBlockMotionSearch / EPZSSubPelBlockSearchBiPred (me_epzs.c:2390, :2728) on the device
@@ -259,10 +273,16 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
     assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
     # the device did the work: plane sets, and the searches of the mode under test
-    pattern = "plain_subpel" in case or "bipred_subpel" in case or "pattern_subpel" in case
-    c = _served(err, ("plane sets", "bi_sub") if "bipred_subpel" in case else ("plane sets",) if "pattern_subpel" in case else ("plane sets", "subpel") if pattern else ("plane sets", "fullpel", "subpel") if "full_search_mode" in case or "full_search_rdopt0" in case
+    pattern = "plain_subpel" in case or "bipred_subpel" in case or "pattern_subpel" in case or case.endswith("_epzs")
+    c = _served(err, ("plane sets", "bi_sub") if "bipred_subpel" in case else ("plane sets",) if "pattern_subpel" in case or case.endswith("_epzs") else ("plane sets", "subpel") if pattern else ("plane sets", "fullpel", "subpel") if "full_search_mode" in case or "full_search_rdopt0" in case
                 else ("plane sets", "ffs", "subpel"))
-    if not pattern and "full_search" not in case:
+    if case.startswith("interlace_"):
+        import re
+        m = re.search(r"interlace: (\d+) macroblock visits searched on a field view of an MBAFF frame, (\d+) on the fields of field pictures", err)
+        assert m, err[-800:]
+        n_mbaff, n_field_pic = map(int, m.groups())
+        assert (n_mbaff > 100) == ("mbaff" in case) and (n_field_pic > 100) == ("picture" in case), (case, m.group(0))
+    if not pattern and "full_search" not in case and "mbaff" not in case:
         # fast full search: one launch per PartitionMotionSearch call, and the device's own motion vector predictors agreed with the
         # reference's SetMotionVectorPredictor on every block search they were used for
         assert c["pms_launches"] > 0 and c["pms_served"] > 0 and c["pms_missed"] == 0, c
@@ -282,7 +302,7 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
             assert n_smp > 1000 and n_smp_full > 100, m.group(0)
         elif "EPZSSubPelME=0" not in args:
             assert n_epzs > 1000 and (n_epzs_bi > 0 or "baseline" in args[1]), m.group(0)
-    if pattern:
+    if pattern or case.startswith("interlace_"):
         # the device did serve these modes: verify mode counts the SubPelBlockMotionSearch calls it answered (and compares each)
         import re
         r = subprocess.run([os.path.join(REF_DIR, "lencod_cuda")] + args, cwd=str(a), capture_output=True, text=True, timeout=1500,
