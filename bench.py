@@ -50,7 +50,17 @@ def bench_config(world, sub_metric=2):
             "metrics": "SAD fpel / %s hpel,qpel" % ("SAD", "SSE", "SATD")[sub_metric],
             "parallelism": "gop-sharded x%d, no collective" % world,
             "l2": "256 MB write between timed steps (L2 flush) and ~250 MB working set per step",
-            "predictors": "synthetic per-partition predictors (pan + jitter), seed 21"}
+            "predictors": "synthetic per-partition predictors (pan + jitter), seed 21",
+            "host_transfer": "pinned job / result arrays in place" if host_transfer_mode(world) != "0"
+                             else "pinned job / result arrays through four pipelined copy chunks (8 processes share the host)"}
+
+
+def host_transfer_mode(world):
+    """How me_cuda_frame_search moves the pinned caller arrays (library switch ME_CUDA_ZEROCOPY; the library does not choose by
+    itself): "1" read and written in place by the kernels, "0" four pipelined copy chunks.  Measured on this pool's boxes, ms per
+    step end to end at 1 / 2 / 4 / 8 processes per host (profiles/r02p_e2e_variants.txt): in place 2.60 / 2.65 / 2.76 / 3.14-3.18,
+    chunked 2.94 / 2.95 / 2.92 / 2.98 -- kernel-issued PCIe accesses win until eight processes share the host's root complex."""
+    return os.environ.get("ME_CUDA_ZEROCOPY") or ("0" if world >= 8 else "1")
 
 
 def env_int(name, default):
@@ -303,6 +313,7 @@ def main():
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the motion-estimation path has no CPU fallback")
+    os.environ["ME_CUDA_ZEROCOPY"] = host_transfer_mode(world)      # read by the library at its first batch
     torch.cuda.set_device(local)
     if world > 1:
         # NCCL writes its version banner to STDOUT when the communicator comes up; stdout carries the one JSON line only, so
