@@ -219,6 +219,44 @@ me_ffs_surfaces_kernel(MeRefDev ref, const uint8_t *__restrict__ cur, int cur_pi
   for (int p = 0; p < ME_NUM_PARTITIONS; p++) surf[(size_t)p * P + s] = part[p];
 }
 
+// The same surfaces for pictures of more than 8 bits per sample (16-bit planes and current picture): plain scalar arithmetic, window
+// read from plane (0,0) of the picture's plane set with clamped coordinates (its 20-sample border and the clamp are both pure edge
+// replication, i.e. JM's origin clamp, refbuf.c:37).  No chroma terms (refused at init for such pictures).
+template <bool SSE>
+__global__ void __launch_bounds__(128)
+me_ffs_surfaces16_kernel(MeRefDev ref, const uint16_t *__restrict__ cur, int cur_pitch, int opix_x, int opix_y,
+                         int cx, int cy, int R, int32_t *__restrict__ surf /* [41][P] in spiral order */)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ uint16_t curs[256];
+  uint16_t *win = reinterpret_cast<uint16_t *>(smem);
+  const int n = 2 * R + 16, tp = n + 1, side = 2 * R + 1, P = side * side;
+  const uint16_t *plane = reinterpret_cast<const uint16_t *>(ref.planes);
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+    const int y = i / n, x = i - y * n;
+    const int sy = me_clamp(cy - R + y + ME_PAD, 0, ref.hp - 1), sx = me_clamp(cx - R + x + ME_PAD, 0, ref.wp - 1);
+    win[y * tp + x] = plane[(size_t)sy * ref.pitch + sx];
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) curs[i] = cur[(size_t)(opix_y + (i >> 4)) * cur_pitch + opix_x + (i & 15)];
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const int dy = idx / side, dx = idx - dy * side;
+  int leaf[16], part[ME_NUM_PARTITIONS];
+#pragma unroll
+  for (int b = 0; b < 16; b++) leaf[b] = 0;
+  for (int row = 0; row < 16; row++)
+#pragma unroll
+    for (int col = 0; col < 16; col++) {
+      const int d = (int)win[(dy + row) * tp + dx + col] - (int)curs[row * 16 + col];
+      leaf[(row >> 2) * 4 + (col >> 2)] += SSE ? d * d : abs(d);
+    }
+  me_aggregate(leaf, part);
+  const int s = me_spiral_index(dx - R, dy - R);
+#pragma unroll
+  for (int p = 0; p < ME_NUM_PARTITIONS; p++) surf[(size_t)p * P + s] = part[p];
+}
+
 // ... then one argmin per block search (FastFullPelBlockMotionSearch, me_fullfast.c:833-903)
 __global__ void __launch_bounds__(256)
 me_ffs_block_kernel(const int32_t *__restrict__ surf_p, int setup_range, int offx, int offy, int pmv_x, int pmv_y,
@@ -254,6 +292,15 @@ extern "C" void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, 
   size_t smem = (size_t)(n + 1) * tp + 16;
   if (sse) me_ffs_surfaces_kernel<true><<<(P + 127) / 128, 128, smem, st>>>(*ref, cur, cur_pitch, opix_x, opix_y, cx, cy, R, *chroma, surf);
   else     me_ffs_surfaces_kernel<false><<<(P + 127) / 128, 128, smem, st>>>(*ref, cur, cur_pitch, opix_x, opix_y, cx, cy, R, *chroma, surf);
+}
+
+extern "C" void me_launch_ffs_surfaces16(const MeRefDev *ref, const uint16_t *cur, int cur_pitch, int opix_x, int opix_y,
+                                         int cx, int cy, int R, int sse, int32_t *surf, cudaStream_t st)
+{
+  const int n = 2 * R + 16, P = (2 * R + 1) * (2 * R + 1);
+  const size_t smem = (size_t)n * (n + 1) * sizeof(uint16_t);      // 41.8 KB at R = 64: inside the default limit
+  if (sse) me_ffs_surfaces16_kernel<true><<<(P + 127) / 128, 128, smem, st>>>(*ref, cur, cur_pitch, opix_x, opix_y, cx, cy, R, surf);
+  else     me_ffs_surfaces16_kernel<false><<<(P + 127) / 128, 128, smem, st>>>(*ref, cur, cur_pitch, opix_x, opix_y, cx, cy, R, surf);
 }
 
 extern "C" void me_launch_ffs_block(const int32_t *surf_p, int setup_range, int offx, int offy, int pmv_x, int pmv_y,

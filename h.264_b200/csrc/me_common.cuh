@@ -49,6 +49,10 @@ struct MeCfgDev {
   // frame batch on caller memory the host has not read (pinned arrays handed through): a validation kernel in front of the searches
   // stores 1 + the index of the first job with a field outside what the kernels index with; the batch kernels then return at once
   const int *abort_flag;        // nullptr: jobs validated on the host
+  // more than 8 bits per sample (imgpel is u16 in the reference, global.h:50): planes and current picture hold 16-bit samples --
+  // pitch / plane_stride of MeRefDev count samples either way; served by the drop-in kernels instantiated for uint16_t
+  int pel16;                    // 0: 8-bit samples
+  int max_pel;                  // img->max_imgpel_value: (1 << bit depth) - 1
 };
 
 // partition tables (order documented in include/me_cuda.h)
@@ -127,6 +131,15 @@ __device__ __forceinline__ const uint8_t *me_umv_ptr(const MeRefDev &r, int y4, 
   int xp = me_clamp(x4 >> 2, 0, r.w + 2 * ME_PAD - 1 - 16);
   int yp = me_clamp(y4 >> 2, 0, r.h + 2 * ME_PAD - 1 - 16);
   return r.planes + (size_t)(((y4 & 3) << 2) | (x4 & 3)) * r.plane_stride + (size_t)yp * r.pitch + xp;
+}
+
+// the same for planes of samples of type Pel (uint8_t / uint16_t): pitch and plane_stride count samples
+template <typename Pel>
+__device__ __forceinline__ const Pel *me_umv_ptr_p(const MeRefDev &r, int y4, int x4)
+{
+  int xp = me_clamp(x4 >> 2, 0, r.w + 2 * ME_PAD - 1 - 16);
+  int yp = me_clamp(y4 >> 2, 0, r.h + 2 * ME_PAD - 1 - 16);
+  return reinterpret_cast<const Pel *>(r.planes) + (size_t)(((y4 & 3) << 2) | (x4 & 3)) * r.plane_stride + (size_t)yp * r.pitch + xp;
 }
 
 // ---- chroma sub-images (getSubImagesChroma, img_chroma.c:374-440) evaluated on the fly: sub-image (sy, sx) at padded-plane

@@ -40,6 +40,9 @@ struct MeFullPelArgs {
 extern "C" {
 void me_launch_planes(const uint8_t *src, int src_stride, int w, int h, uint8_t *planes, int pitch, size_t plane_stride,
                       uint8_t *search, int spad, int spitch, cudaStream_t st);
+void me_launch_planes16(const uint16_t *src, int src_stride, int w, int h, uint16_t *planes, int pitch, size_t plane_stride, int max_pel, cudaStream_t st);
+void me_launch_ffs_surfaces16(const MeRefDev *ref, const uint16_t *cur, int cur_pitch, int opix_x, int opix_y, int cx, int cy, int R, int sse,
+                              int32_t *surf, cudaStream_t st);
 void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_stride, int wp, int hp, uint16_t *dst, cudaStream_t st);
 void me_launch_check_jobs(const MeJob *jobs, int n_jobs, int n_refs0, int n_refs1, int width, int height, int *bad, cudaStream_t st);
 void me_launch_luma_prediction(const void *blocks, int n, int bsx, int bsy, const MeRefDev *table, uint8_t *pred, cudaStream_t st);
@@ -134,6 +137,7 @@ struct State {
   // current picture
   uint8_t *d_cur = nullptr;
   int cur_pitch = 0;
+  int pel_bytes = 1;            // 2: pictures of more than 8 bits per sample (cfg.pel16): 16-bit planes and current picture
   int cur_h = 0;                // rows of the picture last set (the initialised height, or half of it: a field picture)
   // what the drop-in calls read as the current picture: the buffer itself, or one field of it (me_cuda_select_current_view)
   int view = 0; const uint8_t *cur_view = nullptr; int cur_view_pitch = 0, cur_view_h = 0;
@@ -388,6 +392,18 @@ int create_ref_common(const uint8_t *d_luma, int stride, int w, int h, cudaStrea
   d.spad = (g.cfg.search_range + 32 + 1) & ~1;      // even: the search plane is written four bytes at a time
   d.sw = w + 2 * d.spad; d.sh = h + 2 * d.spad;
   d.spitch = align_up(d.sw, 128);
+  if (g.pel_bytes == 2) {
+    // 16-bit samples: pitch / plane_stride count samples; no search-plane copy, no tensor maps (the throughput kernels are 8-bit)
+    CK(cudaMalloc((void **)&r.planes, d.plane_stride * 16 * sizeof(uint16_t)));
+    r.search = nullptr; d.planes = r.planes; d.search = nullptr; d.spad = d.sw = d.sh = d.spitch = 0;
+    r.has_map = r.has_pmap = false;
+    { ScopedTimer t(0, st); me_launch_planes16((const uint16_t *)d_luma, stride, w, h, (uint16_t *)r.planes, d.pitch, d.plane_stride, g.cfg.max_pel, st); }
+    g.launches += 1;
+    CK(cudaGetLastError());
+    r.used = true; r.written_on = st; r.gen = ++g.gen_counter;
+    *out = (me_ref_handle)(slot + 1);
+    return 0;
+  }
   CK(cudaMalloc((void **)&r.planes, d.plane_stride * 16));
   CK(cudaMalloc((void **)&r.search, (size_t)d.spitch * d.sh));
   d.planes = r.planes; d.search = r.search;
@@ -447,7 +463,7 @@ void apply_view(int view)
 {
   const int par = view == 2 ? 1 : 0, mul = view ? 2 : 1;
   g.view = view;
-  g.cur_view = g.d_cur + (size_t)par * g.cur_pitch;
+  g.cur_view = g.d_cur + (size_t)par * g.cur_pitch * g.pel_bytes;
   g.cur_view_pitch = g.cur_pitch * mul;
   g.cur_view_h = g.cur_h / mul;
   if (g.d_cur_c) {
@@ -456,6 +472,15 @@ void apply_view(int view)
   }
 }
 void picture_set(int h) { g.cur_h = h; apply_view(0); }
+
+// More than 8 bits per sample: served by the row-pointer entry points (imgpel rows, as the reference holds its pictures) and the
+// drop-in searches of the fast-full-search path; everything else says so instead of treating 16-bit samples as bytes.
+int only8(const char *who)
+{
+  if (g.inited && g.pel_bytes != 1)
+    return fail(1, "%s: not available for pictures of %d bits per sample (8-bit only)", who, g.p.bit_depth);
+  return 0;
+}
 
 }  // namespace
 
@@ -469,7 +494,9 @@ int me_cuda_init(const me_cuda_params *p)
   if (!p) return fail(1, "me_cuda_init: null parameters");
   if (p->abi_version != ME_CUDA_ABI_VERSION) return fail(1, "ABI version %d, library is %d", p->abi_version, ME_CUDA_ABI_VERSION);
   if (g.inited) me_cuda_shutdown();
-  if (p->bit_depth != 8) return fail(1, "bit depth %d not supported (8-bit content only)", p->bit_depth);
+  if (p->bit_depth < 8 || p->bit_depth > 14) return fail(1, "bit depth %d outside 8..14", p->bit_depth);
+  if (p->bit_depth > 8 && (p->chroma_me_enable || p->weighted_me))
+    return fail(1, "bit depth %d: chroma-aware and weighted-prediction ME are implemented for 8-bit pictures only", p->bit_depth);
   if (p->chroma_me_enable < 0 || p->chroma_me_enable > 2) return fail(1, "ChromaMEEnable %d outside 0..2", p->chroma_me_enable);
   if (p->chroma_me_enable) {
     if (p->yuv_format < 1 || p->yuv_format > 3)
@@ -490,6 +517,8 @@ int me_cuda_init(const me_cuda_params *p)
   if (prop.major < 10) return fail(2, "device %s is sm_%d%d; libme_cuda is built for sm_100a only", prop.name, prop.major, prop.minor);
   g = State();
   g.p = *p; g.device = dev;
+  g.pel_bytes = p->bit_depth > 8 ? 2 : 1;
+  g.cfg.pel16 = p->bit_depth > 8; g.cfg.max_pel = (1 << p->bit_depth) - 1;
   g.cfg.search_range = p->search_range; g.cfg.rdopt = p->rdopt; g.cfg.full_search = p->full_search;
   for (int i = 0; i < 3; i++) g.cfg.metric[i] = p->me_metric[i];
   g.cfg.transform8x8 = p->transform8x8 != 0;
@@ -511,9 +540,9 @@ int me_cuda_init(const me_cuda_params *p)
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&g.ev_order, cudaEventDisableTiming));
   g.cur_pitch = align_up(p->width, 128);
-  CK(cudaMalloc((void **)&g.d_cur, (size_t)g.cur_pitch * p->height));
+  CK(cudaMalloc((void **)&g.d_cur, (size_t)g.cur_pitch * p->height * g.pel_bytes));
   CK(cudaMalloc((void **)&g.d_table, sizeof g.h_table));
-  g.has_cur_map = me_make_tensor_map_2d(g.cur_map.bytes, g.d_cur, p->width, p->height, g.cur_pitch, 16, 16) == 0;
+  g.has_cur_map = g.pel_bytes == 1 && me_make_tensor_map_2d(g.cur_map.bytes, g.d_cur, p->width, p->height, g.cur_pitch, 16, 16) == 0;
   picture_set(p->height);
   CK(cudaHostAlloc((void **)&g.h_result, 64, cudaHostAllocMapped));
   CK(cudaHostGetDevicePointer((void **)&g.d_result, g.h_result, 0));
@@ -610,6 +639,7 @@ int me_cuda_subpel_region_stats(int enable, int64_t *served, int64_t *total)
 int me_cuda_ref_create_device(const void *d_luma, int stride, int w, int h, void *stream, me_ref_handle *out)
 {
   g.spec.valid = false;
+  if (int rc = only8("me_cuda_ref_create_device")) return rc;
   if (int rc = check_size(w, h)) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
   if (int rc = enter_stream(st)) return rc;
@@ -620,6 +650,7 @@ int me_cuda_ref_create_device(const void *d_luma, int stride, int w, int h, void
 int me_cuda_ref_create_u8(const uint8_t *luma, int stride, int w, int h, me_ref_handle *out)
 {
   g.spec.valid = false;
+  if (int rc = only8("me_cuda_ref_create_u8")) return rc;
   if (int rc = check_size(w, h)) return rc;
   size_t bytes = (size_t)w * h;
   if (int rc = ensure_pin(bytes)) return rc;
@@ -634,17 +665,39 @@ int me_cuda_ref_create(const me_imgpel *const *rows, int w, int h, me_imgpel ***
 {
   g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
-  size_t bytes = (size_t)w * h;
+  size_t bytes = (size_t)w * h * g.pel_bytes;
   if (int rc = ensure_pin(bytes)) return rc;
   if (int rc = ensure_stage(bytes)) return rc;
   CK(cudaStreamSynchronize(g.stream));
   for (int y = 0; y < h; y++) {
     const me_imgpel *s = rows[y];
+    if (g.pel_bytes == 2) { memcpy(g.h_pin + (size_t)y * w * 2, s, (size_t)w * 2); continue; }     // imgpel is the 16-bit sample
     uint8_t *d = g.h_pin + (size_t)y * w;
     for (int x = 0; x < w; x++) d[x] = (uint8_t)s[x];
   }
   CK(cudaMemcpyAsync(g_d_stage, g.h_pin, bytes, cudaMemcpyHostToDevice, g.stream));
   if (int rc = create_ref_common(g_d_stage, w, w, h, g.stream, out)) return rc;
+  if (host_sub && g.pel_bytes == 2) {
+    // 16-bit planes go back as they are
+    RefPic *r = ref_of(*out);
+    const int wp = r->dev.wp, hp = r->dev.hp;
+    const size_t n = (size_t)16 * wp * hp;
+    if (g.wide_elems < n) {
+      if (g.d_wide) cudaFree(g.d_wide);
+      if (g.h_wide) cudaFreeHost(g.h_wide);
+      g.d_wide = nullptr; g.h_wide = nullptr; g.wide_elems = 0;
+      CK(cudaMalloc((void **)&g.d_wide, n * sizeof(uint16_t)));
+      CK(cudaMallocHost((void **)&g.h_wide, n * sizeof(uint16_t)));
+      g.wide_elems = n;
+    }
+    CK(cudaMemcpy2DAsync(g.h_wide, (size_t)wp * 2, r->planes, (size_t)r->dev.pitch * 2, (size_t)wp * 2, (size_t)16 * hp, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (int fy = 0; fy < 4; fy++)
+      for (int fx = 0; fx < 4; fx++)
+        for (int y = 0; y < hp; y++)
+          memcpy(host_sub[fy][fx][y], g.h_wide + ((size_t)(fy * 4 + fx) * hp + y) * wp, (size_t)wp * sizeof(uint16_t));
+    return 0;
+  }
   if (host_sub) {
     // the encoder's motion compensation still reads imgY_sub on the host (macroblock.c:816): hand the planes back
     RefPic *r = ref_of(*out);
@@ -688,6 +741,7 @@ int me_cuda_ref_download_plane(me_ref_handle h, int fy, int fx, uint8_t *dst, in
   RefPic *r = ref_of(h);
   if (!r) return fail(3, "me_cuda_ref_download_plane: invalid handle %d", (int)h);
   if (fy < 0 || fy > 3 || fx < 0 || fx > 3) return fail(1, "plane index out of range");
+  if (int rc = only8("me_cuda_ref_download_plane")) return rc;
   CK(cudaMemcpy2DAsync(dst, dst_stride, r->planes + (size_t)(fy * 4 + fx) * r->dev.plane_stride, r->dev.pitch,
                        r->dev.wp, r->dev.hp, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
@@ -697,6 +751,7 @@ int me_cuda_ref_download_plane(me_ref_handle h, int fy, int fx, uint8_t *dst, in
 int me_cuda_ref_update_device(me_ref_handle hd, const void *d_luma, int stride, int w, int h, void *stream)
 {
   g.spec.valid = false;
+  if (int rc = only8("me_cuda_ref_update_device")) return rc;
   if (int rc = check_size(w, h)) return rc;
   if (RefPic *r = ref_of(hd)) if (r->dev.w != w || r->dev.h != h) return fail(1, "me_cuda_ref_update_device: a %dx%d picture into a %dx%d slot", w, h, r->dev.w, r->dev.h);
   cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
@@ -708,6 +763,7 @@ int me_cuda_ref_update_device(me_ref_handle hd, const void *d_luma, int stride, 
 int me_cuda_ref_update_u8(me_ref_handle hd, const uint8_t *luma, int stride, int w, int h)
 {
   g.spec.valid = false;
+  if (int rc = only8("me_cuda_ref_update_u8")) return rc;
   if (int rc = check_size(w, h)) return rc;
   if (RefPic *r = ref_of(hd)) if (r->dev.w != w || r->dev.h != h) return fail(1, "me_cuda_ref_update_u8: a %dx%d picture into a %dx%d slot", w, h, r->dev.w, r->dev.h);
   size_t bytes = (size_t)w * h;
@@ -745,6 +801,7 @@ int me_cuda_kernel_time_ms(int which, double *total_ms, int *n_launches)
 int me_cuda_set_current_device(const void *d_luma, int stride, int w, int h, void *stream)
 {
   g.spec.valid = false;
+  if (int rc = only8("me_cuda_set_current_device")) return rc;
   if (int rc = check_size(w, h)) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
   if (int rc = enter_stream(st)) return rc;
@@ -756,6 +813,7 @@ int me_cuda_set_current_device(const void *d_luma, int stride, int w, int h, voi
 int me_cuda_set_current_u8(const uint8_t *luma, int stride, int w, int h)
 {
   g.spec.valid = false;
+  if (int rc = only8("me_cuda_set_current_u8")) return rc;
   if (int rc = check_size(w, h)) return rc;
   CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, luma, stride, w, h, cudaMemcpyHostToDevice, g.stream));
   picture_set(h);
@@ -766,15 +824,16 @@ int me_cuda_set_current(const me_imgpel *const *rows, int w, int h)
 {
   g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
-  size_t bytes = (size_t)w * h;
+  size_t bytes = (size_t)w * h * g.pel_bytes;
   if (int rc = ensure_pin(bytes)) return rc;
   CK(cudaStreamSynchronize(g.stream));
   for (int y = 0; y < h; y++) {
     const me_imgpel *s = rows[y];
+    if (g.pel_bytes == 2) { memcpy(g.h_pin + (size_t)y * w * 2, s, (size_t)w * 2); continue; }
     uint8_t *d = g.h_pin + (size_t)y * w;
     for (int x = 0; x < w; x++) d[x] = (uint8_t)s[x];
   }
-  CK(cudaMemcpy2DAsync(g.d_cur, g.cur_pitch, g.h_pin, w, w, h, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpy2DAsync(g.d_cur, (size_t)g.cur_pitch * g.pel_bytes, g.h_pin, (size_t)w * g.pel_bytes, (size_t)w * g.pel_bytes, h, cudaMemcpyHostToDevice, g.stream));
   picture_set(h);
   return 0;
 }
@@ -906,6 +965,7 @@ int me_cuda_set_slice_type(int t) { g.slice_type = t; g.spec.valid = false; retu
 
 int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom)
 {
+  if (apply) if (int rc = only8("me_cuda_set_bipred_weights (weighted bi-prediction)")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (list < 0 || list > 1) return fail(1, "me_cuda_set_bipred_weights: list %d out of range", list);
   MeBiW w = {};
@@ -938,6 +998,7 @@ int me_cuda_set_bipred_chroma_weights(int list, int component, int weight1, int 
 
 int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset, int log_denom)
 {
+  if (apply) if (int rc = only8("me_cuda_set_ref_weights (weighted-prediction ME)")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (list < 0 || list > 1 || ref < 0 || ref >= ME_MAX_REFS) return fail(1, "me_cuda_set_ref_weights: (list %d, ref %d) out of range", list, ref);
   WeightSet w;
@@ -989,6 +1050,9 @@ int me_cuda_ffs_setup(int list, int ref, int pmv16_x, int pmv16_y)
   if (!g.d_surf[list][ref]) CK(cudaMalloc((void **)&g.d_surf[list][ref], sizeof(int32_t) * (size_t)ME_NUM_PARTITIONS * P));
   const MeRefDev *dev;
   if (int rc = search_planes(list, ref, r, &dev, nullptr, nullptr, nullptr, nullptr)) return rc;
+  if (g.pel_bytes == 2)
+    me_launch_ffs_surfaces16(dev, (const uint16_t *)g.cur_view, g.cur_view_pitch, g.opix_x, g.opix_y, cx, cy, R, g.cfg.metric[0] != 0, g.d_surf[list][ref], g.stream);
+  else
   me_launch_ffs_surfaces(dev, g.cur_view, g.cur_view_pitch, g.opix_x, g.opix_y, cx, cy, R, g.cfg.metric[0] != 0, &g.cfg.chroma, g.d_surf[list][ref], g.stream);
   g.launches++;
   CK(cudaGetLastError());
@@ -1199,6 +1263,7 @@ int me_cuda_FullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic
                                      short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
                                      int search_range, int min_mcost, int lambda_factor)
 {
+  if (only8("me_cuda_FullPelBlockMotionSearch")) { fatal("me_cuda_FullPelBlockMotionSearch"); return ME_INT_MAX; }
   g.spec.valid = false;
   RefPic *r = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
   if (!r) { fail(1, "me_cuda_FullPelBlockMotionSearch: (list %d, ref %d) not in the reference lists", list, (int)ref); fatal("fullpel"); return ME_INT_MAX; }
@@ -1326,6 +1391,7 @@ static int subpel_pattern(const char *who, const MePatArgs &pa, short ref, int l
                           int pmv_x, int pmv_y, short *mv_x, short *mv_y, const short *s_mv, int search_pos2, int search_pos4,
                           int min_mcost, int lam0, int lam1, int lam2, int check0)
 {
+  if (only8("the sub-pel stages of the pattern searches")) { fatal("the sub-pel stages of the pattern searches"); return ME_INT_MAX; }
   g.spec.valid = false;
   if (blocktype < 1 || blocktype > 7) { fail(1, "%s: block type %d", who, blocktype); fatal(who); return ME_INT_MAX; }
   MeSubpelArgs a{};
@@ -1412,6 +1478,7 @@ static int use_basic_only()
 
 int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, void *d_out_int, void *stream)
 {
+  if (int rc = only8("me_cuda_frame_search")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_jobs <= 0) return 0;
   if (g.view) return fail(1, "me_cuda_frame_search: a field view of the current picture is selected (the frame batch reads the picture as uploaded: upload the field itself)");
@@ -1478,6 +1545,7 @@ static int check_jobs(const me_mb_job *jobs, int first, int n)
 
 int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, me_mb_result_int *out_int)
 {
+  if (int rc = only8("me_cuda_frame_search")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_jobs <= 0) return 0;
   // Pinned (page-locked) caller buffers are visible to the device under unified addressing: the kernels then read the job array and
@@ -1640,6 +1708,7 @@ static int mc_stage(const void *src, size_t in, size_t out, uint8_t **d_in, uint
 
 int me_cuda_luma_prediction(const me_pred_block *blocks, int n, int bsx, int bsy, uint8_t *pred)
 {
+  if (int rc = only8("me_cuda_luma_prediction")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n <= 0) return 0;
   if ((bsx != 4 && bsx != 8 && bsx != 16) || (bsy != 4 && bsy != 8 && bsy != 16)) return fail(1, "me_cuda_luma_prediction: block size %d x %d", bsx, bsy);
@@ -1659,6 +1728,7 @@ int me_cuda_luma_prediction(const me_pred_block *blocks, int n, int bsx, int bsy
 
 int me_cuda_pred_cost8x8(const me_pred_block *blocks, int n_regions, int metric, int32_t *cost4, int32_t *cost8)
 {
+  if (int rc = only8("me_cuda_pred_cost8x8")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_regions <= 0) return 0;
   if (metric < 0 || metric > 2) return fail(1, "me_cuda_pred_cost8x8: metric %d", metric);
@@ -1694,6 +1764,13 @@ int me_cuda_ref_download_region(me_ref_handle h, int fy, int fx, int x0, int y0,
   uint8_t *d_in, *d_out, *h_out;
   uint32_t dummy = 0;
   if (r->written_on && r->written_on != g.stream) CK(cudaStreamSynchronize(r->written_on));
+  if (g.pel_bytes == 2) {          // 16-bit planes: the rectangle as it is
+    const uint16_t *src = (const uint16_t *)r->planes + (size_t)(fy * 4 + fx) * r->dev.plane_stride + (size_t)y0 * r->dev.pitch + x0;
+    CK(cudaMemcpy2DAsync(dst, (size_t)dst_stride * sizeof(uint16_t), src, (size_t)r->dev.pitch * sizeof(uint16_t), (size_t)w * sizeof(uint16_t), hgt,
+                         cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+  }
   if (int rc = mc_stage(&dummy, sizeof dummy, bytes, &d_in, &d_out, &h_out)) return rc;
   me_launch_widen_region(r->planes + (size_t)(fy * 4 + fx) * r->dev.plane_stride, r->dev.pitch, x0, y0, w, hgt, (uint16_t *)d_out, g.stream);
   g.launches++;
@@ -1713,6 +1790,7 @@ int me_cuda_ref_download_region(me_ref_handle h, int fy, int fx, int x0, int y0,
 int me_cuda_deblock_frame(me_imgpel *const *y_rows, me_imgpel *const *u_rows, me_imgpel *const *v_rows, int w, int h, int cw, int ch,
                           const me_deblock_mb *mbs)
 {
+  if (int rc = only8("me_cuda_deblock_frame")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (w <= 0 || h <= 0 || (w & 15) || (h & 15)) return fail(1, "me_cuda_deblock_frame: picture size %d x %d", w, h);
   const bool chroma = u_rows && v_rows;
@@ -1757,6 +1835,7 @@ int me_cuda_deblock_frame(me_imgpel *const *y_rows, me_imgpel *const *u_rows, me
 
 int me_cuda_ref_create_deblocked(int w, int h, me_imgpel ****host_sub, me_ref_handle *out)
 {
+  if (int rc = only8("me_cuda_ref_create_deblocked")) return rc;
   g.spec.valid = false;
   if (int rc = check_size(w, h)) return rc;
   if (!g.db_valid || g.db_w != w || g.db_h != h) return fail(1, "me_cuda_ref_create_deblocked: no deblocked %d x %d picture on the device", w, h);
@@ -1766,6 +1845,7 @@ int me_cuda_ref_create_deblocked(int w, int h, me_imgpel ****host_sub, me_ref_ha
 
 int me_cuda_frame_bipred(const me_bipred_job *jobs, int n_jobs, int refinements, int search_range, int subpel, me_bipred_result *out)
 {
+  if (int rc = only8("me_cuda_frame_bipred")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_jobs <= 0) return 0;
   if (g.list_n[0] < 1 || g.list_n[1] < 1) return fail(1, "me_cuda_frame_bipred needs a reference picture in both lists");

@@ -231,3 +231,51 @@ extern "C" void me_launch_weight_planes(const uint8_t *src, uint8_t *dst, size_t
   me_weight_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), n16,
                                                             weight, offset, log_denom);
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// The 16 planes of a picture with more than 8 bits per sample (imgpel is u16 in the reference, global.h:50): 16-bit samples
+// in and out, the clips of getSubImagesLuma at img->max_imgpel_value (img_luma.c:45-639).  One thread per position of the padded
+// plane computes all sixteen values from the picture with clamped coordinates -- the padded integer plane is pure edge
+// replication, so every clamp the reference applies to padded-plane indices equals a clamp of picture coordinates.
+// 16-bit pictures are not on the throughput path: no byte tricks, no search-plane copy (the searches read plane (0,0)).
+__global__ void __launch_bounds__(256)
+me_planes16_kernel(const uint16_t *__restrict__ src, int src_stride /* samples */, int w, int h, uint16_t *__restrict__ planes,
+                   int pitch /* samples */, size_t plane_stride /* samples */, int max_pel)
+{
+  const int wp = w + 2 * ME_PAD, hp = h + 2 * ME_PAD;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= wp || y >= hp) return;
+  auto L = [&](int yy, int xx) -> int {
+    return (int)src[(size_t)me_clamp(yy - ME_PAD, 0, h - 1) * src_stride + me_clamp(xx - ME_PAD, 0, w - 1)];
+  };
+  auto clip = [&](int v) -> int { return me_clamp(v, 0, max_pel); };
+  auto hsum = [&](int yy, int xx) -> int {       // unrounded horizontal six-tap sum (getHorSubImageSixTap, img_luma.c:181-280)
+    return 20 * (L(yy, xx) + L(yy, xx + 1)) - 5 * (L(yy, xx - 1) + L(yy, xx + 2)) + (L(yy, xx - 2) + L(yy, xx + 3));
+  };
+  auto vhalf = [&](int yy, int xx) -> int {      // getVerSubImageSixTap, img_luma.c:293-380
+    return clip((20 * (L(yy, xx) + L(yy + 1, xx)) - 5 * (L(yy - 1, xx) + L(yy + 2, xx)) + (L(yy - 2, xx) + L(yy + 3, xx)) + 16) >> 5);
+  };
+  int hs[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) hs[k] = hsum(y - 2 + k, x);
+  const int g = L(y, x), gx1 = L(y, x + 1), gy1 = L(y + 1, x);
+  const int b = clip((hs[2] + 16) >> 5), by1 = clip((hs[3] + 16) >> 5);
+  const int hv = vhalf(y, x), hx1 = vhalf(y, x + 1);
+  const int j = clip((20 * (hs[2] + hs[3]) - 5 * (hs[1] + hs[4]) + (hs[0] + hs[5]) + 512) >> 10);      // getVerSubImageSixTapTmp :390-470
+  const size_t o = (size_t)y * pitch + x;
+  auto put = [&](int fy, int fx, int v) { planes[(size_t)(fy * 4 + fx) * plane_stride + o] = (uint16_t)v; };
+  put(0, 0, g); put(0, 2, b); put(2, 0, hv); put(2, 2, j);
+  put(0, 1, (g + b + 1) >> 1);   put(1, 0, (g + hv + 1) >> 1);  put(1, 1, (b + hv + 1) >> 1);    // quarter-pel positions, img_luma.c:483-639
+  put(1, 2, (b + j + 1) >> 1);   put(2, 1, (hv + j + 1) >> 1);
+  put(0, 3, (b + gx1 + 1) >> 1); put(1, 3, (b + hx1 + 1) >> 1); put(2, 3, (j + hx1 + 1) >> 1);
+  put(3, 0, (hv + gy1 + 1) >> 1); put(3, 1, (hv + by1 + 1) >> 1); put(3, 2, (j + by1 + 1) >> 1);
+  put(3, 3, (by1 + hx1 + 1) >> 1);
+}
+
+extern "C" void me_launch_planes16(const uint16_t *src, int src_stride, int w, int h, uint16_t *planes, int pitch, size_t plane_stride,
+                                   int max_pel, cudaStream_t st)
+{
+  const int wp = w + 2 * ME_PAD, hp = h + 2 * ME_PAD;
+  dim3 grid((wp + 31) / 32, (hp + 7) / 8);
+  me_planes16_kernel<<<grid, 256, 0, st>>>(src, src_stride, w, h, planes, pitch, plane_stride, max_pel);
+}

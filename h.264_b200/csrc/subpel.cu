@@ -78,13 +78,14 @@ __device__ __forceinline__ int bipred_pel(int p1, int p2, const MeBiW &w)
 // case only: the 8x8 branch of computeBiPredSATD2 reads the eighth sample of every row without advancing its source pointer
 // (me_distortion.c:1015), so each row of the ORIGINAL block starts one sample further left than the row above -- linear
 // index by*bsx + bx + y*(bsx-1) + x into the bsx-wide copy of the block (mv-search.c:607-611).  Reproduced as is.
-template <int N>
-__device__ __forceinline__ int tile_dist(int metric, const uint8_t *__restrict__ blk, int src_pitch, int bsx, int bx, int by,
-                                         const uint8_t *__restrict__ p1, int pitch1,
-                                         const uint8_t *__restrict__ p2, int pitch2, const MeBiW &bw)
+// Pel: uint8_t, or uint16_t for pictures of more than 8 bits per sample (the drop-in kernels are instantiated for both)
+template <int N, typename Pel>
+__device__ __forceinline__ int tile_dist(int metric, const Pel *__restrict__ blk, int src_pitch, int bsx, int bx, int by,
+                                         const Pel *__restrict__ p1, int pitch1,
+                                         const Pel *__restrict__ p2, int pitch2, const MeBiW &bw)
 {
   int d[N * N];
-  const uint8_t *src = blk + by * src_pitch + bx;
+  const Pel *src = blk + by * src_pitch + bx;
   const bool skew = N == 8 && metric == 2 && p2 && bw.apply;
 #pragma unroll
   for (int y = 0; y < N; y++)
@@ -109,10 +110,11 @@ __device__ __forceinline__ int tile_dist(int metric, const uint8_t *__restrict__
 
 // The reference fetches SAD blocks with one origin clamp per block and SATD tiles with one per tile; both are served by
 // this helper: (bx,by) = tile offset inside the block, `per_tile` selects where the clamp applies.
-__device__ __forceinline__ const uint8_t *tile_ptr(const MeRefDev &r, int x4, int y4, int bx, int by, bool per_tile)
+template <typename Pel>
+__device__ __forceinline__ const Pel *tile_ptr(const MeRefDev &r, int x4, int y4, int bx, int by, bool per_tile)
 {
-  if (per_tile) return me_umv_ptr(r, y4 + (by << 2), x4 + (bx << 2));
-  return me_umv_ptr(r, y4, x4) + (size_t)by * r.pitch + bx;
+  if (per_tile) return me_umv_ptr_p<Pel>(r, y4 + (by << 2), x4 + (bx << 2));
+  return me_umv_ptr_p<Pel>(r, y4, x4) + (size_t)by * r.pitch + bx;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -172,11 +174,11 @@ me_subpel_batch_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDe
       int x4 = ((job.opix_x + 4 * px + ME_PAD) << 2) + mv_s[p][0] + step * c_sp_x[c];
       int y4 = ((job.opix_y + 4 * py + ME_PAD) << 2) + mv_s[p][1] + step * c_sp_y[c];
       int bx = 4 * (tx - px), by = 4 * (ty - py);
-      const uint8_t *rp = tile_ptr(ref, x4, y4, bx, by, metric == 2);
+      const uint8_t *rp = tile_ptr<uint8_t>(ref, x4, y4, bx, by, metric == 2);
       const uint8_t *sp = &cur_s[4 * ty][4 * tx];
       const MeBiW nobw = { 0, 0, 0, 0, 0, { 0, 0 }, { 0, 0 }, { 0, 0 } };
-      int d = use8 ? tile_dist<8>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw)
-                   : tile_dist<4>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw);
+      int d = use8 ? tile_dist<8, uint8_t>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw)
+                   : tile_dist<4, uint8_t>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw);
       // chroma terms of computeSAD / computeSSE (me_distortion.c:376-402, :1069-1091): once per block, by the lane of its first tile
       if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && ref.chroma[0])
         for (int k = 0; k < 2; k++)
@@ -230,7 +232,8 @@ struct BlockScratch {
 
 // One block, both sub-pel levels.  bi == 0: SubPelBlockMotionSearch (r1 searched).  bi == 1: SubPelBlockSearchBiPred, r1 read at
 // the fixed vector (s_mv), r2 at the candidate.  Called by all threads of the CTA; returns the result to all of them.
-__device__ void subpel_block(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch,
+template <typename Pel>
+__device__ void subpel_block(const MeRefDev &r1, const MeRefDev &r2, const Pel *__restrict__ cur, int cur_pitch,
                              const MeCfgDev &cfg, const MeSubpelArgs &a, BlockScratch &sc, int &out_mvx, int &out_mvy, int &out_cost)
 {
   const int tid = threadIdx.x;
@@ -256,23 +259,25 @@ __device__ void subpel_block(const MeRefDev &r1, const MeRefDev &r2, const uint8
       int bx = (tile % tw) * n, by = (tile / tw) * n;
       int x4 = ((a.pic_pix_x + ME_PAD) << 2) + sc.mv_s[0] + step * c_sp_x[c];
       int y4 = ((a.pic_pix_y + ME_PAD) << 2) + sc.mv_s[1] + step * c_sp_y[c];
-      const uint8_t *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
+      const Pel *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
       int d;
       if (!a.bi) {
-        const uint8_t *rp = tile_ptr(r1, x4, y4, bx, by, metric == 2);
-        d = use8 ? tile_dist<8>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw)
-                 : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw);
+        const Pel *rp = tile_ptr<Pel>(r1, x4, y4, bx, by, metric == 2);
+        d = use8 ? tile_dist<8, Pel>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw)
+                 : tile_dist<4, Pel>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw);
       } else {
         int fx4 = ((a.pic_pix_x + ME_PAD) << 2) + a.s_mv_x, fy4 = ((a.pic_pix_y + ME_PAD) << 2) + a.s_mv_y;
-        const uint8_t *p1 = tile_ptr(r1, fx4, fy4, bx, by, metric == 2);
-        const uint8_t *p2 = tile_ptr(r2, x4, y4, bx, by, metric == 2);
-        d = use8 ? tile_dist<8>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw)
-                 : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
+        const Pel *p1 = tile_ptr<Pel>(r1, fx4, fy4, bx, by, metric == 2);
+        const Pel *p2 = tile_ptr<Pel>(r2, x4, y4, bx, by, metric == 2);
+        d = use8 ? tile_dist<8, Pel>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw)
+                 : tile_dist<4, Pel>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
+        if constexpr (sizeof(Pel) == 1)                     // chroma terms: 8-bit pictures only (refused at init otherwise)
         if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0] && r2.chroma[0])      // computeBiPredSAD1 :516-543
           for (int k = 0; k < 2; k++)
             d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, fx4, fy4, &r2, x4, y4,
                                                  a.bw.apply, a.bw.cw1[k], a.bw.cw2[k], a.bw.cobi[k], a.bw.denom);
       }
+      if constexpr (sizeof(Pel) == 1)
       if (!a.bi && cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0])                // computeSAD / SSE :376-402
         for (int k = 0; k < 2; k++)
           d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, x4, y4, nullptr, 0, 0);
@@ -342,18 +347,18 @@ __device__ void pattern_grid(const MeRefDev &r1, const MeRefDev &r2, const uint8
     const int y4 = ((a.pic_pix_y + ME_PAD) << 2) + cy0 + step * (c / W - E);
     int d;
     if (!a.bi) {
-      const uint8_t *rp = tile_ptr(r1, x4, y4, bx, by, metric == 2);
-      d = use8 ? tile_dist<8>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw)
-               : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw);
+      const uint8_t *rp = tile_ptr<uint8_t>(r1, x4, y4, bx, by, metric == 2);
+      d = use8 ? tile_dist<8, uint8_t>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw)
+               : tile_dist<4, uint8_t>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw);
       if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0])                        // computeSAD / SSE, me_distortion.c:376-402
         for (int k = 0; k < 2; k++)
           d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, x4, y4, nullptr, 0, 0);
     } else {
       const int fx4 = ((a.pic_pix_x + ME_PAD) << 2) + a.s_mv_x, fy4 = ((a.pic_pix_y + ME_PAD) << 2) + a.s_mv_y;
-      const uint8_t *p1 = tile_ptr(r1, fx4, fy4, bx, by, metric == 2);
-      const uint8_t *p2 = tile_ptr(r2, x4, y4, bx, by, metric == 2);
-      d = use8 ? tile_dist<8>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw)
-               : tile_dist<4>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
+      const uint8_t *p1 = tile_ptr<uint8_t>(r1, fx4, fy4, bx, by, metric == 2);
+      const uint8_t *p2 = tile_ptr<uint8_t>(r2, x4, y4, bx, by, metric == 2);
+      d = use8 ? tile_dist<8, uint8_t>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw)
+               : tile_dist<4, uint8_t>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
       if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0] && r2.chroma[0])         // computeBiPredSAD1 :516-543
         for (int k = 0; k < 2; k++)
           d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, fx4, fy4, &r2, x4, y4,
@@ -520,8 +525,9 @@ me_subpel_pattern_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ c
   }
 }
 
+template <typename Pel>
 __global__ void __launch_bounds__(128)
-me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const Pel *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                         MeSubpelArgs a, int *result /* mvx, mvy, cost, ticket */, int ticket)
 {
   __shared__ BlockScratch sc;
@@ -538,9 +544,10 @@ me_subpel_single_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cu
 // (mv-search.c:745 -> :770-774 mv <<= 2 -> :785-788 -> :823): one launch and one host wake-up instead of two.  The host
 // hands the second result out when the reference's SubPelBlockMotionSearch call arrives with exactly the predicted
 // arguments, and runs the plain kernel otherwise.  result: {mvx, mvy, cost, ticket, sub mvx, sub mvy, sub cost}.
+template <typename Pel>
 __global__ void __launch_bounds__(256)
 me_ffs_block_subpel_kernel(const int32_t *__restrict__ surf_p, int setup_range, int offx, int offy, int search_range, int min_mcost,
-                           int rdopt, MeRefDev r1, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                           int rdopt, MeRefDev r1, const Pel *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                            MeSubpelArgs a /* block, predictor, lambda[3], check0 = everything but mv == 0 */, int *result, int ticket)
 {
   __shared__ BlockScratch sc;
@@ -614,8 +621,9 @@ __device__ void pms_predictor(const PmsState &st, int ref_frame, int bx4, int by
   pmx = pm[0]; pmy = pm[1];
 }
 
+template <typename Pel>
 __global__ void __launch_bounds__(256)
-me_pms_group_kernel(const __grid_constant__ MePmsParams P, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg /* sub-pel stage */,
+me_pms_group_kernel(const __grid_constant__ MePmsParams P, const Pel *__restrict__ cur, int cur_pitch, MeCfgDev cfg /* sub-pel stage */,
                     int rdopt, MePmsRecord *result /* mapped host memory: [slot][list-ref][4] */, int *done_count, int *ticket_out, int ticket)
 {
   __shared__ BlockScratch sc;
@@ -704,8 +712,8 @@ __device__ int fullpel_dist(const MeRefDev &r, const uint8_t *__restrict__ cur, 
     for (int by = 0; by < bsy; by += n)
       for (int bx = 0; bx < bsx; bx += n) {
         const uint8_t *rp = me_umv_ptr(r, y4 + (by << 2), x4 + (bx << 2));
-        m += use8 ? tile_dist<8>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw)
-                  : tile_dist<4>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw);
+        m += use8 ? tile_dist<8, uint8_t>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw)
+                  : tile_dist<4, uint8_t>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw);
         if (use_thr && m > thr) return m;
       }
     return m;
@@ -781,7 +789,8 @@ struct MeBiFullArgs {
 };
 
 // one bi-predictive integer-pel search; called by all threads of the CTA, returns the result to all of them
-__device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch,
+template <typename Pel>
+__device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const Pel *__restrict__ cur, int cur_pitch,
                                   const MeCfgDev &cfg, const MeBiFullArgs &a, BlockScratch &sc, int &out_mvx, int &out_mvy, int &out_cost)
 {
   const int P = (2 * a.search_range + 1) * (2 * a.search_range + 1);
@@ -792,7 +801,7 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
   const int c1x = (short)(a.pic_pix_x + a.s_mv_x), c1y = (short)(a.pic_pix_y + a.s_mv_y);
   const int px1 = (a.pic_pix_x << 2) + a.pmv_x1, py1 = (a.pic_pix_y << 2) + a.pmv_y1;
   const int px2 = (a.pic_pix_x << 2) + a.pmv_x2, py2 = (a.pic_pix_y << 2) + a.pmv_y2;
-  const uint8_t *p1 = me_umv_ptr(r1, (c1y << 2) + 4 * ME_PAD, (c1x << 2) + 4 * ME_PAD);
+  const Pel *p1 = me_umv_ptr_p<Pel>(r1, (c1y << 2) + 4 * ME_PAD, (c1x << 2) + 4 * ME_PAD);
   const int fixed_cost = me_mv_cost(a.lambda, c1x << 2, c1y << 2, px1, py1);
   unsigned long long best = ~0ull;
   for (int s = threadIdx.x; s < P; s += blockDim.x) {
@@ -800,19 +809,19 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
     me_spiral_xy(s, dx, dy);
     int cx = (c2x + dx) << 2, cy = (c2y + dy) << 2;
     int mc = fixed_cost + me_mv_cost(a.lambda, cx, cy, px2, py2);
-    const uint8_t *p2 = me_umv_ptr(r2, cy + 4 * ME_PAD, cx + 4 * ME_PAD);
+    const Pel *p2 = me_umv_ptr_p<Pel>(r2, cy + 4 * ME_PAD, cx + 4 * ME_PAD);
     int d = 0;
     if (metric == 2) {
       // computeBiPredSATD1 / SATD2 (me_distortion.c:824, :907): Hadamard SAD tile by tile, each tile with its own origin clamp
       const bool use8 = cfg.transform8x8 && a.blocktype <= 4;
       const int n = use8 ? 8 : 4;
-      const uint8_t *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
+      const Pel *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
       for (int by = 0; by < bsy; by += n)
         for (int bx = 0; bx < bsx; bx += n) {
-          const uint8_t *t1 = me_umv_ptr(r1, (c1y << 2) + 4 * ME_PAD + (by << 2), (c1x << 2) + 4 * ME_PAD + (bx << 2));
-          const uint8_t *t2 = me_umv_ptr(r2, cy + 4 * ME_PAD + (by << 2), cx + 4 * ME_PAD + (bx << 2));
-          d += use8 ? tile_dist<8>(2, blk, cur_pitch, bsx, bx, by, t1, r1.pitch, t2, r2.pitch, a.bw)
-                    : tile_dist<4>(2, blk, cur_pitch, bsx, bx, by, t1, r1.pitch, t2, r2.pitch, a.bw);
+          const Pel *t1 = me_umv_ptr_p<Pel>(r1, (c1y << 2) + 4 * ME_PAD + (by << 2), (c1x << 2) + 4 * ME_PAD + (bx << 2));
+          const Pel *t2 = me_umv_ptr_p<Pel>(r2, cy + 4 * ME_PAD + (by << 2), cx + 4 * ME_PAD + (bx << 2));
+          d += use8 ? tile_dist<8, Pel>(2, blk, cur_pitch, bsx, bx, by, t1, r1.pitch, t2, r2.pitch, a.bw)
+                    : tile_dist<4, Pel>(2, blk, cur_pitch, bsx, bx, by, t1, r1.pitch, t2, r2.pitch, a.bw);
         }
     } else
     for (int y = 0; y < bsy; y++)
@@ -821,6 +830,7 @@ __device__ void bipred_full_block(const MeRefDev &r1, const MeRefDev &r2, const 
                 - bipred_pel(p1[(size_t)y * r1.pitch + x], p2[(size_t)y * r2.pitch + x], a.bw);
         d += metric ? e * e : abs(e);                      // computeBiPred1[F_PEL] / computeBiPred2[F_PEL]: SAD, SSE
       }
+    if constexpr (sizeof(Pel) == 1)
     if (cfg.chroma.on && metric != 2 && r1.chroma[0] && r2.chroma[0])     // computeBiPredSAD1, me_distortion.c:516-543
       for (int k = 0; k < 2; k++)
         d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, (c1x << 2) + 4 * ME_PAD,
@@ -914,15 +924,18 @@ __device__ void bipred_full_block_sad(const MeRefDev &r1, const MeRefDev &r2, co
   out_mvx = a.mv_x + dx; out_mvy = a.mv_y + dy; out_cost = cost;
 }
 
+template <typename Pel>
 __global__ void __launch_bounds__(256)
-me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+me_bipred_full_kernel(MeRefDev r1, MeRefDev r2, const Pel *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                       MeBiFullArgs a, int *result, int ticket)
 {
   __shared__ BlockScratch sc;
-  __shared__ BiFastScratch fs;
   int mvx, mvy, cost;
-  if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE && !a.bw.apply && !cfg.chroma.on) bipred_full_block_sad(r1, r2, cur, cur_pitch, a, sc, fs, mvx, mvy, cost);
-  else bipred_full_block(r1, r2, cur, cur_pitch, cfg, a, sc, mvx, mvy, cost);
+  if constexpr (sizeof(Pel) == 1) {
+    __shared__ BiFastScratch fs;                          // the byte-SIMD path: 8-bit pictures
+    if (cfg.metric[0] == 0 && a.search_range <= BI_FAST_RANGE && !a.bw.apply && !cfg.chroma.on) bipred_full_block_sad(r1, r2, cur, cur_pitch, a, sc, fs, mvx, mvy, cost);
+    else bipred_full_block(r1, r2, cur, cur_pitch, cfg, a, sc, mvx, mvy, cost);
+  } else bipred_full_block(r1, r2, cur, cur_pitch, cfg, a, sc, mvx, mvy, cost);
   if (threadIdx.x == 0) {
     result[0] = mvx; result[1] = mvy; result[2] = cost;
     __threadfence_system();
@@ -1040,20 +1053,31 @@ extern "C" void me_launch_ffs_block_subpel(const int32_t *surf_p, int setup_rang
                                            int rdopt, const MeRefDev *r1, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                                            const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st)
 {
-  me_ffs_block_subpel_kernel<<<1, 256, 0, st>>>(surf_p, setup_range, offx, offy, search_range, min_mcost, rdopt, *r1, cur, cur_pitch,
-                                                *cfg, *a, result, ticket);
+  if (cfg->pel16)
+    me_ffs_block_subpel_kernel<uint16_t><<<1, 256, 0, st>>>(surf_p, setup_range, offx, offy, search_range, min_mcost, rdopt, *r1,
+                                                            reinterpret_cast<const uint16_t *>(cur), cur_pitch, *cfg, *a, result, ticket);
+  else
+    me_ffs_block_subpel_kernel<uint8_t><<<1, 256, 0, st>>>(surf_p, setup_range, offx, offy, search_range, min_mcost, rdopt, *r1, cur, cur_pitch,
+                                                           *cfg, *a, result, ticket);
 }
 
 extern "C" void me_launch_pms_group(const MePmsParams *p, const uint8_t *cur, int cur_pitch, const MeCfgDev *sub_cfg, int rdopt,
                                     MePmsRecord *result, int *done_count, int *ticket_out, int ticket, cudaStream_t st)
 {
-  me_pms_group_kernel<<<p->n_items * p->n_refs, 256, 0, st>>>(*p, cur, cur_pitch, *sub_cfg, rdopt, result, done_count, ticket_out, ticket);
+  if (sub_cfg->pel16)
+    me_pms_group_kernel<uint16_t><<<p->n_items * p->n_refs, 256, 0, st>>>(*p, reinterpret_cast<const uint16_t *>(cur), cur_pitch, *sub_cfg, rdopt,
+                                                                          result, done_count, ticket_out, ticket);
+  else
+    me_pms_group_kernel<uint8_t><<<p->n_items * p->n_refs, 256, 0, st>>>(*p, cur, cur_pitch, *sub_cfg, rdopt, result, done_count, ticket_out, ticket);
 }
 
 extern "C" void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
                                         const MeCfgDev *cfg, const MeSubpelArgs *a, int *result, int ticket, cudaStream_t st)
 {
-  me_subpel_single_kernel<<<1, 128, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, result, ticket);
+  if (cfg->pel16)
+    me_subpel_single_kernel<uint16_t><<<1, 128, 0, st>>>(*r1, r2 ? *r2 : *r1, reinterpret_cast<const uint16_t *>(cur), cur_pitch, *cfg, *a, result, ticket);
+  else
+    me_subpel_single_kernel<uint8_t><<<1, 128, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, result, ticket);
 }
 
 extern "C" void me_launch_subpel_pattern(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
@@ -1071,5 +1095,8 @@ extern "C" void me_launch_fullpel_block(const MeRefDev *r, const uint8_t *cur, i
 extern "C" void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
                                       const MeCfgDev *cfg, const MeBiFullArgs *a, int *result, int ticket, cudaStream_t st)
 {
-  me_bipred_full_kernel<<<1, 256, 0, st>>>(*r1, *r2, cur, cur_pitch, *cfg, *a, result, ticket);
+  if (cfg->pel16)
+    me_bipred_full_kernel<uint16_t><<<1, 256, 0, st>>>(*r1, *r2, reinterpret_cast<const uint16_t *>(cur), cur_pitch, *cfg, *a, result, ticket);
+  else
+    me_bipred_full_kernel<uint8_t><<<1, 256, 0, st>>>(*r1, *r2, cur, cur_pitch, *cfg, *a, result, ticket);
 }

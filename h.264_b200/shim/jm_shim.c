@@ -101,6 +101,7 @@ static long served_ffs = 0, served_fullpel = 0, served_subpel = 0, served_bi_ful
 static long served_field_mbs = 0, served_field_pictures_mbs = 0;   /* macroblocks searched on a field view: MBAFF field macroblocks, field pictures */
 static long served_pattern[5] = {0, 0, 0, 0, 0}, served_pattern_bi = 0;   /* sub-pel stages of the pattern searches, by pattern */
 static long served_bid_cost = 0, served_direct_cost = 0, paged_tiles = 0, paged_bytes = 0;
+static int hbd = 0;             /* more than 8 bits per sample */
 static int use_mc = 1;          /* BIDPartitionCost / GetDirectCost8x8 on the device (ME_CUDA_MC=0: the reference's host code) */
 static int lazy_planes = 1;     /* imgY_sub paged in on demand (ME_CUDA_HOST_PLANES=1: all planes copied back at creation) */
 static int poison_planes = 0;
@@ -230,7 +231,12 @@ void __wrap_Init_Motion_Search_Module(void)
     L.set_error_handler(on_library_error);
     p.abi_version = ME_CUDA_ABI_VERSION;
     p.width = img->width; p.height = img->height;
-    p.bit_depth = (img->max_imgpel_value == 255) ? 8 : 16;
+    /* more than 8 bits per sample (imgpel is u16, global.h:50): the fast-full-search path -- plane sets, block searches, plain and
+     * bi-predictive refinements, one launch per PartitionMotionSearch -- runs on 16-bit planes; the other stages stay the reference's
+     * host code in such runs (hbd below), reading the planes through the paging line accessors */
+    p.bit_depth = img->bitdepth_luma;
+    hbd = img->bitdepth_luma > 8;
+    if (hbd && IS_INDEPENDENT(input) && img->bitdepth_chroma != img->bitdepth_luma) die("4:4:4 independent mode with different luma / chroma bit depths");
     p.search_range = input->search_range;
     p.max_num_references = img->max_num_references;
     p.rdopt = input->rdopt;
@@ -248,7 +254,7 @@ void __wrap_Init_Motion_Search_Module(void)
     active = 1;
     verify = getenv("ME_CUDA_VERIFY") && atoi(getenv("ME_CUDA_VERIFY"));
     use_pms = !(getenv("ME_CUDA_PMS") && !atoi(getenv("ME_CUDA_PMS")));
-    use_mc = !(getenv("ME_CUDA_MC") && !atoi(getenv("ME_CUDA_MC")));
+    use_mc = !(getenv("ME_CUDA_MC") && !atoi(getenv("ME_CUDA_MC"))) && !hbd;
     lazy_planes = !(getenv("ME_CUDA_HOST_PLANES") && atoi(getenv("ME_CUDA_HOST_PLANES")));
     poison_planes = getenv("ME_CUDA_POISON_PLANES") && atoi(getenv("ME_CUDA_POISON_PLANES"));
     use_deblock = !(getenv("ME_CUDA_DEBLOCK") && !atoi(getenv("ME_CUDA_DEBLOCK")));
@@ -608,7 +614,7 @@ int __wrap_FullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int p
                                     short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
                                     int search_range, int min_mcost, int lambda_factor)
 {
-  if (!active)
+  if (!active || hbd)
     return __real_FullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                            mv_x, mv_y, search_range, min_mcost, lambda_factor);
   mb_sync();
@@ -722,7 +728,7 @@ int __real_EPZSSubPelBlockMotionSearch(imgpel *, short, int, int, int, int, shor
 int __wrap_EPZSSubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
                                        short pred_mv[2], short mv[2], int search_pos2, int search_pos4, int min_mcost, int *lambda)
 {
-  if (!active)
+  if (!active || hbd)
     return __real_EPZSSubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv, mv, search_pos2, search_pos4, min_mcost, lambda);
   mb_sync();
   keep_reference_side_effects(list, ref);
@@ -743,7 +749,7 @@ int __wrap_EPZSSubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, in
                                        short *pred_mv1, short *pred_mv2, short mv[2], short s_mv[2],
                                        int search_pos2, int search_pos4, int min_mcost, int *lambda)
 {
-  if (!active)
+  if (!active || hbd)
     return __real_EPZSSubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv1, pred_mv2, mv, s_mv,
                                               search_pos2, search_pos4, min_mcost, lambda);
   mb_sync();
@@ -779,7 +785,7 @@ int __real_##NAME(imgpel *, short, int, int, int, int, short, short, short *, sh
 int __wrap_##NAME(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, short pred_mv_x, short pred_mv_y, \
                   short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor)                     \
 {                                                                                                                                   \
-  if (!active)                                                                                                                      \
+  if (!active || hbd)                                                                                                               \
     return __real_##NAME(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2,       \
                          search_pos4, min_mcost, lambda_factor);                                                                    \
   mb_sync();                                                                                                                        \

@@ -128,7 +128,9 @@ def test_mode_decision_costs_and_paged_planes(tmp_path, me_lib_path, args, want)
                                   "epzs_pattern_subpel", "epzs_pattern_subpel_weighted", "umhex_pattern_subpel_chroma_sad",
                                   "umhex_simple_pattern_subpel_rdopt0",
                                   "interlace_field_pictures", "interlace_picture_adaptive", "interlace_mbaff_field_macroblocks",
-                                  "interlace_mbaff_adaptive", "interlace_picture_and_mbaff_adaptive_chroma_me", "interlace_field_pictures_epzs"])
+                                  "interlace_mbaff_adaptive", "interlace_picture_and_mbaff_adaptive_chroma_me", "interlace_field_pictures_epzs",
+                                  "high_bit_depth_10_bframes", "high_bit_depth_12_bframes", "high_bit_depth_10_sad_sse_rdopt0",
+                                  "high_bit_depth_10_field_pictures"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -236,6 +238,17 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
                  "interlace_mbaff_adaptive": ["-p", "MbInterlace=2"],
                  "interlace_picture_and_mbaff_adaptive_chroma_me": ["-p", "PicInterlace=2", "-p", "MbInterlace=2", "-p", "ChromaMEEnable=2"],
                  "interlace_field_pictures_epzs": ["-p", "PicInterlace=1", "-p", "SearchMode=3"]}[case]
+    elif case.startswith("high_bit_depth_"):
+        # SURVEY.md 8(f) row 4, last third: more than 8 bits per sample (imgpel u16): 16-bit plane sets, block searches, plain and
+        # bi-predictive refinements and the launch per PartitionMotionSearch on 16-bit samples.  Input: the reference's QCIF clip
+        # shifted up with random low bits (hbd.yuv, 16-bit little-endian samples).
+        bits = 12 if "_12_" in case else 10
+        args = ["-d", "encoder.cfg", "-p", "InputFile=hbd.yuv", "-p", "BitDepthLuma=%d" % bits, "-p", "BitDepthChroma=%d" % bits,
+                "-p", "ProfileIDC=%d" % (122 if bits == 12 else 110), "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+        if "sad_sse_rdopt0" in case:
+            args += ["-p", "MEDistortionHPel=0", "-p", "MEDistortionQPel=1", "-p", "RDOptimization=0", "-p", "Transform8x8Mode=0"]
+        if "field_pictures" in case:
+            args += ["-p", "PicInterlace=1", "-p", "ReferenceReorder=0", "-p", "PocMemoryManagement=0"]
     elif case == "epzs_pattern_subpel":
         # SURVEY.md 8(f) row 4, second half: EPZS as shipped (EPZSSubPelME = EPZSSubPelMEBiPred = EPZSSubPelGrid = 1):
         # EPZSSubPelBlockMotionSearch / EPZSSubPelBlockSearchBiPred (me_epzs.c:2390, :2728) on the device
@@ -263,6 +276,11 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
                 "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
     for d in (a, b):
         _prep(str(d))
+        if "InputFile=hbd.yuv" in args:
+            import numpy as np
+            src = np.fromfile(os.path.join(REF_DIR, "fixtures", "foreman_part_qcif.yuv"), np.uint8).astype(np.uint16)
+            sh = bits - 8
+            ((src << sh) + np.random.default_rng(5).integers(0, 1 << sh, src.shape).astype(np.uint16)).astype("<u2").tofile(str(d / "hbd.yuv"))
         if "InputFile=syn.yuv" in args:
             wdt = int([a for a in args if a.startswith("SourceWidth=")][0].split("=")[1])
             hgt = int([a for a in args if a.startswith("SourceHeight=")][0].split("=")[1])
@@ -302,7 +320,7 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
             assert n_smp > 1000 and n_smp_full > 100, m.group(0)
         elif "EPZSSubPelME=0" not in args:
             assert n_epzs > 1000 and (n_epzs_bi > 0 or "baseline" in args[1]), m.group(0)
-    if pattern or case.startswith("interlace_"):
+    if pattern or case.startswith("interlace_") or case.startswith("high_bit_depth_"):
         # the device did serve these modes: verify mode counts the SubPelBlockMotionSearch calls it answered (and compares each)
         import re
         r = subprocess.run([os.path.join(REF_DIR, "lencod_cuda")] + args, cwd=str(a), capture_output=True, text=True, timeout=1500,
