@@ -139,11 +139,13 @@ class MeCuda:
 
     def __init__(self, width, height, search_range=32, max_num_references=5, rdopt=1, full_search=2,
                  me_metric=(0, 2, 2), transform8x8=0, mv_limits=(-511, 511), device=-1, lib_path=LIB_PATH,
-                 chroma_me=0, chroma_me_weight=1, yuv_format=1):
+                 chroma_me=0, chroma_me_weight=1, yuv_format=1, bit_depth=8):
+        """bit_depth > 8: pictures are uint16 arrays and go through the row-pointer entry points (ref_create_imgpel,
+        set_current_imgpel); the fast-full-search drop-in path serves them, the 8-bit-only entry points refuse"""
         self.L = load_library(lib_path)
         p = Params()
         p.abi_version = 1
-        p.width, p.height, p.bit_depth = width, height, 8
+        p.width, p.height, p.bit_depth = width, height, bit_depth
         p.search_range, p.max_num_references, p.rdopt, p.full_search = search_range, max_num_references, rdopt, full_search
         for i in range(3):
             p.me_metric[i] = me_metric[i]
@@ -238,6 +240,13 @@ class MeCuda:
     def set_current(self, luma):
         luma = np.ascontiguousarray(luma, np.uint8)
         self._check(self.L.me_cuda_set_current_u8(luma.ctypes.data, luma.strides[0], luma.shape[1], luma.shape[0]))
+
+    def set_current_imgpel(self, luma_u16):
+        """JM-style entry (me_cuda_set_current): rows of 16-bit samples, as the reference holds imgY_org"""
+        luma_u16 = np.ascontiguousarray(luma_u16, np.uint16)
+        hgt, wid = luma_u16.shape
+        rows = (C.c_void_p * hgt)(*[luma_u16.ctypes.data + y * luma_u16.strides[0] for y in range(hgt)])
+        self._check(self.L.me_cuda_set_current(rows, wid, hgt))
 
     def set_ref_list(self, lst, handles):
         arr = (C.c_int32 * max(1, len(handles)))(*handles)

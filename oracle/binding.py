@@ -11,6 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle_me.so")
+LIB16 = os.path.join(HERE, "liboracle_me16.so")     # the same source compiled with 16-bit samples (more than 8 bits per sample)
 
 NUM_PART = 41
 PART_TYPE = [1, 2, 2, 3, 3, 4, 4, 4, 4] + [5] * 8 + [6] * 8 + [7] * 16
@@ -54,19 +55,39 @@ assert RESULT_DTYPE.itemsize == 328 and C.sizeof(MbResult) == 328
 
 
 def build(force=False):
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "me_oracle.c")):
+    src = os.path.getmtime(os.path.join(HERE, "me_oracle.c"))
+    if force or any(not os.path.exists(f) or os.path.getmtime(f) < src for f in (LIB, LIB16)):
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     return LIB
 
 
-_lib = None
+_libs = {}
+_bits = 8
+
+
+def set_bit_depth(bits=8):
+    """8: the 8-bit oracle (default).  9..14: the 16-bit build, clips at (1 << bits) - 1; pictures are uint16 arrays then."""
+    global _bits
+    _bits = int(bits)
+    if _bits > 8:
+        lib().ora_set_max_pel((1 << _bits) - 1)
+
+
+def pel_dtype():
+    return np.uint16 if _bits > 8 else np.uint8
+
+
+def _stride(a):
+    """row stride of a picture in samples (the C side indexes sample pointers)"""
+    return a.strides[0] // a.itemsize
 
 
 def lib():
-    global _lib
+    path = LIB16 if _bits > 8 else LIB
+    _lib = _libs.get(path)
     if _lib is None:
         build()
-        L = C.CDLL(LIB)
+        L = C.CDLL(path)
         vp, ip, sp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_short)
         L.ora_ref_create.restype = vp
         L.ora_ref_create.argtypes = [vp, C.c_int, C.c_int, C.c_int]
@@ -80,6 +101,7 @@ def lib():
         L.ora_set_bipred_weights.argtypes = [C.c_int] * 6
         L.ora_select_bipred_list.argtypes = [C.c_int]
         L.ora_set_bipred_chroma_weights.argtypes = [C.c_int] * 5
+        L.ora_set_max_pel.argtypes = [C.c_int]
         L.ora_spiral.argtypes = [C.c_int, vp, vp]
         L.ora_mvbits.argtypes = [C.c_int]
         L.ora_mv_cost.argtypes = [C.c_int] * 5
@@ -106,12 +128,17 @@ def lib():
         L.ora_smpumhex_full_subpel.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp] + [C.c_int] * 7 + [sp, sp] + [C.c_int] * 6
         L.ora_mb_search.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, vp]
         L.ora_mb_bipred.argtypes = [C.POINTER(OraCfg), vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
-        L.ora_luma_prediction.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
-        L.ora_deblock_frame.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]
-        L.ora_get_skip_cost_mb.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
-        L.ora_get_direct_cost8x8.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, ip]
-        L.ora_bid_partition_cost.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
-        _lib = L
+        if path == LIB:
+            L.ora_luma_prediction.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+        if path == LIB:
+            L.ora_deblock_frame.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        if path == LIB:
+            L.ora_get_skip_cost_mb.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
+        if path == LIB:
+            L.ora_get_direct_cost8x8.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, ip]
+        if path == LIB:
+            L.ora_bid_partition_cost.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib = _libs[path] = L
     return _lib
 
 
@@ -138,16 +165,17 @@ class Ref:
     """16 quarter-pel planes of one reconstructed luma picture (uint8 HxW)."""
 
     def __init__(self, luma):
-        luma = np.ascontiguousarray(luma, np.uint8)
+        luma = np.ascontiguousarray(luma, pel_dtype())
         self.h, self.w = luma.shape
+        self.dtype = luma.dtype
         self.hp, self.wp = self.h + 40, self.w + 40
         self._luma = luma
-        self.ptr = lib().ora_ref_create(luma.ctypes.data, luma.strides[0], self.w, self.h)
+        self.ptr = lib().ora_ref_create(luma.ctypes.data, _stride(luma), self.w, self.h)
 
     def plane(self, fy, fx):
         p = lib().ora_ref_plane(self.ptr, fy, fx)
-        buf = (C.c_uint8 * (self.hp * self.wp)).from_address(p)
-        return np.frombuffer(buf, np.uint8).reshape(self.hp, self.wp)
+        buf = ((C.c_uint16 if self.dtype == np.uint16 else C.c_uint8) * (self.hp * self.wp)).from_address(p)
+        return np.frombuffer(buf, self.dtype).reshape(self.hp, self.wp)
 
     def planes(self):
         return np.stack([np.stack([self.plane(fy, fx) for fx in range(4)]) for fy in range(4)])
@@ -155,7 +183,7 @@ class Ref:
     def set_chroma(self, u, v):
         """ChromaMEEnable: the picture's reconstructed chroma planes (uint8, same shape)"""
         u, v = np.ascontiguousarray(u, np.uint8), np.ascontiguousarray(v, np.uint8)
-        lib().ora_ref_set_chroma(self.ptr, u.ctypes.data, v.ctypes.data, u.strides[0], u.shape[1], u.shape[0])
+        lib().ora_ref_set_chroma(self.ptr, u.ctypes.data, v.ctypes.data, _stride(u), u.shape[1], u.shape[0])
 
     def set_chroma444(self, ref_u, ref_v):
         """4:4:4: the plane sets (Ref objects, kept alive by the caller) built from the picture's U and V planes"""
@@ -181,7 +209,7 @@ class Ref:
 def fullpel_block(cfg, cur, ref, ppx, ppy, bt, ref_idx, slice_type, pmvx, pmvy, mvx, mvy, search_range, min_mcost, lam):
     """FullPelBlockMotionSearch (SearchMode = -1): returns (mv_x, mv_y, cost), vectors in integer pel"""
     mx, my = C.c_short(mvx), C.c_short(mvy)
-    cost = lib().ora_fullpel_block(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr, ppx, ppy, bt, ref_idx, slice_type,
+    cost = lib().ora_fullpel_block(C.byref(cfg), cur.ctypes.data, _stride(cur), ref.ptr, ppx, ppy, bt, ref_idx, slice_type,
                                    pmvx, pmvy, C.byref(mx), C.byref(my), search_range, min_mcost, lam)
     return mx.value, my.value, cost
 
@@ -197,7 +225,7 @@ def set_chroma(enable, weight=0, cur_u=None, cur_v=None, shift=(3, 3)):
         return
     cur_u, cur_v = np.ascontiguousarray(cur_u, np.uint8), np.ascontiguousarray(cur_v, np.uint8)
     _chroma_keep[:] = [cur_u, cur_v]
-    lib().ora_set_chroma(int(enable), int(weight), cur_u.ctypes.data, cur_v.ctypes.data, cur_u.strides[0], shift[0], shift[1])
+    lib().ora_set_chroma(int(enable), int(weight), cur_u.ctypes.data, cur_v.ctypes.data, _stride(cur_u), shift[0], shift[1])
 
 
 def set_bipred_weights(lst, apply, w1=32, w2=32, offset_bi=0, log_denom=5):
@@ -220,7 +248,7 @@ def _shorts(*vals):
 def ffs_surfaces(cfg, cur, ref, opix_x, opix_y, cx, cy, rng):
     P = (2 * rng + 1) ** 2
     out = np.zeros((NUM_PART, P), np.int32)
-    lib().ora_ffs_surfaces(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr, opix_x, opix_y, cx, cy, rng,
+    lib().ora_ffs_surfaces(C.byref(cfg), cur.ctypes.data, _stride(cur), ref.ptr, opix_x, opix_y, cx, cy, rng,
                            out.ctypes.data)
     return out
 
@@ -243,7 +271,7 @@ def subpel(cfg, cur, ref, pic_pix_x, pic_pix_y, blocktype, ref_idx, slice_type, 
            min_mcost, lam, search_pos2=9, search_pos4=9):
     mx, my = _shorts(mv_x, mv_y)
     lam3 = (C.c_int * 3)(*lam)
-    cost = lib().ora_subpel(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr, pic_pix_x, pic_pix_y, blocktype,
+    cost = lib().ora_subpel(C.byref(cfg), cur.ctypes.data, _stride(cur), ref.ptr, pic_pix_x, pic_pix_y, blocktype,
                             ref_idx, slice_type, pmv_x, pmv_y, C.byref(mx), C.byref(my), search_pos2, search_pos4,
                             min_mcost, lam3)
     return mx.value, my.value, cost
@@ -252,7 +280,7 @@ def subpel(cfg, cur, ref, pic_pix_x, pic_pix_y, blocktype, ref_idx, slice_type, 
 def bipred_fullpel(cfg, cur, ref1, ref2, pic_pix_x, pic_pix_y, blocktype, pmv1, pmv2, mv, s_mv, search_range,
                    min_mcost, lam):
     mx, my, sx, sy = _shorts(mv[0], mv[1], s_mv[0], s_mv[1])
-    cost = lib().ora_bipred_fullpel(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref1.ptr, ref2.ptr,
+    cost = lib().ora_bipred_fullpel(C.byref(cfg), cur.ctypes.data, _stride(cur), ref1.ptr, ref2.ptr,
                                     pic_pix_x, pic_pix_y, blocktype, pmv1[0], pmv1[1], pmv2[0], pmv2[1],
                                     C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy), search_range, min_mcost, lam)
     return mx.value, my.value, cost
@@ -262,7 +290,7 @@ def bipred_subpel(cfg, cur, ref1, ref2, pic_pix_x, pic_pix_y, blocktype, pmv, mv
                   search_pos2=9, search_pos4=9):
     mx, my, sx, sy = _shorts(mv[0], mv[1], s_mv[0], s_mv[1])
     lam3 = (C.c_int * 3)(*lam)
-    cost = lib().ora_bipred_subpel(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref1.ptr, ref2.ptr,
+    cost = lib().ora_bipred_subpel(C.byref(cfg), cur.ctypes.data, _stride(cur), ref1.ptr, ref2.ptr,
                                    pic_pix_x, pic_pix_y, blocktype, pmv[0], pmv[1],
                                    C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy), search_pos2, search_pos4,
                                    min_mcost, lam3)
@@ -274,7 +302,7 @@ def bipred_subpel(cfg, cur, ref1, ref2, pic_pix_x, pic_pix_y, blocktype, pmv, mv
 def subpel_pattern(cfg, cur, ref, pattern, pic_pix_x, pic_pix_y, blocktype, ref_idx, slice_type, pmv, mv, min_mcost, lam,
                    search_pos2=9, search_pos4=9, subthres=0, uplayer=(0, 0), thresholds=(1000, 400)):
     mx, my = _shorts(mv[0], mv[1])
-    L, a = lib(), (C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr, pic_pix_x, pic_pix_y, blocktype)
+    L, a = lib(), (C.byref(cfg), cur.ctypes.data, _stride(cur), ref.ptr, pic_pix_x, pic_pix_y, blocktype)
     if pattern == 1:
         cost = L.ora_epzs_subpel(*a, pmv[0], pmv[1], C.byref(mx), C.byref(my), search_pos2, search_pos4, min_mcost, (C.c_int * 3)(*lam), subthres)
     elif pattern == 2:
@@ -292,7 +320,7 @@ def subpel_pattern(cfg, cur, ref, pattern, pic_pix_x, pic_pix_y, blocktype, ref_
 def epzs_subpel_bipred(cfg, cur, ref1, ref2, pic_pix_x, pic_pix_y, blocktype, pmv1, pmv2, mv, s_mv, min_mcost, lam,
                        search_pos2=9, search_pos4=9):
     mx, my, sx, sy = _shorts(mv[0], mv[1], s_mv[0], s_mv[1])
-    cost = lib().ora_epzs_subpel_bipred(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref1.ptr, ref2.ptr, pic_pix_x, pic_pix_y, blocktype,
+    cost = lib().ora_epzs_subpel_bipred(C.byref(cfg), cur.ctypes.data, _stride(cur), ref1.ptr, ref2.ptr, pic_pix_x, pic_pix_y, blocktype,
                                         pmv1[0], pmv1[1], pmv2[0], pmv2[1], C.byref(mx), C.byref(my), C.byref(sx), C.byref(sy),
                                         search_pos2, search_pos4, min_mcost, (C.c_int * 3)(*lam))
     return mx.value, my.value, cost
@@ -310,7 +338,7 @@ def mb_bipred(cfg, cur, ref_l0, ref_l1, jobs, refinements, search_range, subpel)
     out = np.zeros(len(jobs), BIPRED_RESULT_DTYPE)
     L = lib()
     for i in range(len(jobs)):
-        L.ora_mb_bipred(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref_l0.ptr, ref_l1.ptr,
+        L.ora_mb_bipred(C.byref(cfg), cur.ctypes.data, _stride(cur), ref_l0.ptr, ref_l1.ptr,
                         jobs.ctypes.data + i * BIPRED_JOB_DTYPE.itemsize, refinements, search_range, subpel,
                         out.ctypes.data + i * BIPRED_RESULT_DTYPE.itemsize)
     return out
@@ -323,7 +351,7 @@ def mb_search(cfg, cur, ref, jobs):
     out_int = np.zeros(len(jobs), RESULT_DTYPE)
     L = lib()
     for i in range(len(jobs)):
-        L.ora_mb_search(C.byref(cfg), cur.ctypes.data, cur.strides[0], ref.ptr,
+        L.ora_mb_search(C.byref(cfg), cur.ctypes.data, _stride(cur), ref.ptr,
                         jobs.ctypes.data + i * JOB_DTYPE.itemsize,
                         out.ctypes.data + i * RESULT_DTYPE.itemsize,
                         out_int.ctypes.data + i * RESULT_DTYPE.itemsize)
@@ -356,7 +384,7 @@ def get_skip_cost_mb(cur, list0, list1, blocks16, rdopt, transform8x8, metric=2)
     cur = np.ascontiguousarray(cur, np.uint8)
     b = np.ascontiguousarray(blocks16, PRED_BLOCK_DTYPE)
     a0, a1 = _ref_array(list0), _ref_array(list1)
-    return lib().ora_get_skip_cost_mb(cur.ctypes.data, cur.strides[0], a0, a1, b.ctypes.data, rdopt, transform8x8, metric)
+    return lib().ora_get_skip_cost_mb(cur.ctypes.data, _stride(cur), a0, a1, b.ctypes.data, rdopt, transform8x8, metric)
 
 
 def get_direct_cost8x8(cur, list0, list1, blocks16, block, rdopt, transform8x8, metric=2, cost8x8=0):
@@ -364,7 +392,7 @@ def get_direct_cost8x8(cur, list0, list1, blocks16, block, rdopt, transform8x8, 
     b = np.ascontiguousarray(blocks16, PRED_BLOCK_DTYPE)
     a0, a1 = _ref_array(list0), _ref_array(list1)
     c8 = C.c_int(cost8x8)
-    c = lib().ora_get_direct_cost8x8(cur.ctypes.data, cur.strides[0], a0, a1, b.ctypes.data, block, rdopt, transform8x8, metric, C.byref(c8))
+    c = lib().ora_get_direct_cost8x8(cur.ctypes.data, _stride(cur), a0, a1, b.ctypes.data, block, rdopt, transform8x8, metric, C.byref(c8))
     return c, c8.value
 
 
@@ -374,7 +402,7 @@ def bid_partition_cost(cur, list0, list1, blocks16, pmv16, blocktype, block8x8, 
     pm = np.ascontiguousarray(pmv16, np.int16)
     assert pm.shape == (16, 2, 2)
     a0, a1 = _ref_array(list0), _ref_array(list1)
-    return lib().ora_bid_partition_cost(cur.ctypes.data, cur.strides[0], a0, a1, b.ctypes.data, pm.ctypes.data, blocktype, block8x8,
+    return lib().ora_bid_partition_cost(cur.ctypes.data, _stride(cur), a0, a1, b.ctypes.data, pm.ctypes.data, blocktype, block8x8,
                                         lambda_factor, transform8x8, metric)
 
 
@@ -391,8 +419,8 @@ def deblock_frame(y, u, v, mbs):
     mbs = np.ascontiguousarray(mbs, DEBLOCK_MB_DTYPE)
     assert len(mbs) == (w // 16) * (h // 16)
     if u is None:
-        lib().ora_deblock_frame(y.ctypes.data, y.strides[0], None, None, 0, w, h, mbs.ctypes.data)
+        lib().ora_deblock_frame(y.ctypes.data, _stride(y), None, None, 0, w, h, mbs.ctypes.data)
         return y, None, None
     u, v = np.array(u, np.uint8, order="C"), np.array(v, np.uint8, order="C")
-    lib().ora_deblock_frame(y.ctypes.data, y.strides[0], u.ctypes.data, v.ctypes.data, u.strides[0], w, h, mbs.ctypes.data)
+    lib().ora_deblock_frame(y.ctypes.data, _stride(y), u.ctypes.data, v.ctypes.data, _stride(u), w, h, mbs.ctypes.data)
     return y, u, v

@@ -16,6 +16,10 @@
 #define PAD ME_IMG_PAD
 
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* img->max_imgpel_value: 255, or (1 << bit depth) - 1 in the 16-bit build (ORA_PEL16; ora_set_max_pel) */
+static int g_max_pel = 255;
+void ora_set_max_pel(int v) { g_max_pel = v; }
 static inline int iabs_(int v) { return v < 0 ? -v : v; }
 
 /* ------------------------------------------------------------------------------------------------ tables */
@@ -74,16 +78,16 @@ int ora_mv_cost(int f, int cx, int cy, int px, int py)
 
 /* ------------------------------------------------------------------------------------------------ planes */
 
-ora_ref *ora_ref_create(const uint8_t *luma, int stride, int w, int h)
+ora_ref *ora_ref_create(const ora_pel *luma, int stride, int w, int h)
 {
   ora_ref *r = (ora_ref *)calloc(1, sizeof *r);
   int wp = w + 2 * PAD, hp = h + 2 * PAD, x, y, fy, fx;
   int32_t *tmp = (int32_t *)malloc(sizeof(int32_t) * (size_t)wp * hp);
-  uint8_t *G, *b, *hh, *j;
+  ora_pel *G, *b, *hh, *j;
   r->w = w; r->h = h; r->wp = wp; r->hp = hp;
   for (fy = 0; fy < 4; fy++)
     for (fx = 0; fx < 4; fx++)
-      r->plane[fy][fx] = (uint8_t *)malloc((size_t)wp * hp);
+      r->plane[fy][fx] = (ora_pel *)malloc((size_t)wp * hp * sizeof(ora_pel));
   G = r->plane[0][0]; b = r->plane[0][2]; hh = r->plane[2][0]; j = r->plane[2][2];
 
 #define AT(P, yy, xx) ((P)[(size_t)(yy) * wp + (xx)])
@@ -100,39 +104,39 @@ ora_ref *ora_ref_create(const uint8_t *luma, int stride, int w, int h)
       int s = 20 * (AT(G, y, x) + AT(G, y, CX(x + 1))) - 5 * (AT(G, y, CX(x - 1)) + AT(G, y, CX(x + 2)))
               + (AT(G, y, CX(x - 2)) + AT(G, y, CX(x + 3)));
       AT(tmp, y, x) = s;
-      AT(b, y, x) = (uint8_t)clampi((s + 16) >> 5, 0, 255);
+      AT(b, y, x) = (ora_pel)clampi((s + 16) >> 5, 0, g_max_pel);
     }
   /* vertical half-pel (getVerSubImageSixTap, img_luma.c:293-380) */
   for (y = 0; y < hp; y++)
     for (x = 0; x < wp; x++) {
       int s = 20 * (AT(G, y, x) + AT(G, CY(y + 1), x)) - 5 * (AT(G, CY(y - 1), x) + AT(G, CY(y + 2), x))
               + (AT(G, CY(y - 2), x) + AT(G, CY(y + 3), x));
-      AT(hh, y, x) = (uint8_t)clampi((s + 16) >> 5, 0, 255);
+      AT(hh, y, x) = (ora_pel)clampi((s + 16) >> 5, 0, g_max_pel);
     }
   /* centre half-pel from the unrounded horizontal sums (getVerSubImageSixTapTmp, img_luma.c:390-470) */
   for (y = 0; y < hp; y++)
     for (x = 0; x < wp; x++) {
       int s = 20 * (AT(tmp, y, x) + AT(tmp, CY(y + 1), x)) - 5 * (AT(tmp, CY(y - 1), x) + AT(tmp, CY(y + 2), x))
               + (AT(tmp, CY(y - 2), x) + AT(tmp, CY(y + 3), x));
-      AT(j, y, x) = (uint8_t)clampi((s + 512) >> 10, 0, 255);
+      AT(j, y, x) = (ora_pel)clampi((s + 512) >> 10, 0, g_max_pel);
     }
   /* quarter-pel positions: rounded averages of two neighbours (img_luma.c:483-639) */
   for (y = 0; y < hp; y++)
     for (x = 0; x < wp; x++) {
       int x1 = CX(x + 1), y1 = CY(y + 1);
       int g = AT(G, y, x), bb = AT(b, y, x), hv = AT(hh, y, x), jj = AT(j, y, x);
-      AT(r->plane[0][1], y, x) = (uint8_t)((g + bb + 1) >> 1);
-      AT(r->plane[1][0], y, x) = (uint8_t)((g + hv + 1) >> 1);
-      AT(r->plane[1][1], y, x) = (uint8_t)((bb + hv + 1) >> 1);
-      AT(r->plane[1][2], y, x) = (uint8_t)((bb + jj + 1) >> 1);
-      AT(r->plane[2][1], y, x) = (uint8_t)((hv + jj + 1) >> 1);
-      AT(r->plane[0][3], y, x) = (uint8_t)((bb + AT(G, y, x1) + 1) >> 1);
-      AT(r->plane[1][3], y, x) = (uint8_t)((bb + AT(hh, y, x1) + 1) >> 1);
-      AT(r->plane[2][3], y, x) = (uint8_t)((jj + AT(hh, y, x1) + 1) >> 1);
-      AT(r->plane[3][0], y, x) = (uint8_t)((hv + AT(G, y1, x) + 1) >> 1);
-      AT(r->plane[3][1], y, x) = (uint8_t)((hv + AT(b, y1, x) + 1) >> 1);
-      AT(r->plane[3][2], y, x) = (uint8_t)((jj + AT(b, y1, x) + 1) >> 1);
-      AT(r->plane[3][3], y, x) = (uint8_t)((AT(b, y1, x) + AT(hh, y, x1) + 1) >> 1);
+      AT(r->plane[0][1], y, x) = (ora_pel)((g + bb + 1) >> 1);
+      AT(r->plane[1][0], y, x) = (ora_pel)((g + hv + 1) >> 1);
+      AT(r->plane[1][1], y, x) = (ora_pel)((bb + hv + 1) >> 1);
+      AT(r->plane[1][2], y, x) = (ora_pel)((bb + jj + 1) >> 1);
+      AT(r->plane[2][1], y, x) = (ora_pel)((hv + jj + 1) >> 1);
+      AT(r->plane[0][3], y, x) = (ora_pel)((bb + AT(G, y, x1) + 1) >> 1);
+      AT(r->plane[1][3], y, x) = (ora_pel)((bb + AT(hh, y, x1) + 1) >> 1);
+      AT(r->plane[2][3], y, x) = (ora_pel)((jj + AT(hh, y, x1) + 1) >> 1);
+      AT(r->plane[3][0], y, x) = (ora_pel)((hv + AT(G, y1, x) + 1) >> 1);
+      AT(r->plane[3][1], y, x) = (ora_pel)((hv + AT(b, y1, x) + 1) >> 1);
+      AT(r->plane[3][2], y, x) = (ora_pel)((jj + AT(b, y1, x) + 1) >> 1);
+      AT(r->plane[3][3], y, x) = (ora_pel)((AT(b, y1, x) + AT(hh, y, x1) + 1) >> 1);
     }
 #undef AT
 #undef CX
@@ -151,7 +155,7 @@ void ora_ref_destroy(ora_ref *r)
   free(r);
 }
 
-const uint8_t *ora_ref_plane(const ora_ref *r, int fy, int fx) { return r->plane[fy][fx]; }
+const ora_pel *ora_ref_plane(const ora_ref *r, int fy, int fx) { return r->plane[fy][fx]; }
 
 void ora_ref_set_weights(ora_ref *r, int apply, int weight, int offset, int log_denom)
 {
@@ -164,13 +168,13 @@ void ora_ref_set_weights(ora_ref *r, int apply, int weight, int offset, int log_
 static inline int refpel(const ora_ref *r, int v)
 {
   if (!r->wp_apply) return v;
-  return clampi(((r->wp_weight * v + (r->wp_denom ? 1 << (r->wp_denom - 1) : 0)) >> r->wp_denom) + r->wp_offset, 0, 255);
+  return clampi(((r->wp_weight * v + (r->wp_denom ? 1 << (r->wp_denom - 1) : 0)) >> r->wp_denom) + r->wp_offset, 0, g_max_pel);
 }
 
 /* UMVLine4X (refbuf.c:37-43) with size_x_pad = w + 2*20 - 1 - 16 (mbuffer.c:421-422).  FastLine4X (refbuf.c:25)
  * yields the same pixels whenever the reference chooses it: it is only chosen where the clamp is a no-op or where
  * both addresses lie in the edge-replicated region in which every plane is constant along the row / column. */
-const uint8_t *ora_umv_line(const ora_ref *r, int y4, int x4)
+const ora_pel *ora_umv_line(const ora_ref *r, int y4, int x4)
 {
   int xp = clampi(x4 >> 2, 0, r->w + 2 * PAD - 1 - 16);
   int yp = clampi(y4 >> 2, 0, r->h + 2 * PAD - 1 - 16);
@@ -181,24 +185,24 @@ const uint8_t *ora_umv_line(const ora_ref *r, int y4, int x4)
 
 static struct {
   int enable, weight, stride, shift_x, shift_y;
-  const uint8_t *cur[2];
+  const ora_pel *cur[2];
 } g_cr;
 /* weighted bi-prediction state (see ora_set_bipred_weights below); c*: the two chroma components */
 static struct { int apply, w1, w2, obi, denom, cw1[2], cw2[2], cobi[2]; } g_bw[2], g_bw_cur;
 
-void ora_set_chroma(int enable, int weight, const uint8_t *cur_u, const uint8_t *cur_v, int stride, int shift_x, int shift_y)
+void ora_set_chroma(int enable, int weight, const ora_pel *cur_u, const ora_pel *cur_v, int stride, int shift_x, int shift_y)
 {
   g_cr.enable = enable; g_cr.weight = weight; g_cr.cur[0] = cur_u; g_cr.cur[1] = cur_v; g_cr.stride = stride;
   g_cr.shift_x = shift_x; g_cr.shift_y = shift_y;
 }
 
-void ora_ref_set_chroma(ora_ref *r, const uint8_t *u, const uint8_t *v, int stride, int cw, int ch)
+void ora_ref_set_chroma(ora_ref *r, const ora_pel *u, const ora_pel *v, int stride, int cw, int ch)
 {
   int k, y;
   for (k = 0; k < 2; k++) {
-    const uint8_t *src = k ? v : u;
+    const ora_pel *src = k ? v : u;
     free(r->crec[k]);
-    r->crec[k] = (uint8_t *)malloc((size_t)cw * ch);
+    r->crec[k] = (ora_pel *)malloc((size_t)cw * ch);
     for (y = 0; y < ch; y++) memcpy(r->crec[k] + (size_t)y * cw, src + (size_t)y * stride, cw);
   }
   r->cw = cw; r->ch = ch;
@@ -228,7 +232,7 @@ static int cr_pel(const ora_ref *r, int k, int ypos, int xpos, int sy, int sx)
   int y0 = clampi(jy, 0, r->ch - 1), y1 = clampi(jy + 1, 0, r->ch - 1), x0 = clampi(ix, 0, r->cw - 1), x1 = clampi(ix + 1, 0, r->cw - 1);
   int kk = sy << (3 - g_cr.shift_y), ll = sx << (3 - g_cr.shift_x);          /* vertical / horizontal offset in eighths */
   int w01 = (8 - kk) * ll, w00 = ((8 - kk) << 3) - w01, w11 = kk * ll, w10 = (kk << 3) - w11;
-  const uint8_t *p = r->crec[k];
+  const ora_pel *p = r->crec[k];
   return (w00 * p[(size_t)y0 * r->cw + x0] + w01 * p[(size_t)y0 * r->cw + x1] +
           w10 * p[(size_t)y1 * r->cw + x0] + w11 * p[(size_t)y1 * r->cw + x1] + 32) >> 6;
 }
@@ -306,7 +310,7 @@ void ora_search_centre(const ora_cfg *c, int ref, int opix_x, int opix_y, int pm
 
 /* SetupFastFullPelSearch main loop (me_fullfast.c:619-774, unweighted luma branch) + SetupLargerBlocks (:210-273).
  * dist_method is SAD for MEErrorMetric[0]==0 and squared error for anything else (me_fullfast.c:512). */
-void ora_ffs_surfaces(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+void ora_ffs_surfaces(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                       int opix_x, int opix_y, int centre_x, int centre_y, int range, int32_t *surf)
 {
   int P = ora_num_positions(range), pos, p, by, bx, y, x;
@@ -314,7 +318,7 @@ void ora_ffs_surfaces(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
   int leaf[16];
   ora_spiral(range, sx, sy);
   for (pos = 0; pos < P; pos++) {
-    const uint8_t *rp = ora_umv_line(r, (centre_y + sy[pos] + PAD) << 2, (centre_x + sx[pos] + PAD) << 2);
+    const ora_pel *rp = ora_umv_line(r, (centre_y + sy[pos] + PAD) << 2, (centre_x + sx[pos] + PAD) << 2);
     memset(leaf, 0, sizeof leaf);
     for (y = 0; y < 16; y++)
       for (x = 0; x < 16; x++) {
@@ -423,18 +427,18 @@ int ora_hadamard8x8(const int *d)
 
 /* computeSAD (me_distortion.c:351-405), luma only.  The reference's early exits return partial sums that the
  * callers then discard (they are >= the running minimum), so the full sum is equivalent. */
-int ora_sad_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4)
+int ora_sad_block(const ora_pel *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4)
 {
-  const uint8_t *rp = ora_umv_line(r, y4, x4);
+  const ora_pel *rp = ora_umv_line(r, y4, x4);
   int x, y, s = 0;
   for (y = 0; y < bsy; y++)
     for (x = 0; x < bsx; x++) s += iabs_((int)src[(size_t)y * src_stride + x] - refpel(r, rp[(size_t)y * r->wp + x]));
   return s;
 }
 
-static int sse_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4)
+static int sse_block(const ora_pel *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4)
 {
-  const uint8_t *rp = ora_umv_line(r, y4, x4);
+  const ora_pel *rp = ora_umv_line(r, y4, x4);
   int x, y, s = 0;
   for (y = 0; y < bsy; y++)
     for (x = 0; x < bsx; x++) {
@@ -446,12 +450,12 @@ static int sse_block(const uint8_t *src, int src_stride, int bsx, int bsy, const
 
 /* computeSATD (me_distortion.c:657-726): the reference fetches every 4x4 (or 8x8) tile with its own get_line call,
  * i.e. the origin clamp applies per tile. */
-int ora_satd_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4, int use8x8)
+int ora_satd_block(const ora_pel *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4, int use8x8)
 {
   int n = use8x8 ? 8 : 4, bx, by, x, y, s = 0, d[64];
   for (by = 0; by < bsy; by += n)
     for (bx = 0; bx < bsx; bx += n) {
-      const uint8_t *rp = ora_umv_line(r, y4 + (by << 2), x4 + (bx << 2));
+      const ora_pel *rp = ora_umv_line(r, y4 + (by << 2), x4 + (bx << 2));
       for (y = 0; y < n; y++)
         for (x = 0; x < n; x++)
           d[y * n + x] = (int)src[(size_t)(by + y) * src_stride + bx + x] - refpel(r, rp[(size_t)y * r->wp + x]);
@@ -465,7 +469,7 @@ static int cr_block_dist(int sse, int pic_pix_x, int pic_pix_y, int bsx, int bsy
 
 /* pic_pix_x / y: position of the block in the picture (for the chroma terms of computeSAD / computeSSE, me_distortion.c:376-402,
  * :1069-1091, when the global ChromaMEEnable is set; computeSATD has none) */
-static int unipred(const ora_cfg *c, int level, const uint8_t *src, int stride, int bsx, int bsy,
+static int unipred(const ora_cfg *c, int level, const ora_pel *src, int stride, int bsx, int bsy,
                    const ora_ref *r, int x4, int y4, int use8x8, int pic_pix_x, int pic_pix_y)
 {
   int chroma = (g_cr.enable && has_chroma(r) && c->metric[level] != 2)
@@ -494,7 +498,7 @@ static int start_hp(const ora_cfg *c) { return (c->chroma_me == 1 || c->metric[0
 static int start_qp(const ora_cfg *c) { return (c->chroma_me == 1 || c->metric[1] != c->metric[2]) ? 0 : 1; }
 
 /* SubPelBlockMotionSearch (me_fullsearch.c:341-511) */
-int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type,
                int pmv_x, int pmv_y, short *mv_x, short *mv_y, int search_pos2, int search_pos4,
                int min_mcost, const int *lambda)
@@ -505,7 +509,7 @@ int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_r
   int p4x = (pic_pix_x + PAD) << 2, p4y = (pic_pix_y + PAD) << 2;
   int shp = start_hp(c), sqp = start_qp(c);
   int max_pos2 = (!shp && search_pos2 < 1) ? 1 : search_pos2;
-  const uint8_t *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
+  const ora_pel *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
   int16_t sx[9], sy[9];
   ora_block_size(blocktype, &bsx, &bsy);
   first_spiral(9, sx, sy);
@@ -536,7 +540,7 @@ int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_r
  * threshold, me_distortion.c:366,1066; computeSATD: after every tile when the sum exceeds it, :689).  For a threshold below
  * the full distortion the partial sum comes back.  Everywhere else on this path the caller discards such a candidate, so
  * the full sum is equivalent; FullPelBlockMotionSearch is the exception (see below). */
-static int unipred_exit(const ora_cfg *c, const uint8_t *src, int stride, int bsx, int bsy, const ora_ref *r, int x4, int y4,
+static int unipred_exit(const ora_cfg *c, const ora_pel *src, int stride, int bsx, int bsy, const ora_ref *r, int x4, int y4,
                         int use8x8, int thr, int pic_pix_x, int pic_pix_y)
 {
   int metric = c->metric[0], m = 0, x, y;
@@ -549,7 +553,7 @@ static int unipred_exit(const ora_cfg *c, const uint8_t *src, int stride, int bs
       }
     return m;
   } else {
-    const uint8_t *rp = ora_umv_line(r, y4, x4);
+    const ora_pel *rp = ora_umv_line(r, y4, x4);
     for (y = 0; y < bsy; y++) {
       for (x = 0; x < bsx; x++) {
         int d = (int)src[(size_t)y * stride + x] - refpel(r, rp[(size_t)y * r->wp + x]);
@@ -585,7 +589,7 @@ static int unipred_exit(const ora_cfg *c, const uint8_t *src, int stride, int bs
  * caller's min_mcost = INT_MAX and a negative mcost that difference wraps to a negative int, the distortion function leaves
  * after its first row (first tile for SATD) and the candidate is accepted with that partial sum.  This happens for the first
  * spiral position of blocks at picture origin under !rdopt, and the encoder's decisions depend on it -- reproduced. */
-int ora_fullpel_block(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_fullpel_block(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                       int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type,
                       int pmv_x, int pmv_y, short *mv_x, short *mv_y, int search_range, int min_mcost, int lambda_factor)
 {
@@ -595,7 +599,7 @@ int ora_fullpel_block(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
   int center_x = pic_pix_x + *mv_x, center_y = pic_pix_y + *mv_y;
   int check_for_00 = (blocktype == 1 && !c->rdopt && slice_type != ME_B_SLICE && ref == 0);
   int use8x8 = c->transform8x8 && blocktype <= 4;
-  const uint8_t *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
+  const ora_pel *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
   ora_block_size(blocktype, &bsx, &bsy);
   ora_spiral(search_range, sx, sy);
   for (pos = 0; pos < P; pos++) {
@@ -642,18 +646,18 @@ static inline int bipel(int p1, int p2)
 {
   if (!g_bw_cur.apply) return (p1 + p2 + 1) >> 1;
   return clampi(((g_bw_cur.w1 * p1 + g_bw_cur.w2 * p2 + 2 * (g_bw_cur.denom ? 1 << (g_bw_cur.denom - 1) : 0)) >> (g_bw_cur.denom + 1))
-                + g_bw_cur.obi, 0, 255);
+                + g_bw_cur.obi, 0, g_max_pel);
 }
 
 /* computeBiPredSAD1 / computeBiPredSATD1 (me_distortion.c:482-548, 824-899): prediction = (p1 + p2 + 1) >> 1.
  * SAD fetches each picture once per block; SATD once per transform tile. */
-static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stride, int bsx, int bsy,
+static int bipred_dist(const ora_cfg *c, int level, const ora_pel *src, int stride, int bsx, int bsy,
                        const ora_ref *r1, int x41, int y41, const ora_ref *r2, int x42, int y42, int use8x8,
                        int pic_pix_x, int pic_pix_y)
 {
   int metric = c->metric[level], s = 0, x, y, bx, by, d[64];
   if (metric == 0 || metric == 1) {
-    const uint8_t *a = ora_umv_line(r1, y41, x41), *b = ora_umv_line(r2, y42, x42);
+    const ora_pel *a = ora_umv_line(r1, y41, x41), *b = ora_umv_line(r2, y42, x42);
     for (y = 0; y < bsy; y++)
       for (x = 0; x < bsx; x++) {
         int e = (int)src[(size_t)y * stride + x] - bipel(a[(size_t)y * r1->wp + x], b[(size_t)y * r2->wp + x]);
@@ -666,8 +670,8 @@ static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stri
     int n = use8x8 ? 8 : 4;
     for (by = 0; by < bsy; by += n)
       for (bx = 0; bx < bsx; bx += n) {
-        const uint8_t *a = ora_umv_line(r1, y41 + (by << 2), x41 + (bx << 2));
-        const uint8_t *b = ora_umv_line(r2, y42 + (by << 2), x42 + (bx << 2));
+        const ora_pel *a = ora_umv_line(r1, y41 + (by << 2), x41 + (bx << 2));
+        const ora_pel *b = ora_umv_line(r2, y42 + (by << 2), x42 + (bx << 2));
         for (y = 0; y < n; y++)
           for (x = 0; x < n; x++)
             if (use8x8 && g_bw_cur.apply) {
@@ -687,7 +691,7 @@ static int bipred_dist(const ora_cfg *c, int level, const uint8_t *src, int stri
 /* FullPelBlockMotionBiPred (me_fullsearch.c:164-332), unweighted.  r1 = listX[list][ref] read at the fixed vector
  * (s_mv), r2 = listX[list^1][0] read at the candidate.  Vectors are integer pel.  Note the reference stores the
  * centres in `short` (:196-199). */
-int ora_bipred_fullpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+int ora_bipred_fullpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
                        int pic_pix_x, int pic_pix_y, int blocktype,
                        int pmv_x1, int pmv_y1, int pmv_x2, int pmv_y2,
                        short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
@@ -699,7 +703,7 @@ int ora_bipred_fullpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, con
   int px2 = (pic_pix_x << 2) + pmv_x2, py2 = (pic_pix_y << 2) + pmv_y2;
   short cx0 = (short)(pic_pix_x + *mv_x), cy0 = (short)(pic_pix_y + *mv_y);
   short fx0 = (short)(pic_pix_x + *s_mv_x), fy0 = (short)(pic_pix_y + *s_mv_y);
-  const uint8_t *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
+  const ora_pel *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
   ora_block_size(blocktype, &bsx, &bsy);
   ora_spiral(search_range, sx, sy);
   for (pos = 0; pos < P; pos++) {
@@ -718,7 +722,7 @@ int ora_bipred_fullpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, con
 
 /* SubPelBlockSearchBiPred (me_fullsearch.c:520-754), unweighted.  Vectors are quarter pel; only the searched
  * vector carries a rate term (:666, :729). */
-int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+int ora_bipred_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
                       int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y,
                       short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
                       int search_pos2, int search_pos4, int min_mcost, const int *lambda)
@@ -729,7 +733,7 @@ int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
   int smx = *s_mv_x + p4x, smy = *s_mv_y + p4y;
   int shp = start_hp(c), sqp = start_qp(c);
   int max_pos2 = (!shp && search_pos2 < 1) ? 1 : search_pos2;
-  const uint8_t *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
+  const ora_pel *src = cur + (size_t)pic_pix_y * cur_stride + pic_pix_x;
   int16_t sx[9], sy[9];
   ora_block_size(blocktype, &bsx, &bsy);
   first_spiral(9, sx, sy);
@@ -759,7 +763,7 @@ int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
 /* PartitionMotionSearch -> BlockMotionSearch (mv-search.c:1378, :560) for the 41 partitions of one
  * (macroblock, list, ref): integer-pel search (:745), mv <<= 2 (:770-774), min_mcost reset when the half-pel
  * metric differs (:785-788), sub-pel refinement with 9/9 positions (:823). */
-void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+void ora_mb_search(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                    const me_mb_job *job, me_mb_result *out, me_mb_result_int *out_int)
 {
   int range = ora_setup_range(c, job->ref), P = ora_num_positions(range), p, cx, cy;
@@ -795,7 +799,7 @@ void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const o
  * other one fixed, the cost carries over, the range is BiPredMESearchRange >> i); back to quarter pel (:976-982); one
  * sub-pel refinement of bimv with mv fixed (:984-1001) and, for BiPredMESubPel == 2, one of mv with bimv fixed
  * (:1004-1021).  The vectors are kept in `short` like the reference does. */
-void ora_mb_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *l0, const ora_ref *l1,
+void ora_mb_bipred(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *l0, const ora_ref *l1,
                    const me_bipred_job *job, int refinements, int search_range, int subpel, me_bipred_result *out)
 {
   const ora_ref *refs[2] = { l0, l1 };
@@ -850,6 +854,7 @@ void ora_mb_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const o
   out->iterlist = iterlist;
 }
 
+#ifndef ORA_PEL16   /* motion-compensated prediction, mode-decision costs and deblocking: restated for 8-bit pictures only */
 /* ------------------------------------------------------------------------------------------------ prediction / mode-decision costs */
 
 /* OneComponentLumaPrediction (macroblock.c:807-827): the block's rows start at UMVLine4X(plane set, y, x) (refbuf.c:37) and follow
@@ -1102,6 +1107,8 @@ void ora_deblock_frame(uint8_t *y, int ystride, uint8_t *u, uint8_t *v, int cstr
     }
 }
 
+#endif /* !ORA_PEL16 */
+
 /* ------------------------------------------------------------------------------------------------ sub-pel stages of the pattern searches
  * (SURVEY.md 8f row 4).  Every candidate is scored with the FULL distortion: the thresholds the reference hands to computeUniPred /
  * computeBiPred on these paths only ever cut a candidate that the comparison after the call rejects anyway (a partial sum above the
@@ -1110,7 +1117,7 @@ void ora_deblock_frame(uint8_t *y, int ystride, uint8_t *u, uint8_t *v, int cstr
  * pattern inside the padded plane, where the clamp of UMVLine4X is the identity -- so the clamped access serves both. */
 
 typedef struct pat_ctx {
-  const ora_cfg *c; const uint8_t *src; int stride, bsx, bsy, use8x8, ppx, ppy, p4x, p4y;
+  const ora_cfg *c; const ora_pel *src; int stride, bsx, bsy, use8x8, ppx, ppy, p4x, p4y;
   const ora_ref *r1, *r2;      /* r2 != NULL: bi-predictive, r1 read at the fixed vector (smx, smy), r2 at the candidate */
   int smx, smy, pmvx, pmvy, fixed_rate_lambda_level, s_mv_x, s_mv_y, pmv2x, pmv2y;
 } pat_ctx;
@@ -1171,7 +1178,7 @@ static int epzs_level(const pat_ctx *k, int level, int lam, int step, int hp, in
   return 0;
 }
 
-static void pat_init(pat_ctx *k, const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+static void pat_init(pat_ctx *k, const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
                      int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y)
 {
   memset(k, 0, sizeof *k);
@@ -1183,7 +1190,7 @@ static void pat_init(pat_ctx *k, const ora_cfg *c, const uint8_t *cur, int cur_s
 }
 
 /* EPZSSubPelBlockMotionSearch (me_epzs.c:2390-2720).  subthres = subthres[blocktype] (:354) */
-int ora_epzs_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_epzs_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                     int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
                     int search_pos2, int search_pos4, int min_mcost, const int *lambda, int subthres)
 {
@@ -1199,7 +1206,7 @@ int ora_epzs_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const 
 
 /* EPZSSubPelBlockSearchBiPred (me_epzs.c:2728-3125): r1 = listX[list][ref] read at the fixed vector s_mv, r2 = listX[list ^ 1][0] read
  * at the candidate; both vectors carry a rate term; no early return (:2894 is commented out in the reference) */
-int ora_epzs_subpel_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+int ora_epzs_subpel_bipred(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
                            int pic_pix_x, int pic_pix_y, int blocktype, int pmv1_x, int pmv1_y, int pmv2_x, int pmv2_y,
                            short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
                            int search_pos2, int search_pos4, int min_mcost, const int *lambda)
@@ -1264,7 +1271,7 @@ static int umhex_walk(const pat_ctx *k, int smp, int lam, int uplayer_x, int upl
   return min_mcost;
 }
 
-int ora_umhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_umhex_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                      int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
                      int min_mcost, int lambda_factor)
 {
@@ -1275,7 +1282,7 @@ int ora_umhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const
 
 static const int8_t smp_shift[8] = { 0, 0, 1, 1, 2, 3, 3, 1 };                    /* block_type_shift_factor, me_umhexsmp.c:46 */
 
-int ora_smpumhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_smpumhex_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                         int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
                         int min_mcost, int lambda_factor, int uplayer_x, int uplayer_y, int threshold1, int threshold3)
 {
@@ -1287,7 +1294,7 @@ int ora_smpumhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, co
 
 /* smpUMHEXFullSubPelBlockMotionSearch (me_umhexsmp.c:422-608): the nine half-pel and nine quarter-pel positions of the plain
  * refinement, both scored with the quarter-pel metric and factor, each loop left as soon as the minimum is below SubPelThreshold3 */
-int ora_smpumhex_full_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_smpumhex_full_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                              int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type, int pmv_x, int pmv_y,
                              short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor,
                              int threshold1, int threshold3)

@@ -17,6 +17,15 @@
 extern "C" {
 #endif
 
+/* sample type: 8-bit pictures, or -- the same source compiled with -DORA_PEL16 into liboracle_me16.so -- pictures of more than 8 bits
+ * per sample (imgpel is u16 in the reference, global.h:50); strides count samples.  ora_set_max_pel: img->max_imgpel_value */
+#ifdef ORA_PEL16
+typedef uint16_t ora_pel;
+#else
+typedef uint8_t ora_pel;
+#endif
+void ora_set_max_pel(int max_pel_value);
+
 typedef struct ora_cfg {
   int search_range;        /* input->search_range */
   int rdopt;               /* input->rdopt */
@@ -29,12 +38,12 @@ typedef struct ora_cfg {
 
 typedef struct ora_ref {
   int w, h, wp, hp;        /* picture and padded (+40) sizes */
-  uint8_t *plane[4][4];    /* [vertical fraction][horizontal fraction], hp rows of wp bytes */
+  ora_pel *plane[4][4];    /* [vertical fraction][horizontal fraction], hp rows of wp bytes */
   /* weighted-prediction ME (UseWeightedReferenceME): every reference sample of a UNI-predictive distortion becomes
    * clip1(((wp_weight * p + wp_round) >> wp_denom) + wp_offset) (me_fullfast.c:653, me_distortion.c:413-480, :734-822) */
   int wp_apply, wp_weight, wp_offset, wp_denom;
   /* reconstructed chroma (StorablePicture::imgUV), for ChromaMEEnable; NULL when not set */
-  uint8_t *crec[2];
+  ora_pel *crec[2];
   int cw, ch;
   /* 4:4:4: the chroma sub-images are made by the luma interpolator (image.c:1647-1657): the plane sets of U and V (not owned) */
   const struct ora_ref *c444[2];
@@ -50,30 +59,30 @@ extern const int8_t ora_part_blk[ME_NUM_PARTITIONS];     /* top-left 4x4 block i
 void ora_block_size(int blocktype, int *bsx, int *bsy);
 
 /* quarter-pel planes (getSubImagesLuma, img_luma.c:45-639) */
-ora_ref *ora_ref_create(const uint8_t *luma, int stride, int w, int h);
+ora_ref *ora_ref_create(const ora_pel *luma, int stride, int w, int h);
 void     ora_ref_destroy(ora_ref *r);
-const uint8_t *ora_ref_plane(const ora_ref *r, int fy, int fx);
+const ora_pel *ora_ref_plane(const ora_ref *r, int fy, int fx);
 /* weights of the (list, ref) entry this picture is searched as: wp_weight / wp_offset [list][ref][0], luma_log_weight_denom */
 void     ora_ref_set_weights(ora_ref *r, int apply, int weight, int offset, int log_denom);
 
 /* ChromaMEEnable: reconstructed chroma planes of a reference picture (copied) */
-void ora_ref_set_chroma(ora_ref *r, const uint8_t *u, const uint8_t *v, int stride, int cw, int ch);
+void ora_ref_set_chroma(ora_ref *r, const ora_pel *u, const ora_pel *v, int stride, int cw, int ch);
 /* 4:4:4 (chroma_shift 2, 2): the quarter-pel plane sets built from the picture's U and V planes */
 void ora_ref_set_chroma444(ora_ref *r, const ora_ref *u, const ora_ref *v);
 /* chroma state of the NEXT search call: the global ChromaMEEnable as that call sees it (me_distortion.c:56; mv-search.c:612, :779),
  * input->ChromaMEWeight, the original chroma planes (imgUV_org) and chroma_shift_x / chroma_shift_y (lencod.c:2856-2879:
  * 3,3 for 4:2:0; 3,2 for 4:2:2) */
-void ora_set_chroma(int enable, int weight, const uint8_t *cur_u, const uint8_t *cur_v, int stride, int shift_x, int shift_y);
+void ora_set_chroma(int enable, int weight, const ora_pel *cur_u, const ora_pel *cur_v, int stride, int shift_x, int shift_y);
 
 /* plane access with JM's origin clamp (UMVLine4X, refbuf.c:37): pointer to the first pixel of a block row */
-const uint8_t *ora_umv_line(const ora_ref *r, int y4, int x4);
+const ora_pel *ora_umv_line(const ora_ref *r, int y4, int x4);
 
 /* integer-pel fast full search */
 int  ora_setup_range(const ora_cfg *c, int ref);
 void ora_search_centre(const ora_cfg *c, int ref, int opix_x, int opix_y, int pmv16_x, int pmv16_y,
                        int *centre_x, int *centre_y);
 /* surf: 41 surfaces of ora_num_positions(range) ints each, partition order of me_cuda.h */
-void ora_ffs_surfaces(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+void ora_ffs_surfaces(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                       int opix_x, int opix_y, int centre_x, int centre_y, int range, int32_t *surf);
 int  ora_ffs_block(const ora_cfg *c, const int32_t *surf_p, int setup_range, int opix_x, int opix_y,
                    int centre_x, int centre_y, int pmv_x, int pmv_y, int search_range, int min_mcost,
@@ -82,19 +91,19 @@ int  ora_ffs_block(const ora_cfg *c, const int32_t *surf_p, int setup_range, int
 int  ora_block_search_range(const ora_cfg *c, int ref, int blocktype);
 
 /* distortion */
-int ora_sad_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4);
-int ora_satd_block(const uint8_t *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4, int use8x8);
+int ora_sad_block(const ora_pel *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4);
+int ora_satd_block(const ora_pel *src, int src_stride, int bsx, int bsy, const ora_ref *r, int x4, int y4, int use8x8);
 int ora_hadamard4x4(const int *d);
 int ora_hadamard8x8(const int *d);
 
 /* sub-pel refinement (SubPelBlockMotionSearch, me_fullsearch.c:341) */
-int ora_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type,
                int pmv_x, int pmv_y, short *mv_x, short *mv_y, int search_pos2, int search_pos4,
                int min_mcost, const int *lambda);
 
 /* per-block full search (FullPelBlockMotionSearch, me_fullsearch.c:47): SearchMode = -1 */
-int ora_fullpel_block(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_fullpel_block(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                       int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type,
                       int pmv_x, int pmv_y, short *mv_x, short *mv_y, int search_range, int min_mcost, int lambda_factor);
 
@@ -105,12 +114,12 @@ void ora_select_bipred_list(int list);
 void ora_set_bipred_chroma_weights(int list, int component, int weight1, int weight2, int offset_bi);   /* after ora_set_bipred_weights */
 
 /* bi-predictive searches (me_fullsearch.c:164, :520): r1 is read at the fixed vector, r2 at the candidate */
-int ora_bipred_fullpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+int ora_bipred_fullpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
                        int pic_pix_x, int pic_pix_y, int blocktype,
                        int pmv_x1, int pmv_y1, int pmv_x2, int pmv_y2,
                        short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
                        int search_range, int min_mcost, int lambda_factor);
-int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+int ora_bipred_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
                       int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y,
                       short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
                       int search_pos2, int search_pos4, int min_mcost, const int *lambda);
@@ -119,33 +128,34 @@ int ora_bipred_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, cons
  * Vectors are quarter pel.  State the reference keeps in file statics / globals arrives as arguments:
  * subthres = subthres[blocktype] (me_epzs.c:354); uplayer_x / y = smpUMHEX_pred_MV_uplayer_X / _Y (me_umhexsmp.c:1203-1214);
  * threshold1 / threshold3 = SubPelThreshold1 / SubPelThreshold3 (me_umhexsmp.c:106-107), shifted inside by the block type */
-int ora_epzs_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_epzs_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                     int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
                     int search_pos2, int search_pos4, int min_mcost, const int *lambda, int subthres);
-int ora_epzs_subpel_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
+int ora_epzs_subpel_bipred(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r1, const ora_ref *r2,
                            int pic_pix_x, int pic_pix_y, int blocktype, int pmv1_x, int pmv1_y, int pmv2_x, int pmv2_y,
                            short *mv_x, short *mv_y, const short *s_mv_x, const short *s_mv_y,
                            int search_pos2, int search_pos4, int min_mcost, const int *lambda);
-int ora_umhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_umhex_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                      int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
                      int min_mcost, int lambda_factor);
-int ora_smpumhex_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_smpumhex_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                         int pic_pix_x, int pic_pix_y, int blocktype, int pmv_x, int pmv_y, short *mv_x, short *mv_y,
                         int min_mcost, int lambda_factor, int uplayer_x, int uplayer_y, int threshold1, int threshold3);
-int ora_smpumhex_full_subpel(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+int ora_smpumhex_full_subpel(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                              int pic_pix_x, int pic_pix_y, int blocktype, int ref, int slice_type, int pmv_x, int pmv_y,
                              short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor,
                              int threshold1, int threshold3);
 
 /* one batch job = PartitionMotionSearch for all 41 partitions of one (macroblock, list, ref) */
-void ora_mb_search(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *r,
+void ora_mb_search(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *r,
                    const me_mb_job *job, me_mb_result *out, me_mb_result_int *out_int);
 
 /* one bi-predictive batch job = the block of BlockMotionSearch at mv-search.c:864-1034 (block type 1, reference 0):
  * l0 / l1 = reference 0 of list 0 / list 1 */
-void ora_mb_bipred(const ora_cfg *c, const uint8_t *cur, int cur_stride, const ora_ref *l0, const ora_ref *l1,
+void ora_mb_bipred(const ora_cfg *c, const ora_pel *cur, int cur_stride, const ora_ref *l0, const ora_ref *l1,
                    const me_bipred_job *job, int refinements, int search_range, int subpel, me_bipred_result *out);
 
+#ifndef ORA_PEL16
 /* ---- motion-compensated prediction and the mode-decision costs built on it (include/me_cuda.h: me_pred_block).
  * list0 / list1: the reference lists as arrays of pictures; blocks[4 * by + bx]: what LumaPrediction does for the 4x4 block
  * (bx, by) of the macroblock.  Reference: macroblock.c:807-930, me_distortion.c:76-137, mv-search.c:1052-1128, :1136-1181, :1273-1325 */
@@ -163,6 +173,8 @@ int  ora_bid_partition_cost(const uint8_t *cur, int cur_stride, const ora_ref *c
 /* ---- DeblockFrame (loopFilter.c:87-253) with the boundary strengths given per macroblock (include/me_cuda.h: me_deblock_mb);
  * frame pictures, no MBAFF, 8 bit, 4:2:0 (u, v non-NULL) or 4:0:0.  In place. */
 void ora_deblock_frame(uint8_t *y, int ystride, uint8_t *u, uint8_t *v, int cstride, int w, int h, const me_deblock_mb *mbs);
+
+#endif /* !ORA_PEL16 */
 
 #ifdef __cplusplus
 }

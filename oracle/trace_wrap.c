@@ -25,7 +25,7 @@
  *
  * Output (directory named by env ME_TRACE_DIR, default "."):
  *   trace.bin          fixed-size records, 32 little-endian int32 each (layout: REC_* below)
- *   cur_<n>.y          original luma of coded picture n (8-bit, W*H bytes); with ChromaMEEnable also cur_<n>.u / .v
+ *   cur_<n>.y          original luma of coded picture n (W*H bytes; 16-bit little-endian samples when the bit depth exceeds 8, as all dumps then); with ChromaMEEnable also cur_<n>.u / .v
  *   ref_<id>.y         reconstructed luma a set of quarter-pel planes was built from; with ChromaMEEnable also ref_<id>.u / .v
  *   ref_<id>.sub       the 16 planes as the reference produced them, [4][4][H+40][W+40] bytes
  *                      (only when ME_TRACE_PLANES=1)
@@ -104,6 +104,7 @@ static void dump_luma(const char *name, imgpel **rows, int w, int h)
   f = fopen(path, "wb");
   if (!f) { perror(path); exit(97); }
   for (y = 0; y < h; y++) {
+    if (img->bitdepth_luma > 8) { fwrite(rows[y], sizeof(imgpel), w, f); continue; }   /* more than 8 bits: the 16-bit samples as they are */
     for (x = 0; x < w; x++) line[x] = (unsigned char)rows[y][x];
     fwrite(line, 1, w, f);
   }
@@ -126,6 +127,7 @@ static void dump_current_if_needed(void)
   rec[0] = REC_CURPIC; rec[1] = coded_pic_no; rec[2] = img->type; rec[3] = img->width; rec[4] = img->height;
   rec[5] = img->framepoc; rec[6] = img->qp;
   rec[7] = input->ChromaMEEnable; rec[8] = input->ChromaMEWeight; rec[9] = img->yuv_format; rec[10] = img->width_cr; rec[11] = img->height_cr;
+  rec[12] = img->bitdepth_luma;               /* > 8: the picture dumps hold 16-bit samples */
   put(rec);
 }
 
@@ -170,6 +172,7 @@ void __wrap_getSubImagesLuma(StorablePicture *s)
     for (fy = 0; fy < 4; fy++)
       for (fx = 0; fx < 4; fx++)
         for (y = 0; y < hp; y++) {
+          if (img->bitdepth_luma > 8) { fwrite(s->imgY_sub[fy][fx][y], sizeof(imgpel), wp, f); continue; }
           for (x = 0; x < wp; x++) line[x] = (unsigned char)s->imgY_sub[fy][fx][y][x];
           fwrite(line, 1, wp, f);
         }

@@ -60,7 +60,13 @@ PATTERN_CASES = {
 }
 
 
+# more than 8 bits per sample: 16-bit pictures and plane sets (High 10, BitDepthLuma = 10)
+HBD_CASES = {
+    "hbd10": dict(search_range=16, full_search=2, metric=(0, 2, 2), mv_limits=(-511, 511)),
+}
+
+
 def golden_trace(name):
     from trace_util import Trace, cfg_from_trace
     tr = Trace.load_npz(os.path.join(GOLDEN, name + ".npz"))
-    return tr, cfg_from_trace(tr, **(GOLDEN_CASES.get(name) or PATTERN_CASES[name]))
+    return tr, cfg_from_trace(tr, **(GOLDEN_CASES.get(name) or PATTERN_CASES.get(name) or HBD_CASES[name]))

@@ -184,6 +184,7 @@ def main():
         crc["wpbc"] = planes_crc(tr, d)
     epzs(crc, md5s)
     patterns(crc, md5s)
+    hbd(crc, md5s)
     big(md5s)
     json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
     json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
@@ -278,8 +279,36 @@ def patterns(crc, md5s, only=None):
             crc[case] = planes_crc(tr, d)
 
 
+def write_hbd_clip(path, bits, seed=5):
+    """the reference's QCIF clip shifted up to `bits` bits with random low bits, 16-bit little-endian samples"""
+    src = np.fromfile(os.path.join(REF, "fixtures", "foreman_part_qcif.yuv"), np.uint8).astype(np.uint16)
+    sh = bits - 8
+    ((src << sh) + np.random.default_rng(seed).integers(0, 1 << sh, src.shape).astype(np.uint16)).astype("<u2").tofile(path)
+
+
+def hbd(crc, md5s):
+    """hbd10: encoder.cfg in High 10 with BitDepthLuma = BitDepthChroma = 10 (I-B-P, bi-predictive ME, 8x8 transform, SR 16, 2 references):
+    16-bit pictures and plane sets (last third).  Every 4th macroblock is kept; pictures are stored as uint16."""
+    with tempfile.TemporaryDirectory() as d:
+        write_hbd_clip(os.path.join(d, "hbd.yuv"), 10)
+        run_trace(d, ["-d", "encoder.cfg", "-p", "InputFile=hbd.yuv", "-p", "BitDepthLuma=10", "-p", "BitDepthChroma=10", "-p", "ProfileIDC=110",
+                      "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"])
+        md5s["hbd10"] = {"test.264": md5(os.path.join(d, "test.264"))}
+        tr = Trace(d)
+        assert tr.bits == 10 and tr.ref(tr.ref_ids()[0]).dtype == np.uint16 and int(tr.ref(tr.ref_ids()[0]).max()) > 255
+        assert len(tr.of_type(REC_FFS)) > 10000 and len(tr.of_type(REC_BI_FULL)) > 500
+        tr.save_npz(os.path.join(HERE, "hbd10.npz"), keep_mask(tr, 4))
+        crc["hbd10"] = planes_crc(tr, d)
+
+
 if __name__ == "__main__":
-    if sys.argv[1:2] == ["patterns"]:               # add these cases without rewriting the other fixtures
+    if sys.argv[1:2] == ["hbd"]:                      # add this case without rewriting the other fixtures
+        crc = json.load(open(os.path.join(HERE, "planes_crc.json")))
+        md5s = json.load(open(os.path.join(HERE, "bitstream_md5.json")))
+        hbd(crc, md5s)
+        json.dump(crc, open(os.path.join(HERE, "planes_crc.json"), "w"), indent=1)
+        json.dump(md5s, open(os.path.join(HERE, "bitstream_md5.json"), "w"), indent=1)
+    elif sys.argv[1:2] == ["patterns"]:               # add these cases without rewriting the other fixtures
         crc = json.load(open(os.path.join(HERE, "planes_crc.json")))
         md5s = json.load(open(os.path.join(HERE, "bitstream_md5.json")))
         patterns(crc, md5s, sys.argv[2:] or None)

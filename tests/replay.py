@@ -36,6 +36,7 @@ class OracleAdapter:
     def __init__(self, trace, cfgkw):
         from oracle import binding as ob
         self.ob = ob
+        ob.set_bit_depth(trace.bits)          # more than 8 bits per sample: the 16-bit build of the oracle (reset in close())
         self.cfg = ob.make_cfg(**cfgkw)
         self.refs = {i: ob.Ref(trace.ref(i)) for i in trace.ref_ids()}
         self.surf = {}
@@ -127,6 +128,7 @@ class OracleAdapter:
     def close(self):
         for r in list(self.refs.values()) + self.crefs:
             r.close()
+        self.ob.set_bit_depth(8)
 
 
 class CudaAdapter:
@@ -141,8 +143,9 @@ class CudaAdapter:
         ckw = dict(chroma_me=self.ci["enable"], chroma_me_weight=self.ci["weight"], yuv_format=self.ci["yuv_format"]) if self.ci else {}
         self.me = MeCuda(w, h, search_range=cfgkw["search_range"], max_num_references=max_refs, rdopt=cfgkw["rdopt"],
                          full_search=cfgkw["full_search"], me_metric=cfgkw["metric"], transform8x8=cfgkw["transform8x8"],
-                         mv_limits=(cfgkw["mv_limit_min_y"], cfgkw["mv_limit_max_y"]), **ckw)
-        self.handles = {i: self.me.ref_create(trace.ref(i)) for i in trace.ref_ids()}
+                         mv_limits=(cfgkw["mv_limit_min_y"], cfgkw["mv_limit_max_y"]), bit_depth=trace.bits, **ckw)
+        self.hbd = trace.bits > 8
+        self.handles = {i: (self.me.ref_create_imgpel(trace.ref(i))[0] if self.hbd else self.me.ref_create(trace.ref(i))) for i in trace.ref_ids()}
         if self.ci:
             for i, hd in list(self.handles.items()):
                 u, v = trace.chroma("ref", i)
@@ -152,7 +155,10 @@ class CudaAdapter:
                     self.me.ref_set_chroma(hd, u, v)
 
     def begin_picture(self, cur, slice_type, lists, pic=None):
-        self.me.set_current(cur)
+        if self.hbd:
+            self.me.set_current_imgpel(cur)
+        else:
+            self.me.set_current(cur)
         if self.ci:
             self.me.set_current_chroma(*self.trace.chroma("cur", pic))
         self.me.set_slice_type(slice_type)

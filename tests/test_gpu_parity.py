@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, PATTERN_CASES, golden_trace
+from conftest import GOLDEN_CASES, HBD_CASES, PATTERN_CASES, golden_trace
 from replay import CudaAdapter, replay, pattern_counts
 
 pytestmark = pytest.mark.gpu
@@ -108,6 +108,44 @@ def test_dropin_pattern_subpel_calls_match_reference_trace(pkg, case):
     for name, (n, bad) in res.items():
         assert not bad, (case, name, n, len(bad), bad[:3])
     pattern_counts(case, res)
+
+
+def test_high_bit_depth_planes_and_dropin_calls(pkg, oracle_lib):
+    """more than 8 bits per sample: 10-bit pictures as 16-bit samples through the row-pointer entry points --
+    the 16 planes pixel-exact against the 16-bit build of the oracle and the reference's own CRCs, every kept call of the unmodified
+    reference replayed through the drop-in ABI, and the 8-bit-only entry points refusing loudly"""
+    import json, zlib
+    from conftest import GOLDEN
+    from h264_b200 import MeCudaError
+    tr, cfgkw = golden_trace("hbd10")
+    assert sorted(HBD_CASES) == ["hbd10"] and tr.bits == 10
+    crc = json.load(open(os.path.join(GOLDEN, "planes_crc.json")))["hbd10"]
+    h, w = tr.size[("cur", tr.cur_ids()[0])]
+    oracle_lib.set_bit_depth(10)
+    try:
+        with pkg.MeCuda(w, h, search_range=16, max_num_references=2, transform8x8=cfgkw["transform8x8"], bit_depth=10) as me:
+            for i in tr.ref_ids():
+                hd, sub = me.ref_create_imgpel(tr.ref(i), want_planes=True)
+                ref = oracle_lib.Ref(tr.ref(i))
+                assert sub.dtype == np.uint16 and np.array_equal(sub, ref.planes()), i
+                ref.close()
+                for fy in range(4):
+                    for fx in range(4):
+                        assert zlib.crc32(np.ascontiguousarray(sub[fy, fx]).tobytes()) == crc[str(i)][fy][fx], (i, fy, fx)
+            with pytest.raises(MeCudaError):
+                me.ref_create(tr.ref(tr.ref_ids()[0]).astype(np.uint8))      # 8-bit entry point on a 10-bit library
+            with pytest.raises(MeCudaError):
+                me.frame_search(np.zeros(1, pkg.JOB_DTYPE))                  # the frame batch is 8-bit only
+    finally:
+        oracle_lib.set_bit_depth(8)
+    impl = CudaAdapter(tr, cfgkw, max_refs=2)
+    try:
+        res = replay(tr, impl)
+    finally:
+        impl.close()
+    for name, (n, bad) in res.items():
+        assert not bad, (name, n, len(bad), bad[:3])
+    assert res["ffs"][0] > 3000 and res["subpel"][0] > 3000 and res["bi_full"][0] > 100 and res["bi_sub"][0] > 50
 
 
 # ------------------------------------------------------------------------------------------------ one launch per PartitionMotionSearch

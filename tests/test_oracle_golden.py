@@ -6,20 +6,24 @@ import zlib
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, GOLDEN_CASES, PATTERN_CASES, golden_trace
+from conftest import GOLDEN, GOLDEN_CASES, HBD_CASES, PATTERN_CASES, golden_trace
 from replay import OracleAdapter, replay, pattern_counts
 
 
-@pytest.mark.parametrize("case", sorted(GOLDEN_CASES) + sorted(PATTERN_CASES))
+@pytest.mark.parametrize("case", sorted(GOLDEN_CASES) + sorted(PATTERN_CASES) + sorted(HBD_CASES))
 def test_planes_match_reference_crc(oracle_lib, case):
     tr, _ = golden_trace(case)
     crc = json.load(open(os.path.join(GOLDEN, "planes_crc.json")))[case]
-    for i in tr.ref_ids():
-        ref = oracle_lib.Ref(tr.ref(i))
-        for fy in range(4):
-            for fx in range(4):
-                assert zlib.crc32(ref.plane(fy, fx).tobytes()) == crc[str(i)][fy][fx], (case, i, fy, fx)
-        ref.close()
+    oracle_lib.set_bit_depth(tr.bits)              # hbd10: the 16-bit build, clips at 1023
+    try:
+        for i in tr.ref_ids():
+            ref = oracle_lib.Ref(tr.ref(i))
+            for fy in range(4):
+                for fx in range(4):
+                    assert zlib.crc32(ref.plane(fy, fx).tobytes()) == crc[str(i)][fy][fx], (case, i, fy, fx)
+            ref.close()
+    finally:
+        oracle_lib.set_bit_depth(8)
 
 
 @pytest.mark.parametrize("case", sorted(GOLDEN_CASES))
@@ -34,6 +38,18 @@ def test_calls_match_reference_trace(oracle_lib, case):
     assert (res["ffs"][0] > 1000 or res["fullpel"][0] > 1000 or case == "epzs") and res["subpel"][0] > 1000
     if case == "kat":
         assert res["bi_full"][0] > 100 and res["bi_sub"][0] > 50
+
+
+def test_high_bit_depth_calls_match_reference_trace(oracle_lib):
+    """10-bit pictures (imgpel u16): the 16-bit build of the oracle against every kept call of the unmodified reference"""
+    tr, cfgkw = golden_trace("hbd10")
+    assert tr.bits == 10 and tr.ref(tr.ref_ids()[0]).dtype == np.uint16 and int(tr.ref(tr.ref_ids()[0]).max()) > 255
+    impl = OracleAdapter(tr, cfgkw)
+    res = replay(tr, impl)
+    impl.close()
+    for name, (n, bad) in res.items():
+        assert not bad, (name, n, bad[:3])
+    assert res["ffs"][0] > 3000 and res["subpel"][0] > 3000 and res["bi_full"][0] > 100 and res["bi_sub"][0] > 50
 
 
 @pytest.mark.parametrize("case", sorted(PATTERN_CASES))

@@ -88,3 +88,34 @@ def test_oracle_reproduces_the_pattern_searches_subpel_stages(tmp_path, oracle_l
     for key, (n, bad) in res.items():
         assert not bad, (name, key, n, bad[:3])
     assert res["subpel_pat"][0] > 10000 and (res["bi_sub_pat"][0] > 300 or "bipred" not in name)
+
+
+@pytest.mark.parametrize("bits,profile,extra,metric", [
+    (12, 122, [], (0, 2, 2)),
+    (10, 110, ["-p", "MEDistortionHPel=0", "-p", "MEDistortionQPel=1", "-p", "RDOptimization=0", "-p", "Transform8x8Mode=0"], (0, 0, 1))])
+def test_oracle_reproduces_high_bit_depth_runs(tmp_path, oracle_lib, bits, profile, extra, metric):
+    """more than 8 bits per sample: planes of the live reference pixel-exact in the 16-bit build of the oracle (clips at
+    max_imgpel_value) and every traced call, for 12 bit (High 4:2:2) and for SAD / squared-error refinements without RDO at 10 bit"""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    mg.write_hbd_clip(str(tmp_path / "hbd.yuv"), bits)
+    tr = _trace(str(tmp_path), ["-d", "encoder.cfg", "-p", "InputFile=hbd.yuv", "-p", "BitDepthLuma=%d" % bits, "-p", "BitDepthChroma=%d" % bits,
+                                "-p", "ProfileIDC=%d" % profile, "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"] + extra)
+    assert tr.bits == bits
+    oracle_lib.set_bit_depth(bits)
+    try:
+        for i in tr.ref_ids():
+            ref = oracle_lib.Ref(tr.ref(i))
+            assert ref.planes().dtype == np.uint16 and (ref.planes() == tr.ref_sub(i)).all()
+            ref.close()
+    finally:
+        oracle_lib.set_bit_depth(8)
+    impl = OracleAdapter(tr, cfg_from_trace(tr, search_range=16, full_search=2, metric=metric))
+    res = replay(tr, impl)
+    impl.close()
+    for key, (n, bad) in res.items():
+        assert not bad, (bits, key, n, bad[:3])
+    assert res["ffs"][0] > 15000 and res["bi_full"][0] > 500

@@ -29,16 +29,26 @@ class Trace:
     def of_type(self, t):
         return self.recs[self.recs[:, 0] == t]
 
+    @property
+    def bits(self):
+        """bit depth of the traced run (REC_CURPIC field 12; 0 in fixtures made before the field existed = 8)"""
+        r = self.of_type(REC_CURPIC)
+        return int(r[0][12]) if len(r) and int(r[0][12]) else 8
+
+    @property
+    def dtype(self):
+        return np.uint16 if self.bits > 8 else np.uint8
+
     def cur(self, n):
         if n not in self._cur:
             h, w = self.size[("cur", n)]
-            self._cur[n] = np.fromfile(os.path.join(self.dir, "cur_%d.y" % n), np.uint8).reshape(h, w)
+            self._cur[n] = np.fromfile(os.path.join(self.dir, "cur_%d.y" % n), self.dtype).reshape(h, w)
         return self._cur[n]
 
     def ref(self, i):
         if i not in self._ref:
             h, w = self.size[("ref", i)]
-            self._ref[i] = np.fromfile(os.path.join(self.dir, "ref_%d.y" % i), np.uint8).reshape(h, w)
+            self._ref[i] = np.fromfile(os.path.join(self.dir, "ref_%d.y" % i), self.dtype).reshape(h, w)
         return self._ref[i]
 
     # ChromaMEEnable runs: original / reconstructed chroma planes (REC_CURPIC fields 7..11: ChromaMEEnable, ChromaMEWeight,
@@ -60,7 +70,7 @@ class Trace:
 
     def ref_sub(self, i):
         h, w = self.size[("ref", i)]
-        return np.fromfile(os.path.join(self.dir, "ref_%d.sub" % i), np.uint8).reshape(4, 4, h + 40, w + 40)
+        return np.fromfile(os.path.join(self.dir, "ref_%d.sub" % i), self.dtype).reshape(4, 4, h + 40, w + 40)
 
     def cur_ids(self):
         return sorted(n for (k, n) in self.size if k == "cur")
