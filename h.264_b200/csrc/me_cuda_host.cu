@@ -1263,7 +1263,6 @@ int me_cuda_FullPelBlockMotionSearch(short ref, int list, int pic_pix_x, int pic
                                      short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
                                      int search_range, int min_mcost, int lambda_factor)
 {
-  if (only8("me_cuda_FullPelBlockMotionSearch")) { fatal("me_cuda_FullPelBlockMotionSearch"); return ME_INT_MAX; }
   g.spec.valid = false;
   RefPic *r = (g.inited && list >= 0 && list <= 1 && ref >= 0 && ref < g.list_n[list]) ? ref_of(g.list[list][ref]) : nullptr;
   if (!r) { fail(1, "me_cuda_FullPelBlockMotionSearch: (list %d, ref %d) not in the reference lists", list, (int)ref); fatal("fullpel"); return ME_INT_MAX; }
@@ -1391,7 +1390,6 @@ static int subpel_pattern(const char *who, const MePatArgs &pa, short ref, int l
                           int pmv_x, int pmv_y, short *mv_x, short *mv_y, const short *s_mv, int search_pos2, int search_pos4,
                           int min_mcost, int lam0, int lam1, int lam2, int check0)
 {
-  if (only8("the sub-pel stages of the pattern searches")) { fatal("the sub-pel stages of the pattern searches"); return ME_INT_MAX; }
   g.spec.valid = false;
   if (blocktype < 1 || blocktype > 7) { fail(1, "%s: block type %d", who, blocktype); fatal(who); return ME_INT_MAX; }
   MeSubpelArgs a{};

@@ -322,7 +322,8 @@ __constant__ int8_t c_epzs_y[10] = { 0, 0, 1, 0, -1, 1, 1, -1, -1, 1 };
 
 // costs (vector rate + distortion) of the (2E+1)^2 candidates centre + step * (dx, dy), |dx|, |dy| <= E, into sc.grid[(dy+E)*(2E+1) + dx+E].
 // Called by all threads; ends with a barrier.
-__device__ void pattern_grid(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch, const MeCfgDev &cfg,
+template <typename Pel>
+__device__ void pattern_grid(const MeRefDev &r1, const MeRefDev &r2, const Pel *__restrict__ cur, int cur_pitch, const MeCfgDev &cfg,
                              const MeSubpelArgs &a, const MePatArgs &pa, BlockScratch &sc, int level, int lam, int step, int E)
 {
   const int tid = threadIdx.x, W = 2 * E + 1, ncand = W * W;
@@ -339,7 +340,7 @@ __device__ void pattern_grid(const MeRefDev &r1, const MeRefDev &r2, const uint8
   __syncthreads();
   const bool use8 = cfg.transform8x8 && t <= 4 && metric == 2;
   const int n = use8 ? 8 : 4, tw = bsx / n, th = bsy / n;
-  const uint8_t *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
+  const Pel *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
   for (int i = tid; i < tw * th * ncand; i += blockDim.x) {
     const int c = i % ncand, tile = i / ncand;
     const int bx = (tile % tw) * n, by = (tile / tw) * n;
@@ -347,18 +348,20 @@ __device__ void pattern_grid(const MeRefDev &r1, const MeRefDev &r2, const uint8
     const int y4 = ((a.pic_pix_y + ME_PAD) << 2) + cy0 + step * (c / W - E);
     int d;
     if (!a.bi) {
-      const uint8_t *rp = tile_ptr<uint8_t>(r1, x4, y4, bx, by, metric == 2);
-      d = use8 ? tile_dist<8, uint8_t>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw)
-               : tile_dist<4, uint8_t>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw);
+      const Pel *rp = tile_ptr<Pel>(r1, x4, y4, bx, by, metric == 2);
+      d = use8 ? tile_dist<8, Pel>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw)
+               : tile_dist<4, Pel>(metric, blk, cur_pitch, bsx, bx, by, rp, r1.pitch, nullptr, 0, a.bw);
+      if constexpr (sizeof(Pel) == 1)
       if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0])                        // computeSAD / SSE, me_distortion.c:376-402
         for (int k = 0; k < 2; k++)
           d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, x4, y4, nullptr, 0, 0);
     } else {
       const int fx4 = ((a.pic_pix_x + ME_PAD) << 2) + a.s_mv_x, fy4 = ((a.pic_pix_y + ME_PAD) << 2) + a.s_mv_y;
-      const uint8_t *p1 = tile_ptr<uint8_t>(r1, fx4, fy4, bx, by, metric == 2);
-      const uint8_t *p2 = tile_ptr<uint8_t>(r2, x4, y4, bx, by, metric == 2);
-      d = use8 ? tile_dist<8, uint8_t>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw)
-               : tile_dist<4, uint8_t>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
+      const Pel *p1 = tile_ptr<Pel>(r1, fx4, fy4, bx, by, metric == 2);
+      const Pel *p2 = tile_ptr<Pel>(r2, x4, y4, bx, by, metric == 2);
+      d = use8 ? tile_dist<8, Pel>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw)
+               : tile_dist<4, Pel>(metric, blk, cur_pitch, bsx, bx, by, p1, r1.pitch, p2, r2.pitch, a.bw);
+      if constexpr (sizeof(Pel) == 1)
       if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && r1.chroma[0] && r2.chroma[0])         // computeBiPredSAD1 :516-543
         for (int k = 0; k < 2; k++)
           d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r1, fx4, fy4, &r2, x4, y4,
@@ -450,7 +453,8 @@ __device__ void umhex_walk(const int *grid, bool smp, bool start_hp, const MePat
 }
 
 // One block through the sub-pel stage of a pattern search.  Called by all threads of the CTA; returns the result to all of them.
-__device__ void pattern_block(const MeRefDev &r1, const MeRefDev &r2, const uint8_t *__restrict__ cur, int cur_pitch, const MeCfgDev &cfg,
+template <typename Pel>
+__device__ void pattern_block(const MeRefDev &r1, const MeRefDev &r2, const Pel *__restrict__ cur, int cur_pitch, const MeCfgDev &cfg,
                               const MeSubpelArgs &a, const MePatArgs &pa, BlockScratch &sc, int &out_mvx, int &out_mvy, int &out_cost)
 {
   const int tid = threadIdx.x;
@@ -511,8 +515,9 @@ __device__ void pattern_block(const MeRefDev &r1, const MeRefDev &r2, const uint
   out_mvx = sc.mv_s[0]; out_mvy = sc.mv_s[1]; out_cost = sc.min_sh;
 }
 
+template <typename Pel>
 __global__ void __launch_bounds__(256)
-me_subpel_pattern_kernel(MeRefDev r1, MeRefDev r2, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+me_subpel_pattern_kernel(MeRefDev r1, MeRefDev r2, const Pel *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                          MeSubpelArgs a, MePatArgs pa, int *result /* mvx, mvy, cost, ticket */, int ticket)
 {
   __shared__ BlockScratch sc;
@@ -699,11 +704,12 @@ struct MeFullPelArgs {
 
 // whole-block distortion; thr / use_thr: the reference's early exits (after a row of SAD / SSE when the sum has reached the
 // threshold, after a tile of SATD when it exceeds it), needed for the one position where they change the result (below)
-__device__ int fullpel_dist(const MeRefDev &r, const uint8_t *__restrict__ cur, int cur_pitch, const MeCfgDev &cfg, const MeFullPelArgs &a,
+template <typename Pel>
+__device__ int fullpel_dist(const MeRefDev &r, const Pel *__restrict__ cur, int cur_pitch, const MeCfgDev &cfg, const MeFullPelArgs &a,
                             int x4, int y4, bool use_thr, int thr)
 {
   const int metric = cfg.metric[0], bsx = me_bsx(a.blocktype), bsy = me_bsy(a.blocktype);
-  const uint8_t *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
+  const Pel *blk = cur + (size_t)a.pic_pix_y * cur_pitch + a.pic_pix_x;
   const MeBiW nobw = { 0, 0, 0, 0, 0, { 0, 0 }, { 0, 0 }, { 0, 0 } };
   int m = 0;
   if (metric == 2) {
@@ -711,14 +717,14 @@ __device__ int fullpel_dist(const MeRefDev &r, const uint8_t *__restrict__ cur, 
     const int n = use8 ? 8 : 4;
     for (int by = 0; by < bsy; by += n)
       for (int bx = 0; bx < bsx; bx += n) {
-        const uint8_t *rp = me_umv_ptr(r, y4 + (by << 2), x4 + (bx << 2));
-        m += use8 ? tile_dist<8, uint8_t>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw)
-                  : tile_dist<4, uint8_t>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw);
+        const Pel *rp = me_umv_ptr_p<Pel>(r, y4 + (by << 2), x4 + (bx << 2));
+        m += use8 ? tile_dist<8, Pel>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw)
+                  : tile_dist<4, Pel>(2, blk, cur_pitch, bsx, bx, by, rp, r.pitch, nullptr, 0, nobw);
         if (use_thr && m > thr) return m;
       }
     return m;
   }
-  const uint8_t *rp = me_umv_ptr(r, y4, x4);
+  const Pel *rp = me_umv_ptr_p<Pel>(r, y4, x4);
   for (int y = 0; y < bsy; y++) {
     for (int x = 0; x < bsx; x++) {
       const int d = (int)blk[(size_t)y * cur_pitch + x] - (int)rp[(size_t)y * r.pitch + x];
@@ -726,6 +732,7 @@ __device__ int fullpel_dist(const MeRefDev &r, const uint8_t *__restrict__ cur, 
     }
     if (use_thr && m >= thr) return m;
   }
+  if constexpr (sizeof(Pel) == 1)
   if (cfg.chroma.on && r.chroma[0])
     for (int k = 0; k < 2; k++) {               // me_distortion.c:376-402: one component after the other, same early exit
       m += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, a.pic_pix_x, a.pic_pix_y, bsx, bsy, r, x4, y4, nullptr, 0, 0);
@@ -734,8 +741,9 @@ __device__ int fullpel_dist(const MeRefDev &r, const uint8_t *__restrict__ cur, 
   return m;
 }
 
+template <typename Pel>
 __global__ void __launch_bounds__(256)
-me_fullpel_block_kernel(MeRefDev r, const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg, MeFullPelArgs a, int *result, int ticket)
+me_fullpel_block_kernel(MeRefDev r, const Pel *__restrict__ cur, int cur_pitch, MeCfgDev cfg, MeFullPelArgs a, int *result, int ticket)
 {
   __shared__ unsigned long long red[8];
   const int P = (2 * a.search_range + 1) * (2 * a.search_range + 1);
@@ -1083,13 +1091,19 @@ extern "C" void me_launch_subpel_single(const MeRefDev *r1, const MeRefDev *r2, 
 extern "C" void me_launch_subpel_pattern(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,
                                          const MeCfgDev *cfg, const MeSubpelArgs *a, const MePatArgs *pa, int *result, int ticket, cudaStream_t st)
 {
-  me_subpel_pattern_kernel<<<1, 256, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, *pa, result, ticket);
+  if (cfg->pel16)
+    me_subpel_pattern_kernel<uint16_t><<<1, 256, 0, st>>>(*r1, r2 ? *r2 : *r1, reinterpret_cast<const uint16_t *>(cur), cur_pitch, *cfg, *a, *pa, result, ticket);
+  else
+    me_subpel_pattern_kernel<uint8_t><<<1, 256, 0, st>>>(*r1, r2 ? *r2 : *r1, cur, cur_pitch, *cfg, *a, *pa, result, ticket);
 }
 
 extern "C" void me_launch_fullpel_block(const MeRefDev *r, const uint8_t *cur, int cur_pitch, const MeCfgDev *cfg,
                                         const MeFullPelArgs *a, int *result, int ticket, cudaStream_t st)
 {
-  me_fullpel_block_kernel<<<1, 256, 0, st>>>(*r, cur, cur_pitch, *cfg, *a, result, ticket);
+  if (cfg->pel16)
+    me_fullpel_block_kernel<uint16_t><<<1, 256, 0, st>>>(*r, reinterpret_cast<const uint16_t *>(cur), cur_pitch, *cfg, *a, result, ticket);
+  else
+    me_fullpel_block_kernel<uint8_t><<<1, 256, 0, st>>>(*r, cur, cur_pitch, *cfg, *a, result, ticket);
 }
 
 extern "C" void me_launch_bipred_full(const MeRefDev *r1, const MeRefDev *r2, const uint8_t *cur, int cur_pitch,

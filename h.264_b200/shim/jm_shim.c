@@ -231,9 +231,9 @@ void __wrap_Init_Motion_Search_Module(void)
     L.set_error_handler(on_library_error);
     p.abi_version = ME_CUDA_ABI_VERSION;
     p.width = img->width; p.height = img->height;
-    /* more than 8 bits per sample (imgpel is u16, global.h:50): the fast-full-search path -- plane sets, block searches, plain and
-     * bi-predictive refinements, one launch per PartitionMotionSearch -- runs on 16-bit planes; the other stages stay the reference's
-     * host code in such runs (hbd below), reading the planes through the paging line accessors */
+    /* more than 8 bits per sample (imgpel is u16, global.h:50): plane sets, every search stage and the launch per
+     * PartitionMotionSearch run on 16-bit planes; the prediction costs and the deblocking filter stay the reference's host code in
+     * such runs (hbd below), reading the planes through the paging line accessors; weighted / chroma-aware ME is refused */
     p.bit_depth = img->bitdepth_luma;
     hbd = img->bitdepth_luma > 8;
     if (hbd && IS_INDEPENDENT(input) && img->bitdepth_chroma != img->bitdepth_luma) die("4:4:4 independent mode with different luma / chroma bit depths");
@@ -614,7 +614,7 @@ int __wrap_FullPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int p
                                     short pred_mv_x, short pred_mv_y, short *mv_x, short *mv_y,
                                     int search_range, int min_mcost, int lambda_factor)
 {
-  if (!active || hbd)
+  if (!active)
     return __real_FullPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y,
                                            mv_x, mv_y, search_range, min_mcost, lambda_factor);
   mb_sync();
@@ -728,7 +728,7 @@ int __real_EPZSSubPelBlockMotionSearch(imgpel *, short, int, int, int, int, shor
 int __wrap_EPZSSubPelBlockMotionSearch(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype,
                                        short pred_mv[2], short mv[2], int search_pos2, int search_pos4, int min_mcost, int *lambda)
 {
-  if (!active || hbd)
+  if (!active)
     return __real_EPZSSubPelBlockMotionSearch(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv, mv, search_pos2, search_pos4, min_mcost, lambda);
   mb_sync();
   keep_reference_side_effects(list, ref);
@@ -749,7 +749,7 @@ int __wrap_EPZSSubPelBlockSearchBiPred(imgpel *orig_pic, short ref, int list, in
                                        short *pred_mv1, short *pred_mv2, short mv[2], short s_mv[2],
                                        int search_pos2, int search_pos4, int min_mcost, int *lambda)
 {
-  if (!active || hbd)
+  if (!active)
     return __real_EPZSSubPelBlockSearchBiPred(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv1, pred_mv2, mv, s_mv,
                                               search_pos2, search_pos4, min_mcost, lambda);
   mb_sync();
@@ -785,7 +785,7 @@ int __real_##NAME(imgpel *, short, int, int, int, int, short, short, short *, sh
 int __wrap_##NAME(imgpel *orig_pic, short ref, int list, int pic_pix_x, int pic_pix_y, int blocktype, short pred_mv_x, short pred_mv_y, \
                   short *mv_x, short *mv_y, int search_pos2, int search_pos4, int min_mcost, int lambda_factor)                     \
 {                                                                                                                                   \
-  if (!active || hbd)                                                                                                               \
+  if (!active)                                                                                                                      \
     return __real_##NAME(orig_pic, ref, list, pic_pix_x, pic_pix_y, blocktype, pred_mv_x, pred_mv_y, mv_x, mv_y, search_pos2,       \
                          search_pos4, min_mcost, lambda_factor);                                                                    \
   mb_sync();                                                                                                                        \

@@ -55,12 +55,10 @@ typedef struct me_cuda_params {
   int32_t bit_depth;            /* img->bitdepth_luma, 8..14.  More than 8 (imgpel is u16, global.h:50): plane sets and
                                    the current picture hold 16-bit samples, the clips of the interpolation are at (1 << bit_depth) - 1;
                                    served by the row-pointer entry points (me_cuda_ref_create, me_cuda_set_current,
-                                   me_cuda_ref_download_region) and the fast-full-search drop-in path (me_cuda_ffs_setup, me_cuda_pms_*,
-                                   me_cuda_FastFullPelBlockMotionSearch, me_cuda_SubPelBlockMotionSearch, me_cuda_FullPelBlockMotionBiPred,
-                                   me_cuda_SubPelBlockSearchBiPred, field views included).  Everything else -- the *_u8 / *_device entry
-                                   points, the frame batches, weighted / chroma-aware ME, the other search modes' stages, prediction
-                                   costs, deblocking -- is for 8-bit pictures and fails with a message instead of reading 16-bit samples
-                                   as bytes */
+                                   me_cuda_ref_download_region) and every drop-in search (me_cuda_ffs_setup, me_cuda_pms_*, the block
+                                   searches and refinements of all search modes, field views included).  Everything else -- the *_u8 /
+                                   *_device entry points, the frame batches, weighted / chroma-aware ME, prediction costs, deblocking
+                                   -- is for 8-bit pictures and fails with a message instead of reading 16-bit samples as bytes */
   int32_t search_range;         /* input->search_range */
   int32_t max_num_references;   /* img->max_num_references */
   int32_t rdopt;                /* input->rdopt */

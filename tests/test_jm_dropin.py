@@ -130,7 +130,8 @@ def test_mode_decision_costs_and_paged_planes(tmp_path, me_lib_path, args, want)
                                   "interlace_field_pictures", "interlace_picture_adaptive", "interlace_mbaff_field_macroblocks",
                                   "interlace_mbaff_adaptive", "interlace_picture_and_mbaff_adaptive_chroma_me", "interlace_field_pictures_epzs",
                                   "high_bit_depth_10_bframes", "high_bit_depth_12_bframes", "high_bit_depth_10_sad_sse_rdopt0",
-                                  "high_bit_depth_10_field_pictures"])
+                                  "high_bit_depth_10_field_pictures", "high_bit_depth_10_epzs", "high_bit_depth_10_umhex",
+                                  "high_bit_depth_10_full_search_mode_rdopt0"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -249,6 +250,13 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
             args += ["-p", "MEDistortionHPel=0", "-p", "MEDistortionQPel=1", "-p", "RDOptimization=0", "-p", "Transform8x8Mode=0"]
         if "field_pictures" in case:
             args += ["-p", "PicInterlace=1", "-p", "ReferenceReorder=0", "-p", "PocMemoryManagement=0"]
+        if case.endswith("_epzs"):
+            args += ["-p", "SearchMode=3"]
+        if case.endswith("_umhex"):
+            args += ["-p", "SearchMode=1"]
+        if "full_search_mode" in case:
+            args[1] = "encoder_baseline.cfg"               # no bi-predictive ME: its range must not exceed SearchRange
+            args += ["-p", "SearchMode=-1", "-p", "SearchRange=8", "-p", "RDOptimization=0"]
     elif case == "epzs_pattern_subpel":
         # SURVEY.md 8(f) row 4, second half: EPZS as shipped (EPZSSubPelME = EPZSSubPelMEBiPred = EPZSSubPelGrid = 1):
         # EPZSSubPelBlockMotionSearch / EPZSSubPelBlockSearchBiPred (me_epzs.c:2390, :2728) on the device
@@ -291,8 +299,8 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     assert _md5(str(a / "test.264")) == _md5(str(b / "test.264"))
     assert _md5(str(a / "test_rec.yuv")) == _md5(str(b / "test_rec.yuv"))
     # the device did the work: plane sets, and the searches of the mode under test
-    pattern = "plain_subpel" in case or "bipred_subpel" in case or "pattern_subpel" in case or case.endswith("_epzs")
-    c = _served(err, ("plane sets", "bi_sub") if "bipred_subpel" in case else ("plane sets",) if "pattern_subpel" in case or case.endswith("_epzs") else ("plane sets", "subpel") if pattern else ("plane sets", "fullpel", "subpel") if "full_search_mode" in case or "full_search_rdopt0" in case
+    pattern = "plain_subpel" in case or "bipred_subpel" in case or "pattern_subpel" in case or case.endswith("_epzs") or case.endswith("_umhex")
+    c = _served(err, ("plane sets", "bi_sub") if "bipred_subpel" in case else ("plane sets",) if "pattern_subpel" in case or case.endswith("_epzs") or case.endswith("_umhex") else ("plane sets", "subpel") if pattern else ("plane sets", "fullpel", "subpel") if "full_search_mode" in case or "full_search_rdopt0" in case
                 else ("plane sets", "ffs", "subpel"))
     if case.startswith("interlace_"):
         import re
