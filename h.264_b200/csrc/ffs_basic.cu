@@ -95,15 +95,17 @@ __device__ __forceinline__ void me_aggregate(const int leaf[16], int part[41])
   for (int i = 0; i < 16; i++) part[25 + i] = leaf[i];
 }
 
-template <bool SSE>
+// Pel = uint16_t: pictures of more than 8 bits per sample -- window and macroblock as 16-bit samples, scalar differences, the window
+// read from plane (0,0) with clamped coordinates (no search-plane copy for such pictures), no chroma terms
+template <bool SSE, typename Pel>
 __global__ void __launch_bounds__(256)
 me_ffs_batch_basic_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
-                          const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                          const Pel *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                           MeResultInt *__restrict__ out, const int *__restrict__ job_list)
 {
   if (cfg.abort_flag && *cfg.abort_flag) return;
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ uint32_t curw[64];
+  __shared__ uint32_t curw[sizeof(Pel) == 1 ? 64 : 128];    // the macroblock: 64 words of four 8-bit samples, or 256 16-bit samples
   __shared__ unsigned long long red[8][ME_NUM_PARTITIONS];
   __shared__ int16_t pmv_s[ME_NUM_PARTITIONS][2];
   __shared__ MeJob sjob;
@@ -117,16 +119,28 @@ me_ffs_batch_basic_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRe
   const MeJob &job = sjob;
   const MeRefDev ref = ref_table[job.list * ME_MAX_REFS + job.ref];
   const int R = me_setup_range(cfg, job.ref);
-  const int n = 2 * R + 16, tp = (n + 3) & ~3, side = 2 * R + 1;
+  const int n = 2 * R + 16, tp = sizeof(Pel) == 1 ? (n + 3) & ~3 : n + 1, side = 2 * R + 1;
   int cx, cy;
   me_search_centre(cfg, R, job.opix_x, job.opix_y, job.pmv16[0], job.pmv16[1], cx, cy);
   const int offx = cx - job.opix_x, offy = cy - job.opix_y;
   uint8_t *tile = smem;   // (n+1) rows of tp bytes (+ one spare row: the 5th word of the last window word may be read)
+  Pel *tile16 = reinterpret_cast<Pel *>(smem);              // 16-bit samples: n rows of tp samples
+  Pel *cur16 = reinterpret_cast<Pel *>(curw);               // ... and the macroblock as 256 samples (curw: 64 words; see below)
 
+  if constexpr (sizeof(Pel) == 1) {
   me_load_window(tile, tp, n, ref, cx, cy, R);
   if (threadIdx.x < 64) {
     int row = threadIdx.x >> 2, c = threadIdx.x & 3;
     curw[threadIdx.x] = *reinterpret_cast<const uint32_t *>(cur + (size_t)(job.opix_y + row) * cur_pitch + job.opix_x + 4 * c);
+  }
+  } else {
+    const Pel *plane = reinterpret_cast<const Pel *>(ref.planes);
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+      const int y = i / n, x = i - y * n;
+      const int sy = me_clamp(cy - R + y + ME_PAD, 0, ref.hp - 1), sx = me_clamp(cx - R + x + ME_PAD, 0, ref.wp - 1);
+      tile16[y * tp + x] = plane[(size_t)sy * ref.pitch + sx];
+    }
+    cur16[threadIdx.x] = cur[(size_t)(job.opix_y + (threadIdx.x >> 4)) * cur_pitch + job.opix_x + (threadIdx.x & 15)];
   }
   if (threadIdx.x < ME_NUM_PARTITIONS) { pmv_s[threadIdx.x][0] = job.pmv[threadIdx.x][0]; pmv_s[threadIdx.x][1] = job.pmv[threadIdx.x][1]; }
   __syncthreads();
@@ -141,8 +155,19 @@ me_ffs_batch_basic_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRe
   for (int idx = threadIdx.x; idx < side * side; idx += blockDim.x) {
     int dy = idx / side, dx = idx - dy * side;
     int leaf[16], part[ME_NUM_PARTITIONS];
-    me_leaf16<SSE>(tile, tp, curw, dx, dy, leaf);
-    if (cfg.chroma.on && ref.chroma[0]) me_leaf_chroma(ref, cfg.chroma, SSE, job.opix_x, job.opix_y, cx - R + dx, cy - R + dy, leaf);
+    if constexpr (sizeof(Pel) == 1) {
+      me_leaf16<SSE>(tile, tp, curw, dx, dy, leaf);
+      if (cfg.chroma.on && ref.chroma[0]) me_leaf_chroma(ref, cfg.chroma, SSE, job.opix_x, job.opix_y, cx - R + dx, cy - R + dy, leaf);
+    } else {
+#pragma unroll
+      for (int b = 0; b < 16; b++) leaf[b] = 0;
+      for (int row = 0; row < 16; row++)
+#pragma unroll
+        for (int col = 0; col < 16; col++) {
+          const int d = (int)tile16[(dy + row) * tp + dx + col] - (int)cur16[row * 16 + col];
+          leaf[(row >> 2) * 4 + (col >> 2)] += SSE ? d * d : abs(d);
+        }
+    }
     me_aggregate(leaf, part);
     int sidx = me_spiral_index(dx - R, dy - R);
     bool is00 = (!cfg.rdopt) && dx == dx00 && dy == dy00;
@@ -279,10 +304,19 @@ extern "C" void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const M
   int R = cfg->search_range, n = 2 * R + 16, tp = (n + 3) & ~3;
   size_t smem = (size_t)(n + 1) * tp + 16;
   int grid = job_list ? (n_jobs < 296 ? n_jobs : 296) : n_jobs;
+  if (cfg->pel16) {
+    const uint16_t *cur16 = reinterpret_cast<const uint16_t *>(cur);
+    smem = (size_t)n * (n + 1) * sizeof(uint16_t);          // 41.8 KB at R = 64: inside the default limit
+    if (cfg->metric[0])
+      me_ffs_batch_basic_kernel<true, uint16_t><<<grid, 256, smem, st>>>(jobs, n_jobs, ref_table, cur16, cur_pitch, *cfg, out, job_list);
+    else
+      me_ffs_batch_basic_kernel<false, uint16_t><<<grid, 256, smem, st>>>(jobs, n_jobs, ref_table, cur16, cur_pitch, *cfg, out, job_list);
+    return;
+  }
   if (cfg->metric[0])
-    me_ffs_batch_basic_kernel<true><<<grid, 256, smem, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, out, job_list);
+    me_ffs_batch_basic_kernel<true, uint8_t><<<grid, 256, smem, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, out, job_list);
   else
-    me_ffs_batch_basic_kernel<false><<<grid, 256, smem, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, out, job_list);
+    me_ffs_batch_basic_kernel<false, uint8_t><<<grid, 256, smem, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, out, job_list);
 }
 
 extern "C" void me_launch_ffs_surfaces(const MeRefDev *ref, const uint8_t *cur, int cur_pitch, int opix_x, int opix_y,

@@ -1476,7 +1476,6 @@ static int use_basic_only()
 
 int me_cuda_frame_search_device(const void *d_jobs, int n_jobs, void *d_out, void *d_out_int, void *stream)
 {
-  if (int rc = only8("me_cuda_frame_search")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_jobs <= 0) return 0;
   if (g.view) return fail(1, "me_cuda_frame_search: a field view of the current picture is selected (the frame batch reads the picture as uploaded: upload the field itself)");
@@ -1543,7 +1542,6 @@ static int check_jobs(const me_mb_job *jobs, int first, int n)
 
 int me_cuda_frame_search(const me_mb_job *jobs, int n_jobs, me_mb_result *out, me_mb_result_int *out_int)
 {
-  if (int rc = only8("me_cuda_frame_search")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_jobs <= 0) return 0;
   // Pinned (page-locked) caller buffers are visible to the device under unified addressing: the kernels then read the job array and

@@ -119,16 +119,17 @@ __device__ __forceinline__ const Pel *tile_ptr(const MeRefDev &r, int x4, int y4
 
 // ------------------------------------------------------------------------------------------------------------------
 // batch: one CTA per (macroblock, list, ref) job, all 41 partitions
+template <typename Pel>
 __global__ void __launch_bounds__(256)
 me_subpel_batch_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDev *__restrict__ ref_table,
-                       const uint8_t *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
+                       const Pel *__restrict__ cur, int cur_pitch, MeCfgDev cfg,
                        const MeResultInt *__restrict__ in_int, MeResult *__restrict__ out)
 {
   if (cfg.abort_flag && *cfg.abort_flag) return;
   __shared__ int cost_s[ME_NUM_PARTITIONS][9];
   __shared__ int mv_s[ME_NUM_PARTITIONS][2];
   __shared__ int min_s[ME_NUM_PARTITIONS];
-  __shared__ uint8_t cur_s[16][16];
+  __shared__ Pel cur_s[16][16];
   __shared__ MeJob sjob;
   const int job_id = blockIdx.x;
   if (job_id >= n_jobs) return;
@@ -174,12 +175,13 @@ me_subpel_batch_kernel(const MeJob *__restrict__ jobs, int n_jobs, const MeRefDe
       int x4 = ((job.opix_x + 4 * px + ME_PAD) << 2) + mv_s[p][0] + step * c_sp_x[c];
       int y4 = ((job.opix_y + 4 * py + ME_PAD) << 2) + mv_s[p][1] + step * c_sp_y[c];
       int bx = 4 * (tx - px), by = 4 * (ty - py);
-      const uint8_t *rp = tile_ptr<uint8_t>(ref, x4, y4, bx, by, metric == 2);
-      const uint8_t *sp = &cur_s[4 * ty][4 * tx];
+      const Pel *rp = tile_ptr<Pel>(ref, x4, y4, bx, by, metric == 2);
+      const Pel *sp = &cur_s[4 * ty][4 * tx];
       const MeBiW nobw = { 0, 0, 0, 0, 0, { 0, 0 }, { 0, 0 }, { 0, 0 } };
-      int d = use8 ? tile_dist<8, uint8_t>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw)
-                   : tile_dist<4, uint8_t>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw);
+      int d = use8 ? tile_dist<8, Pel>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw)
+                   : tile_dist<4, Pel>(metric, sp, 16, 16, 0, 0, rp, ref.pitch, nullptr, 0, nobw);
       // chroma terms of computeSAD / computeSSE (me_distortion.c:376-402, :1069-1091): once per block, by the lane of its first tile
+      if constexpr (sizeof(Pel) == 1)
       if (cfg.chroma.on && metric != 2 && bx == 0 && by == 0 && ref.chroma[0])
         for (int k = 0; k < 2; k++)
           d += cfg.chroma.weight * me_cr_block(cfg.chroma, metric, k, job.opix_x + 4 * px, job.opix_y + 4 * py, me_bsx(t), me_bsy(t),
@@ -1045,7 +1047,10 @@ extern "C" void me_launch_subpel_batch(const MeJob *jobs, int n_jobs, const MeRe
                                        int cur_pitch, const MeCfgDev *cfg, const MeResultInt *in_int, MeResult *out,
                                        cudaStream_t st)
 {
-  me_subpel_batch_kernel<<<n_jobs, 256, 0, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, in_int, out);
+  if (cfg->pel16)
+    me_subpel_batch_kernel<uint16_t><<<n_jobs, 256, 0, st>>>(jobs, n_jobs, ref_table, reinterpret_cast<const uint16_t *>(cur), cur_pitch, *cfg, in_int, out);
+  else
+    me_subpel_batch_kernel<uint8_t><<<n_jobs, 256, 0, st>>>(jobs, n_jobs, ref_table, cur, cur_pitch, *cfg, in_int, out);
 }
 
 extern "C" void me_launch_bipred_batch(const me_bipred_job *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur,

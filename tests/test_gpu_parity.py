@@ -124,8 +124,10 @@ def test_high_bit_depth_planes_and_dropin_calls(pkg, oracle_lib):
     oracle_lib.set_bit_depth(10)
     try:
         with pkg.MeCuda(w, h, search_range=16, max_num_references=2, transform8x8=cfgkw["transform8x8"], bit_depth=10) as me:
+            hds = []
             for i in tr.ref_ids():
                 hd, sub = me.ref_create_imgpel(tr.ref(i), want_planes=True)
+                hds.append(hd)
                 ref = oracle_lib.Ref(tr.ref(i))
                 assert sub.dtype == np.uint16 and np.array_equal(sub, ref.planes()), i
                 ref.close()
@@ -135,7 +137,22 @@ def test_high_bit_depth_planes_and_dropin_calls(pkg, oracle_lib):
             with pytest.raises(MeCudaError):
                 me.ref_create(tr.ref(tr.ref_ids()[0]).astype(np.uint8))      # 8-bit entry point on a 10-bit library
             with pytest.raises(MeCudaError):
-                me.frame_search(np.zeros(1, pkg.JOB_DTYPE))                  # the frame batch is 8-bit only
+                me.frame_bipred(np.zeros(1, pkg.BIPRED_JOB_DTYPE), 1, 8, 2)  # the bi-predictive frame batch is 8-bit only
+            # the frame batch on 16-bit samples (general kernels): all 41 partitions of every macroblock against the oracle
+            from h264_b200 import synth
+            ids = tr.ref_ids()
+            cur = tr.cur(tr.cur_ids()[-1])
+            me.set_ref_list(0, hds[:2])
+            me.set_current_imgpel(cur)
+            jobs = synth.synthetic_jobs(w, h, min(2, len(ids)), (334459, 334459, 334459), seed=9)
+            out, out_int = me.frame_search(jobs, want_int=True)
+            ocfg = oracle_lib.make_cfg(search_range=16, transform8x8=cfgkw["transform8x8"])
+            for r in range(min(2, len(ids))):
+                oref = oracle_lib.Ref(tr.ref(ids[r]))
+                sel = np.nonzero(jobs["ref"] == r)[0]
+                exp, exp_int = oracle_lib.mb_search(ocfg, np.ascontiguousarray(cur), oref, jobs[sel])
+                assert np.array_equal(out_int[sel], exp_int) and np.array_equal(out[sel], exp), r
+                oref.close()
     finally:
         oracle_lib.set_bit_depth(8)
     impl = CudaAdapter(tr, cfgkw, max_refs=2)
