@@ -581,7 +581,8 @@ me_ffs_block_subpel_kernel(const int32_t *__restrict__ surf_p, int setup_range, 
 
 // SetMotionVectorPredictor (mv-search.c:87-281), frame macroblocks (no MBAFF): st = ref_idx / mv of the 4x4 blocks around and
 // inside the macroblock ([row + 1][col + 1]); block at 4x4 position (bx4, by4), size bsx x bsy pixels.
-struct PmsState { int8_t ref_idx[5][6]; int16_t mv[5][6][2]; };
+// d_ref / d_mv: MBAFF frames only (mbaff != 0) -- neighbour D of a block in column 0 and row k, sample (-1, 4k - 1) (me_cuda.h)
+struct PmsState { int8_t ref_idx[5][6]; int16_t mv[5][6][2]; int8_t d_ref[4]; int16_t d_mv[4][2]; int mbaff; };
 __device__ void pms_predictor(const PmsState &st, int ref_frame, int bx4, int by4, int bsx, int bsy, int &pmx, int &pmy)
 {
   const int mb_x = 4 * bx4, mb_y = 4 * by4;
@@ -595,7 +596,12 @@ __device__ void pms_predictor(const PmsState &st, int ref_frame, int bx4, int by
     n.ok = st.ref_idx[n.r][n.c] != ME_PMS_UNAVAILABLE;
     return n;
   };
-  const Nb a = nb(mb_x - 1, mb_y), b = nb(mb_x, mb_y - 1), d = nb(mb_x - 1, mb_y - 1);
+  const Nb a = nb(mb_x - 1, mb_y), b = nb(mb_x, mb_y - 1);
+  Nb d = nb(mb_x - 1, mb_y - 1);
+  // MBAFF: in column 0 the neighbour D below the first row lies in the left macroblock pair at sample row mb_y - 1, which need not be
+  // the 4x4 row above A's (frame / field pairs interleave their rows): its own entry, marked by row index -1
+  const bool d_sep = st.mbaff && mb_x == 0 && mb_y > 0;
+  if (d_sep) { d.r = -1; d.c = by4; d.ok = st.d_ref[by4] != ME_PMS_UNAVAILABLE; }
   Nb c = nb(mb_x + bsx, mb_y - 1);
   if (mb_y > 0) {                                                            // mv-search.c:111-131
     if (mb_x < 8) {
@@ -604,7 +610,9 @@ __device__ void pms_predictor(const PmsState &st, int ref_frame, int bx4, int by
     } else if (mb_x + bsx == 16) c.ok = false;
   }
   if (!c.ok) c = d;
-  const int rL = a.ok ? st.ref_idx[a.r][a.c] : -1, rU = b.ok ? st.ref_idx[b.r][b.c] : -1, rUR = c.ok ? st.ref_idx[c.r][c.c] : -1;
+  auto ref_of_nb = [&](const Nb &n) -> int { return !n.ok ? -1 : n.r < 0 ? st.d_ref[n.c] : st.ref_idx[n.r][n.c]; };
+  auto mv_of_nb = [&](const Nb &n, int hv) -> int { return !n.ok ? 0 : n.r < 0 ? st.d_mv[n.c][hv] : st.mv[n.r][n.c][hv]; };
+  const int rL = ref_of_nb(a), rU = ref_of_nb(b), rUR = ref_of_nb(c);
   enum { MEDIAN, L, U, UR };
   int type = MEDIAN;
   if (rL == ref_frame && rU != ref_frame && rUR != ref_frame) type = L;
@@ -619,7 +627,7 @@ __device__ void pms_predictor(const PmsState &st, int ref_frame, int bx4, int by
   }
   int pm[2];
   for (int hv = 0; hv < 2; hv++) {
-    const int ma = a.ok ? st.mv[a.r][a.c][hv] : 0, mb = b.ok ? st.mv[b.r][b.c][hv] : 0, mc = c.ok ? st.mv[c.r][c.c][hv] : 0;
+    const int ma = mv_of_nb(a, hv), mb = mv_of_nb(b, hv), mc = mv_of_nb(c, hv);
     int pv;
     if (type == MEDIAN) pv = !(b.ok || c.ok) ? ma : ma + mb + mc - min(ma, min(mb, mc)) - max(ma, max(mb, mc));
     else pv = type == L ? ma : type == U ? mb : mc;
@@ -643,6 +651,12 @@ me_pms_group_kernel(const __grid_constant__ MePmsParams P, const Pel *__restrict
     const int r = threadIdx.x / 6, c = threadIdx.x - 6 * r;
     st.ref_idx[r][c] = P.st.ref_idx[R.list][r][c];
     st.mv[r][c][0] = P.st.mv[R.list][r][c][0]; st.mv[r][c][1] = P.st.mv[R.list][r][c][1];
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 36) {
+    const int k = threadIdx.x - 32;
+    st.d_ref[k] = P.st.d_left_ref_idx[R.list][k];
+    st.d_mv[k][0] = P.st.d_left_mv[R.list][k][0]; st.d_mv[k][1] = P.st.d_left_mv[R.list][k][1];
+    if (k == 0) st.mbaff = P.st.mbaff;
   }
   __syncthreads();
   int hs[4], vs[4];

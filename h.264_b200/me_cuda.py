@@ -25,14 +25,15 @@ BIPRED_JOB_DTYPE = np.dtype([("opix_x", "<i2"), ("opix_y", "<i2"), ("list", "i1"
 BIPRED_RESULT_DTYPE = np.dtype([("mv", "<i2", (2,)), ("bimv", "<i2", (2,)), ("cost", "<i4"), ("iterlist", "<i4")])
 assert JOB_DTYPE.itemsize == 188 and RESULT_DTYPE.itemsize == 328
 # me_mb_motion: motion state around a macroblock (ref_idx -128 = 4x4 block not available), me_pms_item
-MOTION_DTYPE = np.dtype([("ref_idx", "i1", (2, 5, 6)), ("mv", "<i2", (2, 5, 6, 2))])
+MOTION_DTYPE = np.dtype([("ref_idx", "i1", (2, 5, 6)), ("mv", "<i2", (2, 5, 6, 2)), ("mbaff", "i1"), ("reserved", "i1", (3,)),
+                         ("d_left_ref_idx", "i1", (2, 4)), ("d_left_mv", "<i2", (2, 4, 2))])
 PMS_ITEM_DTYPE = np.dtype([("blocktype", "i1"), ("block8x8", "i1")])
 PMS_UNAVAILABLE = -128
 DEBLOCK_MB_DTYPE = np.dtype([("strength", "u1", (2, 4, 16)), ("qp", "i1"), ("qpc", "i1", (2,)), ("alpha_off", "i1"), ("beta_off", "i1"),
                              ("luma_skip", "u1"), ("reserved", "u1", (10,))])
 assert DEBLOCK_MB_DTYPE.itemsize == 144
 assert BIPRED_JOB_DTYPE.itemsize == 32 and BIPRED_RESULT_DTYPE.itemsize == 16
-assert MOTION_DTYPE.itemsize == 300 and PMS_ITEM_DTYPE.itemsize == 2
+assert MOTION_DTYPE.itemsize == 344 and PMS_ITEM_DTYPE.itemsize == 2
 
 # every symbol include/me_cuda.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [

@@ -93,6 +93,7 @@ static struct {
 
 static int active = 0;          /* GPU path in use for this run */
 static int use_pms = 1;         /* one device launch per PartitionMotionSearch call (ME_CUDA_PMS=0: one per block search) */
+static int use_pms_mbaff = 1;   /* ... also for the macroblocks of an MBAFF frame (ME_CUDA_PMS_MBAFF=0: one launch per block search there) */
 static int verify = 0;          /* ME_CUDA_VERIFY=1: run the reference function too, report any difference, keep the reference result */
 static long n_checked = 0, n_mismatch = 0;
 /* calls the device answered, per wrapped function; printed when the module is cleared so that a run (and the tests around it)
@@ -254,6 +255,7 @@ void __wrap_Init_Motion_Search_Module(void)
     active = 1;
     verify = getenv("ME_CUDA_VERIFY") && atoi(getenv("ME_CUDA_VERIFY"));
     use_pms = !(getenv("ME_CUDA_PMS") && !atoi(getenv("ME_CUDA_PMS")));
+    use_pms_mbaff = !(getenv("ME_CUDA_PMS_MBAFF") && !atoi(getenv("ME_CUDA_PMS_MBAFF")));
     use_mc = !(getenv("ME_CUDA_MC") && !atoi(getenv("ME_CUDA_MC"))) && !hbd;
     lazy_planes = !(getenv("ME_CUDA_HOST_PLANES") && atoi(getenv("ME_CUDA_HOST_PLANES")));
     poison_planes = getenv("ME_CUDA_POISON_PLANES") && atoi(getenv("ME_CUDA_POISON_PLANES"));
@@ -513,31 +515,59 @@ static void pass_bipred_weights(int list, short ref, int subpel)
  * 575-674 searches them one after the other without touching the state outside the block).  The reference function then runs
  * unchanged; its block searches are answered from the launch when their arguments equal what the device used (checked in the
  * library), so a wrong guess costs time, never a different result. */
+/* one cell of the motion state from the neighbour at sample (x, y) relative to the macroblock.  MBAFF frames: reference index and
+ * vertical vector component of a neighbour in another macroblock are converted between frame and field units as
+ * SetMotionVectorPredictor does when it reads them (mv-search.c:140-172, :200-236) -- the conversion depends only on the field
+ * flags of the two macroblocks, both known now */
+static void snapshot_cell(int x, int y, int ok, int nlists, int8_t *ref_idx[2], int16_t *mv[2])
+{
+  PixelPos pix;
+  int l, cur_field = img->MbaffFrameFlag && img->mb_data[img->current_mb_nr].mb_field;
+  if (ok) { getLuma4x4Neighbour(img->current_mb_nr, x, y, &pix); ok = pix.available; }
+  for (l = 0; l < 2; l++) {
+    int ref, mvy;
+    if (!ok || l >= nlists) { *ref_idx[l] = ME_PMS_UNAVAILABLE; continue; }
+    ref = enc_picture->ref_idx[l][pix.pos_y][pix.pos_x];
+    mvy = enc_picture->mv[l][pix.pos_y][pix.pos_x][1];
+    if (img->MbaffFrameFlag && pix.mb_addr != img->current_mb_nr) {
+      int nb_field = img->mb_data[pix.mb_addr].mb_field;
+      if (cur_field && !nb_field) { ref = ref * 2; mvy = mvy / 2; }
+      else if (!cur_field && nb_field) { ref = ref >> 1; mvy = mvy * 2; }
+    }
+    *ref_idx[l] = (int8_t)ref;
+    mv[l][0] = enc_picture->mv[l][pix.pos_y][pix.pos_x][0];
+    mv[l][1] = (int16_t)mvy;
+  }
+}
+
 static void snapshot_motion(me_mb_motion *st)
 {
-  int l, r, c, nlists = (img->type == B_SLICE) ? 2 : 1;
+  int r, c, k, nlists = (img->type == B_SLICE) ? 2 : 1;
+  int mbaff = img->MbaffFrameFlag != 0;
   memset(st, 0, sizeof *st);
+  st->mbaff = (int8_t)mbaff;
   for (r = -1; r < 4; r++)
     for (c = -1; c < 5; c++) {
-      PixelPos pix;
+      int8_t *ri[2] = { &st->ref_idx[0][r + 1][c + 1], &st->ref_idx[1][r + 1][c + 1] };
+      int16_t *mv[2] = { st->mv[0][r + 1][c + 1], st->mv[1][r + 1][c + 1] };
       int ok = !(c == 4 && r >= 0);                       /* right of the macroblock: not available (mb_access.c:143) */
-      if (ok) { getLuma4x4Neighbour(img->current_mb_nr, 4 * c, 4 * r, &pix); ok = pix.available; }
-      for (l = 0; l < 2; l++) {
-        if (!ok || l >= nlists) { st->ref_idx[l][r + 1][c + 1] = ME_PMS_UNAVAILABLE; continue; }
-        st->ref_idx[l][r + 1][c + 1] = enc_picture->ref_idx[l][pix.pos_y][pix.pos_x];
-        st->mv[l][r + 1][c + 1][0] = enc_picture->mv[l][pix.pos_y][pix.pos_x][0];
-        st->mv[l][r + 1][c + 1][1] = enc_picture->mv[l][pix.pos_y][pix.pos_x][1];
-      }
+      /* MBAFF: exactly the sample positions SetMotionVectorPredictor asks getLuma4x4Neighbour for (left column x = -1, row above y = -1) */
+      snapshot_cell(mbaff ? (c < 0 ? -1 : 4 * c) : 4 * c, mbaff ? (r < 0 ? -1 : 4 * r) : 4 * r, ok, nlists, ri, mv);
     }
+  for (k = 0; k < 4; k++) {                                /* neighbour D of the blocks in column 0: sample (-1, 4k - 1) */
+    int8_t *ri[2] = { &st->d_left_ref_idx[0][k], &st->d_left_ref_idx[1][k] };
+    int16_t *mv[2] = { st->d_left_mv[0][k], st->d_left_mv[1][k] };
+    snapshot_cell(-1, 4 * k - 1, mbaff, nlists, ri, mv);
+  }
 }
 
 void __real_PartitionMotionSearch(int blocktype, int block8x8, int *lambda_factor);
 void __wrap_PartitionMotionSearch(int blocktype, int block8x8, int *lambda_factor)
 {
-  /* frame and field pictures; not the macroblocks of an MBAFF frame (SetMotionVectorPredictor scales the neighbours' vectors and
-   * reference indices between frame and field macroblocks there, mv-search.c:111-180: those block searches go one by one) */
-  int on = active && use_pms && input->SearchMode == FAST_FULL_SEARCH && !img->MbaffFrameFlag && !input->DisableSubpelME &&
-           blocktype >= 1 && blocktype <= 7;
+  /* frame pictures, field pictures and MBAFF frames (the motion state goes over with the frame / field conversions of
+   * SetMotionVectorPredictor already applied, snapshot_cell) */
+  int on = active && use_pms && input->SearchMode == FAST_FULL_SEARCH && !input->DisableSubpelME &&
+           blocktype >= 1 && blocktype <= 7 && (use_pms_mbaff || !img->MbaffFrameFlag);
   if (on && !L.pms_cached(blocktype, block8x8)) {
     me_mb_motion st;
     me_pms_item items[ME_PMS_MAX_ITEMS];

@@ -245,7 +245,17 @@ int me_cuda_smpUMHEXFullSubPelBlockMotionSearch(short ref, int list, int pic_pix
 typedef struct me_mb_motion {          /* enc_picture->ref_idx[list] / ->mv[list] of the 4x4 blocks getLuma4x4Neighbour can reach */
   int8_t  ref_idx[2][5][6];            /* [list][row + 1][col + 1], rows -1..3, columns -1..4 of the macroblock's 4x4 grid (column 4: row -1) */
   int16_t mv[2][5][6][2];
-} me_mb_motion;
+  /* MBAFF frames (mbaff != 0).  The neighbour a sample position maps to depends on the frame / field state of both macroblock pairs
+   * (getAffNeighbour, mb_access.c), so the cells above are taken at exactly the positions SetMotionVectorPredictor asks for -- left
+   * column at (-1, 4 * row), row above at (4 * col, -1) -- and the neighbour D of a block in column 0, (-1, 4 * row - 1), which is no
+   * longer the cell of the row above, travels separately in d_left[list][row].  Reference indices and vertical vector components of
+   * cells outside the macroblock arrive already converted between frame and field units (mv-search.c:140-172, :200-236: index * 2 or
+   * >> 1, vector / 2 or * 2): the device-side predictor is the same for both kinds of picture. */
+  int8_t  mbaff;
+  int8_t  reserved[3];
+  int8_t  d_left_ref_idx[2][4];
+  int16_t d_left_mv[2][4][2];
+} me_mb_motion;                        /* 344 bytes */
 typedef struct me_pms_item { int8_t blocktype, block8x8; } me_pms_item;
 int me_cuda_pms_begin(const me_mb_motion *state, int n_items, const me_pms_item *items, const int *lambda_factor /* [3] */);
 int me_cuda_pms_cached(int blocktype, int block8x8);     /* 1: results of this PartitionMotionSearch call are waiting */

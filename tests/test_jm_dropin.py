@@ -40,7 +40,7 @@ def _prep(tmp):
 def _run(exe, args, cwd, env=None):
     e = dict(os.environ)
     e["ME_CUDA_LIB"] = os.path.join(ROOT, "h.264_b200", "libme_cuda.so")
-    for k in ("ME_CUDA_DISABLE", "ME_CUDA_VERIFY", "ME_CUDA_PMS", "ME_CUDA_MC", "ME_CUDA_HOST_PLANES", "ME_CUDA_POISON_PLANES", "ME_CUDA_DEBLOCK"):       # a stray switch must not turn the comparison into reference-vs-reference
+    for k in ("ME_CUDA_DISABLE", "ME_CUDA_VERIFY", "ME_CUDA_PMS", "ME_CUDA_PMS_MBAFF", "ME_CUDA_MC", "ME_CUDA_HOST_PLANES", "ME_CUDA_POISON_PLANES", "ME_CUDA_DEBLOCK"):       # a stray switch must not turn the comparison into reference-vs-reference
         e.pop(k, None)
     if env:
         e.update(env)
@@ -308,7 +308,7 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         assert m, err[-800:]
         n_mbaff, n_field_pic = map(int, m.groups())
         assert (n_mbaff > 100) == ("mbaff" in case) and (n_field_pic > 100) == ("picture" in case), (case, m.group(0))
-    if not pattern and "full_search" not in case and "mbaff" not in case:
+    if not pattern and "full_search" not in case:
         # fast full search: one launch per PartitionMotionSearch call, and the device's own motion vector predictors agreed with the
         # reference's SetMotionVectorPredictor on every block search they were used for
         assert c["pms_launches"] > 0 and c["pms_served"] > 0 and c["pms_missed"] == 0, c
