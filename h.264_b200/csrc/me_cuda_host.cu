@@ -13,7 +13,7 @@
 #include "me_common.cuh"
 
 // ---- kernel launchers (planes.cu, ffs_basic.cu, ffs_tuned.cu, subpel.cu) ----
-struct MeBiW { int apply, w1, w2, obi, denom; int cw1[2], cw2[2], cobi[2]; };   // weighted bi-prediction of one `list` argument (subpel.cu)
+struct MeBiW { int apply, w1, w2, obi, denom; int cw1[2], cw2[2], cobi[2]; int maxv; };   // weighted bi-prediction of one `list` argument (subpel.cu)
 struct MeSubpelArgs {
   int pic_pix_x, pic_pix_y, blocktype;
   int pmv_x, pmv_y, mv_x, mv_y, s_mv_x, s_mv_y;
@@ -50,6 +50,7 @@ void me_launch_pred_cost8x8(const void *blocks, int n_regions, int metric, const
                             int32_t *cost4, int32_t *cost8, cudaStream_t st);
 void me_launch_widen_region(const uint8_t *plane, int pitch, int x0, int y0, int w, int h, uint16_t *dst, cudaStream_t st);
 void me_launch_deblock(uint8_t *Y, int ypitch, uint8_t *U, uint8_t *V, int cpitch, int mbw, int mbh, const void *mbs, int *progress, cudaStream_t st);
+void me_launch_weight_planes16(const uint16_t *src, uint16_t *dst, size_t n, int weight, int offset, int log_denom, int max_pel, cudaStream_t st);
 void me_launch_weight_planes(const uint8_t *src, uint8_t *dst, size_t bytes, int weight, int offset, int log_denom, cudaStream_t st);
 void me_launch_ffs_batch_basic(const MeJob *jobs, int n_jobs, const MeRefDev *ref_table, const uint8_t *cur, int cur_pitch,
                                const MeCfgDev *cfg, MeResultInt *out, const int *job_list, cudaStream_t st);
@@ -301,7 +302,7 @@ int search_planes(int list, int idx, RefPic *r, const MeRefDev **dev, const Tens
   const me_ref_handle h = g.list[list][idx];
   if (!(t.valid && t.src == h && t.src_gen == r->gen && t.w == w)) {
     const MeRefDev &d = r->dev;
-    const size_t pb = d.plane_stride * 16, sb = (size_t)d.spitch * d.sh;
+    const size_t pb = d.plane_stride * 16 * g.pel_bytes, sb = (size_t)d.spitch * d.sh;      // 16-bit pictures have no search plane (sb = 0)
     t.valid = false;
     if (t.planes_bytes != pb || t.search_bytes != sb) {
       CK(cudaStreamSynchronize(g.stream));
@@ -309,17 +310,23 @@ int search_planes(int list, int idx, RefPic *r, const MeRefDev **dev, const Tens
       if (t.search) cudaFree(t.search);
       t.planes = t.search = nullptr; t.planes_bytes = t.search_bytes = 0;
       CK(cudaMalloc((void **)&t.planes, pb));
-      CK(cudaMalloc((void **)&t.search, sb));
+      if (sb) CK(cudaMalloc((void **)&t.search, sb));
       t.planes_bytes = pb; t.search_bytes = sb;
-      t.has_map = false;
-      if (int n = me_ffs_tuned_window(g.cfg.search_range))
-        t.has_map = me_make_tensor_map_2d(t.win_map.bytes, t.search, d.sw, d.sh, d.spitch, n + 16, n) == 0;
-      t.has_pmap = me_make_planes_tensor_map(t.planes_map.bytes, t.planes, d.pitch, d.hp, d.plane_stride) == 0;
+      t.has_map = false; t.has_pmap = false;
+      if (g.pel_bytes == 1) {
+        if (int n = me_ffs_tuned_window(g.cfg.search_range))
+          t.has_map = me_make_tensor_map_2d(t.win_map.bytes, t.search, d.sw, d.sh, d.spitch, n + 16, n) == 0;
+        t.has_pmap = me_make_planes_tensor_map(t.planes_map.bytes, t.planes, d.pitch, d.hp, d.plane_stride) == 0;
+      }
     }
     // everything but the luma planes (geometry, chroma planes) is the picture's own: taken afresh, the slot may have served another picture
     t.dev = d; t.dev.planes = t.planes; t.dev.search = t.search;
     // the planes may have been generated on a caller's stream (me_cuda_ref_create_device / me_cuda_ref_update_device)
     if (r->written_on && r->written_on != g.stream) CK(cudaStreamSynchronize(r->written_on));
+    if (g.pel_bytes == 2) {
+      ScopedTimer tm(0, g.stream);
+      me_launch_weight_planes16((const uint16_t *)r->planes, (uint16_t *)t.planes, d.plane_stride * 16, w.weight, w.offset, w.denom, g.cfg.max_pel, g.stream);
+    } else
     { ScopedTimer tm(0, g.stream);
       me_launch_weight_planes(r->planes, t.planes, pb, w.weight, w.offset, w.denom, g.stream);
       me_launch_weight_planes(r->search, t.search, sb, w.weight, w.offset, w.denom, g.stream); }
@@ -495,8 +502,8 @@ int me_cuda_init(const me_cuda_params *p)
   if (p->abi_version != ME_CUDA_ABI_VERSION) return fail(1, "ABI version %d, library is %d", p->abi_version, ME_CUDA_ABI_VERSION);
   if (g.inited) me_cuda_shutdown();
   if (p->bit_depth < 8 || p->bit_depth > 14) return fail(1, "bit depth %d outside 8..14", p->bit_depth);
-  if (p->bit_depth > 8 && (p->chroma_me_enable || p->weighted_me))
-    return fail(1, "bit depth %d: chroma-aware and weighted-prediction ME are implemented for 8-bit pictures only", p->bit_depth);
+  if (p->bit_depth > 8 && p->chroma_me_enable)
+    return fail(1, "bit depth %d: chroma-aware ME is implemented for 8-bit pictures only", p->bit_depth);
   if (p->chroma_me_enable < 0 || p->chroma_me_enable > 2) return fail(1, "ChromaMEEnable %d outside 0..2", p->chroma_me_enable);
   if (p->chroma_me_enable) {
     if (p->yuv_format < 1 || p->yuv_format > 3)
@@ -965,7 +972,6 @@ int me_cuda_set_slice_type(int t) { g.slice_type = t; g.spec.valid = false; retu
 
 int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, int offset_bi, int log_denom)
 {
-  if (apply) if (int rc = only8("me_cuda_set_bipred_weights (weighted bi-prediction)")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (list < 0 || list > 1) return fail(1, "me_cuda_set_bipred_weights: list %d out of range", list);
   MeBiW w = {};
@@ -974,7 +980,7 @@ int me_cuda_set_bipred_weights(int list, int apply, int weight1, int weight2, in
     // lies in the past; the kernels compute in int
     if (weight1 < -128 || weight1 > 128 || weight2 < -128 || weight2 > 128 || offset_bi < -128 || offset_bi > 127 || log_denom < 0 || log_denom > 7)
       return fail(1, "me_cuda_set_bipred_weights: weights %d, %d / offset %d / log denominator %d out of range", weight1, weight2, offset_bi, log_denom);
-    w.apply = 1; w.w1 = weight1; w.w2 = weight2; w.obi = offset_bi; w.denom = log_denom;
+    w.apply = 1; w.w1 = weight1; w.w2 = weight2; w.obi = offset_bi; w.denom = log_denom; w.maxv = g.cfg.max_pel;
     // chroma: like luma until me_cuda_set_bipred_chroma_weights says otherwise (explicit mode leaves chroma at the default
     // weights, i.e. the plain average; implicit mode gives chroma the luma weights, weighted_prediction.c:243-252)
     for (int k = 0; k < 2; k++) { w.cw1[k] = 1 << log_denom; w.cw2[k] = 1 << log_denom; w.cobi[k] = 0; }
@@ -998,7 +1004,6 @@ int me_cuda_set_bipred_chroma_weights(int list, int component, int weight1, int 
 
 int me_cuda_set_ref_weights(int list, int ref, int apply, int weight, int offset, int log_denom)
 {
-  if (apply) if (int rc = only8("me_cuda_set_ref_weights (weighted-prediction ME)")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (list < 0 || list > 1 || ref < 0 || ref >= ME_MAX_REFS) return fail(1, "me_cuda_set_ref_weights: (list %d, ref %d) out of range", list, ref);
   WeightSet w;

@@ -279,3 +279,21 @@ extern "C" void me_launch_planes16(const uint16_t *src, int src_stride, int w, i
   dim3 grid((wp + 31) / 32, (hp + 7) / 8);
   me_planes16_kernel<<<grid, 256, 0, st>>>(src, src_stride, w, h, planes, pitch, plane_stride, max_pel);
 }
+
+// the same for 16-bit samples (more than 8 bits per sample): computed per sample, clip at img->max_imgpel_value
+__global__ void __launch_bounds__(256)
+me_weight_planes16_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, size_t n, int weight, int offset, int log_denom, int max_pel)
+{
+  const int round = log_denom ? 1 << (log_denom - 1) : 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = (uint16_t)me_clamp(((weight * (int)src[i] + round) >> log_denom) + offset, 0, max_pel);
+}
+
+extern "C" void me_launch_weight_planes16(const uint16_t *src, uint16_t *dst, size_t n, int weight, int offset, int log_denom, int max_pel,
+                                          cudaStream_t st)
+{
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks == 0) return;
+  me_weight_planes16_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n, weight, offset, log_denom, max_pel);
+}

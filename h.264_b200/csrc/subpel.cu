@@ -63,14 +63,14 @@ __device__ __noinline__ int hadamard8(int d[64])
 
 // Weighted bi-prediction (computeBiPred*2, me_distortion.c:556, :907, :1254): what FullPelBlockMotionBiPred /
 // SubPelBlockSearchBiPred derive from their `list` argument (me_fullsearch.c:202-234, :538-590).  Same layout in me_cuda_host.cu.
-struct MeBiW { int apply, w1, w2, obi, denom; int cw1[2], cw2[2], cobi[2]; };   // c*: the same for the two chroma components
+struct MeBiW { int apply, w1, w2, obi, denom; int cw1[2], cw2[2], cobi[2]; int maxv; };   // c*: the same for the two chroma components; maxv: img->max_imgpel_value (set with apply)
 
 // prediction sample of a bi-predictive distortion: (p1 + p2 + 1) >> 1 (me_distortion.c:502), or with weights
 // iClip1(255, ((weight1 * p1 + weight2 * p2 + 2 * wp_luma_round) >> (denom + 1)) + offsetBi)
 __device__ __forceinline__ int bipred_pel(int p1, int p2, const MeBiW &w)
 {
   if (!w.apply) return (p1 + p2 + 1) >> 1;
-  return me_clamp(((w.w1 * p1 + w.w2 * p2 + (w.denom ? 1 << w.denom : 0)) >> (w.denom + 1)) + w.obi, 0, 255);
+  return me_clamp(((w.w1 * p1 + w.w2 * p2 + (w.denom ? 1 << w.denom : 0)) >> (w.denom + 1)) + w.obi, 0, w.maxv);
 }
 
 // distortion of one N x N tile.  metric: 0 SAD, 1 SSE, 2 SATD.  p2 != nullptr: bi-prediction.

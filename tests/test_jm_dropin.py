@@ -131,7 +131,8 @@ def test_mode_decision_costs_and_paged_planes(tmp_path, me_lib_path, args, want)
                                   "interlace_mbaff_adaptive", "interlace_picture_and_mbaff_adaptive_chroma_me", "interlace_field_pictures_epzs",
                                   "high_bit_depth_10_bframes", "high_bit_depth_12_bframes", "high_bit_depth_10_sad_sse_rdopt0",
                                   "high_bit_depth_10_field_pictures", "high_bit_depth_10_epzs", "high_bit_depth_10_umhex",
-                                  "high_bit_depth_10_full_search_mode_rdopt0"])
+                                  "high_bit_depth_10_full_search_mode_rdopt0",
+                                  "high_bit_depth_10_weighted_pred_fade", "high_bit_depth_10_weighted_bipred_fade"])
 def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
     """BASELINE configs (reduced frame counts): lencod_cuda against the plain reference binary on the same input"""
     import sys
@@ -254,6 +255,12 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
             args += ["-p", "SearchMode=3"]
         if case.endswith("_umhex"):
             args += ["-p", "SearchMode=1"]
+        if "weighted_pred_fade" in case:                   # explicit weights, searches on weighted 16-bit reference samples
+            args[1] = "encoder_main.cfg"
+            args += ["-p", "SourceWidth=176", "-p", "SourceHeight=144", "-p", "FramesToBeEncoded=4", "-p", "FrameSkip=0", "-p", "NumberBFrames=0",
+                     "-p", "NumberReferenceFrames=3", "-p", "WeightedPrediction=1", "-p", "UseWeightedReferenceME=1"]
+        if "weighted_bipred_fade" in case:                 # weighted bi-predictive searches (computeBiPred*2), clip at 1023
+            args += ["-p", "FramesToBeEncoded=3", "-p", "WeightedBiprediction=1", "-p", "WeightedPrediction=1"]
         if "full_search_mode" in case:
             args[1] = "encoder_baseline.cfg"               # no bi-predictive ME: its range must not exceed SearchRange
             args += ["-p", "SearchMode=-1", "-p", "SearchRange=8", "-p", "RDOptimization=0"]
@@ -286,7 +293,9 @@ def test_configs_match_reference_encoder(tmp_path, me_lib_path, case):
         _prep(str(d))
         if "InputFile=hbd.yuv" in args:
             import numpy as np
-            src = np.fromfile(os.path.join(REF_DIR, "fixtures", "foreman_part_qcif.yuv"), np.uint8).astype(np.uint16)
+            if "fade" in case:
+                synth.write_yuv420(str(d / "fade8.yuv"), 176, 144, 7, kind="fade")
+            src = np.fromfile(str(d / "fade8.yuv") if "fade" in case else os.path.join(REF_DIR, "fixtures", "foreman_part_qcif.yuv"), np.uint8).astype(np.uint16)
             sh = bits - 8
             ((src << sh) + np.random.default_rng(5).integers(0, 1 << sh, src.shape).astype(np.uint16)).astype("<u2").tofile(str(d / "hbd.yuv"))
         if "InputFile=syn.yuv" in args:

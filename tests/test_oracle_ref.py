@@ -119,3 +119,30 @@ def test_oracle_reproduces_high_bit_depth_runs(tmp_path, oracle_lib, bits, profi
     for key, (n, bad) in res.items():
         assert not bad, (bits, key, n, bad[:3])
     assert res["ffs"][0] > 15000 and res["bi_full"][0] > 500
+
+
+@pytest.mark.parametrize("name,args", [
+    ("weighted_pred", ["-d", "encoder_main.cfg", "-p", "SourceWidth=176", "-p", "SourceHeight=144", "-p", "FramesToBeEncoded=4", "-p", "FrameSkip=0",
+                       "-p", "NumberBFrames=0", "-p", "NumberReferenceFrames=3", "-p", "WeightedPrediction=1", "-p", "UseWeightedReferenceME=1"]),
+    ("weighted_bipred", ["-d", "encoder.cfg", "-p", "NumberReferenceFrames=2", "-p", "FramesToBeEncoded=3", "-p", "WeightedBiprediction=1",
+                         "-p", "WeightedPrediction=1"])])
+def test_oracle_reproduces_weighted_high_bit_depth_runs(tmp_path, oracle_lib, name, args):
+    """10-bit fading clip: weighted reference samples / weighted bi-prediction with the clip at 1023 in the 16-bit build of the oracle"""
+    import numpy as np
+    import h264_b200_pkg  # noqa: F401
+    from h264_b200 import synth
+    from trace_util import REC_FFS, REC_BI_FULL
+    synth.write_yuv420(str(tmp_path / "fade8.yuv"), 176, 144, 7, kind="fade")
+    src = np.fromfile(str(tmp_path / "fade8.yuv"), np.uint8).astype(np.uint16)
+    ((src << 2) + np.random.default_rng(5).integers(0, 4, src.shape).astype(np.uint16)).astype("<u2").tofile(str(tmp_path / "hbd.yuv"))
+    tr = _trace(str(tmp_path), args + ["-p", "InputFile=hbd.yuv", "-p", "BitDepthLuma=10", "-p", "BitDepthChroma=10", "-p", "ProfileIDC=110",
+                                      "-p", "SearchRange=16"])
+    assert tr.bits == 10 and set(tr.of_type(REC_FFS)[:, 29].tolist()) - {32}, "the fading clip must produce non-default weights"
+    if name == "weighted_bipred":
+        assert (tr.of_type(REC_BI_FULL)[:, 29] > 0).all()
+    impl = OracleAdapter(tr, cfg_from_trace(tr, search_range=16, full_search=2))
+    res = replay(tr, impl)
+    impl.close()
+    for key, (n, bad) in res.items():
+        assert not bad, (name, key, n, bad[:3])
+    assert res["ffs"][0] > 20000
