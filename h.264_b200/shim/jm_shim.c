@@ -933,9 +933,9 @@ int __wrap_BIDPartitionCost(Macroblock *currMB, int blocktype, int block8x8, sho
   int step_h = input->part_size[blocktype][0], step_v = input->part_size[blocktype][1];
   int bx = bx0[parttype][block8x8], by = by0[parttype][block8x8];
   int v, h, rx, ry, k, n = 0, mvd_bits = 0, mcost, use8 = input->Transform8x8Mode && blocktype <= 4;
-  /* MBAFF frames: LumaPrediction indexes the weight tables through the field macroblock's list offset and halved reference indices
-   * (macroblock.c:846-860); left to the reference's host code, which reads the planes through the paging line accessors */
-  if (!active || !use_mc || img->MbaffFrameFlag) return __real_BIDPartitionCost(currMB, blocktype, block8x8, ref_l0, ref_l1, lambda_factor);
+  /* MBAFF frames too: LumaPrediction takes its pictures from listX[list + currMB->list_offset] (macroblock.c:862-871) -- the lists
+   * mb_sync has set for this macroblock -- and the reference does not combine weighted prediction with MBAFF (configfile.c:1114) */
+  if (!active || !use_mc) return __real_BIDPartitionCost(currMB, blocktype, block8x8, ref_l0, ref_l1, lambda_factor);
   mb_sync();
   /* motion-vector rate (mv-search.c:1083-1096): host arithmetic on the encoder's own arrays */
   for (v = by; v < by + step_v0; v += step_v)
@@ -973,7 +973,7 @@ int __wrap_GetDirectCost8x8(Macroblock *currMB, int block, int *cost8x8)
   me_pred_block blocks[4];
   int32_t c4, c8;
   int k, bx = (block % 2) * 2, by = (block / 2) * 2, cost, in8 = *cost8x8;
-  if (!active || !use_mc || img->MbaffFrameFlag) return __real_GetDirectCost8x8(currMB, block, cost8x8);
+  if (!active || !use_mc) return __real_GetDirectCost8x8(currMB, block, cost8x8);
   mb_sync();
   for (k = 0; k < 4; k++) {
     int h = bx + (k & 1), v = by + (k >> 1);
