@@ -21,19 +21,21 @@ struct PredBlock {
 static_assert(sizeof(PredBlock) == sizeof(me_pred_block), "me_pred_block layout");
 
 // origin of the block in one list's plane set (OneComponentLumaPrediction, macroblock.c:816)
-__device__ __forceinline__ const uint8_t *block_origin(const MeRefDev *table, const PredBlock &b, int list)
+template <typename Pel = uint8_t>
+__device__ __forceinline__ const Pel *block_origin(const MeRefDev *table, const PredBlock &b, int list)
 {
   const MeRefDev &r = table[list * ME_MAX_REFS + b.ref[list]];
-  return me_umv_ptr(r, ((b.pix_y + ME_PAD) << 2) + b.mv[list][1], ((b.pix_x + ME_PAD) << 2) + b.mv[list][0]);
+  return me_umv_ptr_p<Pel>(r, ((b.pix_y + ME_PAD) << 2) + b.mv[list][1], ((b.pix_x + ME_PAD) << 2) + b.mv[list][0]);
 }
 
 // sample of the prediction from the sample(s) of the listed picture(s) (LumaPrediction, macroblock.c:876-930)
-__device__ __forceinline__ int pred_pel(const PredBlock &b, int l0, int l1)
+// max_pel: img->max_imgpel_value (255 for 8-bit pictures)
+__device__ __forceinline__ int pred_pel(const PredBlock &b, int l0, int l1, int max_pel = 255)
 {
   if (b.apply_weights) {
     const int round = (1 << b.log_denom) >> 1;                        // wp_luma_round (weighted_prediction.c:50)
-    if (b.p_dir == 2) return me_clamp(((b.weight[0] * l0 + b.weight[1] * l1 + 2 * round) >> (b.log_denom + 1)) + b.offset, 0, 255);
-    return me_clamp(((b.weight[0] * (b.p_dir ? l1 : l0) + round) >> b.log_denom) + b.offset, 0, 255);
+    if (b.p_dir == 2) return me_clamp(((b.weight[0] * l0 + b.weight[1] * l1 + 2 * round) >> (b.log_denom + 1)) + b.offset, 0, max_pel);
+    return me_clamp(((b.weight[0] * (b.p_dir ? l1 : l0) + round) >> b.log_denom) + b.offset, 0, max_pel);
   }
   return b.p_dir == 2 ? (l0 + l1 + 1) >> 1 : b.p_dir ? l1 : l0;
 }
@@ -76,9 +78,11 @@ me_luma_prediction_kernel(const PredBlock *__restrict__ blocks, int n, int bsx, 
 
 // one warp per 8x8 region: lane -> row (lane >> 2), columns 2 * (lane & 3) and + 1.  The differences go through shared memory
 // to the lanes that own a transform: lanes 0..3 one 4x4 block each, lanes 8..15 one row / column of the 8x8 transform each.
+// Pel = uint16_t: pictures of more than 8 bits per sample (16-bit planes and current picture, weighted samples clip at max_pel)
+template <typename Pel>
 __global__ void __launch_bounds__(128)
 me_pred_cost8x8_kernel(const PredBlock *__restrict__ blocks, int n_regions, int metric, const MeRefDev *__restrict__ table,
-                       const uint8_t *__restrict__ cur, int cur_pitch, int32_t *__restrict__ cost4, int32_t *__restrict__ cost8)
+                       const Pel *__restrict__ cur, int cur_pitch, int max_pel, int32_t *__restrict__ cost4, int32_t *__restrict__ cost8)
 {
   __shared__ int diff[4][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,18 +96,18 @@ me_pred_cost8x8_kernel(const PredBlock *__restrict__ blocks, int n_regions, int 
       const int j = row & 3, i = col & 3;
       int l0[2] = { 0, 0 }, l1[2] = { 0, 0 };
       if (b.p_dir == 0 || b.p_dir == 2) {
-        const uint8_t *p = block_origin(table, b, 0) + (size_t)j * table[b.ref[0]].pitch + i;
+        const Pel *p = block_origin<Pel>(table, b, 0) + (size_t)j * table[b.ref[0]].pitch + i;
         l0[0] = p[0]; l0[1] = p[1];
       }
       if (b.p_dir == 1 || b.p_dir == 2) {
-        const uint8_t *p = block_origin(table, b, 1) + (size_t)j * table[ME_MAX_REFS + b.ref[1]].pitch + i;
+        const Pel *p = block_origin<Pel>(table, b, 1) + (size_t)j * table[ME_MAX_REFS + b.ref[1]].pitch + i;
         l1[0] = p[0]; l1[1] = p[1];
       }
       // the block's position in the picture: its own pix_x / pix_y (the four blocks of a region are adjacent in the callers, but
       // nothing here relies on it)
-      const uint8_t *c = cur + (size_t)(b.pix_y + j) * cur_pitch + b.pix_x + i;
-      d[8 * row + col] = (int)c[0] - pred_pel(b, l0[0], l1[0]);
-      d[8 * row + col + 1] = (int)c[1] - pred_pel(b, l0[1], l1[1]);
+      const Pel *c = cur + (size_t)(b.pix_y + j) * cur_pitch + b.pix_x + i;
+      d[8 * row + col] = (int)c[0] - pred_pel(b, l0[0], l1[0], max_pel);
+      d[8 * row + col + 1] = (int)c[1] - pred_pel(b, l0[1], l1[1], max_pel);
     }
     __syncwarp();
     if (allowed != 0xffffffffu) {                                    // GetDirectCost8x8: direct mode not allowed for a block of the region
@@ -184,11 +188,15 @@ extern "C" void me_launch_luma_prediction(const void *blocks, int n, int bsx, in
 }
 
 extern "C" void me_launch_pred_cost8x8(const void *blocks, int n_regions, int metric, const MeRefDev *table, const uint8_t *cur,
-                                       int cur_pitch, int32_t *cost4, int32_t *cost8, cudaStream_t st)
+                                       int cur_pitch, int pel16, int max_pel, int32_t *cost4, int32_t *cost8, cudaStream_t st)
 {
   int grid = (n_regions + 3) / 4;
   if (grid > 148 * 8) grid = 148 * 8;
-  me_pred_cost8x8_kernel<<<grid, 128, 0, st>>>((const PredBlock *)blocks, n_regions, metric, table, cur, cur_pitch, cost4, cost8);
+  if (pel16)
+    me_pred_cost8x8_kernel<uint16_t><<<grid, 128, 0, st>>>((const PredBlock *)blocks, n_regions, metric, table, reinterpret_cast<const uint16_t *>(cur),
+                                                            cur_pitch, max_pel, cost4, cost8);
+  else
+    me_pred_cost8x8_kernel<uint8_t><<<grid, 128, 0, st>>>((const PredBlock *)blocks, n_regions, metric, table, cur, cur_pitch, 255, cost4, cost8);
 }
 
 extern "C" void me_launch_widen_region(const uint8_t *plane, int pitch, int x0, int y0, int w, int h, uint16_t *dst, cudaStream_t st)

@@ -47,7 +47,7 @@ void me_launch_widen_planes(const uint8_t *planes, int pitch, size_t plane_strid
 void me_launch_check_jobs(const MeJob *jobs, int n_jobs, int n_refs0, int n_refs1, int width, int height, int *bad, cudaStream_t st);
 void me_launch_luma_prediction(const void *blocks, int n, int bsx, int bsy, const MeRefDev *table, uint8_t *pred, cudaStream_t st);
 void me_launch_pred_cost8x8(const void *blocks, int n_regions, int metric, const MeRefDev *table, const uint8_t *cur, int cur_pitch,
-                            int32_t *cost4, int32_t *cost8, cudaStream_t st);
+                            int pel16, int max_pel, int32_t *cost4, int32_t *cost8, cudaStream_t st);
 void me_launch_widen_region(const uint8_t *plane, int pitch, int x0, int y0, int w, int h, uint16_t *dst, cudaStream_t st);
 void me_launch_deblock(uint8_t *Y, int ypitch, uint8_t *U, uint8_t *V, int cpitch, int mbw, int mbh, const void *mbs, int *progress, cudaStream_t st);
 void me_launch_weight_planes16(const uint16_t *src, uint16_t *dst, size_t n, int weight, int offset, int log_denom, int max_pel, cudaStream_t st);
@@ -1729,7 +1729,6 @@ int me_cuda_luma_prediction(const me_pred_block *blocks, int n, int bsx, int bsy
 
 int me_cuda_pred_cost8x8(const me_pred_block *blocks, int n_regions, int metric, int32_t *cost4, int32_t *cost8)
 {
-  if (int rc = only8("me_cuda_pred_cost8x8")) return rc;
   if (!g.inited) return fail(1, "me_cuda_init has not been called");
   if (n_regions <= 0) return 0;
   if (metric < 0 || metric > 2) return fail(1, "me_cuda_pred_cost8x8: metric %d", metric);
@@ -1739,7 +1738,7 @@ int me_cuda_pred_cost8x8(const me_pred_block *blocks, int n_regions, int metric,
   uint8_t *d_in, *d_out, *h_out;
   if (int rc = mc_stage(blocks, in, out, &d_in, &d_out, &h_out)) return rc;
   int32_t *d4 = (int32_t *)d_out, *d8 = d4 + n_regions;
-  me_launch_pred_cost8x8(d_in, n_regions, metric, g.d_mc_table, g.cur_view, g.cur_view_pitch, d4, d8, g.stream);
+  me_launch_pred_cost8x8(d_in, n_regions, metric, g.d_mc_table, g.cur_view, g.cur_view_pitch, g.pel_bytes == 2, g.cfg.max_pel, d4, d8, g.stream);
   g.launches++;
   CK(cudaGetLastError());
   if (!h_out) {

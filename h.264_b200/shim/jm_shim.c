@@ -233,8 +233,8 @@ void __wrap_Init_Motion_Search_Module(void)
     p.abi_version = ME_CUDA_ABI_VERSION;
     p.width = img->width; p.height = img->height;
     /* more than 8 bits per sample (imgpel is u16, global.h:50): plane sets, every search stage and the launch per
-     * PartitionMotionSearch run on 16-bit planes; the prediction costs and the deblocking filter stay the reference's host code in
-     * such runs (hbd below), reading the planes through the paging line accessors; weighted / chroma-aware ME is refused */
+     * PartitionMotionSearch and the prediction costs run on 16-bit planes; the deblocking filter stays the reference's host code in
+     * such runs; chroma-aware ME is refused */
     p.bit_depth = img->bitdepth_luma;
     hbd = img->bitdepth_luma > 8;
     if (hbd && IS_INDEPENDENT(input) && img->bitdepth_chroma != img->bitdepth_luma) die("4:4:4 independent mode with different luma / chroma bit depths");
@@ -256,7 +256,7 @@ void __wrap_Init_Motion_Search_Module(void)
     verify = getenv("ME_CUDA_VERIFY") && atoi(getenv("ME_CUDA_VERIFY"));
     use_pms = !(getenv("ME_CUDA_PMS") && !atoi(getenv("ME_CUDA_PMS")));
     use_pms_mbaff = !(getenv("ME_CUDA_PMS_MBAFF") && !atoi(getenv("ME_CUDA_PMS_MBAFF")));
-    use_mc = !(getenv("ME_CUDA_MC") && !atoi(getenv("ME_CUDA_MC"))) && !hbd;
+    use_mc = !(getenv("ME_CUDA_MC") && !atoi(getenv("ME_CUDA_MC")));
     lazy_planes = !(getenv("ME_CUDA_HOST_PLANES") && atoi(getenv("ME_CUDA_HOST_PLANES")));
     poison_planes = getenv("ME_CUDA_POISON_PLANES") && atoi(getenv("ME_CUDA_POISON_PLANES"));
     use_deblock = !(getenv("ME_CUDA_DEBLOCK") && !atoi(getenv("ME_CUDA_DEBLOCK")));

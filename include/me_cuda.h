@@ -57,9 +57,10 @@ typedef struct me_cuda_params {
                                    served by the row-pointer entry points (me_cuda_ref_create, me_cuda_set_current,
                                    me_cuda_ref_download_region), every drop-in search (me_cuda_ffs_setup, me_cuda_pms_*, the block
                                    searches and refinements of all search modes, field views included) and me_cuda_frame_search (general
-                                   kernels), weighted-prediction ME included.  Everything else -- the *_u8 / *_device picture entry points,
-                                   me_cuda_frame_bipred, chroma-aware ME, prediction costs, deblocking -- is for 8-bit pictures and fails
-                                   with a message instead of reading 16-bit samples as bytes */
+                                   kernels), weighted-prediction ME included, and me_cuda_pred_cost8x8.  Everything else -- the *_u8 /
+                                   *_device picture entry points, me_cuda_frame_bipred, chroma-aware ME, me_cuda_luma_prediction,
+                                   deblocking -- is for 8-bit pictures and fails with a message instead of reading 16-bit samples as
+                                   bytes */
   int32_t search_range;         /* input->search_range */
   int32_t max_num_references;   /* img->max_num_references */
   int32_t rdopt;                /* input->rdopt */
