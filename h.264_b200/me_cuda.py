@@ -29,6 +29,7 @@ MOTION_DTYPE = np.dtype([("ref_idx", "i1", (2, 5, 6)), ("mv", "<i2", (2, 5, 6, 2
                          ("d_left_ref_idx", "i1", (2, 4)), ("d_left_mv", "<i2", (2, 4, 2))])
 PMS_ITEM_DTYPE = np.dtype([("blocktype", "i1"), ("block8x8", "i1")])
 PMS_UNAVAILABLE = -128
+ABI_VERSION = 2            # ME_CUDA_ABI_VERSION of include/me_cuda.h
 DEBLOCK_MB_DTYPE = np.dtype([("strength", "u1", (2, 4, 16)), ("qp", "i1"), ("qpc", "i1", (2,)), ("alpha_off", "i1"), ("beta_off", "i1"),
                              ("luma_skip", "u1"), ("reserved", "u1", (10,))])
 assert DEBLOCK_MB_DTYPE.itemsize == 144
@@ -145,7 +146,7 @@ class MeCuda:
         set_current_imgpel); the fast-full-search drop-in path serves them, the 8-bit-only entry points refuse"""
         self.L = load_library(lib_path)
         p = Params()
-        p.abi_version = 1
+        p.abi_version = ABI_VERSION
         p.width, p.height, p.bit_depth = width, height, bit_depth
         p.search_range, p.max_num_references, p.rdopt, p.full_search = search_range, max_num_references, rdopt, full_search
         for i in range(3):

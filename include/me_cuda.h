@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ME_CUDA_ABI_VERSION 1
+#define ME_CUDA_ABI_VERSION 2          /* 2: me_mb_motion grew (MBAFF), bit_depth 8..14, pattern sub-pel entry points, field views */
 
 /* JM's pixel type in the FRExt build: `typedef unsigned short imgpel` (lencod/inc/global.h:50). */
 typedef unsigned short me_imgpel;

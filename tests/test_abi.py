@@ -20,6 +20,9 @@ def test_header_and_binding_agree():
     import h264_b200_pkg  # noqa: F401
     from h264_b200 import me_cuda
     assert header_symbols() == sorted(me_cuda.ABI_SYMBOLS)
+    text = open(os.path.join(ROOT, "include", "me_cuda.h")).read()
+    assert int(re.search(r"#define ME_CUDA_ABI_VERSION (\d+)", text).group(1)) == me_cuda.ABI_VERSION
+    assert me_cuda.MOTION_DTYPE.itemsize == 344                    # me_mb_motion
 
 
 def test_library_exports_every_declared_symbol(me_lib_path):
