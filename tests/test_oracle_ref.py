@@ -146,3 +146,29 @@ def test_oracle_reproduces_weighted_high_bit_depth_runs(tmp_path, oracle_lib, na
     for key, (n, bad) in res.items():
         assert not bad, (name, key, n, bad[:3])
     assert res["ffs"][0] > 20000
+
+
+@pytest.mark.parametrize("case", ["epzs_sub", "umhex_sub", "smpumhex_sub", "epzs_chroma_sad", "hbd10"])
+def test_new_tracer_wrappers_do_not_change_the_bitstream(tmp_path, case):
+    """the fixtures of the pattern searches and of the 10-bit run were traced with lencod_trace (wrappers around the five pattern
+    sub-pel functions, 16-bit dumps): the PLAIN reference encoder must write the bitstream whose md5 was committed with them"""
+    import importlib.util
+    import json
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    fx = os.path.join(REF_DIR, "fixtures")
+    for f in os.listdir(fx):
+        if f.endswith(".cfg") or f.endswith(".yuv"):
+            shutil.copy(os.path.join(fx, f), str(tmp_path))
+    if case == "hbd10":
+        mg.write_hbd_clip(str(tmp_path / "hbd.yuv"), 10)
+        args = ["-d", "encoder.cfg", "-p", "InputFile=hbd.yuv", "-p", "BitDepthLuma=10", "-p", "BitDepthChroma=10", "-p", "ProfileIDC=110",
+                "-p", "SearchRange=16", "-p", "NumberReferenceFrames=2"]
+    else:
+        args = mg.PATTERN_CASES[case][0]
+    r = subprocess.run([os.path.join(REF_DIR, "lencod")] + args, cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-800:]
+    want = json.load(open(os.path.join(GOLDEN, "bitstream_md5.json")))[case]["test.264"]
+    assert hashlib.md5(open(tmp_path / "test.264", "rb").read()).hexdigest() == want
