@@ -19,7 +19,8 @@ import h264_b200_pkg
 from h264_b200 import synth
 synth.write_yuv420("syn.yuv", 352, 288, $FRAMES)
 PY
-ARGS="-d encoder_main.cfg -p InputFile=syn.yuv -p SourceWidth=352 -p SourceHeight=288 -p FramesToBeEncoded=$FRAMES -p FrameSkip=0 -p NumberBFrames=0 -p SearchRange=32 -p NumberReferenceFrames=5 -p LevelIDC=51"
+# EXTRA="-p MbInterlace=2 -p ReferenceReorder=0 -p PocMemoryManagement=0 -p LevelIDC=40": the same clip as MBAFF frames (any further -p overrides)
+ARGS="-d encoder_main.cfg -p InputFile=syn.yuv -p SourceWidth=352 -p SourceHeight=288 -p FramesToBeEncoded=$FRAMES -p FrameSkip=0 -p NumberBFrames=0 -p SearchRange=32 -p NumberReferenceFrames=5 -p LevelIDC=51 $EXTRA"
 export ME_CUDA_LIB="$ROOT/h.264_b200/libme_cuda.so"
 unset ME_CUDA_DISABLE ME_CUDA_VERIFY ME_CUDA_PMS
 "$ROOT"/oracle/_ref/lencod $ARGS > cpu.log 2>&1; cp test.264 cpu.264
@@ -40,7 +41,7 @@ def tot(f):
     return float(re.search(r"Total encoding time for the seq\.\s*:\s*([0-9.]+)", open(f).read()).group(1))
 ver = re.search(r"verify mode: (\d+) calls checked, (\d+) mismatches", open("ver.err").read())
 pms = re.search(r"partition-search launches (\d+), block searches answered from them (\d+), argument mismatches (\d+)", open("gpu.err").read())
-print(json.dumps({"clip": "CIF 352x288, $FRAMES pictures IPPP, SR 32, 5 references", "me_seconds": {"lencod": me("cpu.log"), "lencod_cuda_pms": me("gpu.log"), "lencod_cuda_per_block": me("blk.log")},
+print(json.dumps({"clip": "CIF 352x288, $FRAMES pictures IPPP, SR 32, 5 references", "extra_args": "$EXTRA", "me_seconds": {"lencod": me("cpu.log"), "lencod_cuda_pms": me("gpu.log"), "lencod_cuda_per_block": me("blk.log")},
                   "encode_seconds": {"lencod": tot("cpu.log"), "lencod_cuda_pms": tot("gpu.log"), "lencod_cuda_per_block": tot("blk.log")},
                   "me_ratio_pms_over_cpu": round(me("gpu.log") / me("cpu.log"), 4),
                   "verify_calls": int(ver.group(1)), "verify_mismatches": int(ver.group(2)),
