@@ -1015,7 +1015,9 @@ void __wrap_DeblockFrame(ImageParameters *p_img, imgpel **imgY, imgpel ***imgUV)
   static unsigned mbs_cap = 0;
   unsigned i;
   int chroma = imgUV != NULL && p_img->yuv_format == YUV420;
-  if (!active || !use_deblock || p_img->MbaffFrameFlag || p_img->structure != FRAME || p_img->max_imgpel_value != 255 ||
+  /* frame pictures and field pictures (a field is filtered as a picture of its own: same edge loops, GetStrengthNormal with
+   * mvlimit 2, loopFilter.c:162-164); MBAFF frames (GetStrengthMBAff, mixed frame / field edges) stay the reference's host filter */
+  if (!active || !use_deblock || p_img->MbaffFrameFlag || p_img->max_imgpel_value != 255 ||
       (p_img->yuv_format != YUV420 && p_img->yuv_format != YUV400) || (p_img->width & 15) || (p_img->height & 15)) {
     __real_DeblockFrame(p_img, imgY, imgUV);
     return;
@@ -1049,7 +1051,7 @@ void __wrap_DeblockFrame(ImageParameters *p_img, imgpel **imgY, imgpel ***imgUV)
       for (edge = 0; edge < 4; edge++) {
         int sum = 0;
         if (!(edge || EdgeCondition)) continue;
-        GetStrengthNormal(Strength, p_img, (int)i, dir, edge << 2, 4);
+        GetStrengthNormal(Strength, p_img, (int)i, dir, edge << 2, p_img->structure != FRAME ? 2 : 4);     /* mvlimit, loopFilter.c:162-164 */
         for (k = 0; k < 16; k++) sum += Strength[k];
         if (!sum) continue;
         memcpy(r->strength[dir][edge], Strength, 16);
