@@ -357,8 +357,8 @@ int me_cuda_pred_cost8x8(const me_pred_block *blocks, int n_regions, int metric,
  * the binding pages the planes into StorablePicture::imgY_sub on demand with it instead of copying them all back */
 int me_cuda_ref_download_region(me_ref_handle h, int fy, int fx, int x0, int y0, int w, int hgt, me_imgpel *dst, int dst_stride);
 
-/* ---- in-loop deblocking of the coded picture: DeblockFrame (loopFilter.c:87-253) for frame pictures
- * without MBAFF, 8-bit, 4:0:0 / 4:2:0.  The boundary strengths are the encoder's own (GetStrength, loopFilter.c:262): per macroblock
+/* ---- in-loop deblocking of the coded picture: DeblockFrame (loopFilter.c:87-253) for frame pictures and
+ * field pictures (each field a picture of its own) without MBAFF, 8-bit, 4:0:0 / 4:2:0.  The boundary strengths are the encoder's own (GetStrength, loopFilter.c:262): per macroblock
  * and (direction 0 = vertical edges / 1 = horizontal, edge 0..3) the 16 values DeblockMb got for the edges it filters, zeros for the
  * edges it does not (picture / slice boundary, LFDisableIdc, all-zero strengths). ---- */
 typedef struct me_deblock_mb {
